@@ -1,0 +1,594 @@
+// C ABI (include/eicos_b200.h) over the engine.  Host logic that mirrors the reference's
+// Solver object: data ownership, updateData semantics, Information.
+#include "../../include/eicos_b200.h"
+#include "backend.hpp"
+#include "engine.hpp"
+#include "symbolic.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace eicos;
+
+namespace
+{
+thread_local std::string g_error;
+
+int fail(int code, const std::string &msg)
+{
+    g_error = msg;
+    return code;
+}
+
+void info_from_rows(const double *d, const int *i, eicos_info *o)
+{
+    o->pcost = d[S_PCOST];
+    o->dcost = d[S_DCOST];
+    o->pres = d[S_PRES];
+    o->dres = d[S_DRES];
+    o->pinfres = d[S_PINFRES];
+    o->dinfres = d[S_DINFRES];
+    o->gap = d[S_GAP];
+    o->relgap = d[S_RELGAP];
+    o->sigma = d[S_SIGMA];
+    o->mu = d[S_MU];
+    o->step = d[S_STEP];
+    o->step_aff = d[S_STEP_AFF];
+    o->kapovert = d[S_KAPOVERT];
+    o->pinf = i[J_PINF];
+    o->dinf = i[J_DINF];
+    o->has_pinfres = i[J_HAS_PINFRES];
+    o->has_dinfres = i[J_HAS_DINFRES];
+    o->has_relgap = i[J_HAS_RELGAP];
+    o->iter = i[J_ITER];
+    o->iter_max = Settings::iter_max;
+    o->nitref1 = i[J_NIT1];
+    o->nitref2 = i[J_NIT2];
+    o->nitref3 = i[J_NIT3];
+}
+
+struct DeviceBuffer
+{
+    void *p = nullptr;
+    size_t bytes = 0;
+    void ensure(size_t n)
+    {
+        if (n > bytes)
+        {
+            be::dfree(p);
+            p = be::alloc(n);
+            bytes = n;
+        }
+    }
+    ~DeviceBuffer() { be::dfree(p); }
+};
+} // namespace
+
+struct eicos_batch
+{
+    Symbolic S;
+    std::unique_ptr<Engine> eng;
+    dvec rawG, rawA, c, h, b; // unequilibrated data as given by the caller
+    int device = 0, workers = 4;
+    bool timing = false;
+    SolveStats stats;
+    DeviceBuffer din, dout, dint;
+};
+
+struct eicos_solver
+{
+    // The reference keeps c,h,b in equilibrated form and (un)equilibrates in place; so do we.
+    Symbolic S;
+    std::unique_ptr<Engine> eng;
+    dvec c, h, b;
+    bool equilibrated = false;
+    dvec x, y, z, s;
+    eicos_info info;
+    DeviceBuffer dout, dint;
+    int device = 0;
+};
+
+static int default_workers() { return 4; }
+
+extern "C"
+{
+
+const char *eicos_last_error(void) { return g_error.c_str(); }
+
+int eicos_device_count(void)
+{
+#ifndef EICOS_EMU
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+        return 0;
+    return n;
+#else
+    return 1;
+#endif
+}
+
+/* ------------------------------------------------------------------ batched */
+eicos_batch *eicos_batch_setup(int n, int m, int p, int l, int ncones, const int *q,
+                               const double *Gpr, const int *Gjc, const int *Gir,
+                               const double *Apr, const int *Ajc, const int *Air,
+                               const double *c, const double *h, const double *b,
+                               int device, long long capacity, int workers)
+{
+    (void)l;
+    try
+    {
+        if (n < 0 || m < 0 || p < 0 || ncones < 0 || (n > 0 && !c))
+            throw std::invalid_argument("eicos_batch_setup: negative dimension or missing c");
+        std::unique_ptr<eicos_batch> bt(new eicos_batch());
+        bt->device = device;
+        bt->workers = workers > 0 ? workers : default_workers();
+        analyze(bt->S, n, m, p, ncones, q, Gpr, Gjc, Gir, Apr, Ajc, Air, /*serial_width=*/2);
+        const Symbolic &S = bt->S;
+        if (S.G.nnz())
+            bt->rawG.assign(Gpr, Gpr + S.G.nnz());
+        if (S.A.nnz())
+            bt->rawA.assign(Apr, Apr + S.A.nnz());
+        bt->c.assign(c, c + S.n);
+        if (S.m)
+        {
+            if (!h)
+                throw std::invalid_argument("eicos_batch_setup: h missing");
+            bt->h.assign(h, h + S.m);
+        }
+        if (S.p)
+        {
+            if (!b)
+                throw std::invalid_argument("eicos_batch_setup: b missing");
+            bt->b.assign(b, b + S.p);
+        }
+        be::set_device(device);
+        if (capacity <= 0)
+        {
+            capacity = 4096;
+#ifndef EICOS_EMU
+            size_t fr = 0, tot = 0;
+            EI_CUDA(cudaMemGetInfo(&fr, &tot));
+            // rows_total is only known to the engine; estimate it from the symbolic sizes
+            const double per_inst = 8.0 * (2.0 * S.nnzL + 9.0 * S.N + 12.0 * S.m + 4.0 * S.n + 4.0 * S.p + 2.0 * S.l +
+                                           S.Vslot.size() + 8.0 * S.nc + S.qtot + S_COUNT + J_COUNT);
+            capacity = (long long)(0.80 * (double)fr / std::max(per_inst, 8.0));
+            capacity = std::max<long long>(32, std::min<long long>(capacity, 1 << 20));
+            capacity -= capacity % 32;
+#endif
+        }
+        bt->eng.reset(new Engine(bt->S, device, capacity, bt->workers));
+        return bt.release();
+    }
+    catch (const std::exception &e)
+    {
+        g_error = e.what();
+        return nullptr;
+    }
+}
+
+int eicos_batch_update_matrices(eicos_batch *bt, const double *Gpr, const double *Apr)
+{
+    if (!bt)
+        return fail(EICOS_ERR_INVALID, "null handle");
+    try
+    {
+        if (Gpr)
+            bt->rawG.assign(Gpr, Gpr + bt->S.G.nnz());
+        if (Apr)
+            bt->rawA.assign(Apr, Apr + bt->S.A.nnz());
+        refresh_values(bt->S, bt->rawG.data(), bt->rawA.data());
+        bt->eng->upload_values(bt->S);
+        return 0;
+    }
+    catch (const std::exception &e)
+    {
+        return fail(EICOS_ERR_DEVICE, e.what());
+    }
+}
+
+int eicos_batch_solve_device(eicos_batch *bt, int batch,
+                             const double *d_cs, const double *d_hs, const double *d_bs,
+                             double *d_x, double *d_y, double *d_z, double *d_s,
+                             int *d_exitflag, int *d_iters)
+{
+    if (!bt || batch < 0)
+        return fail(EICOS_ERR_INVALID, "null handle or negative batch");
+    try
+    {
+        bt->eng->solve(batch, d_cs, d_hs, d_bs, bt->c.data(), bt->h.data(), bt->b.data(),
+                       d_x, d_y, d_z, d_s, d_exitflag, d_iters, nullptr, nullptr,
+                       /*keep_sticky=*/false, /*pre_equilibrated=*/false, bt->timing, &bt->stats);
+        return 0;
+    }
+    catch (const std::invalid_argument &e)
+    {
+        return fail(EICOS_ERR_INVALID, e.what());
+    }
+    catch (const std::exception &e)
+    {
+        return fail(EICOS_ERR_DEVICE, e.what());
+    }
+}
+
+int eicos_batch_solve(eicos_batch *bt, int batch,
+                      const double *cs, const double *hs, const double *bs,
+                      double *x, double *y, double *z, double *s,
+                      int *exitflag, eicos_info *info)
+{
+    if (!bt || batch < 0)
+        return fail(EICOS_ERR_INVALID, "null handle or negative batch");
+    try
+    {
+        const Symbolic &S = bt->S;
+        be::set_device(bt->device);
+        be::stream_t st = (be::stream_t)(intptr_t)bt->eng->stream();
+        const size_t B = (size_t)batch;
+        const size_t nc_ = cs ? B * S.n : 0, nh_ = hs ? B * S.m : 0, nb_ = bs ? B * S.p : 0;
+        bt->din.ensure((nc_ + nh_ + nb_) * sizeof(double));
+        double *din = (double *)bt->din.p;
+        double *dc = cs ? din : nullptr, *dh = hs ? din + nc_ : nullptr, *db = bs ? din + nc_ + nh_ : nullptr;
+        be::h2d(dc, cs, nc_ * sizeof(double), st);
+        be::h2d(dh, hs, nh_ * sizeof(double), st);
+        be::h2d(db, bs, nb_ * sizeof(double), st);
+        const size_t ox = x ? B * S.n : 0, oy = y ? B * S.p : 0, oz = z ? B * S.m : 0, os = s ? B * S.m : 0;
+        const size_t oi = info ? B * S_WORK_END : 0;
+        bt->dout.ensure((ox + oy + oz + os + oi) * sizeof(double));
+        double *dout = (double *)bt->dout.p;
+        double *dx = x ? dout : nullptr, *dy = y ? dout + ox : nullptr, *dz = z ? dout + ox + oy : nullptr;
+        double *dsl = s ? dout + ox + oy + oz : nullptr, *dinfo = info ? dout + ox + oy + oz + os : nullptr;
+        const size_t ie = B, ii = info ? B * J_WORK_END : 0;
+        bt->dint.ensure((ie + ii) * sizeof(int));
+        int *dexit = (int *)bt->dint.p, *diinfo = info ? dexit + ie : nullptr;
+        bt->eng->solve(batch, dc, dh, db, bt->c.data(), bt->h.data(), bt->b.data(),
+                       dx, dy, dz, dsl, dexit, nullptr, dinfo, diinfo,
+                       false, false, bt->timing, &bt->stats);
+        be::d2h(x, dx, ox * sizeof(double), st);
+        be::d2h(y, dy, oy * sizeof(double), st);
+        be::d2h(z, dz, oz * sizeof(double), st);
+        be::d2h(s, dsl, os * sizeof(double), st);
+        std::vector<int> hexit(ie), hii(ii);
+        std::vector<double> hinfo(oi);
+        be::d2h(hexit.data(), dexit, ie * sizeof(int), st);
+        be::d2h(hii.data(), diinfo, ii * sizeof(int), st);
+        be::d2h(hinfo.data(), dinfo, oi * sizeof(double), st);
+        be::sync(st);
+        if (exitflag)
+            std::copy(hexit.begin(), hexit.end(), exitflag);
+        if (info)
+            for (size_t k = 0; k < B; k++)
+                info_from_rows(hinfo.data() + k * S_WORK_END, hii.data() + k * J_WORK_END, info + k);
+        return 0;
+    }
+    catch (const std::invalid_argument &e)
+    {
+        return fail(EICOS_ERR_INVALID, e.what());
+    }
+    catch (const std::exception &e)
+    {
+        return fail(EICOS_ERR_DEVICE, e.what());
+    }
+}
+
+int eicos_batch_set_timing(eicos_batch *bt, int enabled)
+{
+    if (!bt)
+        return fail(EICOS_ERR_INVALID, "null handle");
+    bt->timing = enabled != 0;
+    return 0;
+}
+
+int eicos_batch_get_stats(const eicos_batch *bt, eicos_batch_stats *o)
+{
+    if (!bt || !o)
+        return fail(EICOS_ERR_INVALID, "null argument");
+    const SolveStats &s = bt->stats;
+    o->chunks = s.chunks;
+    o->ipm_iterations = s.ipm_iterations;
+    o->launches = s.launches;
+    o->ir_rounds = s.ir_rounds;
+    o->ms_total = s.ms_total;
+    o->ms_factor = s.ms_factor;
+    o->ms_solve = s.ms_solve;
+    o->ms_other = s.ms_other;
+    o->factor_launch_tiles = s.factor_launch_tiles;
+    o->solve_launch_tiles = s.solve_launch_tiles;
+    o->factor_launches = s.factor_launches;
+    o->solve_launches = s.solve_launches;
+    return 0;
+}
+
+int eicos_batch_get_dims(const eicos_batch *bt, eicos_batch_dims *o)
+{
+    if (!bt || !o)
+        return fail(EICOS_ERR_INVALID, "null argument");
+    const Symbolic &S = bt->S;
+    o->n = S.n;
+    o->m = S.m;
+    o->p = S.p;
+    o->l = S.l;
+    o->ncones = S.nc;
+    o->dim_K = S.N;
+    o->nnzK = (int)S.Ki.size();
+    o->nnzL = S.nnzL;
+    o->nnzV = (int)S.Vslot.size();
+    o->nnzG = S.G.nnz();
+    o->nnzA = S.A.nnz();
+    o->etree_height = S.height;
+    o->max_col = S.maxcol;
+    o->n_phases = (int)S.phases.size();
+    o->tile_width = Engine::tile_width();
+    o->workers = bt->workers;
+    o->ldl_fma = S.fma_count;
+    o->capacity = bt->eng->capacity();
+    o->workspace_bytes = (long long)bt->eng->workspace_bytes();
+    o->rows_per_instance = bt->eng->layout().rows_total;
+    return 0;
+}
+
+int eicos_batch_get_symbolic(const eicos_batch *bt, int *pinv, int *parent, int *Lp, int *Li, int *Kp, int *Ki)
+{
+    if (!bt)
+        return fail(EICOS_ERR_INVALID, "null handle");
+    const Symbolic &S = bt->S;
+    if (pinv)
+        std::copy(S.pinv.begin(), S.pinv.end(), pinv);
+    if (parent)
+        std::copy(S.parent.begin(), S.parent.end(), parent);
+    if (Lp)
+        std::copy(S.Lp.begin(), S.Lp.end(), Lp);
+    if (Li)
+        std::copy(S.Li.begin(), S.Li.end(), Li);
+    if (Kp)
+        std::copy(S.Kp.begin(), S.Kp.end(), Kp);
+    if (Ki)
+        std::copy(S.Ki.begin(), S.Ki.end(), Ki);
+    return 0;
+}
+
+int eicos_batch_debug_init(eicos_batch *bt, int batch, const double *cs, const double *hs, const double *bs,
+                           double *Lx, double *D, double *sol1, double *sol2, int *nitref)
+{
+    if (!bt || batch <= 0)
+        return fail(EICOS_ERR_INVALID, "null handle or empty batch");
+    try
+    {
+        const Symbolic &S = bt->S;
+        be::set_device(bt->device);
+        be::stream_t st = (be::stream_t)(intptr_t)bt->eng->stream();
+        const size_t B = (size_t)batch;
+        const size_t nc_ = cs ? B * S.n : 0, nh_ = hs ? B * S.m : 0, nb_ = bs ? B * S.p : 0;
+        bt->din.ensure((nc_ + nh_ + nb_) * sizeof(double));
+        double *din = (double *)bt->din.p;
+        double *dc = cs ? din : nullptr, *dh = hs ? din + nc_ : nullptr, *db = bs ? din + nc_ + nh_ : nullptr;
+        be::h2d(dc, cs, nc_ * sizeof(double), st);
+        be::h2d(dh, hs, nh_ * sizeof(double), st);
+        be::h2d(db, bs, nb_ * sizeof(double), st);
+        be::sync(st);
+        bt->eng->debug_factor_init(batch, dc, dh, db, bt->c.data(), bt->h.data(), bt->b.data(), Lx, D, sol1, sol2, nitref);
+        return 0;
+    }
+    catch (const std::invalid_argument &e)
+    {
+        return fail(EICOS_ERR_INVALID, e.what());
+    }
+    catch (const std::exception &e)
+    {
+        return fail(EICOS_ERR_DEVICE, e.what());
+    }
+}
+
+void *eicos_batch_stream(const eicos_batch *bt) { return bt ? bt->eng->stream() : nullptr; }
+
+void eicos_batch_cleanup(eicos_batch *bt)
+{
+    if (bt)
+    {
+        be::set_device(bt->device);
+        delete bt;
+    }
+}
+
+/* ------------------------------------------------------------------ single instance */
+static void equilibrate_vectors(eicos_solver *s)
+{ // src/eicos.cpp:364-373
+    for (int k = 0; k < s->S.n; k++)
+        s->c[k] /= s->S.xeq[k];
+    for (int k = 0; k < s->S.p; k++)
+        s->b[k] /= s->S.Aeq[k];
+    for (int k = 0; k < s->S.m; k++)
+        s->h[k] /= s->S.Geq[k];
+    s->equilibrated = true;
+}
+
+eicos_solver *eicos_setup(int n, int m, int p, int l, int ncones, const int *q,
+                          const double *Gpr, const int *Gjc, const int *Gir,
+                          const double *Apr, const int *Ajc, const int *Air,
+                          const double *c, const double *h, const double *b, int device)
+{
+    (void)l;
+    try
+    {
+        if (n < 0 || m < 0 || p < 0 || ncones < 0 || (n > 0 && !c))
+            throw std::invalid_argument("eicos_setup: negative dimension or missing c");
+        std::unique_ptr<eicos_solver> s(new eicos_solver());
+        s->device = device;
+        std::memset(&s->info, 0, sizeof(s->info));
+        analyze(s->S, n, m, p, ncones, q, Gpr, Gjc, Gir, Apr, Ajc, Air, 2);
+        const Symbolic &S = s->S;
+        s->c.assign(c, c + S.n);
+        if (S.m)
+        {
+            if (!h)
+                throw std::invalid_argument("eicos_setup: h missing");
+            s->h.assign(h, h + S.m);
+        }
+        if (S.p)
+        {
+            if (!b)
+                throw std::invalid_argument("eicos_setup: b missing");
+            s->b.assign(b, b + S.p);
+        }
+        equilibrate_vectors(s.get());
+        s->x.assign(S.n, 0.0);
+        s->y.assign(S.p, 0.0);
+        s->z.assign(S.m, 0.0);
+        s->s.assign(S.m, 0.0);
+        be::set_device(device);
+        s->eng.reset(new Engine(s->S, device, 1, default_workers()));
+        return s.release();
+    }
+    catch (const std::exception &e)
+    {
+        g_error = e.what();
+        return nullptr;
+    }
+}
+
+static int update_common(eicos_solver *s, bool full, const double *Gpr, const double *Apr,
+                         const double *c, const double *h, const double *b)
+{
+    if (!s)
+        return fail(EICOS_ERR_INVALID, "null handle");
+    try
+    {
+        Symbolic &S = s->S;
+        if (full)
+        { // Eigen overload: everything overwritten, no un-equilibration needed (src/eicos.cpp:2038-2045)
+            if ((S.G.nnz() && !Gpr) || (S.A.nnz() && !Apr) || (S.n && !c) || (S.m && !h) || (S.p && !b))
+                throw std::invalid_argument("eicos_update_data_full: all arrays are required");
+            s->c.assign(c, c + S.n);
+            if (S.m)
+                s->h.assign(h, h + S.m);
+            if (S.p)
+                s->b.assign(b, b + S.p);
+            refresh_values(S, Gpr, Apr);
+        }
+        else
+        { // pointer overload (src/eicos.cpp:2053-2082)
+            if (s->equilibrated)
+            { // unsetEquilibration :389-404
+                unequilibrate(S);
+                for (int k = 0; k < S.n; k++)
+                    s->c[k] *= S.xeq[k];
+                for (int k = 0; k < S.p; k++)
+                    s->b[k] *= S.Aeq[k];
+                for (int k = 0; k < S.m; k++)
+                    s->h[k] *= S.Geq[k];
+                s->equilibrated = false;
+            }
+            if (Gpr)
+            {
+                if (S.m && !h)
+                    throw std::invalid_argument("eicos_update_data: h must accompany Gpr");
+                if (S.m)
+                    s->h.assign(h, h + S.m);
+            }
+            if (Apr)
+            {
+                if (S.p && !b)
+                    throw std::invalid_argument("eicos_update_data: b must accompany Apr");
+                if (S.p)
+                    s->b.assign(b, b + S.p);
+            }
+            if (c)
+                s->c.assign(c, c + S.n);
+            refresh_values(S, Gpr, Apr);
+        }
+        equilibrate_vectors(s);
+        s->eng->upload_values(S);
+        return 0;
+    }
+    catch (const std::invalid_argument &e)
+    {
+        return fail(EICOS_ERR_INVALID, e.what());
+    }
+    catch (const std::exception &e)
+    {
+        return fail(EICOS_ERR_DEVICE, e.what());
+    }
+}
+
+int eicos_update_data(eicos_solver *s, const double *Gpr, const double *Apr,
+                      const double *c, const double *h, const double *b)
+{
+    return update_common(s, false, Gpr, Apr, c, h, b);
+}
+
+int eicos_update_data_full(eicos_solver *s, const double *Gpr, const double *Apr,
+                           const double *c, const double *h, const double *b)
+{
+    return update_common(s, true, Gpr, Apr, c, h, b);
+}
+
+int eicos_solve(eicos_solver *s)
+{
+    if (!s)
+        return fail(EICOS_ERR_INVALID, "null handle");
+    try
+    {
+        const Symbolic &S = s->S;
+        be::set_device(s->device);
+        be::stream_t st = (be::stream_t)(intptr_t)s->eng->stream();
+        const size_t nd = (size_t)S.n + S.p + 2 * (size_t)S.m + S_WORK_END;
+        s->dout.ensure(nd * sizeof(double));
+        s->dint.ensure((1 + J_WORK_END) * sizeof(int));
+        double *dx = (double *)s->dout.p, *dy = dx + S.n, *dz = dy + S.p, *dsl = dz + S.m, *dinfo = dsl + S.m;
+        int *dexit = (int *)s->dint.p, *dii = dexit + 1;
+        s->eng->solve(1, nullptr, nullptr, nullptr, s->c.data(), s->h.data(), s->b.data(),
+                      dx, dy, dz, dsl, dexit, nullptr, dinfo, dii,
+                      /*keep_sticky=*/true, /*pre_equilibrated=*/true, false, nullptr);
+        double hinfo[S_WORK_END];
+        int hi[1 + J_WORK_END];
+        be::d2h(s->x.data(), dx, S.n * sizeof(double), st);
+        be::d2h(s->y.data(), dy, S.p * sizeof(double), st);
+        be::d2h(s->z.data(), dz, S.m * sizeof(double), st);
+        be::d2h(s->s.data(), dsl, S.m * sizeof(double), st);
+        be::d2h(hinfo, dinfo, sizeof(hinfo), st);
+        be::d2h(hi, dexit, sizeof(hi), st);
+        be::sync(st);
+        info_from_rows(hinfo, hi + 1, &s->info);
+        return hi[0];
+    }
+    catch (const std::exception &e)
+    {
+        g_error = e.what();
+        return EXIT_FATAL;
+    }
+}
+
+const double *eicos_solution(const eicos_solver *s) { return s ? s->x.data() : nullptr; }
+
+int eicos_get_duals(const eicos_solver *s, double *y, double *z, double *slack)
+{
+    if (!s)
+        return fail(EICOS_ERR_INVALID, "null handle");
+    if (y)
+        std::copy(s->y.begin(), s->y.end(), y);
+    if (z)
+        std::copy(s->z.begin(), s->z.end(), z);
+    if (slack)
+        std::copy(s->s.begin(), s->s.end(), slack);
+    return 0;
+}
+
+int eicos_get_info(const eicos_solver *s, eicos_info *out)
+{
+    if (!s || !out)
+        return fail(EICOS_ERR_INVALID, "null argument");
+    *out = s->info;
+    return 0;
+}
+
+void eicos_cleanup(eicos_solver *s)
+{
+    if (s)
+    {
+        be::set_device(s->device);
+        delete s;
+    }
+}
+
+} // extern "C"

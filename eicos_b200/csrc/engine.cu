@@ -1,0 +1,541 @@
+// Host orchestration of the batched interior-point loop + the __global__ entry points.
+// Compiled by nvcc for sm_100a (product) or by g++ with -DEICOS_EMU (tests/emu only).
+#include "engine.hpp"
+#include "backend.hpp"
+#include "tile_program.hpp"
+
+#include <algorithm>
+#include <cstdint>
+
+namespace eicos
+{
+
+typedef void (*TileFn)(const Team &, const KArgs &, int);
+
+#ifndef EICOS_EMU
+// thin named wrappers so that profilers show one kernel name per step of the algorithm
+#define EI_DEFINE_KERNEL(name, fn)                                               \
+    __global__ void __launch_bounds__(512) name(const __grid_constant__ KArgs a) \
+    {                                                                            \
+        extern __shared__ double smem[];                                         \
+        Team tm;                                                                 \
+        tm.lane = threadIdx.x & 31;                                              \
+        tm.wk = threadIdx.x >> 5;                                                \
+        tm.nwk = blockDim.x >> 5;                                                \
+        tm.red = smem;                                                           \
+        tm.acc = a.acc_global ? a.acc_global + (size_t)blockIdx.x * tm.nwk * a.P.maxcol * TILE \
+                              : smem + (size_t)tm.nwk * KRED * TILE;             \
+        fn(tm, a, blockIdx.x);                                                   \
+    }
+EI_DEFINE_KERNEL(eicos_load_inputs, tile_load)
+EI_DEFINE_KERNEL(eicos_init, tile_init)
+EI_DEFINE_KERNEL(eicos_ldl_factor, tile_factor)
+EI_DEFINE_KERNEL(eicos_solve_kkt, tile_solve_kkt)
+EI_DEFINE_KERNEL(eicos_init_point, tile_init_point)
+EI_DEFINE_KERNEL(eicos_iter_head, tile_head)
+EI_DEFINE_KERNEL(eicos_iter_mid, tile_mid)
+EI_DEFINE_KERNEL(eicos_iter_tail, tile_tail)
+EI_DEFINE_KERNEL(eicos_store_outputs, tile_store)
+
+#define EI_LAUNCH(name, fn, tiles, threads, smem, stream, args) name<<<(tiles), (threads), (smem), (stream)>>>(args)
+#else
+#define EI_LAUNCH(name, fn, tiles, threads, smem, stream, args)                 \
+    do                                                                          \
+    {                                                                           \
+        std::vector<double> red_((size_t)KRED * TILE + 8);                      \
+        std::vector<double> acc_((size_t)(args).P.maxcol * TILE + 8);           \
+        for (int tile_ = 0; tile_ < (tiles); tile_++)                           \
+        {                                                                       \
+            Team tm_;                                                           \
+            tm_.lane = 0;                                                       \
+            tm_.wk = 0;                                                         \
+            tm_.nwk = 1;                                                        \
+            tm_.red = red_.data();                                              \
+            tm_.acc = acc_.data();                                              \
+            fn(tm_, (args), tile_);                                             \
+        }                                                                       \
+    } while (0)
+#endif
+
+int Engine::tile_width() { return TILE; }
+
+namespace
+{
+template <class T>
+T *upload(const std::vector<T> &v, std::vector<void *> &owned, be::stream_t s)
+{
+    T *d = (T *)be::alloc(v.size() * sizeof(T));
+    be::h2d(d, v.data(), v.size() * sizeof(T), s);
+    owned.push_back(d);
+    return d;
+}
+inline be::stream_t S_(void *p) { return (be::stream_t)(intptr_t)p; }
+} // namespace
+
+void Engine::build_layout(const Symbolic &S)
+{
+    int at = 0;
+    auto take = [&](int rows) {
+        const int o = at;
+        at += rows;
+        return o;
+    };
+    Layout &L = L_;
+    L.c = take(S.n);
+    L.h = take(S.m);
+    L.b = take(S.p);
+    L.x = take(S.n);
+    L.y = take(S.p);
+    L.z = take(S.m);
+    L.s = take(S.m);
+    L.lam = take(S.m);
+    L.bx = take(S.n);
+    L.by = take(S.p);
+    L.bz = take(S.m);
+    L.bs = take(S.m);
+    L.blam = take(S.m);
+    L.rx = take(S.n);
+    L.ry = take(S.p);
+    L.rz = take(S.m);
+    L.lpv = take(S.l);
+    L.lpw = take(S.l);
+    L.cpar = take(S.nc * CP_COUNT);
+    L.cq = take(S.qtot);
+    L.V = take((int)S.Vslot.size());
+    L.Lx = take(S.nnzL);
+    L.LTx = take(S.nnzL);
+    L.D = take(S.N);
+    L.Dinv = take(S.N);
+    L.rhs1 = take(S.N);
+    L.rhs2 = take(S.N);
+    L.sol1 = take(S.N);
+    L.sol2 = take(S.N);
+    L.xw = take(S.N);
+    L.dxr = take(S.N);
+    L.e = take(S.N);
+    L.dsw = take(S.m);
+    L.wdz = take(S.m);
+    L.dsaff = take(S.m);
+    L.ds1 = take(S.m);
+    L.sc = take(S_COUNT);
+    L.rows_total = at;
+    L.irows_total = J_COUNT;
+}
+
+void Engine::upload_pattern(const Symbolic &S)
+{
+    be::stream_t st = S_(stream_);
+    DevPattern &P = P_;
+    P.n = S.n;
+    P.p = S.p;
+    P.m = S.m;
+    P.l = S.l;
+    P.nc = S.nc;
+    P.N = S.N;
+    P.mt = S.mt;
+    P.qtot = S.qtot;
+    P.nnzL = S.nnzL;
+    P.nnzV = (int)S.Vslot.size();
+    P.nphases = (int)S.phases.size();
+    P.maxcol = S.maxcol;
+    P.cone_dim = upload(S.q, owned_, st);
+    P.cone_z = upload(S.cone_z, owned_, st);
+    P.cone_k = upload(S.cone_k, owned_, st);
+    P.cone_q = upload(S.cone_q, owned_, st);
+    P.zk = upload(S.zk, owned_, st);
+    P.Gp = upload(S.G.p, owned_, st);
+    P.Gi = upload(S.G.i, owned_, st);
+    P.Grp = upload(S.Gr.p, owned_, st);
+    P.Grj = upload(S.Gr.j, owned_, st);
+    P.Grv = upload(S.Gr.v, owned_, st);
+    P.Ap = upload(S.A.p, owned_, st);
+    P.Ai = upload(S.A.i, owned_, st);
+    P.Arp = upload(S.Ar.p, owned_, st);
+    P.Arj = upload(S.Ar.j, owned_, st);
+    P.Arv = upload(S.Ar.v, owned_, st);
+    P.Gx = dGx_ = upload(S.G.x, owned_, st);
+    P.Ax = dAx_ = upload(S.A.x, owned_, st);
+    P.xeq = dxeq_ = upload(S.xeq, owned_, st);
+    P.Aeq = dAeq_ = upload(S.Aeq, owned_, st);
+    P.Geq = dGeq_ = upload(S.Geq, owned_, st);
+    P.pinv = upload(S.pinv, owned_, st);
+    P.Lp = upload(S.Lp, owned_, st);
+    P.Li = upload(S.Li, owned_, st);
+    ivec Lio(S.nnzL), Lcsr(S.nnzL);
+    for (int u = 0; u < S.nnzL; u++)
+        Lio[u] = S.pinv[S.Li[u]];
+    for (int t = 0; t < S.nnzL; t++)
+        Lcsr[S.Lr.v[t]] = t;
+    P.Lio = upload(Lio, owned_, st);
+    P.Lcsr = upload(Lcsr, owned_, st);
+    P.Lrp = upload(S.Lr.p, owned_, st);
+    P.Lrj = upload(S.Lr.j, owned_, st);
+    P.KLp = upload(S.KLp, owned_, st);
+    KLslot_ = S.KLslot;
+    ivec klv(S.KLslot.size());
+    dvec klx(S.KLslot.size());
+    for (size_t e = 0; e < S.KLslot.size(); e++)
+    {
+        klv[e] = S.Kvidx[S.KLslot[e]];
+        klx[e] = S.Kshared[S.KLslot[e]];
+    }
+    P.KLvidx = upload(klv, owned_, st);
+    P.KLpos = upload(S.KLpos, owned_, st);
+    P.KLval = dKLval_ = upload(klx, owned_, st);
+    P.upd_tail = upload(S.upd_tail, owned_, st);
+    P.upd_rel_p = upload(S.upd_rel_p, owned_, st);
+    P.upd_rel = upload(S.upd_rel, owned_, st);
+    P.tasks = upload(S.tasks, owned_, st);
+    std::vector<PhaseDev> ph;
+    for (const Phase &f : S.phases)
+        ph.push_back({f.begin, f.end, f.parallel});
+    P.phases = upload(ph, owned_, st);
+    ivec vk;
+    for (int k = 0; k < S.l; k++)
+        vk.push_back(0);
+    for (int d : S.q)
+    {
+        for (int k = 0; k < d + 1; k++)
+            vk.push_back(0); // D block and the v diagonal: -1
+        for (int k = 1; k < d; k++)
+            vk.push_back(1); // v: 0
+        vk.push_back(2);     // u diagonal: +1
+        for (int k = 0; k < d; k++)
+            vk.push_back(1); // u: 0
+    }
+    P.Vkind = upload(vk, owned_, st);
+    be::sync(st);
+}
+
+void Engine::upload_values(const Symbolic &S)
+{
+    be::stream_t st = S_(stream_);
+    be::set_device(device_);
+    be::h2d(dGx_, S.G.x.data(), S.G.x.size() * sizeof(double), st);
+    be::h2d(dAx_, S.A.x.data(), S.A.x.size() * sizeof(double), st);
+    be::h2d(dxeq_, S.xeq.data(), S.xeq.size() * sizeof(double), st);
+    be::h2d(dAeq_, S.Aeq.data(), S.Aeq.size() * sizeof(double), st);
+    be::h2d(dGeq_, S.Geq.data(), S.Geq.size() * sizeof(double), st);
+    dvec klx(KLslot_.size());
+    for (size_t e = 0; e < KLslot_.size(); e++)
+        klx[e] = S.Kshared[KLslot_[e]];
+    be::h2d(dKLval_, klx.data(), klx.size() * sizeof(double), st);
+    be::sync(st);
+}
+
+Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int workers)
+    : device_(device), workers_(std::max(1, std::min(workers, 16)))
+{
+    be::set_device(device_);
+    stream_ = (void *)(intptr_t)be::make_stream();
+#ifdef EICOS_EMU
+    workers_ = 1;
+#endif
+    build_layout(S);
+    upload_pattern(S);
+    cap_tiles_ = std::max<long long>(1, (capacity_instances + TILE - 1) / TILE);
+    ws_bytes_ = (size_t)cap_tiles_ * L_.rows_total * TILE * sizeof(double);
+    ws_ = (double *)be::alloc(ws_bytes_);
+    const size_t ib = (size_t)cap_tiles_ * L_.irows_total * TILE * sizeof(int);
+    iws_ = (int *)be::alloc(ib);
+    be::zero(ws_, ws_bytes_, S_(stream_));
+    be::zero(iws_, ib, S_(stream_));
+    base_vec_ = (double *)be::alloc((size_t)(S.n + S.m + S.p) * sizeof(double));
+    active_count_ = (unsigned int *)be::alloc(sizeof(unsigned int));
+    ir_rounds_ = (unsigned long long *)be::alloc(sizeof(unsigned long long));
+    host_pinned_ = (unsigned int *)be::pinned(4 * sizeof(unsigned long long));
+    smem_common_ = (size_t)workers_ * KRED * TILE * sizeof(double);
+    smem_factor_ = smem_common_ + (size_t)workers_ * S.maxcol * TILE * sizeof(double);
+#ifndef EICOS_EMU
+    const size_t smem_limit = 200 * 1024;
+    if (smem_factor_ > smem_limit)
+    { // column accumulators spill to global memory (one slab per CTA)
+        acc_global_ = (double *)be::alloc((size_t)cap_tiles_ * workers_ * S.maxcol * TILE * sizeof(double));
+        smem_factor_ = smem_common_;
+    }
+    if (smem_factor_ > 48 * 1024)
+        EI_CUDA(cudaFuncSetAttribute(eicos_ldl_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_factor_));
+#endif
+    be::sync(S_(stream_));
+}
+
+Engine::~Engine()
+{
+    be::set_device(device_);
+#ifndef EICOS_EMU
+    for (void *e : events_)
+        cudaEventDestroy((cudaEvent_t)e);
+#endif
+    for (void *p : owned_)
+        be::dfree(p);
+    be::dfree(ws_);
+    be::dfree(iws_);
+    be::dfree(acc_global_);
+    be::dfree(base_vec_);
+    be::dfree(active_count_);
+    be::dfree(ir_rounds_);
+    be::unpin(host_pinned_);
+    be::drop_stream(S_(stream_));
+}
+
+void Engine::solve(int batch, const double *d_c, const double *d_h, const double *d_b,
+                   const double *base_c, const double *base_h, const double *base_b,
+                   double *d_x, double *d_y, double *d_z, double *d_s,
+                   int *d_exit, int *d_iter, double *d_info, int *d_iinfo,
+                   bool keep_sticky, bool pre_equilibrated, bool timing, SolveStats *stats)
+{
+    be::set_device(device_);
+    be::stream_t st = S_(stream_);
+    SolveStats local;
+    SolveStats &stt = stats ? *stats : local;
+    stt = SolveStats();
+    if (batch <= 0)
+        return;
+    if (keep_sticky && batch > cap_tiles_ * TILE)
+        throw std::invalid_argument("keep_sticky needs the whole batch resident");
+
+    KArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.P = P_;
+    a.L = L_;
+    a.ws = ws_;
+    a.iws = iws_;
+    a.acc_global = acc_global_;
+    a.in_c = d_c;
+    a.in_h = d_h;
+    a.in_b = d_b;
+    a.base_c = base_vec_;
+    a.base_h = base_vec_ + P_.n;
+    a.base_b = base_vec_ + P_.n + P_.m;
+    if ((!d_c && P_.n && !base_c) || (!d_h && P_.m && !base_h) || (!d_b && P_.p && !base_b))
+        throw std::invalid_argument("missing problem vector: neither stacked nor base data given");
+    if (base_c)
+        be::h2d(base_vec_, base_c, P_.n * sizeof(double), st);
+    if (base_h)
+        be::h2d(base_vec_ + P_.n, base_h, P_.m * sizeof(double), st);
+    if (base_b)
+        be::h2d(base_vec_ + P_.n + P_.m, base_b, P_.p * sizeof(double), st);
+    be::sync(st); // base_* may be pageable host memory owned by the caller
+    a.out_x = d_x;
+    a.out_y = d_y;
+    a.out_z = d_z;
+    a.out_s = d_s;
+    a.out_exit = d_exit;
+    a.out_iter = d_iter;
+    a.out_info = d_info;
+    a.out_iinfo = d_iinfo;
+    a.keep_sticky = keep_sticky ? 1 : 0;
+    a.pre_equilibrated = pre_equilibrated ? 1 : 0;
+    a.active_count = active_count_;
+    a.ir_rounds = ir_rounds_;
+    a.nitrow = -1;
+    be::zero(ir_rounds_, sizeof(unsigned long long), st);
+
+    const int threads = workers_ * (TILE == 1 ? 1 : 32);
+    (void)threads;
+
+#ifndef EICOS_EMU
+    // event pool for per-class device timing
+    size_t ev_used = 0;
+    auto ev = [&]() -> cudaEvent_t {
+        if (ev_used == events_.size())
+        {
+            cudaEvent_t e;
+            EI_CUDA(cudaEventCreate(&e));
+            events_.push_back(e);
+        }
+        return (cudaEvent_t)events_[ev_used++];
+    };
+    struct Span
+    {
+        cudaEvent_t a, b;
+        int cls;
+    };
+    std::vector<Span> spans;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    if (timing)
+    {
+        ev_begin = ev();
+        EI_CUDA(cudaEventRecord(ev_begin, st));
+    }
+#define EI_TIMED(cls_, stmt)                                  \
+    do                                                        \
+    {                                                         \
+        if (timing && (cls_) >= 0)                            \
+        {                                                     \
+            Span sp_{ev(), ev(), (cls_)};                     \
+            EI_CUDA(cudaEventRecord(sp_.a, st));              \
+            stmt;                                             \
+            EI_CUDA(cudaEventRecord(sp_.b, st));              \
+            spans.push_back(sp_);                             \
+        }                                                     \
+        else                                                  \
+        {                                                     \
+            stmt;                                             \
+        }                                                     \
+        stt.launches++;                                       \
+    } while (0)
+#else
+#define EI_TIMED(cls_, stmt) \
+    do                       \
+    {                        \
+        stmt;                \
+        stt.launches++;      \
+    } while (0)
+#endif
+
+    for (long long first = 0; first < batch; first += cap_tiles_ * TILE)
+    {
+        const int nb = (int)std::min<long long>(batch - first, cap_tiles_ * TILE);
+        const int tiles = (nb + TILE - 1) / TILE;
+        a.batch = nb;
+        a.first = (int)first;
+        stt.chunks++;
+
+        auto factor = [&]() {
+            EI_TIMED(0, EI_LAUNCH(eicos_ldl_factor, tile_factor, tiles, threads, smem_factor_, st, a));
+            stt.factor_launches++;
+            stt.factor_launch_tiles += tiles;
+        };
+        auto kkt = [&](int rhs, int sol, int init, int nitrow) {
+            a.rhs = rhs;
+            a.sol = sol;
+            a.initialize = init;
+            a.nitrow = nitrow;
+            EI_TIMED(1, EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt, tiles, threads, smem_common_, st, a));
+            stt.solve_launches++;
+            stt.solve_launch_tiles += tiles;
+        };
+
+        EI_TIMED(2, EI_LAUNCH(eicos_load_inputs, tile_load, tiles, threads, smem_common_, st, a));
+        EI_TIMED(2, EI_LAUNCH(eicos_init, tile_init, tiles, threads, smem_common_, st, a));
+        factor();
+        kkt(L_.rhs1, L_.sol1, 1, J_NIT1);
+        kkt(L_.rhs2, L_.sol2, 1, J_NIT2);
+        EI_TIMED(2, EI_LAUNCH(eicos_init_point, tile_init_point, tiles, threads, smem_common_, st, a));
+
+        for (int it = 0; it <= Settings::iter_max + 1; it++)
+        {
+            be::zero(active_count_, sizeof(unsigned int), st);
+            EI_TIMED(2, EI_LAUNCH(eicos_iter_head, tile_head, tiles, threads, smem_common_, st, a));
+            stt.ipm_iterations++;
+            be::d2h(host_pinned_, active_count_, sizeof(unsigned int), st);
+            be::sync(st);
+            if (host_pinned_[0] == 0)
+                break;
+            factor();
+            kkt(L_.rhs1, L_.sol1, 0, -1);
+            kkt(L_.rhs2, L_.sol2, 0, -1);
+            EI_TIMED(2, EI_LAUNCH(eicos_iter_mid, tile_mid, tiles, threads, smem_common_, st, a));
+            kkt(L_.rhs2, L_.sol2, 0, J_NIT3);
+            EI_TIMED(2, EI_LAUNCH(eicos_iter_tail, tile_tail, tiles, threads, smem_common_, st, a));
+        }
+        EI_TIMED(2, EI_LAUNCH(eicos_store_outputs, tile_store, tiles, threads, smem_common_, st, a));
+    }
+    be::d2h(host_pinned_ + 2, ir_rounds_, sizeof(unsigned long long), st);
+#ifndef EICOS_EMU
+    if (timing)
+    {
+        ev_end = ev();
+        EI_CUDA(cudaEventRecord(ev_end, st));
+    }
+    EI_CUDA(cudaGetLastError());
+#endif
+    be::sync(st);
+    std::memcpy(&stt.ir_rounds, host_pinned_ + 2, sizeof(unsigned long long));
+#ifndef EICOS_EMU
+    if (timing)
+    {
+        float ms = 0;
+        EI_CUDA(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+        stt.ms_total = ms;
+        for (const Span &sp : spans)
+        {
+            EI_CUDA(cudaEventElapsedTime(&ms, sp.a, sp.b));
+            (sp.cls == 0 ? stt.ms_factor : sp.cls == 1 ? stt.ms_solve : stt.ms_other) += ms;
+        }
+    }
+#endif
+#undef EI_TIMED
+}
+
+void Engine::debug_factor_init(int batch, const double *d_c, const double *d_h, const double *d_b,
+                               const double *base_c, const double *base_h, const double *base_b,
+                               double *h_Lx, double *h_D, double *h_sol1, double *h_sol2, int *h_nit)
+{
+    be::set_device(device_);
+    be::stream_t st = S_(stream_);
+    if (batch > cap_tiles_ * TILE)
+        throw std::invalid_argument("debug_factor_init: batch exceeds workspace capacity");
+    KArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.P = P_;
+    a.L = L_;
+    a.ws = ws_;
+    a.iws = iws_;
+    a.acc_global = acc_global_;
+    a.in_c = d_c;
+    a.in_h = d_h;
+    a.in_b = d_b;
+    a.base_c = base_vec_;
+    a.base_h = base_vec_ + P_.n;
+    a.base_b = base_vec_ + P_.n + P_.m;
+    if (base_c)
+        be::h2d(base_vec_, base_c, P_.n * sizeof(double), st);
+    if (base_h)
+        be::h2d(base_vec_ + P_.n, base_h, P_.m * sizeof(double), st);
+    if (base_b)
+        be::h2d(base_vec_ + P_.n + P_.m, base_b, P_.p * sizeof(double), st);
+    be::sync(st);
+    a.batch = batch;
+    a.first = 0;
+    a.nitrow = -1;
+    const int tiles = (batch + TILE - 1) / TILE;
+    const int threads = workers_ * (TILE == 1 ? 1 : 32);
+    (void)threads;
+    EI_LAUNCH(eicos_load_inputs, tile_load, tiles, threads, smem_common_, st, a);
+    EI_LAUNCH(eicos_init, tile_init, tiles, threads, smem_common_, st, a);
+    EI_LAUNCH(eicos_ldl_factor, tile_factor, tiles, threads, smem_factor_, st, a);
+    a.rhs = L_.rhs1;
+    a.sol = L_.sol1;
+    a.initialize = 1;
+    a.nitrow = J_NIT1;
+    EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt, tiles, threads, smem_common_, st, a);
+    a.rhs = L_.rhs2;
+    a.sol = L_.sol2;
+    a.nitrow = J_NIT2;
+    EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt, tiles, threads, smem_common_, st, a);
+    be::sync(st);
+    // gather rows back to instance-major host arrays
+    const size_t tile_doubles = (size_t)L_.rows_total * TILE;
+    std::vector<double> buf(tile_doubles);
+    std::vector<int> ibuf((size_t)L_.irows_total * TILE);
+    for (int t = 0; t < tiles; t++)
+    {
+        be::d2h(buf.data(), ws_ + t * tile_doubles, tile_doubles * sizeof(double), st);
+        be::d2h(ibuf.data(), iws_ + (size_t)t * L_.irows_total * TILE, ibuf.size() * sizeof(int), st);
+        be::sync(st);
+        for (int lane = 0; lane < TILE; lane++)
+        {
+            const long long inst = (long long)t * TILE + lane;
+            if (inst >= batch)
+                break;
+            auto grab = [&](double *dst, int row0, int rows) {
+                if (dst)
+                    for (int r = 0; r < rows; r++)
+                        dst[inst * rows + r] = buf[(size_t)(row0 + r) * TILE + lane];
+            };
+            grab(h_Lx, L_.Lx, P_.nnzL);
+            grab(h_D, L_.D, P_.N);
+            grab(h_sol1, L_.sol1, P_.N);
+            grab(h_sol2, L_.sol2, P_.N);
+            if (h_nit)
+            {
+                h_nit[inst * 2 + 0] = ibuf[(size_t)J_NIT1 * TILE + lane];
+                h_nit[inst * 2 + 1] = ibuf[(size_t)J_NIT2 * TILE + lane];
+            }
+        }
+    }
+}
+
+} // namespace eicos

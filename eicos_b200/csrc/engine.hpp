@@ -1,0 +1,86 @@
+// Batched interior-point engine for one device: owns the shared pattern data, the per-instance
+// workspace (tiled SoA, see layout.hpp) and the launch sequence of Solver::solve
+// (reference src/eicos.cpp:848-1262).
+#pragma once
+
+#include "layout.hpp"
+#include "symbolic.hpp"
+
+#include <cstddef>
+#include <vector>
+
+namespace eicos
+{
+
+struct SolveStats
+{
+    int chunks = 0;
+    int ipm_iterations = 0;          // head launches over all chunks
+    long long launches = 0;          // kernels launched
+    unsigned long long ir_rounds = 0; // triangular-solve rounds executed (tile-rounds, all solveKKT calls)
+    double ms_total = 0, ms_factor = 0, ms_solve = 0, ms_other = 0; // device time by kernel class (CUDA events)
+    long long factor_launch_tiles = 0, solve_launch_tiles = 0;      // tiles covered by the timed launches
+    int factor_launches = 0, solve_launches = 0;
+};
+
+class Engine
+{
+  public:
+    // capacity_instances: how many instances the workspace holds at once (larger batches are
+    // processed in chunks); workers: warps per CTA.
+    Engine(const Symbolic &S, int device, long long capacity_instances, int workers);
+    ~Engine();
+    Engine(const Engine &) = delete;
+    Engine &operator=(const Engine &) = delete;
+
+    // re-upload the shared numeric values after refresh_values() (updateData with new G/A)
+    void upload_values(const Symbolic &S);
+
+    // Solve `batch` instances.  d_c/d_h/d_b: instance-major DEVICE arrays of raw (unequilibrated)
+    // data, or null to use base_* (host arrays, shared by all instances).  Outputs are DEVICE
+    // arrays (instance-major), any may be null.  Blocks until the results are complete.
+    void solve(int batch, const double *d_c, const double *d_h, const double *d_b,
+               const double *base_c, const double *base_h, const double *base_b,
+               double *d_x, double *d_y, double *d_z, double *d_s,
+               int *d_exit, int *d_iter, double *d_info, int *d_iinfo,
+               bool keep_sticky, bool pre_equilibrated, bool timing, SolveStats *stats);
+
+    // debug entry points (GPU unit tests): run the initial factorisation / one KKT solve for
+    // instance-major data and copy raw factor values back (host pointers, may be null)
+    void debug_factor_init(int batch, const double *d_c, const double *d_h, const double *d_b,
+                           const double *base_c, const double *base_h, const double *base_b,
+                           double *h_Lx, double *h_D, double *h_sol1, double *h_sol2, int *h_nit);
+
+    void *stream() const { return stream_; }
+    int device() const { return device_; }
+    long long capacity() const { return cap_tiles_ * (long long)tile_width(); }
+    size_t workspace_bytes() const { return ws_bytes_; }
+    const Layout &layout() const { return L_; }
+    static int tile_width();
+
+  private:
+    void build_layout(const Symbolic &S);
+    void upload_pattern(const Symbolic &S);
+
+    int device_ = 0, workers_ = 4;
+    long long cap_tiles_ = 0;
+    size_t ws_bytes_ = 0;
+    void *stream_ = nullptr;
+    Layout L_{};
+    DevPattern P_{};
+    double *ws_ = nullptr;
+    int *iws_ = nullptr;
+    double *acc_global_ = nullptr;
+    double *base_vec_ = nullptr; // device copy of base c|h|b
+    unsigned int *active_count_ = nullptr;
+    unsigned long long *ir_rounds_ = nullptr;
+    unsigned int *host_pinned_ = nullptr;
+    size_t smem_factor_ = 0, smem_common_ = 0;
+    std::vector<void *> owned_; // device allocations holding pattern data
+    // positions of value arrays that upload_values() rewrites
+    double *dGx_ = nullptr, *dAx_ = nullptr, *dxeq_ = nullptr, *dAeq_ = nullptr, *dGeq_ = nullptr, *dKLval_ = nullptr;
+    std::vector<int> KLslot_;
+    std::vector<void *> events_;
+};
+
+} // namespace eicos

@@ -1,0 +1,1412 @@
+// The per-tile interior-point program: every step of EiCOS's Solver::solve (reference
+// src/eicos.cpp:848-1262) for TILE instances at a time, lane = instance.
+//
+// One CTA owns one tile.  Its warps ("workers") split rows / cones / elimination-tree tasks among
+// themselves and meet at CTA barriers; per-instance reductions over a vector run down the rows in
+// each worker and are combined through shared memory in a fixed order, so every warp of the CTA
+// holds bit-identical per-lane scalars and all control flow is uniform across the CTA.
+//
+// The same source compiles two ways:
+//   * nvcc (default): TILE = 32, workers = warps of the CTA  -> the product.
+//   * -DEICOS_EMU (tests/emu only): TILE = 1, one worker, plain C++ -> lets the CPU-only test
+//     tier execute the kernel logic against the oracle.  It is never linked into the product.
+#pragma once
+
+#include "layout.hpp"
+#include "symbolic.hpp"
+
+#include <cfloat>
+#include <cmath>
+
+#ifdef EICOS_EMU
+#define EI_DEV inline
+#define EI_LDG(p) (*(p))
+#else
+#include <cuda_runtime.h>
+#define EI_DEV __device__ __forceinline__
+#define EI_LDG(p) __ldg(p)
+#endif
+
+namespace eicos
+{
+
+#ifdef EICOS_EMU
+constexpr int TILE = 1;
+#else
+constexpr int TILE = 32;
+#endif
+constexpr int KRED = 17; // widest block reduction (head kernel)
+
+struct KArgs
+{
+    DevPattern P;
+    Layout L;
+    double *ws; // [tiles][rows_total][TILE]
+    int *iws;   // [tiles][irows_total][TILE]
+    double *acc_global; // factor accumulators when they do not fit shared memory, else null
+    int batch;  // instances handled by this launch's chunk
+    int first;  // global index (within the device's batch) of the chunk's first instance
+    // instance-major device buffers for load/store (any may be null)
+    const double *in_c, *in_h, *in_b;
+    const double *base_c, *base_h, *base_b; // raw vectors shared by the batch (used when in_* is null)
+    double *out_x, *out_y, *out_z, *out_s;
+    int *out_exit, *out_iter;
+    double *out_info; // [batch][S_WORK_END]
+    int *out_iinfo;   // [batch][J_WORK_END]
+    // solveKKT parameters
+    int rhs, sol, initialize, nitrow;
+    int keep_sticky;
+    int pre_equilibrated; // inputs are already divided by the equilibration vectors
+    unsigned int *active_count; // device counter: instances still iterating after the head step
+    unsigned long long *ir_rounds; // device counter: refinement rounds executed (tile-rounds)
+};
+
+struct Team
+{
+    int lane, wk, nwk;
+    double *red; // [nwk][KRED][TILE]
+    double *acc; // [nwk][maxcol][TILE]
+#ifdef EICOS_EMU
+    void sync() const {}
+    bool all(bool v) const { return v; }
+    bool any(bool v) const { return v; }
+#else
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ bool all(bool v) const { return __all_sync(0xffffffffu, v); }
+    __device__ __forceinline__ bool any(bool v) const { return __any_sync(0xffffffffu, v); }
+#endif
+};
+
+// ------------------------------------------------------------------ small helpers
+#define ROWD(base, r) (base)[(size_t)(r) * TILE + tm.lane]
+
+EI_DEV bool ei_isnan(double v) { return v != v; }
+EI_DEV double dmax(double a, double b) { return a > b ? a : b; } // std::max(a,b) semantics (returns a on ties / NaN in b)
+EI_DEV double dmin(double a, double b) { return b < a ? b : a; } // std::min(a,b)
+
+template <int K>
+EI_DEV void team_sum(const Team &tm, double (&v)[K])
+{
+    if (tm.nwk == 1)
+        return;
+    tm.sync();
+    for (int i = 0; i < K; i++)
+        tm.red[(size_t)(tm.wk * K + i) * TILE + tm.lane] = v[i];
+    tm.sync();
+    for (int i = 0; i < K; i++)
+    {
+        double s = 0.0;
+        for (int w = 0; w < tm.nwk; w++)
+            s += tm.red[(size_t)(w * K + i) * TILE + tm.lane];
+        v[i] = s;
+    }
+}
+
+template <int K>
+EI_DEV void team_max(const Team &tm, double (&v)[K])
+{
+    if (tm.nwk == 1)
+        return;
+    tm.sync();
+    for (int i = 0; i < K; i++)
+        tm.red[(size_t)(tm.wk * K + i) * TILE + tm.lane] = v[i];
+    tm.sync();
+    for (int i = 0; i < K; i++)
+    {
+        double s = tm.red[(size_t)i * TILE + tm.lane];
+        for (int w = 1; w < tm.nwk; w++)
+            s = dmax(s, tm.red[(size_t)(w * K + i) * TILE + tm.lane]);
+        v[i] = s;
+    }
+}
+
+template <int K>
+EI_DEV void team_min(const Team &tm, double (&v)[K])
+{
+    if (tm.nwk == 1)
+        return;
+    tm.sync();
+    for (int i = 0; i < K; i++)
+        tm.red[(size_t)(tm.wk * K + i) * TILE + tm.lane] = v[i];
+    tm.sync();
+    for (int i = 0; i < K; i++)
+    {
+        double s = tm.red[(size_t)i * TILE + tm.lane];
+        for (int w = 1; w < tm.nwk; w++)
+            s = dmin(s, tm.red[(size_t)(w * K + i) * TILE + tm.lane]);
+        v[i] = s;
+    }
+}
+
+// A z-shaped vector: compact (rows base+i) or embedded in a KKT-space vector (rows base+zk[i]).
+struct ZRef
+{
+    int base;
+    const int *map;
+    EI_DEV int row(int i) const { return base + (map ? EI_LDG(map + i) : i); }
+};
+
+struct TileMem
+{
+    double *T;
+    int *I;
+};
+
+EI_DEV TileMem tile_mem(const KArgs &a, int tile)
+{
+    TileMem t;
+    t.T = a.ws + (size_t)tile * a.L.rows_total * TILE;
+    t.I = a.iws + (size_t)tile * a.L.irows_total * TILE;
+    return t;
+}
+
+EI_DEV bool lane_active(const Team &tm, const TileMem &t) { return ROWD(t.I, J_STATUS) == ST_ACTIVE; }
+
+// ------------------------------------------------------------------ W products (src/eicos.cpp:485-507)
+// out = W * in for the lanes' current scalings.  One worker per cone; LP rows strided over workers.
+EI_DEV void cone_scale(const Team &tm, const KArgs &a, double *T, const ZRef in, const ZRef out, bool write)
+{
+    const DevPattern &P = a.P;
+    const Layout &L = a.L;
+    for (int k = tm.wk; k < P.l; k += tm.nwk)
+    {
+        const double v = ROWD(T, L.lpw + k) * ROWD(T, in.row(k));
+        if (write)
+            ROWD(T, out.row(k)) = v;
+    }
+    for (int c = tm.wk; c < P.nc; c += tm.nwk)
+    {
+        const int d = EI_LDG(P.cone_dim + c), zs = EI_LDG(P.cone_z + c), qo = EI_LDG(P.cone_q + c);
+        const double *cp = T + (size_t)(L.cpar + c * CP_COUNT) * TILE + tm.lane;
+        const double eta = cp[CP_ETA * TILE], ca = cp[CP_A * TILE];
+        double zeta = 0.0;
+        for (int k = 1; k < d; k++)
+            zeta += ROWD(T, L.cq + qo + k - 1) * ROWD(T, in.row(zs + k));
+        const double z0 = ROWD(T, in.row(zs));
+        const double factor = z0 + zeta / (1. + ca);
+        if (write)
+        {
+            ROWD(T, out.row(zs)) = eta * (ca * z0 + zeta);
+            for (int k = 1; k < d; k++)
+                ROWD(T, out.row(zs + k)) = eta * (ROWD(T, in.row(zs + k)) + factor * ROWD(T, L.cq + qo + k - 1));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ line search (src/eicos.cpp:1380-1469)
+// lambda, ds, dz are compact m-vectors (row offsets).  Returns the clamped step for every lane.
+// TODO(parity): the reference's `continue` on lknorm2<=0 skips the cone offset advance; here later
+// cones keep their own offsets (differs only after lambda has already left the cone).
+EI_DEV double line_search(const Team &tm, const KArgs &a, double *T, int lam, int ds, int dz,
+                          double tau, double dtau, double kap, double dkap)
+{
+    const DevPattern &P = a.P;
+    double alpha;
+    double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}; // rhomin, sigmamin, min over cones of 1/conic_step
+    for (int k = tm.wk; k < P.l; k += tm.nwk)
+    {
+        const double lk = ROWD(T, lam + k);
+        mn[0] = dmin(mn[0], ROWD(T, ds + k) / lk);
+        mn[1] = dmin(mn[1], ROWD(T, dz + k) / lk);
+    }
+    for (int c = tm.wk; c < P.nc; c += tm.nwk)
+    {
+        const int d = EI_LDG(P.cone_dim + c), zs = EI_LDG(P.cone_z + c);
+        const double l0 = ROWD(T, lam + zs);
+        double sq = 0.0;
+        for (int k = 1; k < d; k++)
+        {
+            const double v = ROWD(T, lam + zs + k);
+            sq += v * v;
+        }
+        const double lknorm2 = l0 * l0 - sq;
+        if (lknorm2 <= 0.)
+            continue;
+        const double lknorm = sqrt(lknorm2);
+        const double lknorminv = 1. / lknorm;
+        const double lk0 = l0 / lknorm;
+        double dsdot = 0.0, dzdot = 0.0;
+        for (int k = 1; k < d; k++)
+        {
+            const double lkb = ROWD(T, lam + zs + k) / lknorm;
+            dsdot += lkb * ROWD(T, ds + zs + k);
+            dzdot += lkb * ROWD(T, dz + zs + k);
+        }
+        const double ds0 = ROWD(T, ds + zs), dz0 = ROWD(T, dz + zs);
+        const double lds = lk0 * ds0 - dsdot, ldz = lk0 * dz0 - dzdot;
+        const double rho0 = lknorminv * lds, sig0 = lknorminv * ldz;
+        const double frho = (lds + ds0) / (lk0 + 1.), fsig = (ldz + dz0) / (lk0 + 1.);
+        double ar = 0.0, as = 0.0;
+        for (int k = 1; k < d; k++)
+        {
+            const double lkb = ROWD(T, lam + zs + k) / lknorm;
+            const double r = lknorminv * (ROWD(T, ds + zs + k) - frho * lkb);
+            const double s = lknorminv * (ROWD(T, dz + zs + k) - fsig * lkb);
+            ar += r * r;
+            as += s * s;
+        }
+        const double rhonorm = sqrt(ar) - rho0, signorm = sqrt(as) - sig0;
+        const double conic_step = dmax(0., dmax(signorm, rhonorm));
+        if (conic_step != 0.)
+            mn[2] = dmin(mn[2], 1. / conic_step);
+    }
+    team_min<3>(tm, mn);
+    if (P.l > 0)
+    {
+        const double rhomin = mn[0], sigmamin = mn[1];
+        const double eps = 1e-13;
+        if (-sigmamin > -rhomin)
+            alpha = sigmamin < 0. ? 1. / (-sigmamin) : 1. / eps;
+        else
+            alpha = rhomin < 0. ? 1. / (-rhomin) : 1. / eps;
+    }
+    else
+        alpha = 10.;
+    const double mt = -tau / dtau, mk = -kap / dkap;
+    if (mt > 0. && mt < alpha)
+        alpha = mt;
+    if (mk > 0. && mk < alpha)
+        alpha = mk;
+    alpha = dmin(mn[2], alpha);
+    // std::clamp(alpha, stepmin, stepmax)
+    if (alpha < Settings::stepmin)
+        alpha = Settings::stepmin;
+    else if (Settings::stepmax < alpha)
+        alpha = Settings::stepmax;
+    return alpha;
+}
+
+// ------------------------------------------------------------------ numeric LDL' (Eigen factorize, src/eicos.cpp:900,1164)
+// Left-looking by column on the fixed pattern, walking the level schedule of the elimination
+// tree.  Column j: gather its KKT entries, subtract the contribution of every earlier column k
+// with L(j,k) != 0 (row j of L, read from the row-ordered copy; the tail of column k below row j
+// is a contiguous run of rows), divide by the pivot and store the column in both orders.
+EI_DEV void factor_column(const Team &tm, const KArgs &a, double *T, int *I, int j, bool act)
+{
+    const DevPattern &P = a.P;
+    const Layout &L = a.L;
+    const int base = EI_LDG(P.Lp + j), cnt = EI_LDG(P.Lp + j + 1) - base;
+    double *acc = tm.acc + (size_t)tm.wk * P.maxcol * TILE + tm.lane;
+    for (int q = 0; q < cnt; q++)
+        acc[(size_t)q * TILE] = 0.0;
+    double d = 0.0;
+    for (int e = EI_LDG(P.KLp + j), e1 = EI_LDG(P.KLp + j + 1); e < e1; e++)
+    {
+        const int vi = EI_LDG(P.KLvidx + e), pos = EI_LDG(P.KLpos + e);
+        const double val = vi >= 0 ? ROWD(T, L.V + vi) : EI_LDG(P.KLval + e);
+        if (pos < 0)
+            d = val;
+        else
+            acc[(size_t)pos * TILE] = val;
+    }
+    for (int t = EI_LDG(P.Lrp + j), t1 = EI_LDG(P.Lrp + j + 1); t < t1; t++)
+    {
+        const int k = EI_LDG(P.Lrj + t);
+        const double ljk = ROWD(T, L.LTx + t);
+        const double w = ljk * ROWD(T, L.D + k);
+        d -= ljk * w;
+        int r = EI_LDG(P.upd_rel_p + t);
+        for (int u = EI_LDG(P.upd_tail + t), u1 = EI_LDG(P.Lp + k + 1); u < u1; u++, r++)
+            acc[(size_t)EI_LDG(P.upd_rel + r) * TILE] -= ROWD(T, L.Lx + u) * w;
+    }
+    ROWD(T, L.D + j) = d;
+    ROWD(T, L.Dinv + j) = 1.0 / d;
+    if (d == 0.0 && act)
+        ROWD(I, J_STATUS) = EXIT_FATAL; // Eigen reports NumericalIssue only on an exactly zero pivot
+    for (int q = 0; q < cnt; q++)
+    {
+        const double lv = acc[(size_t)q * TILE] / d;
+        ROWD(T, L.Lx + base + q) = lv;
+        ROWD(T, L.LTx + EI_LDG(P.Lcsr + base + q)) = lv;
+    }
+}
+
+EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
+{
+    const TileMem t = tile_mem(a, tile);
+    const bool act = lane_active(tm, t);
+    if (!tm.any(act))
+        return;
+    const DevPattern &P = a.P;
+    for (int ph = 0; ph < P.nphases; ph++)
+    {
+        const PhaseDev f = P.phases[ph];
+        if (f.parallel)
+        {
+            for (int q = f.begin + tm.wk; q < f.end; q += tm.nwk)
+                factor_column(tm, a, t.T, t.I, EI_LDG(P.tasks + q), act);
+        }
+        else if (tm.wk == 0)
+        {
+            for (int q = f.begin; q < f.end; q++)
+                factor_column(tm, a, t.T, t.I, EI_LDG(P.tasks + q), act);
+        }
+        tm.sync();
+    }
+}
+
+// ------------------------------------------------------------------ triangular solves (Eigen solve, src/eicos.cpp:1477,1599)
+// forward:  xw = L^-1 P rhs      (rows of L, dot form; the permutation is folded into the gather)
+// backward: out = P' L^-T D^-1 xw (columns of L, dot form; results land in KKT order directly)
+EI_DEV void ldl_forward(const Team &tm, const KArgs &a, double *T, int rhs)
+{
+    const DevPattern &P = a.P;
+    const Layout &L = a.L;
+    for (int ph = 0; ph < P.nphases; ph++)
+    {
+        const PhaseDev f = P.phases[ph];
+        const int step = f.parallel ? tm.nwk : 1;
+        if (f.parallel || tm.wk == 0)
+            for (int q = f.begin + (f.parallel ? tm.wk : 0); q < f.end; q += step)
+            {
+                const int i = EI_LDG(P.tasks + q);
+                double v = ROWD(T, rhs + EI_LDG(P.pinv + i));
+                for (int t = EI_LDG(P.Lrp + i), t1 = EI_LDG(P.Lrp + i + 1); t < t1; t++)
+                    v -= ROWD(T, L.LTx + t) * ROWD(T, L.xw + EI_LDG(P.Lrj + t));
+                ROWD(T, L.xw + i) = v;
+            }
+        tm.sync();
+    }
+}
+
+// mode 0: out = solution.  mode 1: out = refinement step, and x += step for lanes with `cont`.
+EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int out, int x, bool cont)
+{
+    const DevPattern &P = a.P;
+    const Layout &L = a.L;
+    for (int ph = P.nphases - 1; ph >= 0; ph--)
+    {
+        const PhaseDev f = P.phases[ph];
+        if (f.parallel || tm.wk == 0)
+        {
+            const int step = f.parallel ? tm.nwk : 1;
+            for (int q = f.end - 1 - (f.parallel ? tm.wk : 0); q >= f.begin; q -= step)
+            {
+                const int j = EI_LDG(P.tasks + q);
+                double v = ROWD(T, L.Dinv + j) * ROWD(T, L.xw + j);
+                for (int u = EI_LDG(P.Lp + j), u1 = EI_LDG(P.Lp + j + 1); u < u1; u++)
+                    v -= ROWD(T, L.Lx + u) * ROWD(T, out + EI_LDG(P.Lio + u));
+                const int o = EI_LDG(P.pinv + j);
+                ROWD(T, out + o) = v;
+                if (x >= 0 && cont)
+                    ROWD(T, x + o) += v;
+            }
+        }
+        tm.sync();
+    }
+}
+
+// ------------------------------------------------------------------ KKT residual for iterative refinement (src/eicos.cpp:1511-1576)
+// e = rhs - Ktrue * x with the un-regularised scaling block (identity while initialising),
+// returns ||e||_inf per lane.
+EI_DEV double kkt_residual(const Team &tm, const KArgs &a, double *T, int rhs, int x, bool initialize)
+{
+    const DevPattern &P = a.P;
+    const Layout &L = a.L;
+    const double delta = Settings::deltastat;
+    const int n = P.n, p = P.p, zb = P.n + P.p;
+    double nerr[1] = {0.0};
+    for (int j = tm.wk; j < n; j += tm.nwk)
+    {
+        double v = ROWD(T, rhs + j);
+        for (int k = EI_LDG(P.Gp + j), k1 = EI_LDG(P.Gp + j + 1); k < k1; k++)
+            v -= EI_LDG(P.Gx + k) * ROWD(T, x + zb + EI_LDG(P.zk + EI_LDG(P.Gi + k)));
+        for (int k = EI_LDG(P.Ap + j), k1 = EI_LDG(P.Ap + j + 1); k < k1; k++)
+            v -= EI_LDG(P.Ax + k) * ROWD(T, x + n + EI_LDG(P.Ai + k));
+        v -= delta * ROWD(T, x + j);
+        ROWD(T, L.e + j) = v;
+        nerr[0] = dmax(nerr[0], fabs(v));
+    }
+    for (int i = tm.wk; i < p; i += tm.nwk)
+    {
+        double v = ROWD(T, rhs + n + i);
+        for (int t = EI_LDG(P.Arp + i), t1 = EI_LDG(P.Arp + i + 1); t < t1; t++)
+            v -= EI_LDG(P.Ax + EI_LDG(P.Arv + t)) * ROWD(T, x + EI_LDG(P.Arj + t));
+        v += delta * ROWD(T, x + n + i);
+        ROWD(T, L.e + n + i) = v;
+        nerr[0] = dmax(nerr[0], fabs(v));
+    }
+    for (int i = tm.wk; i < P.l; i += tm.nwk)
+    {
+        double g = 0.0;
+        for (int t = EI_LDG(P.Grp + i), t1 = EI_LDG(P.Grp + i + 1); t < t1; t++)
+            g += EI_LDG(P.Gx + EI_LDG(P.Grv + t)) * ROWD(T, x + EI_LDG(P.Grj + t));
+        const double dz = ROWD(T, x + zb + i);
+        double v = ROWD(T, rhs + zb + i) - g + delta * dz;
+        v += initialize ? dz : ROWD(T, L.lpv + i) * dz;
+        ROWD(T, L.e + zb + i) = v;
+        nerr[0] = dmax(nerr[0], fabs(v));
+    }
+    for (int c = tm.wk; c < P.nc; c += tm.nwk)
+    {
+        const int d = EI_LDG(P.cone_dim + c), zs = EI_LDG(P.cone_z + c), qo = EI_LDG(P.cone_q + c);
+        const int kb = zb + EI_LDG(P.cone_k + c); // KKT row of the cone's first entry
+        const double *cp = T + (size_t)(L.cpar + c * CP_COUNT) * TILE + tm.lane;
+        const double eta2 = cp[CP_ETA2 * TILE], d1 = cp[CP_D1 * TILE], u0 = cp[CP_U0 * TILE];
+        const double u1 = cp[CP_U1 * TILE], v1 = cp[CP_V1 * TILE];
+        const double x1 = ROWD(T, x + kb), x3 = ROWD(T, x + kb + d), x4 = ROWD(T, x + kb + d + 1);
+        double qtx2 = 0.0;
+        for (int k = 1; k < d; k++)
+            qtx2 += ROWD(T, L.cq + qo + k - 1) * ROWD(T, x + kb + k);
+        const double vu = v1 * x3 + u1 * x4;
+        for (int k = 0; k < d; k++)
+        {
+            const int i = zs + k;
+            double g = 0.0;
+            for (int t = EI_LDG(P.Grp + i), t1 = EI_LDG(P.Grp + i + 1); t < t1; t++)
+                g += EI_LDG(P.Gx + EI_LDG(P.Grv + t)) * ROWD(T, x + EI_LDG(P.Grj + t));
+            const double xk = ROWD(T, x + kb + k);
+            double v = ROWD(T, rhs + kb + k) - g;
+            if (k < d - 1)
+                v += delta * xk;
+            else
+                v -= delta * xk;
+            if (initialize)
+                v += xk;
+            else if (k == 0)
+                v += eta2 * (d1 * x1 + u0 * x4);
+            else
+                v += eta2 * (xk + vu * ROWD(T, L.cq + qo + k - 1));
+            ROWD(T, L.e + kb + k) = v;
+            nerr[0] = dmax(nerr[0], fabs(v));
+        }
+        const double e3 = initialize ? x3 : eta2 * (v1 * qtx2 + x3);
+        const double e4 = initialize ? x4 : eta2 * (u0 * x1 + u1 * qtx2 - x4);
+        ROWD(T, L.e + kb + d) = e3;
+        ROWD(T, L.e + kb + d + 1) = e4;
+        nerr[0] = dmax(nerr[0], dmax(fabs(e3), fabs(e4)));
+    }
+    team_max<1>(tm, nerr);
+    return nerr[0];
+}
+
+// ------------------------------------------------------------------ solveKKT (src/eicos.cpp:1471-1620)
+// sol = K^-1 rhs followed by up to nitref refinement rounds; every lane stops on its own
+// criterion, the tile loops until all of its lanes have stopped.
+EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
+{
+    const TileMem t = tile_mem(a, tile);
+    const bool act = lane_active(tm, t);
+    if (!tm.any(act))
+        return;
+    const DevPattern &P = a.P;
+    const Layout &L = a.L;
+    double *T = t.T;
+    const int rhs = a.rhs, sol = a.sol;
+    const bool init = a.initialize != 0;
+
+    double mx[1] = {0.0};
+    for (int r = tm.wk; r < P.N; r += tm.nwk)
+        mx[0] = dmax(mx[0], fabs(ROWD(T, rhs + r)));
+    team_max<1>(tm, mx);
+    const double threshold = (1. + mx[0]) * Settings::linsysacc;
+
+    ldl_forward(tm, a, T, rhs);
+    ldl_backward(tm, a, T, sol, -1, false);
+
+    double nerr_prev = DBL_MAX;
+    int kref = 0;
+    bool done = !act;
+    unsigned rounds = 0;
+    for (;;)
+    {
+        const double nerr = kkt_residual(tm, a, T, rhs, sol, init);
+        bool rollback = false;
+        if (!done)
+        {
+            if (kref > 0 && nerr > nerr_prev)
+            {
+                rollback = true;
+                kref--;
+                done = true;
+            }
+            else if (kref == Settings::nitref || nerr < threshold || (kref > 0 && nerr_prev < Settings::irerrfact * nerr))
+                done = true;
+            else
+                nerr_prev = nerr;
+        }
+        if (tm.any(rollback))
+        { // x -= dx_ref for the lanes whose last refinement made things worse
+            for (int r = tm.wk; r < P.N; r += tm.nwk)
+                if (rollback)
+                    ROWD(T, sol + r) -= ROWD(T, L.dxr + r);
+        }
+        if (tm.all(done))
+            break;
+        tm.sync(); // e complete before the forward sweep gathers it
+        ldl_forward(tm, a, T, L.e);
+        ldl_backward(tm, a, T, L.dxr, sol, !done);
+        if (!done)
+            kref++;
+        rounds++;
+    }
+    tm.sync();
+    if (tm.wk == 0)
+    {
+        if (act && a.nitrow >= 0)
+            ROWD(t.I, a.nitrow) = kref;
+#ifndef EICOS_EMU
+        if (tm.lane == 0 && a.ir_rounds)
+            atomicAdd(a.ir_rounds, (unsigned long long)(rounds + 1));
+#endif
+    }
+}
+
+// ------------------------------------------------------------------ start of a solve (src/eicos.cpp:855-894)
+EI_DEV void tile_init(const Team &tm, const KArgs &a, int tile)
+{
+    const TileMem t = tile_mem(a, tile);
+    const DevPattern &P = a.P;
+    const Layout &L = a.L;
+    double *T = t.T;
+    const int zb = P.n + P.p;
+    const bool valid = tile * TILE + tm.lane < a.batch;
+    if (tm.wk == 0)
+    {
+        ROWD(t.I, J_STATUS) = valid ? (int)ST_ACTIVE : (int)EXIT_FATAL;
+        if (!a.keep_sticky)
+        {
+            ROWD(t.I, J_HAS_PINFRES) = 0;
+            ROWD(t.I, J_HAS_DINFRES) = 0;
+            ROWD(t.I, J_HAS_RELGAP) = 0;
+            ROWD(T, L.sc + S_PINFRES) = 0.0;
+            ROWD(T, L.sc + S_DINFRES) = 0.0;
+            ROWD(T, L.sc + S_RELGAP) = 0.0;
+        }
+    }
+    for (int k = tm.wk; k < P.nnzV; k += tm.nwk)
+    { // resetKKTScalings :807-846
+        const int kind = EI_LDG(P.Vkind + k);
+        ROWD(T, L.V + k) = kind == 0 ? -1.0 : (kind == 1 ? 0.0 : 1.0);
+    }
+    for (int r = tm.wk; r < P.N; r += tm.nwk)
+    {
+        ROWD(T, L.rhs1 + r) = 0.0;
+        ROWD(T, L.rhs2 + r) = 0.0;
+    }
+    tm.sync();
+    double nr[3] = {0.0, 0.0, 0.0};
+    for (int j = tm.wk; j < P.n; j += tm.nwk)
+    {
+        const double cj = ROWD(T, L.c + j);
+        ROWD(T, L.rhs2 + j) = -cj;
+        nr[0] += cj * cj;
+    }
+    for (int i = tm.wk; i < P.p; i += tm.nwk)
+    {
+        const double bi = ROWD(T, L.b + i);
+        ROWD(T, L.rhs1 + P.n + i) = bi;
+        nr[1] += bi * bi;
+    }
+    for (int i = tm.wk; i < P.m; i += tm.nwk)
+    {
+        const double hi = ROWD(T, L.h + i);
+        ROWD(T, L.rhs1 + zb + EI_LDG(P.zk + i)) = hi;
+        nr[2] += hi * hi;
+    }
+    team_sum<3>(tm, nr);
+    if (tm.wk == 0)
+    {
+        ROWD(T, L.sc + S_RESX0) = dmax(1., sqrt(nr[0]));
+        ROWD(T, L.sc + S_RESY0) = dmax(1., sqrt(nr[1]));
+        ROWD(T, L.sc + S_RESZ0) = dmax(1., sqrt(nr[2]));
+    }
+}
+
+// bringToCone (src/eicos.cpp:761-805): dst = sign*src + (1+alpha) e
+EI_DEV void bring_to_cone(const Team &tm, const KArgs &a, double *T, int src_kkt, double sign, int dst, bool write)
+{
+    const DevPattern &P = a.P;
+    double al[1] = {-Settings::gamma};
+    for (int k = tm.wk; k < P.l; k += tm.nwk)
+    {
+        const double r = sign * ROWD(T, src_kkt + k);
+        if (r <= 0 && -r > al[0])
+            al[0] = -r;
+    }
+    for (int c = tm.wk; c < P.nc; c += tm.nwk)
+    {
+        const int d = EI_LDG(P.cone_dim + c), kb = EI_LDG(P.cone_k + c);
+        double sq = 0.0;
+        for (int k = 1; k < d; k++)
+        {
+            const double v = sign * ROWD(T, src_kkt + kb + k);
+            sq += v * v;
+        }
+        const double cres = sign * ROWD(T, src_kkt + kb) - sqrt(sq);
+        if (cres <= 0 && -cres > al[0])
+            al[0] = -cres;
+    }
+    team_max<1>(tm, al);
+    const double alpha = al[0] + 1.;
+    if (!write)
+        return;
+    for (int k = tm.wk; k < P.l; k += tm.nwk)
+        ROWD(T, dst + k) = sign * ROWD(T, src_kkt + k) + alpha;
+    for (int c = tm.wk; c < P.nc; c += tm.nwk)
+    {
+        const int d = EI_LDG(P.cone_dim + c), kb = EI_LDG(P.cone_k + c), zs = EI_LDG(P.cone_z + c);
+        ROWD(T, dst + zs) = sign * ROWD(T, src_kkt + kb) + alpha;
+        for (int k = 1; k < d; k++)
+            ROWD(T, dst + zs + k) = sign * ROWD(T, src_kkt + kb + k);
+    }
+}
+
+// initial point (src/eicos.cpp:933-992), after the two initial KKT solves
+EI_DEV void tile_init_point(const Team &tm, const KArgs &a, int tile)
+{
+    const TileMem t = tile_mem(a, tile);
+    const bool act = lane_active(tm, t);
+    if (!tm.any(act))
+        return;
+    const DevPattern &P = a.P;
+    const Layout &L = a.L;
+    double *T = t.T;
+    const int zb = P.n + P.p;
+    for (int j = tm.wk; j < P.n; j += tm.nwk)
+    {
+        if (act)
+            ROWD(T, L.x + j) = ROWD(T, L.sol1 + j);
+        ROWD(T, L.rhs1 + j) = -ROWD(T, L.c + j);
+    }
+    for (int i = tm.wk; i < P.p; i += tm.nwk)
+        if (act)
+            ROWD(T, L.y + i) = ROWD(T, L.sol2 + P.n + i);
+    bring_to_cone(tm, a, T, L.sol1 + zb, -1.0, L.s, act);
+    bring_to_cone(tm, a, T, L.sol2 + zb, 1.0, L.z, act);
+    if (tm.wk == 0 && act)
+    {
+        ROWD(T, L.sc + S_KAP) = 1.;
+        ROWD(T, L.sc + S_TAU) = 1.;
+        ROWD(T, L.sc + S_STEP) = 0.;
+        ROWD(T, L.sc + S_STEP_AFF) = 0.;
+        ROWD(T, L.sc + S_PRES_PREV) = DBL_MAX;
+        ROWD(t.I, J_PINF) = 0;
+        ROWD(t.I, J_DINF) = 0;
+        ROWD(t.I, J_ITER) = 0;
+    }
+}
+
+// ------------------------------------------------------------------ per-lane scalar state of `Work` + `Information`
+struct WState
+{
+    double d[S_WORK_END];
+    int i[J_WORK_END];
+};
+
+EI_DEV void ws_load(const Team &tm, const double *T, const int *I, int sc, int soff, int ioff, WState &w)
+{
+    for (int k = 0; k < S_WORK_END; k++)
+        w.d[k] = ROWD(T, sc + soff + k);
+    for (int k = 0; k < J_WORK_END; k++)
+        w.i[k] = ROWD(I, ioff + k);
+}
+EI_DEV void ws_store(const Team &tm, double *T, int *I, int sc, int soff, int ioff, const WState &w)
+{
+    for (int k = 0; k < S_WORK_END; k++)
+        ROWD(T, sc + soff + k) = w.d[k];
+    for (int k = 0; k < J_WORK_END; k++)
+        ROWD(I, ioff + k) = w.i[k];
+}
+
+// Information::isBetterThan (src/eicos.cpp:23-68)
+EI_DEV bool ws_better(const WState &a, const WState &o)
+{
+    const bool gapmu = (a.d[S_GAP] > 0. && o.d[S_GAP] > 0. && a.d[S_GAP] < o.d[S_GAP]) &&
+                       (a.d[S_MU] > 0. && a.d[S_MU] < o.d[S_MU]);
+    if (a.i[J_HAS_PINFRES] && a.d[S_KAPOVERT] > 1.)
+    {
+        if (o.i[J_HAS_PINFRES])
+            return gapmu && (a.d[S_PINFRES] > 0. && a.d[S_PINFRES] < o.d[S_PRES]);
+        return gapmu;
+    }
+    return gapmu && (a.d[S_PRES] > 0. && a.d[S_PRES] < o.d[S_PRES]) &&
+           (a.d[S_DRES] > 0. && a.d[S_DRES] < o.d[S_DRES]) &&
+           (a.d[S_KAPOVERT] > 0. && a.d[S_KAPOVERT] < o.d[S_KAPOVERT]);
+}
+
+// checkExitConditions (src/eicos.cpp:526-641).  An empty std::optional compares "less than"
+// any double there, which is what the (!has || v < tol) terms reproduce.
+EI_DEV int ws_check_exit(WState &w, bool reduced)
+{
+    const double feastol = reduced ? Settings::feastol_inacc : Settings::feastol;
+    const double abstol = reduced ? Settings::abstol_inacc : Settings::abstol;
+    const double reltol = reduced ? Settings::reltol_inacc : Settings::reltol;
+    const double tau = w.d[S_TAU], kap = w.d[S_KAP];
+    if ((-w.d[S_CX] > 0. || -w.d[S_BY] - w.d[S_HZ] >= -abstol) &&
+        (w.d[S_PRES] < feastol && w.d[S_DRES] < feastol) &&
+        (w.d[S_GAP] < abstol || !w.i[J_HAS_RELGAP] || w.d[S_RELGAP] < reltol))
+    {
+        w.i[J_PINF] = 0;
+        w.i[J_DINF] = 0;
+        return reduced ? EXIT_OPTIMAL + EXIT_INACC : EXIT_OPTIMAL;
+    }
+    else if (w.i[J_HAS_DINFRES] && w.d[S_DINFRES] < feastol && tau < kap)
+    {
+        w.i[J_PINF] = 0;
+        w.i[J_DINF] = 1;
+        return reduced ? EXIT_DINF + EXIT_INACC : EXIT_DINF;
+    }
+    else if ((w.i[J_HAS_PINFRES] && w.d[S_PINFRES] < feastol && tau < kap) ||
+             (tau < feastol && kap < feastol && (!w.i[J_HAS_PINFRES] || w.d[S_PINFRES] < feastol)))
+    {
+        w.i[J_PINF] = 1;
+        w.i[J_DINF] = 0;
+        return reduced ? EXIT_PINF + EXIT_INACC : EXIT_PINF;
+    }
+    return EXIT_NOT_CONVERGED;
+}
+
+// ------------------------------------------------------------------ NT scaling of one cone (src/eicos.cpp:419-474)
+struct ConeScaling
+{
+    int stage; // 0 ok, 1 failed the residual test (nothing assigned), 2 failed c^2/u0^2 - d (eta, q assigned)
+    double eta, eta2, a, d1, u0, u1, v1, w, snorm, znorm, gamma;
+};
+
+EI_DEV ConeScaling cone_scaling(const Team &tm, const double *T, int srow, int zrow, int d)
+{
+    ConeScaling r;
+    const double s0 = ROWD(T, srow), z0 = ROWD(T, zrow);
+    double ss = 0.0, zz = 0.0;
+    for (int k = 1; k < d; k++)
+    {
+        const double sv = ROWD(T, srow + k), zv = ROWD(T, zrow + k);
+        ss += sv * sv;
+        zz += zv * zv;
+    }
+    const double sres = s0 * s0 - ss, zres = z0 * z0 - zz;
+    r.stage = 0;
+    if (sres <= 0 || zres <= 0)
+    {
+        r.stage = 1;
+        return r;
+    }
+    r.snorm = sqrt(sres);
+    r.znorm = sqrt(zres);
+    r.eta2 = r.snorm / r.znorm;
+    r.eta = sqrt(r.eta2);
+    double g = 0.0;
+    for (int k = 0; k < d; k++)
+        g += (ROWD(T, srow + k) / r.snorm) * (ROWD(T, zrow + k) / r.znorm);
+    g = sqrt(0.5 * (1. + g));
+    r.gamma = g;
+    const double av = (0.5 / g) * (s0 / r.snorm + z0 / r.znorm);
+    double w = 0.0;
+    for (int k = 1; k < d; k++)
+    {
+        const double qk = (0.5 / g) * (ROWD(T, srow + k) / r.snorm - ROWD(T, zrow + k) / r.znorm);
+        w += qk * qk;
+    }
+    const double cc = (1. + av) + w / (1. + av);
+    const double dd = 1. + 2. / (1. + av) + w / ((1. + av) * (1. + av));
+    const double d1 = dmax(0., 0.5 * (av * av + w * (1. - (cc * cc) / (1. + w * dd))));
+    const double u0sq = av * av + w - d1;
+    const double c2byu02 = (cc * cc) / u0sq;
+    if (c2byu02 - dd <= 0)
+    {
+        r.stage = 2;
+        return r;
+    }
+    r.d1 = d1;
+    r.u0 = sqrt(u0sq);
+    r.u1 = sqrt(c2byu02);
+    r.v1 = sqrt(c2byu02 - dd);
+    r.a = av;
+    r.w = w;
+    return r;
+}
+
+// ------------------------------------------------------------------ head of an iteration
+// computeResiduals + updateStatistics + safeguards / exit tests + best-iterate bookkeeping
+// (src/eicos.cpp:997-1158), then for the lanes that keep iterating: updateScalings,
+// updateKKTScalings and RHSaffine (:1160-1162, :1176).  Lanes that stop are back-scaled in place.
+EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
+{
+    const TileMem t = tile_mem(a, tile);
+    const bool act = lane_active(tm, t);
+    if (!tm.any(act))
+        return;
+    const DevPattern &P = a.P;
+    const Layout &L = a.L;
+    double *T = t.T;
+    int *I = t.I;
+    const int n = P.n, p = P.p, m = P.m, zb = P.n + P.p;
+    const double tau = ROWD(T, L.sc + S_TAU), kap = ROWD(T, L.sc + S_KAP);
+
+    enum { HX2, RX2, CX, NX2, HY2, RY2, BY, NY2, HZ2, RZ2, HZ, NZ2, NS2, GAP, NRED };
+    double r[NRED];
+    for (int k = 0; k < NRED; k++)
+        r[k] = 0.0;
+    for (int j = tm.wk; j < n; j += tm.nwk)
+    {
+        double v = 0.0;
+        for (int k = EI_LDG(P.Gp + j), k1 = EI_LDG(P.Gp + j + 1); k < k1; k++)
+            v -= EI_LDG(P.Gx + k) * ROWD(T, L.z + EI_LDG(P.Gi + k));
+        for (int k = EI_LDG(P.Ap + j), k1 = EI_LDG(P.Ap + j + 1); k < k1; k++)
+            v -= EI_LDG(P.Ax + k) * ROWD(T, L.y + EI_LDG(P.Ai + k));
+        r[HX2] += v * v;
+        const double cj = ROWD(T, L.c + j), xj = ROWD(T, L.x + j);
+        v -= tau * cj;
+        ROWD(T, L.rx + j) = v;
+        r[RX2] += v * v;
+        r[CX] += cj * xj;
+        r[NX2] += xj * xj;
+    }
+    for (int i = tm.wk; i < p; i += tm.nwk)
+    {
+        double v = 0.0;
+        for (int q = EI_LDG(P.Arp + i), q1 = EI_LDG(P.Arp + i + 1); q < q1; q++)
+            v += EI_LDG(P.Ax + EI_LDG(P.Arv + q)) * ROWD(T, L.x + EI_LDG(P.Arj + q));
+        r[HY2] += v * v;
+        const double bi = ROWD(T, L.b + i), yi = ROWD(T, L.y + i);
+        v -= tau * bi;
+        ROWD(T, L.ry + i) = v;
+        r[RY2] += v * v;
+        r[BY] += bi * yi;
+        r[NY2] += yi * yi;
+    }
+    for (int i = tm.wk; i < m; i += tm.nwk)
+    {
+        const double si = ROWD(T, L.s + i), zi = ROWD(T, L.z + i), hi = ROWD(T, L.h + i);
+        double v = si;
+        for (int q = EI_LDG(P.Grp + i), q1 = EI_LDG(P.Grp + i + 1); q < q1; q++)
+            v += EI_LDG(P.Gx + EI_LDG(P.Grv + q)) * ROWD(T, L.x + EI_LDG(P.Grj + q));
+        r[HZ2] += v * v;
+        v -= tau * hi;
+        ROWD(T, L.rz + i) = v;
+        r[RZ2] += v * v;
+        r[HZ] += hi * zi;
+        r[NZ2] += zi * zi;
+        r[NS2] += si * si;
+        r[GAP] += si * zi;
+    }
+    team_sum<NRED>(tm, r);
+
+    // ---- updateStatistics (:691-728) on registers; every warp computes the same values
+    WState w, best;
+    ws_load(tm, T, I, L.sc, 0, 0, w);
+    ws_load(tm, T, I, L.sc, S_BEST, J_BEST, best);
+    const double hresx = sqrt(r[HX2]), hresy = sqrt(r[HY2]), hresz = sqrt(r[HZ2]);
+    const double nx = sqrt(r[NX2]), ny = sqrt(r[NY2]), nz = sqrt(r[NZ2]), ns = sqrt(r[NS2]);
+    const double cx = r[CX], by = p > 0 ? r[BY] : 0., hz = r[HZ];
+    const double rt = kap + cx + by + hz;
+    w.d[S_CX] = cx;
+    w.d[S_BY] = by;
+    w.d[S_HZ] = hz;
+    w.d[S_GAP] = r[GAP];
+    w.d[S_MU] = (r[GAP] + kap * tau) / ((P.l + P.nc) + 1);
+    w.d[S_KAPOVERT] = kap / tau;
+    w.d[S_PCOST] = cx / tau;
+    w.d[S_DCOST] = -(hz + by) / tau;
+    if (w.d[S_PCOST] < 0.)
+    {
+        w.i[J_HAS_RELGAP] = 1;
+        w.d[S_RELGAP] = w.d[S_GAP] / (-w.d[S_PCOST]);
+    }
+    else if (w.d[S_DCOST] > 0.)
+    {
+        w.i[J_HAS_RELGAP] = 1;
+        w.d[S_RELGAP] = w.d[S_GAP] / w.d[S_DCOST];
+    }
+    else
+        w.i[J_HAS_RELGAP] = 0;
+    const double resx0 = ROWD(T, L.sc + S_RESX0), resy0 = ROWD(T, L.sc + S_RESY0), resz0 = ROWD(T, L.sc + S_RESZ0);
+    const double nry = p > 0 ? sqrt(r[RY2]) / dmax(resy0 + nx, 1.) : 0.;
+    const double nrz = sqrt(r[RZ2]) / dmax(resz0 + nx + ns, 1.);
+    w.d[S_PRES] = dmax(nry, nrz) / tau;
+    w.d[S_DRES] = sqrt(r[RX2]) / dmax(resx0 + ny + nz, 1.) / tau;
+    if ((hz + by) / dmax(ny + nz, 1.) < -Settings::reltol)
+    {
+        w.i[J_HAS_PINFRES] = 1;
+        w.d[S_PINFRES] = hresx / dmax(ny + nz, 1.);
+    }
+    if (cx / dmax(nx, 1.) < -Settings::reltol)
+    {
+        w.i[J_HAS_DINFRES] = 1;
+        w.d[S_DINFRES] = dmax(hresy / dmax(nx, 1.), hresz / dmax(nx + ns, 1.));
+    }
+
+    // ---- safeguards, exit tests, best iterate (:1010-1158)
+    const int iter = w.i[J_ITER];
+    double pres_prev = ROWD(T, L.sc + S_PRES_PREV);
+    int code = ST_ACTIVE;
+    bool restore = false, save = false;
+    if (act)
+    {
+        if (iter > 0 && (w.d[S_PRES] > Settings::safeguard * pres_prev || w.d[S_GAP] < 0.))
+        {
+            restore = true;
+            w = best;
+            code = ws_check_exit(w, true);
+            if (code == EXIT_NOT_CONVERGED)
+                code = EXIT_NUMERICS;
+        }
+        else
+        {
+            pres_prev = w.d[S_PRES];
+            code = ws_check_exit(w, false);
+            if (code == EXIT_NOT_CONVERGED)
+            {
+                if (iter > 0 && w.d[S_STEP] == Settings::stepmin * Settings::gamma)
+                {
+                    restore = true;
+                    w = best;
+                    code = ws_check_exit(w, true);
+                    if (code == EXIT_NOT_CONVERGED)
+                        code = EXIT_NUMERICS;
+                }
+                else if (iter == Settings::iter_max)
+                {
+                    if (!ws_better(w, best))
+                    {
+                        restore = true;
+                        w = best;
+                    }
+                    code = ws_check_exit(w, true);
+                    if (code == EXIT_NOT_CONVERGED)
+                        code = EXIT_MAXIT;
+                }
+                else if (ei_isnan(w.d[S_PCOST]))
+                {
+                    if (!(iter == 0 || ws_better(w, best)))
+                    {
+                        restore = true;
+                        w = best;
+                        code = ws_check_exit(w, true);
+                        if (code == EXIT_NOT_CONVERGED)
+                            code = EXIT_NUMERICS;
+                    } // else: the reference leaves not_converged_yet (-87) in place (:1117-1121)
+                }
+                else
+                    code = ST_ACTIVE;
+            }
+        }
+        if (code == ST_ACTIVE && (iter == 0 || ws_better(w, best)))
+        {
+            save = true;
+            best = w;
+        }
+    }
+    const bool fin = act && code != ST_ACTIVE;
+    const bool cont = act && !fin;
+    tm.sync(); // every warp has read the old state rows before warp 0 overwrites them
+    if (tm.wk == 0 && act)
+    {
+        ws_store(tm, T, I, L.sc, 0, 0, w);
+        if (save)
+            ws_store(tm, T, I, L.sc, S_BEST, J_BEST, best);
+        ROWD(T, L.sc + S_RT) = rt;
+        ROWD(T, L.sc + S_PRES_PREV) = pres_prev;
+        ROWD(I, J_STATUS) = code;
+    }
+
+    // ---- vector part of `w = w_best` / `w_best = w`, and backscale (:1271-1277) for finished lanes
+    const double ftau = w.d[S_TAU];
+    if (tm.any(restore || save || fin))
+    {
+        for (int j = tm.wk; j < n; j += tm.nwk)
+        {
+            double v = ROWD(T, L.x + j);
+            if (restore)
+                v = ROWD(T, L.bx + j);
+            if (save)
+                ROWD(T, L.bx + j) = v;
+            if (fin)
+                v = v / (EI_LDG(P.xeq + j) * ftau);
+            if (restore || fin)
+                ROWD(T, L.x + j) = v;
+        }
+        for (int i = tm.wk; i < p; i += tm.nwk)
+        {
+            double v = ROWD(T, L.y + i);
+            if (restore)
+                v = ROWD(T, L.by + i);
+            if (save)
+                ROWD(T, L.by + i) = v;
+            if (fin)
+                v = v / (EI_LDG(P.Aeq + i) * ftau);
+            if (restore || fin)
+                ROWD(T, L.y + i) = v;
+        }
+        for (int i = tm.wk; i < m; i += tm.nwk)
+        {
+            double zv = ROWD(T, L.z + i), sv = ROWD(T, L.s + i), lv = ROWD(T, L.lam + i);
+            if (restore)
+            {
+                zv = ROWD(T, L.bz + i);
+                sv = ROWD(T, L.bs + i);
+                lv = ROWD(T, L.blam + i);
+            }
+            if (save)
+            {
+                ROWD(T, L.bz + i) = zv;
+                ROWD(T, L.bs + i) = sv;
+                ROWD(T, L.blam + i) = lv;
+            }
+            if (fin)
+            {
+                const double ge = EI_LDG(P.Geq + i);
+                zv = zv / (ge * ftau);
+                sv = sv * (ge / ftau);
+            }
+            if (restore || fin)
+            {
+                ROWD(T, L.z + i) = zv;
+                ROWD(T, L.s + i) = sv;
+                ROWD(T, L.lam + i) = lv;
+            }
+        }
+    }
+    if (!tm.any(cont))
+        return;
+#ifndef EICOS_EMU
+    if (tm.wk == 0 && a.active_count)
+    {
+        const unsigned bal = __ballot_sync(0xffffffffu, cont);
+        if (tm.lane == 0)
+            atomicAdd(a.active_count, (unsigned)__popc(bal));
+    }
+#else
+    if (a.active_count && cont)
+        *a.active_count += 1;
+#endif
+
+    // ---- updateScalings (:411-479); its return value is ignored by the caller (:1160), so after a
+    // failure at cone c the LP part and cones < c are new, cone c is partly new and lambda is stale.
+    for (int k = tm.wk; k < P.l; k += tm.nwk)
+    {
+        const double v = ROWD(T, L.s + k) / ROWD(T, L.z + k);
+        if (cont)
+        {
+            ROWD(T, L.lpv + k) = v;
+            ROWD(T, L.lpw + k) = sqrt(v);
+        }
+    }
+    double ff[1] = {(double)P.nc};
+    for (int c = tm.wk; c < P.nc; c += tm.nwk)
+    {
+        const ConeScaling cs = cone_scaling(tm, T, L.s + EI_LDG(P.cone_z + c), L.z + EI_LDG(P.cone_z + c), EI_LDG(P.cone_dim + c));
+        if (cs.stage != 0)
+            ff[0] = dmin(ff[0], (double)c);
+    }
+    team_min<1>(tm, ff);
+    const int first_fail = (int)ff[0];
+    for (int c = tm.wk; c < P.nc; c += tm.nwk)
+    {
+        if (!cont || c > first_fail)
+            continue; // (divergent per lane, cone-local work only)
+        const int d = EI_LDG(P.cone_dim + c), zs = EI_LDG(P.cone_z + c), qo = EI_LDG(P.cone_q + c);
+        const ConeScaling cs = cone_scaling(tm, T, L.s + zs, L.z + zs, d);
+        if (cs.stage == 1)
+            continue;
+        double *cp = T + (size_t)(L.cpar + c * CP_COUNT) * TILE + tm.lane;
+        cp[CP_ETA2 * TILE] = cs.eta2;
+        cp[CP_ETA * TILE] = cs.eta;
+        for (int k = 1; k < d; k++)
+            ROWD(T, L.cq + qo + k - 1) = (0.5 / cs.gamma) * (ROWD(T, L.s + zs + k) / cs.snorm - ROWD(T, L.z + zs + k) / cs.znorm);
+        if (cs.stage == 2)
+            continue;
+        cp[CP_D1 * TILE] = cs.d1;
+        cp[CP_U0 * TILE] = cs.u0;
+        cp[CP_U1 * TILE] = cs.u1;
+        cp[CP_V1 * TILE] = cs.v1;
+        cp[CP_A * TILE] = cs.a;
+        cp[CP_W * TILE] = cs.w;
+    }
+    tm.sync();
+    cone_scale(tm, a, T, ZRef{L.z, nullptr}, ZRef{L.lam, nullptr}, cont && first_fail == P.nc);
+
+    // ---- updateKKTScalings (:1691-1732) into the V rows, RHSaffine (:1670-1689) into rhs2
+    const double delta = Settings::deltastat;
+    for (int k = tm.wk; k < P.l; k += tm.nwk)
+        ROWD(T, L.V + k) = -ROWD(T, L.lpv + k) - delta;
+    for (int c = tm.wk; c < P.nc; c += tm.nwk)
+    {
+        const int d = EI_LDG(P.cone_dim + c), zs = EI_LDG(P.cone_z + c), qo = EI_LDG(P.cone_q + c);
+        const double *cp = T + (size_t)(L.cpar + c * CP_COUNT) * TILE + tm.lane;
+        const double eta2 = cp[CP_ETA2 * TILE], d1 = cp[CP_D1 * TILE], u0 = cp[CP_U0 * TILE];
+        const double u1 = cp[CP_U1 * TILE], v1 = cp[CP_V1 * TILE];
+        int vb = L.V + P.l + 3 * (zs - P.l) + c; // cones before c contributed sum(3 dim + 1) entries
+        ROWD(T, vb++) = -eta2 * d1 - delta;
+        for (int k = 1; k < d; k++)
+            ROWD(T, vb++) = -eta2 - delta;
+        ROWD(T, vb++) = -eta2;
+        for (int k = 1; k < d; k++)
+            ROWD(T, vb++) = -eta2 * v1 * ROWD(T, L.cq + qo + k - 1);
+        ROWD(T, vb++) = eta2 + delta;
+        ROWD(T, vb++) = -eta2 * u0;
+        for (int k = 1; k < d; k++)
+            ROWD(T, vb++) = -eta2 * u1 * ROWD(T, L.cq + qo + k - 1);
+    }
+    for (int j = tm.wk; j < n; j += tm.nwk)
+        ROWD(T, L.rhs2 + j) = ROWD(T, L.rx + j);
+    for (int i = tm.wk; i < p; i += tm.nwk)
+        ROWD(T, L.rhs2 + n + i) = -ROWD(T, L.ry + i);
+    for (int i = tm.wk; i < m; i += tm.nwk)
+        ROWD(T, L.rhs2 + zb + EI_LDG(P.zk + i)) = ROWD(T, L.s + i) - ROWD(T, L.rz + i);
+    for (int c = tm.wk; c < P.nc; c += tm.nwk)
+    {
+        const int kb = zb + EI_LDG(P.cone_k + c) + EI_LDG(P.cone_dim + c);
+        ROWD(T, L.rhs2 + kb) = 0.0;
+        ROWD(T, L.rhs2 + kb + 1) = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------ affine step -> centering -> combined RHS
+// (src/eicos.cpp:1181-1210 with RHScombined :1282-1325, conicProduct :1357, conicDivision :1330)
+EI_DEV void tile_mid(const Team &tm, const KArgs &a, int tile)
+{
+    const TileMem t = tile_mem(a, tile);
+    const bool act = lane_active(tm, t);
+    if (!tm.any(act))
+        return;
+    const DevPattern &P = a.P;
+    const Layout &L = a.L;
+    double *T = t.T;
+    const int n = P.n, p = P.p, m = P.m, zb = P.n + P.p;
+    const double tau = ROWD(T, L.sc + S_TAU), kap = ROWD(T, L.sc + S_KAP), rt = ROWD(T, L.sc + S_RT);
+    const double mu = ROWD(T, L.sc + S_MU);
+
+    double dt[6] = {0, 0, 0, 0, 0, 0};
+    for (int j = tm.wk; j < n; j += tm.nwk)
+    {
+        const double cj = ROWD(T, L.c + j);
+        dt[0] += cj * ROWD(T, L.sol1 + j);
+        dt[3] += cj * ROWD(T, L.sol2 + j);
+    }
+    for (int i = tm.wk; i < p; i += tm.nwk)
+    {
+        const double bi = ROWD(T, L.b + i);
+        dt[1] += bi * ROWD(T, L.sol1 + n + i);
+        dt[4] += bi * ROWD(T, L.sol2 + n + i);
+    }
+    for (int i = tm.wk; i < m; i += tm.nwk)
+    {
+        const double hi = ROWD(T, L.h + i);
+        const int kr = zb + EI_LDG(P.zk + i);
+        dt[2] += hi * ROWD(T, L.sol1 + kr);
+        dt[5] += hi * ROWD(T, L.sol2 + kr);
+    }
+    team_sum<6>(tm, dt);
+    const double dtau_denom = kap / tau - dt[0] - dt[1] - dt[2];
+    const double dtauaff = (rt - kap + dt[3] + dt[4] + dt[5]) / dtau_denom;
+    for (int i = tm.wk; i < m; i += tm.nwk)
+    {
+        const int kr = zb + EI_LDG(P.zk + i);
+        ROWD(T, L.sol2 + kr) += dtauaff * ROWD(T, L.sol1 + kr);
+    }
+    tm.sync();
+    cone_scale(tm, a, T, ZRef{L.sol2 + zb, P.zk}, ZRef{L.wdz, nullptr}, true);
+    tm.sync();
+    for (int i = tm.wk; i < m; i += tm.nwk)
+        ROWD(T, L.dsw + i) = -ROWD(T, L.wdz + i) - ROWD(T, L.lam + i);
+    tm.sync();
+    const double dkapaff = -kap - kap / tau * dtauaff;
+    const double step_aff = line_search(tm, a, T, L.lam, L.dsw, L.wdz, tau, dtauaff, kap, dkapaff);
+    const double om = 1. - step_aff;
+    double sigma = om * om * om; // std::pow(x, 3)
+    if (sigma < Settings::sigmamin)
+        sigma = Settings::sigmamin;
+    else if (Settings::sigmamax < sigma)
+        sigma = Settings::sigmamax;
+    if (tm.wk == 0 && act)
+    {
+        ROWD(T, L.sc + S_DTAU_DENOM) = dtau_denom;
+        ROWD(T, L.sc + S_DTAUAFF) = dtauaff;
+        ROWD(T, L.sc + S_DKAPAFF) = dkapaff;
+        ROWD(T, L.sc + S_STEP_AFF) = step_aff;
+        ROWD(T, L.sc + S_SIGMA) = sigma;
+    }
+
+    // RHScombined
+    const double sigmamu = sigma * mu, oms = 1. - sigma;
+    for (int r = tm.wk; r < n + p; r += tm.nwk)
+        ROWD(T, L.rhs2 + r) *= oms;
+    for (int k = tm.wk; k < P.l; k += tm.nwk)
+    {
+        const double lk = ROWD(T, L.lam + k);
+        double d1 = lk * lk;
+        d1 += ROWD(T, L.dsw + k) * ROWD(T, L.wdz + k);
+        d1 -= sigmamu;
+        const double q = d1 / lk; // conicDivision, LP part
+        ROWD(T, L.dsw + k) = q;
+        ROWD(T, L.rhs2 + zb + k) = -oms * ROWD(T, L.rz + k) + ROWD(T, L.lpw + k) * q;
+    }
+    for (int c = tm.wk; c < P.nc; c += tm.nwk)
+    {
+        const int d = EI_LDG(P.cone_dim + c), zs = EI_LDG(P.cone_z + c), qo = EI_LDG(P.cone_q + c);
+        const int kb = zb + EI_LDG(P.cone_k + c);
+        const double *cp = T + (size_t)(L.cpar + c * CP_COUNT) * TILE + tm.lane;
+        const double eta = cp[CP_ETA * TILE], ca = cp[CP_A * TILE];
+        // ds1 = lambda o lambda ; ds2 = (W\ds_aff) o (W dz_aff)
+        const double l0 = ROWD(T, L.lam + zs), u0 = ROWD(T, L.dsw + zs), v0 = ROWD(T, L.wdz + zs);
+        double ll = 0.0, uv = 0.0;
+        for (int k = 0; k < d; k++)
+        {
+            const double lk = ROWD(T, L.lam + zs + k);
+            ll += lk * lk;
+            uv += ROWD(T, L.dsw + zs + k) * ROWD(T, L.wdz + zs + k);
+        }
+        double w0 = ll - sigmamu;
+        w0 += uv;
+        ROWD(T, L.ds1 + zs) = w0;
+        for (int k = 1; k < d; k++)
+        {
+            const double lk = ROWD(T, L.lam + zs + k);
+            double v = l0 * lk + l0 * lk;
+            v += u0 * ROWD(T, L.wdz + zs + k) + v0 * ROWD(T, L.dsw + zs + k);
+            ROWD(T, L.ds1 + zs + k) = v;
+        }
+        // dsw = lambda \ ds1
+        double rho = 0.0, zeta = 0.0;
+        for (int k = 1; k < d; k++)
+        {
+            const double lk = ROWD(T, L.lam + zs + k);
+            rho += lk * lk;
+            zeta += lk * ROWD(T, L.ds1 + zs + k);
+        }
+        rho = l0 * l0 - rho;
+        const double factor = (zeta / l0 - w0) / rho;
+        const double q0 = (l0 * w0 - zeta) / rho;
+        ROWD(T, L.dsw + zs) = q0;
+        for (int k = 1; k < d; k++)
+            ROWD(T, L.dsw + zs + k) = factor * ROWD(T, L.lam + zs + k) + ROWD(T, L.ds1 + zs + k) / l0;
+        // ds1 = W * dsw, then the cone rows of rhs2
+        double zt = 0.0;
+        for (int k = 1; k < d; k++)
+            zt += ROWD(T, L.cq + qo + k - 1) * ROWD(T, L.dsw + zs + k);
+        const double fz = q0 + zt / (1. + ca);
+        ROWD(T, L.rhs2 + kb) = -oms * ROWD(T, L.rz + zs) + eta * (ca * q0 + zt);
+        for (int k = 1; k < d; k++)
+            ROWD(T, L.rhs2 + kb + k) = -oms * ROWD(T, L.rz + zs + k) +
+                                       eta * (ROWD(T, L.dsw + zs + k) + fz * ROWD(T, L.cq + qo + k - 1));
+        ROWD(T, L.rhs2 + kb + d) = 0.0;
+        ROWD(T, L.rhs2 + kb + d + 1) = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------ combined step and iterate update (src/eicos.cpp:1214-1252)
+EI_DEV void tile_tail(const Team &tm, const KArgs &a, int tile)
+{
+    const TileMem t = tile_mem(a, tile);
+    const bool act = lane_active(tm, t);
+    if (!tm.any(act))
+        return;
+    const DevPattern &P = a.P;
+    const Layout &L = a.L;
+    double *T = t.T;
+    const int n = P.n, p = P.p, m = P.m, zb = P.n + P.p;
+    const double tau = ROWD(T, L.sc + S_TAU), kap = ROWD(T, L.sc + S_KAP), rt = ROWD(T, L.sc + S_RT);
+    const double mu = ROWD(T, L.sc + S_MU), sigma = ROWD(T, L.sc + S_SIGMA);
+    const double dtau_denom = ROWD(T, L.sc + S_DTAU_DENOM), dtauaff = ROWD(T, L.sc + S_DTAUAFF);
+    const double dkapaff = ROWD(T, L.sc + S_DKAPAFF);
+
+    double dt[3] = {0, 0, 0};
+    for (int j = tm.wk; j < n; j += tm.nwk)
+        dt[0] += ROWD(T, L.c + j) * ROWD(T, L.sol2 + j);
+    for (int i = tm.wk; i < p; i += tm.nwk)
+        dt[1] += ROWD(T, L.b + i) * ROWD(T, L.sol2 + n + i);
+    for (int i = tm.wk; i < m; i += tm.nwk)
+        dt[2] += ROWD(T, L.h + i) * ROWD(T, L.sol2 + zb + EI_LDG(P.zk + i));
+    team_sum<3>(tm, dt);
+    const double bkap = kap * tau + dkapaff * dtauaff - sigma * mu;
+    const double dtau = ((1. - sigma) * rt - bkap / tau + dt[0] + dt[1] + dt[2]) / dtau_denom;
+    for (int r = tm.wk; r < P.N; r += tm.nwk)
+        ROWD(T, L.sol2 + r) += dtau * ROWD(T, L.sol1 + r);
+    tm.sync();
+    cone_scale(tm, a, T, ZRef{L.sol2 + zb, P.zk}, ZRef{L.wdz, nullptr}, true);
+    tm.sync();
+    for (int i = tm.wk; i < m; i += tm.nwk)
+        ROWD(T, L.dsw + i) = -(ROWD(T, L.dsw + i) + ROWD(T, L.wdz + i));
+    tm.sync();
+    const double dkap = -(bkap + kap * dtau) / tau;
+    const double step = Settings::gamma * line_search(tm, a, T, L.lam, L.dsw, L.wdz, tau, dtau, kap, dkap);
+    cone_scale(tm, a, T, ZRef{L.dsw, nullptr}, ZRef{L.dsaff, nullptr}, true);
+    tm.sync();
+    if (!act)
+        return; // no barriers below
+    for (int j = tm.wk; j < n; j += tm.nwk)
+        ROWD(T, L.x + j) += step * ROWD(T, L.sol2 + j);
+    for (int i = tm.wk; i < p; i += tm.nwk)
+        ROWD(T, L.y + i) += step * ROWD(T, L.sol2 + n + i);
+    for (int i = tm.wk; i < m; i += tm.nwk)
+    {
+        ROWD(T, L.z + i) += step * ROWD(T, L.sol2 + zb + EI_LDG(P.zk + i));
+        ROWD(T, L.s + i) += step * ROWD(T, L.dsaff + i);
+    }
+    if (tm.wk == 0)
+    {
+        ROWD(T, L.sc + S_KAP) = kap + step * dkap;
+        ROWD(T, L.sc + S_TAU) = tau + step * dtau;
+        ROWD(T, L.sc + S_STEP) = step;
+        ROWD(t.I, J_ITER) += 1;
+    }
+}
+
+// ------------------------------------------------------------------ data in / results out
+// Inputs are instance-major (what the C ABI receives); they are equilibrated on the way in
+// (c / x_equil, h / G_equil, b / A_equil : src/eicos.cpp:364-371).
+EI_DEV void tile_load(const Team &tm, const KArgs &a, int tile)
+{
+    const TileMem t = tile_mem(a, tile);
+    const DevPattern &P = a.P;
+    const Layout &L = a.L;
+    int inst = tile * TILE + tm.lane;
+    if (inst >= a.batch)
+        inst = a.batch - 1; // padding lanes replay the last instance; their results are never stored
+    const size_t g = (size_t)a.first + inst;
+    for (int j = tm.wk; j < P.n; j += tm.nwk)
+    {
+        const double v = a.in_c ? a.in_c[g * P.n + j] : EI_LDG(a.base_c + j);
+        ROWD(t.T, L.c + j) = a.pre_equilibrated ? v : v / EI_LDG(P.xeq + j);
+    }
+    for (int i = tm.wk; i < P.m; i += tm.nwk)
+    {
+        const double v = a.in_h ? a.in_h[g * P.m + i] : EI_LDG(a.base_h + i);
+        ROWD(t.T, L.h + i) = a.pre_equilibrated ? v : v / EI_LDG(P.Geq + i);
+    }
+    for (int i = tm.wk; i < P.p; i += tm.nwk)
+    {
+        const double v = a.in_b ? a.in_b[g * P.p + i] : EI_LDG(a.base_b + i);
+        ROWD(t.T, L.b + i) = a.pre_equilibrated ? v : v / EI_LDG(P.Aeq + i);
+    }
+}
+
+EI_DEV void tile_store(const Team &tm, const KArgs &a, int tile)
+{
+    const TileMem t = tile_mem(a, tile);
+    const DevPattern &P = a.P;
+    const Layout &L = a.L;
+    const int inst = tile * TILE + tm.lane;
+    if (inst >= a.batch)
+        return;
+    const size_t g = (size_t)a.first + inst;
+    if (a.out_x)
+        for (int j = tm.wk; j < P.n; j += tm.nwk)
+            a.out_x[g * P.n + j] = ROWD(t.T, L.x + j);
+    if (a.out_y)
+        for (int i = tm.wk; i < P.p; i += tm.nwk)
+            a.out_y[g * P.p + i] = ROWD(t.T, L.y + i);
+    if (a.out_z)
+        for (int i = tm.wk; i < P.m; i += tm.nwk)
+            a.out_z[g * P.m + i] = ROWD(t.T, L.z + i);
+    if (a.out_s)
+        for (int i = tm.wk; i < P.m; i += tm.nwk)
+            a.out_s[g * P.m + i] = ROWD(t.T, L.s + i);
+    if (tm.wk == 0)
+    {
+        if (a.out_exit)
+            a.out_exit[g] = ROWD(t.I, J_STATUS);
+        if (a.out_iter)
+            a.out_iter[g] = ROWD(t.I, J_ITER);
+        if (a.out_info)
+            for (int k = 0; k < S_WORK_END; k++)
+                a.out_info[g * S_WORK_END + k] = ROWD(t.T, L.sc + k);
+        if (a.out_iinfo)
+            for (int k = 0; k < J_WORK_END; k++)
+                a.out_iinfo[g * J_WORK_END + k] = ROWD(t.I, k);
+    }
+}
+
+} // namespace eicos

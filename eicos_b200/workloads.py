@@ -1,0 +1,115 @@
+"""Synthetic workloads for the parity tests and bench.py (host-side numpy only).
+
+* `perturbed(P, batch, ...)` - BASELINE.json configs[2]: one fixture, `batch` instances with
+  h and b perturbed entry-wise, h_b = h (1 + rel u), u ~ U(-1,1); zeros stay zero; G, A, c shared.
+* `soc_mpc(...)` - a builder-defined SOC-bearing MPC problem (the reference's MPC01 data file is
+  missing from the checkout): 2-D double integrator, horizon T, tracking cost
+  through second-order cones.  NOT reference data.
+"""
+import numpy as np
+
+
+def perturbed(P, batch, rel=0.05, seed=1234, vary=("h", "b")):
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    out = {}
+    for k in ("c", "h", "b"):
+        if k in vary and np.asarray(P[k]).size:
+            base = np.asarray(P[k], dtype=np.float64)
+            u = rng.uniform(-1.0, 1.0, size=(batch, base.size))
+            out[k + "s"] = base[None, :] * (1.0 + rel * u)
+        else:
+            out[k + "s"] = None
+    return out
+
+
+def _csc(M):
+    """dense -> (pr, jc, ir) with rows ascending per column, explicit zeros dropped"""
+    M = np.asarray(M, dtype=np.float64)
+    jc, ir, pr = [0], [], []
+    for j in range(M.shape[1]):
+        nz = np.nonzero(M[:, j])[0]
+        ir.extend(nz.tolist())
+        pr.extend(M[nz, j].tolist())
+        jc.append(len(ir))
+    return np.array(pr), np.array(jc, np.int32), np.array(ir, np.int32)
+
+
+def soc_mpc(T=20, dt=0.25, umax=2.0, vmax=3.0, x0=(4.0, -3.0, 0.5, 0.0), ref=(0.0, 0.0, 0.0, 0.0), rho=0.1):
+    """min sum_k t_k + rho r_k   s.t.  x_{k+1} = Ad x_k + Bd u_k, x_0 given,
+    |v_k| <= vmax (LP), r_k <= umax (LP), ||u_k|| <= r_k (SOC dim 3), ||x_{k+1} - ref|| <= t_k (SOC dim 5).
+    Variables per stage k=0..T-1: u_k (2), r_k, t_k, x_{k+1} (4)  -> n = 8 T."""
+    Ad = np.eye(4)
+    Ad[0, 2] = Ad[1, 3] = dt
+    Bd = np.zeros((4, 2))
+    Bd[0, 0] = Bd[1, 1] = 0.5 * dt * dt
+    Bd[2, 0] = Bd[3, 1] = dt
+    nv = 8
+    n = nv * T
+    iu, ir_, it, ix = 0, 2, 3, 4
+    c = np.zeros(n)
+    A = np.zeros((4 * T, n))
+    b = np.zeros(4 * T)
+    for k in range(T):
+        o = nv * k
+        c[o + it] = 1.0
+        c[o + ir_] = rho
+        A[4 * k:4 * k + 4, o + ix:o + ix + 4] = np.eye(4)
+        A[4 * k:4 * k + 4, o + iu:o + iu + 2] = -Bd
+        if k == 0:
+            b[0:4] = Ad @ np.asarray(x0, dtype=np.float64)
+        else:
+            A[4 * k:4 * k + 4, o - nv + ix:o - nv + ix + 4] = -Ad
+    rows_lp = 5 * T
+    m = rows_lp + 3 * T + 5 * T
+    G = np.zeros((m, n))
+    h = np.zeros(m)
+    r = 0
+    for k in range(T):
+        o = nv * k
+        for d in (2, 3):  # |v| <= vmax
+            G[r, o + ix + d] = 1.0
+            h[r] = vmax
+            r += 1
+            G[r, o + ix + d] = -1.0
+            h[r] = vmax
+            r += 1
+        G[r, o + ir_] = 1.0  # r_k <= umax
+        h[r] = umax
+        r += 1
+    q = []
+    for k in range(T):  # (r_k; u_k) in Q^3
+        o = nv * k
+        G[r, o + ir_] = -1.0
+        G[r + 1, o + iu] = -1.0
+        G[r + 2, o + iu + 1] = -1.0
+        r += 3
+        q.append(3)
+    for k in range(T):  # (t_k; x_{k+1} - ref) in Q^5
+        o = nv * k
+        G[r, o + it] = -1.0
+        for d in range(4):
+            G[r + 1 + d, o + ix + d] = -1.0
+            h[r + 1 + d] = -ref[d]
+        r += 5
+        q.append(5)
+    assert r == m
+    Gpr, Gjc, Gir = _csc(G)
+    Apr, Ajc, Air = _csc(A)
+    return dict(n=n, m=m, p=4 * T, l=rows_lp, ncones=len(q), q=np.array(q, np.int32),
+                Gpr=Gpr, Gjc=Gjc, Gir=Gir, Apr=Apr, Ajc=Ajc, Air=Air, c=c, h=h, b=b,
+                meta=dict(T=T, Ad=Ad, nv=nv))
+
+
+def soc_mpc_batch(P, batch, seed=7):
+    """Per-instance initial state (enters b) and reference (enters h); everything else shared."""
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    T, Ad = P["meta"]["T"], P["meta"]["Ad"]
+    bs = np.repeat(P["b"][None, :], batch, axis=0)
+    hs = np.repeat(P["h"][None, :], batch, axis=0)
+    x0 = rng.uniform(-5, 5, size=(batch, 4)) * np.array([1, 1, 0.3, 0.3])
+    ref = rng.uniform(-1, 1, size=(batch, 4)) * np.array([1, 1, 0, 0])
+    bs[:, 0:4] = x0 @ Ad.T
+    base = 5 * T + 3 * T
+    for k in range(T):
+        hs[:, base + 5 * k + 1: base + 5 * k + 5] = -ref
+    return dict(cs=None, hs=hs, bs=bs)
