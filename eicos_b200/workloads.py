@@ -2,21 +2,27 @@
 
 * `perturbed(P, batch, ...)` - BASELINE.json configs[2]: one fixture, `batch` instances with
   h and b perturbed entry-wise, h_b = h (1 + rel u), u ~ U(-1,1); zeros stay zero; G, A, c shared.
+  MPC_REL is the perturbation bench.py uses on MPC02: b +-2 %, h +-0.2 % - every instance stays feasible (MPC02 has paired bounds
+  39 <= x <= 39.3, so +-5 % on h makes two thirds of the instances primal infeasible; +-5 % on b about 2 %).
 * `soc_mpc(...)` - a builder-defined SOC-bearing MPC problem (the reference's MPC01 data file is
   missing from the checkout): 2-D double integrator, horizon T, tracking cost
   through second-order cones.  NOT reference data.
 """
 import numpy as np
 
+MPC_REL = {"h": 0.002, "b": 0.02}
+
 
 def perturbed(P, batch, rel=0.05, seed=1234, vary=("h", "b")):
+    """rel: one float, or a dict per vector, e.g. {"h": 0.002, "b": 0.05}."""
     rng = np.random.Generator(np.random.Philox(key=seed))
     out = {}
     for k in ("c", "h", "b"):
-        if k in vary and np.asarray(P[k]).size:
+        r = rel.get(k, 0.0) if isinstance(rel, dict) else rel
+        if k in vary and np.asarray(P[k]).size and r:
             base = np.asarray(P[k], dtype=np.float64)
             u = rng.uniform(-1.0, 1.0, size=(batch, base.size))
-            out[k + "s"] = base[None, :] * (1.0 + rel * u)
+            out[k + "s"] = base[None, :] * (1.0 + r * u)
         else:
             out[k + "s"] = None
     return out

@@ -1978,7 +1978,7 @@ double ora_batch_run(int n, int m, int p, int l, int ncones, const int *q,
                      int batch,
                      const double *Gs, const double *As,
                      const double *cs, const double *hs, const double *bs,
-                     int nthreads,
+                     int nthreads, int reset_sticky,
                      int *exitflags, int *iters, double *xs, double *ys, double *zs, double *ss,
                      double *pcosts)
 {
@@ -2002,6 +2002,11 @@ double ora_batch_run(int n, int m, int p, int l, int ncones, const int *q,
             const double *hi = hs ? hs + (size_t)i * m : h;
             const double *bi = bs ? bs + (size_t)i * p : b;
             S->update_data_ptr(Gi, Ai, ci, hi, bi);
+            if (reset_sticky)
+            { /* a fresh Solver has empty pinfres/dinfres; the reference never clears them (:720-728) */
+                S->w.i.has_pinfres = S->w.i.has_dinfres = false;
+                S->w.i.pinfres = S->w.i.dinfres = 0.0;
+            }
             const int code = S->solve();
             if (exitflags)
                 exitflags[i] = code;

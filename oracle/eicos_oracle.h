@@ -75,6 +75,10 @@ void ora_debug_get_data(void *solver, double *Gpr, double *Apr, double *c, doubl
  * instance i of its slice: updateData(Gpr_i|base, Apr_i|base, c_i|base, h_i, b_i)
  * + solve().  Stacked arrays are instance-major; a NULL stacked pointer means
  * "every instance uses the base array".  Outputs may be NULL.
+ * reset_sticky != 0 clears Information::pinfres/dinfres before every solve, which makes each
+ * instance behave like a freshly constructed Solver (the batched API's definition); with 0 the
+ * flags carry over from the previous instance solved by the same thread exactly as a reused
+ * reference Solver would (they are never cleared there, src/eicos.cpp:720-728).
  * Returns wall seconds spent in the update+solve loop (construction excluded).
  */
 double ora_batch_run(int n, int m, int p, int l, int ncones, const int *q,
@@ -84,7 +88,7 @@ double ora_batch_run(int n, int m, int p, int l, int ncones, const int *q,
                      int batch,
                      const double *Gs, const double *As,
                      const double *cs, const double *hs, const double *bs,
-                     int nthreads,
+                     int nthreads, int reset_sticky,
                      int *exitflags, int *iters, double *xs, double *ys, double *zs, double *ss,
                      double *pcosts);
 

@@ -83,7 +83,7 @@ def lib():
         L.ora_debug_get_data.argtypes = [C.c_void_p] + [_dp] * 5
         L.ora_batch_run.restype = C.c_double
         L.ora_batch_run.argtypes = ([C.c_int] * 5 + [_ip, _dp, _ip, _ip, _dp, _ip, _ip, _dp, _dp, _dp] +
-                                    [C.c_int] + [_dp] * 5 + [C.c_int] + [_ip, _ip] + [_dp] * 5)
+                                    [C.c_int] + [_dp] * 5 + [C.c_int, C.c_int] + [_ip, _ip] + [_dp] * 5)
         _lib = L
     return _lib
 
@@ -201,7 +201,7 @@ class OracleSolver:
         return xe, Ae, Ge
 
 
-def batch_run(P, batch, Gs=None, As=None, cs=None, hs=None, bs=None, nthreads=1, want_solution=True):
+def batch_run(P, batch, Gs=None, As=None, cs=None, hs=None, bs=None, nthreads=1, want_solution=True, reset_sticky=True):
     """CPU baseline driver: one solver per thread, updateData + solve per instance."""
     keep, args = _problem_args(P)
     n, m, p = args[0], args[1], args[2]
@@ -212,6 +212,6 @@ def batch_run(P, batch, Gs=None, As=None, cs=None, hs=None, bs=None, nthreads=1,
         xs, ys, zs, ss = np.zeros((batch, n)), np.zeros((batch, p)), np.zeros((batch, m)), np.zeros((batch, m))
     else:
         xs = ys = zs = ss = None
-    secs = lib().ora_batch_run(*args, batch, *[_d(v) for v in st], int(nthreads),
+    secs = lib().ora_batch_run(*args, batch, *[_d(v) for v in st], int(nthreads), int(reset_sticky),
                                _i(ex), _i(it), _d(xs), _d(ys), _d(zs), _d(ss), _d(pc))
     return dict(seconds=secs, exit=ex, iter=it, pcost=pc, x=xs, y=ys, z=zs, s=ss)
