@@ -1,10 +1,10 @@
 import sys, time, json
-sys.path.insert(0, '.')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from oracle import OracleSolver, load_fixture, batch_run
 import eicos_b200
 from eicos_b200.workloads import perturbed
-names = sorted(json.load(open('tests/golden/fixtures/manifest.json')).keys(), key=str.lower)
+names = sorted(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests/golden/fixtures/manifest.json'))).keys(), key=str.lower)
 bad = 0
 for nm in names:
     P = load_fixture(nm)
