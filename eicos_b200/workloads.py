@@ -40,7 +40,7 @@ def _csc(M):
     return np.array(pr), np.array(jc, np.int32), np.array(ir, np.int32)
 
 
-def soc_mpc(T=20, dt=0.25, umax=2.0, vmax=3.0, x0=(4.0, -3.0, 0.5, 0.0), ref=(0.0, 0.0, 0.0, 0.0), rho=0.1):
+def soc_mpc(T=20, dt=0.25, umax=0.5, vmax=3.0, x0=(4.0, -3.0, 0.5, 0.0), ref=(0.0, 0.0, 0.0, 0.0), rho=0.1):
     """min sum_k t_k + rho r_k   s.t.  x_{k+1} = Ad x_k + Bd u_k, x_0 given,
     |v_k| <= vmax (LP), r_k <= umax (LP), ||u_k|| <= r_k (SOC dim 3), ||x_{k+1} - ref|| <= t_k (SOC dim 5).
     Variables per stage k=0..T-1: u_k (2), r_k, t_k, x_{k+1} (4)  -> n = 8 T."""
