@@ -6,54 +6,69 @@
 
 #include <algorithm>
 #include <cstdint>
+#ifdef EICOS_EMU
+#include <thread>
+#endif
 
 namespace eicos
 {
 
-typedef void (*TileFn)(const Team &, const KArgs &, int);
-
 #ifndef EICOS_EMU
 // thin named wrappers so that profilers show one kernel name per step of the algorithm
-#define EI_DEFINE_KERNEL(name, fn)                                               \
-    __global__ void __launch_bounds__(512) name(const __grid_constant__ KArgs a) \
-    {                                                                            \
-        extern __shared__ double smem[];                                         \
-        Team tm;                                                                 \
-        tm.lane = threadIdx.x & 31;                                              \
-        tm.wk = threadIdx.x >> 5;                                                \
-        tm.nwk = blockDim.x >> 5;                                                \
-        tm.red = smem;                                                           \
+#define EI_DEFINE_KERNEL(name, fn, minblocks)                                                  \
+    __global__ void __launch_bounds__(EI_MAX_THREADS, minblocks) name(const __grid_constant__ KArgs a) \
+    {                                                                                          \
+        extern __shared__ double smem[];                                                       \
+        Team tm;                                                                               \
+        tm.lane = threadIdx.x & 31;                                                            \
+        tm.wk = threadIdx.x >> 5;                                                              \
+        tm.nwk = blockDim.x >> 5;                                                              \
+        tm.red = smem;                                                                         \
         tm.acc = a.acc_global ? a.acc_global + (size_t)blockIdx.x * tm.nwk * a.P.maxcol * TILE \
-                              : smem + (size_t)tm.nwk * KRED * TILE;             \
-        fn(tm, a, blockIdx.x);                                                   \
+                              : smem + (size_t)tm.nwk * KRED * TILE;                           \
+        fn(tm, a, blockIdx.x);                                                                 \
     }
-EI_DEFINE_KERNEL(eicos_load_inputs, tile_load)
-EI_DEFINE_KERNEL(eicos_init, tile_init)
-EI_DEFINE_KERNEL(eicos_ldl_factor, tile_factor)
-EI_DEFINE_KERNEL(eicos_solve_kkt, tile_solve_kkt)
-EI_DEFINE_KERNEL(eicos_init_point, tile_init_point)
-EI_DEFINE_KERNEL(eicos_iter_head, tile_head)
-EI_DEFINE_KERNEL(eicos_iter_mid, tile_mid)
-EI_DEFINE_KERNEL(eicos_iter_tail, tile_tail)
-EI_DEFINE_KERNEL(eicos_store_outputs, tile_store)
+#define EI_MAX_THREADS 256
+EI_DEFINE_KERNEL(eicos_load_inputs, tile_load, 4)
+EI_DEFINE_KERNEL(eicos_init, tile_init, 4)
+EI_DEFINE_KERNEL(eicos_ldl_factor, tile_factor, 4)
+EI_DEFINE_KERNEL(eicos_solve_kkt, tile_solve_kkt, 4)
+EI_DEFINE_KERNEL(eicos_init_point, tile_init_point, 4)
+EI_DEFINE_KERNEL(eicos_iter_head, tile_head, 2)
+EI_DEFINE_KERNEL(eicos_iter_mid, tile_mid, 4)
+EI_DEFINE_KERNEL(eicos_iter_tail, tile_tail, 4)
+EI_DEFINE_KERNEL(eicos_store_outputs, tile_store, 4)
 
 #define EI_LAUNCH(name, fn, tiles, threads, smem, stream, args) name<<<(tiles), (threads), (smem), (stream)>>>(args)
 #else
-#define EI_LAUNCH(name, fn, tiles, threads, smem, stream, args)                 \
-    do                                                                          \
-    {                                                                           \
-        std::vector<double> red_((size_t)KRED * TILE + 8);                      \
-        std::vector<double> acc_((size_t)(args).P.maxcol * TILE + 8);           \
-        for (int tile_ = 0; tile_ < (tiles); tile_++)                           \
-        {                                                                       \
-            Team tm_;                                                           \
-            tm_.lane = 0;                                                       \
-            tm_.wk = 0;                                                         \
-            tm_.nwk = 1;                                                        \
-            tm_.red = red_.data();                                              \
-            tm_.acc = acc_.data();                                              \
-            fn(tm_, (args), tile_);                                             \
-        }                                                                       \
+#define EI_MAX_THREADS 256
+// emulator: one std::thread per worker of a tile, CTA barrier = std::barrier
+#define EI_LAUNCH(name, fn, tiles, threads, smem, stream, args)                                   \
+    do                                                                                            \
+    {                                                                                             \
+        const int nw_ = (threads);                                                                \
+        std::vector<double> red_((size_t)nw_ * KRED * TILE + 8);                                  \
+        std::vector<double> acc_((size_t)nw_ * (args).P.maxcol * TILE + 8);                       \
+        for (int tile_ = 0; tile_ < (tiles); tile_++)                                             \
+        {                                                                                         \
+            std::barrier<> bar_(nw_);                                                             \
+            auto body_ = [&](int wk_) {                                                           \
+                Team tm_;                                                                         \
+                tm_.lane = 0;                                                                     \
+                tm_.wk = wk_;                                                                     \
+                tm_.nwk = nw_;                                                                    \
+                tm_.red = red_.data();                                                            \
+                tm_.acc = acc_.data();                                                            \
+                tm_.bar = nw_ > 1 ? &bar_ : nullptr;                                              \
+                fn(tm_, (args), tile_);                                                           \
+            };                                                                                    \
+            std::vector<std::thread> th_;                                                         \
+            for (int wk_ = 1; wk_ < nw_; wk_++)                                                   \
+                th_.emplace_back(body_, wk_);                                                     \
+            body_(0);                                                                             \
+            for (auto &t_ : th_)                                                                  \
+                t_.join();                                                                        \
+        }                                                                                         \
     } while (0)
 #endif
 
@@ -70,6 +85,14 @@ T *upload(const std::vector<T> &v, std::vector<void *> &owned, be::stream_t s)
     return d;
 }
 inline be::stream_t S_(void *p) { return (be::stream_t)(intptr_t)p; }
+
+dvec expanded_geq(const Symbolic &S)
+{
+    dvec g(S.mt, 1.0);
+    for (int i = 0; i < S.m; i++)
+        g[S.zk[i]] = S.Geq[i];
+    return g;
+}
 } // namespace
 
 void Engine::build_layout(const Symbolic &S)
@@ -81,22 +104,14 @@ void Engine::build_layout(const Symbolic &S)
         return o;
     };
     Layout &L = L_;
-    L.c = take(S.n);
-    L.h = take(S.m);
-    L.b = take(S.p);
-    L.x = take(S.n);
-    L.y = take(S.p);
-    L.z = take(S.m);
-    L.s = take(S.m);
-    L.lam = take(S.m);
-    L.bx = take(S.n);
-    L.by = take(S.p);
-    L.bz = take(S.m);
-    L.bs = take(S.m);
-    L.blam = take(S.m);
-    L.rx = take(S.n);
-    L.ry = take(S.p);
-    L.rz = take(S.m);
+    L.chb = take(S.N);
+    L.w = take(S.N);
+    L.s = take(S.mt);
+    L.lam = take(S.mt);
+    L.wb = take(S.N);
+    L.bs = take(S.mt);
+    L.blam = take(S.mt);
+    L.r = take(S.N);
     L.lpv = take(S.l);
     L.lpw = take(S.l);
     L.cpar = take(S.nc * CP_COUNT);
@@ -113,10 +128,10 @@ void Engine::build_layout(const Symbolic &S)
     L.xw = take(S.N);
     L.dxr = take(S.N);
     L.e = take(S.N);
-    L.dsw = take(S.m);
-    L.wdz = take(S.m);
-    L.dsaff = take(S.m);
-    L.ds1 = take(S.m);
+    L.dsw = take(S.mt);
+    L.wdz = take(S.mt);
+    L.dsaff = take(S.mt);
+    L.ds1 = take(S.mt);
     L.sc = take(S_COUNT);
     L.rows_total = at;
     L.irows_total = J_COUNT;
@@ -125,6 +140,8 @@ void Engine::build_layout(const Symbolic &S)
 void Engine::upload_pattern(const Symbolic &S)
 {
     be::stream_t st = S_(stream_);
+    build_streams(S, workers_, H_);
+    Lp_ = S.Lp;
     DevPattern &P = P_;
     P.n = S.n;
     P.p = S.p;
@@ -139,57 +156,31 @@ void Engine::upload_pattern(const Symbolic &S)
     P.nphases = (int)S.phases.size();
     P.maxcol = S.maxcol;
     P.cone_dim = upload(S.q, owned_, st);
-    P.cone_z = upload(S.cone_z, owned_, st);
     P.cone_k = upload(S.cone_k, owned_, st);
     P.cone_q = upload(S.cone_q, owned_, st);
     P.zk = upload(S.zk, owned_, st);
-    P.Gp = upload(S.G.p, owned_, st);
-    P.Gi = upload(S.G.i, owned_, st);
-    P.Grp = upload(S.Gr.p, owned_, st);
-    P.Grj = upload(S.Gr.j, owned_, st);
-    P.Grv = upload(S.Gr.v, owned_, st);
-    P.Ap = upload(S.A.p, owned_, st);
-    P.Ai = upload(S.A.i, owned_, st);
-    P.Arp = upload(S.Ar.p, owned_, st);
-    P.Arj = upload(S.Ar.j, owned_, st);
-    P.Arv = upload(S.Ar.v, owned_, st);
-    P.Gx = dGx_ = upload(S.G.x, owned_, st);
-    P.Ax = dAx_ = upload(S.A.x, owned_, st);
     P.xeq = dxeq_ = upload(S.xeq, owned_, st);
     P.Aeq = dAeq_ = upload(S.Aeq, owned_, st);
-    P.Geq = dGeq_ = upload(S.Geq, owned_, st);
-    P.pinv = upload(S.pinv, owned_, st);
-    P.Lp = upload(S.Lp, owned_, st);
-    P.Li = upload(S.Li, owned_, st);
-    ivec Lio(S.nnzL), Lcsr(S.nnzL);
-    for (int u = 0; u < S.nnzL; u++)
-        Lio[u] = S.pinv[S.Li[u]];
-    for (int t = 0; t < S.nnzL; t++)
-        Lcsr[S.Lr.v[t]] = t;
-    P.Lio = upload(Lio, owned_, st);
-    P.Lcsr = upload(Lcsr, owned_, st);
-    P.Lrp = upload(S.Lr.p, owned_, st);
-    P.Lrj = upload(S.Lr.j, owned_, st);
-    P.KLp = upload(S.KLp, owned_, st);
-    KLslot_ = S.KLslot;
-    ivec klv(S.KLslot.size());
-    dvec klx(S.KLslot.size());
-    for (size_t e = 0; e < S.KLslot.size(); e++)
-    {
-        klv[e] = S.Kvidx[S.KLslot[e]];
-        klx[e] = S.Kshared[S.KLslot[e]];
-    }
-    P.KLvidx = upload(klv, owned_, st);
-    P.KLpos = upload(S.KLpos, owned_, st);
-    P.KLval = dKLval_ = upload(klx, owned_, st);
-    P.upd_tail = upload(S.upd_tail, owned_, st);
-    P.upd_rel_p = upload(S.upd_rel_p, owned_, st);
-    P.upd_rel = upload(S.upd_rel, owned_, st);
-    P.tasks = upload(S.tasks, owned_, st);
-    std::vector<PhaseDev> ph;
-    for (const Phase &f : S.phases)
-        ph.push_back({f.begin, f.end, f.parallel});
-    P.phases = upload(ph, owned_, st);
+    P.GeqE = dGeq_ = upload(expanded_geq(S), owned_, st);
+    P.fw = upload(H_.fw, owned_, st);
+    P.fw_seg = upload(H_.fw_seg, owned_, st);
+    P.bw = upload(H_.bw, owned_, st);
+    P.bw_seg = upload(H_.bw_seg, owned_, st);
+    P.fa = upload(H_.fa, owned_, st);
+    P.fa_seg = upload(H_.fa_seg, owned_, st);
+    P.fa_val = dfa_val_ = upload(H_.fa_val, owned_, st);
+    P.rx = upload(H_.rx, owned_, st);
+    P.rx_seg = upload(H_.rx_seg, owned_, st);
+    P.rx_val = drx_val_ = upload(H_.rx_val, owned_, st);
+    P.ry = upload(H_.ry, owned_, st);
+    P.ry_seg = upload(H_.ry_seg, owned_, st);
+    P.ry_val = dry_val_ = upload(H_.ry_val, owned_, st);
+    P.rz = upload(H_.rz, owned_, st);
+    P.rz_seg = upload(H_.rz_seg, owned_, st);
+    P.rz_val = drz_val_ = upload(H_.rz_val, owned_, st);
+    P.rc = upload(H_.rc, owned_, st);
+    P.rc_seg = upload(H_.rc_seg, owned_, st);
+    P.rc_val = drc_val_ = upload(H_.rc_val, owned_, st);
     ivec vk;
     for (int k = 0; k < S.l; k++)
         vk.push_back(0);
@@ -211,26 +202,24 @@ void Engine::upload_values(const Symbolic &S)
 {
     be::stream_t st = S_(stream_);
     be::set_device(device_);
-    be::h2d(dGx_, S.G.x.data(), S.G.x.size() * sizeof(double), st);
-    be::h2d(dAx_, S.A.x.data(), S.A.x.size() * sizeof(double), st);
+    refresh_stream_values(S, H_);
+    const dvec ge = expanded_geq(S);
     be::h2d(dxeq_, S.xeq.data(), S.xeq.size() * sizeof(double), st);
     be::h2d(dAeq_, S.Aeq.data(), S.Aeq.size() * sizeof(double), st);
-    be::h2d(dGeq_, S.Geq.data(), S.Geq.size() * sizeof(double), st);
-    dvec klx(KLslot_.size());
-    for (size_t e = 0; e < KLslot_.size(); e++)
-        klx[e] = S.Kshared[KLslot_[e]];
-    be::h2d(dKLval_, klx.data(), klx.size() * sizeof(double), st);
+    be::h2d(dGeq_, ge.data(), ge.size() * sizeof(double), st);
+    be::h2d(dfa_val_, H_.fa_val.data(), H_.fa_val.size() * sizeof(double), st);
+    be::h2d(drx_val_, H_.rx_val.data(), H_.rx_val.size() * sizeof(double), st);
+    be::h2d(dry_val_, H_.ry_val.data(), H_.ry_val.size() * sizeof(double), st);
+    be::h2d(drz_val_, H_.rz_val.data(), H_.rz_val.size() * sizeof(double), st);
+    be::h2d(drc_val_, H_.rc_val.data(), H_.rc_val.size() * sizeof(double), st);
     be::sync(st);
 }
 
 Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int workers)
-    : device_(device), workers_(std::max(1, std::min(workers, 16)))
+    : device_(device), workers_(std::max(1, std::min(workers, EI_MAX_THREADS / 32 > 0 ? EI_MAX_THREADS / 32 : 1)))
 {
     be::set_device(device_);
     stream_ = (void *)(intptr_t)be::make_stream();
-#ifdef EICOS_EMU
-    workers_ = 1;
-#endif
     build_layout(S);
     upload_pattern(S);
     cap_tiles_ = std::max<long long>(1, (capacity_instances + TILE - 1) / TILE);
@@ -506,7 +495,7 @@ void Engine::debug_factor_init(int batch, const double *d_c, const double *d_h, 
     a.nitrow = J_NIT2;
     EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt, tiles, threads, smem_common_, st, a);
     be::sync(st);
-    // gather rows back to instance-major host arrays
+    // gather rows back to instance-major host arrays; L comes back in CSC order
     const size_t tile_doubles = (size_t)L_.rows_total * TILE;
     std::vector<double> buf(tile_doubles);
     std::vector<int> ibuf((size_t)L_.irows_total * TILE);
@@ -525,7 +514,10 @@ void Engine::debug_factor_init(int batch, const double *d_c, const double *d_h, 
                     for (int r = 0; r < rows; r++)
                         dst[inst * rows + r] = buf[(size_t)(row0 + r) * TILE + lane];
             };
-            grab(h_Lx, L_.Lx, P_.nnzL);
+            if (h_Lx)
+                for (int j = 0; j < P_.N; j++)
+                    for (int u = Lp_[j]; u < Lp_[j + 1]; u++)
+                        h_Lx[inst * P_.nnzL + u] = buf[(size_t)(L_.Lx + H_.bw_base[j] + (u - Lp_[j])) * TILE + lane];
             grab(h_D, L_.D, P_.N);
             grab(h_sol1, L_.sol1, P_.N);
             grab(h_sol2, L_.sol2, P_.N);

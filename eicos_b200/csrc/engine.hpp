@@ -4,6 +4,7 @@
 #pragma once
 
 #include "layout.hpp"
+#include "streams.hpp"
 #include "symbolic.hpp"
 
 #include <cstddef>
@@ -78,8 +79,10 @@ class Engine
     size_t smem_factor_ = 0, smem_common_ = 0;
     std::vector<void *> owned_; // device allocations holding pattern data
     // positions of value arrays that upload_values() rewrites
-    double *dGx_ = nullptr, *dAx_ = nullptr, *dxeq_ = nullptr, *dAeq_ = nullptr, *dGeq_ = nullptr, *dKLval_ = nullptr;
-    std::vector<int> KLslot_;
+    double *dxeq_ = nullptr, *dAeq_ = nullptr, *dGeq_ = nullptr;
+    double *dfa_val_ = nullptr, *drx_val_ = nullptr, *dry_val_ = nullptr, *drz_val_ = nullptr, *drc_val_ = nullptr;
+    HostStreams H_;        // host copy of the instruction streams (value streams are rebuilt on updateData)
+    std::vector<int> Lp_;  // column pointers of L (debug extraction)
     std::vector<void *> events_;
 };
 

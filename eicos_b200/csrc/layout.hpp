@@ -5,8 +5,13 @@
 //   of ROWS; row r of tile t is the TILE consecutive doubles  ws[(t*rows_total + r)*TILE + lane].
 //   A warp that walks rows therefore issues one fully coalesced 256-byte access per row whatever the
 //   row index is, and all rows of one tile are contiguous (column slices of L are contiguous runs).
-//   Index data (patterns, maps, schedules) is shared by the whole batch and read with warp-uniform
-//   loads.
+//   Index data (instruction streams, see streams.hpp) is shared by the whole batch.
+//
+// Index spaces: "KKT space" = [x (n) | y (p) | z expanded (mt = m + 2 nc)], the row order of the
+// reference's KKT matrix (src/eicos.cpp:1776-1819): every second-order cone of dimension d owns d
+// rows followed by 2 expansion slots.  ALL z-shaped vectors (z, s, lambda, h, rz, ...) use the
+// expanded index here, with the slot rows held at zero, so that one gather index serves the
+// iterate, the residuals and the KKT-space solution vectors alike.
 #pragma once
 
 #include <cstddef>
@@ -52,24 +57,24 @@ enum IntRow : int
     J_BEST = J_WORK_END,
     J_BEST_END = J_BEST + J_WORK_END,
     J_STATUS = J_BEST_END, // ST_ACTIVE or the exit code
-    J_SCALEFAIL,           // first cone whose scaling update failed this iteration (or nc)
     J_COUNT
 };
 
 // Row offsets of every per-instance array inside a tile's workspace block.
 struct Layout
 {
-    int c, h, b;                    // equilibrated problem vectors
-    int x, y, z, s, lam;            // current iterate (Work)
-    int bx, by, bz, bs, blam;       // best iterate (w_best)
-    int rx, ry, rz;                 // residuals
-    int lpv, lpw;                   // LP cone scalings
-    int cpar, cq;                   // SOC scalings: 8 rows per cone (CP_*), q vectors
+    int chb;                        // [c | b | h] equilibrated problem vectors, KKT-shaped (N rows)
+    int w;                          // current iterate [x | y | z] (N rows)
+    int s, lam;                     // slacks, scaled variable (mt rows each)
+    int wb, bs, blam;               // best iterate (w_best)
+    int r;                          // residuals [rx | ry | rz] (N rows)
+    int lpv, lpw;                   // LP cone scalings (l rows each)
+    int cpar, cq;                   // SOC scalings: CP_COUNT rows per cone, q vectors
     int V;                          // scaling block values of the KKT matrix (cacheIndices order)
-    int Lx, LTx, D, Dinv;           // factor: columns, rows (copy), pivots, reciprocals
-    int rhs1, rhs2, sol1, sol2;     // KKT-space vectors (length N)
-    int xw, dxr, e;                 // triangular-solve work vector, refinement step, residual
-    int dsw, wdz, dsaff, ds1;       // dsaff_by_W, W_times_dzaff, dsaff, scratch (length m)
+    int Lx, LTx, D, Dinv;           // factor: by columns (backward-sweep order), by rows (forward-sweep order), pivots, reciprocals
+    int rhs1, rhs2, sol1, sol2;     // KKT-space vectors (N rows)
+    int xw, dxr, e;                 // triangular-solve work vector, refinement step, residual (N rows)
+    int dsw, wdz, dsaff, ds1;       // dsaff_by_W, W_times_dzaff, dsaff, scratch (mt rows)
     int sc;                         // S_COUNT scalar rows
     int rows_total;
     int irows_total;                // integer rows (J_COUNT)
@@ -80,25 +85,18 @@ enum ConeParam : int
     CP_ETA, CP_ETA2, CP_A, CP_D1, CP_U0, CP_U1, CP_V1, CP_W, CP_COUNT
 };
 
-struct PhaseDev
-{
-    int begin, end, parallel;
-};
-
 // Shared index data on the device (all pointers are device pointers).
 struct DevPattern
 {
     int n, p, m, l, nc, N, mt, qtot, nnzL, nnzV, nphases, maxcol;
-    const int *cone_dim, *cone_z, *cone_k, *cone_q, *zk;
-    const int *Gp, *Gi, *Grp, *Grj, *Grv;
-    const int *Ap, *Ai, *Arp, *Arj, *Arv;
-    const double *Gx, *Ax, *xeq, *Aeq, *Geq;
-    const int *pinv, *Lp, *Li, *Lio, *Lcsr, *Lrp, *Lrj;
-    const int *KLp, *KLvidx, *KLpos;
-    const double *KLval;
-    const int *upd_tail, *upd_rel_p, *upd_rel;
-    const int *tasks;
-    const PhaseDev *phases;
+    const int *cone_dim, *cone_k, *cone_q; // per cone: dimension, first expanded index, first q row
+    const int *zk;                         // compact z index -> expanded index (load / store only)
+    const double *xeq, *Aeq, *GeqE;        // equilibration vectors (GeqE is expanded, 1 in the slots)
+    // instruction streams (streams.hpp)
+    const int *fw, *fw_seg, *bw, *bw_seg, *fa, *fa_seg;
+    const double *fa_val;
+    const int *rx, *rx_seg, *ry, *ry_seg, *rz, *rz_seg, *rc, *rc_seg;
+    const double *rx_val, *ry_val, *rz_val, *rc_val;
     const int *Vkind; // per V entry: what resetKKTScalings writes (0 -> -1, 1 -> 0, 2 -> +1)
 };
 

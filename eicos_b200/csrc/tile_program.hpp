@@ -5,6 +5,8 @@
 // themselves and meet at CTA barriers; per-instance reductions over a vector run down the rows in
 // each worker and are combined through shared memory in a fixed order, so every warp of the CTA
 // holds bit-identical per-lane scalars and all control flow is uniform across the CTA.
+// Sparse structure is never looked up through CSR/CSC arrays on the device: each worker decodes
+// its own instruction stream (streams.hpp) with coalesced chunk loads + warp shuffles.
 //
 // The same source compiles two ways:
 //   * nvcc (default): TILE = 32, workers = warps of the CTA  -> the product.
@@ -13,18 +15,22 @@
 #pragma once
 
 #include "layout.hpp"
+#include "streams.hpp"
 #include "symbolic.hpp"
 
 #include <cfloat>
 #include <cmath>
 
 #ifdef EICOS_EMU
+#include <barrier>
 #define EI_DEV inline
 #define EI_LDG(p) (*(p))
+#define EI_PREFETCH(p) ((void)0)
 #else
 #include <cuda_runtime.h>
 #define EI_DEV __device__ __forceinline__
 #define EI_LDG(p) __ldg(p)
+#define EI_PREFETCH(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #endif
 
 namespace eicos
@@ -35,7 +41,8 @@ constexpr int TILE = 1;
 #else
 constexpr int TILE = 32;
 #endif
-constexpr int KRED = 17; // widest block reduction (head kernel)
+constexpr int KRED = 17;    // widest block reduction
+constexpr int PF_ROWS = 24; // how many value rows ahead the sweeps prefetch into L2
 
 struct KArgs
 {
@@ -58,7 +65,7 @@ struct KArgs
     int keep_sticky;
     int pre_equilibrated; // inputs are already divided by the equilibration vectors
     unsigned int *active_count; // device counter: instances still iterating after the head step
-    unsigned long long *ir_rounds; // device counter: refinement rounds executed (tile-rounds)
+    unsigned long long *ir_rounds; // device counter: solve rounds executed (tile-rounds)
 };
 
 struct Team
@@ -67,13 +74,87 @@ struct Team
     double *red; // [nwk][KRED][TILE]
     double *acc; // [nwk][maxcol][TILE]
 #ifdef EICOS_EMU
-    void sync() const {}
+    std::barrier<> *bar; // workers of a tile are real threads in the emulator
+    void sync() const
+    {
+        if (bar)
+            bar->arrive_and_wait();
+    }
     bool all(bool v) const { return v; }
     bool any(bool v) const { return v; }
 #else
     __device__ __forceinline__ void sync() const { __syncthreads(); }
     __device__ __forceinline__ bool all(bool v) const { return __all_sync(0xffffffffu, v); }
     __device__ __forceinline__ bool any(bool v) const { return __any_sync(0xffffffffu, v); }
+#endif
+};
+
+// ------------------------------------------------------------------ instruction stream readers
+// All lanes of the warp call get() together (never under a per-lane branch).
+struct IStream
+{
+#ifdef EICOS_EMU
+    const int *p;
+    EI_DEV void open(const int *base, int) { p = base; }
+    EI_DEV int get() { return *p++; }
+#else
+    const int *p;
+    int cur, nxt, pos, lane;
+    EI_DEV void open(const int *base, int lane_)
+    {
+        lane = lane_;
+        cur = __ldg(base + lane);
+        nxt = __ldg(base + STREAM_CHUNK + lane);
+        p = base + 2 * STREAM_CHUNK;
+        pos = 0;
+    }
+    EI_DEV int get()
+    {
+        if (pos == STREAM_CHUNK)
+        {
+            cur = nxt;
+            nxt = __ldg(p + lane);
+            p += STREAM_CHUNK;
+            pos = 0;
+        }
+        const int v = __shfl_sync(0xffffffffu, cur, pos);
+        ++pos;
+        return v;
+    }
+#endif
+};
+
+struct DStream
+{
+#ifdef EICOS_EMU
+    const double *p;
+    EI_DEV void open(const double *base, int) { p = base; }
+    EI_DEV double get() { return *p++; }
+#else
+    const double *p;
+    double cur, nxt;
+    int pos, lane;
+    EI_DEV void open(const double *base, int lane_)
+    {
+        lane = lane_;
+        cur = __ldg(base + lane);
+        nxt = __ldg(base + STREAM_CHUNK + lane);
+        p = base + 2 * STREAM_CHUNK;
+        pos = 0;
+    }
+    EI_DEV double get()
+    {
+        if (pos == STREAM_CHUNK)
+        {
+            cur = nxt;
+            nxt = __ldg(p + lane);
+            p += STREAM_CHUNK;
+            pos = 0;
+        }
+        const double v = __shfl_sync(0xffffffffu, cur, pos);
+        ++pos;
+        return v;
+    }
 #endif
 };
 
@@ -138,14 +219,6 @@ EI_DEV void team_min(const Team &tm, double (&v)[K])
     }
 }
 
-// A z-shaped vector: compact (rows base+i) or embedded in a KKT-space vector (rows base+zk[i]).
-struct ZRef
-{
-    int base;
-    const int *map;
-    EI_DEV int row(int i) const { return base + (map ? EI_LDG(map + i) : i); }
-};
-
 struct TileMem
 {
     double *T;
@@ -162,39 +235,52 @@ EI_DEV TileMem tile_mem(const KArgs &a, int tile)
 
 EI_DEV bool lane_active(const Team &tm, const TileMem &t) { return ROWD(t.I, J_STATUS) == ST_ACTIVE; }
 
+// sum_k val_k * vec[idx_k] folded into `v` with sign: one mat-vec row from a row-set stream
+EI_DEV double row_accumulate(const Team &tm, IStream &is, DStream &ds, const double *T, int vec, double v, double sign)
+{
+    const int cnt = is.get();
+    for (int k = 0; k < cnt; k++)
+    {
+        const int idx = is.get();
+        const double val = ds.get();
+        v += (sign * val) * ROWD(T, vec + idx);
+    }
+    return v;
+}
+
 // ------------------------------------------------------------------ W products (src/eicos.cpp:485-507)
-// out = W * in for the lanes' current scalings.  One worker per cone; LP rows strided over workers.
-EI_DEV void cone_scale(const Team &tm, const KArgs &a, double *T, const ZRef in, const ZRef out, bool write)
+// out = W * in for the lanes' current scalings; in/out are z-shaped (expanded) row offsets.
+EI_DEV void cone_scale(const Team &tm, const KArgs &a, double *T, int in, int out, bool write)
 {
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     for (int k = tm.wk; k < P.l; k += tm.nwk)
     {
-        const double v = ROWD(T, L.lpw + k) * ROWD(T, in.row(k));
+        const double v = ROWD(T, L.lpw + k) * ROWD(T, in + k);
         if (write)
-            ROWD(T, out.row(k)) = v;
+            ROWD(T, out + k) = v;
     }
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     {
-        const int d = EI_LDG(P.cone_dim + c), zs = EI_LDG(P.cone_z + c), qo = EI_LDG(P.cone_q + c);
+        const int d = EI_LDG(P.cone_dim + c), ks = EI_LDG(P.cone_k + c), qo = EI_LDG(P.cone_q + c);
         const double *cp = T + (size_t)(L.cpar + c * CP_COUNT) * TILE + tm.lane;
         const double eta = cp[CP_ETA * TILE], ca = cp[CP_A * TILE];
         double zeta = 0.0;
         for (int k = 1; k < d; k++)
-            zeta += ROWD(T, L.cq + qo + k - 1) * ROWD(T, in.row(zs + k));
-        const double z0 = ROWD(T, in.row(zs));
+            zeta += ROWD(T, L.cq + qo + k - 1) * ROWD(T, in + ks + k);
+        const double z0 = ROWD(T, in + ks);
         const double factor = z0 + zeta / (1. + ca);
         if (write)
         {
-            ROWD(T, out.row(zs)) = eta * (ca * z0 + zeta);
+            ROWD(T, out + ks) = eta * (ca * z0 + zeta);
             for (int k = 1; k < d; k++)
-                ROWD(T, out.row(zs + k)) = eta * (ROWD(T, in.row(zs + k)) + factor * ROWD(T, L.cq + qo + k - 1));
+                ROWD(T, out + ks + k) = eta * (ROWD(T, in + ks + k) + factor * ROWD(T, L.cq + qo + k - 1));
         }
     }
 }
 
 // ------------------------------------------------------------------ line search (src/eicos.cpp:1380-1469)
-// lambda, ds, dz are compact m-vectors (row offsets).  Returns the clamped step for every lane.
+// lambda, ds, dz are z-shaped row offsets.  Returns the clamped step for every lane.
 // TODO(parity): the reference's `continue` on lknorm2<=0 skips the cone offset advance; here later
 // cones keep their own offsets (differs only after lambda has already left the cone).
 EI_DEV double line_search(const Team &tm, const KArgs &a, double *T, int lam, int ds, int dz,
@@ -211,7 +297,7 @@ EI_DEV double line_search(const Team &tm, const KArgs &a, double *T, int lam, in
     }
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     {
-        const int d = EI_LDG(P.cone_dim + c), zs = EI_LDG(P.cone_z + c);
+        const int d = EI_LDG(P.cone_dim + c), zs = EI_LDG(P.cone_k + c);
         const double l0 = ROWD(T, lam + zs);
         double sq = 0.0;
         for (int k = 1; k < d; k++)
@@ -279,48 +365,9 @@ EI_DEV double line_search(const Team &tm, const KArgs &a, double *T, int lam, in
 // ------------------------------------------------------------------ numeric LDL' (Eigen factorize, src/eicos.cpp:900,1164)
 // Left-looking by column on the fixed pattern, walking the level schedule of the elimination
 // tree.  Column j: gather its KKT entries, subtract the contribution of every earlier column k
-// with L(j,k) != 0 (row j of L, read from the row-ordered copy; the tail of column k below row j
-// is a contiguous run of rows), divide by the pivot and store the column in both orders.
-EI_DEV void factor_column(const Team &tm, const KArgs &a, double *T, int *I, int j, bool act)
-{
-    const DevPattern &P = a.P;
-    const Layout &L = a.L;
-    const int base = EI_LDG(P.Lp + j), cnt = EI_LDG(P.Lp + j + 1) - base;
-    double *acc = tm.acc + (size_t)tm.wk * P.maxcol * TILE + tm.lane;
-    for (int q = 0; q < cnt; q++)
-        acc[(size_t)q * TILE] = 0.0;
-    double d = 0.0;
-    for (int e = EI_LDG(P.KLp + j), e1 = EI_LDG(P.KLp + j + 1); e < e1; e++)
-    {
-        const int vi = EI_LDG(P.KLvidx + e), pos = EI_LDG(P.KLpos + e);
-        const double val = vi >= 0 ? ROWD(T, L.V + vi) : EI_LDG(P.KLval + e);
-        if (pos < 0)
-            d = val;
-        else
-            acc[(size_t)pos * TILE] = val;
-    }
-    for (int t = EI_LDG(P.Lrp + j), t1 = EI_LDG(P.Lrp + j + 1); t < t1; t++)
-    {
-        const int k = EI_LDG(P.Lrj + t);
-        const double ljk = ROWD(T, L.LTx + t);
-        const double w = ljk * ROWD(T, L.D + k);
-        d -= ljk * w;
-        int r = EI_LDG(P.upd_rel_p + t);
-        for (int u = EI_LDG(P.upd_tail + t), u1 = EI_LDG(P.Lp + k + 1); u < u1; u++, r++)
-            acc[(size_t)EI_LDG(P.upd_rel + r) * TILE] -= ROWD(T, L.Lx + u) * w;
-    }
-    ROWD(T, L.D + j) = d;
-    ROWD(T, L.Dinv + j) = 1.0 / d;
-    if (d == 0.0 && act)
-        ROWD(I, J_STATUS) = EXIT_FATAL; // Eigen reports NumericalIssue only on an exactly zero pivot
-    for (int q = 0; q < cnt; q++)
-    {
-        const double lv = acc[(size_t)q * TILE] / d;
-        ROWD(T, L.Lx + base + q) = lv;
-        ROWD(T, L.LTx + EI_LDG(P.Lcsr + base + q)) = lv;
-    }
-}
-
+// with L(j,k) != 0 (row j of L is a contiguous run of the row-ordered copy; the tail of column k
+// below row j is a contiguous run of the column-ordered copy), divide by the pivot and store the
+// column in both orders.  Everything structural comes from the worker's instruction stream.
 EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
 {
     const TileMem t = tile_mem(a, tile);
@@ -328,68 +375,167 @@ EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
     if (!tm.any(act))
         return;
     const DevPattern &P = a.P;
+    const Layout &L = a.L;
+    double *T = t.T;
+    double *acc = tm.acc + (size_t)tm.wk * P.maxcol * TILE + tm.lane;
+    bool zero_pivot = false;
     for (int ph = 0; ph < P.nphases; ph++)
     {
-        const PhaseDev f = P.phases[ph];
-        if (f.parallel)
+        const int *seg = P.fa_seg + ((size_t)ph * tm.nwk + tm.wk) * 3;
+        const int nt = EI_LDG(seg + 1);
+        if (nt > 0)
         {
-            for (int q = f.begin + tm.wk; q < f.end; q += tm.nwk)
-                factor_column(tm, a, t.T, t.I, EI_LDG(P.tasks + q), act);
-        }
-        else if (tm.wk == 0)
-        {
-            for (int q = f.begin; q < f.end; q++)
-                factor_column(tm, a, t.T, t.I, EI_LDG(P.tasks + q), act);
+            IStream is;
+            DStream ds;
+            is.open(P.fa + EI_LDG(seg), tm.lane);
+            ds.open(P.fa_val + EI_LDG(seg + 2), tm.lane);
+            for (int q = 0; q < nt; q++)
+            {
+                const int j = is.get(), cnt = is.get(), nK = is.get(), nR = is.get();
+                const int bwb = is.get(), fwb = is.get();
+                for (int c = 0; c < cnt; c++)
+                    acc[(size_t)c * TILE] = 0.0;
+                double d = 0.0;
+                for (int e = 0; e < nK; e++)
+                {
+                    const int vi = is.get(), pos = is.get();
+                    const double val = vi >= 0 ? ROWD(T, L.V + vi) : ds.get();
+                    if (pos < 0)
+                        d = val;
+                    else
+                        acc[(size_t)pos * TILE] = val;
+                }
+                const double *lrow = T + (size_t)(L.LTx + fwb) * TILE + tm.lane;
+                for (int r = 0; r < nR; r++)
+                {
+                    const int k = is.get(), tp = is.get(), tl = is.get();
+                    const double ljk = lrow[(size_t)r * TILE];
+                    const double w = ljk * ROWD(T, L.D + k);
+                    d -= ljk * w;
+                    const double *lcol = T + (size_t)(L.Lx + tp) * TILE + tm.lane;
+                    for (int u = 0; u < tl; u++)
+                    {
+                        const int rel = is.get();
+                        acc[(size_t)rel * TILE] -= lcol[(size_t)u * TILE] * w;
+                    }
+                }
+                ROWD(T, L.D + j) = d;
+                ROWD(T, L.Dinv + j) = 1.0 / d;
+                zero_pivot = zero_pivot || (d == 0.0); // Eigen reports NumericalIssue only on an exactly zero pivot
+                double *lout = T + (size_t)(L.Lx + bwb) * TILE + tm.lane;
+                for (int c = 0; c < cnt; c++)
+                {
+                    const int fp = is.get();
+                    const double lv = acc[(size_t)c * TILE] / d;
+                    lout[(size_t)c * TILE] = lv;
+                    ROWD(T, L.LTx + fp) = lv;
+                }
+            }
         }
         tm.sync();
     }
+    if (zero_pivot && act)
+        ROWD(t.I, J_STATUS) = EXIT_FATAL;
 }
 
 // ------------------------------------------------------------------ triangular solves (Eigen solve, src/eicos.cpp:1477,1599)
-// forward:  xw = L^-1 P rhs      (rows of L, dot form; the permutation is folded into the gather)
+// forward:  xw = L^-1 P rhs       (rows of L, dot form; the permutation is folded into the gather)
 // backward: out = P' L^-T D^-1 xw (columns of L, dot form; results land in KKT order directly)
+// Stream layout per worker and phase: hdr(0) hdr(1) ent(0) hdr(2) ent(1) ... so that the header of
+// the next task (and the load of its right-hand side) is issued before the current task's entries.
 EI_DEV void ldl_forward(const Team &tm, const KArgs &a, double *T, int rhs)
 {
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     for (int ph = 0; ph < P.nphases; ph++)
     {
-        const PhaseDev f = P.phases[ph];
-        const int step = f.parallel ? tm.nwk : 1;
-        if (f.parallel || tm.wk == 0)
-            for (int q = f.begin + (f.parallel ? tm.wk : 0); q < f.end; q += step)
+        const int *seg = P.fw_seg + ((size_t)ph * tm.nwk + tm.wk) * 3;
+        const int nt = EI_LDG(seg + 1);
+        if (nt > 0)
+        {
+            IStream is;
+            is.open(P.fw + EI_LDG(seg), tm.lane);
+            const double *lv = T + (size_t)(L.LTx + EI_LDG(seg + 2)) * TILE + tm.lane;
+            double p1 = 0.0, p2 = 0.0;
+            int i = is.get(), r = is.get(), cnt = is.get();
+            double v = ROWD(T, rhs + r);
+            for (int q = 0; q < nt; q++)
             {
-                const int i = EI_LDG(P.tasks + q);
-                double v = ROWD(T, rhs + EI_LDG(P.pinv + i));
-                for (int t = EI_LDG(P.Lrp + i), t1 = EI_LDG(P.Lrp + i + 1); t < t1; t++)
-                    v -= ROWD(T, L.LTx + t) * ROWD(T, L.xw + EI_LDG(P.Lrj + t));
+                int ni = 0, ncnt = 0;
+                double nv = 0.0;
+                if (q + 1 < nt)
+                {
+                    ni = is.get();
+                    r = is.get();
+                    ncnt = is.get();
+                    nv = ROWD(T, rhs + r);
+                }
+                for (int k = 0; k < cnt; k++)
+                {
+                    const int c = is.get();
+                    EI_PREFETCH(lv + (size_t)PF_ROWS * TILE);
+                    const double lval = *lv;
+                    lv += TILE;
+                    const double xv = c >= 0 ? ROWD(T, L.xw + c) : (c == FWD_PREV1 ? p1 : p2);
+                    v -= lval * xv;
+                }
                 ROWD(T, L.xw + i) = v;
+                p2 = p1;
+                p1 = v;
+                i = ni;
+                cnt = ncnt;
+                v = nv;
             }
+        }
         tm.sync();
     }
 }
 
-// mode 0: out = solution.  mode 1: out = refinement step, and x += step for lanes with `cont`.
+// out = solution (KKT order).  If x >= 0: additionally x += solution for the lanes with `cont`.
 EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int out, int x, bool cont)
 {
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     for (int ph = P.nphases - 1; ph >= 0; ph--)
     {
-        const PhaseDev f = P.phases[ph];
-        if (f.parallel || tm.wk == 0)
+        const int *seg = P.bw_seg + ((size_t)ph * tm.nwk + tm.wk) * 3;
+        const int nt = EI_LDG(seg + 1);
+        if (nt > 0)
         {
-            const int step = f.parallel ? tm.nwk : 1;
-            for (int q = f.end - 1 - (f.parallel ? tm.wk : 0); q >= f.begin; q -= step)
+            IStream is;
+            is.open(P.bw + EI_LDG(seg), tm.lane);
+            const double *lv = T + (size_t)(L.Lx + EI_LDG(seg + 2)) * TILE + tm.lane;
+            double p1 = 0.0, p2 = 0.0;
+            int j = is.get(), o = is.get(), cnt = is.get();
+            double v = ROWD(T, L.Dinv + j) * ROWD(T, L.xw + j);
+            for (int q = 0; q < nt; q++)
             {
-                const int j = EI_LDG(P.tasks + q);
-                double v = ROWD(T, L.Dinv + j) * ROWD(T, L.xw + j);
-                for (int u = EI_LDG(P.Lp + j), u1 = EI_LDG(P.Lp + j + 1); u < u1; u++)
-                    v -= ROWD(T, L.Lx + u) * ROWD(T, out + EI_LDG(P.Lio + u));
-                const int o = EI_LDG(P.pinv + j);
+                int no = 0, ncnt = 0;
+                double nv = 0.0;
+                if (q + 1 < nt)
+                {
+                    j = is.get();
+                    no = is.get();
+                    ncnt = is.get();
+                    nv = ROWD(T, L.Dinv + j) * ROWD(T, L.xw + j);
+                }
+                for (int k = 0; k < cnt; k++)
+                {
+                    const int c = is.get();
+                    EI_PREFETCH(lv + (size_t)PF_ROWS * TILE);
+                    const double lval = *lv;
+                    lv += TILE;
+                    const double xv = c >= 0 ? ROWD(T, out + c) : (c == FWD_PREV1 ? p1 : p2);
+                    v -= lval * xv;
+                }
                 ROWD(T, out + o) = v;
                 if (x >= 0 && cont)
                     ROWD(T, x + o) += v;
+                p2 = p1;
+                p1 = v;
+                o = no;
+                cnt = ncnt;
+                v = nv;
             }
         }
         tm.sync();
@@ -406,75 +552,85 @@ EI_DEV double kkt_residual(const Team &tm, const KArgs &a, double *T, int rhs, i
     const double delta = Settings::deltastat;
     const int n = P.n, p = P.p, zb = P.n + P.p;
     double nerr[1] = {0.0};
-    for (int j = tm.wk; j < n; j += tm.nwk)
+    IStream is;
+    DStream ds;
+    if (n > 0)
     {
-        double v = ROWD(T, rhs + j);
-        for (int k = EI_LDG(P.Gp + j), k1 = EI_LDG(P.Gp + j + 1); k < k1; k++)
-            v -= EI_LDG(P.Gx + k) * ROWD(T, x + zb + EI_LDG(P.zk + EI_LDG(P.Gi + k)));
-        for (int k = EI_LDG(P.Ap + j), k1 = EI_LDG(P.Ap + j + 1); k < k1; k++)
-            v -= EI_LDG(P.Ax + k) * ROWD(T, x + n + EI_LDG(P.Ai + k));
-        v -= delta * ROWD(T, x + j);
-        ROWD(T, L.e + j) = v;
-        nerr[0] = dmax(nerr[0], fabs(v));
-    }
-    for (int i = tm.wk; i < p; i += tm.nwk)
-    {
-        double v = ROWD(T, rhs + n + i);
-        for (int t = EI_LDG(P.Arp + i), t1 = EI_LDG(P.Arp + i + 1); t < t1; t++)
-            v -= EI_LDG(P.Ax + EI_LDG(P.Arv + t)) * ROWD(T, x + EI_LDG(P.Arj + t));
-        v += delta * ROWD(T, x + n + i);
-        ROWD(T, L.e + n + i) = v;
-        nerr[0] = dmax(nerr[0], fabs(v));
-    }
-    for (int i = tm.wk; i < P.l; i += tm.nwk)
-    {
-        double g = 0.0;
-        for (int t = EI_LDG(P.Grp + i), t1 = EI_LDG(P.Grp + i + 1); t < t1; t++)
-            g += EI_LDG(P.Gx + EI_LDG(P.Grv + t)) * ROWD(T, x + EI_LDG(P.Grj + t));
-        const double dz = ROWD(T, x + zb + i);
-        double v = ROWD(T, rhs + zb + i) - g + delta * dz;
-        v += initialize ? dz : ROWD(T, L.lpv + i) * dz;
-        ROWD(T, L.e + zb + i) = v;
-        nerr[0] = dmax(nerr[0], fabs(v));
-    }
-    for (int c = tm.wk; c < P.nc; c += tm.nwk)
-    {
-        const int d = EI_LDG(P.cone_dim + c), zs = EI_LDG(P.cone_z + c), qo = EI_LDG(P.cone_q + c);
-        const int kb = zb + EI_LDG(P.cone_k + c); // KKT row of the cone's first entry
-        const double *cp = T + (size_t)(L.cpar + c * CP_COUNT) * TILE + tm.lane;
-        const double eta2 = cp[CP_ETA2 * TILE], d1 = cp[CP_D1 * TILE], u0 = cp[CP_U0 * TILE];
-        const double u1 = cp[CP_U1 * TILE], v1 = cp[CP_V1 * TILE];
-        const double x1 = ROWD(T, x + kb), x3 = ROWD(T, x + kb + d), x4 = ROWD(T, x + kb + d + 1);
-        double qtx2 = 0.0;
-        for (int k = 1; k < d; k++)
-            qtx2 += ROWD(T, L.cq + qo + k - 1) * ROWD(T, x + kb + k);
-        const double vu = v1 * x3 + u1 * x4;
-        for (int k = 0; k < d; k++)
+        is.open(P.rx + EI_LDG(P.rx_seg + tm.wk * 2), tm.lane);
+        ds.open(P.rx_val + EI_LDG(P.rx_seg + tm.wk * 2 + 1), tm.lane);
+        for (int j = tm.wk; j < n; j += tm.nwk)
         {
-            const int i = zs + k;
-            double g = 0.0;
-            for (int t = EI_LDG(P.Grp + i), t1 = EI_LDG(P.Grp + i + 1); t < t1; t++)
-                g += EI_LDG(P.Gx + EI_LDG(P.Grv + t)) * ROWD(T, x + EI_LDG(P.Grj + t));
-            const double xk = ROWD(T, x + kb + k);
-            double v = ROWD(T, rhs + kb + k) - g;
-            if (k < d - 1)
-                v += delta * xk;
-            else
-                v -= delta * xk;
-            if (initialize)
-                v += xk;
-            else if (k == 0)
-                v += eta2 * (d1 * x1 + u0 * x4);
-            else
-                v += eta2 * (xk + vu * ROWD(T, L.cq + qo + k - 1));
-            ROWD(T, L.e + kb + k) = v;
+            double v = row_accumulate(tm, is, ds, T, x, ROWD(T, rhs + j), -1.0);
+            v -= delta * ROWD(T, x + j);
+            ROWD(T, L.e + j) = v;
             nerr[0] = dmax(nerr[0], fabs(v));
         }
-        const double e3 = initialize ? x3 : eta2 * (v1 * qtx2 + x3);
-        const double e4 = initialize ? x4 : eta2 * (u0 * x1 + u1 * qtx2 - x4);
-        ROWD(T, L.e + kb + d) = e3;
-        ROWD(T, L.e + kb + d + 1) = e4;
-        nerr[0] = dmax(nerr[0], dmax(fabs(e3), fabs(e4)));
+    }
+    if (p > 0)
+    {
+        is.open(P.ry + EI_LDG(P.ry_seg + tm.wk * 2), tm.lane);
+        ds.open(P.ry_val + EI_LDG(P.ry_seg + tm.wk * 2 + 1), tm.lane);
+        for (int i = tm.wk; i < p; i += tm.nwk)
+        {
+            double v = row_accumulate(tm, is, ds, T, x, ROWD(T, rhs + n + i), -1.0);
+            v += delta * ROWD(T, x + n + i);
+            ROWD(T, L.e + n + i) = v;
+            nerr[0] = dmax(nerr[0], fabs(v));
+        }
+    }
+    if (P.l > 0)
+    {
+        is.open(P.rz + EI_LDG(P.rz_seg + tm.wk * 2), tm.lane);
+        ds.open(P.rz_val + EI_LDG(P.rz_seg + tm.wk * 2 + 1), tm.lane);
+        for (int i = tm.wk; i < P.l; i += tm.nwk)
+        {
+            const double dz = ROWD(T, x + zb + i);
+            double v = row_accumulate(tm, is, ds, T, x, ROWD(T, rhs + zb + i), -1.0);
+            v += delta * dz;
+            v += initialize ? dz : ROWD(T, L.lpv + i) * dz;
+            ROWD(T, L.e + zb + i) = v;
+            nerr[0] = dmax(nerr[0], fabs(v));
+        }
+    }
+    if (P.nc > 0)
+    {
+        is.open(P.rc + EI_LDG(P.rc_seg + tm.wk * 2), tm.lane);
+        ds.open(P.rc_val + EI_LDG(P.rc_seg + tm.wk * 2 + 1), tm.lane);
+        for (int c = tm.wk; c < P.nc; c += tm.nwk)
+        {
+            const int d = is.get(), ks = is.get(), qo = is.get();
+            const int kb = zb + ks; // KKT row of the cone's first entry
+            const double *cp = T + (size_t)(L.cpar + c * CP_COUNT) * TILE + tm.lane;
+            const double eta2 = cp[CP_ETA2 * TILE], d1 = cp[CP_D1 * TILE], u0 = cp[CP_U0 * TILE];
+            const double u1 = cp[CP_U1 * TILE], v1 = cp[CP_V1 * TILE];
+            const double x1 = ROWD(T, x + kb), x3 = ROWD(T, x + kb + d), x4 = ROWD(T, x + kb + d + 1);
+            double qtx2 = 0.0;
+            for (int k = 1; k < d; k++)
+                qtx2 += ROWD(T, L.cq + qo + k - 1) * ROWD(T, x + kb + k);
+            const double vu = v1 * x3 + u1 * x4;
+            for (int k = 0; k < d; k++)
+            {
+                const double xk = ROWD(T, x + kb + k);
+                double v = row_accumulate(tm, is, ds, T, x, ROWD(T, rhs + kb + k), -1.0);
+                if (k < d - 1)
+                    v += delta * xk;
+                else
+                    v -= delta * xk;
+                if (initialize)
+                    v += xk;
+                else if (k == 0)
+                    v += eta2 * (d1 * x1 + u0 * x4);
+                else
+                    v += eta2 * (xk + vu * ROWD(T, L.cq + qo + k - 1));
+                ROWD(T, L.e + kb + k) = v;
+                nerr[0] = dmax(nerr[0], fabs(v));
+            }
+            const double e3 = initialize ? x3 : eta2 * (v1 * qtx2 + x3);
+            const double e4 = initialize ? x4 : eta2 * (u0 * x1 + u1 * qtx2 - x4);
+            ROWD(T, L.e + kb + d) = e3;
+            ROWD(T, L.e + kb + d + 1) = e4;
+            nerr[0] = dmax(nerr[0], dmax(fabs(e3), fabs(e4)));
+        }
     }
     team_max<1>(tm, nerr);
     return nerr[0];
@@ -559,7 +715,7 @@ EI_DEV void tile_init(const Team &tm, const KArgs &a, int tile)
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     double *T = t.T;
-    const int zb = P.n + P.p;
+    const int n = P.n, zb = P.n + P.p;
     const bool valid = tile * TILE + tm.lane < a.batch;
     if (tm.wk == 0)
     {
@@ -579,30 +735,28 @@ EI_DEV void tile_init(const Team &tm, const KArgs &a, int tile)
         const int kind = EI_LDG(P.Vkind + k);
         ROWD(T, L.V + k) = kind == 0 ? -1.0 : (kind == 1 ? 0.0 : 1.0);
     }
-    for (int r = tm.wk; r < P.N; r += tm.nwk)
-    {
-        ROWD(T, L.rhs1 + r) = 0.0;
-        ROWD(T, L.rhs2 + r) = 0.0;
-    }
-    tm.sync();
+    // rhs1 = [0; b; h], rhs2 = [-c; 0; 0]; resx0.. = max(1, ||c||), ... (:865-894)
     double nr[3] = {0.0, 0.0, 0.0};
-    for (int j = tm.wk; j < P.n; j += tm.nwk)
+    for (int r = tm.wk; r < n; r += tm.nwk)
     {
-        const double cj = ROWD(T, L.c + j);
-        ROWD(T, L.rhs2 + j) = -cj;
-        nr[0] += cj * cj;
+        const double v = ROWD(T, L.chb + r);
+        ROWD(T, L.rhs1 + r) = 0.0;
+        ROWD(T, L.rhs2 + r) = -v;
+        nr[0] += v * v;
     }
-    for (int i = tm.wk; i < P.p; i += tm.nwk)
+    for (int r = n + tm.wk; r < zb; r += tm.nwk)
     {
-        const double bi = ROWD(T, L.b + i);
-        ROWD(T, L.rhs1 + P.n + i) = bi;
-        nr[1] += bi * bi;
+        const double v = ROWD(T, L.chb + r);
+        ROWD(T, L.rhs1 + r) = v;
+        ROWD(T, L.rhs2 + r) = 0.0;
+        nr[1] += v * v;
     }
-    for (int i = tm.wk; i < P.m; i += tm.nwk)
+    for (int r = zb + tm.wk; r < P.N; r += tm.nwk)
     {
-        const double hi = ROWD(T, L.h + i);
-        ROWD(T, L.rhs1 + zb + EI_LDG(P.zk + i)) = hi;
-        nr[2] += hi * hi;
+        const double v = ROWD(T, L.chb + r);
+        ROWD(T, L.rhs1 + r) = v;
+        ROWD(T, L.rhs2 + r) = 0.0;
+        nr[2] += v * v;
     }
     team_sum<3>(tm, nr);
     if (tm.wk == 0)
@@ -613,14 +767,14 @@ EI_DEV void tile_init(const Team &tm, const KArgs &a, int tile)
     }
 }
 
-// bringToCone (src/eicos.cpp:761-805): dst = sign*src + (1+alpha) e
-EI_DEV void bring_to_cone(const Team &tm, const KArgs &a, double *T, int src_kkt, double sign, int dst, bool write)
+// bringToCone (src/eicos.cpp:761-805): dst = sign*src + (1+alpha) e ; src, dst z-shaped row offsets
+EI_DEV void bring_to_cone(const Team &tm, const KArgs &a, double *T, int src, double sign, int dst, bool write)
 {
     const DevPattern &P = a.P;
     double al[1] = {-Settings::gamma};
     for (int k = tm.wk; k < P.l; k += tm.nwk)
     {
-        const double r = sign * ROWD(T, src_kkt + k);
+        const double r = sign * ROWD(T, src + k);
         if (r <= 0 && -r > al[0])
             al[0] = -r;
     }
@@ -630,10 +784,10 @@ EI_DEV void bring_to_cone(const Team &tm, const KArgs &a, double *T, int src_kkt
         double sq = 0.0;
         for (int k = 1; k < d; k++)
         {
-            const double v = sign * ROWD(T, src_kkt + kb + k);
+            const double v = sign * ROWD(T, src + kb + k);
             sq += v * v;
         }
-        const double cres = sign * ROWD(T, src_kkt + kb) - sqrt(sq);
+        const double cres = sign * ROWD(T, src + kb) - sqrt(sq);
         if (cres <= 0 && -cres > al[0])
             al[0] = -cres;
     }
@@ -642,13 +796,13 @@ EI_DEV void bring_to_cone(const Team &tm, const KArgs &a, double *T, int src_kkt
     if (!write)
         return;
     for (int k = tm.wk; k < P.l; k += tm.nwk)
-        ROWD(T, dst + k) = sign * ROWD(T, src_kkt + k) + alpha;
+        ROWD(T, dst + k) = sign * ROWD(T, src + k) + alpha;
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     {
-        const int d = EI_LDG(P.cone_dim + c), kb = EI_LDG(P.cone_k + c), zs = EI_LDG(P.cone_z + c);
-        ROWD(T, dst + zs) = sign * ROWD(T, src_kkt + kb) + alpha;
+        const int d = EI_LDG(P.cone_dim + c), kb = EI_LDG(P.cone_k + c);
+        ROWD(T, dst + kb) = sign * ROWD(T, src + kb) + alpha;
         for (int k = 1; k < d; k++)
-            ROWD(T, dst + zs + k) = sign * ROWD(T, src_kkt + kb + k);
+            ROWD(T, dst + kb + k) = sign * ROWD(T, src + kb + k);
     }
 }
 
@@ -662,18 +816,18 @@ EI_DEV void tile_init_point(const Team &tm, const KArgs &a, int tile)
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     double *T = t.T;
-    const int zb = P.n + P.p;
-    for (int j = tm.wk; j < P.n; j += tm.nwk)
+    const int n = P.n, zb = P.n + P.p;
+    for (int j = tm.wk; j < n; j += tm.nwk)
     {
         if (act)
-            ROWD(T, L.x + j) = ROWD(T, L.sol1 + j);
-        ROWD(T, L.rhs1 + j) = -ROWD(T, L.c + j);
+            ROWD(T, L.w + j) = ROWD(T, L.sol1 + j);
+        ROWD(T, L.rhs1 + j) = -ROWD(T, L.chb + j);
     }
     for (int i = tm.wk; i < P.p; i += tm.nwk)
         if (act)
-            ROWD(T, L.y + i) = ROWD(T, L.sol2 + P.n + i);
+            ROWD(T, L.w + n + i) = ROWD(T, L.sol2 + n + i);
     bring_to_cone(tm, a, T, L.sol1 + zb, -1.0, L.s, act);
-    bring_to_cone(tm, a, T, L.sol2 + zb, 1.0, L.z, act);
+    bring_to_cone(tm, a, T, L.sol2 + zb, 1.0, L.w + zb, act);
     if (tm.wk == 0 && act)
     {
         ROWD(T, L.sc + S_KAP) = 1.;
@@ -831,55 +985,88 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
     const Layout &L = a.L;
     double *T = t.T;
     int *I = t.I;
-    const int n = P.n, p = P.p, m = P.m, zb = P.n + P.p;
+    const int n = P.n, p = P.p, zb = P.n + P.p;
     const double tau = ROWD(T, L.sc + S_TAU), kap = ROWD(T, L.sc + S_KAP);
 
     enum { HX2, RX2, CX, NX2, HY2, RY2, BY, NY2, HZ2, RZ2, HZ, NZ2, NS2, GAP, NRED };
     double r[NRED];
     for (int k = 0; k < NRED; k++)
         r[k] = 0.0;
-    for (int j = tm.wk; j < n; j += tm.nwk)
+    IStream is;
+    DStream ds;
+    if (n > 0)
     {
-        double v = 0.0;
-        for (int k = EI_LDG(P.Gp + j), k1 = EI_LDG(P.Gp + j + 1); k < k1; k++)
-            v -= EI_LDG(P.Gx + k) * ROWD(T, L.z + EI_LDG(P.Gi + k));
-        for (int k = EI_LDG(P.Ap + j), k1 = EI_LDG(P.Ap + j + 1); k < k1; k++)
-            v -= EI_LDG(P.Ax + k) * ROWD(T, L.y + EI_LDG(P.Ai + k));
-        r[HX2] += v * v;
-        const double cj = ROWD(T, L.c + j), xj = ROWD(T, L.x + j);
-        v -= tau * cj;
-        ROWD(T, L.rx + j) = v;
-        r[RX2] += v * v;
-        r[CX] += cj * xj;
-        r[NX2] += xj * xj;
+        is.open(P.rx + EI_LDG(P.rx_seg + tm.wk * 2), tm.lane);
+        ds.open(P.rx_val + EI_LDG(P.rx_seg + tm.wk * 2 + 1), tm.lane);
+        for (int j = tm.wk; j < n; j += tm.nwk)
+        {
+            const double cj = ROWD(T, L.chb + j), xj = ROWD(T, L.w + j);
+            double v = row_accumulate(tm, is, ds, T, L.w, 0.0, -1.0);
+            r[HX2] += v * v;
+            v -= tau * cj;
+            ROWD(T, L.r + j) = v;
+            r[RX2] += v * v;
+            r[CX] += cj * xj;
+            r[NX2] += xj * xj;
+        }
     }
-    for (int i = tm.wk; i < p; i += tm.nwk)
+    if (p > 0)
     {
-        double v = 0.0;
-        for (int q = EI_LDG(P.Arp + i), q1 = EI_LDG(P.Arp + i + 1); q < q1; q++)
-            v += EI_LDG(P.Ax + EI_LDG(P.Arv + q)) * ROWD(T, L.x + EI_LDG(P.Arj + q));
-        r[HY2] += v * v;
-        const double bi = ROWD(T, L.b + i), yi = ROWD(T, L.y + i);
-        v -= tau * bi;
-        ROWD(T, L.ry + i) = v;
-        r[RY2] += v * v;
-        r[BY] += bi * yi;
-        r[NY2] += yi * yi;
+        is.open(P.ry + EI_LDG(P.ry_seg + tm.wk * 2), tm.lane);
+        ds.open(P.ry_val + EI_LDG(P.ry_seg + tm.wk * 2 + 1), tm.lane);
+        for (int i = tm.wk; i < p; i += tm.nwk)
+        {
+            const double bi = ROWD(T, L.chb + n + i), yi = ROWD(T, L.w + n + i);
+            double v = row_accumulate(tm, is, ds, T, L.w, 0.0, 1.0);
+            r[HY2] += v * v;
+            v -= tau * bi;
+            ROWD(T, L.r + n + i) = v;
+            r[RY2] += v * v;
+            r[BY] += bi * yi;
+            r[NY2] += yi * yi;
+        }
     }
-    for (int i = tm.wk; i < m; i += tm.nwk)
+    if (P.l > 0)
     {
-        const double si = ROWD(T, L.s + i), zi = ROWD(T, L.z + i), hi = ROWD(T, L.h + i);
-        double v = si;
-        for (int q = EI_LDG(P.Grp + i), q1 = EI_LDG(P.Grp + i + 1); q < q1; q++)
-            v += EI_LDG(P.Gx + EI_LDG(P.Grv + q)) * ROWD(T, L.x + EI_LDG(P.Grj + q));
-        r[HZ2] += v * v;
-        v -= tau * hi;
-        ROWD(T, L.rz + i) = v;
-        r[RZ2] += v * v;
-        r[HZ] += hi * zi;
-        r[NZ2] += zi * zi;
-        r[NS2] += si * si;
-        r[GAP] += si * zi;
+        is.open(P.rz + EI_LDG(P.rz_seg + tm.wk * 2), tm.lane);
+        ds.open(P.rz_val + EI_LDG(P.rz_seg + tm.wk * 2 + 1), tm.lane);
+        for (int i = tm.wk; i < P.l; i += tm.nwk)
+        {
+            const double si = ROWD(T, L.s + i), zi = ROWD(T, L.w + zb + i), hi = ROWD(T, L.chb + zb + i);
+            double v = row_accumulate(tm, is, ds, T, L.w, si, 1.0);
+            r[HZ2] += v * v;
+            v -= tau * hi;
+            ROWD(T, L.r + zb + i) = v;
+            r[RZ2] += v * v;
+            r[HZ] += hi * zi;
+            r[NZ2] += zi * zi;
+            r[NS2] += si * si;
+            r[GAP] += si * zi;
+        }
+    }
+    if (P.nc > 0)
+    {
+        is.open(P.rc + EI_LDG(P.rc_seg + tm.wk * 2), tm.lane);
+        ds.open(P.rc_val + EI_LDG(P.rc_seg + tm.wk * 2 + 1), tm.lane);
+        for (int c = tm.wk; c < P.nc; c += tm.nwk)
+        {
+            const int d = is.get(), ks = is.get();
+            (void)is.get();
+            for (int k = 0; k < d; k++)
+            {
+                const int e = ks + k;
+                const double si = ROWD(T, L.s + e), zi = ROWD(T, L.w + zb + e), hi = ROWD(T, L.chb + zb + e);
+                double v = row_accumulate(tm, is, ds, T, L.w, si, 1.0);
+                r[HZ2] += v * v;
+                v -= tau * hi;
+                ROWD(T, L.r + zb + e) = v;
+                r[RZ2] += v * v;
+                r[HZ] += hi * zi;
+                r[NZ2] += zi * zi;
+                r[NS2] += si * si;
+                r[GAP] += si * zi;
+            }
+        }
     }
     team_sum<NRED>(tm, r);
 
@@ -1005,56 +1192,40 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
     const double ftau = w.d[S_TAU];
     if (tm.any(restore || save || fin))
     {
-        for (int j = tm.wk; j < n; j += tm.nwk)
+        for (int q = tm.wk; q < P.N; q += tm.nwk)
         {
-            double v = ROWD(T, L.x + j);
+            double v = ROWD(T, L.w + q);
             if (restore)
-                v = ROWD(T, L.bx + j);
+                v = ROWD(T, L.wb + q);
             if (save)
-                ROWD(T, L.bx + j) = v;
+                ROWD(T, L.wb + q) = v;
             if (fin)
-                v = v / (EI_LDG(P.xeq + j) * ftau);
+            {
+                const double eq = q < n ? EI_LDG(P.xeq + q) : (q < zb ? EI_LDG(P.Aeq + q - n) : EI_LDG(P.GeqE + q - zb));
+                v = v / (eq * ftau);
+            }
             if (restore || fin)
-                ROWD(T, L.x + j) = v;
+                ROWD(T, L.w + q) = v;
         }
-        for (int i = tm.wk; i < p; i += tm.nwk)
+        for (int e = tm.wk; e < P.mt; e += tm.nwk)
         {
-            double v = ROWD(T, L.y + i);
-            if (restore)
-                v = ROWD(T, L.by + i);
-            if (save)
-                ROWD(T, L.by + i) = v;
-            if (fin)
-                v = v / (EI_LDG(P.Aeq + i) * ftau);
-            if (restore || fin)
-                ROWD(T, L.y + i) = v;
-        }
-        for (int i = tm.wk; i < m; i += tm.nwk)
-        {
-            double zv = ROWD(T, L.z + i), sv = ROWD(T, L.s + i), lv = ROWD(T, L.lam + i);
+            double sv = ROWD(T, L.s + e), lv = ROWD(T, L.lam + e);
             if (restore)
             {
-                zv = ROWD(T, L.bz + i);
-                sv = ROWD(T, L.bs + i);
-                lv = ROWD(T, L.blam + i);
+                sv = ROWD(T, L.bs + e);
+                lv = ROWD(T, L.blam + e);
             }
             if (save)
             {
-                ROWD(T, L.bz + i) = zv;
-                ROWD(T, L.bs + i) = sv;
-                ROWD(T, L.blam + i) = lv;
+                ROWD(T, L.bs + e) = sv;
+                ROWD(T, L.blam + e) = lv;
             }
             if (fin)
-            {
-                const double ge = EI_LDG(P.Geq + i);
-                zv = zv / (ge * ftau);
-                sv = sv * (ge / ftau);
-            }
+                sv = sv * (EI_LDG(P.GeqE + e) / ftau);
             if (restore || fin)
             {
-                ROWD(T, L.z + i) = zv;
-                ROWD(T, L.s + i) = sv;
-                ROWD(T, L.lam + i) = lv;
+                ROWD(T, L.s + e) = sv;
+                ROWD(T, L.lam + e) = lv;
             }
         }
     }
@@ -1068,54 +1239,60 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
             atomicAdd(a.active_count, (unsigned)__popc(bal));
     }
 #else
-    if (a.active_count && cont)
+    if (tm.wk == 0 && a.active_count && cont)
         *a.active_count += 1;
 #endif
 
     // ---- updateScalings (:411-479); its return value is ignored by the caller (:1160), so after a
     // failure at cone c the LP part and cones < c are new, cone c is partly new and lambda is stale.
+    const int sz = L.w + zb; // z rows of the iterate
     for (int k = tm.wk; k < P.l; k += tm.nwk)
     {
-        const double v = ROWD(T, L.s + k) / ROWD(T, L.z + k);
+        const double v = ROWD(T, L.s + k) / ROWD(T, sz + k);
         if (cont)
         {
             ROWD(T, L.lpv + k) = v;
             ROWD(T, L.lpw + k) = sqrt(v);
         }
     }
-    double ff[1] = {(double)P.nc};
-    for (int c = tm.wk; c < P.nc; c += tm.nwk)
+    int first_fail = P.nc;
+    if (P.nc > 0)
     {
-        const ConeScaling cs = cone_scaling(tm, T, L.s + EI_LDG(P.cone_z + c), L.z + EI_LDG(P.cone_z + c), EI_LDG(P.cone_dim + c));
-        if (cs.stage != 0)
-            ff[0] = dmin(ff[0], (double)c);
+        double ff[1] = {(double)P.nc};
+        for (int c = tm.wk; c < P.nc; c += tm.nwk)
+        {
+            const int ks = EI_LDG(P.cone_k + c);
+            const ConeScaling cs = cone_scaling(tm, T, L.s + ks, sz + ks, EI_LDG(P.cone_dim + c));
+            if (cs.stage != 0)
+                ff[0] = dmin(ff[0], (double)c);
+        }
+        team_min<1>(tm, ff);
+        first_fail = (int)ff[0];
+        for (int c = tm.wk; c < P.nc; c += tm.nwk)
+        {
+            if (!cont || c > first_fail)
+                continue; // (divergent per lane, cone-local work only)
+            const int d = EI_LDG(P.cone_dim + c), ks = EI_LDG(P.cone_k + c), qo = EI_LDG(P.cone_q + c);
+            const ConeScaling cs = cone_scaling(tm, T, L.s + ks, sz + ks, d);
+            if (cs.stage == 1)
+                continue;
+            double *cp = T + (size_t)(L.cpar + c * CP_COUNT) * TILE + tm.lane;
+            cp[CP_ETA2 * TILE] = cs.eta2;
+            cp[CP_ETA * TILE] = cs.eta;
+            for (int k = 1; k < d; k++)
+                ROWD(T, L.cq + qo + k - 1) = (0.5 / cs.gamma) * (ROWD(T, L.s + ks + k) / cs.snorm - ROWD(T, sz + ks + k) / cs.znorm);
+            if (cs.stage == 2)
+                continue;
+            cp[CP_D1 * TILE] = cs.d1;
+            cp[CP_U0 * TILE] = cs.u0;
+            cp[CP_U1 * TILE] = cs.u1;
+            cp[CP_V1 * TILE] = cs.v1;
+            cp[CP_A * TILE] = cs.a;
+            cp[CP_W * TILE] = cs.w;
+        }
+        tm.sync();
     }
-    team_min<1>(tm, ff);
-    const int first_fail = (int)ff[0];
-    for (int c = tm.wk; c < P.nc; c += tm.nwk)
-    {
-        if (!cont || c > first_fail)
-            continue; // (divergent per lane, cone-local work only)
-        const int d = EI_LDG(P.cone_dim + c), zs = EI_LDG(P.cone_z + c), qo = EI_LDG(P.cone_q + c);
-        const ConeScaling cs = cone_scaling(tm, T, L.s + zs, L.z + zs, d);
-        if (cs.stage == 1)
-            continue;
-        double *cp = T + (size_t)(L.cpar + c * CP_COUNT) * TILE + tm.lane;
-        cp[CP_ETA2 * TILE] = cs.eta2;
-        cp[CP_ETA * TILE] = cs.eta;
-        for (int k = 1; k < d; k++)
-            ROWD(T, L.cq + qo + k - 1) = (0.5 / cs.gamma) * (ROWD(T, L.s + zs + k) / cs.snorm - ROWD(T, L.z + zs + k) / cs.znorm);
-        if (cs.stage == 2)
-            continue;
-        cp[CP_D1 * TILE] = cs.d1;
-        cp[CP_U0 * TILE] = cs.u0;
-        cp[CP_U1 * TILE] = cs.u1;
-        cp[CP_V1 * TILE] = cs.v1;
-        cp[CP_A * TILE] = cs.a;
-        cp[CP_W * TILE] = cs.w;
-    }
-    tm.sync();
-    cone_scale(tm, a, T, ZRef{L.z, nullptr}, ZRef{L.lam, nullptr}, cont && first_fail == P.nc);
+    cone_scale(tm, a, T, sz, L.lam, cont && first_fail == P.nc);
 
     // ---- updateKKTScalings (:1691-1732) into the V rows, RHSaffine (:1670-1689) into rhs2
     const double delta = Settings::deltastat;
@@ -1123,11 +1300,12 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
         ROWD(T, L.V + k) = -ROWD(T, L.lpv + k) - delta;
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     {
-        const int d = EI_LDG(P.cone_dim + c), zs = EI_LDG(P.cone_z + c), qo = EI_LDG(P.cone_q + c);
+        const int d = EI_LDG(P.cone_dim + c), ks = EI_LDG(P.cone_k + c), qo = EI_LDG(P.cone_q + c);
         const double *cp = T + (size_t)(L.cpar + c * CP_COUNT) * TILE + tm.lane;
         const double eta2 = cp[CP_ETA2 * TILE], d1 = cp[CP_D1 * TILE], u0 = cp[CP_U0 * TILE];
         const double u1 = cp[CP_U1 * TILE], v1 = cp[CP_V1 * TILE];
-        int vb = L.V + P.l + 3 * (zs - P.l) + c; // cones before c contributed sum(3 dim + 1) entries
+        // cones before c contributed sum(3 dim + 1) V entries; ks - 2c - l = sum of their dims
+        int vb = L.V + P.l + 3 * (ks - 2 * c - P.l) + c;
         ROWD(T, vb++) = -eta2 * d1 - delta;
         for (int k = 1; k < d; k++)
             ROWD(T, vb++) = -eta2 - delta;
@@ -1139,17 +1317,10 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
         for (int k = 1; k < d; k++)
             ROWD(T, vb++) = -eta2 * u1 * ROWD(T, L.cq + qo + k - 1);
     }
-    for (int j = tm.wk; j < n; j += tm.nwk)
-        ROWD(T, L.rhs2 + j) = ROWD(T, L.rx + j);
-    for (int i = tm.wk; i < p; i += tm.nwk)
-        ROWD(T, L.rhs2 + n + i) = -ROWD(T, L.ry + i);
-    for (int i = tm.wk; i < m; i += tm.nwk)
-        ROWD(T, L.rhs2 + zb + EI_LDG(P.zk + i)) = ROWD(T, L.s + i) - ROWD(T, L.rz + i);
-    for (int c = tm.wk; c < P.nc; c += tm.nwk)
-    {
-        const int kb = zb + EI_LDG(P.cone_k + c) + EI_LDG(P.cone_dim + c);
-        ROWD(T, L.rhs2 + kb) = 0.0;
-        ROWD(T, L.rhs2 + kb + 1) = 0.0;
+    for (int q = tm.wk; q < P.N; q += tm.nwk)
+    { // [rx; -ry; s - rz], the slot rows of s and rz are zero
+        const double rv = ROWD(T, L.r + q);
+        ROWD(T, L.rhs2 + q) = q < n ? rv : (q < zb ? -rv : ROWD(T, L.s + q - zb) - rv);
     }
 }
 
@@ -1164,43 +1335,50 @@ EI_DEV void tile_mid(const Team &tm, const KArgs &a, int tile)
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     double *T = t.T;
-    const int n = P.n, p = P.p, m = P.m, zb = P.n + P.p;
+    const int n = P.n, p = P.p, zb = P.n + P.p;
     const double tau = ROWD(T, L.sc + S_TAU), kap = ROWD(T, L.sc + S_KAP), rt = ROWD(T, L.sc + S_RT);
     const double mu = ROWD(T, L.sc + S_MU);
 
+    // c'dx, b'dy, h'dz for both solutions; the slot rows of h are zero but are skipped anyway
     double dt[6] = {0, 0, 0, 0, 0, 0};
-    for (int j = tm.wk; j < n; j += tm.nwk)
+    for (int q = tm.wk; q < n; q += tm.nwk)
     {
-        const double cj = ROWD(T, L.c + j);
-        dt[0] += cj * ROWD(T, L.sol1 + j);
-        dt[3] += cj * ROWD(T, L.sol2 + j);
+        const double cv = ROWD(T, L.chb + q);
+        dt[0] += cv * ROWD(T, L.sol1 + q);
+        dt[3] += cv * ROWD(T, L.sol2 + q);
     }
-    for (int i = tm.wk; i < p; i += tm.nwk)
+    for (int q = n + tm.wk; q < zb; q += tm.nwk)
     {
-        const double bi = ROWD(T, L.b + i);
-        dt[1] += bi * ROWD(T, L.sol1 + n + i);
-        dt[4] += bi * ROWD(T, L.sol2 + n + i);
+        const double cv = ROWD(T, L.chb + q);
+        dt[1] += cv * ROWD(T, L.sol1 + q);
+        dt[4] += cv * ROWD(T, L.sol2 + q);
     }
-    for (int i = tm.wk; i < m; i += tm.nwk)
+    for (int q = zb + tm.wk; q < zb + P.l; q += tm.nwk)
     {
-        const double hi = ROWD(T, L.h + i);
-        const int kr = zb + EI_LDG(P.zk + i);
-        dt[2] += hi * ROWD(T, L.sol1 + kr);
-        dt[5] += hi * ROWD(T, L.sol2 + kr);
+        const double cv = ROWD(T, L.chb + q);
+        dt[2] += cv * ROWD(T, L.sol1 + q);
+        dt[5] += cv * ROWD(T, L.sol2 + q);
+    }
+    for (int c = tm.wk; c < P.nc; c += tm.nwk)
+    {
+        const int d = EI_LDG(P.cone_dim + c), kb = zb + EI_LDG(P.cone_k + c);
+        for (int k = 0; k < d; k++)
+        {
+            const double hv = ROWD(T, L.chb + kb + k);
+            dt[2] += hv * ROWD(T, L.sol1 + kb + k);
+            dt[5] += hv * ROWD(T, L.sol2 + kb + k);
+        }
     }
     team_sum<6>(tm, dt);
     const double dtau_denom = kap / tau - dt[0] - dt[1] - dt[2];
     const double dtauaff = (rt - kap + dt[3] + dt[4] + dt[5]) / dtau_denom;
-    for (int i = tm.wk; i < m; i += tm.nwk)
-    {
-        const int kr = zb + EI_LDG(P.zk + i);
-        ROWD(T, L.sol2 + kr) += dtauaff * ROWD(T, L.sol1 + kr);
-    }
+    for (int e = tm.wk; e < P.mt; e += tm.nwk) // dz2 += dtauaff * dz1 (slot rows are never read again)
+        ROWD(T, L.sol2 + zb + e) += dtauaff * ROWD(T, L.sol1 + zb + e);
     tm.sync();
-    cone_scale(tm, a, T, ZRef{L.sol2 + zb, P.zk}, ZRef{L.wdz, nullptr}, true);
+    cone_scale(tm, a, T, L.sol2 + zb, L.wdz, true);
     tm.sync();
-    for (int i = tm.wk; i < m; i += tm.nwk)
-        ROWD(T, L.dsw + i) = -ROWD(T, L.wdz + i) - ROWD(T, L.lam + i);
+    for (int e = tm.wk; e < P.mt; e += tm.nwk)
+        ROWD(T, L.dsw + e) = -ROWD(T, L.wdz + e) - ROWD(T, L.lam + e);
     tm.sync();
     const double dkapaff = -kap - kap / tau * dtauaff;
     const double step_aff = line_search(tm, a, T, L.lam, L.dsw, L.wdz, tau, dtauaff, kap, dkapaff);
@@ -1231,12 +1409,12 @@ EI_DEV void tile_mid(const Team &tm, const KArgs &a, int tile)
         d1 -= sigmamu;
         const double q = d1 / lk; // conicDivision, LP part
         ROWD(T, L.dsw + k) = q;
-        ROWD(T, L.rhs2 + zb + k) = -oms * ROWD(T, L.rz + k) + ROWD(T, L.lpw + k) * q;
+        ROWD(T, L.rhs2 + zb + k) = -oms * ROWD(T, L.r + zb + k) + ROWD(T, L.lpw + k) * q;
     }
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     {
-        const int d = EI_LDG(P.cone_dim + c), zs = EI_LDG(P.cone_z + c), qo = EI_LDG(P.cone_q + c);
-        const int kb = zb + EI_LDG(P.cone_k + c);
+        const int d = EI_LDG(P.cone_dim + c), zs = EI_LDG(P.cone_k + c), qo = EI_LDG(P.cone_q + c);
+        const int kb = zb + zs;
         const double *cp = T + (size_t)(L.cpar + c * CP_COUNT) * TILE + tm.lane;
         const double eta = cp[CP_ETA * TILE], ca = cp[CP_A * TILE];
         // ds1 = lambda o lambda ; ds2 = (W\ds_aff) o (W dz_aff)
@@ -1277,9 +1455,9 @@ EI_DEV void tile_mid(const Team &tm, const KArgs &a, int tile)
         for (int k = 1; k < d; k++)
             zt += ROWD(T, L.cq + qo + k - 1) * ROWD(T, L.dsw + zs + k);
         const double fz = q0 + zt / (1. + ca);
-        ROWD(T, L.rhs2 + kb) = -oms * ROWD(T, L.rz + zs) + eta * (ca * q0 + zt);
+        ROWD(T, L.rhs2 + kb) = -oms * ROWD(T, L.r + kb) + eta * (ca * q0 + zt);
         for (int k = 1; k < d; k++)
-            ROWD(T, L.rhs2 + kb + k) = -oms * ROWD(T, L.rz + zs + k) +
+            ROWD(T, L.rhs2 + kb + k) = -oms * ROWD(T, L.r + kb + k) +
                                        eta * (ROWD(T, L.dsw + zs + k) + fz * ROWD(T, L.cq + qo + k - 1));
         ROWD(T, L.rhs2 + kb + d) = 0.0;
         ROWD(T, L.rhs2 + kb + d + 1) = 0.0;
@@ -1296,45 +1474,52 @@ EI_DEV void tile_tail(const Team &tm, const KArgs &a, int tile)
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     double *T = t.T;
-    const int n = P.n, p = P.p, m = P.m, zb = P.n + P.p;
+    const int n = P.n, zb = P.n + P.p;
     const double tau = ROWD(T, L.sc + S_TAU), kap = ROWD(T, L.sc + S_KAP), rt = ROWD(T, L.sc + S_RT);
     const double mu = ROWD(T, L.sc + S_MU), sigma = ROWD(T, L.sc + S_SIGMA);
     const double dtau_denom = ROWD(T, L.sc + S_DTAU_DENOM), dtauaff = ROWD(T, L.sc + S_DTAUAFF);
     const double dkapaff = ROWD(T, L.sc + S_DKAPAFF);
 
     double dt[3] = {0, 0, 0};
-    for (int j = tm.wk; j < n; j += tm.nwk)
-        dt[0] += ROWD(T, L.c + j) * ROWD(T, L.sol2 + j);
-    for (int i = tm.wk; i < p; i += tm.nwk)
-        dt[1] += ROWD(T, L.b + i) * ROWD(T, L.sol2 + n + i);
-    for (int i = tm.wk; i < m; i += tm.nwk)
-        dt[2] += ROWD(T, L.h + i) * ROWD(T, L.sol2 + zb + EI_LDG(P.zk + i));
+    for (int q = tm.wk; q < n; q += tm.nwk)
+        dt[0] += ROWD(T, L.chb + q) * ROWD(T, L.sol2 + q);
+    for (int q = n + tm.wk; q < zb; q += tm.nwk)
+        dt[1] += ROWD(T, L.chb + q) * ROWD(T, L.sol2 + q);
+    for (int q = zb + tm.wk; q < zb + P.l; q += tm.nwk)
+        dt[2] += ROWD(T, L.chb + q) * ROWD(T, L.sol2 + q);
+    for (int c = tm.wk; c < P.nc; c += tm.nwk)
+    {
+        const int d = EI_LDG(P.cone_dim + c), kb = zb + EI_LDG(P.cone_k + c);
+        for (int k = 0; k < d; k++)
+            dt[2] += ROWD(T, L.chb + kb + k) * ROWD(T, L.sol2 + kb + k);
+    }
     team_sum<3>(tm, dt);
     const double bkap = kap * tau + dkapaff * dtauaff - sigma * mu;
     const double dtau = ((1. - sigma) * rt - bkap / tau + dt[0] + dt[1] + dt[2]) / dtau_denom;
     for (int r = tm.wk; r < P.N; r += tm.nwk)
         ROWD(T, L.sol2 + r) += dtau * ROWD(T, L.sol1 + r);
     tm.sync();
-    cone_scale(tm, a, T, ZRef{L.sol2 + zb, P.zk}, ZRef{L.wdz, nullptr}, true);
+    cone_scale(tm, a, T, L.sol2 + zb, L.wdz, true);
     tm.sync();
-    for (int i = tm.wk; i < m; i += tm.nwk)
-        ROWD(T, L.dsw + i) = -(ROWD(T, L.dsw + i) + ROWD(T, L.wdz + i));
+    for (int e = tm.wk; e < P.mt; e += tm.nwk)
+        ROWD(T, L.dsw + e) = -(ROWD(T, L.dsw + e) + ROWD(T, L.wdz + e));
     tm.sync();
     const double dkap = -(bkap + kap * dtau) / tau;
     const double step = Settings::gamma * line_search(tm, a, T, L.lam, L.dsw, L.wdz, tau, dtau, kap, dkap);
-    cone_scale(tm, a, T, ZRef{L.dsw, nullptr}, ZRef{L.dsaff, nullptr}, true);
+    cone_scale(tm, a, T, L.dsw, L.dsaff, true);
     tm.sync();
     if (!act)
         return; // no barriers below
-    for (int j = tm.wk; j < n; j += tm.nwk)
-        ROWD(T, L.x + j) += step * ROWD(T, L.sol2 + j);
-    for (int i = tm.wk; i < p; i += tm.nwk)
-        ROWD(T, L.y + i) += step * ROWD(T, L.sol2 + n + i);
-    for (int i = tm.wk; i < m; i += tm.nwk)
-    {
-        ROWD(T, L.z + i) += step * ROWD(T, L.sol2 + zb + EI_LDG(P.zk + i));
-        ROWD(T, L.s + i) += step * ROWD(T, L.dsaff + i);
+    for (int q = tm.wk; q < zb + P.l; q += tm.nwk)
+        ROWD(T, L.w + q) += step * ROWD(T, L.sol2 + q);
+    for (int c = tm.wk; c < P.nc; c += tm.nwk)
+    { // cone rows of z; the expansion slots of the iterate stay zero
+        const int d = EI_LDG(P.cone_dim + c), kb = zb + EI_LDG(P.cone_k + c);
+        for (int k = 0; k < d; k++)
+            ROWD(T, L.w + kb + k) += step * ROWD(T, L.sol2 + kb + k);
     }
+    for (int e = tm.wk; e < P.mt; e += tm.nwk)
+        ROWD(T, L.s + e) += step * ROWD(T, L.dsaff + e);
     if (tm.wk == 0)
     {
         ROWD(T, L.sc + S_KAP) = kap + step * dkap;
@@ -1346,30 +1531,32 @@ EI_DEV void tile_tail(const Team &tm, const KArgs &a, int tile)
 
 // ------------------------------------------------------------------ data in / results out
 // Inputs are instance-major (what the C ABI receives); they are equilibrated on the way in
-// (c / x_equil, h / G_equil, b / A_equil : src/eicos.cpp:364-371).
+// (c / x_equil, h / G_equil, b / A_equil : src/eicos.cpp:364-371) and land KKT-shaped in `chb`.
 EI_DEV void tile_load(const Team &tm, const KArgs &a, int tile)
 {
     const TileMem t = tile_mem(a, tile);
     const DevPattern &P = a.P;
     const Layout &L = a.L;
+    const int n = P.n, zb = P.n + P.p;
     int inst = tile * TILE + tm.lane;
     if (inst >= a.batch)
         inst = a.batch - 1; // padding lanes replay the last instance; their results are never stored
     const size_t g = (size_t)a.first + inst;
-    for (int j = tm.wk; j < P.n; j += tm.nwk)
+    for (int j = tm.wk; j < n; j += tm.nwk)
     {
-        const double v = a.in_c ? a.in_c[g * P.n + j] : EI_LDG(a.base_c + j);
-        ROWD(t.T, L.c + j) = a.pre_equilibrated ? v : v / EI_LDG(P.xeq + j);
-    }
-    for (int i = tm.wk; i < P.m; i += tm.nwk)
-    {
-        const double v = a.in_h ? a.in_h[g * P.m + i] : EI_LDG(a.base_h + i);
-        ROWD(t.T, L.h + i) = a.pre_equilibrated ? v : v / EI_LDG(P.Geq + i);
+        const double v = a.in_c ? a.in_c[g * n + j] : EI_LDG(a.base_c + j);
+        ROWD(t.T, L.chb + j) = a.pre_equilibrated ? v : v / EI_LDG(P.xeq + j);
     }
     for (int i = tm.wk; i < P.p; i += tm.nwk)
     {
         const double v = a.in_b ? a.in_b[g * P.p + i] : EI_LDG(a.base_b + i);
-        ROWD(t.T, L.b + i) = a.pre_equilibrated ? v : v / EI_LDG(P.Aeq + i);
+        ROWD(t.T, L.chb + n + i) = a.pre_equilibrated ? v : v / EI_LDG(P.Aeq + i);
+    }
+    for (int i = tm.wk; i < P.m; i += tm.nwk)
+    {
+        const double v = a.in_h ? a.in_h[g * P.m + i] : EI_LDG(a.base_h + i);
+        const int e = EI_LDG(P.zk + i);
+        ROWD(t.T, L.chb + zb + e) = a.pre_equilibrated ? v : v / EI_LDG(P.GeqE + e);
     }
 }
 
@@ -1378,22 +1565,23 @@ EI_DEV void tile_store(const Team &tm, const KArgs &a, int tile)
     const TileMem t = tile_mem(a, tile);
     const DevPattern &P = a.P;
     const Layout &L = a.L;
+    const int n = P.n, zb = P.n + P.p;
     const int inst = tile * TILE + tm.lane;
     if (inst >= a.batch)
         return;
     const size_t g = (size_t)a.first + inst;
     if (a.out_x)
-        for (int j = tm.wk; j < P.n; j += tm.nwk)
-            a.out_x[g * P.n + j] = ROWD(t.T, L.x + j);
+        for (int j = tm.wk; j < n; j += tm.nwk)
+            a.out_x[g * n + j] = ROWD(t.T, L.w + j);
     if (a.out_y)
         for (int i = tm.wk; i < P.p; i += tm.nwk)
-            a.out_y[g * P.p + i] = ROWD(t.T, L.y + i);
+            a.out_y[g * P.p + i] = ROWD(t.T, L.w + n + i);
     if (a.out_z)
         for (int i = tm.wk; i < P.m; i += tm.nwk)
-            a.out_z[g * P.m + i] = ROWD(t.T, L.z + i);
+            a.out_z[g * P.m + i] = ROWD(t.T, L.w + zb + EI_LDG(P.zk + i));
     if (a.out_s)
         for (int i = tm.wk; i < P.m; i += tm.nwk)
-            a.out_s[g * P.m + i] = ROWD(t.T, L.s + i);
+            a.out_s[g * P.m + i] = ROWD(t.T, L.s + EI_LDG(P.zk + i));
     if (tm.wk == 0)
     {
         if (a.out_exit)

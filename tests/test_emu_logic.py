@@ -57,7 +57,7 @@ def test_batched_perturbed_parity(oracle_mod, emu_lib, name, rel, batch):
     P = oracle_mod.load_fixture(name)
     W = perturbed(P, batch, rel=rel, seed=3)
     ref = oracle_mod.batch_run(P, batch, hs=W["hs"], bs=W["bs"], nthreads=2)
-    B = BatchSolver(P, lib=emu_lib, capacity=4)  # forces several chunks
+    B = BatchSolver(P, lib=emu_lib, capacity=4, workers=3)  # several chunks; 3 workers = 3 threads + barriers in the emulator
     out = B.solve(batch, hs=W["hs"], bs=W["bs"])
     assert np.array_equal(out["exit"], ref["exit"])
     assert np.array_equal(out["iter"], ref["iter"])
@@ -73,7 +73,7 @@ def test_batched_soc_mpc_parity(oracle_mod, emu_lib):
     P = soc_mpc(T=12)
     W = soc_mpc_batch(P, 10)
     ref = oracle_mod.batch_run(P, 10, hs=W["hs"], bs=W["bs"], nthreads=2)
-    out = BatchSolver(P, lib=emu_lib, capacity=16).solve(10, hs=W["hs"], bs=W["bs"])
+    out = BatchSolver(P, lib=emu_lib, capacity=16, workers=4).solve(10, hs=W["hs"], bs=W["bs"])
     assert np.array_equal(out["exit"], ref["exit"]) and np.array_equal(out["iter"], ref["iter"])
     for k in "xs":
         assert relerr(out[k], ref[k]) <= TOL, k
