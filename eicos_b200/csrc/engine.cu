@@ -24,8 +24,9 @@ namespace eicos
         tm.wk = threadIdx.x >> 5;                                                              \
         tm.nwk = blockDim.x >> 5;                                                              \
         tm.red = smem;                                                                         \
+        tm.stage = smem + (size_t)tm.nwk * KRED * TILE + (size_t)tm.wk * STAGE_SLOTS * TILE + tm.lane; \
         tm.acc = a.acc_global ? a.acc_global + (size_t)blockIdx.x * tm.nwk * a.P.maxcol * TILE \
-                              : smem + (size_t)tm.nwk * KRED * TILE;                           \
+                              : smem + (size_t)tm.nwk * (KRED + STAGE_SLOTS) * TILE;           \
         fn(tm, a, blockIdx.x);                                                                 \
     }
 #define EI_MAX_THREADS 256
@@ -49,6 +50,7 @@ EI_DEFINE_KERNEL(eicos_store_outputs, tile_store, 4)
         const int nw_ = (threads);                                                                \
         std::vector<double> red_((size_t)nw_ * KRED * TILE + 8);                                  \
         std::vector<double> acc_((size_t)nw_ * (args).P.maxcol * TILE + 8);                       \
+        std::vector<double> stg_((size_t)nw_ * STAGE_SLOTS * TILE + 8);                           \
         for (int tile_ = 0; tile_ < (tiles); tile_++)                                             \
         {                                                                                         \
             std::barrier<> bar_(nw_);                                                             \
@@ -59,6 +61,7 @@ EI_DEFINE_KERNEL(eicos_store_outputs, tile_store, 4)
                 tm_.nwk = nw_;                                                                    \
                 tm_.red = red_.data();                                                            \
                 tm_.acc = acc_.data();                                                            \
+                tm_.stage = stg_.data() + (size_t)wk_ * STAGE_SLOTS * TILE;                       \
                 tm_.bar = nw_ > 1 ? &bar_ : nullptr;                                              \
                 fn(tm_, (args), tile_);                                                           \
             };                                                                                    \
@@ -155,6 +158,8 @@ void Engine::upload_pattern(const Symbolic &S)
     P.nnzV = (int)S.Vslot.size();
     P.nphases = (int)S.phases.size();
     P.maxcol = S.maxcol;
+    P.nph_fw = H_.nph_fw;
+    P.nph_bw = H_.nph_bw;
     P.cone_dim = upload(S.q, owned_, st);
     P.cone_k = upload(S.cone_k, owned_, st);
     P.cone_q = upload(S.cone_q, owned_, st);
@@ -233,7 +238,7 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
     active_count_ = (unsigned int *)be::alloc(sizeof(unsigned int));
     ir_rounds_ = (unsigned long long *)be::alloc(sizeof(unsigned long long));
     host_pinned_ = (unsigned int *)be::pinned(4 * sizeof(unsigned long long));
-    smem_common_ = (size_t)workers_ * KRED * TILE * sizeof(double);
+    smem_common_ = (size_t)workers_ * (KRED + STAGE_SLOTS) * TILE * sizeof(double);
     smem_factor_ = smem_common_ + (size_t)workers_ * S.maxcol * TILE * sizeof(double);
 #ifndef EICOS_EMU
     const size_t smem_limit = 200 * 1024;
@@ -244,6 +249,14 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
     }
     if (smem_factor_ > 48 * 1024)
         EI_CUDA(cudaFuncSetAttribute(eicos_ldl_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_factor_));
+    if (smem_common_ > 48 * 1024)
+    {
+        const void *ks[] = {(const void *)eicos_load_inputs, (const void *)eicos_init, (const void *)eicos_solve_kkt,
+                            (const void *)eicos_init_point, (const void *)eicos_iter_head, (const void *)eicos_iter_mid,
+                            (const void *)eicos_iter_tail, (const void *)eicos_store_outputs};
+        for (const void *k : ks)
+            EI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_common_));
+    }
 #endif
     be::sync(S_(stream_));
 }
@@ -515,9 +528,8 @@ void Engine::debug_factor_init(int batch, const double *d_c, const double *d_h, 
                         dst[inst * rows + r] = buf[(size_t)(row0 + r) * TILE + lane];
             };
             if (h_Lx)
-                for (int j = 0; j < P_.N; j++)
-                    for (int u = Lp_[j]; u < Lp_[j + 1]; u++)
-                        h_Lx[inst * P_.nnzL + u] = buf[(size_t)(L_.Lx + H_.bw_base[j] + (u - Lp_[j])) * TILE + lane];
+                for (int u = 0; u < P_.nnzL; u++)
+                    h_Lx[inst * P_.nnzL + u] = buf[(size_t)(L_.Lx + H_.bw_pos[u]) * TILE + lane];
             grab(h_D, L_.D, P_.N);
             grab(h_sol1, L_.sol1, P_.N);
             grab(h_sol2, L_.sol2, P_.N);

@@ -71,8 +71,9 @@ struct KArgs
 struct Team
 {
     int lane, wk, nwk;
-    double *red; // [nwk][KRED][TILE]
-    double *acc; // [nwk][maxcol][TILE]
+    double *red;   // [nwk][KRED][TILE]
+    double *acc;   // [nwk][maxcol][TILE]   (factor kernel only)
+    double *stage; // this worker's staging slots + lane: slot s lives at stage[s * TILE]
 #ifdef EICOS_EMU
     std::barrier<> *bar; // workers of a tile are real threads in the emulator
     void sync() const
@@ -235,7 +236,31 @@ EI_DEV TileMem tile_mem(const KArgs &a, int tile)
 
 EI_DEV bool lane_active(const Team &tm, const TileMem &t) { return ROWD(t.I, J_STATUS) == ST_ACTIVE; }
 
-// sum_k val_k * vec[idx_k] folded into `v` with sign: one mat-vec row from a row-set stream
+// ------------------------------------------------------------------ asynchronous staging
+// A warp issues in order, so a load that is consumed right away limits it to ~2 loads in flight.
+// Independent work is therefore done block-wise: pass 1 issues every load of the block into this
+// worker's shared-memory slots with cp.async (no register dependency, up to STAGE_SLOTS rows =
+// 8 KB in flight per warp), pass 2 re-walks the same stream words and computes from shared memory.
+// Each lane only ever reads the slot words it wrote itself, so cp.async.wait_all is the only fence.
+EI_DEV void stage_issue(double *slot_lane, const double *src_lane)
+{
+#ifdef EICOS_EMU
+    *slot_lane = *src_lane;
+#else
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(slot_lane);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(src_lane) : "memory");
+#endif
+}
+EI_DEV void stage_wait()
+{
+#ifndef EICOS_EMU
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
+EI_DEV const double *rowp(const Team &tm, const double *T, int row) { return T + (size_t)row * TILE + tm.lane; }
+
+// sum_k val_k * vec[idx_k] folded into `v` with sign: one mat-vec row straight from global memory
 EI_DEV double row_accumulate(const Team &tm, IStream &is, DStream &ds, const double *T, int vec, double v, double sign)
 {
     const int cnt = is.get();
@@ -246,6 +271,63 @@ EI_DEV double row_accumulate(const Team &tm, IStream &is, DStream &ds, const dou
         v += (sign * val) * ROWD(T, vec + idx);
     }
     return v;
+}
+
+// Walks one worker's share of a mat-vec row set (rows first, first+nwk, ...) block by block.
+//   extra(row, k)  -> row offset of the k-th extra operand of `row` (k < NEX), staged with the gathers
+//   finish(row, ex, v) receives the extras and v = init(ex) + sum sign*val*vec[idx]
+template <int NEX, class Extra, class Init, class Finish>
+EI_DEV void rowset_run(const Team &tm, const double *T, const int *stream, const double *vals, const int *seg,
+                       int first, int vec, double sign, Extra extra, Init init, Finish finish)
+{
+    IStream is;
+    DStream ds;
+    is.open(stream + EI_LDG(seg + tm.wk * 3), tm.lane);
+    ds.open(vals + EI_LDG(seg + tm.wk * 3 + 1), tm.lane);
+    const int nblocks = EI_LDG(seg + tm.wk * 3 + 2);
+    int row = first + tm.wk;
+    for (int b = 0; b < nblocks; b++)
+    {
+        const int nr = is.get();
+        if (nr < 0)
+        { // oversize row: no staging
+            double ex[NEX > 0 ? NEX : 1];
+            for (int k = 0; k < NEX; k++)
+                ex[k] = *rowp(tm, T, extra(row, k));
+            const double v = row_accumulate(tm, is, ds, T, vec, init(ex), sign);
+            finish(row, ex, v);
+            row += tm.nwk;
+            continue;
+        }
+        const IStream mark = is;
+        double *sp = tm.stage;
+        int rr = row;
+        for (int t = 0; t < nr; t++, rr += tm.nwk)
+        {
+            for (int k = 0; k < NEX; k++, sp += TILE)
+                stage_issue(sp, rowp(tm, T, extra(rr, k)));
+            const int cnt = is.get();
+            for (int k = 0; k < cnt; k++, sp += TILE)
+                stage_issue(sp, rowp(tm, T, vec + is.get()));
+        }
+        stage_wait();
+        is = mark;
+        sp = tm.stage;
+        for (int t = 0; t < nr; t++, row += tm.nwk)
+        {
+            double ex[NEX > 0 ? NEX : 1];
+            for (int k = 0; k < NEX; k++, sp += TILE)
+                ex[k] = *sp;
+            double v = init(ex);
+            const int cnt = is.get();
+            for (int k = 0; k < cnt; k++, sp += TILE)
+            {
+                (void)is.get();
+                v += (sign * ds.get()) * *sp;
+            }
+            finish(row, ex, v);
+        }
+    }
 }
 
 // ------------------------------------------------------------------ W products (src/eicos.cpp:485-507)
@@ -392,7 +474,6 @@ EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
             for (int q = 0; q < nt; q++)
             {
                 const int j = is.get(), cnt = is.get(), nK = is.get(), nR = is.get();
-                const int bwb = is.get(), fwb = is.get();
                 for (int c = 0; c < cnt; c++)
                     acc[(size_t)c * TILE] = 0.0;
                 double d = 0.0;
@@ -405,29 +486,26 @@ EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
                     else
                         acc[(size_t)pos * TILE] = val;
                 }
-                const double *lrow = T + (size_t)(L.LTx + fwb) * TILE + tm.lane;
                 for (int r = 0; r < nR; r++)
                 {
-                    const int k = is.get(), tp = is.get(), tl = is.get();
-                    const double ljk = lrow[(size_t)r * TILE];
+                    const int k = is.get(), fp = is.get(), tl = is.get();
+                    const double ljk = ROWD(T, L.LTx + fp);
                     const double w = ljk * ROWD(T, L.D + k);
                     d -= ljk * w;
-                    const double *lcol = T + (size_t)(L.Lx + tp) * TILE + tm.lane;
                     for (int u = 0; u < tl; u++)
                     {
-                        const int rel = is.get();
-                        acc[(size_t)rel * TILE] -= lcol[(size_t)u * TILE] * w;
+                        const int rel = is.get(), bp = is.get();
+                        acc[(size_t)rel * TILE] -= ROWD(T, L.Lx + bp) * w;
                     }
                 }
                 ROWD(T, L.D + j) = d;
                 ROWD(T, L.Dinv + j) = 1.0 / d;
                 zero_pivot = zero_pivot || (d == 0.0); // Eigen reports NumericalIssue only on an exactly zero pivot
-                double *lout = T + (size_t)(L.Lx + bwb) * TILE + tm.lane;
                 for (int c = 0; c < cnt; c++)
                 {
-                    const int fp = is.get();
+                    const int bp = is.get(), fp = is.get();
                     const double lv = acc[(size_t)c * TILE] / d;
-                    lout[(size_t)c * TILE] = lv;
+                    ROWD(T, L.Lx + bp) = lv;
                     ROWD(T, L.LTx + fp) = lv;
                 }
             }
@@ -441,50 +519,101 @@ EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
 // ------------------------------------------------------------------ triangular solves (Eigen solve, src/eicos.cpp:1477,1599)
 // forward:  xw = L^-1 P rhs       (rows of L, dot form; the permutation is folded into the gather)
 // backward: out = P' L^-T D^-1 xw (columns of L, dot form; results land in KKT order directly)
-// Stream layout per worker and phase: hdr(0) hdr(1) ent(0) hdr(2) ent(1) ... so that the header of
-// the next task (and the load of its right-hand side) is issued before the current task's entries.
+// Phases come from the sweep's own stream (streams.hpp): block phases hold independent tasks that
+// are staged asynchronously; serial phases hold the chains of the elimination tree, reduced to the
+// recurrence between their own members (results of the last three tasks are forwarded in registers).
+// Serial stream layout: hdr(0) hdr(1) ent(0) hdr(2) ent(1) ..., so the start value of the next task
+// is already being loaded while the current one is computed.
 EI_DEV void ldl_forward(const Team &tm, const KArgs &a, double *T, int rhs)
 {
     const DevPattern &P = a.P;
     const Layout &L = a.L;
-    for (int ph = 0; ph < P.nphases; ph++)
+    for (int ph = 0; ph < P.nph_fw; ph++)
     {
-        const int *seg = P.fw_seg + ((size_t)ph * tm.nwk + tm.wk) * 3;
-        const int nt = EI_LDG(seg + 1);
-        if (nt > 0)
+        const int *seg = P.fw_seg + ((size_t)ph * tm.nwk + tm.wk) * 4;
+        const int count = EI_LDG(seg + 1);
+        if (count > 0)
         {
             IStream is;
             is.open(P.fw + EI_LDG(seg), tm.lane);
             const double *lv = T + (size_t)(L.LTx + EI_LDG(seg + 2)) * TILE + tm.lane;
-            double p1 = 0.0, p2 = 0.0;
-            int i = is.get(), r = is.get(), cnt = is.get();
-            double v = ROWD(T, rhs + r);
-            for (int q = 0; q < nt; q++)
+            if (EI_LDG(seg + 3) == SEG_BLOCKS)
             {
-                int ni = 0, ncnt = 0;
-                double nv = 0.0;
-                if (q + 1 < nt)
+                for (int b = 0; b < count; b++)
                 {
-                    ni = is.get();
-                    r = is.get();
-                    ncnt = is.get();
-                    nv = ROWD(T, rhs + r);
+                    const int nt = is.get();
+                    if (nt < 0)
+                    { // oversize row: straight from global memory
+                        const int i = is.get(), r = is.get(), cnt = is.get();
+                        double v = r >= 0 ? ROWD(T, rhs + r) : ROWD(T, L.xw + i);
+                        for (int k = 0; k < cnt; k++, lv += TILE)
+                            v -= *lv * ROWD(T, L.xw + is.get());
+                        ROWD(T, L.xw + i) = v;
+                        continue;
+                    }
+                    const IStream mark = is;
+                    double *sp = tm.stage;
+                    for (int t = 0; t < nt; t++)
+                    {
+                        const int i = is.get(), r = is.get(), cnt = is.get();
+                        stage_issue(sp, r >= 0 ? rowp(tm, T, rhs + r) : rowp(tm, T, L.xw + i));
+                        sp += TILE;
+                        for (int k = 0; k < cnt; k++, lv += TILE, sp += 2 * TILE)
+                        {
+                            stage_issue(sp, lv);
+                            stage_issue(sp + TILE, rowp(tm, T, L.xw + is.get()));
+                        }
+                    }
+                    stage_wait();
+                    is = mark;
+                    sp = tm.stage;
+                    for (int t = 0; t < nt; t++)
+                    {
+                        const int i = is.get();
+                        (void)is.get();
+                        const int cnt = is.get();
+                        double v = *sp;
+                        sp += TILE;
+                        for (int k = 0; k < cnt; k++, sp += 2 * TILE)
+                        {
+                            (void)is.get();
+                            v -= sp[0] * sp[TILE];
+                        }
+                        ROWD(T, L.xw + i) = v;
+                    }
                 }
-                for (int k = 0; k < cnt; k++)
+            }
+            else
+            {
+                double p1 = 0.0, p2 = 0.0, p3 = 0.0;
+                int i = is.get(), r = is.get(), cnt = is.get();
+                double v = r >= 0 ? ROWD(T, rhs + r) : ROWD(T, L.xw + i);
+                for (int q = 0; q < count; q++)
                 {
-                    const int c = is.get();
-                    EI_PREFETCH(lv + (size_t)PF_ROWS * TILE);
-                    const double lval = *lv;
-                    lv += TILE;
-                    const double xv = c >= 0 ? ROWD(T, L.xw + c) : (c == FWD_PREV1 ? p1 : p2);
-                    v -= lval * xv;
+                    int ni = 0, ncnt = 0;
+                    double nv = 0.0;
+                    if (q + 1 < count)
+                    {
+                        ni = is.get();
+                        r = is.get();
+                        ncnt = is.get();
+                        nv = r >= 0 ? ROWD(T, rhs + r) : ROWD(T, L.xw + ni);
+                    }
+                    for (int k = 0; k < cnt; k++, lv += TILE)
+                    {
+                        const int c = is.get();
+                        EI_PREFETCH(lv + (size_t)PF_ROWS * TILE);
+                        const double xv = c >= 0 ? ROWD(T, L.xw + c) : (c == FWD_PREV1 ? p1 : (c == FWD_PREV2 ? p2 : p3));
+                        v -= *lv * xv;
+                    }
+                    ROWD(T, L.xw + i) = v;
+                    p3 = p2;
+                    p2 = p1;
+                    p1 = v;
+                    i = ni;
+                    cnt = ncnt;
+                    v = nv;
                 }
-                ROWD(T, L.xw + i) = v;
-                p2 = p1;
-                p1 = v;
-                i = ni;
-                cnt = ncnt;
-                v = nv;
             }
         }
         tm.sync();
@@ -492,50 +621,110 @@ EI_DEV void ldl_forward(const Team &tm, const KArgs &a, double *T, int rhs)
 }
 
 // out = solution (KKT order).  If x >= 0: additionally x += solution for the lanes with `cont`.
+// Task header: [xw/Dinv row j | INIT_PARTIAL, out row o | ~o for the external part of a chain task].
 EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int out, int x, bool cont)
 {
     const DevPattern &P = a.P;
     const Layout &L = a.L;
-    for (int ph = P.nphases - 1; ph >= 0; ph--)
+    const bool accumulate = x >= 0 && cont;
+    for (int ph = 0; ph < P.nph_bw; ph++)
     {
-        const int *seg = P.bw_seg + ((size_t)ph * tm.nwk + tm.wk) * 3;
-        const int nt = EI_LDG(seg + 1);
-        if (nt > 0)
+        const int *seg = P.bw_seg + ((size_t)ph * tm.nwk + tm.wk) * 4;
+        const int count = EI_LDG(seg + 1);
+        if (count > 0)
         {
             IStream is;
             is.open(P.bw + EI_LDG(seg), tm.lane);
             const double *lv = T + (size_t)(L.Lx + EI_LDG(seg + 2)) * TILE + tm.lane;
-            double p1 = 0.0, p2 = 0.0;
-            int j = is.get(), o = is.get(), cnt = is.get();
-            double v = ROWD(T, L.Dinv + j) * ROWD(T, L.xw + j);
-            for (int q = 0; q < nt; q++)
+            if (EI_LDG(seg + 3) == SEG_BLOCKS)
             {
-                int no = 0, ncnt = 0;
-                double nv = 0.0;
-                if (q + 1 < nt)
+                for (int b = 0; b < count; b++)
                 {
-                    j = is.get();
-                    no = is.get();
-                    ncnt = is.get();
-                    nv = ROWD(T, L.Dinv + j) * ROWD(T, L.xw + j);
+                    const int nt = is.get();
+                    if (nt < 0)
+                    {
+                        const int j = is.get(), oe = is.get(), cnt = is.get();
+                        const int o = oe >= 0 ? oe : ~oe;
+                        double v = j >= 0 ? ROWD(T, L.Dinv + j) * ROWD(T, L.xw + j) : ROWD(T, out + o);
+                        for (int k = 0; k < cnt; k++, lv += TILE)
+                            v -= *lv * ROWD(T, out + is.get());
+                        ROWD(T, out + o) = v;
+                        if (accumulate && oe >= 0)
+                            ROWD(T, x + o) += v;
+                        continue;
+                    }
+                    const IStream mark = is;
+                    double *sp = tm.stage;
+                    for (int t = 0; t < nt; t++)
+                    {
+                        const int j = is.get(), oe = is.get(), cnt = is.get();
+                        if (j >= 0)
+                        {
+                            stage_issue(sp, rowp(tm, T, L.Dinv + j));
+                            stage_issue(sp + TILE, rowp(tm, T, L.xw + j));
+                        }
+                        else
+                            stage_issue(sp, rowp(tm, T, out + (oe >= 0 ? oe : ~oe)));
+                        sp += 2 * TILE;
+                        for (int k = 0; k < cnt; k++, lv += TILE, sp += 2 * TILE)
+                        {
+                            stage_issue(sp, lv);
+                            stage_issue(sp + TILE, rowp(tm, T, out + is.get()));
+                        }
+                    }
+                    stage_wait();
+                    is = mark;
+                    sp = tm.stage;
+                    for (int t = 0; t < nt; t++)
+                    {
+                        const int j = is.get(), oe = is.get(), cnt = is.get();
+                        const int o = oe >= 0 ? oe : ~oe;
+                        double v = j >= 0 ? sp[0] * sp[TILE] : sp[0];
+                        sp += 2 * TILE;
+                        for (int k = 0; k < cnt; k++, sp += 2 * TILE)
+                        {
+                            (void)is.get();
+                            v -= sp[0] * sp[TILE];
+                        }
+                        ROWD(T, out + o) = v;
+                        if (accumulate && oe >= 0)
+                            ROWD(T, x + o) += v;
+                    }
                 }
-                for (int k = 0; k < cnt; k++)
+            }
+            else
+            {
+                double p1 = 0.0, p2 = 0.0, p3 = 0.0;
+                int j = is.get(), o = is.get(), cnt = is.get();
+                double v = j >= 0 ? ROWD(T, L.Dinv + j) * ROWD(T, L.xw + j) : ROWD(T, out + o);
+                for (int q = 0; q < count; q++)
                 {
-                    const int c = is.get();
-                    EI_PREFETCH(lv + (size_t)PF_ROWS * TILE);
-                    const double lval = *lv;
-                    lv += TILE;
-                    const double xv = c >= 0 ? ROWD(T, out + c) : (c == FWD_PREV1 ? p1 : p2);
-                    v -= lval * xv;
+                    int no = 0, ncnt = 0;
+                    double nv = 0.0;
+                    if (q + 1 < count)
+                    {
+                        j = is.get();
+                        no = is.get();
+                        ncnt = is.get();
+                        nv = j >= 0 ? ROWD(T, L.Dinv + j) * ROWD(T, L.xw + j) : ROWD(T, out + no);
+                    }
+                    for (int k = 0; k < cnt; k++, lv += TILE)
+                    {
+                        const int c = is.get();
+                        EI_PREFETCH(lv + (size_t)PF_ROWS * TILE);
+                        const double xv = c >= 0 ? ROWD(T, out + c) : (c == FWD_PREV1 ? p1 : (c == FWD_PREV2 ? p2 : p3));
+                        v -= *lv * xv;
+                    }
+                    ROWD(T, out + o) = v;
+                    if (accumulate)
+                        ROWD(T, x + o) += v;
+                    p3 = p2;
+                    p2 = p1;
+                    p1 = v;
+                    o = no;
+                    cnt = ncnt;
+                    v = nv;
                 }
-                ROWD(T, out + o) = v;
-                if (x >= 0 && cont)
-                    ROWD(T, x + o) += v;
-                p2 = p1;
-                p1 = v;
-                o = no;
-                cnt = ncnt;
-                v = nv;
             }
         }
         tm.sync();
@@ -551,49 +740,43 @@ EI_DEV double kkt_residual(const Team &tm, const KArgs &a, double *T, int rhs, i
     const Layout &L = a.L;
     const double delta = Settings::deltastat;
     const int n = P.n, p = P.p, zb = P.n + P.p;
-    double nerr[1] = {0.0};
-    IStream is;
-    DStream ds;
+    double nerr = 0.0;
     if (n > 0)
-    {
-        is.open(P.rx + EI_LDG(P.rx_seg + tm.wk * 2), tm.lane);
-        ds.open(P.rx_val + EI_LDG(P.rx_seg + tm.wk * 2 + 1), tm.lane);
-        for (int j = tm.wk; j < n; j += tm.nwk)
-        {
-            double v = row_accumulate(tm, is, ds, T, x, ROWD(T, rhs + j), -1.0);
-            v -= delta * ROWD(T, x + j);
-            ROWD(T, L.e + j) = v;
-            nerr[0] = dmax(nerr[0], fabs(v));
-        }
-    }
+        rowset_run<2>(
+            tm, T, P.rx, P.rx_val, P.rx_seg, 0, x, -1.0,
+            [&](int j, int k) { return (k == 0 ? rhs : x) + j; },
+            [&](const double *ex) { return ex[0]; },
+            [&](int j, const double *ex, double v) {
+                v -= delta * ex[1];
+                ROWD(T, L.e + j) = v;
+                nerr = dmax(nerr, fabs(v));
+            });
     if (p > 0)
-    {
-        is.open(P.ry + EI_LDG(P.ry_seg + tm.wk * 2), tm.lane);
-        ds.open(P.ry_val + EI_LDG(P.ry_seg + tm.wk * 2 + 1), tm.lane);
-        for (int i = tm.wk; i < p; i += tm.nwk)
-        {
-            double v = row_accumulate(tm, is, ds, T, x, ROWD(T, rhs + n + i), -1.0);
-            v += delta * ROWD(T, x + n + i);
-            ROWD(T, L.e + n + i) = v;
-            nerr[0] = dmax(nerr[0], fabs(v));
-        }
-    }
+        rowset_run<2>(
+            tm, T, P.ry, P.ry_val, P.ry_seg, 0, x, -1.0,
+            [&](int i, int k) { return (k == 0 ? rhs : x) + n + i; },
+            [&](const double *ex) { return ex[0]; },
+            [&](int i, const double *ex, double v) {
+                v += delta * ex[1];
+                ROWD(T, L.e + n + i) = v;
+                nerr = dmax(nerr, fabs(v));
+            });
     if (P.l > 0)
-    {
-        is.open(P.rz + EI_LDG(P.rz_seg + tm.wk * 2), tm.lane);
-        ds.open(P.rz_val + EI_LDG(P.rz_seg + tm.wk * 2 + 1), tm.lane);
-        for (int i = tm.wk; i < P.l; i += tm.nwk)
-        {
-            const double dz = ROWD(T, x + zb + i);
-            double v = row_accumulate(tm, is, ds, T, x, ROWD(T, rhs + zb + i), -1.0);
-            v += delta * dz;
-            v += initialize ? dz : ROWD(T, L.lpv + i) * dz;
-            ROWD(T, L.e + zb + i) = v;
-            nerr[0] = dmax(nerr[0], fabs(v));
-        }
-    }
+        rowset_run<3>(
+            tm, T, P.rz, P.rz_val, P.rz_seg, 0, x, -1.0,
+            [&](int i, int k) { return k == 0 ? rhs + zb + i : (k == 1 ? x + zb + i : L.lpv + i); },
+            [&](const double *ex) { return ex[0]; },
+            [&](int i, const double *ex, double v) {
+                const double dz = ex[1];
+                v += delta * dz;
+                v += initialize ? dz : ex[2] * dz;
+                ROWD(T, L.e + zb + i) = v;
+                nerr = dmax(nerr, fabs(v));
+            });
     if (P.nc > 0)
     {
+        IStream is;
+        DStream ds;
         is.open(P.rc + EI_LDG(P.rc_seg + tm.wk * 2), tm.lane);
         ds.open(P.rc_val + EI_LDG(P.rc_seg + tm.wk * 2 + 1), tm.lane);
         for (int c = tm.wk; c < P.nc; c += tm.nwk)
@@ -623,17 +806,18 @@ EI_DEV double kkt_residual(const Team &tm, const KArgs &a, double *T, int rhs, i
                 else
                     v += eta2 * (xk + vu * ROWD(T, L.cq + qo + k - 1));
                 ROWD(T, L.e + kb + k) = v;
-                nerr[0] = dmax(nerr[0], fabs(v));
+                nerr = dmax(nerr, fabs(v));
             }
             const double e3 = initialize ? x3 : eta2 * (v1 * qtx2 + x3);
             const double e4 = initialize ? x4 : eta2 * (u0 * x1 + u1 * qtx2 - x4);
             ROWD(T, L.e + kb + d) = e3;
             ROWD(T, L.e + kb + d + 1) = e4;
-            nerr[0] = dmax(nerr[0], dmax(fabs(e3), fabs(e4)));
+            nerr = dmax(nerr, dmax(fabs(e3), fabs(e4)));
         }
     }
-    team_max<1>(tm, nerr);
-    return nerr[0];
+    double red[1] = {nerr};
+    team_max<1>(tm, red);
+    return red[0];
 }
 
 // ------------------------------------------------------------------ solveKKT (src/eicos.cpp:1471-1620)
@@ -992,60 +1176,54 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
     double r[NRED];
     for (int k = 0; k < NRED; k++)
         r[k] = 0.0;
-    IStream is;
-    DStream ds;
     if (n > 0)
-    {
-        is.open(P.rx + EI_LDG(P.rx_seg + tm.wk * 2), tm.lane);
-        ds.open(P.rx_val + EI_LDG(P.rx_seg + tm.wk * 2 + 1), tm.lane);
-        for (int j = tm.wk; j < n; j += tm.nwk)
-        {
-            const double cj = ROWD(T, L.chb + j), xj = ROWD(T, L.w + j);
-            double v = row_accumulate(tm, is, ds, T, L.w, 0.0, -1.0);
-            r[HX2] += v * v;
-            v -= tau * cj;
-            ROWD(T, L.r + j) = v;
-            r[RX2] += v * v;
-            r[CX] += cj * xj;
-            r[NX2] += xj * xj;
-        }
-    }
+        rowset_run<2>(
+            tm, T, P.rx, P.rx_val, P.rx_seg, 0, L.w, -1.0,
+            [&](int j, int k) { return (k == 0 ? L.chb : L.w) + j; },
+            [&](const double *) { return 0.0; },
+            [&](int j, const double *ex, double v) {
+                const double cj = ex[0], xj = ex[1];
+                r[HX2] += v * v;
+                v -= tau * cj;
+                ROWD(T, L.r + j) = v;
+                r[RX2] += v * v;
+                r[CX] += cj * xj;
+                r[NX2] += xj * xj;
+            });
     if (p > 0)
-    {
-        is.open(P.ry + EI_LDG(P.ry_seg + tm.wk * 2), tm.lane);
-        ds.open(P.ry_val + EI_LDG(P.ry_seg + tm.wk * 2 + 1), tm.lane);
-        for (int i = tm.wk; i < p; i += tm.nwk)
-        {
-            const double bi = ROWD(T, L.chb + n + i), yi = ROWD(T, L.w + n + i);
-            double v = row_accumulate(tm, is, ds, T, L.w, 0.0, 1.0);
-            r[HY2] += v * v;
-            v -= tau * bi;
-            ROWD(T, L.r + n + i) = v;
-            r[RY2] += v * v;
-            r[BY] += bi * yi;
-            r[NY2] += yi * yi;
-        }
-    }
+        rowset_run<2>(
+            tm, T, P.ry, P.ry_val, P.ry_seg, 0, L.w, 1.0,
+            [&](int i, int k) { return (k == 0 ? L.chb : L.w) + n + i; },
+            [&](const double *) { return 0.0; },
+            [&](int i, const double *ex, double v) {
+                const double bi = ex[0], yi = ex[1];
+                r[HY2] += v * v;
+                v -= tau * bi;
+                ROWD(T, L.r + n + i) = v;
+                r[RY2] += v * v;
+                r[BY] += bi * yi;
+                r[NY2] += yi * yi;
+            });
     if (P.l > 0)
-    {
-        is.open(P.rz + EI_LDG(P.rz_seg + tm.wk * 2), tm.lane);
-        ds.open(P.rz_val + EI_LDG(P.rz_seg + tm.wk * 2 + 1), tm.lane);
-        for (int i = tm.wk; i < P.l; i += tm.nwk)
-        {
-            const double si = ROWD(T, L.s + i), zi = ROWD(T, L.w + zb + i), hi = ROWD(T, L.chb + zb + i);
-            double v = row_accumulate(tm, is, ds, T, L.w, si, 1.0);
-            r[HZ2] += v * v;
-            v -= tau * hi;
-            ROWD(T, L.r + zb + i) = v;
-            r[RZ2] += v * v;
-            r[HZ] += hi * zi;
-            r[NZ2] += zi * zi;
-            r[NS2] += si * si;
-            r[GAP] += si * zi;
-        }
-    }
+        rowset_run<3>(
+            tm, T, P.rz, P.rz_val, P.rz_seg, 0, L.w, 1.0,
+            [&](int i, int k) { return k == 0 ? L.s + i : (k == 1 ? L.w + zb + i : L.chb + zb + i); },
+            [&](const double *ex) { return ex[0]; },
+            [&](int i, const double *ex, double v) {
+                const double si = ex[0], zi = ex[1], hi = ex[2];
+                r[HZ2] += v * v;
+                v -= tau * hi;
+                ROWD(T, L.r + zb + i) = v;
+                r[RZ2] += v * v;
+                r[HZ] += hi * zi;
+                r[NZ2] += zi * zi;
+                r[NS2] += si * si;
+                r[GAP] += si * zi;
+            });
     if (P.nc > 0)
     {
+        IStream is;
+        DStream ds;
         is.open(P.rc + EI_LDG(P.rc_seg + tm.wk * 2), tm.lane);
         ds.open(P.rc_val + EI_LDG(P.rc_seg + tm.wk * 2 + 1), tm.lane);
         for (int c = tm.wk; c < P.nc; c += tm.nwk)
