@@ -20,7 +20,8 @@ namespace eicos
     {                                                                                          \
         extern __shared__ double smem[];                                                       \
         Team tm;                                                                               \
-        tm.lane = threadIdx.x & 31;                                                            \
+        tm.pl = threadIdx.x & 31;                                                              \
+        tm.lane = tm.pl * VEC;                                                                 \
         tm.wk = threadIdx.x >> 5;                                                              \
         tm.nwk = blockDim.x >> 5;                                                              \
         tm.red = smem;                                                                         \
@@ -30,15 +31,15 @@ namespace eicos
         fn(tm, a, blockIdx.x);                                                                 \
     }
 #define EI_MAX_THREADS 256
-EI_DEFINE_KERNEL(eicos_load_inputs, tile_load, 4)
-EI_DEFINE_KERNEL(eicos_init, tile_init, 4)
-EI_DEFINE_KERNEL(eicos_ldl_factor, tile_factor, 4)
-EI_DEFINE_KERNEL(eicos_solve_kkt, tile_solve_kkt, 4)
-EI_DEFINE_KERNEL(eicos_init_point, tile_init_point, 4)
+EI_DEFINE_KERNEL(eicos_load_inputs, tile_load, 2)
+EI_DEFINE_KERNEL(eicos_init, tile_init, 2)
+EI_DEFINE_KERNEL(eicos_ldl_factor, tile_factor, 2)
+EI_DEFINE_KERNEL(eicos_solve_kkt, tile_solve_kkt, 2)
+EI_DEFINE_KERNEL(eicos_init_point, tile_init_point, 2)
 EI_DEFINE_KERNEL(eicos_iter_head, tile_head, 2)
-EI_DEFINE_KERNEL(eicos_iter_mid, tile_mid, 4)
-EI_DEFINE_KERNEL(eicos_iter_tail, tile_tail, 4)
-EI_DEFINE_KERNEL(eicos_store_outputs, tile_store, 4)
+EI_DEFINE_KERNEL(eicos_iter_mid, tile_mid, 2)
+EI_DEFINE_KERNEL(eicos_iter_tail, tile_tail, 2)
+EI_DEFINE_KERNEL(eicos_store_outputs, tile_store, 2)
 
 #define EI_LAUNCH(name, fn, tiles, threads, smem, stream, args) name<<<(tiles), (threads), (smem), (stream)>>>(args)
 #else
@@ -57,6 +58,7 @@ EI_DEFINE_KERNEL(eicos_store_outputs, tile_store, 4)
             auto body_ = [&](int wk_) {                                                           \
                 Team tm_;                                                                         \
                 tm_.lane = 0;                                                                     \
+                tm_.pl = 0;                                                                       \
                 tm_.wk = wk_;                                                                     \
                 tm_.nwk = nw_;                                                                    \
                 tm_.red = red_.data();                                                            \
@@ -333,7 +335,7 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
     a.nitrow = -1;
     be::zero(ir_rounds_, sizeof(unsigned long long), st);
 
-    const int threads = workers_ * (TILE == 1 ? 1 : 32);
+    const int threads = workers_ * (LANES == 1 ? 1 : 32);
     (void)threads;
 
 #ifndef EICOS_EMU
@@ -493,7 +495,7 @@ void Engine::debug_factor_init(int batch, const double *d_c, const double *d_h, 
     a.first = 0;
     a.nitrow = -1;
     const int tiles = (batch + TILE - 1) / TILE;
-    const int threads = workers_ * (TILE == 1 ? 1 : 32);
+    const int threads = workers_ * (LANES == 1 ? 1 : 32);
     (void)threads;
     EI_LAUNCH(eicos_load_inputs, tile_load, tiles, threads, smem_common_, st, a);
     EI_LAUNCH(eicos_init, tile_init, tiles, threads, smem_common_, st, a);

@@ -1,17 +1,20 @@
 // The per-tile interior-point program: every step of EiCOS's Solver::solve (reference
-// src/eicos.cpp:848-1262) for TILE instances at a time, lane = instance.
+// src/eicos.cpp:848-1262) for TILE = LANES x VEC instances at a time.
 //
-// One CTA owns one tile.  Its warps ("workers") split rows / cones / elimination-tree tasks among
-// themselves and meet at CTA barriers; per-instance reductions over a vector run down the rows in
-// each worker and are combined through shared memory in a fixed order, so every warp of the CTA
-// holds bit-identical per-lane scalars and all control flow is uniform across the CTA.
-// Sparse structure is never looked up through CSR/CSC arrays on the device: each worker decodes
-// its own instruction stream (streams.hpp) with coalesced chunk loads + warp shuffles.
+// One CTA owns one tile.  Lane l of a warp owns VEC consecutive instances of the tile, so a row of a
+// per-instance array is read with ONE 16-byte vector load per lane (512 B per warp for VEC = 2):
+// every index decode, address computation and loop step is amortised over VEC instances.  The warps
+// ("workers") of the CTA split rows / cones / elimination-tree tasks among themselves and meet at
+// CTA barriers; per-instance reductions over a vector run down the rows in each worker and are
+// combined through shared memory in a fixed order, so every warp holds bit-identical per-instance
+// scalars and all control flow is uniform across the CTA.
+// Sparse structure is never looked up through CSR/CSC arrays on the device: each worker decodes its
+// own instruction stream (streams.hpp) with coalesced chunk loads + warp shuffles.
 //
 // The same source compiles two ways:
-//   * nvcc (default): TILE = 32, workers = warps of the CTA  -> the product.
-//   * -DEICOS_EMU (tests/emu only): TILE = 1, one worker, plain C++ -> lets the CPU-only test
-//     tier execute the kernel logic against the oracle.  It is never linked into the product.
+//   * nvcc (default): LANES = 32, workers = warps of the CTA  -> the product.
+//   * -DEICOS_EMU (tests/emu only): LANES = 1, workers = host threads, plain C++ -> lets the
+//     CPU-only test tier execute the kernel logic against the oracle.  Never linked into the product.
 #pragma once
 
 #include "layout.hpp"
@@ -33,16 +36,103 @@
 #define EI_PREFETCH(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #endif
 
+#ifndef EICOS_VEC
+#define EICOS_VEC 2
+#endif
+
 namespace eicos
 {
 
 #ifdef EICOS_EMU
-constexpr int TILE = 1;
+constexpr int LANES = 1;
 #else
-constexpr int TILE = 32;
+constexpr int LANES = 32;
 #endif
-constexpr int KRED = 17;    // widest block reduction
-constexpr int PF_ROWS = 24; // how many value rows ahead the sweeps prefetch into L2
+constexpr int VEC = EICOS_VEC;       // instances per lane
+constexpr int TILE = LANES * VEC;    // instances per tile = doubles per row
+constexpr int KRED = 14;             // widest block reduction
+constexpr int PF_ROWS = 24;          // how many value rows ahead the serial sweeps prefetch into L2
+
+// ------------------------------------------------------------------ VEC-wide values
+struct alignas(VEC >= 2 ? 16 : 8) vd
+{
+    double v[VEC];
+};
+struct vb
+{
+    bool v[VEC];
+};
+#define VFOR for (int c_ = 0; c_ < VEC; c_++)
+
+EI_DEV vd vset(double s)
+{
+    vd r;
+    VFOR r.v[c_] = s;
+    return r;
+}
+EI_DEV vd operator+(vd a, vd b) { VFOR a.v[c_] += b.v[c_]; return a; }
+EI_DEV vd operator-(vd a, vd b) { VFOR a.v[c_] -= b.v[c_]; return a; }
+EI_DEV vd operator*(vd a, vd b) { VFOR a.v[c_] *= b.v[c_]; return a; }
+EI_DEV vd operator/(vd a, vd b) { VFOR a.v[c_] /= b.v[c_]; return a; }
+EI_DEV vd operator-(vd a) { VFOR a.v[c_] = -a.v[c_]; return a; }
+EI_DEV vd operator+(vd a, double b) { VFOR a.v[c_] += b; return a; }
+EI_DEV vd operator-(vd a, double b) { VFOR a.v[c_] -= b; return a; }
+EI_DEV vd operator+(double b, vd a) { VFOR a.v[c_] = b + a.v[c_]; return a; }
+EI_DEV vd operator-(double b, vd a) { VFOR a.v[c_] = b - a.v[c_]; return a; }
+EI_DEV vd operator*(vd a, double b) { VFOR a.v[c_] *= b; return a; }
+EI_DEV vd operator*(double b, vd a) { VFOR a.v[c_] = b * a.v[c_]; return a; }
+EI_DEV vd operator/(vd a, double b) { VFOR a.v[c_] /= b; return a; }
+EI_DEV vd operator/(double b, vd a) { VFOR a.v[c_] = b / a.v[c_]; return a; }
+EI_DEV vd &operator+=(vd &a, vd b) { VFOR a.v[c_] += b.v[c_]; return a; }
+EI_DEV vd &operator-=(vd &a, vd b) { VFOR a.v[c_] -= b.v[c_]; return a; }
+EI_DEV vd vsqrt(vd a) { VFOR a.v[c_] = sqrt(a.v[c_]); return a; }
+EI_DEV vd vabs(vd a) { VFOR a.v[c_] = fabs(a.v[c_]); return a; }
+EI_DEV bool ei_isnan(double v) { return v != v; }
+EI_DEV double dmax(double a, double b) { return a > b ? a : b; } // std::max(a,b) semantics (returns a on ties / NaN in b)
+EI_DEV double dmin(double a, double b) { return b < a ? b : a; } // std::min(a,b)
+EI_DEV vd vmax(vd a, vd b) { VFOR a.v[c_] = dmax(a.v[c_], b.v[c_]); return a; }
+EI_DEV vd vmin(vd a, vd b) { VFOR a.v[c_] = dmin(a.v[c_], b.v[c_]); return a; }
+EI_DEV vd vsel(vb m, vd a, vd b) { VFOR a.v[c_] = m.v[c_] ? a.v[c_] : b.v[c_]; return a; }
+EI_DEV vb vbset(bool s)
+{
+    vb r;
+    VFOR r.v[c_] = s;
+    return r;
+}
+EI_DEV vb operator&&(vb a, vb b) { VFOR a.v[c_] = a.v[c_] && b.v[c_]; return a; }
+EI_DEV vb operator||(vb a, vb b) { VFOR a.v[c_] = a.v[c_] || b.v[c_]; return a; }
+EI_DEV vb operator!(vb a) { VFOR a.v[c_] = !a.v[c_]; return a; }
+EI_DEV bool vany(vb a)
+{
+    bool r = false;
+    VFOR r = r || a.v[c_];
+    return r;
+}
+EI_DEV bool vall(vb a)
+{
+    bool r = true;
+    VFOR r = r && a.v[c_];
+    return r;
+}
+
+EI_DEV vd vload(const double *p) { return *reinterpret_cast<const vd *>(p); }
+EI_DEV void vstore(double *p, vd v) { *reinterpret_cast<vd *>(p) = v; }
+
+// proxy for one row of the tile as seen by this lane (VEC instances)
+struct RowRef
+{
+    double *p;
+    EI_DEV operator vd() const { return vload(p); }
+    EI_DEV void operator=(vd v) const { vstore(p, v); }
+    EI_DEV void operator=(double s) const { vstore(p, vset(s)); }
+    EI_DEV void operator+=(vd v) const { vstore(p, vload(p) + v); }
+    EI_DEV void operator-=(vd v) const { vstore(p, vload(p) - v); }
+    EI_DEV void operator*=(double s) const { vstore(p, vload(p) * s); }
+    EI_DEV void operator*=(vd s) const { vstore(p, vload(p) * s); }
+    EI_DEV void operator=(const RowRef &o) const { vstore(p, vload(o.p)); }
+};
+#define ROWD(base, r) (RowRef{(base) + (size_t)(r) * TILE + tm.lane})
+#define ROWC(base, r, c) ((base)[(size_t)(r) * TILE + tm.lane + (c)])
 
 struct KArgs
 {
@@ -70,7 +160,9 @@ struct KArgs
 
 struct Team
 {
-    int lane, wk, nwk;
+    int lane;      // element offset of this lane inside a row (= physical lane * VEC)
+    int pl;        // physical lane inside the warp
+    int wk, nwk;
     double *red;   // [nwk][KRED][TILE]
     double *acc;   // [nwk][maxcol][TILE]   (factor kernel only)
     double *stage; // this worker's staging slots + lane: slot s lives at stage[s * TILE]
@@ -81,12 +173,12 @@ struct Team
         if (bar)
             bar->arrive_and_wait();
     }
-    bool all(bool v) const { return v; }
-    bool any(bool v) const { return v; }
+    bool all(vb v) const { return vall(v); }
+    bool any(vb v) const { return vany(v); }
 #else
     __device__ __forceinline__ void sync() const { __syncthreads(); }
-    __device__ __forceinline__ bool all(bool v) const { return __all_sync(0xffffffffu, v); }
-    __device__ __forceinline__ bool any(bool v) const { return __any_sync(0xffffffffu, v); }
+    __device__ __forceinline__ bool all(vb v) const { return __all_sync(0xffffffffu, vall(v)); }
+    __device__ __forceinline__ bool any(vb v) const { return __any_sync(0xffffffffu, vany(v)); }
 #endif
 };
 
@@ -159,65 +251,38 @@ struct DStream
 #endif
 };
 
-// ------------------------------------------------------------------ small helpers
-#define ROWD(base, r) (base)[(size_t)(r) * TILE + tm.lane]
-
-EI_DEV bool ei_isnan(double v) { return v != v; }
-EI_DEV double dmax(double a, double b) { return a > b ? a : b; } // std::max(a,b) semantics (returns a on ties / NaN in b)
-EI_DEV double dmin(double a, double b) { return b < a ? b : a; } // std::min(a,b)
-
-template <int K>
-EI_DEV void team_sum(const Team &tm, double (&v)[K])
+// ------------------------------------------------------------------ block reductions (fixed order)
+template <int K, class Op>
+EI_DEV void team_reduce(const Team &tm, vd (&v)[K], Op op)
 {
     if (tm.nwk == 1)
         return;
     tm.sync();
     for (int i = 0; i < K; i++)
-        tm.red[(size_t)(tm.wk * K + i) * TILE + tm.lane] = v[i];
+        vstore(tm.red + (size_t)(tm.wk * K + i) * TILE + tm.lane, v[i]);
     tm.sync();
     for (int i = 0; i < K; i++)
     {
-        double s = 0.0;
-        for (int w = 0; w < tm.nwk; w++)
-            s += tm.red[(size_t)(w * K + i) * TILE + tm.lane];
+        vd s = vload(tm.red + (size_t)i * TILE + tm.lane);
+        for (int w = 1; w < tm.nwk; w++)
+            s = op(s, vload(tm.red + (size_t)(w * K + i) * TILE + tm.lane));
         v[i] = s;
     }
 }
-
 template <int K>
-EI_DEV void team_max(const Team &tm, double (&v)[K])
+EI_DEV void team_sum(const Team &tm, vd (&v)[K])
 {
-    if (tm.nwk == 1)
-        return;
-    tm.sync();
-    for (int i = 0; i < K; i++)
-        tm.red[(size_t)(tm.wk * K + i) * TILE + tm.lane] = v[i];
-    tm.sync();
-    for (int i = 0; i < K; i++)
-    {
-        double s = tm.red[(size_t)i * TILE + tm.lane];
-        for (int w = 1; w < tm.nwk; w++)
-            s = dmax(s, tm.red[(size_t)(w * K + i) * TILE + tm.lane]);
-        v[i] = s;
-    }
+    team_reduce<K>(tm, v, [](vd a, vd b) { return a + b; });
 }
-
 template <int K>
-EI_DEV void team_min(const Team &tm, double (&v)[K])
+EI_DEV void team_max(const Team &tm, vd (&v)[K])
 {
-    if (tm.nwk == 1)
-        return;
-    tm.sync();
-    for (int i = 0; i < K; i++)
-        tm.red[(size_t)(tm.wk * K + i) * TILE + tm.lane] = v[i];
-    tm.sync();
-    for (int i = 0; i < K; i++)
-    {
-        double s = tm.red[(size_t)i * TILE + tm.lane];
-        for (int w = 1; w < tm.nwk; w++)
-            s = dmin(s, tm.red[(size_t)(w * K + i) * TILE + tm.lane]);
-        v[i] = s;
-    }
+    team_reduce<K>(tm, v, [](vd a, vd b) { return vmax(a, b); });
+}
+template <int K>
+EI_DEV void team_min(const Team &tm, vd (&v)[K])
+{
+    team_reduce<K>(tm, v, [](vd a, vd b) { return vmin(a, b); });
 }
 
 struct TileMem
@@ -234,21 +299,30 @@ EI_DEV TileMem tile_mem(const KArgs &a, int tile)
     return t;
 }
 
-EI_DEV bool lane_active(const Team &tm, const TileMem &t) { return ROWD(t.I, J_STATUS) == ST_ACTIVE; }
+EI_DEV vb lane_active(const Team &tm, const TileMem &t)
+{
+    vb r;
+    VFOR r.v[c_] = ROWC(t.I, J_STATUS, c_) == ST_ACTIVE;
+    return r;
+}
 
 // ------------------------------------------------------------------ asynchronous staging
 // A warp issues in order, so a load that is consumed right away limits it to ~2 loads in flight.
 // Independent work is therefore done block-wise: pass 1 issues every load of the block into this
-// worker's shared-memory slots with cp.async (no register dependency, up to STAGE_SLOTS rows =
-// 8 KB in flight per warp), pass 2 re-walks the same stream words and computes from shared memory.
-// Each lane only ever reads the slot words it wrote itself, so cp.async.wait_all is the only fence.
+// worker's shared-memory slots with cp.async (no register dependency), pass 2 re-walks the same
+// stream words and computes from shared memory.  Each lane only ever reads the slot words it wrote
+// itself, so cp.async.wait_all is the only fence needed.
 EI_DEV void stage_issue(double *slot_lane, const double *src_lane)
 {
 #ifdef EICOS_EMU
-    *slot_lane = *src_lane;
+    vstore(slot_lane, vload(src_lane));
 #else
     const unsigned sa = (unsigned)__cvta_generic_to_shared(slot_lane);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(src_lane) : "memory");
+    if (VEC == 2)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src_lane) : "memory");
+    else
+        for (int c = 0; c < VEC; c++)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + 8 * c), "l"(src_lane + c) : "memory");
 #endif
 }
 EI_DEV void stage_wait()
@@ -261,14 +335,14 @@ EI_DEV void stage_wait()
 EI_DEV const double *rowp(const Team &tm, const double *T, int row) { return T + (size_t)row * TILE + tm.lane; }
 
 // sum_k val_k * vec[idx_k] folded into `v` with sign: one mat-vec row straight from global memory
-EI_DEV double row_accumulate(const Team &tm, IStream &is, DStream &ds, const double *T, int vec, double v, double sign)
+EI_DEV vd row_accumulate(const Team &tm, IStream &is, DStream &ds, const double *T, int vec, vd v, double sign)
 {
     const int cnt = is.get();
     for (int k = 0; k < cnt; k++)
     {
         const int idx = is.get();
         const double val = ds.get();
-        v += (sign * val) * ROWD(T, vec + idx);
+        v += (sign * val) * vload(rowp(tm, T, vec + idx));
     }
     return v;
 }
@@ -278,23 +352,23 @@ EI_DEV double row_accumulate(const Team &tm, IStream &is, DStream &ds, const dou
 //   finish(row, ex, v) receives the extras and v = init(ex) + sum sign*val*vec[idx]
 template <int NEX, class Extra, class Init, class Finish>
 EI_DEV void rowset_run(const Team &tm, const double *T, const int *stream, const double *vals, const int *seg,
-                       int first, int vec, double sign, Extra extra, Init init, Finish finish)
+                       int vec, double sign, Extra extra, Init init, Finish finish)
 {
     IStream is;
     DStream ds;
-    is.open(stream + EI_LDG(seg + tm.wk * 3), tm.lane);
-    ds.open(vals + EI_LDG(seg + tm.wk * 3 + 1), tm.lane);
+    is.open(stream + EI_LDG(seg + tm.wk * 3), tm.pl);
+    ds.open(vals + EI_LDG(seg + tm.wk * 3 + 1), tm.pl);
     const int nblocks = EI_LDG(seg + tm.wk * 3 + 2);
-    int row = first + tm.wk;
+    int row = tm.wk;
     for (int b = 0; b < nblocks; b++)
     {
         const int nr = is.get();
         if (nr < 0)
         { // oversize row: no staging
-            double ex[NEX > 0 ? NEX : 1];
+            vd ex[NEX > 0 ? NEX : 1];
             for (int k = 0; k < NEX; k++)
-                ex[k] = *rowp(tm, T, extra(row, k));
-            const double v = row_accumulate(tm, is, ds, T, vec, init(ex), sign);
+                ex[k] = vload(rowp(tm, T, extra(row, k)));
+            const vd v = row_accumulate(tm, is, ds, T, vec, init(ex), sign);
             finish(row, ex, v);
             row += tm.nwk;
             continue;
@@ -315,15 +389,15 @@ EI_DEV void rowset_run(const Team &tm, const double *T, const int *stream, const
         sp = tm.stage;
         for (int t = 0; t < nr; t++, row += tm.nwk)
         {
-            double ex[NEX > 0 ? NEX : 1];
+            vd ex[NEX > 0 ? NEX : 1];
             for (int k = 0; k < NEX; k++, sp += TILE)
-                ex[k] = *sp;
-            double v = init(ex);
+                ex[k] = vload(sp);
+            vd v = init(ex);
             const int cnt = is.get();
             for (int k = 0; k < cnt; k++, sp += TILE)
             {
                 (void)is.get();
-                v += (sign * ds.get()) * *sp;
+                v += (sign * ds.get()) * vload(sp);
             }
             finish(row, ex, v);
         }
@@ -331,136 +405,145 @@ EI_DEV void rowset_run(const Team &tm, const double *T, const int *stream, const
 }
 
 // ------------------------------------------------------------------ W products (src/eicos.cpp:485-507)
-// out = W * in for the lanes' current scalings; in/out are z-shaped (expanded) row offsets.
-EI_DEV void cone_scale(const Team &tm, const KArgs &a, double *T, int in, int out, bool write)
+// out = W * in for the instances' current scalings; in/out are z-shaped (expanded) row offsets.
+EI_DEV void cone_scale(const Team &tm, const KArgs &a, double *T, int in, int out, vb write)
 {
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     for (int k = tm.wk; k < P.l; k += tm.nwk)
     {
-        const double v = ROWD(T, L.lpw + k) * ROWD(T, in + k);
-        if (write)
-            ROWD(T, out + k) = v;
+        const vd v = vd(ROWD(T, L.lpw + k)) * vd(ROWD(T, in + k));
+        ROWD(T, out + k) = vsel(write, v, ROWD(T, out + k));
     }
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     {
         const int d = EI_LDG(P.cone_dim + c), ks = EI_LDG(P.cone_k + c), qo = EI_LDG(P.cone_q + c);
-        const double *cp = T + (size_t)(L.cpar + c * CP_COUNT) * TILE + tm.lane;
-        const double eta = cp[CP_ETA * TILE], ca = cp[CP_A * TILE];
-        double zeta = 0.0;
-        for (int k = 1; k < d; k++)
-            zeta += ROWD(T, L.cq + qo + k - 1) * ROWD(T, in + ks + k);
-        const double z0 = ROWD(T, in + ks);
-        const double factor = z0 + zeta / (1. + ca);
-        if (write)
+        VFOR
         {
-            ROWD(T, out + ks) = eta * (ca * z0 + zeta);
+            const double eta = ROWC(T, L.cpar + c * CP_COUNT + CP_ETA, c_), ca = ROWC(T, L.cpar + c * CP_COUNT + CP_A, c_);
+            double zeta = 0.0;
             for (int k = 1; k < d; k++)
-                ROWD(T, out + ks + k) = eta * (ROWD(T, in + ks + k) + factor * ROWD(T, L.cq + qo + k - 1));
+                zeta += ROWC(T, L.cq + qo + k - 1, c_) * ROWC(T, in + ks + k, c_);
+            const double z0 = ROWC(T, in + ks, c_);
+            const double factor = z0 + zeta / (1. + ca);
+            if (write.v[c_])
+            {
+                ROWC(T, out + ks, c_) = eta * (ca * z0 + zeta);
+                for (int k = 1; k < d; k++)
+                    ROWC(T, out + ks + k, c_) = eta * (ROWC(T, in + ks + k, c_) + factor * ROWC(T, L.cq + qo + k - 1, c_));
+            }
         }
     }
 }
 
 // ------------------------------------------------------------------ line search (src/eicos.cpp:1380-1469)
-// lambda, ds, dz are z-shaped row offsets.  Returns the clamped step for every lane.
+// lambda, ds, dz are z-shaped row offsets.  Returns the clamped step for every instance.
 // TODO(parity): the reference's `continue` on lknorm2<=0 skips the cone offset advance; here later
 // cones keep their own offsets (differs only after lambda has already left the cone).
-EI_DEV double line_search(const Team &tm, const KArgs &a, double *T, int lam, int ds, int dz,
-                          double tau, double dtau, double kap, double dkap)
+EI_DEV vd line_search(const Team &tm, const KArgs &a, double *T, int lam, int ds, int dz,
+                      vd tau, vd dtau, vd kap, vd dkap)
 {
     const DevPattern &P = a.P;
-    double alpha;
-    double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}; // rhomin, sigmamin, min over cones of 1/conic_step
+    vd mn[3] = {vset(DBL_MAX), vset(DBL_MAX), vset(DBL_MAX)}; // rhomin, sigmamin, min over cones of 1/conic_step
     for (int k = tm.wk; k < P.l; k += tm.nwk)
     {
-        const double lk = ROWD(T, lam + k);
-        mn[0] = dmin(mn[0], ROWD(T, ds + k) / lk);
-        mn[1] = dmin(mn[1], ROWD(T, dz + k) / lk);
+        const vd lk = ROWD(T, lam + k);
+        mn[0] = vmin(mn[0], vd(ROWD(T, ds + k)) / lk);
+        mn[1] = vmin(mn[1], vd(ROWD(T, dz + k)) / lk);
     }
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     {
         const int d = EI_LDG(P.cone_dim + c), zs = EI_LDG(P.cone_k + c);
-        const double l0 = ROWD(T, lam + zs);
-        double sq = 0.0;
-        for (int k = 1; k < d; k++)
+        VFOR
         {
-            const double v = ROWD(T, lam + zs + k);
-            sq += v * v;
+            const double l0 = ROWC(T, lam + zs, c_);
+            double sq = 0.0;
+            for (int k = 1; k < d; k++)
+            {
+                const double v = ROWC(T, lam + zs + k, c_);
+                sq += v * v;
+            }
+            const double lknorm2 = l0 * l0 - sq;
+            if (lknorm2 <= 0.)
+                continue;
+            const double lknorm = sqrt(lknorm2);
+            const double lknorminv = 1. / lknorm;
+            const double lk0 = l0 / lknorm;
+            double dsdot = 0.0, dzdot = 0.0;
+            for (int k = 1; k < d; k++)
+            {
+                const double lkb = ROWC(T, lam + zs + k, c_) / lknorm;
+                dsdot += lkb * ROWC(T, ds + zs + k, c_);
+                dzdot += lkb * ROWC(T, dz + zs + k, c_);
+            }
+            const double ds0 = ROWC(T, ds + zs, c_), dz0 = ROWC(T, dz + zs, c_);
+            const double lds = lk0 * ds0 - dsdot, ldz = lk0 * dz0 - dzdot;
+            const double rho0 = lknorminv * lds, sig0 = lknorminv * ldz;
+            const double frho = (lds + ds0) / (lk0 + 1.), fsig = (ldz + dz0) / (lk0 + 1.);
+            double ar = 0.0, as = 0.0;
+            for (int k = 1; k < d; k++)
+            {
+                const double lkb = ROWC(T, lam + zs + k, c_) / lknorm;
+                const double r = lknorminv * (ROWC(T, ds + zs + k, c_) - frho * lkb);
+                const double s = lknorminv * (ROWC(T, dz + zs + k, c_) - fsig * lkb);
+                ar += r * r;
+                as += s * s;
+            }
+            const double rhonorm = sqrt(ar) - rho0, signorm = sqrt(as) - sig0;
+            const double conic_step = dmax(0., dmax(signorm, rhonorm));
+            if (conic_step != 0.)
+                mn[2].v[c_] = dmin(mn[2].v[c_], 1. / conic_step);
         }
-        const double lknorm2 = l0 * l0 - sq;
-        if (lknorm2 <= 0.)
-            continue;
-        const double lknorm = sqrt(lknorm2);
-        const double lknorminv = 1. / lknorm;
-        const double lk0 = l0 / lknorm;
-        double dsdot = 0.0, dzdot = 0.0;
-        for (int k = 1; k < d; k++)
-        {
-            const double lkb = ROWD(T, lam + zs + k) / lknorm;
-            dsdot += lkb * ROWD(T, ds + zs + k);
-            dzdot += lkb * ROWD(T, dz + zs + k);
-        }
-        const double ds0 = ROWD(T, ds + zs), dz0 = ROWD(T, dz + zs);
-        const double lds = lk0 * ds0 - dsdot, ldz = lk0 * dz0 - dzdot;
-        const double rho0 = lknorminv * lds, sig0 = lknorminv * ldz;
-        const double frho = (lds + ds0) / (lk0 + 1.), fsig = (ldz + dz0) / (lk0 + 1.);
-        double ar = 0.0, as = 0.0;
-        for (int k = 1; k < d; k++)
-        {
-            const double lkb = ROWD(T, lam + zs + k) / lknorm;
-            const double r = lknorminv * (ROWD(T, ds + zs + k) - frho * lkb);
-            const double s = lknorminv * (ROWD(T, dz + zs + k) - fsig * lkb);
-            ar += r * r;
-            as += s * s;
-        }
-        const double rhonorm = sqrt(ar) - rho0, signorm = sqrt(as) - sig0;
-        const double conic_step = dmax(0., dmax(signorm, rhonorm));
-        if (conic_step != 0.)
-            mn[2] = dmin(mn[2], 1. / conic_step);
     }
     team_min<3>(tm, mn);
-    if (P.l > 0)
+    vd res;
+    VFOR
     {
-        const double rhomin = mn[0], sigmamin = mn[1];
-        const double eps = 1e-13;
-        if (-sigmamin > -rhomin)
-            alpha = sigmamin < 0. ? 1. / (-sigmamin) : 1. / eps;
+        double alpha;
+        if (P.l > 0)
+        {
+            const double rhomin = mn[0].v[c_], sigmamin = mn[1].v[c_];
+            const double eps = 1e-13;
+            if (-sigmamin > -rhomin)
+                alpha = sigmamin < 0. ? 1. / (-sigmamin) : 1. / eps;
+            else
+                alpha = rhomin < 0. ? 1. / (-rhomin) : 1. / eps;
+        }
         else
-            alpha = rhomin < 0. ? 1. / (-rhomin) : 1. / eps;
+            alpha = 10.;
+        const double mt = -tau.v[c_] / dtau.v[c_], mk = -kap.v[c_] / dkap.v[c_];
+        if (mt > 0. && mt < alpha)
+            alpha = mt;
+        if (mk > 0. && mk < alpha)
+            alpha = mk;
+        alpha = dmin(mn[2].v[c_], alpha);
+        // std::clamp(alpha, stepmin, stepmax)
+        if (alpha < Settings::stepmin)
+            alpha = Settings::stepmin;
+        else if (Settings::stepmax < alpha)
+            alpha = Settings::stepmax;
+        res.v[c_] = alpha;
     }
-    else
-        alpha = 10.;
-    const double mt = -tau / dtau, mk = -kap / dkap;
-    if (mt > 0. && mt < alpha)
-        alpha = mt;
-    if (mk > 0. && mk < alpha)
-        alpha = mk;
-    alpha = dmin(mn[2], alpha);
-    // std::clamp(alpha, stepmin, stepmax)
-    if (alpha < Settings::stepmin)
-        alpha = Settings::stepmin;
-    else if (Settings::stepmax < alpha)
-        alpha = Settings::stepmax;
-    return alpha;
+    return res;
 }
 
 // ------------------------------------------------------------------ numeric LDL' (Eigen factorize, src/eicos.cpp:900,1164)
 // Left-looking by column on the fixed pattern, walking the level schedule of the elimination
 // tree.  Column j: gather its KKT entries, subtract the contribution of every earlier column k
-// with L(j,k) != 0 (row j of L is a contiguous run of the row-ordered copy; the tail of column k
-// below row j is a contiguous run of the column-ordered copy), divide by the pivot and store the
-// column in both orders.  Everything structural comes from the worker's instruction stream.
+// with L(j,k) != 0, divide by the pivot and store the column in both orders (LTx for the forward
+// sweep, Lx for the backward sweep).  Everything structural, including the storage row of every L
+// entry, comes from the worker's instruction stream.
 EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
 {
     const TileMem t = tile_mem(a, tile);
-    const bool act = lane_active(tm, t);
+    const vb act = lane_active(tm, t);
     if (!tm.any(act))
         return;
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     double *T = t.T;
     double *acc = tm.acc + (size_t)tm.wk * P.maxcol * TILE + tm.lane;
-    bool zero_pivot = false;
+    vb zero_pivot = vbset(false);
     for (int ph = 0; ph < P.nphases; ph++)
     {
         const int *seg = P.fa_seg + ((size_t)ph * tm.nwk + tm.wk) * 3;
@@ -469,42 +552,43 @@ EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
         {
             IStream is;
             DStream ds;
-            is.open(P.fa + EI_LDG(seg), tm.lane);
-            ds.open(P.fa_val + EI_LDG(seg + 2), tm.lane);
+            is.open(P.fa + EI_LDG(seg), tm.pl);
+            ds.open(P.fa_val + EI_LDG(seg + 2), tm.pl);
             for (int q = 0; q < nt; q++)
             {
                 const int j = is.get(), cnt = is.get(), nK = is.get(), nR = is.get();
                 for (int c = 0; c < cnt; c++)
-                    acc[(size_t)c * TILE] = 0.0;
-                double d = 0.0;
+                    vstore(acc + (size_t)c * TILE, vset(0.0));
+                vd d = vset(0.0);
                 for (int e = 0; e < nK; e++)
                 {
                     const int vi = is.get(), pos = is.get();
-                    const double val = vi >= 0 ? ROWD(T, L.V + vi) : ds.get();
+                    const vd val = vi >= 0 ? vd(ROWD(T, L.V + vi)) : vset(ds.get());
                     if (pos < 0)
                         d = val;
                     else
-                        acc[(size_t)pos * TILE] = val;
+                        vstore(acc + (size_t)pos * TILE, val);
                 }
                 for (int r = 0; r < nR; r++)
                 {
                     const int k = is.get(), fp = is.get(), tl = is.get();
-                    const double ljk = ROWD(T, L.LTx + fp);
-                    const double w = ljk * ROWD(T, L.D + k);
+                    const vd ljk = ROWD(T, L.LTx + fp);
+                    const vd w = ljk * vd(ROWD(T, L.D + k));
                     d -= ljk * w;
                     for (int u = 0; u < tl; u++)
                     {
                         const int rel = is.get(), bp = is.get();
-                        acc[(size_t)rel * TILE] -= ROWD(T, L.Lx + bp) * w;
+                        double *ap = acc + (size_t)rel * TILE;
+                        vstore(ap, vload(ap) - vd(ROWD(T, L.Lx + bp)) * w);
                     }
                 }
                 ROWD(T, L.D + j) = d;
                 ROWD(T, L.Dinv + j) = 1.0 / d;
-                zero_pivot = zero_pivot || (d == 0.0); // Eigen reports NumericalIssue only on an exactly zero pivot
+                VFOR zero_pivot.v[c_] = zero_pivot.v[c_] || (d.v[c_] == 0.0); // Eigen: NumericalIssue only on an exactly zero pivot
                 for (int c = 0; c < cnt; c++)
                 {
                     const int bp = is.get(), fp = is.get();
-                    const double lv = acc[(size_t)c * TILE] / d;
+                    const vd lv = vload(acc + (size_t)c * TILE) / d;
                     ROWD(T, L.Lx + bp) = lv;
                     ROWD(T, L.LTx + fp) = lv;
                 }
@@ -512,8 +596,7 @@ EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
         }
         tm.sync();
     }
-    if (zero_pivot && act)
-        ROWD(t.I, J_STATUS) = EXIT_FATAL;
+    VFOR if (zero_pivot.v[c_] && act.v[c_]) ROWC(t.I, J_STATUS, c_) = EXIT_FATAL;
 }
 
 // ------------------------------------------------------------------ triangular solves (Eigen solve, src/eicos.cpp:1477,1599)
@@ -535,7 +618,7 @@ EI_DEV void ldl_forward(const Team &tm, const KArgs &a, double *T, int rhs)
         if (count > 0)
         {
             IStream is;
-            is.open(P.fw + EI_LDG(seg), tm.lane);
+            is.open(P.fw + EI_LDG(seg), tm.pl);
             const double *lv = T + (size_t)(L.LTx + EI_LDG(seg + 2)) * TILE + tm.lane;
             if (EI_LDG(seg + 3) == SEG_BLOCKS)
             {
@@ -545,9 +628,9 @@ EI_DEV void ldl_forward(const Team &tm, const KArgs &a, double *T, int rhs)
                     if (nt < 0)
                     { // oversize row: straight from global memory
                         const int i = is.get(), r = is.get(), cnt = is.get();
-                        double v = r >= 0 ? ROWD(T, rhs + r) : ROWD(T, L.xw + i);
+                        vd v = r >= 0 ? vd(ROWD(T, rhs + r)) : vd(ROWD(T, L.xw + i));
                         for (int k = 0; k < cnt; k++, lv += TILE)
-                            v -= *lv * ROWD(T, L.xw + is.get());
+                            v -= vload(lv) * vd(ROWD(T, L.xw + is.get()));
                         ROWD(T, L.xw + i) = v;
                         continue;
                     }
@@ -572,12 +655,12 @@ EI_DEV void ldl_forward(const Team &tm, const KArgs &a, double *T, int rhs)
                         const int i = is.get();
                         (void)is.get();
                         const int cnt = is.get();
-                        double v = *sp;
+                        vd v = vload(sp);
                         sp += TILE;
                         for (int k = 0; k < cnt; k++, sp += 2 * TILE)
                         {
                             (void)is.get();
-                            v -= sp[0] * sp[TILE];
+                            v -= vload(sp) * vload(sp + TILE);
                         }
                         ROWD(T, L.xw + i) = v;
                     }
@@ -585,26 +668,26 @@ EI_DEV void ldl_forward(const Team &tm, const KArgs &a, double *T, int rhs)
             }
             else
             {
-                double p1 = 0.0, p2 = 0.0, p3 = 0.0;
+                vd p1 = vset(0.0), p2 = vset(0.0), p3 = vset(0.0);
                 int i = is.get(), r = is.get(), cnt = is.get();
-                double v = r >= 0 ? ROWD(T, rhs + r) : ROWD(T, L.xw + i);
+                vd v = r >= 0 ? vd(ROWD(T, rhs + r)) : vd(ROWD(T, L.xw + i));
                 for (int q = 0; q < count; q++)
                 {
                     int ni = 0, ncnt = 0;
-                    double nv = 0.0;
+                    vd nv = vset(0.0);
                     if (q + 1 < count)
                     {
                         ni = is.get();
                         r = is.get();
                         ncnt = is.get();
-                        nv = r >= 0 ? ROWD(T, rhs + r) : ROWD(T, L.xw + ni);
+                        nv = r >= 0 ? vd(ROWD(T, rhs + r)) : vd(ROWD(T, L.xw + ni));
                     }
                     for (int k = 0; k < cnt; k++, lv += TILE)
                     {
                         const int c = is.get();
                         EI_PREFETCH(lv + (size_t)PF_ROWS * TILE);
-                        const double xv = c >= 0 ? ROWD(T, L.xw + c) : (c == FWD_PREV1 ? p1 : (c == FWD_PREV2 ? p2 : p3));
-                        v -= *lv * xv;
+                        const vd xv = c >= 0 ? vd(ROWD(T, L.xw + c)) : (c == FWD_PREV1 ? p1 : (c == FWD_PREV2 ? p2 : p3));
+                        v -= vload(lv) * xv;
                     }
                     ROWD(T, L.xw + i) = v;
                     p3 = p2;
@@ -620,13 +703,14 @@ EI_DEV void ldl_forward(const Team &tm, const KArgs &a, double *T, int rhs)
     }
 }
 
-// out = solution (KKT order).  If x >= 0: additionally x += solution for the lanes with `cont`.
+// out = solution (KKT order).  If x >= 0: additionally x += solution for the instances with `cont`.
 // Task header: [xw/Dinv row j | INIT_PARTIAL, out row o | ~o for the external part of a chain task].
-EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int out, int x, bool cont)
+EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int out, int x, vb cont)
 {
     const DevPattern &P = a.P;
     const Layout &L = a.L;
-    const bool accumulate = x >= 0 && cont;
+    const bool accumulate = x >= 0;
+    const vd zero = vset(0.0);
     for (int ph = 0; ph < P.nph_bw; ph++)
     {
         const int *seg = P.bw_seg + ((size_t)ph * tm.nwk + tm.wk) * 4;
@@ -634,7 +718,7 @@ EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int out, int
         if (count > 0)
         {
             IStream is;
-            is.open(P.bw + EI_LDG(seg), tm.lane);
+            is.open(P.bw + EI_LDG(seg), tm.pl);
             const double *lv = T + (size_t)(L.Lx + EI_LDG(seg + 2)) * TILE + tm.lane;
             if (EI_LDG(seg + 3) == SEG_BLOCKS)
             {
@@ -645,12 +729,12 @@ EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int out, int
                     {
                         const int j = is.get(), oe = is.get(), cnt = is.get();
                         const int o = oe >= 0 ? oe : ~oe;
-                        double v = j >= 0 ? ROWD(T, L.Dinv + j) * ROWD(T, L.xw + j) : ROWD(T, out + o);
+                        vd v = j >= 0 ? vd(ROWD(T, L.Dinv + j)) * vd(ROWD(T, L.xw + j)) : vd(ROWD(T, out + o));
                         for (int k = 0; k < cnt; k++, lv += TILE)
-                            v -= *lv * ROWD(T, out + is.get());
+                            v -= vload(lv) * vd(ROWD(T, out + is.get()));
                         ROWD(T, out + o) = v;
                         if (accumulate && oe >= 0)
-                            ROWD(T, x + o) += v;
+                            ROWD(T, x + o) += vsel(cont, v, zero);
                         continue;
                     }
                     const IStream mark = is;
@@ -679,45 +763,45 @@ EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int out, int
                     {
                         const int j = is.get(), oe = is.get(), cnt = is.get();
                         const int o = oe >= 0 ? oe : ~oe;
-                        double v = j >= 0 ? sp[0] * sp[TILE] : sp[0];
+                        vd v = j >= 0 ? vload(sp) * vload(sp + TILE) : vload(sp);
                         sp += 2 * TILE;
                         for (int k = 0; k < cnt; k++, sp += 2 * TILE)
                         {
                             (void)is.get();
-                            v -= sp[0] * sp[TILE];
+                            v -= vload(sp) * vload(sp + TILE);
                         }
                         ROWD(T, out + o) = v;
                         if (accumulate && oe >= 0)
-                            ROWD(T, x + o) += v;
+                            ROWD(T, x + o) += vsel(cont, v, zero);
                     }
                 }
             }
             else
             {
-                double p1 = 0.0, p2 = 0.0, p3 = 0.0;
+                vd p1 = zero, p2 = zero, p3 = zero;
                 int j = is.get(), o = is.get(), cnt = is.get();
-                double v = j >= 0 ? ROWD(T, L.Dinv + j) * ROWD(T, L.xw + j) : ROWD(T, out + o);
+                vd v = j >= 0 ? vd(ROWD(T, L.Dinv + j)) * vd(ROWD(T, L.xw + j)) : vd(ROWD(T, out + o));
                 for (int q = 0; q < count; q++)
                 {
                     int no = 0, ncnt = 0;
-                    double nv = 0.0;
+                    vd nv = zero;
                     if (q + 1 < count)
                     {
                         j = is.get();
                         no = is.get();
                         ncnt = is.get();
-                        nv = j >= 0 ? ROWD(T, L.Dinv + j) * ROWD(T, L.xw + j) : ROWD(T, out + no);
+                        nv = j >= 0 ? vd(ROWD(T, L.Dinv + j)) * vd(ROWD(T, L.xw + j)) : vd(ROWD(T, out + no));
                     }
                     for (int k = 0; k < cnt; k++, lv += TILE)
                     {
                         const int c = is.get();
                         EI_PREFETCH(lv + (size_t)PF_ROWS * TILE);
-                        const double xv = c >= 0 ? ROWD(T, out + c) : (c == FWD_PREV1 ? p1 : (c == FWD_PREV2 ? p2 : p3));
-                        v -= *lv * xv;
+                        const vd xv = c >= 0 ? vd(ROWD(T, out + c)) : (c == FWD_PREV1 ? p1 : (c == FWD_PREV2 ? p2 : p3));
+                        v -= vload(lv) * xv;
                     }
                     ROWD(T, out + o) = v;
                     if (accumulate)
-                        ROWD(T, x + o) += v;
+                        ROWD(T, x + o) += vsel(cont, v, zero);
                     p3 = p2;
                     p2 = p1;
                     p1 = v;
@@ -733,68 +817,68 @@ EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int out, int
 
 // ------------------------------------------------------------------ KKT residual for iterative refinement (src/eicos.cpp:1511-1576)
 // e = rhs - Ktrue * x with the un-regularised scaling block (identity while initialising),
-// returns ||e||_inf per lane.
-EI_DEV double kkt_residual(const Team &tm, const KArgs &a, double *T, int rhs, int x, bool initialize)
+// returns ||e||_inf per instance.
+EI_DEV vd kkt_residual(const Team &tm, const KArgs &a, double *T, int rhs, int x, bool initialize)
 {
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     const double delta = Settings::deltastat;
     const int n = P.n, p = P.p, zb = P.n + P.p;
-    double nerr = 0.0;
+    vd nerr = vset(0.0);
     if (n > 0)
         rowset_run<2>(
-            tm, T, P.rx, P.rx_val, P.rx_seg, 0, x, -1.0,
+            tm, T, P.rx, P.rx_val, P.rx_seg, x, -1.0,
             [&](int j, int k) { return (k == 0 ? rhs : x) + j; },
-            [&](const double *ex) { return ex[0]; },
-            [&](int j, const double *ex, double v) {
+            [&](const vd *ex) { return ex[0]; },
+            [&](int j, const vd *ex, vd v) {
                 v -= delta * ex[1];
                 ROWD(T, L.e + j) = v;
-                nerr = dmax(nerr, fabs(v));
+                nerr = vmax(nerr, vabs(v));
             });
     if (p > 0)
         rowset_run<2>(
-            tm, T, P.ry, P.ry_val, P.ry_seg, 0, x, -1.0,
+            tm, T, P.ry, P.ry_val, P.ry_seg, x, -1.0,
             [&](int i, int k) { return (k == 0 ? rhs : x) + n + i; },
-            [&](const double *ex) { return ex[0]; },
-            [&](int i, const double *ex, double v) {
+            [&](const vd *ex) { return ex[0]; },
+            [&](int i, const vd *ex, vd v) {
                 v += delta * ex[1];
                 ROWD(T, L.e + n + i) = v;
-                nerr = dmax(nerr, fabs(v));
+                nerr = vmax(nerr, vabs(v));
             });
     if (P.l > 0)
         rowset_run<3>(
-            tm, T, P.rz, P.rz_val, P.rz_seg, 0, x, -1.0,
+            tm, T, P.rz, P.rz_val, P.rz_seg, x, -1.0,
             [&](int i, int k) { return k == 0 ? rhs + zb + i : (k == 1 ? x + zb + i : L.lpv + i); },
-            [&](const double *ex) { return ex[0]; },
-            [&](int i, const double *ex, double v) {
-                const double dz = ex[1];
+            [&](const vd *ex) { return ex[0]; },
+            [&](int i, const vd *ex, vd v) {
+                const vd dz = ex[1];
                 v += delta * dz;
                 v += initialize ? dz : ex[2] * dz;
                 ROWD(T, L.e + zb + i) = v;
-                nerr = dmax(nerr, fabs(v));
+                nerr = vmax(nerr, vabs(v));
             });
     if (P.nc > 0)
     {
         IStream is;
         DStream ds;
-        is.open(P.rc + EI_LDG(P.rc_seg + tm.wk * 2), tm.lane);
-        ds.open(P.rc_val + EI_LDG(P.rc_seg + tm.wk * 2 + 1), tm.lane);
+        is.open(P.rc + EI_LDG(P.rc_seg + tm.wk * 2), tm.pl);
+        ds.open(P.rc_val + EI_LDG(P.rc_seg + tm.wk * 2 + 1), tm.pl);
         for (int c = tm.wk; c < P.nc; c += tm.nwk)
         {
             const int d = is.get(), ks = is.get(), qo = is.get();
             const int kb = zb + ks; // KKT row of the cone's first entry
-            const double *cp = T + (size_t)(L.cpar + c * CP_COUNT) * TILE + tm.lane;
-            const double eta2 = cp[CP_ETA2 * TILE], d1 = cp[CP_D1 * TILE], u0 = cp[CP_U0 * TILE];
-            const double u1 = cp[CP_U1 * TILE], v1 = cp[CP_V1 * TILE];
-            const double x1 = ROWD(T, x + kb), x3 = ROWD(T, x + kb + d), x4 = ROWD(T, x + kb + d + 1);
-            double qtx2 = 0.0;
+            const int cp = L.cpar + c * CP_COUNT;
+            const vd eta2 = ROWD(T, cp + CP_ETA2), d1 = ROWD(T, cp + CP_D1), u0 = ROWD(T, cp + CP_U0);
+            const vd u1 = ROWD(T, cp + CP_U1), v1 = ROWD(T, cp + CP_V1);
+            const vd x1 = ROWD(T, x + kb), x3 = ROWD(T, x + kb + d), x4 = ROWD(T, x + kb + d + 1);
+            vd qtx2 = vset(0.0);
             for (int k = 1; k < d; k++)
-                qtx2 += ROWD(T, L.cq + qo + k - 1) * ROWD(T, x + kb + k);
-            const double vu = v1 * x3 + u1 * x4;
+                qtx2 += vd(ROWD(T, L.cq + qo + k - 1)) * vd(ROWD(T, x + kb + k));
+            const vd vu = v1 * x3 + u1 * x4;
             for (int k = 0; k < d; k++)
             {
-                const double xk = ROWD(T, x + kb + k);
-                double v = row_accumulate(tm, is, ds, T, x, ROWD(T, rhs + kb + k), -1.0);
+                const vd xk = ROWD(T, x + kb + k);
+                vd v = row_accumulate(tm, is, ds, T, x, ROWD(T, rhs + kb + k), -1.0);
                 if (k < d - 1)
                     v += delta * xk;
                 else
@@ -804,29 +888,29 @@ EI_DEV double kkt_residual(const Team &tm, const KArgs &a, double *T, int rhs, i
                 else if (k == 0)
                     v += eta2 * (d1 * x1 + u0 * x4);
                 else
-                    v += eta2 * (xk + vu * ROWD(T, L.cq + qo + k - 1));
+                    v += eta2 * (xk + vu * vd(ROWD(T, L.cq + qo + k - 1)));
                 ROWD(T, L.e + kb + k) = v;
-                nerr = dmax(nerr, fabs(v));
+                nerr = vmax(nerr, vabs(v));
             }
-            const double e3 = initialize ? x3 : eta2 * (v1 * qtx2 + x3);
-            const double e4 = initialize ? x4 : eta2 * (u0 * x1 + u1 * qtx2 - x4);
+            const vd e3 = initialize ? x3 : eta2 * (v1 * qtx2 + x3);
+            const vd e4 = initialize ? x4 : eta2 * (u0 * x1 + u1 * qtx2 - x4);
             ROWD(T, L.e + kb + d) = e3;
             ROWD(T, L.e + kb + d + 1) = e4;
-            nerr = dmax(nerr, dmax(fabs(e3), fabs(e4)));
+            nerr = vmax(nerr, vmax(vabs(e3), vabs(e4)));
         }
     }
-    double red[1] = {nerr};
+    vd red[1] = {nerr};
     team_max<1>(tm, red);
     return red[0];
 }
 
 // ------------------------------------------------------------------ solveKKT (src/eicos.cpp:1471-1620)
-// sol = K^-1 rhs followed by up to nitref refinement rounds; every lane stops on its own
-// criterion, the tile loops until all of its lanes have stopped.
+// sol = K^-1 rhs followed by up to nitref refinement rounds; every instance stops on its own
+// criterion, the tile loops until all of its instances have stopped.
 EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
 {
     const TileMem t = tile_mem(a, tile);
-    const bool act = lane_active(tm, t);
+    const vb act = lane_active(tm, t);
     if (!tm.any(act))
         return;
     const DevPattern &P = a.P;
@@ -835,58 +919,60 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
     const int rhs = a.rhs, sol = a.sol;
     const bool init = a.initialize != 0;
 
-    double mx[1] = {0.0};
+    vd mx[1] = {vset(0.0)};
     for (int r = tm.wk; r < P.N; r += tm.nwk)
-        mx[0] = dmax(mx[0], fabs(ROWD(T, rhs + r)));
+        mx[0] = vmax(mx[0], vabs(ROWD(T, rhs + r)));
     team_max<1>(tm, mx);
-    const double threshold = (1. + mx[0]) * Settings::linsysacc;
+    const vd threshold = (1. + mx[0]) * Settings::linsysacc;
 
     ldl_forward(tm, a, T, rhs);
-    ldl_backward(tm, a, T, sol, -1, false);
+    ldl_backward(tm, a, T, sol, -1, vbset(false));
 
-    double nerr_prev = DBL_MAX;
-    int kref = 0;
-    bool done = !act;
+    vd nerr_prev = vset(DBL_MAX);
+    int kref[VEC];
+    vb done = !act;
+    VFOR kref[c_] = 0;
     unsigned rounds = 0;
     for (;;)
     {
-        const double nerr = kkt_residual(tm, a, T, rhs, sol, init);
-        bool rollback = false;
-        if (!done)
+        const vd nerr = kkt_residual(tm, a, T, rhs, sol, init);
+        vb rollback = vbset(false);
+        VFOR
         {
-            if (kref > 0 && nerr > nerr_prev)
+            if (done.v[c_])
+                continue;
+            if (kref[c_] > 0 && nerr.v[c_] > nerr_prev.v[c_])
             {
-                rollback = true;
-                kref--;
-                done = true;
+                rollback.v[c_] = true;
+                kref[c_]--;
+                done.v[c_] = true;
             }
-            else if (kref == Settings::nitref || nerr < threshold || (kref > 0 && nerr_prev < Settings::irerrfact * nerr))
-                done = true;
+            else if (kref[c_] == Settings::nitref || nerr.v[c_] < threshold.v[c_] ||
+                     (kref[c_] > 0 && nerr_prev.v[c_] < Settings::irerrfact * nerr.v[c_]))
+                done.v[c_] = true;
             else
-                nerr_prev = nerr;
+                nerr_prev.v[c_] = nerr.v[c_];
         }
         if (tm.any(rollback))
-        { // x -= dx_ref for the lanes whose last refinement made things worse
+        { // x -= dx_ref for the instances whose last refinement made things worse
             for (int r = tm.wk; r < P.N; r += tm.nwk)
-                if (rollback)
-                    ROWD(T, sol + r) -= ROWD(T, L.dxr + r);
+                ROWD(T, sol + r) -= vsel(rollback, ROWD(T, L.dxr + r), vset(0.0));
         }
         if (tm.all(done))
             break;
         tm.sync(); // e complete before the forward sweep gathers it
         ldl_forward(tm, a, T, L.e);
         ldl_backward(tm, a, T, L.dxr, sol, !done);
-        if (!done)
-            kref++;
+        VFOR if (!done.v[c_]) kref[c_]++;
         rounds++;
     }
     tm.sync();
     if (tm.wk == 0)
     {
-        if (act && a.nitrow >= 0)
-            ROWD(t.I, a.nitrow) = kref;
+        if (a.nitrow >= 0)
+            VFOR if (act.v[c_]) ROWC(t.I, a.nitrow, c_) = kref[c_];
 #ifndef EICOS_EMU
-        if (tm.lane == 0 && a.ir_rounds)
+        if (tm.pl == 0 && a.ir_rounds)
             atomicAdd(a.ir_rounds, (unsigned long long)(rounds + 1));
 #endif
     }
@@ -900,18 +986,21 @@ EI_DEV void tile_init(const Team &tm, const KArgs &a, int tile)
     const Layout &L = a.L;
     double *T = t.T;
     const int n = P.n, zb = P.n + P.p;
-    const bool valid = tile * TILE + tm.lane < a.batch;
     if (tm.wk == 0)
     {
-        ROWD(t.I, J_STATUS) = valid ? (int)ST_ACTIVE : (int)EXIT_FATAL;
-        if (!a.keep_sticky)
+        VFOR
         {
-            ROWD(t.I, J_HAS_PINFRES) = 0;
-            ROWD(t.I, J_HAS_DINFRES) = 0;
-            ROWD(t.I, J_HAS_RELGAP) = 0;
-            ROWD(T, L.sc + S_PINFRES) = 0.0;
-            ROWD(T, L.sc + S_DINFRES) = 0.0;
-            ROWD(T, L.sc + S_RELGAP) = 0.0;
+            const bool valid = tile * TILE + tm.lane + c_ < a.batch;
+            ROWC(t.I, J_STATUS, c_) = valid ? (int)ST_ACTIVE : (int)EXIT_FATAL;
+            if (!a.keep_sticky)
+            {
+                ROWC(t.I, J_HAS_PINFRES, c_) = 0;
+                ROWC(t.I, J_HAS_DINFRES, c_) = 0;
+                ROWC(t.I, J_HAS_RELGAP, c_) = 0;
+                ROWC(T, L.sc + S_PINFRES, c_) = 0.0;
+                ROWC(T, L.sc + S_DINFRES, c_) = 0.0;
+                ROWC(T, L.sc + S_RELGAP, c_) = 0.0;
+            }
         }
     }
     for (int k = tm.wk; k < P.nnzV; k += tm.nwk)
@@ -920,24 +1009,24 @@ EI_DEV void tile_init(const Team &tm, const KArgs &a, int tile)
         ROWD(T, L.V + k) = kind == 0 ? -1.0 : (kind == 1 ? 0.0 : 1.0);
     }
     // rhs1 = [0; b; h], rhs2 = [-c; 0; 0]; resx0.. = max(1, ||c||), ... (:865-894)
-    double nr[3] = {0.0, 0.0, 0.0};
+    vd nr[3] = {vset(0.0), vset(0.0), vset(0.0)};
     for (int r = tm.wk; r < n; r += tm.nwk)
     {
-        const double v = ROWD(T, L.chb + r);
+        const vd v = ROWD(T, L.chb + r);
         ROWD(T, L.rhs1 + r) = 0.0;
         ROWD(T, L.rhs2 + r) = -v;
         nr[0] += v * v;
     }
     for (int r = n + tm.wk; r < zb; r += tm.nwk)
     {
-        const double v = ROWD(T, L.chb + r);
+        const vd v = ROWD(T, L.chb + r);
         ROWD(T, L.rhs1 + r) = v;
         ROWD(T, L.rhs2 + r) = 0.0;
         nr[1] += v * v;
     }
     for (int r = zb + tm.wk; r < P.N; r += tm.nwk)
     {
-        const double v = ROWD(T, L.chb + r);
+        const vd v = ROWD(T, L.chb + r);
         ROWD(T, L.rhs1 + r) = v;
         ROWD(T, L.rhs2 + r) = 0.0;
         nr[2] += v * v;
@@ -945,48 +1034,44 @@ EI_DEV void tile_init(const Team &tm, const KArgs &a, int tile)
     team_sum<3>(tm, nr);
     if (tm.wk == 0)
     {
-        ROWD(T, L.sc + S_RESX0) = dmax(1., sqrt(nr[0]));
-        ROWD(T, L.sc + S_RESY0) = dmax(1., sqrt(nr[1]));
-        ROWD(T, L.sc + S_RESZ0) = dmax(1., sqrt(nr[2]));
+        ROWD(T, L.sc + S_RESX0) = vmax(vset(1.), vsqrt(nr[0]));
+        ROWD(T, L.sc + S_RESY0) = vmax(vset(1.), vsqrt(nr[1]));
+        ROWD(T, L.sc + S_RESZ0) = vmax(vset(1.), vsqrt(nr[2]));
     }
 }
 
 // bringToCone (src/eicos.cpp:761-805): dst = sign*src + (1+alpha) e ; src, dst z-shaped row offsets
-EI_DEV void bring_to_cone(const Team &tm, const KArgs &a, double *T, int src, double sign, int dst, bool write)
+EI_DEV void bring_to_cone(const Team &tm, const KArgs &a, double *T, int src, double sign, int dst, vb write)
 {
     const DevPattern &P = a.P;
-    double al[1] = {-Settings::gamma};
+    vd al[1] = {vset(-Settings::gamma)};
     for (int k = tm.wk; k < P.l; k += tm.nwk)
     {
-        const double r = sign * ROWD(T, src + k);
-        if (r <= 0 && -r > al[0])
-            al[0] = -r;
+        const vd r = sign * vd(ROWD(T, src + k));
+        VFOR if (r.v[c_] <= 0 && -r.v[c_] > al[0].v[c_]) al[0].v[c_] = -r.v[c_];
     }
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     {
         const int d = EI_LDG(P.cone_dim + c), kb = EI_LDG(P.cone_k + c);
-        double sq = 0.0;
+        vd sq = vset(0.0);
         for (int k = 1; k < d; k++)
         {
-            const double v = sign * ROWD(T, src + kb + k);
+            const vd v = sign * vd(ROWD(T, src + kb + k));
             sq += v * v;
         }
-        const double cres = sign * ROWD(T, src + kb) - sqrt(sq);
-        if (cres <= 0 && -cres > al[0])
-            al[0] = -cres;
+        const vd cres = sign * vd(ROWD(T, src + kb)) - vsqrt(sq);
+        VFOR if (cres.v[c_] <= 0 && -cres.v[c_] > al[0].v[c_]) al[0].v[c_] = -cres.v[c_];
     }
     team_max<1>(tm, al);
-    const double alpha = al[0] + 1.;
-    if (!write)
-        return;
+    const vd alpha = al[0] + 1.;
     for (int k = tm.wk; k < P.l; k += tm.nwk)
-        ROWD(T, dst + k) = sign * ROWD(T, src + k) + alpha;
+        ROWD(T, dst + k) = vsel(write, sign * vd(ROWD(T, src + k)) + alpha, ROWD(T, dst + k));
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     {
         const int d = EI_LDG(P.cone_dim + c), kb = EI_LDG(P.cone_k + c);
-        ROWD(T, dst + kb) = sign * ROWD(T, src + kb) + alpha;
+        ROWD(T, dst + kb) = vsel(write, sign * vd(ROWD(T, src + kb)) + alpha, ROWD(T, dst + kb));
         for (int k = 1; k < d; k++)
-            ROWD(T, dst + kb + k) = sign * ROWD(T, src + kb + k);
+            ROWD(T, dst + kb + k) = vsel(write, sign * vd(ROWD(T, src + kb + k)), ROWD(T, dst + kb + k));
     }
 }
 
@@ -994,7 +1079,7 @@ EI_DEV void bring_to_cone(const Team &tm, const KArgs &a, double *T, int src, do
 EI_DEV void tile_init_point(const Team &tm, const KArgs &a, int tile)
 {
     const TileMem t = tile_mem(a, tile);
-    const bool act = lane_active(tm, t);
+    const vb act = lane_active(tm, t);
     if (!tm.any(act))
         return;
     const DevPattern &P = a.P;
@@ -1003,48 +1088,47 @@ EI_DEV void tile_init_point(const Team &tm, const KArgs &a, int tile)
     const int n = P.n, zb = P.n + P.p;
     for (int j = tm.wk; j < n; j += tm.nwk)
     {
-        if (act)
-            ROWD(T, L.w + j) = ROWD(T, L.sol1 + j);
-        ROWD(T, L.rhs1 + j) = -ROWD(T, L.chb + j);
+        ROWD(T, L.w + j) = vsel(act, ROWD(T, L.sol1 + j), ROWD(T, L.w + j));
+        ROWD(T, L.rhs1 + j) = -vd(ROWD(T, L.chb + j));
     }
     for (int i = tm.wk; i < P.p; i += tm.nwk)
-        if (act)
-            ROWD(T, L.w + n + i) = ROWD(T, L.sol2 + n + i);
+        ROWD(T, L.w + n + i) = vsel(act, ROWD(T, L.sol2 + n + i), ROWD(T, L.w + n + i));
     bring_to_cone(tm, a, T, L.sol1 + zb, -1.0, L.s, act);
     bring_to_cone(tm, a, T, L.sol2 + zb, 1.0, L.w + zb, act);
-    if (tm.wk == 0 && act)
-    {
-        ROWD(T, L.sc + S_KAP) = 1.;
-        ROWD(T, L.sc + S_TAU) = 1.;
-        ROWD(T, L.sc + S_STEP) = 0.;
-        ROWD(T, L.sc + S_STEP_AFF) = 0.;
-        ROWD(T, L.sc + S_PRES_PREV) = DBL_MAX;
-        ROWD(t.I, J_PINF) = 0;
-        ROWD(t.I, J_DINF) = 0;
-        ROWD(t.I, J_ITER) = 0;
-    }
+    if (tm.wk == 0)
+        VFOR if (act.v[c_])
+        {
+            ROWC(T, L.sc + S_KAP, c_) = 1.;
+            ROWC(T, L.sc + S_TAU, c_) = 1.;
+            ROWC(T, L.sc + S_STEP, c_) = 0.;
+            ROWC(T, L.sc + S_STEP_AFF, c_) = 0.;
+            ROWC(T, L.sc + S_PRES_PREV, c_) = DBL_MAX;
+            ROWC(t.I, J_PINF, c_) = 0;
+            ROWC(t.I, J_DINF, c_) = 0;
+            ROWC(t.I, J_ITER, c_) = 0;
+        }
 }
 
-// ------------------------------------------------------------------ per-lane scalar state of `Work` + `Information`
+// ------------------------------------------------------------------ per-instance scalar state of `Work` + `Information`
 struct WState
 {
     double d[S_WORK_END];
     int i[J_WORK_END];
 };
 
-EI_DEV void ws_load(const Team &tm, const double *T, const int *I, int sc, int soff, int ioff, WState &w)
+EI_DEV void ws_load(const Team &tm, const double *T, const int *I, int sc, int soff, int ioff, int c, WState &w)
 {
     for (int k = 0; k < S_WORK_END; k++)
-        w.d[k] = ROWD(T, sc + soff + k);
+        w.d[k] = ROWC(T, sc + soff + k, c);
     for (int k = 0; k < J_WORK_END; k++)
-        w.i[k] = ROWD(I, ioff + k);
+        w.i[k] = ROWC(I, ioff + k, c);
 }
-EI_DEV void ws_store(const Team &tm, double *T, int *I, int sc, int soff, int ioff, const WState &w)
+EI_DEV void ws_store(const Team &tm, double *T, int *I, int sc, int soff, int ioff, int c, const WState &w)
 {
     for (int k = 0; k < S_WORK_END; k++)
-        ROWD(T, sc + soff + k) = w.d[k];
+        ROWC(T, sc + soff + k, c) = w.d[k];
     for (int k = 0; k < J_WORK_END; k++)
-        ROWD(I, ioff + k) = w.i[k];
+        ROWC(I, ioff + k, c) = w.i[k];
 }
 
 // Information::isBetterThan (src/eicos.cpp:23-68)
@@ -1095,21 +1179,21 @@ EI_DEV int ws_check_exit(WState &w, bool reduced)
     return EXIT_NOT_CONVERGED;
 }
 
-// ------------------------------------------------------------------ NT scaling of one cone (src/eicos.cpp:419-474)
+// ------------------------------------------------------------------ NT scaling of one cone, one instance (src/eicos.cpp:419-474)
 struct ConeScaling
 {
     int stage; // 0 ok, 1 failed the residual test (nothing assigned), 2 failed c^2/u0^2 - d (eta, q assigned)
     double eta, eta2, a, d1, u0, u1, v1, w, snorm, znorm, gamma;
 };
 
-EI_DEV ConeScaling cone_scaling(const Team &tm, const double *T, int srow, int zrow, int d)
+EI_DEV ConeScaling cone_scaling(const Team &tm, const double *T, int srow, int zrow, int d, int c)
 {
     ConeScaling r;
-    const double s0 = ROWD(T, srow), z0 = ROWD(T, zrow);
+    const double s0 = ROWC(T, srow, c), z0 = ROWC(T, zrow, c);
     double ss = 0.0, zz = 0.0;
     for (int k = 1; k < d; k++)
     {
-        const double sv = ROWD(T, srow + k), zv = ROWD(T, zrow + k);
+        const double sv = ROWC(T, srow + k, c), zv = ROWC(T, zrow + k, c);
         ss += sv * sv;
         zz += zv * zv;
     }
@@ -1126,14 +1210,14 @@ EI_DEV ConeScaling cone_scaling(const Team &tm, const double *T, int srow, int z
     r.eta = sqrt(r.eta2);
     double g = 0.0;
     for (int k = 0; k < d; k++)
-        g += (ROWD(T, srow + k) / r.snorm) * (ROWD(T, zrow + k) / r.znorm);
+        g += (ROWC(T, srow + k, c) / r.snorm) * (ROWC(T, zrow + k, c) / r.znorm);
     g = sqrt(0.5 * (1. + g));
     r.gamma = g;
     const double av = (0.5 / g) * (s0 / r.snorm + z0 / r.znorm);
     double w = 0.0;
     for (int k = 1; k < d; k++)
     {
-        const double qk = (0.5 / g) * (ROWD(T, srow + k) / r.snorm - ROWD(T, zrow + k) / r.znorm);
+        const double qk = (0.5 / g) * (ROWC(T, srow + k, c) / r.snorm - ROWC(T, zrow + k, c) / r.znorm);
         w += qk * qk;
     }
     const double cc = (1. + av) + w / (1. + av);
@@ -1157,12 +1241,12 @@ EI_DEV ConeScaling cone_scaling(const Team &tm, const double *T, int srow, int z
 
 // ------------------------------------------------------------------ head of an iteration
 // computeResiduals + updateStatistics + safeguards / exit tests + best-iterate bookkeeping
-// (src/eicos.cpp:997-1158), then for the lanes that keep iterating: updateScalings,
-// updateKKTScalings and RHSaffine (:1160-1162, :1176).  Lanes that stop are back-scaled in place.
+// (src/eicos.cpp:997-1158), then for the instances that keep iterating: updateScalings,
+// updateKKTScalings and RHSaffine (:1160-1162, :1176).  Instances that stop are back-scaled in place.
 EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
 {
     const TileMem t = tile_mem(a, tile);
-    const bool act = lane_active(tm, t);
+    const vb act = lane_active(tm, t);
     if (!tm.any(act))
         return;
     const DevPattern &P = a.P;
@@ -1170,19 +1254,20 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
     double *T = t.T;
     int *I = t.I;
     const int n = P.n, p = P.p, zb = P.n + P.p;
-    const double tau = ROWD(T, L.sc + S_TAU), kap = ROWD(T, L.sc + S_KAP);
+    const vd tau = ROWD(T, L.sc + S_TAU), kap = ROWD(T, L.sc + S_KAP);
 
     enum { HX2, RX2, CX, NX2, HY2, RY2, BY, NY2, HZ2, RZ2, HZ, NZ2, NS2, GAP, NRED };
-    double r[NRED];
+    static_assert(NRED <= KRED, "reduction buffer too small");
+    vd r[NRED];
     for (int k = 0; k < NRED; k++)
-        r[k] = 0.0;
+        r[k] = vset(0.0);
     if (n > 0)
         rowset_run<2>(
-            tm, T, P.rx, P.rx_val, P.rx_seg, 0, L.w, -1.0,
+            tm, T, P.rx, P.rx_val, P.rx_seg, L.w, -1.0,
             [&](int j, int k) { return (k == 0 ? L.chb : L.w) + j; },
-            [&](const double *) { return 0.0; },
-            [&](int j, const double *ex, double v) {
-                const double cj = ex[0], xj = ex[1];
+            [&](const vd *) { return vset(0.0); },
+            [&](int j, const vd *ex, vd v) {
+                const vd cj = ex[0], xj = ex[1];
                 r[HX2] += v * v;
                 v -= tau * cj;
                 ROWD(T, L.r + j) = v;
@@ -1192,11 +1277,11 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
             });
     if (p > 0)
         rowset_run<2>(
-            tm, T, P.ry, P.ry_val, P.ry_seg, 0, L.w, 1.0,
+            tm, T, P.ry, P.ry_val, P.ry_seg, L.w, 1.0,
             [&](int i, int k) { return (k == 0 ? L.chb : L.w) + n + i; },
-            [&](const double *) { return 0.0; },
-            [&](int i, const double *ex, double v) {
-                const double bi = ex[0], yi = ex[1];
+            [&](const vd *) { return vset(0.0); },
+            [&](int i, const vd *ex, vd v) {
+                const vd bi = ex[0], yi = ex[1];
                 r[HY2] += v * v;
                 v -= tau * bi;
                 ROWD(T, L.r + n + i) = v;
@@ -1204,28 +1289,28 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
                 r[BY] += bi * yi;
                 r[NY2] += yi * yi;
             });
+    const auto zrow = [&](int e, vd si, vd zi, vd hi, vd v) {
+        r[HZ2] += v * v;
+        v -= tau * hi;
+        ROWD(T, L.r + zb + e) = v;
+        r[RZ2] += v * v;
+        r[HZ] += hi * zi;
+        r[NZ2] += zi * zi;
+        r[NS2] += si * si;
+        r[GAP] += si * zi;
+    };
     if (P.l > 0)
         rowset_run<3>(
-            tm, T, P.rz, P.rz_val, P.rz_seg, 0, L.w, 1.0,
+            tm, T, P.rz, P.rz_val, P.rz_seg, L.w, 1.0,
             [&](int i, int k) { return k == 0 ? L.s + i : (k == 1 ? L.w + zb + i : L.chb + zb + i); },
-            [&](const double *ex) { return ex[0]; },
-            [&](int i, const double *ex, double v) {
-                const double si = ex[0], zi = ex[1], hi = ex[2];
-                r[HZ2] += v * v;
-                v -= tau * hi;
-                ROWD(T, L.r + zb + i) = v;
-                r[RZ2] += v * v;
-                r[HZ] += hi * zi;
-                r[NZ2] += zi * zi;
-                r[NS2] += si * si;
-                r[GAP] += si * zi;
-            });
+            [&](const vd *ex) { return ex[0]; },
+            [&](int i, const vd *ex, vd v) { zrow(i, ex[0], ex[1], ex[2], v); });
     if (P.nc > 0)
     {
         IStream is;
         DStream ds;
-        is.open(P.rc + EI_LDG(P.rc_seg + tm.wk * 2), tm.lane);
-        ds.open(P.rc_val + EI_LDG(P.rc_seg + tm.wk * 2 + 1), tm.lane);
+        is.open(P.rc + EI_LDG(P.rc_seg + tm.wk * 2), tm.pl);
+        ds.open(P.rc_val + EI_LDG(P.rc_seg + tm.wk * 2 + 1), tm.pl);
         for (int c = tm.wk; c < P.nc; c += tm.nwk)
         {
             const int d = is.get(), ks = is.get();
@@ -1233,178 +1318,170 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
             for (int k = 0; k < d; k++)
             {
                 const int e = ks + k;
-                const double si = ROWD(T, L.s + e), zi = ROWD(T, L.w + zb + e), hi = ROWD(T, L.chb + zb + e);
-                double v = row_accumulate(tm, is, ds, T, L.w, si, 1.0);
-                r[HZ2] += v * v;
-                v -= tau * hi;
-                ROWD(T, L.r + zb + e) = v;
-                r[RZ2] += v * v;
-                r[HZ] += hi * zi;
-                r[NZ2] += zi * zi;
-                r[NS2] += si * si;
-                r[GAP] += si * zi;
+                const vd si = ROWD(T, L.s + e), zi = ROWD(T, L.w + zb + e), hi = ROWD(T, L.chb + zb + e);
+                zrow(e, si, zi, hi, row_accumulate(tm, is, ds, T, L.w, si, 1.0));
             }
         }
     }
     team_sum<NRED>(tm, r);
 
-    // ---- updateStatistics (:691-728) on registers; every warp computes the same values
-    WState w, best;
-    ws_load(tm, T, I, L.sc, 0, 0, w);
-    ws_load(tm, T, I, L.sc, S_BEST, J_BEST, best);
-    const double hresx = sqrt(r[HX2]), hresy = sqrt(r[HY2]), hresz = sqrt(r[HZ2]);
-    const double nx = sqrt(r[NX2]), ny = sqrt(r[NY2]), nz = sqrt(r[NZ2]), ns = sqrt(r[NS2]);
-    const double cx = r[CX], by = p > 0 ? r[BY] : 0., hz = r[HZ];
-    const double rt = kap + cx + by + hz;
-    w.d[S_CX] = cx;
-    w.d[S_BY] = by;
-    w.d[S_HZ] = hz;
-    w.d[S_GAP] = r[GAP];
-    w.d[S_MU] = (r[GAP] + kap * tau) / ((P.l + P.nc) + 1);
-    w.d[S_KAPOVERT] = kap / tau;
-    w.d[S_PCOST] = cx / tau;
-    w.d[S_DCOST] = -(hz + by) / tau;
-    if (w.d[S_PCOST] < 0.)
+    // ---- per instance: updateStatistics (:691-728), safeguards, exit tests, best iterate (:1010-1158).
+    //      Every warp computes the same values; warp 0 writes them back.
+    vb restore = vbset(false), save = vbset(false), fin = vbset(false), cont = vbset(false);
+    vd ftau = tau;
+    WState wsv[VEC], bsv[VEC];
+    double rtv[VEC], ppv[VEC];
+    int codev[VEC];
+    VFOR
     {
-        w.i[J_HAS_RELGAP] = 1;
-        w.d[S_RELGAP] = w.d[S_GAP] / (-w.d[S_PCOST]);
-    }
-    else if (w.d[S_DCOST] > 0.)
-    {
-        w.i[J_HAS_RELGAP] = 1;
-        w.d[S_RELGAP] = w.d[S_GAP] / w.d[S_DCOST];
-    }
-    else
-        w.i[J_HAS_RELGAP] = 0;
-    const double resx0 = ROWD(T, L.sc + S_RESX0), resy0 = ROWD(T, L.sc + S_RESY0), resz0 = ROWD(T, L.sc + S_RESZ0);
-    const double nry = p > 0 ? sqrt(r[RY2]) / dmax(resy0 + nx, 1.) : 0.;
-    const double nrz = sqrt(r[RZ2]) / dmax(resz0 + nx + ns, 1.);
-    w.d[S_PRES] = dmax(nry, nrz) / tau;
-    w.d[S_DRES] = sqrt(r[RX2]) / dmax(resx0 + ny + nz, 1.) / tau;
-    if ((hz + by) / dmax(ny + nz, 1.) < -Settings::reltol)
-    {
-        w.i[J_HAS_PINFRES] = 1;
-        w.d[S_PINFRES] = hresx / dmax(ny + nz, 1.);
-    }
-    if (cx / dmax(nx, 1.) < -Settings::reltol)
-    {
-        w.i[J_HAS_DINFRES] = 1;
-        w.d[S_DINFRES] = dmax(hresy / dmax(nx, 1.), hresz / dmax(nx + ns, 1.));
-    }
-
-    // ---- safeguards, exit tests, best iterate (:1010-1158)
-    const int iter = w.i[J_ITER];
-    double pres_prev = ROWD(T, L.sc + S_PRES_PREV);
-    int code = ST_ACTIVE;
-    bool restore = false, save = false;
-    if (act)
-    {
-        if (iter > 0 && (w.d[S_PRES] > Settings::safeguard * pres_prev || w.d[S_GAP] < 0.))
+        const int c = c_;
+        WState &w = wsv[c], &best = bsv[c];
+        ws_load(tm, T, I, L.sc, 0, 0, c, w);
+        ws_load(tm, T, I, L.sc, S_BEST, J_BEST, c, best);
+        const double tau_c = tau.v[c], kap_c = kap.v[c];
+        const double hresx = sqrt(r[HX2].v[c]), hresy = sqrt(r[HY2].v[c]), hresz = sqrt(r[HZ2].v[c]);
+        const double nx = sqrt(r[NX2].v[c]), ny = sqrt(r[NY2].v[c]), nz = sqrt(r[NZ2].v[c]), ns = sqrt(r[NS2].v[c]);
+        const double cx = r[CX].v[c], by = p > 0 ? r[BY].v[c] : 0., hz = r[HZ].v[c];
+        const double rt = kap_c + cx + by + hz;
+        w.d[S_CX] = cx;
+        w.d[S_BY] = by;
+        w.d[S_HZ] = hz;
+        w.d[S_GAP] = r[GAP].v[c];
+        w.d[S_MU] = (r[GAP].v[c] + kap_c * tau_c) / ((P.l + P.nc) + 1);
+        w.d[S_KAPOVERT] = kap_c / tau_c;
+        w.d[S_PCOST] = cx / tau_c;
+        w.d[S_DCOST] = -(hz + by) / tau_c;
+        if (w.d[S_PCOST] < 0.)
         {
-            restore = true;
-            w = best;
-            code = ws_check_exit(w, true);
-            if (code == EXIT_NOT_CONVERGED)
-                code = EXIT_NUMERICS;
+            w.i[J_HAS_RELGAP] = 1;
+            w.d[S_RELGAP] = w.d[S_GAP] / (-w.d[S_PCOST]);
+        }
+        else if (w.d[S_DCOST] > 0.)
+        {
+            w.i[J_HAS_RELGAP] = 1;
+            w.d[S_RELGAP] = w.d[S_GAP] / w.d[S_DCOST];
         }
         else
+            w.i[J_HAS_RELGAP] = 0;
+        const double resx0 = ROWC(T, L.sc + S_RESX0, c), resy0 = ROWC(T, L.sc + S_RESY0, c), resz0 = ROWC(T, L.sc + S_RESZ0, c);
+        const double nry = p > 0 ? sqrt(r[RY2].v[c]) / dmax(resy0 + nx, 1.) : 0.;
+        const double nrz = sqrt(r[RZ2].v[c]) / dmax(resz0 + nx + ns, 1.);
+        w.d[S_PRES] = dmax(nry, nrz) / tau_c;
+        w.d[S_DRES] = sqrt(r[RX2].v[c]) / dmax(resx0 + ny + nz, 1.) / tau_c;
+        if ((hz + by) / dmax(ny + nz, 1.) < -Settings::reltol)
         {
-            pres_prev = w.d[S_PRES];
-            code = ws_check_exit(w, false);
-            if (code == EXIT_NOT_CONVERGED)
+            w.i[J_HAS_PINFRES] = 1;
+            w.d[S_PINFRES] = hresx / dmax(ny + nz, 1.);
+        }
+        if (cx / dmax(nx, 1.) < -Settings::reltol)
+        {
+            w.i[J_HAS_DINFRES] = 1;
+            w.d[S_DINFRES] = dmax(hresy / dmax(nx, 1.), hresz / dmax(nx + ns, 1.));
+        }
+
+        const int iter = w.i[J_ITER];
+        double pres_prev = ROWC(T, L.sc + S_PRES_PREV, c);
+        int code = ST_ACTIVE;
+        bool rst = false, sav = false;
+        if (act.v[c])
+        {
+            if (iter > 0 && (w.d[S_PRES] > Settings::safeguard * pres_prev || w.d[S_GAP] < 0.))
             {
-                if (iter > 0 && w.d[S_STEP] == Settings::stepmin * Settings::gamma)
+                rst = true;
+                w = best;
+                code = ws_check_exit(w, true);
+                if (code == EXIT_NOT_CONVERGED)
+                    code = EXIT_NUMERICS;
+            }
+            else
+            {
+                pres_prev = w.d[S_PRES];
+                code = ws_check_exit(w, false);
+                if (code == EXIT_NOT_CONVERGED)
                 {
-                    restore = true;
-                    w = best;
-                    code = ws_check_exit(w, true);
-                    if (code == EXIT_NOT_CONVERGED)
-                        code = EXIT_NUMERICS;
-                }
-                else if (iter == Settings::iter_max)
-                {
-                    if (!ws_better(w, best))
+                    if (iter > 0 && w.d[S_STEP] == Settings::stepmin * Settings::gamma)
                     {
-                        restore = true;
-                        w = best;
-                    }
-                    code = ws_check_exit(w, true);
-                    if (code == EXIT_NOT_CONVERGED)
-                        code = EXIT_MAXIT;
-                }
-                else if (ei_isnan(w.d[S_PCOST]))
-                {
-                    if (!(iter == 0 || ws_better(w, best)))
-                    {
-                        restore = true;
+                        rst = true;
                         w = best;
                         code = ws_check_exit(w, true);
                         if (code == EXIT_NOT_CONVERGED)
                             code = EXIT_NUMERICS;
-                    } // else: the reference leaves not_converged_yet (-87) in place (:1117-1121)
+                    }
+                    else if (iter == Settings::iter_max)
+                    {
+                        if (!ws_better(w, best))
+                        {
+                            rst = true;
+                            w = best;
+                        }
+                        code = ws_check_exit(w, true);
+                        if (code == EXIT_NOT_CONVERGED)
+                            code = EXIT_MAXIT;
+                    }
+                    else if (ei_isnan(w.d[S_PCOST]))
+                    {
+                        if (!(iter == 0 || ws_better(w, best)))
+                        {
+                            rst = true;
+                            w = best;
+                            code = ws_check_exit(w, true);
+                            if (code == EXIT_NOT_CONVERGED)
+                                code = EXIT_NUMERICS;
+                        } // else: the reference leaves not_converged_yet (-87) in place (:1117-1121)
+                    }
+                    else
+                        code = ST_ACTIVE;
                 }
-                else
-                    code = ST_ACTIVE;
+            }
+            if (code == ST_ACTIVE && (iter == 0 || ws_better(w, best)))
+            {
+                sav = true;
+                best = w;
             }
         }
-        if (code == ST_ACTIVE && (iter == 0 || ws_better(w, best)))
-        {
-            save = true;
-            best = w;
-        }
+        restore.v[c] = rst;
+        save.v[c] = sav;
+        fin.v[c] = act.v[c] && code != ST_ACTIVE;
+        cont.v[c] = act.v[c] && code == ST_ACTIVE;
+        ftau.v[c] = w.d[S_TAU];
+        rtv[c] = rt;
+        ppv[c] = pres_prev;
+        codev[c] = code;
     }
-    const bool fin = act && code != ST_ACTIVE;
-    const bool cont = act && !fin;
     tm.sync(); // every warp has read the old state rows before warp 0 overwrites them
-    if (tm.wk == 0 && act)
-    {
-        ws_store(tm, T, I, L.sc, 0, 0, w);
-        if (save)
-            ws_store(tm, T, I, L.sc, S_BEST, J_BEST, best);
-        ROWD(T, L.sc + S_RT) = rt;
-        ROWD(T, L.sc + S_PRES_PREV) = pres_prev;
-        ROWD(I, J_STATUS) = code;
-    }
+    if (tm.wk == 0)
+        VFOR if (act.v[c_])
+        {
+            ws_store(tm, T, I, L.sc, 0, 0, c_, wsv[c_]);
+            if (save.v[c_])
+                ws_store(tm, T, I, L.sc, S_BEST, J_BEST, c_, bsv[c_]);
+            ROWC(T, L.sc + S_RT, c_) = rtv[c_];
+            ROWC(T, L.sc + S_PRES_PREV, c_) = ppv[c_];
+            ROWC(I, J_STATUS, c_) = codev[c_];
+        }
 
-    // ---- vector part of `w = w_best` / `w_best = w`, and backscale (:1271-1277) for finished lanes
-    const double ftau = w.d[S_TAU];
+    // ---- vector part of `w = w_best` / `w_best = w`, and backscale (:1271-1277) for finished instances
     if (tm.any(restore || save || fin))
     {
         for (int q = tm.wk; q < P.N; q += tm.nwk)
         {
-            double v = ROWD(T, L.w + q);
-            if (restore)
-                v = ROWD(T, L.wb + q);
-            if (save)
-                ROWD(T, L.wb + q) = v;
-            if (fin)
-            {
-                const double eq = q < n ? EI_LDG(P.xeq + q) : (q < zb ? EI_LDG(P.Aeq + q - n) : EI_LDG(P.GeqE + q - zb));
-                v = v / (eq * ftau);
-            }
-            if (restore || fin)
-                ROWD(T, L.w + q) = v;
+            vd v = ROWD(T, L.w + q);
+            v = vsel(restore, ROWD(T, L.wb + q), v);
+            ROWD(T, L.wb + q) = vsel(save, v, ROWD(T, L.wb + q));
+            const double eq = q < n ? EI_LDG(P.xeq + q) : (q < zb ? EI_LDG(P.Aeq + q - n) : EI_LDG(P.GeqE + q - zb));
+            v = vsel(fin, v / (eq * ftau), v);
+            ROWD(T, L.w + q) = v;
         }
         for (int e = tm.wk; e < P.mt; e += tm.nwk)
         {
-            double sv = ROWD(T, L.s + e), lv = ROWD(T, L.lam + e);
-            if (restore)
-            {
-                sv = ROWD(T, L.bs + e);
-                lv = ROWD(T, L.blam + e);
-            }
-            if (save)
-            {
-                ROWD(T, L.bs + e) = sv;
-                ROWD(T, L.blam + e) = lv;
-            }
-            if (fin)
-                sv = sv * (EI_LDG(P.GeqE + e) / ftau);
-            if (restore || fin)
-            {
-                ROWD(T, L.s + e) = sv;
-                ROWD(T, L.lam + e) = lv;
-            }
+            vd sv = ROWD(T, L.s + e), lv = ROWD(T, L.lam + e);
+            sv = vsel(restore, ROWD(T, L.bs + e), sv);
+            lv = vsel(restore, ROWD(T, L.blam + e), lv);
+            ROWD(T, L.bs + e) = vsel(save, sv, ROWD(T, L.bs + e));
+            ROWD(T, L.blam + e) = vsel(save, lv, ROWD(T, L.blam + e));
+            sv = vsel(fin, sv * (EI_LDG(P.GeqE + e) / ftau), sv);
+            ROWD(T, L.s + e) = sv;
+            ROWD(T, L.lam + e) = lv;
         }
     }
     if (!tm.any(cont))
@@ -1412,13 +1489,16 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
 #ifndef EICOS_EMU
     if (tm.wk == 0 && a.active_count)
     {
-        const unsigned bal = __ballot_sync(0xffffffffu, cont);
-        if (tm.lane == 0)
-            atomicAdd(a.active_count, (unsigned)__popc(bal));
+        int mine = 0;
+        VFOR mine += cont.v[c_] ? 1 : 0;
+        for (int o = 16; o > 0; o >>= 1)
+            mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if (tm.pl == 0)
+            atomicAdd(a.active_count, (unsigned)mine);
     }
 #else
-    if (tm.wk == 0 && a.active_count && cont)
-        *a.active_count += 1;
+    if (tm.wk == 0 && a.active_count)
+        VFOR if (cont.v[c_]) *a.active_count += 1;
 #endif
 
     // ---- updateScalings (:411-479); its return value is ignored by the caller (:1160), so after a
@@ -1426,80 +1506,84 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
     const int sz = L.w + zb; // z rows of the iterate
     for (int k = tm.wk; k < P.l; k += tm.nwk)
     {
-        const double v = ROWD(T, L.s + k) / ROWD(T, sz + k);
-        if (cont)
-        {
-            ROWD(T, L.lpv + k) = v;
-            ROWD(T, L.lpw + k) = sqrt(v);
-        }
+        const vd v = vd(ROWD(T, L.s + k)) / vd(ROWD(T, sz + k));
+        ROWD(T, L.lpv + k) = vsel(cont, v, ROWD(T, L.lpv + k));
+        ROWD(T, L.lpw + k) = vsel(cont, vsqrt(v), ROWD(T, L.lpw + k));
     }
-    int first_fail = P.nc;
+    vb nofail = vbset(true);
     if (P.nc > 0)
     {
-        double ff[1] = {(double)P.nc};
+        vd ff[1] = {vset((double)P.nc)};
         for (int c = tm.wk; c < P.nc; c += tm.nwk)
         {
-            const int ks = EI_LDG(P.cone_k + c);
-            const ConeScaling cs = cone_scaling(tm, T, L.s + ks, sz + ks, EI_LDG(P.cone_dim + c));
-            if (cs.stage != 0)
-                ff[0] = dmin(ff[0], (double)c);
+            const int ks = EI_LDG(P.cone_k + c), d = EI_LDG(P.cone_dim + c);
+            VFOR
+            {
+                const ConeScaling cs = cone_scaling(tm, T, L.s + ks, sz + ks, d, c_);
+                if (cs.stage != 0)
+                    ff[0].v[c_] = dmin(ff[0].v[c_], (double)c);
+            }
         }
         team_min<1>(tm, ff);
-        first_fail = (int)ff[0];
+        VFOR nofail.v[c_] = (int)ff[0].v[c_] == P.nc;
         for (int c = tm.wk; c < P.nc; c += tm.nwk)
         {
-            if (!cont || c > first_fail)
-                continue; // (divergent per lane, cone-local work only)
             const int d = EI_LDG(P.cone_dim + c), ks = EI_LDG(P.cone_k + c), qo = EI_LDG(P.cone_q + c);
-            const ConeScaling cs = cone_scaling(tm, T, L.s + ks, sz + ks, d);
-            if (cs.stage == 1)
-                continue;
-            double *cp = T + (size_t)(L.cpar + c * CP_COUNT) * TILE + tm.lane;
-            cp[CP_ETA2 * TILE] = cs.eta2;
-            cp[CP_ETA * TILE] = cs.eta;
-            for (int k = 1; k < d; k++)
-                ROWD(T, L.cq + qo + k - 1) = (0.5 / cs.gamma) * (ROWD(T, L.s + ks + k) / cs.snorm - ROWD(T, sz + ks + k) / cs.znorm);
-            if (cs.stage == 2)
-                continue;
-            cp[CP_D1 * TILE] = cs.d1;
-            cp[CP_U0 * TILE] = cs.u0;
-            cp[CP_U1 * TILE] = cs.u1;
-            cp[CP_V1 * TILE] = cs.v1;
-            cp[CP_A * TILE] = cs.a;
-            cp[CP_W * TILE] = cs.w;
+            const int cp = L.cpar + c * CP_COUNT;
+            VFOR
+            {
+                if (!cont.v[c_] || c > (int)ff[0].v[c_])
+                    continue;
+                const ConeScaling cs = cone_scaling(tm, T, L.s + ks, sz + ks, d, c_);
+                if (cs.stage == 1)
+                    continue;
+                ROWC(T, cp + CP_ETA2, c_) = cs.eta2;
+                ROWC(T, cp + CP_ETA, c_) = cs.eta;
+                for (int k = 1; k < d; k++)
+                    ROWC(T, L.cq + qo + k - 1, c_) = (0.5 / cs.gamma) * (ROWC(T, L.s + ks + k, c_) / cs.snorm - ROWC(T, sz + ks + k, c_) / cs.znorm);
+                if (cs.stage == 2)
+                    continue;
+                ROWC(T, cp + CP_D1, c_) = cs.d1;
+                ROWC(T, cp + CP_U0, c_) = cs.u0;
+                ROWC(T, cp + CP_U1, c_) = cs.u1;
+                ROWC(T, cp + CP_V1, c_) = cs.v1;
+                ROWC(T, cp + CP_A, c_) = cs.a;
+                ROWC(T, cp + CP_W, c_) = cs.w;
+            }
         }
         tm.sync();
     }
-    cone_scale(tm, a, T, sz, L.lam, cont && first_fail == P.nc);
+    cone_scale(tm, a, T, sz, L.lam, cont && nofail);
 
     // ---- updateKKTScalings (:1691-1732) into the V rows, RHSaffine (:1670-1689) into rhs2
     const double delta = Settings::deltastat;
     for (int k = tm.wk; k < P.l; k += tm.nwk)
-        ROWD(T, L.V + k) = -ROWD(T, L.lpv + k) - delta;
+        ROWD(T, L.V + k) = -vd(ROWD(T, L.lpv + k)) - delta;
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     {
         const int d = EI_LDG(P.cone_dim + c), ks = EI_LDG(P.cone_k + c), qo = EI_LDG(P.cone_q + c);
-        const double *cp = T + (size_t)(L.cpar + c * CP_COUNT) * TILE + tm.lane;
-        const double eta2 = cp[CP_ETA2 * TILE], d1 = cp[CP_D1 * TILE], u0 = cp[CP_U0 * TILE];
-        const double u1 = cp[CP_U1 * TILE], v1 = cp[CP_V1 * TILE];
+        const int cp = L.cpar + c * CP_COUNT;
+        const vd eta2 = ROWD(T, cp + CP_ETA2), d1 = ROWD(T, cp + CP_D1), u0 = ROWD(T, cp + CP_U0);
+        const vd u1 = ROWD(T, cp + CP_U1), v1 = ROWD(T, cp + CP_V1);
         // cones before c contributed sum(3 dim + 1) V entries; ks - 2c - l = sum of their dims
-        int vb = L.V + P.l + 3 * (ks - 2 * c - P.l) + c;
-        ROWD(T, vb++) = -eta2 * d1 - delta;
+        int vb_ = L.V + P.l + 3 * (ks - 2 * c - P.l) + c;
+        ROWD(T, vb_++) = -(eta2 * d1) - delta;
         for (int k = 1; k < d; k++)
-            ROWD(T, vb++) = -eta2 - delta;
-        ROWD(T, vb++) = -eta2;
+            ROWD(T, vb_++) = -eta2 - delta;
+        ROWD(T, vb_++) = -eta2;
         for (int k = 1; k < d; k++)
-            ROWD(T, vb++) = -eta2 * v1 * ROWD(T, L.cq + qo + k - 1);
-        ROWD(T, vb++) = eta2 + delta;
-        ROWD(T, vb++) = -eta2 * u0;
+            ROWD(T, vb_++) = -(eta2 * v1) * vd(ROWD(T, L.cq + qo + k - 1));
+        ROWD(T, vb_++) = eta2 + delta;
+        ROWD(T, vb_++) = -(eta2 * u0);
         for (int k = 1; k < d; k++)
-            ROWD(T, vb++) = -eta2 * u1 * ROWD(T, L.cq + qo + k - 1);
+            ROWD(T, vb_++) = -(eta2 * u1) * vd(ROWD(T, L.cq + qo + k - 1));
     }
-    for (int q = tm.wk; q < P.N; q += tm.nwk)
-    { // [rx; -ry; s - rz], the slot rows of s and rz are zero
-        const double rv = ROWD(T, L.r + q);
-        ROWD(T, L.rhs2 + q) = q < n ? rv : (q < zb ? -rv : ROWD(T, L.s + q - zb) - rv);
-    }
+    for (int q = tm.wk; q < n; q += tm.nwk)
+        ROWD(T, L.rhs2 + q) = ROWD(T, L.r + q);
+    for (int q = n + tm.wk; q < zb; q += tm.nwk)
+        ROWD(T, L.rhs2 + q) = -vd(ROWD(T, L.r + q));
+    for (int q = zb + tm.wk; q < P.N; q += tm.nwk) // s - rz; the slot rows of s and rz are zero
+        ROWD(T, L.rhs2 + q) = vd(ROWD(T, L.s + q - zb)) - vd(ROWD(T, L.r + q));
 }
 
 // ------------------------------------------------------------------ affine step -> centering -> combined RHS
@@ -1507,136 +1591,144 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
 EI_DEV void tile_mid(const Team &tm, const KArgs &a, int tile)
 {
     const TileMem t = tile_mem(a, tile);
-    const bool act = lane_active(tm, t);
+    const vb act = lane_active(tm, t);
     if (!tm.any(act))
         return;
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     double *T = t.T;
     const int n = P.n, p = P.p, zb = P.n + P.p;
-    const double tau = ROWD(T, L.sc + S_TAU), kap = ROWD(T, L.sc + S_KAP), rt = ROWD(T, L.sc + S_RT);
-    const double mu = ROWD(T, L.sc + S_MU);
+    const vd tau = ROWD(T, L.sc + S_TAU), kap = ROWD(T, L.sc + S_KAP), rt = ROWD(T, L.sc + S_RT);
+    const vd mu = ROWD(T, L.sc + S_MU);
 
     // c'dx, b'dy, h'dz for both solutions; the slot rows of h are zero but are skipped anyway
-    double dt[6] = {0, 0, 0, 0, 0, 0};
+    vd dt[6];
+    for (int k = 0; k < 6; k++)
+        dt[k] = vset(0.0);
     for (int q = tm.wk; q < n; q += tm.nwk)
     {
-        const double cv = ROWD(T, L.chb + q);
-        dt[0] += cv * ROWD(T, L.sol1 + q);
-        dt[3] += cv * ROWD(T, L.sol2 + q);
+        const vd cv = ROWD(T, L.chb + q);
+        dt[0] += cv * vd(ROWD(T, L.sol1 + q));
+        dt[3] += cv * vd(ROWD(T, L.sol2 + q));
     }
     for (int q = n + tm.wk; q < zb; q += tm.nwk)
     {
-        const double cv = ROWD(T, L.chb + q);
-        dt[1] += cv * ROWD(T, L.sol1 + q);
-        dt[4] += cv * ROWD(T, L.sol2 + q);
+        const vd cv = ROWD(T, L.chb + q);
+        dt[1] += cv * vd(ROWD(T, L.sol1 + q));
+        dt[4] += cv * vd(ROWD(T, L.sol2 + q));
     }
     for (int q = zb + tm.wk; q < zb + P.l; q += tm.nwk)
     {
-        const double cv = ROWD(T, L.chb + q);
-        dt[2] += cv * ROWD(T, L.sol1 + q);
-        dt[5] += cv * ROWD(T, L.sol2 + q);
+        const vd cv = ROWD(T, L.chb + q);
+        dt[2] += cv * vd(ROWD(T, L.sol1 + q));
+        dt[5] += cv * vd(ROWD(T, L.sol2 + q));
     }
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     {
         const int d = EI_LDG(P.cone_dim + c), kb = zb + EI_LDG(P.cone_k + c);
         for (int k = 0; k < d; k++)
         {
-            const double hv = ROWD(T, L.chb + kb + k);
-            dt[2] += hv * ROWD(T, L.sol1 + kb + k);
-            dt[5] += hv * ROWD(T, L.sol2 + kb + k);
+            const vd hv = ROWD(T, L.chb + kb + k);
+            dt[2] += hv * vd(ROWD(T, L.sol1 + kb + k));
+            dt[5] += hv * vd(ROWD(T, L.sol2 + kb + k));
         }
     }
     team_sum<6>(tm, dt);
-    const double dtau_denom = kap / tau - dt[0] - dt[1] - dt[2];
-    const double dtauaff = (rt - kap + dt[3] + dt[4] + dt[5]) / dtau_denom;
+    const vd dtau_denom = kap / tau - dt[0] - dt[1] - dt[2];
+    const vd dtauaff = (rt - kap + dt[3] + dt[4] + dt[5]) / dtau_denom;
     for (int e = tm.wk; e < P.mt; e += tm.nwk) // dz2 += dtauaff * dz1 (slot rows are never read again)
-        ROWD(T, L.sol2 + zb + e) += dtauaff * ROWD(T, L.sol1 + zb + e);
+        ROWD(T, L.sol2 + zb + e) += dtauaff * vd(ROWD(T, L.sol1 + zb + e));
     tm.sync();
-    cone_scale(tm, a, T, L.sol2 + zb, L.wdz, true);
+    cone_scale(tm, a, T, L.sol2 + zb, L.wdz, vbset(true));
     tm.sync();
     for (int e = tm.wk; e < P.mt; e += tm.nwk)
-        ROWD(T, L.dsw + e) = -ROWD(T, L.wdz + e) - ROWD(T, L.lam + e);
+        ROWD(T, L.dsw + e) = -vd(ROWD(T, L.wdz + e)) - vd(ROWD(T, L.lam + e));
     tm.sync();
-    const double dkapaff = -kap - kap / tau * dtauaff;
-    const double step_aff = line_search(tm, a, T, L.lam, L.dsw, L.wdz, tau, dtauaff, kap, dkapaff);
-    const double om = 1. - step_aff;
-    double sigma = om * om * om; // std::pow(x, 3)
-    if (sigma < Settings::sigmamin)
-        sigma = Settings::sigmamin;
-    else if (Settings::sigmamax < sigma)
-        sigma = Settings::sigmamax;
-    if (tm.wk == 0 && act)
+    const vd dkapaff = -kap - kap / tau * dtauaff;
+    const vd step_aff = line_search(tm, a, T, L.lam, L.dsw, L.wdz, tau, dtauaff, kap, dkapaff);
+    vd sigma;
+    VFOR
     {
-        ROWD(T, L.sc + S_DTAU_DENOM) = dtau_denom;
-        ROWD(T, L.sc + S_DTAUAFF) = dtauaff;
-        ROWD(T, L.sc + S_DKAPAFF) = dkapaff;
-        ROWD(T, L.sc + S_STEP_AFF) = step_aff;
-        ROWD(T, L.sc + S_SIGMA) = sigma;
+        const double om = 1. - step_aff.v[c_];
+        double sg = om * om * om; // std::pow(x, 3)
+        if (sg < Settings::sigmamin)
+            sg = Settings::sigmamin;
+        else if (Settings::sigmamax < sg)
+            sg = Settings::sigmamax;
+        sigma.v[c_] = sg;
     }
+    if (tm.wk == 0)
+        VFOR if (act.v[c_])
+        {
+            ROWC(T, L.sc + S_DTAU_DENOM, c_) = dtau_denom.v[c_];
+            ROWC(T, L.sc + S_DTAUAFF, c_) = dtauaff.v[c_];
+            ROWC(T, L.sc + S_DKAPAFF, c_) = dkapaff.v[c_];
+            ROWC(T, L.sc + S_STEP_AFF, c_) = step_aff.v[c_];
+            ROWC(T, L.sc + S_SIGMA, c_) = sigma.v[c_];
+        }
 
     // RHScombined
-    const double sigmamu = sigma * mu, oms = 1. - sigma;
+    const vd sigmamu = sigma * mu, oms = 1. - sigma;
     for (int r = tm.wk; r < n + p; r += tm.nwk)
         ROWD(T, L.rhs2 + r) *= oms;
     for (int k = tm.wk; k < P.l; k += tm.nwk)
     {
-        const double lk = ROWD(T, L.lam + k);
-        double d1 = lk * lk;
-        d1 += ROWD(T, L.dsw + k) * ROWD(T, L.wdz + k);
+        const vd lk = ROWD(T, L.lam + k);
+        vd d1 = lk * lk;
+        d1 += vd(ROWD(T, L.dsw + k)) * vd(ROWD(T, L.wdz + k));
         d1 -= sigmamu;
-        const double q = d1 / lk; // conicDivision, LP part
+        const vd q = d1 / lk; // conicDivision, LP part
         ROWD(T, L.dsw + k) = q;
-        ROWD(T, L.rhs2 + zb + k) = -oms * ROWD(T, L.r + zb + k) + ROWD(T, L.lpw + k) * q;
+        ROWD(T, L.rhs2 + zb + k) = -oms * vd(ROWD(T, L.r + zb + k)) + vd(ROWD(T, L.lpw + k)) * q;
     }
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     {
         const int d = EI_LDG(P.cone_dim + c), zs = EI_LDG(P.cone_k + c), qo = EI_LDG(P.cone_q + c);
         const int kb = zb + zs;
-        const double *cp = T + (size_t)(L.cpar + c * CP_COUNT) * TILE + tm.lane;
-        const double eta = cp[CP_ETA * TILE], ca = cp[CP_A * TILE];
+        const int cp = L.cpar + c * CP_COUNT;
+        const vd eta = ROWD(T, cp + CP_ETA), ca = ROWD(T, cp + CP_A);
         // ds1 = lambda o lambda ; ds2 = (W\ds_aff) o (W dz_aff)
-        const double l0 = ROWD(T, L.lam + zs), u0 = ROWD(T, L.dsw + zs), v0 = ROWD(T, L.wdz + zs);
-        double ll = 0.0, uv = 0.0;
+        const vd l0 = ROWD(T, L.lam + zs), u0 = ROWD(T, L.dsw + zs), v0 = ROWD(T, L.wdz + zs);
+        vd ll = vset(0.0), uv = vset(0.0);
         for (int k = 0; k < d; k++)
         {
-            const double lk = ROWD(T, L.lam + zs + k);
+            const vd lk = ROWD(T, L.lam + zs + k);
             ll += lk * lk;
-            uv += ROWD(T, L.dsw + zs + k) * ROWD(T, L.wdz + zs + k);
+            uv += vd(ROWD(T, L.dsw + zs + k)) * vd(ROWD(T, L.wdz + zs + k));
         }
-        double w0 = ll - sigmamu;
+        vd w0 = ll - sigmamu;
         w0 += uv;
         ROWD(T, L.ds1 + zs) = w0;
         for (int k = 1; k < d; k++)
         {
-            const double lk = ROWD(T, L.lam + zs + k);
-            double v = l0 * lk + l0 * lk;
-            v += u0 * ROWD(T, L.wdz + zs + k) + v0 * ROWD(T, L.dsw + zs + k);
+            const vd lk = ROWD(T, L.lam + zs + k);
+            vd v = l0 * lk + l0 * lk;
+            v += u0 * vd(ROWD(T, L.wdz + zs + k)) + v0 * vd(ROWD(T, L.dsw + zs + k));
             ROWD(T, L.ds1 + zs + k) = v;
         }
         // dsw = lambda \ ds1
-        double rho = 0.0, zeta = 0.0;
+        vd rho = vset(0.0), zeta = vset(0.0);
         for (int k = 1; k < d; k++)
         {
-            const double lk = ROWD(T, L.lam + zs + k);
+            const vd lk = ROWD(T, L.lam + zs + k);
             rho += lk * lk;
-            zeta += lk * ROWD(T, L.ds1 + zs + k);
+            zeta += lk * vd(ROWD(T, L.ds1 + zs + k));
         }
         rho = l0 * l0 - rho;
-        const double factor = (zeta / l0 - w0) / rho;
-        const double q0 = (l0 * w0 - zeta) / rho;
+        const vd factor = (zeta / l0 - w0) / rho;
+        const vd q0 = (l0 * w0 - zeta) / rho;
         ROWD(T, L.dsw + zs) = q0;
         for (int k = 1; k < d; k++)
-            ROWD(T, L.dsw + zs + k) = factor * ROWD(T, L.lam + zs + k) + ROWD(T, L.ds1 + zs + k) / l0;
+            ROWD(T, L.dsw + zs + k) = factor * vd(ROWD(T, L.lam + zs + k)) + vd(ROWD(T, L.ds1 + zs + k)) / l0;
         // ds1 = W * dsw, then the cone rows of rhs2
-        double zt = 0.0;
+        vd zt = vset(0.0);
         for (int k = 1; k < d; k++)
-            zt += ROWD(T, L.cq + qo + k - 1) * ROWD(T, L.dsw + zs + k);
-        const double fz = q0 + zt / (1. + ca);
-        ROWD(T, L.rhs2 + kb) = -oms * ROWD(T, L.r + kb) + eta * (ca * q0 + zt);
+            zt += vd(ROWD(T, L.cq + qo + k - 1)) * vd(ROWD(T, L.dsw + zs + k));
+        const vd fz = q0 + zt / (1. + ca);
+        ROWD(T, L.rhs2 + kb) = -oms * vd(ROWD(T, L.r + kb)) + eta * (ca * q0 + zt);
         for (int k = 1; k < d; k++)
-            ROWD(T, L.rhs2 + kb + k) = -oms * ROWD(T, L.r + kb + k) +
-                                       eta * (ROWD(T, L.dsw + zs + k) + fz * ROWD(T, L.cq + qo + k - 1));
+            ROWD(T, L.rhs2 + kb + k) = -oms * vd(ROWD(T, L.r + kb + k)) +
+                                       eta * (vd(ROWD(T, L.dsw + zs + k)) + fz * vd(ROWD(T, L.cq + qo + k - 1)));
         ROWD(T, L.rhs2 + kb + d) = 0.0;
         ROWD(T, L.rhs2 + kb + d + 1) = 0.0;
     }
@@ -1646,65 +1738,64 @@ EI_DEV void tile_mid(const Team &tm, const KArgs &a, int tile)
 EI_DEV void tile_tail(const Team &tm, const KArgs &a, int tile)
 {
     const TileMem t = tile_mem(a, tile);
-    const bool act = lane_active(tm, t);
+    const vb act = lane_active(tm, t);
     if (!tm.any(act))
         return;
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     double *T = t.T;
     const int n = P.n, zb = P.n + P.p;
-    const double tau = ROWD(T, L.sc + S_TAU), kap = ROWD(T, L.sc + S_KAP), rt = ROWD(T, L.sc + S_RT);
-    const double mu = ROWD(T, L.sc + S_MU), sigma = ROWD(T, L.sc + S_SIGMA);
-    const double dtau_denom = ROWD(T, L.sc + S_DTAU_DENOM), dtauaff = ROWD(T, L.sc + S_DTAUAFF);
-    const double dkapaff = ROWD(T, L.sc + S_DKAPAFF);
+    const vd tau = ROWD(T, L.sc + S_TAU), kap = ROWD(T, L.sc + S_KAP), rt = ROWD(T, L.sc + S_RT);
+    const vd mu = ROWD(T, L.sc + S_MU), sigma = ROWD(T, L.sc + S_SIGMA);
+    const vd dtau_denom = ROWD(T, L.sc + S_DTAU_DENOM), dtauaff = ROWD(T, L.sc + S_DTAUAFF);
+    const vd dkapaff = ROWD(T, L.sc + S_DKAPAFF);
 
-    double dt[3] = {0, 0, 0};
+    vd dt[3] = {vset(0.0), vset(0.0), vset(0.0)};
     for (int q = tm.wk; q < n; q += tm.nwk)
-        dt[0] += ROWD(T, L.chb + q) * ROWD(T, L.sol2 + q);
+        dt[0] += vd(ROWD(T, L.chb + q)) * vd(ROWD(T, L.sol2 + q));
     for (int q = n + tm.wk; q < zb; q += tm.nwk)
-        dt[1] += ROWD(T, L.chb + q) * ROWD(T, L.sol2 + q);
+        dt[1] += vd(ROWD(T, L.chb + q)) * vd(ROWD(T, L.sol2 + q));
     for (int q = zb + tm.wk; q < zb + P.l; q += tm.nwk)
-        dt[2] += ROWD(T, L.chb + q) * ROWD(T, L.sol2 + q);
+        dt[2] += vd(ROWD(T, L.chb + q)) * vd(ROWD(T, L.sol2 + q));
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     {
         const int d = EI_LDG(P.cone_dim + c), kb = zb + EI_LDG(P.cone_k + c);
         for (int k = 0; k < d; k++)
-            dt[2] += ROWD(T, L.chb + kb + k) * ROWD(T, L.sol2 + kb + k);
+            dt[2] += vd(ROWD(T, L.chb + kb + k)) * vd(ROWD(T, L.sol2 + kb + k));
     }
     team_sum<3>(tm, dt);
-    const double bkap = kap * tau + dkapaff * dtauaff - sigma * mu;
-    const double dtau = ((1. - sigma) * rt - bkap / tau + dt[0] + dt[1] + dt[2]) / dtau_denom;
+    const vd bkap = kap * tau + dkapaff * dtauaff - sigma * mu;
+    const vd dtau = ((1. - sigma) * rt - bkap / tau + dt[0] + dt[1] + dt[2]) / dtau_denom;
     for (int r = tm.wk; r < P.N; r += tm.nwk)
-        ROWD(T, L.sol2 + r) += dtau * ROWD(T, L.sol1 + r);
+        ROWD(T, L.sol2 + r) += dtau * vd(ROWD(T, L.sol1 + r));
     tm.sync();
-    cone_scale(tm, a, T, L.sol2 + zb, L.wdz, true);
+    cone_scale(tm, a, T, L.sol2 + zb, L.wdz, vbset(true));
     tm.sync();
     for (int e = tm.wk; e < P.mt; e += tm.nwk)
-        ROWD(T, L.dsw + e) = -(ROWD(T, L.dsw + e) + ROWD(T, L.wdz + e));
+        ROWD(T, L.dsw + e) = -(vd(ROWD(T, L.dsw + e)) + vd(ROWD(T, L.wdz + e)));
     tm.sync();
-    const double dkap = -(bkap + kap * dtau) / tau;
-    const double step = Settings::gamma * line_search(tm, a, T, L.lam, L.dsw, L.wdz, tau, dtau, kap, dkap);
-    cone_scale(tm, a, T, L.dsw, L.dsaff, true);
+    const vd dkap = -(bkap + kap * dtau) / tau;
+    const vd step = Settings::gamma * line_search(tm, a, T, L.lam, L.dsw, L.wdz, tau, dtau, kap, dkap);
+    cone_scale(tm, a, T, L.dsw, L.dsaff, vbset(true));
     tm.sync();
-    if (!act)
-        return; // no barriers below
     for (int q = tm.wk; q < zb + P.l; q += tm.nwk)
-        ROWD(T, L.w + q) += step * ROWD(T, L.sol2 + q);
+        ROWD(T, L.w + q) = vsel(act, vd(ROWD(T, L.w + q)) + step * vd(ROWD(T, L.sol2 + q)), ROWD(T, L.w + q));
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     { // cone rows of z; the expansion slots of the iterate stay zero
         const int d = EI_LDG(P.cone_dim + c), kb = zb + EI_LDG(P.cone_k + c);
         for (int k = 0; k < d; k++)
-            ROWD(T, L.w + kb + k) += step * ROWD(T, L.sol2 + kb + k);
+            ROWD(T, L.w + kb + k) = vsel(act, vd(ROWD(T, L.w + kb + k)) + step * vd(ROWD(T, L.sol2 + kb + k)), ROWD(T, L.w + kb + k));
     }
     for (int e = tm.wk; e < P.mt; e += tm.nwk)
-        ROWD(T, L.s + e) += step * ROWD(T, L.dsaff + e);
+        ROWD(T, L.s + e) = vsel(act, vd(ROWD(T, L.s + e)) + step * vd(ROWD(T, L.dsaff + e)), ROWD(T, L.s + e));
     if (tm.wk == 0)
-    {
-        ROWD(T, L.sc + S_KAP) = kap + step * dkap;
-        ROWD(T, L.sc + S_TAU) = tau + step * dtau;
-        ROWD(T, L.sc + S_STEP) = step;
-        ROWD(t.I, J_ITER) += 1;
-    }
+        VFOR if (act.v[c_])
+        {
+            ROWC(T, L.sc + S_KAP, c_) = kap.v[c_] + step.v[c_] * dkap.v[c_];
+            ROWC(T, L.sc + S_TAU, c_) = tau.v[c_] + step.v[c_] * dtau.v[c_];
+            ROWC(T, L.sc + S_STEP, c_) = step.v[c_];
+            ROWC(t.I, J_ITER, c_) += 1;
+        }
 }
 
 // ------------------------------------------------------------------ data in / results out
@@ -1716,25 +1807,28 @@ EI_DEV void tile_load(const Team &tm, const KArgs &a, int tile)
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     const int n = P.n, zb = P.n + P.p;
-    int inst = tile * TILE + tm.lane;
-    if (inst >= a.batch)
-        inst = a.batch - 1; // padding lanes replay the last instance; their results are never stored
-    const size_t g = (size_t)a.first + inst;
-    for (int j = tm.wk; j < n; j += tm.nwk)
+    VFOR
     {
-        const double v = a.in_c ? a.in_c[g * n + j] : EI_LDG(a.base_c + j);
-        ROWD(t.T, L.chb + j) = a.pre_equilibrated ? v : v / EI_LDG(P.xeq + j);
-    }
-    for (int i = tm.wk; i < P.p; i += tm.nwk)
-    {
-        const double v = a.in_b ? a.in_b[g * P.p + i] : EI_LDG(a.base_b + i);
-        ROWD(t.T, L.chb + n + i) = a.pre_equilibrated ? v : v / EI_LDG(P.Aeq + i);
-    }
-    for (int i = tm.wk; i < P.m; i += tm.nwk)
-    {
-        const double v = a.in_h ? a.in_h[g * P.m + i] : EI_LDG(a.base_h + i);
-        const int e = EI_LDG(P.zk + i);
-        ROWD(t.T, L.chb + zb + e) = a.pre_equilibrated ? v : v / EI_LDG(P.GeqE + e);
+        int inst = tile * TILE + tm.lane + c_;
+        if (inst >= a.batch)
+            inst = a.batch - 1; // padding instances replay the last one; their results are never stored
+        const size_t g = (size_t)a.first + inst;
+        for (int j = tm.wk; j < n; j += tm.nwk)
+        {
+            const double v = a.in_c ? a.in_c[g * n + j] : EI_LDG(a.base_c + j);
+            ROWC(t.T, L.chb + j, c_) = a.pre_equilibrated ? v : v / EI_LDG(P.xeq + j);
+        }
+        for (int i = tm.wk; i < P.p; i += tm.nwk)
+        {
+            const double v = a.in_b ? a.in_b[g * P.p + i] : EI_LDG(a.base_b + i);
+            ROWC(t.T, L.chb + n + i, c_) = a.pre_equilibrated ? v : v / EI_LDG(P.Aeq + i);
+        }
+        for (int i = tm.wk; i < P.m; i += tm.nwk)
+        {
+            const double v = a.in_h ? a.in_h[g * P.m + i] : EI_LDG(a.base_h + i);
+            const int e = EI_LDG(P.zk + i);
+            ROWC(t.T, L.chb + zb + e, c_) = a.pre_equilibrated ? v : v / EI_LDG(P.GeqE + e);
+        }
     }
 }
 
@@ -1744,34 +1838,37 @@ EI_DEV void tile_store(const Team &tm, const KArgs &a, int tile)
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     const int n = P.n, zb = P.n + P.p;
-    const int inst = tile * TILE + tm.lane;
-    if (inst >= a.batch)
-        return;
-    const size_t g = (size_t)a.first + inst;
-    if (a.out_x)
-        for (int j = tm.wk; j < n; j += tm.nwk)
-            a.out_x[g * n + j] = ROWD(t.T, L.w + j);
-    if (a.out_y)
-        for (int i = tm.wk; i < P.p; i += tm.nwk)
-            a.out_y[g * P.p + i] = ROWD(t.T, L.w + n + i);
-    if (a.out_z)
-        for (int i = tm.wk; i < P.m; i += tm.nwk)
-            a.out_z[g * P.m + i] = ROWD(t.T, L.w + zb + EI_LDG(P.zk + i));
-    if (a.out_s)
-        for (int i = tm.wk; i < P.m; i += tm.nwk)
-            a.out_s[g * P.m + i] = ROWD(t.T, L.s + EI_LDG(P.zk + i));
-    if (tm.wk == 0)
+    VFOR
     {
-        if (a.out_exit)
-            a.out_exit[g] = ROWD(t.I, J_STATUS);
-        if (a.out_iter)
-            a.out_iter[g] = ROWD(t.I, J_ITER);
-        if (a.out_info)
-            for (int k = 0; k < S_WORK_END; k++)
-                a.out_info[g * S_WORK_END + k] = ROWD(t.T, L.sc + k);
-        if (a.out_iinfo)
-            for (int k = 0; k < J_WORK_END; k++)
-                a.out_iinfo[g * J_WORK_END + k] = ROWD(t.I, k);
+        const int inst = tile * TILE + tm.lane + c_;
+        if (inst >= a.batch)
+            continue;
+        const size_t g = (size_t)a.first + inst;
+        if (a.out_x)
+            for (int j = tm.wk; j < n; j += tm.nwk)
+                a.out_x[g * n + j] = ROWC(t.T, L.w + j, c_);
+        if (a.out_y)
+            for (int i = tm.wk; i < P.p; i += tm.nwk)
+                a.out_y[g * P.p + i] = ROWC(t.T, L.w + n + i, c_);
+        if (a.out_z)
+            for (int i = tm.wk; i < P.m; i += tm.nwk)
+                a.out_z[g * P.m + i] = ROWC(t.T, L.w + zb + EI_LDG(P.zk + i), c_);
+        if (a.out_s)
+            for (int i = tm.wk; i < P.m; i += tm.nwk)
+                a.out_s[g * P.m + i] = ROWC(t.T, L.s + EI_LDG(P.zk + i), c_);
+        if (tm.wk == 0)
+        {
+            if (a.out_exit)
+                a.out_exit[g] = ROWC(t.I, J_STATUS, c_);
+            if (a.out_iter)
+                a.out_iter[g] = ROWC(t.I, J_ITER, c_);
+            if (a.out_info)
+                for (int k = 0; k < S_WORK_END; k++)
+                    a.out_info[g * S_WORK_END + k] = ROWC(t.T, L.sc + k, c_);
+            if (a.out_iinfo)
+                for (int k = 0; k < J_WORK_END; k++)
+                    a.out_iinfo[g * J_WORK_END + k] = ROWC(t.I, k, c_);
+        }
     }
 }
 
