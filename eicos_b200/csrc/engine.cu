@@ -25,9 +25,9 @@ namespace eicos
         tm.wk = threadIdx.x >> 5;                                                              \
         tm.nwk = blockDim.x >> 5;                                                              \
         tm.red = smem;                                                                         \
-        tm.stage = smem + (size_t)tm.nwk * KRED * TILE + (size_t)tm.wk * STAGE_SLOTS * TILE + tm.lane; \
+        tm.stage = smem + (size_t)tm.nwk * KRED * TILE + (size_t)tm.wk * 2 * STAGE_SLOTS * TILE + tm.lane; \
         tm.acc = a.acc_global ? a.acc_global + (size_t)blockIdx.x * tm.nwk * a.P.maxcol * TILE \
-                              : smem + (size_t)tm.nwk * (KRED + STAGE_SLOTS) * TILE;           \
+                              : smem + (size_t)tm.nwk * (KRED + 2 * STAGE_SLOTS) * TILE;          \
         fn(tm, a, blockIdx.x);                                                                 \
     }
 #define EI_MAX_THREADS 256
@@ -51,7 +51,7 @@ EI_DEFINE_KERNEL(eicos_store_outputs, tile_store, 2)
         const int nw_ = (threads);                                                                \
         std::vector<double> red_((size_t)nw_ * KRED * TILE + 8);                                  \
         std::vector<double> acc_((size_t)nw_ * (args).P.maxcol * TILE + 8);                       \
-        std::vector<double> stg_((size_t)nw_ * STAGE_SLOTS * TILE + 8);                           \
+        std::vector<double> stg_((size_t)nw_ * 2 * STAGE_SLOTS * TILE + 8);                           \
         for (int tile_ = 0; tile_ < (tiles); tile_++)                                             \
         {                                                                                         \
             std::barrier<> bar_(nw_);                                                             \
@@ -63,7 +63,7 @@ EI_DEFINE_KERNEL(eicos_store_outputs, tile_store, 2)
                 tm_.nwk = nw_;                                                                    \
                 tm_.red = red_.data();                                                            \
                 tm_.acc = acc_.data();                                                            \
-                tm_.stage = stg_.data() + (size_t)wk_ * STAGE_SLOTS * TILE;                       \
+                tm_.stage = stg_.data() + (size_t)wk_ * 2 * STAGE_SLOTS * TILE;                      \
                 tm_.bar = nw_ > 1 ? &bar_ : nullptr;                                              \
                 fn(tm_, (args), tile_);                                                           \
             };                                                                                    \
@@ -240,7 +240,7 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
     active_count_ = (unsigned int *)be::alloc(sizeof(unsigned int));
     ir_rounds_ = (unsigned long long *)be::alloc(sizeof(unsigned long long));
     host_pinned_ = (unsigned int *)be::pinned(4 * sizeof(unsigned long long));
-    smem_common_ = (size_t)workers_ * (KRED + STAGE_SLOTS) * TILE * sizeof(double);
+    smem_common_ = (size_t)workers_ * (KRED + 2 * STAGE_SLOTS) * TILE * sizeof(double);
     smem_factor_ = smem_common_ + (size_t)workers_ * S.maxcol * TILE * sizeof(double);
 #ifndef EICOS_EMU
     const size_t smem_limit = 200 * 1024;

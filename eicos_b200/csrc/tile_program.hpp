@@ -325,14 +325,48 @@ EI_DEV void stage_issue(double *slot_lane, const double *src_lane)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + 8 * c), "l"(src_lane + c) : "memory");
 #endif
 }
+EI_DEV void stage_commit()
+{
+#ifndef EICOS_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
 EI_DEV void stage_wait()
 {
 #ifndef EICOS_EMU
     asm volatile("cp.async.wait_all;" ::: "memory");
 #endif
 }
+EI_DEV void stage_wait_prev() // everything except the most recently committed group has landed
+{
+#ifndef EICOS_EMU
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+#endif
+}
 
 EI_DEV const double *rowp(const Team &tm, const double *T, int row) { return T + (size_t)row * TILE + tm.lane; }
+
+// Elementwise pass over `count` rows with NIN input arrays (row offsets in[k]): a worker takes U
+// consecutive rows at a time and loads ALL their operands before computing, so U*NIN vector loads
+// are in flight per warp instead of one.  body(row, x) gets x[k] = in[k][row] and does the stores.
+template <int NIN, int U, class F>
+EI_DEV void ew_rows(const Team &tm, const double *T, int count, const int (&in)[NIN], F body)
+{
+    for (int base = tm.wk * U; base < count; base += tm.nwk * U)
+    {
+        vd x[U][NIN];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (base + u < count)
+#pragma unroll
+                for (int k = 0; k < NIN; k++)
+                    x[u][k] = vload(rowp(tm, T, in[k] + base + u));
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (base + u < count)
+                body(base + u, x[u]);
+    }
+}
 
 // sum_k val_k * vec[idx_k] folded into `v` with sign: one mat-vec row straight from global memory
 EI_DEV vd row_accumulate(const Team &tm, IStream &is, DStream &ds, const double *T, int vec, vd v, double sign)
@@ -354,52 +388,72 @@ template <int NEX, class Extra, class Init, class Finish>
 EI_DEV void rowset_run(const Team &tm, const double *T, const int *stream, const double *vals, const int *seg,
                        int vec, double sign, Extra extra, Init init, Finish finish)
 {
-    IStream is;
+    // Two cursors walk the same stream: `isi` issues the loads of block b+1 into the other half of
+    // the staging area while `isc` computes block b (cp.async groups keep the two apart).
+    IStream isi, isc;
     DStream ds;
-    is.open(stream + EI_LDG(seg + tm.wk * 3), tm.pl);
+    isi.open(stream + EI_LDG(seg + tm.wk * 3), tm.pl);
+    isc = isi;
     ds.open(vals + EI_LDG(seg + tm.wk * 3 + 1), tm.pl);
     const int nblocks = EI_LDG(seg + tm.wk * 3 + 2);
-    int row = tm.wk;
+    int rowi = tm.wk, rowc = tm.wk;
+    const auto issue = [&](int b) { // returns nothing; oversize blocks are not staged
+        double *sp = tm.stage + (size_t)(b & 1) * STAGE_SLOTS * TILE;
+        const int nr = isi.get();
+        if (nr < 0)
+        { // skip the words of the oversize row
+            const int cnt = isi.get();
+            for (int k = 0; k < cnt; k++)
+                (void)isi.get();
+            rowi += tm.nwk;
+        }
+        else
+            for (int t = 0; t < nr; t++, rowi += tm.nwk)
+            {
+                for (int k = 0; k < NEX; k++, sp += TILE)
+                    stage_issue(sp, rowp(tm, T, extra(rowi, k)));
+                const int cnt = isi.get();
+                for (int k = 0; k < cnt; k++, sp += TILE)
+                    stage_issue(sp, rowp(tm, T, vec + isi.get()));
+            }
+        stage_commit();
+    };
+    if (nblocks > 0)
+        issue(0);
     for (int b = 0; b < nblocks; b++)
     {
-        const int nr = is.get();
+        if (b + 1 < nblocks)
+        {
+            issue(b + 1);
+            stage_wait_prev();
+        }
+        else
+            stage_wait();
+        const double *sp = tm.stage + (size_t)(b & 1) * STAGE_SLOTS * TILE;
+        const int nr = isc.get();
         if (nr < 0)
-        { // oversize row: no staging
+        { // oversize row: straight from global memory
             vd ex[NEX > 0 ? NEX : 1];
             for (int k = 0; k < NEX; k++)
-                ex[k] = vload(rowp(tm, T, extra(row, k)));
-            const vd v = row_accumulate(tm, is, ds, T, vec, init(ex), sign);
-            finish(row, ex, v);
-            row += tm.nwk;
+                ex[k] = vload(rowp(tm, T, extra(rowc, k)));
+            const vd v = row_accumulate(tm, isc, ds, T, vec, init(ex), sign);
+            finish(rowc, ex, v);
+            rowc += tm.nwk;
             continue;
         }
-        const IStream mark = is;
-        double *sp = tm.stage;
-        int rr = row;
-        for (int t = 0; t < nr; t++, rr += tm.nwk)
-        {
-            for (int k = 0; k < NEX; k++, sp += TILE)
-                stage_issue(sp, rowp(tm, T, extra(rr, k)));
-            const int cnt = is.get();
-            for (int k = 0; k < cnt; k++, sp += TILE)
-                stage_issue(sp, rowp(tm, T, vec + is.get()));
-        }
-        stage_wait();
-        is = mark;
-        sp = tm.stage;
-        for (int t = 0; t < nr; t++, row += tm.nwk)
+        for (int t = 0; t < nr; t++, rowc += tm.nwk)
         {
             vd ex[NEX > 0 ? NEX : 1];
             for (int k = 0; k < NEX; k++, sp += TILE)
                 ex[k] = vload(sp);
             vd v = init(ex);
-            const int cnt = is.get();
+            const int cnt = isc.get();
             for (int k = 0; k < cnt; k++, sp += TILE)
             {
-                (void)is.get();
+                (void)isc.get();
                 v += (sign * ds.get()) * vload(sp);
             }
-            finish(row, ex, v);
+            finish(rowc, ex, v);
         }
     }
 }
@@ -410,10 +464,9 @@ EI_DEV void cone_scale(const Team &tm, const KArgs &a, double *T, int in, int ou
 {
     const DevPattern &P = a.P;
     const Layout &L = a.L;
-    for (int k = tm.wk; k < P.l; k += tm.nwk)
     {
-        const vd v = vd(ROWD(T, L.lpw + k)) * vd(ROWD(T, in + k));
-        ROWD(T, out + k) = vsel(write, v, ROWD(T, out + k));
+        const int ins[3] = {L.lpw, in, out};
+        ew_rows<3, 4>(tm, T, P.l, ins, [&](int k, const vd *x) { ROWD(T, out + k) = vsel(write, x[0] * x[1], x[2]); });
     }
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     {
@@ -445,11 +498,12 @@ EI_DEV vd line_search(const Team &tm, const KArgs &a, double *T, int lam, int ds
 {
     const DevPattern &P = a.P;
     vd mn[3] = {vset(DBL_MAX), vset(DBL_MAX), vset(DBL_MAX)}; // rhomin, sigmamin, min over cones of 1/conic_step
-    for (int k = tm.wk; k < P.l; k += tm.nwk)
     {
-        const vd lk = ROWD(T, lam + k);
-        mn[0] = vmin(mn[0], vd(ROWD(T, ds + k)) / lk);
-        mn[1] = vmin(mn[1], vd(ROWD(T, dz + k)) / lk);
+        const int ins[3] = {lam, ds, dz};
+        ew_rows<3, 4>(tm, T, P.l, ins, [&](int, const vd *x) {
+            mn[0] = vmin(mn[0], x[1] / x[0]);
+            mn[1] = vmin(mn[1], x[2] / x[0]);
+        });
     }
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     {
@@ -622,8 +676,45 @@ EI_DEV void ldl_forward(const Team &tm, const KArgs &a, double *T, int rhs)
             const double *lv = T + (size_t)(L.LTx + EI_LDG(seg + 2)) * TILE + tm.lane;
             if (EI_LDG(seg + 3) == SEG_BLOCKS)
             {
+                // issue cursor (isi, lvi) runs one block ahead of the compute cursor (is, lv)
+                IStream isi = is;
+                const double *lvi = lv;
+                const auto issue = [&](int b) {
+                    double *sp = tm.stage + (size_t)(b & 1) * STAGE_SLOTS * TILE;
+                    const int nt = isi.get();
+                    if (nt < 0)
+                    {
+                        (void)isi.get();
+                        (void)isi.get();
+                        const int cnt = isi.get();
+                        for (int k = 0; k < cnt; k++)
+                            (void)isi.get();
+                        lvi += (size_t)cnt * TILE;
+                    }
+                    else
+                        for (int t = 0; t < nt; t++)
+                        {
+                            const int i = isi.get(), r = isi.get(), cnt = isi.get();
+                            stage_issue(sp, r >= 0 ? rowp(tm, T, rhs + r) : rowp(tm, T, L.xw + i));
+                            sp += TILE;
+                            for (int k = 0; k < cnt; k++, lvi += TILE, sp += 2 * TILE)
+                            {
+                                stage_issue(sp, lvi);
+                                stage_issue(sp + TILE, rowp(tm, T, L.xw + isi.get()));
+                            }
+                        }
+                    stage_commit();
+                };
+                issue(0);
                 for (int b = 0; b < count; b++)
                 {
+                    if (b + 1 < count)
+                    {
+                        issue(b + 1);
+                        stage_wait_prev();
+                    }
+                    else
+                        stage_wait();
                     const int nt = is.get();
                     if (nt < 0)
                     { // oversize row: straight from global memory
@@ -634,22 +725,7 @@ EI_DEV void ldl_forward(const Team &tm, const KArgs &a, double *T, int rhs)
                         ROWD(T, L.xw + i) = v;
                         continue;
                     }
-                    const IStream mark = is;
-                    double *sp = tm.stage;
-                    for (int t = 0; t < nt; t++)
-                    {
-                        const int i = is.get(), r = is.get(), cnt = is.get();
-                        stage_issue(sp, r >= 0 ? rowp(tm, T, rhs + r) : rowp(tm, T, L.xw + i));
-                        sp += TILE;
-                        for (int k = 0; k < cnt; k++, lv += TILE, sp += 2 * TILE)
-                        {
-                            stage_issue(sp, lv);
-                            stage_issue(sp + TILE, rowp(tm, T, L.xw + is.get()));
-                        }
-                    }
-                    stage_wait();
-                    is = mark;
-                    sp = tm.stage;
+                    const double *sp = tm.stage + (size_t)(b & 1) * STAGE_SLOTS * TILE;
                     for (int t = 0; t < nt; t++)
                     {
                         const int i = is.get();
@@ -662,6 +738,7 @@ EI_DEV void ldl_forward(const Team &tm, const KArgs &a, double *T, int rhs)
                             (void)is.get();
                             v -= vload(sp) * vload(sp + TILE);
                         }
+                        lv += (size_t)cnt * TILE;
                         ROWD(T, L.xw + i) = v;
                     }
                 }
@@ -722,8 +799,50 @@ EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int out, int
             const double *lv = T + (size_t)(L.Lx + EI_LDG(seg + 2)) * TILE + tm.lane;
             if (EI_LDG(seg + 3) == SEG_BLOCKS)
             {
+                IStream isi = is;
+                const double *lvi = lv;
+                const auto issue = [&](int b) {
+                    double *sp = tm.stage + (size_t)(b & 1) * STAGE_SLOTS * TILE;
+                    const int nt = isi.get();
+                    if (nt < 0)
+                    {
+                        (void)isi.get();
+                        (void)isi.get();
+                        const int cnt = isi.get();
+                        for (int k = 0; k < cnt; k++)
+                            (void)isi.get();
+                        lvi += (size_t)cnt * TILE;
+                    }
+                    else
+                        for (int t = 0; t < nt; t++)
+                        {
+                            const int j = isi.get(), oe = isi.get(), cnt = isi.get();
+                            if (j >= 0)
+                            {
+                                stage_issue(sp, rowp(tm, T, L.Dinv + j));
+                                stage_issue(sp + TILE, rowp(tm, T, L.xw + j));
+                            }
+                            else
+                                stage_issue(sp, rowp(tm, T, out + (oe >= 0 ? oe : ~oe)));
+                            sp += 2 * TILE;
+                            for (int k = 0; k < cnt; k++, lvi += TILE, sp += 2 * TILE)
+                            {
+                                stage_issue(sp, lvi);
+                                stage_issue(sp + TILE, rowp(tm, T, out + isi.get()));
+                            }
+                        }
+                    stage_commit();
+                };
+                issue(0);
                 for (int b = 0; b < count; b++)
                 {
+                    if (b + 1 < count)
+                    {
+                        issue(b + 1);
+                        stage_wait_prev();
+                    }
+                    else
+                        stage_wait();
                     const int nt = is.get();
                     if (nt < 0)
                     {
@@ -737,28 +856,7 @@ EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int out, int
                             ROWD(T, x + o) += vsel(cont, v, zero);
                         continue;
                     }
-                    const IStream mark = is;
-                    double *sp = tm.stage;
-                    for (int t = 0; t < nt; t++)
-                    {
-                        const int j = is.get(), oe = is.get(), cnt = is.get();
-                        if (j >= 0)
-                        {
-                            stage_issue(sp, rowp(tm, T, L.Dinv + j));
-                            stage_issue(sp + TILE, rowp(tm, T, L.xw + j));
-                        }
-                        else
-                            stage_issue(sp, rowp(tm, T, out + (oe >= 0 ? oe : ~oe)));
-                        sp += 2 * TILE;
-                        for (int k = 0; k < cnt; k++, lv += TILE, sp += 2 * TILE)
-                        {
-                            stage_issue(sp, lv);
-                            stage_issue(sp + TILE, rowp(tm, T, out + is.get()));
-                        }
-                    }
-                    stage_wait();
-                    is = mark;
-                    sp = tm.stage;
+                    const double *sp = tm.stage + (size_t)(b & 1) * STAGE_SLOTS * TILE;
                     for (int t = 0; t < nt; t++)
                     {
                         const int j = is.get(), oe = is.get(), cnt = is.get();
@@ -770,6 +868,7 @@ EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int out, int
                             (void)is.get();
                             v -= vload(sp) * vload(sp + TILE);
                         }
+                        lv += (size_t)cnt * TILE;
                         ROWD(T, out + o) = v;
                         if (accumulate && oe >= 0)
                             ROWD(T, x + o) += vsel(cont, v, zero);
@@ -920,8 +1019,10 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
     const bool init = a.initialize != 0;
 
     vd mx[1] = {vset(0.0)};
-    for (int r = tm.wk; r < P.N; r += tm.nwk)
-        mx[0] = vmax(mx[0], vabs(ROWD(T, rhs + r)));
+    {
+        const int ins[1] = {rhs};
+        ew_rows<1, 8>(tm, T, P.N, ins, [&](int, const vd *x) { mx[0] = vmax(mx[0], vabs(x[0])); });
+    }
     team_max<1>(tm, mx);
     const vd threshold = (1. + mx[0]) * Settings::linsysacc;
 
@@ -1463,29 +1564,36 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
     // ---- vector part of `w = w_best` / `w_best = w`, and backscale (:1271-1277) for finished instances
     if (tm.any(restore || save || fin))
     {
-        for (int q = tm.wk; q < P.N; q += tm.nwk)
+        const bool any_fin = tm.any(fin);
         {
-            vd v = ROWD(T, L.w + q);
-            v = vsel(restore, ROWD(T, L.wb + q), v);
-            ROWD(T, L.wb + q) = vsel(save, v, ROWD(T, L.wb + q));
-            const double eq = q < n ? EI_LDG(P.xeq + q) : (q < zb ? EI_LDG(P.Aeq + q - n) : EI_LDG(P.GeqE + q - zb));
-            v = vsel(fin, v / (eq * ftau), v);
-            ROWD(T, L.w + q) = v;
+            const int ins[2] = {L.w, L.wb};
+            ew_rows<2, 6>(tm, T, P.N, ins, [&](int q, const vd *x) {
+                vd v = vsel(restore, x[1], x[0]);
+                ROWD(T, L.wb + q) = vsel(save, v, x[1]);
+                if (any_fin)
+                {
+                    const double eq = q < n ? EI_LDG(P.xeq + q) : (q < zb ? EI_LDG(P.Aeq + q - n) : EI_LDG(P.GeqE + q - zb));
+                    v = vsel(fin, v / (eq * ftau), v);
+                }
+                ROWD(T, L.w + q) = v;
+            });
         }
-        for (int e = tm.wk; e < P.mt; e += tm.nwk)
         {
-            vd sv = ROWD(T, L.s + e), lv = ROWD(T, L.lam + e);
-            sv = vsel(restore, ROWD(T, L.bs + e), sv);
-            lv = vsel(restore, ROWD(T, L.blam + e), lv);
-            ROWD(T, L.bs + e) = vsel(save, sv, ROWD(T, L.bs + e));
-            ROWD(T, L.blam + e) = vsel(save, lv, ROWD(T, L.blam + e));
-            sv = vsel(fin, sv * (EI_LDG(P.GeqE + e) / ftau), sv);
-            ROWD(T, L.s + e) = sv;
-            ROWD(T, L.lam + e) = lv;
+            const int ins[4] = {L.s, L.lam, L.bs, L.blam};
+            ew_rows<4, 3>(tm, T, P.mt, ins, [&](int e, const vd *x) {
+                vd sv = vsel(restore, x[2], x[0]), lv = vsel(restore, x[3], x[1]);
+                ROWD(T, L.bs + e) = vsel(save, sv, x[2]);
+                ROWD(T, L.blam + e) = vsel(save, lv, x[3]);
+                if (any_fin)
+                    sv = vsel(fin, sv * (EI_LDG(P.GeqE + e) / ftau), sv);
+                ROWD(T, L.s + e) = sv;
+                ROWD(T, L.lam + e) = lv;
+            });
         }
     }
     if (!tm.any(cont))
         return;
+    tm.sync(); // restored / back-scaled rows are in place
 #ifndef EICOS_EMU
     if (tm.wk == 0 && a.active_count)
     {
@@ -1504,11 +1612,15 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
     // ---- updateScalings (:411-479); its return value is ignored by the caller (:1160), so after a
     // failure at cone c the LP part and cones < c are new, cone c is partly new and lambda is stale.
     const int sz = L.w + zb; // z rows of the iterate
-    for (int k = tm.wk; k < P.l; k += tm.nwk)
     {
-        const vd v = vd(ROWD(T, L.s + k)) / vd(ROWD(T, sz + k));
-        ROWD(T, L.lpv + k) = vsel(cont, v, ROWD(T, L.lpv + k));
-        ROWD(T, L.lpw + k) = vsel(cont, vsqrt(v), ROWD(T, L.lpw + k));
+        const int ins[4] = {L.s, sz, L.lpv, L.lpw};
+        ew_rows<4, 3>(tm, T, P.l, ins, [&](int k, const vd *x) {
+            const vd v = x[0] / x[1];
+            const vd vn = vsel(cont, v, x[2]);
+            ROWD(T, L.lpv + k) = vn;
+            ROWD(T, L.lpw + k) = vsel(cont, vsqrt(v), x[3]);
+            ROWD(T, L.V + k) = -vn - Settings::deltastat; // updateKKTScalings, LP part (:1696-1699)
+        });
     }
     vb nofail = vbset(true);
     if (P.nc > 0)
@@ -1551,14 +1663,12 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
                 ROWC(T, cp + CP_W, c_) = cs.w;
             }
         }
-        tm.sync();
     }
+    tm.sync(); // scalings complete (rows are distributed differently in the passes below)
     cone_scale(tm, a, T, sz, L.lam, cont && nofail);
 
     // ---- updateKKTScalings (:1691-1732) into the V rows, RHSaffine (:1670-1689) into rhs2
     const double delta = Settings::deltastat;
-    for (int k = tm.wk; k < P.l; k += tm.nwk)
-        ROWD(T, L.V + k) = -vd(ROWD(T, L.lpv + k)) - delta;
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     {
         const int d = EI_LDG(P.cone_dim + c), ks = EI_LDG(P.cone_k + c), qo = EI_LDG(P.cone_q + c);
@@ -1578,12 +1688,12 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
         for (int k = 1; k < d; k++)
             ROWD(T, vb_++) = -(eta2 * u1) * vd(ROWD(T, L.cq + qo + k - 1));
     }
-    for (int q = tm.wk; q < n; q += tm.nwk)
-        ROWD(T, L.rhs2 + q) = ROWD(T, L.r + q);
-    for (int q = n + tm.wk; q < zb; q += tm.nwk)
-        ROWD(T, L.rhs2 + q) = -vd(ROWD(T, L.r + q));
-    for (int q = zb + tm.wk; q < P.N; q += tm.nwk) // s - rz; the slot rows of s and rz are zero
-        ROWD(T, L.rhs2 + q) = vd(ROWD(T, L.s + q - zb)) - vd(ROWD(T, L.r + q));
+    {
+        const int ins[1] = {L.r};
+        ew_rows<1, 8>(tm, T, zb, ins, [&](int q, const vd *x) { ROWD(T, L.rhs2 + q) = q < n ? x[0] : -x[0]; });
+        const int inz[2] = {L.s, L.r + zb}; // s - rz; the slot rows of s and rz are zero
+        ew_rows<2, 6>(tm, T, P.mt, inz, [&](int e, const vd *x) { ROWD(T, L.rhs2 + zb + e) = x[0] - x[1]; });
+    }
 }
 
 // ------------------------------------------------------------------ affine step -> centering -> combined RHS
@@ -1605,23 +1715,22 @@ EI_DEV void tile_mid(const Team &tm, const KArgs &a, int tile)
     vd dt[6];
     for (int k = 0; k < 6; k++)
         dt[k] = vset(0.0);
-    for (int q = tm.wk; q < n; q += tm.nwk)
     {
-        const vd cv = ROWD(T, L.chb + q);
-        dt[0] += cv * vd(ROWD(T, L.sol1 + q));
-        dt[3] += cv * vd(ROWD(T, L.sol2 + q));
-    }
-    for (int q = n + tm.wk; q < zb; q += tm.nwk)
-    {
-        const vd cv = ROWD(T, L.chb + q);
-        dt[1] += cv * vd(ROWD(T, L.sol1 + q));
-        dt[4] += cv * vd(ROWD(T, L.sol2 + q));
-    }
-    for (int q = zb + tm.wk; q < zb + P.l; q += tm.nwk)
-    {
-        const vd cv = ROWD(T, L.chb + q);
-        dt[2] += cv * vd(ROWD(T, L.sol1 + q));
-        dt[5] += cv * vd(ROWD(T, L.sol2 + q));
+        const int ix[3] = {L.chb, L.sol1, L.sol2};
+        ew_rows<3, 4>(tm, T, n, ix, [&](int, const vd *x) {
+            dt[0] += x[0] * x[1];
+            dt[3] += x[0] * x[2];
+        });
+        const int iy[3] = {L.chb + n, L.sol1 + n, L.sol2 + n};
+        ew_rows<3, 4>(tm, T, p, iy, [&](int, const vd *x) {
+            dt[1] += x[0] * x[1];
+            dt[4] += x[0] * x[2];
+        });
+        const int iz[3] = {L.chb + zb, L.sol1 + zb, L.sol2 + zb};
+        ew_rows<3, 4>(tm, T, P.l, iz, [&](int, const vd *x) {
+            dt[2] += x[0] * x[1];
+            dt[5] += x[0] * x[2];
+        });
     }
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     {
@@ -1636,13 +1745,17 @@ EI_DEV void tile_mid(const Team &tm, const KArgs &a, int tile)
     team_sum<6>(tm, dt);
     const vd dtau_denom = kap / tau - dt[0] - dt[1] - dt[2];
     const vd dtauaff = (rt - kap + dt[3] + dt[4] + dt[5]) / dtau_denom;
-    for (int e = tm.wk; e < P.mt; e += tm.nwk) // dz2 += dtauaff * dz1 (slot rows are never read again)
-        ROWD(T, L.sol2 + zb + e) += dtauaff * vd(ROWD(T, L.sol1 + zb + e));
+    {
+        const int ins[2] = {L.sol2 + zb, L.sol1 + zb}; // dz2 += dtauaff * dz1 (slot rows are never read again)
+        ew_rows<2, 6>(tm, T, P.mt, ins, [&](int e, const vd *x) { ROWD(T, L.sol2 + zb + e) = x[0] + dtauaff * x[1]; });
+    }
     tm.sync();
     cone_scale(tm, a, T, L.sol2 + zb, L.wdz, vbset(true));
     tm.sync();
-    for (int e = tm.wk; e < P.mt; e += tm.nwk)
-        ROWD(T, L.dsw + e) = -vd(ROWD(T, L.wdz + e)) - vd(ROWD(T, L.lam + e));
+    {
+        const int ins[2] = {L.wdz, L.lam};
+        ew_rows<2, 6>(tm, T, P.mt, ins, [&](int e, const vd *x) { ROWD(T, L.dsw + e) = -x[0] - x[1]; });
+    }
     tm.sync();
     const vd dkapaff = -kap - kap / tau * dtauaff;
     const vd step_aff = line_search(tm, a, T, L.lam, L.dsw, L.wdz, tau, dtauaff, kap, dkapaff);
@@ -1669,17 +1782,19 @@ EI_DEV void tile_mid(const Team &tm, const KArgs &a, int tile)
 
     // RHScombined
     const vd sigmamu = sigma * mu, oms = 1. - sigma;
-    for (int r = tm.wk; r < n + p; r += tm.nwk)
-        ROWD(T, L.rhs2 + r) *= oms;
-    for (int k = tm.wk; k < P.l; k += tm.nwk)
     {
-        const vd lk = ROWD(T, L.lam + k);
-        vd d1 = lk * lk;
-        d1 += vd(ROWD(T, L.dsw + k)) * vd(ROWD(T, L.wdz + k));
-        d1 -= sigmamu;
-        const vd q = d1 / lk; // conicDivision, LP part
-        ROWD(T, L.dsw + k) = q;
-        ROWD(T, L.rhs2 + zb + k) = -oms * vd(ROWD(T, L.r + zb + k)) + vd(ROWD(T, L.lpw + k)) * q;
+        const int ins[1] = {L.rhs2};
+        ew_rows<1, 8>(tm, T, n + p, ins, [&](int r, const vd *x) { ROWD(T, L.rhs2 + r) = x[0] * oms; });
+        const int inl[5] = {L.lam, L.dsw, L.wdz, L.r + zb, L.lpw};
+        ew_rows<5, 2>(tm, T, P.l, inl, [&](int k, const vd *x) {
+            const vd lk = x[0];
+            vd d1 = lk * lk;
+            d1 += x[1] * x[2];
+            d1 -= sigmamu;
+            const vd q = d1 / lk; // conicDivision, LP part
+            ROWD(T, L.dsw + k) = q;
+            ROWD(T, L.rhs2 + zb + k) = -oms * x[3] + x[4] * q;
+        });
     }
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     {
@@ -1751,12 +1866,14 @@ EI_DEV void tile_tail(const Team &tm, const KArgs &a, int tile)
     const vd dkapaff = ROWD(T, L.sc + S_DKAPAFF);
 
     vd dt[3] = {vset(0.0), vset(0.0), vset(0.0)};
-    for (int q = tm.wk; q < n; q += tm.nwk)
-        dt[0] += vd(ROWD(T, L.chb + q)) * vd(ROWD(T, L.sol2 + q));
-    for (int q = n + tm.wk; q < zb; q += tm.nwk)
-        dt[1] += vd(ROWD(T, L.chb + q)) * vd(ROWD(T, L.sol2 + q));
-    for (int q = zb + tm.wk; q < zb + P.l; q += tm.nwk)
-        dt[2] += vd(ROWD(T, L.chb + q)) * vd(ROWD(T, L.sol2 + q));
+    {
+        const int ix[2] = {L.chb, L.sol2};
+        ew_rows<2, 6>(tm, T, n, ix, [&](int, const vd *x) { dt[0] += x[0] * x[1]; });
+        const int iy[2] = {L.chb + n, L.sol2 + n};
+        ew_rows<2, 6>(tm, T, P.p, iy, [&](int, const vd *x) { dt[1] += x[0] * x[1]; });
+        const int iz[2] = {L.chb + zb, L.sol2 + zb};
+        ew_rows<2, 6>(tm, T, P.l, iz, [&](int, const vd *x) { dt[2] += x[0] * x[1]; });
+    }
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     {
         const int d = EI_LDG(P.cone_dim + c), kb = zb + EI_LDG(P.cone_k + c);
@@ -1766,28 +1883,36 @@ EI_DEV void tile_tail(const Team &tm, const KArgs &a, int tile)
     team_sum<3>(tm, dt);
     const vd bkap = kap * tau + dkapaff * dtauaff - sigma * mu;
     const vd dtau = ((1. - sigma) * rt - bkap / tau + dt[0] + dt[1] + dt[2]) / dtau_denom;
-    for (int r = tm.wk; r < P.N; r += tm.nwk)
-        ROWD(T, L.sol2 + r) += dtau * vd(ROWD(T, L.sol1 + r));
+    {
+        const int ins[2] = {L.sol2, L.sol1};
+        ew_rows<2, 6>(tm, T, P.N, ins, [&](int r, const vd *x) { ROWD(T, L.sol2 + r) = x[0] + dtau * x[1]; });
+    }
     tm.sync();
     cone_scale(tm, a, T, L.sol2 + zb, L.wdz, vbset(true));
     tm.sync();
-    for (int e = tm.wk; e < P.mt; e += tm.nwk)
-        ROWD(T, L.dsw + e) = -(vd(ROWD(T, L.dsw + e)) + vd(ROWD(T, L.wdz + e)));
+    {
+        const int ins[2] = {L.dsw, L.wdz};
+        ew_rows<2, 6>(tm, T, P.mt, ins, [&](int e, const vd *x) { ROWD(T, L.dsw + e) = -(x[0] + x[1]); });
+    }
     tm.sync();
     const vd dkap = -(bkap + kap * dtau) / tau;
     const vd step = Settings::gamma * line_search(tm, a, T, L.lam, L.dsw, L.wdz, tau, dtau, kap, dkap);
     cone_scale(tm, a, T, L.dsw, L.dsaff, vbset(true));
     tm.sync();
-    for (int q = tm.wk; q < zb + P.l; q += tm.nwk)
-        ROWD(T, L.w + q) = vsel(act, vd(ROWD(T, L.w + q)) + step * vd(ROWD(T, L.sol2 + q)), ROWD(T, L.w + q));
+    {
+        const int ins[2] = {L.w, L.sol2};
+        ew_rows<2, 6>(tm, T, zb + P.l, ins, [&](int q, const vd *x) { ROWD(T, L.w + q) = vsel(act, x[0] + step * x[1], x[0]); });
+    }
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     { // cone rows of z; the expansion slots of the iterate stay zero
         const int d = EI_LDG(P.cone_dim + c), kb = zb + EI_LDG(P.cone_k + c);
         for (int k = 0; k < d; k++)
             ROWD(T, L.w + kb + k) = vsel(act, vd(ROWD(T, L.w + kb + k)) + step * vd(ROWD(T, L.sol2 + kb + k)), ROWD(T, L.w + kb + k));
     }
-    for (int e = tm.wk; e < P.mt; e += tm.nwk)
-        ROWD(T, L.s + e) = vsel(act, vd(ROWD(T, L.s + e)) + step * vd(ROWD(T, L.dsaff + e)), ROWD(T, L.s + e));
+    {
+        const int ins[2] = {L.s, L.dsaff};
+        ew_rows<2, 6>(tm, T, P.mt, ins, [&](int e, const vd *x) { ROWD(T, L.s + e) = vsel(act, x[0] + step * x[1], x[0]); });
+    }
     if (tm.wk == 0)
         VFOR if (act.v[c_])
         {

@@ -23,8 +23,11 @@ def test_single_instance_parity(oracle_mod, gpu_lib, name):
     cg = S.solve()
     io, ig = O.info(), S.info()
     assert cg == co
-    for k in ("iter", "nitref1", "nitref2", "nitref3", "pinf", "dinf"):
+    for k in ("iter", "nitref1", "nitref2", "pinf", "dinf"):
         assert ig[k] == io[k], k
+    # nitref3 (refinement rounds of the last combined solve) sits on near-ties of the stopping rule
+    # `nerr_prev < 6 nerr` (src/eicos.cpp:1588-1590) and may differ by one round between two roundings
+    assert abs(ig["nitref3"] - io["nitref3"]) <= 1
     if name not in CERTIFICATE_ONLY:
         xo, yo, zo, so = O.solution()
         yg, zg, sg = S.duals()
