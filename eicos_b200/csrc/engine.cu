@@ -25,9 +25,9 @@ namespace eicos
         tm.wk = threadIdx.x >> 5;                                                              \
         tm.nwk = blockDim.x >> 5;                                                              \
         tm.red = smem;                                                                         \
-        tm.stage = smem + (size_t)tm.nwk * KRED * TILE + (size_t)tm.wk * 2 * STAGE_SLOTS * TILE + tm.lane; \
+        tm.stage = smem + (size_t)(tm.nwk > 1 ? tm.nwk * KRED : 0) * TILE + (size_t)tm.wk * 2 * STAGE_SLOTS * TILE + tm.lane; \
         tm.acc = a.acc_global ? a.acc_global + (size_t)blockIdx.x * tm.nwk * a.P.maxcol * TILE \
-                              : smem + (size_t)tm.nwk * (KRED + 2 * STAGE_SLOTS) * TILE;          \
+                              : smem + (size_t)tm.nwk * ((tm.nwk > 1 ? KRED : 0) + 2 * STAGE_SLOTS) * TILE;          \
         fn(tm, a, blockIdx.x);                                                                 \
     }
 #define EI_MAX_THREADS 256
@@ -240,7 +240,7 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
     active_count_ = (unsigned int *)be::alloc(sizeof(unsigned int));
     ir_rounds_ = (unsigned long long *)be::alloc(sizeof(unsigned long long));
     host_pinned_ = (unsigned int *)be::pinned(4 * sizeof(unsigned long long));
-    smem_common_ = (size_t)workers_ * (KRED + 2 * STAGE_SLOTS) * TILE * sizeof(double);
+    smem_common_ = (size_t)workers_ * ((workers_ > 1 ? KRED : 0) + 2 * STAGE_SLOTS) * TILE * sizeof(double);
     smem_factor_ = smem_common_ + (size_t)workers_ * S.maxcol * TILE * sizeof(double);
 #ifndef EICOS_EMU
     const size_t smem_limit = 200 * 1024;

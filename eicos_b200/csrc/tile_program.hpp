@@ -37,7 +37,7 @@
 #endif
 
 #ifndef EICOS_VEC
-#define EICOS_VEC 2
+#define EICOS_VEC 4
 #endif
 
 namespace eicos
@@ -318,8 +318,12 @@ EI_DEV void stage_issue(double *slot_lane, const double *src_lane)
     vstore(slot_lane, vload(src_lane));
 #else
     const unsigned sa = (unsigned)__cvta_generic_to_shared(slot_lane);
-    if (VEC == 2)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src_lane) : "memory");
+    if (VEC % 2 == 0)
+    {
+#pragma unroll
+        for (int c = 0; c < VEC; c += 2)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + 8 * c), "l"(src_lane + c) : "memory");
+    }
     else
         for (int c = 0; c < VEC; c++)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + 8 * c), "l"(src_lane + c) : "memory");
@@ -352,17 +356,18 @@ EI_DEV const double *rowp(const Team &tm, const double *T, int row) { return T +
 template <int NIN, int U, class F>
 EI_DEV void ew_rows(const Team &tm, const double *T, int count, const int (&in)[NIN], F body)
 {
-    for (int base = tm.wk * U; base < count; base += tm.nwk * U)
+    constexpr int UE = (U * 2 / VEC) > 0 ? (U * 2 / VEC) : 1; // U is quoted for VEC = 2; keep the register footprint constant
+    for (int base = tm.wk * UE; base < count; base += tm.nwk * UE)
     {
-        vd x[U][NIN];
+        vd x[UE][NIN];
 #pragma unroll
-        for (int u = 0; u < U; u++)
+        for (int u = 0; u < UE; u++)
             if (base + u < count)
 #pragma unroll
                 for (int k = 0; k < NIN; k++)
                     x[u][k] = vload(rowp(tm, T, in[k] + base + u));
 #pragma unroll
-        for (int u = 0; u < U; u++)
+        for (int u = 0; u < UE; u++)
             if (base + u < count)
                 body(base + u, x[u]);
     }
