@@ -225,6 +225,11 @@ void Engine::upload_values(const Symbolic &S)
 Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int workers)
     : device_(device), workers_(std::max(1, std::min(workers, EI_MAX_THREADS / 32 > 0 ? EI_MAX_THREADS / 32 : 1)))
 {
+    { // keep the per-CTA shared memory (reductions + two staging buffers per worker) within ~96 KB
+        const size_t per_worker = (size_t)(KRED + 2 * STAGE_SLOTS) * TILE * sizeof(double);
+        const int fit = (int)std::max<size_t>(1, (128 * 1024) / per_worker);
+        workers_ = std::min(workers_, fit);
+    }
     be::set_device(device_);
     stream_ = (void *)(intptr_t)be::make_stream();
     build_layout(S);

@@ -28,7 +28,7 @@ namespace eicos
 
 constexpr int STREAM_CHUNK = 32;  // words per cooperative load
 constexpr int STREAM_PAD = 96;    // readable words after the last used one (two chunks of lookahead)
-constexpr int STAGE_SLOTS = 24;   // rows per staging buffer (one slot = TILE doubles); a worker owns two buffers
+constexpr int STAGE_SLOTS = 12;   // rows per staging buffer (one slot = TILE doubles); a worker owns two buffers
 constexpr int FWD_PREV1 = -1;     // gather code: result of the previous task of this worker
 constexpr int FWD_PREV2 = -2;     // ... of the task before that
 constexpr int FWD_PREV3 = -3;

@@ -37,7 +37,7 @@
 #endif
 
 #ifndef EICOS_VEC
-#define EICOS_VEC 4
+#define EICOS_VEC 2
 #endif
 
 namespace eicos
@@ -50,7 +50,7 @@ constexpr int LANES = 32;
 #endif
 constexpr int VEC = EICOS_VEC;       // instances per lane
 constexpr int TILE = LANES * VEC;    // instances per tile = doubles per row
-constexpr int KRED = 14;             // widest block reduction
+constexpr int KRED = 7;              // rows per worker in the shared reduction buffer
 constexpr int PF_ROWS = 24;          // how many value rows ahead the serial sweeps prefetch into L2
 
 // ------------------------------------------------------------------ VEC-wide values
@@ -131,8 +131,8 @@ struct RowRef
     EI_DEV void operator*=(vd s) const { vstore(p, vload(p) * s); }
     EI_DEV void operator=(const RowRef &o) const { vstore(p, vload(o.p)); }
 };
-#define ROWD(base, r) (RowRef{(base) + (size_t)(r) * TILE + tm.lane})
-#define ROWC(base, r, c) ((base)[(size_t)(r) * TILE + tm.lane + (c)])
+#define ROWD(base, r) (RowRef{(base) + (size_t)(r) * TILE})
+#define ROWC(base, r, c) ((base)[(size_t)(r) * TILE + (c)])
 
 struct KArgs
 {
@@ -191,14 +191,15 @@ struct IStream
     EI_DEV void open(const int *base, int) { p = base; }
     EI_DEV int get() { return *p++; }
 #else
-    const int *p;
-    int cur, nxt, pos, lane;
-    EI_DEV void open(const int *base, int lane_)
+    const int *base; // warp-uniform
+    int off;         // word offset of the chunk after `nxt`, plus this lane
+    int cur, nxt, pos;
+    EI_DEV void open(const int *b, int lane)
     {
-        lane = lane_;
-        cur = __ldg(base + lane);
-        nxt = __ldg(base + STREAM_CHUNK + lane);
-        p = base + 2 * STREAM_CHUNK;
+        base = b;
+        cur = __ldg(b + lane);
+        nxt = __ldg(b + STREAM_CHUNK + lane);
+        off = 2 * STREAM_CHUNK + lane;
         pos = 0;
     }
     EI_DEV int get()
@@ -206,8 +207,8 @@ struct IStream
         if (pos == STREAM_CHUNK)
         {
             cur = nxt;
-            nxt = __ldg(p + lane);
-            p += STREAM_CHUNK;
+            nxt = __ldg(base + off);
+            off += STREAM_CHUNK;
             pos = 0;
         }
         const int v = __shfl_sync(0xffffffffu, cur, pos);
@@ -224,15 +225,15 @@ struct DStream
     EI_DEV void open(const double *base, int) { p = base; }
     EI_DEV double get() { return *p++; }
 #else
-    const double *p;
+    const double *base;
+    int off, pos;
     double cur, nxt;
-    int pos, lane;
-    EI_DEV void open(const double *base, int lane_)
+    EI_DEV void open(const double *b, int lane)
     {
-        lane = lane_;
-        cur = __ldg(base + lane);
-        nxt = __ldg(base + STREAM_CHUNK + lane);
-        p = base + 2 * STREAM_CHUNK;
+        base = b;
+        cur = __ldg(b + lane);
+        nxt = __ldg(b + STREAM_CHUNK + lane);
+        off = 2 * STREAM_CHUNK + lane;
         pos = 0;
     }
     EI_DEV double get()
@@ -240,8 +241,8 @@ struct DStream
         if (pos == STREAM_CHUNK)
         {
             cur = nxt;
-            nxt = __ldg(p + lane);
-            p += STREAM_CHUNK;
+            nxt = __ldg(base + off);
+            off += STREAM_CHUNK;
             pos = 0;
         }
         const double v = __shfl_sync(0xffffffffu, cur, pos);
@@ -257,16 +258,20 @@ EI_DEV void team_reduce(const Team &tm, vd (&v)[K], Op op)
 {
     if (tm.nwk == 1)
         return;
-    tm.sync();
-    for (int i = 0; i < K; i++)
-        vstore(tm.red + (size_t)(tm.wk * K + i) * TILE + tm.lane, v[i]);
-    tm.sync();
-    for (int i = 0; i < K; i++)
-    {
-        vd s = vload(tm.red + (size_t)i * TILE + tm.lane);
-        for (int w = 1; w < tm.nwk; w++)
-            s = op(s, vload(tm.red + (size_t)(w * K + i) * TILE + tm.lane));
-        v[i] = s;
+    for (int i0 = 0; i0 < K; i0 += KRED)
+    { // the shared buffer holds KRED rows per worker: wide reductions go through it in rounds
+        const int kn = K - i0 < KRED ? K - i0 : KRED;
+        tm.sync();
+        for (int i = 0; i < kn; i++)
+            vstore(tm.red + (size_t)(tm.wk * KRED + i) * TILE + tm.lane, v[i0 + i]);
+        tm.sync();
+        for (int i = 0; i < kn; i++)
+        {
+            vd s = vload(tm.red + (size_t)i * TILE + tm.lane);
+            for (int w = 1; w < tm.nwk; w++)
+                s = op(s, vload(tm.red + (size_t)(w * KRED + i) * TILE + tm.lane));
+            v[i0 + i] = s;
+        }
     }
 }
 template <int K>
@@ -291,11 +296,13 @@ struct TileMem
     int *I;
 };
 
-EI_DEV TileMem tile_mem(const KArgs &a, int tile)
+// Base pointers of a tile as seen by this lane: the lane's element offset is folded in once, so a
+// row access is base + row * TILE (one IMAD.WIDE).
+EI_DEV TileMem tile_mem(const Team &tm, const KArgs &a, int tile)
 {
     TileMem t;
-    t.T = a.ws + (size_t)tile * a.L.rows_total * TILE;
-    t.I = a.iws + (size_t)tile * a.L.irows_total * TILE;
+    t.T = a.ws + (size_t)tile * a.L.rows_total * TILE + tm.lane;
+    t.I = a.iws + (size_t)tile * a.L.irows_total * TILE + tm.lane;
     return t;
 }
 
@@ -348,7 +355,7 @@ EI_DEV void stage_wait_prev() // everything except the most recently committed g
 #endif
 }
 
-EI_DEV const double *rowp(const Team &tm, const double *T, int row) { return T + (size_t)row * TILE + tm.lane; }
+EI_DEV const double *rowp(const Team &, const double *T, int row) { return T + (size_t)row * TILE; }
 
 // Elementwise pass over `count` rows with NIN input arrays (row offsets in[k]): a worker takes U
 // consecutive rows at a time and loads ALL their operands before computing, so U*NIN vector loads
@@ -594,7 +601,7 @@ EI_DEV vd line_search(const Team &tm, const KArgs &a, double *T, int lam, int ds
 // entry, comes from the worker's instruction stream.
 EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
 {
-    const TileMem t = tile_mem(a, tile);
+    const TileMem t = tile_mem(tm, a, tile);
     const vb act = lane_active(tm, t);
     if (!tm.any(act))
         return;
@@ -678,7 +685,7 @@ EI_DEV void ldl_forward(const Team &tm, const KArgs &a, double *T, int rhs)
         {
             IStream is;
             is.open(P.fw + EI_LDG(seg), tm.pl);
-            const double *lv = T + (size_t)(L.LTx + EI_LDG(seg + 2)) * TILE + tm.lane;
+            const double *lv = T + (size_t)(L.LTx + EI_LDG(seg + 2)) * TILE;
             if (EI_LDG(seg + 3) == SEG_BLOCKS)
             {
                 // issue cursor (isi, lvi) runs one block ahead of the compute cursor (is, lv)
@@ -801,7 +808,7 @@ EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int out, int
         {
             IStream is;
             is.open(P.bw + EI_LDG(seg), tm.pl);
-            const double *lv = T + (size_t)(L.Lx + EI_LDG(seg + 2)) * TILE + tm.lane;
+            const double *lv = T + (size_t)(L.Lx + EI_LDG(seg + 2)) * TILE;
             if (EI_LDG(seg + 3) == SEG_BLOCKS)
             {
                 IStream isi = is;
@@ -1013,7 +1020,7 @@ EI_DEV vd kkt_residual(const Team &tm, const KArgs &a, double *T, int rhs, int x
 // criterion, the tile loops until all of its instances have stopped.
 EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
 {
-    const TileMem t = tile_mem(a, tile);
+    const TileMem t = tile_mem(tm, a, tile);
     const vb act = lane_active(tm, t);
     if (!tm.any(act))
         return;
@@ -1087,7 +1094,7 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
 // ------------------------------------------------------------------ start of a solve (src/eicos.cpp:855-894)
 EI_DEV void tile_init(const Team &tm, const KArgs &a, int tile)
 {
-    const TileMem t = tile_mem(a, tile);
+    const TileMem t = tile_mem(tm, a, tile);
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     double *T = t.T;
@@ -1184,7 +1191,7 @@ EI_DEV void bring_to_cone(const Team &tm, const KArgs &a, double *T, int src, do
 // initial point (src/eicos.cpp:933-992), after the two initial KKT solves
 EI_DEV void tile_init_point(const Team &tm, const KArgs &a, int tile)
 {
-    const TileMem t = tile_mem(a, tile);
+    const TileMem t = tile_mem(tm, a, tile);
     const vb act = lane_active(tm, t);
     if (!tm.any(act))
         return;
@@ -1351,7 +1358,7 @@ EI_DEV ConeScaling cone_scaling(const Team &tm, const double *T, int srow, int z
 // updateKKTScalings and RHSaffine (:1160-1162, :1176).  Instances that stop are back-scaled in place.
 EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
 {
-    const TileMem t = tile_mem(a, tile);
+    const TileMem t = tile_mem(tm, a, tile);
     const vb act = lane_active(tm, t);
     if (!tm.any(act))
         return;
@@ -1363,7 +1370,6 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
     const vd tau = ROWD(T, L.sc + S_TAU), kap = ROWD(T, L.sc + S_KAP);
 
     enum { HX2, RX2, CX, NX2, HY2, RY2, BY, NY2, HZ2, RZ2, HZ, NZ2, NS2, GAP, NRED };
-    static_assert(NRED <= KRED, "reduction buffer too small");
     vd r[NRED];
     for (int k = 0; k < NRED; k++)
         r[k] = vset(0.0);
@@ -1705,7 +1711,7 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
 // (src/eicos.cpp:1181-1210 with RHScombined :1282-1325, conicProduct :1357, conicDivision :1330)
 EI_DEV void tile_mid(const Team &tm, const KArgs &a, int tile)
 {
-    const TileMem t = tile_mem(a, tile);
+    const TileMem t = tile_mem(tm, a, tile);
     const vb act = lane_active(tm, t);
     if (!tm.any(act))
         return;
@@ -1857,7 +1863,7 @@ EI_DEV void tile_mid(const Team &tm, const KArgs &a, int tile)
 // ------------------------------------------------------------------ combined step and iterate update (src/eicos.cpp:1214-1252)
 EI_DEV void tile_tail(const Team &tm, const KArgs &a, int tile)
 {
-    const TileMem t = tile_mem(a, tile);
+    const TileMem t = tile_mem(tm, a, tile);
     const vb act = lane_active(tm, t);
     if (!tm.any(act))
         return;
@@ -1933,7 +1939,7 @@ EI_DEV void tile_tail(const Team &tm, const KArgs &a, int tile)
 // (c / x_equil, h / G_equil, b / A_equil : src/eicos.cpp:364-371) and land KKT-shaped in `chb`.
 EI_DEV void tile_load(const Team &tm, const KArgs &a, int tile)
 {
-    const TileMem t = tile_mem(a, tile);
+    const TileMem t = tile_mem(tm, a, tile);
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     const int n = P.n, zb = P.n + P.p;
@@ -1964,7 +1970,7 @@ EI_DEV void tile_load(const Team &tm, const KArgs &a, int tile)
 
 EI_DEV void tile_store(const Team &tm, const KArgs &a, int tile)
 {
-    const TileMem t = tile_mem(a, tile);
+    const TileMem t = tile_mem(tm, a, tile);
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     const int n = P.n, zb = P.n + P.p;
