@@ -91,7 +91,15 @@ struct eicos_solver
     int device = 0;
 };
 
-static int default_workers() { return 4; }
+// Warps per CTA (= workers per tile).  A tile is one CTA and runs a long dependent program, so the
+// machine is filled by tiles x workers: aim at ~14 warps per SM (measured optimum on B200: 2 workers
+// for 1024 tiles), more workers when there are few tiles, capped by the engine's shared-memory fit.
+static int default_workers(long long instances)
+{
+    const double tiles_per_sm = (double)((instances + Engine::tile_width() - 1) / Engine::tile_width()) / 148.0;
+    int w = (int)(14.0 / std::max(tiles_per_sm, 0.01) + 0.5);
+    return std::max(1, std::min(w, 8));
+}
 
 extern "C"
 {
@@ -124,7 +132,6 @@ eicos_batch *eicos_batch_setup(int n, int m, int p, int l, int ncones, const int
             throw std::invalid_argument("eicos_batch_setup: negative dimension or missing c");
         std::unique_ptr<eicos_batch> bt(new eicos_batch());
         bt->device = device;
-        bt->workers = workers > 0 ? workers : default_workers();
         analyze(bt->S, n, m, p, ncones, q, Gpr, Gjc, Gir, Apr, Ajc, Air, /*serial_width=*/2);
         const Symbolic &S = bt->S;
         if (S.G.nnz())
@@ -159,7 +166,9 @@ eicos_batch *eicos_batch_setup(int n, int m, int p, int l, int ncones, const int
             capacity -= capacity % 32;
 #endif
         }
+        bt->workers = workers > 0 ? workers : default_workers(capacity);
         bt->eng.reset(new Engine(bt->S, device, capacity, bt->workers));
+        bt->workers = bt->eng->workers();
         return bt.release();
     }
     catch (const std::exception &e)
@@ -437,7 +446,7 @@ eicos_solver *eicos_setup(int n, int m, int p, int l, int ncones, const int *q,
         s->z.assign(S.m, 0.0);
         s->s.assign(S.m, 0.0);
         be::set_device(device);
-        s->eng.reset(new Engine(s->S, device, 1, default_workers()));
+        s->eng.reset(new Engine(s->S, device, 1, default_workers(1)));
         return s.release();
     }
     catch (const std::exception &e)

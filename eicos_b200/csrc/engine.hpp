@@ -54,6 +54,7 @@ class Engine
 
     void *stream() const { return stream_; }
     int device() const { return device_; }
+    int workers() const { return workers_; }
     long long capacity() const { return cap_tiles_ * (long long)tile_width(); }
     size_t workspace_bytes() const { return ws_bytes_; }
     const Layout &layout() const { return L_; }
