@@ -162,6 +162,7 @@ void Engine::upload_pattern(const Symbolic &S)
     P.maxcol = S.maxcol;
     P.nph_fw = H_.nph_fw;
     P.nph_bw = H_.nph_bw;
+    P.nph_fa = H_.nph_fa;
     P.cone_dim = upload(S.q, owned_, st);
     P.cone_k = upload(S.cone_k, owned_, st);
     P.cone_q = upload(S.cone_q, owned_, st);

@@ -89,7 +89,7 @@ enum ConeParam : int
 struct DevPattern
 {
     int n, p, m, l, nc, N, mt, qtot, nnzL, nnzV, nphases, maxcol;
-    int nph_fw, nph_bw; // phases of the forward / backward sweep streams (chains are split, streams.hpp)
+    int nph_fw, nph_bw, nph_fa; // phases of the forward / backward / factor streams (chains are split, streams.hpp)
     const int *cone_dim, *cone_k, *cone_q; // per cone: dimension, first expanded index, first q row
     const int *zk;                         // compact z index -> expanded index (load / store only)
     const double *xeq, *Aeq, *GeqE;        // equilibration vectors (GeqE is expanded, 1 in the slots)

@@ -332,28 +332,33 @@ void build_streams(const Symbolic &S, int W, HostStreams &H)
         pad_tail(H.bw);
     }
 
-    // ---- numeric factorisation, left-looking by column (every position explicit)
+    // ---- numeric factorisation, left-looking by column (every position explicit).
+    // Task = [j, kind, cnt, nK, nR] {kind 2: cnt x bwpos of the stored partial column}
+    //        nK x [vidx, pos]  groups of <= FA_GROUP row entries: headers [k, fwpos, tail len] then
+    //        their tails (rel, bwpos) ...  cnt x [bwpos, fwpos].
+    // kind 0: whole column.  Columns of a serial phase (a chain of the elimination tree) are split:
+    // kind 1 = contributions of columns OUTSIDE the chain, done in a parallel phase, partial column
+    // stored un-normalised in D / Lx; kind 2 = chain task continuing such a partial; kind 3 = chain
+    // task without external contributions.
     ivec Lcsr(S.nnzL);
     for (int t = 0; t < S.nnzL; t++)
         Lcsr[S.Lr.v[t]] = t;
-    H.fa_seg.assign((size_t)nph * W * 3, 0);
-    for (int ph = 0; ph < nph; ph++)
-        for (int w = 0; w < W; w++)
-        {
-            align_chunk(H.fa);
-            align_chunk(H.fa_val);
-            const ivec tk = worker_tasks(S, S.phases[ph], w, W, false);
-            int *seg = &H.fa_seg[((size_t)ph * W + w) * 3];
-            seg[0] = (int)H.fa.size();
-            seg[1] = (int)tk.size();
-            seg[2] = (int)H.fa_val.size();
-            for (int j : tk)
-            {
-                const int cnt = S.Lp[j + 1] - S.Lp[j];
-                H.fa.push_back(j);
-                H.fa.push_back(cnt);
-                H.fa.push_back(S.KLp[j + 1] - S.KLp[j]);
-                H.fa.push_back(S.Lr.p[j + 1] - S.Lr.p[j]);
+    H.fa_seg.clear();
+    H.nph_fa = 0;
+    {
+        ivec where(S.N, -1);
+        auto emit_task = [&](int j, int kind, const ivec &rows /* CSR indices t */) {
+            const int cnt = S.Lp[j + 1] - S.Lp[j];
+            const bool with_k = kind != 2;
+            H.fa.push_back(j);
+            H.fa.push_back(kind);
+            H.fa.push_back(cnt);
+            H.fa.push_back(with_k ? S.KLp[j + 1] - S.KLp[j] : 0);
+            H.fa.push_back((int)rows.size());
+            if (kind == 2)
+                for (int q = 0; q < cnt; q++)
+                    H.fa.push_back(H.bw_pos[S.Lp[j] + q]);
+            if (with_k)
                 for (int e = S.KLp[j]; e < S.KLp[j + 1]; e++)
                 {
                     const int slot = S.KLslot[e], vi = S.Kvidx[slot];
@@ -362,27 +367,96 @@ void build_streams(const Symbolic &S, int W, HostStreams &H)
                     if (vi < 0)
                         H.fa_val.push_back(S.Kshared[slot]);
                 }
-                for (int t = S.Lr.p[j]; t < S.Lr.p[j + 1]; t++)
+            for (size_t g = 0; g < rows.size(); g += FA_GROUP)
+            {
+                const size_t ge = std::min(rows.size(), g + FA_GROUP);
+                for (size_t r = g; r < ge; r++)
                 {
-                    const int k = S.Lr.j[t];
-                    const int u0 = S.upd_tail[t], len = S.Lp[k + 1] - u0;
+                    const int t = rows[r], k = S.Lr.j[t];
                     H.fa.push_back(k);
                     H.fa.push_back(H.fw_pos[t]);
-                    H.fa.push_back(len);
-                    for (int r = 0; r < len; r++)
+                    H.fa.push_back(S.Lp[k + 1] - S.upd_tail[t]);
+                }
+                for (size_t r = g; r < ge; r++)
+                {
+                    const int t = rows[r], k = S.Lr.j[t];
+                    const int u0 = S.upd_tail[t], len = S.Lp[k + 1] - u0;
+                    for (int q = 0; q < len; q++)
                     {
-                        H.fa.push_back(S.upd_rel[S.upd_rel_p[t] + r]);
-                        H.fa.push_back(H.bw_pos[u0 + r]);
+                        H.fa.push_back(S.upd_rel[S.upd_rel_p[t] + q]);
+                        H.fa.push_back(H.bw_pos[u0 + q]);
                     }
                 }
-                for (int q = 0; q < cnt; q++)
+            }
+            for (int q = 0; q < cnt; q++)
+            {
+                const int u = S.Lp[j] + q;
+                H.fa.push_back(H.bw_pos[u]);
+                H.fa.push_back(H.fw_pos[Lcsr[u]]);
+            }
+        };
+        auto emit_phase = [&](const std::vector<std::vector<std::pair<int, std::pair<int, ivec>>>> &pw) {
+            for (int w = 0; w < W; w++)
+            {
+                align_chunk(H.fa);
+                align_chunk(H.fa_val);
+                H.fa_seg.insert(H.fa_seg.end(), {(int)H.fa.size(), (int)pw[w].size(), (int)H.fa_val.size()});
+                for (const auto &tk : pw[w])
+                    emit_task(tk.first, tk.second.first, tk.second.second);
+            }
+            H.nph_fa++;
+        };
+        auto all_rows = [&](int j) {
+            ivec r;
+            for (int t = S.Lr.p[j]; t < S.Lr.p[j + 1]; t++)
+                r.push_back(t);
+            return r;
+        };
+        for (int ph = 0; ph < nph; ph++)
+        {
+            const Phase &f = S.phases[ph];
+            std::vector<std::vector<std::pair<int, std::pair<int, ivec>>>> pw(W);
+            if (f.parallel)
+            {
+                for (int w = 0; w < W; w++)
+                    for (int j : worker_tasks(S, f, w, W, false))
+                        pw[w].push_back({j, {0, all_rows(j)}});
+                emit_phase(pw);
+                continue;
+            }
+            const ivec tk = worker_tasks(S, f, 0, W, false);
+            for (size_t a = 0; a < tk.size(); a++)
+                where[tk[a]] = (int)a;
+            std::vector<char> has_ext(tk.size(), 0);
+            int rr = 0;
+            for (size_t a = 0; a < tk.size(); a++)
+            {
+                ivec ext;
+                for (int t = S.Lr.p[tk[a]]; t < S.Lr.p[tk[a] + 1]; t++)
+                    if (where[S.Lr.j[t]] < 0)
+                        ext.push_back(t);
+                if (!ext.empty())
                 {
-                    const int u = S.Lp[j] + q;
-                    H.fa.push_back(H.bw_pos[u]);
-                    H.fa.push_back(H.fw_pos[Lcsr[u]]);
+                    has_ext[a] = 1;
+                    pw[rr++ % W].push_back({tk[a], {1, ext}});
                 }
             }
+            if (rr > 0)
+                emit_phase(pw);
+            std::vector<std::vector<std::pair<int, std::pair<int, ivec>>>> cw(W);
+            for (size_t a = 0; a < tk.size(); a++)
+            {
+                ivec in;
+                for (int t = S.Lr.p[tk[a]]; t < S.Lr.p[tk[a] + 1]; t++)
+                    if (where[S.Lr.j[t]] >= 0)
+                        in.push_back(t);
+                cw[0].push_back({tk[a], {has_ext[a] ? 2 : 3, in}});
+            }
+            emit_phase(cw);
+            for (int j : tk)
+                where[j] = -1;
         }
+    }
     pad_tail(H.fa);
     pad_tail(H.fa_val);
 

@@ -33,6 +33,7 @@ constexpr int FWD_PREV1 = -1;     // gather code: result of the previous task of
 constexpr int FWD_PREV2 = -2;     // ... of the task before that
 constexpr int FWD_PREV3 = -3;
 constexpr int INIT_PARTIAL = -1;  // task header: the start value is the partial result already stored in the output row
+constexpr int FA_GROUP = 4;        // row entries of a factor task whose operands are loaded together
 constexpr int ROW_EXTRA_SLOTS = 4; // staging slots a mat-vec row may use besides its gathers
 
 enum SegKind : int
@@ -45,7 +46,7 @@ struct HostStreams
 {
     int workers = 1;
     // triangular sweeps: phases in PROCESSING order; seg = [phase][worker]{int offset, count, first value row, kind}
-    int nph_fw = 0, nph_bw = 0;
+    int nph_fw = 0, nph_bw = 0, nph_fa = 0;
     ivec fw, fw_seg, bw, bw_seg;
     ivec fw_pos, bw_pos; // storage row (inside LTx / Lx) of CSR entry t / CSC entry u
     // factorisation: seg = [phase][worker]{int offset, tasks, double offset}

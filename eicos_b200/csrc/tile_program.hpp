@@ -610,7 +610,7 @@ EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
     double *T = t.T;
     double *acc = tm.acc + (size_t)tm.wk * P.maxcol * TILE + tm.lane;
     vb zero_pivot = vbset(false);
-    for (int ph = 0; ph < P.nphases; ph++)
+    for (int ph = 0; ph < P.nph_fa; ph++)
     {
         const int *seg = P.fa_seg + ((size_t)ph * tm.nwk + tm.wk) * 3;
         const int nt = EI_LDG(seg + 1);
@@ -622,10 +622,20 @@ EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
             ds.open(P.fa_val + EI_LDG(seg + 2), tm.pl);
             for (int q = 0; q < nt; q++)
             {
-                const int j = is.get(), cnt = is.get(), nK = is.get(), nR = is.get();
-                for (int c = 0; c < cnt; c++)
-                    vstore(acc + (size_t)c * TILE, vset(0.0));
-                vd d = vset(0.0);
+                const int j = is.get(), kind = is.get(), cnt = is.get(), nK = is.get(), nR = is.get();
+                vd d;
+                if (kind == 2)
+                { // continue the partial column left by the external part
+                    d = ROWD(T, L.D + j);
+                    for (int c = 0; c < cnt; c++)
+                        vstore(acc + (size_t)c * TILE, ROWD(T, L.Lx + is.get()));
+                }
+                else
+                {
+                    d = vset(0.0);
+                    for (int c = 0; c < cnt; c++)
+                        vstore(acc + (size_t)c * TILE, vset(0.0));
+                }
                 for (int e = 0; e < nK; e++)
                 {
                     const int vi = is.get(), pos = is.get();
@@ -635,18 +645,69 @@ EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
                     else
                         vstore(acc + (size_t)pos * TILE, val);
                 }
-                for (int r = 0; r < nR; r++)
-                {
-                    const int k = is.get(), fp = is.get(), tl = is.get();
-                    const vd ljk = ROWD(T, L.LTx + fp);
-                    const vd w = ljk * vd(ROWD(T, L.D + k));
-                    d -= ljk * w;
-                    for (int u = 0; u < tl; u++)
+                for (int r0 = 0; r0 < nR; r0 += FA_GROUP)
+                { // operands of up to FA_GROUP row entries are loaded before any of them is used
+                    int tl[FA_GROUP];
+                    vd w[FA_GROUP];
                     {
-                        const int rel = is.get(), bp = is.get();
-                        double *ap = acc + (size_t)rel * TILE;
-                        vstore(ap, vload(ap) - vd(ROWD(T, L.Lx + bp)) * w);
+                        int k[FA_GROUP], fp[FA_GROUP];
+                        vd ljk[FA_GROUP], dk[FA_GROUP];
+#pragma unroll
+                        for (int u = 0; u < FA_GROUP; u++)
+                        {
+                            tl[u] = 0;
+                            if (r0 + u < nR)
+                            {
+                                k[u] = is.get();
+                                fp[u] = is.get();
+                                tl[u] = is.get();
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < FA_GROUP; u++)
+                            if (r0 + u < nR)
+                            {
+                                ljk[u] = ROWD(T, L.LTx + fp[u]);
+                                dk[u] = ROWD(T, L.D + k[u]);
+                            }
+#pragma unroll
+                        for (int u = 0; u < FA_GROUP; u++)
+                            if (r0 + u < nR)
+                            {
+                                w[u] = ljk[u] * dk[u];
+                                d -= ljk[u] * w[u];
+                            }
                     }
+#pragma unroll
+                    for (int u = 0; u < FA_GROUP; u++)
+                    {
+                        int t0 = 0;
+                        for (; t0 + 2 <= tl[u]; t0 += 2)
+                        {
+                            const int rel0 = is.get(), bp0 = is.get(), rel1 = is.get(), bp1 = is.get();
+                            const vd l0 = ROWD(T, L.Lx + bp0), l1 = ROWD(T, L.Lx + bp1);
+                            double *a0 = acc + (size_t)rel0 * TILE, *a1 = acc + (size_t)rel1 * TILE;
+                            vstore(a0, vload(a0) - l0 * w[u]);
+                            vstore(a1, vload(a1) - l1 * w[u]);
+                        }
+                        for (; t0 < tl[u]; t0++)
+                        {
+                            const int rel = is.get(), bp = is.get();
+                            double *ap = acc + (size_t)rel * TILE;
+                            vstore(ap, vload(ap) - vd(ROWD(T, L.Lx + bp)) * w[u]);
+                        }
+                    }
+                }
+                if (kind == 1)
+                { // external part only: leave the un-normalised partial column for the chain task
+                    ROWD(T, L.D + j) = d;
+                    for (int c = 0; c < cnt; c++)
+                    {
+                        const int bp = is.get();
+                        (void)is.get();
+                        ROWD(T, L.Lx + bp) = vload(acc + (size_t)c * TILE);
+                    }
+                    continue;
                 }
                 ROWD(T, L.D + j) = d;
                 ROWD(T, L.Dinv + j) = 1.0 / d;
@@ -663,6 +724,34 @@ EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
         tm.sync();
     }
     VFOR if (zero_pivot.v[c_] && act.v[c_]) ROWC(t.I, J_STATUS, c_) = EXIT_FATAL;
+}
+
+// v - sum_k L[k] * vec[gather_k] for a row too long for the staging buffers: six entries at a time,
+// all twelve loads issued before the first multiply-add.
+EI_DEV vd long_row(const Team &tm, IStream &is, const double *T, const double *lv, int vec, int cnt, vd v)
+{
+    constexpr int U = 6;
+    int k = 0;
+    for (; k + U <= cnt; k += U, lv += (size_t)U * TILE)
+    {
+        int c[U];
+        vd l[U], g[U];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            c[u] = is.get();
+#pragma unroll
+        for (int u = 0; u < U; u++)
+        {
+            l[u] = vload(lv + (size_t)u * TILE);
+            g[u] = vload(rowp(tm, T, vec + c[u]));
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            v -= l[u] * g[u];
+    }
+    for (; k < cnt; k++, lv += TILE)
+        v -= vload(lv) * vload(rowp(tm, T, vec + is.get()));
+    return v;
 }
 
 // ------------------------------------------------------------------ triangular solves (Eigen solve, src/eicos.cpp:1477,1599)
@@ -732,8 +821,8 @@ EI_DEV void ldl_forward(const Team &tm, const KArgs &a, double *T, int rhs)
                     { // oversize row: straight from global memory
                         const int i = is.get(), r = is.get(), cnt = is.get();
                         vd v = r >= 0 ? vd(ROWD(T, rhs + r)) : vd(ROWD(T, L.xw + i));
-                        for (int k = 0; k < cnt; k++, lv += TILE)
-                            v -= vload(lv) * vd(ROWD(T, L.xw + is.get()));
+                        v = long_row(tm, is, T, lv, L.xw, cnt, v);
+                        lv += (size_t)cnt * TILE;
                         ROWD(T, L.xw + i) = v;
                         continue;
                     }
@@ -861,8 +950,8 @@ EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int out, int
                         const int j = is.get(), oe = is.get(), cnt = is.get();
                         const int o = oe >= 0 ? oe : ~oe;
                         vd v = j >= 0 ? vd(ROWD(T, L.Dinv + j)) * vd(ROWD(T, L.xw + j)) : vd(ROWD(T, out + o));
-                        for (int k = 0; k < cnt; k++, lv += TILE)
-                            v -= vload(lv) * vd(ROWD(T, out + is.get()));
+                        v = long_row(tm, is, T, lv, out, cnt, v);
+                        lv += (size_t)cnt * TILE;
                         ROWD(T, out + o) = v;
                         if (accumulate && oe >= 0)
                             ROWD(T, x + o) += vsel(cont, v, zero);
