@@ -35,7 +35,7 @@ class BatchStats(C.Structure):
                 ("ir_rounds", C.c_ulonglong), ("ms_total", C.c_double), ("ms_factor", C.c_double),
                 ("ms_solve", C.c_double), ("ms_other", C.c_double),
                 ("factor_launch_tiles", C.c_longlong), ("solve_launch_tiles", C.c_longlong),
-                ("factor_launches", C.c_int), ("solve_launches", C.c_int)]
+                ("factor_launches", C.c_int), ("solve_launches", C.c_int), ("compactions", C.c_int)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -55,7 +55,7 @@ EXPORTS = [
     "eicos_setup", "eicos_update_data", "eicos_update_data_full", "eicos_solve", "eicos_solution",
     "eicos_get_duals", "eicos_get_info", "eicos_cleanup",
     "eicos_batch_setup", "eicos_batch_update_matrices", "eicos_batch_solve", "eicos_batch_solve_device",
-    "eicos_batch_set_timing", "eicos_batch_get_stats", "eicos_batch_get_dims", "eicos_batch_get_symbolic",
+    "eicos_batch_set_timing", "eicos_batch_set_compaction", "eicos_batch_get_stats", "eicos_batch_get_dims", "eicos_batch_get_symbolic",
     "eicos_batch_debug_init", "eicos_batch_stream", "eicos_batch_cleanup",
     "eicos_last_error", "eicos_device_count",
 ]
@@ -110,6 +110,8 @@ class Library:
         L.eicos_batch_solve_device.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 9
         L.eicos_batch_set_timing.restype = C.c_int
         L.eicos_batch_set_timing.argtypes = [C.c_void_p, C.c_int]
+        L.eicos_batch_set_compaction.restype = C.c_int
+        L.eicos_batch_set_compaction.argtypes = [C.c_void_p, C.c_int]
         L.eicos_batch_get_stats.restype = C.c_int
         L.eicos_batch_get_stats.argtypes = [C.c_void_p, C.POINTER(BatchStats)]
         L.eicos_batch_get_dims.restype = C.c_int
@@ -248,6 +250,9 @@ class BatchSolver:
 
     def set_timing(self, on=True):
         self.lib.check(self.lib.L.eicos_batch_set_timing(self.h, int(on)))
+
+    def set_compaction(self, on=True):
+        self.lib.check(self.lib.L.eicos_batch_set_compaction(self.h, int(on)))
 
     def stats(self):
         s = BatchStats()

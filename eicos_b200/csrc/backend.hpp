@@ -38,6 +38,11 @@ inline void dfree(void *p) { cudaFree(p); }
 inline void h2d(void *d, const void *h, size_t n, stream_t s) { if (n) EI_CUDA(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); }
 inline void d2h(void *h, const void *d, size_t n, stream_t s) { if (n) EI_CUDA(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); }
 inline void zero(void *d, size_t n, stream_t s) { if (n) EI_CUDA(cudaMemsetAsync(d, 0, n, s)); }
+inline void d2h_2d(void *h, size_t hpitch, const void *d, size_t dpitch, size_t width, size_t rows, stream_t s)
+{
+    if (width && rows)
+        EI_CUDA(cudaMemcpy2DAsync(h, hpitch, d, dpitch, width, rows, cudaMemcpyDeviceToHost, s));
+}
 inline void sync(stream_t s) { EI_CUDA(cudaStreamSynchronize(s)); }
 inline stream_t make_stream()
 {
@@ -69,6 +74,11 @@ inline void dfree(void *p) { std::free(p); }
 inline void h2d(void *d, const void *h, size_t n, stream_t) { if (n) std::memcpy(d, h, n); }
 inline void d2h(void *h, const void *d, size_t n, stream_t) { if (n) std::memcpy(h, d, n); }
 inline void zero(void *d, size_t n, stream_t) { if (n) std::memset(d, 0, n); }
+inline void d2h_2d(void *h, size_t hpitch, const void *d, size_t dpitch, size_t width, size_t rows, stream_t)
+{
+    for (size_t r = 0; r < rows; r++)
+        std::memcpy((char *)h + r * hpitch, (const char *)d + r * dpitch, width);
+}
 inline void sync(stream_t) {}
 inline stream_t make_stream() { return 0; }
 inline void drop_stream(stream_t) {}

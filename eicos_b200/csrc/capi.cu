@@ -289,6 +289,14 @@ int eicos_batch_set_timing(eicos_batch *bt, int enabled)
     return 0;
 }
 
+int eicos_batch_set_compaction(eicos_batch *bt, int enabled)
+{
+    if (!bt)
+        return fail(EICOS_ERR_INVALID, "null handle");
+    bt->eng->set_compaction(enabled != 0);
+    return 0;
+}
+
 int eicos_batch_get_stats(const eicos_batch *bt, eicos_batch_stats *o)
 {
     if (!bt || !o)
@@ -306,6 +314,7 @@ int eicos_batch_get_stats(const eicos_batch *bt, eicos_batch_stats *o)
     o->solve_launch_tiles = s.solve_launch_tiles;
     o->factor_launches = s.factor_launches;
     o->solve_launches = s.solve_launches;
+    o->compactions = s.compactions;
     return 0;
 }
 

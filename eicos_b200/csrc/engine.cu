@@ -42,6 +42,15 @@ EI_DEFINE_KERNEL(eicos_iter_tail, tile_tail, 2)
 EI_DEFINE_KERNEL(eicos_store_outputs, tile_store, 2)
 
 #define EI_LAUNCH(name, fn, tiles, threads, smem, stream, args) name<<<(tiles), (threads), (smem), (stream)>>>(args)
+
+__global__ void eicos_compact(const __grid_constant__ KArgs a, const __grid_constant__ MoveRanges mr, const int *moves)
+{
+    const int src = moves[2 * blockIdx.x], dst = moves[2 * blockIdx.x + 1];
+    compact_move(a, mr, src, dst, threadIdx.x, blockDim.x);
+    __syncthreads();
+    if (threadIdx.x == 0)
+        compact_vacate(a, src);
+}
 #else
 #define EI_MAX_THREADS 256
 // emulator: one std::thread per worker of a tile, CTA barrier = std::barrier
@@ -75,6 +84,17 @@ EI_DEFINE_KERNEL(eicos_store_outputs, tile_store, 2)
                 t_.join();                                                                        \
         }                                                                                         \
     } while (0)
+#endif
+
+#ifdef EICOS_EMU
+static void eicos_compact_emu(const KArgs &a, const MoveRanges &mr, const int *moves, int nmoves)
+{
+    for (int q = 0; q < nmoves; q++)
+    {
+        compact_move(a, mr, moves[2 * q], moves[2 * q + 1], 0, 1);
+        compact_vacate(a, moves[2 * q]);
+    }
+}
 #endif
 
 int Engine::tile_width() { return TILE; }
@@ -246,6 +266,10 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
     active_count_ = (unsigned int *)be::alloc(sizeof(unsigned int));
     ir_rounds_ = (unsigned long long *)be::alloc(sizeof(unsigned long long));
     host_pinned_ = (unsigned int *)be::pinned(4 * sizeof(unsigned long long));
+    const size_t slots = (size_t)cap_tiles_ * TILE;
+    moves_dev_ = (int *)be::alloc(2 * slots * sizeof(int));
+    status_host_ = (int *)be::pinned(slots * sizeof(int));
+    moves_host_ = (int *)be::pinned(2 * slots * sizeof(int));
     smem_common_ = (size_t)workers_ * ((workers_ > 1 ? KRED : 0) + 2 * STAGE_SLOTS) * TILE * sizeof(double);
     smem_factor_ = smem_common_ + (size_t)workers_ * S.maxcol * TILE * sizeof(double);
 #ifndef EICOS_EMU
@@ -285,6 +309,9 @@ Engine::~Engine()
     be::dfree(active_count_);
     be::dfree(ir_rounds_);
     be::unpin(host_pinned_);
+    be::dfree(moves_dev_);
+    be::unpin(status_host_);
+    be::unpin(moves_host_);
     be::drop_stream(S_(stream_));
 }
 
@@ -397,7 +424,7 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
     for (long long first = 0; first < batch; first += cap_tiles_ * TILE)
     {
         const int nb = (int)std::min<long long>(batch - first, cap_tiles_ * TILE);
-        const int tiles = (nb + TILE - 1) / TILE;
+        int tiles = (nb + TILE - 1) / TILE;
         a.batch = nb;
         a.first = (int)first;
         stt.chunks++;
@@ -431,8 +458,59 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
             stt.ipm_iterations++;
             be::d2h(host_pinned_, active_count_, sizeof(unsigned int), st);
             be::sync(st);
-            if (host_pinned_[0] == 0)
+            const long long nactive = host_pinned_[0];
+            if (nactive == 0)
                 break;
+            // ---- active-set compaction: when enough instances have finished, store their results and
+            // pack the survivors into the leading tiles so that later launches cover fewer tiles
+            if (compaction_ && !keep_sticky && tiles >= 8 && nactive * 4 <= (long long)tiles * TILE * 3)
+            {
+                EI_TIMED(2, EI_LAUNCH(eicos_store_outputs, tile_store, tiles, threads, smem_common_, st, a));
+                be::d2h_2d(status_host_, TILE * sizeof(int), iws_ + (size_t)J_STATUS * TILE,
+                           (size_t)L_.irows_total * TILE * sizeof(int), TILE * sizeof(int), tiles, st);
+                be::sync(st);
+                const int new_tiles = (int)((nactive + TILE - 1) / TILE);
+                int nmoves = 0, hole = 0;
+                const int keep = new_tiles * TILE;
+                for (int src = keep; src < tiles * TILE; src++)
+                {
+                    if (status_host_[src] != ST_ACTIVE)
+                        continue;
+                    while (hole < keep && status_host_[hole] == ST_ACTIVE)
+                        hole++;
+                    if (hole >= keep)
+                        throw std::logic_error("compaction: no free slot");
+                    moves_host_[2 * nmoves] = src;
+                    moves_host_[2 * nmoves + 1] = hole++;
+                    nmoves++;
+                }
+                if (nmoves > 0)
+                {
+                    be::h2d(moves_dev_, moves_host_, 2 * (size_t)nmoves * sizeof(int), st);
+                    MoveRanges mr;
+                    // rows that are live between the head step and the rest of the iteration (everything
+                    // else - factor, solutions, work vectors - is recomputed): problem data, iterate and best
+                    // iterate (contiguous), residuals, scalings + scaling block (contiguous), both right-hand
+                    // sides (contiguous), scalars
+                    const int rr[12] = {L_.chb, P_.N,
+                                        L_.w, (L_.blam + P_.mt) - L_.w,
+                                        L_.r, P_.N,
+                                        L_.lpv, (L_.V + P_.nnzV) - L_.lpv,
+                                        L_.rhs1, 2 * P_.N,
+                                        L_.sc, S_COUNT};
+                    mr.n = 6;
+                    for (int k = 0; k < 12; k++)
+                        mr.r[k] = rr[k];
+#ifndef EICOS_EMU
+                    eicos_compact<<<nmoves, 128, 0, st>>>(a, mr, moves_dev_);
+#else
+                    eicos_compact_emu(a, mr, moves_dev_, nmoves);
+#endif
+                    stt.launches++;
+                    stt.compactions++;
+                }
+                tiles = new_tiles;
+            }
             factor();
             kkt(L_.rhs1, L_.sol1, 0, -1);
             kkt(L_.rhs2, L_.sol2, 0, -1);

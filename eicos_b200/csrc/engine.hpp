@@ -15,7 +15,7 @@ namespace eicos
 
 struct SolveStats
 {
-    int chunks = 0;
+    int chunks = 0, compactions = 0;
     int ipm_iterations = 0;          // head launches over all chunks
     long long launches = 0;          // kernels launched
     unsigned long long ir_rounds = 0; // triangular-solve rounds executed (tile-rounds, all solveKKT calls)
@@ -55,6 +55,7 @@ class Engine
     void *stream() const { return stream_; }
     int device() const { return device_; }
     int workers() const { return workers_; }
+    void set_compaction(bool on) { compaction_ = on; }
     long long capacity() const { return cap_tiles_ * (long long)tile_width(); }
     size_t workspace_bytes() const { return ws_bytes_; }
     const Layout &layout() const { return L_; }
@@ -77,6 +78,8 @@ class Engine
     unsigned int *active_count_ = nullptr;
     unsigned long long *ir_rounds_ = nullptr;
     unsigned int *host_pinned_ = nullptr;
+    int *moves_dev_ = nullptr, *status_host_ = nullptr, *moves_host_ = nullptr; // active-set compaction
+    bool compaction_ = true;
     size_t smem_factor_ = 0, smem_common_ = 0;
     std::vector<void *> owned_; // device allocations holding pattern data
     // positions of value arrays that upload_values() rewrites

@@ -57,6 +57,8 @@ enum IntRow : int
     J_BEST = J_WORK_END,
     J_BEST_END = J_BEST + J_WORK_END,
     J_STATUS = J_BEST_END, // ST_ACTIVE or the exit code
+    J_INST,                // index of the instance inside the device batch (-1: padding / vacated slot)
+    J_STORED,              // results already written to the output buffers
     J_COUNT
 };
 

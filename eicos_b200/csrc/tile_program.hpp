@@ -1194,6 +1194,8 @@ EI_DEV void tile_init(const Team &tm, const KArgs &a, int tile)
         {
             const bool valid = tile * TILE + tm.lane + c_ < a.batch;
             ROWC(t.I, J_STATUS, c_) = valid ? (int)ST_ACTIVE : (int)EXIT_FATAL;
+            ROWC(t.I, J_INST, c_) = valid ? a.first + tile * TILE + tm.lane + c_ : -1;
+            ROWC(t.I, J_STORED, c_) = 0;
             if (!a.keep_sticky)
             {
                 ROWC(t.I, J_HAS_PINFRES, c_) = 0;
@@ -2059,16 +2061,18 @@ EI_DEV void tile_load(const Team &tm, const KArgs &a, int tile)
 
 EI_DEV void tile_store(const Team &tm, const KArgs &a, int tile)
 {
+    // Writes the results of every instance of the tile that has finished and has not been stored yet
+    // (called once at the end, and before a compaction frees the slots of finished instances).
     const TileMem t = tile_mem(tm, a, tile);
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     const int n = P.n, zb = P.n + P.p;
     VFOR
     {
-        const int inst = tile * TILE + tm.lane + c_;
-        if (inst >= a.batch)
+        const int inst = ROWC(t.I, J_INST, c_);
+        if (inst < 0 || ROWC(t.I, J_STORED, c_) || ROWC(t.I, J_STATUS, c_) == ST_ACTIVE)
             continue;
-        const size_t g = (size_t)a.first + inst;
+        const size_t g = (size_t)inst;
         if (a.out_x)
             for (int j = tm.wk; j < n; j += tm.nwk)
                 a.out_x[g * n + j] = ROWC(t.T, L.w + j, c_);
@@ -2095,6 +2099,38 @@ EI_DEV void tile_store(const Team &tm, const KArgs &a, int tile)
                     a.out_iinfo[g * J_WORK_END + k] = ROWC(t.I, k, c_);
         }
     }
+    tm.sync();
+    if (tm.wk == 0)
+        VFOR if (ROWC(t.I, J_INST, c_) >= 0 && ROWC(t.I, J_STATUS, c_) != ST_ACTIVE) ROWC(t.I, J_STORED, c_) = 1;
+}
+
+// ------------------------------------------------------------------ active-set compaction
+// Moves one still-active instance from slot `src` to the free slot `dst` (slot = tile * TILE + lane
+// position): the rows that carry state across iterations are copied, everything else is recomputed.
+struct MoveRanges
+{
+    int n;        // number of (first row, rows) pairs
+    int r[12];
+};
+EI_DEV void compact_move(const KArgs &a, const MoveRanges &mr, int src, int dst, int tid, int nthreads)
+{
+    const size_t st = (size_t)(src / TILE), dt = (size_t)(dst / TILE);
+    const int sl = src % TILE, dl = dst % TILE;
+    const double *S = a.ws + st * a.L.rows_total * TILE + sl;
+    double *D = a.ws + dt * a.L.rows_total * TILE + dl;
+    for (int q = 0; q < mr.n; q++)
+        for (int r = mr.r[2 * q] + tid, e = mr.r[2 * q] + mr.r[2 * q + 1]; r < e; r += nthreads)
+            D[(size_t)r * TILE] = S[(size_t)r * TILE];
+    int *SI = a.iws + st * a.L.irows_total * TILE + sl, *DI = a.iws + dt * a.L.irows_total * TILE + dl;
+    for (int r = tid; r < J_COUNT; r += nthreads)
+        DI[(size_t)r * TILE] = SI[(size_t)r * TILE];
+}
+EI_DEV void compact_vacate(const KArgs &a, int src)
+{ // the source slot becomes an empty, already-stored, inactive slot
+    int *SI = a.iws + (size_t)(src / TILE) * a.L.irows_total * TILE + src % TILE;
+    SI[(size_t)J_STATUS * TILE] = EXIT_FATAL;
+    SI[(size_t)J_INST * TILE] = -1;
+    SI[(size_t)J_STORED * TILE] = 1;
 }
 
 } // namespace eicos

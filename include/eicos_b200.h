@@ -121,10 +121,15 @@ typedef struct eicos_batch_stats
     double ms_total, ms_factor, ms_solve, ms_other; /* device time (CUDA events) of the last solve */
     long long factor_launch_tiles, solve_launch_tiles;
     int factor_launches, solve_launches;
+    int compactions; /* active-set compactions performed */
 } eicos_batch_stats;
 
 /* Per-kernel-class device timing of the LAST eicos_batch_solve* call (enable first). */
 int eicos_batch_set_timing(eicos_batch *bt, int enabled);
+/* Active-set compaction (on by default): when at most 3/4 of the resident instances are still
+ * iterating, results of the finished ones are written out and the survivors are packed into fewer
+ * tiles.  Results do not depend on it. */
+int eicos_batch_set_compaction(eicos_batch *bt, int enabled);
 int eicos_batch_get_stats(const eicos_batch *bt, eicos_batch_stats *out);
 
 typedef struct eicos_batch_dims

@@ -123,3 +123,23 @@ def test_initial_factor_and_solves(oracle_mod, emu_lib):
             # not to machine precision.  Iterative refinement (solveKKT) is what removes this.
             assert np.max(np.abs(r["D"][b] - Do) / np.maximum(1.0, np.abs(Do))) <= 1e-7
             assert np.max(np.abs(r["Lx"][b] - Lo), initial=0.0) <= 1e-9 * max(1.0, np.max(np.abs(Lo), initial=0.0))
+
+
+def test_compaction_is_transparent(oracle_mod, emu_lib):
+    """Active-set compaction (finished instances stored early, survivors packed into fewer tiles) must
+    not change a single bit of the results."""
+    from eicos_b200.binding import BatchSolver
+    from eicos_b200.workloads import perturbed
+    P = oracle_mod.load_fixture("update_data_1")
+    batch = 300
+    W = perturbed(P, batch, rel=0.05, seed=9)
+    B = BatchSolver(P, lib=emu_lib, capacity=batch, workers=2)
+    a = B.solve(batch, hs=W["hs"], bs=W["bs"])
+    assert B.stats()["compactions"] >= 1
+    B.set_compaction(False)
+    b = B.solve(batch, hs=W["hs"], bs=W["bs"])
+    assert B.stats()["compactions"] == 0
+    for k in ("x", "y", "z", "s", "exit", "iter"):
+        assert np.array_equal(a[k], b[k]), k
+    ref = oracle_mod.batch_run(P, batch, hs=W["hs"], bs=W["bs"], nthreads=8)
+    assert np.array_equal(a["exit"], ref["exit"]) and np.array_equal(a["iter"], ref["iter"])

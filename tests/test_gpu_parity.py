@@ -193,3 +193,23 @@ def test_full_size_mpc02_properties(oracle_mod, gpu_lib):
     ref = oracle_mod.batch_run(P, 64, hs=W["hs"][:64], bs=W["bs"][:64], nthreads=8)
     assert np.array_equal(ref["exit"], out["exit"][:64])
     assert relerr(out["x"][:64], ref["x"]) <= TOL
+
+
+def test_compaction_is_transparent(oracle_mod, gpu_lib):
+    """Active-set compaction (finished instances stored early, survivors packed into fewer tiles) must
+    not change a single bit of the results."""
+    from eicos_b200.binding import BatchSolver
+    from eicos_b200.workloads import perturbed
+    P = oracle_mod.load_fixture("update_data_1")
+    batch = 300
+    W = perturbed(P, batch, rel=0.05, seed=9)
+    B = BatchSolver(P, lib=gpu_lib, capacity=batch, workers=2)
+    a = B.solve(batch, hs=W["hs"], bs=W["bs"])
+    assert B.stats()["compactions"] >= 1
+    B.set_compaction(False)
+    b = B.solve(batch, hs=W["hs"], bs=W["bs"])
+    assert B.stats()["compactions"] == 0
+    for k in ("x", "y", "z", "s", "exit", "iter"):
+        assert np.array_equal(a[k], b[k]), k
+    ref = oracle_mod.batch_run(P, batch, hs=W["hs"], bs=W["bs"], nthreads=8)
+    assert np.array_equal(a["exit"], ref["exit"]) and np.array_equal(a["iter"], ref["iter"])

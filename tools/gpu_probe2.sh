@@ -15,4 +15,4 @@ if [ "$1" == "ncu1" ]; then
   tail -3 gpurun_out/tile1/log.txt
   exit 0
 fi
-run 64 2; run 65536 2; run 65536 3
+run 64 2; run 65536 2
