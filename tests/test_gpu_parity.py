@@ -201,7 +201,7 @@ def test_compaction_is_transparent(oracle_mod, gpu_lib):
     from eicos_b200.binding import BatchSolver
     from eicos_b200.workloads import perturbed
     P = oracle_mod.load_fixture("update_data_1")
-    batch = 300
+    batch = 1500  # 24 tiles of 64 instances: compaction needs at least 8 tiles
     W = perturbed(P, batch, rel=0.05, seed=9)
     B = BatchSolver(P, lib=gpu_lib, capacity=batch, workers=2)
     a = B.solve(batch, hs=W["hs"], bs=W["bs"])
