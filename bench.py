@@ -309,6 +309,11 @@ def main():
                                "share_of_step": ms_factor / ms_kernels if ms_kernels else None,
                                "traffic": (traffic or {}).get("eicos_ldl_factor")}}
 
+    # where the tiles spend their time inside eicos_solve_kkt (clock64 per phase, summed over tiles)
+    pc = np.sum([s["kkt_phase_cycles"] for s in stats], axis=0).astype(float)
+    phase_share = dict(zip(("rhs_norm", "forward", "backward", "residual", "bookkeeping"),
+                           (pc / max(pc.sum(), 1.0)).round(4).tolist()))
+
     cpu = None
     if not args.no_cpu_baseline:
         cpu = cpu_baseline(P, gen, host_cores())
@@ -328,6 +333,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(sum(s["launches"] for s in stats)),
             "kernel_ms": {"solve_kkt": ms_solve, "ldl_factor": ms_factor, "other": ms_other},
+            "kkt_phase_share": phase_share,
             "clocks": clocks}
     print(json.dumps(line), flush=True)
     if world > 1:

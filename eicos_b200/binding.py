@@ -35,10 +35,13 @@ class BatchStats(C.Structure):
                 ("ir_rounds", C.c_ulonglong), ("ms_total", C.c_double), ("ms_factor", C.c_double),
                 ("ms_solve", C.c_double), ("ms_other", C.c_double),
                 ("factor_launch_tiles", C.c_longlong), ("solve_launch_tiles", C.c_longlong),
-                ("factor_launches", C.c_int), ("solve_launches", C.c_int), ("compactions", C.c_int)]
+                ("factor_launches", C.c_int), ("solve_launches", C.c_int), ("compactions", C.c_int),
+                ("kkt_phase_cycles", C.c_ulonglong * 5)]
 
     def asdict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["kkt_phase_cycles"] = list(d["kkt_phase_cycles"])
+        return d
 
 
 class BatchDims(C.Structure):

@@ -91,14 +91,16 @@ struct eicos_solver
     int device = 0;
 };
 
-// Warps per CTA (= workers per tile).  A tile is one CTA and runs a long dependent program, so the
-// machine is filled by tiles x workers: aim at ~14 warps per SM (measured optimum on B200: 2 workers
-// for 1024 tiles), more workers when there are few tiles, capped by the engine's shared-memory fit.
+// Warps per CTA (= workers per tile).  The factorisation and the triangular sweeps are run by one
+// warp per tile (slot programs, streams.hpp); extra workers only share the mat-vec rows and the
+// vector passes.  A full machine (>= 7 tiles per SM) is best served by one worker; small batches get
+// more so that the vector passes are not left to a handful of warps.
 static int default_workers(long long instances)
 {
     const double tiles_per_sm = (double)((instances + Engine::tile_width() - 1) / Engine::tile_width()) / 148.0;
-    int w = (int)(14.0 / std::max(tiles_per_sm, 0.01) + 0.5);
-    return std::max(1, std::min(w, 8));
+    if (tiles_per_sm >= 3.0)
+        return 1;
+    return tiles_per_sm >= 1.0 ? 2 : 4;
 }
 
 extern "C"
@@ -315,6 +317,8 @@ int eicos_batch_get_stats(const eicos_batch *bt, eicos_batch_stats *o)
     o->factor_launches = s.factor_launches;
     o->solve_launches = s.solve_launches;
     o->compactions = s.compactions;
+    for (int k = 0; k < 5; k++)
+        o->kkt_phase_cycles[k] = s.kkt_phase_cycles[k];
     return 0;
 }
 

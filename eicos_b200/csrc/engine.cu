@@ -26,8 +26,7 @@ namespace eicos
         tm.nwk = blockDim.x >> 5;                                                              \
         tm.red = smem;                                                                         \
         tm.stage = smem + (size_t)(tm.nwk > 1 ? tm.nwk * KRED : 0) * TILE + (size_t)tm.wk * 2 * STAGE_SLOTS * TILE + tm.lane; \
-        tm.acc = a.acc_global ? a.acc_global + (size_t)blockIdx.x * tm.nwk * a.P.maxcol * TILE \
-                              : smem + (size_t)tm.nwk * ((tm.nwk > 1 ? KRED : 0) + 2 * STAGE_SLOTS) * TILE;          \
+        tm.extra = smem + (size_t)tm.nwk * ((tm.nwk > 1 ? KRED : 0) + 2 * STAGE_SLOTS) * TILE + tm.lane;             \
         fn(tm, a, blockIdx.x);                                                                 \
     }
 #define EI_MAX_THREADS 256
@@ -59,7 +58,7 @@ __global__ void eicos_compact(const __grid_constant__ KArgs a, const __grid_cons
     {                                                                                             \
         const int nw_ = (threads);                                                                \
         std::vector<double> red_((size_t)nw_ * KRED * TILE + 8);                                  \
-        std::vector<double> acc_((size_t)nw_ * (args).P.maxcol * TILE + 8);                       \
+        std::vector<double> ext_(((size_t)std::max((args).P.sw_slots, (args).P.fa_slots) + 2 * (args).P.maxcol) * TILE + 8); \
         std::vector<double> stg_((size_t)nw_ * 2 * STAGE_SLOTS * TILE + 8);                           \
         for (int tile_ = 0; tile_ < (tiles); tile_++)                                             \
         {                                                                                         \
@@ -71,7 +70,7 @@ __global__ void eicos_compact(const __grid_constant__ KArgs a, const __grid_cons
                 tm_.wk = wk_;                                                                     \
                 tm_.nwk = nw_;                                                                    \
                 tm_.red = red_.data();                                                            \
-                tm_.acc = acc_.data();                                                            \
+                tm_.extra = ext_.data();                                                          \
                 tm_.stage = stg_.data() + (size_t)wk_ * 2 * STAGE_SLOTS * TILE;                      \
                 tm_.bar = nw_ > 1 ? &bar_ : nullptr;                                              \
                 fn(tm_, (args), tile_);                                                           \
@@ -96,6 +95,9 @@ static void eicos_compact_emu(const KArgs &a, const MoveRanges &mr, const int *m
     }
 }
 #endif
+
+// shared-memory budget of the slot programs (rows of TILE doubles per CTA)
+constexpr int MAX_SW_SLOTS = 24, MAX_FA_SLOTS = 48, MAX_COLBUF_ROWS = 16;
 
 int Engine::tile_width() { return TILE; }
 
@@ -143,9 +145,7 @@ void Engine::build_layout(const Symbolic &S)
     L.cq = take(S.qtot);
     L.V = take((int)S.Vslot.size());
     L.Lx = take(S.nnzL);
-    L.LTx = take(S.nnzL);
     L.D = take(S.N);
-    L.Dinv = take(S.N);
     L.rhs1 = take(S.N);
     L.rhs2 = take(S.N);
     L.sol1 = take(S.N);
@@ -165,7 +165,7 @@ void Engine::build_layout(const Symbolic &S)
 void Engine::upload_pattern(const Symbolic &S)
 {
     be::stream_t st = S_(stream_);
-    build_streams(S, workers_, H_);
+    build_streams(S, L_, workers_, MAX_SW_SLOTS, MAX_FA_SLOTS, H_);
     Lp_ = S.Lp;
     DevPattern &P = P_;
     P.n = S.n;
@@ -180,9 +180,11 @@ void Engine::upload_pattern(const Symbolic &S)
     P.nnzV = (int)S.Vslot.size();
     P.nphases = (int)S.phases.size();
     P.maxcol = S.maxcol;
-    P.nph_fw = H_.nph_fw;
-    P.nph_bw = H_.nph_bw;
-    P.nph_fa = H_.nph_fa;
+    P.fw_nld = H_.fw_nld;
+    P.bw_nld = H_.bw_nld;
+    P.fa_nld = H_.fa_nld;
+    P.sw_slots = H_.sw_slots;
+    P.fa_slots = H_.fa_slots;
     P.cone_dim = upload(S.q, owned_, st);
     P.cone_k = upload(S.cone_k, owned_, st);
     P.cone_q = upload(S.cone_q, owned_, st);
@@ -191,11 +193,11 @@ void Engine::upload_pattern(const Symbolic &S)
     P.Aeq = dAeq_ = upload(S.Aeq, owned_, st);
     P.GeqE = dGeq_ = upload(expanded_geq(S), owned_, st);
     P.fw = upload(H_.fw, owned_, st);
-    P.fw_seg = upload(H_.fw_seg, owned_, st);
+    P.fw_ld = upload(H_.fw_ld, owned_, st);
     P.bw = upload(H_.bw, owned_, st);
-    P.bw_seg = upload(H_.bw_seg, owned_, st);
+    P.bw_ld = upload(H_.bw_ld, owned_, st);
     P.fa = upload(H_.fa, owned_, st);
-    P.fa_seg = upload(H_.fa_seg, owned_, st);
+    P.fa_ld = upload(H_.fa_ld, owned_, st);
     P.fa_val = dfa_val_ = upload(H_.fa_val, owned_, st);
     P.rx = upload(H_.rx, owned_, st);
     P.rx_seg = upload(H_.rx_seg, owned_, st);
@@ -230,7 +232,7 @@ void Engine::upload_values(const Symbolic &S)
 {
     be::stream_t st = S_(stream_);
     be::set_device(device_);
-    refresh_stream_values(S, H_);
+    refresh_stream_values(S, L_, H_);
     const dvec ge = expanded_geq(S);
     be::h2d(dxeq_, S.xeq.data(), S.xeq.size() * sizeof(double), st);
     be::h2d(dAeq_, S.Aeq.data(), S.Aeq.size() * sizeof(double), st);
@@ -264,20 +266,20 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
     be::zero(iws_, ib, S_(stream_));
     base_vec_ = (double *)be::alloc((size_t)(S.n + S.m + S.p) * sizeof(double));
     active_count_ = (unsigned int *)be::alloc(sizeof(unsigned int));
-    ir_rounds_ = (unsigned long long *)be::alloc(sizeof(unsigned long long));
-    host_pinned_ = (unsigned int *)be::pinned(4 * sizeof(unsigned long long));
+    ir_rounds_ = (unsigned long long *)be::alloc(8 * sizeof(unsigned long long)); // [0] rounds, [1..5] phase cycles
+    host_pinned_ = (unsigned int *)be::pinned(12 * sizeof(unsigned long long));
     const size_t slots = (size_t)cap_tiles_ * TILE;
     moves_dev_ = (int *)be::alloc(2 * slots * sizeof(int));
     status_host_ = (int *)be::pinned(slots * sizeof(int));
     moves_host_ = (int *)be::pinned(2 * slots * sizeof(int));
-    smem_common_ = (size_t)workers_ * ((workers_ > 1 ? KRED : 0) + 2 * STAGE_SLOTS) * TILE * sizeof(double);
-    smem_factor_ = smem_common_ + (size_t)workers_ * S.maxcol * TILE * sizeof(double);
+    const size_t smem_base = (size_t)workers_ * ((workers_ > 1 ? KRED : 0) + 2 * STAGE_SLOTS) * TILE * sizeof(double);
+    smem_common_ = smem_base + (size_t)H_.sw_slots * TILE * sizeof(double);
+    smem_factor_ = smem_base + (size_t)(H_.fa_slots + 2 * S.maxcol) * TILE * sizeof(double);
 #ifndef EICOS_EMU
-    const size_t smem_limit = 200 * 1024;
-    if (smem_factor_ > smem_limit)
-    { // column accumulators spill to global memory (one slab per CTA)
-        acc_global_ = (double *)be::alloc((size_t)cap_tiles_ * workers_ * S.maxcol * TILE * sizeof(double));
-        smem_factor_ = smem_common_;
+    if (2 * S.maxcol > MAX_COLBUF_ROWS)
+    { // the column buffers of the factorisation spill to global memory (one slab per tile)
+        acc_global_ = (double *)be::alloc((size_t)cap_tiles_ * 2 * S.maxcol * TILE * sizeof(double));
+        smem_factor_ = smem_base + (size_t)H_.fa_slots * TILE * sizeof(double);
     }
     if (smem_factor_ > 48 * 1024)
         EI_CUDA(cudaFuncSetAttribute(eicos_ldl_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_factor_));
@@ -366,7 +368,7 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
     a.active_count = active_count_;
     a.ir_rounds = ir_rounds_;
     a.nitrow = -1;
-    be::zero(ir_rounds_, sizeof(unsigned long long), st);
+    be::zero(ir_rounds_, 8 * sizeof(unsigned long long), st);
 
     const int threads = workers_ * (LANES == 1 ? 1 : 32);
     (void)threads;
@@ -520,7 +522,7 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
         }
         EI_TIMED(2, EI_LAUNCH(eicos_store_outputs, tile_store, tiles, threads, smem_common_, st, a));
     }
-    be::d2h(host_pinned_ + 2, ir_rounds_, sizeof(unsigned long long), st);
+    be::d2h(host_pinned_ + 2, ir_rounds_, 8 * sizeof(unsigned long long), st);
 #ifndef EICOS_EMU
     if (timing)
     {
@@ -531,6 +533,7 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
 #endif
     be::sync(st);
     std::memcpy(&stt.ir_rounds, host_pinned_ + 2, sizeof(unsigned long long));
+    std::memcpy(stt.kkt_phase_cycles, host_pinned_ + 4, 5 * sizeof(unsigned long long));
 #ifndef EICOS_EMU
     if (timing)
     {
@@ -615,7 +618,7 @@ void Engine::debug_factor_init(int batch, const double *d_c, const double *d_h, 
             };
             if (h_Lx)
                 for (int u = 0; u < P_.nnzL; u++)
-                    h_Lx[inst * P_.nnzL + u] = buf[(size_t)(L_.Lx + H_.bw_pos[u]) * TILE + lane];
+                    h_Lx[inst * P_.nnzL + u] = buf[(size_t)(L_.Lx + u) * TILE + lane];
             grab(h_D, L_.D, P_.N);
             grab(h_sol1, L_.sol1, P_.N);
             grab(h_sol2, L_.sol2, P_.N);

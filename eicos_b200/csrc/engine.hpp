@@ -19,6 +19,7 @@ struct SolveStats
     int ipm_iterations = 0;          // head launches over all chunks
     long long launches = 0;          // kernels launched
     unsigned long long ir_rounds = 0; // triangular-solve rounds executed (tile-rounds, all solveKKT calls)
+    unsigned long long kkt_phase_cycles[5] = {0, 0, 0, 0, 0}; // norm, forward, backward, residual, bookkeeping (summed over tiles)
     double ms_total = 0, ms_factor = 0, ms_solve = 0, ms_other = 0; // device time by kernel class (CUDA events)
     long long factor_launch_tiles = 0, solve_launch_tiles = 0;      // tiles covered by the timed launches
     int factor_launches = 0, solve_launches = 0;

@@ -73,7 +73,7 @@ struct Layout
     int lpv, lpw;                   // LP cone scalings (l rows each)
     int cpar, cq;                   // SOC scalings: CP_COUNT rows per cone, q vectors
     int V;                          // scaling block values of the KKT matrix (cacheIndices order)
-    int Lx, LTx, D, Dinv;           // factor: by columns (backward-sweep order), by rows (forward-sweep order), pivots, reciprocals
+    int Lx, D;                      // factor: L column-major (CSC order of the symbolic pattern), pivots
     int rhs1, rhs2, sol1, sol2;     // KKT-space vectors (N rows)
     int xw, dxr, e;                 // triangular-solve work vector, refinement step, residual (N rows)
     int dsw, wdz, dsaff, ds1;       // dsaff_by_W, W_times_dzaff, dsaff, scratch (mt rows)
@@ -91,12 +91,13 @@ enum ConeParam : int
 struct DevPattern
 {
     int n, p, m, l, nc, N, mt, qtot, nnzL, nnzV, nphases, maxcol;
-    int nph_fw, nph_bw, nph_fa; // phases of the forward / backward / factor streams (chains are split, streams.hpp)
     const int *cone_dim, *cone_k, *cone_q; // per cone: dimension, first expanded index, first q row
     const int *zk;                         // compact z index -> expanded index (load / store only)
     const double *xeq, *Aeq, *GeqE;        // equilibration vectors (GeqE is expanded, 1 in the slots)
     // instruction streams (streams.hpp)
-    const int *fw, *fw_seg, *bw, *bw_seg, *fa, *fa_seg;
+    // slot programs (streams.hpp): ops, load lists (+ length in words), shared-memory slots they use
+    const int *fw, *fw_ld, *bw, *bw_ld, *fa, *fa_ld;
+    int fw_nld, bw_nld, fa_nld, sw_slots, fa_slots;
     const double *fa_val;
     const int *rx, *rx_seg, *ry, *ry_seg, *rz, *rz_seg, *rc, *rc_seg;
     const double *rx_val, *ry_val, *rz_val, *rc_val;

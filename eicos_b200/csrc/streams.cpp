@@ -29,210 +29,6 @@ void pad_tail(dvec &s)
     s.insert(s.end(), STREAM_PAD, 0.0);
 }
 
-// tasks of worker w in a phase of the elimination-tree schedule, in the order the device walks them
-ivec worker_tasks(const Symbolic &S, const Phase &f, int w, int W, bool backward)
-{
-    ivec t;
-    if (f.parallel)
-    {
-        if (!backward)
-            for (int q = f.begin + w; q < f.end; q += W)
-                t.push_back(S.tasks[q]);
-        else
-            for (int q = f.end - 1 - w; q >= f.begin; q -= W)
-                t.push_back(S.tasks[q]);
-    }
-    else if (w == 0)
-    {
-        if (!backward)
-            for (int q = f.begin; q < f.end; q++)
-                t.push_back(S.tasks[q]);
-        else
-            for (int q = f.end - 1; q >= f.begin; q--)
-                t.push_back(S.tasks[q]);
-    }
-    return t;
-}
-
-// One task of a triangular sweep: out = init - sum_k L[src_k] * vec[gather_k]
-struct SweepTask
-{
-    int h0, h1;   // header words (meaning depends on the direction, see tile_program.hpp)
-    ivec gather;  // row to gather from, or a FWD_PREV* code
-    ivec src;     // natural index of the L value (CSR index t for forward, CSC index u for backward)
-};
-
-struct SweepBuilder
-{
-    int W;
-    int init_slots; // staging slots the start value of a task needs (1 forward, 2 backward)
-    ivec &stream, &seg, &pos;
-    int nphases = 0, next_pos = 0;
-
-    SweepBuilder(int W_, int init_slots_, ivec &stream_, ivec &seg_, ivec &pos_)
-        : W(W_), init_slots(init_slots_), stream(stream_), seg(seg_), pos(pos_) {}
-
-    int assign(const SweepTask &t)
-    {
-        const int first = next_pos;
-        for (int s : t.src)
-            pos[s] = next_pos++;
-        return first;
-    }
-
-    // independent tasks, already distributed over the workers
-    void parallel_phase(const std::vector<std::vector<SweepTask>> &per_worker)
-    {
-        for (int w = 0; w < W; w++)
-        {
-            align_chunk(stream);
-            const std::vector<SweepTask> &tk = per_worker[w];
-            const int ioff = (int)stream.size(), voff = next_pos;
-            int nblocks = 0;
-            size_t a = 0;
-            while (a < tk.size())
-            {
-                int slots = init_slots + 2 * (int)tk[a].gather.size();
-                size_t b = a + 1;
-                if (slots > STAGE_SLOTS)
-                    stream.push_back(-1); // oversize task: processed without staging
-                else
-                {
-                    while (b < tk.size() && slots + init_slots + 2 * (int)tk[b].gather.size() <= STAGE_SLOTS)
-                    {
-                        slots += init_slots + 2 * (int)tk[b].gather.size();
-                        b++;
-                    }
-                    stream.push_back((int)(b - a));
-                }
-                for (size_t q = a; q < b; q++)
-                {
-                    assign(tk[q]);
-                    stream.push_back(tk[q].h0);
-                    stream.push_back(tk[q].h1);
-                    stream.push_back((int)tk[q].gather.size());
-                    stream.insert(stream.end(), tk[q].gather.begin(), tk[q].gather.end());
-                }
-                nblocks++;
-                a = b;
-            }
-            seg.insert(seg.end(), {ioff, nblocks, voff, (int)SEG_BLOCKS});
-        }
-        nphases++;
-    }
-
-    // a dependent chain, walked by worker 0
-    void serial_phase(const std::vector<SweepTask> &tk)
-    {
-        for (int w = 0; w < W; w++)
-        {
-            align_chunk(stream);
-            const int ioff = (int)stream.size(), voff = next_pos;
-            if (w != 0)
-            {
-                seg.insert(seg.end(), {ioff, 0, voff, (int)SEG_SERIAL});
-                continue;
-            }
-            auto header = [&](size_t a) {
-                stream.push_back(tk[a].h0);
-                stream.push_back(tk[a].h1);
-                stream.push_back((int)tk[a].gather.size());
-            };
-            if (!tk.empty())
-                header(0);
-            for (size_t a = 0; a < tk.size(); a++)
-            { // the header of task a+1 precedes the entries of task a (software pipelining on the device)
-                if (a + 1 < tk.size())
-                    header(a + 1);
-                assign(tk[a]);
-                stream.insert(stream.end(), tk[a].gather.begin(), tk[a].gather.end());
-            }
-            seg.insert(seg.end(), {ioff, (int)tk.size(), voff, (int)SEG_SERIAL});
-        }
-        nphases++;
-    }
-};
-
-// Schedules one sweep.  `entries(j)` lists (other index, natural value index) of task j;
-// `header` fills the two header words of a task (kind: 0 whole task, 1 external part of a chain task,
-// 2 chain task that continues a stored partial result, 3 chain task without external part).
-template <class Entries, class Header, class GatherRow>
-void schedule_sweep(const Symbolic &S, int W, bool backward, SweepBuilder &B, Entries entries, Header header, GatherRow gather_row)
-{
-    const int nph = (int)S.phases.size();
-    ivec where(S.N, -1); // position inside the current serial phase
-    for (int step = 0; step < nph; step++)
-    {
-        const int ph = backward ? nph - 1 - step : step;
-        const Phase &f = S.phases[ph];
-        if (f.parallel)
-        {
-            std::vector<std::vector<SweepTask>> pw(W);
-            for (int w = 0; w < W; w++)
-                for (int j : worker_tasks(S, f, w, W, backward))
-                {
-                    SweepTask t;
-                    header(j, 0, t);
-                    for (auto &e : entries(j))
-                    {
-                        t.gather.push_back(gather_row(e.first));
-                        t.src.push_back(e.second);
-                    }
-                    pw[w].push_back(std::move(t));
-                }
-            B.parallel_phase(pw);
-            continue;
-        }
-        const ivec tk = worker_tasks(S, f, 0, W, backward);
-        for (size_t a = 0; a < tk.size(); a++)
-            where[tk[a]] = (int)a;
-        // external part: terms that come from phases already processed -> one parallel phase
-        std::vector<std::vector<SweepTask>> pw(W);
-        std::vector<char> has_ext(tk.size(), 0);
-        int rr = 0;
-        for (size_t a = 0; a < tk.size(); a++)
-        {
-            SweepTask t;
-            header(tk[a], 1, t);
-            for (auto &e : entries(tk[a]))
-                if (where[e.first] < 0)
-                {
-                    t.gather.push_back(gather_row(e.first));
-                    t.src.push_back(e.second);
-                }
-            if (!t.gather.empty())
-            {
-                has_ext[a] = 1;
-                pw[rr++ % W].push_back(std::move(t));
-            }
-        }
-        if (rr > 0)
-            B.parallel_phase(pw);
-        // internal part: the recurrence along the chain
-        std::vector<SweepTask> chain;
-        for (size_t a = 0; a < tk.size(); a++)
-        {
-            SweepTask t;
-            header(tk[a], has_ext[a] ? 2 : 3, t);
-            for (auto &e : entries(tk[a]))
-            {
-                const int wpos = where[e.first];
-                if (wpos < 0)
-                    continue;
-                const int dist = (int)a - wpos;
-                if (dist <= 0)
-                    throw std::logic_error("serial phase: dependency on a later task");
-                t.gather.push_back(dist == 1 ? FWD_PREV1 : dist == 2 ? FWD_PREV2 : dist == 3 ? FWD_PREV3 : gather_row(e.first));
-                t.src.push_back(e.second);
-            }
-            chain.push_back(std::move(t));
-        }
-        B.serial_phase(chain);
-        for (int j : tk)
-            where[j] = -1;
-    }
-}
-
 // mat-vec row set for one worker: blocks of rows whose gathers fit the staging slots
 template <class Emit>
 void rowset(int rows, int W, ivec &s, dvec &v, ivec &seg, Emit &&emit)
@@ -278,187 +74,234 @@ void rowset(int rows, int W, ivec &s, dvec &v, ivec &seg, Emit &&emit)
     pad_tail(s);
     pad_tail(v);
 }
+// Shared-memory slots for the live ranges of a slot program (linear scan: a value gets a slot when
+// it is first touched and gives it back after its last use; when none is free it lives at home).
+struct SlotPool
+{
+    ivec free_;
+    int top = 0; // slots ever used
+    long long home = 0;
+    explicit SlotPool(int n)
+    {
+        for (int s = n - 1; s >= 0; s--)
+            free_.push_back(s);
+    }
+    int take(int home_row)
+    {
+        if (free_.empty())
+        {
+            home++;
+            return SLOT_HOME + home_row;
+        }
+        const int s = free_.back();
+        free_.pop_back();
+        top = std::max(top, s + 1);
+        return s;
+    }
+    void give(int code)
+    {
+        if (code >= 0 && code < SLOT_HOME)
+            free_.push_back(code);
+    }
+};
+
+// ---- forward sweep  xw = L^-1 P rhs, column by column in elimination order (scatter form, the
+// order Eigen's own forward substitution uses): step k consumes the accumulator of row k and
+// subtracts L(i,k) x_k from the accumulators of the rows i of column k.  An accumulator starts from
+// its right-hand-side row on the first touch.
+//   ops:   [src, cnt, cnt x target]        load list: [rhs_k if untouched] { L(i,k) [rhs_i on a first touch] }
+void build_forward(const Symbolic &S, const Layout &L, int max_slots, HostStreams &H)
+{
+    SlotPool pool(max_slots);
+    ivec code(S.N, -1);
+    for (int k = 0; k < S.N; k++)
+    {
+        if (code[k] < 0)
+        {
+            H.fw.push_back(SRC_FIFO);
+            H.fw_ld.push_back(~S.pinv[k]);
+        }
+        else
+            H.fw.push_back(code[k]);
+        H.fw.push_back(S.Lp[k + 1] - S.Lp[k]);
+        for (int u = S.Lp[k]; u < S.Lp[k + 1]; u++)
+        {
+            const int i = S.Li[u];
+            H.fw_ld.push_back(L.Lx + u);
+            if (code[i] < 0)
+            {
+                code[i] = pool.take(L.xw + i);
+                H.fw.push_back(code[i] | (OPK_FIFO << OPK_SHIFT));
+                H.fw_ld.push_back(~S.pinv[i]);
+            }
+            else
+                H.fw.push_back(code[i]);
+        }
+        pool.give(code[k]);
+    }
+    H.fw_nld = (int)H.fw_ld.size();
+    H.sw_slots = std::max(H.sw_slots, pool.top);
+    H.sw_home += pool.home;
+    pad_tail(H.fw);
+    pad_tail(H.fw_ld);
+}
+
+// ---- backward sweep  out = P' L^-T D^-1 xw, columns in reverse elimination order (dot form):
+// step k gathers the finished entries i of column k.  A finished entry is kept in a slot until the
+// first column of its row has used it; its home is its own output row (relative to `out`).
+//   ops:   [out row, keep code | -1, cnt, cnt x gather]
+//   load list: D_k, xw_k, { L(i,k) }, ~out row (accumulated solution; skipped on a plain solve)
+void build_backward(const Symbolic &S, const Layout &L, int max_slots, HostStreams &H)
+{
+    SlotPool pool(max_slots);
+    ivec code(S.N, -1), minrow(S.N, -1);
+    for (int i = 0; i < S.N; i++)
+        if (S.Lr.p[i + 1] > S.Lr.p[i])
+        {
+            int mn = S.N;
+            for (int t = S.Lr.p[i]; t < S.Lr.p[i + 1]; t++)
+                mn = std::min(mn, S.Lr.j[t]);
+            minrow[i] = mn;
+        }
+    for (int k = S.N - 1; k >= 0; k--)
+    {
+        const int o = S.pinv[k];
+        H.bw_ld.push_back(L.D + k);
+        H.bw_ld.push_back(L.xw + k);
+        H.bw.push_back(o);
+        const size_t keep_at = H.bw.size();
+        H.bw.push_back(-1);
+        H.bw.push_back(S.Lp[k + 1] - S.Lp[k]);
+        for (int u = S.Lp[k]; u < S.Lp[k + 1]; u++)
+        {
+            H.bw_ld.push_back(L.Lx + u);
+            H.bw.push_back(code[S.Li[u]]);
+        }
+        for (int u = S.Lp[k]; u < S.Lp[k + 1]; u++)
+            if (minrow[S.Li[u]] == k)
+                pool.give(code[S.Li[u]]);
+        if (minrow[k] >= 0)
+        {
+            code[k] = pool.take(o);
+            H.bw[keep_at] = code[k] < SLOT_HOME ? code[k] : -1;
+        }
+        H.bw_ld.push_back(~o);
+    }
+    H.bw_nld = (int)H.bw_ld.size();
+    H.sw_slots = std::max(H.sw_slots, pool.top);
+    H.sw_home += pool.home;
+    pad_tail(H.bw);
+    pad_tail(H.bw_ld);
+}
+
+// ---- numeric factorisation, right-looking in elimination order.  Every entry (i,j) of L and every
+// pivot owns an accumulator that starts from the KKT value (shared constant, per-instance scaling
+// value, or 0 for fill) on its first touch.  Step k: d = acc(k,k); for the rows i of column k
+// a_i = acc(i,k), l_i = a_i / d (stored, column-major = the order both sweeps stream it in); then
+// for every pair i1 >= i2 of the column  acc(i1,i2) -= l_i2 * a_i1  (the products Eigen's
+// up-looking kernel forms, accumulated in ascending k).
+//   ops:   [src_d, cnt, cnt x src, cnt(cnt+1)/2 x target]   constants in fa_val, V rows in the load list
+void build_factor(const Symbolic &S, const Layout &L, int max_slots, HostStreams &H)
+{
+    struct Init
+    {
+        int kind = OPK_ZERO, vrow = -1;
+        double c = 0.0;
+    };
+    std::vector<Init> di(S.N), ei(S.nnzL);
+    for (int j = 0; j < S.N; j++)
+        for (int e = S.KLp[j]; e < S.KLp[j + 1]; e++)
+        {
+            const int slot = S.KLslot[e], vi = S.Kvidx[slot], pos = S.KLpos[e];
+            Init &t = pos < 0 ? di[j] : ei[S.Lp[j] + pos];
+            if (vi >= 0)
+            {
+                t.kind = OPK_FIFO;
+                t.vrow = L.V + vi;
+            }
+            else
+            {
+                t.kind = OPK_CONST;
+                t.c = S.Kshared[slot];
+            }
+        }
+    SlotPool pool(max_slots);
+    ivec dcode(S.N, -1), ecode(S.nnzL, -1);
+    const auto source = [&](int code, const Init &t) {
+        if (code >= 0)
+            H.fa.push_back(code);
+        else if (t.kind == OPK_FIFO)
+        {
+            H.fa.push_back(SRC_FIFO);
+            H.fa_ld.push_back(t.vrow);
+        }
+        else if (t.kind == OPK_CONST)
+        {
+            H.fa.push_back(SRC_CONST);
+            H.fa_val.push_back(t.c);
+        }
+        else
+            H.fa.push_back(SRC_ZERO);
+    };
+    const auto target = [&](int &code, const Init &t, int home_row) {
+        if (code >= 0)
+        {
+            H.fa.push_back(code);
+            return;
+        }
+        code = pool.take(home_row);
+        H.fa.push_back(code | (t.kind << OPK_SHIFT));
+        if (t.kind == OPK_FIFO)
+            H.fa_ld.push_back(t.vrow);
+        else if (t.kind == OPK_CONST)
+            H.fa_val.push_back(t.c);
+    };
+    for (int k = 0; k < S.N; k++)
+    {
+        const int u0 = S.Lp[k], cnt = S.Lp[k + 1] - u0;
+        source(dcode[k], di[k]);
+        H.fa.push_back(cnt);
+        for (int e = 0; e < cnt; e++)
+            source(ecode[u0 + e], ei[u0 + e]);
+        for (int e1 = 0; e1 < cnt; e1++)
+        {
+            const int i1 = S.Li[u0 + e1];
+            for (int e2 = 0; e2 < e1; e2++)
+            {
+                const int i2 = S.Li[u0 + e2];
+                const int *b = S.Li.data() + S.Lp[i2], *e = S.Li.data() + S.Lp[i2 + 1];
+                const int *f = std::lower_bound(b, e, i1);
+                if (f == e || *f != i1)
+                    throw std::logic_error("factor program: update outside the pattern of L");
+                const int ut = (int)(f - S.Li.data());
+                target(ecode[ut], ei[ut], L.Lx + ut);
+            }
+            target(dcode[i1], di[i1], L.D + i1);
+        }
+        pool.give(dcode[k]);
+        for (int e = 0; e < cnt; e++)
+            pool.give(ecode[u0 + e]);
+    }
+    H.fa_nld = (int)H.fa_ld.size();
+    H.fa_slots = pool.top;
+    H.fa_home = pool.home;
+    pad_tail(H.fa);
+    pad_tail(H.fa_ld);
+    pad_tail(H.fa_val);
+}
 } // namespace
 
-void build_streams(const Symbolic &S, int W, HostStreams &H)
+void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, int max_fa_slots, HostStreams &H)
 {
     H = HostStreams();
     H.workers = W;
-    const int nph = (int)S.phases.size();
-    H.fw_pos.assign(S.nnzL, -1);
-    H.bw_pos.assign(S.nnzL, -1);
-
-    // ---- forward sweep: rows of L.  header = [xw row i, rhs row pinv[i] | INIT_PARTIAL]
-    {
-        SweepBuilder B(W, 1, H.fw, H.fw_seg, H.fw_pos);
-        schedule_sweep(
-            S, W, false, B,
-            [&](int i) {
-                std::vector<std::pair<int, int>> e;
-                for (int t = S.Lr.p[i]; t < S.Lr.p[i + 1]; t++)
-                    e.push_back({S.Lr.j[t], t});
-                return e;
-            },
-            [&](int i, int kind, SweepTask &t) { // kind: 0 whole row, 1 external part, 2 chain after an external part, 3 chain
-                t.h0 = i;
-                t.h1 = kind == 2 ? INIT_PARTIAL : S.pinv[i];
-            },
-            [&](int c) { return c; });
-        H.nph_fw = B.nphases;
-        if (B.next_pos != S.nnzL)
-            throw std::logic_error("forward stream does not cover L");
-        pad_tail(H.fw);
-    }
-    // ---- backward sweep: columns of L, results land in KKT order.
-    //      header = [xw/Dinv row j | INIT_PARTIAL, out row pinv[j]]
-    {
-        SweepBuilder B(W, 2, H.bw, H.bw_seg, H.bw_pos);
-        schedule_sweep(
-            S, W, true, B,
-            [&](int j) {
-                std::vector<std::pair<int, int>> e;
-                for (int u = S.Lp[j]; u < S.Lp[j + 1]; u++)
-                    e.push_back({S.Li[u], u});
-                return e;
-            },
-            [&](int j, int kind, SweepTask &t) { // an external part stores a partial result: out row encoded as ~row
-                t.h0 = kind == 2 ? INIT_PARTIAL : j;
-                t.h1 = kind == 1 ? ~S.pinv[j] : S.pinv[j];
-            },
-            [&](int r) { return S.pinv[r]; });
-        H.nph_bw = B.nphases;
-        if (B.next_pos != S.nnzL)
-            throw std::logic_error("backward stream does not cover L");
-        pad_tail(H.bw);
-    }
-
-    // ---- numeric factorisation, left-looking by column (every position explicit).
-    // Task = [j, kind, cnt, nK, nR] {kind 2: cnt x bwpos of the stored partial column}
-    //        nK x [vidx, pos]  groups of <= FA_GROUP row entries: headers [k, fwpos, tail len] then
-    //        their tails (rel, bwpos) ...  cnt x [bwpos, fwpos].
-    // kind 0: whole column.  Columns of a serial phase (a chain of the elimination tree) are split:
-    // kind 1 = contributions of columns OUTSIDE the chain, done in a parallel phase, partial column
-    // stored un-normalised in D / Lx; kind 2 = chain task continuing such a partial; kind 3 = chain
-    // task without external contributions.
-    ivec Lcsr(S.nnzL);
-    for (int t = 0; t < S.nnzL; t++)
-        Lcsr[S.Lr.v[t]] = t;
-    H.fa_seg.clear();
-    H.nph_fa = 0;
-    {
-        ivec where(S.N, -1);
-        auto emit_task = [&](int j, int kind, const ivec &rows /* CSR indices t */) {
-            const int cnt = S.Lp[j + 1] - S.Lp[j];
-            const bool with_k = kind != 2;
-            H.fa.push_back(j);
-            H.fa.push_back(kind);
-            H.fa.push_back(cnt);
-            H.fa.push_back(with_k ? S.KLp[j + 1] - S.KLp[j] : 0);
-            H.fa.push_back((int)rows.size());
-            if (kind == 2)
-                for (int q = 0; q < cnt; q++)
-                    H.fa.push_back(H.bw_pos[S.Lp[j] + q]);
-            if (with_k)
-                for (int e = S.KLp[j]; e < S.KLp[j + 1]; e++)
-                {
-                    const int slot = S.KLslot[e], vi = S.Kvidx[slot];
-                    H.fa.push_back(vi);
-                    H.fa.push_back(S.KLpos[e]);
-                    if (vi < 0)
-                        H.fa_val.push_back(S.Kshared[slot]);
-                }
-            for (size_t g = 0; g < rows.size(); g += FA_GROUP)
-            {
-                const size_t ge = std::min(rows.size(), g + FA_GROUP);
-                for (size_t r = g; r < ge; r++)
-                {
-                    const int t = rows[r], k = S.Lr.j[t];
-                    H.fa.push_back(k);
-                    H.fa.push_back(H.fw_pos[t]);
-                    H.fa.push_back(S.Lp[k + 1] - S.upd_tail[t]);
-                }
-                for (size_t r = g; r < ge; r++)
-                {
-                    const int t = rows[r], k = S.Lr.j[t];
-                    const int u0 = S.upd_tail[t], len = S.Lp[k + 1] - u0;
-                    for (int q = 0; q < len; q++)
-                    {
-                        H.fa.push_back(S.upd_rel[S.upd_rel_p[t] + q]);
-                        H.fa.push_back(H.bw_pos[u0 + q]);
-                    }
-                }
-            }
-            for (int q = 0; q < cnt; q++)
-            {
-                const int u = S.Lp[j] + q;
-                H.fa.push_back(H.bw_pos[u]);
-                H.fa.push_back(H.fw_pos[Lcsr[u]]);
-            }
-        };
-        auto emit_phase = [&](const std::vector<std::vector<std::pair<int, std::pair<int, ivec>>>> &pw) {
-            for (int w = 0; w < W; w++)
-            {
-                align_chunk(H.fa);
-                align_chunk(H.fa_val);
-                H.fa_seg.insert(H.fa_seg.end(), {(int)H.fa.size(), (int)pw[w].size(), (int)H.fa_val.size()});
-                for (const auto &tk : pw[w])
-                    emit_task(tk.first, tk.second.first, tk.second.second);
-            }
-            H.nph_fa++;
-        };
-        auto all_rows = [&](int j) {
-            ivec r;
-            for (int t = S.Lr.p[j]; t < S.Lr.p[j + 1]; t++)
-                r.push_back(t);
-            return r;
-        };
-        for (int ph = 0; ph < nph; ph++)
-        {
-            const Phase &f = S.phases[ph];
-            std::vector<std::vector<std::pair<int, std::pair<int, ivec>>>> pw(W);
-            if (f.parallel)
-            {
-                for (int w = 0; w < W; w++)
-                    for (int j : worker_tasks(S, f, w, W, false))
-                        pw[w].push_back({j, {0, all_rows(j)}});
-                emit_phase(pw);
-                continue;
-            }
-            const ivec tk = worker_tasks(S, f, 0, W, false);
-            for (size_t a = 0; a < tk.size(); a++)
-                where[tk[a]] = (int)a;
-            std::vector<char> has_ext(tk.size(), 0);
-            int rr = 0;
-            for (size_t a = 0; a < tk.size(); a++)
-            {
-                ivec ext;
-                for (int t = S.Lr.p[tk[a]]; t < S.Lr.p[tk[a] + 1]; t++)
-                    if (where[S.Lr.j[t]] < 0)
-                        ext.push_back(t);
-                if (!ext.empty())
-                {
-                    has_ext[a] = 1;
-                    pw[rr++ % W].push_back({tk[a], {1, ext}});
-                }
-            }
-            if (rr > 0)
-                emit_phase(pw);
-            std::vector<std::vector<std::pair<int, std::pair<int, ivec>>>> cw(W);
-            for (size_t a = 0; a < tk.size(); a++)
-            {
-                ivec in;
-                for (int t = S.Lr.p[tk[a]]; t < S.Lr.p[tk[a] + 1]; t++)
-                    if (where[S.Lr.j[t]] >= 0)
-                        in.push_back(t);
-                cw[0].push_back({tk[a], {has_ext[a] ? 2 : 3, in}});
-            }
-            emit_phase(cw);
-            for (int j : tk)
-                where[j] = -1;
-        }
-    }
-    pad_tail(H.fa);
-    pad_tail(H.fa_val);
+    for (int k = 0; k < S.N; k++)
+        for (int u = S.Lp[k]; u + 1 < S.Lp[k + 1]; u++)
+            if (S.Li[u] >= S.Li[u + 1])
+                throw std::logic_error("columns of L must have ascending rows");
+    build_forward(S, L, max_sw_slots, H);
+    build_backward(S, L, max_sw_slots, H);
+    build_factor(S, L, max_fa_slots, H);
 
     // ---- mat-vec row sets (K-space gather indices); a row = [cnt, idx...]
     const int n = S.n, p = S.p, zb = S.n + S.p;
@@ -513,10 +356,10 @@ void build_streams(const Symbolic &S, int W, HostStreams &H)
     pad_tail(H.rc_val);
 }
 
-void refresh_stream_values(const Symbolic &S, HostStreams &H)
+void refresh_stream_values(const Symbolic &S, const Layout &L, HostStreams &H)
 {
     HostStreams fresh;
-    build_streams(S, H.workers, fresh);
+    build_streams(S, L, H.workers, std::max(H.sw_slots, 1), std::max(H.fa_slots, 1), fresh);
     H.fa_val.swap(fresh.fa_val);
     H.rx_val.swap(fresh.rx_val);
     H.ry_val.swap(fresh.ry_val);

@@ -1,21 +1,26 @@
-// Per-worker instruction streams for the device kernels.
+// Instruction streams for the device kernels.
 //
-// Problems they solve (profiles/r01a, r01b):
-//  * walking CSR/CSC index arrays with warp-uniform loads costs one full memory latency per INDEX
-//    (Lrp[i] -> Lrj[t] -> x[...]).  Every worker (warp) of a CTA instead gets its own contiguous
-//    int32 stream holding, in execution order, everything it will need; the warp loads 32 stream
-//    words with ONE coalesced access one chunk ahead of use and broadcasts them with shuffles.
-//    Values shared by the batch (equilibrated A/G entries, +-delta) travel in a parallel double
-//    stream; per-instance values (L, D, vectors) are addressed by ROW (layout.hpp).
-//  * warps issue in order, so a load that is consumed immediately gives a memory-level parallelism
-//    of ~2 per warp.  Independent work is therefore cut into BLOCKS: the device first issues every
-//    load of a block asynchronously into shared memory (cp.async), then computes.  The host decides
-//    the block boundaries (slot budget) so the device never has to look ahead.
-//  * rows of a serial phase (a chain of the elimination tree) mostly gather from EARLIER phases;
-//    those terms are split off into a parallel "external" phase, leaving a short recurrence.
+// Problems they solve (profiles/r01a .. r01d):
+//  * walking CSR/CSC index arrays with warp-uniform loads costs one full memory latency per INDEX.
+//    A warp instead reads contiguous int32 streams holding, in execution order, everything it will
+//    need: 32 words per coalesced access, one chunk ahead of use, broadcast with shuffles.  Values
+//    shared by the batch (equilibrated A/G entries, +-delta) travel in a parallel double stream;
+//    per-instance values (L, D, vectors) are addressed by ROW (layout.hpp).
+//  * a warp issues in order, so a load that is consumed immediately gives a memory-level
+//    parallelism of ~2.  Every global READ of the factorisation and of the triangular sweeps is
+//    therefore known to the host in consumption order ("load list") and runs through a FIFO of
+//    shared-memory rows filled by cp.async FIFO_ROWS ahead of the consumer (tile_program.hpp: Fifo).
+//  * gathers through the solution vector / the partially factorised matrix re-read rows from HBM.
+//    AMD orderings are local: in elimination order almost every value is consumed within a few
+//    dozen steps of being produced.  The host therefore compiles the three numeric kernels into
+//    "slot programs": every intermediate value (accumulator of a forward-sweep row, finished entry
+//    of the backward sweep, Schur accumulator of an L entry) is given a shared-memory slot for its
+//    live range by a linear-scan allocator; values that do not get a slot fall back to their home
+//    row in HBM.  What is left as HBM traffic is the algorithmic minimum: L, D and V once, the
+//    right-hand side in, the solution out.
 //
-// The layout of a stream depends on the number of workers per CTA, so streams are built by the
-// engine (not by analyze()).
+// The triangular sweeps and the factorisation are run by ONE warp per tile (elimination order,
+// no barriers); the mat-vec row sets are split over the workers of the CTA.
 #pragma once
 
 #include "layout.hpp"
@@ -28,29 +33,43 @@ namespace eicos
 
 constexpr int STREAM_CHUNK = 32;  // words per cooperative load
 constexpr int STREAM_PAD = 96;    // readable words after the last used one (two chunks of lookahead)
-constexpr int STAGE_SLOTS = 12;   // rows per staging buffer (one slot = TILE doubles); a worker owns two buffers
-constexpr int FWD_PREV1 = -1;     // gather code: result of the previous task of this worker
-constexpr int FWD_PREV2 = -2;     // ... of the task before that
-constexpr int FWD_PREV3 = -3;
-constexpr int INIT_PARTIAL = -1;  // task header: the start value is the partial result already stored in the output row
-constexpr int FA_GROUP = 4;        // row entries of a factor task whose operands are loaded together
+constexpr int STAGE_SLOTS = 16;   // rows per staging buffer (one slot = TILE doubles); a worker owns two buffers
 constexpr int ROW_EXTRA_SLOTS = 4; // staging slots a mat-vec row may use besides its gathers
 
-enum SegKind : int
+// FIFO of asynchronously loaded rows: FIFO_GROUPS cp.async groups of FIFO_GROUP rows.  It lives in
+// the two staging buffers of worker 0.
+constexpr int FIFO_GROUP = 8;
+constexpr int FIFO_GROUPS = 4;
+constexpr int FIFO_ROWS = FIFO_GROUP * FIFO_GROUPS;
+static_assert(FIFO_ROWS == 2 * STAGE_SLOTS, "the FIFO ring aliases worker 0's staging buffers");
+static_assert((FIFO_ROWS & (FIFO_ROWS - 1)) == 0 && (FIFO_GROUP & (FIFO_GROUP - 1)) == 0, "powers of two");
+
+// Operand words of the slot programs: code < SLOT_HOME is a shared-memory slot, anything else the
+// home row (code - SLOT_HOME, relative to the program's home base).  Bits 28..29 of a TARGET word
+// say how the accumulator starts on its first touch.
+constexpr int SLOT_HOME = 1 << 16;
+constexpr int OP_CODE_MASK = (1 << 28) - 1;
+constexpr int OPK_SHIFT = 28;
+enum OpKind : int
 {
-    SEG_BLOCKS = 0, // count = number of blocks; block = [ntasks | -1 (one oversize task)] tasks...
-    SEG_SERIAL = 1  // count = number of tasks; layout hdr(0) hdr(1) ent(0) hdr(2) ent(1) ...
+    OPK_RMW = 0,   // accumulator already holds a value
+    OPK_ZERO = 1,  // first touch, starts from 0 (fill entry)
+    OPK_CONST = 2, // first touch, starts from the next word of the double stream
+    OPK_FIFO = 3   // first touch, starts from the next row of the FIFO
 };
+// Source words (a value that is consumed): an operand code, or one of
+constexpr int SRC_FIFO = -1, SRC_CONST = -2, SRC_ZERO = -3;
+// Load-list words: row >= 0 is relative to the tile base; ~row (< 0) is relative to the run-time
+// vector of the sweep (right-hand side / accumulated solution) and is skipped when there is none.
 
 struct HostStreams
 {
     int workers = 1;
-    // triangular sweeps: phases in PROCESSING order; seg = [phase][worker]{int offset, count, first value row, kind}
-    int nph_fw = 0, nph_bw = 0, nph_fa = 0;
-    ivec fw, fw_seg, bw, bw_seg;
-    ivec fw_pos, bw_pos; // storage row (inside LTx / Lx) of CSR entry t / CSC entry u
-    // factorisation: seg = [phase][worker]{int offset, tasks, double offset}
-    ivec fa, fa_seg;
+    // slot programs (one warp): ops, load list (+ its length in words), shared-memory slots used
+    ivec fw, fw_ld, bw, bw_ld, fa, fa_ld;
+    int fw_nld = 0, bw_nld = 0, fa_nld = 0;
+    int sw_slots = 0, fa_slots = 0;
+    long long sw_home = 0, fa_home = 0; // operands that did not get a slot (statistics)
     dvec fa_val;
     // mat-vec row sets: seg = [worker]{int offset, double offset, blocks}
     ivec rx, rx_seg, ry, ry_seg, rz, rz_seg, rc, rc_seg;
@@ -59,9 +78,10 @@ struct HostStreams
 
 // K-space / expanded indexing used by the row sets: x rows [0,n), y rows [n,n+p), z rows
 // n+p+e with e the expanded cone index (2 unused slots after every second-order cone).
-void build_streams(const Symbolic &S, int workers, HostStreams &H);
+// max_sw_slots / max_fa_slots: shared-memory slots the sweeps / the factorisation may use.
+void build_streams(const Symbolic &S, const Layout &L, int workers, int max_sw_slots, int max_fa_slots, HostStreams &H);
 
 // shared values change with updateData: rebuild only the double streams
-void refresh_stream_values(const Symbolic &S, HostStreams &H);
+void refresh_stream_values(const Symbolic &S, const Layout &L, HostStreams &H);
 
 } // namespace eicos

@@ -29,11 +29,13 @@
 #define EI_DEV inline
 #define EI_LDG(p) (*(p))
 #define EI_PREFETCH(p) ((void)0)
+#define EI_CLOCK() 0ll
 #else
 #include <cuda_runtime.h>
 #define EI_DEV __device__ __forceinline__
 #define EI_LDG(p) __ldg(p)
 #define EI_PREFETCH(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#define EI_CLOCK() clock64()
 #endif
 
 #ifndef EICOS_VEC
@@ -51,7 +53,6 @@ constexpr int LANES = 32;
 constexpr int VEC = EICOS_VEC;       // instances per lane
 constexpr int TILE = LANES * VEC;    // instances per tile = doubles per row
 constexpr int KRED = 7;              // rows per worker in the shared reduction buffer
-constexpr int PF_ROWS = 24;          // how many value rows ahead the serial sweeps prefetch into L2
 
 // ------------------------------------------------------------------ VEC-wide values
 struct alignas(VEC >= 2 ? 16 : 8) vd
@@ -140,7 +141,7 @@ struct KArgs
     Layout L;
     double *ws; // [tiles][rows_total][TILE]
     int *iws;   // [tiles][irows_total][TILE]
-    double *acc_global; // factor accumulators when they do not fit shared memory, else null
+    double *acc_global; // factor column buffers [tile][2 maxcol][TILE] when they do not fit shared memory, else null
     int batch;  // instances handled by this launch's chunk
     int first;  // global index (within the device's batch) of the chunk's first instance
     // instance-major device buffers for load/store (any may be null)
@@ -155,7 +156,7 @@ struct KArgs
     int keep_sticky;
     int pre_equilibrated; // inputs are already divided by the equilibration vectors
     unsigned int *active_count; // device counter: instances still iterating after the head step
-    unsigned long long *ir_rounds; // device counter: solve rounds executed (tile-rounds)
+    unsigned long long *ir_rounds; // device counters: [0] solve rounds executed (tile-rounds), [1..5] cycles per solve_kkt phase
 };
 
 struct Team
@@ -164,8 +165,8 @@ struct Team
     int pl;        // physical lane inside the warp
     int wk, nwk;
     double *red;   // [nwk][KRED][TILE]
-    double *acc;   // [nwk][maxcol][TILE]   (factor kernel only)
     double *stage; // this worker's staging slots + lane: slot s lives at stage[s * TILE]
+    double *extra; // shared memory behind the staging buffers (+ lane): slots of the slot programs, column buffers
 #ifdef EICOS_EMU
     std::barrier<> *bar; // workers of a tile are real threads in the emulator
     void sync() const
@@ -593,426 +594,207 @@ EI_DEV vd line_search(const Team &tm, const KArgs &a, double *T, int lam, int ds
     return res;
 }
 
+// ------------------------------------------------------------------ FIFO of asynchronously loaded rows
+// Every global read of the factorisation and of the sweeps is known to the host in consumption
+// order (the program's load list).  The warp keeps FIFO_GROUPS - 1 cp.async groups of FIFO_GROUP rows
+// in flight ahead of the row it is consuming, so the memory latency never meets a dependent
+// instruction.  Each lane copies and later reads only its own 8 * VEC bytes of a row, so
+// cp.async.wait_group is the only synchronisation needed.
+struct Fifo
+{
+    IStream ld;
+    double *ring;      // FIFO_ROWS rows of shared memory (+ lane)
+    const double *T;   // tile base (+ lane): words >= 0
+    const double *rb;  // run-time vector (+ lane): words < 0; null = such rows are not loaded
+    int left;          // words left in the load list
+    int head, tail;    // producer / consumer ring row
+
+    EI_DEV void issue_group()
+    {
+        int n = 0;
+        while (n < FIFO_GROUP && left > 0)
+        {
+            const int w = ld.get();
+            left--;
+            if (w < 0 && !rb)
+                continue;
+            stage_issue(ring + (size_t)head * TILE, w >= 0 ? T + (size_t)w * TILE : rb + (size_t)(~w) * TILE);
+            head = (head + 1) & (FIFO_ROWS - 1);
+            n++;
+        }
+        stage_commit();
+    }
+    EI_DEV void open(const Team &tm, const int *list, int nwords, const double *T_, const double *rb_)
+    {
+        ld.open(list, tm.pl);
+        ring = tm.stage;
+        T = T_;
+        rb = rb_;
+        left = nwords;
+        head = tail = 0;
+        for (int g = 0; g < FIFO_GROUPS - 1; g++)
+            issue_group();
+    }
+    EI_DEV vd pop()
+    {
+        if ((tail & (FIFO_GROUP - 1)) == 0)
+        { // entering a new group: refill the one just drained, then wait for this one
+            issue_group();
+#ifndef EICOS_EMU
+            asm volatile("cp.async.wait_group %0;" ::"n"(FIFO_GROUPS - 1) : "memory");
+#endif
+        }
+        const vd v = vload(ring + (size_t)tail * TILE);
+        tail = (tail + 1) & (FIFO_ROWS - 1);
+        return v;
+    }
+    EI_DEV void close() { stage_wait(); }
+};
+
+// operand of a slot program: shared-memory slot or home row (streams.hpp)
+EI_DEV double *opnd(double *slots, double *home, int code)
+{
+    return code < SLOT_HOME ? slots + (size_t)code * TILE : home + (size_t)(code - SLOT_HOME) * TILE;
+}
+
 // ------------------------------------------------------------------ numeric LDL' (Eigen factorize, src/eicos.cpp:900,1164)
-// Left-looking by column on the fixed pattern, walking the level schedule of the elimination
-// tree.  Column j: gather its KKT entries, subtract the contribution of every earlier column k
-// with L(j,k) != 0, divide by the pivot and store the column in both orders (LTx for the forward
-// sweep, Lx for the backward sweep).  Everything structural, including the storage row of every L
-// entry, comes from the worker's instruction stream.
+// Right-looking in elimination order, one warp per tile, driven by the factor program
+// (streams.cpp: build_factor).  Step k takes the finished accumulators of column k, writes the pivot
+// and the column of L (column-major, contiguous), and applies the Schur updates of the column to the
+// accumulators of later entries - shared-memory slots for the (short) live range of each entry.
+// HBM traffic: the scaling block V in (FIFO), L and D out.  Same products as Eigen's up-looking
+// kernel (l_small_row * unscaled a_large_row), accumulated in ascending column order.
 EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
 {
     const TileMem t = tile_mem(tm, a, tile);
     const vb act = lane_active(tm, t);
     if (!tm.any(act))
         return;
+    if (tm.wk != 0)
+        return;
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     double *T = t.T;
-    double *acc = tm.acc + (size_t)tm.wk * P.maxcol * TILE + tm.lane;
+    double *slots = tm.extra;
+    double *colA = a.acc_global ? a.acc_global + (size_t)tile * 2 * P.maxcol * TILE + tm.lane : tm.extra + (size_t)P.fa_slots * TILE;
+    double *colL = colA + (size_t)P.maxcol * TILE;
     vb zero_pivot = vbset(false);
-    for (int ph = 0; ph < P.nph_fa; ph++)
+    IStream is;
+    DStream ds;
+    Fifo ff;
+    is.open(P.fa, tm.pl);
+    ds.open(P.fa_val, tm.pl);
+    ff.open(tm, P.fa_ld, P.fa_nld, T, nullptr);
+    const auto fetch = [&](int src) -> vd {
+        if (src >= 0)
+            return vload(opnd(slots, T, src));
+        if (src == SRC_FIFO)
+            return ff.pop();
+        return vset(src == SRC_CONST ? ds.get() : 0.0);
+    };
+    double *Dp = T + (size_t)L.D * TILE, *Lp = T + (size_t)L.Lx * TILE;
+    for (int k = 0; k < P.N; k++, Dp += TILE)
     {
-        const int *seg = P.fa_seg + ((size_t)ph * tm.nwk + tm.wk) * 3;
-        const int nt = EI_LDG(seg + 1);
-        if (nt > 0)
+        const int dsrc = is.get(), cnt = is.get();
+        const vd d = fetch(dsrc);
+        vstore(Dp, d);
+        VFOR zero_pivot.v[c_] = zero_pivot.v[c_] || (d.v[c_] == 0.0); // Eigen: NumericalIssue only on an exactly zero pivot
+        for (int e = 0; e < cnt; e++, Lp += TILE)
         {
-            IStream is;
-            DStream ds;
-            is.open(P.fa + EI_LDG(seg), tm.pl);
-            ds.open(P.fa_val + EI_LDG(seg + 2), tm.pl);
-            for (int q = 0; q < nt; q++)
+            const vd av = fetch(is.get());
+            const vd lv = av / d;
+            vstore(colA + (size_t)e * TILE, av);
+            vstore(colL + (size_t)e * TILE, lv);
+            vstore(Lp, lv);
+        }
+        for (int e1 = 0; e1 < cnt; e1++)
+        {
+            const vd a1 = vload(colA + (size_t)e1 * TILE);
+            for (int e2 = 0; e2 <= e1; e2++)
             {
-                const int j = is.get(), kind = is.get(), cnt = is.get(), nK = is.get(), nR = is.get();
-                vd d;
-                if (kind == 2)
-                { // continue the partial column left by the external part
-                    d = ROWD(T, L.D + j);
-                    for (int c = 0; c < cnt; c++)
-                        vstore(acc + (size_t)c * TILE, ROWD(T, L.Lx + is.get()));
-                }
+                const int tw = is.get();
+                const int kind = tw >> OPK_SHIFT;
+                double *tp = opnd(slots, T, tw & OP_CODE_MASK);
+                vd init;
+                if (kind == OPK_RMW)
+                    init = vload(tp);
+                else if (kind == OPK_FIFO)
+                    init = ff.pop();
                 else
-                {
-                    d = vset(0.0);
-                    for (int c = 0; c < cnt; c++)
-                        vstore(acc + (size_t)c * TILE, vset(0.0));
-                }
-                for (int e = 0; e < nK; e++)
-                {
-                    const int vi = is.get(), pos = is.get();
-                    const vd val = vi >= 0 ? vd(ROWD(T, L.V + vi)) : vset(ds.get());
-                    if (pos < 0)
-                        d = val;
-                    else
-                        vstore(acc + (size_t)pos * TILE, val);
-                }
-                for (int r0 = 0; r0 < nR; r0 += FA_GROUP)
-                { // operands of up to FA_GROUP row entries are loaded before any of them is used
-                    int tl[FA_GROUP];
-                    vd w[FA_GROUP];
-                    {
-                        int k[FA_GROUP], fp[FA_GROUP];
-                        vd ljk[FA_GROUP], dk[FA_GROUP];
-#pragma unroll
-                        for (int u = 0; u < FA_GROUP; u++)
-                        {
-                            tl[u] = 0;
-                            if (r0 + u < nR)
-                            {
-                                k[u] = is.get();
-                                fp[u] = is.get();
-                                tl[u] = is.get();
-                            }
-                        }
-#pragma unroll
-                        for (int u = 0; u < FA_GROUP; u++)
-                            if (r0 + u < nR)
-                            {
-                                ljk[u] = ROWD(T, L.LTx + fp[u]);
-                                dk[u] = ROWD(T, L.D + k[u]);
-                            }
-#pragma unroll
-                        for (int u = 0; u < FA_GROUP; u++)
-                            if (r0 + u < nR)
-                            {
-                                w[u] = ljk[u] * dk[u];
-                                d -= ljk[u] * w[u];
-                            }
-                    }
-#pragma unroll
-                    for (int u = 0; u < FA_GROUP; u++)
-                    {
-                        int t0 = 0;
-                        for (; t0 + 2 <= tl[u]; t0 += 2)
-                        {
-                            const int rel0 = is.get(), bp0 = is.get(), rel1 = is.get(), bp1 = is.get();
-                            const vd l0 = ROWD(T, L.Lx + bp0), l1 = ROWD(T, L.Lx + bp1);
-                            double *a0 = acc + (size_t)rel0 * TILE, *a1 = acc + (size_t)rel1 * TILE;
-                            vstore(a0, vload(a0) - l0 * w[u]);
-                            vstore(a1, vload(a1) - l1 * w[u]);
-                        }
-                        for (; t0 < tl[u]; t0++)
-                        {
-                            const int rel = is.get(), bp = is.get();
-                            double *ap = acc + (size_t)rel * TILE;
-                            vstore(ap, vload(ap) - vd(ROWD(T, L.Lx + bp)) * w[u]);
-                        }
-                    }
-                }
-                if (kind == 1)
-                { // external part only: leave the un-normalised partial column for the chain task
-                    ROWD(T, L.D + j) = d;
-                    for (int c = 0; c < cnt; c++)
-                    {
-                        const int bp = is.get();
-                        (void)is.get();
-                        ROWD(T, L.Lx + bp) = vload(acc + (size_t)c * TILE);
-                    }
-                    continue;
-                }
-                ROWD(T, L.D + j) = d;
-                ROWD(T, L.Dinv + j) = 1.0 / d;
-                VFOR zero_pivot.v[c_] = zero_pivot.v[c_] || (d.v[c_] == 0.0); // Eigen: NumericalIssue only on an exactly zero pivot
-                for (int c = 0; c < cnt; c++)
-                {
-                    const int bp = is.get(), fp = is.get();
-                    const vd lv = vload(acc + (size_t)c * TILE) / d;
-                    ROWD(T, L.Lx + bp) = lv;
-                    ROWD(T, L.LTx + fp) = lv;
-                }
+                    init = vset(kind == OPK_CONST ? ds.get() : 0.0);
+                vstore(tp, init - vload(colL + (size_t)e2 * TILE) * a1);
             }
         }
-        tm.sync();
     }
+    ff.close();
     VFOR if (zero_pivot.v[c_] && act.v[c_]) ROWC(t.I, J_STATUS, c_) = EXIT_FATAL;
 }
 
-// v - sum_k L[k] * vec[gather_k] for a row too long for the staging buffers: six entries at a time,
-// all twelve loads issued before the first multiply-add.
-EI_DEV vd long_row(const Team &tm, IStream &is, const double *T, const double *lv, int vec, int cnt, vd v)
-{
-    constexpr int U = 6;
-    int k = 0;
-    for (; k + U <= cnt; k += U, lv += (size_t)U * TILE)
-    {
-        int c[U];
-        vd l[U], g[U];
-#pragma unroll
-        for (int u = 0; u < U; u++)
-            c[u] = is.get();
-#pragma unroll
-        for (int u = 0; u < U; u++)
-        {
-            l[u] = vload(lv + (size_t)u * TILE);
-            g[u] = vload(rowp(tm, T, vec + c[u]));
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++)
-            v -= l[u] * g[u];
-    }
-    for (; k < cnt; k++, lv += TILE)
-        v -= vload(lv) * vload(rowp(tm, T, vec + is.get()));
-    return v;
-}
-
 // ------------------------------------------------------------------ triangular solves (Eigen solve, src/eicos.cpp:1477,1599)
-// forward:  xw = L^-1 P rhs       (rows of L, dot form; the permutation is folded into the gather)
-// backward: out = P' L^-T D^-1 xw (columns of L, dot form; results land in KKT order directly)
-// Phases come from the sweep's own stream (streams.hpp): block phases hold independent tasks that
-// are staged asynchronously; serial phases hold the chains of the elimination tree, reduced to the
-// recurrence between their own members (results of the last three tasks are forwarded in registers).
-// Serial stream layout: hdr(0) hdr(1) ent(0) hdr(2) ent(1) ..., so the start value of the next task
-// is already being loaded while the current one is computed.
+// forward:  xw = L^-1 P rhs       scatter form by columns of L in elimination order - exactly the
+//                                 summation order of Eigen's forward substitution; the permutation is
+//                                 folded into the right-hand-side loads.
+// backward: out = P' L^-T D^-1 xw dot form by columns in reverse order; results land in KKT order.
+// Both stream the single column-major copy of L through the FIFO (forward ascending, backward
+// descending) and keep every intermediate value in a shared-memory slot for its live range
+// (streams.cpp: build_forward / build_backward).  One warp per tile, no barriers inside a sweep.
 EI_DEV void ldl_forward(const Team &tm, const KArgs &a, double *T, int rhs)
 {
     const DevPattern &P = a.P;
     const Layout &L = a.L;
-    for (int ph = 0; ph < P.nph_fw; ph++)
+    double *slots = tm.extra;
+    IStream is;
+    Fifo ff;
+    is.open(P.fw, tm.pl);
+    ff.open(tm, P.fw_ld, P.fw_nld, T, T + (size_t)rhs * TILE);
+    double *xp = T + (size_t)L.xw * TILE;
+    for (int k = 0; k < P.N; k++, xp += TILE)
     {
-        const int *seg = P.fw_seg + ((size_t)ph * tm.nwk + tm.wk) * 4;
-        const int count = EI_LDG(seg + 1);
-        if (count > 0)
+        const int src = is.get(), cnt = is.get();
+        const vd x = src >= 0 ? vload(opnd(slots, T, src)) : ff.pop();
+        vstore(xp, x);
+        for (int e = 0; e < cnt; e++)
         {
-            IStream is;
-            is.open(P.fw + EI_LDG(seg), tm.pl);
-            const double *lv = T + (size_t)(L.LTx + EI_LDG(seg + 2)) * TILE;
-            if (EI_LDG(seg + 3) == SEG_BLOCKS)
-            {
-                // issue cursor (isi, lvi) runs one block ahead of the compute cursor (is, lv)
-                IStream isi = is;
-                const double *lvi = lv;
-                const auto issue = [&](int b) {
-                    double *sp = tm.stage + (size_t)(b & 1) * STAGE_SLOTS * TILE;
-                    const int nt = isi.get();
-                    if (nt < 0)
-                    {
-                        (void)isi.get();
-                        (void)isi.get();
-                        const int cnt = isi.get();
-                        for (int k = 0; k < cnt; k++)
-                            (void)isi.get();
-                        lvi += (size_t)cnt * TILE;
-                    }
-                    else
-                        for (int t = 0; t < nt; t++)
-                        {
-                            const int i = isi.get(), r = isi.get(), cnt = isi.get();
-                            stage_issue(sp, r >= 0 ? rowp(tm, T, rhs + r) : rowp(tm, T, L.xw + i));
-                            sp += TILE;
-                            for (int k = 0; k < cnt; k++, lvi += TILE, sp += 2 * TILE)
-                            {
-                                stage_issue(sp, lvi);
-                                stage_issue(sp + TILE, rowp(tm, T, L.xw + isi.get()));
-                            }
-                        }
-                    stage_commit();
-                };
-                issue(0);
-                for (int b = 0; b < count; b++)
-                {
-                    if (b + 1 < count)
-                    {
-                        issue(b + 1);
-                        stage_wait_prev();
-                    }
-                    else
-                        stage_wait();
-                    const int nt = is.get();
-                    if (nt < 0)
-                    { // oversize row: straight from global memory
-                        const int i = is.get(), r = is.get(), cnt = is.get();
-                        vd v = r >= 0 ? vd(ROWD(T, rhs + r)) : vd(ROWD(T, L.xw + i));
-                        v = long_row(tm, is, T, lv, L.xw, cnt, v);
-                        lv += (size_t)cnt * TILE;
-                        ROWD(T, L.xw + i) = v;
-                        continue;
-                    }
-                    const double *sp = tm.stage + (size_t)(b & 1) * STAGE_SLOTS * TILE;
-                    for (int t = 0; t < nt; t++)
-                    {
-                        const int i = is.get();
-                        (void)is.get();
-                        const int cnt = is.get();
-                        vd v = vload(sp);
-                        sp += TILE;
-                        for (int k = 0; k < cnt; k++, sp += 2 * TILE)
-                        {
-                            (void)is.get();
-                            v -= vload(sp) * vload(sp + TILE);
-                        }
-                        lv += (size_t)cnt * TILE;
-                        ROWD(T, L.xw + i) = v;
-                    }
-                }
-            }
-            else
-            {
-                vd p1 = vset(0.0), p2 = vset(0.0), p3 = vset(0.0);
-                int i = is.get(), r = is.get(), cnt = is.get();
-                vd v = r >= 0 ? vd(ROWD(T, rhs + r)) : vd(ROWD(T, L.xw + i));
-                for (int q = 0; q < count; q++)
-                {
-                    int ni = 0, ncnt = 0;
-                    vd nv = vset(0.0);
-                    if (q + 1 < count)
-                    {
-                        ni = is.get();
-                        r = is.get();
-                        ncnt = is.get();
-                        nv = r >= 0 ? vd(ROWD(T, rhs + r)) : vd(ROWD(T, L.xw + ni));
-                    }
-                    for (int k = 0; k < cnt; k++, lv += TILE)
-                    {
-                        const int c = is.get();
-                        EI_PREFETCH(lv + (size_t)PF_ROWS * TILE);
-                        const vd xv = c >= 0 ? vd(ROWD(T, L.xw + c)) : (c == FWD_PREV1 ? p1 : (c == FWD_PREV2 ? p2 : p3));
-                        v -= vload(lv) * xv;
-                    }
-                    ROWD(T, L.xw + i) = v;
-                    p3 = p2;
-                    p2 = p1;
-                    p1 = v;
-                    i = ni;
-                    cnt = ncnt;
-                    v = nv;
-                }
-            }
+            const int tw = is.get();
+            const vd l = ff.pop();
+            double *tp = opnd(slots, T, tw & OP_CODE_MASK);
+            const vd init = (tw >> OPK_SHIFT) == OPK_FIFO ? ff.pop() : vload(tp);
+            vstore(tp, init - l * x);
         }
-        tm.sync();
     }
+    ff.close();
 }
 
 // out = solution (KKT order).  If x >= 0: additionally x += solution for the instances with `cont`.
-// Task header: [xw/Dinv row j | INIT_PARTIAL, out row o | ~o for the external part of a chain task].
 EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int out, int x, vb cont)
 {
     const DevPattern &P = a.P;
-    const Layout &L = a.L;
+    double *slots = tm.extra;
     const bool accumulate = x >= 0;
     const vd zero = vset(0.0);
-    for (int ph = 0; ph < P.nph_bw; ph++)
+    double *op = T + (size_t)out * TILE;
+    double *xp = accumulate ? T + (size_t)x * TILE : nullptr;
+    IStream is;
+    Fifo ff;
+    is.open(P.bw, tm.pl);
+    ff.open(tm, P.bw_ld, P.bw_nld, T, xp);
+    for (int k = 0; k < P.N; k++)
     {
-        const int *seg = P.bw_seg + ((size_t)ph * tm.nwk + tm.wk) * 4;
-        const int count = EI_LDG(seg + 1);
-        if (count > 0)
+        const int o = is.get(), keep = is.get(), cnt = is.get();
+        const vd d = ff.pop();
+        vd v = (1.0 / d) * ff.pop(); // Eigen: diag.inverse() * x
+        for (int e = 0; e < cnt; e++)
         {
-            IStream is;
-            is.open(P.bw + EI_LDG(seg), tm.pl);
-            const double *lv = T + (size_t)(L.Lx + EI_LDG(seg + 2)) * TILE;
-            if (EI_LDG(seg + 3) == SEG_BLOCKS)
-            {
-                IStream isi = is;
-                const double *lvi = lv;
-                const auto issue = [&](int b) {
-                    double *sp = tm.stage + (size_t)(b & 1) * STAGE_SLOTS * TILE;
-                    const int nt = isi.get();
-                    if (nt < 0)
-                    {
-                        (void)isi.get();
-                        (void)isi.get();
-                        const int cnt = isi.get();
-                        for (int k = 0; k < cnt; k++)
-                            (void)isi.get();
-                        lvi += (size_t)cnt * TILE;
-                    }
-                    else
-                        for (int t = 0; t < nt; t++)
-                        {
-                            const int j = isi.get(), oe = isi.get(), cnt = isi.get();
-                            if (j >= 0)
-                            {
-                                stage_issue(sp, rowp(tm, T, L.Dinv + j));
-                                stage_issue(sp + TILE, rowp(tm, T, L.xw + j));
-                            }
-                            else
-                                stage_issue(sp, rowp(tm, T, out + (oe >= 0 ? oe : ~oe)));
-                            sp += 2 * TILE;
-                            for (int k = 0; k < cnt; k++, lvi += TILE, sp += 2 * TILE)
-                            {
-                                stage_issue(sp, lvi);
-                                stage_issue(sp + TILE, rowp(tm, T, out + isi.get()));
-                            }
-                        }
-                    stage_commit();
-                };
-                issue(0);
-                for (int b = 0; b < count; b++)
-                {
-                    if (b + 1 < count)
-                    {
-                        issue(b + 1);
-                        stage_wait_prev();
-                    }
-                    else
-                        stage_wait();
-                    const int nt = is.get();
-                    if (nt < 0)
-                    {
-                        const int j = is.get(), oe = is.get(), cnt = is.get();
-                        const int o = oe >= 0 ? oe : ~oe;
-                        vd v = j >= 0 ? vd(ROWD(T, L.Dinv + j)) * vd(ROWD(T, L.xw + j)) : vd(ROWD(T, out + o));
-                        v = long_row(tm, is, T, lv, out, cnt, v);
-                        lv += (size_t)cnt * TILE;
-                        ROWD(T, out + o) = v;
-                        if (accumulate && oe >= 0)
-                            ROWD(T, x + o) += vsel(cont, v, zero);
-                        continue;
-                    }
-                    const double *sp = tm.stage + (size_t)(b & 1) * STAGE_SLOTS * TILE;
-                    for (int t = 0; t < nt; t++)
-                    {
-                        const int j = is.get(), oe = is.get(), cnt = is.get();
-                        const int o = oe >= 0 ? oe : ~oe;
-                        vd v = j >= 0 ? vload(sp) * vload(sp + TILE) : vload(sp);
-                        sp += 2 * TILE;
-                        for (int k = 0; k < cnt; k++, sp += 2 * TILE)
-                        {
-                            (void)is.get();
-                            v -= vload(sp) * vload(sp + TILE);
-                        }
-                        lv += (size_t)cnt * TILE;
-                        ROWD(T, out + o) = v;
-                        if (accumulate && oe >= 0)
-                            ROWD(T, x + o) += vsel(cont, v, zero);
-                    }
-                }
-            }
-            else
-            {
-                vd p1 = zero, p2 = zero, p3 = zero;
-                int j = is.get(), o = is.get(), cnt = is.get();
-                vd v = j >= 0 ? vd(ROWD(T, L.Dinv + j)) * vd(ROWD(T, L.xw + j)) : vd(ROWD(T, out + o));
-                for (int q = 0; q < count; q++)
-                {
-                    int no = 0, ncnt = 0;
-                    vd nv = zero;
-                    if (q + 1 < count)
-                    {
-                        j = is.get();
-                        no = is.get();
-                        ncnt = is.get();
-                        nv = j >= 0 ? vd(ROWD(T, L.Dinv + j)) * vd(ROWD(T, L.xw + j)) : vd(ROWD(T, out + no));
-                    }
-                    for (int k = 0; k < cnt; k++, lv += TILE)
-                    {
-                        const int c = is.get();
-                        EI_PREFETCH(lv + (size_t)PF_ROWS * TILE);
-                        const vd xv = c >= 0 ? vd(ROWD(T, out + c)) : (c == FWD_PREV1 ? p1 : (c == FWD_PREV2 ? p2 : p3));
-                        v -= vload(lv) * xv;
-                    }
-                    ROWD(T, out + o) = v;
-                    if (accumulate)
-                        ROWD(T, x + o) += vsel(cont, v, zero);
-                    p3 = p2;
-                    p2 = p1;
-                    p1 = v;
-                    o = no;
-                    cnt = ncnt;
-                    v = nv;
-                }
-            }
+            const int g = is.get();
+            v -= ff.pop() * vload(opnd(slots, op, g));
         }
-        tm.sync();
+        vstore(op + (size_t)o * TILE, v);
+        if (keep >= 0)
+            vstore(slots + (size_t)keep * TILE, v);
+        if (accumulate)
+            vstore(xp + (size_t)o * TILE, ff.pop() + vsel(cont, v, zero));
     }
+    ff.close();
 }
 
 // ------------------------------------------------------------------ KKT residual for iterative refinement (src/eicos.cpp:1511-1576)
@@ -1119,6 +901,8 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
     const int rhs = a.rhs, sol = a.sol;
     const bool init = a.initialize != 0;
 
+    long long ck[5] = {0, 0, 0, 0, 0}, c0 = EI_CLOCK(), c1;
+#define EI_PHASE(k) (c1 = EI_CLOCK(), ck[k] += c1 - c0, c0 = c1)
     vd mx[1] = {vset(0.0)};
     {
         const int ins[1] = {rhs};
@@ -1127,8 +911,16 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
     team_max<1>(tm, mx);
     const vd threshold = (1. + mx[0]) * Settings::linsysacc;
 
-    ldl_forward(tm, a, T, rhs);
-    ldl_backward(tm, a, T, sol, -1, vbset(false));
+    tm.sync(); // (workers > 1) everybody has read rhs before worker 0 reuses the staging buffers
+    EI_PHASE(0);
+    if (tm.wk == 0)
+    {
+        ldl_forward(tm, a, T, rhs);
+        EI_PHASE(1);
+        ldl_backward(tm, a, T, sol, -1, vbset(false));
+        EI_PHASE(2);
+    }
+    tm.sync();
 
     vd nerr_prev = vset(DBL_MAX);
     int kref[VEC];
@@ -1138,6 +930,7 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
     for (;;)
     {
         const vd nerr = kkt_residual(tm, a, T, rhs, sol, init);
+        EI_PHASE(3);
         vb rollback = vbset(false);
         VFOR
         {
@@ -1162,9 +955,16 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
         }
         if (tm.all(done))
             break;
-        tm.sync(); // e complete before the forward sweep gathers it
-        ldl_forward(tm, a, T, L.e);
-        ldl_backward(tm, a, T, L.dxr, sol, !done);
+        tm.sync(); // e complete before the forward sweep loads it
+        EI_PHASE(4);
+        if (tm.wk == 0)
+        {
+            ldl_forward(tm, a, T, L.e);
+            EI_PHASE(1);
+            ldl_backward(tm, a, T, L.dxr, sol, !done);
+            EI_PHASE(2);
+        }
+        tm.sync();
         VFOR if (!done.v[c_]) kref[c_]++;
         rounds++;
     }
@@ -1175,9 +975,15 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
             VFOR if (act.v[c_]) ROWC(t.I, a.nitrow, c_) = kref[c_];
 #ifndef EICOS_EMU
         if (tm.pl == 0 && a.ir_rounds)
+        {
             atomicAdd(a.ir_rounds, (unsigned long long)(rounds + 1));
+            EI_PHASE(4);
+            for (int k = 0; k < 5; k++)
+                atomicAdd(a.ir_rounds + 1 + k, (unsigned long long)ck[k]);
+        }
 #endif
     }
+#undef EI_PHASE
 }
 
 // ------------------------------------------------------------------ start of a solve (src/eicos.cpp:855-894)

@@ -122,6 +122,9 @@ typedef struct eicos_batch_stats
     long long factor_launch_tiles, solve_launch_tiles;
     int factor_launches, solve_launches;
     int compactions; /* active-set compactions performed */
+    /* SM clock cycles the tiles spent in the phases of eicos_solve_kkt, summed over tiles and launches:
+     * right-hand-side norm, forward sweep, backward sweep, refinement residual, bookkeeping */
+    unsigned long long kkt_phase_cycles[5];
 } eicos_batch_stats;
 
 /* Per-kernel-class device timing of the LAST eicos_batch_solve* call (enable first). */
