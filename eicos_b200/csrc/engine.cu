@@ -25,8 +25,10 @@ namespace eicos
         tm.wk = threadIdx.x >> 5;                                                              \
         tm.nwk = blockDim.x >> 5;                                                              \
         tm.red = smem;                                                                         \
-        tm.stage = smem + (size_t)(tm.nwk > 1 ? tm.nwk * KRED : 0) * TILE + (size_t)tm.wk * 2 * STAGE_SLOTS * TILE + tm.lane; \
-        tm.extra = smem + (size_t)tm.nwk * ((tm.nwk > 1 ? KRED : 0) + 2 * STAGE_SLOTS) * TILE + tm.lane;             \
+        /* [reduction rows][worker 0: staging = FIFO ring][slots, column buffers][staging of workers 1..] */ \
+        double *st0_ = smem + (size_t)(tm.nwk > 1 ? tm.nwk * KRED : 0) * TILE + tm.lane;             \
+        tm.extra = st0_ + (size_t)2 * STAGE_SLOTS * TILE;                                          \
+        tm.stage = tm.wk == 0 ? st0_ : tm.extra + ((size_t)a.xrows + (size_t)(tm.wk - 1) * 2 * STAGE_SLOTS) * TILE; \
         fn(tm, a, blockIdx.x);                                                                 \
     }
 #define EI_MAX_THREADS 256
@@ -58,8 +60,8 @@ __global__ void eicos_compact(const __grid_constant__ KArgs a, const __grid_cons
     {                                                                                             \
         const int nw_ = (threads);                                                                \
         std::vector<double> red_((size_t)nw_ * KRED * TILE + 8);                                  \
-        std::vector<double> ext_(((size_t)std::max((args).P.sw_slots, (args).P.fa_slots) + 2 * (args).P.maxcol) * TILE + 8); \
-        std::vector<double> stg_((size_t)nw_ * 2 * STAGE_SLOTS * TILE + 8);                           \
+        const size_t xr_ = (size_t)std::max((args).P.sw_slots, (args).P.fa_slots) + 2 * (args).P.maxcol; \
+        std::vector<double> stg_(((size_t)nw_ * 2 * STAGE_SLOTS + xr_) * TILE + 8);                \
         for (int tile_ = 0; tile_ < (tiles); tile_++)                                             \
         {                                                                                         \
             std::barrier<> bar_(nw_);                                                             \
@@ -70,8 +72,8 @@ __global__ void eicos_compact(const __grid_constant__ KArgs a, const __grid_cons
                 tm_.wk = wk_;                                                                     \
                 tm_.nwk = nw_;                                                                    \
                 tm_.red = red_.data();                                                            \
-                tm_.extra = ext_.data();                                                          \
-                tm_.stage = stg_.data() + (size_t)wk_ * 2 * STAGE_SLOTS * TILE;                      \
+                tm_.extra = stg_.data() + (size_t)2 * STAGE_SLOTS * TILE;                         \
+                tm_.stage = wk_ == 0 ? stg_.data() : tm_.extra + (xr_ + (size_t)(wk_ - 1) * 2 * STAGE_SLOTS) * TILE; \
                 tm_.bar = nw_ > 1 ? &bar_ : nullptr;                                              \
                 fn(tm_, (args), tile_);                                                           \
             };                                                                                    \
@@ -146,6 +148,7 @@ void Engine::build_layout(const Symbolic &S)
     L.V = take((int)S.Vslot.size());
     L.Lx = take(S.nnzL);
     L.D = take(S.N);
+    L.Dinv = take(S.N);
     L.rhs1 = take(S.N);
     L.rhs2 = take(S.N);
     L.sol1 = take(S.N);
@@ -185,6 +188,7 @@ void Engine::upload_pattern(const Symbolic &S)
     P.fa_nld = H_.fa_nld;
     P.sw_slots = H_.sw_slots;
     P.fa_slots = H_.fa_slots;
+    P.sw_direct = H_.sw_direct > 0 ? 1 : 0;
     P.cone_dim = upload(S.q, owned_, st);
     P.cone_k = upload(S.cone_k, owned_, st);
     P.cone_q = upload(S.cone_q, owned_, st);
@@ -274,13 +278,16 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
     moves_host_ = (int *)be::pinned(2 * slots * sizeof(int));
     const size_t smem_base = (size_t)workers_ * ((workers_ > 1 ? KRED : 0) + 2 * STAGE_SLOTS) * TILE * sizeof(double);
     smem_common_ = smem_base + (size_t)H_.sw_slots * TILE * sizeof(double);
-    smem_factor_ = smem_base + (size_t)(H_.fa_slots + 2 * S.maxcol) * TILE * sizeof(double);
+    xrows_factor_ = H_.fa_slots + 2 * S.maxcol;
 #ifndef EICOS_EMU
     if (2 * S.maxcol > MAX_COLBUF_ROWS)
     { // the column buffers of the factorisation spill to global memory (one slab per tile)
         acc_global_ = (double *)be::alloc((size_t)cap_tiles_ * 2 * S.maxcol * TILE * sizeof(double));
-        smem_factor_ = smem_base + (size_t)H_.fa_slots * TILE * sizeof(double);
+        xrows_factor_ = H_.fa_slots;
     }
+#endif
+    smem_factor_ = smem_base + (size_t)xrows_factor_ * TILE * sizeof(double);
+#ifndef EICOS_EMU
     if (smem_factor_ > 48 * 1024)
         EI_CUDA(cudaFuncSetAttribute(eicos_ldl_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_factor_));
     if (smem_common_ > 48 * 1024)
@@ -368,6 +375,7 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
     a.active_count = active_count_;
     a.ir_rounds = ir_rounds_;
     a.nitrow = -1;
+    a.xrows = P_.sw_slots;
     be::zero(ir_rounds_, 8 * sizeof(unsigned long long), st);
 
     const int threads = workers_ * (LANES == 1 ? 1 : 32);
@@ -432,7 +440,9 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
         stt.chunks++;
 
         auto factor = [&]() {
+            a.xrows = xrows_factor_;
             EI_TIMED(0, EI_LAUNCH(eicos_ldl_factor, tile_factor, tiles, threads, smem_factor_, st, a));
+            a.xrows = P_.sw_slots;
             stt.factor_launches++;
             stt.factor_launch_tiles += tiles;
         };
@@ -581,12 +591,15 @@ void Engine::debug_factor_init(int batch, const double *d_c, const double *d_h, 
     a.batch = batch;
     a.first = 0;
     a.nitrow = -1;
+    a.xrows = P_.sw_slots;
     const int tiles = (batch + TILE - 1) / TILE;
     const int threads = workers_ * (LANES == 1 ? 1 : 32);
     (void)threads;
     EI_LAUNCH(eicos_load_inputs, tile_load, tiles, threads, smem_common_, st, a);
     EI_LAUNCH(eicos_init, tile_init, tiles, threads, smem_common_, st, a);
+    a.xrows = xrows_factor_;
     EI_LAUNCH(eicos_ldl_factor, tile_factor, tiles, threads, smem_factor_, st, a);
+    a.xrows = P_.sw_slots;
     a.rhs = L_.rhs1;
     a.sol = L_.sol1;
     a.initialize = 1;

@@ -82,6 +82,7 @@ class Engine
     int *moves_dev_ = nullptr, *status_host_ = nullptr, *moves_host_ = nullptr; // active-set compaction
     bool compaction_ = true;
     size_t smem_factor_ = 0, smem_common_ = 0;
+    int xrows_factor_ = 0; // shared-memory rows behind the FIFO ring in the factor kernel (slots + column buffers)
     std::vector<void *> owned_; // device allocations holding pattern data
     // positions of value arrays that upload_values() rewrites
     double *dxeq_ = nullptr, *dAeq_ = nullptr, *dGeq_ = nullptr;

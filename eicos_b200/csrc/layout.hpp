@@ -73,7 +73,7 @@ struct Layout
     int lpv, lpw;                   // LP cone scalings (l rows each)
     int cpar, cq;                   // SOC scalings: CP_COUNT rows per cone, q vectors
     int V;                          // scaling block values of the KKT matrix (cacheIndices order)
-    int Lx, D;                      // factor: L column-major (CSC order of the symbolic pattern), pivots
+    int Lx, D, Dinv;                // factor: L column-major (CSC order of the symbolic pattern), pivots, reciprocals
     int rhs1, rhs2, sol1, sol2;     // KKT-space vectors (N rows)
     int xw, dxr, e;                 // triangular-solve work vector, refinement step, residual (N rows)
     int dsw, wdz, dsaff, ds1;       // dsaff_by_W, W_times_dzaff, dsaff, scratch (mt rows)
@@ -98,6 +98,7 @@ struct DevPattern
     // slot programs (streams.hpp): ops, load lists (+ length in words), shared-memory slots they use
     const int *fw, *fw_ld, *bw, *bw_ld, *fa, *fa_ld;
     int fw_nld, bw_nld, fa_nld, sw_slots, fa_slots;
+    int sw_direct; // the sweep programs contain operands read straight from global memory
     const double *fa_val;
     const int *rx, *rx_seg, *ry, *ry_seg, *rz, *rz_seg, *rc, *rc_seg;
     const double *rx_val, *ry_val, *rz_val, *rc_val;

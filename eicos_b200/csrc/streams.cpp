@@ -2,6 +2,7 @@
 #include "streams.hpp"
 
 #include <algorithm>
+#include <cstdint>
 #include <stdexcept>
 
 namespace eicos
@@ -105,91 +106,209 @@ struct SlotPool
     }
 };
 
-// ---- forward sweep  xw = L^-1 P rhs, column by column in elimination order (scatter form, the
-// order Eigen's own forward substitution uses): step k consumes the accumulator of row k and
-// subtracts L(i,k) x_k from the accumulators of the rows i of column k.  An accumulator starts from
-// its right-hand-side row on the first touch.
-//   ops:   [src, cnt, cnt x target]        load list: [rhs_k if untouched] { L(i,k) [rhs_i on a first touch] }
+// Host model of the device FIFO: every pop appends the row to the load list and returns the ring row
+// the device will find it in.
+struct FifoSim
+{
+    ivec &ld;
+    int npop = 0;
+    explicit FifoSim(ivec &l) : ld(l) {}
+    int pop(int base, int row)
+    {
+        if (row < 0 || row > LD_ROW_MASK)
+            throw std::logic_error("load list: row out of range");
+        ld.push_back((base << LD_BASE_SHIFT) | row);
+        return npop++ % FIFO_ROWS;
+    }
+    // does a check point that makes `pops` pops, the first one being pop number `first`, enter a new group?
+    static bool crosses(int first, int pops)
+    {
+        if (pops <= 0)
+            return false;
+        const int before = first == 0 ? 0 : (first - 1) / FIFO_GROUP + 1;
+        return (first + pops - 1) / FIFO_GROUP + 1 > before;
+    }
+    // A value written to global memory when `prod` pops had been made may be loaded through the FIFO as
+    // pop number j only if the group of j is issued afterwards (sync points come up to FIFO_GROUP - 1
+    // pops early, the first FIFO_AHEAD groups are issued before the program starts).
+    static bool far_safe(int prod, int j)
+    {
+        const int g = j / FIFO_GROUP;
+        return g >= FIFO_AHEAD && prod <= (g - FIFO_AHEAD) * FIFO_GROUP - FIFO_GROUP;
+    }
+};
+
+// Shared-memory slots for the values of a sweep, Belady style: a value gets a slot when it is
+// produced; when none is free the live value whose next use is furthest away loses its slot (it is
+// still at home in global memory).  Use times are step numbers of the sweep.
+struct SlotCache
+{
+    const std::vector<ivec> &uses;
+    ivec holder, slot_of, ptr;
+    int top = 0;
+    SlotCache(int slots, const std::vector<ivec> &u) : uses(u), holder(slots, -1), slot_of(u.size(), -1), ptr(u.size(), 0) {}
+    int next_use(int v) const { return ptr[v] < (int)uses[v].size() ? uses[v][ptr[v]] : INT32_MAX; }
+    void used(int v)
+    {
+        ptr[v]++;
+        if (ptr[v] == (int)uses[v].size() && slot_of[v] >= 0)
+        {
+            holder[slot_of[v]] = -1;
+            slot_of[v] = -1;
+        }
+    }
+    int alloc(int v)
+    {
+        if (uses[v].empty())
+            return -1;
+        int s = -1;
+        for (int q = 0; q < (int)holder.size() && s < 0; q++)
+            if (holder[q] < 0)
+                s = q;
+        if (s < 0)
+        {
+            int far = -1;
+            for (int q = 0; q < (int)holder.size(); q++)
+                if (far < 0 || next_use(holder[q]) > next_use(holder[far]))
+                    far = q;
+            if (far < 0 || next_use(holder[far]) <= next_use(v))
+                return -1;
+            slot_of[holder[far]] = -1;
+            s = far;
+        }
+        holder[s] = v;
+        slot_of[v] = s;
+        top = std::max(top, s + 1);
+        return s;
+    }
+};
+
+// Emits the pair words of one row and sets the sync flags at the device's check points (groups of
+// SW_UNROLL pairs, then single pairs).  operand(q) appends the q-th pair: it pops the L value and
+// resolves the gathered value, returning the pair word without flags.
+template <class Pair>
+void emit_pairs(ivec &ops, FifoSim &F, int cnt, Pair pair)
+{
+    const int cnt4 = cnt / SW_UNROLL * SW_UNROLL;
+    int q = 0;
+    while (q < cnt)
+    {
+        const int len = q < cnt4 ? SW_UNROLL : 1;
+        const int first = F.npop;
+        const size_t at = ops.size();
+        for (int r = 0; r < len; r++)
+            ops.push_back(pair(q + r));
+        if (FifoSim::crosses(first, F.npop - first))
+            ops[at] |= SW_SYNC_PAIR;
+        q += len;
+    }
+}
+
+int pair_word(int lrow, int opnd)
+{
+    if (opnd < 0 || opnd >= (1 << (31 - SW_OPND_SHIFT)))
+        throw std::logic_error("sweep program: operand out of range");
+    return lrow | (opnd << SW_OPND_SHIFT);
+}
+
+// ---- forward sweep  xw = L^-1 P rhs, rows of L in elimination order, dot form in ascending column
+// order (the summation order of Eigen's column-oriented forward substitution).  L is stored once,
+// column-major; the row-order walk is just the order of the load list.
+//   row i: [cnt | sync, keep | rhs ring row << 8] cnt x pair
 void build_forward(const Symbolic &S, const Layout &L, int max_slots, HostStreams &H)
 {
-    SlotPool pool(max_slots);
-    ivec code(S.N, -1);
+    std::vector<ivec> uses(S.N);
     for (int k = 0; k < S.N; k++)
+        uses[k].assign(S.Li.begin() + S.Lp[k], S.Li.begin() + S.Lp[k + 1]);
+    SlotCache cache(max_slots, uses);
+    FifoSim F(H.fw_ld);
+    ivec prod(S.N, 0);
+    for (int i = 0; i < S.N; i++)
     {
-        if (code[k] < 0)
-        {
-            H.fw.push_back(SRC_FIFO);
-            H.fw_ld.push_back(~S.pinv[k]);
-        }
-        else
-            H.fw.push_back(code[k]);
-        H.fw.push_back(S.Lp[k + 1] - S.Lp[k]);
-        for (int u = S.Lp[k]; u < S.Lp[k + 1]; u++)
-        {
-            const int i = S.Li[u];
-            H.fw_ld.push_back(L.Lx + u);
-            if (code[i] < 0)
+        const int cnt = S.Lr.p[i + 1] - S.Lr.p[i];
+        const int first = F.npop;
+        const int rhs_row = F.pop(1, S.pinv[i]);
+        H.fw.push_back(cnt | (FifoSim::crosses(first, 1) ? SW_SYNC_HDR : 0));
+        const size_t w1 = H.fw.size();
+        H.fw.push_back(0);
+        emit_pairs(H.fw, F, cnt, [&](int q) {
+            const int t = S.Lr.p[i] + q, k = S.Lr.j[t];
+            const int lrow = F.pop(0, L.Lx + S.Lr.v[t]);
+            int opnd;
+            if (cache.slot_of[k] >= 0)
+                opnd = FIFO_ROWS + cache.slot_of[k];
+            else if (FifoSim::far_safe(prod[k], F.npop))
             {
-                code[i] = pool.take(L.xw + i);
-                H.fw.push_back(code[i] | (OPK_FIFO << OPK_SHIFT));
-                H.fw_ld.push_back(~S.pinv[i]);
+                opnd = F.pop(0, L.xw + k);
+                H.sw_far++;
             }
             else
-                H.fw.push_back(code[i]);
-        }
-        pool.give(code[k]);
+            {
+                opnd = SW_DIRECT + L.xw + k;
+                H.sw_direct++;
+            }
+            cache.used(k);
+            return pair_word(lrow, opnd);
+        });
+        const int s = cache.alloc(i);
+        H.fw[w1] = (s >= 0 ? FIFO_ROWS + s : SW_NO_KEEP) | (rhs_row << 8);
+        prod[i] = F.npop;
     }
     H.fw_nld = (int)H.fw_ld.size();
-    H.sw_slots = std::max(H.sw_slots, pool.top);
-    H.sw_home += pool.home;
+    H.sw_slots = std::max(H.sw_slots, cache.top);
     pad_tail(H.fw);
     pad_tail(H.fw_ld);
 }
 
-// ---- backward sweep  out = P' L^-T D^-1 xw, columns in reverse elimination order (dot form):
-// step k gathers the finished entries i of column k.  A finished entry is kept in a slot until the
-// first column of its row has used it; its home is its own output row (relative to `out`).
-//   ops:   [out row, keep code | -1, cnt, cnt x gather]
-//   load list: D_k, xw_k, { L(i,k) }, ~out row (accumulated solution; skipped on a plain solve)
+// ---- backward sweep  out = P' L^-T D^-1 xw, columns in reverse elimination order (dot form, Eigen's
+// order); results land in KKT order.  The home of a finished entry is its output row.
+//   column k: [cnt | sync, keep | 1/d ring row << 8 | xw ring row << 16 | accumulated-solution ring row << 24, out row] cnt x pair
 void build_backward(const Symbolic &S, const Layout &L, int max_slots, HostStreams &H)
 {
-    SlotPool pool(max_slots);
-    ivec code(S.N, -1), minrow(S.N, -1);
+    std::vector<ivec> uses(S.N); // value i is used by the columns of row i, latest column first
     for (int i = 0; i < S.N; i++)
-        if (S.Lr.p[i + 1] > S.Lr.p[i])
-        {
-            int mn = S.N;
-            for (int t = S.Lr.p[i]; t < S.Lr.p[i + 1]; t++)
-                mn = std::min(mn, S.Lr.j[t]);
-            minrow[i] = mn;
-        }
+        for (int t = S.Lr.p[i + 1] - 1; t >= S.Lr.p[i]; t--)
+            uses[i].push_back(S.N - 1 - S.Lr.j[t]);
+    for (const ivec &u : uses)
+        if (!std::is_sorted(u.begin(), u.end()))
+            throw std::logic_error("rows of L must have ascending columns");
+    SlotCache cache(max_slots, uses);
+    FifoSim F(H.bw_ld);
+    ivec prod(S.N, 0);
     for (int k = S.N - 1; k >= 0; k--)
     {
-        const int o = S.pinv[k];
-        H.bw_ld.push_back(L.D + k);
-        H.bw_ld.push_back(L.xw + k);
+        const int o = S.pinv[k], cnt = S.Lp[k + 1] - S.Lp[k];
+        const int first = F.npop;
+        const int drow = F.pop(0, L.Dinv + k), xrow = F.pop(0, L.xw + k), arow = F.pop(2, o);
+        H.bw.push_back(cnt | (FifoSim::crosses(first, 3) ? SW_SYNC_HDR : 0));
+        const size_t w1 = H.bw.size();
+        H.bw.push_back(0);
         H.bw.push_back(o);
-        const size_t keep_at = H.bw.size();
-        H.bw.push_back(-1);
-        H.bw.push_back(S.Lp[k + 1] - S.Lp[k]);
-        for (int u = S.Lp[k]; u < S.Lp[k + 1]; u++)
-        {
-            H.bw_ld.push_back(L.Lx + u);
-            H.bw.push_back(code[S.Li[u]]);
-        }
-        for (int u = S.Lp[k]; u < S.Lp[k + 1]; u++)
-            if (minrow[S.Li[u]] == k)
-                pool.give(code[S.Li[u]]);
-        if (minrow[k] >= 0)
-        {
-            code[k] = pool.take(o);
-            H.bw[keep_at] = code[k] < SLOT_HOME ? code[k] : -1;
-        }
-        H.bw_ld.push_back(~o);
+        emit_pairs(H.bw, F, cnt, [&](int q) {
+            const int u = S.Lp[k] + q, i = S.Li[u];
+            const int lrow = F.pop(0, L.Lx + u);
+            int opnd;
+            if (cache.slot_of[i] >= 0)
+                opnd = FIFO_ROWS + cache.slot_of[i];
+            else if (FifoSim::far_safe(prod[i], F.npop))
+            {
+                opnd = F.pop(1, S.pinv[i]);
+                H.sw_far++;
+            }
+            else
+            {
+                opnd = SW_DIRECT + S.pinv[i];
+                H.sw_direct++;
+            }
+            cache.used(i);
+            return pair_word(lrow, opnd);
+        });
+        const int s = cache.alloc(k);
+        H.bw[w1] = (s >= 0 ? FIFO_ROWS + s : SW_NO_KEEP) | (drow << 8) | (xrow << 16) | (arow << 24);
+        prod[k] = F.npop;
     }
     H.bw_nld = (int)H.bw_ld.size();
-    H.sw_slots = std::max(H.sw_slots, pool.top);
-    H.sw_home += pool.home;
+    H.sw_slots = std::max(H.sw_slots, cache.top);
     pad_tail(H.bw);
     pad_tail(H.bw_ld);
 }

@@ -33,20 +33,44 @@ namespace eicos
 
 constexpr int STREAM_CHUNK = 32;  // words per cooperative load
 constexpr int STREAM_PAD = 96;    // readable words after the last used one (two chunks of lookahead)
-constexpr int STAGE_SLOTS = 16;   // rows per staging buffer (one slot = TILE doubles); a worker owns two buffers
+constexpr int STAGE_SLOTS = 20;   // rows per staging buffer (one slot = TILE doubles); a worker owns two buffers
 constexpr int ROW_EXTRA_SLOTS = 4; // staging slots a mat-vec row may use besides its gathers
 
-// FIFO of asynchronously loaded rows: FIFO_GROUPS cp.async groups of FIFO_GROUP rows.  It lives in
-// the two staging buffers of worker 0.
+// FIFO of asynchronously loaded rows: a ring of FIFO_SLOTS cp.async groups of FIFO_GROUP rows, of which
+// FIFO_AHEAD are in flight ahead of the group being consumed and one is slack (the host-placed sync
+// points may come up to FIFO_GROUP - 1 rows early).  It lives in the two staging buffers of worker 0.
+// The host simulates the FIFO while it builds a program, so operands name their ring row directly
+// and the device never counts pops.
 constexpr int FIFO_GROUP = 8;
-constexpr int FIFO_GROUPS = 4;
-constexpr int FIFO_ROWS = FIFO_GROUP * FIFO_GROUPS;
+constexpr int FIFO_SLOTS = 5;
+constexpr int FIFO_AHEAD = 3;
+constexpr int FIFO_ROWS = FIFO_GROUP * FIFO_SLOTS;
 static_assert(FIFO_ROWS == 2 * STAGE_SLOTS, "the FIFO ring aliases worker 0's staging buffers");
-static_assert((FIFO_ROWS & (FIFO_ROWS - 1)) == 0 && (FIFO_GROUP & (FIFO_GROUP - 1)) == 0, "powers of two");
+static_assert(FIFO_SLOTS >= FIFO_AHEAD + 2, "ring = consumed group + slack group + groups in flight");
 
-// Operand words of the slot programs: code < SLOT_HOME is a shared-memory slot, anything else the
-// home row (code - SLOT_HOME, relative to the program's home base).  Bits 28..29 of a TARGET word
-// say how the accumulator starts on its first touch.
+// ---- load-list words (all programs): bits 30..31 select the base, the rest is the row
+//      0 = tile base, 1 / 2 = run-time vectors of the sweep (rhs | out, accumulated solution)
+constexpr int LD_BASE_SHIFT = 30;
+constexpr int LD_ROW_MASK = (1 << 30) - 1;
+
+// ---- triangular sweeps: dot-form row programs.  Shared-memory rows are numbered ring first
+// ([0, FIFO_ROWS)), then the slots.
+//   header word 0: number of pairs | SW_SYNC_HDR            (sync = issue the next FIFO group, wait for the current one)
+//   header word 1: keep row (0xFF none) | ring rows of the start operands << 8, 16, 24
+//   backward only, header word 2: output row
+//   pair word: ring row of the L value | SW_SYNC_PAIR | operand << SW_OPND_SHIFT
+//              operand < SW_DIRECT: shared-memory row; else global row (operand - SW_DIRECT) of the home vector
+constexpr int SW_SYNC_HDR = 1 << 31;
+constexpr int SW_CNT_MASK = 0x7fffffff;
+constexpr int SW_SYNC_PAIR = 1 << 8;
+constexpr int SW_OPND_SHIFT = 9;
+constexpr int SW_DIRECT = 256;
+constexpr int SW_NO_KEEP = 0xFF;
+constexpr int SW_UNROLL = 4; // pairs per sync check point on the device
+
+// ---- factorisation: operand codes.  code < SLOT_HOME is a shared-memory slot, anything else the
+// home row (code - SLOT_HOME, relative to the tile base).  Bits 28..29 of a TARGET word say how the
+// accumulator starts on its first touch.
 constexpr int SLOT_HOME = 1 << 16;
 constexpr int OP_CODE_MASK = (1 << 28) - 1;
 constexpr int OPK_SHIFT = 28;
@@ -59,8 +83,6 @@ enum OpKind : int
 };
 // Source words (a value that is consumed): an operand code, or one of
 constexpr int SRC_FIFO = -1, SRC_CONST = -2, SRC_ZERO = -3;
-// Load-list words: row >= 0 is relative to the tile base; ~row (< 0) is relative to the run-time
-// vector of the sweep (right-hand side / accumulated solution) and is skipped when there is none.
 
 struct HostStreams
 {
@@ -69,7 +91,7 @@ struct HostStreams
     ivec fw, fw_ld, bw, bw_ld, fa, fa_ld;
     int fw_nld = 0, bw_nld = 0, fa_nld = 0;
     int sw_slots = 0, fa_slots = 0;
-    long long sw_home = 0, fa_home = 0; // operands that did not get a slot (statistics)
+    long long sw_far = 0, sw_direct = 0, fa_home = 0; // operands served by far gathers / direct global loads / home rows (statistics)
     dvec fa_val;
     // mat-vec row sets: seg = [worker]{int offset, double offset, blocks}
     ivec rx, rx_seg, ry, ry_seg, rz, rz_seg, rc, rc_seg;

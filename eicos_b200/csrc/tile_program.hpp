@@ -142,6 +142,7 @@ struct KArgs
     double *ws; // [tiles][rows_total][TILE]
     int *iws;   // [tiles][irows_total][TILE]
     double *acc_global; // factor column buffers [tile][2 maxcol][TILE] when they do not fit shared memory, else null
+    int xrows;  // rows of shared memory between worker 0's staging buffers and the other workers' (slots, column buffers)
     int batch;  // instances handled by this launch's chunk
     int first;  // global index (within the device's batch) of the chunk's first instance
     // instance-major device buffers for load/store (any may be null)
@@ -596,56 +597,60 @@ EI_DEV vd line_search(const Team &tm, const KArgs &a, double *T, int lam, int ds
 
 // ------------------------------------------------------------------ FIFO of asynchronously loaded rows
 // Every global read of the factorisation and of the sweeps is known to the host in consumption
-// order (the program's load list).  The warp keeps FIFO_GROUPS - 1 cp.async groups of FIFO_GROUP rows
-// in flight ahead of the row it is consuming, so the memory latency never meets a dependent
-// instruction.  Each lane copies and later reads only its own 8 * VEC bytes of a row, so
-// cp.async.wait_group is the only synchronisation needed.
+// order (the program's load list).  The warp keeps FIFO_AHEAD cp.async groups of FIFO_GROUP rows in
+// flight ahead of the group it is consuming, so the memory latency never meets a dependent
+// instruction.  The host simulates the ring while it builds a program: operands name their ring
+// row directly and sync points are flags in the program (streams.hpp).  Each lane copies and later
+// reads only its own 8 * VEC bytes of a row, so cp.async.wait_group is the only synchronisation.
 struct Fifo
 {
     IStream ld;
-    double *ring;      // FIFO_ROWS rows of shared memory (+ lane)
-    const double *T;   // tile base (+ lane): words >= 0
-    const double *rb;  // run-time vector (+ lane): words < 0; null = such rows are not loaded
-    int left;          // words left in the load list
-    int head, tail;    // producer / consumer ring row
+    double *ring;                // FIFO_ROWS rows of shared memory (+ lane)
+    const double *b0, *b1, *b2;  // load bases (+ lane): tile, run-time vectors 1 and 2
+    int left;                    // words left in the load list
+    int head;                    // producer ring row
 
     EI_DEV void issue_group()
     {
-        int n = 0;
-        while (n < FIFO_GROUP && left > 0)
+        const int n = left < FIFO_GROUP ? left : FIFO_GROUP;
+        for (int r = 0; r < n; r++)
         {
             const int w = ld.get();
-            left--;
-            if (w < 0 && !rb)
-                continue;
-            stage_issue(ring + (size_t)head * TILE, w >= 0 ? T + (size_t)w * TILE : rb + (size_t)(~w) * TILE);
-            head = (head + 1) & (FIFO_ROWS - 1);
-            n++;
+            const int sel = (unsigned)w >> LD_BASE_SHIFT;
+            const double *base = sel == 0 ? b0 : (sel == 1 ? b1 : b2);
+            stage_issue(ring + (size_t)(head + r) * TILE, base + (size_t)(w & LD_ROW_MASK) * TILE);
         }
+        left -= n;
+        head = head + FIFO_GROUP == FIFO_ROWS ? 0 : head + FIFO_GROUP;
         stage_commit();
     }
-    EI_DEV void open(const Team &tm, const int *list, int nwords, const double *T_, const double *rb_)
+    EI_DEV void open(const Team &tm, const int *list, int nwords, const double *T, const double *r1, const double *r2)
     {
         ld.open(list, tm.pl);
         ring = tm.stage;
-        T = T_;
-        rb = rb_;
+        b0 = T;
+        b1 = r1;
+        b2 = r2;
         left = nwords;
-        head = tail = 0;
-        for (int g = 0; g < FIFO_GROUPS - 1; g++)
+        head = 0;
+        for (int g = 0; g < FIFO_AHEAD; g++)
             issue_group();
     }
+    EI_DEV void sync() // entering a new group: issue the next one, wait for this one
+    {
+        issue_group();
+#ifndef EICOS_EMU
+        asm volatile("cp.async.wait_group %0;" ::"n"(FIFO_AHEAD) : "memory");
+#endif
+    }
+    // sequential consumption (factor program): the device counts the rows itself
+    int tail;
     EI_DEV vd pop()
     {
         if ((tail & (FIFO_GROUP - 1)) == 0)
-        { // entering a new group: refill the one just drained, then wait for this one
-            issue_group();
-#ifndef EICOS_EMU
-            asm volatile("cp.async.wait_group %0;" ::"n"(FIFO_GROUPS - 1) : "memory");
-#endif
-        }
+            sync();
         const vd v = vload(ring + (size_t)tail * TILE);
-        tail = (tail + 1) & (FIFO_ROWS - 1);
+        tail = tail + 1 == FIFO_ROWS ? 0 : tail + 1;
         return v;
     }
     EI_DEV void close() { stage_wait(); }
@@ -684,7 +689,8 @@ EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
     Fifo ff;
     is.open(P.fa, tm.pl);
     ds.open(P.fa_val, tm.pl);
-    ff.open(tm, P.fa_ld, P.fa_nld, T, nullptr);
+    ff.open(tm, P.fa_ld, P.fa_nld, T, T, T);
+    ff.tail = 0;
     const auto fetch = [&](int src) -> vd {
         if (src >= 0)
             return vload(opnd(slots, T, src));
@@ -693,11 +699,13 @@ EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
         return vset(src == SRC_CONST ? ds.get() : 0.0);
     };
     double *Dp = T + (size_t)L.D * TILE, *Lp = T + (size_t)L.Lx * TILE;
+    const size_t dinv_off = (size_t)(L.Dinv - L.D) * TILE;
     for (int k = 0; k < P.N; k++, Dp += TILE)
     {
         const int dsrc = is.get(), cnt = is.get();
         const vd d = fetch(dsrc);
         vstore(Dp, d);
+        vstore(Dp + dinv_off, 1.0 / d); // the backward sweep multiplies by the reciprocal, like Eigen
         VFOR zero_pivot.v[c_] = zero_pivot.v[c_] || (d.v[c_] == 0.0); // Eigen: NumericalIssue only on an exactly zero pivot
         for (int e = 0; e < cnt; e++, Lp += TILE)
         {
@@ -731,70 +739,125 @@ EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
 }
 
 // ------------------------------------------------------------------ triangular solves (Eigen solve, src/eicos.cpp:1477,1599)
-// forward:  xw = L^-1 P rhs       scatter form by columns of L in elimination order - exactly the
-//                                 summation order of Eigen's forward substitution; the permutation is
-//                                 folded into the right-hand-side loads.
-// backward: out = P' L^-T D^-1 xw dot form by columns in reverse order; results land in KKT order.
-// Both stream the single column-major copy of L through the FIFO (forward ascending, backward
-// descending) and keep every intermediate value in a shared-memory slot for its live range
-// (streams.cpp: build_forward / build_backward).  One warp per tile, no barriers inside a sweep.
-EI_DEV void ldl_forward(const Team &tm, const KArgs &a, double *T, int rhs)
+// forward:  xw = L^-1 P rhs         rows of L in elimination order, dot form in ascending column order
+//                                   (the summation order of Eigen's forward substitution); the
+//                                   permutation is folded into the right-hand-side loads.
+// backward: out = P' L^-T D^-1 xw   columns in reverse order, dot form; results land in KKT order.
+// Both are row programs (streams.cpp: build_forward / build_backward) run by one warp per tile with
+// no barrier inside: every global read comes through the FIFO, every gathered value that is still
+// live sits in a shared-memory slot, and each pair word names the two shared-memory rows it
+// multiplies.  DIRECT: the program contains operands that must be read straight from global memory
+// (only when the slots do not cover the live values of the pattern).
+template <bool DIRECT>
+EI_DEV vd sweep_operand(const double *sm, const double *home, int code)
+{
+    if (DIRECT && code >= SW_DIRECT)
+        return vload(home + (size_t)(code - SW_DIRECT) * TILE);
+    return vload(sm + (size_t)code * TILE);
+}
+
+template <bool DIRECT>
+EI_DEV vd sweep_pairs(IStream &is, Fifo &ff, const double *sm, const double *home, int cnt, vd v)
+{
+    int e = 0;
+    for (; e + SW_UNROLL <= cnt; e += SW_UNROLL)
+    {
+        int p[SW_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SW_UNROLL; u++)
+            p[u] = is.get();
+        if (p[0] & SW_SYNC_PAIR)
+            ff.sync();
+        vd l[SW_UNROLL], g[SW_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SW_UNROLL; u++)
+        {
+            l[u] = vload(sm + (size_t)(p[u] & 0xff) * TILE);
+            g[u] = sweep_operand<DIRECT>(sm, home, (int)((unsigned)p[u] >> SW_OPND_SHIFT));
+        }
+#pragma unroll
+        for (int u = 0; u < SW_UNROLL; u++)
+            v -= l[u] * g[u];
+    }
+    for (; e < cnt; e++)
+    {
+        const int p = is.get();
+        if (p & SW_SYNC_PAIR)
+            ff.sync();
+        v -= vload(sm + (size_t)(p & 0xff) * TILE) * sweep_operand<DIRECT>(sm, home, (int)((unsigned)p >> SW_OPND_SHIFT));
+    }
+    return v;
+}
+
+template <bool DIRECT>
+EI_DEV void ldl_forward_t(const Team &tm, const KArgs &a, double *T, int rhs)
 {
     const DevPattern &P = a.P;
-    const Layout &L = a.L;
-    double *slots = tm.extra;
+    double *sm = tm.stage; // ring rows, then the slots
     IStream is;
     Fifo ff;
     is.open(P.fw, tm.pl);
-    ff.open(tm, P.fw_ld, P.fw_nld, T, T + (size_t)rhs * TILE);
-    double *xp = T + (size_t)L.xw * TILE;
-    for (int k = 0; k < P.N; k++, xp += TILE)
+    ff.open(tm, P.fw_ld, P.fw_nld, T, T + (size_t)rhs * TILE, T);
+    double *xp = T + (size_t)a.L.xw * TILE;
+    for (int i = 0; i < P.N; i++, xp += TILE)
     {
-        const int src = is.get(), cnt = is.get();
-        const vd x = src >= 0 ? vload(opnd(slots, T, src)) : ff.pop();
-        vstore(xp, x);
-        for (int e = 0; e < cnt; e++)
-        {
-            const int tw = is.get();
-            const vd l = ff.pop();
-            double *tp = opnd(slots, T, tw & OP_CODE_MASK);
-            const vd init = (tw >> OPK_SHIFT) == OPK_FIFO ? ff.pop() : vload(tp);
-            vstore(tp, init - l * x);
-        }
+        const int w0 = is.get(), w1 = is.get();
+        if (w0 < 0)
+            ff.sync();
+        vd v = vload(sm + (size_t)((w1 >> 8) & 0xff) * TILE);
+        v = sweep_pairs<DIRECT>(is, ff, sm, T, w0 & SW_CNT_MASK, v);
+        vstore(xp, v);
+        const int keep = w1 & 0xff;
+        if (keep != SW_NO_KEEP)
+            vstore(sm + (size_t)keep * TILE, v);
     }
     ff.close();
 }
+EI_DEV void ldl_forward(const Team &tm, const KArgs &a, double *T, int rhs)
+{
+    if (a.P.sw_direct)
+        ldl_forward_t<true>(tm, a, T, rhs);
+    else
+        ldl_forward_t<false>(tm, a, T, rhs);
+}
 
 // out = solution (KKT order).  If x >= 0: additionally x += solution for the instances with `cont`.
-EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int out, int x, vb cont)
+template <bool DIRECT>
+EI_DEV void ldl_backward_t(const Team &tm, const KArgs &a, double *T, int out, int x, vb cont)
 {
     const DevPattern &P = a.P;
-    double *slots = tm.extra;
+    double *sm = tm.stage;
     const bool accumulate = x >= 0;
     const vd zero = vset(0.0);
     double *op = T + (size_t)out * TILE;
-    double *xp = accumulate ? T + (size_t)x * TILE : nullptr;
+    double *xp = T + (size_t)(accumulate ? x : out) * TILE; // a plain solve loads (and ignores) its own output rows
     IStream is;
     Fifo ff;
     is.open(P.bw, tm.pl);
-    ff.open(tm, P.bw_ld, P.bw_nld, T, xp);
+    ff.open(tm, P.bw_ld, P.bw_nld, T, op, xp);
     for (int k = 0; k < P.N; k++)
     {
-        const int o = is.get(), keep = is.get(), cnt = is.get();
-        const vd d = ff.pop();
-        vd v = (1.0 / d) * ff.pop(); // Eigen: diag.inverse() * x
-        for (int e = 0; e < cnt; e++)
-        {
-            const int g = is.get();
-            v -= ff.pop() * vload(opnd(slots, op, g));
-        }
+        const int w0 = is.get(), w1 = is.get(), o = is.get();
+        if (w0 < 0)
+            ff.sync();
+        vd v = vload(sm + (size_t)((w1 >> 8) & 0xff) * TILE) * vload(sm + (size_t)((w1 >> 16) & 0xff) * TILE); // Eigen: diag.inverse() * x
+        const vd xa = vload(sm + (size_t)((unsigned)w1 >> 24) * TILE); // read now: a long column recycles the ring row
+        v = sweep_pairs<DIRECT>(is, ff, sm, op, w0 & SW_CNT_MASK, v);
         vstore(op + (size_t)o * TILE, v);
-        if (keep >= 0)
-            vstore(slots + (size_t)keep * TILE, v);
+        const int keep = w1 & 0xff;
+        if (keep != SW_NO_KEEP)
+            vstore(sm + (size_t)keep * TILE, v);
         if (accumulate)
-            vstore(xp + (size_t)o * TILE, ff.pop() + vsel(cont, v, zero));
+            vstore(xp + (size_t)o * TILE, xa + vsel(cont, v, zero));
     }
     ff.close();
+}
+EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int out, int x, vb cont)
+{
+    if (a.P.sw_direct)
+        ldl_backward_t<true>(tm, a, T, out, x, cont);
+    else
+        ldl_backward_t<false>(tm, a, T, out, x, cont);
 }
 
 // ------------------------------------------------------------------ KKT residual for iterative refinement (src/eicos.cpp:1511-1576)
