@@ -99,7 +99,8 @@ static void eicos_compact_emu(const KArgs &a, const MoveRanges &mr, const int *m
 #endif
 
 // shared-memory budget of the slot programs (rows of TILE doubles per CTA)
-constexpr int MAX_SW_SLOTS = 24, MAX_FA_SLOTS = 48, MAX_COLBUF_ROWS = 16;
+// (one warp per tile wants 7 CTAs per SM: ring 32 rows + 28 rows here = 30 KB per CTA at TILE = 64)
+constexpr int MAX_SW_SLOTS = 24, MAX_FA_SLOTS = 20, MAX_COLBUF_ROWS = 8;
 
 int Engine::tile_width() { return TILE; }
 
@@ -186,7 +187,7 @@ void Engine::upload_pattern(const Symbolic &S)
     P.fw_nld = H_.fw_nld;
     P.bw_nld = H_.bw_nld;
     P.fa_nld = H_.fa_nld;
-    P.sw_slots = H_.sw_slots;
+    P.sw_slots = H_.sw_slots + 1; // rows behind the ring: the zero row, then the slots
     P.fa_slots = H_.fa_slots;
     P.sw_direct = H_.sw_direct > 0 ? 1 : 0;
     P.cone_dim = upload(S.q, owned_, st);
@@ -277,7 +278,7 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
     status_host_ = (int *)be::pinned(slots * sizeof(int));
     moves_host_ = (int *)be::pinned(2 * slots * sizeof(int));
     const size_t smem_base = (size_t)workers_ * ((workers_ > 1 ? KRED : 0) + 2 * STAGE_SLOTS) * TILE * sizeof(double);
-    smem_common_ = smem_base + (size_t)H_.sw_slots * TILE * sizeof(double);
+    smem_common_ = smem_base + (size_t)P_.sw_slots * TILE * sizeof(double);
     xrows_factor_ = H_.fa_slots + 2 * S.maxcol;
 #ifndef EICOS_EMU
     if (2 * S.maxcol > MAX_COLBUF_ROWS)

@@ -183,24 +183,25 @@ struct SlotCache
     }
 };
 
-// Emits the pair words of one row and sets the sync flags at the device's check points (groups of
-// SW_UNROLL pairs, then single pairs).  operand(q) appends the q-th pair: it pops the L value and
-// resolves the gathered value, returning the pair word without flags.
+// Emits the pair words of one row behind its `hdr` header words (already pushed, the first at
+// w0) and sets the sync flags: one check point per 16-byte record.  pair(q) appends nothing itself;
+// it pops the L value, resolves the gathered value and returns the pair word without flags.
 template <class Pair>
-void emit_pairs(ivec &ops, FifoSim &F, int cnt, Pair pair)
+void emit_pairs(ivec &ops, FifoSim &F, size_t w0, int hdr, int first_pop, int cnt, Pair pair)
 {
-    const int cnt4 = cnt / SW_UNROLL * SW_UNROLL;
     int q = 0;
+    for (int r = hdr; r < 4; r++)
+        ops.push_back(q < cnt ? pair(q++) : SW_PAD_PAIR);
+    if (FifoSim::crosses(first_pop, F.npop - first_pop))
+        ops[w0] |= SW_SYNC_HDR;
     while (q < cnt)
     {
-        const int len = q < cnt4 ? SW_UNROLL : 1;
         const int first = F.npop;
         const size_t at = ops.size();
-        for (int r = 0; r < len; r++)
-            ops.push_back(pair(q + r));
+        for (int r = 0; r < 4; r++)
+            ops.push_back(q < cnt ? pair(q++) : SW_PAD_PAIR);
         if (FifoSim::crosses(first, F.npop - first))
             ops[at] |= SW_SYNC_PAIR;
-        q += len;
     }
 }
 
@@ -228,15 +229,15 @@ void build_forward(const Symbolic &S, const Layout &L, int max_slots, HostStream
         const int cnt = S.Lr.p[i + 1] - S.Lr.p[i];
         const int first = F.npop;
         const int rhs_row = F.pop(1, S.pinv[i]);
-        H.fw.push_back(cnt | (FifoSim::crosses(first, 1) ? SW_SYNC_HDR : 0));
-        const size_t w1 = H.fw.size();
+        const size_t w1 = H.fw.size() + 1;
+        H.fw.push_back(cnt);
         H.fw.push_back(0);
-        emit_pairs(H.fw, F, cnt, [&](int q) {
+        emit_pairs(H.fw, F, w1 - 1, 2, first, cnt, [&](int q) {
             const int t = S.Lr.p[i] + q, k = S.Lr.j[t];
             const int lrow = F.pop(0, L.Lx + S.Lr.v[t]);
             int opnd;
             if (cache.slot_of[k] >= 0)
-                opnd = FIFO_ROWS + cache.slot_of[k];
+                opnd = SW_SLOT0 + cache.slot_of[k];
             else if (FifoSim::far_safe(prod[k], F.npop))
             {
                 opnd = F.pop(0, L.xw + k);
@@ -251,7 +252,7 @@ void build_forward(const Symbolic &S, const Layout &L, int max_slots, HostStream
             return pair_word(lrow, opnd);
         });
         const int s = cache.alloc(i);
-        H.fw[w1] = (s >= 0 ? FIFO_ROWS + s : SW_NO_KEEP) | (rhs_row << 8);
+        H.fw[w1] = (s >= 0 ? SW_SLOT0 + s : SW_NO_KEEP) | (rhs_row << 8);
         prod[i] = F.npop;
     }
     H.fw_nld = (int)H.fw_ld.size();
@@ -280,16 +281,16 @@ void build_backward(const Symbolic &S, const Layout &L, int max_slots, HostStrea
         const int o = S.pinv[k], cnt = S.Lp[k + 1] - S.Lp[k];
         const int first = F.npop;
         const int drow = F.pop(0, L.Dinv + k), xrow = F.pop(0, L.xw + k), arow = F.pop(2, o);
-        H.bw.push_back(cnt | (FifoSim::crosses(first, 3) ? SW_SYNC_HDR : 0));
-        const size_t w1 = H.bw.size();
+        const size_t w1 = H.bw.size() + 1;
+        H.bw.push_back(cnt);
         H.bw.push_back(0);
         H.bw.push_back(o);
-        emit_pairs(H.bw, F, cnt, [&](int q) {
+        emit_pairs(H.bw, F, w1 - 1, 3, first, cnt, [&](int q) {
             const int u = S.Lp[k] + q, i = S.Li[u];
             const int lrow = F.pop(0, L.Lx + u);
             int opnd;
             if (cache.slot_of[i] >= 0)
-                opnd = FIFO_ROWS + cache.slot_of[i];
+                opnd = SW_SLOT0 + cache.slot_of[i];
             else if (FifoSim::far_safe(prod[i], F.npop))
             {
                 opnd = F.pop(1, S.pinv[i]);
@@ -304,7 +305,7 @@ void build_backward(const Symbolic &S, const Layout &L, int max_slots, HostStrea
             return pair_word(lrow, opnd);
         });
         const int s = cache.alloc(k);
-        H.bw[w1] = (s >= 0 ? FIFO_ROWS + s : SW_NO_KEEP) | (drow << 8) | (xrow << 16) | (arow << 24);
+        H.bw[w1] = (s >= 0 ? SW_SLOT0 + s : SW_NO_KEEP) | (drow << 8) | (xrow << 16) | (arow << 24);
         prod[k] = F.npop;
     }
     H.bw_nld = (int)H.bw_ld.size();

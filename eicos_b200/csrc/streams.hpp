@@ -33,7 +33,7 @@ namespace eicos
 
 constexpr int STREAM_CHUNK = 32;  // words per cooperative load
 constexpr int STREAM_PAD = 96;    // readable words after the last used one (two chunks of lookahead)
-constexpr int STAGE_SLOTS = 20;   // rows per staging buffer (one slot = TILE doubles); a worker owns two buffers
+constexpr int STAGE_SLOTS = 16;   // rows per staging buffer (one slot = TILE doubles); a worker owns two buffers
 constexpr int ROW_EXTRA_SLOTS = 4; // staging slots a mat-vec row may use besides its gathers
 
 // FIFO of asynchronously loaded rows: a ring of FIFO_SLOTS cp.async groups of FIFO_GROUP rows, of which
@@ -42,8 +42,8 @@ constexpr int ROW_EXTRA_SLOTS = 4; // staging slots a mat-vec row may use beside
 // The host simulates the FIFO while it builds a program, so operands name their ring row directly
 // and the device never counts pops.
 constexpr int FIFO_GROUP = 8;
-constexpr int FIFO_SLOTS = 5;
-constexpr int FIFO_AHEAD = 3;
+constexpr int FIFO_SLOTS = 4;
+constexpr int FIFO_AHEAD = 2;
 constexpr int FIFO_ROWS = FIFO_GROUP * FIFO_SLOTS;
 static_assert(FIFO_ROWS == 2 * STAGE_SLOTS, "the FIFO ring aliases worker 0's staging buffers");
 static_assert(FIFO_SLOTS >= FIFO_AHEAD + 2, "ring = consumed group + slack group + groups in flight");
@@ -53,20 +53,26 @@ static_assert(FIFO_SLOTS >= FIFO_AHEAD + 2, "ring = consumed group + slack group
 constexpr int LD_BASE_SHIFT = 30;
 constexpr int LD_ROW_MASK = (1 << 30) - 1;
 
-// ---- triangular sweeps: dot-form row programs.  Shared-memory rows are numbered ring first
-// ([0, FIFO_ROWS)), then the slots.
-//   header word 0: number of pairs | SW_SYNC_HDR            (sync = issue the next FIFO group, wait for the current one)
-//   header word 1: keep row (0xFF none) | ring rows of the start operands << 8, 16, 24
-//   backward only, header word 2: output row
+// ---- triangular sweeps: dot-form row programs made of 16-byte records that the warp reads with
+// one uniform 128-bit load each.  Shared-memory rows are numbered ring first ([0, FIFO_ROWS)), then
+// one row of zeros (SW_ZERO_ROW), then the slots.
+//   first record of a row: [number of pairs | SW_SYNC_HDR,
+//                           keep row (0xFF none) | ring rows of the start operands << 8, 16, 24,
+//                           (backward only) output row, pairs...]
+//   further records: 4 pairs each, SW_SYNC_PAIR on the first one   (sync = issue the next FIFO group,
+//                           wait for the current one; it covers every pop of its record)
 //   pair word: ring row of the L value | SW_SYNC_PAIR | operand << SW_OPND_SHIFT
 //              operand < SW_DIRECT: shared-memory row; else global row (operand - SW_DIRECT) of the home vector
+//   the last record of a row is padded with pairs that multiply the zero row by itself.
 constexpr int SW_SYNC_HDR = 1 << 31;
 constexpr int SW_CNT_MASK = 0x7fffffff;
 constexpr int SW_SYNC_PAIR = 1 << 8;
 constexpr int SW_OPND_SHIFT = 9;
 constexpr int SW_DIRECT = 256;
 constexpr int SW_NO_KEEP = 0xFF;
-constexpr int SW_UNROLL = 4; // pairs per sync check point on the device
+constexpr int SW_ZERO_ROW = FIFO_ROWS;
+constexpr int SW_SLOT0 = FIFO_ROWS + 1;
+constexpr int SW_PAD_PAIR = SW_ZERO_ROW | (SW_ZERO_ROW << SW_OPND_SHIFT);
 
 // ---- factorisation: operand codes.  code < SLOT_HOME is a shared-memory slot, anything else the
 // home row (code - SLOT_HOME, relative to the tile base).  Bits 28..29 of a TARGET word say how the

@@ -119,6 +119,74 @@ EI_DEV bool vall(vb a)
 EI_DEV vd vload(const double *p) { return *reinterpret_cast<const vd *>(p); }
 EI_DEV void vstore(double *p, vd v) { *reinterpret_cast<vd *>(p) = v; }
 
+// 16-byte record of an instruction stream, read by the whole warp from one address (one broadcast
+// transaction through the read-only path; the line stays in L1 for the next three records)
+#ifdef EICOS_EMU
+struct i4
+{
+    int x, y, z, w;
+};
+EI_DEV i4 ldg4(const int *p) { return i4{p[0], p[1], p[2], p[3]}; }
+#else
+typedef int4 i4;
+EI_DEV i4 ldg4(const int *p) { return __ldg(reinterpret_cast<const int4 *>(p)); }
+#endif
+
+// Rows of the worker's shared memory (FIFO ring, zero row, slots) addressed by row number.  On the
+// device these are 32-bit shared-window addresses and explicit ld/st.shared, so that the compiler
+// neither widens them to generic pointers nor reorders them around the cp.async traffic.
+#ifdef EICOS_EMU
+typedef double *smem_t;
+EI_DEV smem_t smem_of(double *p) { return p; }
+EI_DEV vd sm_load(smem_t b, int row) { return vload(b + (size_t)row * TILE); }
+EI_DEV void sm_store(smem_t b, int row, vd v) { vstore(b + (size_t)row * TILE, v); }
+EI_DEV void sm_fill(smem_t b, int row, const double *src) { vstore(b + (size_t)row * TILE, vload(src)); }
+#else
+typedef unsigned smem_t;
+EI_DEV smem_t smem_of(double *p) { return (unsigned)__cvta_generic_to_shared(p); }
+EI_DEV vd sm_load(smem_t b, int row)
+{
+    vd r;
+    const unsigned a = b + (unsigned)row * (unsigned)(TILE * sizeof(double));
+    if (VEC % 2 == 0)
+    {
+#pragma unroll
+        for (int c = 0; c < VEC; c += 2)
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.v[c]), "=d"(r.v[c + 1]) : "r"(a + 8 * c));
+    }
+    else
+        for (int c = 0; c < VEC; c++)
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r.v[c]) : "r"(a + 8 * c));
+    return r;
+}
+EI_DEV void sm_store(smem_t b, int row, vd v)
+{
+    const unsigned a = b + (unsigned)row * (unsigned)(TILE * sizeof(double));
+    if (VEC % 2 == 0)
+    {
+#pragma unroll
+        for (int c = 0; c < VEC; c += 2)
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a + 8 * c), "d"(v.v[c]), "d"(v.v[c + 1]) : "memory");
+    }
+    else
+        for (int c = 0; c < VEC; c++)
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(a + 8 * c), "d"(v.v[c]) : "memory");
+}
+EI_DEV void sm_fill(smem_t b, int row, const double *src) // asynchronous copy of one row (this lane's part)
+{
+    const unsigned a = b + (unsigned)row * (unsigned)(TILE * sizeof(double));
+    if (VEC % 2 == 0)
+    {
+#pragma unroll
+        for (int c = 0; c < VEC; c += 2)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a + 8 * c), "l"(src + c) : "memory");
+    }
+    else
+        for (int c = 0; c < VEC; c++)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(a + 8 * c), "l"(src + c) : "memory");
+}
+#endif
+
 // proxy for one row of the tile as seen by this lane (VEC instances)
 struct RowRef
 {
@@ -602,32 +670,59 @@ EI_DEV vd line_search(const Team &tm, const KArgs &a, double *T, int lam, int ds
 // instruction.  The host simulates the ring while it builds a program: operands name their ring
 // row directly and sync points are flags in the program (streams.hpp).  Each lane copies and later
 // reads only its own 8 * VEC bytes of a row, so cp.async.wait_group is the only synchronisation.
+// The load list itself is read one group (two 16-byte records) ahead.
 struct Fifo
 {
-    IStream ld;
-    double *ring;                // FIFO_ROWS rows of shared memory (+ lane)
+    const int *lp;               // next group of the load list to fetch
+    i4 wa, wb;                   // the group that will be issued next
+    smem_t ring;                 // FIFO_ROWS rows of shared memory (this lane's part)
     const double *b0, *b1, *b2;  // load bases (+ lane): tile, run-time vectors 1 and 2
     int left;                    // words left in the load list
     int head;                    // producer ring row
 
+    EI_DEV void issue_row(int r, int w) const
+    {
+        const int sel = (unsigned)w >> LD_BASE_SHIFT;
+        const double *base = sel == 0 ? b0 : (sel == 1 ? b1 : b2);
+        sm_fill(ring, head + r, base + (size_t)(w & LD_ROW_MASK) * TILE);
+    }
     EI_DEV void issue_group()
     {
-        const int n = left < FIFO_GROUP ? left : FIFO_GROUP;
-        for (int r = 0; r < n; r++)
+        const i4 a = wa, b = wb;
+        wa = ldg4(lp);
+        wb = ldg4(lp + 4);
+        lp += FIFO_GROUP;
+        if (left >= FIFO_GROUP)
         {
-            const int w = ld.get();
-            const int sel = (unsigned)w >> LD_BASE_SHIFT;
-            const double *base = sel == 0 ? b0 : (sel == 1 ? b1 : b2);
-            stage_issue(ring + (size_t)(head + r) * TILE, base + (size_t)(w & LD_ROW_MASK) * TILE);
+            issue_row(0, a.x);
+            issue_row(1, a.y);
+            issue_row(2, a.z);
+            issue_row(3, a.w);
+            issue_row(4, b.x);
+            issue_row(5, b.y);
+            issue_row(6, b.z);
+            issue_row(7, b.w);
+            left -= FIFO_GROUP;
         }
-        left -= n;
+        else
+        {
+            const int w[FIFO_GROUP] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int r = 0; r < FIFO_GROUP; r++)
+                if (r < left)
+                    issue_row(r, w[r]);
+            left = 0;
+        }
         head = head + FIFO_GROUP == FIFO_ROWS ? 0 : head + FIFO_GROUP;
         stage_commit();
     }
     EI_DEV void open(const Team &tm, const int *list, int nwords, const double *T, const double *r1, const double *r2)
     {
-        ld.open(list, tm.pl);
-        ring = tm.stage;
+        static_assert(FIFO_GROUP == 8, "issue_group reads the load list as two 4-word records");
+        lp = list + FIFO_GROUP;
+        wa = ldg4(list);
+        wb = ldg4(list + 4);
+        ring = smem_of(tm.stage);
         b0 = T;
         b1 = r1;
         b2 = r2;
@@ -649,7 +744,7 @@ struct Fifo
     {
         if ((tail & (FIFO_GROUP - 1)) == 0)
             sync();
-        const vd v = vload(ring + (size_t)tail * TILE);
+        const vd v = sm_load(ring, tail);
         tail = tail + 1 == FIFO_ROWS ? 0 : tail + 1;
         return v;
     }
@@ -749,42 +844,43 @@ EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
 // multiplies.  DIRECT: the program contains operands that must be read straight from global memory
 // (only when the slots do not cover the live values of the pattern).
 template <bool DIRECT>
-EI_DEV vd sweep_operand(const double *sm, const double *home, int code)
+EI_DEV vd sweep_operand(smem_t sm, const double *home, int code)
 {
     if (DIRECT && code >= SW_DIRECT)
         return vload(home + (size_t)(code - SW_DIRECT) * TILE);
-    return vload(sm + (size_t)code * TILE);
+    return sm_load(sm, code);
 }
 
-template <bool DIRECT>
-EI_DEV vd sweep_pairs(IStream &is, Fifo &ff, const double *sm, const double *home, int cnt, vd v)
+// v -= sum over the pairs p0..: all operand loads first, then the multiply-adds in order
+template <bool DIRECT, int NP>
+EI_DEV vd sweep_pairs(smem_t sm, const double *home, const int (&p)[NP], vd v)
 {
-    int e = 0;
-    for (; e + SW_UNROLL <= cnt; e += SW_UNROLL)
+    vd l[NP], g[NP];
+#pragma unroll
+    for (int u = 0; u < NP; u++)
     {
-        int p[SW_UNROLL];
-#pragma unroll
-        for (int u = 0; u < SW_UNROLL; u++)
-            p[u] = is.get();
-        if (p[0] & SW_SYNC_PAIR)
-            ff.sync();
-        vd l[SW_UNROLL], g[SW_UNROLL];
-#pragma unroll
-        for (int u = 0; u < SW_UNROLL; u++)
-        {
-            l[u] = vload(sm + (size_t)(p[u] & 0xff) * TILE);
-            g[u] = sweep_operand<DIRECT>(sm, home, (int)((unsigned)p[u] >> SW_OPND_SHIFT));
-        }
-#pragma unroll
-        for (int u = 0; u < SW_UNROLL; u++)
-            v -= l[u] * g[u];
+        l[u] = sm_load(sm, p[u] & 0xff);
+        g[u] = sweep_operand<DIRECT>(sm, home, (int)((unsigned)p[u] >> SW_OPND_SHIFT));
     }
-    for (; e < cnt; e++)
+#pragma unroll
+    for (int u = 0; u < NP; u++)
+        v -= l[u] * g[u];
+    return v;
+}
+
+// the records of a row behind its first one (4 pairs each), read one record ahead
+template <bool DIRECT>
+EI_DEV vd sweep_tail(const int *rp, int nrec, Fifo &ff, smem_t sm, const double *home, vd v)
+{
+    i4 nx = ldg4(rp + 4);
+    for (int q = 1; q < nrec; q++)
     {
-        const int p = is.get();
-        if (p & SW_SYNC_PAIR)
+        const i4 pr = nx;
+        nx = ldg4(rp + 4 * (q + 1));
+        if (pr.x & SW_SYNC_PAIR)
             ff.sync();
-        v -= vload(sm + (size_t)(p & 0xff) * TILE) * sweep_operand<DIRECT>(sm, home, (int)((unsigned)p >> SW_OPND_SHIFT));
+        const int p[4] = {pr.x, pr.y, pr.z, pr.w};
+        v = sweep_pairs<DIRECT, 4>(sm, home, p, v);
     }
     return v;
 }
@@ -793,23 +889,35 @@ template <bool DIRECT>
 EI_DEV void ldl_forward_t(const Team &tm, const KArgs &a, double *T, int rhs)
 {
     const DevPattern &P = a.P;
-    double *sm = tm.stage; // ring rows, then the slots
-    IStream is;
+    const smem_t sm = smem_of(tm.stage); // ring rows, zero row, slots
+    sm_store(sm, SW_ZERO_ROW, vset(0.0));
     Fifo ff;
-    is.open(P.fw, tm.pl);
     ff.open(tm, P.fw_ld, P.fw_nld, T, T + (size_t)rhs * TILE, T);
+    const int *rp = P.fw;
+    i4 rec = ldg4(rp);
     double *xp = T + (size_t)a.L.xw * TILE;
     for (int i = 0; i < P.N; i++, xp += TILE)
     {
-        const int w0 = is.get(), w1 = is.get();
-        if (w0 < 0)
+        const int cnt = rec.x & SW_CNT_MASK;
+        const int nrec = (cnt + 2 + 3) >> 2;
+        const int *np = rp + 4 * nrec;
+        const i4 nx = ldg4(np); // first record of the next row
+        if (rec.x < 0)
             ff.sync();
-        vd v = vload(sm + (size_t)((w1 >> 8) & 0xff) * TILE);
-        v = sweep_pairs<DIRECT>(is, ff, sm, T, w0 & SW_CNT_MASK, v);
+        vd v = sm_load(sm, (rec.y >> 8) & 0xff);
+        if (cnt > 0)
+        {
+            const int p[2] = {rec.z, rec.w};
+            v = sweep_pairs<DIRECT, 2>(sm, T, p, v);
+            if (nrec > 1)
+                v = sweep_tail<DIRECT>(rp, nrec, ff, sm, T, v);
+        }
         vstore(xp, v);
-        const int keep = w1 & 0xff;
+        const int keep = rec.y & 0xff;
         if (keep != SW_NO_KEEP)
-            vstore(sm + (size_t)keep * TILE, v);
+            sm_store(sm, keep, v);
+        rp = np;
+        rec = nx;
     }
     ff.close();
 }
@@ -826,29 +934,42 @@ template <bool DIRECT>
 EI_DEV void ldl_backward_t(const Team &tm, const KArgs &a, double *T, int out, int x, vb cont)
 {
     const DevPattern &P = a.P;
-    double *sm = tm.stage;
+    const smem_t sm = smem_of(tm.stage);
+    sm_store(sm, SW_ZERO_ROW, vset(0.0));
     const bool accumulate = x >= 0;
     const vd zero = vset(0.0);
     double *op = T + (size_t)out * TILE;
     double *xp = T + (size_t)(accumulate ? x : out) * TILE; // a plain solve loads (and ignores) its own output rows
-    IStream is;
     Fifo ff;
-    is.open(P.bw, tm.pl);
     ff.open(tm, P.bw_ld, P.bw_nld, T, op, xp);
+    const int *rp = P.bw;
+    i4 rec = ldg4(rp);
     for (int k = 0; k < P.N; k++)
     {
-        const int w0 = is.get(), w1 = is.get(), o = is.get();
-        if (w0 < 0)
+        const int cnt = rec.x & SW_CNT_MASK;
+        const int nrec = (cnt + 3 + 3) >> 2;
+        const int *np = rp + 4 * nrec;
+        const i4 nx = ldg4(np);
+        if (rec.x < 0)
             ff.sync();
-        vd v = vload(sm + (size_t)((w1 >> 8) & 0xff) * TILE) * vload(sm + (size_t)((w1 >> 16) & 0xff) * TILE); // Eigen: diag.inverse() * x
-        const vd xa = vload(sm + (size_t)((unsigned)w1 >> 24) * TILE); // read now: a long column recycles the ring row
-        v = sweep_pairs<DIRECT>(is, ff, sm, op, w0 & SW_CNT_MASK, v);
+        vd v = sm_load(sm, (rec.y >> 8) & 0xff) * sm_load(sm, (rec.y >> 16) & 0xff); // Eigen: diag.inverse() * x
+        const vd xa = sm_load(sm, (int)((unsigned)rec.y >> 24)); // read now: a long column recycles the ring row
+        if (cnt > 0)
+        {
+            const int p[1] = {rec.w};
+            v = sweep_pairs<DIRECT, 1>(sm, op, p, v);
+            if (nrec > 1)
+                v = sweep_tail<DIRECT>(rp, nrec, ff, sm, op, v);
+        }
+        const int o = rec.z;
         vstore(op + (size_t)o * TILE, v);
-        const int keep = w1 & 0xff;
+        const int keep = rec.y & 0xff;
         if (keep != SW_NO_KEEP)
-            vstore(sm + (size_t)keep * TILE, v);
+            sm_store(sm, keep, v);
         if (accumulate)
             vstore(xp + (size_t)o * TILE, xa + vsel(cont, v, zero));
+        rp = np;
+        rec = nx;
     }
     ff.close();
 }
