@@ -203,6 +203,11 @@ void Engine::upload_pattern(const Symbolic &S)
     P.bw_ld = upload(H_.bw_ld, owned_, st);
     P.fa = upload(H_.fa, owned_, st);
     P.fa_ld = upload(H_.fa_ld, owned_, st);
+    P.mv = upload(H_.mv, owned_, st);
+    P.mv_ld = upload(H_.mv_ld, owned_, st);
+    P.mv_val = dmv_val_ = upload(H_.mv_val, owned_, st);
+    P.mv_nld = H_.mv_nld;
+    P.mv_rows = H_.mv_rows;
     P.fa_val = dfa_val_ = upload(H_.fa_val, owned_, st);
     P.rx = upload(H_.rx, owned_, st);
     P.rx_seg = upload(H_.rx_seg, owned_, st);
@@ -243,6 +248,7 @@ void Engine::upload_values(const Symbolic &S)
     be::h2d(dAeq_, S.Aeq.data(), S.Aeq.size() * sizeof(double), st);
     be::h2d(dGeq_, ge.data(), ge.size() * sizeof(double), st);
     be::h2d(dfa_val_, H_.fa_val.data(), H_.fa_val.size() * sizeof(double), st);
+    be::h2d(dmv_val_, H_.mv_val.data(), H_.mv_val.size() * sizeof(double), st);
     be::h2d(drx_val_, H_.rx_val.data(), H_.rx_val.size() * sizeof(double), st);
     be::h2d(dry_val_, H_.ry_val.data(), H_.ry_val.size() * sizeof(double), st);
     be::h2d(drz_val_, H_.rz_val.data(), H_.rz_val.size() * sizeof(double), st);

@@ -96,8 +96,9 @@ struct DevPattern
     const double *xeq, *Aeq, *GeqE;        // equilibration vectors (GeqE is expanded, 1 in the slots)
     // instruction streams (streams.hpp)
     // slot programs (streams.hpp): ops, load lists (+ length in words), shared-memory slots they use
-    const int *fw, *fw_ld, *bw, *bw_ld, *fa, *fa_ld;
-    int fw_nld, bw_nld, fa_nld, sw_slots, fa_slots;
+    const int *fw, *fw_ld, *bw, *bw_ld, *fa, *fa_ld, *mv, *mv_ld;
+    const double *mv_val;
+    int fw_nld, bw_nld, fa_nld, mv_nld, mv_rows, sw_slots, fa_slots;
     int sw_direct; // the sweep programs contain operands read straight from global memory
     const double *fa_val;
     const int *rx, *rx_seg, *ry, *ry_seg, *rz, *rz_seg, *rc, *rc_seg;

@@ -159,7 +159,7 @@ struct SlotCache
     }
     int alloc(int v)
     {
-        if (uses[v].empty())
+        if (next_use(v) == INT32_MAX)
             return -1;
         int s = -1;
         for (int q = 0; q < (int)holder.size() && s < 0; q++)
@@ -314,6 +314,106 @@ void build_backward(const Symbolic &S, const Layout &L, int max_slots, HostStrea
     pad_tail(H.bw_ld);
 }
 
+// ---- KKT mat-vec program (streams.hpp).  Rows = x, y and LP-z rows in elimination order; the
+// pairs of a row keep the order of the CSC / CSR data (G entries before A entries in an x row).
+void build_matvec(const Symbolic &S, const Layout &L, int max_slots, HostStreams &H)
+{
+    const int n = S.n, p = S.p, zb = S.n + S.p, nrows = zb + S.l;
+    ivec order;
+    for (int r = 0; r < nrows; r++)
+        order.push_back(r);
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return S.P[a] < S.P[b]; });
+    std::vector<std::vector<std::pair<int, double>>> ent(nrows);
+    for (int j = 0; j < n; j++)
+    {
+        for (int k = S.G.p[j]; k < S.G.p[j + 1]; k++)
+            ent[j].push_back({zb + S.zk[S.G.i[k]], S.G.x[k]});
+        for (int k = S.A.p[j]; k < S.A.p[j + 1]; k++)
+            ent[j].push_back({n + S.A.i[k], S.A.x[k]});
+    }
+    for (int i = 0; i < p; i++)
+        for (int t = S.Ar.p[i]; t < S.Ar.p[i + 1]; t++)
+            ent[n + i].push_back({S.Ar.j[t], S.A.x[S.Ar.v[t]]});
+    for (int i = 0; i < S.l; i++)
+        for (int t = S.Gr.p[i]; t < S.Gr.p[i + 1]; t++)
+            ent[zb + i].push_back({S.Gr.j[t], S.G.x[S.Gr.v[t]]});
+    std::vector<ivec> uses(S.N);
+    for (int t = 0; t < nrows; t++)
+    {
+        const int r = order[t];
+        uses[r].push_back(t);
+        for (auto &e : ent[r])
+            uses[e.first].push_back(t);
+    }
+    for (ivec &u : uses)
+        std::sort(u.begin(), u.end());
+    SlotCache cache(max_slots, uses);
+    FifoSim F(H.mv_ld);
+    // resolves one operand: (operand row, keep row)
+    const auto operand = [&](int c) {
+        std::pair<int, int> r;
+        if (cache.slot_of[c] >= 0)
+        {
+            r = {SW_SLOT0 + cache.slot_of[c], SW_NO_KEEP};
+            cache.used(c);
+        }
+        else
+        {
+            r.first = F.pop(2, c);
+            cache.used(c);
+            const int s = cache.alloc(c);
+            r.second = s >= 0 ? SW_SLOT0 + s : SW_NO_KEEP;
+        }
+        return r;
+    };
+    for (int t = 0; t < nrows; t++)
+    {
+        const int r = order[t], cnt = (int)ent[r].size();
+        const int kind = r < n ? MV_X : (r < zb ? MV_Y : MV_Z);
+        if (cnt > MV_CNT_MASK)
+            throw std::logic_error("mat-vec program: row too long");
+        const int first = F.npop;
+        const int ex0 = F.pop(1, r);
+        const auto own = operand(r);
+        const int ex1 = kind == MV_Z ? F.pop(3, r - zb) : SW_ZERO_ROW;
+        const size_t w0 = H.mv.size();
+        H.mv.push_back(cnt | (kind << MV_KIND_SHIFT));
+        H.mv.push_back(ex0 | (own.first << 8) | (own.second << 16) | (ex1 << 24));
+        H.mv.push_back(r);
+        int q = 0;
+        const auto pair = [&]() {
+            if (q >= cnt)
+            {
+                H.mv_val.push_back(0.0);
+                return MV_PAD_PAIR;
+            }
+            const auto o = operand(ent[r][q].first);
+            H.mv_val.push_back(ent[r][q].second);
+            q++;
+            return o.first | (o.second << 8);
+        };
+        H.mv.push_back(pair());
+        H.mv_val.push_back(0.0); // first record: {c0, 0}
+        if (FifoSim::crosses(first, F.npop - first))
+            H.mv[w0] |= SW_SYNC_HDR;
+        while (q < cnt)
+        {
+            const int f = F.npop;
+            const size_t at = H.mv.size();
+            for (int k = 0; k < 4; k++)
+                H.mv.push_back(pair());
+            if (FifoSim::crosses(f, F.npop - f))
+                H.mv[at] |= MV_SYNC_PAIR;
+        }
+    }
+    H.mv_rows = nrows;
+    H.mv_nld = (int)H.mv_ld.size();
+    H.sw_slots = std::max(H.sw_slots, cache.top);
+    pad_tail(H.mv);
+    pad_tail(H.mv_ld);
+    pad_tail(H.mv_val);
+}
+
 // ---- numeric factorisation, right-looking in elimination order.  Every entry (i,j) of L and every
 // pivot owns an accumulator that starts from the KKT value (shared constant, per-instance scaling
 // value, or 0 for fill) on its first touch.  Step k: d = acc(k,k); for the rows i of column k
@@ -422,6 +522,7 @@ void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, 
     build_forward(S, L, max_sw_slots, H);
     build_backward(S, L, max_sw_slots, H);
     build_factor(S, L, max_fa_slots, H);
+    build_matvec(S, L, max_sw_slots, H);
 
     // ---- mat-vec row sets (K-space gather indices); a row = [cnt, idx...]
     const int n = S.n, p = S.p, zb = S.n + S.p;
@@ -481,6 +582,7 @@ void refresh_stream_values(const Symbolic &S, const Layout &L, HostStreams &H)
     HostStreams fresh;
     build_streams(S, L, H.workers, std::max(H.sw_slots, 1), std::max(H.fa_slots, 1), fresh);
     H.fa_val.swap(fresh.fa_val);
+    H.mv_val.swap(fresh.mv_val);
     H.rx_val.swap(fresh.rx_val);
     H.ry_val.swap(fresh.ry_val);
     H.rz_val.swap(fresh.rz_val);

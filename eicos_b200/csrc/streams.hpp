@@ -50,6 +50,7 @@ static_assert(FIFO_SLOTS >= FIFO_AHEAD + 2, "ring = consumed group + slack group
 
 // ---- load-list words (all programs): bits 30..31 select the base, the rest is the row
 //      0 = tile base, 1 / 2 = run-time vectors of the sweep (rhs | out, accumulated solution)
+//      (3 = second run-time vector of the mat-vec program)
 constexpr int LD_BASE_SHIFT = 30;
 constexpr int LD_ROW_MASK = (1 << 30) - 1;
 
@@ -74,6 +75,28 @@ constexpr int SW_ZERO_ROW = FIFO_ROWS;
 constexpr int SW_SLOT0 = FIFO_ROWS + 1;
 constexpr int SW_PAD_PAIR = SW_ZERO_ROW | (SW_ZERO_ROW << SW_OPND_SHIFT);
 
+// ---- KKT mat-vec program (refinement residual, computeResiduals): one row program over the x, y
+// and LP rows of [0 A' G'; A 0 0; G 0 0] in elimination order, where the rows that share operands
+// are neighbours.  Coefficients are shared by the batch and travel in a parallel stream of 16-byte
+// double records; every operand row is loaded once through the FIFO and kept in a slot while it
+// has further uses (Belady), so the traffic is the vectors themselves.
+//   first record: [number of pairs | kind << MV_KIND_SHIFT | SW_SYNC_HDR,
+//                  ring row of extra 0 | own operand << 8 | own keep << 16 | ring row of extra 1 << 24,
+//                  K-space row, pair 0]            coefficients: {c0, 0}
+//   further records: 4 pairs, MV_SYNC_PAIR on the first   coefficients: {c, c} {c, c}
+//   pair word: operand row | keep row << 8 (0xFF none) | MV_SYNC_PAIR
+//   load list bases: 1 = vector of extra 0 (rhs | c,b,h), 2 = operand vector, 3 = vector of extra 1 (LP scalings | s)
+constexpr int MV_KIND_SHIFT = 24;
+constexpr int MV_CNT_MASK = (1 << MV_KIND_SHIFT) - 1;
+constexpr int MV_SYNC_PAIR = 1 << 16;
+constexpr int MV_PAD_PAIR = SW_ZERO_ROW | (SW_NO_KEEP << 8);
+enum MvKind : int
+{
+    MV_X = 0, // row of the x block: -(G' z + A' y)
+    MV_Y = 1, // row of the y block: A x
+    MV_Z = 2  // LP row of the z block: G x
+};
+
 // ---- factorisation: operand codes.  code < SLOT_HOME is a shared-memory slot, anything else the
 // home row (code - SLOT_HOME, relative to the tile base).  Bits 28..29 of a TARGET word say how the
 // accumulator starts on its first touch.
@@ -94,8 +117,9 @@ struct HostStreams
 {
     int workers = 1;
     // slot programs (one warp): ops, load list (+ its length in words), shared-memory slots used
-    ivec fw, fw_ld, bw, bw_ld, fa, fa_ld;
-    int fw_nld = 0, bw_nld = 0, fa_nld = 0;
+    ivec fw, fw_ld, bw, bw_ld, fa, fa_ld, mv, mv_ld;
+    int fw_nld = 0, bw_nld = 0, fa_nld = 0, mv_nld = 0, mv_rows = 0;
+    dvec mv_val;
     int sw_slots = 0, fa_slots = 0;
     long long sw_far = 0, sw_direct = 0, fa_home = 0; // operands served by far gathers / direct global loads / home rows (statistics)
     dvec fa_val;

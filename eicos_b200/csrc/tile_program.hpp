@@ -131,6 +131,19 @@ EI_DEV i4 ldg4(const int *p) { return i4{p[0], p[1], p[2], p[3]}; }
 typedef int4 i4;
 EI_DEV i4 ldg4(const int *p) { return __ldg(reinterpret_cast<const int4 *>(p)); }
 #endif
+struct alignas(16) d2
+{
+    double x, y;
+};
+EI_DEV d2 ldg2(const double *p)
+{
+#ifdef EICOS_EMU
+    return d2{p[0], p[1]};
+#else
+    const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+    return d2{v.x, v.y};
+#endif
+}
 
 // Rows of the worker's shared memory (FIFO ring, zero row, slots) addressed by row number.  On the
 // device these are 32-bit shared-window addresses and explicit ld/st.shared, so that the compiler
@@ -676,14 +689,14 @@ struct Fifo
     const int *lp;               // next group of the load list to fetch
     i4 wa, wb;                   // the group that will be issued next
     smem_t ring;                 // FIFO_ROWS rows of shared memory (this lane's part)
-    const double *b0, *b1, *b2;  // load bases (+ lane): tile, run-time vectors 1 and 2
+    const double *b0, *b1, *b2, *b3; // load bases (+ lane): tile, run-time vectors 1..3
     int left;                    // words left in the load list
     int head;                    // producer ring row
 
     EI_DEV void issue_row(int r, int w) const
     {
         const int sel = (unsigned)w >> LD_BASE_SHIFT;
-        const double *base = sel == 0 ? b0 : (sel == 1 ? b1 : b2);
+        const double *base = sel == 0 ? b0 : (sel == 1 ? b1 : (sel == 2 ? b2 : b3));
         sm_fill(ring, head + r, base + (size_t)(w & LD_ROW_MASK) * TILE);
     }
     EI_DEV void issue_group()
@@ -716,8 +729,10 @@ struct Fifo
         head = head + FIFO_GROUP == FIFO_ROWS ? 0 : head + FIFO_GROUP;
         stage_commit();
     }
-    EI_DEV void open(const Team &tm, const int *list, int nwords, const double *T, const double *r1, const double *r2)
+    EI_DEV void open(const Team &tm, const int *list, int nwords, const double *T, const double *r1, const double *r2,
+                     const double *r3 = nullptr)
     {
+        b3 = r3 ? r3 : T;
         static_assert(FIFO_GROUP == 8, "issue_group reads the load list as two 4-word records");
         lp = list + FIFO_GROUP;
         wa = ldg4(list);
@@ -981,6 +996,91 @@ EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int out, int
         ldl_backward_t<false>(tm, a, T, out, x, cont);
 }
 
+// ------------------------------------------------------------------ KKT mat-vec program (streams.hpp, streams.cpp: build_matvec)
+// For every x, y and LP row r of the KKT matrix, in elimination order:
+//   v = init(kind, ex0, own, ex1) + sum_k (sign[kind] * coefficient_k) * vec[column_k];  finish(kind, r, v, ex0, own, ex1)
+// ex0 = v1[r], own = vec[r], ex1 = v3[r - n - p] (LP rows only).  One warp; every operand row comes
+// through the FIFO once and stays in a shared-memory slot while it has further uses.
+template <class Init, class Finish>
+EI_DEV void mv_run(const Team &tm, const KArgs &a, const double *T, const double *v1, const double *vec, const double *v3,
+                   double sx, double sy, double sz, Init init, Finish finish)
+{
+    const DevPattern &P = a.P;
+    const smem_t sm = smem_of(tm.stage);
+    sm_store(sm, SW_ZERO_ROW, vset(0.0));
+    Fifo ff;
+    ff.open(tm, P.mv_ld, P.mv_nld, T, v1, vec, v3);
+    const int *rp = P.mv;
+    const double *vp = P.mv_val;
+    i4 rec = ldg4(rp);
+    d2 cv = ldg2(vp);
+    for (int t = 0; t < P.mv_rows; t++)
+    {
+        const int cnt = rec.x & MV_CNT_MASK, kind = (rec.x >> MV_KIND_SHIFT) & 3;
+        const int nrec = (cnt + 3 + 3) >> 2;
+        const int *np = rp + 4 * nrec;
+        const double *nvp = vp + 2 + 4 * (nrec - 1);
+        const i4 nx = ldg4(np);
+        const d2 ncv = ldg2(nvp);
+        if (rec.x < 0)
+            ff.sync();
+        const vd ex0 = sm_load(sm, rec.y & 0xff), own = sm_load(sm, (rec.y >> 8) & 0xff);
+        const vd ex1 = sm_load(sm, (int)((unsigned)rec.y >> 24));
+        const int okeep = (rec.y >> 16) & 0xff;
+        if (okeep != SW_NO_KEEP)
+            sm_store(sm, okeep, own);
+        const double sgn = kind == MV_X ? sx : (kind == MV_Y ? sy : sz);
+        vd v = init(kind, ex0, own, ex1);
+        if (cnt > 0)
+        {
+            {
+                const vd g = sm_load(sm, rec.w & 0xff);
+                const int keep = (rec.w >> 8) & 0xff;
+                if (keep != SW_NO_KEEP)
+                    sm_store(sm, keep, g);
+                v += (sgn * cv.x) * g;
+            }
+            if (nrec > 1)
+            {
+                i4 pn = ldg4(rp + 4);
+                d2 c0n = ldg2(vp + 2), c1n = ldg2(vp + 4);
+                for (int q = 1; q < nrec; q++)
+                {
+                    const i4 pr = pn;
+                    const d2 c0 = c0n, c1 = c1n;
+                    pn = ldg4(rp + 4 * (q + 1));
+                    c0n = ldg2(vp + 2 + 4 * q);
+                    c1n = ldg2(vp + 4 + 4 * q);
+                    if (pr.x & MV_SYNC_PAIR)
+                        ff.sync();
+                    const int pw[4] = {pr.x, pr.y, pr.z, pr.w};
+                    const double cf[4] = {c0.x, c0.y, c1.x, c1.y};
+                    vd g[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        g[u] = sm_load(sm, pw[u] & 0xff);
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                    {
+                        const int keep = (pw[u] >> 8) & 0xff;
+                        if (keep != SW_NO_KEEP)
+                            sm_store(sm, keep, g[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        v += (sgn * cf[u]) * g[u];
+                }
+            }
+        }
+        finish(kind, rec.z, v, ex0, own, ex1);
+        rp = np;
+        vp = nvp;
+        rec = nx;
+        cv = ncv;
+    }
+    ff.close();
+}
+
 // ------------------------------------------------------------------ KKT residual for iterative refinement (src/eicos.cpp:1511-1576)
 // e = rhs - Ktrue * x with the un-regularised scaling block (identity while initialising),
 // returns ||e||_inf per instance.
@@ -991,36 +1091,20 @@ EI_DEV vd kkt_residual(const Team &tm, const KArgs &a, double *T, int rhs, int x
     const double delta = Settings::deltastat;
     const int n = P.n, p = P.p, zb = P.n + P.p;
     vd nerr = vset(0.0);
-    if (n > 0)
-        rowset_run<2>(
-            tm, T, P.rx, P.rx_val, P.rx_seg, x, -1.0,
-            [&](int j, int k) { return (k == 0 ? rhs : x) + j; },
-            [&](const vd *ex) { return ex[0]; },
-            [&](int j, const vd *ex, vd v) {
-                v -= delta * ex[1];
-                ROWD(T, L.e + j) = v;
-                nerr = vmax(nerr, vabs(v));
-            });
-    if (p > 0)
-        rowset_run<2>(
-            tm, T, P.ry, P.ry_val, P.ry_seg, x, -1.0,
-            [&](int i, int k) { return (k == 0 ? rhs : x) + n + i; },
-            [&](const vd *ex) { return ex[0]; },
-            [&](int i, const vd *ex, vd v) {
-                v += delta * ex[1];
-                ROWD(T, L.e + n + i) = v;
-                nerr = vmax(nerr, vabs(v));
-            });
-    if (P.l > 0)
-        rowset_run<3>(
-            tm, T, P.rz, P.rz_val, P.rz_seg, x, -1.0,
-            [&](int i, int k) { return k == 0 ? rhs + zb + i : (k == 1 ? x + zb + i : L.lpv + i); },
-            [&](const vd *ex) { return ex[0]; },
-            [&](int i, const vd *ex, vd v) {
-                const vd dz = ex[1];
-                v += delta * dz;
-                v += initialize ? dz : ex[2] * dz;
-                ROWD(T, L.e + zb + i) = v;
+    if (tm.wk == 0 && P.mv_rows > 0)
+        mv_run(
+            tm, a, T, T + (size_t)rhs * TILE, T + (size_t)x * TILE, T + (size_t)L.lpv * TILE, -1.0, -1.0, -1.0,
+            [&](int, vd ex0, vd, vd) { return ex0; },
+            [&](int kind, int r, vd v, vd, vd own, vd ex1) {
+                if (kind == MV_X)
+                    v -= delta * own;
+                else
+                {
+                    v += delta * own;
+                    if (kind == MV_Z)
+                        v += initialize ? own : ex1 * own;
+                }
+                ROWD(T, L.e + r) = v;
                 nerr = vmax(nerr, vabs(v));
             });
     if (P.nc > 0)
@@ -1454,34 +1538,6 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
     vd r[NRED];
     for (int k = 0; k < NRED; k++)
         r[k] = vset(0.0);
-    if (n > 0)
-        rowset_run<2>(
-            tm, T, P.rx, P.rx_val, P.rx_seg, L.w, -1.0,
-            [&](int j, int k) { return (k == 0 ? L.chb : L.w) + j; },
-            [&](const vd *) { return vset(0.0); },
-            [&](int j, const vd *ex, vd v) {
-                const vd cj = ex[0], xj = ex[1];
-                r[HX2] += v * v;
-                v -= tau * cj;
-                ROWD(T, L.r + j) = v;
-                r[RX2] += v * v;
-                r[CX] += cj * xj;
-                r[NX2] += xj * xj;
-            });
-    if (p > 0)
-        rowset_run<2>(
-            tm, T, P.ry, P.ry_val, P.ry_seg, L.w, 1.0,
-            [&](int i, int k) { return (k == 0 ? L.chb : L.w) + n + i; },
-            [&](const vd *) { return vset(0.0); },
-            [&](int i, const vd *ex, vd v) {
-                const vd bi = ex[0], yi = ex[1];
-                r[HY2] += v * v;
-                v -= tau * bi;
-                ROWD(T, L.r + n + i) = v;
-                r[RY2] += v * v;
-                r[BY] += bi * yi;
-                r[NY2] += yi * yi;
-            });
     const auto zrow = [&](int e, vd si, vd zi, vd hi, vd v) {
         r[HZ2] += v * v;
         v -= tau * hi;
@@ -1492,12 +1548,35 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
         r[NS2] += si * si;
         r[GAP] += si * zi;
     };
-    if (P.l > 0)
-        rowset_run<3>(
-            tm, T, P.rz, P.rz_val, P.rz_seg, L.w, 1.0,
-            [&](int i, int k) { return k == 0 ? L.s + i : (k == 1 ? L.w + zb + i : L.chb + zb + i); },
-            [&](const vd *ex) { return ex[0]; },
-            [&](int i, const vd *ex, vd v) { zrow(i, ex[0], ex[1], ex[2], v); });
+    if (tm.wk == 0 && P.mv_rows > 0)
+        mv_run(
+            tm, a, T, T + (size_t)L.chb * TILE, T + (size_t)L.w * TILE, T + (size_t)L.s * TILE, -1.0, 1.0, 1.0,
+            [&](int kind, vd, vd, vd ex1) { return kind == MV_Z ? ex1 : vset(0.0); },
+            [&](int kind, int q, vd v, vd ex0, vd own, vd ex1) {
+                if (kind == MV_Z)
+                {
+                    zrow(q - zb, ex1, own, ex0, v);
+                    return;
+                }
+                if (kind == MV_X)
+                { // ex0 = c_j, own = x_j
+                    r[HX2] += v * v;
+                    v -= tau * ex0;
+                    ROWD(T, L.r + q) = v;
+                    r[RX2] += v * v;
+                    r[CX] += ex0 * own;
+                    r[NX2] += own * own;
+                }
+                else
+                { // ex0 = b_i, own = y_i
+                    r[HY2] += v * v;
+                    v -= tau * ex0;
+                    ROWD(T, L.r + q) = v;
+                    r[RY2] += v * v;
+                    r[BY] += ex0 * own;
+                    r[NY2] += own * own;
+                }
+            });
     if (P.nc > 0)
     {
         IStream is;
