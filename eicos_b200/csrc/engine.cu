@@ -198,13 +198,28 @@ void Engine::upload_pattern(const Symbolic &S)
     P.Aeq = dAeq_ = upload(S.Aeq, owned_, st);
     P.GeqE = dGeq_ = upload(expanded_geq(S), owned_, st);
     P.fw = upload(H_.fw, owned_, st);
-    P.fw_ld = upload(H_.fw_ld, owned_, st);
+    // materialise the load lists: base selector (streams.hpp) -> row offset of the vector it stands for
+    const auto variant = [&](const ivec &list, int r1, int r2, int r3) {
+        ivec out(list.size());
+        const int off[4] = {0, r1, r2, r3};
+        for (size_t k = 0; k < list.size(); k++)
+            out[k] = (list[k] & LD_ROW_MASK) + off[(unsigned)list[k] >> LD_BASE_SHIFT];
+        return upload(out, owned_, st);
+    };
+    P.fw_ld[0] = variant(H_.fw_ld, L_.rhs1, 0, 0);
+    P.fw_ld[1] = variant(H_.fw_ld, L_.rhs2, 0, 0);
+    P.fw_ld[2] = variant(H_.fw_ld, L_.e, 0, 0);
     P.bw = upload(H_.bw, owned_, st);
-    P.bw_ld = upload(H_.bw_ld, owned_, st);
+    P.bw_ld[0] = variant(H_.bw_ld, L_.sol1, L_.sol1, 0); // a plain solve loads (and ignores) its own output rows
+    P.bw_ld[1] = variant(H_.bw_ld, L_.sol2, L_.sol2, 0);
+    P.bw_ld[2] = variant(H_.bw_ld, L_.dxr, L_.sol1, 0);
+    P.bw_ld[3] = variant(H_.bw_ld, L_.dxr, L_.sol2, 0);
     P.fa = upload(H_.fa, owned_, st);
     P.fa_ld = upload(H_.fa_ld, owned_, st);
     P.mv = upload(H_.mv, owned_, st);
-    P.mv_ld = upload(H_.mv_ld, owned_, st);
+    P.mv_ld[0] = variant(H_.mv_ld, L_.rhs1, L_.sol1, L_.lpv);
+    P.mv_ld[1] = variant(H_.mv_ld, L_.rhs2, L_.sol2, L_.lpv);
+    P.mv_ld[2] = variant(H_.mv_ld, L_.chb, L_.w, L_.s);
     P.mv_val = dmv_val_ = upload(H_.mv_val, owned_, st);
     P.mv_nld = H_.mv_nld;
     P.mv_rows = H_.mv_rows;
@@ -456,6 +471,7 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
         auto kkt = [&](int rhs, int sol, int init, int nitrow) {
             a.rhs = rhs;
             a.sol = sol;
+            a.variant = rhs == L_.rhs1 ? LDV_SOL1 : LDV_SOL2;
             a.initialize = init;
             a.nitrow = nitrow;
             EI_TIMED(1, EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt, tiles, threads, smem_common_, st, a));
@@ -609,11 +625,13 @@ void Engine::debug_factor_init(int batch, const double *d_c, const double *d_h, 
     a.xrows = P_.sw_slots;
     a.rhs = L_.rhs1;
     a.sol = L_.sol1;
+    a.variant = LDV_SOL1;
     a.initialize = 1;
     a.nitrow = J_NIT1;
     EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt, tiles, threads, smem_common_, st, a);
     a.rhs = L_.rhs2;
     a.sol = L_.sol2;
+    a.variant = LDV_SOL2;
     a.nitrow = J_NIT2;
     EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt, tiles, threads, smem_common_, st, a);
     be::sync(st);

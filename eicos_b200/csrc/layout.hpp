@@ -82,6 +82,15 @@ struct Layout
     int irows_total;                // integer rows (J_COUNT)
 };
 
+// index of a materialised load list (DevPattern::fw_ld / bw_ld / mv_ld)
+enum LdVariant : int
+{
+    LDV_SOL1 = 0,   // rhs1 -> sol1
+    LDV_SOL2 = 1,   // rhs2 -> sol2
+    LDV_REFINE = 2, // forward: rhs = e; backward: LDV_REFINE + {0, 1}: out = dxr, accumulated into sol1 / sol2
+    LDV_HEAD = 2    // mat-vec: computeResiduals (chb, w, s)
+};
+
 enum ConeParam : int
 {
     CP_ETA, CP_ETA2, CP_A, CP_D1, CP_U0, CP_U1, CP_V1, CP_W, CP_COUNT
@@ -96,7 +105,11 @@ struct DevPattern
     const double *xeq, *Aeq, *GeqE;        // equilibration vectors (GeqE is expanded, 1 in the slots)
     // instruction streams (streams.hpp)
     // slot programs (streams.hpp): ops, load lists (+ length in words), shared-memory slots they use
-    const int *fw, *fw_ld, *bw, *bw_ld, *fa, *fa_ld, *mv, *mv_ld;
+    // Load lists are materialised per use (absolute rows of the tile, so that issuing a load is one
+    // multiply-add): forward [rhs1, rhs2, e]; backward [sol1, sol2, dxr += into sol1, dxr += into sol2];
+    // mat-vec [rhs1/sol1, rhs2/sol2, computeResiduals].
+    const int *fw, *bw, *fa, *fa_ld, *mv;
+    const int *fw_ld[3], *bw_ld[4], *mv_ld[3];
     const double *mv_val;
     int fw_nld, bw_nld, fa_nld, mv_nld, mv_rows, sw_slots, fa_slots;
     int sw_direct; // the sweep programs contain operands read straight from global memory

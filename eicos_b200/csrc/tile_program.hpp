@@ -34,7 +34,7 @@
 #include <cuda_runtime.h>
 #define EI_DEV __device__ __forceinline__
 #define EI_LDG(p) __ldg(p)
-#define EI_PREFETCH(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#define EI_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
 #define EI_CLOCK() clock64()
 #endif
 
@@ -118,6 +118,8 @@ EI_DEV bool vall(vb a)
 
 EI_DEV vd vload(const double *p) { return *reinterpret_cast<const vd *>(p); }
 EI_DEV void vstore(double *p, vd v) { *reinterpret_cast<vd *>(p) = v; }
+
+constexpr int PF_AHEAD = 64; // 4-byte words (two 128-byte lines) the stream readers prefetch ahead into L1
 
 // 16-byte record of an instruction stream, read by the whole warp from one address (one broadcast
 // transaction through the read-only path; the line stays in L1 for the next three records)
@@ -235,6 +237,7 @@ struct KArgs
     int *out_iinfo;   // [batch][J_WORK_END]
     // solveKKT parameters
     int rhs, sol, initialize, nitrow;
+    int variant; // 0: rhs1 -> sol1, 1: rhs2 -> sol2 (selects the materialised load lists, LdVariant)
     int keep_sticky;
     int pre_equilibrated; // inputs are already divided by the equilibration vectors
     unsigned int *active_count; // device counter: instances still iterating after the head step
@@ -689,21 +692,20 @@ struct Fifo
     const int *lp;               // next group of the load list to fetch
     i4 wa, wb;                   // the group that will be issued next
     smem_t ring;                 // FIFO_ROWS rows of shared memory (this lane's part)
-    const double *b0, *b1, *b2, *b3; // load bases (+ lane): tile, run-time vectors 1..3
+    const double *b0;            // tile base (+ lane); the words of the (materialised, layout.hpp) load list are rows of the tile
     int left;                    // words left in the load list
     int head;                    // producer ring row
 
     EI_DEV void issue_row(int r, int w) const
     {
-        const int sel = (unsigned)w >> LD_BASE_SHIFT;
-        const double *base = sel == 0 ? b0 : (sel == 1 ? b1 : (sel == 2 ? b2 : b3));
-        sm_fill(ring, head + r, base + (size_t)(w & LD_ROW_MASK) * TILE);
+        sm_fill(ring, head + r, b0 + (size_t)w * TILE);
     }
     EI_DEV void issue_group()
     {
         const i4 a = wa, b = wb;
         wa = ldg4(lp);
         wb = ldg4(lp + 4);
+        EI_PREFETCH(lp + PF_AHEAD);
         lp += FIFO_GROUP;
         if (left >= FIFO_GROUP)
         {
@@ -729,18 +731,14 @@ struct Fifo
         head = head + FIFO_GROUP == FIFO_ROWS ? 0 : head + FIFO_GROUP;
         stage_commit();
     }
-    EI_DEV void open(const Team &tm, const int *list, int nwords, const double *T, const double *r1, const double *r2,
-                     const double *r3 = nullptr)
+    EI_DEV void open(const Team &tm, const int *list, int nwords, const double *T)
     {
-        b3 = r3 ? r3 : T;
         static_assert(FIFO_GROUP == 8, "issue_group reads the load list as two 4-word records");
         lp = list + FIFO_GROUP;
         wa = ldg4(list);
         wb = ldg4(list + 4);
         ring = smem_of(tm.stage);
         b0 = T;
-        b1 = r1;
-        b2 = r2;
         left = nwords;
         head = 0;
         for (int g = 0; g < FIFO_AHEAD; g++)
@@ -799,7 +797,7 @@ EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
     Fifo ff;
     is.open(P.fa, tm.pl);
     ds.open(P.fa_val, tm.pl);
-    ff.open(tm, P.fa_ld, P.fa_nld, T, T, T);
+    ff.open(tm, P.fa_ld, P.fa_nld, T);
     ff.tail = 0;
     const auto fetch = [&](int src) -> vd {
         if (src >= 0)
@@ -901,13 +899,13 @@ EI_DEV vd sweep_tail(const int *rp, int nrec, Fifo &ff, smem_t sm, const double 
 }
 
 template <bool DIRECT>
-EI_DEV void ldl_forward_t(const Team &tm, const KArgs &a, double *T, int rhs)
+EI_DEV void ldl_forward_t(const Team &tm, const KArgs &a, double *T, int variant)
 {
     const DevPattern &P = a.P;
     const smem_t sm = smem_of(tm.stage); // ring rows, zero row, slots
     sm_store(sm, SW_ZERO_ROW, vset(0.0));
     Fifo ff;
-    ff.open(tm, P.fw_ld, P.fw_nld, T, T + (size_t)rhs * TILE, T);
+    ff.open(tm, P.fw_ld[variant], P.fw_nld, T);
     const int *rp = P.fw;
     i4 rec = ldg4(rp);
     double *xp = T + (size_t)a.L.xw * TILE;
@@ -917,6 +915,7 @@ EI_DEV void ldl_forward_t(const Team &tm, const KArgs &a, double *T, int rhs)
         const int nrec = (cnt + 2 + 3) >> 2;
         const int *np = rp + 4 * nrec;
         const i4 nx = ldg4(np); // first record of the next row
+        EI_PREFETCH(np + PF_AHEAD);
         if (rec.x < 0)
             ff.sync();
         vd v = sm_load(sm, (rec.y >> 8) & 0xff);
@@ -936,17 +935,18 @@ EI_DEV void ldl_forward_t(const Team &tm, const KArgs &a, double *T, int rhs)
     }
     ff.close();
 }
-EI_DEV void ldl_forward(const Team &tm, const KArgs &a, double *T, int rhs)
+// variant: which right-hand side the load list was materialised for (LdVariant, layout.hpp)
+EI_DEV void ldl_forward(const Team &tm, const KArgs &a, double *T, int variant)
 {
     if (a.P.sw_direct)
-        ldl_forward_t<true>(tm, a, T, rhs);
+        ldl_forward_t<true>(tm, a, T, variant);
     else
-        ldl_forward_t<false>(tm, a, T, rhs);
+        ldl_forward_t<false>(tm, a, T, variant);
 }
 
 // out = solution (KKT order).  If x >= 0: additionally x += solution for the instances with `cont`.
 template <bool DIRECT>
-EI_DEV void ldl_backward_t(const Team &tm, const KArgs &a, double *T, int out, int x, vb cont)
+EI_DEV void ldl_backward_t(const Team &tm, const KArgs &a, double *T, int variant, int out, int x, vb cont)
 {
     const DevPattern &P = a.P;
     const smem_t sm = smem_of(tm.stage);
@@ -956,7 +956,7 @@ EI_DEV void ldl_backward_t(const Team &tm, const KArgs &a, double *T, int out, i
     double *op = T + (size_t)out * TILE;
     double *xp = T + (size_t)(accumulate ? x : out) * TILE; // a plain solve loads (and ignores) its own output rows
     Fifo ff;
-    ff.open(tm, P.bw_ld, P.bw_nld, T, op, xp);
+    ff.open(tm, P.bw_ld[variant], P.bw_nld, T);
     const int *rp = P.bw;
     i4 rec = ldg4(rp);
     for (int k = 0; k < P.N; k++)
@@ -965,6 +965,7 @@ EI_DEV void ldl_backward_t(const Team &tm, const KArgs &a, double *T, int out, i
         const int nrec = (cnt + 3 + 3) >> 2;
         const int *np = rp + 4 * nrec;
         const i4 nx = ldg4(np);
+        EI_PREFETCH(np + PF_AHEAD);
         if (rec.x < 0)
             ff.sync();
         vd v = sm_load(sm, (rec.y >> 8) & 0xff) * sm_load(sm, (rec.y >> 16) & 0xff); // Eigen: diag.inverse() * x
@@ -988,12 +989,12 @@ EI_DEV void ldl_backward_t(const Team &tm, const KArgs &a, double *T, int out, i
     }
     ff.close();
 }
-EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int out, int x, vb cont)
+EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int variant, int out, int x, vb cont)
 {
     if (a.P.sw_direct)
-        ldl_backward_t<true>(tm, a, T, out, x, cont);
+        ldl_backward_t<true>(tm, a, T, variant, out, x, cont);
     else
-        ldl_backward_t<false>(tm, a, T, out, x, cont);
+        ldl_backward_t<false>(tm, a, T, variant, out, x, cont);
 }
 
 // ------------------------------------------------------------------ KKT mat-vec program (streams.hpp, streams.cpp: build_matvec)
@@ -1002,14 +1003,14 @@ EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int out, int
 // ex0 = v1[r], own = vec[r], ex1 = v3[r - n - p] (LP rows only).  One warp; every operand row comes
 // through the FIFO once and stays in a shared-memory slot while it has further uses.
 template <class Init, class Finish>
-EI_DEV void mv_run(const Team &tm, const KArgs &a, const double *T, const double *v1, const double *vec, const double *v3,
+EI_DEV void mv_run(const Team &tm, const KArgs &a, const double *T, int variant,
                    double sx, double sy, double sz, Init init, Finish finish)
 {
     const DevPattern &P = a.P;
     const smem_t sm = smem_of(tm.stage);
     sm_store(sm, SW_ZERO_ROW, vset(0.0));
     Fifo ff;
-    ff.open(tm, P.mv_ld, P.mv_nld, T, v1, vec, v3);
+    ff.open(tm, P.mv_ld[variant], P.mv_nld, T);
     const int *rp = P.mv;
     const double *vp = P.mv_val;
     i4 rec = ldg4(rp);
@@ -1022,6 +1023,8 @@ EI_DEV void mv_run(const Team &tm, const KArgs &a, const double *T, const double
         const double *nvp = vp + 2 + 4 * (nrec - 1);
         const i4 nx = ldg4(np);
         const d2 ncv = ldg2(nvp);
+        EI_PREFETCH(np + PF_AHEAD);
+        EI_PREFETCH(nvp + PF_AHEAD / 2);
         if (rec.x < 0)
             ff.sync();
         const vd ex0 = sm_load(sm, rec.y & 0xff), own = sm_load(sm, (rec.y >> 8) & 0xff);
@@ -1084,7 +1087,7 @@ EI_DEV void mv_run(const Team &tm, const KArgs &a, const double *T, const double
 // ------------------------------------------------------------------ KKT residual for iterative refinement (src/eicos.cpp:1511-1576)
 // e = rhs - Ktrue * x with the un-regularised scaling block (identity while initialising),
 // returns ||e||_inf per instance.
-EI_DEV vd kkt_residual(const Team &tm, const KArgs &a, double *T, int rhs, int x, bool initialize)
+EI_DEV vd kkt_residual(const Team &tm, const KArgs &a, double *T, int variant, int rhs, int x, bool initialize)
 {
     const DevPattern &P = a.P;
     const Layout &L = a.L;
@@ -1093,7 +1096,7 @@ EI_DEV vd kkt_residual(const Team &tm, const KArgs &a, double *T, int rhs, int x
     vd nerr = vset(0.0);
     if (tm.wk == 0 && P.mv_rows > 0)
         mv_run(
-            tm, a, T, T + (size_t)rhs * TILE, T + (size_t)x * TILE, T + (size_t)L.lpv * TILE, -1.0, -1.0, -1.0,
+            tm, a, T, variant, -1.0, -1.0, -1.0,
             [&](int, vd ex0, vd, vd) { return ex0; },
             [&](int kind, int r, vd v, vd, vd own, vd ex1) {
                 if (kind == MV_X)
@@ -1183,9 +1186,9 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
     EI_PHASE(0);
     if (tm.wk == 0)
     {
-        ldl_forward(tm, a, T, rhs);
+        ldl_forward(tm, a, T, a.variant);
         EI_PHASE(1);
-        ldl_backward(tm, a, T, sol, -1, vbset(false));
+        ldl_backward(tm, a, T, a.variant, sol, -1, vbset(false));
         EI_PHASE(2);
     }
     tm.sync();
@@ -1197,7 +1200,7 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
     unsigned rounds = 0;
     for (;;)
     {
-        const vd nerr = kkt_residual(tm, a, T, rhs, sol, init);
+        const vd nerr = kkt_residual(tm, a, T, a.variant, rhs, sol, init);
         EI_PHASE(3);
         vb rollback = vbset(false);
         VFOR
@@ -1227,9 +1230,9 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
         EI_PHASE(4);
         if (tm.wk == 0)
         {
-            ldl_forward(tm, a, T, L.e);
+            ldl_forward(tm, a, T, LDV_REFINE);
             EI_PHASE(1);
-            ldl_backward(tm, a, T, L.dxr, sol, !done);
+            ldl_backward(tm, a, T, LDV_REFINE + a.variant, L.dxr, sol, !done);
             EI_PHASE(2);
         }
         tm.sync();
@@ -1550,7 +1553,7 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
     };
     if (tm.wk == 0 && P.mv_rows > 0)
         mv_run(
-            tm, a, T, T + (size_t)L.chb * TILE, T + (size_t)L.w * TILE, T + (size_t)L.s * TILE, -1.0, 1.0, 1.0,
+            tm, a, T, LDV_HEAD, -1.0, 1.0, 1.0,
             [&](int kind, vd, vd, vd ex1) { return kind == MV_Z ? ex1 : vset(0.0); },
             [&](int kind, int q, vd v, vd ex0, vd own, vd ex1) {
                 if (kind == MV_Z)
