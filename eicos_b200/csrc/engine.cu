@@ -25,8 +25,9 @@ namespace eicos
         tm.wk = threadIdx.x >> 5;                                                              \
         tm.nwk = blockDim.x >> 5;                                                              \
         tm.red = smem;                                                                         \
-        /* [reduction rows][worker 0: staging = FIFO ring][slots, column buffers][staging of workers 1..] */ \
-        double *st0_ = smem + (size_t)(tm.nwk > 1 ? tm.nwk * KRED : 0) * TILE + tm.lane;             \
+        /* [reduction rows][program-stream buffers][worker 0: staging = FIFO ring][slots, column buffers][staging of workers 1..] */ \
+        tm.pbuf = smem + (size_t)(tm.nwk > 1 ? tm.nwk * KRED : 0) * TILE;                           \
+        double *st0_ = tm.pbuf + PS_DOUBLES + tm.lane;                                             \
         tm.extra = st0_ + (size_t)2 * STAGE_SLOTS * TILE;                                          \
         tm.stage = tm.wk == 0 ? st0_ : tm.extra + ((size_t)a.xrows + (size_t)(tm.wk - 1) * 2 * STAGE_SLOTS) * TILE; \
         fn(tm, a, blockIdx.x);                                                                 \
@@ -62,6 +63,7 @@ __global__ void eicos_compact(const __grid_constant__ KArgs a, const __grid_cons
         std::vector<double> red_((size_t)nw_ * KRED * TILE + 8);                                  \
         const size_t xr_ = (size_t)std::max((args).P.sw_slots, (args).P.fa_slots) + 2 * (args).P.maxcol; \
         std::vector<double> stg_(((size_t)nw_ * 2 * STAGE_SLOTS + xr_) * TILE + 8);                \
+        std::vector<double> pb_(PS_DOUBLES + 8);                                                   \
         for (int tile_ = 0; tile_ < (tiles); tile_++)                                             \
         {                                                                                         \
             std::barrier<> bar_(nw_);                                                             \
@@ -73,6 +75,7 @@ __global__ void eicos_compact(const __grid_constant__ KArgs a, const __grid_cons
                 tm_.nwk = nw_;                                                                    \
                 tm_.red = red_.data();                                                            \
                 tm_.extra = stg_.data() + (size_t)2 * STAGE_SLOTS * TILE;                         \
+                tm_.pbuf = pb_.data();                                                            \
                 tm_.stage = wk_ == 0 ? stg_.data() : tm_.extra + (xr_ + (size_t)(wk_ - 1) * 2 * STAGE_SLOTS) * TILE; \
                 tm_.bar = nw_ > 1 ? &bar_ : nullptr;                                              \
                 fn(tm_, (args), tile_);                                                           \
@@ -298,7 +301,8 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
     moves_dev_ = (int *)be::alloc(2 * slots * sizeof(int));
     status_host_ = (int *)be::pinned(slots * sizeof(int));
     moves_host_ = (int *)be::pinned(2 * slots * sizeof(int));
-    const size_t smem_base = (size_t)workers_ * ((workers_ > 1 ? KRED : 0) + 2 * STAGE_SLOTS) * TILE * sizeof(double);
+    const size_t smem_base = (size_t)workers_ * ((workers_ > 1 ? KRED : 0) + 2 * STAGE_SLOTS) * TILE * sizeof(double) +
+                             PS_DOUBLES * sizeof(double);
     smem_common_ = smem_base + (size_t)P_.sw_slots * TILE * sizeof(double);
     xrows_factor_ = H_.fa_slots + 2 * S.maxcol;
 #ifndef EICOS_EMU

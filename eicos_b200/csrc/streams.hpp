@@ -32,7 +32,7 @@ namespace eicos
 {
 
 constexpr int STREAM_CHUNK = 32;  // words per cooperative load
-constexpr int STREAM_PAD = 192;   // readable words after the last used one (record lookahead + L1 prefetch distance)
+constexpr int STREAM_PAD = 640;   // readable words after the last used one (the stream readers fetch up to four 128-word chunks ahead)
 constexpr int STAGE_SLOTS = 16;   // rows per staging buffer (one slot = TILE doubles); a worker owns two buffers
 constexpr int ROW_EXTRA_SLOTS = 4; // staging slots a mat-vec row may use besides its gathers
 

@@ -119,8 +119,6 @@ EI_DEV bool vall(vb a)
 EI_DEV vd vload(const double *p) { return *reinterpret_cast<const vd *>(p); }
 EI_DEV void vstore(double *p, vd v) { *reinterpret_cast<vd *>(p) = v; }
 
-constexpr int PF_AHEAD = 64; // 4-byte words (two 128-byte lines) the stream readers prefetch ahead into L1
-
 // 16-byte record of an instruction stream, read by the whole warp from one address (one broadcast
 // transaction through the read-only path; the line stays in L1 for the next three records)
 #ifdef EICOS_EMU
@@ -252,6 +250,7 @@ struct Team
     double *red;   // [nwk][KRED][TILE]
     double *stage; // this worker's staging slots + lane: slot s lives at stage[s * TILE]
     double *extra; // shared memory behind the staging buffers (+ lane): slots of the slot programs, column buffers
+    double *pbuf;  // worker 0: PS_STREAMS x PS_BYTES of shared memory for the program-stream readers (no lane offset)
 #ifdef EICOS_EMU
     std::barrier<> *bar; // workers of a tile are real threads in the emulator
     void sync() const
@@ -679,6 +678,88 @@ EI_DEV vd line_search(const Team &tm, const KArgs &a, double *T, int lam, int ds
     return res;
 }
 
+// ------------------------------------------------------------------ program-stream reader
+// Sequential reader of a program stream (16-byte records).  L1 allocates by 32-byte sector, so
+// record-sized loads from global memory pay an L2 round trip every other record (profiles/r01e).
+// Instead the warp fetches the stream 512 bytes at a time (one coalesced 16-byte load per lane, a
+// whole chunk ahead of use), parks it in a 1 KB double buffer in shared memory and reads records
+// from there with broadcast 128-bit loads, one record ahead of use.
+constexpr int PS_BYTES = 1024; // shared memory per stream
+constexpr int PS_STREAMS = 3;  // streams a kernel reads at the same time (ops, load list, coefficients)
+constexpr int PS_DOUBLES = PS_STREAMS * PS_BYTES / 8;
+#ifdef EICOS_EMU
+struct PStream
+{
+    const int *p;
+    EI_DEV void open(const Team &, const void *base, int) { p = (const int *)base; }
+    EI_DEV i4 get()
+    {
+        const i4 r = ldg4(p);
+        p += 4;
+        return r;
+    }
+};
+#else
+struct PStream
+{
+    const int *g; // next chunk to fetch from global memory (+ this lane's 16 bytes)
+    i4 nextv;     // the chunk after the two in the buffer (this lane's part)
+    i4 look;      // the record get() will return
+    unsigned buf, pa;
+    static __device__ __forceinline__ i4 lds(unsigned a)
+    {
+        i4 r;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+        return r;
+    }
+    static __device__ __forceinline__ void sts(unsigned a, i4 v)
+    {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+    __device__ __forceinline__ void open(const Team &tm, const void *base, int k)
+    {
+        const int *b = (const int *)base + 4 * tm.pl;
+        buf = (unsigned)__cvta_generic_to_shared(tm.pbuf) + (unsigned)k * PS_BYTES;
+        __syncwarp();
+        sts(buf + 16 * tm.pl, ldg4(b));
+        sts(buf + 512 + 16 * tm.pl, ldg4(b + 128));
+        g = b + 256;
+        nextv = ldg4(g);
+        g += 128;
+        __syncwarp();
+        look = lds(buf);
+        pa = 16;
+    }
+    __device__ __forceinline__ i4 get()
+    {
+        const i4 r = look;
+        look = lds(buf + pa);
+        pa += 16;
+        if ((pa & 511) == 0)
+        { // the half behind pa has been read completely: it takes the prefetched chunk
+            const unsigned half = (pa & 512) ^ 512;
+            __syncwarp();
+            sts(buf + half + 16 * (threadIdx.x & 31), nextv);
+            nextv = ldg4(g);
+            g += 128;
+            __syncwarp();
+            pa &= PS_BYTES - 1;
+        }
+        return r;
+    }
+};
+#endif
+EI_DEV d2 as_d2(i4 r)
+{
+#ifdef EICOS_EMU
+    d2 v;
+    std::memcpy(&v, &r, sizeof(v));
+    return v;
+#else
+    return d2{__hiloint2double(r.y, r.x), __hiloint2double(r.w, r.z)};
+#endif
+}
+
 // ------------------------------------------------------------------ FIFO of asynchronously loaded rows
 // Every global read of the factorisation and of the sweeps is known to the host in consumption
 // order (the program's load list).  The warp keeps FIFO_AHEAD cp.async groups of FIFO_GROUP rows in
@@ -689,24 +770,16 @@ EI_DEV vd line_search(const Team &tm, const KArgs &a, double *T, int lam, int ds
 // The load list itself is read one group (two 16-byte records) ahead.
 struct Fifo
 {
-    const int *lp;               // next group of the load list to fetch
-    i4 wa, wb;                   // the group that will be issued next
+    PStream ld;                  // the load list: FIFO_GROUP words = two records per group
     smem_t ring;                 // FIFO_ROWS rows of shared memory (this lane's part)
     const double *b0;            // tile base (+ lane); the words of the (materialised, layout.hpp) load list are rows of the tile
     int left;                    // words left in the load list
     int head;                    // producer ring row
 
-    EI_DEV void issue_row(int r, int w) const
-    {
-        sm_fill(ring, head + r, b0 + (size_t)w * TILE);
-    }
+    EI_DEV void issue_row(int r, int w) const { sm_fill(ring, head + r, b0 + (size_t)w * TILE); }
     EI_DEV void issue_group()
     {
-        const i4 a = wa, b = wb;
-        wa = ldg4(lp);
-        wb = ldg4(lp + 4);
-        EI_PREFETCH(lp + PF_AHEAD);
-        lp += FIFO_GROUP;
+        const i4 a = ld.get(), b = ld.get();
         if (left >= FIFO_GROUP)
         {
             issue_row(0, a.x);
@@ -731,12 +804,11 @@ struct Fifo
         head = head + FIFO_GROUP == FIFO_ROWS ? 0 : head + FIFO_GROUP;
         stage_commit();
     }
-    EI_DEV void open(const Team &tm, const int *list, int nwords, const double *T)
+    // stream: which PStream buffer of the worker the load list uses
+    EI_DEV void open(const Team &tm, const int *list, int nwords, const double *T, int stream)
     {
         static_assert(FIFO_GROUP == 8, "issue_group reads the load list as two 4-word records");
-        lp = list + FIFO_GROUP;
-        wa = ldg4(list);
-        wb = ldg4(list + 4);
+        ld.open(tm, list, stream);
         ring = smem_of(tm.stage);
         b0 = T;
         left = nwords;
@@ -797,7 +869,7 @@ EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
     Fifo ff;
     is.open(P.fa, tm.pl);
     ds.open(P.fa_val, tm.pl);
-    ff.open(tm, P.fa_ld, P.fa_nld, T);
+    ff.open(tm, P.fa_ld, P.fa_nld, T, 0);
     ff.tail = 0;
     const auto fetch = [&](int src) -> vd {
         if (src >= 0)
@@ -881,15 +953,13 @@ EI_DEV vd sweep_pairs(smem_t sm, const double *home, const int (&p)[NP], vd v)
     return v;
 }
 
-// the records of a row behind its first one (4 pairs each), read one record ahead
+// the records of a row behind its first one (4 pairs each)
 template <bool DIRECT>
-EI_DEV vd sweep_tail(const int *rp, int nrec, Fifo &ff, smem_t sm, const double *home, vd v)
+EI_DEV vd sweep_tail(PStream &ops, int nrec, Fifo &ff, smem_t sm, const double *home, vd v)
 {
-    i4 nx = ldg4(rp + 4);
     for (int q = 1; q < nrec; q++)
     {
-        const i4 pr = nx;
-        nx = ldg4(rp + 4 * (q + 1));
+        const i4 pr = ops.get();
         if (pr.x & SW_SYNC_PAIR)
             ff.sync();
         const int p[4] = {pr.x, pr.y, pr.z, pr.w};
@@ -904,18 +974,15 @@ EI_DEV void ldl_forward_t(const Team &tm, const KArgs &a, double *T, int variant
     const DevPattern &P = a.P;
     const smem_t sm = smem_of(tm.stage); // ring rows, zero row, slots
     sm_store(sm, SW_ZERO_ROW, vset(0.0));
+    PStream ops;
     Fifo ff;
-    ff.open(tm, P.fw_ld[variant], P.fw_nld, T);
-    const int *rp = P.fw;
-    i4 rec = ldg4(rp);
+    ops.open(tm, P.fw, 0);
+    ff.open(tm, P.fw_ld[variant], P.fw_nld, T, 1);
     double *xp = T + (size_t)a.L.xw * TILE;
     for (int i = 0; i < P.N; i++, xp += TILE)
     {
+        const i4 rec = ops.get();
         const int cnt = rec.x & SW_CNT_MASK;
-        const int nrec = (cnt + 2 + 3) >> 2;
-        const int *np = rp + 4 * nrec;
-        const i4 nx = ldg4(np); // first record of the next row
-        EI_PREFETCH(np + PF_AHEAD);
         if (rec.x < 0)
             ff.sync();
         vd v = sm_load(sm, (rec.y >> 8) & 0xff);
@@ -923,15 +990,13 @@ EI_DEV void ldl_forward_t(const Team &tm, const KArgs &a, double *T, int variant
         {
             const int p[2] = {rec.z, rec.w};
             v = sweep_pairs<DIRECT, 2>(sm, T, p, v);
-            if (nrec > 1)
-                v = sweep_tail<DIRECT>(rp, nrec, ff, sm, T, v);
+            if (cnt > 2)
+                v = sweep_tail<DIRECT>(ops, (cnt + 2 + 3) >> 2, ff, sm, T, v);
         }
         vstore(xp, v);
         const int keep = rec.y & 0xff;
         if (keep != SW_NO_KEEP)
             sm_store(sm, keep, v);
-        rp = np;
-        rec = nx;
     }
     ff.close();
 }
@@ -954,18 +1019,15 @@ EI_DEV void ldl_backward_t(const Team &tm, const KArgs &a, double *T, int varian
     const bool accumulate = x >= 0;
     const vd zero = vset(0.0);
     double *op = T + (size_t)out * TILE;
-    double *xp = T + (size_t)(accumulate ? x : out) * TILE; // a plain solve loads (and ignores) its own output rows
+    double *xp = T + (size_t)(accumulate ? x : out) * TILE;
+    PStream ops;
     Fifo ff;
-    ff.open(tm, P.bw_ld[variant], P.bw_nld, T);
-    const int *rp = P.bw;
-    i4 rec = ldg4(rp);
+    ops.open(tm, P.bw, 0);
+    ff.open(tm, P.bw_ld[variant], P.bw_nld, T, 1);
     for (int k = 0; k < P.N; k++)
     {
+        const i4 rec = ops.get();
         const int cnt = rec.x & SW_CNT_MASK;
-        const int nrec = (cnt + 3 + 3) >> 2;
-        const int *np = rp + 4 * nrec;
-        const i4 nx = ldg4(np);
-        EI_PREFETCH(np + PF_AHEAD);
         if (rec.x < 0)
             ff.sync();
         vd v = sm_load(sm, (rec.y >> 8) & 0xff) * sm_load(sm, (rec.y >> 16) & 0xff); // Eigen: diag.inverse() * x
@@ -974,8 +1036,8 @@ EI_DEV void ldl_backward_t(const Team &tm, const KArgs &a, double *T, int varian
         {
             const int p[1] = {rec.w};
             v = sweep_pairs<DIRECT, 1>(sm, op, p, v);
-            if (nrec > 1)
-                v = sweep_tail<DIRECT>(rp, nrec, ff, sm, op, v);
+            if (cnt > 1)
+                v = sweep_tail<DIRECT>(ops, (cnt + 3 + 3) >> 2, ff, sm, op, v);
         }
         const int o = rec.z;
         vstore(op + (size_t)o * TILE, v);
@@ -984,8 +1046,6 @@ EI_DEV void ldl_backward_t(const Team &tm, const KArgs &a, double *T, int varian
             sm_store(sm, keep, v);
         if (accumulate)
             vstore(xp + (size_t)o * TILE, xa + vsel(cont, v, zero));
-        rp = np;
-        rec = nx;
     }
     ff.close();
 }
@@ -1009,22 +1069,16 @@ EI_DEV void mv_run(const Team &tm, const KArgs &a, const double *T, int variant,
     const DevPattern &P = a.P;
     const smem_t sm = smem_of(tm.stage);
     sm_store(sm, SW_ZERO_ROW, vset(0.0));
+    PStream ops, vals;
     Fifo ff;
-    ff.open(tm, P.mv_ld[variant], P.mv_nld, T);
-    const int *rp = P.mv;
-    const double *vp = P.mv_val;
-    i4 rec = ldg4(rp);
-    d2 cv = ldg2(vp);
+    ops.open(tm, P.mv, 0);
+    vals.open(tm, P.mv_val, 2);
+    ff.open(tm, P.mv_ld[variant], P.mv_nld, T, 1);
     for (int t = 0; t < P.mv_rows; t++)
     {
+        const i4 rec = ops.get();
+        const d2 cv = as_d2(vals.get());
         const int cnt = rec.x & MV_CNT_MASK, kind = (rec.x >> MV_KIND_SHIFT) & 3;
-        const int nrec = (cnt + 3 + 3) >> 2;
-        const int *np = rp + 4 * nrec;
-        const double *nvp = vp + 2 + 4 * (nrec - 1);
-        const i4 nx = ldg4(np);
-        const d2 ncv = ldg2(nvp);
-        EI_PREFETCH(np + PF_AHEAD);
-        EI_PREFETCH(nvp + PF_AHEAD / 2);
         if (rec.x < 0)
             ff.sync();
         const vd ex0 = sm_load(sm, rec.y & 0xff), own = sm_load(sm, (rec.y >> 8) & 0xff);
@@ -1043,43 +1097,32 @@ EI_DEV void mv_run(const Team &tm, const KArgs &a, const double *T, int variant,
                     sm_store(sm, keep, g);
                 v += (sgn * cv.x) * g;
             }
-            if (nrec > 1)
+            const int nrec = (cnt + 3 + 3) >> 2;
+            for (int q = 1; q < nrec; q++)
             {
-                i4 pn = ldg4(rp + 4);
-                d2 c0n = ldg2(vp + 2), c1n = ldg2(vp + 4);
-                for (int q = 1; q < nrec; q++)
+                const i4 pr = ops.get();
+                const d2 c0 = as_d2(vals.get()), c1 = as_d2(vals.get());
+                if (pr.x & MV_SYNC_PAIR)
+                    ff.sync();
+                const int pw[4] = {pr.x, pr.y, pr.z, pr.w};
+                const double cf[4] = {c0.x, c0.y, c1.x, c1.y};
+                vd g[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    g[u] = sm_load(sm, pw[u] & 0xff);
+#pragma unroll
+                for (int u = 0; u < 4; u++)
                 {
-                    const i4 pr = pn;
-                    const d2 c0 = c0n, c1 = c1n;
-                    pn = ldg4(rp + 4 * (q + 1));
-                    c0n = ldg2(vp + 2 + 4 * q);
-                    c1n = ldg2(vp + 4 + 4 * q);
-                    if (pr.x & MV_SYNC_PAIR)
-                        ff.sync();
-                    const int pw[4] = {pr.x, pr.y, pr.z, pr.w};
-                    const double cf[4] = {c0.x, c0.y, c1.x, c1.y};
-                    vd g[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        g[u] = sm_load(sm, pw[u] & 0xff);
-#pragma unroll
-                    for (int u = 0; u < 4; u++)
-                    {
-                        const int keep = (pw[u] >> 8) & 0xff;
-                        if (keep != SW_NO_KEEP)
-                            sm_store(sm, keep, g[u]);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        v += (sgn * cf[u]) * g[u];
+                    const int keep = (pw[u] >> 8) & 0xff;
+                    if (keep != SW_NO_KEEP)
+                        sm_store(sm, keep, g[u]);
                 }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    v += (sgn * cf[u]) * g[u];
             }
         }
         finish(kind, rec.z, v, ex0, own, ex1);
-        rp = np;
-        vp = nvp;
-        rec = nx;
-        cv = ncv;
     }
     ff.close();
 }
