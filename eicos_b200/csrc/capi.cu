@@ -91,16 +91,13 @@ struct eicos_solver
     int device = 0;
 };
 
-// Warps per CTA (= workers per tile).  The factorisation and the triangular sweeps are run by one
-// warp per tile (slot programs, streams.hpp); extra workers only share the mat-vec rows and the
-// vector passes.  A full machine (>= 7 tiles per SM) is best served by one worker; small batches get
-// more so that the vector passes are not left to a handful of warps.
+// Warps per CTA of the vector kernels (= workers per tile).  The factorisation, the triangular
+// sweeps and the KKT mat-vecs are programs run by ONE warp per tile (streams.hpp); the remaining
+// kernels are element-wise passes and reductions over the rows of a tile, split over `workers` warps.
 static int default_workers(long long instances)
 {
-    const double tiles_per_sm = (double)((instances + Engine::tile_width() - 1) / Engine::tile_width()) / 148.0;
-    if (tiles_per_sm >= 3.0)
-        return 1;
-    return tiles_per_sm >= 1.0 ? 2 : 4;
+    (void)instances;
+    return 4;
 }
 
 extern "C"

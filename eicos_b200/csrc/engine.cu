@@ -25,11 +25,11 @@ namespace eicos
         tm.wk = threadIdx.x >> 5;                                                              \
         tm.nwk = blockDim.x >> 5;                                                              \
         tm.red = smem;                                                                         \
-        /* [reduction rows][program-stream buffers][worker 0: staging = FIFO ring][slots, column buffers][staging of workers 1..] */ \
+        /* vector kernels (several warps): [reduction rows]; program kernels (one warp):              \
+           [program-stream buffers][staging = FIFO ring][zero row, slots, column buffers] */        \
         tm.pbuf = smem + (size_t)(tm.nwk > 1 ? tm.nwk * KRED : 0) * TILE;                           \
-        double *st0_ = tm.pbuf + PS_DOUBLES + tm.lane;                                             \
-        tm.extra = st0_ + (size_t)2 * STAGE_SLOTS * TILE;                                          \
-        tm.stage = tm.wk == 0 ? st0_ : tm.extra + ((size_t)a.xrows + (size_t)(tm.wk - 1) * 2 * STAGE_SLOTS) * TILE; \
+        tm.stage = tm.pbuf + PS_DOUBLES + tm.lane;                                                 \
+        tm.extra = tm.stage + (size_t)2 * STAGE_SLOTS * TILE;                                      \
         fn(tm, a, blockIdx.x);                                                                 \
     }
 #define EI_MAX_THREADS 256
@@ -38,6 +38,7 @@ EI_DEFINE_KERNEL(eicos_init, tile_init, 2)
 EI_DEFINE_KERNEL(eicos_ldl_factor, tile_factor, 2)
 EI_DEFINE_KERNEL(eicos_solve_kkt, tile_solve_kkt, 2)
 EI_DEFINE_KERNEL(eicos_init_point, tile_init_point, 2)
+EI_DEFINE_KERNEL(eicos_residuals, tile_resid, 2)
 EI_DEFINE_KERNEL(eicos_iter_head, tile_head, 2)
 EI_DEFINE_KERNEL(eicos_iter_mid, tile_mid, 2)
 EI_DEFINE_KERNEL(eicos_iter_tail, tile_tail, 2)
@@ -76,7 +77,7 @@ __global__ void eicos_compact(const __grid_constant__ KArgs a, const __grid_cons
                 tm_.red = red_.data();                                                            \
                 tm_.extra = stg_.data() + (size_t)2 * STAGE_SLOTS * TILE;                         \
                 tm_.pbuf = pb_.data();                                                            \
-                tm_.stage = wk_ == 0 ? stg_.data() : tm_.extra + (xr_ + (size_t)(wk_ - 1) * 2 * STAGE_SLOTS) * TILE; \
+                tm_.stage = stg_.data();                                                          \
                 tm_.bar = nw_ > 1 ? &bar_ : nullptr;                                              \
                 fn(tm_, (args), tile_);                                                           \
             };                                                                                    \
@@ -227,15 +228,6 @@ void Engine::upload_pattern(const Symbolic &S)
     P.mv_nld = H_.mv_nld;
     P.mv_rows = H_.mv_rows;
     P.fa_val = dfa_val_ = upload(H_.fa_val, owned_, st);
-    P.rx = upload(H_.rx, owned_, st);
-    P.rx_seg = upload(H_.rx_seg, owned_, st);
-    P.rx_val = drx_val_ = upload(H_.rx_val, owned_, st);
-    P.ry = upload(H_.ry, owned_, st);
-    P.ry_seg = upload(H_.ry_seg, owned_, st);
-    P.ry_val = dry_val_ = upload(H_.ry_val, owned_, st);
-    P.rz = upload(H_.rz, owned_, st);
-    P.rz_seg = upload(H_.rz_seg, owned_, st);
-    P.rz_val = drz_val_ = upload(H_.rz_val, owned_, st);
     P.rc = upload(H_.rc, owned_, st);
     P.rc_seg = upload(H_.rc_seg, owned_, st);
     P.rc_val = drc_val_ = upload(H_.rc_val, owned_, st);
@@ -267,9 +259,6 @@ void Engine::upload_values(const Symbolic &S)
     be::h2d(dGeq_, ge.data(), ge.size() * sizeof(double), st);
     be::h2d(dfa_val_, H_.fa_val.data(), H_.fa_val.size() * sizeof(double), st);
     be::h2d(dmv_val_, H_.mv_val.data(), H_.mv_val.size() * sizeof(double), st);
-    be::h2d(drx_val_, H_.rx_val.data(), H_.rx_val.size() * sizeof(double), st);
-    be::h2d(dry_val_, H_.ry_val.data(), H_.ry_val.size() * sizeof(double), st);
-    be::h2d(drz_val_, H_.rz_val.data(), H_.rz_val.size() * sizeof(double), st);
     be::h2d(drc_val_, H_.rc_val.data(), H_.rc_val.size() * sizeof(double), st);
     be::sync(st);
 }
@@ -277,11 +266,6 @@ void Engine::upload_values(const Symbolic &S)
 Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int workers)
     : device_(device), workers_(std::max(1, std::min(workers, EI_MAX_THREADS / 32 > 0 ? EI_MAX_THREADS / 32 : 1)))
 {
-    { // keep the per-CTA shared memory (reductions + two staging buffers per worker) within ~96 KB
-        const size_t per_worker = (size_t)(KRED + 2 * STAGE_SLOTS) * TILE * sizeof(double);
-        const int fit = (int)std::max<size_t>(1, (128 * 1024) / per_worker);
-        workers_ = std::min(workers_, fit);
-    }
     be::set_device(device_);
     stream_ = (void *)(intptr_t)be::make_stream();
     build_layout(S);
@@ -301,9 +285,10 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
     moves_dev_ = (int *)be::alloc(2 * slots * sizeof(int));
     status_host_ = (int *)be::pinned(slots * sizeof(int));
     moves_host_ = (int *)be::pinned(2 * slots * sizeof(int));
-    const size_t smem_base = (size_t)workers_ * ((workers_ > 1 ? KRED : 0) + 2 * STAGE_SLOTS) * TILE * sizeof(double) +
-                             PS_DOUBLES * sizeof(double);
-    smem_common_ = smem_base + (size_t)P_.sw_slots * TILE * sizeof(double);
+    // program kernels (one warp per tile): stream buffers + FIFO ring + slots; vector kernels: reduction rows only
+    const size_t smem_base = ((size_t)2 * STAGE_SLOTS * TILE + PS_DOUBLES) * sizeof(double);
+    smem_prog_ = smem_base + (size_t)P_.sw_slots * TILE * sizeof(double);
+    smem_common_ = workers_ > 1 ? (size_t)workers_ * KRED * TILE * sizeof(double) : 0;
     xrows_factor_ = H_.fa_slots + 2 * S.maxcol;
 #ifndef EICOS_EMU
     if (2 * S.maxcol > MAX_COLBUF_ROWS)
@@ -316,11 +301,16 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
 #ifndef EICOS_EMU
     if (smem_factor_ > 48 * 1024)
         EI_CUDA(cudaFuncSetAttribute(eicos_ldl_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_factor_));
+    if (smem_prog_ > 48 * 1024)
+    {
+        EI_CUDA(cudaFuncSetAttribute(eicos_solve_kkt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prog_));
+        EI_CUDA(cudaFuncSetAttribute(eicos_residuals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prog_));
+    }
     if (smem_common_ > 48 * 1024)
     {
-        const void *ks[] = {(const void *)eicos_load_inputs, (const void *)eicos_init, (const void *)eicos_solve_kkt,
-                            (const void *)eicos_init_point, (const void *)eicos_iter_head, (const void *)eicos_iter_mid,
-                            (const void *)eicos_iter_tail, (const void *)eicos_store_outputs};
+        const void *ks[] = {(const void *)eicos_load_inputs, (const void *)eicos_init, (const void *)eicos_init_point,
+                            (const void *)eicos_iter_head, (const void *)eicos_iter_mid, (const void *)eicos_iter_tail,
+                            (const void *)eicos_store_outputs};
         for (const void *k : ks)
             EI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_common_));
     }
@@ -404,8 +394,9 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
     a.xrows = P_.sw_slots;
     be::zero(ir_rounds_, 8 * sizeof(unsigned long long), st);
 
-    const int threads = workers_ * (LANES == 1 ? 1 : 32);
+    const int threads = workers_ * (LANES == 1 ? 1 : 32), threads1 = LANES == 1 ? 1 : 32;
     (void)threads;
+    (void)threads1;
 
 #ifndef EICOS_EMU
     // event pool for per-class device timing
@@ -467,7 +458,7 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
 
         auto factor = [&]() {
             a.xrows = xrows_factor_;
-            EI_TIMED(0, EI_LAUNCH(eicos_ldl_factor, tile_factor, tiles, threads, smem_factor_, st, a));
+            EI_TIMED(0, EI_LAUNCH(eicos_ldl_factor, tile_factor, tiles, threads1, smem_factor_, st, a));
             a.xrows = P_.sw_slots;
             stt.factor_launches++;
             stt.factor_launch_tiles += tiles;
@@ -478,7 +469,7 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
             a.variant = rhs == L_.rhs1 ? LDV_SOL1 : LDV_SOL2;
             a.initialize = init;
             a.nitrow = nitrow;
-            EI_TIMED(1, EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt, tiles, threads, smem_common_, st, a));
+            EI_TIMED(1, EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt, tiles, threads1, smem_prog_, st, a));
             stt.solve_launches++;
             stt.solve_launch_tiles += tiles;
         };
@@ -493,6 +484,7 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
         for (int it = 0; it <= Settings::iter_max + 1; it++)
         {
             be::zero(active_count_, sizeof(unsigned int), st);
+            EI_TIMED(2, EI_LAUNCH(eicos_residuals, tile_resid, tiles, threads1, smem_prog_, st, a));
             EI_TIMED(2, EI_LAUNCH(eicos_iter_head, tile_head, tiles, threads, smem_common_, st, a));
             stt.ipm_iterations++;
             be::d2h(host_pinned_, active_count_, sizeof(unsigned int), st);
@@ -620,24 +612,25 @@ void Engine::debug_factor_init(int batch, const double *d_c, const double *d_h, 
     a.nitrow = -1;
     a.xrows = P_.sw_slots;
     const int tiles = (batch + TILE - 1) / TILE;
-    const int threads = workers_ * (LANES == 1 ? 1 : 32);
+    const int threads = workers_ * (LANES == 1 ? 1 : 32), threads1 = LANES == 1 ? 1 : 32;
     (void)threads;
+    (void)threads1;
     EI_LAUNCH(eicos_load_inputs, tile_load, tiles, threads, smem_common_, st, a);
     EI_LAUNCH(eicos_init, tile_init, tiles, threads, smem_common_, st, a);
     a.xrows = xrows_factor_;
-    EI_LAUNCH(eicos_ldl_factor, tile_factor, tiles, threads, smem_factor_, st, a);
+    EI_LAUNCH(eicos_ldl_factor, tile_factor, tiles, threads1, smem_factor_, st, a);
     a.xrows = P_.sw_slots;
     a.rhs = L_.rhs1;
     a.sol = L_.sol1;
     a.variant = LDV_SOL1;
     a.initialize = 1;
     a.nitrow = J_NIT1;
-    EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt, tiles, threads, smem_common_, st, a);
+    EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt, tiles, threads1, smem_prog_, st, a);
     a.rhs = L_.rhs2;
     a.sol = L_.sol2;
     a.variant = LDV_SOL2;
     a.nitrow = J_NIT2;
-    EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt, tiles, threads, smem_common_, st, a);
+    EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt, tiles, threads1, smem_prog_, st, a);
     be::sync(st);
     // gather rows back to instance-major host arrays; L comes back in CSC order
     const size_t tile_doubles = (size_t)L_.rows_total * TILE;

@@ -81,13 +81,13 @@ class Engine
     unsigned int *host_pinned_ = nullptr;
     int *moves_dev_ = nullptr, *status_host_ = nullptr, *moves_host_ = nullptr; // active-set compaction
     bool compaction_ = true;
-    size_t smem_factor_ = 0, smem_common_ = 0;
+    size_t smem_factor_ = 0, smem_common_ = 0, smem_prog_ = 0; // factor kernel / vector kernels / one-warp program kernels
     int xrows_factor_ = 0; // shared-memory rows behind the FIFO ring in the factor kernel (slots + column buffers)
     std::vector<void *> owned_; // device allocations holding pattern data
     // positions of value arrays that upload_values() rewrites
     double *dxeq_ = nullptr, *dAeq_ = nullptr, *dGeq_ = nullptr;
     double *dmv_val_ = nullptr;
-    double *dfa_val_ = nullptr, *drx_val_ = nullptr, *dry_val_ = nullptr, *drz_val_ = nullptr, *drc_val_ = nullptr;
+    double *dfa_val_ = nullptr, *drc_val_ = nullptr;
     HostStreams H_;        // host copy of the instruction streams (value streams are rebuilt on updateData)
     std::vector<int> Lp_;  // column pointers of L (debug extraction)
     std::vector<void *> events_;

@@ -46,7 +46,8 @@ enum ScalarRow : int
     S_RT = S_BEST_END, S_NX, S_NY, S_NZ, S_NS, S_HRESX, S_HRESY, S_HRESZ,
     S_RESX0, S_RESY0, S_RESZ0, S_PRES_PREV,
     S_DTAU_DENOM, S_DTAUAFF, S_DKAPAFF,
-    S_COUNT
+    S_RED,                 // the 14 sums of computeResiduals, handed from eicos_residuals to eicos_iter_head
+    S_COUNT = S_RED + 14
 };
 
 // integer rows
@@ -114,8 +115,8 @@ struct DevPattern
     int fw_nld, bw_nld, fa_nld, mv_nld, mv_rows, sw_slots, fa_slots;
     int sw_direct; // the sweep programs contain operands read straight from global memory
     const double *fa_val;
-    const int *rx, *rx_seg, *ry, *ry_seg, *rz, *rz_seg, *rc, *rc_seg;
-    const double *rx_val, *ry_val, *rz_val, *rc_val;
+    const int *rc, *rc_seg; // second-order-cone rows of G, rc_seg = [cone]{int offset, double offset}
+    const double *rc_val;
     const int *Vkind; // per V entry: what resetKKTScalings writes (0 -> -1, 1 -> 0, 2 -> +1)
 };
 

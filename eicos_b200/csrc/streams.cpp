@@ -30,51 +30,6 @@ void pad_tail(dvec &s)
     s.insert(s.end(), STREAM_PAD, 0.0);
 }
 
-// mat-vec row set for one worker: blocks of rows whose gathers fit the staging slots
-template <class Emit>
-void rowset(int rows, int W, ivec &s, dvec &v, ivec &seg, Emit &&emit)
-{
-    seg.assign((size_t)W * 3, 0);
-    for (int w = 0; w < W; w++)
-    {
-        align_chunk(s);
-        align_chunk(v);
-        seg[w * 3] = (int)s.size();
-        seg[w * 3 + 1] = (int)v.size();
-        int nblocks = 0;
-        std::vector<ivec> rowwords;
-        for (int r = w; r < rows; r += W)
-        {
-            ivec words;
-            emit(r, words, v);
-            rowwords.push_back(std::move(words));
-        }
-        size_t a = 0;
-        while (a < rowwords.size())
-        {
-            int slots = (int)rowwords[a].size() - 1 + ROW_EXTRA_SLOTS;
-            size_t b = a + 1;
-            if (slots > STAGE_SLOTS)
-                s.push_back(-1);
-            else
-            {
-                while (b < rowwords.size() && slots + (int)rowwords[b].size() - 1 + ROW_EXTRA_SLOTS <= STAGE_SLOTS)
-                {
-                    slots += (int)rowwords[b].size() - 1 + ROW_EXTRA_SLOTS;
-                    b++;
-                }
-                s.push_back((int)(b - a));
-            }
-            for (size_t q = a; q < b; q++)
-                s.insert(s.end(), rowwords[q].begin(), rowwords[q].end());
-            nblocks++;
-            a = b;
-        }
-        seg[w * 3 + 2] = nblocks;
-    }
-    pad_tail(s);
-    pad_tail(v);
-}
 // Shared-memory slots for the live ranges of a slot program (linear scan: a value gets a slot when
 // it is first touched and gives it back after its last use; when none is free it lives at home).
 struct SlotPool
@@ -524,53 +479,26 @@ void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, 
     build_factor(S, L, max_fa_slots, H);
     build_matvec(S, L, max_sw_slots, H);
 
-    // ---- mat-vec row sets (K-space gather indices); a row = [cnt, idx...]
-    const int n = S.n, p = S.p, zb = S.n + S.p;
-    rowset(n, W, H.rx, H.rx_val, H.rx_seg, [&](int j, ivec &s, dvec &v) {
-        s.push_back((S.G.p[j + 1] - S.G.p[j]) + (S.A.p[j + 1] - S.A.p[j]));
-        for (int k = S.G.p[j]; k < S.G.p[j + 1]; k++)
-        {
-            s.push_back(zb + S.zk[S.G.i[k]]);
-            v.push_back(S.G.x[k]);
-        }
-        for (int k = S.A.p[j]; k < S.A.p[j + 1]; k++)
-        {
-            s.push_back(n + S.A.i[k]);
-            v.push_back(S.A.x[k]);
-        }
-    });
-    rowset(p, W, H.ry, H.ry_val, H.ry_seg, [&](int i, ivec &s, dvec &v) {
-        s.push_back(S.Ar.p[i + 1] - S.Ar.p[i]);
-        for (int t = S.Ar.p[i]; t < S.Ar.p[i + 1]; t++)
-        {
-            s.push_back(S.Ar.j[t]);
-            v.push_back(S.A.x[S.Ar.v[t]]);
-        }
-    });
-    auto grow = [&](int i, ivec &s, dvec &v) {
-        s.push_back(S.Gr.p[i + 1] - S.Gr.p[i]);
-        for (int t = S.Gr.p[i]; t < S.Gr.p[i + 1]; t++)
-        {
-            s.push_back(S.Gr.j[t]);
-            v.push_back(S.G.x[S.Gr.v[t]]);
-        }
-    };
-    rowset(S.l, W, H.rz, H.rz_val, H.rz_seg, grow);
-    // cones: [dim, first expanded index, first q row] then one row per cone entry (no staging)
-    H.rc_seg.assign((size_t)W * 2, 0);
-    for (int w = 0; w < W; w++)
+    // ---- second-order-cone rows of G (residuals of the cone block are evaluated cone by cone):
+    // per cone [dim, first expanded index, first q row] then one row [cnt, idx...] per cone entry;
+    // rc_seg = [cone]{int offset, double offset}
+    H.rc_seg.assign((size_t)S.nc * 2, 0);
+    for (int c = 0; c < S.nc; c++)
     {
-        align_chunk(H.rc);
-        align_chunk(H.rc_val);
-        H.rc_seg[w * 2] = (int)H.rc.size();
-        H.rc_seg[w * 2 + 1] = (int)H.rc_val.size();
-        for (int c = w; c < S.nc; c += W)
+        H.rc_seg[c * 2] = (int)H.rc.size();
+        H.rc_seg[c * 2 + 1] = (int)H.rc_val.size();
+        H.rc.push_back(S.q[c]);
+        H.rc.push_back(S.cone_k[c]);
+        H.rc.push_back(S.cone_q[c]);
+        for (int k = 0; k < S.q[c]; k++)
         {
-            H.rc.push_back(S.q[c]);
-            H.rc.push_back(S.cone_k[c]);
-            H.rc.push_back(S.cone_q[c]);
-            for (int k = 0; k < S.q[c]; k++)
-                grow(S.cone_z[c] + k, H.rc, H.rc_val);
+            const int i = S.cone_z[c] + k;
+            H.rc.push_back(S.Gr.p[i + 1] - S.Gr.p[i]);
+            for (int t = S.Gr.p[i]; t < S.Gr.p[i + 1]; t++)
+            {
+                H.rc.push_back(S.Gr.j[t]);
+                H.rc_val.push_back(S.G.x[S.Gr.v[t]]);
+            }
         }
     }
     pad_tail(H.rc);
@@ -583,9 +511,6 @@ void refresh_stream_values(const Symbolic &S, const Layout &L, HostStreams &H)
     build_streams(S, L, H.workers, std::max(H.sw_slots, 1), std::max(H.fa_slots, 1), fresh);
     H.fa_val.swap(fresh.fa_val);
     H.mv_val.swap(fresh.mv_val);
-    H.rx_val.swap(fresh.rx_val);
-    H.ry_val.swap(fresh.ry_val);
-    H.rz_val.swap(fresh.rz_val);
     H.rc_val.swap(fresh.rc_val);
 }
 

@@ -34,7 +34,6 @@ namespace eicos
 constexpr int STREAM_CHUNK = 32;  // words per cooperative load
 constexpr int STREAM_PAD = 640;   // readable words after the last used one (the stream readers fetch up to four 128-word chunks ahead)
 constexpr int STAGE_SLOTS = 16;   // rows per staging buffer (one slot = TILE doubles); a worker owns two buffers
-constexpr int ROW_EXTRA_SLOTS = 4; // staging slots a mat-vec row may use besides its gathers
 
 // FIFO of asynchronously loaded rows: a ring of FIFO_SLOTS cp.async groups of FIFO_GROUP rows, of which
 // FIFO_AHEAD are in flight ahead of the group being consumed and one is slack (the host-placed sync
@@ -123,9 +122,9 @@ struct HostStreams
     int sw_slots = 0, fa_slots = 0;
     long long sw_far = 0, sw_direct = 0, fa_home = 0; // operands served by far gathers / direct global loads / home rows (statistics)
     dvec fa_val;
-    // mat-vec row sets: seg = [worker]{int offset, double offset, blocks}
-    ivec rx, rx_seg, ry, ry_seg, rz, rz_seg, rc, rc_seg;
-    dvec rx_val, ry_val, rz_val, rc_val;
+    // second-order-cone rows of G: rc_seg = [cone]{int offset, double offset}
+    ivec rc, rc_seg;
+    dvec rc_val;
 };
 
 // K-space / expanded indexing used by the row sets: x rows [0,n), y rows [n,n+p), z rows

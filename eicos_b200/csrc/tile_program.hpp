@@ -478,83 +478,6 @@ EI_DEV vd row_accumulate(const Team &tm, IStream &is, DStream &ds, const double 
     return v;
 }
 
-// Walks one worker's share of a mat-vec row set (rows first, first+nwk, ...) block by block.
-//   extra(row, k)  -> row offset of the k-th extra operand of `row` (k < NEX), staged with the gathers
-//   finish(row, ex, v) receives the extras and v = init(ex) + sum sign*val*vec[idx]
-template <int NEX, class Extra, class Init, class Finish>
-EI_DEV void rowset_run(const Team &tm, const double *T, const int *stream, const double *vals, const int *seg,
-                       int vec, double sign, Extra extra, Init init, Finish finish)
-{
-    // Two cursors walk the same stream: `isi` issues the loads of block b+1 into the other half of
-    // the staging area while `isc` computes block b (cp.async groups keep the two apart).
-    IStream isi, isc;
-    DStream ds;
-    isi.open(stream + EI_LDG(seg + tm.wk * 3), tm.pl);
-    isc = isi;
-    ds.open(vals + EI_LDG(seg + tm.wk * 3 + 1), tm.pl);
-    const int nblocks = EI_LDG(seg + tm.wk * 3 + 2);
-    int rowi = tm.wk, rowc = tm.wk;
-    const auto issue = [&](int b) { // returns nothing; oversize blocks are not staged
-        double *sp = tm.stage + (size_t)(b & 1) * STAGE_SLOTS * TILE;
-        const int nr = isi.get();
-        if (nr < 0)
-        { // skip the words of the oversize row
-            const int cnt = isi.get();
-            for (int k = 0; k < cnt; k++)
-                (void)isi.get();
-            rowi += tm.nwk;
-        }
-        else
-            for (int t = 0; t < nr; t++, rowi += tm.nwk)
-            {
-                for (int k = 0; k < NEX; k++, sp += TILE)
-                    stage_issue(sp, rowp(tm, T, extra(rowi, k)));
-                const int cnt = isi.get();
-                for (int k = 0; k < cnt; k++, sp += TILE)
-                    stage_issue(sp, rowp(tm, T, vec + isi.get()));
-            }
-        stage_commit();
-    };
-    if (nblocks > 0)
-        issue(0);
-    for (int b = 0; b < nblocks; b++)
-    {
-        if (b + 1 < nblocks)
-        {
-            issue(b + 1);
-            stage_wait_prev();
-        }
-        else
-            stage_wait();
-        const double *sp = tm.stage + (size_t)(b & 1) * STAGE_SLOTS * TILE;
-        const int nr = isc.get();
-        if (nr < 0)
-        { // oversize row: straight from global memory
-            vd ex[NEX > 0 ? NEX : 1];
-            for (int k = 0; k < NEX; k++)
-                ex[k] = vload(rowp(tm, T, extra(rowc, k)));
-            const vd v = row_accumulate(tm, isc, ds, T, vec, init(ex), sign);
-            finish(rowc, ex, v);
-            rowc += tm.nwk;
-            continue;
-        }
-        for (int t = 0; t < nr; t++, rowc += tm.nwk)
-        {
-            vd ex[NEX > 0 ? NEX : 1];
-            for (int k = 0; k < NEX; k++, sp += TILE)
-                ex[k] = vload(sp);
-            vd v = init(ex);
-            const int cnt = isc.get();
-            for (int k = 0; k < cnt; k++, sp += TILE)
-            {
-                (void)isc.get();
-                v += (sign * ds.get()) * vload(sp);
-            }
-            finish(rowc, ex, v);
-        }
-    }
-}
-
 // ------------------------------------------------------------------ W products (src/eicos.cpp:485-507)
 // out = W * in for the instances' current scalings; in/out are z-shaped (expanded) row offsets.
 EI_DEV void cone_scale(const Team &tm, const KArgs &a, double *T, int in, int out, vb write)
@@ -1155,12 +1078,12 @@ EI_DEV vd kkt_residual(const Team &tm, const KArgs &a, double *T, int variant, i
             });
     if (P.nc > 0)
     {
-        IStream is;
-        DStream ds;
-        is.open(P.rc + EI_LDG(P.rc_seg + tm.wk * 2), tm.pl);
-        ds.open(P.rc_val + EI_LDG(P.rc_seg + tm.wk * 2 + 1), tm.pl);
         for (int c = tm.wk; c < P.nc; c += tm.nwk)
         {
+            IStream is;
+            DStream ds;
+            is.open(P.rc + EI_LDG(P.rc_seg + c * 2), tm.pl);
+            ds.open(P.rc_val + EI_LDG(P.rc_seg + c * 2 + 1), tm.pl);
             const int d = is.get(), ks = is.get(), qo = is.get();
             const int kb = zb + ks; // KKT row of the cone's first entry
             const int cp = L.cpar + c * CP_COUNT;
@@ -1563,11 +1486,10 @@ EI_DEV ConeScaling cone_scaling(const Team &tm, const double *T, int srow, int z
     return r;
 }
 
-// ------------------------------------------------------------------ head of an iteration
-// computeResiduals + updateStatistics + safeguards / exit tests + best-iterate bookkeeping
-// (src/eicos.cpp:997-1158), then for the instances that keep iterating: updateScalings,
-// updateKKTScalings and RHSaffine (:1160-1162, :1176).  Instances that stop are back-scaled in place.
-EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
+// ------------------------------------------------------------------ computeResiduals (src/eicos.cpp:643-689)
+// rx = -A'y - G'z, ry = A x, rz = s + G x (each before and after the tau terms) and the sums the
+// statistics need; one warp per tile (KKT mat-vec program), results in `r` and the S_RED rows.
+EI_DEV void tile_resid(const Team &tm, const KArgs &a, int tile)
 {
     const TileMem t = tile_mem(tm, a, tile);
     const vb act = lane_active(tm, t);
@@ -1625,12 +1547,12 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
             });
     if (P.nc > 0)
     {
-        IStream is;
-        DStream ds;
-        is.open(P.rc + EI_LDG(P.rc_seg + tm.wk * 2), tm.pl);
-        ds.open(P.rc_val + EI_LDG(P.rc_seg + tm.wk * 2 + 1), tm.pl);
         for (int c = tm.wk; c < P.nc; c += tm.nwk)
         {
+            IStream is;
+            DStream ds;
+            is.open(P.rc + EI_LDG(P.rc_seg + c * 2), tm.pl);
+            ds.open(P.rc_val + EI_LDG(P.rc_seg + c * 2 + 1), tm.pl);
             const int d = is.get(), ks = is.get();
             (void)is.get();
             for (int k = 0; k < d; k++)
@@ -1642,6 +1564,32 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
         }
     }
     team_sum<NRED>(tm, r);
+    if (tm.wk == 0)
+        for (int k = 0; k < NRED; k++)
+            ROWD(T, L.sc + S_RED + k) = r[k];
+}
+
+// ------------------------------------------------------------------ head of an iteration
+// computeResiduals + updateStatistics + safeguards / exit tests + best-iterate bookkeeping
+// (src/eicos.cpp:997-1158), then for the instances that keep iterating: updateScalings,
+// updateKKTScalings and RHSaffine (:1160-1162, :1176).  Instances that stop are back-scaled in place.
+EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
+{
+    const TileMem t = tile_mem(tm, a, tile);
+    const vb act = lane_active(tm, t);
+    if (!tm.any(act))
+        return;
+    const DevPattern &P = a.P;
+    const Layout &L = a.L;
+    double *T = t.T;
+    int *I = t.I;
+    const int n = P.n, p = P.p, zb = P.n + P.p;
+    const vd tau = ROWD(T, L.sc + S_TAU), kap = ROWD(T, L.sc + S_KAP);
+    enum { HX2, RX2, CX, NX2, HY2, RY2, BY, NY2, HZ2, RZ2, HZ, NZ2, NS2, GAP, NRED };
+    static_assert(NRED == 14, "S_RED holds 14 rows");
+    vd r[NRED];
+    for (int k = 0; k < NRED; k++)
+        r[k] = ROWD(T, L.sc + S_RED + k);
 
     // ---- per instance: updateStatistics (:691-728), safeguards, exit tests, best iterate (:1010-1158).
     //      Every warp computes the same values; warp 0 writes them back.
