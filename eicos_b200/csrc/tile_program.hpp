@@ -672,6 +672,29 @@ struct PStream
     }
 };
 #endif
+// word-at-a-time views of a program stream (factor program)
+struct WStream
+{
+    PStream ps;
+    i4 cur;
+    int k;
+    EI_DEV void open(const Team &tm, const void *base, int stream)
+    {
+        ps.open(tm, base, stream);
+        k = 4;
+    }
+    EI_DEV int get()
+    {
+        if (k == 4)
+        {
+            cur = ps.get();
+            k = 0;
+        }
+        const int w = k == 0 ? cur.x : (k == 1 ? cur.y : (k == 2 ? cur.z : cur.w));
+        k++;
+        return w;
+    }
+};
 EI_DEV d2 as_d2(i4 r)
 {
 #ifdef EICOS_EMU
@@ -682,6 +705,29 @@ EI_DEV d2 as_d2(i4 r)
     return d2{__hiloint2double(r.y, r.x), __hiloint2double(r.w, r.z)};
 #endif
 }
+
+struct DWStream
+{
+    PStream ps;
+    d2 cur;
+    int k;
+    EI_DEV void open(const Team &tm, const void *base, int stream)
+    {
+        ps.open(tm, base, stream);
+        k = 2;
+    }
+    EI_DEV double get()
+    {
+        if (k == 2)
+        {
+            cur = as_d2(ps.get());
+            k = 0;
+        }
+        const double v = k == 0 ? cur.x : cur.y;
+        k++;
+        return v;
+    }
+};
 
 // ------------------------------------------------------------------ FIFO of asynchronously loaded rows
 // Every global read of the factorisation and of the sweeps is known to the host in consumption
@@ -787,11 +833,11 @@ EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
     double *colA = a.acc_global ? a.acc_global + (size_t)tile * 2 * P.maxcol * TILE + tm.lane : tm.extra + (size_t)P.fa_slots * TILE;
     double *colL = colA + (size_t)P.maxcol * TILE;
     vb zero_pivot = vbset(false);
-    IStream is;
-    DStream ds;
+    WStream is;
+    DWStream ds;
     Fifo ff;
-    is.open(P.fa, tm.pl);
-    ds.open(P.fa_val, tm.pl);
+    is.open(tm, P.fa, 1);
+    ds.open(tm, P.fa_val, 2);
     ff.open(tm, P.fa_ld, P.fa_nld, T, 0);
     ff.tail = 0;
     const auto fetch = [&](int src) -> vd {
