@@ -194,6 +194,7 @@ void Engine::upload_pattern(const Symbolic &S)
     P.sw_slots = H_.sw_slots + 1; // rows behind the ring: the zero row, then the slots
     P.fa_slots = H_.fa_slots;
     P.sw_direct = H_.sw_direct > 0 ? 1 : 0;
+    P.fa_fast = H_.fa_fast;
     P.cone_dim = upload(S.q, owned_, st);
     P.cone_k = upload(S.cone_k, owned_, st);
     P.cone_q = upload(S.cone_q, owned_, st);
@@ -289,9 +290,9 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
     const size_t smem_base = ((size_t)2 * STAGE_SLOTS * TILE + PS_DOUBLES) * sizeof(double);
     smem_prog_ = smem_base + (size_t)P_.sw_slots * TILE * sizeof(double);
     smem_common_ = workers_ > 1 ? (size_t)workers_ * KRED * TILE * sizeof(double) : 0;
-    xrows_factor_ = H_.fa_slots + 2 * S.maxcol;
+    xrows_factor_ = H_.fa_slots + (H_.fa_fast ? 0 : 2 * S.maxcol); // record form keeps the column in registers
 #ifndef EICOS_EMU
-    if (2 * S.maxcol > MAX_COLBUF_ROWS)
+    if (!H_.fa_fast && 2 * S.maxcol > MAX_COLBUF_ROWS)
     { // the column buffers of the factorisation spill to global memory (one slab per tile)
         acc_global_ = (double *)be::alloc((size_t)cap_tiles_ * 2 * S.maxcol * TILE * sizeof(double));
         xrows_factor_ = H_.fa_slots;

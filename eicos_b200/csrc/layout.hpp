@@ -114,6 +114,7 @@ struct DevPattern
     const double *mv_val;
     int fw_nld, bw_nld, fa_nld, mv_nld, mv_rows, sw_slots, fa_slots;
     int sw_direct; // the sweep programs contain operands read straight from global memory
+    int fa_fast;   // the factor program is in record form (streams.hpp)
     const double *fa_val;
     const int *rc, *rc_seg; // second-order-cone rows of G, rc_seg = [cone]{int offset, double offset}
     const double *rc_val;

@@ -464,6 +464,152 @@ void build_factor(const Symbolic &S, const Layout &L, int max_slots, HostStreams
     pad_tail(H.fa_ld);
     pad_tail(H.fa_val);
 }
+// ---- numeric factorisation in record form (streams.hpp); same right-looking algorithm and the
+// same arithmetic as build_factor, but every operand is a shared-memory row known to the host.
+// Returns false (leaving H untouched) when the pattern does not qualify.
+bool build_factor_fast(const Symbolic &S, const Layout &L, int max_slots, HostStreams &H)
+{
+    if (S.maxcol > FA_FAST_COL)
+        return false;
+    struct Init
+    {
+        int kind = FA_ZERO, vrow = -1;
+        double c = 0.0;
+    };
+    std::vector<Init> di(S.N), ei(S.nnzL);
+    for (int j = 0; j < S.N; j++)
+        for (int e = S.KLp[j]; e < S.KLp[j + 1]; e++)
+        {
+            const int slot = S.KLslot[e], vi = S.Kvidx[slot], pos = S.KLpos[e];
+            Init &t = pos < 0 ? di[j] : ei[S.Lp[j] + pos];
+            if (vi >= 0)
+            {
+                t.kind = FA_ROW;
+                t.vrow = L.V + vi;
+            }
+            else
+            {
+                t.kind = FA_CONST;
+                t.c = S.Kshared[slot];
+            }
+        }
+    ivec ops, ld;
+    dvec val;
+    SlotPool pool(max_slots);
+    FifoSim F(ld);
+    ivec dcode(S.N, -1), ecode(S.nnzL, -1); // slot of a touched accumulator
+    const int slot0 = FIFO_ROWS;
+    const auto source = [&](int code, const Init &t) {
+        if (code >= 0)
+            return slot0 + code;
+        if (t.kind == FA_ROW)
+            return F.pop(0, t.vrow);
+        if (t.kind == FA_CONST)
+        {
+            val.push_back(t.c);
+            return FA_CONST << FA_KIND_SHIFT;
+        }
+        return FA_ZERO << FA_KIND_SHIFT;
+    };
+    bool ok = true;
+    const auto target = [&](int &code, const Init &t, int home_row) {
+        if (code >= 0)
+            return (slot0 + code) | ((slot0 + code) << 8);
+        code = pool.take(home_row);
+        if (code >= SLOT_HOME)
+        {
+            ok = false;
+            return 0;
+        }
+        const int row = slot0 + code;
+        if (t.kind == FA_ROW)
+            return row | (F.pop(0, t.vrow) << 8);
+        if (t.kind == FA_CONST)
+        {
+            val.push_back(t.c);
+            return row | (FA_CONST << FA_KIND_SHIFT);
+        }
+        return row | (FA_ZERO << FA_KIND_SHIFT);
+    };
+    // a record = 4 words whose pops start at `first`
+    const auto close_record = [&](size_t at, int first) {
+        if (FifoSim::crosses(first, F.npop - first))
+            ops[at] |= FA_SYNC;
+    };
+    for (int k = 0; k < S.N && ok; k++)
+    {
+        const int u0 = S.Lp[k], cnt = S.Lp[k + 1] - u0;
+        int first = F.npop;
+        size_t at = ops.size();
+        ops.push_back(source(dcode[k], di[k]));
+        ops.push_back(cnt);
+        for (int e = 0; e < 2; e++)
+            ops.push_back(e < cnt ? source(ecode[u0 + e], ei[u0 + e]) : 0);
+        close_record(at, first);
+        if (cnt > 2)
+        {
+            first = F.npop;
+            at = ops.size();
+            for (int e = 2; e < 4; e++)
+                ops.push_back(e < cnt ? source(ecode[u0 + e], ei[u0 + e]) : 0);
+            ops.push_back(0);
+            ops.push_back(0);
+            close_record(at, first);
+        }
+        int inrec = 0;
+        for (int e1 = 0; e1 < cnt && ok; e1++)
+        {
+            const int i1 = S.Li[u0 + e1];
+            for (int e2 = 0; e2 <= e1 && ok; e2++)
+            {
+                if (inrec == 0)
+                {
+                    first = F.npop;
+                    at = ops.size();
+                }
+                if (e2 < e1)
+                {
+                    const int i2 = S.Li[u0 + e2];
+                    const int *b = S.Li.data() + S.Lp[i2], *e = S.Li.data() + S.Lp[i2 + 1];
+                    const int *f = std::lower_bound(b, e, i1);
+                    if (f == e || *f != i1)
+                        throw std::logic_error("factor program: update outside the pattern of L");
+                    const int ut = (int)(f - S.Li.data());
+                    ops.push_back(target(ecode[ut], ei[ut], L.Lx + ut));
+                }
+                else
+                    ops.push_back(target(dcode[i1], di[i1], L.D + i1));
+                if (++inrec == 4)
+                {
+                    close_record(at, first);
+                    inrec = 0;
+                }
+            }
+        }
+        if (inrec > 0)
+        {
+            while (inrec++ < 4)
+                ops.push_back(0);
+            close_record(at, first);
+        }
+        pool.give(dcode[k]);
+        for (int e = 0; e < cnt; e++)
+            pool.give(ecode[u0 + e]);
+    }
+    if (!ok || slot0 + pool.top > 255)
+        return false;
+    H.fa.swap(ops);
+    H.fa_ld.swap(ld);
+    H.fa_val.swap(val);
+    H.fa_nld = (int)H.fa_ld.size();
+    H.fa_slots = pool.top;
+    H.fa_home = 0;
+    H.fa_fast = 1;
+    pad_tail(H.fa);
+    pad_tail(H.fa_ld);
+    pad_tail(H.fa_val);
+    return true;
+}
 } // namespace
 
 void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, int max_fa_slots, HostStreams &H)
@@ -476,7 +622,8 @@ void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, 
                 throw std::logic_error("columns of L must have ascending rows");
     build_forward(S, L, max_sw_slots, H);
     build_backward(S, L, max_sw_slots, H);
-    build_factor(S, L, max_fa_slots, H);
+    if (!build_factor_fast(S, L, max_fa_slots, H))
+        build_factor(S, L, max_fa_slots, H);
     build_matvec(S, L, max_sw_slots, H);
 
     // ---- second-order-cone rows of G (residuals of the cone block are evaluated cone by cone):

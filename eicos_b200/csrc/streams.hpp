@@ -96,7 +96,27 @@ enum MvKind : int
     MV_Z = 2  // LP row of the z block: G x
 };
 
-// ---- factorisation: operand codes.  code < SLOT_HOME is a shared-memory slot, anything else the
+// ---- factorisation, record form (patterns whose columns of L have at most FA_FAST_COL entries and
+// whose live accumulators all fit the slots - e.g. MPC problems): 16-byte records, shared-memory rows
+// named directly (ring row of a scaling value, slot of an accumulator), Schur updates unrolled on
+// the device with the column in registers.
+//   step k: [source of d, number of entries, source 0, source 1] [source 2, source 3, -, -] (if > 2 entries)
+//           then the targets of the pairs (e1, e2 <= e1) in order, four per record
+//   source word: row | kind << FA_KIND_SHIFT | FA_SYNC     kind: FA_ROW (read the row), FA_ZERO, FA_CONST (next coefficient)
+//   target word: accumulator row | start row << 8 | kind << FA_KIND_SHIFT | FA_SYNC
+//                (start row = the accumulator itself, or the ring row of the scaling value it starts from)
+//   FA_SYNC on the first word of a record covers the pops of that record.
+constexpr int FA_FAST_COL = 4;
+constexpr int FA_KIND_SHIFT = 16;
+constexpr int FA_SYNC = 1 << 30;
+enum FaKind : int
+{
+    FA_ROW = 0,
+    FA_ZERO = 1,
+    FA_CONST = 2
+};
+
+// ---- factorisation, general form: operand codes.  code < SLOT_HOME is a shared-memory slot, anything else the
 // home row (code - SLOT_HOME, relative to the tile base).  Bits 28..29 of a TARGET word say how the
 // accumulator starts on its first touch.
 constexpr int SLOT_HOME = 1 << 16;
@@ -120,6 +140,7 @@ struct HostStreams
     int fw_nld = 0, bw_nld = 0, fa_nld = 0, mv_nld = 0, mv_rows = 0;
     dvec mv_val;
     int sw_slots = 0, fa_slots = 0;
+    int fa_fast = 0; // the factor program is in record form
     long long sw_far = 0, sw_direct = 0, fa_home = 0; // operands served by far gathers / direct global loads / home rows (statistics)
     dvec fa_val;
     // second-order-cone rows of G: rc_seg = [cone]{int offset, double offset}

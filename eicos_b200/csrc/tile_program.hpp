@@ -811,6 +811,115 @@ EI_DEV double *opnd(double *slots, double *home, int code)
     return code < SLOT_HOME ? slots + (size_t)code * TILE : home + (size_t)(code - SLOT_HOME) * TILE;
 }
 
+// ------------------------------------------------------------------ numeric LDL', record form (streams.hpp: FA_*)
+// Columns of at most FA_FAST_COL entries: the column lives in registers, the Schur updates are
+// unrolled, every operand is a shared-memory row named by the program.
+EI_DEV void tile_factor_fast(const Team &tm, const KArgs &a, const TileMem &t, vb act)
+{
+    const DevPattern &P = a.P;
+    const Layout &L = a.L;
+    double *T = t.T;
+    const smem_t sm = smem_of(tm.stage); // ring rows, then the slots
+    vb zero_pivot = vbset(false);
+    PStream ops;
+    DWStream ds;
+    Fifo ff;
+    ops.open(tm, P.fa, 1);
+    ds.open(tm, P.fa_val, 2);
+    ff.open(tm, P.fa_ld, P.fa_nld, T, 0);
+    const auto src = [&](int w) -> vd {
+        const int kind = (w >> FA_KIND_SHIFT) & 3;
+        if (kind == FA_ROW)
+            return sm_load(sm, w & 0xff);
+        return vset(kind == FA_CONST ? ds.get() : 0.0);
+    };
+    const auto upd = [&](int w, vd l2, vd a1) {
+        const int kind = (w >> FA_KIND_SHIFT) & 3;
+        vd init;
+        if (kind == FA_ROW)
+            init = sm_load(sm, (w >> 8) & 0xff);
+        else
+            init = vset(kind == FA_CONST ? ds.get() : 0.0);
+        sm_store(sm, w & 0xff, init - l2 * a1);
+    };
+    double *Dp = T + (size_t)L.D * TILE, *Lp = T + (size_t)L.Lx * TILE;
+    const size_t dinv_off = (size_t)(L.Dinv - L.D) * TILE;
+    for (int k = 0; k < P.N; k++, Dp += TILE)
+    {
+        const i4 r0 = ops.get();
+        if (r0.x & FA_SYNC)
+            ff.sync();
+        const int cnt = r0.y;
+        const vd d = src(r0.x);
+        const vd rd = 1.0 / d;
+        vstore(Dp, d);
+        vstore(Dp + dinv_off, rd);
+        VFOR zero_pivot.v[c_] = zero_pivot.v[c_] || (d.v[c_] == 0.0);
+        if (cnt == 0)
+            continue;
+        vd av[FA_FAST_COL], lv[FA_FAST_COL];
+        av[0] = src(r0.z);
+        lv[0] = av[0] / d;
+        vstore(Lp, lv[0]);
+        Lp += TILE;
+        if (cnt > 1)
+        {
+            av[1] = src(r0.w);
+            lv[1] = av[1] / d;
+            vstore(Lp, lv[1]);
+            Lp += TILE;
+        }
+        if (cnt > 2)
+        {
+            const i4 r1 = ops.get();
+            if (r1.x & FA_SYNC)
+                ff.sync();
+            av[2] = src(r1.x);
+            lv[2] = av[2] / d;
+            vstore(Lp, lv[2]);
+            Lp += TILE;
+            if (cnt > 3)
+            {
+                av[3] = src(r1.y);
+                lv[3] = av[3] / d;
+                vstore(Lp, lv[3]);
+                Lp += TILE;
+            }
+        }
+        // Schur updates, pairs (e1, e2 <= e1) in order: acc(i1, i2) -= l(i2) * a(i1)
+        const i4 t0 = ops.get();
+        if (t0.x & FA_SYNC)
+            ff.sync();
+        upd(t0.x, lv[0], av[0]);
+        if (cnt > 1)
+        {
+            upd(t0.y, lv[0], av[1]);
+            upd(t0.z, lv[1], av[1]);
+            if (cnt > 2)
+            {
+                upd(t0.w, lv[0], av[2]);
+                const i4 t1 = ops.get();
+                if (t1.x & FA_SYNC)
+                    ff.sync();
+                upd(t1.x, lv[1], av[2]);
+                upd(t1.y, lv[2], av[2]);
+                if (cnt > 3)
+                {
+                    upd(t1.z, lv[0], av[3]);
+                    upd(t1.w, lv[1], av[3]);
+                    const i4 t2 = ops.get();
+                    if (t2.x & FA_SYNC)
+                        ff.sync();
+                    upd(t2.x, lv[2], av[3]);
+                    upd(t2.y, lv[3], av[3]);
+                }
+            }
+        }
+    }
+    ff.close();
+    VFOR if (zero_pivot.v[c_] && act.v[c_]) ROWC(t.I, J_STATUS, c_) = EXIT_FATAL;
+}
+
 // ------------------------------------------------------------------ numeric LDL' (Eigen factorize, src/eicos.cpp:900,1164)
 // Right-looking in elimination order, one warp per tile, driven by the factor program
 // (streams.cpp: build_factor).  Step k takes the finished accumulators of column k, writes the pivot
@@ -826,6 +935,11 @@ EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
         return;
     if (tm.wk != 0)
         return;
+    if (a.P.fa_fast)
+    {
+        tile_factor_fast(tm, a, t, act);
+        return;
+    }
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     double *T = t.T;
