@@ -859,13 +859,13 @@ EI_DEV void tile_factor_fast(const Team &tm, const KArgs &a, const TileMem &t, v
             continue;
         vd av[FA_FAST_COL], lv[FA_FAST_COL];
         av[0] = src(r0.z);
-        lv[0] = av[0] / d;
+        lv[0] = av[0] * rd;
         vstore(Lp, lv[0]);
         Lp += TILE;
         if (cnt > 1)
         {
             av[1] = src(r0.w);
-            lv[1] = av[1] / d;
+            lv[1] = av[1] * rd;
             vstore(Lp, lv[1]);
             Lp += TILE;
         }
@@ -875,13 +875,13 @@ EI_DEV void tile_factor_fast(const Team &tm, const KArgs &a, const TileMem &t, v
             if (r1.x & FA_SYNC)
                 ff.sync();
             av[2] = src(r1.x);
-            lv[2] = av[2] / d;
+            lv[2] = av[2] * rd;
             vstore(Lp, lv[2]);
             Lp += TILE;
             if (cnt > 3)
             {
                 av[3] = src(r1.y);
-                lv[3] = av[3] / d;
+                lv[3] = av[3] * rd;
                 vstore(Lp, lv[3]);
                 Lp += TILE;
             }
