@@ -480,10 +480,11 @@ EI_DEV vd row_accumulate(const Team &tm, IStream &is, DStream &ds, const double 
 
 // ------------------------------------------------------------------ W products (src/eicos.cpp:485-507)
 // out = W * in for the instances' current scalings; in/out are z-shaped (expanded) row offsets.
-EI_DEV void cone_scale(const Team &tm, const KArgs &a, double *T, int in, int out, vb write)
+EI_DEV void cone_scale(const Team &tm, const KArgs &a, double *T, int in, int out, vb write, bool lp = true)
 {
     const DevPattern &P = a.P;
     const Layout &L = a.L;
+    if (lp)
     {
         const int ins[3] = {L.lpw, in, out};
         ew_rows<3, 4>(tm, T, P.l, ins, [&](int k, const vd *x) { ROWD(T, out + k) = vsel(write, x[0] * x[1], x[2]); });
@@ -513,11 +514,13 @@ EI_DEV void cone_scale(const Team &tm, const KArgs &a, double *T, int in, int ou
 // lambda, ds, dz are z-shaped row offsets.  Returns the clamped step for every instance.
 // TODO(parity): the reference's `continue` on lknorm2<=0 skips the cone offset advance; here later
 // cones keep their own offsets (differs only after lambda has already left the cone).
+// lp = false: the caller has already folded the LP rows into m0 = min ds/lambda, m1 = min dz/lambda.
 EI_DEV vd line_search(const Team &tm, const KArgs &a, double *T, int lam, int ds, int dz,
-                      vd tau, vd dtau, vd kap, vd dkap)
+                      vd tau, vd dtau, vd kap, vd dkap, bool lp = true, vd m0 = vset(DBL_MAX), vd m1 = vset(DBL_MAX))
 {
     const DevPattern &P = a.P;
-    vd mn[3] = {vset(DBL_MAX), vset(DBL_MAX), vset(DBL_MAX)}; // rhomin, sigmamin, min over cones of 1/conic_step
+    vd mn[3] = {m0, m1, vset(DBL_MAX)}; // rhomin, sigmamin, min over cones of 1/conic_step
+    if (lp)
     {
         const int ins[3] = {lam, ds, dz};
         ew_rows<3, 4>(tm, T, P.l, ins, [&](int, const vd *x) {
@@ -1887,7 +1890,18 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
         }
 
     // ---- vector part of `w = w_best` / `w_best = w`, and backscale (:1271-1277) for finished instances
-    if (tm.any(restore || save || fin))
+    if (!tm.any(restore || fin) && tm.all(save || !act))
+    { // common case: every active instance improves its best iterate and nobody stops -> plain copies
+        // (inactive lanes of w_best are never read again)
+        const int ins[1] = {L.w};
+        ew_rows<1, 8>(tm, T, P.N, ins, [&](int q, const vd *x) { ROWD(T, L.wb + q) = x[0]; });
+        const int inz[2] = {L.s, L.lam};
+        ew_rows<2, 6>(tm, T, P.mt, inz, [&](int e, const vd *x) {
+            ROWD(T, L.bs + e) = x[0];
+            ROWD(T, L.blam + e) = x[1];
+        });
+    }
+    else if (tm.any(restore || save || fin))
     {
         const bool any_fin = tm.any(fin);
         {
@@ -1937,6 +1951,33 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
     // ---- updateScalings (:411-479); its return value is ignored by the caller (:1160), so after a
     // failure at cone c the LP part and cones < c are new, cone c is partly new and lambda is stale.
     const int sz = L.w + zb; // z rows of the iterate
+    const bool lp_only = P.nc == 0; // then lambda = W z is folded into the LP pass
+    if (lp_only && tm.all(cont))
+    {
+        const int ins[2] = {L.s, sz};
+        ew_rows<2, 6>(tm, T, P.l, ins, [&](int k, const vd *x) {
+            const vd v = x[0] / x[1];
+            const vd w = vsqrt(v);
+            ROWD(T, L.lpv + k) = v;
+            ROWD(T, L.lpw + k) = w;
+            ROWD(T, L.V + k) = -v - Settings::deltastat; // updateKKTScalings, LP part (:1696-1699)
+            ROWD(T, L.lam + k) = w * x[1];                // scale(): lambda = W z
+        });
+    }
+    else if (lp_only)
+    {
+        const int ins[5] = {L.s, sz, L.lpv, L.lpw, L.lam};
+        ew_rows<5, 2>(tm, T, P.l, ins, [&](int k, const vd *x) {
+            const vd v = x[0] / x[1];
+            const vd vn = vsel(cont, v, x[2]);
+            const vd wn = vsel(cont, vsqrt(v), x[3]);
+            ROWD(T, L.lpv + k) = vn;
+            ROWD(T, L.lpw + k) = wn;
+            ROWD(T, L.V + k) = -vn - Settings::deltastat;
+            ROWD(T, L.lam + k) = vsel(cont, wn * x[1], x[4]);
+        });
+    }
+    else
     {
         const int ins[4] = {L.s, sz, L.lpv, L.lpw};
         ew_rows<4, 3>(tm, T, P.l, ins, [&](int k, const vd *x) {
@@ -1990,7 +2031,8 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
         }
     }
     tm.sync(); // scalings complete (rows are distributed differently in the passes below)
-    cone_scale(tm, a, T, sz, L.lam, cont && nofail);
+    if (!lp_only)
+        cone_scale(tm, a, T, sz, L.lam, cont && nofail);
 
     // ---- updateKKTScalings (:1691-1732) into the V rows, RHSaffine (:1670-1689) into rhs2
     const double delta = Settings::deltastat;
@@ -2070,20 +2112,35 @@ EI_DEV void tile_mid(const Team &tm, const KArgs &a, int tile)
     team_sum<6>(tm, dt);
     const vd dtau_denom = kap / tau - dt[0] - dt[1] - dt[2];
     const vd dtauaff = (rt - kap + dt[3] + dt[4] + dt[5]) / dtau_denom;
+    // LP rows in one pass: dz2 += dtauaff * dz1, W dz, ds = -(W dz) - lambda, min ratios of the line search
+    vd m0 = vset(DBL_MAX), m1 = vset(DBL_MAX);
     {
-        const int ins[2] = {L.sol2 + zb, L.sol1 + zb}; // dz2 += dtauaff * dz1 (slot rows are never read again)
-        ew_rows<2, 6>(tm, T, P.mt, ins, [&](int e, const vd *x) { ROWD(T, L.sol2 + zb + e) = x[0] + dtauaff * x[1]; });
+        const int ins[4] = {L.sol2 + zb, L.sol1 + zb, L.lpw, L.lam};
+        ew_rows<4, 3>(tm, T, P.l, ins, [&](int k, const vd *x) {
+            const vd dz = x[0] + dtauaff * x[1];
+            const vd wd = x[2] * dz;
+            const vd ds = -wd - x[3];
+            ROWD(T, L.sol2 + zb + k) = dz;
+            ROWD(T, L.wdz + k) = wd;
+            ROWD(T, L.dsw + k) = ds;
+            m0 = vmin(m0, ds / x[3]);
+            m1 = vmin(m1, wd / x[3]);
+        });
     }
-    tm.sync();
-    cone_scale(tm, a, T, L.sol2 + zb, L.wdz, vbset(true));
-    tm.sync();
-    {
-        const int ins[2] = {L.wdz, L.lam};
-        ew_rows<2, 6>(tm, T, P.mt, ins, [&](int e, const vd *x) { ROWD(T, L.dsw + e) = -x[0] - x[1]; });
+    if (P.mt > P.l)
+    { // cone rows: the same steps, pass by pass (slot rows are never read again)
+        const int cz = zb + P.l, nr = P.mt - P.l;
+        const int ins[2] = {L.sol2 + cz, L.sol1 + cz};
+        ew_rows<2, 6>(tm, T, nr, ins, [&](int e, const vd *x) { ROWD(T, L.sol2 + cz + e) = x[0] + dtauaff * x[1]; });
+        tm.sync();
+        cone_scale(tm, a, T, L.sol2 + zb, L.wdz, vbset(true), false);
+        tm.sync();
+        const int in2[2] = {L.wdz + P.l, L.lam + P.l};
+        ew_rows<2, 6>(tm, T, nr, in2, [&](int e, const vd *x) { ROWD(T, L.dsw + P.l + e) = -x[0] - x[1]; });
+        tm.sync();
     }
-    tm.sync();
     const vd dkapaff = -kap - kap / tau * dtauaff;
-    const vd step_aff = line_search(tm, a, T, L.lam, L.dsw, L.wdz, tau, dtauaff, kap, dkapaff);
+    const vd step_aff = line_search(tm, a, T, L.lam, L.dsw, L.wdz, tau, dtauaff, kap, dkapaff, false, m0, m1);
     vd sigma;
     VFOR
     {
@@ -2210,23 +2267,50 @@ EI_DEV void tile_tail(const Team &tm, const KArgs &a, int tile)
     const vd dtau = ((1. - sigma) * rt - bkap / tau + dt[0] + dt[1] + dt[2]) / dtau_denom;
     {
         const int ins[2] = {L.sol2, L.sol1};
-        ew_rows<2, 6>(tm, T, P.N, ins, [&](int r, const vd *x) { ROWD(T, L.sol2 + r) = x[0] + dtau * x[1]; });
+        ew_rows<2, 6>(tm, T, zb, ins, [&](int r, const vd *x) { ROWD(T, L.sol2 + r) = x[0] + dtau * x[1]; });
     }
-    tm.sync();
-    cone_scale(tm, a, T, L.sol2 + zb, L.wdz, vbset(true));
-    tm.sync();
+    // LP rows in one pass: dz += dtau * dz1, W dz, ds = -(ds + W dz), min ratios of the line search
+    vd m0 = vset(DBL_MAX), m1 = vset(DBL_MAX);
     {
-        const int ins[2] = {L.dsw, L.wdz};
-        ew_rows<2, 6>(tm, T, P.mt, ins, [&](int e, const vd *x) { ROWD(T, L.dsw + e) = -(x[0] + x[1]); });
+        const int ins[5] = {L.sol2 + zb, L.sol1 + zb, L.lpw, L.dsw, L.lam};
+        ew_rows<5, 2>(tm, T, P.l, ins, [&](int k, const vd *x) {
+            const vd dz = x[0] + dtau * x[1];
+            const vd wd = x[2] * dz;
+            const vd ds = -(x[3] + wd);
+            ROWD(T, L.sol2 + zb + k) = dz;
+            ROWD(T, L.dsw + k) = ds;
+            m0 = vmin(m0, ds / x[4]);
+            m1 = vmin(m1, wd / x[4]);
+        });
     }
-    tm.sync();
+    if (P.mt > P.l)
+    { // cone rows: pass by pass
+        const int cz = zb + P.l, nr = P.mt - P.l;
+        const int ins[2] = {L.sol2 + cz, L.sol1 + cz};
+        ew_rows<2, 6>(tm, T, nr, ins, [&](int e, const vd *x) { ROWD(T, L.sol2 + cz + e) = x[0] + dtau * x[1]; });
+        tm.sync();
+        cone_scale(tm, a, T, L.sol2 + zb, L.wdz, vbset(true), false);
+        tm.sync();
+        const int in2[2] = {L.dsw + P.l, L.wdz + P.l};
+        ew_rows<2, 6>(tm, T, nr, in2, [&](int e, const vd *x) { ROWD(T, L.dsw + P.l + e) = -(x[0] + x[1]); });
+        tm.sync();
+    }
     const vd dkap = -(bkap + kap * dtau) / tau;
-    const vd step = Settings::gamma * line_search(tm, a, T, L.lam, L.dsw, L.wdz, tau, dtau, kap, dkap);
-    cone_scale(tm, a, T, L.dsw, L.dsaff, vbset(true));
-    tm.sync();
+    const vd step = Settings::gamma * line_search(tm, a, T, L.lam, L.dsw, L.wdz, tau, dtau, kap, dkap, false, m0, m1);
+    if (P.mt > P.l)
+    {
+        cone_scale(tm, a, T, L.dsw, L.dsaff, vbset(true), false);
+        tm.sync();
+    }
     {
         const int ins[2] = {L.w, L.sol2};
-        ew_rows<2, 6>(tm, T, zb + P.l, ins, [&](int q, const vd *x) { ROWD(T, L.w + q) = vsel(act, x[0] + step * x[1], x[0]); });
+        ew_rows<2, 6>(tm, T, zb, ins, [&](int q, const vd *x) { ROWD(T, L.w + q) = vsel(act, x[0] + step * x[1], x[0]); });
+        // LP rows: z += step * dz and s += step * (W ds) in one pass
+        const int inl[5] = {L.w + zb, L.sol2 + zb, L.s, L.lpw, L.dsw};
+        ew_rows<5, 2>(tm, T, P.l, inl, [&](int k, const vd *x) {
+            ROWD(T, L.w + zb + k) = vsel(act, x[0] + step * x[1], x[0]);
+            ROWD(T, L.s + k) = vsel(act, x[2] + step * (x[3] * x[4]), x[2]);
+        });
     }
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     { // cone rows of z; the expansion slots of the iterate stay zero
@@ -2234,9 +2318,10 @@ EI_DEV void tile_tail(const Team &tm, const KArgs &a, int tile)
         for (int k = 0; k < d; k++)
             ROWD(T, L.w + kb + k) = vsel(act, vd(ROWD(T, L.w + kb + k)) + step * vd(ROWD(T, L.sol2 + kb + k)), ROWD(T, L.w + kb + k));
     }
+    if (P.mt > P.l)
     {
-        const int ins[2] = {L.s, L.dsaff};
-        ew_rows<2, 6>(tm, T, P.mt, ins, [&](int e, const vd *x) { ROWD(T, L.s + e) = vsel(act, x[0] + step * x[1], x[0]); });
+        const int ins[2] = {L.s + P.l, L.dsaff + P.l};
+        ew_rows<2, 6>(tm, T, P.mt - P.l, ins, [&](int e, const vd *x) { ROWD(T, L.s + P.l + e) = vsel(act, x[0] + step * x[1], x[0]); });
     }
     if (tm.wk == 0)
         VFOR if (act.v[c_])
