@@ -1054,8 +1054,9 @@ EI_DEV vd sweep_tail(PStream &ops, int nrec, Fifo &ff, smem_t sm, const double *
     return v;
 }
 
+// Returns max |rhs| over the rows (solveKKT's stopping threshold, src/eicos.cpp:1590).
 template <bool DIRECT>
-EI_DEV void ldl_forward_t(const Team &tm, const KArgs &a, double *T, int variant)
+EI_DEV vd ldl_forward_t(const Team &tm, const KArgs &a, double *T, int variant)
 {
     const DevPattern &P = a.P;
     const smem_t sm = smem_of(tm.stage); // ring rows, zero row, slots
@@ -1065,6 +1066,7 @@ EI_DEV void ldl_forward_t(const Team &tm, const KArgs &a, double *T, int variant
     ops.open(tm, P.fw, 0);
     ff.open(tm, P.fw_ld[variant], P.fw_nld, T, 1);
     double *xp = T + (size_t)a.L.xw * TILE;
+    vd mx = vset(0.0);
     for (int i = 0; i < P.N; i++, xp += TILE)
     {
         const i4 rec = ops.get();
@@ -1072,6 +1074,7 @@ EI_DEV void ldl_forward_t(const Team &tm, const KArgs &a, double *T, int variant
         if (rec.x < 0)
             ff.sync();
         vd v = sm_load(sm, (rec.y >> 8) & 0xff);
+        mx = vmax(mx, vabs(v));
         if (cnt > 0)
         {
             const int p[2] = {rec.z, rec.w};
@@ -1085,14 +1088,14 @@ EI_DEV void ldl_forward_t(const Team &tm, const KArgs &a, double *T, int variant
             sm_store(sm, keep, v);
     }
     ff.close();
+    return mx;
 }
 // variant: which right-hand side the load list was materialised for (LdVariant, layout.hpp)
-EI_DEV void ldl_forward(const Team &tm, const KArgs &a, double *T, int variant)
+EI_DEV vd ldl_forward(const Team &tm, const KArgs &a, double *T, int variant)
 {
     if (a.P.sw_direct)
-        ldl_forward_t<true>(tm, a, T, variant);
-    else
-        ldl_forward_t<false>(tm, a, T, variant);
+        return ldl_forward_t<true>(tm, a, T, variant);
+    return ldl_forward_t<false>(tm, a, T, variant);
 }
 
 // out = solution (KKT order).  If x >= 0: additionally x += solution for the instances with `cont`.
@@ -1303,23 +1306,17 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
 
     long long ck[5] = {0, 0, 0, 0, 0}, c0 = EI_CLOCK(), c1;
 #define EI_PHASE(k) (c1 = EI_CLOCK(), ck[k] += c1 - c0, c0 = c1)
-    vd mx[1] = {vset(0.0)};
-    {
-        const int ins[1] = {rhs};
-        ew_rows<1, 8>(tm, T, P.N, ins, [&](int, const vd *x) { mx[0] = vmax(mx[0], vabs(x[0])); });
-    }
-    team_max<1>(tm, mx);
-    const vd threshold = (1. + mx[0]) * Settings::linsysacc;
-
-    tm.sync(); // (workers > 1) everybody has read rhs before worker 0 reuses the staging buffers
+    vd mx[1] = {vset(0.0)}; // max |rhs|, picked up by the forward sweep as it loads the rows
     EI_PHASE(0);
     if (tm.wk == 0)
     {
-        ldl_forward(tm, a, T, a.variant);
+        mx[0] = ldl_forward(tm, a, T, a.variant);
         EI_PHASE(1);
         ldl_backward(tm, a, T, a.variant, sol, -1, vbset(false));
         EI_PHASE(2);
     }
+    team_max<1>(tm, mx); // (workers > 1: worker 0 holds the value, the others 0)
+    const vd threshold = (1. + mx[0]) * Settings::linsysacc;
     tm.sync();
 
     vd nerr_prev = vset(DBL_MAX);
@@ -1359,7 +1356,7 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
         EI_PHASE(4);
         if (tm.wk == 0)
         {
-            ldl_forward(tm, a, T, LDV_REFINE);
+            (void)ldl_forward(tm, a, T, LDV_REFINE);
             EI_PHASE(1);
             ldl_backward(tm, a, T, LDV_REFINE + a.variant, L.dxr, sol, !done);
             EI_PHASE(2);
