@@ -54,11 +54,20 @@ class BatchDims(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class ProgramStats(C.Structure):
+    _fields_ = [("sw_slots", C.c_int), ("fa_slots", C.c_int), ("fa_fast", C.c_int),
+                ("sw_far", C.c_longlong), ("sw_direct", C.c_longlong), ("fa_home", C.c_longlong),
+                ("fw_loads", C.c_int), ("bw_loads", C.c_int), ("fa_loads", C.c_int), ("mv_loads", C.c_int)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 EXPORTS = [
     "eicos_setup", "eicos_update_data", "eicos_update_data_full", "eicos_solve", "eicos_solution",
     "eicos_get_duals", "eicos_get_info", "eicos_cleanup",
     "eicos_batch_setup", "eicos_batch_update_matrices", "eicos_batch_solve", "eicos_batch_solve_device",
-    "eicos_batch_set_timing", "eicos_batch_set_compaction", "eicos_batch_get_stats", "eicos_batch_get_dims", "eicos_batch_get_symbolic",
+    "eicos_batch_set_timing", "eicos_batch_set_compaction", "eicos_batch_get_stats", "eicos_batch_get_dims", "eicos_batch_get_program_stats", "eicos_batch_get_symbolic",
     "eicos_batch_debug_init", "eicos_batch_stream", "eicos_batch_cleanup",
     "eicos_last_error", "eicos_device_count",
 ]
@@ -117,6 +126,8 @@ class Library:
         L.eicos_batch_set_compaction.argtypes = [C.c_void_p, C.c_int]
         L.eicos_batch_get_stats.restype = C.c_int
         L.eicos_batch_get_stats.argtypes = [C.c_void_p, C.POINTER(BatchStats)]
+        L.eicos_batch_get_program_stats.restype = C.c_int
+        L.eicos_batch_get_program_stats.argtypes = [C.c_void_p, C.POINTER(ProgramStats)]
         L.eicos_batch_get_dims.restype = C.c_int
         L.eicos_batch_get_dims.argtypes = [C.c_void_p, C.POINTER(BatchDims)]
         L.eicos_batch_get_symbolic.restype = C.c_int
@@ -237,6 +248,11 @@ class BatchSolver:
         d = BatchDims()
         self.lib.check(self.lib.L.eicos_batch_get_dims(self.h, C.byref(d)))
         return d.asdict()
+
+    def program_stats(self):
+        p = ProgramStats()
+        self.lib.check(self.lib.L.eicos_batch_get_program_stats(self.h, C.byref(p)))
+        return p.asdict()
 
     def symbolic(self):
         d = self.dims()

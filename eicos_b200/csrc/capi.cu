@@ -347,6 +347,24 @@ int eicos_batch_get_dims(const eicos_batch *bt, eicos_batch_dims *o)
     return 0;
 }
 
+int eicos_batch_get_program_stats(const eicos_batch *bt, eicos_program_stats *o)
+{
+    if (!bt || !o)
+        return fail(EICOS_ERR_INVALID, "null argument");
+    const ProgramStats p = bt->eng->program_stats();
+    o->sw_slots = p.sw_slots;
+    o->fa_slots = p.fa_slots;
+    o->fa_fast = p.fa_fast;
+    o->sw_far = p.sw_far;
+    o->sw_direct = p.sw_direct;
+    o->fa_home = p.fa_home;
+    o->fw_loads = p.fw_loads;
+    o->bw_loads = p.bw_loads;
+    o->fa_loads = p.fa_loads;
+    o->mv_loads = p.mv_loads;
+    return 0;
+}
+
 int eicos_batch_get_symbolic(const eicos_batch *bt, int *pinv, int *parent, int *Lp, int *Li, int *Kp, int *Ki)
 {
     if (!bt)

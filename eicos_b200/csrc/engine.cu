@@ -173,7 +173,14 @@ void Engine::build_layout(const Symbolic &S)
 void Engine::upload_pattern(const Symbolic &S)
 {
     be::stream_t st = S_(stream_);
-    build_streams(S, L_, workers_, MAX_SW_SLOTS, MAX_FA_SLOTS, H_);
+    // slot budgets; the environment overrides exist for the tests, which shrink them to force the
+    // far-gather / direct-operand / general-form paths on small patterns
+    int sw_budget = MAX_SW_SLOTS, fa_budget = MAX_FA_SLOTS;
+    if (const char *v = std::getenv("EICOS_MAX_SW_SLOTS"))
+        sw_budget = std::max(1, std::min(MAX_SW_SLOTS, std::atoi(v)));
+    if (const char *v = std::getenv("EICOS_MAX_FA_SLOTS"))
+        fa_budget = std::max(1, std::min(MAX_FA_SLOTS, std::atoi(v)));
+    build_streams(S, L_, workers_, sw_budget, fa_budget, H_);
     Lp_ = S.Lp;
     DevPattern &P = P_;
     P.n = S.n;
@@ -339,6 +346,22 @@ Engine::~Engine()
     be::unpin(status_host_);
     be::unpin(moves_host_);
     be::drop_stream(S_(stream_));
+}
+
+ProgramStats Engine::program_stats() const
+{
+    ProgramStats p;
+    p.sw_slots = H_.sw_slots;
+    p.fa_slots = H_.fa_slots;
+    p.fa_fast = H_.fa_fast;
+    p.sw_far = H_.sw_far;
+    p.sw_direct = H_.sw_direct;
+    p.fa_home = H_.fa_home;
+    p.fw_loads = H_.fw_nld;
+    p.bw_loads = H_.bw_nld;
+    p.fa_loads = H_.fa_nld;
+    p.mv_loads = H_.mv_nld;
+    return p;
 }
 
 void Engine::solve(int batch, const double *d_c, const double *d_h, const double *d_b,

@@ -25,6 +25,14 @@ struct SolveStats
     int factor_launches = 0, solve_launches = 0;
 };
 
+// what the program compiler (streams.cpp) produced for this pattern
+struct ProgramStats
+{
+    int sw_slots = 0, fa_slots = 0, fa_fast = 0;
+    long long sw_far = 0, sw_direct = 0, fa_home = 0; // operands served by far gathers / direct loads / home rows
+    int fw_loads = 0, bw_loads = 0, fa_loads = 0, mv_loads = 0; // rows each program reads from HBM per run
+};
+
 class Engine
 {
   public:
@@ -53,6 +61,7 @@ class Engine
                            const double *base_c, const double *base_h, const double *base_b,
                            double *h_Lx, double *h_D, double *h_sol1, double *h_sol2, int *h_nit);
 
+    ProgramStats program_stats() const;
     void *stream() const { return stream_; }
     int device() const { return device_; }
     int workers() const { return workers_; }

@@ -145,6 +145,18 @@ typedef struct eicos_batch_dims
 } eicos_batch_dims;
 int eicos_batch_get_dims(const eicos_batch *bt, eicos_batch_dims *out);
 
+/* What the host-side program compiler produced for this pattern (eicos_b200/csrc/streams.cpp): the
+ * factorisation, the triangular sweeps and the KKT mat-vecs run as programs whose intermediate values
+ * live in shared-memory slots and whose global reads are known in advance (load lists). */
+typedef struct eicos_program_stats
+{
+    int sw_slots, fa_slots; /* shared-memory slots used by the sweeps + mat-vec / by the factorisation */
+    int fa_fast;            /* 1: record-form factor program (narrow columns), 0: general form */
+    long long sw_far, sw_direct, fa_home; /* operands served by far gathers / direct global loads / home rows */
+    int fw_loads, bw_loads, fa_loads, mv_loads; /* rows each program reads from HBM per run */
+} eicos_program_stats;
+int eicos_batch_get_program_stats(const eicos_batch *bt, eicos_program_stats *out);
+
 /* Symbolic results for parity checks (any pointer may be NULL): pinv[dim_K] = original KKT index
  * of the k-th pivot (what Eigen's AMDOrdering returns), parent[dim_K] = elimination tree,
  * Lp[dim_K+1]/Li[nnzL] = pattern of L, Kp[dim_K+1]/Ki[nnzK] = upper KKT pattern. */

@@ -213,3 +213,36 @@ def test_compaction_is_transparent(oracle_mod, gpu_lib):
         assert np.array_equal(a[k], b[k]), k
     ref = oracle_mod.batch_run(P, batch, hs=W["hs"], bs=W["bs"], nthreads=8)
     assert np.array_equal(a["exit"], ref["exit"]) and np.array_equal(a["iter"], ref["iter"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,sw,fa", [("update_data_1", 2, 2), ("lp_afiro", 3, 4), ("MPC02", 3, 6)])
+def test_starved_slots_on_device(oracle_mod, gpu_lib, monkeypatch, name, sw, fa):
+    """Shrunk slot budgets push the CUDA kernels through the far-gather, direct-operand and
+    general-form factor paths; the results must be bit-identical to the roomy programs and match
+    the oracle."""
+    from eicos_b200.binding import BatchSolver
+    from eicos_b200.workloads import MPC_REL, perturbed
+    P = oracle_mod.load_fixture(name)
+    batch = 70  # two tiles, the second one ragged
+    W = perturbed(P, batch, rel=MPC_REL if name == "MPC02" else 0.02, seed=4)
+    roomy = BatchSolver(P, lib=gpu_lib, capacity=batch)
+    a = roomy.solve(batch, hs=W["hs"], bs=W["bs"])
+    monkeypatch.setenv("EICOS_MAX_SW_SLOTS", str(sw))
+    monkeypatch.setenv("EICOS_MAX_FA_SLOTS", str(fa))
+    starved = BatchSolver(P, lib=gpu_lib, capacity=batch)
+    ps = starved.program_stats()
+    assert ps["sw_slots"] <= sw and ps["fa_slots"] <= fa and ps["sw_far"] + ps["sw_direct"] > 0
+    b = starved.solve(batch, hs=W["hs"], bs=W["bs"])
+    same_factor = ps["fa_fast"] == roomy.program_stats()["fa_fast"]
+    for k in ("exit", "iter"):
+        assert np.array_equal(a[k], b[k]), k
+    for k in ("x", "y", "z", "s"):
+        if same_factor:
+            assert np.array_equal(a[k], b[k]), k
+        else:  # record form multiplies by the reciprocal pivot, general form divides
+            assert relerr(a[k], b[k]) <= TOL, k
+    ref = oracle_mod.batch_run(P, batch, hs=W["hs"], bs=W["bs"], nthreads=8)
+    assert np.array_equal(b["exit"], ref["exit"]) and np.array_equal(b["iter"], ref["iter"])
+    for k in "xyzs":
+        assert relerr(b[k], ref[k]) <= TOL, k
