@@ -16,4 +16,8 @@ echo "== ncu full: solve_kkt"
 ncu --set full --clock-control none --import-source on -k regex:eicos_solve_kkt -s 8 -c 2 -f -o $OUT/prof_solve_kkt $SMALL > $OUT/prof_solve.log 2>&1
 echo "== ncu full: ldl_factor"
 ncu --set full --clock-control none --import-source on -k regex:eicos_ldl_factor -s 3 -c 2 -f -o $OUT/prof_ldl_factor $SMALL > $OUT/prof_factor.log 2>&1
+echo "== ncu DRAM traffic per launch at the bench batch (one pass, two metrics)"
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "regex:eicos_(solve_kkt|ldl_factor)" --csv --log-file $OUT/traffic.csv \
+  python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > $OUT/traffic.log 2>&1
+python tools/ncu_traffic.py $OUT/traffic.csv $OUT/ncu_traffic.json
 ls -la $OUT
