@@ -15,7 +15,8 @@ namespace eicos
 
 #ifndef EICOS_EMU
 // thin named wrappers so that profilers show one kernel name per step of the algorithm
-#define EI_DEFINE_KERNEL(name, fn, minblocks)                                                  \
+#define EI_DEFINE_KERNEL(name, fn, minblocks) EI_DEFINE_KERNEL_(name, fn, minblocks, 0)
+#define EI_DEFINE_KERNEL_(name, fn, minblocks, JOBS)                                           \
     __global__ void __launch_bounds__(EI_MAX_THREADS, minblocks) name(const __grid_constant__ KArgs a) \
     {                                                                                          \
         extern __shared__ double smem[];                                                       \
@@ -30,13 +31,14 @@ namespace eicos
         tm.pbuf = smem + (size_t)(tm.nwk > 1 ? tm.nwk * KRED : 0) * TILE;                           \
         tm.stage = tm.pbuf + PS_DOUBLES + tm.lane;                                                 \
         tm.extra = tm.stage + (size_t)2 * STAGE_SLOTS * TILE;                                      \
-        fn(tm, a, blockIdx.x);                                                                 \
+        tm.job = JOBS ? (int)(blockIdx.x % (unsigned)a.njobs) : 0;                                 \
+        fn(tm, a, JOBS ? (int)(blockIdx.x / (unsigned)a.njobs) : (int)blockIdx.x);                                                                 \
     }
 #define EI_MAX_THREADS 256
 EI_DEFINE_KERNEL(eicos_load_inputs, tile_load, 2)
 EI_DEFINE_KERNEL(eicos_init, tile_init, 2)
 EI_DEFINE_KERNEL(eicos_ldl_factor, tile_factor, 2)
-EI_DEFINE_KERNEL(eicos_solve_kkt, tile_solve_kkt, 2)
+EI_DEFINE_KERNEL_(eicos_solve_kkt, tile_solve_kkt, 2, 1) /* grid = tiles x jobs, job fastest */
 EI_DEFINE_KERNEL(eicos_init_point, tile_init_point, 2)
 EI_DEFINE_KERNEL(eicos_residuals, tile_resid, 2)
 EI_DEFINE_KERNEL(eicos_iter_head, tile_head, 2)
@@ -45,6 +47,8 @@ EI_DEFINE_KERNEL(eicos_iter_tail, tile_tail, 2)
 EI_DEFINE_KERNEL(eicos_store_outputs, tile_store, 2)
 
 #define EI_LAUNCH(name, fn, tiles, threads, smem, stream, args) name<<<(tiles), (threads), (smem), (stream)>>>(args)
+#define EI_LAUNCH_JOBS(name, fn, tiles, njobs, threads, smem, stream, args) \
+    name<<<(tiles) * (njobs), (threads), (smem), (stream)>>>(args)
 
 __global__ void eicos_compact(const __grid_constant__ KArgs a, const __grid_constant__ MoveRanges mr, const int *moves)
 {
@@ -57,16 +61,18 @@ __global__ void eicos_compact(const __grid_constant__ KArgs a, const __grid_cons
 #else
 #define EI_MAX_THREADS 256
 // emulator: one std::thread per worker of a tile, CTA barrier = std::barrier
-#define EI_LAUNCH(name, fn, tiles, threads, smem, stream, args)                                   \
+#define EI_LAUNCH(name, fn, tiles, threads, smem, stream, args) EI_LAUNCH_JOBS(name, fn, tiles, 1, threads, smem, stream, args)
+#define EI_LAUNCH_JOBS(name, fn, tiles, njobs, threads, smem, stream, args)                       \
     do                                                                                            \
     {                                                                                             \
-        const int nw_ = (threads);                                                                \
+        const int nw_ = (threads), nj_ = (njobs);                                                                \
         std::vector<double> red_((size_t)nw_ * KRED * TILE + 8);                                  \
         const size_t xr_ = (size_t)std::max((args).P.sw_slots, (args).P.fa_slots) + 2 * (args).P.maxcol; \
         std::vector<double> stg_(((size_t)nw_ * 2 * STAGE_SLOTS + xr_) * TILE + 8);                \
         std::vector<double> pb_(PS_DOUBLES + 8);                                                   \
-        for (int tile_ = 0; tile_ < (tiles); tile_++)                                             \
+        for (int cta_ = 0; cta_ < (tiles) * nj_; cta_++)                                          \
         {                                                                                         \
+            const int tile_ = cta_ / nj_;                                                         \
             std::barrier<> bar_(nw_);                                                             \
             auto body_ = [&](int wk_) {                                                           \
                 Team tm_;                                                                         \
@@ -74,6 +80,7 @@ __global__ void eicos_compact(const __grid_constant__ KArgs a, const __grid_cons
                 tm_.pl = 0;                                                                       \
                 tm_.wk = wk_;                                                                     \
                 tm_.nwk = nw_;                                                                    \
+                tm_.job = cta_ % nj_;                                                             \
                 tm_.red = red_.data();                                                            \
                 tm_.extra = stg_.data() + (size_t)2 * STAGE_SLOTS * TILE;                         \
                 tm_.pbuf = pb_.data();                                                            \
@@ -161,6 +168,9 @@ void Engine::build_layout(const Symbolic &S)
     L.xw = take(S.N);
     L.dxr = take(S.N);
     L.e = take(S.N);
+    L.xw2 = take(S.N);
+    L.dxr2 = take(S.N);
+    L.e2 = take(S.N);
     L.dsw = take(S.mt);
     L.wdz = take(S.mt);
     L.dsaff = take(S.mt);
@@ -218,14 +228,16 @@ void Engine::upload_pattern(const Symbolic &S)
             out[k] = (list[k] & LD_ROW_MASK) + off[(unsigned)list[k] >> LD_BASE_SHIFT];
         return upload(out, owned_, st);
     };
-    P.fw_ld[0] = variant(H_.fw_ld, L_.rhs1, 0, 0);
-    P.fw_ld[1] = variant(H_.fw_ld, L_.rhs2, 0, 0);
-    P.fw_ld[2] = variant(H_.fw_ld, L_.e, 0, 0);
+    // sweeps: list 2 * set + refinement (layout.hpp: LdVariant)
+    P.fw_ld[0] = variant(H_.fw_ld, L_.rhs1, 0, L_.xw);
+    P.fw_ld[1] = variant(H_.fw_ld, L_.e, 0, L_.xw);
+    P.fw_ld[2] = variant(H_.fw_ld, L_.rhs2, 0, L_.xw2);
+    P.fw_ld[3] = variant(H_.fw_ld, L_.e2, 0, L_.xw2);
     P.bw = upload(H_.bw, owned_, st);
-    P.bw_ld[0] = variant(H_.bw_ld, L_.sol1, L_.sol1, 0); // a plain solve loads (and ignores) its own output rows
-    P.bw_ld[1] = variant(H_.bw_ld, L_.sol2, L_.sol2, 0);
-    P.bw_ld[2] = variant(H_.bw_ld, L_.dxr, L_.sol1, 0);
-    P.bw_ld[3] = variant(H_.bw_ld, L_.dxr, L_.sol2, 0);
+    P.bw_ld[0] = variant(H_.bw_ld, L_.sol1, L_.sol1, L_.xw); // a plain solve loads (and ignores) its own output rows
+    P.bw_ld[1] = variant(H_.bw_ld, L_.dxr, L_.sol1, L_.xw);
+    P.bw_ld[2] = variant(H_.bw_ld, L_.sol2, L_.sol2, L_.xw2);
+    P.bw_ld[3] = variant(H_.bw_ld, L_.dxr2, L_.sol2, L_.xw2);
     P.fa = upload(H_.fa, owned_, st);
     P.fa_ld = upload(H_.fa_ld, owned_, st);
     P.mv = upload(H_.mv, owned_, st);
@@ -414,7 +426,7 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
     a.pre_equilibrated = pre_equilibrated ? 1 : 0;
     a.active_count = active_count_;
     a.ir_rounds = ir_rounds_;
-    a.nitrow = -1;
+    a.njobs = 1;
     a.xrows = P_.sw_slots;
     be::zero(ir_rounds_, 8 * sizeof(unsigned long long), st);
 
@@ -487,22 +499,30 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
             stt.factor_launches++;
             stt.factor_launch_tiles += tiles;
         };
-        auto kkt = [&](int rhs, int sol, int init, int nitrow) {
-            a.rhs = rhs;
-            a.sol = sol;
-            a.variant = rhs == L_.rhs1 ? LDV_SOL1 : LDV_SOL2;
+        // solveKKT launches: one job, or the two solves of an iteration that share the factor and do
+        // not depend on each other (rhs1 -> sol1 and rhs2 -> sol2), as CTAs (tile, job) of one launch -
+        // same traffic when the machine is full, half the latency when it is not
+        auto kkt_launch = [&](int njobs, int init) {
+            a.njobs = njobs;
             a.initialize = init;
-            a.nitrow = nitrow;
-            EI_TIMED(1, EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt, tiles, threads1, smem_prog_, st, a));
+            EI_TIMED(1, EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt, tiles, njobs, threads1, smem_prog_, st, a));
             stt.solve_launches++;
-            stt.solve_launch_tiles += tiles;
+            stt.solve_launch_tiles += (long long)tiles * njobs;
+        };
+        auto kkt_pair = [&](int init, int nit1, int nit2) {
+            a.job[0] = {L_.rhs1, L_.sol1, nit1, 0};
+            a.job[1] = {L_.rhs2, L_.sol2, nit2, 1};
+            kkt_launch(2, init);
+        };
+        auto kkt_rhs2 = [&](int nitrow) {
+            a.job[0] = {L_.rhs2, L_.sol2, nitrow, 1};
+            kkt_launch(1, 0);
         };
 
         EI_TIMED(2, EI_LAUNCH(eicos_load_inputs, tile_load, tiles, threads, smem_common_, st, a));
         EI_TIMED(2, EI_LAUNCH(eicos_init, tile_init, tiles, threads, smem_common_, st, a));
         factor();
-        kkt(L_.rhs1, L_.sol1, 1, J_NIT1);
-        kkt(L_.rhs2, L_.sol2, 1, J_NIT2);
+        kkt_pair(1, J_NIT1, J_NIT2);
         EI_TIMED(2, EI_LAUNCH(eicos_init_point, tile_init_point, tiles, threads, smem_common_, st, a));
 
         for (int it = 0; it <= Settings::iter_max + 1; it++)
@@ -567,10 +587,9 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
                 tiles = new_tiles;
             }
             factor();
-            kkt(L_.rhs1, L_.sol1, 0, -1);
-            kkt(L_.rhs2, L_.sol2, 0, -1);
+            kkt_pair(0, -1, -1);
             EI_TIMED(2, EI_LAUNCH(eicos_iter_mid, tile_mid, tiles, threads, smem_common_, st, a));
-            kkt(L_.rhs2, L_.sol2, 0, J_NIT3);
+            kkt_rhs2(J_NIT3);
             EI_TIMED(2, EI_LAUNCH(eicos_iter_tail, tile_tail, tiles, threads, smem_common_, st, a));
         }
         EI_TIMED(2, EI_LAUNCH(eicos_store_outputs, tile_store, tiles, threads, smem_common_, st, a));
@@ -633,7 +652,6 @@ void Engine::debug_factor_init(int batch, const double *d_c, const double *d_h, 
     be::sync(st);
     a.batch = batch;
     a.first = 0;
-    a.nitrow = -1;
     a.xrows = P_.sw_slots;
     const int tiles = (batch + TILE - 1) / TILE;
     const int threads = workers_ * (LANES == 1 ? 1 : 32), threads1 = LANES == 1 ? 1 : 32;
@@ -644,17 +662,11 @@ void Engine::debug_factor_init(int batch, const double *d_c, const double *d_h, 
     a.xrows = xrows_factor_;
     EI_LAUNCH(eicos_ldl_factor, tile_factor, tiles, threads1, smem_factor_, st, a);
     a.xrows = P_.sw_slots;
-    a.rhs = L_.rhs1;
-    a.sol = L_.sol1;
-    a.variant = LDV_SOL1;
     a.initialize = 1;
-    a.nitrow = J_NIT1;
-    EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt, tiles, threads1, smem_prog_, st, a);
-    a.rhs = L_.rhs2;
-    a.sol = L_.sol2;
-    a.variant = LDV_SOL2;
-    a.nitrow = J_NIT2;
-    EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt, tiles, threads1, smem_prog_, st, a);
+    a.njobs = 2;
+    a.job[0] = {L_.rhs1, L_.sol1, J_NIT1, 0};
+    a.job[1] = {L_.rhs2, L_.sol2, J_NIT2, 1};
+    EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt, tiles, 2, threads1, smem_prog_, st, a);
     be::sync(st);
     // gather rows back to instance-major host arrays; L comes back in CSC order
     const size_t tile_doubles = (size_t)L_.rows_total * TILE;

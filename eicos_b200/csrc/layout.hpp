@@ -77,6 +77,7 @@ struct Layout
     int Lx, D, Dinv;                // factor: L column-major (CSC order of the symbolic pattern), pivots, reciprocals
     int rhs1, rhs2, sol1, sol2;     // KKT-space vectors (N rows)
     int xw, dxr, e;                 // triangular-solve work vector, refinement step, residual (N rows)
+    int xw2, dxr2, e2;              // the same for the second of two concurrent solves (job set 1)
     int dsw, wdz, dsaff, ds1;       // dsaff_by_W, W_times_dzaff, dsaff, scratch (mt rows)
     int sc;                         // S_COUNT scalar rows
     int rows_total;
@@ -86,9 +87,9 @@ struct Layout
 // index of a materialised load list (DevPattern::fw_ld / bw_ld / mv_ld)
 enum LdVariant : int
 {
-    LDV_SOL1 = 0,   // rhs1 -> sol1
-    LDV_SOL2 = 1,   // rhs2 -> sol2
-    LDV_REFINE = 2, // forward: rhs = e; backward: LDV_REFINE + {0, 1}: out = dxr, accumulated into sol1 / sol2
+    LDV_SOL1 = 0,   // set 0: rhs1 -> sol1
+    LDV_SOL2 = 1,   // set 1: rhs2 -> sol2
+    LDV_REFINE = 1, // sweeps: list 2 * set + LDV_REFINE: rhs = e of the set, out = dxr of the set, accumulated into its sol
     LDV_HEAD = 2    // mat-vec: computeResiduals (chb, w, s)
 };
 
@@ -108,9 +109,11 @@ struct DevPattern
     // slot programs (streams.hpp): ops, load lists (+ length in words), shared-memory slots they use
     // Load lists are materialised per use (absolute rows of the tile, so that issuing a load is one
     // multiply-add): forward [rhs1, rhs2, e]; backward [sol1, sol2, dxr += into sol1, dxr += into sol2];
-    // mat-vec [rhs1/sol1, rhs2/sol2, computeResiduals].
+    // mat-vec [rhs1/sol1, rhs2/sol2, computeResiduals].  Sweep lists: index = 2 * set + refinement, where
+    // set 0 = (rhs1, sol1) with work vectors xw/dxr/e and set 1 = (rhs2, sol2) with xw2/dxr2/e2, so
+    // that the two solves of an iteration that share a factor can run at the same time.
     const int *fw, *bw, *fa, *fa_ld, *mv;
-    const int *fw_ld[3], *bw_ld[4], *mv_ld[3];
+    const int *fw_ld[4], *bw_ld[4], *mv_ld[3];
     const double *mv_val;
     int fw_nld, bw_nld, fa_nld, mv_nld, mv_rows, sw_slots, fa_slots;
     int sw_direct; // the sweep programs contain operands read straight from global memory

@@ -195,12 +195,12 @@ void build_forward(const Symbolic &S, const Layout &L, int max_slots, HostStream
                 opnd = SW_SLOT0 + cache.slot_of[k];
             else if (FifoSim::far_safe(prod[k], F.npop))
             {
-                opnd = F.pop(0, L.xw + k);
+                opnd = F.pop(3, k); // the work vector xw of the running solve
                 H.sw_far++;
             }
             else
             {
-                opnd = SW_DIRECT + L.xw + k;
+                opnd = SW_DIRECT + k; // relative to xw
                 H.sw_direct++;
             }
             cache.used(k);
@@ -235,7 +235,7 @@ void build_backward(const Symbolic &S, const Layout &L, int max_slots, HostStrea
     {
         const int o = S.pinv[k], cnt = S.Lp[k + 1] - S.Lp[k];
         const int first = F.npop;
-        const int drow = F.pop(0, L.Dinv + k), xrow = F.pop(0, L.xw + k), arow = F.pop(2, o);
+        const int drow = F.pop(0, L.Dinv + k), xrow = F.pop(3, k), arow = F.pop(2, o);
         const size_t w1 = H.bw.size() + 1;
         H.bw.push_back(cnt);
         H.bw.push_back(0);

@@ -48,8 +48,8 @@ static_assert(FIFO_ROWS == 2 * STAGE_SLOTS, "the FIFO ring aliases worker 0's st
 static_assert(FIFO_SLOTS >= FIFO_AHEAD + 2, "ring = consumed group + slack group + groups in flight");
 
 // ---- load-list words (all programs): bits 30..31 select the base, the rest is the row
-//      0 = tile base, 1 / 2 = run-time vectors of the sweep (rhs | out, accumulated solution)
-//      (3 = second run-time vector of the mat-vec program)
+//      0 = tile base, 1 / 2 = run-time vectors of the sweep (rhs | out, accumulated solution),
+//      3 = the work vector xw of the sweeps / the second extra vector of the mat-vec program
 constexpr int LD_BASE_SHIFT = 30;
 constexpr int LD_ROW_MASK = (1 << 30) - 1;
 

@@ -234,8 +234,12 @@ struct KArgs
     double *out_info; // [batch][S_WORK_END]
     int *out_iinfo;   // [batch][J_WORK_END]
     // solveKKT parameters
-    int rhs, sol, initialize, nitrow;
-    int variant; // 0: rhs1 -> sol1, 1: rhs2 -> sol2 (selects the materialised load lists, LdVariant)
+    // solveKKT jobs of this launch: CTA = (tile, job).  set 0: rhs1 -> sol1, set 1: rhs2 -> sol2 (LdVariant)
+    struct KktJob
+    {
+        int rhs, sol, nitrow, set;
+    } job[2];
+    int njobs, initialize;
     int keep_sticky;
     int pre_equilibrated; // inputs are already divided by the equilibration vectors
     unsigned int *active_count; // device counter: instances still iterating after the head step
@@ -247,6 +251,7 @@ struct Team
     int lane;      // element offset of this lane inside a row (= physical lane * VEC)
     int pl;        // physical lane inside the warp
     int wk, nwk;
+    int job;       // eicos_solve_kkt: which of the launch's solveKKT jobs this CTA runs
     double *red;   // [nwk][KRED][TILE]
     double *stage; // this worker's staging slots + lane: slot s lives at stage[s * TILE]
     double *extra; // shared memory behind the staging buffers (+ lane): slots of the slot programs, column buffers
@@ -1056,7 +1061,7 @@ EI_DEV vd sweep_tail(PStream &ops, int nrec, Fifo &ff, smem_t sm, const double *
 
 // Returns max |rhs| over the rows (solveKKT's stopping threshold, src/eicos.cpp:1590).
 template <bool DIRECT>
-EI_DEV vd ldl_forward_t(const Team &tm, const KArgs &a, double *T, int variant)
+EI_DEV vd ldl_forward_t(const Team &tm, const KArgs &a, double *T, int variant, int xw)
 {
     const DevPattern &P = a.P;
     const smem_t sm = smem_of(tm.stage); // ring rows, zero row, slots
@@ -1065,7 +1070,8 @@ EI_DEV vd ldl_forward_t(const Team &tm, const KArgs &a, double *T, int variant)
     Fifo ff;
     ops.open(tm, P.fw, 0);
     ff.open(tm, P.fw_ld[variant], P.fw_nld, T, 1);
-    double *xp = T + (size_t)a.L.xw * TILE;
+    double *xp = T + (size_t)xw * TILE;
+    double *const xhome = xp; // direct operands are rows of xw
     vd mx = vset(0.0);
     for (int i = 0; i < P.N; i++, xp += TILE)
     {
@@ -1078,9 +1084,9 @@ EI_DEV vd ldl_forward_t(const Team &tm, const KArgs &a, double *T, int variant)
         if (cnt > 0)
         {
             const int p[2] = {rec.z, rec.w};
-            v = sweep_pairs<DIRECT, 2>(sm, T, p, v);
+            v = sweep_pairs<DIRECT, 2>(sm, xhome, p, v);
             if (cnt > 2)
-                v = sweep_tail<DIRECT>(ops, (cnt + 2 + 3) >> 2, ff, sm, T, v);
+                v = sweep_tail<DIRECT>(ops, (cnt + 2 + 3) >> 2, ff, sm, xhome, v);
         }
         vstore(xp, v);
         const int keep = rec.y & 0xff;
@@ -1090,12 +1096,12 @@ EI_DEV vd ldl_forward_t(const Team &tm, const KArgs &a, double *T, int variant)
     ff.close();
     return mx;
 }
-// variant: which right-hand side the load list was materialised for (LdVariant, layout.hpp)
-EI_DEV vd ldl_forward(const Team &tm, const KArgs &a, double *T, int variant)
+// variant: which vectors the load list was materialised for (LdVariant, layout.hpp); xw: work vector it fills
+EI_DEV vd ldl_forward(const Team &tm, const KArgs &a, double *T, int variant, int xw)
 {
     if (a.P.sw_direct)
-        return ldl_forward_t<true>(tm, a, T, variant);
-    return ldl_forward_t<false>(tm, a, T, variant);
+        return ldl_forward_t<true>(tm, a, T, variant, xw);
+    return ldl_forward_t<false>(tm, a, T, variant, xw);
 }
 
 // out = solution (KKT order).  If x >= 0: additionally x += solution for the instances with `cont`.
@@ -1219,7 +1225,7 @@ EI_DEV void mv_run(const Team &tm, const KArgs &a, const double *T, int variant,
 // ------------------------------------------------------------------ KKT residual for iterative refinement (src/eicos.cpp:1511-1576)
 // e = rhs - Ktrue * x with the un-regularised scaling block (identity while initialising),
 // returns ||e||_inf per instance.
-EI_DEV vd kkt_residual(const Team &tm, const KArgs &a, double *T, int variant, int rhs, int x, bool initialize)
+EI_DEV vd kkt_residual(const Team &tm, const KArgs &a, double *T, int variant, int rhs, int x, int erow, bool initialize)
 {
     const DevPattern &P = a.P;
     const Layout &L = a.L;
@@ -1239,7 +1245,7 @@ EI_DEV vd kkt_residual(const Team &tm, const KArgs &a, double *T, int variant, i
                     if (kind == MV_Z)
                         v += initialize ? own : ex1 * own;
                 }
-                ROWD(T, L.e + r) = v;
+                ROWD(T, erow + r) = v;
                 nerr = vmax(nerr, vabs(v));
             });
     if (P.nc > 0)
@@ -1274,13 +1280,13 @@ EI_DEV vd kkt_residual(const Team &tm, const KArgs &a, double *T, int variant, i
                     v += eta2 * (d1 * x1 + u0 * x4);
                 else
                     v += eta2 * (xk + vu * vd(ROWD(T, L.cq + qo + k - 1)));
-                ROWD(T, L.e + kb + k) = v;
+                ROWD(T, erow + kb + k) = v;
                 nerr = vmax(nerr, vabs(v));
             }
             const vd e3 = initialize ? x3 : eta2 * (v1 * qtx2 + x3);
             const vd e4 = initialize ? x4 : eta2 * (u0 * x1 + u1 * qtx2 - x4);
-            ROWD(T, L.e + kb + d) = e3;
-            ROWD(T, L.e + kb + d + 1) = e4;
+            ROWD(T, erow + kb + d) = e3;
+            ROWD(T, erow + kb + d + 1) = e4;
             nerr = vmax(nerr, vmax(vabs(e3), vabs(e4)));
         }
     }
@@ -1301,7 +1307,9 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     double *T = t.T;
-    const int rhs = a.rhs, sol = a.sol;
+    const KArgs::KktJob jb = a.job[tm.job];
+    const int rhs = jb.rhs, sol = jb.sol, set = jb.set;
+    const int xw = set ? L.xw2 : L.xw, dxr = set ? L.dxr2 : L.dxr, erow = set ? L.e2 : L.e;
     const bool init = a.initialize != 0;
 
     long long ck[5] = {0, 0, 0, 0, 0}, c0 = EI_CLOCK(), c1;
@@ -1310,9 +1318,9 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
     EI_PHASE(0);
     if (tm.wk == 0)
     {
-        mx[0] = ldl_forward(tm, a, T, a.variant);
+        mx[0] = ldl_forward(tm, a, T, 2 * set, xw);
         EI_PHASE(1);
-        ldl_backward(tm, a, T, a.variant, sol, -1, vbset(false));
+        ldl_backward(tm, a, T, 2 * set, sol, -1, vbset(false));
         EI_PHASE(2);
     }
     team_max<1>(tm, mx); // (workers > 1: worker 0 holds the value, the others 0)
@@ -1326,7 +1334,7 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
     unsigned rounds = 0;
     for (;;)
     {
-        const vd nerr = kkt_residual(tm, a, T, a.variant, rhs, sol, init);
+        const vd nerr = kkt_residual(tm, a, T, set, rhs, sol, erow, init);
         EI_PHASE(3);
         vb rollback = vbset(false);
         VFOR
@@ -1348,7 +1356,7 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
         if (tm.any(rollback))
         { // x -= dx_ref for the instances whose last refinement made things worse
             for (int r = tm.wk; r < P.N; r += tm.nwk)
-                ROWD(T, sol + r) -= vsel(rollback, ROWD(T, L.dxr + r), vset(0.0));
+                ROWD(T, sol + r) -= vsel(rollback, ROWD(T, dxr + r), vset(0.0));
         }
         if (tm.all(done))
             break;
@@ -1356,9 +1364,9 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
         EI_PHASE(4);
         if (tm.wk == 0)
         {
-            (void)ldl_forward(tm, a, T, LDV_REFINE);
+            (void)ldl_forward(tm, a, T, 2 * set + LDV_REFINE, xw);
             EI_PHASE(1);
-            ldl_backward(tm, a, T, LDV_REFINE + a.variant, L.dxr, sol, !done);
+            ldl_backward(tm, a, T, 2 * set + LDV_REFINE, dxr, sol, !done);
             EI_PHASE(2);
         }
         tm.sync();
@@ -1368,8 +1376,8 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
     tm.sync();
     if (tm.wk == 0)
     {
-        if (a.nitrow >= 0)
-            VFOR if (act.v[c_]) ROWC(t.I, a.nitrow, c_) = kref[c_];
+        if (jb.nitrow >= 0)
+            VFOR if (act.v[c_]) ROWC(t.I, jb.nitrow, c_) = kref[c_];
 #ifndef EICOS_EMU
         if (tm.pl == 0 && a.ir_rounds)
         {
