@@ -47,7 +47,7 @@ class BatchStats(C.Structure):
 class BatchDims(C.Structure):
     _fields_ = [(k, C.c_int) for k in
                 ("n", "m", "p", "l", "ncones", "dim_K", "nnzK", "nnzL", "nnzV", "nnzG", "nnzA",
-                 "etree_height", "max_col", "n_phases", "tile_width", "workers")] + \
+                 "etree_height", "max_col", "tile_width", "workers")] + \
                [(k, C.c_longlong) for k in ("ldl_fma", "capacity", "workspace_bytes", "rows_per_instance")]
 
     def asdict(self):

@@ -131,7 +131,7 @@ eicos_batch *eicos_batch_setup(int n, int m, int p, int l, int ncones, const int
             throw std::invalid_argument("eicos_batch_setup: negative dimension or missing c");
         std::unique_ptr<eicos_batch> bt(new eicos_batch());
         bt->device = device;
-        analyze(bt->S, n, m, p, ncones, q, Gpr, Gjc, Gir, Apr, Ajc, Air, /*serial_width=*/2);
+        analyze(bt->S, n, m, p, ncones, q, Gpr, Gjc, Gir, Apr, Ajc, Air);
         const Symbolic &S = bt->S;
         if (S.G.nnz())
             bt->rawG.assign(Gpr, Gpr + S.G.nnz());
@@ -337,7 +337,6 @@ int eicos_batch_get_dims(const eicos_batch *bt, eicos_batch_dims *o)
     o->nnzA = S.A.nnz();
     o->etree_height = S.height;
     o->max_col = S.maxcol;
-    o->n_phases = (int)S.phases.size();
     o->tile_width = Engine::tile_width();
     o->workers = bt->workers;
     o->ldl_fma = S.fma_count;
@@ -453,7 +452,7 @@ eicos_solver *eicos_setup(int n, int m, int p, int l, int ncones, const int *q,
         std::unique_ptr<eicos_solver> s(new eicos_solver());
         s->device = device;
         std::memset(&s->info, 0, sizeof(s->info));
-        analyze(s->S, n, m, p, ncones, q, Gpr, Gjc, Gir, Apr, Ajc, Air, 2);
+        analyze(s->S, n, m, p, ncones, q, Gpr, Gjc, Gir, Apr, Ajc, Air);
         const Symbolic &S = s->S;
         s->c.assign(c, c + S.n);
         if (S.m)

@@ -203,7 +203,6 @@ void Engine::upload_pattern(const Symbolic &S)
     P.qtot = S.qtot;
     P.nnzL = S.nnzL;
     P.nnzV = (int)S.Vslot.size();
-    P.nphases = (int)S.phases.size();
     P.maxcol = S.maxcol;
     P.fw_nld = H_.fw_nld;
     P.bw_nld = H_.bw_nld;

@@ -101,7 +101,7 @@ enum ConeParam : int
 // Shared index data on the device (all pointers are device pointers).
 struct DevPattern
 {
-    int n, p, m, l, nc, N, mt, qtot, nnzL, nnzV, nphases, maxcol;
+    int n, p, m, l, nc, N, mt, qtot, nnzL, nnzV, maxcol;
     const int *cone_dim, *cone_k, *cone_q; // per cone: dimension, first expanded index, first q row
     const int *zk;                         // compact z index -> expanded index (load / store only)
     const double *xeq, *Aeq, *GeqE;        // equilibration vectors (GeqE is expanded, 1 in the slots)

@@ -310,7 +310,8 @@ static void order_and_factor_pattern(Symbolic &S)
         }
 }
 
-static void build_schedule(Symbolic &S, int serial_width)
+// elimination-tree height, widest column of L, multiply-adds of one numeric factorisation
+static void build_shape(Symbolic &S)
 {
     const int N = S.N;
     S.level.assign(N, 0);
@@ -319,57 +320,18 @@ static void build_schedule(Symbolic &S, int serial_width)
             S.level[S.parent[j]] = std::max(S.level[S.parent[j]], S.level[j] + 1);
     S.height = N ? *std::max_element(S.level.begin(), S.level.end()) + 1 : 0;
     S.maxcol = 0;
-    for (int j = 0; j < N; j++)
-        S.maxcol = std::max(S.maxcol, S.Lp[j + 1] - S.Lp[j]);
-    S.tasks.resize(N);
-    std::iota(S.tasks.begin(), S.tasks.end(), 0);
-    std::stable_sort(S.tasks.begin(), S.tasks.end(), [&](int a, int b) { return S.level[a] < S.level[b]; });
-    ivec lp(S.height + 1, 0);
-    for (int j = 0; j < N; j++)
-        lp[S.level[j] + 1]++;
-    std::partial_sum(lp.begin(), lp.end(), lp.begin());
-    S.phases.clear();
-    for (int h = 0; h < S.height; h++)
-    {
-        const int w = lp[h + 1] - lp[h];
-        if (w > serial_width)
-            S.phases.push_back({lp[h], lp[h + 1], 1});
-        else if (!S.phases.empty() && !S.phases.back().parallel)
-            S.phases.back().end = lp[h + 1];
-        else
-            S.phases.push_back({lp[h], lp[h + 1], 0});
-    }
-
-    // left-looking update streams: for row j of L and each k in it, the tail of column k below j
-    S.upd_tail.assign(S.nnzL, 0);
-    S.upd_rel_p.assign(S.nnzL + 1, 0);
-    S.upd_rel.clear();
     S.fma_count = 0;
     for (int j = 0; j < N; j++)
-        for (int t = S.Lr.p[j]; t < S.Lr.p[j + 1]; t++)
-        {
-            const int k = S.Lr.j[t];
-            const int tail = S.Lr.v[t] + 1;
-            S.upd_tail[t] = tail;
-            S.upd_rel_p[t] = (int)S.upd_rel.size();
-            const int *b0 = S.Li.data() + S.Lp[j], *e = S.Li.data() + S.Lp[j + 1];
-            const int *b = b0;
-            for (int u = tail; u < S.Lp[k + 1]; u++)
-            {
-                const int *f = std::lower_bound(b, e, S.Li[u]);
-                if (f == e || *f != S.Li[u])
-                    throw std::logic_error("column tail outside the pattern of its ancestor");
-                S.upd_rel.push_back((int)(f - b0));
-                b = f + 1; // both lists ascend
-            }
-            S.fma_count += S.Lp[k + 1] - tail + 1;
-        }
-    S.upd_rel_p[S.nnzL] = (int)S.upd_rel.size();
+    {
+        const long long c = S.Lp[j + 1] - S.Lp[j];
+        S.maxcol = std::max(S.maxcol, (int)c);
+        S.fma_count += c * (c + 1) / 2; // Schur updates of column j (right-looking)
+    }
 }
 
 void analyze(Symbolic &S, int n, int m, int p, int ncones, const int *q,
              const double *Gpr, const int *Gjc, const int *Gir,
-             const double *Apr, const int *Ajc, const int *Air, int serial_width)
+             const double *Apr, const int *Ajc, const int *Air)
 {
     // a NULL triple means "matrix absent" (src/eicos.cpp:103-117); then the matching dimension is 0
     const bool hasG = Gpr && Gjc && Gir, hasA = Apr && Ajc && Air;
@@ -442,7 +404,7 @@ void analyze(Symbolic &S, int n, int m, int p, int ncones, const int *q,
     build_kkt(S);
     fill_shared_values(S);
     order_and_factor_pattern(S);
-    build_schedule(S, serial_width);
+    build_shape(S);
 }
 
 void unequilibrate(Symbolic &S)

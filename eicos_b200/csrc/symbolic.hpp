@@ -7,8 +7,8 @@
 //   - Eigen::SimplicialLDLT::analyzePattern   call site src/eicos.cpp:897 (AMD ordering, elimination
 //                                             tree, column counts) - run ONCE per pattern here instead of
 //                                             once per solve()
-// and adds what only the GPU needs: CSR views, the level schedule of the elimination tree and
-// the flat index streams the factor / solve kernels walk.
+// and adds what only the GPU needs: CSR views of G, A and L (the programs the numeric kernels run
+// are compiled from these by streams.cpp).
 #pragma once
 
 #include <cstdint>
@@ -46,14 +46,6 @@ struct CsrView
     ivec p, j, v;
 };
 
-// One phase of the level schedule: `parallel` phases spread independent tasks over the warps of a
-// CTA (barrier at the end); serial phases are runs of narrow levels walked by warp 0 alone.
-struct Phase
-{
-    int begin, end; // range into the task list
-    int parallel;
-};
-
 struct Symbolic
 {
     // ---- dimensions (src/eicos.cpp:152-165)
@@ -86,28 +78,20 @@ struct Symbolic
     // ---- permuted KKT, lower-triangular by columns: what column j of the factorisation consumes
     ivec KLp, KLslot, KLpos; // entry range per column; K slot; position inside L column j (-1 = diagonal)
 
-    // ---- level schedule
+    // ---- shape of the factor
     ivec level;              // etree height of every column (0 = leaf)
-    ivec tasks;              // columns ordered by (level, index)
-    std::vector<Phase> phases;
     int height = 0, maxcol = 0;
-
-    // ---- left-looking update streams (factor kernel)
-    ivec upd_tail;  // per CSR entry t=(j,k): CSC position of the first entry of column k below row j
-    ivec upd_rel_p; // per CSR entry: start in `upd_rel`; length = Lp[k+1]-upd_tail[t]
-    ivec upd_rel;   // position inside column j's accumulator of each tail row
-    long long fma_count = 0;
+    long long fma_count = 0; // multiply-adds of one numeric factorisation
 };
 
 // Row/column infinity-norm equilibration of G and A in place (src/eicos.cpp:302-362); cones share
 // one row scale.  c/h/b are NOT touched here (they are per instance).
 void equilibrate(Csc &G, Csc &A, int l, const ivec &q, dvec &xeq, dvec &Aeq, dvec &Geq);
 
-// Builds everything above from the (unequilibrated) problem matrices. serial_width: levels with at
-// most this many columns are merged into serial phases.
+// Builds everything above from the (unequilibrated) problem matrices.
 void analyze(Symbolic &S, int n, int m, int p, int ncones, const int *q,
              const double *Gpr, const int *Gjc, const int *Gir,
-             const double *Apr, const int *Ajc, const int *Air, int serial_width);
+             const double *Apr, const int *Ajc, const int *Air);
 
 // Undo the equilibration of the stored G/A values by multiplying the scales back in
 // (restore(), src/eicos.cpp:376-392 - not bit-exact with the original data, like the reference).

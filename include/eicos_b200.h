@@ -138,7 +138,7 @@ int eicos_batch_get_stats(const eicos_batch *bt, eicos_batch_stats *out);
 typedef struct eicos_batch_dims
 {
     int n, m, p, l, ncones, dim_K, nnzK, nnzL, nnzV, nnzG, nnzA;
-    int etree_height, max_col, n_phases, tile_width, workers;
+    int etree_height, max_col, tile_width, workers;
     long long ldl_fma; /* multiply-adds of one numeric factorisation */
     long long capacity;
     long long workspace_bytes, rows_per_instance;
