@@ -2,14 +2,18 @@
 // src/eicos.cpp:848-1262) for TILE = LANES x VEC instances at a time.
 //
 // One CTA owns one tile.  Lane l of a warp owns VEC consecutive instances of the tile, so a row of a
-// per-instance array is read with ONE 16-byte vector load per lane (512 B per warp for VEC = 2):
-// every index decode, address computation and loop step is amortised over VEC instances.  The warps
-// ("workers") of the CTA split rows / cones / elimination-tree tasks among themselves and meet at
-// CTA barriers; per-instance reductions over a vector run down the rows in each worker and are
-// combined through shared memory in a fixed order, so every warp holds bit-identical per-instance
-// scalars and all control flow is uniform across the CTA.
-// Sparse structure is never looked up through CSR/CSC arrays on the device: each worker decodes its
-// own instruction stream (streams.hpp) with coalesced chunk loads + warp shuffles.
+// per-instance array is moved with ONE 16-byte access per lane (512 B per warp for VEC = 2): every
+// index decode, address computation and loop step is amortised over VEC instances, and the
+// sparsity pattern never diverges inside a warp.
+//   * Program kernels (numeric LDL', triangular sweeps, KKT mat-vecs): ONE warp per tile walks a
+//     program compiled on the host (streams.hpp) in elimination order.  Global reads arrive through
+//     a cp.async FIFO whose ring rows the program names directly; intermediate values sit in
+//     shared-memory slots for their live range; the program itself is read through a small
+//     shared-memory double buffer.  Nothing inside such a kernel needs a barrier.
+//   * Vector kernels (statistics, scalings, right-hand sides, line search, iterate update): the
+//     warps ("workers") of the CTA split the rows; per-instance reductions run down the rows in
+//     each worker and are combined through shared memory in a fixed order, so every warp holds
+//     bit-identical per-instance scalars and all control flow is uniform across the CTA.
 //
 // The same source compiles two ways:
 //   * nvcc (default): LANES = 32, workers = warps of the CTA  -> the product.
@@ -403,29 +407,7 @@ EI_DEV vb lane_active(const Team &tm, const TileMem &t)
     return r;
 }
 
-// ------------------------------------------------------------------ asynchronous staging
-// A warp issues in order, so a load that is consumed right away limits it to ~2 loads in flight.
-// Independent work is therefore done block-wise: pass 1 issues every load of the block into this
-// worker's shared-memory slots with cp.async (no register dependency), pass 2 re-walks the same
-// stream words and computes from shared memory.  Each lane only ever reads the slot words it wrote
-// itself, so cp.async.wait_all is the only fence needed.
-EI_DEV void stage_issue(double *slot_lane, const double *src_lane)
-{
-#ifdef EICOS_EMU
-    vstore(slot_lane, vload(src_lane));
-#else
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(slot_lane);
-    if (VEC % 2 == 0)
-    {
-#pragma unroll
-        for (int c = 0; c < VEC; c += 2)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + 8 * c), "l"(src_lane + c) : "memory");
-    }
-    else
-        for (int c = 0; c < VEC; c++)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + 8 * c), "l"(src_lane + c) : "memory");
-#endif
-}
+// ------------------------------------------------------------------ cp.async group control (the FIFO below)
 EI_DEV void stage_commit()
 {
 #ifndef EICOS_EMU
@@ -438,13 +420,6 @@ EI_DEV void stage_wait()
     asm volatile("cp.async.wait_all;" ::: "memory");
 #endif
 }
-EI_DEV void stage_wait_prev() // everything except the most recently committed group has landed
-{
-#ifndef EICOS_EMU
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-#endif
-}
-
 EI_DEV const double *rowp(const Team &, const double *T, int row) { return T + (size_t)row * TILE; }
 
 // Elementwise pass over `count` rows with NIN input arrays (row offsets in[k]): a worker takes U
