@@ -297,6 +297,8 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
+        if traffic.get("_workload") != args.workload or traffic.get("_batch_per_gpu") != batch:
+            traffic = None  # the ncu capture is of another configuration
     roofline = {"bound": "hbm", "kernel": "eicos_solve_kkt", "achieved": solve_gbs, "peak": peak, "unit": "GB/s",
                 "frac": solve_gbs / peak, "peak_source": peak_src,
                 "traffic": (traffic or {}).get("eicos_solve_kkt"),

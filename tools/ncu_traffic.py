@@ -18,5 +18,7 @@ for r in rows[hi + 1:]:
 out = {k: tot[k] / max(len(launches[k]), 1) for k in tot}
 out["_note"] = "bytes per launch, averaged over %s launches of `bench.py --steps 1 --warmup 1` under ncu (dram__bytes_read.sum + dram__bytes_write.sum)" % \
     {k: len(v) for k, v in launches.items()}
+out["_workload"] = sys.argv[3] if len(sys.argv) > 3 else "mpc02"
+out["_batch_per_gpu"] = int(sys.argv[4]) if len(sys.argv) > 4 else 65536
 json.dump(out, open(sys.argv[2], "w"), indent=1)
 print(json.dumps(out))
