@@ -206,6 +206,7 @@ void Engine::upload_pattern(const Symbolic &S)
     P.maxcol = S.maxcol;
     P.fw_nld = H_.fw_nld;
     P.bw_nld = H_.bw_nld;
+    P.bwp_nld = H_.bwp_nld;
     P.fa_nld = H_.fa_nld;
     P.sw_slots = H_.sw_slots + 1; // rows behind the ring: the zero row, then the slots
     P.fa_slots = H_.fa_slots;
@@ -233,9 +234,10 @@ void Engine::upload_pattern(const Symbolic &S)
     P.fw_ld[2] = variant(H_.fw_ld, L_.rhs2, 0, L_.xw2);
     P.fw_ld[3] = variant(H_.fw_ld, L_.e2, 0, L_.xw2);
     P.bw = upload(H_.bw, owned_, st);
-    P.bw_ld[0] = variant(H_.bw_ld, L_.sol1, L_.sol1, L_.xw); // a plain solve loads (and ignores) its own output rows
+    P.bwp = upload(H_.bwp, owned_, st);
+    P.bw_ld[0] = variant(H_.bwp_ld, L_.sol1, 0, L_.xw); // plain solve: its own program (no solution rows to add to)
     P.bw_ld[1] = variant(H_.bw_ld, L_.dxr, L_.sol1, L_.xw);
-    P.bw_ld[2] = variant(H_.bw_ld, L_.sol2, L_.sol2, L_.xw2);
+    P.bw_ld[2] = variant(H_.bwp_ld, L_.sol2, 0, L_.xw2);
     P.bw_ld[3] = variant(H_.bw_ld, L_.dxr2, L_.sol2, L_.xw2);
     P.fa = upload(H_.fa, owned_, st);
     P.fa_ld = upload(H_.fa_ld, owned_, st);

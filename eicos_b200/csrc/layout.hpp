@@ -112,10 +112,10 @@ struct DevPattern
     // mat-vec [rhs1/sol1, rhs2/sol2, computeResiduals].  Sweep lists: index = 2 * set + refinement, where
     // set 0 = (rhs1, sol1) with work vectors xw/dxr/e and set 1 = (rhs2, sol2) with xw2/dxr2/e2, so
     // that the two solves of an iteration that share a factor can run at the same time.
-    const int *fw, *bw, *fa, *fa_ld, *mv;
+    const int *fw, *bw, *bwp, *fa, *fa_ld, *mv; // bwp: backward sweep without accumulation (list 2 * set)
     const int *fw_ld[4], *bw_ld[4], *mv_ld[3];
     const double *mv_val;
-    int fw_nld, bw_nld, fa_nld, mv_nld, mv_rows, sw_slots, fa_slots;
+    int fw_nld, bw_nld, bwp_nld, fa_nld, mv_nld, mv_rows, sw_slots, fa_slots;
     int sw_direct; // the sweep programs contain operands read straight from global memory
     int fa_fast;   // the factor program is in record form (streams.hpp)
     const double *fa_val;

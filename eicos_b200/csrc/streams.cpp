@@ -219,8 +219,11 @@ void build_forward(const Symbolic &S, const Layout &L, int max_slots, HostStream
 // ---- backward sweep  out = P' L^-T D^-1 xw, columns in reverse elimination order (dot form, Eigen's
 // order); results land in KKT order.  The home of a finished entry is its output row.
 //   column k: [cnt | sync, keep | 1/d ring row << 8 | xw ring row << 16 | accumulated-solution ring row << 24, out row] cnt x pair
-void build_backward(const Symbolic &S, const Layout &L, int max_slots, HostStreams &H)
+// accumulate: the program also loads the row of the solution it adds its result to (refinement
+// rounds); the plain program of the first solve leaves those loads out.
+void build_backward(const Symbolic &S, const Layout &L, int max_slots, HostStreams &H, bool accumulate)
 {
+    ivec &ops = accumulate ? H.bw : H.bwp, &ld = accumulate ? H.bw_ld : H.bwp_ld;
     std::vector<ivec> uses(S.N); // value i is used by the columns of row i, latest column first
     for (int i = 0; i < S.N; i++)
         for (int t = S.Lr.p[i + 1] - 1; t >= S.Lr.p[i]; t--)
@@ -229,18 +232,18 @@ void build_backward(const Symbolic &S, const Layout &L, int max_slots, HostStrea
         if (!std::is_sorted(u.begin(), u.end()))
             throw std::logic_error("rows of L must have ascending columns");
     SlotCache cache(max_slots, uses);
-    FifoSim F(H.bw_ld);
+    FifoSim F(ld);
     ivec prod(S.N, 0);
     for (int k = S.N - 1; k >= 0; k--)
     {
         const int o = S.pinv[k], cnt = S.Lp[k + 1] - S.Lp[k];
         const int first = F.npop;
-        const int drow = F.pop(0, L.Dinv + k), xrow = F.pop(3, k), arow = F.pop(2, o);
-        const size_t w1 = H.bw.size() + 1;
-        H.bw.push_back(cnt);
-        H.bw.push_back(0);
-        H.bw.push_back(o);
-        emit_pairs(H.bw, F, w1 - 1, 3, first, cnt, [&](int q) {
+        const int drow = F.pop(0, L.Dinv + k), xrow = F.pop(3, k), arow = accumulate ? F.pop(2, o) : SW_ZERO_ROW;
+        const size_t w1 = ops.size() + 1;
+        ops.push_back(cnt);
+        ops.push_back(0);
+        ops.push_back(o);
+        emit_pairs(ops, F, w1 - 1, 3, first, cnt, [&](int q) {
             const int u = S.Lp[k] + q, i = S.Li[u];
             const int lrow = F.pop(0, L.Lx + u);
             int opnd;
@@ -260,13 +263,13 @@ void build_backward(const Symbolic &S, const Layout &L, int max_slots, HostStrea
             return pair_word(lrow, opnd);
         });
         const int s = cache.alloc(k);
-        H.bw[w1] = (s >= 0 ? SW_SLOT0 + s : SW_NO_KEEP) | (drow << 8) | (xrow << 16) | (arow << 24);
+        ops[w1] = (s >= 0 ? SW_SLOT0 + s : SW_NO_KEEP) | (drow << 8) | (xrow << 16) | (arow << 24);
         prod[k] = F.npop;
     }
-    H.bw_nld = (int)H.bw_ld.size();
+    (accumulate ? H.bw_nld : H.bwp_nld) = (int)ld.size();
     H.sw_slots = std::max(H.sw_slots, cache.top);
-    pad_tail(H.bw);
-    pad_tail(H.bw_ld);
+    pad_tail(ops);
+    pad_tail(ld);
 }
 
 // ---- KKT mat-vec program (streams.hpp).  Rows = x, y and LP-z rows in elimination order; the
@@ -621,7 +624,8 @@ void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, 
             if (S.Li[u] >= S.Li[u + 1])
                 throw std::logic_error("columns of L must have ascending rows");
     build_forward(S, L, max_sw_slots, H);
-    build_backward(S, L, max_sw_slots, H);
+    build_backward(S, L, max_sw_slots, H, true);
+    build_backward(S, L, max_sw_slots, H, false);
     if (!build_factor_fast(S, L, max_fa_slots, H))
         build_factor(S, L, max_fa_slots, H);
     build_matvec(S, L, max_sw_slots, H);

@@ -136,8 +136,8 @@ struct HostStreams
 {
     int workers = 1;
     // slot programs (one warp): ops, load list (+ its length in words), shared-memory slots used
-    ivec fw, fw_ld, bw, bw_ld, fa, fa_ld, mv, mv_ld;
-    int fw_nld = 0, bw_nld = 0, fa_nld = 0, mv_nld = 0, mv_rows = 0;
+    ivec fw, fw_ld, bw, bw_ld, bwp, bwp_ld, fa, fa_ld, mv, mv_ld; // bwp: backward sweep of a plain solve (no accumulation)
+    int fw_nld = 0, bw_nld = 0, bwp_nld = 0, fa_nld = 0, mv_nld = 0, mv_rows = 0;
     dvec mv_val;
     int sw_slots = 0, fa_slots = 0;
     int fa_fast = 0; // the factor program is in record form

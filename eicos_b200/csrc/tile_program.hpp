@@ -1092,8 +1092,8 @@ EI_DEV void ldl_backward_t(const Team &tm, const KArgs &a, double *T, int varian
     double *xp = T + (size_t)(accumulate ? x : out) * TILE;
     PStream ops;
     Fifo ff;
-    ops.open(tm, P.bw, 0);
-    ff.open(tm, P.bw_ld[variant], P.bw_nld, T, 1);
+    ops.open(tm, accumulate ? P.bw : P.bwp, 0);
+    ff.open(tm, P.bw_ld[variant], accumulate ? P.bw_nld : P.bwp_nld, T, 1);
     for (int k = 0; k < P.N; k++)
     {
         const i4 rec = ops.get();
