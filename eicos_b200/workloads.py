@@ -119,3 +119,69 @@ def soc_mpc_batch(P, batch, seed=7):
     for k in range(T):
         hs[:, base + 5 * k + 1: base + 5 * k + 5] = -ref
     return dict(cs=None, hs=hs, bs=bs)
+
+
+def synthetic_socp(n=2000, m=3000, ncones=500, p=200, seed=7):
+    """BASELINE.json configs[3] in the concrete form SURVEY.md 8(d) proposes (the literal statement -
+    500 cones uniform on 3..10 inside m = 3000 rows - is inconsistent): cone dims q_i = 3 + floor(8 u_i^2),
+    resampled until sum q <= m - 100; l = m - sum q LP rows; G has 4 entries per row, three inside a
+    +-16 column window around row * n / m plus one uniform column (bounded fill); A has 3 per row by
+    the same rule; values N(0,1).  Feasible by construction: x0 ~ N(0,1), s0 and z0 strictly interior,
+    y0 ~ N(0,1), h = G x0 + s0, b = A x0, c = -G' z0 - A' y0.  NOT reference data."""
+    rng = np.random.default_rng(seed)
+    while True:
+        q = (3 + np.floor(8.0 * rng.random(ncones) ** 2)).astype(np.int32)
+        if q.sum() <= m - 100:
+            break
+    l = int(m - q.sum())
+
+    def banded(rows, per_row):
+        M = {}
+        for r in range(rows):
+            centre = r * n // rows
+            cols = set()
+            while len(cols) < per_row - 1:
+                cols.add(int(np.clip(centre + rng.integers(-16, 17), 0, n - 1)))
+            while len(cols) < per_row:
+                cols.add(int(rng.integers(0, n)))
+            for c in cols:
+                M[(r, c)] = rng.standard_normal()
+        return M
+
+    def to_csc(M, rows):
+        by_col = [[] for _ in range(n)]
+        for (r, c), v in M.items():
+            by_col[c].append((r, v))
+        pr, ir, jc = [], [], [0]
+        for c in range(n):
+            for r, v in sorted(by_col[c]):
+                ir.append(r)
+                pr.append(v)
+            jc.append(len(ir))
+        return np.array(pr), np.array(jc, np.int32), np.array(ir, np.int32)
+
+    Gm, Am = banded(m, 4), banded(p, 3)
+    Gpr, Gjc, Gir = to_csc(Gm, m)
+    Apr, Ajc, Air = to_csc(Am, p)
+
+    def matvec(pr, jc, ir, rows, x):
+        out = np.zeros(rows)
+        for c in range(n):
+            sl = slice(jc[c], jc[c + 1])
+            out[ir[sl]] += pr[sl] * x[c]
+        return out
+
+    def rmatvec(pr, jc, ir, y):
+        return np.array([np.dot(pr[jc[c]:jc[c + 1]], y[ir[jc[c]:jc[c + 1]]]) for c in range(n)])
+
+    x0, y0 = rng.standard_normal(n), rng.standard_normal(p)
+    s0, z0 = np.abs(rng.standard_normal(m)) + 0.5, np.abs(rng.standard_normal(m)) + 0.5
+    at = l
+    for d in q:
+        s0[at] = np.linalg.norm(s0[at + 1:at + d]) + 1.0
+        z0[at] = np.linalg.norm(z0[at + 1:at + d]) + 1.0
+        at += d
+    return dict(n=n, m=m, p=p, l=l, ncones=int(ncones), q=q,
+                Gpr=Gpr, Gjc=Gjc, Gir=Gir, Apr=Apr, Ajc=Ajc, Air=Air,
+                c=-rmatvec(Gpr, Gjc, Gir, z0) - rmatvec(Apr, Ajc, Air, y0),
+                h=matvec(Gpr, Gjc, Gir, m, x0) + s0, b=matvec(Apr, Ajc, Air, p, x0))

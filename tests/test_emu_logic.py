@@ -143,3 +143,20 @@ def test_compaction_is_transparent(oracle_mod, emu_lib):
         assert np.array_equal(a[k], b[k]), k
     ref = oracle_mod.batch_run(P, batch, hs=W["hs"], bs=W["bs"], nthreads=8)
     assert np.array_equal(a["exit"], ref["exit"]) and np.array_equal(a["iter"], ref["iter"])
+
+
+def test_synthetic_socp_config4_small(oracle_mod, emu_lib):
+    """BASELINE.json configs[3] (random sparse SOCP with many small cones, SURVEY.md 8d recipe) at a size
+    the CPU tier finishes in seconds; h, b and c differ per instance.  At the literal size (n=2000,
+    m=3000, 500 cones) the recipe's uniform columns fill L to 1.57 M entries with a 1628-wide trailing
+    front - DESIGN.md section 8."""
+    from eicos_b200.binding import BatchSolver
+    from eicos_b200.workloads import perturbed, synthetic_socp
+    P = synthetic_socp(n=200, m=300, ncones=50, p=20, seed=7)
+    W = perturbed(P, 6, rel=0.01, seed=3, vary=("h", "b", "c"))
+    ref = oracle_mod.batch_run(P, 6, cs=W["cs"], hs=W["hs"], bs=W["bs"], nthreads=4)
+    out = BatchSolver(P, lib=emu_lib, capacity=6).solve(6, cs=W["cs"], hs=W["hs"], bs=W["bs"])
+    assert np.array_equal(out["exit"], ref["exit"]) and np.array_equal(out["iter"], ref["iter"])
+    assert np.all(ref["exit"] == 0)
+    for k in "xyzs":
+        assert relerr(out[k], ref[k]) <= TOL, k
