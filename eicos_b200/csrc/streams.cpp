@@ -623,6 +623,12 @@ void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, 
         for (int u = S.Lp[k]; u + 1 < S.Lp[k + 1]; u++)
             if (S.Li[u] >= S.Li[u + 1])
                 throw std::logic_error("columns of L must have ascending rows");
+    // The factor program has one word per Schur update.  Patterns that fill into large dense fronts
+    // (hundreds of millions of updates) belong to a supernodal / dense-front path, which this engine
+    // does not have yet: refuse instead of compiling a multi-gigabyte program.
+    if (S.fma_count > MAX_FACTOR_UPDATES)
+        throw std::runtime_error("pattern fills too much for the row-program factorisation (" + std::to_string(S.fma_count) +
+                                 " Schur updates per factorisation; limit " + std::to_string(MAX_FACTOR_UPDATES) + ")");
     build_forward(S, L, max_sw_slots, H);
     build_backward(S, L, max_sw_slots, H, true);
     build_backward(S, L, max_sw_slots, H, false);

@@ -26,11 +26,13 @@
 #include "layout.hpp"
 #include "symbolic.hpp"
 
+#include <string>
 #include <vector>
 
 namespace eicos
 {
 
+constexpr long long MAX_FACTOR_UPDATES = 100LL * 1000 * 1000; // Schur updates per factorisation a factor program may hold
 constexpr int STREAM_CHUNK = 32;  // words per cooperative load
 constexpr int STREAM_PAD = 640;   // readable words after the last used one (the stream readers fetch up to four 128-word chunks ahead)
 constexpr int STAGE_SLOTS = 16;   // rows per staging buffer (one slot = TILE doubles); a worker owns two buffers

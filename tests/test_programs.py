@@ -73,3 +73,13 @@ def test_slot_budget_does_not_change_bits(oracle_mod, emu_lib, monkeypatch):
     for k in ("x", "y", "z", "s"):
         assert np.array_equal(outs[0][k], outs[1][k]), k
     assert np.array_equal(outs[0]["iter"], outs[1]["iter"])
+
+
+def test_catastrophic_fill_is_refused(oracle_mod, emu_lib):
+    """configs[3] at its literal size fills L to 1.57 M entries (8.3e8 Schur updates per factorisation):
+    setup must fail with a clear message instead of compiling a multi-gigabyte factor program."""
+    from eicos_b200.binding import BatchSolver
+    from eicos_b200.workloads import synthetic_socp
+    P = synthetic_socp()
+    with pytest.raises(RuntimeError, match="fills too much"):
+        BatchSolver(P, lib=emu_lib, capacity=1)
