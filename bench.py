@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mpc02", choices=["mpc02", "socmpc"])
+    ap.add_argument("--workload", default="mpc02", choices=["mpc02", "socmpc", "lp25fv47"])
     ap.add_argument("--batch", type=int, default=65536, help="instances per GPU (weak) or in total (strong)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--workers", type=int, default=0)
@@ -59,6 +59,13 @@ def make_problem(workload):
         name = ("MPC02 (reference test/MPC/MPC02.h; stands in for the missing MPC01) x{B} per GPU, "
                 "h*(1+-0.2%) b*(1+-2%) per instance via updateData, G/A/c shared")
         return P, name, lambda batch, seed: perturbed(P, batch, rel=MPC_REL, seed=seed)
+    if workload == "lp25fv47":  # BASELINE.json configs[4]: c and b perturbed by 1 %
+        d = np.load(os.path.join(ROOT, "tests", "golden", "fixtures", "lp_25fv47.npz"))
+        P = {k: d[k] for k in d.files}
+        for k in ("n", "m", "p", "l", "ncones"):
+            P[k] = int(P[k])
+        name = "lp_25fv47 (reference test/LPnetlib/lp_25fv47.h) x{B} per GPU, c*(1+-1%) b*(1+-1%) per instance, G/A/h shared"
+        return P, name, lambda batch, seed: perturbed(P, batch, rel=0.01, seed=seed, vary=("c", "b"))
     P = soc_mpc(T=40)
     name = "builder-defined SOC MPC (2-D double integrator, T=40, 80 cones of dim 3/5) x{B} per GPU, x0/ref per instance"
     return P, name, lambda batch, seed: soc_mpc_batch(P, batch, seed=seed)
@@ -134,16 +141,17 @@ def run_reference(args, rank, world):
     import oracle
     cores = host_cores()
     probe = gen(max(2 * cores, 8), 990)
-    t = oracle.batch_run(P, len(probe["hs"]), hs=probe["hs"], bs=probe["bs"], nthreads=cores, want_solution=False)["seconds"]
-    per = max(t / len(probe["hs"]), 1e-6)
+    nprobe = max(2 * cores, 8)
+    t = oracle.batch_run(P, nprobe, cs=probe.get("cs"), hs=probe["hs"], bs=probe["bs"], nthreads=cores, want_solution=False)["seconds"]
+    per = max(t / nprobe, 1e-6)
     total_steps = args.steps + args.warmup
     sample = int(min(4096, max(cores, (120.0 / total_steps) / per)))  # whole run within a few minutes
     W = gen(sample, 1234)
     for _ in range(args.warmup):
-        oracle.batch_run(P, sample, hs=W["hs"], bs=W["bs"], nthreads=cores, want_solution=False)
+        oracle.batch_run(P, sample, cs=W.get("cs"), hs=W["hs"], bs=W["bs"], nthreads=cores, want_solution=False)
     secs, exits = 0.0, None
     for _ in range(args.steps):
-        r = oracle.batch_run(P, sample, hs=W["hs"], bs=W["bs"], nthreads=cores, want_solution=False)
+        r = oracle.batch_run(P, sample, cs=W.get("cs"), hs=W["hs"], bs=W["bs"], nthreads=cores, want_solution=False)
         secs += r["seconds"]
         exits = r["exit"]
     value = args.steps * sample / secs
@@ -188,8 +196,9 @@ def main():
         seed = 1234 + rank
     n, m, p = P["n"], P["m"], P["p"]
     W = gen(batch, seed)
-    hs_h = torch.from_numpy(np.ascontiguousarray(W["hs"])).pin_memory()
-    bs_h = torch.from_numpy(np.ascontiguousarray(W["bs"])).pin_memory()
+    # per-instance stacks (pinned host copies); a vector the workload does not vary stays shared (None)
+    host = {k: (torch.from_numpy(np.ascontiguousarray(W[k])).pin_memory() if W.get(k) is not None else None)
+            for k in ("cs", "hs", "bs")}
     x_h = torch.empty((batch, n), dtype=torch.float64).pin_memory()
     exit_h = torch.empty((batch,), dtype=torch.int32).pin_memory()
 
@@ -197,22 +206,24 @@ def main():
     dims = solver.dims()
     stream = torch.cuda.ExternalStream(solver.stream(), device=dev)
 
-    hs_d, bs_d = hs_h.to(dev), bs_h.to(dev)
+    devb = {k: (v.to(dev) if v is not None else None) for k, v in host.items()}
+    dptr = {k: (v.data_ptr() if v is not None else 0) for k, v in devb.items()}
     x_d = torch.empty((batch, n), dtype=torch.float64, device=dev)
     exit_d = torch.empty((batch,), dtype=torch.int32, device=dev)
     iter_d = torch.empty((batch,), dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
 
     def step_device():
-        solver.solve_device(batch, d_hs=hs_d.data_ptr(), d_bs=bs_d.data_ptr(), d_x=x_d.data_ptr(),
+        solver.solve_device(batch, d_cs=dptr["cs"], d_hs=dptr["hs"], d_bs=dptr["bs"], d_x=x_d.data_ptr(),
                             d_exit=exit_d.data_ptr(), d_iter=iter_d.data_ptr())
 
     def step_host():
         L = solver.lib.L
         import ctypes as C
         dp = C.POINTER(C.c_double)
+        hp = {k: (C.cast(v.data_ptr(), dp) if v is not None else None) for k, v in host.items()}
         solver.lib.check(L.eicos_batch_solve(
-            solver.h, batch, None, C.cast(hs_h.data_ptr(), dp), C.cast(bs_h.data_ptr(), dp),
+            solver.h, batch, hp["cs"], hp["hs"], hp["bs"],
             C.cast(x_h.data_ptr(), dp), None, None, None,
             C.cast(exit_h.data_ptr(), C.POINTER(C.c_int)), None))
 
@@ -261,7 +272,8 @@ def main():
             step_host()
         ms_e = timed(step_host, args.steps)
         e2e = {"value": total_batch * args.steps / (ms_e * 1e-3), "unit": "solves/s",
-               "h2d_bytes_per_step": int(batch * (m + p) * 8), "d2h_bytes_per_step": int(batch * (n * 8 + 4)),
+               "h2d_bytes_per_step": int(sum(v.numel() * 8 for v in host.values() if v is not None)),
+               "d2h_bytes_per_step": int(batch * (n * 8 + 4)),
                "ms_per_step": ms_e / args.steps,
                "api": "eicos_batch_solve (include/eicos_b200.h): pinned host h,b in; x and exit flags out"}
         assert np.array_equal(exit_h.numpy(), exits)
