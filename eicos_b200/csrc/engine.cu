@@ -249,9 +249,6 @@ void Engine::upload_pattern(const Symbolic &S)
     P.mv_nld = H_.mv_nld;
     P.mv_rows = H_.mv_rows;
     P.fa_val = dfa_val_ = upload(H_.fa_val, owned_, st);
-    P.rc = upload(H_.rc, owned_, st);
-    P.rc_seg = upload(H_.rc_seg, owned_, st);
-    P.rc_val = drc_val_ = upload(H_.rc_val, owned_, st);
     ivec vk;
     for (int k = 0; k < S.l; k++)
         vk.push_back(0);
@@ -280,7 +277,6 @@ void Engine::upload_values(const Symbolic &S)
     be::h2d(dGeq_, ge.data(), ge.size() * sizeof(double), st);
     be::h2d(dfa_val_, H_.fa_val.data(), H_.fa_val.size() * sizeof(double), st);
     be::h2d(dmv_val_, H_.mv_val.data(), H_.mv_val.size() * sizeof(double), st);
-    be::h2d(drc_val_, H_.rc_val.data(), H_.rc_val.size() * sizeof(double), st);
     be::sync(st);
 }
 

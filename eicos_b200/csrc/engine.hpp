@@ -96,7 +96,7 @@ class Engine
     // positions of value arrays that upload_values() rewrites
     double *dxeq_ = nullptr, *dAeq_ = nullptr, *dGeq_ = nullptr;
     double *dmv_val_ = nullptr;
-    double *dfa_val_ = nullptr, *drc_val_ = nullptr;
+    double *dfa_val_ = nullptr;
     HostStreams H_;        // host copy of the instruction streams (value streams are rebuilt on updateData)
     std::vector<int> Lp_;  // column pointers of L (debug extraction)
     std::vector<void *> events_;

@@ -119,8 +119,6 @@ struct DevPattern
     int sw_direct; // the sweep programs contain operands read straight from global memory
     int fa_fast;   // the factor program is in record form (streams.hpp)
     const double *fa_val;
-    const int *rc, *rc_seg; // second-order-cone rows of G, rc_seg = [cone]{int offset, double offset}
-    const double *rc_val;
     const int *Vkind; // per V entry: what resetKKTScalings writes (0 -> -1, 1 -> 0, 2 -> +1)
 };
 

@@ -272,16 +272,20 @@ void build_backward(const Symbolic &S, const Layout &L, int max_slots, HostStrea
     pad_tail(ld);
 }
 
-// ---- KKT mat-vec program (streams.hpp).  Rows = x, y and LP-z rows in elimination order; the
-// pairs of a row keep the order of the CSC / CSR data (G entries before A entries in an x row).
+// ---- KKT mat-vec program (streams.hpp).  Rows = x, y and z rows (the two expansion slots of every
+// second-order cone excepted) in elimination order; the pairs of a row keep the order of the
+// CSC / CSR data (G entries before A entries in an x row).
 void build_matvec(const Symbolic &S, const Layout &L, int max_slots, HostStreams &H)
 {
-    const int n = S.n, p = S.p, zb = S.n + S.p, nrows = zb + S.l;
+    const int n = S.n, p = S.p, zb = S.n + S.p;
     ivec order;
-    for (int r = 0; r < nrows; r++)
+    for (int r = 0; r < zb; r++)
         order.push_back(r);
+    for (int i = 0; i < S.m; i++)
+        order.push_back(zb + S.zk[i]); // K-space row of z entry i (expanded index)
+    const int nrows = (int)order.size();
     std::sort(order.begin(), order.end(), [&](int a, int b) { return S.P[a] < S.P[b]; });
-    std::vector<std::vector<std::pair<int, double>>> ent(nrows);
+    std::vector<std::vector<std::pair<int, double>>> ent(S.N);
     for (int j = 0; j < n; j++)
     {
         for (int k = S.G.p[j]; k < S.G.p[j + 1]; k++)
@@ -292,9 +296,9 @@ void build_matvec(const Symbolic &S, const Layout &L, int max_slots, HostStreams
     for (int i = 0; i < p; i++)
         for (int t = S.Ar.p[i]; t < S.Ar.p[i + 1]; t++)
             ent[n + i].push_back({S.Ar.j[t], S.A.x[S.Ar.v[t]]});
-    for (int i = 0; i < S.l; i++)
+    for (int i = 0; i < S.m; i++)
         for (int t = S.Gr.p[i]; t < S.Gr.p[i + 1]; t++)
-            ent[zb + i].push_back({S.Gr.j[t], S.G.x[S.Gr.v[t]]});
+            ent[zb + S.zk[i]].push_back({S.Gr.j[t], S.G.x[S.Gr.v[t]]});
     std::vector<ivec> uses(S.N);
     for (int t = 0; t < nrows; t++)
     {
@@ -327,13 +331,13 @@ void build_matvec(const Symbolic &S, const Layout &L, int max_slots, HostStreams
     for (int t = 0; t < nrows; t++)
     {
         const int r = order[t], cnt = (int)ent[r].size();
-        const int kind = r < n ? MV_X : (r < zb ? MV_Y : MV_Z);
+        const int kind = r < n ? MV_X : (r < zb ? MV_Y : (r < zb + S.l ? MV_Z : MV_ZC));
         if (cnt > MV_CNT_MASK)
             throw std::logic_error("mat-vec program: row too long");
         const int first = F.npop;
         const int ex0 = F.pop(1, r);
         const auto own = operand(r);
-        const int ex1 = kind == MV_Z ? F.pop(3, r - zb) : SW_ZERO_ROW;
+        const int ex1 = kind >= MV_Z ? F.pop(3, r - zb) : SW_ZERO_ROW;
         const size_t w0 = H.mv.size();
         H.mv.push_back(cnt | (kind << MV_KIND_SHIFT));
         H.mv.push_back(ex0 | (own.first << 8) | (own.second << 16) | (ex1 << 24));
@@ -636,30 +640,6 @@ void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, 
         build_factor(S, L, max_fa_slots, H);
     build_matvec(S, L, max_sw_slots, H);
 
-    // ---- second-order-cone rows of G (residuals of the cone block are evaluated cone by cone):
-    // per cone [dim, first expanded index, first q row] then one row [cnt, idx...] per cone entry;
-    // rc_seg = [cone]{int offset, double offset}
-    H.rc_seg.assign((size_t)S.nc * 2, 0);
-    for (int c = 0; c < S.nc; c++)
-    {
-        H.rc_seg[c * 2] = (int)H.rc.size();
-        H.rc_seg[c * 2 + 1] = (int)H.rc_val.size();
-        H.rc.push_back(S.q[c]);
-        H.rc.push_back(S.cone_k[c]);
-        H.rc.push_back(S.cone_q[c]);
-        for (int k = 0; k < S.q[c]; k++)
-        {
-            const int i = S.cone_z[c] + k;
-            H.rc.push_back(S.Gr.p[i + 1] - S.Gr.p[i]);
-            for (int t = S.Gr.p[i]; t < S.Gr.p[i + 1]; t++)
-            {
-                H.rc.push_back(S.Gr.j[t]);
-                H.rc_val.push_back(S.G.x[S.Gr.v[t]]);
-            }
-        }
-    }
-    pad_tail(H.rc);
-    pad_tail(H.rc_val);
 }
 
 void refresh_stream_values(const Symbolic &S, const Layout &L, HostStreams &H)
@@ -668,7 +648,6 @@ void refresh_stream_values(const Symbolic &S, const Layout &L, HostStreams &H)
     build_streams(S, L, H.workers, std::max(H.sw_slots, 1), std::max(H.fa_slots, 1), fresh);
     H.fa_val.swap(fresh.fa_val);
     H.mv_val.swap(fresh.mv_val);
-    H.rc_val.swap(fresh.rc_val);
 }
 
 } // namespace eicos

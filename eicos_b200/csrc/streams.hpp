@@ -33,7 +33,7 @@ namespace eicos
 {
 
 constexpr long long MAX_FACTOR_UPDATES = 100LL * 1000 * 1000; // Schur updates per factorisation a factor program may hold
-constexpr int STREAM_CHUNK = 32;  // words per cooperative load
+constexpr int STREAM_CHUNK = 32;  // streams are padded to multiples of this many words
 constexpr int STREAM_PAD = 640;   // readable words after the last used one (the stream readers fetch up to four 128-word chunks ahead)
 constexpr int STAGE_SLOTS = 16;   // rows per staging buffer (one slot = TILE doubles); a worker owns two buffers
 
@@ -77,7 +77,7 @@ constexpr int SW_SLOT0 = FIFO_ROWS + 1;
 constexpr int SW_PAD_PAIR = SW_ZERO_ROW | (SW_ZERO_ROW << SW_OPND_SHIFT);
 
 // ---- KKT mat-vec program (refinement residual, computeResiduals): one row program over the x, y
-// and LP rows of [0 A' G'; A 0 0; G 0 0] in elimination order, where the rows that share operands
+// and z rows of [0 A' G'; A 0 0; G 0 0] in elimination order, where the rows that share operands
 // are neighbours.  Coefficients are shared by the batch and travel in a parallel stream of 16-byte
 // double records; every operand row is loaded once through the FIFO and kept in a slot while it
 // has further uses (Belady), so the traffic is the vectors themselves.
@@ -95,7 +95,8 @@ enum MvKind : int
 {
     MV_X = 0, // row of the x block: -(G' z + A' y)
     MV_Y = 1, // row of the y block: A x
-    MV_Z = 2  // LP row of the z block: G x
+    MV_Z = 2, // LP row of the z block: G x
+    MV_ZC = 3 // row of a second-order cone: G x (the cone block itself is applied cone by cone afterwards)
 };
 
 // ---- factorisation, record form (patterns whose columns of L have at most FA_FAST_COL entries and
@@ -145,9 +146,6 @@ struct HostStreams
     int fa_fast = 0; // the factor program is in record form
     long long sw_far = 0, sw_direct = 0, fa_home = 0; // operands served by far gathers / direct global loads / home rows (statistics)
     dvec fa_val;
-    // second-order-cone rows of G: rc_seg = [cone]{int offset, double offset}
-    ivec rc, rc_seg;
-    dvec rc_val;
 };
 
 // K-space / expanded indexing used by the row sets: x rows [0,n), y rows [n,n+p), z rows

@@ -276,76 +276,6 @@ struct Team
 #endif
 };
 
-// ------------------------------------------------------------------ instruction stream readers
-// All lanes of the warp call get() together (never under a per-lane branch).
-struct IStream
-{
-#ifdef EICOS_EMU
-    const int *p;
-    EI_DEV void open(const int *base, int) { p = base; }
-    EI_DEV int get() { return *p++; }
-#else
-    const int *base; // warp-uniform
-    int off;         // word offset of the chunk after `nxt`, plus this lane
-    int cur, nxt, pos;
-    EI_DEV void open(const int *b, int lane)
-    {
-        base = b;
-        cur = __ldg(b + lane);
-        nxt = __ldg(b + STREAM_CHUNK + lane);
-        off = 2 * STREAM_CHUNK + lane;
-        pos = 0;
-    }
-    EI_DEV int get()
-    {
-        if (pos == STREAM_CHUNK)
-        {
-            cur = nxt;
-            nxt = __ldg(base + off);
-            off += STREAM_CHUNK;
-            pos = 0;
-        }
-        const int v = __shfl_sync(0xffffffffu, cur, pos);
-        ++pos;
-        return v;
-    }
-#endif
-};
-
-struct DStream
-{
-#ifdef EICOS_EMU
-    const double *p;
-    EI_DEV void open(const double *base, int) { p = base; }
-    EI_DEV double get() { return *p++; }
-#else
-    const double *base;
-    int off, pos;
-    double cur, nxt;
-    EI_DEV void open(const double *b, int lane)
-    {
-        base = b;
-        cur = __ldg(b + lane);
-        nxt = __ldg(b + STREAM_CHUNK + lane);
-        off = 2 * STREAM_CHUNK + lane;
-        pos = 0;
-    }
-    EI_DEV double get()
-    {
-        if (pos == STREAM_CHUNK)
-        {
-            cur = nxt;
-            nxt = __ldg(base + off);
-            off += STREAM_CHUNK;
-            pos = 0;
-        }
-        const double v = __shfl_sync(0xffffffffu, cur, pos);
-        ++pos;
-        return v;
-    }
-#endif
-};
-
 // ------------------------------------------------------------------ block reductions (fixed order)
 template <int K, class Op>
 EI_DEV void team_reduce(const Team &tm, vd (&v)[K], Op op)
@@ -443,19 +373,6 @@ EI_DEV void ew_rows(const Team &tm, const double *T, int count, const int (&in)[
             if (base + u < count)
                 body(base + u, x[u]);
     }
-}
-
-// sum_k val_k * vec[idx_k] folded into `v` with sign: one mat-vec row straight from global memory
-EI_DEV vd row_accumulate(const Team &tm, IStream &is, DStream &ds, const double *T, int vec, vd v, double sign)
-{
-    const int cnt = is.get();
-    for (int k = 0; k < cnt; k++)
-    {
-        const int idx = is.get();
-        const double val = ds.get();
-        v += (sign * val) * vload(rowp(tm, T, vec + idx));
-    }
-    return v;
 }
 
 // ------------------------------------------------------------------ W products (src/eicos.cpp:485-507)
@@ -1200,18 +1117,23 @@ EI_DEV void mv_run(const Team &tm, const KArgs &a, const double *T, int variant,
 // ------------------------------------------------------------------ KKT residual for iterative refinement (src/eicos.cpp:1511-1576)
 // e = rhs - Ktrue * x with the un-regularised scaling block (identity while initialising),
 // returns ||e||_inf per instance.
-EI_DEV vd kkt_residual(const Team &tm, const KArgs &a, double *T, int variant, int rhs, int x, int erow, bool initialize)
+EI_DEV vd kkt_residual(const Team &tm, const KArgs &a, double *T, int variant, int x, int erow, bool initialize)
 {
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     const double delta = Settings::deltastat;
-    const int n = P.n, p = P.p, zb = P.n + P.p;
+    const int zb = P.n + P.p;
     vd nerr = vset(0.0);
     if (tm.wk == 0 && P.mv_rows > 0)
         mv_run(
             tm, a, T, variant, -1.0, -1.0, -1.0,
             [&](int, vd ex0, vd, vd) { return ex0; },
             [&](int kind, int r, vd v, vd, vd own, vd ex1) {
+                if (kind == MV_ZC)
+                { // cone row: rhs - G x only; the cone block is added below
+                    ROWD(T, erow + r) = v;
+                    return;
+                }
                 if (kind == MV_X)
                     v -= delta * own;
                 else
@@ -1225,13 +1147,10 @@ EI_DEV vd kkt_residual(const Team &tm, const KArgs &a, double *T, int variant, i
             });
     if (P.nc > 0)
     {
+        tm.sync(); // (workers > 1) the partial cone rows written by worker 0 are visible
         for (int c = tm.wk; c < P.nc; c += tm.nwk)
         {
-            IStream is;
-            DStream ds;
-            is.open(P.rc + EI_LDG(P.rc_seg + c * 2), tm.pl);
-            ds.open(P.rc_val + EI_LDG(P.rc_seg + c * 2 + 1), tm.pl);
-            const int d = is.get(), ks = is.get(), qo = is.get();
+            const int d = EI_LDG(P.cone_dim + c), ks = EI_LDG(P.cone_k + c), qo = EI_LDG(P.cone_q + c);
             const int kb = zb + ks; // KKT row of the cone's first entry
             const int cp = L.cpar + c * CP_COUNT;
             const vd eta2 = ROWD(T, cp + CP_ETA2), d1 = ROWD(T, cp + CP_D1), u0 = ROWD(T, cp + CP_U0);
@@ -1244,7 +1163,7 @@ EI_DEV vd kkt_residual(const Team &tm, const KArgs &a, double *T, int variant, i
             for (int k = 0; k < d; k++)
             {
                 const vd xk = ROWD(T, x + kb + k);
-                vd v = row_accumulate(tm, is, ds, T, x, ROWD(T, rhs + kb + k), -1.0);
+                vd v = ROWD(T, erow + kb + k); // rhs - G x from the mat-vec program
                 if (k < d - 1)
                     v += delta * xk;
                 else
@@ -1283,7 +1202,7 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
     const Layout &L = a.L;
     double *T = t.T;
     const KArgs::KktJob jb = a.job[tm.job];
-    const int rhs = jb.rhs, sol = jb.sol, set = jb.set;
+    const int sol = jb.sol, set = jb.set; // (jb.rhs is baked into the materialised load lists of the set)
     const int xw = set ? L.xw2 : L.xw, dxr = set ? L.dxr2 : L.dxr, erow = set ? L.e2 : L.e;
     const bool init = a.initialize != 0;
 
@@ -1309,7 +1228,7 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
     unsigned rounds = 0;
     for (;;)
     {
-        const vd nerr = kkt_residual(tm, a, T, set, rhs, sol, erow, init);
+        const vd nerr = kkt_residual(tm, a, T, set, sol, erow, init);
         EI_PHASE(3);
         vb rollback = vbset(false);
         VFOR
@@ -1641,9 +1560,8 @@ EI_DEV void tile_resid(const Team &tm, const KArgs &a, int tile)
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     double *T = t.T;
-    int *I = t.I;
-    const int n = P.n, p = P.p, zb = P.n + P.p;
-    const vd tau = ROWD(T, L.sc + S_TAU), kap = ROWD(T, L.sc + S_KAP);
+    const int zb = P.n + P.p;
+    const vd tau = ROWD(T, L.sc + S_TAU);
 
     enum { HX2, RX2, CX, NX2, HY2, RY2, BY, NY2, HZ2, RZ2, HZ, NZ2, NS2, GAP, NRED };
     vd r[NRED];
@@ -1662,10 +1580,10 @@ EI_DEV void tile_resid(const Team &tm, const KArgs &a, int tile)
     if (tm.wk == 0 && P.mv_rows > 0)
         mv_run(
             tm, a, T, LDV_HEAD, -1.0, 1.0, 1.0,
-            [&](int kind, vd, vd, vd ex1) { return kind == MV_Z ? ex1 : vset(0.0); },
+            [&](int kind, vd, vd, vd ex1) { return kind >= MV_Z ? ex1 : vset(0.0); },
             [&](int kind, int q, vd v, vd ex0, vd own, vd ex1) {
-                if (kind == MV_Z)
-                {
+                if (kind >= MV_Z)
+                { // LP and cone rows alike: rz = s + G x
                     zrow(q - zb, ex1, own, ex0, v);
                     return;
                 }
@@ -1688,24 +1606,6 @@ EI_DEV void tile_resid(const Team &tm, const KArgs &a, int tile)
                     r[NY2] += own * own;
                 }
             });
-    if (P.nc > 0)
-    {
-        for (int c = tm.wk; c < P.nc; c += tm.nwk)
-        {
-            IStream is;
-            DStream ds;
-            is.open(P.rc + EI_LDG(P.rc_seg + c * 2), tm.pl);
-            ds.open(P.rc_val + EI_LDG(P.rc_seg + c * 2 + 1), tm.pl);
-            const int d = is.get(), ks = is.get();
-            (void)is.get();
-            for (int k = 0; k < d; k++)
-            {
-                const int e = ks + k;
-                const vd si = ROWD(T, L.s + e), zi = ROWD(T, L.w + zb + e), hi = ROWD(T, L.chb + zb + e);
-                zrow(e, si, zi, hi, row_accumulate(tm, is, ds, T, L.w, si, 1.0));
-            }
-        }
-    }
     team_sum<NRED>(tm, r);
     if (tm.wk == 0)
         for (int k = 0; k < NRED; k++)
