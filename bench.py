@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mpc02", choices=["mpc02", "socmpc", "lp25fv47"])
+    ap.add_argument("--workload", default="mpc02", choices=["mpc02", "mpc02pim", "socmpc", "lp25fv47"])
     ap.add_argument("--batch", type=int, default=65536, help="instances per GPU (weak) or in total (strong)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--workers", type=int, default=0)
@@ -50,7 +50,21 @@ def parse_args():
 
 def make_problem(workload):
     """Problem data + a function producing the per-instance stacks for `batch` instances."""
-    from eicos_b200.workloads import MPC_REL, perturbed, soc_mpc, soc_mpc_batch
+    from eicos_b200.workloads import MPC_REL, perturbed, perturbed_matrices, soc_mpc, soc_mpc_batch
+    if workload == "mpc02pim":  # SURVEY.md 8f row 1: every instance brings its own G / A values (linearised dynamics)
+        d = np.load(os.path.join(ROOT, "tests", "golden", "fixtures", "MPC02.npz"))
+        P = {k: d[k] for k in d.files}
+        for k in ("n", "m", "p", "l", "ncones"):
+            P[k] = int(P[k])
+        name = ("MPC02 (reference test/MPC/MPC02.h) x{B} per GPU, per-instance G*(1+-0.1%) A*(1+-0.1%) values on the shared "
+                "pattern plus h*(1+-0.2%) b*(1+-2%), via updateData(Gpr, Apr, c, h, b); equilibration per instance on the device")
+
+        def gen(batch, seed):
+            W = perturbed(P, batch, rel=MPC_REL, seed=seed)
+            M = perturbed_matrices(P, batch, rel=0.001, seed=seed + 50000)
+            W["Gs"], W["As"] = M["Gs"], M["As"]
+            return W
+        return P, name, gen
     if workload == "mpc02":
         d = np.load(os.path.join(ROOT, "tests", "golden", "fixtures", "MPC02.npz"))
         P = {k: d[k] for k in d.files}
@@ -83,11 +97,11 @@ def cpu_baseline(P, gen, cores, seconds_target=15.0):
     import oracle
     probe_n = max(2 * cores, 8)
     W = gen(probe_n, 991)
-    t = oracle.batch_run(P, probe_n, hs=W["hs"], bs=W["bs"], cs=W.get("cs"), nthreads=cores, want_solution=False)["seconds"]
+    t = oracle.batch_run(P, probe_n, Gs=W.get("Gs"), As=W.get("As"), hs=W["hs"], bs=W["bs"], cs=W.get("cs"), nthreads=cores, want_solution=False)["seconds"]
     per = max(t / probe_n, 1e-6)
     sample = int(min(8192, max(probe_n, seconds_target / per)))
     W = gen(sample, 992)
-    r = oracle.batch_run(P, sample, hs=W["hs"], bs=W["bs"], cs=W.get("cs"), nthreads=cores, want_solution=False)
+    r = oracle.batch_run(P, sample, Gs=W.get("Gs"), As=W.get("As"), hs=W["hs"], bs=W["bs"], cs=W.get("cs"), nthreads=cores, want_solution=False)
     return {"value": sample / r["seconds"], "unit": "solves/s", "cores": cores, "kind": "port",
             "sample": f"{sample} instances of the same workload, {cores} threads, one solver per thread, "
                       f"updateData+solve per instance (includes re-equilibration and the per-solve AMD ordering), "
@@ -142,16 +156,16 @@ def run_reference(args, rank, world):
     cores = host_cores()
     probe = gen(max(2 * cores, 8), 990)
     nprobe = max(2 * cores, 8)
-    t = oracle.batch_run(P, nprobe, cs=probe.get("cs"), hs=probe["hs"], bs=probe["bs"], nthreads=cores, want_solution=False)["seconds"]
+    t = oracle.batch_run(P, nprobe, Gs=probe.get("Gs"), As=probe.get("As"), cs=probe.get("cs"), hs=probe["hs"], bs=probe["bs"], nthreads=cores, want_solution=False)["seconds"]
     per = max(t / nprobe, 1e-6)
     total_steps = args.steps + args.warmup
     sample = int(min(4096, max(cores, (120.0 / total_steps) / per)))  # whole run within a few minutes
     W = gen(sample, 1234)
     for _ in range(args.warmup):
-        oracle.batch_run(P, sample, cs=W.get("cs"), hs=W["hs"], bs=W["bs"], nthreads=cores, want_solution=False)
+        oracle.batch_run(P, sample, Gs=W.get("Gs"), As=W.get("As"), cs=W.get("cs"), hs=W["hs"], bs=W["bs"], nthreads=cores, want_solution=False)
     secs, exits = 0.0, None
     for _ in range(args.steps):
-        r = oracle.batch_run(P, sample, cs=W.get("cs"), hs=W["hs"], bs=W["bs"], nthreads=cores, want_solution=False)
+        r = oracle.batch_run(P, sample, Gs=W.get("Gs"), As=W.get("As"), cs=W.get("cs"), hs=W["hs"], bs=W["bs"], nthreads=cores, want_solution=False)
         secs += r["seconds"]
         exits = r["exit"]
     value = args.steps * sample / secs
@@ -198,11 +212,12 @@ def main():
     W = gen(batch, seed)
     # per-instance stacks (pinned host copies); a vector the workload does not vary stays shared (None)
     host = {k: (torch.from_numpy(np.ascontiguousarray(W[k])).pin_memory() if W.get(k) is not None else None)
-            for k in ("cs", "hs", "bs")}
+            for k in ("cs", "hs", "bs", "Gs", "As")}
+    pim = host["Gs"] is not None or host["As"] is not None
     x_h = torch.empty((batch, n), dtype=torch.float64).pin_memory()
     exit_h = torch.empty((batch,), dtype=torch.int32).pin_memory()
 
-    solver = eicos_b200.BatchSolver(P, device=local, capacity=batch, workers=args.workers)
+    solver = eicos_b200.BatchSolver(P, device=local, capacity=batch, workers=args.workers, instance_matrices=pim)
     dims = solver.dims()
     stream = torch.cuda.ExternalStream(solver.stream(), device=dev)
 
@@ -214,7 +229,7 @@ def main():
     torch.cuda.synchronize()
 
     def step_device():
-        solver.solve_device(batch, d_cs=dptr["cs"], d_hs=dptr["hs"], d_bs=dptr["bs"], d_x=x_d.data_ptr(),
+        solver.solve_device(batch, d_Gs=dptr["Gs"], d_As=dptr["As"], d_cs=dptr["cs"], d_hs=dptr["hs"], d_bs=dptr["bs"], d_x=x_d.data_ptr(),
                             d_exit=exit_d.data_ptr(), d_iter=iter_d.data_ptr())
 
     def step_host():
@@ -222,8 +237,8 @@ def main():
         import ctypes as C
         dp = C.POINTER(C.c_double)
         hp = {k: (C.cast(v.data_ptr(), dp) if v is not None else None) for k, v in host.items()}
-        solver.lib.check(L.eicos_batch_solve(
-            solver.h, batch, hp["cs"], hp["hs"], hp["bs"],
+        solver.lib.check(L.eicos_batch_solve_matrices(
+            solver.h, batch, hp["Gs"], hp["As"], hp["cs"], hp["hs"], hp["bs"],
             C.cast(x_h.data_ptr(), dp), None, None, None,
             C.cast(exit_h.data_ptr(), C.POINTER(C.c_int)), None))
 
@@ -275,7 +290,8 @@ def main():
                "h2d_bytes_per_step": int(sum(v.numel() * 8 for v in host.values() if v is not None)),
                "d2h_bytes_per_step": int(batch * (n * 8 + 4)),
                "ms_per_step": ms_e / args.steps,
-               "api": "eicos_batch_solve (include/eicos_b200.h): pinned host h,b in; x and exit flags out"}
+               "api": ("eicos_batch_solve_matrices (include/eicos_b200.h): pinned host G,A,h,b in; x and exit flags out" if pim else
+                       "eicos_batch_solve (include/eicos_b200.h): pinned host h,b in; x and exit flags out")}
         assert np.array_equal(exit_h.numpy(), exits)
 
     if rank != 0:
@@ -301,9 +317,11 @@ def main():
     factor_tiles = sum(s["factor_launch_tiles"] for s in stats)
     # algorithmic bytes (shared-A/G variant): one solve round = triangular solves
     # 8(2 nnzL + 3N) + refinement residual 8*4N per instance; a launch processes tile-rounds x 32 lanes
-    bytes_round = 8.0 * (2 * nnzL + 7 * N) * tile
+    # (per-instance matrices: the residual also reads every G / A value once, the factorisation too)
+    nnzGA = (int(np.asarray(P["Gpr"]).size) + int(np.asarray(P["Apr"]).size)) if pim else 0
+    bytes_round = 8.0 * (2 * nnzL + 7 * N + nnzGA) * tile
     solve_gbs = rounds * bytes_round / (ms_solve * 1e-3) / 1e9 if ms_solve > 0 else 0.0
-    bytes_factor = 8.0 * (nnzV + nnzL + N) * tile
+    bytes_factor = 8.0 * (nnzV + nnzL + N + nnzGA) * tile
     factor_gbs = factor_tiles * bytes_factor / (ms_factor * 1e-3) / 1e9 if ms_factor > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")

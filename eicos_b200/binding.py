@@ -66,7 +66,8 @@ class ProgramStats(C.Structure):
 EXPORTS = [
     "eicos_setup", "eicos_update_data", "eicos_update_data_full", "eicos_solve", "eicos_solution",
     "eicos_get_duals", "eicos_get_info", "eicos_cleanup",
-    "eicos_batch_setup", "eicos_batch_update_matrices", "eicos_batch_solve", "eicos_batch_solve_device",
+    "eicos_batch_setup", "eicos_batch_setup_ex", "eicos_batch_update_matrices", "eicos_batch_solve",
+    "eicos_batch_solve_matrices", "eicos_batch_solve_device", "eicos_batch_solve_matrices_device",
     "eicos_batch_set_timing", "eicos_batch_set_compaction", "eicos_batch_get_stats", "eicos_batch_get_dims", "eicos_batch_get_program_stats", "eicos_batch_get_symbolic",
     "eicos_batch_debug_init", "eicos_batch_stream", "eicos_batch_cleanup",
     "eicos_last_error", "eicos_device_count",
@@ -114,12 +115,18 @@ class Library:
         L.eicos_cleanup.argtypes = [C.c_void_p]
         L.eicos_batch_setup.restype = C.c_void_p
         L.eicos_batch_setup.argtypes = setup_args + [C.c_int, C.c_longlong, C.c_int]
+        L.eicos_batch_setup_ex.restype = C.c_void_p
+        L.eicos_batch_setup_ex.argtypes = setup_args + [C.c_int, C.c_longlong, C.c_int, C.c_int]
+        L.eicos_batch_solve_matrices.restype = C.c_int
+        L.eicos_batch_solve_matrices.argtypes = [C.c_void_p, C.c_int] + [_dp] * 9 + [_ip, C.POINTER(Info)]
         L.eicos_batch_update_matrices.restype = C.c_int
         L.eicos_batch_update_matrices.argtypes = [C.c_void_p, _dp, _dp]
         L.eicos_batch_solve.restype = C.c_int
         L.eicos_batch_solve.argtypes = [C.c_void_p, C.c_int] + [_dp] * 7 + [_ip, C.POINTER(Info)]
         L.eicos_batch_solve_device.restype = C.c_int
         L.eicos_batch_solve_device.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 9
+        L.eicos_batch_solve_matrices_device.restype = C.c_int
+        L.eicos_batch_solve_matrices_device.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 11
         L.eicos_batch_set_timing.restype = C.c_int
         L.eicos_batch_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.eicos_batch_set_compaction.restype = C.c_int
@@ -224,12 +231,17 @@ class Solver:
 
 
 class BatchSolver:
-    """Batched overload: one pattern + shared G/A values, stacked per-instance c/h/b."""
+    """Batched overload: one pattern + shared G/A values, stacked per-instance c/h/b.
+    instance_matrices=True: instances may also bring their own G/A values (solve(..., Gs=, As=))."""
 
-    def __init__(self, problem, device=0, capacity=0, workers=0, lib=None):
+    INSTANCE_MATRICES = 1
+
+    def __init__(self, problem, device=0, capacity=0, workers=0, lib=None, instance_matrices=False):
         self.lib = lib or load()
         self._keep, args, (self.n, self.m, self.p) = _problem_args(problem)
-        self.h = self.lib.L.eicos_batch_setup(*args, int(device), int(capacity), int(workers))
+        self.nnzG, self.nnzA = int(np.asarray(problem["Gpr"]).size), int(np.asarray(problem["Apr"]).size)
+        self.h = self.lib.L.eicos_batch_setup_ex(*args, int(device), int(capacity), int(workers),
+                                                 self.INSTANCE_MATRICES if instance_matrices else 0)
         if not self.h:
             raise RuntimeError("eicos_batch_setup failed: " + self.lib.last_error())
 
@@ -281,10 +293,10 @@ class BatchSolver:
     def stream(self):
         return self.lib.L.eicos_batch_stream(self.h)
 
-    def solve(self, batch, cs=None, hs=None, bs=None, want=("x", "y", "z", "s"), want_info=True):
+    def solve(self, batch, cs=None, hs=None, bs=None, want=("x", "y", "z", "s"), want_info=True, Gs=None, As=None):
         """Host buffers in, host buffers out (copies included)."""
-        cs, hs, bs = (_arr(v, np.float64) for v in (cs, hs, bs))
-        for a, k in ((cs, self.n), (hs, self.m), (bs, self.p)):
+        cs, hs, bs, Gs, As = (_arr(v, np.float64) for v in (cs, hs, bs, Gs, As))
+        for a, k in ((cs, self.n), (hs, self.m), (bs, self.p), (Gs, self.nnzG), (As, self.nnzA)):
             if a is not None and a.size != batch * k:
                 raise ValueError("stacked vector has the wrong size")
         out = {}
@@ -294,8 +306,8 @@ class BatchSolver:
         out["s"] = np.zeros((batch, self.m)) if "s" in want else None
         ex = np.zeros(batch, np.int32)
         info = (Info * batch)() if want_info else None
-        self.lib.check(self.lib.L.eicos_batch_solve(
-            self.h, int(batch), _d(cs), _d(hs), _d(bs),
+        self.lib.check(self.lib.L.eicos_batch_solve_matrices(
+            self.h, int(batch), _d(Gs), _d(As), _d(cs), _d(hs), _d(bs),
             _d(out["x"]), _d(out["y"]), _d(out["z"]), _d(out["s"]), _i(ex), info))
         out["exit"] = ex
         if want_info:
@@ -303,10 +315,10 @@ class BatchSolver:
             out["iter"] = np.array([i["iter"] for i in out["info"]], np.int32)
         return out
 
-    def solve_device(self, batch, d_cs=0, d_hs=0, d_bs=0, d_x=0, d_y=0, d_z=0, d_s=0, d_exit=0, d_iter=0):
+    def solve_device(self, batch, d_cs=0, d_hs=0, d_bs=0, d_x=0, d_y=0, d_z=0, d_s=0, d_exit=0, d_iter=0, d_Gs=0, d_As=0):
         """Raw device pointers (ints); results stay in HBM."""
-        self.lib.check(self.lib.L.eicos_batch_solve_device(
-            self.h, int(batch), *[C.c_void_p(int(v) or None) for v in (d_cs, d_hs, d_bs, d_x, d_y, d_z, d_s, d_exit, d_iter)]))
+        self.lib.check(self.lib.L.eicos_batch_solve_matrices_device(
+            self.h, int(batch), *[C.c_void_p(int(v) or None) for v in (d_Gs, d_As, d_cs, d_hs, d_bs, d_x, d_y, d_z, d_s, d_exit, d_iter)]))
 
     def debug_init(self, batch, cs=None, hs=None, bs=None):
         d = self.dims()

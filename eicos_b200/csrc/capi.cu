@@ -75,7 +75,7 @@ struct eicos_batch
     int device = 0, workers = 4;
     bool timing = false;
     SolveStats stats;
-    DeviceBuffer din, dout, dint;
+    DeviceBuffer din, dout, dint, dmat;
 };
 
 struct eicos_solver
@@ -124,7 +124,17 @@ eicos_batch *eicos_batch_setup(int n, int m, int p, int l, int ncones, const int
                                const double *c, const double *h, const double *b,
                                int device, long long capacity, int workers)
 {
+    return eicos_batch_setup_ex(n, m, p, l, ncones, q, Gpr, Gjc, Gir, Apr, Ajc, Air, c, h, b, device, capacity, workers, 0);
+}
+
+eicos_batch *eicos_batch_setup_ex(int n, int m, int p, int l, int ncones, const int *q,
+                                  const double *Gpr, const int *Gjc, const int *Gir,
+                                  const double *Apr, const int *Ajc, const int *Air,
+                                  const double *c, const double *h, const double *b,
+                                  int device, long long capacity, int workers, int flags)
+{
     (void)l;
+    const bool pim = (flags & EICOS_BATCH_INSTANCE_MATRICES) != 0;
     try
     {
         if (n < 0 || m < 0 || p < 0 || ncones < 0 || (n > 0 && !c))
@@ -158,15 +168,16 @@ eicos_batch *eicos_batch_setup(int n, int m, int p, int l, int ncones, const int
             size_t fr = 0, tot = 0;
             EI_CUDA(cudaMemGetInfo(&fr, &tot));
             // rows_total is only known to the engine; estimate it from the symbolic sizes
-            const double per_inst = 8.0 * (2.0 * S.nnzL + 9.0 * S.N + 12.0 * S.m + 4.0 * S.n + 4.0 * S.p + 2.0 * S.l +
-                                           S.Vslot.size() + 8.0 * S.nc + S.qtot + S_COUNT + J_COUNT);
+            const double per_inst = 8.0 * (2.0 * S.nnzL + 13.0 * S.N + 12.0 * S.m + 4.0 * S.n + 4.0 * S.p + 2.0 * S.l +
+                                           S.Vslot.size() + 8.0 * S.nc + S.qtot + S_COUNT + J_COUNT +
+                                           (pim ? (double)S.G.nnz() + S.A.nnz() + S.N : 0.0));
             capacity = (long long)(0.80 * (double)fr / std::max(per_inst, 8.0));
             capacity = std::max<long long>(32, std::min<long long>(capacity, 1 << 20));
             capacity -= capacity % 32;
 #endif
         }
         bt->workers = workers > 0 ? workers : default_workers(capacity);
-        bt->eng.reset(new Engine(bt->S, device, capacity, bt->workers));
+        bt->eng.reset(new Engine(bt->S, device, capacity, bt->workers, pim));
         bt->workers = bt->eng->workers();
         return bt.release();
     }
@@ -202,10 +213,23 @@ int eicos_batch_solve_device(eicos_batch *bt, int batch,
                              double *d_x, double *d_y, double *d_z, double *d_s,
                              int *d_exitflag, int *d_iters)
 {
+    return eicos_batch_solve_matrices_device(bt, batch, nullptr, nullptr, d_cs, d_hs, d_bs, d_x, d_y, d_z, d_s,
+                                             d_exitflag, d_iters);
+}
+
+int eicos_batch_solve_matrices_device(eicos_batch *bt, int batch, const double *d_Gs, const double *d_As,
+                                      const double *d_cs, const double *d_hs, const double *d_bs,
+                                      double *d_x, double *d_y, double *d_z, double *d_s,
+                                      int *d_exitflag, int *d_iters)
+{
     if (!bt || batch < 0)
         return fail(EICOS_ERR_INVALID, "null handle or negative batch");
+    if ((d_Gs || d_As) && !bt->eng->instance_matrices())
+        return fail(EICOS_ERR_INVALID, "per-instance matrices need a handle from eicos_batch_setup_ex(..., EICOS_BATCH_INSTANCE_MATRICES)");
     try
     {
+        if (bt->eng->instance_matrices())
+            bt->eng->set_matrices(d_Gs, d_As, bt->rawG.data(), bt->rawA.data());
         bt->eng->solve(batch, d_cs, d_hs, d_bs, bt->c.data(), bt->h.data(), bt->b.data(),
                        d_x, d_y, d_z, d_s, d_exitflag, d_iters, nullptr, nullptr,
                        /*keep_sticky=*/false, /*pre_equilibrated=*/false, bt->timing, &bt->stats);
@@ -226,14 +250,33 @@ int eicos_batch_solve(eicos_batch *bt, int batch,
                       double *x, double *y, double *z, double *s,
                       int *exitflag, eicos_info *info)
 {
+    return eicos_batch_solve_matrices(bt, batch, nullptr, nullptr, cs, hs, bs, x, y, z, s, exitflag, info);
+}
+
+int eicos_batch_solve_matrices(eicos_batch *bt, int batch, const double *Gs, const double *As,
+                               const double *cs, const double *hs, const double *bs,
+                               double *x, double *y, double *z, double *s,
+                               int *exitflag, eicos_info *info)
+{
     if (!bt || batch < 0)
         return fail(EICOS_ERR_INVALID, "null handle or negative batch");
+    if ((Gs || As) && !bt->eng->instance_matrices())
+        return fail(EICOS_ERR_INVALID, "per-instance matrices need a handle from eicos_batch_setup_ex(..., EICOS_BATCH_INSTANCE_MATRICES)");
     try
     {
         const Symbolic &S = bt->S;
         be::set_device(bt->device);
         be::stream_t st = (be::stream_t)(intptr_t)bt->eng->stream();
         const size_t B = (size_t)batch;
+        if (bt->eng->instance_matrices())
+        { // stacks of raw matrix values (instance-major); missing ones fall back to the setup matrices
+            const size_t ng = Gs ? B * S.G.nnz() : 0, na = As ? B * S.A.nnz() : 0;
+            bt->dmat.ensure((ng + na) * sizeof(double));
+            double *dm = (double *)bt->dmat.p;
+            be::h2d(dm, Gs, ng * sizeof(double), st);
+            be::h2d(dm + ng, As, na * sizeof(double), st);
+            bt->eng->set_matrices(Gs ? dm : nullptr, As ? dm + ng : nullptr, bt->rawG.data(), bt->rawA.data());
+        }
         const size_t nc_ = cs ? B * S.n : 0, nh_ = hs ? B * S.m : 0, nb_ = bs ? B * S.p : 0;
         bt->din.ensure((nc_ + nh_ + nb_) * sizeof(double));
         double *din = (double *)bt->din.p;

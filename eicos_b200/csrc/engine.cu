@@ -36,6 +36,7 @@ namespace eicos
     }
 #define EI_MAX_THREADS 256
 EI_DEFINE_KERNEL(eicos_load_inputs, tile_load, 2)
+EI_DEFINE_KERNEL(eicos_equilibrate, tile_equil, 2)
 EI_DEFINE_KERNEL(eicos_init, tile_init, 2)
 EI_DEFINE_KERNEL(eicos_ldl_factor, tile_factor, 2)
 EI_DEFINE_KERNEL_(eicos_solve_kkt, tile_solve_kkt, 2, 1) /* grid = tiles x jobs, job fastest */
@@ -175,6 +176,9 @@ void Engine::build_layout(const Symbolic &S)
     L.wdz = take(S.mt);
     L.dsaff = take(S.mt);
     L.ds1 = take(S.mt);
+    L.Gx = take(pim_ ? S.G.nnz() : 0);
+    L.Ax = take(pim_ ? S.A.nnz() : 0);
+    L.eq = take(pim_ ? S.N : 0);
     L.sc = take(S_COUNT);
     L.rows_total = at;
     L.irows_total = J_COUNT;
@@ -190,7 +194,7 @@ void Engine::upload_pattern(const Symbolic &S)
         sw_budget = std::max(1, std::min(MAX_SW_SLOTS, std::atoi(v)));
     if (const char *v = std::getenv("EICOS_MAX_FA_SLOTS"))
         fa_budget = std::max(1, std::min(MAX_FA_SLOTS, std::atoi(v)));
-    build_streams(S, L_, workers_, sw_budget, fa_budget, H_);
+    build_streams(S, L_, workers_, sw_budget, fa_budget, H_, pim_);
     Lp_ = S.Lp;
     DevPattern &P = P_;
     P.n = S.n;
@@ -212,6 +216,21 @@ void Engine::upload_pattern(const Symbolic &S)
     P.fa_slots = H_.fa_slots;
     P.sw_direct = H_.sw_direct > 0 ? 1 : 0;
     P.fa_fast = H_.fa_fast;
+    P.pim = pim_ ? 1 : 0;
+    P.nnzG = S.G.nnz();
+    P.nnzA = S.A.nnz();
+    if (pim_)
+    {
+        P.Gp = upload(S.G.p, owned_, st);
+        P.Gi = upload(S.G.i, owned_, st);
+        P.Ap = upload(S.A.p, owned_, st);
+        P.Ai = upload(S.A.i, owned_, st);
+        P.Grp = upload(S.Gr.p, owned_, st);
+        P.Grv = upload(S.Gr.v, owned_, st);
+        P.Arp = upload(S.Ar.p, owned_, st);
+        P.Arv = upload(S.Ar.v, owned_, st);
+        P.cone_z = upload(S.cone_z, owned_, st);
+    }
     P.cone_dim = upload(S.q, owned_, st);
     P.cone_k = upload(S.cone_k, owned_, st);
     P.cone_q = upload(S.cone_q, owned_, st);
@@ -270,7 +289,7 @@ void Engine::upload_values(const Symbolic &S)
 {
     be::stream_t st = S_(stream_);
     be::set_device(device_);
-    refresh_stream_values(S, L_, H_);
+    refresh_stream_values(S, L_, H_, pim_);
     const dvec ge = expanded_geq(S);
     be::h2d(dxeq_, S.xeq.data(), S.xeq.size() * sizeof(double), st);
     be::h2d(dAeq_, S.Aeq.data(), S.Aeq.size() * sizeof(double), st);
@@ -280,8 +299,9 @@ void Engine::upload_values(const Symbolic &S)
     be::sync(st);
 }
 
-Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int workers)
-    : device_(device), workers_(std::max(1, std::min(workers, EI_MAX_THREADS / 32 > 0 ? EI_MAX_THREADS / 32 : 1)))
+Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int workers, bool instance_matrices)
+    : device_(device), workers_(std::max(1, std::min(workers, EI_MAX_THREADS / 32 > 0 ? EI_MAX_THREADS / 32 : 1))),
+      pim_(instance_matrices), nnzG_(S.G.nnz()), nnzA_(S.A.nnz())
 {
     be::set_device(device_);
     stream_ = (void *)(intptr_t)be::make_stream();
@@ -295,6 +315,8 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
     be::zero(ws_, ws_bytes_, S_(stream_));
     be::zero(iws_, ib, S_(stream_));
     base_vec_ = (double *)be::alloc((size_t)(S.n + S.m + S.p) * sizeof(double));
+    if (pim_)
+        base_mat_ = (double *)be::alloc((size_t)(nnzG_ + nnzA_ + 1) * sizeof(double));
     active_count_ = (unsigned int *)be::alloc(sizeof(unsigned int));
     ir_rounds_ = (unsigned long long *)be::alloc(8 * sizeof(unsigned long long)); // [0] rounds, [1..5] phase cycles
     host_pinned_ = (unsigned int *)be::pinned(12 * sizeof(unsigned long long));
@@ -325,7 +347,8 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
     }
     if (smem_common_ > 48 * 1024)
     {
-        const void *ks[] = {(const void *)eicos_load_inputs, (const void *)eicos_init, (const void *)eicos_init_point,
+        const void *ks[] = {(const void *)eicos_load_inputs, (const void *)eicos_equilibrate, (const void *)eicos_init,
+                            (const void *)eicos_init_point,
                             (const void *)eicos_iter_head, (const void *)eicos_iter_mid, (const void *)eicos_iter_tail,
                             (const void *)eicos_store_outputs};
         for (const void *k : ks)
@@ -348,6 +371,7 @@ Engine::~Engine()
     be::dfree(iws_);
     be::dfree(acc_global_);
     be::dfree(base_vec_);
+    be::dfree(base_mat_);
     be::dfree(active_count_);
     be::dfree(ir_rounds_);
     be::unpin(host_pinned_);
@@ -355,6 +379,23 @@ Engine::~Engine()
     be::unpin(status_host_);
     be::unpin(moves_host_);
     be::drop_stream(S_(stream_));
+}
+
+void Engine::set_matrices(const double *d_G, const double *d_A, const double *base_G, const double *base_A)
+{
+    if (!pim_)
+        throw std::invalid_argument("the handle was not set up for per-instance matrices");
+    be::set_device(device_);
+    be::stream_t st = S_(stream_);
+    mat_dG_ = d_G;
+    mat_dA_ = d_A;
+    if ((!d_G && nnzG_ && !base_G) || (!d_A && nnzA_ && !base_A))
+        throw std::invalid_argument("missing matrix values: neither stacked nor base data given");
+    if (base_G)
+        be::h2d(base_mat_, base_G, (size_t)nnzG_ * sizeof(double), st);
+    if (base_A)
+        be::h2d(base_mat_ + nnzG_, base_A, (size_t)nnzA_ * sizeof(double), st);
+    be::sync(st);
 }
 
 ProgramStats Engine::program_stats() const
@@ -411,6 +452,10 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
     if (base_b)
         be::h2d(base_vec_ + P_.n + P_.m, base_b, P_.p * sizeof(double), st);
     be::sync(st); // base_* may be pageable host memory owned by the caller
+    a.in_G = mat_dG_;
+    a.in_A = mat_dA_;
+    a.base_G = base_mat_;
+    a.base_A = base_mat_ ? base_mat_ + nnzG_ : nullptr;
     a.out_x = d_x;
     a.out_y = d_y;
     a.out_z = d_z;
@@ -517,6 +562,8 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
         };
 
         EI_TIMED(2, EI_LAUNCH(eicos_load_inputs, tile_load, tiles, threads, smem_common_, st, a));
+        if (pim_)
+            EI_TIMED(2, EI_LAUNCH(eicos_equilibrate, tile_equil, tiles, threads, smem_common_, st, a));
         EI_TIMED(2, EI_LAUNCH(eicos_init, tile_init, tiles, threads, smem_common_, st, a));
         factor();
         kkt_pair(1, J_NIT1, J_NIT2);
@@ -564,14 +611,16 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
                     // else - factor, solutions, work vectors - is recomputed): problem data, iterate and best
                     // iterate (contiguous), residuals, scalings + scaling block (contiguous), both right-hand
                     // sides (contiguous), scalars
-                    const int rr[12] = {L_.chb, P_.N,
+                    // (per-instance matrices: also the equilibrated G / A values and the equilibration vectors)
+                    const int rr[14] = {L_.chb, P_.N,
                                         L_.w, (L_.blam + P_.mt) - L_.w,
                                         L_.r, P_.N,
                                         L_.lpv, (L_.V + P_.nnzV) - L_.lpv,
                                         L_.rhs1, 2 * P_.N,
-                                        L_.sc, S_COUNT};
-                    mr.n = 6;
-                    for (int k = 0; k < 12; k++)
+                                        L_.sc, S_COUNT,
+                                        L_.Gx, L_.sc - L_.Gx};
+                    mr.n = 7;
+                    for (int k = 0; k < 14; k++)
                         mr.r[k] = rr[k];
 #ifndef EICOS_EMU
                     eicos_compact<<<nmoves, 128, 0, st>>>(a, mr, moves_dev_);
@@ -654,7 +703,13 @@ void Engine::debug_factor_init(int batch, const double *d_c, const double *d_h, 
     const int threads = workers_ * (LANES == 1 ? 1 : 32), threads1 = LANES == 1 ? 1 : 32;
     (void)threads;
     (void)threads1;
+    a.in_G = mat_dG_;
+    a.in_A = mat_dA_;
+    a.base_G = base_mat_;
+    a.base_A = base_mat_ ? base_mat_ + nnzG_ : nullptr;
     EI_LAUNCH(eicos_load_inputs, tile_load, tiles, threads, smem_common_, st, a);
+    if (pim_)
+        EI_LAUNCH(eicos_equilibrate, tile_equil, tiles, threads, smem_common_, st, a);
     EI_LAUNCH(eicos_init, tile_init, tiles, threads, smem_common_, st, a);
     a.xrows = xrows_factor_;
     EI_LAUNCH(eicos_ldl_factor, tile_factor, tiles, threads1, smem_factor_, st, a);

@@ -38,10 +38,18 @@ class Engine
   public:
     // capacity_instances: how many instances the workspace holds at once (larger batches are
     // processed in chunks); workers: warps per CTA.
-    Engine(const Symbolic &S, int device, long long capacity_instances, int workers);
+    // instance_matrices: every instance brings its own G / A values (same pattern); they are
+    // equilibrated on the device and the programs read them as rows of the workspace.
+    Engine(const Symbolic &S, int device, long long capacity_instances, int workers, bool instance_matrices = false);
     ~Engine();
     Engine(const Engine &) = delete;
     Engine &operator=(const Engine &) = delete;
+
+    // per-instance-matrices mode: the matrices of the NEXT solve().  d_G / d_A: instance-major DEVICE
+    // arrays of raw values [batch x nnzG], [batch x nnzA], or null to use base_G / base_A (host arrays
+    // of raw values shared by all instances).
+    void set_matrices(const double *d_G, const double *d_A, const double *base_G, const double *base_A);
+    bool instance_matrices() const { return pim_; }
 
     // re-upload the shared numeric values after refresh_values() (updateData with new G/A)
     void upload_values(const Symbolic &S);
@@ -76,6 +84,10 @@ class Engine
     void upload_pattern(const Symbolic &S);
 
     int device_ = 0, workers_ = 4;
+    bool pim_ = false;
+    const double *mat_dG_ = nullptr, *mat_dA_ = nullptr; // matrices of the next solve (pim)
+    double *base_mat_ = nullptr;                         // device copy of the shared raw G | A values (pim)
+    int nnzG_ = 0, nnzA_ = 0;
     long long cap_tiles_ = 0;
     size_t ws_bytes_ = 0;
     void *stream_ = nullptr;

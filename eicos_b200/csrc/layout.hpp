@@ -79,6 +79,8 @@ struct Layout
     int xw, dxr, e;                 // triangular-solve work vector, refinement step, residual (N rows)
     int xw2, dxr2, e2;              // the same for the second of two concurrent solves (job set 1)
     int dsw, wdz, dsaff, ds1;       // dsaff_by_W, W_times_dzaff, dsaff, scratch (mt rows)
+    int Gx, Ax, eq;                 // per-instance-matrices mode: equilibrated G / A values (CSC order), and the
+                                    // equilibration vectors KKT-shaped [x_equil | A_equil | G_equil expanded] (N rows)
     int sc;                         // S_COUNT scalar rows
     int rows_total;
     int irows_total;                // integer rows (J_COUNT)
@@ -118,6 +120,10 @@ struct DevPattern
     int fw_nld, bw_nld, bwp_nld, fa_nld, mv_nld, mv_rows, sw_slots, fa_slots;
     int sw_direct; // the sweep programs contain operands read straight from global memory
     int fa_fast;   // the factor program is in record form (streams.hpp)
+    // per-instance-matrices mode (every instance has its own G / A values): 1, and the index arrays
+    // the on-device equilibration walks (CSC of G and A, their CSR views as row pointer + value index)
+    int pim, nnzG, nnzA;
+    const int *Gp, *Gi, *Ap, *Ai, *Grp, *Grv, *Arp, *Arv, *cone_z;
     const double *fa_val;
     const int *Vkind; // per V entry: what resetKKTScalings writes (0 -> -1, 1 -> 0, 2 -> +1)
 };

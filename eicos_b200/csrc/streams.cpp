@@ -275,7 +275,7 @@ void build_backward(const Symbolic &S, const Layout &L, int max_slots, HostStrea
 // ---- KKT mat-vec program (streams.hpp).  Rows = x, y and z rows (the two expansion slots of every
 // second-order cone excepted) in elimination order; the pairs of a row keep the order of the
 // CSC / CSR data (G entries before A entries in an x row).
-void build_matvec(const Symbolic &S, const Layout &L, int max_slots, HostStreams &H)
+void build_matvec(const Symbolic &S, const Layout &L, int max_slots, HostStreams &H, bool pim)
 {
     const int n = S.n, p = S.p, zb = S.n + S.p;
     ivec order;
@@ -286,19 +286,32 @@ void build_matvec(const Symbolic &S, const Layout &L, int max_slots, HostStreams
     const int nrows = (int)order.size();
     std::sort(order.begin(), order.end(), [&](int a, int b) { return S.P[a] < S.P[b]; });
     std::vector<std::vector<std::pair<int, double>>> ent(S.N);
+    std::vector<ivec> crow(S.N); // per entry: workspace row of the per-instance coefficient (pim)
     for (int j = 0; j < n; j++)
     {
         for (int k = S.G.p[j]; k < S.G.p[j + 1]; k++)
+        {
             ent[j].push_back({zb + S.zk[S.G.i[k]], S.G.x[k]});
+            crow[j].push_back(L.Gx + k);
+        }
         for (int k = S.A.p[j]; k < S.A.p[j + 1]; k++)
+        {
             ent[j].push_back({n + S.A.i[k], S.A.x[k]});
+            crow[j].push_back(L.Ax + k);
+        }
     }
     for (int i = 0; i < p; i++)
         for (int t = S.Ar.p[i]; t < S.Ar.p[i + 1]; t++)
+        {
             ent[n + i].push_back({S.Ar.j[t], S.A.x[S.Ar.v[t]]});
+            crow[n + i].push_back(L.Ax + S.Ar.v[t]);
+        }
     for (int i = 0; i < S.m; i++)
         for (int t = S.Gr.p[i]; t < S.Gr.p[i + 1]; t++)
+        {
             ent[zb + S.zk[i]].push_back({S.Gr.j[t], S.G.x[S.Gr.v[t]]});
+            crow[zb + S.zk[i]].push_back(L.Gx + S.Gr.v[t]);
+        }
     std::vector<ivec> uses(S.N);
     for (int t = 0; t < nrows; t++)
     {
@@ -342,6 +355,35 @@ void build_matvec(const Symbolic &S, const Layout &L, int max_slots, HostStreams
         H.mv.push_back(cnt | (kind << MV_KIND_SHIFT));
         H.mv.push_back(ex0 | (own.first << 8) | (own.second << 16) | (ex1 << 24));
         H.mv.push_back(r);
+        if (pim)
+        { // coefficients are rows too: [coefficient ring row | operand | keep], four pairs per further record
+            H.mv.push_back(0);
+            if (FifoSim::crosses(first, F.npop - first))
+                H.mv[w0] |= SW_SYNC_HDR;
+            int q = 0, ntail = 0;
+            while (q < cnt)
+            {
+                const int f = F.npop;
+                const size_t at = H.mv.size();
+                for (int k = 0; k < 4; k++)
+                {
+                    if (q >= cnt)
+                    {
+                        H.mv.push_back(MVP_PAD_PAIR);
+                        continue;
+                    }
+                    const int cr = F.pop(0, crow[r][q]);
+                    const auto o = operand(ent[r][q].first);
+                    H.mv.push_back(cr | (o.first << 8) | (o.second << 16));
+                    q++;
+                }
+                if (FifoSim::crosses(f, F.npop - f))
+                    H.mv[at] |= MVP_SYNC;
+                ntail++;
+            }
+            H.mv[w0] = (H.mv[w0] & ~MV_CNT_MASK) | ntail;
+            continue;
+        }
         int q = 0;
         const auto pair = [&]() {
             if (q >= cnt)
@@ -376,6 +418,15 @@ void build_matvec(const Symbolic &S, const Layout &L, int max_slots, HostStreams
     pad_tail(H.mv_val);
 }
 
+// per K slot: row of the workspace holding the per-instance A / G value (per-instance-matrices mode), or -1
+ivec ag_rows(const Symbolic &S, const Layout &L)
+{
+    ivec row(S.Ki.size(), -1);
+    for (size_t k = 0; k < S.AGslot.size(); k++)
+        row[S.AGslot[k]] = S.AGsrc[k] >= 0 ? L.Ax + S.AGsrc[k] : L.Gx + (-S.AGsrc[k] - 1);
+    return row;
+}
+
 // ---- numeric factorisation, right-looking in elimination order.  Every entry (i,j) of L and every
 // pivot owns an accumulator that starts from the KKT value (shared constant, per-instance scaling
 // value, or 0 for fill) on its first touch.  Step k: d = acc(k,k); for the rows i of column k
@@ -383,23 +434,24 @@ void build_matvec(const Symbolic &S, const Layout &L, int max_slots, HostStreams
 // for every pair i1 >= i2 of the column  acc(i1,i2) -= l_i2 * a_i1  (the products Eigen's
 // up-looking kernel forms, accumulated in ascending k).
 //   ops:   [src_d, cnt, cnt x src, cnt(cnt+1)/2 x target]   constants in fa_val, V rows in the load list
-void build_factor(const Symbolic &S, const Layout &L, int max_slots, HostStreams &H)
+void build_factor(const Symbolic &S, const Layout &L, int max_slots, HostStreams &H, bool pim)
 {
     struct Init
     {
         int kind = OPK_ZERO, vrow = -1;
         double c = 0.0;
     };
+    const ivec agrow = pim ? ag_rows(S, L) : ivec(S.Ki.size(), -1);
     std::vector<Init> di(S.N), ei(S.nnzL);
     for (int j = 0; j < S.N; j++)
         for (int e = S.KLp[j]; e < S.KLp[j + 1]; e++)
         {
             const int slot = S.KLslot[e], vi = S.Kvidx[slot], pos = S.KLpos[e];
             Init &t = pos < 0 ? di[j] : ei[S.Lp[j] + pos];
-            if (vi >= 0)
+            if (vi >= 0 || agrow[slot] >= 0)
             {
                 t.kind = OPK_FIFO;
-                t.vrow = L.V + vi;
+                t.vrow = vi >= 0 ? L.V + vi : agrow[slot];
             }
             else
             {
@@ -474,7 +526,7 @@ void build_factor(const Symbolic &S, const Layout &L, int max_slots, HostStreams
 // ---- numeric factorisation in record form (streams.hpp); same right-looking algorithm and the
 // same arithmetic as build_factor, but every operand is a shared-memory row known to the host.
 // Returns false (leaving H untouched) when the pattern does not qualify.
-bool build_factor_fast(const Symbolic &S, const Layout &L, int max_slots, HostStreams &H)
+bool build_factor_fast(const Symbolic &S, const Layout &L, int max_slots, HostStreams &H, bool pim)
 {
     if (S.maxcol > FA_FAST_COL)
         return false;
@@ -483,16 +535,17 @@ bool build_factor_fast(const Symbolic &S, const Layout &L, int max_slots, HostSt
         int kind = FA_ZERO, vrow = -1;
         double c = 0.0;
     };
+    const ivec agrow = pim ? ag_rows(S, L) : ivec(S.Ki.size(), -1);
     std::vector<Init> di(S.N), ei(S.nnzL);
     for (int j = 0; j < S.N; j++)
         for (int e = S.KLp[j]; e < S.KLp[j + 1]; e++)
         {
             const int slot = S.KLslot[e], vi = S.Kvidx[slot], pos = S.KLpos[e];
             Init &t = pos < 0 ? di[j] : ei[S.Lp[j] + pos];
-            if (vi >= 0)
+            if (vi >= 0 || agrow[slot] >= 0)
             {
                 t.kind = FA_ROW;
-                t.vrow = L.V + vi;
+                t.vrow = vi >= 0 ? L.V + vi : agrow[slot];
             }
             else
             {
@@ -619,7 +672,7 @@ bool build_factor_fast(const Symbolic &S, const Layout &L, int max_slots, HostSt
 }
 } // namespace
 
-void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, int max_fa_slots, HostStreams &H)
+void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, int max_fa_slots, HostStreams &H, bool pim)
 {
     H = HostStreams();
     H.workers = W;
@@ -636,16 +689,16 @@ void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, 
     build_forward(S, L, max_sw_slots, H);
     build_backward(S, L, max_sw_slots, H, true);
     build_backward(S, L, max_sw_slots, H, false);
-    if (!build_factor_fast(S, L, max_fa_slots, H))
-        build_factor(S, L, max_fa_slots, H);
-    build_matvec(S, L, max_sw_slots, H);
+    if (!build_factor_fast(S, L, max_fa_slots, H, pim))
+        build_factor(S, L, max_fa_slots, H, pim);
+    build_matvec(S, L, max_sw_slots, H, pim);
 
 }
 
-void refresh_stream_values(const Symbolic &S, const Layout &L, HostStreams &H)
+void refresh_stream_values(const Symbolic &S, const Layout &L, HostStreams &H, bool pim)
 {
     HostStreams fresh;
-    build_streams(S, L, H.workers, std::max(H.sw_slots, 1), std::max(H.fa_slots, 1), fresh);
+    build_streams(S, L, H.workers, std::max(H.sw_slots, 1), std::max(H.fa_slots, 1), fresh, pim);
     H.fa_val.swap(fresh.fa_val);
     H.mv_val.swap(fresh.mv_val);
 }

@@ -91,6 +91,10 @@ constexpr int MV_KIND_SHIFT = 24;
 constexpr int MV_CNT_MASK = (1 << MV_KIND_SHIFT) - 1;
 constexpr int MV_SYNC_PAIR = 1 << 16;
 constexpr int MV_PAD_PAIR = SW_ZERO_ROW | (SW_NO_KEEP << 8);
+// per-instance-matrices form: no coefficient stream; the first record holds no pair and its word 0
+// counts the further records; pair word = ring row of the coefficient | operand << 8 | keep << 16 | MVP_SYNC
+constexpr int MVP_SYNC = 1 << 30;
+constexpr int MVP_PAD_PAIR = SW_ZERO_ROW | (SW_ZERO_ROW << 8) | (SW_NO_KEEP << 16);
 enum MvKind : int
 {
     MV_X = 0, // row of the x block: -(G' z + A' y)
@@ -151,9 +155,12 @@ struct HostStreams
 // K-space / expanded indexing used by the row sets: x rows [0,n), y rows [n,n+p), z rows
 // n+p+e with e the expanded cone index (2 unused slots after every second-order cone).
 // max_sw_slots / max_fa_slots: shared-memory slots the sweeps / the factorisation may use.
-void build_streams(const Symbolic &S, const Layout &L, int workers, int max_sw_slots, int max_fa_slots, HostStreams &H);
+// pim: per-instance-matrices mode - the A / G entries of the KKT matrix are rows of the workspace
+// (Layout::Ax, Gx) instead of shared coefficients.
+void build_streams(const Symbolic &S, const Layout &L, int workers, int max_sw_slots, int max_fa_slots, HostStreams &H,
+                   bool pim = false);
 
 // shared values change with updateData: rebuild only the double streams
-void refresh_stream_values(const Symbolic &S, const Layout &L, HostStreams &H);
+void refresh_stream_values(const Symbolic &S, const Layout &L, HostStreams &H, bool pim = false);
 
 } // namespace eicos

@@ -233,6 +233,8 @@ struct KArgs
     // instance-major device buffers for load/store (any may be null)
     const double *in_c, *in_h, *in_b;
     const double *base_c, *base_h, *base_b; // raw vectors shared by the batch (used when in_* is null)
+    const double *in_G, *in_A;              // per-instance-matrices mode: instance-major raw G / A values (may be null)
+    const double *base_G, *base_A;          // ... and the raw values shared by the batch (used when in_G / in_A is null)
     double *out_x, *out_y, *out_z, *out_s;
     int *out_exit, *out_iter;
     double *out_info; // [batch][S_WORK_END]
@@ -1114,6 +1116,61 @@ EI_DEV void mv_run(const Team &tm, const KArgs &a, const double *T, int variant,
     ff.close();
 }
 
+// The same for per-instance matrices: every coefficient is a row of the workspace that arrives
+// through the FIFO like the operands (streams.hpp: MVP_*).
+template <class Init, class Finish>
+EI_DEV void mv_run_pim(const Team &tm, const KArgs &a, const double *T, int variant,
+                       double sx, double sy, double sz, Init init, Finish finish)
+{
+    const DevPattern &P = a.P;
+    const smem_t sm = smem_of(tm.stage);
+    sm_store(sm, SW_ZERO_ROW, vset(0.0));
+    PStream ops;
+    Fifo ff;
+    ops.open(tm, P.mv, 0);
+    ff.open(tm, P.mv_ld[variant], P.mv_nld, T, 1);
+    for (int t = 0; t < P.mv_rows; t++)
+    {
+        const i4 rec = ops.get();
+        const int ntail = rec.x & MV_CNT_MASK, kind = (rec.x >> MV_KIND_SHIFT) & 3;
+        if (rec.x < 0)
+            ff.sync();
+        const vd ex0 = sm_load(sm, rec.y & 0xff), own = sm_load(sm, (rec.y >> 8) & 0xff);
+        const vd ex1 = sm_load(sm, (int)((unsigned)rec.y >> 24));
+        const int okeep = (rec.y >> 16) & 0xff;
+        if (okeep != SW_NO_KEEP)
+            sm_store(sm, okeep, own);
+        const double sgn = kind == MV_X ? sx : (kind == MV_Y ? sy : sz);
+        vd v = init(kind, ex0, own, ex1);
+        for (int q = 0; q < ntail; q++)
+        {
+            const i4 pr = ops.get();
+            if (pr.x & MVP_SYNC)
+                ff.sync();
+            const int pw[4] = {pr.x, pr.y, pr.z, pr.w};
+            vd c[4], g[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+            {
+                c[u] = sm_load(sm, pw[u] & 0x3f);
+                g[u] = sm_load(sm, (pw[u] >> 8) & 0xff);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+            {
+                const int keep = (pw[u] >> 16) & 0xff;
+                if (keep != SW_NO_KEEP)
+                    sm_store(sm, keep, g[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                v += (sgn * c[u]) * g[u];
+        }
+        finish(kind, rec.z, v, ex0, own, ex1);
+    }
+    ff.close();
+}
+
 // ------------------------------------------------------------------ KKT residual for iterative refinement (src/eicos.cpp:1511-1576)
 // e = rhs - Ktrue * x with the un-regularised scaling block (identity while initialising),
 // returns ||e||_inf per instance.
@@ -1124,27 +1181,31 @@ EI_DEV vd kkt_residual(const Team &tm, const KArgs &a, double *T, int variant, i
     const double delta = Settings::deltastat;
     const int zb = P.n + P.p;
     vd nerr = vset(0.0);
+    const auto mv_init = [&](int, vd ex0, vd, vd) { return ex0; };
+    const auto mv_finish = [&](int kind, int r, vd v, vd, vd own, vd ex1) {
+        if (kind == MV_ZC)
+        { // cone row: rhs - G x only; the cone block is added below
+            ROWD(T, erow + r) = v;
+            return;
+        }
+        if (kind == MV_X)
+            v -= delta * own;
+        else
+        {
+            v += delta * own;
+            if (kind == MV_Z)
+                v += initialize ? own : ex1 * own;
+        }
+        ROWD(T, erow + r) = v;
+        nerr = vmax(nerr, vabs(v));
+    };
     if (tm.wk == 0 && P.mv_rows > 0)
-        mv_run(
-            tm, a, T, variant, -1.0, -1.0, -1.0,
-            [&](int, vd ex0, vd, vd) { return ex0; },
-            [&](int kind, int r, vd v, vd, vd own, vd ex1) {
-                if (kind == MV_ZC)
-                { // cone row: rhs - G x only; the cone block is added below
-                    ROWD(T, erow + r) = v;
-                    return;
-                }
-                if (kind == MV_X)
-                    v -= delta * own;
-                else
-                {
-                    v += delta * own;
-                    if (kind == MV_Z)
-                        v += initialize ? own : ex1 * own;
-                }
-                ROWD(T, erow + r) = v;
-                nerr = vmax(nerr, vabs(v));
-            });
+    {
+        if (P.pim)
+            mv_run_pim(tm, a, T, variant, -1.0, -1.0, -1.0, mv_init, mv_finish);
+        else
+            mv_run(tm, a, T, variant, -1.0, -1.0, -1.0, mv_init, mv_finish);
+    }
     if (P.nc > 0)
     {
         tm.sync(); // (workers > 1) the partial cone rows written by worker 0 are visible
@@ -1577,11 +1638,8 @@ EI_DEV void tile_resid(const Team &tm, const KArgs &a, int tile)
         r[NS2] += si * si;
         r[GAP] += si * zi;
     };
-    if (tm.wk == 0 && P.mv_rows > 0)
-        mv_run(
-            tm, a, T, LDV_HEAD, -1.0, 1.0, 1.0,
-            [&](int kind, vd, vd, vd ex1) { return kind >= MV_Z ? ex1 : vset(0.0); },
-            [&](int kind, int q, vd v, vd ex0, vd own, vd ex1) {
+    const auto mv_init = [&](int kind, vd, vd, vd ex1) { return kind >= MV_Z ? ex1 : vset(0.0); };
+    const auto mv_finish = [&](int kind, int q, vd v, vd ex0, vd own, vd ex1) {
                 if (kind >= MV_Z)
                 { // LP and cone rows alike: rz = s + G x
                     zrow(q - zb, ex1, own, ex0, v);
@@ -1605,7 +1663,14 @@ EI_DEV void tile_resid(const Team &tm, const KArgs &a, int tile)
                     r[BY] += ex0 * own;
                     r[NY2] += own * own;
                 }
-            });
+            };
+    if (tm.wk == 0 && P.mv_rows > 0)
+    {
+        if (P.pim)
+            mv_run_pim(tm, a, T, LDV_HEAD, -1.0, 1.0, 1.0, mv_init, mv_finish);
+        else
+            mv_run(tm, a, T, LDV_HEAD, -1.0, 1.0, 1.0, mv_init, mv_finish);
+    }
     team_sum<NRED>(tm, r);
     if (tm.wk == 0)
         for (int k = 0; k < NRED; k++)
@@ -1789,7 +1854,9 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
             ew_rows<2, 6>(tm, T, P.N, ins, [&](int q, const vd *x) {
                 vd v = vsel(restore, x[1], x[0]);
                 ROWD(T, L.wb + q) = vsel(save, v, x[1]);
-                if (any_fin)
+                if (any_fin && P.pim)
+                    v = vsel(fin, v / (vd(ROWD(T, L.eq + q)) * ftau), v);
+                else if (any_fin)
                 {
                     const double eq = q < n ? EI_LDG(P.xeq + q) : (q < zb ? EI_LDG(P.Aeq + q - n) : EI_LDG(P.GeqE + q - zb));
                     v = vsel(fin, v / (eq * ftau), v);
@@ -1803,7 +1870,9 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
                 vd sv = vsel(restore, x[2], x[0]), lv = vsel(restore, x[3], x[1]);
                 ROWD(T, L.bs + e) = vsel(save, sv, x[2]);
                 ROWD(T, L.blam + e) = vsel(save, lv, x[3]);
-                if (any_fin)
+                if (any_fin && P.pim)
+                    sv = vsel(fin, sv * (vd(ROWD(T, L.eq + zb + e)) / ftau), sv);
+                else if (any_fin)
                     sv = vsel(fin, sv * (EI_LDG(P.GeqE + e) / ftau), sv);
                 ROWD(T, L.s + e) = sv;
                 ROWD(T, L.lam + e) = lv;
@@ -2228,6 +2297,20 @@ EI_DEV void tile_load(const Team &tm, const KArgs &a, int tile)
         if (inst >= a.batch)
             inst = a.batch - 1; // padding instances replay the last one; their results are never stored
         const size_t g = (size_t)a.first + inst;
+        if (P.pim)
+        { // raw data in; eicos_equilibrate scales matrices and vectors per instance
+            for (int j = tm.wk; j < n; j += tm.nwk)
+                ROWC(t.T, L.chb + j, c_) = a.in_c ? a.in_c[g * n + j] : EI_LDG(a.base_c + j);
+            for (int i = tm.wk; i < P.p; i += tm.nwk)
+                ROWC(t.T, L.chb + n + i, c_) = a.in_b ? a.in_b[g * P.p + i] : EI_LDG(a.base_b + i);
+            for (int i = tm.wk; i < P.m; i += tm.nwk)
+                ROWC(t.T, L.chb + zb + EI_LDG(P.zk + i), c_) = a.in_h ? a.in_h[g * P.m + i] : EI_LDG(a.base_h + i);
+            for (int k = tm.wk; k < P.nnzG; k += tm.nwk)
+                ROWC(t.T, L.Gx + k, c_) = a.in_G ? a.in_G[g * P.nnzG + k] : EI_LDG(a.base_G + k);
+            for (int k = tm.wk; k < P.nnzA; k += tm.nwk)
+                ROWC(t.T, L.Ax + k, c_) = a.in_A ? a.in_A[g * P.nnzA + k] : EI_LDG(a.base_A + k);
+            continue;
+        }
         for (int j = tm.wk; j < n; j += tm.nwk)
         {
             const double v = a.in_c ? a.in_c[g * n + j] : EI_LDG(a.base_c + j);
@@ -2244,6 +2327,91 @@ EI_DEV void tile_load(const Team &tm, const KArgs &a, int tile)
             const int e = EI_LDG(P.zk + i);
             ROWC(t.T, L.chb + zb + e, c_) = a.pre_equilibrated ? v : v / EI_LDG(P.GeqE + e);
         }
+    }
+}
+
+// ------------------------------------------------------------------ on-device equilibration (per-instance-matrices mode)
+// setEquilibration (src/eicos.cpp:302-374) for every instance of the tile: equil_iters rounds of
+// column / row infinity-norm scaling of [A; G] (the rows of a second-order cone share the sum of
+// their norms), rows first then columns as two separate divisions, scales accumulated into
+// x_equil / A_equil / G_equil; then c, b, h are divided by them.  Work vectors: xw.
+EI_DEV void tile_equil(const Team &tm, const KArgs &a, int tile)
+{
+    const TileMem t = tile_mem(tm, a, tile);
+    const DevPattern &P = a.P;
+    const Layout &L = a.L;
+    double *T = t.T;
+    const int n = P.n, p = P.p, zb = P.n + P.p;
+    const int cs = L.xw, ra = L.xw + n, rg = L.xw + zb; // column scales, row scales of A, of G (z index, not expanded)
+    const auto root = [](vd v) {
+        VFOR v.v[c_] = fabs(v.v[c_]) < 1e-6 ? 1.0 : sqrt(v.v[c_]);
+        return v;
+    };
+    for (int r = tm.wk; r < P.N; r += tm.nwk)
+        ROWD(T, L.eq + r) = 1.0;
+    tm.sync();
+    for (int round = 0; round < Settings::equil_iters; round++)
+    {
+        for (int j = tm.wk; j < n; j += tm.nwk)
+        { // maxCols over A then G (:267)
+            vd mx = vset(0.0);
+            for (int k = EI_LDG(P.Ap + j); k < EI_LDG(P.Ap + j + 1); k++)
+                mx = vmax(vabs(ROWD(T, L.Ax + k)), mx);
+            for (int k = EI_LDG(P.Gp + j); k < EI_LDG(P.Gp + j + 1); k++)
+                mx = vmax(vabs(ROWD(T, L.Gx + k)), mx);
+            ROWD(T, cs + j) = mx;
+        }
+        for (int i = tm.wk; i < p; i += tm.nwk)
+        { // maxRows (:256)
+            vd mx = vset(0.0);
+            for (int q = EI_LDG(P.Arp + i); q < EI_LDG(P.Arp + i + 1); q++)
+                mx = vmax(vabs(ROWD(T, L.Ax + EI_LDG(P.Arv + q))), mx);
+            ROWD(T, ra + i) = mx;
+        }
+        for (int i = tm.wk; i < P.m; i += tm.nwk)
+        {
+            vd mx = vset(0.0);
+            for (int q = EI_LDG(P.Grp + i); q < EI_LDG(P.Grp + i + 1); q++)
+                mx = vmax(vabs(ROWD(T, L.Gx + EI_LDG(P.Grv + q))), mx);
+            ROWD(T, rg + i) = mx;
+        }
+        tm.sync();
+        for (int c = tm.wk; c < P.nc; c += tm.nwk)
+        { // every row of a cone gets the sum over the cone (:338-344)
+            const int d = EI_LDG(P.cone_dim + c), z0 = EI_LDG(P.cone_z + c);
+            vd tot = vset(0.0);
+            for (int k = 0; k < d; k++)
+                tot += vd(ROWD(T, rg + z0 + k));
+            for (int k = 0; k < d; k++)
+                ROWD(T, rg + z0 + k) = tot;
+        }
+        tm.sync();
+        for (int r = tm.wk; r < zb + P.m; r += tm.nwk)
+            ROWD(T, cs + r) = root(ROWD(T, cs + r));
+        tm.sync();
+        for (int j = tm.wk; j < n; j += tm.nwk)
+        { // rows first, then columns: two divisions per entry (:353-356)
+            const vd cj = ROWD(T, cs + j);
+            for (int k = EI_LDG(P.Ap + j); k < EI_LDG(P.Ap + j + 1); k++)
+                ROWD(T, L.Ax + k) = vd(ROWD(T, L.Ax + k)) / vd(ROWD(T, ra + EI_LDG(P.Ai + k))) / cj;
+            for (int k = EI_LDG(P.Gp + j); k < EI_LDG(P.Gp + j + 1); k++)
+                ROWD(T, L.Gx + k) = vd(ROWD(T, L.Gx + k)) / vd(ROWD(T, rg + EI_LDG(P.Gi + k))) / cj;
+            ROWD(T, L.eq + j) *= cj;
+        }
+        for (int i = tm.wk; i < p; i += tm.nwk)
+            ROWD(T, L.eq + n + i) *= vd(ROWD(T, ra + i));
+        for (int i = tm.wk; i < P.m; i += tm.nwk)
+            ROWD(T, L.eq + zb + EI_LDG(P.zk + i)) *= vd(ROWD(T, rg + i));
+        tm.sync();
+    }
+    for (int j = tm.wk; j < n; j += tm.nwk)
+        ROWD(T, L.chb + j) = vd(ROWD(T, L.chb + j)) / vd(ROWD(T, L.eq + j));
+    for (int i = tm.wk; i < p; i += tm.nwk)
+        ROWD(T, L.chb + n + i) = vd(ROWD(T, L.chb + n + i)) / vd(ROWD(T, L.eq + n + i));
+    for (int i = tm.wk; i < P.m; i += tm.nwk)
+    {
+        const int e = EI_LDG(P.zk + i);
+        ROWD(T, L.chb + zb + e) = vd(ROWD(T, L.chb + zb + e)) / vd(ROWD(T, L.eq + zb + e));
     }
 }
 
@@ -2298,7 +2466,7 @@ EI_DEV void tile_store(const Team &tm, const KArgs &a, int tile)
 struct MoveRanges
 {
     int n;        // number of (first row, rows) pairs
-    int r[12];
+    int r[14];
 };
 EI_DEV void compact_move(const KArgs &a, const MoveRanges &mr, int src, int dst, int tid, int nthreads)
 {

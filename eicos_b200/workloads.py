@@ -28,6 +28,30 @@ def perturbed(P, batch, rel=0.05, seed=1234, vary=("h", "b")):
     return out
 
 
+def perturbed_matrices(P, batch, rel=0.01, seed=77, scale_spread=0.0):
+    """Per-instance G / A VALUES on the shared pattern (what updateData(Gpr, Apr, ...) feeds the
+    reference one instance at a time): entry-wise G_b = G (1 + rel u), u ~ U(-1,1).  scale_spread > 0
+    also multiplies every instance's G rows of the LP cone and A rows by 10^(spread v), v ~ U(-1,1)
+    per row, so that the per-instance equilibration really differs between instances; the matching
+    h / b stacks are returned scaled the same way (the feasible set is unchanged by a row scaling)."""
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    G0, A0 = np.asarray(P["Gpr"], np.float64), np.asarray(P["Apr"], np.float64)
+    Gs = G0[None, :] * (1.0 + rel * rng.uniform(-1.0, 1.0, size=(batch, G0.size)))
+    As = A0[None, :] * (1.0 + rel * rng.uniform(-1.0, 1.0, size=(batch, A0.size))) if A0.size else None
+    out = {"Gs": Gs, "As": As, "hs": None, "bs": None}
+    if scale_spread:
+        m, p, l = int(P["m"]), int(P["p"]), int(P["l"])
+        rs = np.ones((batch, m))
+        rs[:, :l] = 10.0 ** (scale_spread * rng.uniform(-1.0, 1.0, size=(batch, l)))
+        out["Gs"] = Gs * rs[:, np.asarray(P["Gir"], np.int64)]
+        out["hs"] = np.asarray(P["h"], np.float64)[None, :] * rs
+        if A0.size:
+            ra = 10.0 ** (scale_spread * rng.uniform(-1.0, 1.0, size=(batch, p)))
+            out["As"] = As * ra[:, np.asarray(P["Air"], np.int64)]
+            out["bs"] = np.asarray(P["b"], np.float64)[None, :] * ra
+    return out
+
+
 def _csc(M):
     """dense -> (pr, jc, ir) with rows ascending per column, explicit zeros dropped"""
     M = np.asarray(M, dtype=np.float64)

@@ -93,6 +93,17 @@ eicos_batch *eicos_batch_setup(int n, int m, int p, int l, int ncones, const int
                                const double *c, const double *h, const double *b,
                                int device, long long capacity, int workers);
 
+/* The same with flags.  EICOS_BATCH_INSTANCE_MATRICES: every instance may bring its own G / A VALUES
+ * (same pattern) - what the reference does with updateData(Gpr, Apr, c, h, b) + solve per instance
+ * (src/eicos.cpp:2053-2082): the matrices are equilibrated per instance on the device
+ * (setEquilibration, src/eicos.cpp:302-374) and the KKT programs read them per instance. */
+#define EICOS_BATCH_INSTANCE_MATRICES 1
+eicos_batch *eicos_batch_setup_ex(int n, int m, int p, int l, int ncones, const int *q,
+                                  const double *Gpr, const int *Gjc, const int *Gir,
+                                  const double *Apr, const int *Ajc, const int *Air,
+                                  const double *c, const double *h, const double *b,
+                                  int device, long long capacity, int workers, int flags);
+
 /* New shared matrix values for the whole batch (both or either; NULL = keep the last raw
  * values); re-equilibrates and refreshes the KKT values like updateData (src/eicos.cpp:2076-2081). */
 int eicos_batch_update_matrices(eicos_batch *bt, const double *Gpr, const double *Apr);
@@ -106,12 +117,27 @@ int eicos_batch_solve(eicos_batch *bt, int batch,
                       double *x, double *y, double *z, double *s,
                       int *exitflag, eicos_info *info);
 
+/* eicos_batch_solve with per-instance matrix values: Gs [batch x nnzG], As [batch x nnzA], instance-major,
+ * in the CSC order of the setup matrices; NULL = the setup values for every instance.  Needs a handle
+ * from eicos_batch_setup_ex(..., EICOS_BATCH_INSTANCE_MATRICES). */
+int eicos_batch_solve_matrices(eicos_batch *bt, int batch, const double *Gs, const double *As,
+                               const double *cs, const double *hs, const double *bs,
+                               double *x, double *y, double *z, double *s,
+                               int *exitflag, eicos_info *info);
+
 /* Same with DEVICE buffers (already resident in HBM; results stay on the device).
  * iters may be NULL.  Runs on the engine's own stream and returns after it has drained. */
 int eicos_batch_solve_device(eicos_batch *bt, int batch,
                              const double *d_cs, const double *d_hs, const double *d_bs,
                              double *d_x, double *d_y, double *d_z, double *d_s,
                              int *d_exitflag, int *d_iters);
+
+/* eicos_batch_solve_matrices with DEVICE buffers: d_Gs [batch x nnzG], d_As [batch x nnzA] instance-major
+ * raw values in HBM (NULL = the setup values for every instance). */
+int eicos_batch_solve_matrices_device(eicos_batch *bt, int batch, const double *d_Gs, const double *d_As,
+                                      const double *d_cs, const double *d_hs, const double *d_bs,
+                                      double *d_x, double *d_y, double *d_z, double *d_s,
+                                      int *d_exitflag, int *d_iters);
 
 typedef struct eicos_batch_stats
 {

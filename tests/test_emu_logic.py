@@ -160,3 +160,84 @@ def test_synthetic_socp_config4_small(oracle_mod, emu_lib):
     assert np.all(ref["exit"] == 0)
     for k in "xyzs":
         assert relerr(out[k], ref[k]) <= TOL, k
+
+
+# ---------------------------------------------------------------- per-instance matrices
+def _pim_case(oracle_mod, lib, P, batch, W, cap, workers, nthreads=2):
+    """BatchSolver(instance_matrices=True) against the oracle's updateData(Gpr, Apr, c, h, b) + solve per
+    instance (src/eicos.cpp:2053-2082): setEquilibration runs per instance on the device."""
+    from eicos_b200.binding import BatchSolver
+    ref = oracle_mod.batch_run(P, batch, Gs=W.get("Gs"), As=W.get("As"), hs=W.get("hs"), bs=W.get("bs"), nthreads=nthreads)
+    B = BatchSolver(P, lib=lib, capacity=cap, workers=workers, instance_matrices=True)
+    out = B.solve(batch, hs=W.get("hs"), bs=W.get("bs"), Gs=W.get("Gs"), As=W.get("As"))
+    assert np.array_equal(out["exit"], ref["exit"])
+    assert np.array_equal(out["iter"], ref["iter"])
+    ok = ref["exit"] == 0
+    assert ok.any()
+    return out, ref, ok
+
+
+@pytest.mark.parametrize("name,batch,spread", [("update_data_1", 12, 0.0), ("update_data_1", 9, 1.0), ("lp_afiro", 6, 0.5),
+                                               ("MPC02", 4, 0.0)])
+def test_instance_matrices_parity(oracle_mod, emu_lib, name, batch, spread):
+    from eicos_b200.workloads import perturbed_matrices
+    P = oracle_mod.load_fixture(name)
+    W = perturbed_matrices(P, batch, rel=0.01, seed=11, scale_spread=spread)
+    out, ref, ok = _pim_case(oracle_mod, emu_lib, P, batch, W, cap=4, workers=3)
+    for k in "xyzs":
+        assert relerr(out[k][ok], ref[k][ok]) <= TOL, k
+
+
+def test_instance_matrices_partial_and_shared(oracle_mod, emu_lib):
+    """Only G stacked (A shared), nothing stacked (every instance = the setup problem), and a handle
+    without the flag refusing matrices."""
+    from eicos_b200.binding import BatchSolver
+    from eicos_b200.workloads import perturbed, perturbed_matrices
+    P = oracle_mod.load_fixture("update_data_1")
+    W = perturbed_matrices(P, 7, rel=0.02, seed=2)
+    V = perturbed(P, 7, rel=0.03, seed=4)
+    for Wc in ({"Gs": W["Gs"], "hs": V["hs"]}, {"As": W["As"], "bs": V["bs"]}, {"hs": V["hs"], "bs": V["bs"]}):
+        out, ref, ok = _pim_case(oracle_mod, emu_lib, P, 7, Wc, cap=8, workers=2)
+        for k in "xyzs":
+            assert relerr(out[k][ok], ref[k][ok]) <= TOL, k
+    plain = BatchSolver(P, lib=emu_lib, capacity=8)
+    with pytest.raises(RuntimeError, match="per-instance matrices"):
+        plain.solve(7, Gs=W["Gs"])
+    pim = BatchSolver(P, lib=emu_lib, capacity=8, instance_matrices=True)
+    with pytest.raises(ValueError):
+        pim.solve(7, Gs=W["Gs"][:, :-1])
+
+
+def test_instance_matrices_soc(oracle_mod, emu_lib):
+    """Second-order cones: the rows of a cone share one equilibration scale (src/eicos.cpp:338-344)."""
+    from eicos_b200.workloads import soc_mpc, soc_mpc_batch, perturbed_matrices
+    P = soc_mpc(T=8)
+    W = soc_mpc_batch(P, 6)
+    M = perturbed_matrices(P, 6, rel=0.005, seed=9)
+    out, ref, ok = _pim_case(oracle_mod, emu_lib, P, 6, {"Gs": M["Gs"], "As": M["As"], "hs": W["hs"], "bs": W["bs"]},
+                             cap=4, workers=4)
+    for k in "xs":
+        assert relerr(out[k][ok], ref[k][ok]) <= TOL, k
+    for k in "yz":  # duals at a cone apex: see test_batched_soc_mpc_parity
+        assert relerr(out[k][ok], ref[k][ok]) <= 1e-5, k
+
+
+def test_instance_matrices_compaction(oracle_mod, emu_lib):
+    """Compaction moves the per-instance matrices and equilibration vectors with the survivors."""
+    from eicos_b200.binding import BatchSolver
+    from eicos_b200.workloads import perturbed_matrices
+    P = oracle_mod.load_fixture("update_data_1")
+    batch = 300
+    W = perturbed_matrices(P, batch, rel=0.03, seed=21, scale_spread=0.7)
+    B = BatchSolver(P, lib=emu_lib, capacity=batch, workers=2, instance_matrices=True)
+    a = B.solve(batch, hs=W["hs"], bs=W["bs"], Gs=W["Gs"], As=W["As"])
+    assert B.stats()["compactions"] >= 1
+    B.set_compaction(False)
+    b = B.solve(batch, hs=W["hs"], bs=W["bs"], Gs=W["Gs"], As=W["As"])
+    assert B.stats()["compactions"] == 0
+    for k in ("x", "y", "z", "s", "exit", "iter"):
+        assert np.array_equal(a[k], b[k]), k
+    ref = oracle_mod.batch_run(P, batch, Gs=W["Gs"], As=W["As"], hs=W["hs"], bs=W["bs"], nthreads=8)
+    assert np.array_equal(a["exit"], ref["exit"]) and np.array_equal(a["iter"], ref["iter"])
+    ok = ref["exit"] == 0
+    assert relerr(a["x"][ok], ref["x"][ok]) <= TOL

@@ -290,3 +290,75 @@ def test_lp25fv47_config5(oracle_mod, gpu_lib):
     assert relerr(out["x"][ok], ref["x"][ok]) <= 1e-6
     pc = np.array([i["pcost"] for i in out["info"]])
     assert np.max(np.abs(pc[ok] - ref["pcost"][ok]) / np.maximum(1, np.abs(ref["pcost"][ok]))) <= TOL
+
+
+# ---------------------------------------------------------------- per-instance matrices
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,batch,cap,spread", [
+    ("update_data_1", 100, 256, 1.0),   # ragged tile, row scales spread over two decades per instance
+    ("lp_afiro", 70, 64, 0.5),          # two chunks
+    ("lp_blend", 33, 64, 0.0),
+    ("MPC02", 72, 64, 0.0),             # configs[2] shape with per-instance G / A values, chunked
+])
+def test_instance_matrices_parity(oracle_mod, gpu_lib, name, batch, cap, spread):
+    """BatchSolver(instance_matrices=True): every instance brings its own G / A values, equilibrated on the
+    device; against the oracle's updateData(Gpr, Apr, c, h, b) + solve per instance (src/eicos.cpp:2053-2082)."""
+    from eicos_b200 import BatchSolver
+    from eicos_b200.workloads import perturbed_matrices
+    P = oracle_mod.load_fixture(name)
+    W = perturbed_matrices(P, batch, rel=0.01, seed=11, scale_spread=spread)
+    ref = oracle_mod.batch_run(P, batch, Gs=W["Gs"], As=W["As"], hs=W["hs"], bs=W["bs"], nthreads=8)
+    B = BatchSolver(P, lib=gpu_lib, capacity=cap, instance_matrices=True)
+    out = B.solve(batch, hs=W["hs"], bs=W["bs"], Gs=W["Gs"], As=W["As"])
+    assert np.array_equal(out["exit"], ref["exit"])
+    assert np.array_equal(out["iter"], ref["iter"])
+    ok = ref["exit"] == 0
+    assert ok.any()
+    for k in "xyzs":
+        assert relerr(out[k][ok], ref[k][ok]) <= TOL, k
+    # the same handle with shared matrices again: identical to the plain batched path, bit for bit
+    out2 = B.solve(batch)
+    plain = BatchSolver(P, lib=gpu_lib, capacity=cap).solve(batch)
+    assert np.array_equal(out2["exit"], plain["exit"]) and np.array_equal(out2["iter"], plain["iter"])
+    assert relerr(out2["x"], plain["x"]) <= 1e-12
+
+
+@pytest.mark.gpu
+def test_instance_matrices_soc(oracle_mod, gpu_lib):
+    from eicos_b200 import BatchSolver
+    from eicos_b200.workloads import soc_mpc, soc_mpc_batch, perturbed_matrices
+    P = soc_mpc(T=20)
+    W = soc_mpc_batch(P, 200)
+    M = perturbed_matrices(P, 200, rel=0.005, seed=9)
+    ref = oracle_mod.batch_run(P, 200, Gs=M["Gs"], As=M["As"], hs=W["hs"], bs=W["bs"], nthreads=8)
+    B = BatchSolver(P, lib=gpu_lib, capacity=256, instance_matrices=True)
+    out = B.solve(200, hs=W["hs"], bs=W["bs"], Gs=M["Gs"], As=M["As"])
+    assert np.array_equal(out["exit"], ref["exit"]) and np.array_equal(out["iter"], ref["iter"])
+    ok = ref["exit"] == 0
+    for k in "xs":
+        assert relerr(out[k][ok], ref[k][ok]) <= TOL, k
+    for k in "yz":  # duals at a cone apex: see test_batched_soc_mpc_parity
+        err = np.max(np.abs(out[k] - ref[k]), axis=1) / np.maximum(1.0, np.max(np.abs(ref[k]), axis=1))
+        assert np.mean(err <= TOL) >= 0.9 and err.max() <= 1e-5, (k, err.max())
+
+
+@pytest.mark.gpu
+def test_instance_matrices_compaction(oracle_mod, gpu_lib):
+    """Active-set compaction moves the per-instance matrices and equilibration vectors with the survivors."""
+    from eicos_b200 import BatchSolver
+    from eicos_b200.workloads import perturbed_matrices
+    P = oracle_mod.load_fixture("update_data_1")
+    batch = 1500  # 24 tiles: compaction needs at least 8
+    W = perturbed_matrices(P, batch, rel=0.03, seed=21, scale_spread=0.7)
+    B = BatchSolver(P, lib=gpu_lib, capacity=batch, workers=2, instance_matrices=True)
+    a = B.solve(batch, hs=W["hs"], bs=W["bs"], Gs=W["Gs"], As=W["As"])
+    assert B.stats()["compactions"] >= 1
+    B.set_compaction(False)
+    b = B.solve(batch, hs=W["hs"], bs=W["bs"], Gs=W["Gs"], As=W["As"])
+    assert B.stats()["compactions"] == 0
+    for k in ("x", "y", "z", "s", "exit", "iter"):
+        assert np.array_equal(a[k], b[k]), k
+    ref = oracle_mod.batch_run(P, batch, Gs=W["Gs"], As=W["As"], hs=W["hs"], bs=W["bs"], nthreads=8)
+    assert np.array_equal(a["exit"], ref["exit"]) and np.array_equal(a["iter"], ref["iter"])
+    ok = ref["exit"] == 0
+    assert relerr(a["x"][ok], ref["x"][ok]) <= TOL
