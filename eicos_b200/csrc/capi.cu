@@ -267,50 +267,62 @@ int eicos_batch_solve_matrices(eicos_batch *bt, int batch, const double *Gs, con
         const Symbolic &S = bt->S;
         be::set_device(bt->device);
         be::stream_t st = (be::stream_t)(intptr_t)bt->eng->stream();
-        const size_t B = (size_t)batch;
-        if (bt->eng->instance_matrices())
-        { // stacks of raw matrix values (instance-major); missing ones fall back to the setup matrices
-            const size_t ng = Gs ? B * S.G.nnz() : 0, na = As ? B * S.A.nnz() : 0;
-            bt->dmat.ensure((ng + na) * sizeof(double));
-            double *dm = (double *)bt->dmat.p;
-            be::h2d(dm, Gs, ng * sizeof(double), st);
-            be::h2d(dm + ng, As, na * sizeof(double), st);
-            bt->eng->set_matrices(Gs ? dm : nullptr, As ? dm + ng : nullptr, bt->rawG.data(), bt->rawA.data());
+        // The device staging buffers hold one SEGMENT of at most `capacity` instances (= one resident
+        // chunk of the engine), so their size is bounded by the handle, not by the caller's batch.
+        const size_t cap = (size_t)std::max<long long>(1, bt->eng->capacity());
+        const size_t nG = (size_t)S.G.nnz(), nA = (size_t)S.A.nnz();
+        SolveStats total;
+        for (size_t first = 0; first < (size_t)batch || first == 0; first += cap)
+        {
+            const size_t B = std::min(cap, (size_t)batch - first);
+            if (bt->eng->instance_matrices())
+            { // stacks of raw matrix values (instance-major); missing ones fall back to the setup matrices
+                const size_t ng = Gs ? B * nG : 0, na = As ? B * nA : 0;
+                bt->dmat.ensure((ng + na) * sizeof(double));
+                double *dm = (double *)bt->dmat.p;
+                be::h2d(dm, Gs ? Gs + first * nG : nullptr, ng * sizeof(double), st);
+                be::h2d(dm + ng, As ? As + first * nA : nullptr, na * sizeof(double), st);
+                bt->eng->set_matrices(Gs ? dm : nullptr, As ? dm + ng : nullptr, bt->rawG.data(), bt->rawA.data());
+            }
+            const size_t nc_ = cs ? B * S.n : 0, nh_ = hs ? B * S.m : 0, nb_ = bs ? B * S.p : 0;
+            bt->din.ensure((nc_ + nh_ + nb_) * sizeof(double));
+            double *din = (double *)bt->din.p;
+            double *dc = cs ? din : nullptr, *dh = hs ? din + nc_ : nullptr, *db = bs ? din + nc_ + nh_ : nullptr;
+            be::h2d(dc, cs ? cs + first * S.n : nullptr, nc_ * sizeof(double), st);
+            be::h2d(dh, hs ? hs + first * S.m : nullptr, nh_ * sizeof(double), st);
+            be::h2d(db, bs ? bs + first * S.p : nullptr, nb_ * sizeof(double), st);
+            const size_t ox = x ? B * S.n : 0, oy = y ? B * S.p : 0, oz = z ? B * S.m : 0, os = s ? B * S.m : 0;
+            const size_t oi = info ? B * S_WORK_END : 0;
+            bt->dout.ensure((ox + oy + oz + os + oi) * sizeof(double));
+            double *dout = (double *)bt->dout.p;
+            double *dx = x ? dout : nullptr, *dy = y ? dout + ox : nullptr, *dz = z ? dout + ox + oy : nullptr;
+            double *dsl = s ? dout + ox + oy + oz : nullptr, *dinfo = info ? dout + ox + oy + oz + os : nullptr;
+            const size_t ie = B, ii = info ? B * J_WORK_END : 0;
+            bt->dint.ensure((ie + ii) * sizeof(int));
+            int *dexit = (int *)bt->dint.p, *diinfo = info ? dexit + ie : nullptr;
+            bt->eng->solve((int)B, dc, dh, db, bt->c.data(), bt->h.data(), bt->b.data(),
+                           dx, dy, dz, dsl, dexit, nullptr, dinfo, diinfo,
+                           false, false, bt->timing, &bt->stats);
+            be::d2h(x ? x + first * S.n : nullptr, dx, ox * sizeof(double), st);
+            be::d2h(y ? y + first * S.p : nullptr, dy, oy * sizeof(double), st);
+            be::d2h(z ? z + first * S.m : nullptr, dz, oz * sizeof(double), st);
+            be::d2h(s ? s + first * S.m : nullptr, dsl, os * sizeof(double), st);
+            std::vector<int> hexit(ie), hii(ii);
+            std::vector<double> hinfo(oi);
+            be::d2h(hexit.data(), dexit, ie * sizeof(int), st);
+            be::d2h(hii.data(), diinfo, ii * sizeof(int), st);
+            be::d2h(hinfo.data(), dinfo, oi * sizeof(double), st);
+            be::sync(st);
+            if (exitflag)
+                std::copy(hexit.begin(), hexit.end(), exitflag + first);
+            if (info)
+                for (size_t k = 0; k < B; k++)
+                    info_from_rows(hinfo.data() + k * S_WORK_END, hii.data() + k * J_WORK_END, info + first + k);
+            total += bt->stats;
+            if (batch == 0)
+                break;
         }
-        const size_t nc_ = cs ? B * S.n : 0, nh_ = hs ? B * S.m : 0, nb_ = bs ? B * S.p : 0;
-        bt->din.ensure((nc_ + nh_ + nb_) * sizeof(double));
-        double *din = (double *)bt->din.p;
-        double *dc = cs ? din : nullptr, *dh = hs ? din + nc_ : nullptr, *db = bs ? din + nc_ + nh_ : nullptr;
-        be::h2d(dc, cs, nc_ * sizeof(double), st);
-        be::h2d(dh, hs, nh_ * sizeof(double), st);
-        be::h2d(db, bs, nb_ * sizeof(double), st);
-        const size_t ox = x ? B * S.n : 0, oy = y ? B * S.p : 0, oz = z ? B * S.m : 0, os = s ? B * S.m : 0;
-        const size_t oi = info ? B * S_WORK_END : 0;
-        bt->dout.ensure((ox + oy + oz + os + oi) * sizeof(double));
-        double *dout = (double *)bt->dout.p;
-        double *dx = x ? dout : nullptr, *dy = y ? dout + ox : nullptr, *dz = z ? dout + ox + oy : nullptr;
-        double *dsl = s ? dout + ox + oy + oz : nullptr, *dinfo = info ? dout + ox + oy + oz + os : nullptr;
-        const size_t ie = B, ii = info ? B * J_WORK_END : 0;
-        bt->dint.ensure((ie + ii) * sizeof(int));
-        int *dexit = (int *)bt->dint.p, *diinfo = info ? dexit + ie : nullptr;
-        bt->eng->solve(batch, dc, dh, db, bt->c.data(), bt->h.data(), bt->b.data(),
-                       dx, dy, dz, dsl, dexit, nullptr, dinfo, diinfo,
-                       false, false, bt->timing, &bt->stats);
-        be::d2h(x, dx, ox * sizeof(double), st);
-        be::d2h(y, dy, oy * sizeof(double), st);
-        be::d2h(z, dz, oz * sizeof(double), st);
-        be::d2h(s, dsl, os * sizeof(double), st);
-        std::vector<int> hexit(ie), hii(ii);
-        std::vector<double> hinfo(oi);
-        be::d2h(hexit.data(), dexit, ie * sizeof(int), st);
-        be::d2h(hii.data(), diinfo, ii * sizeof(int), st);
-        be::d2h(hinfo.data(), dinfo, oi * sizeof(double), st);
-        be::sync(st);
-        if (exitflag)
-            std::copy(hexit.begin(), hexit.end(), exitflag);
-        if (info)
-            for (size_t k = 0; k < B; k++)
-                info_from_rows(hinfo.data() + k * S_WORK_END, hii.data() + k * J_WORK_END, info + k);
+        bt->stats = total;
         return 0;
     }
     catch (const std::invalid_argument &e)

@@ -23,6 +23,18 @@ struct SolveStats
     double ms_total = 0, ms_factor = 0, ms_solve = 0, ms_other = 0; // device time by kernel class (CUDA events)
     long long factor_launch_tiles = 0, solve_launch_tiles = 0;      // tiles covered by the timed launches
     int factor_launches = 0, solve_launches = 0;
+
+    SolveStats &operator+=(const SolveStats &o)
+    { // a batch solved in several segments (capi.cu)
+        chunks += o.chunks, compactions += o.compactions, ipm_iterations += o.ipm_iterations;
+        launches += o.launches, ir_rounds += o.ir_rounds;
+        for (int k = 0; k < 5; k++)
+            kkt_phase_cycles[k] += o.kkt_phase_cycles[k];
+        ms_total += o.ms_total, ms_factor += o.ms_factor, ms_solve += o.ms_solve, ms_other += o.ms_other;
+        factor_launch_tiles += o.factor_launch_tiles, solve_launch_tiles += o.solve_launch_tiles;
+        factor_launches += o.factor_launches, solve_launches += o.solve_launches;
+        return *this;
+    }
 };
 
 // what the program compiler (streams.cpp) produced for this pattern
