@@ -14,7 +14,6 @@ computed independently with scipy (see make_objectives.py).
 """
 import json
 import os
-import re
 import sys
 
 import numpy as np
@@ -22,57 +21,15 @@ import numpy as np
 REF = os.environ.get("EICOS_REFERENCE", "/root/reference")
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fixtures")
 
-ARR = re.compile(r"(?:static\s+)?(idxint|pfloat)\s+(\w+)\s*\[\s*\d*\s*\]\s*=\s*\{([^}]*)\}\s*;", re.S)
-SCL = re.compile(r"(?:static\s+)?(idxint|pfloat)\s+(\w+)\s*=\s*([-+0-9.eE]+)\s*;")
-
-ALIAS = {"Gx": "Gpr", "Gp": "Gjc", "Gi": "Gir", "Ax": "Apr", "Ap": "Ajc", "Ai": "Air"}
-KEYS = ["n", "m", "p", "l", "ncones", "q", "c", "h", "b", "Gpr", "Gjc", "Gir", "Apr", "Ajc", "Air"]
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
+from eicos_b200.ecos_format import KEYS, parse_header as parse, select as canon, finish as _finish  # noqa: E402
 
 
-def parse(path):
-    txt = open(path).read()
-    out = {}
-    for ty, name, body in ARR.findall(txt):
-        vals = [v for v in re.split(r"[,\s]+", body.strip()) if v]
-        out[name] = np.array([float(v) for v in vals], dtype=np.float64 if ty == "pfloat" else np.int32)
-        if ty == "idxint":
-            out[name] = out[name].astype(np.int32)
-    for ty, name, val in SCL.findall(txt):
-        out[name] = int(val) if ty == "idxint" else float(val)
-    return out
-
-
-def canon(raw, prefix, suffix=""):
-    """Pick `<prefix><key><suffix>` entries (with ECOS aliases) into canonical keys."""
-    d = {}
-    for k in KEYS:
-        for cand in [k] + [a for a, b in ALIAS.items() if b == k]:
-            for nm in (prefix + cand + suffix, prefix + cand):
-                if nm in raw:
-                    d[k] = raw[nm]
-                    break
-            if k in d:
-                break
-    return d
-
-
-def finish(d, n=None, m=None, p=None, l=None, ncones=None):
-    for k, v in dict(n=n, m=m, p=p, l=l, ncones=ncones).items():
-        if v is not None:
-            d[k] = v
-    d.setdefault("p", 0)
-    d.setdefault("ncones", 0)
-    for k in ("q", "Gjc", "Gir", "Ajc", "Air"):
-        d[k] = np.asarray(d.get(k, np.zeros(0)), dtype=np.int32)
-    for k in ("c", "h", "b", "Gpr", "Apr"):
-        d[k] = np.asarray(d.get(k, np.zeros(0)), dtype=np.float64)
+def finish(d, **dims):
+    """ecos_format.finish with the scalar dtypes the committed .npz files were written with."""
+    d = _finish(d, **dims)
     for k in ("n", "m", "p", "l", "ncones"):
         d[k] = np.int32(d[k])
-    assert d["c"].size == d["n"] and d["h"].size == d["m"] and d["b"].size == d["p"], (d["n"], d["m"], d["p"])
-    if d["Gpr"].size:
-        assert d["Gjc"].size == d["n"] + 1 and d["Gjc"][-1] == d["Gpr"].size == d["Gir"].size
-    if d["Apr"].size:
-        assert d["Ajc"].size == d["n"] + 1 and d["Ajc"][-1] == d["Apr"].size == d["Air"].size
     return d
 
 

@@ -241,3 +241,18 @@ def test_instance_matrices_compaction(oracle_mod, emu_lib):
     assert np.array_equal(a["exit"], ref["exit"]) and np.array_equal(a["iter"], ref["iter"])
     ok = ref["exit"] == 0
     assert relerr(a["x"][ok], ref["x"][ok]) <= TOL
+
+
+def test_instance_matrices_handle_follows_update_matrices(oracle_mod, emu_lib):
+    """eicos_batch_update_matrices on a per-instance-matrices handle replaces the values instances fall back to."""
+    from eicos_b200.binding import BatchSolver
+    from eicos_b200.workloads import perturbed
+    P1, P2 = oracle_mod.load_fixture("update_data_1"), oracle_mod.load_fixture("update_data_2")
+    W = perturbed(P2, 5, rel=0.02, seed=12)
+    B = BatchSolver(P1, lib=emu_lib, capacity=8, instance_matrices=True)
+    B.update_matrices(P2["Gpr"], P2["Apr"])
+    out = B.solve(5, cs=np.tile(P2["c"], (5, 1)), hs=W["hs"], bs=W["bs"])
+    ref = oracle_mod.batch_run(P2, 5, hs=W["hs"], bs=W["bs"], nthreads=2)
+    assert np.array_equal(out["exit"], ref["exit"]) and np.array_equal(out["iter"], ref["iter"])
+    for k in "xyzs":
+        assert relerr(out[k], ref[k]) <= TOL, k
