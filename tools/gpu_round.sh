@@ -9,6 +9,7 @@ echo "== pytest -m gpu"; python -m pytest tests -x -q -m gpu 2>&1 | tail -15 | t
 echo "== smoke"; python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee $OUT/smoke.txt
 echo "== bench"; python bench.py 2>$OUT/bench.err | tee $OUT/bench.json | cut -c1-1500; tail -5 $OUT/bench.err
 echo "== bench reference"; python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | tee $OUT/bench_reference.json | cut -c1-400
+echo "== bench mpc02pim (per-instance matrices)"; python bench.py --workload mpc02pim 2>$OUT/bench_pim.err | tee $OUT/bench_pim.json | cut -c1-600; tail -3 $OUT/bench_pim.err
 SMALL="python bench.py --batch 4096 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline"
 echo "== ncu launch list"
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:eicos_ --csv --log-file $OUT/launches.csv $SMALL > $OUT/launches.log 2>&1
