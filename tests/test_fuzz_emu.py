@@ -1,6 +1,6 @@
 """Randomised parity (tools/fuzz_emu.py): random small SOCPs with irregular sparsity, random slot budgets
 and worker counts, shared and per-instance matrices, kernel emulator against the oracle.  A bounded
-slice of the sweep (the full one - 750 problems, 4500 instances - is recorded in DESIGN.md section 6)."""
+slice of the sweep (the full one - 1500 problems, 9000 solves - is recorded in DESIGN.md section 6)."""
 import os
 import sys
 
