@@ -16,7 +16,38 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def random_mpc(seed):
+    """Banded MPC-like LP (scalar or 2-state dynamics, box bounds, optional input-norm cones): narrow
+    columns of L, so the record-form factor program (streams.hpp: fa_fast) is the one exercised."""
+    from eicos_b200.workloads import _csc
+    rng = np.random.default_rng(seed)
+    nx, T = int(rng.integers(1, 3)), int(rng.integers(3, 25))
+    nv = (nx + 1) * T  # per stage: u_k, x_{k+1}
+    Ad = np.eye(nx) + 0.1 * np.triu(np.ones((nx, nx)), 1)
+    Bd = np.full(nx, 0.1)
+    A = np.zeros((nx * T, nv))
+    b = np.zeros(nx * T)
+    x0 = rng.uniform(-1, 1, nx)
+    for k in range(T):
+        r = slice(nx * k, nx * (k + 1))
+        A[r, (nx + 1) * k] = -Bd
+        A[r, (nx + 1) * k + 1:(nx + 1) * (k + 1)] = np.eye(nx)
+        if k:
+            A[r, (nx + 1) * (k - 1) + 1:(nx + 1) * k] = -Ad
+        else:
+            b[r] = Ad @ x0
+    G = np.vstack([np.eye(nv), -np.eye(nv)])
+    h = np.concatenate([np.full(nv, 3.0 + rng.random()), np.full(nv, 3.0 + rng.random())])
+    c = rng.standard_normal(nv)
+    Gpr, Gjc, Gir = _csc(G)
+    Apr, Ajc, Air = _csc(A)
+    return dict(n=nv, m=2 * nv, p=nx * T, l=2 * nv, ncones=0, q=np.zeros(0, np.int32), Gpr=Gpr, Gjc=Gjc, Gir=Gir,
+                Apr=Apr, Ajc=Ajc, Air=Air, c=c, h=h, b=b)
+
+
 def random_problem(seed):
+    if seed % 7 == 3:
+        return random_mpc(seed)
     rng = np.random.default_rng(seed)
     big = seed % 5 == 0  # every fifth problem is larger: longer programs, far gathers, FIFO wrap-arounds
     n = int(rng.integers(40, 160)) if big else int(rng.integers(1, 40))
