@@ -2331,6 +2331,48 @@ EI_DEV void tile_load(const Team &tm, const KArgs &a, int tile)
 }
 
 // ------------------------------------------------------------------ on-device equilibration (per-instance-matrices mode)
+// max |row| over the entries k0..k1-1 of an index walk, folded into mx in walk order; the row loads of
+// four entries are issued before the first compare so that they overlap (the walk is latency-bound).
+template <class RowOf>
+EI_DEV vd equil_max_abs(const double *T, int k0, int k1, vd mx, RowOf row)
+{
+    int k = k0;
+    for (; k + 4 <= k1; k += 4)
+    {
+        vd v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            v[u] = vload(T + (size_t)row(k + u) * TILE);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            mx = vmax(vabs(v[u]), mx);
+    }
+    for (; k < k1; k++)
+        mx = vmax(vabs(vload(T + (size_t)row(k) * TILE)), mx);
+    return mx;
+}
+
+// entries k0..k1-1 of a CSC column: value /= row scale, then /= column scale (two divisions, src/eicos.cpp:353-356)
+EI_DEV void equil_scale_column(double *T, int val0, int scale0, const int *rows, int k0, int k1, vd cj)
+{
+    int k = k0;
+    for (; k + 4 <= k1; k += 4)
+    {
+        vd v[4], r[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+        {
+            v[u] = vload(T + (size_t)(val0 + k + u) * TILE);
+            r[u] = vload(T + (size_t)(scale0 + EI_LDG(rows + k + u)) * TILE);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            vstore(T + (size_t)(val0 + k + u) * TILE, v[u] / r[u] / cj);
+    }
+    for (; k < k1; k++)
+        ROWD(T, val0 + k) = vd(ROWD(T, val0 + k)) / vd(ROWD(T, scale0 + EI_LDG(rows + k))) / cj;
+}
+
 // setEquilibration (src/eicos.cpp:302-374) for every instance of the tile: equil_iters rounds of
 // column / row infinity-norm scaling of [A; G] (the rows of a second-order cone share the sum of
 // their norms), rows first then columns as two separate divisions, scales accumulated into
@@ -2354,27 +2396,15 @@ EI_DEV void tile_equil(const Team &tm, const KArgs &a, int tile)
     {
         for (int j = tm.wk; j < n; j += tm.nwk)
         { // maxCols over A then G (:267)
-            vd mx = vset(0.0);
-            for (int k = EI_LDG(P.Ap + j); k < EI_LDG(P.Ap + j + 1); k++)
-                mx = vmax(vabs(ROWD(T, L.Ax + k)), mx);
-            for (int k = EI_LDG(P.Gp + j); k < EI_LDG(P.Gp + j + 1); k++)
-                mx = vmax(vabs(ROWD(T, L.Gx + k)), mx);
-            ROWD(T, cs + j) = mx;
+            vd mx = equil_max_abs(T, EI_LDG(P.Ap + j), EI_LDG(P.Ap + j + 1), vset(0.0), [&](int k) { return L.Ax + k; });
+            ROWD(T, cs + j) = equil_max_abs(T, EI_LDG(P.Gp + j), EI_LDG(P.Gp + j + 1), mx, [&](int k) { return L.Gx + k; });
         }
-        for (int i = tm.wk; i < p; i += tm.nwk)
-        { // maxRows (:256)
-            vd mx = vset(0.0);
-            for (int q = EI_LDG(P.Arp + i); q < EI_LDG(P.Arp + i + 1); q++)
-                mx = vmax(vabs(ROWD(T, L.Ax + EI_LDG(P.Arv + q))), mx);
-            ROWD(T, ra + i) = mx;
-        }
+        for (int i = tm.wk; i < p; i += tm.nwk) // maxRows (:256)
+            ROWD(T, ra + i) = equil_max_abs(T, EI_LDG(P.Arp + i), EI_LDG(P.Arp + i + 1), vset(0.0),
+                                            [&](int q) { return L.Ax + EI_LDG(P.Arv + q); });
         for (int i = tm.wk; i < P.m; i += tm.nwk)
-        {
-            vd mx = vset(0.0);
-            for (int q = EI_LDG(P.Grp + i); q < EI_LDG(P.Grp + i + 1); q++)
-                mx = vmax(vabs(ROWD(T, L.Gx + EI_LDG(P.Grv + q))), mx);
-            ROWD(T, rg + i) = mx;
-        }
+            ROWD(T, rg + i) = equil_max_abs(T, EI_LDG(P.Grp + i), EI_LDG(P.Grp + i + 1), vset(0.0),
+                                            [&](int q) { return L.Gx + EI_LDG(P.Grv + q); });
         tm.sync();
         for (int c = tm.wk; c < P.nc; c += tm.nwk)
         { // every row of a cone gets the sum over the cone (:338-344)
@@ -2392,10 +2422,8 @@ EI_DEV void tile_equil(const Team &tm, const KArgs &a, int tile)
         for (int j = tm.wk; j < n; j += tm.nwk)
         { // rows first, then columns: two divisions per entry (:353-356)
             const vd cj = ROWD(T, cs + j);
-            for (int k = EI_LDG(P.Ap + j); k < EI_LDG(P.Ap + j + 1); k++)
-                ROWD(T, L.Ax + k) = vd(ROWD(T, L.Ax + k)) / vd(ROWD(T, ra + EI_LDG(P.Ai + k))) / cj;
-            for (int k = EI_LDG(P.Gp + j); k < EI_LDG(P.Gp + j + 1); k++)
-                ROWD(T, L.Gx + k) = vd(ROWD(T, L.Gx + k)) / vd(ROWD(T, rg + EI_LDG(P.Gi + k))) / cj;
+            equil_scale_column(T, L.Ax, ra, P.Ai, EI_LDG(P.Ap + j), EI_LDG(P.Ap + j + 1), cj);
+            equil_scale_column(T, L.Gx, rg, P.Gi, EI_LDG(P.Gp + j), EI_LDG(P.Gp + j + 1), cj);
             ROWD(T, L.eq + j) *= cj;
         }
         for (int i = tm.wk; i < p; i += tm.nwk)
