@@ -15,9 +15,11 @@ namespace eicos
 
 #ifndef EICOS_EMU
 // thin named wrappers so that profilers show one kernel name per step of the algorithm
-#define EI_DEFINE_KERNEL(name, fn, minblocks) EI_DEFINE_KERNEL_(name, fn, minblocks, 0)
-#define EI_DEFINE_KERNEL_(name, fn, minblocks, JOBS)                                           \
-    __global__ void __launch_bounds__(EI_MAX_THREADS, minblocks) name(const __grid_constant__ KArgs a) \
+#define EI_DEFINE_KERNEL(name, fn, minblocks) EI_DEFINE_KERNEL_(name, fn, EI_MAX_THREADS, minblocks, 0)
+/* one-warp program kernels: no register cap below the hardware's (a handful of CTAs per SM, limited by shared memory) */
+#define EI_DEFINE_KERNEL1(name, fn) EI_DEFINE_KERNEL_(name, fn, 32, 8, 0)
+#define EI_DEFINE_KERNEL_(name, fn, maxthreads, minblocks, JOBS)                                           \
+    __global__ void __launch_bounds__(maxthreads, minblocks) name(const __grid_constant__ KArgs a) \
     {                                                                                          \
         extern __shared__ double smem[];                                                       \
         Team tm;                                                                               \
@@ -26,8 +28,9 @@ namespace eicos
         tm.wk = threadIdx.x >> 5;                                                              \
         tm.nwk = blockDim.x >> 5;                                                              \
         tm.red = smem;                                                                         \
-        /* vector kernels (several warps): [reduction rows]; program kernels (one warp):              \
-           [program-stream buffers][staging = FIFO ring][zero row, slots, column buffers] */        \
+        /* vector kernels (several warps): [reduction rows]; factor kernel (one warp): [program-stream   \
+           buffers][staging = FIFO ring][slots, column buffers]; solveKKT / residual kernels (one warp):  \
+           the pipes of tile_program.hpp (ops ring, mbarriers, rows) at pbuf */                      \
         tm.pbuf = smem + (size_t)(tm.nwk > 1 ? tm.nwk * KRED : 0) * TILE;                           \
         tm.stage = tm.pbuf + PS_DOUBLES + tm.lane;                                                 \
         tm.extra = tm.stage + (size_t)2 * STAGE_SLOTS * TILE;                                      \
@@ -38,10 +41,11 @@ namespace eicos
 EI_DEFINE_KERNEL(eicos_load_inputs, tile_load, 2)
 EI_DEFINE_KERNEL(eicos_equilibrate, tile_equil, 2)
 EI_DEFINE_KERNEL(eicos_init, tile_init, 2)
-EI_DEFINE_KERNEL(eicos_ldl_factor, tile_factor, 2)
-EI_DEFINE_KERNEL_(eicos_solve_kkt, tile_solve_kkt, 2, 1) /* grid = tiles x jobs, job fastest */
+EI_DEFINE_KERNEL1(eicos_ldl_factor, tile_factor)
+EI_DEFINE_KERNEL1(eicos_solve_kkt, tile_solve_kkt<1>)     /* one solveKKT per tile */
+EI_DEFINE_KERNEL1(eicos_solve_kkt_pair, tile_solve_kkt<2>) /* two solveKKT that share the factor, one pass over L */
 EI_DEFINE_KERNEL(eicos_init_point, tile_init_point, 2)
-EI_DEFINE_KERNEL(eicos_residuals, tile_resid, 2)
+EI_DEFINE_KERNEL1(eicos_residuals, tile_resid)
 EI_DEFINE_KERNEL(eicos_iter_head, tile_head, 2)
 EI_DEFINE_KERNEL(eicos_iter_mid, tile_mid, 2)
 EI_DEFINE_KERNEL(eicos_iter_tail, tile_tail, 2)
@@ -68,9 +72,9 @@ __global__ void eicos_compact(const __grid_constant__ KArgs a, const __grid_cons
     {                                                                                             \
         const int nw_ = (threads), nj_ = (njobs);                                                                \
         std::vector<double> red_((size_t)nw_ * KRED * TILE + 8);                                  \
-        const size_t xr_ = (size_t)std::max((args).P.sw_slots, (args).P.fa_slots) + 2 * (args).P.maxcol; \
+        const size_t xr_ = (size_t)(args).P.fa_slots + 2 * (args).P.maxcol;                           \
         std::vector<double> stg_(((size_t)nw_ * 2 * STAGE_SLOTS + xr_) * TILE + 8);                \
-        std::vector<double> pb_(PS_DOUBLES + 8);                                                   \
+        std::vector<double> pb_(std::max<size_t>(PS_DOUBLES, pipe_smem_doubles(std::max((args).P.sw_rows[0], (args).P.sw_rows[1]))) + 8); \
         for (int cta_ = 0; cta_ < (tiles) * nj_; cta_++)                                          \
         {                                                                                         \
             const int tile_ = cta_ / nj_;                                                         \
@@ -208,13 +212,8 @@ void Engine::upload_pattern(const Symbolic &S)
     P.nnzL = S.nnzL;
     P.nnzV = (int)S.Vslot.size();
     P.maxcol = S.maxcol;
-    P.fw_nld = H_.fw_nld;
-    P.bw_nld = H_.bw_nld;
-    P.bwp_nld = H_.bwp_nld;
     P.fa_nld = H_.fa_nld;
-    P.sw_slots = H_.sw_slots + 1; // rows behind the ring: the zero row, then the slots
     P.fa_slots = H_.fa_slots;
-    P.sw_direct = H_.sw_direct > 0 ? 1 : 0;
     P.fa_fast = H_.fa_fast;
     P.pim = pim_ ? 1 : 0;
     P.nnzG = S.G.nnz();
@@ -238,35 +237,50 @@ void Engine::upload_pattern(const Symbolic &S)
     P.xeq = dxeq_ = upload(S.xeq, owned_, st);
     P.Aeq = dAeq_ = upload(S.Aeq, owned_, st);
     P.GeqE = dGeq_ = upload(expanded_geq(S), owned_, st);
-    P.fw = upload(H_.fw, owned_, st);
-    // materialise the load lists: base selector (streams.hpp) -> row offset of the vector it stands for
-    const auto variant = [&](const ivec &list, int r1, int r2, int r3) {
+    // row programs: record streams as they are, load lists materialised per use
+    // (selector -> row offset of the vector it stands for, streams.hpp; LD_NONE stays)
+    const auto prog = [&](const Program &h, DevProgram &d, int **keep = nullptr) {
+        int *o = upload(h.ops, owned_, st);
+        d.ops = o;
+        d.nchunks = h.nchunks;
+        d.nld = h.nld;
+        if (keep)
+            *keep = o;
+    };
+    const auto variant = [&](const ivec &list, int a1, int a2, int a3, int b1 = 0, int b2 = 0, int b3 = 0) {
         ivec out(list.size());
-        const int off[4] = {0, r1, r2, r3};
+        const int off[8] = {0, a1, a2, a3, 0, b1, b2, b3};
         for (size_t k = 0; k < list.size(); k++)
-            out[k] = (list[k] & LD_ROW_MASK) + off[(unsigned)list[k] >> LD_BASE_SHIFT];
+            out[k] = list[k] == LD_NONE ? LD_NONE : (list[k] & LD_ROW_MASK2) + off[(unsigned)list[k] >> LD_SEL_SHIFT];
         return upload(out, owned_, st);
     };
-    // sweeps: list 2 * set + refinement (layout.hpp: LdVariant)
-    P.fw_ld[0] = variant(H_.fw_ld, L_.rhs1, 0, L_.xw);
-    P.fw_ld[1] = variant(H_.fw_ld, L_.e, 0, L_.xw);
-    P.fw_ld[2] = variant(H_.fw_ld, L_.rhs2, 0, L_.xw2);
-    P.fw_ld[3] = variant(H_.fw_ld, L_.e2, 0, L_.xw2);
-    P.bw = upload(H_.bw, owned_, st);
-    P.bwp = upload(H_.bwp, owned_, st);
-    P.bw_ld[0] = variant(H_.bwp_ld, L_.sol1, 0, L_.xw); // plain solve: its own program (no solution rows to add to)
-    P.bw_ld[1] = variant(H_.bw_ld, L_.dxr, L_.sol1, L_.xw);
-    P.bw_ld[2] = variant(H_.bwp_ld, L_.sol2, 0, L_.xw2);
-    P.bw_ld[3] = variant(H_.bw_ld, L_.dxr2, L_.sol2, L_.xw2);
+    for (int k = 0; k < 2; k++)
+    {
+        prog(H_.fw[k], P.fw[k]);
+        prog(H_.bw[k], P.bw[k]);
+        prog(H_.bwp[k], P.bwp[k]);
+        prog(H_.mv[k], P.mv[k], &dmv_ops_[k]);
+        P.sw_rows[k] = std::max(std::max(H_.fw[k].slot_rows, H_.bw[k].slot_rows), std::max(H_.bwp[k].slot_rows, H_.mv[k].slot_rows));
+    }
+    const int rhs[2] = {L_.rhs1, L_.rhs2}, sol[2] = {L_.sol1, L_.sol2}, xw[2] = {L_.xw, L_.xw2};
+    const int dxr[2] = {L_.dxr, L_.dxr2}, er[2] = {L_.e, L_.e2};
+    for (int set = 0; set < 2; set++)
+    { // forward: 1 = right-hand side, 3 = xw; backward: 1 = output, 2 = accumulated solution, 3 = xw
+        P.fw_ld1[set][0] = variant(H_.fw[0].ld, rhs[set], 0, xw[set]);
+        P.fw_ld1[set][1] = variant(H_.fw[0].ld, er[set], 0, xw[set]);
+        P.bw_ld1[set][0] = variant(H_.bwp[0].ld, sol[set], 0, xw[set]);
+        P.bw_ld1[set][1] = variant(H_.bw[0].ld, dxr[set], sol[set], xw[set]);
+        P.mv_ld1[set] = variant(H_.mv[0].ld, rhs[set], sol[set], L_.lpv);
+    }
+    P.mv_ld1[LDV_HEAD] = variant(H_.mv[0].ld, L_.chb, L_.w, L_.s);
+    P.fw_ld2[0] = variant(H_.fw[1].ld, rhs[0], 0, xw[0], rhs[1], 0, xw[1]);
+    P.fw_ld2[1] = variant(H_.fw[1].ld, er[0], 0, xw[0], er[1], 0, xw[1]);
+    P.bw_ld2[0] = variant(H_.bwp[1].ld, sol[0], 0, xw[0], sol[1], 0, xw[1]);
+    P.bw_ld2[1] = variant(H_.bw[1].ld, dxr[0], sol[0], xw[0], dxr[1], sol[1], xw[1]);
+    P.mv_ld2 = variant(H_.mv[1].ld, rhs[0], sol[0], L_.lpv, rhs[1], sol[1], 0);
+    P.mv_rows = H_.mv_rows;
     P.fa = upload(H_.fa, owned_, st);
     P.fa_ld = upload(H_.fa_ld, owned_, st);
-    P.mv = upload(H_.mv, owned_, st);
-    P.mv_ld[0] = variant(H_.mv_ld, L_.rhs1, L_.sol1, L_.lpv);
-    P.mv_ld[1] = variant(H_.mv_ld, L_.rhs2, L_.sol2, L_.lpv);
-    P.mv_ld[2] = variant(H_.mv_ld, L_.chb, L_.w, L_.s);
-    P.mv_val = dmv_val_ = upload(H_.mv_val, owned_, st);
-    P.mv_nld = H_.mv_nld;
-    P.mv_rows = H_.mv_rows;
     P.fa_val = dfa_val_ = upload(H_.fa_val, owned_, st);
     ivec vk;
     for (int k = 0; k < S.l; k++)
@@ -295,7 +309,8 @@ void Engine::upload_values(const Symbolic &S)
     be::h2d(dAeq_, S.Aeq.data(), S.Aeq.size() * sizeof(double), st);
     be::h2d(dGeq_, ge.data(), ge.size() * sizeof(double), st);
     be::h2d(dfa_val_, H_.fa_val.data(), H_.fa_val.size() * sizeof(double), st);
-    be::h2d(dmv_val_, H_.mv_val.data(), H_.mv_val.size() * sizeof(double), st);
+    for (int k = 0; k < 2; k++) // the mat-vec programs carry the shared coefficients inline
+        be::h2d(dmv_ops_[k], H_.mv[k].ops.data(), H_.mv[k].ops.size() * sizeof(int), st);
     be::sync(st);
 }
 
@@ -304,6 +319,8 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
       pim_(instance_matrices), nnzG_(S.G.nnz()), nnzA_(S.A.nnz())
 {
     be::set_device(device_);
+    if (const char *v = std::getenv("EICOS_PAIR_SOLVES"))
+        pair_solves_ = std::atoi(v) != 0;
     stream_ = (void *)(intptr_t)be::make_stream();
     build_layout(S);
     upload_pattern(S);
@@ -326,7 +343,8 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
     moves_host_ = (int *)be::pinned(2 * slots * sizeof(int));
     // program kernels (one warp per tile): stream buffers + FIFO ring + slots; vector kernels: reduction rows only
     const size_t smem_base = ((size_t)2 * STAGE_SLOTS * TILE + PS_DOUBLES) * sizeof(double);
-    smem_prog_ = smem_base + (size_t)P_.sw_slots * TILE * sizeof(double);
+    for (int k = 0; k < 2; k++)
+        smem_prog_[k] = pipe_smem_doubles(P_.sw_rows[k]) * sizeof(double);
     smem_common_ = workers_ > 1 ? (size_t)workers_ * KRED * TILE * sizeof(double) : 0;
     xrows_factor_ = H_.fa_slots + (H_.fa_fast ? 0 : 2 * S.maxcol); // record form keeps the column in registers
 #ifndef EICOS_EMU
@@ -340,11 +358,13 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
 #ifndef EICOS_EMU
     if (smem_factor_ > 48 * 1024)
         EI_CUDA(cudaFuncSetAttribute(eicos_ldl_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_factor_));
-    if (smem_prog_ > 48 * 1024)
+    if (smem_prog_[0] > 48 * 1024)
     {
-        EI_CUDA(cudaFuncSetAttribute(eicos_solve_kkt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prog_));
-        EI_CUDA(cudaFuncSetAttribute(eicos_residuals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prog_));
+        EI_CUDA(cudaFuncSetAttribute(eicos_solve_kkt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prog_[0]));
+        EI_CUDA(cudaFuncSetAttribute(eicos_residuals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prog_[0]));
     }
+    if (smem_prog_[1] > 48 * 1024)
+        EI_CUDA(cudaFuncSetAttribute(eicos_solve_kkt_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prog_[1]));
     if (smem_common_ > 48 * 1024)
     {
         const void *ks[] = {(const void *)eicos_load_inputs, (const void *)eicos_equilibrate, (const void *)eicos_init,
@@ -407,10 +427,10 @@ ProgramStats Engine::program_stats() const
     p.sw_far = H_.sw_far;
     p.sw_direct = H_.sw_direct;
     p.fa_home = H_.fa_home;
-    p.fw_loads = H_.fw_nld;
-    p.bw_loads = H_.bw_nld;
+    p.fw_loads = H_.fw[0].nld;
+    p.bw_loads = H_.bw[0].nld;
     p.fa_loads = H_.fa_nld;
-    p.mv_loads = H_.mv_nld;
+    p.mv_loads = H_.mv[0].nld;
     return p;
 }
 
@@ -469,7 +489,7 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
     a.active_count = active_count_;
     a.ir_rounds = ir_rounds_;
     a.njobs = 1;
-    a.xrows = P_.sw_slots;
+    a.xrows = 0;
     be::zero(ir_rounds_, 8 * sizeof(unsigned long long), st);
 
     const int threads = workers_ * (LANES == 1 ? 1 : 32), threads1 = LANES == 1 ? 1 : 32;
@@ -537,28 +557,41 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
         auto factor = [&]() {
             a.xrows = xrows_factor_;
             EI_TIMED(0, EI_LAUNCH(eicos_ldl_factor, tile_factor, tiles, threads1, smem_factor_, st, a));
-            a.xrows = P_.sw_slots;
+            a.xrows = 0;
             stt.factor_launches++;
             stt.factor_launch_tiles += tiles;
         };
         // solveKKT launches: one job, or the two solves of an iteration that share the factor and do
         // not depend on each other (rhs1 -> sol1 and rhs2 -> sol2), as CTAs (tile, job) of one launch -
         // same traffic when the machine is full, half the latency when it is not
-        auto kkt_launch = [&](int njobs, int init) {
-            a.njobs = njobs;
-            a.initialize = init;
-            EI_TIMED(1, EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt, tiles, njobs, threads1, smem_prog_, st, a));
-            stt.solve_launches++;
-            stt.solve_launch_tiles += (long long)tiles * njobs;
-        };
+        // solveKKT launches: one job, or the two solves of an iteration that share the factor and do
+        // not depend on each other (rhs1 -> sol1 and rhs2 -> sol2) in ONE pass over L per sweep
         auto kkt_pair = [&](int init, int nit1, int nit2) {
             a.job[0] = {L_.rhs1, L_.sol1, nit1, 0};
             a.job[1] = {L_.rhs2, L_.sol2, nit2, 1};
-            kkt_launch(2, init);
+            a.njobs = 2;
+            a.initialize = init;
+            if (pair_solves_)
+            {
+                EI_TIMED(1, EI_LAUNCH(eicos_solve_kkt_pair, tile_solve_kkt<2>, tiles, threads1, smem_prog_[1], st, a));
+                stt.solve_launches++;
+            }
+            else
+            { // (diagnostic switch) the same two solves as two one-job launches
+                EI_TIMED(1, EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt<1>, tiles, threads1, smem_prog_[0], st, a));
+                a.job[0] = a.job[1];
+                EI_TIMED(1, EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt<1>, tiles, threads1, smem_prog_[0], st, a));
+                stt.solve_launches += 2;
+            }
+            stt.solve_launch_tiles += (long long)tiles * 2;
         };
         auto kkt_rhs2 = [&](int nitrow) {
             a.job[0] = {L_.rhs2, L_.sol2, nitrow, 1};
-            kkt_launch(1, 0);
+            a.njobs = 1;
+            a.initialize = 0;
+            EI_TIMED(1, EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt<1>, tiles, threads1, smem_prog_[0], st, a));
+            stt.solve_launches++;
+            stt.solve_launch_tiles += tiles;
         };
 
         EI_TIMED(2, EI_LAUNCH(eicos_load_inputs, tile_load, tiles, threads, smem_common_, st, a));
@@ -572,7 +605,7 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
         for (int it = 0; it <= Settings::iter_max + 1; it++)
         {
             be::zero(active_count_, sizeof(unsigned int), st);
-            EI_TIMED(2, EI_LAUNCH(eicos_residuals, tile_resid, tiles, threads1, smem_prog_, st, a));
+            EI_TIMED(2, EI_LAUNCH(eicos_residuals, tile_resid, tiles, threads1, smem_prog_[0], st, a));
             EI_TIMED(2, EI_LAUNCH(eicos_iter_head, tile_head, tiles, threads, smem_common_, st, a));
             stt.ipm_iterations++;
             be::d2h(host_pinned_, active_count_, sizeof(unsigned int), st);
@@ -698,7 +731,7 @@ void Engine::debug_factor_init(int batch, const double *d_c, const double *d_h, 
     be::sync(st);
     a.batch = batch;
     a.first = 0;
-    a.xrows = P_.sw_slots;
+    a.xrows = 0;
     const int tiles = (batch + TILE - 1) / TILE;
     const int threads = workers_ * (LANES == 1 ? 1 : 32), threads1 = LANES == 1 ? 1 : 32;
     (void)threads;
@@ -713,12 +746,12 @@ void Engine::debug_factor_init(int batch, const double *d_c, const double *d_h, 
     EI_LAUNCH(eicos_init, tile_init, tiles, threads, smem_common_, st, a);
     a.xrows = xrows_factor_;
     EI_LAUNCH(eicos_ldl_factor, tile_factor, tiles, threads1, smem_factor_, st, a);
-    a.xrows = P_.sw_slots;
+    a.xrows = 0;
     a.initialize = 1;
     a.njobs = 2;
     a.job[0] = {L_.rhs1, L_.sol1, J_NIT1, 0};
     a.job[1] = {L_.rhs2, L_.sol2, J_NIT2, 1};
-    EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt, tiles, 2, threads1, smem_prog_, st, a);
+    EI_LAUNCH(eicos_solve_kkt_pair, tile_solve_kkt<2>, tiles, threads1, smem_prog_[1], st, a);
     be::sync(st);
     // gather rows back to instance-major host arrays; L comes back in CSC order
     const size_t tile_doubles = (size_t)L_.rows_total * TILE;

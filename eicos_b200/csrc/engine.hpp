@@ -114,12 +114,13 @@ class Engine
     unsigned int *host_pinned_ = nullptr;
     int *moves_dev_ = nullptr, *status_host_ = nullptr, *moves_host_ = nullptr; // active-set compaction
     bool compaction_ = true;
-    size_t smem_factor_ = 0, smem_common_ = 0, smem_prog_ = 0; // factor kernel / vector kernels / one-warp program kernels
+    bool pair_solves_ = true; // the two independent solves of an iteration in one pass over L (EICOS_PAIR_SOLVES=0: two launches)
+    size_t smem_factor_ = 0, smem_common_ = 0, smem_prog_[2] = {0, 0}; // factor kernel / vector kernels / solveKKT + residual kernels (NR = 1, 2)
     int xrows_factor_ = 0; // shared-memory rows behind the FIFO ring in the factor kernel (slots + column buffers)
     std::vector<void *> owned_; // device allocations holding pattern data
     // positions of value arrays that upload_values() rewrites
     double *dxeq_ = nullptr, *dAeq_ = nullptr, *dGeq_ = nullptr;
-    double *dmv_val_ = nullptr;
+    int *dmv_ops_[2] = {nullptr, nullptr};
     double *dfa_val_ = nullptr;
     HostStreams H_;        // host copy of the instruction streams (value streams are rebuilt on updateData)
     std::vector<int> Lp_;  // column pointers of L (debug extraction)

@@ -46,6 +46,7 @@ enum ScalarRow : int
     S_RT = S_BEST_END, S_NX, S_NY, S_NZ, S_NS, S_HRESX, S_HRESY, S_HRESZ,
     S_RESX0, S_RESY0, S_RESZ0, S_PRES_PREV,
     S_DTAU_DENOM, S_DTAUAFF, S_DKAPAFF,
+    S_RHSMAX1, S_RHSMAX2,  // max |rhs1|, max |rhs2|: kept by the kernels that write the right-hand sides (solveKKT's stopping threshold)
     S_RED,                 // the 14 sums of computeResiduals, handed from eicos_residuals to eicos_iter_head
     S_COUNT = S_RED + 14
 };
@@ -86,13 +87,19 @@ struct Layout
     int irows_total;                // integer rows (J_COUNT)
 };
 
-// index of a materialised load list (DevPattern::fw_ld / bw_ld / mv_ld)
+// index of a materialised mat-vec load list (DevPattern::mv_ld1)
 enum LdVariant : int
 {
-    LDV_SOL1 = 0,   // set 0: rhs1 -> sol1
-    LDV_SOL2 = 1,   // set 1: rhs2 -> sol2
-    LDV_REFINE = 1, // sweeps: list 2 * set + LDV_REFINE: rhs = e of the set, out = dxr of the set, accumulated into its sol
-    LDV_HEAD = 2    // mat-vec: computeResiduals (chb, w, s)
+    LDV_SOL1 = 0, // set 0: rhs1 / sol1
+    LDV_SOL2 = 1, // set 1: rhs2 / sol2
+    LDV_HEAD = 2  // computeResiduals (chb, w, s)
+};
+
+// one pipe-form row program on the device (streams.hpp: Program)
+struct DevProgram
+{
+    const int *ops;
+    int nchunks, nld;
 };
 
 enum ConeParam : int
@@ -107,18 +114,19 @@ struct DevPattern
     const int *cone_dim, *cone_k, *cone_q; // per cone: dimension, first expanded index, first q row
     const int *zk;                         // compact z index -> expanded index (load / store only)
     const double *xeq, *Aeq, *GeqE;        // equilibration vectors (GeqE is expanded, 1 in the slots)
-    // instruction streams (streams.hpp)
-    // slot programs (streams.hpp): ops, load lists (+ length in words), shared-memory slots they use
-    // Load lists are materialised per use (absolute rows of the tile, so that issuing a load is one
-    // multiply-add): forward [rhs1, rhs2, e]; backward [sol1, sol2, dxr += into sol1, dxr += into sol2];
-    // mat-vec [rhs1/sol1, rhs2/sol2, computeResiduals].  Sweep lists: index = 2 * set + refinement, where
-    // set 0 = (rhs1, sol1) with work vectors xw/dxr/e and set 1 = (rhs2, sol2) with xw2/dxr2/e2, so
-    // that the two solves of an iteration that share a factor can run at the same time.
-    const int *fw, *bw, *bwp, *fa, *fa_ld, *mv; // bwp: backward sweep without accumulation (list 2 * set)
-    const int *fw_ld[4], *bw_ld[4], *mv_ld[3];
-    const double *mv_val;
-    int fw_nld, bw_nld, bwp_nld, fa_nld, mv_nld, mv_rows, sw_slots, fa_slots;
-    int sw_direct; // the sweep programs contain operands read straight from global memory
+    // Row programs (streams.hpp), index = NR - 1, and their load lists, materialised per use (absolute
+    // rows of the tile): a job set is (rhs1, sol1) with work vectors xw / dxr / e (set 0) or (rhs2, sol2)
+    // with xw2 / dxr2 / e2 (set 1).  One-job lists: [set][first solve | refinement round]; pair lists (both
+    // sets in one pass): [first solve | refinement round].  The backward sweep of a first solve runs the
+    // plain program bwp, a refinement round the accumulating program bw.
+    DevProgram fw[2], bw[2], bwp[2], mv[2];
+    const int *fw_ld1[2][2], *bw_ld1[2][2], *mv_ld1[3];
+    const int *fw_ld2[2], *bw_ld2[2], *mv_ld2;
+    int mv_rows;
+    int sw_rows[2]; // shared-memory rows behind PR_SLOT0 the programs of NR = 1 / 2 use
+    // factor program (FIFO form)
+    const int *fa, *fa_ld;
+    int fa_nld, fa_slots;
     int fa_fast;   // the factor program is in record form (streams.hpp)
     // per-instance-matrices mode (every instance has its own G / A values): 1, and the index arrays
     // the on-device equilibration walks (CSC of G and A, their CSR views as row pointer + value index)

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstring>
 #include <stdexcept>
 
 namespace eicos
@@ -138,92 +139,267 @@ struct SlotCache
     }
 };
 
-// Emits the pair words of one row behind its `hdr` header words (already pushed, the first at
-// w0) and sets the sync flags: one check point per 16-byte record.  pair(q) appends nothing itself;
-// it pops the L value, resolves the gathered value and returns the pair word without flags.
-template <class Pair>
-void emit_pairs(ivec &ops, FifoSim &F, size_t w0, int hdr, int first_pop, int cnt, Pair pair)
+// ------------------------------------------------------------------ pipe-form row programs (streams.hpp)
+int field(int row)
 {
-    int q = 0;
-    for (int r = hdr; r < 4; r++)
-        ops.push_back(q < cnt ? pair(q++) : SW_PAD_PAIR);
-    if (FifoSim::crosses(first_pop, F.npop - first_pop))
-        ops[w0] |= SW_SYNC_HDR;
-    while (q < cnt)
-    {
-        const int first = F.npop;
-        const size_t at = ops.size();
-        for (int r = 0; r < 4; r++)
-            ops.push_back(q < cnt ? pair(q++) : SW_PAD_PAIR);
-        if (FifoSim::crosses(first, F.npop - first))
-            ops[at] |= SW_SYNC_PAIR;
-    }
+    if (row < 0 || row >= PR_MAX_ROWS)
+        throw std::logic_error("row program: shared-memory row out of range");
+    return row << PR_FIELD_SHIFT;
 }
 
-int pair_word(int lrow, int opnd)
+// Host model of the data ring and writer of the record stream.  A record is opened with begin(),
+// makes its pops, and is closed with end(), which derives the acquire / release counts from the
+// pops made in between.
+struct Emitter
 {
-    if (opnd < 0 || opnd >= (1 << (31 - SW_OPND_SHIFT)))
-        throw std::logic_error("sweep program: operand out of range");
-    return lrow | (opnd << SW_OPND_SHIFT);
+    Program &P;
+    const int NR;
+    int npop = 0, released = 0;
+    int rec_first = 0;
+    struct RelAt
+    {
+        size_t word;
+        int fence_bit;
+    };
+    std::vector<RelAt> rel_at; // release number -> record word holding its flags
+    Emitter(Program &p, int nr) : P(p), NR(nr) {}
+
+    int pop(int sel, int row)
+    {
+        if (row < 0 || row > LD_ROW_MASK2)
+            throw std::logic_error("load list: row out of range");
+        P.ld.push_back((sel << LD_SEL_SHIFT) | row);
+        return npop++ % RING_ROWS;
+    }
+    void pad()
+    {
+        P.ld.push_back(LD_NONE);
+        npop++;
+        P.pads++;
+    }
+    bool aligned() const { return NR == 1 || npop % 2 == 0; }
+    // vector pop: one row per job, adjacent ring rows (the caller may first hoist a single pop to align)
+    int vpop(int sel, int row)
+    {
+        if (!aligned())
+            pad();
+        const int r = pop(sel, row);
+        if (NR == 2)
+            pop(sel + LD_JOB_B, row);
+        return r;
+    }
+    void begin() { rec_first = npop; }
+    // May a value whose producing record ended when `prod_after` pops had been made be loaded through the
+    // ring as the next pop?  Its group is refilled when group G - RING_GROUPS is released, which happens
+    // at the end of the record that makes pop 8 (G - RING_GROUPS + 1) - 1; the producer must be an
+    // earlier record.  (The first RING_GROUPS groups are issued before the program starts.)
+    bool far_safe(int prod_after) const
+    {
+        const int at = aligned() ? npop : npop + 1;
+        const int G = at / RING_GROUP;
+        return G >= RING_GROUPS && prod_after < RING_GROUP * (G - RING_GROUPS + 1);
+    }
+    // the refill of the group the next pop lands in must be preceded by a proxy fence
+    void fence_next_pop()
+    {
+        const int at = aligned() ? npop : npop + 1;
+        const int G = at / RING_GROUP;
+        const RelAt &r = rel_at.at(G - RING_GROUPS);
+        P.ops[r.word] |= r.fence_bit;
+    }
+    void end(int w0, int w1, int w2, int w3, bool header)
+    {
+        const int nacq = (npop + RING_GROUP - 1) / RING_GROUP - (rec_first + RING_GROUP - 1) / RING_GROUP;
+        const int nrel = npop / RING_GROUP - released;
+        if (nacq > 3 || nrel > 3 || nacq < 0 || nrel < 0)
+            throw std::logic_error("row program: a record spans too many ring groups");
+        const size_t at = P.ops.size();
+        if (header)
+            w0 |= (nacq << PH_NACQ_SHIFT) | (nrel << PH_NREL_SHIFT);
+        else
+        {
+            if (w0 & ((1 << PR_FIELD_SHIFT) - 1))
+                throw std::logic_error("row program: flag bits of a tail record are in use");
+            w0 |= (nacq << PT_NACQ_SHIFT) | (nrel << PT_NREL_SHIFT);
+        }
+        for (int k = 0; k < nrel; k++)
+            rel_at.push_back({at, header ? PH_FENCE : PT_FENCE});
+        released += nrel;
+        P.ops.push_back(w0);
+        P.ops.push_back(w1);
+        P.ops.push_back(w2);
+        P.ops.push_back(w3);
+    }
+    void finish(int slot_rows)
+    {
+        begin();
+        end(PH_END, 0, 0, 0, true);
+        P.nchunks = (int)((P.ops.size() + OPS_CHUNK_WORDS - 1) / OPS_CHUNK_WORDS);
+        while (P.ops.size() % OPS_CHUNK_WORDS)
+            P.ops.push_back(0);
+        P.ops.insert(P.ops.end(), OPS_CHUNK_WORDS, 0); // the record look-ahead may read one record past END
+        P.nld = (int)P.ld.size();
+        while (P.ld.size() % RING_ROWS)
+            P.ld.push_back(LD_NONE);
+        P.ld.insert(P.ld.end(), 2 * RING_ROWS, LD_NONE); // the lanes read their next word two rounds ahead
+        P.slot_rows = slot_rows;
+    }
+};
+
+// one multiply-add of a dot-form row: the L value (single pop) and the gathered vector value
+struct PairSrc
+{
+    int lrow;    // workspace row of the L value
+    int value;   // index of the gathered value (slot cache / producer bookkeeping)
+    int far_sel; // load-list selector of the vector the value lives in
+    int far_row; // its row inside that vector
+};
+
+// Emits one dot-form row: header record (with up to `ninl` pairs inline) + tail records.
+//   pre()      makes the header's own pops (right-hand side, pivot, ...); called once the header is open
+//   header(rp) closes the header record: rp.w0 = tail counts / form flags for word 0, rp.inl = inline pair words
+struct RowPairs
+{
+    int inl[2] = {PR_PAD_PAIR, PR_PAD_PAIR};
+    int w0 = 0;
+};
+
+template <class Pre, class Header>
+void emit_row(Emitter &E, SlotCache &cache, const ivec &prod, const std::vector<PairSrc> &pairs, int ninl, Program &P,
+              Pre pre, Header header)
+{
+    const int cnt = (int)pairs.size(), NR = E.NR;
+    // kind of every gathered value: 0 slot, 1 far (through the ring), 2 direct (straight from global memory).
+    // far_safe() only gets easier as the pop position advances, so testing at the current position is safe.
+    ivec kind(cnt);
+    bool slow = false;
+    for (int q = 0; q < cnt; q++)
+    {
+        kind[q] = cache.slot_of[pairs[q].value] >= 0 ? 0 : (E.far_safe(prod[pairs[q].value]) ? 1 : 2);
+        slow = slow || kind[q] == 2;
+    }
+    const auto operand = [&](int q) -> int { // field of pair q's gathered value
+        const PairSrc &pr = pairs[q];
+        int f;
+        if (kind[q] == 0)
+            f = field(PR_SLOT0 + NR * cache.slot_of[pr.value]);
+        else
+        {
+            if (!E.aligned())
+                E.pad();
+            if (!E.far_safe(prod[pr.value]))
+                throw std::logic_error("row program: far operand not safe at emission");
+            E.fence_next_pop();
+            f = field(E.vpop(pr.far_sel, pr.far_row));
+            P.far++;
+        }
+        cache.used(pr.value);
+        return f;
+    };
+    E.begin();
+    RowPairs rp;
+    if (slow)
+    { // one record per pair: [L field | flags, 0 = field in word 2 / 1 = global row in word 2, value, -]
+        if (cnt > PH_NTAIL_MASK)
+            throw std::logic_error("row program: row too long for the slow form");
+        pre();
+        rp.w0 = PH_SLOW | cnt;
+        header(rp);
+        for (int q = 0; q < cnt; q++)
+        {
+            const PairSrc &pr = pairs[q];
+            E.begin();
+            const int lf = field(E.pop(0, pr.lrow));
+            if (kind[q] == 2)
+            {
+                cache.used(pr.value);
+                P.direct++;
+                E.end(lf, 1, pr.far_row, 0, false);
+            }
+            else
+                E.end(lf, 0, operand(q), 0, false);
+        }
+        return;
+    }
+    int q = 0;
+    const auto pair_word = [&](int qq, int lfield = -1) {
+        const int lf = lfield >= 0 ? lfield : field(E.pop(0, pairs[qq].lrow));
+        const int of = operand(qq);
+        return lf | (of << 16);
+    };
+    const int rest = cnt > ninl ? cnt - ninl : 0;
+    const int n4 = rest / 4, r4 = rest % 4;
+    // remainder 1..2 -> one 2-pair record; remainder 3 -> one more 4-pair record
+    const int ntail4 = n4 + (r4 == 3 ? 1 : 0), has2 = (r4 == 1 || r4 == 2) ? 1 : 0;
+    if (ntail4 > PH_NTAIL_MASK)
+        throw std::logic_error("row program: row too long");
+    rp.w0 = ntail4 | (has2 ? PH_HAS2 : 0) | (cnt > 0 && ninl > 0 ? PH_INLINE : 0);
+    // NR = 2: vector pops want an even ring position; an L pop made first realigns it without padding
+    int hoisted = -1;
+    if (!E.aligned() && cnt > 0 && ninl > 0)
+        hoisted = field(E.pop(0, pairs[0].lrow));
+    pre();
+    for (int k = 0; k < ninl && q < cnt; k++, q++)
+        rp.inl[k] = pair_word(q, k == 0 ? hoisted : -1);
+    header(rp);
+    for (int t = 0; t < ntail4; t++)
+    {
+        E.begin();
+        int w[4];
+        for (int k = 0; k < 4; k++)
+            w[k] = q < cnt ? pair_word(q++) : PR_PAD_PAIR;
+        E.end(w[0], w[1], w[2], w[3], false);
+    }
+    if (has2)
+    {
+        E.begin();
+        int w[2];
+        for (int k = 0; k < 2; k++)
+            w[k] = q < cnt ? pair_word(q++) : PR_PAD_PAIR;
+        E.end(w[0], w[1], 0, 0, false);
+    }
 }
 
 // ---- forward sweep  xw = L^-1 P rhs, rows of L in elimination order, dot form in ascending column
 // order (the summation order of Eigen's column-oriented forward substitution).  L is stored once,
 // column-major; the row-order walk is just the order of the load list.
-//   row i: [cnt | sync, keep | rhs ring row << 8] cnt x pair
-void build_forward(const Symbolic &S, const Layout &L, int max_slots, HostStreams &H)
+// Load-list selectors: 1 = right-hand side (KKT order), 3 = the work vector xw (far gathers).
+void build_forward(const Symbolic &S, const Layout &L, int NR, int max_values, Program &P)
 {
     std::vector<ivec> uses(S.N);
     for (int k = 0; k < S.N; k++)
         uses[k].assign(S.Li.begin() + S.Lp[k], S.Li.begin() + S.Lp[k + 1]);
-    SlotCache cache(max_slots, uses);
-    FifoSim F(H.fw_ld);
+    SlotCache cache(max_values, uses);
+    Emitter E(P, NR);
     ivec prod(S.N, 0);
+    std::vector<PairSrc> pairs;
     for (int i = 0; i < S.N; i++)
     {
-        const int cnt = S.Lr.p[i + 1] - S.Lr.p[i];
-        const int first = F.npop;
-        const int rhs_row = F.pop(1, S.pinv[i]);
-        const size_t w1 = H.fw.size() + 1;
-        H.fw.push_back(cnt);
-        H.fw.push_back(0);
-        emit_pairs(H.fw, F, w1 - 1, 2, first, cnt, [&](int q) {
-            const int t = S.Lr.p[i] + q, k = S.Lr.j[t];
-            const int lrow = F.pop(0, L.Lx + S.Lr.v[t]);
-            int opnd;
-            if (cache.slot_of[k] >= 0)
-                opnd = SW_SLOT0 + cache.slot_of[k];
-            else if (FifoSim::far_safe(prod[k], F.npop))
-            {
-                opnd = F.pop(3, k); // the work vector xw of the running solve
-                H.sw_far++;
-            }
-            else
-            {
-                opnd = SW_DIRECT + k; // relative to xw
-                H.sw_direct++;
-            }
-            cache.used(k);
-            return pair_word(lrow, opnd);
-        });
+        pairs.clear();
+        for (int t = S.Lr.p[i]; t < S.Lr.p[i + 1]; t++)
+            pairs.push_back({L.Lx + S.Lr.v[t], S.Lr.j[t], 3, S.Lr.j[t]});
+        int rhs_field = 0;
+        size_t hdr_at = 0;
+        emit_row(
+            E, cache, prod, pairs, 2, P, [&]() { rhs_field = field(E.vpop(1, S.pinv[i])); },
+            [&](const RowPairs &rp) {
+                hdr_at = P.ops.size();
+                E.end(rp.w0, rhs_field, rp.inl[0], rp.inl[1], true);
+            });
         const int s = cache.alloc(i);
-        H.fw[w1] = (s >= 0 ? SW_SLOT0 + s : SW_NO_KEEP) | (rhs_row << 8);
-        prod[i] = F.npop;
+        P.ops[hdr_at + 1] |= field(s >= 0 ? PR_SLOT0 + NR * s : PR_TRASH) << 16;
+        prod[i] = E.npop;
     }
-    H.fw_nld = (int)H.fw_ld.size();
-    H.sw_slots = std::max(H.sw_slots, cache.top);
-    pad_tail(H.fw);
-    pad_tail(H.fw_ld);
+    E.finish(NR * cache.top);
 }
 
 // ---- backward sweep  out = P' L^-T D^-1 xw, columns in reverse elimination order (dot form, Eigen's
 // order); results land in KKT order.  The home of a finished entry is its output row.
-//   column k: [cnt | sync, keep | 1/d ring row << 8 | xw ring row << 16 | accumulated-solution ring row << 24, out row] cnt x pair
 // accumulate: the program also loads the row of the solution it adds its result to (refinement
 // rounds); the plain program of the first solve leaves those loads out.
-void build_backward(const Symbolic &S, const Layout &L, int max_slots, HostStreams &H, bool accumulate)
+// Load-list selectors: 1 = output vector (far gathers), 2 = accumulated solution, 3 = xw.
+void build_backward(const Symbolic &S, const Layout &L, int NR, int max_values, Program &P, bool accumulate)
 {
-    ivec &ops = accumulate ? H.bw : H.bwp, &ld = accumulate ? H.bw_ld : H.bwp_ld;
     std::vector<ivec> uses(S.N); // value i is used by the columns of row i, latest column first
     for (int i = 0; i < S.N; i++)
         for (int t = S.Lr.p[i + 1] - 1; t >= S.Lr.p[i]; t--)
@@ -231,51 +407,58 @@ void build_backward(const Symbolic &S, const Layout &L, int max_slots, HostStrea
     for (const ivec &u : uses)
         if (!std::is_sorted(u.begin(), u.end()))
             throw std::logic_error("rows of L must have ascending columns");
-    SlotCache cache(max_slots, uses);
-    FifoSim F(ld);
+    SlotCache cache(max_values, uses);
+    Emitter E(P, NR);
     ivec prod(S.N, 0);
+    std::vector<PairSrc> pairs;
     for (int k = S.N - 1; k >= 0; k--)
     {
-        const int o = S.pinv[k], cnt = S.Lp[k + 1] - S.Lp[k];
-        const int first = F.npop;
-        const int drow = F.pop(0, L.Dinv + k), xrow = F.pop(3, k), arow = accumulate ? F.pop(2, o) : SW_ZERO_ROW;
-        const size_t w1 = ops.size() + 1;
-        ops.push_back(cnt);
-        ops.push_back(0);
-        ops.push_back(o);
-        emit_pairs(ops, F, w1 - 1, 3, first, cnt, [&](int q) {
-            const int u = S.Lp[k] + q, i = S.Li[u];
-            const int lrow = F.pop(0, L.Lx + u);
-            int opnd;
-            if (cache.slot_of[i] >= 0)
-                opnd = SW_SLOT0 + cache.slot_of[i];
-            else if (FifoSim::far_safe(prod[i], F.npop))
-            {
-                opnd = F.pop(1, S.pinv[i]);
-                H.sw_far++;
-            }
-            else
-            {
-                opnd = SW_DIRECT + S.pinv[i];
-                H.sw_direct++;
-            }
-            cache.used(i);
-            return pair_word(lrow, opnd);
-        });
+        const int o = S.pinv[k];
+        pairs.clear();
+        for (int u = S.Lp[k]; u < S.Lp[k + 1]; u++)
+            pairs.push_back({L.Lx + u, S.Li[u], 1, S.pinv[S.Li[u]]});
+        int dfield = 0, xfield = 0, afield = field(PR_ZERO);
+        bool dpopped = false;
+        size_t hdr_at = 0;
+        emit_row(
+            E, cache, prod, pairs, 0, P,
+            [&]() {
+                if (!E.aligned()) // the single pop first realigns the ring for the vector pops
+                {
+                    dfield = field(E.pop(0, L.Dinv + k));
+                    dpopped = true;
+                }
+                xfield = field(E.vpop(3, k));
+                if (accumulate)
+                    afield = field(E.vpop(2, o));
+                if (!dpopped)
+                    dfield = field(E.pop(0, L.Dinv + k));
+            },
+            [&](const RowPairs &rp) {
+                hdr_at = P.ops.size();
+                E.end(rp.w0, dfield | (xfield << 16), afield << 16, o, true);
+            });
         const int s = cache.alloc(k);
-        ops[w1] = (s >= 0 ? SW_SLOT0 + s : SW_NO_KEEP) | (drow << 8) | (xrow << 16) | (arow << 24);
-        prod[k] = F.npop;
+        P.ops[hdr_at + 2] |= field(s >= 0 ? PR_SLOT0 + NR * s : PR_TRASH);
+        prod[k] = E.npop;
     }
-    (accumulate ? H.bw_nld : H.bwp_nld) = (int)ld.size();
-    H.sw_slots = std::max(H.sw_slots, cache.top);
-    pad_tail(ops);
-    pad_tail(ld);
+    E.finish(NR * cache.top);
 }
 
 // ---- KKT mat-vec program (streams.hpp).  Rows = x, y and z rows (the two expansion slots of every
 // second-order cone excepted) in elimination order; the pairs of a row keep the order of the
 // CSC / CSR data (G entries before A entries in an x row).
-void build_matvec(const Symbolic &S, const Layout &L, int max_slots, HostStreams &H, bool pim)
+// Load-list selectors: 1 = vector of extra 0 (rhs | c,b,h), 2 = operand vector, 3 = vector of extra 1
+// (LP scalings | s; one row per instance even in a pair program).
+void push_double(ivec &ops, double v)
+{
+    int32_t w[2];
+    std::memcpy(w, &v, sizeof(v));
+    ops.push_back(w[0]);
+    ops.push_back(w[1]);
+}
+
+void build_matvec(const Symbolic &S, const Layout &L, int NR, int max_values, Program &P, int &mv_rows, bool pim)
 {
     const int n = S.n, p = S.p, zb = S.n + S.p;
     ivec order;
@@ -322,100 +505,101 @@ void build_matvec(const Symbolic &S, const Layout &L, int max_slots, HostStreams
     }
     for (ivec &u : uses)
         std::sort(u.begin(), u.end());
-    SlotCache cache(max_slots, uses);
-    FifoSim F(H.mv_ld);
-    // resolves one operand: (operand row, keep row)
+    SlotCache cache(max_values, uses);
+    Emitter E(P, NR);
+    // resolves one operand: (operand field, keep field)
     const auto operand = [&](int c) {
         std::pair<int, int> r;
         if (cache.slot_of[c] >= 0)
         {
-            r = {SW_SLOT0 + cache.slot_of[c], SW_NO_KEEP};
+            r = {field(PR_SLOT0 + NR * cache.slot_of[c]), field(PR_TRASH)};
             cache.used(c);
         }
         else
         {
-            r.first = F.pop(2, c);
+            r.first = field(E.vpop(2, c));
             cache.used(c);
             const int s = cache.alloc(c);
-            r.second = s >= 0 ? SW_SLOT0 + s : SW_NO_KEEP;
+            r.second = field(s >= 0 ? PR_SLOT0 + NR * s : PR_TRASH);
         }
         return r;
     };
+    const int pad_pair = field(PR_ZERO) | (field(PR_TRASH) << 16);
     for (int t = 0; t < nrows; t++)
     {
         const int r = order[t], cnt = (int)ent[r].size();
         const int kind = r < n ? MV_X : (r < zb ? MV_Y : (r < zb + S.l ? MV_Z : MV_ZC));
-        if (cnt > MV_CNT_MASK)
-            throw std::logic_error("mat-vec program: row too long");
-        const int first = F.npop;
-        const int ex0 = F.pop(1, r);
+        E.begin();
+        int ex1 = field(PR_ZERO);
+        bool ex1_popped = false;
+        if (kind >= MV_Z && !E.aligned())
+        {
+            ex1 = field(E.pop(3, r - zb));
+            ex1_popped = true;
+        }
+        const int ex0 = field(E.vpop(1, r));
         const auto own = operand(r);
-        const int ex1 = kind >= MV_Z ? F.pop(3, r - zb) : SW_ZERO_ROW;
-        const size_t w0 = H.mv.size();
-        H.mv.push_back(cnt | (kind << MV_KIND_SHIFT));
-        H.mv.push_back(ex0 | (own.first << 8) | (own.second << 16) | (ex1 << 24));
-        H.mv.push_back(r);
+        if (kind >= MV_Z && !ex1_popped)
+            ex1 = field(E.pop(3, r - zb));
+        const int per = pim ? 2 : 4; // pairs per full group
+        const int ng = cnt / per, rem = cnt % per;
+        // shared coefficients: remainder 1..2 -> a 2-pair group, 3 -> one more full group; pim: remainder 1 -> one more record
+        const int ngroups = pim ? ng + (rem ? 1 : 0) : ng + (rem == 3 ? 1 : 0);
+        const int has2 = !pim && (rem == 1 || rem == 2);
+        if (ngroups > PH_NTAIL_MASK)
+            throw std::logic_error("mat-vec program: row too long");
+        E.end(ngroups | (has2 ? PH_HAS2 : 0) | (kind << PH_KIND_SHIFT), ex0 | (own.first << 16), own.second | (ex1 << 16), r, true);
+        int q = 0;
         if (pim)
-        { // coefficients are rows too: [coefficient ring row | operand | keep], four pairs per further record
-            H.mv.push_back(0);
-            if (FifoSim::crosses(first, F.npop - first))
-                H.mv[w0] |= SW_SYNC_HDR;
-            int q = 0, ntail = 0;
-            while (q < cnt)
+        { // [coefficient field | operand field << 16, keep field] x 2 per record
+            for (int g = 0; g < ngroups; g++)
             {
-                const int f = F.npop;
-                const size_t at = H.mv.size();
-                for (int k = 0; k < 4; k++)
+                E.begin();
+                int w[4];
+                for (int k = 0; k < 2; k++)
                 {
                     if (q >= cnt)
                     {
-                        H.mv.push_back(MVP_PAD_PAIR);
+                        w[2 * k] = PR_PAD_PAIR;
+                        w[2 * k + 1] = field(PR_TRASH);
                         continue;
                     }
-                    const int cr = F.pop(0, crow[r][q]);
+                    const int cf = field(E.pop(0, crow[r][q]));
                     const auto o = operand(ent[r][q].first);
-                    H.mv.push_back(cr | (o.first << 8) | (o.second << 16));
+                    w[2 * k] = cf | (o.first << 16);
+                    w[2 * k + 1] = o.second;
                     q++;
                 }
-                if (FifoSim::crosses(f, F.npop - f))
-                    H.mv[at] |= MVP_SYNC;
-                ntail++;
+                E.end(w[0], w[1], w[2], w[3], false);
             }
-            H.mv[w0] = (H.mv[w0] & ~MV_CNT_MASK) | ntail;
             continue;
         }
-        int q = 0;
-        const auto pair = [&]() {
-            if (q >= cnt)
+        const auto group = [&](int np) { // np pairs + their coefficients
+            E.begin();
+            int w[4] = {pad_pair, pad_pair, 0, 0};
+            double c[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int k = 0; k < np; k++)
             {
-                H.mv_val.push_back(0.0);
-                return MV_PAD_PAIR;
+                w[k] = pad_pair;
+                if (q < cnt)
+                {
+                    const auto o = operand(ent[r][q].first);
+                    w[k] = o.first | (o.second << 16);
+                    c[k] = ent[r][q].second;
+                    q++;
+                }
             }
-            const auto o = operand(ent[r][q].first);
-            H.mv_val.push_back(ent[r][q].second);
-            q++;
-            return o.first | (o.second << 8);
+            E.end(w[0], w[1], w[2], w[3], false);
+            for (int k = 0; k < np; k++)
+                push_double(P.ops, c[k]);
         };
-        H.mv.push_back(pair());
-        H.mv_val.push_back(0.0); // first record: {c0, 0}
-        if (FifoSim::crosses(first, F.npop - first))
-            H.mv[w0] |= SW_SYNC_HDR;
-        while (q < cnt)
-        {
-            const int f = F.npop;
-            const size_t at = H.mv.size();
-            for (int k = 0; k < 4; k++)
-                H.mv.push_back(pair());
-            if (FifoSim::crosses(f, F.npop - f))
-                H.mv[at] |= MV_SYNC_PAIR;
-        }
+        for (int g = 0; g < ngroups; g++)
+            group(4);
+        if (has2)
+            group(2);
     }
-    H.mv_rows = nrows;
-    H.mv_nld = (int)H.mv_ld.size();
-    H.sw_slots = std::max(H.sw_slots, cache.top);
-    pad_tail(H.mv);
-    pad_tail(H.mv_ld);
-    pad_tail(H.mv_val);
+    mv_rows = nrows;
+    E.finish(NR * cache.top);
 }
 
 // per K slot: row of the workspace holding the per-instance A / G value (per-instance-matrices mode), or -1
@@ -686,13 +870,22 @@ void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, 
     if (S.fma_count > MAX_FACTOR_UPDATES)
         throw std::runtime_error("pattern fills too much for the row-program factorisation (" + std::to_string(S.fma_count) +
                                  " Schur updates per factorisation; limit " + std::to_string(MAX_FACTOR_UPDATES) + ")");
-    build_forward(S, L, max_sw_slots, H);
-    build_backward(S, L, max_sw_slots, H, true);
-    build_backward(S, L, max_sw_slots, H, false);
+    for (int NR = 1; NR <= 2; NR++)
+    {
+        const int maxv = std::max(1, std::min(max_sw_slots, (PR_MAX_ROWS - PR_SLOT0) / NR));
+        const char *dbg = std::getenv("EICOS_DBG_STARVE");
+        const int dm = dbg ? std::atoi(dbg) : 0;
+        build_forward(S, L, NR, dm & 1 ? 2 : maxv, H.fw[NR - 1]);
+        build_backward(S, L, NR, dm & 2 ? 2 : maxv, H.bw[NR - 1], true);
+        build_backward(S, L, NR, dm & 4 ? 2 : maxv, H.bwp[NR - 1], false);
+        build_matvec(S, L, NR, dm & 8 ? 2 : maxv, H.mv[NR - 1], H.mv_rows, pim);
+        for (const Program *q : {&H.fw[NR - 1], &H.bw[NR - 1], &H.bwp[NR - 1], &H.mv[NR - 1]})
+            H.sw_slots = std::max(H.sw_slots, q->slot_rows / NR);
+    }
+    H.sw_far = H.fw[0].far + H.bw[0].far;
+    H.sw_direct = H.fw[0].direct + H.bw[0].direct;
     if (!build_factor_fast(S, L, max_fa_slots, H, pim))
         build_factor(S, L, max_fa_slots, H, pim);
-    build_matvec(S, L, max_sw_slots, H, pim);
-
 }
 
 void refresh_stream_values(const Symbolic &S, const Layout &L, HostStreams &H, bool pim)
@@ -700,7 +893,12 @@ void refresh_stream_values(const Symbolic &S, const Layout &L, HostStreams &H, b
     HostStreams fresh;
     build_streams(S, L, H.workers, std::max(H.sw_slots, 1), std::max(H.fa_slots, 1), fresh, pim);
     H.fa_val.swap(fresh.fa_val);
-    H.mv_val.swap(fresh.mv_val);
+    for (int k = 0; k < 2; k++)
+    {
+        if (fresh.mv[k].ops.size() != H.mv[k].ops.size())
+            throw std::logic_error("mat-vec program changed shape on a value refresh");
+        H.mv[k].ops.swap(fresh.mv[k].ops);
+    }
 }
 
 } // namespace eicos

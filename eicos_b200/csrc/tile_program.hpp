@@ -90,6 +90,17 @@ EI_DEV vd operator/(vd a, double b) { VFOR a.v[c_] /= b; return a; }
 EI_DEV vd operator/(double b, vd a) { VFOR a.v[c_] = b / a.v[c_]; return a; }
 EI_DEV vd &operator+=(vd &a, vd b) { VFOR a.v[c_] += b.v[c_]; return a; }
 EI_DEV vd &operator-=(vd &a, vd b) { VFOR a.v[c_] -= b.v[c_]; return a; }
+// v - a * b with one rounding, spelled out so that every code path (and the CPU emulator) fuses alike
+EI_DEV vd vfnma(vd v, vd a, vd b)
+{
+    VFOR v.v[c_] = fma(-a.v[c_], b.v[c_], v.v[c_]);
+    return v;
+}
+EI_DEV vd vfnma(vd v, double a, vd b)
+{
+    VFOR v.v[c_] = fma(-a, b.v[c_], v.v[c_]);
+    return v;
+}
 EI_DEV vd vsqrt(vd a) { VFOR a.v[c_] = sqrt(a.v[c_]); return a; }
 EI_DEV vd vabs(vd a) { VFOR a.v[c_] = fabs(a.v[c_]); return a; }
 EI_DEV bool ei_isnan(double v) { return v != v; }
@@ -318,8 +329,9 @@ EI_DEV void team_min(const Team &tm, vd (&v)[K])
 
 struct TileMem
 {
-    double *T;
+    double *T;        // tile base + this lane's element offset
     int *I;
+    const double *Tb; // tile base (row 0, lane 0): source of whole-row bulk copies
 };
 
 // Base pointers of a tile as seen by this lane: the lane's element offset is folded in once, so a
@@ -327,6 +339,7 @@ struct TileMem
 EI_DEV TileMem tile_mem(const Team &tm, const KArgs &a, int tile)
 {
     TileMem t;
+    t.Tb = a.ws + (size_t)tile * a.L.rows_total * TILE;
     t.T = a.ws + (size_t)tile * a.L.rows_total * TILE + tm.lane;
     t.I = a.iws + (size_t)tile * a.L.irows_total * TILE + tm.lane;
     return t;
@@ -903,289 +916,630 @@ EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
     VFOR if (zero_pivot.v[c_] && act.v[c_]) ROWC(t.I, J_STATUS, c_) = EXIT_FATAL;
 }
 
+// ------------------------------------------------------------------ TMA bulk copies and mbarriers (sm_100a)
+#ifndef EICOS_EMU
+EI_DEV void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+EI_DEV void mbar_inval(unsigned bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory"); }
+EI_DEV void mbar_arrive(unsigned bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+EI_DEV void mbar_arrive_expect(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+EI_DEV bool mbar_try_wait(unsigned bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+EI_DEV void mbar_wait(unsigned bar, unsigned parity)
+{
+    while (!mbar_try_wait(bar, parity))
+    {
+    }
+}
+// one row (or one chunk of a record stream) global -> shared, completion counted on the mbarrier
+EI_DEV void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// global / shared writes made through the generic proxy before this point are visible to later bulk copies
+EI_DEV void proxy_fence() { asm volatile("fence.proxy.async;" ::: "memory"); }
+#endif
+
+// ------------------------------------------------------------------ the two pipes of a program warp (streams.hpp)
+// Shared memory of one program warp: [ops ring][mbarriers][rows: data ring, zero rows, trash rows, slots].
+constexpr int ROW_BYTES = TILE * (int)sizeof(double);
+constexpr int OPS_RING_BYTES = OPS_CHUNKS * OPS_CHUNK_WORDS * 4;
+constexpr int PIPE_BAR_BYTES = 64;  // OPS_CHUNKS mbarriers
+constexpr int PIPE_HEAD_DOUBLES = (OPS_RING_BYTES + PIPE_BAR_BYTES) / 8;
+#ifndef EICOS_EMU
+static_assert(ROW_BYTES == (1 << PR_FIELD_SHIFT), "a field is the byte offset of a 512-byte row");
+#endif
+inline size_t pipe_smem_doubles(int slot_rows) { return PIPE_HEAD_DOUBLES + (size_t)(PR_SLOT0 + slot_rows) * TILE; }
+
+struct Pipes
+{
+#ifdef EICOS_EMU
+    double *rows;    // rows region
+    const int *opsp; // next record
+    const int *list; // load list
+    const double *Tb;
+    int nld, rel;
+    EI_DEV void init(const Team &tm, double *mem) { rows = mem + PIPE_HEAD_DOUBLES; }
+    EI_DEV void refill(int G)
+    { // group G of the load list lands in its ring rows (the producer at its eagerest)
+        for (int k = 0; k < RING_GROUP; k++)
+        {
+            const int idx = G * RING_GROUP + k;
+            if (idx < nld && list[idx] != LD_NONE)
+                std::memcpy(rows + (size_t)(idx % RING_ROWS) * TILE, Tb + (size_t)list[idx] * TILE, ROW_BYTES);
+        }
+    }
+    EI_DEV void open(const Team &, const DevProgram &pr, const int *ld, const double *tile_base)
+    {
+        opsp = pr.ops;
+        list = ld;
+        nld = pr.nld;
+        Tb = tile_base;
+        rel = 0;
+        for (int c = 0; c < VEC; c++)
+            for (int r = 0; r < 2; r++)
+                rows[(size_t)(PR_ZERO + r) * TILE + c] = 0.0;
+        for (int G = 0; G < RING_GROUPS; G++)
+            refill(G);
+    }
+    EI_DEV i4 get()
+    {
+        const i4 r = ldg4(opsp);
+        opsp += 4;
+        return r;
+    }
+    EI_DEV void acquire(int) {}
+    EI_DEV void release(int n, bool)
+    {
+        for (; n > 0; n--, rel++)
+            refill(rel + RING_GROUPS);
+    }
+    EI_DEV void close() {}
+    EI_DEV vd ld(int f) const { return vload(rows + (size_t)(f >> PR_FIELD_SHIFT) * TILE); }
+    EI_DEV vd ld2(int f) const { return vload(rows + (size_t)((f >> PR_FIELD_SHIFT) + 1) * TILE); }
+    EI_DEV void st(int f, vd v) const { vstore(rows + (size_t)(f >> PR_FIELD_SHIFT) * TILE, v); }
+    EI_DEV void st2(int f, vd v) const { vstore(rows + (size_t)((f >> PR_FIELD_SHIFT) + 1) * TILE, v); }
+#else
+    unsigned rows; // shared address of the rows region + this lane's 16 bytes
+    unsigned opsb; // shared address of the ops ring
+    unsigned bars; // mbarriers of the ops chunks
+    int pl;
+    bool inited;
+    // data ring: rows arrive by cp.async (every lane moves its 16 bytes of a row: the rows of a program are
+    // gathered from all over the tile, one address per row), one commit group per ring group
+    const int *listp; // load list, two groups ahead of the consumer
+    i4 nw0, nw1;      // the words of the next refill
+    const char *Tl;   // tile base + this lane's 16 bytes
+    // ops ring: the record stream arrives in 512-byte chunks by TMA bulk copies (one elected lane)
+    const int *opsg;  // global chunk pointer of the next refill
+    int nchunks, fetched, cons;
+    unsigned pos, head; // byte position of the next record; ring group the next refill lands in
+    i4 look;
+
+    __device__ __forceinline__ void init(const Team &tm, double *mem)
+    {
+        pl = tm.pl;
+        opsb = (unsigned)__cvta_generic_to_shared(mem);
+        bars = opsb + OPS_RING_BYTES;
+        rows = bars + PIPE_BAR_BYTES + 16u * pl;
+        inited = false;
+    }
+    static __device__ __forceinline__ i4 lds4(unsigned a)
+    {
+        i4 r;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+        return r;
+    }
+    __device__ __forceinline__ void issue_row(unsigned dst, int w) const
+    { // ring row <- workspace row w of the tile (LD_NONE: alignment padding, nothing to copy)
+        if (w != LD_NONE)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(Tl + (size_t)w * ROW_BYTES) : "memory");
+    }
+    __device__ __forceinline__ void issue_group()
+    { // the next RING_GROUP words of the load list into ring group `head`; their successors are fetched for next time
+        const unsigned d = rows + head * (RING_GROUP * ROW_BYTES);
+        issue_row(d, nw0.x);
+        issue_row(d + ROW_BYTES, nw0.y);
+        issue_row(d + 2 * ROW_BYTES, nw0.z);
+        issue_row(d + 3 * ROW_BYTES, nw0.w);
+        issue_row(d + 4 * ROW_BYTES, nw1.x);
+        issue_row(d + 5 * ROW_BYTES, nw1.y);
+        issue_row(d + 6 * ROW_BYTES, nw1.z);
+        issue_row(d + 7 * ROW_BYTES, nw1.w);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        head = (head + 1) % RING_GROUPS;
+        nw0 = ldg4(listp);
+        nw1 = ldg4(listp + 4);
+        listp += RING_GROUP;
+    }
+    __device__ __forceinline__ void issue_chunk()
+    { // next chunk of the record stream into its ring position (lane 0 only)
+        const unsigned slot = (unsigned)fetched % OPS_CHUNKS;
+        const unsigned bar = bars + 8u * slot;
+        mbar_arrive_expect(bar, OPS_CHUNK_WORDS * 4);
+        bulk_g2s(opsb + slot * (OPS_CHUNK_WORDS * 4), opsg, OPS_CHUNK_WORDS * 4, bar);
+    }
+    __device__ __forceinline__ void open(const Team &, const DevProgram &pr, const int *ld, const double *tile_base)
+    {
+        static_assert(RING_GROUP == 8, "issue_group reads the load list as two 4-word records");
+        __syncwarp();
+        if (pl == 0)
+        {
+            for (int b = 0; b < OPS_CHUNKS; b++)
+            {
+                if (inited)
+                    mbar_inval(bars + 8u * b);
+                mbar_init(bars + 8u * b, 1);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        inited = true;
+        __syncwarp();
+        // zero rows (both jobs)
+        asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(rows + PR_ZERO * ROW_BYTES), "d"(0.0) : "memory");
+        asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(rows + (PR_ZERO + 1) * ROW_BYTES), "d"(0.0) : "memory");
+        // ops ring
+        nchunks = pr.nchunks;
+        opsg = pr.ops;
+        fetched = 0;
+        cons = 0;
+        pos = 0;
+        for (int c = 0; c < OPS_CHUNKS && c < nchunks; c++)
+        {
+            if (pl == 0)
+                issue_chunk();
+            fetched++;
+            opsg += OPS_CHUNK_WORDS;
+        }
+        // data ring: the first RING_GROUPS groups of the load list (the list is padded with LD_NONE)
+        Tl = (const char *)tile_base + 16 * pl;
+        head = 0;
+        nw0 = ldg4(ld);
+        nw1 = ldg4(ld + 4);
+        listp = ld + RING_GROUP;
+        for (int g = 0; g < RING_GROUPS; g++)
+            issue_group();
+        mbar_wait(bars, 0);
+        look = lds4(opsb);
+    }
+    __device__ __forceinline__ void chunk_boundary()
+    { // the chunk behind pos has been read completely: it takes the next chunk of the stream
+        cons++;
+        if (fetched < nchunks)
+        {
+            if (pl == 0)
+                issue_chunk();
+            fetched++;
+            opsg += OPS_CHUNK_WORDS;
+        }
+        if (cons < fetched) // (the look-ahead of the END record may step past the last chunk)
+            mbar_wait(bars + 8u * ((unsigned)cons % OPS_CHUNKS), ((unsigned)cons / OPS_CHUNKS) & 1u);
+    }
+    __device__ __forceinline__ i4 get()
+    {
+        const i4 r = look;
+        pos += 16;
+        if ((pos & (OPS_CHUNK_WORDS * 4 - 1)) == 0)
+            chunk_boundary();
+        look = lds4(opsb + (pos & (OPS_RING_BYTES - 1)));
+        return r;
+    }
+    // Group G is commit group G; when the consumer first touches it, at most two newer groups have been
+    // committed behind it per further group it needs (one commit per release, RING_GROUPS at the start).
+    __device__ __forceinline__ void acquire(int n)
+    {
+        if (n == 1)
+            asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else if (n == 2)
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __device__ __forceinline__ void release(int n, bool)
+    { // n groups are consumed: they take the next groups of the load list
+        for (; n > 0; n--)
+            issue_group();
+    }
+    __device__ __forceinline__ void close()
+    { // nothing may still be in flight when the pipes are re-opened or the CTA exits
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        for (int c = cons + 1; c < fetched; c++)
+            mbar_wait(bars + 8u * ((unsigned)c % OPS_CHUNKS), ((unsigned)c / OPS_CHUNKS) & 1u);
+    }
+    __device__ __forceinline__ vd ld(int f) const
+    {
+        vd r;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "r"(rows + (unsigned)f));
+        return r;
+    }
+    __device__ __forceinline__ vd ld2(int f) const
+    {
+        vd r;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+512];" : "=d"(r.v[0]), "=d"(r.v[1]) : "r"(rows + (unsigned)f));
+        return r;
+    }
+    __device__ __forceinline__ void st(int f, vd v) const
+    {
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(rows + (unsigned)f), "d"(v.v[0]), "d"(v.v[1]) : "memory");
+    }
+    __device__ __forceinline__ void st2(int f, vd v) const
+    {
+        asm volatile("st.shared.v2.f64 [%0+512], {%1, %2};" ::"r"(rows + (unsigned)f), "d"(v.v[0]), "d"(v.v[1]) : "memory");
+    }
+#endif
+};
+
+// ------------------------------------------------------------------ record decoding helpers
+EI_DEV int f_lo(int w) { return w & PR_FIELD_MASK; }
+EI_DEV int f_hi(int w) { return (int)((unsigned)w >> 16); }
+constexpr int PH_CTRL_MASK = PH_END | (3 << PH_NACQ_SHIFT);
+constexpr int PH_PAIRS_MASK = PH_NTAIL_MASK | PH_HAS2 | PH_INLINE | PH_SLOW;
+constexpr int PT_FLAG_MASK = (1 << PR_FIELD_SHIFT) - 1;
+
+// acquire what the header record needs; returns false on the END record
+EI_DEV bool pipe_header(Pipes &pp, int w0)
+{
+    if (w0 & PH_CTRL_MASK)
+    {
+        if (w0 < 0)
+            return false;
+        pp.acquire((w0 >> PH_NACQ_SHIFT) & 3);
+    }
+    return true;
+}
+EI_DEV void pipe_header_release(Pipes &pp, int w0)
+{
+    const int nrel = (w0 >> PH_NREL_SHIFT) & 3;
+    if (nrel)
+        pp.release(nrel, (w0 & PH_FENCE) != 0);
+}
+EI_DEV void pipe_tail_acquire(Pipes &pp, int w0)
+{
+    if (w0 & (3 << PT_NACQ_SHIFT))
+        pp.acquire((w0 >> PT_NACQ_SHIFT) & 3);
+}
+EI_DEV void pipe_tail_release(Pipes &pp, int w0)
+{
+    if (w0 & (3 << PT_NREL_SHIFT))
+        pp.release((w0 >> PT_NREL_SHIFT) & 3, (w0 & PT_FENCE) != 0);
+}
+
 // ------------------------------------------------------------------ triangular solves (Eigen solve, src/eicos.cpp:1477,1599)
 // forward:  xw = L^-1 P rhs         rows of L in elimination order, dot form in ascending column order
 //                                   (the summation order of Eigen's forward substitution); the
 //                                   permutation is folded into the right-hand-side loads.
 // backward: out = P' L^-T D^-1 xw   columns in reverse order, dot form; results land in KKT order.
-// Both are row programs (streams.cpp: build_forward / build_backward) run by one warp per tile with
-// no barrier inside: every global read comes through the FIFO, every gathered value that is still
-// live sits in a shared-memory slot, and each pair word names the two shared-memory rows it
-// multiplies.  DIRECT: the program contains operands that must be read straight from global memory
-// (only when the slots do not cover the live values of the pattern).
-template <bool DIRECT>
-EI_DEV vd sweep_operand(smem_t sm, const double *home, int code)
-{
-    if (DIRECT && code >= SW_DIRECT)
-        return vload(home + (size_t)(code - SW_DIRECT) * TILE);
-    return sm_load(sm, code);
-}
+// Both are pipe-form row programs (streams.hpp, streams.cpp: build_forward / build_backward) run by one
+// warp per tile with no barrier inside.  NR = 2 solves two right-hand sides in one pass over L.
 
-// v -= sum over the pairs p0..: all operand loads first, then the multiply-adds in order
-template <bool DIRECT, int NP>
-EI_DEV vd sweep_pairs(smem_t sm, const double *home, const int (&p)[NP], vd v)
+// v[j] -= l * g[j] for NP pairs: all operand loads first, then the multiply-adds in order
+template <int NR, int NP>
+EI_DEV void dot_pairs(const Pipes &pp, const int (&w)[NP], vd (&v)[NR])
 {
-    vd l[NP], g[NP];
+    vd l[NP], g[NP][NR];
 #pragma unroll
     for (int u = 0; u < NP; u++)
     {
-        l[u] = sm_load(sm, p[u] & 0xff);
-        g[u] = sweep_operand<DIRECT>(sm, home, (int)((unsigned)p[u] >> SW_OPND_SHIFT));
+        l[u] = pp.ld(f_lo(w[u]));
+        g[u][0] = pp.ld(f_hi(w[u]));
+        if (NR == 2)
+            g[u][NR - 1] = pp.ld2(f_hi(w[u]));
     }
 #pragma unroll
     for (int u = 0; u < NP; u++)
-        v -= l[u] * g[u];
-    return v;
+#pragma unroll
+        for (int j = 0; j < NR; j++)
+            v[j] = vfnma(v[j], l[u], g[u][j]);
 }
 
-// the records of a row behind its first one (4 pairs each)
-template <bool DIRECT>
-EI_DEV vd sweep_tail(PStream &ops, int nrec, Fifo &ff, smem_t sm, const double *home, vd v)
+// the pairs of a row behind its header: inline pairs, 4-pair records, a 2-pair record; or the slow form
+template <int NR>
+EI_DEV void dot_row(Pipes &pp, const i4 &h, bool inline_pairs, double *const (&home)[NR], vd (&v)[NR])
 {
-    for (int q = 1; q < nrec; q++)
-    {
-        const i4 pr = ops.get();
-        if (pr.x & SW_SYNC_PAIR)
-            ff.sync();
-        const int p[4] = {pr.x, pr.y, pr.z, pr.w};
-        v = sweep_pairs<DIRECT, 4>(sm, home, p, v);
-    }
-    return v;
-}
-
-// Returns max |rhs| over the rows (solveKKT's stopping threshold, src/eicos.cpp:1590).
-template <bool DIRECT>
-EI_DEV vd ldl_forward_t(const Team &tm, const KArgs &a, double *T, int variant, int xw)
-{
-    const DevPattern &P = a.P;
-    const smem_t sm = smem_of(tm.stage); // ring rows, zero row, slots
-    sm_store(sm, SW_ZERO_ROW, vset(0.0));
-    PStream ops;
-    Fifo ff;
-    ops.open(tm, P.fw, 0);
-    ff.open(tm, P.fw_ld[variant], P.fw_nld, T, 1);
-    double *xp = T + (size_t)xw * TILE;
-    double *const xhome = xp; // direct operands are rows of xw
-    vd mx = vset(0.0);
-    for (int i = 0; i < P.N; i++, xp += TILE)
-    {
-        const i4 rec = ops.get();
-        const int cnt = rec.x & SW_CNT_MASK;
-        if (rec.x < 0)
-            ff.sync();
-        vd v = sm_load(sm, (rec.y >> 8) & 0xff);
-        mx = vmax(mx, vabs(v));
-        if (cnt > 0)
+    if (h.x & PH_SLOW)
+    { // one pair per record, operands possibly straight from global memory
+        pipe_header_release(pp, h.x);
+        const int cnt = h.x & PH_NTAIL_MASK;
+        for (int q = 0; q < cnt; q++)
         {
-            const int p[2] = {rec.z, rec.w};
-            v = sweep_pairs<DIRECT, 2>(sm, xhome, p, v);
-            if (cnt > 2)
-                v = sweep_tail<DIRECT>(ops, (cnt + 2 + 3) >> 2, ff, sm, xhome, v);
+            const i4 r = pp.get();
+            pipe_tail_acquire(pp, r.x);
+            const vd l = pp.ld(f_lo(r.x));
+#pragma unroll
+            for (int j = 0; j < NR; j++)
+            {
+                vd g;
+                if (r.y)
+                    g = vload(home[j] + (size_t)r.z * TILE);
+                else
+                    g = j == 0 ? pp.ld(r.z) : pp.ld2(r.z);
+                v[j] = vfnma(v[j], l, g);
+            }
+            pipe_tail_release(pp, r.x);
         }
-        vstore(xp, v);
-        const int keep = rec.y & 0xff;
-        if (keep != SW_NO_KEEP)
-            sm_store(sm, keep, v);
+        return;
     }
-    ff.close();
-    return mx;
-}
-// variant: which vectors the load list was materialised for (LdVariant, layout.hpp); xw: work vector it fills
-EI_DEV vd ldl_forward(const Team &tm, const KArgs &a, double *T, int variant, int xw)
-{
-    if (a.P.sw_direct)
-        return ldl_forward_t<true>(tm, a, T, variant, xw);
-    return ldl_forward_t<false>(tm, a, T, variant, xw);
+    if (inline_pairs && (h.x & PH_INLINE))
+    {
+        const int w[2] = {h.z, h.w};
+        dot_pairs<NR, 2>(pp, w, v);
+    }
+    pipe_header_release(pp, h.x);
+    const int ntail4 = h.x & PH_NTAIL_MASK;
+    for (int t = 0; t < ntail4; t++)
+    {
+        const i4 r = pp.get();
+        pipe_tail_acquire(pp, r.x);
+        const int w[4] = {r.x, r.y, r.z, r.w};
+        dot_pairs<NR, 4>(pp, w, v);
+        pipe_tail_release(pp, r.x);
+    }
+    if (h.x & PH_HAS2)
+    {
+        const i4 r = pp.get();
+        pipe_tail_acquire(pp, r.x);
+        const int w[2] = {r.x, r.y};
+        dot_pairs<NR, 2>(pp, w, v);
+        pipe_tail_release(pp, r.x);
+    }
 }
 
-// out = solution (KKT order).  If x >= 0: additionally x += solution for the instances with `cont`.
-template <bool DIRECT>
-EI_DEV void ldl_backward_t(const Team &tm, const KArgs &a, double *T, int variant, int out, int x, vb cont)
+// xw[j]: work vector job j fills.  ld: the materialised load list of this use (layout.hpp).
+template <int NR>
+EI_DEV void ldl_forward(const Team &tm, Pipes &pp, const DevProgram &pr, const int *ld, const double *Tb, double *T,
+                        const int (&xw)[NR])
 {
-    const DevPattern &P = a.P;
-    const smem_t sm = smem_of(tm.stage);
-    sm_store(sm, SW_ZERO_ROW, vset(0.0));
-    const bool accumulate = x >= 0;
+    pp.open(tm, pr, ld, Tb);
+    double *xp[NR], *home[NR];
+#pragma unroll
+    for (int j = 0; j < NR; j++)
+        xp[j] = home[j] = T + (size_t)xw[j] * TILE;
+    for (;;)
+    {
+        const i4 h = pp.get();
+        if (!pipe_header(pp, h.x))
+            break;
+        vd v[NR];
+        v[0] = pp.ld(f_lo(h.y));
+        if (NR == 2)
+            v[NR - 1] = pp.ld2(f_lo(h.y));
+        if (h.x & PH_PAIRS_MASK)
+            dot_row<NR>(pp, h, true, home, v);
+        else
+            pipe_header_release(pp, h.x);
+        const int keep = f_hi(h.y);
+#pragma unroll
+        for (int j = 0; j < NR; j++)
+        {
+            vstore(xp[j], v[j]);
+            xp[j] += TILE;
+        }
+        pp.st(keep, v[0]);
+        if (NR == 2)
+            pp.st2(keep, v[NR - 1]);
+    }
+    pp.close();
+}
+
+// out[j] = solution (KKT order).  ACC: additionally x[j] += solution for the instances with cont[j].
+template <int NR, bool ACC>
+EI_DEV void ldl_backward(const Team &tm, Pipes &pp, const DevProgram &pr, const int *ld, const double *Tb, double *T,
+                         const int (&out)[NR], const int (&x)[NR], const vb (&cont)[NR])
+{
+    pp.open(tm, pr, ld, Tb);
     const vd zero = vset(0.0);
-    double *op = T + (size_t)out * TILE;
-    double *xp = T + (size_t)(accumulate ? x : out) * TILE;
-    PStream ops;
-    Fifo ff;
-    ops.open(tm, accumulate ? P.bw : P.bwp, 0);
-    ff.open(tm, P.bw_ld[variant], accumulate ? P.bw_nld : P.bwp_nld, T, 1);
-    for (int k = 0; k < P.N; k++)
+    double *op[NR], *xp[NR];
+#pragma unroll
+    for (int j = 0; j < NR; j++)
     {
-        const i4 rec = ops.get();
-        const int cnt = rec.x & SW_CNT_MASK;
-        if (rec.x < 0)
-            ff.sync();
-        vd v = sm_load(sm, (rec.y >> 8) & 0xff) * sm_load(sm, (rec.y >> 16) & 0xff); // Eigen: diag.inverse() * x
-        const vd xa = sm_load(sm, (int)((unsigned)rec.y >> 24)); // read now: a long column recycles the ring row
-        if (cnt > 0)
-        {
-            const int p[1] = {rec.w};
-            v = sweep_pairs<DIRECT, 1>(sm, op, p, v);
-            if (cnt > 1)
-                v = sweep_tail<DIRECT>(ops, (cnt + 3 + 3) >> 2, ff, sm, op, v);
-        }
-        const int o = rec.z;
-        vstore(op + (size_t)o * TILE, v);
-        const int keep = rec.y & 0xff;
-        if (keep != SW_NO_KEEP)
-            sm_store(sm, keep, v);
-        if (accumulate)
-            vstore(xp + (size_t)o * TILE, xa + vsel(cont, v, zero));
+        op[j] = T + (size_t)out[j] * TILE;
+        xp[j] = T + (size_t)(ACC ? x[j] : out[j]) * TILE;
     }
-    ff.close();
-}
-EI_DEV void ldl_backward(const Team &tm, const KArgs &a, double *T, int variant, int out, int x, vb cont)
-{
-    if (a.P.sw_direct)
-        ldl_backward_t<true>(tm, a, T, variant, out, x, cont);
-    else
-        ldl_backward_t<false>(tm, a, T, variant, out, x, cont);
+    for (;;)
+    {
+        const i4 h = pp.get();
+        if (!pipe_header(pp, h.x))
+            break;
+        const vd di = pp.ld(f_lo(h.y)); // Eigen: diag.inverse() * x
+        vd v[NR], xa[NR];
+        v[0] = di * pp.ld(f_hi(h.y));
+        if (NR == 2)
+            v[NR - 1] = di * pp.ld2(f_hi(h.y));
+        if (ACC)
+        {
+            xa[0] = pp.ld(f_hi(h.z));
+            if (NR == 2)
+                xa[NR - 1] = pp.ld2(f_hi(h.z));
+        }
+        if (h.x & PH_PAIRS_MASK)
+            dot_row<NR>(pp, h, false, op, v);
+        else
+            pipe_header_release(pp, h.x);
+        const size_t o = (size_t)h.w * TILE;
+        const int keep = f_lo(h.z);
+#pragma unroll
+        for (int j = 0; j < NR; j++)
+        {
+            vstore(op[j] + o, v[j]);
+            if (ACC)
+                vstore(xp[j] + o, xa[j] + vsel(cont[j], v[j], zero));
+        }
+        pp.st(keep, v[0]);
+        if (NR == 2)
+            pp.st2(keep, v[NR - 1]);
+    }
+    pp.close();
 }
 
 // ------------------------------------------------------------------ KKT mat-vec program (streams.hpp, streams.cpp: build_matvec)
-// For every x, y and LP row r of the KKT matrix, in elimination order:
-//   v = init(kind, ex0, own, ex1) + sum_k (sign[kind] * coefficient_k) * vec[column_k];  finish(kind, r, v, ex0, own, ex1)
-// ex0 = v1[r], own = vec[r], ex1 = v3[r - n - p] (LP rows only).  One warp; every operand row comes
-// through the FIFO once and stays in a shared-memory slot while it has further uses.
-template <class Init, class Finish>
-EI_DEV void mv_run(const Team &tm, const KArgs &a, const double *T, int variant,
-                   double sx, double sy, double sz, Init init, Finish finish)
+// For every x, y and z row r of the KKT matrix, in elimination order and for every job j:
+//   v = init(kind, ex0, own, ex1) - sum_k coefficient_k * vec[column_k];  finish(j, kind, r, v, ex0, own, ex1)
+// ex0 = v1[r], own = vec[r], ex1 = v3[r - n - p] (z rows only; one row per instance).  One warp; every
+// operand row comes through the ring once and stays in a shared-memory slot while it has further uses.
+// The sum is always SUBTRACTED (callers that want init + sum negate init and the result: bit-identical).
+template <int NR, bool PIM, class Init, class Finish>
+EI_DEV void mv_run(const Team &tm, Pipes &pp, const DevProgram &pr, const int *ld, const double *Tb, Init init, Finish finish)
 {
-    const DevPattern &P = a.P;
-    const smem_t sm = smem_of(tm.stage);
-    sm_store(sm, SW_ZERO_ROW, vset(0.0));
-    PStream ops, vals;
-    Fifo ff;
-    ops.open(tm, P.mv, 0);
-    vals.open(tm, P.mv_val, 2);
-    ff.open(tm, P.mv_ld[variant], P.mv_nld, T, 1);
-    for (int t = 0; t < P.mv_rows; t++)
+    pp.open(tm, pr, ld, Tb);
+    for (;;)
     {
-        const i4 rec = ops.get();
-        const d2 cv = as_d2(vals.get());
-        const int cnt = rec.x & MV_CNT_MASK, kind = (rec.x >> MV_KIND_SHIFT) & 3;
-        if (rec.x < 0)
-            ff.sync();
-        const vd ex0 = sm_load(sm, rec.y & 0xff), own = sm_load(sm, (rec.y >> 8) & 0xff);
-        const vd ex1 = sm_load(sm, (int)((unsigned)rec.y >> 24));
-        const int okeep = (rec.y >> 16) & 0xff;
-        if (okeep != SW_NO_KEEP)
-            sm_store(sm, okeep, own);
-        const double sgn = kind == MV_X ? sx : (kind == MV_Y ? sy : sz);
-        vd v = init(kind, ex0, own, ex1);
-        if (cnt > 0)
+        const i4 h = pp.get();
+        if (!pipe_header(pp, h.x))
+            break;
+        const int kind = (h.x >> PH_KIND_SHIFT) & 3;
+        vd ex0[NR], own[NR], v[NR];
+        ex0[0] = pp.ld(f_lo(h.y));
+        own[0] = pp.ld(f_hi(h.y));
+        if (NR == 2)
         {
-            {
-                const vd g = sm_load(sm, rec.w & 0xff);
-                const int keep = (rec.w >> 8) & 0xff;
-                if (keep != SW_NO_KEEP)
-                    sm_store(sm, keep, g);
-                v += (sgn * cv.x) * g;
-            }
-            const int nrec = (cnt + 3 + 3) >> 2;
-            for (int q = 1; q < nrec; q++)
-            {
-                const i4 pr = ops.get();
-                const d2 c0 = as_d2(vals.get()), c1 = as_d2(vals.get());
-                if (pr.x & MV_SYNC_PAIR)
-                    ff.sync();
-                const int pw[4] = {pr.x, pr.y, pr.z, pr.w};
-                const double cf[4] = {c0.x, c0.y, c1.x, c1.y};
-                vd g[4];
+            ex0[NR - 1] = pp.ld2(f_lo(h.y));
+            own[NR - 1] = pp.ld2(f_hi(h.y));
+        }
+        const vd ex1 = pp.ld(f_hi(h.z));
+        pp.st(f_lo(h.z), own[0]);
+        if (NR == 2)
+            pp.st2(f_lo(h.z), own[NR - 1]);
 #pragma unroll
-                for (int u = 0; u < 4; u++)
-                    g[u] = sm_load(sm, pw[u] & 0xff);
+        for (int j = 0; j < NR; j++)
+            v[j] = init(kind, ex0[j], own[j], ex1);
+        pipe_header_release(pp, h.x);
+        const int ng = h.x & PH_NTAIL_MASK;
+        if (PIM)
+        { // [coefficient field | operand field << 16, keep field] x 2 per record
+            for (int q = 0; q < ng; q++)
+            {
+                const i4 r = pp.get();
+                pipe_tail_acquire(pp, r.x);
+                const int pw[2] = {r.x, r.z}, kw[2] = {r.y, r.w};
+                vd c[2], g[2][NR];
+#pragma unroll
+                for (int u = 0; u < 2; u++)
+                {
+                    c[u] = pp.ld(f_lo(pw[u]));
+                    g[u][0] = pp.ld(f_hi(pw[u]));
+                    if (NR == 2)
+                        g[u][NR - 1] = pp.ld2(f_hi(pw[u]));
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++)
+                {
+                    pp.st(f_lo(kw[u]), g[u][0]);
+                    if (NR == 2)
+                        pp.st2(f_lo(kw[u]), g[u][NR - 1]);
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++)
+#pragma unroll
+                    for (int j = 0; j < NR; j++)
+                        v[j] = vfnma(v[j], c[u], g[u][j]);
+                pipe_tail_release(pp, r.x);
+            }
+        }
+        else
+        {
+            for (int q = 0; q < ng; q++)
+            {
+                const i4 r = pp.get();
+                const d2 c0 = as_d2(pp.get()), c1 = as_d2(pp.get());
+                pipe_tail_acquire(pp, r.x);
+                const int pw[4] = {r.x, r.y, r.z, r.w};
+                const double cf[4] = {c0.x, c0.y, c1.x, c1.y};
+                vd g[4][NR];
 #pragma unroll
                 for (int u = 0; u < 4; u++)
                 {
-                    const int keep = (pw[u] >> 8) & 0xff;
-                    if (keep != SW_NO_KEEP)
-                        sm_store(sm, keep, g[u]);
+                    g[u][0] = pp.ld(f_lo(pw[u]));
+                    if (NR == 2)
+                        g[u][NR - 1] = pp.ld2(f_lo(pw[u]));
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++)
-                    v += (sgn * cf[u]) * g[u];
+                {
+                    pp.st(f_hi(pw[u]), g[u][0]);
+                    if (NR == 2)
+                        pp.st2(f_hi(pw[u]), g[u][NR - 1]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+#pragma unroll
+                    for (int j = 0; j < NR; j++)
+                        v[j] = vfnma(v[j], cf[u], g[u][j]);
+                pipe_tail_release(pp, r.x);
+            }
+            if (h.x & PH_HAS2)
+            {
+                const i4 r = pp.get();
+                const d2 c0 = as_d2(pp.get());
+                pipe_tail_acquire(pp, r.x);
+                const int pw[2] = {r.x, r.y};
+                const double cf[2] = {c0.x, c0.y};
+                vd g[2][NR];
+#pragma unroll
+                for (int u = 0; u < 2; u++)
+                {
+                    g[u][0] = pp.ld(f_lo(pw[u]));
+                    if (NR == 2)
+                        g[u][NR - 1] = pp.ld2(f_lo(pw[u]));
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++)
+                {
+                    pp.st(f_hi(pw[u]), g[u][0]);
+                    if (NR == 2)
+                        pp.st2(f_hi(pw[u]), g[u][NR - 1]);
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++)
+#pragma unroll
+                    for (int j = 0; j < NR; j++)
+                        v[j] = vfnma(v[j], cf[u], g[u][j]);
+                pipe_tail_release(pp, r.x);
             }
         }
-        finish(kind, rec.z, v, ex0, own, ex1);
+#pragma unroll
+        for (int j = 0; j < NR; j++)
+            finish(j, kind, h.w, v[j], ex0[j], own[j], ex1);
     }
-    ff.close();
-}
-
-// The same for per-instance matrices: every coefficient is a row of the workspace that arrives
-// through the FIFO like the operands (streams.hpp: MVP_*).
-template <class Init, class Finish>
-EI_DEV void mv_run_pim(const Team &tm, const KArgs &a, const double *T, int variant,
-                       double sx, double sy, double sz, Init init, Finish finish)
-{
-    const DevPattern &P = a.P;
-    const smem_t sm = smem_of(tm.stage);
-    sm_store(sm, SW_ZERO_ROW, vset(0.0));
-    PStream ops;
-    Fifo ff;
-    ops.open(tm, P.mv, 0);
-    ff.open(tm, P.mv_ld[variant], P.mv_nld, T, 1);
-    for (int t = 0; t < P.mv_rows; t++)
-    {
-        const i4 rec = ops.get();
-        const int ntail = rec.x & MV_CNT_MASK, kind = (rec.x >> MV_KIND_SHIFT) & 3;
-        if (rec.x < 0)
-            ff.sync();
-        const vd ex0 = sm_load(sm, rec.y & 0xff), own = sm_load(sm, (rec.y >> 8) & 0xff);
-        const vd ex1 = sm_load(sm, (int)((unsigned)rec.y >> 24));
-        const int okeep = (rec.y >> 16) & 0xff;
-        if (okeep != SW_NO_KEEP)
-            sm_store(sm, okeep, own);
-        const double sgn = kind == MV_X ? sx : (kind == MV_Y ? sy : sz);
-        vd v = init(kind, ex0, own, ex1);
-        for (int q = 0; q < ntail; q++)
-        {
-            const i4 pr = ops.get();
-            if (pr.x & MVP_SYNC)
-                ff.sync();
-            const int pw[4] = {pr.x, pr.y, pr.z, pr.w};
-            vd c[4], g[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-            {
-                c[u] = sm_load(sm, pw[u] & 0x3f);
-                g[u] = sm_load(sm, (pw[u] >> 8) & 0xff);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-            {
-                const int keep = (pw[u] >> 16) & 0xff;
-                if (keep != SW_NO_KEEP)
-                    sm_store(sm, keep, g[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-                v += (sgn * c[u]) * g[u];
-        }
-        finish(kind, rec.z, v, ex0, own, ex1);
-    }
-    ff.close();
+    pp.close();
 }
 
 // ------------------------------------------------------------------ KKT residual for iterative refinement (src/eicos.cpp:1511-1576)
-// e = rhs - Ktrue * x with the un-regularised scaling block (identity while initialising),
-// returns ||e||_inf per instance.
-EI_DEV vd kkt_residual(const Team &tm, const KArgs &a, double *T, int variant, int x, int erow, bool initialize)
+// e[j] = rhs[j] - Ktrue * x[j] with the un-regularised scaling block (identity while initialising),
+// nerr[j] = ||e[j]||_inf per instance.  mvld: the materialised mat-vec load list of this use.
+template <int NR>
+EI_DEV void kkt_residual(const Team &tm, const KArgs &a, Pipes &pp, const TileMem &t, const int *mvld, const int (&x)[NR],
+                         const int (&erow)[NR], bool initialize, vd (&nerr)[NR])
 {
     const DevPattern &P = a.P;
     const Layout &L = a.L;
+    double *T = t.T;
     const double delta = Settings::deltastat;
     const int zb = P.n + P.p;
-    vd nerr = vset(0.0);
+#pragma unroll
+    for (int j = 0; j < NR; j++)
+        nerr[j] = vset(0.0);
     const auto mv_init = [&](int, vd ex0, vd, vd) { return ex0; };
-    const auto mv_finish = [&](int kind, int r, vd v, vd, vd own, vd ex1) {
+    const auto mv_finish = [&](int j, int kind, int r, vd v, vd, vd own, vd ex1) {
         if (kind == MV_ZC)
         { // cone row: rhs - G x only; the cone block is added below
-            ROWD(T, erow + r) = v;
+            ROWD(T, erow[j] + r) = v;
             return;
         }
         if (kind == MV_X)
@@ -1196,15 +1550,15 @@ EI_DEV vd kkt_residual(const Team &tm, const KArgs &a, double *T, int variant, i
             if (kind == MV_Z)
                 v += initialize ? own : ex1 * own;
         }
-        ROWD(T, erow + r) = v;
-        nerr = vmax(nerr, vabs(v));
+        ROWD(T, erow[j] + r) = v;
+        nerr[j] = vmax(nerr[j], vabs(v));
     };
     if (tm.wk == 0 && P.mv_rows > 0)
     {
         if (P.pim)
-            mv_run_pim(tm, a, T, variant, -1.0, -1.0, -1.0, mv_init, mv_finish);
+            mv_run<NR, true>(tm, pp, P.mv[NR - 1], mvld, t.Tb, mv_init, mv_finish);
         else
-            mv_run(tm, a, T, variant, -1.0, -1.0, -1.0, mv_init, mv_finish);
+            mv_run<NR, false>(tm, pp, P.mv[NR - 1], mvld, t.Tb, mv_init, mv_finish);
     }
     if (P.nc > 0)
     {
@@ -1216,43 +1570,48 @@ EI_DEV vd kkt_residual(const Team &tm, const KArgs &a, double *T, int variant, i
             const int cp = L.cpar + c * CP_COUNT;
             const vd eta2 = ROWD(T, cp + CP_ETA2), d1 = ROWD(T, cp + CP_D1), u0 = ROWD(T, cp + CP_U0);
             const vd u1 = ROWD(T, cp + CP_U1), v1 = ROWD(T, cp + CP_V1);
-            const vd x1 = ROWD(T, x + kb), x3 = ROWD(T, x + kb + d), x4 = ROWD(T, x + kb + d + 1);
-            vd qtx2 = vset(0.0);
-            for (int k = 1; k < d; k++)
-                qtx2 += vd(ROWD(T, L.cq + qo + k - 1)) * vd(ROWD(T, x + kb + k));
-            const vd vu = v1 * x3 + u1 * x4;
-            for (int k = 0; k < d; k++)
+            for (int j = 0; j < NR; j++)
             {
-                const vd xk = ROWD(T, x + kb + k);
-                vd v = ROWD(T, erow + kb + k); // rhs - G x from the mat-vec program
-                if (k < d - 1)
-                    v += delta * xk;
-                else
-                    v -= delta * xk;
-                if (initialize)
-                    v += xk;
-                else if (k == 0)
-                    v += eta2 * (d1 * x1 + u0 * x4);
-                else
-                    v += eta2 * (xk + vu * vd(ROWD(T, L.cq + qo + k - 1)));
-                ROWD(T, erow + kb + k) = v;
-                nerr = vmax(nerr, vabs(v));
+                const int xj = x[j], ej = erow[j];
+                const vd x1 = ROWD(T, xj + kb), x3 = ROWD(T, xj + kb + d), x4 = ROWD(T, xj + kb + d + 1);
+                vd qtx2 = vset(0.0);
+                for (int k = 1; k < d; k++)
+                    qtx2 += vd(ROWD(T, L.cq + qo + k - 1)) * vd(ROWD(T, xj + kb + k));
+                const vd vu = v1 * x3 + u1 * x4;
+                for (int k = 0; k < d; k++)
+                {
+                    const vd xk = ROWD(T, xj + kb + k);
+                    vd v = ROWD(T, ej + kb + k); // rhs - G x from the mat-vec program
+                    if (k < d - 1)
+                        v += delta * xk;
+                    else
+                        v -= delta * xk;
+                    if (initialize)
+                        v += xk;
+                    else if (k == 0)
+                        v += eta2 * (d1 * x1 + u0 * x4);
+                    else
+                        v += eta2 * (xk + vu * vd(ROWD(T, L.cq + qo + k - 1)));
+                    ROWD(T, ej + kb + k) = v;
+                    nerr[j] = vmax(nerr[j], vabs(v));
+                }
+                const vd e3 = initialize ? x3 : eta2 * (v1 * qtx2 + x3);
+                const vd e4 = initialize ? x4 : eta2 * (u0 * x1 + u1 * qtx2 - x4);
+                ROWD(T, ej + kb + d) = e3;
+                ROWD(T, ej + kb + d + 1) = e4;
+                nerr[j] = vmax(nerr[j], vmax(vabs(e3), vabs(e4)));
             }
-            const vd e3 = initialize ? x3 : eta2 * (v1 * qtx2 + x3);
-            const vd e4 = initialize ? x4 : eta2 * (u0 * x1 + u1 * qtx2 - x4);
-            ROWD(T, erow + kb + d) = e3;
-            ROWD(T, erow + kb + d + 1) = e4;
-            nerr = vmax(nerr, vmax(vabs(e3), vabs(e4)));
         }
     }
-    vd red[1] = {nerr};
-    team_max<1>(tm, red);
-    return red[0];
+    team_max<NR>(tm, nerr);
 }
 
 // ------------------------------------------------------------------ solveKKT (src/eicos.cpp:1471-1620)
 // sol = K^-1 rhs followed by up to nitref refinement rounds; every instance stops on its own
-// criterion, the tile loops until all of its instances have stopped.
+// criterion, the tile loops until all of its instances have stopped.  NR = 2: the two solves of an
+// iteration that share the factor (rhs1 -> sol1, rhs2 -> sol2) in one pass over L per sweep; a job whose
+// instances have all stopped rides along with its accumulation masked off.
+template <int NR>
 EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
 {
     const TileMem t = tile_mem(tm, a, tile);
@@ -1262,84 +1621,144 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     double *T = t.T;
-    const KArgs::KktJob jb = a.job[tm.job];
-    const int sol = jb.sol, set = jb.set; // (jb.rhs is baked into the materialised load lists of the set)
-    const int xw = set ? L.xw2 : L.xw, dxr = set ? L.dxr2 : L.dxr, erow = set ? L.e2 : L.e;
     const bool init = a.initialize != 0;
+    int sol[NR], xw[NR], dxr[NR], erow[NR], nitrow[NR];
+    vd threshold[NR];
+#pragma unroll
+    for (int j = 0; j < NR; j++)
+    {
+        const KArgs::KktJob jb = a.job[j];
+        const int set = jb.set; // (jb.rhs is baked into the materialised load lists of the set)
+        sol[j] = jb.sol;
+        nitrow[j] = jb.nitrow;
+        xw[j] = set ? L.xw2 : L.xw;
+        dxr[j] = set ? L.dxr2 : L.dxr;
+        erow[j] = set ? L.e2 : L.e;
+        // max |rhs| is kept up to date by the kernels that write the right-hand sides (src/eicos.cpp:1590)
+        threshold[j] = (1. + vd(ROWD(T, L.sc + (set ? S_RHSMAX2 : S_RHSMAX1)))) * Settings::linsysacc;
+    }
+    const int set0 = a.job[0].set;
+    const int *fw_ld[2], *bw_ld[2], *mv_ld;
+    if (NR == 1)
+    {
+        fw_ld[0] = P.fw_ld1[set0][0], fw_ld[1] = P.fw_ld1[set0][1];
+        bw_ld[0] = P.bw_ld1[set0][0], bw_ld[1] = P.bw_ld1[set0][1];
+        mv_ld = P.mv_ld1[set0];
+    }
+    else
+    {
+        fw_ld[0] = P.fw_ld2[0], fw_ld[1] = P.fw_ld2[1];
+        bw_ld[0] = P.bw_ld2[0], bw_ld[1] = P.bw_ld2[1];
+        mv_ld = P.mv_ld2;
+    }
+    Pipes pp;
+    pp.init(tm, tm.pbuf);
 
     long long ck[5] = {0, 0, 0, 0, 0}, c0 = EI_CLOCK(), c1;
 #define EI_PHASE(k) (c1 = EI_CLOCK(), ck[k] += c1 - c0, c0 = c1)
-    vd mx[1] = {vset(0.0)}; // max |rhs|, picked up by the forward sweep as it loads the rows
-    EI_PHASE(0);
+    vb nocont[NR];
+#pragma unroll
+    for (int j = 0; j < NR; j++)
+        nocont[j] = vbset(false);
     if (tm.wk == 0)
     {
-        mx[0] = ldl_forward(tm, a, T, 2 * set, xw);
+        ldl_forward<NR>(tm, pp, P.fw[NR - 1], fw_ld[0], t.Tb, T, xw);
         EI_PHASE(1);
-        ldl_backward(tm, a, T, 2 * set, sol, -1, vbset(false));
+        ldl_backward<NR, false>(tm, pp, P.bwp[NR - 1], bw_ld[0], t.Tb, T, sol, sol, nocont);
         EI_PHASE(2);
     }
-    team_max<1>(tm, mx); // (workers > 1: worker 0 holds the value, the others 0)
-    const vd threshold = (1. + mx[0]) * Settings::linsysacc;
     tm.sync();
 
-    vd nerr_prev = vset(DBL_MAX);
-    int kref[VEC];
-    vb done = !act;
-    VFOR kref[c_] = 0;
+    vd nerr_prev[NR];
+    int kref[NR][VEC];
+    vb done[NR];
+#pragma unroll
+    for (int j = 0; j < NR; j++)
+    {
+        nerr_prev[j] = vset(DBL_MAX);
+        done[j] = !act;
+        VFOR kref[j][c_] = 0;
+    }
     unsigned rounds = 0;
     for (;;)
     {
-        const vd nerr = kkt_residual(tm, a, T, set, sol, erow, init);
+        vd nerr[NR];
+        kkt_residual<NR>(tm, a, pp, t, mv_ld, sol, erow, init, nerr);
         EI_PHASE(3);
-        vb rollback = vbset(false);
-        VFOR
+        bool all_done = true;
+#pragma unroll
+        for (int j = 0; j < NR; j++)
         {
-            if (done.v[c_])
-                continue;
-            if (kref[c_] > 0 && nerr.v[c_] > nerr_prev.v[c_])
+            vb rollback = vbset(false);
+            VFOR
             {
-                rollback.v[c_] = true;
-                kref[c_]--;
-                done.v[c_] = true;
+                if (done[j].v[c_])
+                    continue;
+                if (kref[j][c_] > 0 && nerr[j].v[c_] > nerr_prev[j].v[c_])
+                {
+                    rollback.v[c_] = true;
+                    kref[j][c_]--;
+                    done[j].v[c_] = true;
+                }
+                else if (kref[j][c_] == Settings::nitref || nerr[j].v[c_] < threshold[j].v[c_] ||
+                         (kref[j][c_] > 0 && nerr_prev[j].v[c_] < Settings::irerrfact * nerr[j].v[c_]))
+                    done[j].v[c_] = true;
+                else
+                    nerr_prev[j].v[c_] = nerr[j].v[c_];
             }
-            else if (kref[c_] == Settings::nitref || nerr.v[c_] < threshold.v[c_] ||
-                     (kref[c_] > 0 && nerr_prev.v[c_] < Settings::irerrfact * nerr.v[c_]))
-                done.v[c_] = true;
-            else
-                nerr_prev.v[c_] = nerr.v[c_];
+            if (tm.any(rollback))
+            { // x -= dx_ref for the instances whose last refinement made things worse
+                for (int r = tm.wk; r < P.N; r += tm.nwk)
+                    ROWD(T, sol[j] + r) -= vsel(rollback, ROWD(T, dxr[j] + r), vset(0.0));
+            }
+            all_done = all_done && tm.all(done[j]);
         }
-        if (tm.any(rollback))
-        { // x -= dx_ref for the instances whose last refinement made things worse
-            for (int r = tm.wk; r < P.N; r += tm.nwk)
-                ROWD(T, sol + r) -= vsel(rollback, ROWD(T, dxr + r), vset(0.0));
-        }
-        if (tm.all(done))
+        if (all_done)
             break;
         tm.sync(); // e complete before the forward sweep loads it
         EI_PHASE(4);
         if (tm.wk == 0)
         {
-            (void)ldl_forward(tm, a, T, 2 * set + LDV_REFINE, xw);
+            vb cont[NR];
+#pragma unroll
+            for (int j = 0; j < NR; j++)
+                cont[j] = !done[j];
+            ldl_forward<NR>(tm, pp, P.fw[NR - 1], fw_ld[1], t.Tb, T, xw);
             EI_PHASE(1);
-            ldl_backward(tm, a, T, 2 * set + LDV_REFINE, dxr, sol, !done);
+            ldl_backward<NR, true>(tm, pp, P.bw[NR - 1], bw_ld[1], t.Tb, T, dxr, sol, cont);
             EI_PHASE(2);
         }
         tm.sync();
-        VFOR if (!done.v[c_]) kref[c_]++;
+#pragma unroll
+        for (int j = 0; j < NR; j++)
+            VFOR if (!done[j].v[c_]) kref[j][c_]++;
         rounds++;
     }
     tm.sync();
     if (tm.wk == 0)
     {
-        if (jb.nitrow >= 0)
-            VFOR if (act.v[c_]) ROWC(t.I, jb.nitrow, c_) = kref[c_];
+#pragma unroll
+        for (int j = 0; j < NR; j++)
+            if (nitrow[j] >= 0)
+                VFOR if (act.v[c_]) ROWC(t.I, nitrow[j], c_) = kref[j][c_];
 #ifndef EICOS_EMU
-        if (tm.pl == 0 && a.ir_rounds)
+        if (a.ir_rounds)
         {
-            atomicAdd(a.ir_rounds, (unsigned long long)(rounds + 1));
-            EI_PHASE(4);
-            for (int k = 0; k < 5; k++)
-                atomicAdd(a.ir_rounds + 1 + k, (unsigned long long)ck[k]);
+            // [0] tile-rounds (sweep pairs x jobs), [6] lane-rounds: sweep pairs each instance needed
+            int lane_rounds = 0;
+#pragma unroll
+            for (int j = 0; j < NR; j++)
+                VFOR if (act.v[c_]) lane_rounds += kref[j][c_] + 1;
+            for (int o = 16; o > 0; o >>= 1)
+                lane_rounds += __shfl_xor_sync(0xffffffffu, lane_rounds, o);
+            if (tm.pl == 0)
+            {
+                atomicAdd(a.ir_rounds, (unsigned long long)(rounds + 1) * NR);
+                atomicAdd(a.ir_rounds + 6, (unsigned long long)lane_rounds);
+                EI_PHASE(4);
+                for (int k = 0; k < 5; k++)
+                    atomicAdd(a.ir_rounds + 1 + k, (unsigned long long)ck[k]);
+            }
         }
 #endif
     }
@@ -1380,12 +1799,14 @@ EI_DEV void tile_init(const Team &tm, const KArgs &a, int tile)
     }
     // rhs1 = [0; b; h], rhs2 = [-c; 0; 0]; resx0.. = max(1, ||c||), ... (:865-894)
     vd nr[3] = {vset(0.0), vset(0.0), vset(0.0)};
+    vd mx[2] = {vset(0.0), vset(0.0)}; // max |rhs1|, max |rhs2| (solveKKT's stopping threshold, src/eicos.cpp:1590)
     for (int r = tm.wk; r < n; r += tm.nwk)
     {
         const vd v = ROWD(T, L.chb + r);
         ROWD(T, L.rhs1 + r) = 0.0;
         ROWD(T, L.rhs2 + r) = -v;
         nr[0] += v * v;
+        mx[1] = vmax(mx[1], vabs(v));
     }
     for (int r = n + tm.wk; r < zb; r += tm.nwk)
     {
@@ -1393,6 +1814,7 @@ EI_DEV void tile_init(const Team &tm, const KArgs &a, int tile)
         ROWD(T, L.rhs1 + r) = v;
         ROWD(T, L.rhs2 + r) = 0.0;
         nr[1] += v * v;
+        mx[0] = vmax(mx[0], vabs(v));
     }
     for (int r = zb + tm.wk; r < P.N; r += tm.nwk)
     {
@@ -1400,13 +1822,17 @@ EI_DEV void tile_init(const Team &tm, const KArgs &a, int tile)
         ROWD(T, L.rhs1 + r) = v;
         ROWD(T, L.rhs2 + r) = 0.0;
         nr[2] += v * v;
+        mx[0] = vmax(mx[0], vabs(v));
     }
     team_sum<3>(tm, nr);
+    team_max<2>(tm, mx);
     if (tm.wk == 0)
     {
         ROWD(T, L.sc + S_RESX0) = vmax(vset(1.), vsqrt(nr[0]));
         ROWD(T, L.sc + S_RESY0) = vmax(vset(1.), vsqrt(nr[1]));
         ROWD(T, L.sc + S_RESZ0) = vmax(vset(1.), vsqrt(nr[2]));
+        ROWD(T, L.sc + S_RHSMAX1) = mx[0];
+        ROWD(T, L.sc + S_RHSMAX2) = mx[1];
     }
 }
 
@@ -1473,6 +1899,8 @@ EI_DEV void tile_init_point(const Team &tm, const KArgs &a, int tile)
             ROWC(T, L.sc + S_STEP, c_) = 0.;
             ROWC(T, L.sc + S_STEP_AFF, c_) = 0.;
             ROWC(T, L.sc + S_PRES_PREV, c_) = DBL_MAX;
+            // rhs1 = [-c; b; h] from here on (S_RHSMAX2 still holds max |c| from eicos_init)
+            ROWC(T, L.sc + S_RHSMAX1, c_) = dmax(ROWC(T, L.sc + S_RHSMAX1, c_), ROWC(T, L.sc + S_RHSMAX2, c_));
             ROWC(t.I, J_PINF, c_) = 0;
             ROWC(t.I, J_DINF, c_) = 0;
             ROWC(t.I, J_ITER, c_) = 0;
@@ -1638,11 +2066,13 @@ EI_DEV void tile_resid(const Team &tm, const KArgs &a, int tile)
         r[NS2] += si * si;
         r[GAP] += si * zi;
     };
-    const auto mv_init = [&](int kind, vd, vd, vd ex1) { return kind >= MV_Z ? ex1 : vset(0.0); };
-    const auto mv_finish = [&](int kind, int q, vd v, vd ex0, vd own, vd ex1) {
+    // mv_run subtracts the row sum; the y and z rows want it added: start from the negated initial value
+    // and negate the result (bit-identical, rounding is symmetric)
+    const auto mv_init = [&](int kind, vd, vd, vd ex1) { return kind >= MV_Z ? -ex1 : (kind == MV_Y ? vset(-0.0) : vset(0.0)); };
+    const auto mv_finish = [&](int, int kind, int q, vd v, vd ex0, vd own, vd ex1) {
                 if (kind >= MV_Z)
                 { // LP and cone rows alike: rz = s + G x
-                    zrow(q - zb, ex1, own, ex0, v);
+                    zrow(q - zb, ex1, own, ex0, -v);
                     return;
                 }
                 if (kind == MV_X)
@@ -1656,6 +2086,7 @@ EI_DEV void tile_resid(const Team &tm, const KArgs &a, int tile)
                 }
                 else
                 { // ex0 = b_i, own = y_i
+                    v = -v;
                     r[HY2] += v * v;
                     v -= tau * ex0;
                     ROWD(T, L.r + q) = v;
@@ -1666,10 +2097,12 @@ EI_DEV void tile_resid(const Team &tm, const KArgs &a, int tile)
             };
     if (tm.wk == 0 && P.mv_rows > 0)
     {
+        Pipes pp;
+        pp.init(tm, tm.pbuf);
         if (P.pim)
-            mv_run_pim(tm, a, T, LDV_HEAD, -1.0, 1.0, 1.0, mv_init, mv_finish);
+            mv_run<1, true>(tm, pp, P.mv[0], P.mv_ld1[LDV_HEAD], t.Tb, mv_init, mv_finish);
         else
-            mv_run(tm, a, T, LDV_HEAD, -1.0, 1.0, 1.0, mv_init, mv_finish);
+            mv_run<1, false>(tm, pp, P.mv[0], P.mv_ld1[LDV_HEAD], t.Tb, mv_init, mv_finish);
     }
     team_sum<NRED>(tm, r);
     if (tm.wk == 0)
@@ -2005,10 +2438,21 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
             ROWD(T, vb_++) = -(eta2 * u1) * vd(ROWD(T, L.cq + qo + k - 1));
     }
     {
+        vd mx[1] = {vset(0.0)}; // max |rhs2| for the affine solve
         const int ins[1] = {L.r};
-        ew_rows<1, 8>(tm, T, zb, ins, [&](int q, const vd *x) { ROWD(T, L.rhs2 + q) = q < n ? x[0] : -x[0]; });
+        ew_rows<1, 8>(tm, T, zb, ins, [&](int q, const vd *x) {
+            ROWD(T, L.rhs2 + q) = q < n ? x[0] : -x[0];
+            mx[0] = vmax(mx[0], vabs(x[0]));
+        });
         const int inz[2] = {L.s, L.r + zb}; // s - rz; the slot rows of s and rz are zero
-        ew_rows<2, 6>(tm, T, P.mt, inz, [&](int e, const vd *x) { ROWD(T, L.rhs2 + zb + e) = x[0] - x[1]; });
+        ew_rows<2, 6>(tm, T, P.mt, inz, [&](int e, const vd *x) {
+            const vd v = x[0] - x[1];
+            ROWD(T, L.rhs2 + zb + e) = v;
+            mx[0] = vmax(mx[0], vabs(v));
+        });
+        team_max<1>(tm, mx);
+        if (tm.wk == 0)
+            ROWD(T, L.sc + S_RHSMAX2) = vsel(cont, mx[0], ROWD(T, L.sc + S_RHSMAX2));
     }
 }
 
@@ -2113,9 +2557,14 @@ EI_DEV void tile_mid(const Team &tm, const KArgs &a, int tile)
 
     // RHScombined
     const vd sigmamu = sigma * mu, oms = 1. - sigma;
+    vd mx[1] = {vset(0.0)}; // max |rhs2| for the combined solve
     {
         const int ins[1] = {L.rhs2};
-        ew_rows<1, 8>(tm, T, n + p, ins, [&](int r, const vd *x) { ROWD(T, L.rhs2 + r) = x[0] * oms; });
+        ew_rows<1, 8>(tm, T, n + p, ins, [&](int r, const vd *x) {
+            const vd v = x[0] * oms;
+            ROWD(T, L.rhs2 + r) = v;
+            mx[0] = vmax(mx[0], vabs(v));
+        });
         const int inl[5] = {L.lam, L.dsw, L.wdz, L.r + zb, L.lpw};
         ew_rows<5, 2>(tm, T, P.l, inl, [&](int k, const vd *x) {
             const vd lk = x[0];
@@ -2124,7 +2573,9 @@ EI_DEV void tile_mid(const Team &tm, const KArgs &a, int tile)
             d1 -= sigmamu;
             const vd q = d1 / lk; // conicDivision, LP part
             ROWD(T, L.dsw + k) = q;
-            ROWD(T, L.rhs2 + zb + k) = -oms * x[3] + x[4] * q;
+            const vd v = -oms * x[3] + x[4] * q;
+            ROWD(T, L.rhs2 + zb + k) = v;
+            mx[0] = vmax(mx[0], vabs(v));
         });
     }
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
@@ -2171,13 +2622,24 @@ EI_DEV void tile_mid(const Team &tm, const KArgs &a, int tile)
         for (int k = 1; k < d; k++)
             zt += vd(ROWD(T, L.cq + qo + k - 1)) * vd(ROWD(T, L.dsw + zs + k));
         const vd fz = q0 + zt / (1. + ca);
-        ROWD(T, L.rhs2 + kb) = -oms * vd(ROWD(T, L.r + kb)) + eta * (ca * q0 + zt);
+        {
+            const vd v = -oms * vd(ROWD(T, L.r + kb)) + eta * (ca * q0 + zt);
+            ROWD(T, L.rhs2 + kb) = v;
+            mx[0] = vmax(mx[0], vabs(v));
+        }
         for (int k = 1; k < d; k++)
-            ROWD(T, L.rhs2 + kb + k) = -oms * vd(ROWD(T, L.r + kb + k)) +
-                                       eta * (vd(ROWD(T, L.dsw + zs + k)) + fz * vd(ROWD(T, L.cq + qo + k - 1)));
+        {
+            const vd v = -oms * vd(ROWD(T, L.r + kb + k)) +
+                         eta * (vd(ROWD(T, L.dsw + zs + k)) + fz * vd(ROWD(T, L.cq + qo + k - 1)));
+            ROWD(T, L.rhs2 + kb + k) = v;
+            mx[0] = vmax(mx[0], vabs(v));
+        }
         ROWD(T, L.rhs2 + kb + d) = 0.0;
         ROWD(T, L.rhs2 + kb + d + 1) = 0.0;
     }
+    team_max<1>(tm, mx);
+    if (tm.wk == 0)
+        ROWD(T, L.sc + S_RHSMAX2) = vsel(act, mx[0], ROWD(T, L.sc + S_RHSMAX2));
 }
 
 // ------------------------------------------------------------------ combined step and iterate update (src/eicos.cpp:1214-1252)
