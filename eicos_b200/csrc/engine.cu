@@ -42,8 +42,7 @@ EI_DEFINE_KERNEL(eicos_load_inputs, tile_load, 2)
 EI_DEFINE_KERNEL(eicos_equilibrate, tile_equil, 2)
 EI_DEFINE_KERNEL(eicos_init, tile_init, 2)
 EI_DEFINE_KERNEL1(eicos_ldl_factor, tile_factor)
-EI_DEFINE_KERNEL1(eicos_solve_kkt, tile_solve_kkt<1>)     /* one solveKKT per tile */
-EI_DEFINE_KERNEL1(eicos_solve_kkt_pair, tile_solve_kkt<2>) /* two solveKKT that share the factor, one pass over L */
+EI_DEFINE_KERNEL_(eicos_solve_kkt, tile_solve_kkt, 32, 8, 1) /* CTA = (tile, job): one solveKKT each */
 EI_DEFINE_KERNEL(eicos_init_point, tile_init_point, 2)
 EI_DEFINE_KERNEL1(eicos_residuals, tile_resid)
 EI_DEFINE_KERNEL(eicos_iter_head, tile_head, 2)
@@ -74,7 +73,7 @@ __global__ void eicos_compact(const __grid_constant__ KArgs a, const __grid_cons
         std::vector<double> red_((size_t)nw_ * KRED * TILE + 8);                                  \
         const size_t xr_ = (size_t)(args).P.fa_slots + 2 * (args).P.maxcol;                           \
         std::vector<double> stg_(((size_t)nw_ * 2 * STAGE_SLOTS + xr_) * TILE + 8);                \
-        std::vector<double> pb_(std::max<size_t>(PS_DOUBLES, pipe_smem_doubles(std::max((args).P.sw_rows[0], (args).P.sw_rows[1]))) + 8); \
+        std::vector<double> pb_(std::max<size_t>(PS_DOUBLES, machine_smem_doubles((args).P.sw_rows)) + 8); \
         for (int cta_ = 0; cta_ < (tiles) * nj_; cta_++)                                          \
         {                                                                                         \
             const int tile_ = cta_ / nj_;                                                         \
@@ -237,47 +236,39 @@ void Engine::upload_pattern(const Symbolic &S)
     P.xeq = dxeq_ = upload(S.xeq, owned_, st);
     P.Aeq = dAeq_ = upload(S.Aeq, owned_, st);
     P.GeqE = dGeq_ = upload(expanded_geq(S), owned_, st);
-    // row programs: record streams as they are, load lists materialised per use
-    // (selector -> row offset of the vector it stands for, streams.hpp; LD_NONE stays)
-    const auto prog = [&](const Program &h, DevProgram &d, int **keep = nullptr) {
+    // machine programs: record streams as they are, load lists materialised per use
+    // (selector -> row offset of the vector it stands for, streams.hpp; M_LD_NONE stays)
+    const auto prog = [&](const MachineCode &h, DevMachine &d, int **keep = nullptr) {
         int *o = upload(h.ops, owned_, st);
         d.ops = o;
         d.nchunks = h.nchunks;
-        d.nld = h.nld;
         if (keep)
             *keep = o;
     };
-    const auto variant = [&](const ivec &list, int a1, int a2, int a3, int b1 = 0, int b2 = 0, int b3 = 0) {
+    const auto variant = [&](const ivec &list, int a1, int a2, int a3, int a4 = 0, int a5 = 0) {
         ivec out(list.size());
-        const int off[8] = {0, a1, a2, a3, 0, b1, b2, b3};
+        const int off[8] = {0, a1, a2, a3, a4, a5, 0, 0};
         for (size_t k = 0; k < list.size(); k++)
-            out[k] = list[k] == LD_NONE ? LD_NONE : (list[k] & LD_ROW_MASK2) + off[(unsigned)list[k] >> LD_SEL_SHIFT];
+            out[k] = list[k] == M_LD_NONE ? M_LD_NONE : (list[k] & M_LD_ROW_MASK) + off[((unsigned)list[k] >> M_LD_SEL_SHIFT) & 7];
         return upload(out, owned_, st);
     };
-    for (int k = 0; k < 2; k++)
-    {
-        prog(H_.fw[k], P.fw[k]);
-        prog(H_.bw[k], P.bw[k]);
-        prog(H_.bwp[k], P.bwp[k]);
-        prog(H_.mv[k], P.mv[k], &dmv_ops_[k]);
-        P.sw_rows[k] = std::max(std::max(H_.fw[k].slot_rows, H_.bw[k].slot_rows), std::max(H_.bwp[k].slot_rows, H_.mv[k].slot_rows));
-    }
+    prog(H_.fw, P.fw);
+    prog(H_.bw, P.bw);
+    prog(H_.bwp, P.bwp);
+    prog(H_.mv, P.mv, &dmv_ops_[0]);
+    prog(H_.rs, P.rs, &dmv_ops_[1]);
+    P.sw_rows = H_.sw_slots;
     const int rhs[2] = {L_.rhs1, L_.rhs2}, sol[2] = {L_.sol1, L_.sol2}, xw[2] = {L_.xw, L_.xw2};
     const int dxr[2] = {L_.dxr, L_.dxr2}, er[2] = {L_.e, L_.e2};
     for (int set = 0; set < 2; set++)
     { // forward: 1 = right-hand side, 3 = xw; backward: 1 = output, 2 = accumulated solution, 3 = xw
-        P.fw_ld1[set][0] = variant(H_.fw[0].ld, rhs[set], 0, xw[set]);
-        P.fw_ld1[set][1] = variant(H_.fw[0].ld, er[set], 0, xw[set]);
-        P.bw_ld1[set][0] = variant(H_.bwp[0].ld, sol[set], 0, xw[set]);
-        P.bw_ld1[set][1] = variant(H_.bw[0].ld, dxr[set], sol[set], xw[set]);
-        P.mv_ld1[set] = variant(H_.mv[0].ld, rhs[set], sol[set], L_.lpv);
+        P.fw_ld[set][0] = variant(H_.fw.ld, rhs[set], 0, xw[set]);
+        P.fw_ld[set][1] = variant(H_.fw.ld, er[set], 0, xw[set]);
+        P.bw_ld[set][0] = variant(H_.bwp.ld, sol[set], 0, xw[set]);
+        P.bw_ld[set][1] = variant(H_.bw.ld, dxr[set], sol[set], xw[set]);
+        P.mv_ld[set] = variant(H_.mv.ld, rhs[set], sol[set], L_.lpv, er[set]);
     }
-    P.mv_ld1[LDV_HEAD] = variant(H_.mv[0].ld, L_.chb, L_.w, L_.s);
-    P.fw_ld2[0] = variant(H_.fw[1].ld, rhs[0], 0, xw[0], rhs[1], 0, xw[1]);
-    P.fw_ld2[1] = variant(H_.fw[1].ld, er[0], 0, xw[0], er[1], 0, xw[1]);
-    P.bw_ld2[0] = variant(H_.bwp[1].ld, sol[0], 0, xw[0], sol[1], 0, xw[1]);
-    P.bw_ld2[1] = variant(H_.bw[1].ld, dxr[0], sol[0], xw[0], dxr[1], sol[1], xw[1]);
-    P.mv_ld2 = variant(H_.mv[1].ld, rhs[0], sol[0], L_.lpv, rhs[1], sol[1], 0);
+    P.rs_ld = variant(H_.rs.ld, L_.chb, L_.w, L_.s, L_.r, L_.sc);
     P.mv_rows = H_.mv_rows;
     P.fa = upload(H_.fa, owned_, st);
     P.fa_ld = upload(H_.fa_ld, owned_, st);
@@ -309,8 +300,9 @@ void Engine::upload_values(const Symbolic &S)
     be::h2d(dAeq_, S.Aeq.data(), S.Aeq.size() * sizeof(double), st);
     be::h2d(dGeq_, ge.data(), ge.size() * sizeof(double), st);
     be::h2d(dfa_val_, H_.fa_val.data(), H_.fa_val.size() * sizeof(double), st);
-    for (int k = 0; k < 2; k++) // the mat-vec programs carry the shared coefficients inline
-        be::h2d(dmv_ops_[k], H_.mv[k].ops.data(), H_.mv[k].ops.size() * sizeof(int), st);
+    // the mat-vec programs carry the shared coefficients inline
+    be::h2d(dmv_ops_[0], H_.mv.ops.data(), H_.mv.ops.size() * sizeof(int), st);
+    be::h2d(dmv_ops_[1], H_.rs.ops.data(), H_.rs.ops.size() * sizeof(int), st);
     be::sync(st);
 }
 
@@ -319,8 +311,6 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
       pim_(instance_matrices), nnzG_(S.G.nnz()), nnzA_(S.A.nnz())
 {
     be::set_device(device_);
-    if (const char *v = std::getenv("EICOS_PAIR_SOLVES"))
-        pair_solves_ = std::atoi(v) != 0;
     stream_ = (void *)(intptr_t)be::make_stream();
     build_layout(S);
     upload_pattern(S);
@@ -343,8 +333,7 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
     moves_host_ = (int *)be::pinned(2 * slots * sizeof(int));
     // program kernels (one warp per tile): stream buffers + FIFO ring + slots; vector kernels: reduction rows only
     const size_t smem_base = ((size_t)2 * STAGE_SLOTS * TILE + PS_DOUBLES) * sizeof(double);
-    for (int k = 0; k < 2; k++)
-        smem_prog_[k] = pipe_smem_doubles(P_.sw_rows[k]) * sizeof(double);
+    smem_prog_ = machine_smem_doubles(P_.sw_rows) * sizeof(double);
     smem_common_ = workers_ > 1 ? (size_t)workers_ * KRED * TILE * sizeof(double) : 0;
     xrows_factor_ = H_.fa_slots + (H_.fa_fast ? 0 : 2 * S.maxcol); // record form keeps the column in registers
 #ifndef EICOS_EMU
@@ -358,13 +347,11 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
 #ifndef EICOS_EMU
     if (smem_factor_ > 48 * 1024)
         EI_CUDA(cudaFuncSetAttribute(eicos_ldl_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_factor_));
-    if (smem_prog_[0] > 48 * 1024)
+    if (smem_prog_ > 48 * 1024)
     {
-        EI_CUDA(cudaFuncSetAttribute(eicos_solve_kkt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prog_[0]));
-        EI_CUDA(cudaFuncSetAttribute(eicos_residuals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prog_[0]));
+        EI_CUDA(cudaFuncSetAttribute(eicos_solve_kkt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prog_));
+        EI_CUDA(cudaFuncSetAttribute(eicos_residuals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prog_));
     }
-    if (smem_prog_[1] > 48 * 1024)
-        EI_CUDA(cudaFuncSetAttribute(eicos_solve_kkt_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prog_[1]));
     if (smem_common_ > 48 * 1024)
     {
         const void *ks[] = {(const void *)eicos_load_inputs, (const void *)eicos_equilibrate, (const void *)eicos_init,
@@ -427,10 +414,10 @@ ProgramStats Engine::program_stats() const
     p.sw_far = H_.sw_far;
     p.sw_direct = H_.sw_direct;
     p.fa_home = H_.fa_home;
-    p.fw_loads = H_.fw[0].nld;
-    p.bw_loads = H_.bw[0].nld;
+    p.fw_loads = H_.fw.nld - (int)H_.fw.pads;
+    p.bw_loads = H_.bw.nld - (int)H_.bw.pads;
     p.fa_loads = H_.fa_nld;
-    p.mv_loads = H_.mv[0].nld;
+    p.mv_loads = H_.mv.nld - (int)H_.mv.pads;
     return p;
 }
 
@@ -564,32 +551,20 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
         // solveKKT launches: one job, or the two solves of an iteration that share the factor and do
         // not depend on each other (rhs1 -> sol1 and rhs2 -> sol2), as CTAs (tile, job) of one launch -
         // same traffic when the machine is full, half the latency when it is not
-        // solveKKT launches: one job, or the two solves of an iteration that share the factor and do
-        // not depend on each other (rhs1 -> sol1 and rhs2 -> sol2) in ONE pass over L per sweep
         auto kkt_pair = [&](int init, int nit1, int nit2) {
             a.job[0] = {L_.rhs1, L_.sol1, nit1, 0};
             a.job[1] = {L_.rhs2, L_.sol2, nit2, 1};
             a.njobs = 2;
             a.initialize = init;
-            if (pair_solves_)
-            {
-                EI_TIMED(1, EI_LAUNCH(eicos_solve_kkt_pair, tile_solve_kkt<2>, tiles, threads1, smem_prog_[1], st, a));
-                stt.solve_launches++;
-            }
-            else
-            { // (diagnostic switch) the same two solves as two one-job launches
-                EI_TIMED(1, EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt<1>, tiles, threads1, smem_prog_[0], st, a));
-                a.job[0] = a.job[1];
-                EI_TIMED(1, EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt<1>, tiles, threads1, smem_prog_[0], st, a));
-                stt.solve_launches += 2;
-            }
+            EI_TIMED(1, EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt, tiles, 2, threads1, smem_prog_, st, a));
+            stt.solve_launches++;
             stt.solve_launch_tiles += (long long)tiles * 2;
         };
         auto kkt_rhs2 = [&](int nitrow) {
             a.job[0] = {L_.rhs2, L_.sol2, nitrow, 1};
             a.njobs = 1;
             a.initialize = 0;
-            EI_TIMED(1, EI_LAUNCH(eicos_solve_kkt, tile_solve_kkt<1>, tiles, threads1, smem_prog_[0], st, a));
+            EI_TIMED(1, EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt, tiles, 1, threads1, smem_prog_, st, a));
             stt.solve_launches++;
             stt.solve_launch_tiles += tiles;
         };
@@ -605,7 +580,7 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
         for (int it = 0; it <= Settings::iter_max + 1; it++)
         {
             be::zero(active_count_, sizeof(unsigned int), st);
-            EI_TIMED(2, EI_LAUNCH(eicos_residuals, tile_resid, tiles, threads1, smem_prog_[0], st, a));
+            EI_TIMED(2, EI_LAUNCH(eicos_residuals, tile_resid, tiles, threads1, smem_prog_, st, a));
             EI_TIMED(2, EI_LAUNCH(eicos_iter_head, tile_head, tiles, threads, smem_common_, st, a));
             stt.ipm_iterations++;
             be::d2h(host_pinned_, active_count_, sizeof(unsigned int), st);
@@ -751,7 +726,7 @@ void Engine::debug_factor_init(int batch, const double *d_c, const double *d_h, 
     a.njobs = 2;
     a.job[0] = {L_.rhs1, L_.sol1, J_NIT1, 0};
     a.job[1] = {L_.rhs2, L_.sol2, J_NIT2, 1};
-    EI_LAUNCH(eicos_solve_kkt_pair, tile_solve_kkt<2>, tiles, threads1, smem_prog_[1], st, a);
+    EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt, tiles, 2, threads1, smem_prog_, st, a);
     be::sync(st);
     // gather rows back to instance-major host arrays; L comes back in CSC order
     const size_t tile_doubles = (size_t)L_.rows_total * TILE;

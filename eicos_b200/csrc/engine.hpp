@@ -114,8 +114,7 @@ class Engine
     unsigned int *host_pinned_ = nullptr;
     int *moves_dev_ = nullptr, *status_host_ = nullptr, *moves_host_ = nullptr; // active-set compaction
     bool compaction_ = true;
-    bool pair_solves_ = true; // the two independent solves of an iteration in one pass over L (EICOS_PAIR_SOLVES=0: two launches)
-    size_t smem_factor_ = 0, smem_common_ = 0, smem_prog_[2] = {0, 0}; // factor kernel / vector kernels / solveKKT + residual kernels (NR = 1, 2)
+    size_t smem_factor_ = 0, smem_common_ = 0, smem_prog_ = 0; // factor kernel / vector kernels / solveKKT + residual kernels
     int xrows_factor_ = 0; // shared-memory rows behind the FIFO ring in the factor kernel (slots + column buffers)
     std::vector<void *> owned_; // device allocations holding pattern data
     // positions of value arrays that upload_values() rewrites

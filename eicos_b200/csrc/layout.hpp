@@ -87,19 +87,11 @@ struct Layout
     int irows_total;                // integer rows (J_COUNT)
 };
 
-// index of a materialised mat-vec load list (DevPattern::mv_ld1)
-enum LdVariant : int
-{
-    LDV_SOL1 = 0, // set 0: rhs1 / sol1
-    LDV_SOL2 = 1, // set 1: rhs2 / sol2
-    LDV_HEAD = 2  // computeResiduals (chb, w, s)
-};
-
-// one pipe-form row program on the device (streams.hpp: Program)
-struct DevProgram
+// one program of the FMA machine on the device (machine.hpp: MachineCode)
+struct DevMachine
 {
     const int *ops;
-    int nchunks, nld;
+    int nchunks;
 };
 
 enum ConeParam : int
@@ -114,16 +106,14 @@ struct DevPattern
     const int *cone_dim, *cone_k, *cone_q; // per cone: dimension, first expanded index, first q row
     const int *zk;                         // compact z index -> expanded index (load / store only)
     const double *xeq, *Aeq, *GeqE;        // equilibration vectors (GeqE is expanded, 1 in the slots)
-    // Row programs (streams.hpp), index = NR - 1, and their load lists, materialised per use (absolute
-    // rows of the tile): a job set is (rhs1, sol1) with work vectors xw / dxr / e (set 0) or (rhs2, sol2)
-    // with xw2 / dxr2 / e2 (set 1).  One-job lists: [set][first solve | refinement round]; pair lists (both
-    // sets in one pass): [first solve | refinement round].  The backward sweep of a first solve runs the
-    // plain program bwp, a refinement round the accumulating program bw.
-    DevProgram fw[2], bw[2], bwp[2], mv[2];
-    const int *fw_ld1[2][2], *bw_ld1[2][2], *mv_ld1[3];
-    const int *fw_ld2[2], *bw_ld2[2], *mv_ld2;
+    // Machine programs (machine.hpp, streams.cpp) and their load lists, materialised per use (absolute rows
+    // of the tile): a job set is (rhs1, sol1) with work vectors xw / dxr / e (set 0) or (rhs2, sol2) with
+    // xw2 / dxr2 / e2 (set 1); [set][first solve | refinement round].  The backward sweep of a first solve
+    // runs the plain program bwp, a refinement round the accumulating program bw.
+    DevMachine fw, bw, bwp, mv, rs;
+    const int *fw_ld[2][2], *bw_ld[2][2], *mv_ld[2], *rs_ld;
     int mv_rows;
-    int sw_rows[2]; // shared-memory rows behind PR_SLOT0 the programs of NR = 1 / 2 use
+    int sw_rows; // shared-memory rows behind M_ROW_SLOT0 the programs use
     // factor program (FIFO form)
     const int *fa, *fa_ld;
     int fa_nld, fa_slots;

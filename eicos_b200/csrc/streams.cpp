@@ -3,6 +3,8 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -94,512 +96,263 @@ struct FifoSim
     }
 };
 
-// Shared-memory slots for the values of a sweep, Belady style: a value gets a slot when it is
-// produced; when none is free the live value whose next use is furthest away loses its slot (it is
-// still at home in global memory).  Use times are step numbers of the sweep.
-struct SlotCache
-{
-    const std::vector<ivec> &uses;
-    ivec holder, slot_of, ptr;
-    int top = 0;
-    SlotCache(int slots, const std::vector<ivec> &u) : uses(u), holder(slots, -1), slot_of(u.size(), -1), ptr(u.size(), 0) {}
-    int next_use(int v) const { return ptr[v] < (int)uses[v].size() ? uses[v][ptr[v]] : INT32_MAX; }
-    void used(int v)
-    {
-        ptr[v]++;
-        if (ptr[v] == (int)uses[v].size() && slot_of[v] >= 0)
-        {
-            holder[slot_of[v]] = -1;
-            slot_of[v] = -1;
-        }
-    }
-    int alloc(int v)
-    {
-        if (next_use(v) == INT32_MAX)
-            return -1;
-        int s = -1;
-        for (int q = 0; q < (int)holder.size() && s < 0; q++)
-            if (holder[q] < 0)
-                s = q;
-        if (s < 0)
-        {
-            int far = -1;
-            for (int q = 0; q < (int)holder.size(); q++)
-                if (far < 0 || next_use(holder[q]) > next_use(holder[far]))
-                    far = q;
-            if (far < 0 || next_use(holder[far]) <= next_use(v))
-                return -1;
-            slot_of[holder[far]] = -1;
-            s = far;
-        }
-        holder[s] = v;
-        slot_of[v] = s;
-        top = std::max(top, s + 1);
-        return s;
-    }
-};
+// ------------------------------------------------------------------ machine programs (machine.hpp)
 
-// ------------------------------------------------------------------ pipe-form row programs (streams.hpp)
-int field(int row)
+// ---- forward sweep  xw = L^-1 P rhs, rows of L in dot form in ascending column order (the summation
+// order of Eigen's column-oriented forward substitution).  L is stored once, column-major; the row-order
+// walk is just the order of the load list.  Row i:  x_i = rhs[pinv i] - sum_k L(i,k) x_k, one operation per
+// entry, chained through the partial sum.  Selectors: 1 = right-hand side (KKT order), 3 = xw (out vector).
+void build_forward(const Symbolic &S, const Layout &L, MProgram &P)
 {
-    if (row < 0 || row >= PR_MAX_ROWS)
-        throw std::logic_error("row program: shared-memory row out of range");
-    return row << PR_FIELD_SHIFT;
-}
-
-// Host model of the data ring and writer of the record stream.  A record is opened with begin(),
-// makes its pops, and is closed with end(), which derives the acquire / release counts from the
-// pops made in between.
-struct Emitter
-{
-    Program &P;
-    const int NR;
-    int npop = 0, released = 0;
-    int rec_first = 0;
-    struct RelAt
-    {
-        size_t word;
-        int fence_bit;
-    };
-    std::vector<RelAt> rel_at; // release number -> record word holding its flags
-    Emitter(Program &p, int nr) : P(p), NR(nr) {}
-
-    int pop(int sel, int row)
-    {
-        if (row < 0 || row > LD_ROW_MASK2)
-            throw std::logic_error("load list: row out of range");
-        P.ld.push_back((sel << LD_SEL_SHIFT) | row);
-        return npop++ % RING_ROWS;
-    }
-    void pad()
-    {
-        P.ld.push_back(LD_NONE);
-        npop++;
-        P.pads++;
-    }
-    bool aligned() const { return NR == 1 || npop % 2 == 0; }
-    // vector pop: one row per job, adjacent ring rows (the caller may first hoist a single pop to align)
-    int vpop(int sel, int row)
-    {
-        if (!aligned())
-            pad();
-        const int r = pop(sel, row);
-        if (NR == 2)
-            pop(sel + LD_JOB_B, row);
-        return r;
-    }
-    void begin() { rec_first = npop; }
-    // May a value whose producing record ended when `prod_after` pops had been made be loaded through the
-    // ring as the next pop?  Its group is refilled when group G - RING_GROUPS is released, which happens
-    // at the end of the record that makes pop 8 (G - RING_GROUPS + 1) - 1; the producer must be an
-    // earlier record.  (The first RING_GROUPS groups are issued before the program starts.)
-    bool far_safe(int prod_after) const
-    {
-        const int at = aligned() ? npop : npop + 1;
-        const int G = at / RING_GROUP;
-        return G >= RING_GROUPS && prod_after < RING_GROUP * (G - RING_GROUPS + 1);
-    }
-    // the refill of the group the next pop lands in must be preceded by a proxy fence
-    void fence_next_pop()
-    {
-        const int at = aligned() ? npop : npop + 1;
-        const int G = at / RING_GROUP;
-        const RelAt &r = rel_at.at(G - RING_GROUPS);
-        P.ops[r.word] |= r.fence_bit;
-    }
-    void end(int w0, int w1, int w2, int w3, bool header)
-    {
-        const int nacq = (npop + RING_GROUP - 1) / RING_GROUP - (rec_first + RING_GROUP - 1) / RING_GROUP;
-        const int nrel = npop / RING_GROUP - released;
-        if (nacq > 3 || nrel > 3 || nacq < 0 || nrel < 0)
-            throw std::logic_error("row program: a record spans too many ring groups");
-        const size_t at = P.ops.size();
-        if (header)
-            w0 |= (nacq << PH_NACQ_SHIFT) | (nrel << PH_NREL_SHIFT);
-        else
-        {
-            if (w0 & ((1 << PR_FIELD_SHIFT) - 1))
-                throw std::logic_error("row program: flag bits of a tail record are in use");
-            w0 |= (nacq << PT_NACQ_SHIFT) | (nrel << PT_NREL_SHIFT);
-        }
-        for (int k = 0; k < nrel; k++)
-            rel_at.push_back({at, header ? PH_FENCE : PT_FENCE});
-        released += nrel;
-        P.ops.push_back(w0);
-        P.ops.push_back(w1);
-        P.ops.push_back(w2);
-        P.ops.push_back(w3);
-    }
-    void finish(int slot_rows)
-    {
-        begin();
-        end(PH_END, 0, 0, 0, true);
-        P.nchunks = (int)((P.ops.size() + OPS_CHUNK_WORDS - 1) / OPS_CHUNK_WORDS);
-        while (P.ops.size() % OPS_CHUNK_WORDS)
-            P.ops.push_back(0);
-        P.ops.insert(P.ops.end(), OPS_CHUNK_WORDS, 0); // the record look-ahead may read one record past END
-        P.nld = (int)P.ld.size();
-        while (P.ld.size() % RING_ROWS)
-            P.ld.push_back(LD_NONE);
-        P.ld.insert(P.ld.end(), 2 * RING_ROWS, LD_NONE); // the lanes read their next word two rounds ahead
-        P.slot_rows = slot_rows;
-    }
-};
-
-// one multiply-add of a dot-form row: the L value (single pop) and the gathered vector value
-struct PairSrc
-{
-    int lrow;    // workspace row of the L value
-    int value;   // index of the gathered value (slot cache / producer bookkeeping)
-    int far_sel; // load-list selector of the vector the value lives in
-    int far_row; // its row inside that vector
-};
-
-// Emits one dot-form row: header record (with up to `ninl` pairs inline) + tail records.
-//   pre()      makes the header's own pops (right-hand side, pivot, ...); called once the header is open
-//   header(rp) closes the header record: rp.w0 = tail counts / form flags for word 0, rp.inl = inline pair words
-struct RowPairs
-{
-    int inl[2] = {PR_PAD_PAIR, PR_PAD_PAIR};
-    int w0 = 0;
-};
-
-template <class Pre, class Header>
-void emit_row(Emitter &E, SlotCache &cache, const ivec &prod, const std::vector<PairSrc> &pairs, int ninl, Program &P,
-              Pre pre, Header header)
-{
-    const int cnt = (int)pairs.size(), NR = E.NR;
-    // kind of every gathered value: 0 slot, 1 far (through the ring), 2 direct (straight from global memory).
-    // far_safe() only gets easier as the pop position advances, so testing at the current position is safe.
-    ivec kind(cnt);
-    bool slow = false;
-    for (int q = 0; q < cnt; q++)
-    {
-        kind[q] = cache.slot_of[pairs[q].value] >= 0 ? 0 : (E.far_safe(prod[pairs[q].value]) ? 1 : 2);
-        slow = slow || kind[q] == 2;
-    }
-    const auto operand = [&](int q) -> int { // field of pair q's gathered value
-        const PairSrc &pr = pairs[q];
-        int f;
-        if (kind[q] == 0)
-            f = field(PR_SLOT0 + NR * cache.slot_of[pr.value]);
-        else
-        {
-            if (!E.aligned())
-                E.pad();
-            if (!E.far_safe(prod[pr.value]))
-                throw std::logic_error("row program: far operand not safe at emission");
-            E.fence_next_pop();
-            f = field(E.vpop(pr.far_sel, pr.far_row));
-            P.far++;
-        }
-        cache.used(pr.value);
-        return f;
-    };
-    E.begin();
-    RowPairs rp;
-    if (slow)
-    { // one record per pair: [L field | flags, 0 = field in word 2 / 1 = global row in word 2, value, -]
-        if (cnt > PH_NTAIL_MASK)
-            throw std::logic_error("row program: row too long for the slow form");
-        pre();
-        rp.w0 = PH_SLOW | cnt;
-        header(rp);
-        for (int q = 0; q < cnt; q++)
-        {
-            const PairSrc &pr = pairs[q];
-            E.begin();
-            const int lf = field(E.pop(0, pr.lrow));
-            if (kind[q] == 2)
-            {
-                cache.used(pr.value);
-                P.direct++;
-                E.end(lf, 1, pr.far_row, 0, false);
-            }
-            else
-                E.end(lf, 0, operand(q), 0, false);
-        }
-        return;
-    }
-    int q = 0;
-    const auto pair_word = [&](int qq, int lfield = -1) {
-        const int lf = lfield >= 0 ? lfield : field(E.pop(0, pairs[qq].lrow));
-        const int of = operand(qq);
-        return lf | (of << 16);
-    };
-    const int rest = cnt > ninl ? cnt - ninl : 0;
-    const int n4 = rest / 4, r4 = rest % 4;
-    // remainder 1..2 -> one 2-pair record; remainder 3 -> one more 4-pair record
-    const int ntail4 = n4 + (r4 == 3 ? 1 : 0), has2 = (r4 == 1 || r4 == 2) ? 1 : 0;
-    if (ntail4 > PH_NTAIL_MASK)
-        throw std::logic_error("row program: row too long");
-    rp.w0 = ntail4 | (has2 ? PH_HAS2 : 0) | (cnt > 0 && ninl > 0 ? PH_INLINE : 0);
-    // NR = 2: vector pops want an even ring position; an L pop made first realigns it without padding
-    int hoisted = -1;
-    if (!E.aligned() && cnt > 0 && ninl > 0)
-        hoisted = field(E.pop(0, pairs[0].lrow));
-    pre();
-    for (int k = 0; k < ninl && q < cnt; k++, q++)
-        rp.inl[k] = pair_word(q, k == 0 ? hoisted : -1);
-    header(rp);
-    for (int t = 0; t < ntail4; t++)
-    {
-        E.begin();
-        int w[4];
-        for (int k = 0; k < 4; k++)
-            w[k] = q < cnt ? pair_word(q++) : PR_PAD_PAIR;
-        E.end(w[0], w[1], w[2], w[3], false);
-    }
-    if (has2)
-    {
-        E.begin();
-        int w[2];
-        for (int k = 0; k < 2; k++)
-            w[k] = q < cnt ? pair_word(q++) : PR_PAD_PAIR;
-        E.end(w[0], w[1], 0, 0, false);
-    }
-}
-
-// ---- forward sweep  xw = L^-1 P rhs, rows of L in elimination order, dot form in ascending column
-// order (the summation order of Eigen's column-oriented forward substitution).  L is stored once,
-// column-major; the row-order walk is just the order of the load list.
-// Load-list selectors: 1 = right-hand side (KKT order), 3 = the work vector xw (far gathers).
-void build_forward(const Symbolic &S, const Layout &L, int NR, int max_values, Program &P)
-{
-    std::vector<ivec> uses(S.N);
-    for (int k = 0; k < S.N; k++)
-        uses[k].assign(S.Li.begin() + S.Lp[k], S.Li.begin() + S.Lp[k + 1]);
-    SlotCache cache(max_values, uses);
-    Emitter E(P, NR);
-    ivec prod(S.N, 0);
-    std::vector<PairSrc> pairs;
+    ivec xval(S.N, -1);
     for (int i = 0; i < S.N; i++)
     {
-        pairs.clear();
-        for (int t = S.Lr.p[i]; t < S.Lr.p[i + 1]; t++)
-            pairs.push_back({L.Lx + S.Lr.v[t], S.Lr.j[t], 3, S.Lr.j[t]});
-        int rhs_field = 0;
-        size_t hdr_at = 0;
-        emit_row(
-            E, cache, prod, pairs, 2, P, [&]() { rhs_field = field(E.vpop(1, S.pinv[i])); },
-            [&](const RowPairs &rp) {
-                hdr_at = P.ops.size();
-                E.end(rp.w0, rhs_field, rp.inl[0], rp.inl[1], true);
-            });
-        const int s = cache.alloc(i);
-        P.ops[hdr_at + 1] |= field(s >= 0 ? PR_SLOT0 + NR * s : PR_TRASH) << 16;
-        prod[i] = E.npop;
+        const int t0 = S.Lr.p[i], cnt = S.Lr.p[i + 1] - t0;
+        int prev = -1;
+        for (int q = 0; q < std::max(cnt, 1); q++)
+        {
+            MOp op;
+            op.c = q == 0 ? MSrc::load(1, S.pinv[i]) : MSrc::value(prev);
+            if (cnt > 0)
+            {
+                op.a = MSrc::load(0, L.Lx + S.Lr.v[t0 + q]);
+                op.b = MSrc::value(xval[S.Lr.j[t0 + q]]);
+            }
+            op.dst = prev = P.new_value(3, i);
+            if (q == std::max(cnt, 1) - 1)
+            {
+                op.flags |= MF_OUT;
+                op.out_row = i;
+            }
+            P.ops.push_back(op);
+        }
+        xval[i] = prev;
     }
-    E.finish(NR * cache.top);
 }
 
 // ---- backward sweep  out = P' L^-T D^-1 xw, columns in reverse elimination order (dot form, Eigen's
-// order); results land in KKT order.  The home of a finished entry is its output row.
-// accumulate: the program also loads the row of the solution it adds its result to (refinement
-// rounds); the plain program of the first solve leaves those loads out.
-// Load-list selectors: 1 = output vector (far gathers), 2 = accumulated solution, 3 = xw.
-void build_backward(const Symbolic &S, const Layout &L, int NR, int max_values, Program &P, bool accumulate)
+// order); results land in KKT order.  Column k:  v = (1/d_k) xw_k;  v -= L(i,k) x_i for the rows of the
+// column; out[pinv k] = v.  accumulate: the last operation of a column also hands the row of the accumulated
+// solution to the finish functor (x += v for the instances that continue refining).
+// Selectors: 1 = output vector, 2 = accumulated solution, 3 = xw.
+void build_backward(const Symbolic &S, const Layout &L, MProgram &P, bool accumulate)
 {
-    std::vector<ivec> uses(S.N); // value i is used by the columns of row i, latest column first
-    for (int i = 0; i < S.N; i++)
-        for (int t = S.Lr.p[i + 1] - 1; t >= S.Lr.p[i]; t--)
-            uses[i].push_back(S.N - 1 - S.Lr.j[t]);
-    for (const ivec &u : uses)
-        if (!std::is_sorted(u.begin(), u.end()))
-            throw std::logic_error("rows of L must have ascending columns");
-    SlotCache cache(max_values, uses);
-    Emitter E(P, NR);
-    ivec prod(S.N, 0);
-    std::vector<PairSrc> pairs;
+    ivec xval(S.N, -1);
     for (int k = S.N - 1; k >= 0; k--)
     {
-        const int o = S.pinv[k];
-        pairs.clear();
-        for (int u = S.Lp[k]; u < S.Lp[k + 1]; u++)
-            pairs.push_back({L.Lx + u, S.Li[u], 1, S.pinv[S.Li[u]]});
-        int dfield = 0, xfield = 0, afield = field(PR_ZERO);
-        bool dpopped = false;
-        size_t hdr_at = 0;
-        emit_row(
-            E, cache, prod, pairs, 0, P,
-            [&]() {
-                if (!E.aligned()) // the single pop first realigns the ring for the vector pops
-                {
-                    dfield = field(E.pop(0, L.Dinv + k));
-                    dpopped = true;
-                }
-                xfield = field(E.vpop(3, k));
+        const int o = S.pinv[k], u0 = S.Lp[k], cnt = S.Lp[k + 1] - u0;
+        int prev = -1;
+        for (int q = 0; q <= cnt; q++)
+        {
+            MOp op;
+            if (q == 0)
+            { // Eigen: diag.inverse() * x  (a product: 1/d * xw + (-0))
+                op.c = MSrc::negzero();
+                op.a = MSrc::load(0, L.Dinv + k);
+                op.b = MSrc::load(3, k);
+                op.flags |= MF_POS;
+            }
+            else
+            {
+                op.c = MSrc::value(prev);
+                op.a = MSrc::load(0, L.Lx + u0 + q - 1);
+                op.b = MSrc::value(xval[S.Li[u0 + q - 1]]);
+            }
+            op.dst = prev = P.new_value(1, o);
+            if (q == cnt)
+            {
+                op.flags |= MF_OUT;
+                op.out_row = o;
                 if (accumulate)
-                    afield = field(E.vpop(2, o));
-                if (!dpopped)
-                    dfield = field(E.pop(0, L.Dinv + k));
-            },
-            [&](const RowPairs &rp) {
-                hdr_at = P.ops.size();
-                E.end(rp.w0, dfield | (xfield << 16), afield << 16, o, true);
-            });
-        const int s = cache.alloc(k);
-        P.ops[hdr_at + 2] |= field(s >= 0 ? PR_SLOT0 + NR * s : PR_TRASH);
-        prod[k] = E.npop;
+                {
+                    op.flags |= MF_FIN | (FIN_ACC << MF_KIND_SHIFT);
+                    op.x3 = MSrc::load(2, o);
+                }
+            }
+            P.ops.push_back(op);
+        }
+        xval[k] = prev;
     }
-    E.finish(NR * cache.top);
 }
 
-// ---- KKT mat-vec program (streams.hpp).  Rows = x, y and z rows (the two expansion slots of every
-// second-order cone excepted) in elimination order; the pairs of a row keep the order of the
-// CSC / CSR data (G entries before A entries in an x row).
-// Load-list selectors: 1 = vector of extra 0 (rhs | c,b,h), 2 = operand vector, 3 = vector of extra 1
-// (LP scalings | s; one row per instance even in a pair program).
-void push_double(ivec &ops, double v)
+// ---- the rows of the KKT mat-vecs: x, y and z rows (the two expansion slots of every second-order cone
+// excepted) in elimination order; the entries of a row keep the order of the CSC / CSR data (G entries
+// before A entries in an x row).
+struct MatvecRows
 {
-    int32_t w[2];
-    std::memcpy(w, &v, sizeof(v));
-    ops.push_back(w[0]);
-    ops.push_back(w[1]);
-}
-
-void build_matvec(const Symbolic &S, const Layout &L, int NR, int max_values, Program &P, int &mv_rows, bool pim)
+    ivec order;
+    std::vector<std::vector<std::pair<int, double>>> ent; // per K row: (K column, shared coefficient)
+    std::vector<ivec> crow;                                // ... and the workspace row of the per-instance coefficient (pim)
+};
+void matvec_rows(const Symbolic &S, const Layout &L, MatvecRows &R)
 {
     const int n = S.n, p = S.p, zb = S.n + S.p;
-    ivec order;
     for (int r = 0; r < zb; r++)
-        order.push_back(r);
+        R.order.push_back(r);
     for (int i = 0; i < S.m; i++)
-        order.push_back(zb + S.zk[i]); // K-space row of z entry i (expanded index)
-    const int nrows = (int)order.size();
-    std::sort(order.begin(), order.end(), [&](int a, int b) { return S.P[a] < S.P[b]; });
-    std::vector<std::vector<std::pair<int, double>>> ent(S.N);
-    std::vector<ivec> crow(S.N); // per entry: workspace row of the per-instance coefficient (pim)
+        R.order.push_back(zb + S.zk[i]); // K-space row of z entry i (expanded index)
+    std::sort(R.order.begin(), R.order.end(), [&](int a, int b) { return S.P[a] < S.P[b]; });
+    R.ent.assign(S.N, {});
+    R.crow.assign(S.N, {});
     for (int j = 0; j < n; j++)
     {
         for (int k = S.G.p[j]; k < S.G.p[j + 1]; k++)
         {
-            ent[j].push_back({zb + S.zk[S.G.i[k]], S.G.x[k]});
-            crow[j].push_back(L.Gx + k);
+            R.ent[j].push_back({zb + S.zk[S.G.i[k]], S.G.x[k]});
+            R.crow[j].push_back(L.Gx + k);
         }
         for (int k = S.A.p[j]; k < S.A.p[j + 1]; k++)
         {
-            ent[j].push_back({n + S.A.i[k], S.A.x[k]});
-            crow[j].push_back(L.Ax + k);
+            R.ent[j].push_back({n + S.A.i[k], S.A.x[k]});
+            R.crow[j].push_back(L.Ax + k);
         }
     }
     for (int i = 0; i < p; i++)
         for (int t = S.Ar.p[i]; t < S.Ar.p[i + 1]; t++)
         {
-            ent[n + i].push_back({S.Ar.j[t], S.A.x[S.Ar.v[t]]});
-            crow[n + i].push_back(L.Ax + S.Ar.v[t]);
+            R.ent[n + i].push_back({S.Ar.j[t], S.A.x[S.Ar.v[t]]});
+            R.crow[n + i].push_back(L.Ax + S.Ar.v[t]);
         }
     for (int i = 0; i < S.m; i++)
         for (int t = S.Gr.p[i]; t < S.Gr.p[i + 1]; t++)
         {
-            ent[zb + S.zk[i]].push_back({S.Gr.j[t], S.G.x[S.Gr.v[t]]});
-            crow[zb + S.zk[i]].push_back(L.Gx + S.Gr.v[t]);
+            R.ent[zb + S.zk[i]].push_back({S.Gr.j[t], S.G.x[S.Gr.v[t]]});
+            R.crow[zb + S.zk[i]].push_back(L.Gx + S.Gr.v[t]);
         }
-    std::vector<ivec> uses(S.N);
-    for (int t = 0; t < nrows; t++)
+}
+int mv_kind(const Symbolic &S, int r)
+{
+    const int zb = S.n + S.p;
+    return r < S.n ? MV_X : (r < zb ? MV_Y : (r < zb + S.l ? MV_Z : MV_ZC));
+}
+
+// ---- residual of the iterative refinement  e = rhs - Ktrue x  (src/eicos.cpp:1511-1576), LP part:
+//   row r:  v = rhs_r - sum_k coefficient_k x_k;  x rows: v -= delta x_r;  y rows: v += delta x_r;
+//   LP z rows: v += delta x_r, v += w_r^2 x_r (x_r alone while the scalings are the identity: MF_AONE);
+//   rows of second-order cones stop after the sum (the cone block is applied cone by cone afterwards).
+// The vector x is an external value per row: gathered once, parked in a slot while it has further uses.
+// Selectors: 1 = rhs, 2 = x, 3 = LP scalings, 4 = e (out vector).
+void build_matvec(const Symbolic &S, const Layout &L, MProgram &P, int &mv_rows, bool pim)
+{
+    MatvecRows R;
+    matvec_rows(S, L, R);
+    const int zb = S.n + S.p;
+    const double delta = Settings::deltastat;
+    P.keep_loads = true;
+    ivec xv(S.N);
+    for (int c = 0; c < S.N; c++)
+        xv[c] = P.new_value(2, c);
+    for (int r : R.order)
     {
-        const int r = order[t];
-        uses[r].push_back(t);
-        for (auto &e : ent[r])
-            uses[e.first].push_back(t);
+        const int kind = mv_kind(S, r);
+        std::vector<MOp> row;
+        for (size_t q = 0; q < R.ent[r].size(); q++)
+        {
+            MOp op;
+            op.a = pim ? MSrc::load(0, R.crow[r][q]) : MSrc::constant(R.ent[r][q].second);
+            op.b = MSrc::value(xv[R.ent[r][q].first]);
+            row.push_back(op);
+        }
+        if (kind != MV_ZC)
+        {
+            MOp op;
+            op.a = MSrc::constant(kind == MV_X ? delta : -delta);
+            op.b = MSrc::value(xv[r]);
+            row.push_back(op);
+        }
+        if (kind == MV_Z)
+        {
+            MOp op;
+            op.a = MSrc::load(3, r - zb);
+            op.b = MSrc::value(xv[r]);
+            op.flags |= MF_POS | MF_AONE;
+            row.push_back(op);
+        }
+        if (row.empty())
+            row.push_back(MOp());
+        int prev = -1;
+        for (size_t q = 0; q < row.size(); q++)
+        {
+            MOp &op = row[q];
+            op.c = q == 0 ? MSrc::load(1, r) : MSrc::value(prev);
+            op.dst = prev = P.new_value(4, r);
+            if (q + 1 == row.size())
+            {
+                op.flags |= MF_OUT;
+                op.out_row = r;
+                if (kind != MV_ZC)
+                    op.flags |= MF_FIN | (FIN_ABSMAX << MF_KIND_SHIFT);
+            }
+            P.ops.push_back(op);
+        }
     }
-    for (ivec &u : uses)
-        std::sort(u.begin(), u.end());
-    SlotCache cache(max_values, uses);
-    Emitter E(P, NR);
-    // resolves one operand: (operand field, keep field)
-    const auto operand = [&](int c) {
-        std::pair<int, int> r;
-        if (cache.slot_of[c] >= 0)
-        {
-            r = {field(PR_SLOT0 + NR * cache.slot_of[c]), field(PR_TRASH)};
-            cache.used(c);
-        }
-        else
-        {
-            r.first = field(E.vpop(2, c));
-            cache.used(c);
-            const int s = cache.alloc(c);
-            r.second = field(s >= 0 ? PR_SLOT0 + NR * s : PR_TRASH);
-        }
-        return r;
-    };
-    const int pad_pair = field(PR_ZERO) | (field(PR_TRASH) << 16);
-    for (int t = 0; t < nrows; t++)
+    mv_rows = (int)R.order.size();
+}
+
+// ---- computeResiduals (src/eicos.cpp:643-689): rx = -G'z - A'y - tau c, ry = A x - tau b, rz = s + G x - tau h
+// and the sums of updateStatistics, which the finish functor (tile_program.hpp: ResidFin) collects:
+//   x row:  v = 0 - sum;  PRE (hresx += v^2);  v -= tau c_j  -> out;  FIN (c_j, x_j)
+//   y row:  v = 0 + sum;  PRE;  v -= tau b_i -> out;  FIN (b_i, y_i)
+//   z row:  v = s_i (FIRST: s_i, z_i);  v += sum;  PRE;  v -= tau h_i -> out;  FIN (h_i, z_i)
+// Selectors: 1 = [c | b | h], 2 = [x | y | z], 3 = s, 4 = r (out vector), 5 = scalar rows.
+void build_resid(const Symbolic &S, const Layout &L, MProgram &P, bool pim)
+{
+    MatvecRows R;
+    matvec_rows(S, L, R);
+    const int zb = S.n + S.p;
+    P.keep_loads = true;
+    ivec xv(S.N);
+    for (int c = 0; c < S.N; c++)
+        xv[c] = P.new_value(2, c);
+    // tau: copied into a slot once (an A operand of every row)
+    const int tau_home = P.new_value(5, S_TAU);
+    const int tau = P.new_value(-1, 0);
     {
-        const int r = order[t], cnt = (int)ent[r].size();
-        const int kind = r < n ? MV_X : (r < zb ? MV_Y : (r < zb + S.l ? MV_Z : MV_ZC));
-        E.begin();
-        int ex1 = field(PR_ZERO);
-        bool ex1_popped = false;
-        if (kind >= MV_Z && !E.aligned())
-        {
-            ex1 = field(E.pop(3, r - zb));
-            ex1_popped = true;
-        }
-        const int ex0 = field(E.vpop(1, r));
-        const auto own = operand(r);
-        if (kind >= MV_Z && !ex1_popped)
-            ex1 = field(E.pop(3, r - zb));
-        const int per = pim ? 2 : 4; // pairs per full group
-        const int ng = cnt / per, rem = cnt % per;
-        // shared coefficients: remainder 1..2 -> a 2-pair group, 3 -> one more full group; pim: remainder 1 -> one more record
-        const int ngroups = pim ? ng + (rem ? 1 : 0) : ng + (rem == 3 ? 1 : 0);
-        const int has2 = !pim && (rem == 1 || rem == 2);
-        if (ngroups > PH_NTAIL_MASK)
-            throw std::logic_error("mat-vec program: row too long");
-        E.end(ngroups | (has2 ? PH_HAS2 : 0) | (kind << PH_KIND_SHIFT), ex0 | (own.first << 16), own.second | (ex1 << 16), r, true);
-        int q = 0;
-        if (pim)
-        { // [coefficient field | operand field << 16, keep field] x 2 per record
-            for (int g = 0; g < ngroups; g++)
-            {
-                E.begin();
-                int w[4];
-                for (int k = 0; k < 2; k++)
-                {
-                    if (q >= cnt)
-                    {
-                        w[2 * k] = PR_PAD_PAIR;
-                        w[2 * k + 1] = field(PR_TRASH);
-                        continue;
-                    }
-                    const int cf = field(E.pop(0, crow[r][q]));
-                    const auto o = operand(ent[r][q].first);
-                    w[2 * k] = cf | (o.first << 16);
-                    w[2 * k + 1] = o.second;
-                    q++;
-                }
-                E.end(w[0], w[1], w[2], w[3], false);
-            }
-            continue;
-        }
-        const auto group = [&](int np) { // np pairs + their coefficients
-            E.begin();
-            int w[4] = {pad_pair, pad_pair, 0, 0};
-            double c[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int k = 0; k < np; k++)
-            {
-                w[k] = pad_pair;
-                if (q < cnt)
-                {
-                    const auto o = operand(ent[r][q].first);
-                    w[k] = o.first | (o.second << 16);
-                    c[k] = ent[r][q].second;
-                    q++;
-                }
-            }
-            E.end(w[0], w[1], w[2], w[3], false);
-            for (int k = 0; k < np; k++)
-                push_double(P.ops, c[k]);
-        };
-        for (int g = 0; g < ngroups; g++)
-            group(4);
-        if (has2)
-            group(2);
+        MOp op;
+        op.c = MSrc::value(tau_home);
+        op.dst = tau;
+        P.ops.push_back(op);
     }
-    mv_rows = nrows;
-    E.finish(NR * cache.top);
+    for (int r : R.order)
+    {
+        const int kind = mv_kind(S, r);
+        const bool zrow = kind >= MV_Z;
+        const int pre = kind == MV_X ? RS_PRE_X : (kind == MV_Y ? RS_PRE_Y : RS_PRE_Z);
+        const int fin = kind == MV_X ? RS_FIN_X : (kind == MV_Y ? RS_FIN_Y : RS_FIN_Z);
+        const size_t cnt = R.ent[r].size();
+        int prev = -1;
+        if (zrow)
+        { // v = s_i
+            MOp op;
+            op.c = MSrc::load(3, r - zb);
+            op.x3 = MSrc::value(xv[r]);
+            op.flags |= MF_FIN | ((cnt == 0 ? RS_FIRST_PRE_Z : RS_FIRST_Z) << MF_KIND_SHIFT);
+            op.dst = prev = P.new_value(4, r);
+            P.ops.push_back(op);
+        }
+        for (size_t q = 0; q < cnt; q++)
+        {
+            MOp op;
+            op.c = prev >= 0 ? MSrc::value(prev) : MSrc::zero();
+            op.a = pim ? MSrc::load(0, R.crow[r][q]) : MSrc::constant(R.ent[r][q].second);
+            op.b = MSrc::value(xv[R.ent[r][q].first]);
+            if (kind != MV_X)
+                op.flags |= MF_POS;
+            if (q + 1 == cnt)
+                op.flags |= MF_FIN | (pre << MF_KIND_SHIFT);
+            op.dst = prev = P.new_value(4, r);
+            P.ops.push_back(op);
+        }
+        MOp op; // the tau term
+        op.c = prev >= 0 ? MSrc::value(prev) : MSrc::zero();
+        op.a = MSrc::value(tau);
+        op.b = MSrc::load(1, r);
+        op.x3 = MSrc::value(xv[r]);
+        op.flags |= MF_OUT | MF_FIN | (fin << MF_KIND_SHIFT);
+        op.out_row = r;
+        op.dst = P.new_value(4, r);
+        P.ops.push_back(op);
+    }
 }
 
 // per K slot: row of the workspace holding the per-instance A / G value (per-instance-matrices mode), or -1
@@ -858,6 +611,7 @@ bool build_factor_fast(const Symbolic &S, const Layout &L, int max_slots, HostSt
 
 void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, int max_fa_slots, HostStreams &H, bool pim)
 {
+    constexpr int MACHINE_TUNE_SLOTS = 24; // = the engine's default budget (engine.cu: MAX_SW_SLOTS)
     H = HostStreams();
     H.workers = W;
     for (int k = 0; k < S.N; k++)
@@ -870,20 +624,41 @@ void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, 
     if (S.fma_count > MAX_FACTOR_UPDATES)
         throw std::runtime_error("pattern fills too much for the row-program factorisation (" + std::to_string(S.fma_count) +
                                  " Schur updates per factorisation; limit " + std::to_string(MAX_FACTOR_UPDATES) + ")");
-    for (int NR = 1; NR <= 2; NR++)
     {
-        const int maxv = std::max(1, std::min(max_sw_slots, (PR_MAX_ROWS - PR_SLOT0) / NR));
-        const char *dbg = std::getenv("EICOS_DBG_STARVE");
-        const int dm = dbg ? std::atoi(dbg) : 0;
-        build_forward(S, L, NR, dm & 1 ? 2 : maxv, H.fw[NR - 1]);
-        build_backward(S, L, NR, dm & 2 ? 2 : maxv, H.bw[NR - 1], true);
-        build_backward(S, L, NR, dm & 4 ? 2 : maxv, H.bwp[NR - 1], false);
-        build_matvec(S, L, NR, dm & 8 ? 2 : maxv, H.mv[NR - 1], H.mv_rows, pim);
-        for (const Program *q : {&H.fw[NR - 1], &H.bw[NR - 1], &H.bwp[NR - 1], &H.mv[NR - 1]})
-            H.sw_slots = std::max(H.sw_slots, q->slot_rows / NR);
+        const int slots = std::max(2, max_sw_slots);
+        MProgram pf, pb, pbp, pm, pr;
+        build_forward(S, L, pf);
+        build_backward(S, L, pb, true);
+        build_backward(S, L, pbp, false);
+        build_matvec(S, L, pm, H.mv_rows, pim);
+        build_resid(S, L, pr, pim);
+        const auto compile = [&](const char *name, const MProgram &p, MachineCode &c) {
+            // (diagnostics) EICOS_SCHED_WINDOW_<name> pins the scheduler window of one program
+            const std::string key = std::string("EICOS_SCHED_WINDOW_") + name;
+            if (const char *v = std::getenv(key.c_str()))
+            {
+                setenv("EICOS_SCHED_WINDOW", v, 1);
+                machine_compile(p, slots, c, MACHINE_TUNE_SLOTS);
+                unsetenv("EICOS_SCHED_WINDOW");
+            }
+            else
+                machine_compile(p, slots, c, MACHINE_TUNE_SLOTS);
+        };
+        compile("fw", pf, H.fw);
+        compile("bw", pb, H.bw);
+        compile("bwp", pbp, H.bwp);
+        compile("mv", pm, H.mv);
+        compile("rs", pr, H.rs);
+        for (const MachineCode *q : {&H.fw, &H.bw, &H.bwp, &H.mv, &H.rs})
+            H.sw_slots = std::max(H.sw_slots, q->slot_rows);
+        H.sw_far = H.fw.far + H.bwp.far;
+        if (std::getenv("EICOS_DBG_PROGRAMS"))
+            for (auto nq : {std::make_pair("fw", &H.fw), std::make_pair("bw", &H.bw), std::make_pair("bwp", &H.bwp),
+                            std::make_pair("mv", &H.mv), std::make_pair("rs", &H.rs)})
+                std::fprintf(stderr, "machine %s: ops %lld nop %lld bundles %d loads %d far %lld pads %lld spills %lld slots %d\n", nq.first,
+                             nq.second->nops, nq.second->nnop, nq.second->nbundles, nq.second->nld, nq.second->far, nq.second->pads,
+                             nq.second->spills, nq.second->slot_rows, nq.second->window);
     }
-    H.sw_far = H.fw[0].far + H.bw[0].far;
-    H.sw_direct = H.fw[0].direct + H.bw[0].direct;
     if (!build_factor_fast(S, L, max_fa_slots, H, pim))
         build_factor(S, L, max_fa_slots, H, pim);
 }
@@ -893,11 +668,11 @@ void refresh_stream_values(const Symbolic &S, const Layout &L, HostStreams &H, b
     HostStreams fresh;
     build_streams(S, L, H.workers, std::max(H.sw_slots, 1), std::max(H.fa_slots, 1), fresh, pim);
     H.fa_val.swap(fresh.fa_val);
-    for (int k = 0; k < 2; k++)
-    {
-        if (fresh.mv[k].ops.size() != H.mv[k].ops.size())
+    for (auto pq : {std::make_pair(&H.mv, &fresh.mv), std::make_pair(&H.rs, &fresh.rs)})
+    { // the mat-vec programs carry the shared coefficients inline
+        if (pq.second->ops.size() != pq.first->ops.size())
             throw std::logic_error("mat-vec program changed shape on a value refresh");
-        H.mv[k].ops.swap(fresh.mv[k].ops);
+        pq.first->ops.swap(pq.second->ops);
     }
 }
 

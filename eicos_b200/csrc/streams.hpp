@@ -24,6 +24,7 @@
 #pragma once
 
 #include "layout.hpp"
+#include "machine.hpp"
 #include "symbolic.hpp"
 
 #include <string>
@@ -55,64 +56,26 @@ static_assert(FIFO_SLOTS >= FIFO_AHEAD + 2, "ring = consumed group + slack group
 constexpr int LD_BASE_SHIFT = 30;
 constexpr int LD_ROW_MASK = (1 << 30) - 1;
 
-// ---- row programs of the solveKKT kernels (triangular sweeps, KKT mat-vec), "pipe" form.
-// One warp walks a stream of 16-byte records.  Two shared-memory pipes feed it, both filled by TMA
-// bulk copies (cp.async.bulk, completion on mbarriers) that the warp issues for itself:
-//   * the ops ring: OPS_CHUNKS chunks of 512 bytes of the record stream, refilled a chunk at a time;
-//   * the data ring: RING_ROWS rows (one row = the TILE doubles of one workspace row).  Lane j owns
-//     ring row j: whenever the consumer has finished with group g of RING_GROUP rows, the lanes of
-//     that group copy their next rows (load list word RING_ROWS further on) into place - one 512-byte
-//     bulk copy per lane, all eight in one warp instruction.  RING_ROWS - RING_GROUP rows are in flight
-//     ahead of the consumer.  The host simulates the ring while it compiles a program, so every
-//     operand field names its shared-memory row and the group acquire / release points are flag
-//     bits of the records.
-// Shared-memory rows: [0, RING_ROWS) ring, PR_ZERO (+1) rows of zeros, PR_TRASH (+1) where values
-// without a slot are dumped, PR_SLOT0.. the slots.  A FIELD is 16 bits: row << 9 (the byte offset of
-// the row for 512-byte rows); the low 9 bits of the first field of a record may carry flags.
-// NR = 2 ("pair programs"): the same program solves two right-hand sides in one pass over L - every
-// vector value (right-hand side, solution entry, slot) occupies two adjacent rows (job A, job B),
-// vector pops are aligned to even ring rows, L / D values stay single.
-//
-// Load-list words: selector << LD_SEL_SHIFT | row; selector 0 = absolute row of the tile, 1..3 = run-time
-// vectors of job A, 5..7 = the same vectors of job B (materialised per use, layout.hpp: LdVariant);
-// LD_NONE = no copy (alignment padding).
-constexpr int RING_ROWS = 32, RING_GROUP = 8, RING_GROUPS = RING_ROWS / RING_GROUP;
-constexpr int OPS_CHUNK_WORDS = 128; // 512 bytes = 32 records
-constexpr int OPS_CHUNKS = 4;
-constexpr int PR_ZERO = RING_ROWS, PR_TRASH = RING_ROWS + 2, PR_SLOT0 = RING_ROWS + 4, PR_MAX_ROWS = 128;
-constexpr int PR_FIELD_SHIFT = 9;
-constexpr int LD_SEL_SHIFT = 29;
-constexpr int LD_ROW_MASK2 = (1 << LD_SEL_SHIFT) - 1;
-constexpr int LD_NONE = -1;
-constexpr int LD_JOB_B = 4; // added to a selector: the vector of job B
-// header word 0 (every program): counts in the low bits, then
-constexpr int PH_HAS2 = 1 << 12;      // one 2-pair record follows the 4-pair records
-constexpr int PH_INLINE = 1 << 13;    // the header's own pair words are in use
-constexpr int PH_SLOW = 1 << 14;      // the row's pairs come one per record (operands read straight from global memory)
-constexpr int PH_KIND_SHIFT = 16;     // mat-vec: MvKind (2 bits)
-constexpr int PH_NACQ_SHIFT = 24;     // ring groups to acquire before the record's operands are read (2 bits)
-constexpr int PH_NREL_SHIFT = 26;     // ring groups to release (= refill) after the record (2 bits)
-constexpr int PH_FENCE = 1 << 28;     // the refill reads rows written earlier in this sweep: proxy fence first
-constexpr int PH_END = 1 << 31;
-constexpr int PH_NTAIL_MASK = 0xfff;
-// tail records: the same flags in the low 9 bits of word 0
-constexpr int PT_NACQ_SHIFT = 0, PT_NREL_SHIFT = 2, PT_FENCE = 1 << 4;
-constexpr int PR_FIELD_MASK = 0xfe00;
-//   forward row:   [ntail4 | flags, rhs field | keep field << 16, pair, pair]      pair = L field | operand field << 16
-//   backward col:  [ntail4 | flags, 1/d field | xw field << 16, keep field | accumulated-solution field << 16, out row]
-//   tails:         4 pairs per record (PH_HAS2: a last record with 2), padded with PR_PAD_PAIR
-//   slow rows:     one record per pair [L field | flags, 0 = operand field in word 2 / 1 = global row in word 2, value, -]
-//   mat-vec row:   [ngroups4 | kind | flags, extra-0 field | own field << 16, own keep field | extra-1 field << 16, K row]
-//   mat-vec pairs: groups of 4 = 3 records [p, p, p, p] [c, c] [c, c]; PH_HAS2: a last group [p, p, -, -] [c, c]
-//                  p = operand field | keep field << 16, c = coefficient (double)
-//   (per-instance matrices: groups of 2 = 1 record [coefficient field | operand field << 16, keep field, ...] x 2)
-constexpr int PR_PAD_PAIR = (PR_ZERO << PR_FIELD_SHIFT) | (PR_ZERO << (PR_FIELD_SHIFT + 16));
+// ---- programs of the solveKKT / computeResiduals kernels: FMA-machine code (machine.hpp).
+// Load-list selectors (bits 28.. of a load-list word; materialised into absolute tile rows per use):
+//   0 = absolute row of the tile (L, 1/D, per-instance matrix values, scalar rows)
+//   forward:   1 = right-hand side (KKT order), 3 = work vector xw (the program's out vector)
+//   backward:  1 = output vector (the program's out vector), 2 = accumulated solution, 3 = xw
+//   mat-vec:   1 = vector of the row's start value (rhs), 2 = operand vector, 3 = LP scalings, 4 = out vector e
+//   residuals: 1 = [c | b | h], 2 = iterate [x | y | z], 3 = s, 4 = out vector r, 5 = scalar rows
 enum MvKind : int
 {
     MV_X = 0, // row of the x block: -(G' z + A' y)
     MV_Y = 1, // row of the y block: A x
     MV_Z = 2, // LP row of the z block: G x
     MV_ZC = 3 // row of a second-order cone: G x (the cone block itself is applied cone by cone afterwards)
+};
+// kinds the finish functors of tile_program.hpp see
+enum : int
+{
+    FIN_ACC = 1,    // backward sweep of a refinement round: x[row] += result where the instance continues
+    FIN_ABSMAX = 2, // residual row: nerr = max(nerr, |result|)
+    RS_PRE_X = 3, RS_PRE_Y, RS_PRE_Z, RS_FIN_X, RS_FIN_Y, RS_FIN_Z, RS_FIRST_Z, RS_FIRST_PRE_Z // computeResiduals
 };
 
 // ---- factorisation, record form (patterns whose columns of L have at most FA_FAST_COL entries and
@@ -151,28 +114,18 @@ enum OpKind : int
 // Source words (a value that is consumed): an operand code, or one of
 constexpr int SRC_FIFO = -1, SRC_CONST = -2, SRC_ZERO = -3;
 
-// One compiled row program: record stream (padded to whole chunks), load list (padded), and what it needs.
-struct Program
-{
-    ivec ops, ld;
-    int nchunks = 0; // 512-byte chunks of the record stream up to and including the END record
-    int nld = 0;     // load-list words in use (pops, alignment padding included)
-    int slot_rows = 0; // shared-memory rows it uses behind PR_SLOT0
-    long long far = 0, direct = 0, pads = 0; // statistics: operands gathered through the ring / read straight from global memory / alignment padding pops
-};
-
 struct HostStreams
 {
     int workers = 1;
-    // pipe-form row programs, index = NR - 1 (one / two right-hand sides per pass)
-    Program fw[2], bw[2], bwp[2], mv[2]; // bwp: backward sweep of a plain solve (no accumulation into the solution)
+    // machine programs: forward sweep, backward sweep (accumulating / plain), refinement residual, computeResiduals
+    MachineCode fw, bw, bwp, mv, rs;
     int mv_rows = 0;
     // factor program (FIFO form): ops, load list (+ its length in words), shared-memory slots used
     ivec fa, fa_ld;
     int fa_nld = 0;
-    int sw_slots = 0, fa_slots = 0; // sw_slots: values (not rows) the sweeps / mat-vec keep in slots
+    int sw_slots = 0, fa_slots = 0; // sw_slots: rows the sweeps / mat-vecs keep in slots
     int fa_fast = 0; // the factor program is in record form
-    long long sw_far = 0, sw_direct = 0, fa_home = 0; // operands served by far gathers / direct global loads / home rows (statistics)
+    long long sw_far = 0, sw_direct = 0, fa_home = 0; // values re-read from their home rows (sweeps) / - / home-row accumulators (factor)
     dvec fa_val;
 };
 

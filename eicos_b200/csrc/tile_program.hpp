@@ -957,88 +957,147 @@ EI_DEV void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar
 EI_DEV void proxy_fence() { asm volatile("fence.proxy.async;" ::: "memory"); }
 #endif
 
-// ------------------------------------------------------------------ the two pipes of a program warp (streams.hpp)
-// Shared memory of one program warp: [ops ring][mbarriers][rows: data ring, zero rows, trash rows, slots].
+// ------------------------------------------------------------------ the FMA machine (machine.hpp)
+// Shared memory of one program warp: [ops ring][mbarriers][rows: data ring, 0, -0, scratch, slots].
 constexpr int ROW_BYTES = TILE * (int)sizeof(double);
-constexpr int OPS_RING_BYTES = OPS_CHUNKS * OPS_CHUNK_WORDS * 4;
-constexpr int PIPE_BAR_BYTES = 64;  // OPS_CHUNKS mbarriers
-constexpr int PIPE_HEAD_DOUBLES = (OPS_RING_BYTES + PIPE_BAR_BYTES) / 8;
+constexpr int M_CHUNK_BYTES = M_CHUNK_WORDS * 4;
+constexpr int M_OPS_RING_BYTES = M_CHUNKS * M_CHUNK_BYTES;
+constexpr int M_BAR_BYTES = 64; // M_CHUNKS mbarriers
+constexpr int M_HEAD_DOUBLES = (M_OPS_RING_BYTES + M_BAR_BYTES) / 8;
+constexpr int M_BUNDLE_BYTES = M_BUNDLE_WORDS * 4;
 #ifndef EICOS_EMU
-static_assert(ROW_BYTES == (1 << PR_FIELD_SHIFT), "a field is the byte offset of a 512-byte row");
+static_assert(ROW_BYTES == (1 << M_FIELD_SHIFT), "a field is the byte offset of a 512-byte row");
 #endif
-inline size_t pipe_smem_doubles(int slot_rows) { return PIPE_HEAD_DOUBLES + (size_t)(PR_SLOT0 + slot_rows) * TILE; }
+inline size_t machine_smem_doubles(int slot_rows) { return M_HEAD_DOUBLES + (size_t)(M_ROW_SLOT0 + slot_rows) * TILE; }
 
-struct Pipes
+// what the interpreter compiles in for a kernel (everything else costs no instructions)
+enum : int
+{
+    MC_CONST = 1,  // MF_ACONST / MF_CCONST
+    MC_POS = 2,    // MF_POS
+    MC_BKEEP = 4,  // MF_BKEEP
+    MC_RECIP = 8,  // MF_RECIP
+    MC_FIN = 16,   // MF_FIN
+    MC_OUT2 = 32,  // MF_OUT2
+    MC_AONE = 64,  // MF_AONE
+    MC_X3 = 128    // finish functors read a fourth operand (field w6), loaded with the other operands
+};
+
+// one run of a program on a tile
+struct MRun
+{
+    DevMachine prog;
+    const int *ld;     // materialised load list of this use
+    const double *Tb;  // tile base (row 0, lane 0)
+    double *out, *out2; // out bases (+ this lane's element offset)
+    bool a_one;
+};
+
+EI_DEV d2 words_d2(int lo, int hi)
 {
 #ifdef EICOS_EMU
-    double *rows;    // rows region
-    const int *opsp; // next record
-    const int *list; // load list
-    const double *Tb;
-    int nld, rel;
-    EI_DEV void init(const Team &tm, double *mem) { rows = mem + PIPE_HEAD_DOUBLES; }
-    EI_DEV void refill(int G)
-    { // group G of the load list lands in its ring rows (the producer at its eagerest)
-        for (int k = 0; k < RING_GROUP; k++)
+    d2 v;
+    int w[4] = {lo, hi, 0, 0};
+    std::memcpy(&v.x, w, 8);
+    v.y = 0.0;
+    return v;
+#else
+    return d2{__hiloint2double(hi, lo), 0.0};
+#endif
+}
+
+struct Machine
+{
+#ifdef EICOS_EMU
+    double *rows;
+    EI_DEV void init(const Team &, double *mem) { rows = mem + M_HEAD_DOUBLES; }
+    EI_DEV vd ld(int f) const { return vload(rows + (size_t)(f >> M_FIELD_SHIFT) * TILE); }
+    EI_DEV void st(int f, vd v) const { vstore(rows + (size_t)(f >> M_FIELD_SHIFT) * TILE, v); }
+
+    template <int CFG, class Fin>
+    EI_DEV void run(const Team &, const MRun &r, Fin &fin)
+    {
+        for (int c = 0; c < VEC; c++)
         {
-            const int idx = G * RING_GROUP + k;
-            if (idx < nld && list[idx] != LD_NONE)
-                std::memcpy(rows + (size_t)(idx % RING_ROWS) * TILE, Tb + (size_t)list[idx] * TILE, ROW_BYTES);
+            rows[(size_t)M_ROW_ZERO * TILE + c] = 0.0;
+            rows[(size_t)M_ROW_NEGZERO * TILE + c] = -0.0;
+        }
+        long long issued = 0; // ring groups copied so far
+        const auto refill = [&]() {
+            for (int k = 0; k < M_RING_GROUP; k++)
+            {
+                const long long idx = issued * M_RING_GROUP + k;
+                const int w = r.ld[idx];
+                if (w != M_LD_NONE)
+                    std::memcpy(rows + (size_t)(idx % M_RING_ROWS) * TILE, r.Tb + (size_t)w * TILE, ROW_BYTES);
+            }
+            issued++;
+        };
+        for (int g = 0; g < M_RING_GROUPS; g++)
+            refill();
+        const int *rec = r.prog.ops;
+        for (;; rec += M_BUNDLE_WORDS)
+        {
+            const int ctrl = rec[4];
+            vd res[M_U], bv[M_U], xv[M_U];
+            for (int u = 0; u < M_U; u++)
+            {
+                const int *w = rec + u * M_REC_WORDS;
+                const int f = w[4];
+                const double cst = words_d2(w[6], w[7]).x;
+                xv[u] = (CFG & MC_X3) && (f & MF_X3) ? ld(w[6]) : vset(0.0);
+                vd a = (CFG & MC_CONST) && (f & MF_ACONST) ? vset(cst) : ld(w[0]);
+                const vd b = ld(w[1]);
+                const vd c = (CFG & MC_CONST) && (f & MF_CCONST) ? vset(cst) : ld(w[2]);
+                if ((CFG & MC_AONE) && (f & MF_AONE) && r.a_one)
+                    a = vset(1.0);
+                if ((CFG & MC_POS) && f < 0)
+                    a = -a;
+                vd v = vfnma(c, a, b);
+                if ((CFG & MC_RECIP) && (f & MF_RECIP))
+                    v = 1.0 / c;
+                res[u] = v;
+                bv[u] = b;
+            }
+            for (int u = 0; u < M_U; u++)
+            {
+                const int *w = rec + u * M_REC_WORDS;
+                const int f = w[4];
+                st(w[3], res[u]);
+                if (f & MF_OUT)
+                    vstore(((CFG & MC_OUT2) && (f & MF_OUT2) ? r.out2 : r.out) + (size_t)w[5] * TILE, res[u]);
+                if ((CFG & MC_BKEEP) && (f & MF_BKEEP))
+                    st(w[5], bv[u]);
+                if ((CFG & MC_FIN) && (f & MF_FIN))
+                    fin((f >> MF_KIND_SHIFT) & 15, w[5], res[u], bv[u], xv[u]);
+            }
+            for (int k = (ctrl >> MF_NREL_SHIFT) & 7; k > 0; k--)
+                refill();
+            if (ctrl & MF_END)
+                break;
         }
     }
-    EI_DEV void open(const Team &, const DevProgram &pr, const int *ld, const double *tile_base)
-    {
-        opsp = pr.ops;
-        list = ld;
-        nld = pr.nld;
-        Tb = tile_base;
-        rel = 0;
-        for (int c = 0; c < VEC; c++)
-            for (int r = 0; r < 2; r++)
-                rows[(size_t)(PR_ZERO + r) * TILE + c] = 0.0;
-        for (int G = 0; G < RING_GROUPS; G++)
-            refill(G);
-    }
-    EI_DEV i4 get()
-    {
-        const i4 r = ldg4(opsp);
-        opsp += 4;
-        return r;
-    }
-    EI_DEV void acquire(int) {}
-    EI_DEV void release(int n, bool)
-    {
-        for (; n > 0; n--, rel++)
-            refill(rel + RING_GROUPS);
-    }
-    EI_DEV void close() {}
-    EI_DEV vd ld(int f) const { return vload(rows + (size_t)(f >> PR_FIELD_SHIFT) * TILE); }
-    EI_DEV vd ld2(int f) const { return vload(rows + (size_t)((f >> PR_FIELD_SHIFT) + 1) * TILE); }
-    EI_DEV void st(int f, vd v) const { vstore(rows + (size_t)(f >> PR_FIELD_SHIFT) * TILE, v); }
-    EI_DEV void st2(int f, vd v) const { vstore(rows + (size_t)((f >> PR_FIELD_SHIFT) + 1) * TILE, v); }
 #else
     unsigned rows; // shared address of the rows region + this lane's 16 bytes
     unsigned opsb; // shared address of the ops ring
     unsigned bars; // mbarriers of the ops chunks
     int pl;
     bool inited;
-    // data ring: rows arrive by cp.async (every lane moves its 16 bytes of a row: the rows of a program are
-    // gathered from all over the tile, one address per row), one commit group per ring group
-    const int *listp; // load list, two groups ahead of the consumer
+    // data ring: every lane moves its 16 bytes of a row (cp.async), one commit group per ring group
+    const int *listp; // load list, one group ahead of the refill
     i4 nw0, nw1;      // the words of the next refill
     const char *Tl;   // tile base + this lane's 16 bytes
-    // ops ring: the record stream arrives in 512-byte chunks by TMA bulk copies (one elected lane)
-    const int *opsg;  // global chunk pointer of the next refill
-    int nchunks, fetched, cons;
-    unsigned pos, head; // byte position of the next record; ring group the next refill lands in
-    i4 look;
+    unsigned head;    // ring group the next refill lands in
+    // ops ring: the record stream arrives in 1 KB chunks by TMA bulk copies (one elected lane)
+    const int *opsg;  // global pointer of the next chunk to fetch
+    int nchunks, fetched;
 
     __device__ __forceinline__ void init(const Team &tm, double *mem)
     {
         pl = tm.pl;
         opsb = (unsigned)__cvta_generic_to_shared(mem);
-        bars = opsb + OPS_RING_BYTES;
-        rows = bars + PIPE_BAR_BYTES + 16u * pl;
+        bars = opsb + M_OPS_RING_BYTES;
+        rows = bars + M_BAR_BYTES + 16u * pl;
         inited = false;
     }
     static __device__ __forceinline__ i4 lds4(unsigned a)
@@ -1047,14 +1106,24 @@ struct Pipes
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
         return r;
     }
+    __device__ __forceinline__ vd ld(int f) const
+    {
+        vd r;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "r"(rows + (unsigned)f));
+        return r;
+    }
+    __device__ __forceinline__ void st(int f, vd v) const
+    {
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(rows + (unsigned)f), "d"(v.v[0]), "d"(v.v[1]) : "memory");
+    }
     __device__ __forceinline__ void issue_row(unsigned dst, int w) const
-    { // ring row <- workspace row w of the tile (LD_NONE: alignment padding, nothing to copy)
-        if (w != LD_NONE)
+    { // ring row <- workspace row w of the tile (M_LD_NONE: padding, nothing to copy)
+        if (w != M_LD_NONE)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(Tl + (size_t)w * ROW_BYTES) : "memory");
     }
     __device__ __forceinline__ void issue_group()
-    { // the next RING_GROUP words of the load list into ring group `head`; their successors are fetched for next time
-        const unsigned d = rows + head * (RING_GROUP * ROW_BYTES);
+    { // the next M_RING_GROUP words of the load list into ring group `head`; their successors are fetched for next time
+        const unsigned d = rows + head * (M_RING_GROUP * ROW_BYTES);
         issue_row(d, nw0.x);
         issue_row(d + ROW_BYTES, nw0.y);
         issue_row(d + 2 * ROW_BYTES, nw0.z);
@@ -1064,25 +1133,38 @@ struct Pipes
         issue_row(d + 6 * ROW_BYTES, nw1.z);
         issue_row(d + 7 * ROW_BYTES, nw1.w);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        head = (head + 1) % RING_GROUPS;
+        head = (head + 1) % M_RING_GROUPS;
         nw0 = ldg4(listp);
         nw1 = ldg4(listp + 4);
-        listp += RING_GROUP;
+        listp += M_RING_GROUP;
     }
     __device__ __forceinline__ void issue_chunk()
     { // next chunk of the record stream into its ring position (lane 0 only)
-        const unsigned slot = (unsigned)fetched % OPS_CHUNKS;
+        const unsigned slot = (unsigned)fetched % M_CHUNKS;
         const unsigned bar = bars + 8u * slot;
-        mbar_arrive_expect(bar, OPS_CHUNK_WORDS * 4);
-        bulk_g2s(opsb + slot * (OPS_CHUNK_WORDS * 4), opsg, OPS_CHUNK_WORDS * 4, bar);
+        mbar_arrive_expect(bar, M_CHUNK_BYTES);
+        bulk_g2s(opsb + slot * M_CHUNK_BYTES, opsg, M_CHUNK_BYTES, bar);
     }
-    __device__ __forceinline__ void open(const Team &, const DevProgram &pr, const int *ld, const double *tile_base)
+    static __device__ __forceinline__ void wait_groups(int n)
+    { // n = allowed pending groups + 1
+        if (n == 1)
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        else if (n == 2)
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else if (n == 3)
+            asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else
+            asm volatile("cp.async.wait_group 3;" ::: "memory");
+    }
+
+    template <int CFG, class Fin>
+    __device__ __forceinline__ void run(const Team &, const MRun &r, Fin &fin)
     {
-        static_assert(RING_GROUP == 8, "issue_group reads the load list as two 4-word records");
+        static_assert(M_RING_GROUP == 8 && M_RING_GROUPS == 4, "issue_group / wait_groups are written for 4 groups of 8 rows");
         __syncwarp();
         if (pl == 0)
         {
-            for (int b = 0; b < OPS_CHUNKS; b++)
+            for (int b = 0; b < M_CHUNKS; b++)
             {
                 if (inited)
                     mbar_inval(bars + 8u * b);
@@ -1092,473 +1174,201 @@ struct Pipes
         }
         inited = true;
         __syncwarp();
-        // zero rows (both jobs)
-        asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(rows + PR_ZERO * ROW_BYTES), "d"(0.0) : "memory");
-        asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(rows + (PR_ZERO + 1) * ROW_BYTES), "d"(0.0) : "memory");
+        asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(rows + M_ROW_ZERO * ROW_BYTES), "d"(0.0) : "memory");
+        asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(rows + M_ROW_NEGZERO * ROW_BYTES), "d"(-0.0) : "memory");
         // ops ring
-        nchunks = pr.nchunks;
-        opsg = pr.ops;
+        nchunks = r.prog.nchunks;
+        opsg = r.prog.ops;
         fetched = 0;
-        cons = 0;
-        pos = 0;
-        for (int c = 0; c < OPS_CHUNKS && c < nchunks; c++)
+        for (int c = 0; c < M_CHUNKS && c < nchunks; c++)
         {
             if (pl == 0)
                 issue_chunk();
             fetched++;
-            opsg += OPS_CHUNK_WORDS;
+            opsg += M_CHUNK_WORDS;
         }
-        // data ring: the first RING_GROUPS groups of the load list (the list is padded with LD_NONE)
-        Tl = (const char *)tile_base + 16 * pl;
+        // data ring: the first M_RING_GROUPS groups of the load list (the list is padded with M_LD_NONE)
+        Tl = (const char *)r.Tb + 16 * pl;
         head = 0;
-        nw0 = ldg4(ld);
-        nw1 = ldg4(ld + 4);
-        listp = ld + RING_GROUP;
-        for (int g = 0; g < RING_GROUPS; g++)
+        nw0 = ldg4(r.ld);
+        nw1 = ldg4(r.ld + 4);
+        listp = r.ld + M_RING_GROUP;
+        for (int g = 0; g < M_RING_GROUPS; g++)
             issue_group();
         mbar_wait(bars, 0);
-        look = lds4(opsb);
-    }
-    __device__ __forceinline__ void chunk_boundary()
-    { // the chunk behind pos has been read completely: it takes the next chunk of the stream
-        cons++;
-        if (fetched < nchunks)
+        unsigned pos = 0; // byte position of the current bundle in the ops ring
+        int cons = 0;     // chunk being consumed
+        i4 ra[M_U], rb[M_U];
+#pragma unroll
+        for (int u = 0; u < M_U; u++)
         {
-            if (pl == 0)
-                issue_chunk();
-            fetched++;
-            opsg += OPS_CHUNK_WORDS;
+            ra[u] = lds4(opsb + 32u * u);
+            rb[u] = lds4(opsb + 32u * u + 16u);
         }
-        if (cons < fetched) // (the look-ahead of the END record may step past the last chunk)
-            mbar_wait(bars + 8u * ((unsigned)cons % OPS_CHUNKS), ((unsigned)cons / OPS_CHUNKS) & 1u);
-    }
-    __device__ __forceinline__ i4 get()
-    {
-        const i4 r = look;
-        pos += 16;
-        if ((pos & (OPS_CHUNK_WORDS * 4 - 1)) == 0)
-            chunk_boundary();
-        look = lds4(opsb + (pos & (OPS_RING_BYTES - 1)));
-        return r;
-    }
-    // Group G is commit group G; when the consumer first touches it, at most two newer groups have been
-    // committed behind it per further group it needs (one commit per release, RING_GROUPS at the start).
-    __device__ __forceinline__ void acquire(int n)
-    {
-        if (n == 1)
-            asm volatile("cp.async.wait_group 2;" ::: "memory");
-        else if (n == 2)
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        else
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __device__ __forceinline__ void release(int n, bool)
-    { // n groups are consumed: they take the next groups of the load list
-        for (; n > 0; n--)
-            issue_group();
-    }
-    __device__ __forceinline__ void close()
-    { // nothing may still be in flight when the pipes are re-opened or the CTA exits
+        for (;;)
+        {
+            const int ctrl = rb[0].x;
+            const int nwait = (ctrl >> MF_WAIT_SHIFT) & 7;
+            if (nwait)
+                wait_groups(nwait);
+            // ---- operand loads
+            vd a[M_U], b[M_U], c[M_U], x3[M_U];
+            int fl[M_U], kf[M_U], w5[M_U];
+#pragma unroll
+            for (int u = 0; u < M_U; u++)
+            {
+                fl[u] = rb[u].x;
+                kf[u] = ra[u].w;
+                w5[u] = rb[u].y;
+                b[u] = ld(ra[u].y);
+                if (CFG & MC_X3)
+                {
+                    if (fl[u] & MF_X3)
+                        x3[u] = ld(rb[u].z);
+                    else
+                        x3[u] = vset(0.0);
+                }
+                if (CFG & MC_CONST)
+                {
+                    const double cst = __hiloint2double(rb[u].w, rb[u].z);
+                    if (fl[u] & MF_ACONST)
+                        a[u] = vset(cst);
+                    else
+                        a[u] = ld(ra[u].x);
+                    if (fl[u] & MF_CCONST)
+                        c[u] = vset(cst);
+                    else
+                        c[u] = ld(ra[u].z);
+                }
+                else
+                {
+                    a[u] = ld(ra[u].x);
+                    c[u] = ld(ra[u].z);
+                }
+            }
+            // ---- the records of the next bundle (the chunk behind a boundary was fetched M_CHUNKS - 1 chunks ago)
+            const bool last = (ctrl & MF_END) != 0;
+            pos += M_BUNDLE_BYTES;
+            if ((pos & (M_CHUNK_BYTES - 1)) == 0)
+            {
+                // the chunk just read is free: it takes the next chunk of the stream
+                if (fetched < nchunks)
+                {
+                    if (pl == 0)
+                    {
+                        proxy_fence();
+                        issue_chunk();
+                    }
+                    fetched++;
+                    opsg += M_CHUNK_WORDS;
+                }
+                cons++;
+                if (cons < nchunks)
+                    mbar_wait(bars + 8u * ((unsigned)cons % M_CHUNKS), ((unsigned)cons / M_CHUNKS) & 1u);
+                pos &= M_OPS_RING_BYTES - 1;
+            }
+#pragma unroll
+            for (int u = 0; u < M_U; u++)
+            {
+                ra[u] = lds4(opsb + pos + 32u * u);
+                rb[u] = lds4(opsb + pos + 32u * u + 16u);
+            }
+            // ---- multiply-adds
+            vd res[M_U];
+#pragma unroll
+            for (int u = 0; u < M_U; u++)
+            {
+                vd av = a[u];
+                if ((CFG & MC_AONE) && (fl[u] & MF_AONE) && r.a_one)
+                    av = vset(1.0);
+                if (CFG & MC_POS)
+                { // flip the sign of A where the flag (bit 31) is set
+                    VFOR av.v[c_] = __hiloint2double(__double2hiint(av.v[c_]) ^ (fl[u] & (int)0x80000000), __double2loint(av.v[c_]));
+                }
+                vd v = vfnma(c[u], av, b[u]);
+                if ((CFG & MC_RECIP) && (fl[u] & MF_RECIP))
+                    v = 1.0 / c[u];
+                res[u] = v;
+            }
+            // ---- stores
+#pragma unroll
+            for (int u = 0; u < M_U; u++)
+            {
+                st(kf[u], res[u]);
+                if (fl[u] & MF_OUT)
+                    vstore(((CFG & MC_OUT2) && (fl[u] & MF_OUT2) ? r.out2 : r.out) + (size_t)w5[u] * TILE, res[u]);
+                if ((CFG & MC_BKEEP) && (fl[u] & MF_BKEEP))
+                    st(w5[u], b[u]);
+                if ((CFG & MC_FIN) && (fl[u] & MF_FIN))
+                    fin((fl[u] >> MF_KIND_SHIFT) & 15, w5[u], res[u], b[u], (CFG & MC_X3) ? x3[u] : vset(0.0));
+            }
+            // ---- refills of the ring groups this bundle finished with
+            for (int k = (ctrl >> MF_NREL_SHIFT) & 7; k > 0; k--)
+                issue_group();
+            if (last)
+                break;
+        }
+        // nothing may still be in flight when the machine is re-opened or the CTA exits
         asm volatile("cp.async.wait_all;" ::: "memory");
         for (int c = cons + 1; c < fetched; c++)
-            mbar_wait(bars + 8u * ((unsigned)c % OPS_CHUNKS), ((unsigned)c / OPS_CHUNKS) & 1u);
-    }
-    __device__ __forceinline__ vd ld(int f) const
-    {
-        vd r;
-        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "r"(rows + (unsigned)f));
-        return r;
-    }
-    __device__ __forceinline__ vd ld2(int f) const
-    {
-        vd r;
-        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+512];" : "=d"(r.v[0]), "=d"(r.v[1]) : "r"(rows + (unsigned)f));
-        return r;
-    }
-    __device__ __forceinline__ void st(int f, vd v) const
-    {
-        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(rows + (unsigned)f), "d"(v.v[0]), "d"(v.v[1]) : "memory");
-    }
-    __device__ __forceinline__ void st2(int f, vd v) const
-    {
-        asm volatile("st.shared.v2.f64 [%0+512], {%1, %2};" ::"r"(rows + (unsigned)f), "d"(v.v[0]), "d"(v.v[1]) : "memory");
+            mbar_wait(bars + 8u * ((unsigned)c % M_CHUNKS), ((unsigned)c / M_CHUNKS) & 1u);
     }
 #endif
 };
 
-// ------------------------------------------------------------------ record decoding helpers
-EI_DEV int f_lo(int w) { return w & PR_FIELD_MASK; }
-EI_DEV int f_hi(int w) { return (int)((unsigned)w >> 16); }
-constexpr int PH_CTRL_MASK = PH_END | (3 << PH_NACQ_SHIFT);
-constexpr int PH_PAIRS_MASK = PH_NTAIL_MASK | PH_HAS2 | PH_INLINE | PH_SLOW;
-constexpr int PT_FLAG_MASK = (1 << PR_FIELD_SHIFT) - 1;
+struct NoFin
+{
+    EI_DEV void operator()(int, int, vd, vd, vd) {}
+};
 
-// acquire what the header record needs; returns false on the END record
-EI_DEV bool pipe_header(Pipes &pp, int w0)
+// ------------------------------------------------------------------ triangular solves and KKT residual (machine programs)
+// forward:  xw = L^-1 P rhs         rows of L in dot form, ascending columns (the summation order of Eigen's
+//                                   forward substitution); the permutation is folded into the loads.
+// backward: out = P' L^-T D^-1 xw   columns in reverse order, dot form; results land in KKT order; the
+//                                   accumulating form also does x += out for the instances with `cont`.
+// residual: e = rhs - Ktrue * x     with the un-regularised scaling block (src/eicos.cpp:1511-1576)
+// All three are programs of the FMA machine (streams.cpp: build_forward / build_backward / build_matvec).
+struct AccFin
 {
-    if (w0 & PH_CTRL_MASK)
+    vb cont;
+    double *x; // accumulated solution (+ lane)
+    EI_DEV void operator()(int, int row, vd res, vd, vd xa)
     {
-        if (w0 < 0)
-            return false;
-        pp.acquire((w0 >> PH_NACQ_SHIFT) & 3);
+        vstore(x + (size_t)row * TILE, xa + vsel(cont, res, vset(0.0)));
     }
-    return true;
-}
-EI_DEV void pipe_header_release(Pipes &pp, int w0)
+};
+struct AbsMaxFin
 {
-    const int nrel = (w0 >> PH_NREL_SHIFT) & 3;
-    if (nrel)
-        pp.release(nrel, (w0 & PH_FENCE) != 0);
-}
-EI_DEV void pipe_tail_acquire(Pipes &pp, int w0)
-{
-    if (w0 & (3 << PT_NACQ_SHIFT))
-        pp.acquire((w0 >> PT_NACQ_SHIFT) & 3);
-}
-EI_DEV void pipe_tail_release(Pipes &pp, int w0)
-{
-    if (w0 & (3 << PT_NREL_SHIFT))
-        pp.release((w0 >> PT_NREL_SHIFT) & 3, (w0 & PT_FENCE) != 0);
-}
+    vd nerr;
+    EI_DEV void operator()(int, int, vd res, vd, vd) { nerr = vmax(nerr, vabs(res)); }
+};
 
-// ------------------------------------------------------------------ triangular solves (Eigen solve, src/eicos.cpp:1477,1599)
-// forward:  xw = L^-1 P rhs         rows of L in elimination order, dot form in ascending column order
-//                                   (the summation order of Eigen's forward substitution); the
-//                                   permutation is folded into the right-hand-side loads.
-// backward: out = P' L^-T D^-1 xw   columns in reverse order, dot form; results land in KKT order.
-// Both are pipe-form row programs (streams.hpp, streams.cpp: build_forward / build_backward) run by one
-// warp per tile with no barrier inside.  NR = 2 solves two right-hand sides in one pass over L.
-
-// v[j] -= l * g[j] for NP pairs: all operand loads first, then the multiply-adds in order
-template <int NR, int NP>
-EI_DEV void dot_pairs(const Pipes &pp, const int (&w)[NP], vd (&v)[NR])
-{
-    vd l[NP], g[NP][NR];
-#pragma unroll
-    for (int u = 0; u < NP; u++)
-    {
-        l[u] = pp.ld(f_lo(w[u]));
-        g[u][0] = pp.ld(f_hi(w[u]));
-        if (NR == 2)
-            g[u][NR - 1] = pp.ld2(f_hi(w[u]));
-    }
-#pragma unroll
-    for (int u = 0; u < NP; u++)
-#pragma unroll
-        for (int j = 0; j < NR; j++)
-            v[j] = vfnma(v[j], l[u], g[u][j]);
-}
-
-// the pairs of a row behind its header: inline pairs, 4-pair records, a 2-pair record; or the slow form
-template <int NR>
-EI_DEV void dot_row(Pipes &pp, const i4 &h, bool inline_pairs, double *const (&home)[NR], vd (&v)[NR])
-{
-    if (h.x & PH_SLOW)
-    { // one pair per record, operands possibly straight from global memory
-        pipe_header_release(pp, h.x);
-        const int cnt = h.x & PH_NTAIL_MASK;
-        for (int q = 0; q < cnt; q++)
-        {
-            const i4 r = pp.get();
-            pipe_tail_acquire(pp, r.x);
-            const vd l = pp.ld(f_lo(r.x));
-#pragma unroll
-            for (int j = 0; j < NR; j++)
-            {
-                vd g;
-                if (r.y)
-                    g = vload(home[j] + (size_t)r.z * TILE);
-                else
-                    g = j == 0 ? pp.ld(r.z) : pp.ld2(r.z);
-                v[j] = vfnma(v[j], l, g);
-            }
-            pipe_tail_release(pp, r.x);
-        }
-        return;
-    }
-    if (inline_pairs && (h.x & PH_INLINE))
-    {
-        const int w[2] = {h.z, h.w};
-        dot_pairs<NR, 2>(pp, w, v);
-    }
-    pipe_header_release(pp, h.x);
-    const int ntail4 = h.x & PH_NTAIL_MASK;
-    for (int t = 0; t < ntail4; t++)
-    {
-        const i4 r = pp.get();
-        pipe_tail_acquire(pp, r.x);
-        const int w[4] = {r.x, r.y, r.z, r.w};
-        dot_pairs<NR, 4>(pp, w, v);
-        pipe_tail_release(pp, r.x);
-    }
-    if (h.x & PH_HAS2)
-    {
-        const i4 r = pp.get();
-        pipe_tail_acquire(pp, r.x);
-        const int w[2] = {r.x, r.y};
-        dot_pairs<NR, 2>(pp, w, v);
-        pipe_tail_release(pp, r.x);
-    }
-}
-
-// xw[j]: work vector job j fills.  ld: the materialised load list of this use (layout.hpp).
-template <int NR>
-EI_DEV void ldl_forward(const Team &tm, Pipes &pp, const DevProgram &pr, const int *ld, const double *Tb, double *T,
-                        const int (&xw)[NR])
-{
-    pp.open(tm, pr, ld, Tb);
-    double *xp[NR], *home[NR];
-#pragma unroll
-    for (int j = 0; j < NR; j++)
-        xp[j] = home[j] = T + (size_t)xw[j] * TILE;
-    for (;;)
-    {
-        const i4 h = pp.get();
-        if (!pipe_header(pp, h.x))
-            break;
-        vd v[NR];
-        v[0] = pp.ld(f_lo(h.y));
-        if (NR == 2)
-            v[NR - 1] = pp.ld2(f_lo(h.y));
-        if (h.x & PH_PAIRS_MASK)
-            dot_row<NR>(pp, h, true, home, v);
-        else
-            pipe_header_release(pp, h.x);
-        const int keep = f_hi(h.y);
-#pragma unroll
-        for (int j = 0; j < NR; j++)
-        {
-            vstore(xp[j], v[j]);
-            xp[j] += TILE;
-        }
-        pp.st(keep, v[0]);
-        if (NR == 2)
-            pp.st2(keep, v[NR - 1]);
-    }
-    pp.close();
-}
-
-// out[j] = solution (KKT order).  ACC: additionally x[j] += solution for the instances with cont[j].
-template <int NR, bool ACC>
-EI_DEV void ldl_backward(const Team &tm, Pipes &pp, const DevProgram &pr, const int *ld, const double *Tb, double *T,
-                         const int (&out)[NR], const int (&x)[NR], const vb (&cont)[NR])
-{
-    pp.open(tm, pr, ld, Tb);
-    const vd zero = vset(0.0);
-    double *op[NR], *xp[NR];
-#pragma unroll
-    for (int j = 0; j < NR; j++)
-    {
-        op[j] = T + (size_t)out[j] * TILE;
-        xp[j] = T + (size_t)(ACC ? x[j] : out[j]) * TILE;
-    }
-    for (;;)
-    {
-        const i4 h = pp.get();
-        if (!pipe_header(pp, h.x))
-            break;
-        const vd di = pp.ld(f_lo(h.y)); // Eigen: diag.inverse() * x
-        vd v[NR], xa[NR];
-        v[0] = di * pp.ld(f_hi(h.y));
-        if (NR == 2)
-            v[NR - 1] = di * pp.ld2(f_hi(h.y));
-        if (ACC)
-        {
-            xa[0] = pp.ld(f_hi(h.z));
-            if (NR == 2)
-                xa[NR - 1] = pp.ld2(f_hi(h.z));
-        }
-        if (h.x & PH_PAIRS_MASK)
-            dot_row<NR>(pp, h, false, op, v);
-        else
-            pipe_header_release(pp, h.x);
-        const size_t o = (size_t)h.w * TILE;
-        const int keep = f_lo(h.z);
-#pragma unroll
-        for (int j = 0; j < NR; j++)
-        {
-            vstore(op[j] + o, v[j]);
-            if (ACC)
-                vstore(xp[j] + o, xa[j] + vsel(cont[j], v[j], zero));
-        }
-        pp.st(keep, v[0]);
-        if (NR == 2)
-            pp.st2(keep, v[NR - 1]);
-    }
-    pp.close();
-}
-
-// ------------------------------------------------------------------ KKT mat-vec program (streams.hpp, streams.cpp: build_matvec)
-// For every x, y and z row r of the KKT matrix, in elimination order and for every job j:
-//   v = init(kind, ex0, own, ex1) - sum_k coefficient_k * vec[column_k];  finish(j, kind, r, v, ex0, own, ex1)
-// ex0 = v1[r], own = vec[r], ex1 = v3[r - n - p] (z rows only; one row per instance).  One warp; every
-// operand row comes through the ring once and stays in a shared-memory slot while it has further uses.
-// The sum is always SUBTRACTED (callers that want init + sum negate init and the result: bit-identical).
-template <int NR, bool PIM, class Init, class Finish>
-EI_DEV void mv_run(const Team &tm, Pipes &pp, const DevProgram &pr, const int *ld, const double *Tb, Init init, Finish finish)
-{
-    pp.open(tm, pr, ld, Tb);
-    for (;;)
-    {
-        const i4 h = pp.get();
-        if (!pipe_header(pp, h.x))
-            break;
-        const int kind = (h.x >> PH_KIND_SHIFT) & 3;
-        vd ex0[NR], own[NR], v[NR];
-        ex0[0] = pp.ld(f_lo(h.y));
-        own[0] = pp.ld(f_hi(h.y));
-        if (NR == 2)
-        {
-            ex0[NR - 1] = pp.ld2(f_lo(h.y));
-            own[NR - 1] = pp.ld2(f_hi(h.y));
-        }
-        const vd ex1 = pp.ld(f_hi(h.z));
-        pp.st(f_lo(h.z), own[0]);
-        if (NR == 2)
-            pp.st2(f_lo(h.z), own[NR - 1]);
-#pragma unroll
-        for (int j = 0; j < NR; j++)
-            v[j] = init(kind, ex0[j], own[j], ex1);
-        pipe_header_release(pp, h.x);
-        const int ng = h.x & PH_NTAIL_MASK;
-        if (PIM)
-        { // [coefficient field | operand field << 16, keep field] x 2 per record
-            for (int q = 0; q < ng; q++)
-            {
-                const i4 r = pp.get();
-                pipe_tail_acquire(pp, r.x);
-                const int pw[2] = {r.x, r.z}, kw[2] = {r.y, r.w};
-                vd c[2], g[2][NR];
-#pragma unroll
-                for (int u = 0; u < 2; u++)
-                {
-                    c[u] = pp.ld(f_lo(pw[u]));
-                    g[u][0] = pp.ld(f_hi(pw[u]));
-                    if (NR == 2)
-                        g[u][NR - 1] = pp.ld2(f_hi(pw[u]));
-                }
-#pragma unroll
-                for (int u = 0; u < 2; u++)
-                {
-                    pp.st(f_lo(kw[u]), g[u][0]);
-                    if (NR == 2)
-                        pp.st2(f_lo(kw[u]), g[u][NR - 1]);
-                }
-#pragma unroll
-                for (int u = 0; u < 2; u++)
-#pragma unroll
-                    for (int j = 0; j < NR; j++)
-                        v[j] = vfnma(v[j], c[u], g[u][j]);
-                pipe_tail_release(pp, r.x);
-            }
-        }
-        else
-        {
-            for (int q = 0; q < ng; q++)
-            {
-                const i4 r = pp.get();
-                const d2 c0 = as_d2(pp.get()), c1 = as_d2(pp.get());
-                pipe_tail_acquire(pp, r.x);
-                const int pw[4] = {r.x, r.y, r.z, r.w};
-                const double cf[4] = {c0.x, c0.y, c1.x, c1.y};
-                vd g[4][NR];
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-                {
-                    g[u][0] = pp.ld(f_lo(pw[u]));
-                    if (NR == 2)
-                        g[u][NR - 1] = pp.ld2(f_lo(pw[u]));
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-                {
-                    pp.st(f_hi(pw[u]), g[u][0]);
-                    if (NR == 2)
-                        pp.st2(f_hi(pw[u]), g[u][NR - 1]);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-#pragma unroll
-                    for (int j = 0; j < NR; j++)
-                        v[j] = vfnma(v[j], cf[u], g[u][j]);
-                pipe_tail_release(pp, r.x);
-            }
-            if (h.x & PH_HAS2)
-            {
-                const i4 r = pp.get();
-                const d2 c0 = as_d2(pp.get());
-                pipe_tail_acquire(pp, r.x);
-                const int pw[2] = {r.x, r.y};
-                const double cf[2] = {c0.x, c0.y};
-                vd g[2][NR];
-#pragma unroll
-                for (int u = 0; u < 2; u++)
-                {
-                    g[u][0] = pp.ld(f_lo(pw[u]));
-                    if (NR == 2)
-                        g[u][NR - 1] = pp.ld2(f_lo(pw[u]));
-                }
-#pragma unroll
-                for (int u = 0; u < 2; u++)
-                {
-                    pp.st(f_hi(pw[u]), g[u][0]);
-                    if (NR == 2)
-                        pp.st2(f_hi(pw[u]), g[u][NR - 1]);
-                }
-#pragma unroll
-                for (int u = 0; u < 2; u++)
-#pragma unroll
-                    for (int j = 0; j < NR; j++)
-                        v[j] = vfnma(v[j], cf[u], g[u][j]);
-                pipe_tail_release(pp, r.x);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < NR; j++)
-            finish(j, kind, h.w, v[j], ex0[j], own[j], ex1);
-    }
-    pp.close();
-}
-
-// ------------------------------------------------------------------ KKT residual for iterative refinement (src/eicos.cpp:1511-1576)
-// e[j] = rhs[j] - Ktrue * x[j] with the un-regularised scaling block (identity while initialising),
-// nerr[j] = ||e[j]||_inf per instance.  mvld: the materialised mat-vec load list of this use.
-template <int NR>
-EI_DEV void kkt_residual(const Team &tm, const KArgs &a, Pipes &pp, const TileMem &t, const int *mvld, const int (&x)[NR],
-                         const int (&erow)[NR], bool initialize, vd (&nerr)[NR])
+// e = rhs - Ktrue * x, nerr = ||e||_inf per instance.  mvld: the materialised mat-vec load list of this use.
+EI_DEV void kkt_residual(const Team &tm, const KArgs &a, Machine &mm, const TileMem &t, const int *mvld, int x, int erow,
+                         bool initialize, vd &nerr)
 {
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     double *T = t.T;
     const double delta = Settings::deltastat;
     const int zb = P.n + P.p;
-#pragma unroll
-    for (int j = 0; j < NR; j++)
-        nerr[j] = vset(0.0);
-    const auto mv_init = [&](int, vd ex0, vd, vd) { return ex0; };
-    const auto mv_finish = [&](int j, int kind, int r, vd v, vd, vd own, vd ex1) {
-        if (kind == MV_ZC)
-        { // cone row: rhs - G x only; the cone block is added below
-            ROWD(T, erow[j] + r) = v;
-            return;
-        }
-        if (kind == MV_X)
-            v -= delta * own;
-        else
-        {
-            v += delta * own;
-            if (kind == MV_Z)
-                v += initialize ? own : ex1 * own;
-        }
-        ROWD(T, erow[j] + r) = v;
-        nerr[j] = vmax(nerr[j], vabs(v));
-    };
+    nerr = vset(0.0);
     if (tm.wk == 0 && P.mv_rows > 0)
     {
+        AbsMaxFin fin;
+        fin.nerr = vset(0.0);
+        MRun r;
+        r.prog = P.mv;
+        r.ld = mvld;
+        r.Tb = t.Tb;
+        r.out = T + (size_t)erow * TILE;
+        r.out2 = r.out;
+        r.a_one = initialize;
         if (P.pim)
-            mv_run<NR, true>(tm, pp, P.mv[NR - 1], mvld, t.Tb, mv_init, mv_finish);
+            mm.run<MC_CONST | MC_POS | MC_BKEEP | MC_FIN | MC_AONE>(tm, r, fin);
         else
-            mv_run<NR, false>(tm, pp, P.mv[NR - 1], mvld, t.Tb, mv_init, mv_finish);
+            mm.run<MC_CONST | MC_POS | MC_BKEEP | MC_FIN | MC_AONE>(tm, r, fin);
+        nerr = fin.nerr;
     }
     if (P.nc > 0)
     {
@@ -1570,48 +1380,45 @@ EI_DEV void kkt_residual(const Team &tm, const KArgs &a, Pipes &pp, const TileMe
             const int cp = L.cpar + c * CP_COUNT;
             const vd eta2 = ROWD(T, cp + CP_ETA2), d1 = ROWD(T, cp + CP_D1), u0 = ROWD(T, cp + CP_U0);
             const vd u1 = ROWD(T, cp + CP_U1), v1 = ROWD(T, cp + CP_V1);
-            for (int j = 0; j < NR; j++)
+            const int xj = x, ej = erow;
+            const vd x1 = ROWD(T, xj + kb), x3 = ROWD(T, xj + kb + d), x4 = ROWD(T, xj + kb + d + 1);
+            vd qtx2 = vset(0.0);
+            for (int k = 1; k < d; k++)
+                qtx2 += vd(ROWD(T, L.cq + qo + k - 1)) * vd(ROWD(T, xj + kb + k));
+            const vd vu = v1 * x3 + u1 * x4;
+            for (int k = 0; k < d; k++)
             {
-                const int xj = x[j], ej = erow[j];
-                const vd x1 = ROWD(T, xj + kb), x3 = ROWD(T, xj + kb + d), x4 = ROWD(T, xj + kb + d + 1);
-                vd qtx2 = vset(0.0);
-                for (int k = 1; k < d; k++)
-                    qtx2 += vd(ROWD(T, L.cq + qo + k - 1)) * vd(ROWD(T, xj + kb + k));
-                const vd vu = v1 * x3 + u1 * x4;
-                for (int k = 0; k < d; k++)
-                {
-                    const vd xk = ROWD(T, xj + kb + k);
-                    vd v = ROWD(T, ej + kb + k); // rhs - G x from the mat-vec program
-                    if (k < d - 1)
-                        v += delta * xk;
-                    else
-                        v -= delta * xk;
-                    if (initialize)
-                        v += xk;
-                    else if (k == 0)
-                        v += eta2 * (d1 * x1 + u0 * x4);
-                    else
-                        v += eta2 * (xk + vu * vd(ROWD(T, L.cq + qo + k - 1)));
-                    ROWD(T, ej + kb + k) = v;
-                    nerr[j] = vmax(nerr[j], vabs(v));
-                }
-                const vd e3 = initialize ? x3 : eta2 * (v1 * qtx2 + x3);
-                const vd e4 = initialize ? x4 : eta2 * (u0 * x1 + u1 * qtx2 - x4);
-                ROWD(T, ej + kb + d) = e3;
-                ROWD(T, ej + kb + d + 1) = e4;
-                nerr[j] = vmax(nerr[j], vmax(vabs(e3), vabs(e4)));
+                const vd xk = ROWD(T, xj + kb + k);
+                vd v = ROWD(T, ej + kb + k); // rhs - G x from the mat-vec program
+                if (k < d - 1)
+                    v += delta * xk;
+                else
+                    v -= delta * xk;
+                if (initialize)
+                    v += xk;
+                else if (k == 0)
+                    v += eta2 * (d1 * x1 + u0 * x4);
+                else
+                    v += eta2 * (xk + vu * vd(ROWD(T, L.cq + qo + k - 1)));
+                ROWD(T, ej + kb + k) = v;
+                nerr = vmax(nerr, vabs(v));
             }
+            const vd e3 = initialize ? x3 : eta2 * (v1 * qtx2 + x3);
+            const vd e4 = initialize ? x4 : eta2 * (u0 * x1 + u1 * qtx2 - x4);
+            ROWD(T, ej + kb + d) = e3;
+            ROWD(T, ej + kb + d + 1) = e4;
+            nerr = vmax(nerr, vmax(vabs(e3), vabs(e4)));
         }
     }
-    team_max<NR>(tm, nerr);
+    vd nn[1] = {nerr};
+    team_max<1>(tm, nn);
+    nerr = nn[0];
 }
 
 // ------------------------------------------------------------------ solveKKT (src/eicos.cpp:1471-1620)
 // sol = K^-1 rhs followed by up to nitref refinement rounds; every instance stops on its own
-// criterion, the tile loops until all of its instances have stopped.  NR = 2: the two solves of an
-// iteration that share the factor (rhs1 -> sol1, rhs2 -> sol2) in one pass over L per sweep; a job whose
-// instances have all stopped rides along with its accumulation masked off.
-template <int NR>
+// criterion, the tile loops until all of its instances have stopped.  CTA = (tile, job): the two solves
+// of an iteration that share the factor (rhs1 -> sol1, rhs2 -> sol2) run side by side.
 EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
 {
     const TileMem t = tile_mem(tm, a, tile);
@@ -1622,138 +1429,108 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
     const Layout &L = a.L;
     double *T = t.T;
     const bool init = a.initialize != 0;
-    int sol[NR], xw[NR], dxr[NR], erow[NR], nitrow[NR];
-    vd threshold[NR];
-#pragma unroll
-    for (int j = 0; j < NR; j++)
-    {
-        const KArgs::KktJob jb = a.job[j];
-        const int set = jb.set; // (jb.rhs is baked into the materialised load lists of the set)
-        sol[j] = jb.sol;
-        nitrow[j] = jb.nitrow;
-        xw[j] = set ? L.xw2 : L.xw;
-        dxr[j] = set ? L.dxr2 : L.dxr;
-        erow[j] = set ? L.e2 : L.e;
-        // max |rhs| is kept up to date by the kernels that write the right-hand sides (src/eicos.cpp:1590)
-        threshold[j] = (1. + vd(ROWD(T, L.sc + (set ? S_RHSMAX2 : S_RHSMAX1)))) * Settings::linsysacc;
-    }
-    const int set0 = a.job[0].set;
-    const int *fw_ld[2], *bw_ld[2], *mv_ld;
-    if (NR == 1)
-    {
-        fw_ld[0] = P.fw_ld1[set0][0], fw_ld[1] = P.fw_ld1[set0][1];
-        bw_ld[0] = P.bw_ld1[set0][0], bw_ld[1] = P.bw_ld1[set0][1];
-        mv_ld = P.mv_ld1[set0];
-    }
-    else
-    {
-        fw_ld[0] = P.fw_ld2[0], fw_ld[1] = P.fw_ld2[1];
-        bw_ld[0] = P.bw_ld2[0], bw_ld[1] = P.bw_ld2[1];
-        mv_ld = P.mv_ld2;
-    }
-    Pipes pp;
-    pp.init(tm, tm.pbuf);
+    const KArgs::KktJob jb = a.job[tm.job];
+    const int set = jb.set; // (jb.rhs is baked into the materialised load lists of the set)
+    const int sol = jb.sol, nitrow = jb.nitrow;
+    const int xw = set ? L.xw2 : L.xw, dxr = set ? L.dxr2 : L.dxr, erow = set ? L.e2 : L.e;
+    // max |rhs| is kept up to date by the kernels that write the right-hand sides (src/eicos.cpp:1590)
+    const vd threshold = (1. + vd(ROWD(T, L.sc + (set ? S_RHSMAX2 : S_RHSMAX1)))) * Settings::linsysacc;
+    Machine mm;
+    mm.init(tm, tm.pbuf);
 
     long long ck[5] = {0, 0, 0, 0, 0}, c0 = EI_CLOCK(), c1;
 #define EI_PHASE(k) (c1 = EI_CLOCK(), ck[k] += c1 - c0, c0 = c1)
-    vb nocont[NR];
-#pragma unroll
-    for (int j = 0; j < NR; j++)
-        nocont[j] = vbset(false);
-    if (tm.wk == 0)
-    {
-        ldl_forward<NR>(tm, pp, P.fw[NR - 1], fw_ld[0], t.Tb, T, xw);
+    const auto sweeps = [&](int round, bool accumulate, vb cont) {
+        MRun r;
+        r.Tb = t.Tb;
+        r.a_one = false;
+        r.prog = P.fw;
+        r.ld = P.fw_ld[set][round];
+        r.out = r.out2 = T + (size_t)xw * TILE;
+        NoFin nofin;
+        mm.run<0>(tm, r, nofin);
         EI_PHASE(1);
-        ldl_backward<NR, false>(tm, pp, P.bwp[NR - 1], bw_ld[0], t.Tb, T, sol, sol, nocont);
+        if (accumulate)
+        {
+            AccFin fin;
+            fin.cont = cont;
+            fin.x = T + (size_t)sol * TILE;
+            r.prog = P.bw;
+            r.ld = P.bw_ld[set][1];
+            r.out = r.out2 = T + (size_t)dxr * TILE;
+            mm.run<MC_POS | MC_FIN | MC_X3>(tm, r, fin);
+        }
+        else
+        {
+            r.prog = P.bwp;
+            r.ld = P.bw_ld[set][0];
+            r.out = r.out2 = T + (size_t)sol * TILE;
+            mm.run<MC_POS>(tm, r, nofin);
+        }
         EI_PHASE(2);
-    }
+    };
+    if (tm.wk == 0)
+        sweeps(0, false, vbset(false));
     tm.sync();
 
-    vd nerr_prev[NR];
-    int kref[NR][VEC];
-    vb done[NR];
-#pragma unroll
-    for (int j = 0; j < NR; j++)
-    {
-        nerr_prev[j] = vset(DBL_MAX);
-        done[j] = !act;
-        VFOR kref[j][c_] = 0;
-    }
+    vd nerr_prev = vset(DBL_MAX);
+    int kref[VEC];
+    vb done = !act;
+    VFOR kref[c_] = 0;
     unsigned rounds = 0;
     for (;;)
     {
-        vd nerr[NR];
-        kkt_residual<NR>(tm, a, pp, t, mv_ld, sol, erow, init, nerr);
+        vd nerr;
+        kkt_residual(tm, a, mm, t, P.mv_ld[set], sol, erow, init, nerr);
         EI_PHASE(3);
-        bool all_done = true;
-#pragma unroll
-        for (int j = 0; j < NR; j++)
+        vb rollback = vbset(false);
+        VFOR
         {
-            vb rollback = vbset(false);
-            VFOR
+            if (done.v[c_])
+                continue;
+            if (kref[c_] > 0 && nerr.v[c_] > nerr_prev.v[c_])
             {
-                if (done[j].v[c_])
-                    continue;
-                if (kref[j][c_] > 0 && nerr[j].v[c_] > nerr_prev[j].v[c_])
-                {
-                    rollback.v[c_] = true;
-                    kref[j][c_]--;
-                    done[j].v[c_] = true;
-                }
-                else if (kref[j][c_] == Settings::nitref || nerr[j].v[c_] < threshold[j].v[c_] ||
-                         (kref[j][c_] > 0 && nerr_prev[j].v[c_] < Settings::irerrfact * nerr[j].v[c_]))
-                    done[j].v[c_] = true;
-                else
-                    nerr_prev[j].v[c_] = nerr[j].v[c_];
+                rollback.v[c_] = true;
+                kref[c_]--;
+                done.v[c_] = true;
             }
-            if (tm.any(rollback))
-            { // x -= dx_ref for the instances whose last refinement made things worse
-                for (int r = tm.wk; r < P.N; r += tm.nwk)
-                    ROWD(T, sol[j] + r) -= vsel(rollback, ROWD(T, dxr[j] + r), vset(0.0));
-            }
-            all_done = all_done && tm.all(done[j]);
+            else if (kref[c_] == Settings::nitref || nerr.v[c_] < threshold.v[c_] ||
+                     (kref[c_] > 0 && nerr_prev.v[c_] < Settings::irerrfact * nerr.v[c_]))
+                done.v[c_] = true;
+            else
+                nerr_prev.v[c_] = nerr.v[c_];
         }
-        if (all_done)
+        if (tm.any(rollback))
+        { // x -= dx_ref for the instances whose last refinement made things worse
+            for (int r = tm.wk; r < P.N; r += tm.nwk)
+                ROWD(T, sol + r) -= vsel(rollback, ROWD(T, dxr + r), vset(0.0));
+        }
+        if (tm.all(done))
             break;
         tm.sync(); // e complete before the forward sweep loads it
         EI_PHASE(4);
         if (tm.wk == 0)
-        {
-            vb cont[NR];
-#pragma unroll
-            for (int j = 0; j < NR; j++)
-                cont[j] = !done[j];
-            ldl_forward<NR>(tm, pp, P.fw[NR - 1], fw_ld[1], t.Tb, T, xw);
-            EI_PHASE(1);
-            ldl_backward<NR, true>(tm, pp, P.bw[NR - 1], bw_ld[1], t.Tb, T, dxr, sol, cont);
-            EI_PHASE(2);
-        }
+            sweeps(1, true, !done);
         tm.sync();
-#pragma unroll
-        for (int j = 0; j < NR; j++)
-            VFOR if (!done[j].v[c_]) kref[j][c_]++;
+        VFOR if (!done.v[c_]) kref[c_]++;
         rounds++;
     }
     tm.sync();
     if (tm.wk == 0)
     {
-#pragma unroll
-        for (int j = 0; j < NR; j++)
-            if (nitrow[j] >= 0)
-                VFOR if (act.v[c_]) ROWC(t.I, nitrow[j], c_) = kref[j][c_];
+        if (nitrow >= 0)
+            VFOR if (act.v[c_]) ROWC(t.I, nitrow, c_) = kref[c_];
 #ifndef EICOS_EMU
         if (a.ir_rounds)
         {
-            // [0] tile-rounds (sweep pairs x jobs), [6] lane-rounds: sweep pairs each instance needed
+            // [0] tile-rounds (sweep pairs), [6] lane-rounds: sweep pairs each instance needed
             int lane_rounds = 0;
-#pragma unroll
-            for (int j = 0; j < NR; j++)
-                VFOR if (act.v[c_]) lane_rounds += kref[j][c_] + 1;
+            VFOR if (act.v[c_]) lane_rounds += kref[c_] + 1;
             for (int o = 16; o > 0; o >>= 1)
                 lane_rounds += __shfl_xor_sync(0xffffffffu, lane_rounds, o);
             if (tm.pl == 0)
             {
-                atomicAdd(a.ir_rounds, (unsigned long long)(rounds + 1) * NR);
+                atomicAdd(a.ir_rounds, (unsigned long long)(rounds + 1));
                 atomicAdd(a.ir_rounds + 6, (unsigned long long)lane_rounds);
                 EI_PHASE(4);
                 for (int k = 0; k < 5; k++)
@@ -2039,7 +1816,53 @@ EI_DEV ConeScaling cone_scaling(const Team &tm, const double *T, int srow, int z
 
 // ------------------------------------------------------------------ computeResiduals (src/eicos.cpp:643-689)
 // rx = -A'y - G'z, ry = A x, rz = s + G x (each before and after the tau terms) and the sums the
-// statistics need; one warp per tile (KKT mat-vec program), results in `r` and the S_RED rows.
+// statistics need; one warp per tile runs the machine program of streams.cpp: build_resid, whose
+// finish functor keeps the fourteen sums; results in `r` and the S_RED rows.
+enum { RS_HX2, RS_RX2, RS_CX, RS_NX2, RS_HY2, RS_RY2, RS_BY, RS_NY2, RS_HZ2, RS_RZ2, RS_HZ, RS_NZ2, RS_NS2, RS_GAP, RS_NRED };
+struct ResidFin
+{
+    vd r[RS_NRED];
+    EI_DEV void operator()(int kind, int, vd res, vd b, vd own)
+    {
+        // PRE: res = the row before its tau term; FIN: res = the finished row, b = c_j / b_i / h_i, f3 -> x_j / y_i / z_i;
+        // FIRST_Z: res = s_i, f3 -> z_i
+        if (kind == RS_PRE_X)
+            r[RS_HX2] += res * res;
+        else if (kind == RS_PRE_Y)
+            r[RS_HY2] += res * res;
+        else if (kind == RS_PRE_Z)
+            r[RS_HZ2] += res * res;
+        else
+        {
+            if (kind == RS_FIN_X)
+            {
+                r[RS_RX2] += res * res;
+                r[RS_CX] += b * own;
+                r[RS_NX2] += own * own;
+            }
+            else if (kind == RS_FIN_Y)
+            {
+                r[RS_RY2] += res * res;
+                r[RS_BY] += b * own;
+                r[RS_NY2] += own * own;
+            }
+            else if (kind == RS_FIN_Z)
+            {
+                r[RS_RZ2] += res * res;
+                r[RS_HZ] += b * own;
+                r[RS_NZ2] += own * own;
+            }
+            else
+            { // RS_FIRST_Z, RS_FIRST_PRE_Z
+                r[RS_NS2] += res * res;
+                r[RS_GAP] += res * own;
+                if (kind == RS_FIRST_PRE_Z)
+                    r[RS_HZ2] += res * res;
+            }
+        }
+    }
+};
+
 EI_DEV void tile_resid(const Team &tm, const KArgs &a, int tile)
 {
     const TileMem t = tile_mem(tm, a, tile);
@@ -2049,65 +1872,24 @@ EI_DEV void tile_resid(const Team &tm, const KArgs &a, int tile)
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     double *T = t.T;
-    const int zb = P.n + P.p;
-    const vd tau = ROWD(T, L.sc + S_TAU);
-
-    enum { HX2, RX2, CX, NX2, HY2, RY2, BY, NY2, HZ2, RZ2, HZ, NZ2, NS2, GAP, NRED };
-    vd r[NRED];
-    for (int k = 0; k < NRED; k++)
-        r[k] = vset(0.0);
-    const auto zrow = [&](int e, vd si, vd zi, vd hi, vd v) {
-        r[HZ2] += v * v;
-        v -= tau * hi;
-        ROWD(T, L.r + zb + e) = v;
-        r[RZ2] += v * v;
-        r[HZ] += hi * zi;
-        r[NZ2] += zi * zi;
-        r[NS2] += si * si;
-        r[GAP] += si * zi;
-    };
-    // mv_run subtracts the row sum; the y and z rows want it added: start from the negated initial value
-    // and negate the result (bit-identical, rounding is symmetric)
-    const auto mv_init = [&](int kind, vd, vd, vd ex1) { return kind >= MV_Z ? -ex1 : (kind == MV_Y ? vset(-0.0) : vset(0.0)); };
-    const auto mv_finish = [&](int, int kind, int q, vd v, vd ex0, vd own, vd ex1) {
-                if (kind >= MV_Z)
-                { // LP and cone rows alike: rz = s + G x
-                    zrow(q - zb, ex1, own, ex0, -v);
-                    return;
-                }
-                if (kind == MV_X)
-                { // ex0 = c_j, own = x_j
-                    r[HX2] += v * v;
-                    v -= tau * ex0;
-                    ROWD(T, L.r + q) = v;
-                    r[RX2] += v * v;
-                    r[CX] += ex0 * own;
-                    r[NX2] += own * own;
-                }
-                else
-                { // ex0 = b_i, own = y_i
-                    v = -v;
-                    r[HY2] += v * v;
-                    v -= tau * ex0;
-                    ROWD(T, L.r + q) = v;
-                    r[RY2] += v * v;
-                    r[BY] += ex0 * own;
-                    r[NY2] += own * own;
-                }
-            };
+    ResidFin fin;
+    for (int k = 0; k < RS_NRED; k++)
+        fin.r[k] = vset(0.0);
     if (tm.wk == 0 && P.mv_rows > 0)
     {
-        Pipes pp;
-        pp.init(tm, tm.pbuf);
-        if (P.pim)
-            mv_run<1, true>(tm, pp, P.mv[0], P.mv_ld1[LDV_HEAD], t.Tb, mv_init, mv_finish);
-        else
-            mv_run<1, false>(tm, pp, P.mv[0], P.mv_ld1[LDV_HEAD], t.Tb, mv_init, mv_finish);
+        Machine mm;
+        mm.init(tm, tm.pbuf);
+        MRun r;
+        r.prog = P.rs;
+        r.ld = P.rs_ld;
+        r.Tb = t.Tb;
+        r.out = r.out2 = T + (size_t)L.r * TILE;
+        r.a_one = false;
+        mm.run<MC_CONST | MC_POS | MC_BKEEP | MC_FIN | MC_X3>(tm, r, fin);
     }
-    team_sum<NRED>(tm, r);
     if (tm.wk == 0)
-        for (int k = 0; k < NRED; k++)
-            ROWD(T, L.sc + S_RED + k) = r[k];
+        for (int k = 0; k < RS_NRED; k++)
+            ROWD(T, L.sc + S_RED + k) = fin.r[k];
 }
 
 // ------------------------------------------------------------------ head of an iteration
