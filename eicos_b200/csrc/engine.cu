@@ -28,12 +28,9 @@ namespace eicos
         tm.wk = threadIdx.x >> 5;                                                              \
         tm.nwk = blockDim.x >> 5;                                                              \
         tm.red = smem;                                                                         \
-        /* vector kernels (several warps): [reduction rows]; factor kernel (one warp): [program-stream   \
-           buffers][staging = FIFO ring][slots, column buffers]; solveKKT / residual kernels (one warp):  \
-           the pipes of tile_program.hpp (ops ring, mbarriers, rows) at pbuf */                      \
+        /* vector kernels (several warps): [reduction rows]; program kernels (one warp): the shared  \
+           memory of the FMA machine (ops ring, mbarriers, rows) at pbuf */                          \
         tm.pbuf = smem + (size_t)(tm.nwk > 1 ? tm.nwk * KRED : 0) * TILE;                           \
-        tm.stage = tm.pbuf + PS_DOUBLES + tm.lane;                                                 \
-        tm.extra = tm.stage + (size_t)2 * STAGE_SLOTS * TILE;                                      \
         tm.job = JOBS ? (int)(blockIdx.x % (unsigned)a.njobs) : 0;                                 \
         fn(tm, a, JOBS ? (int)(blockIdx.x / (unsigned)a.njobs) : (int)blockIdx.x);                                                                 \
     }
@@ -71,9 +68,7 @@ __global__ void eicos_compact(const __grid_constant__ KArgs a, const __grid_cons
     {                                                                                             \
         const int nw_ = (threads), nj_ = (njobs);                                                                \
         std::vector<double> red_((size_t)nw_ * KRED * TILE + 8);                                  \
-        const size_t xr_ = (size_t)(args).P.fa_slots + 2 * (args).P.maxcol;                           \
-        std::vector<double> stg_(((size_t)nw_ * 2 * STAGE_SLOTS + xr_) * TILE + 8);                \
-        std::vector<double> pb_(std::max<size_t>(PS_DOUBLES, machine_smem_doubles((args).P.sw_rows)) + 8); \
+        std::vector<double> pb_(machine_smem_doubles(std::max((args).P.sw_budget, (args).P.fa_budget), M_MAX_RING_GROUPS) + 8); \
         for (int cta_ = 0; cta_ < (tiles) * nj_; cta_++)                                          \
         {                                                                                         \
             const int tile_ = cta_ / nj_;                                                         \
@@ -86,9 +81,7 @@ __global__ void eicos_compact(const __grid_constant__ KArgs a, const __grid_cons
                 tm_.nwk = nw_;                                                                    \
                 tm_.job = cta_ % nj_;                                                             \
                 tm_.red = red_.data();                                                            \
-                tm_.extra = stg_.data() + (size_t)2 * STAGE_SLOTS * TILE;                         \
                 tm_.pbuf = pb_.data();                                                            \
-                tm_.stage = stg_.data();                                                          \
                 tm_.bar = nw_ > 1 ? &bar_ : nullptr;                                              \
                 fn(tm_, (args), tile_);                                                           \
             };                                                                                    \
@@ -115,9 +108,20 @@ static void eicos_compact_emu(const KArgs &a, const MoveRanges &mr, const int *m
 
 // shared-memory budget of the slot programs (rows of TILE doubles per CTA)
 // (one warp per tile wants 7 CTAs per SM: ring 32 rows + 28 rows here = 30 KB per CTA at TILE = 64)
-constexpr int MAX_SW_SLOTS = 24, MAX_FA_SLOTS = 20, MAX_COLBUF_ROWS = 8;
+constexpr int MAX_SW_SLOTS = 24, MAX_FA_SLOTS = 32;
 
 int Engine::tile_width() { return TILE; }
+
+// A launch of `ctas` one-warp CTAs runs the deep-ring programs when all of them are resident at the deep
+// ring's shared-memory footprint (then nothing is lost by giving each tile more rows in flight).
+bool Engine::deep_ring(int ctas) const
+{
+    if (force_variant_ >= 0)
+        return force_variant_ > 0;
+    const size_t deep = std::max(smem_prog_[M_VARIANTS - 1], smem_factor_[M_VARIANTS - 1]) + 1024;
+    const long long per_sm = (long long)((size_t)227 * 1024 / deep);
+    return (long long)ctas <= per_sm * sms_;
+}
 
 namespace
 {
@@ -140,7 +144,7 @@ dvec expanded_geq(const Symbolic &S)
 }
 } // namespace
 
-void Engine::build_layout(const Symbolic &S)
+void Engine::build_layout(const Symbolic &S, bool acc_rows)
 {
     int at = 0;
     auto take = [&](int rows) {
@@ -183,6 +187,7 @@ void Engine::build_layout(const Symbolic &S)
     L.Ax = take(pim_ ? S.A.nnz() : 0);
     L.eq = take(pim_ ? S.N : 0);
     L.sc = take(S_COUNT);
+    L.acc = acc_rows ? take(S.nnzL) : -1;
     L.rows_total = at;
     L.irows_total = J_COUNT;
 }
@@ -197,7 +202,17 @@ void Engine::upload_pattern(const Symbolic &S)
         sw_budget = std::max(1, std::min(MAX_SW_SLOTS, std::atoi(v)));
     if (const char *v = std::getenv("EICOS_MAX_FA_SLOTS"))
         fa_budget = std::max(1, std::min(MAX_FA_SLOTS, std::atoi(v)));
-    build_streams(S, L_, workers_, sw_budget, fa_budget, H_, pim_);
+    try
+    {
+        build_streams(S, L_, workers_, sw_budget, fa_budget, H_, pim_);
+    }
+    catch (const MachineOutOfSlots &)
+    { // the factorisation's accumulators do not fit the slots: give them home rows
+        if (L_.acc >= 0)
+            throw;
+        build_layout(S, true);
+        build_streams(S, L_, workers_, sw_budget, fa_budget, H_, pim_);
+    }
     Lp_ = S.Lp;
     DevPattern &P = P_;
     P.n = S.n;
@@ -211,9 +226,6 @@ void Engine::upload_pattern(const Symbolic &S)
     P.nnzL = S.nnzL;
     P.nnzV = (int)S.Vslot.size();
     P.maxcol = S.maxcol;
-    P.fa_nld = H_.fa_nld;
-    P.fa_slots = H_.fa_slots;
-    P.fa_fast = H_.fa_fast;
     P.pim = pim_ ? 1 : 0;
     P.nnzG = S.G.nnz();
     P.nnzA = S.A.nnz();
@@ -242,6 +254,9 @@ void Engine::upload_pattern(const Symbolic &S)
         int *o = upload(h.ops, owned_, st);
         d.ops = o;
         d.nchunks = h.nchunks;
+        d.nld_chunks = h.nld_chunks;
+        d.ring_groups = h.ring_groups;
+        d.ring_row0 = M_ROW_SLOT0 + h.slot_budget;
         if (keep)
             *keep = o;
     };
@@ -252,27 +267,30 @@ void Engine::upload_pattern(const Symbolic &S)
             out[k] = list[k] == M_LD_NONE ? M_LD_NONE : (list[k] & M_LD_ROW_MASK) + off[((unsigned)list[k] >> M_LD_SEL_SHIFT) & 7];
         return upload(out, owned_, st);
     };
-    prog(H_.fw, P.fw);
-    prog(H_.bw, P.bw);
-    prog(H_.bwp, P.bwp);
-    prog(H_.mv, P.mv, &dmv_ops_[0]);
-    prog(H_.rs, P.rs, &dmv_ops_[1]);
-    P.sw_rows = H_.sw_slots;
+    P.sw_budget = H_.fw[0].slot_budget;
+    P.fa_budget = H_.fa[0].slot_budget;
     const int rhs[2] = {L_.rhs1, L_.rhs2}, sol[2] = {L_.sol1, L_.sol2}, xw[2] = {L_.xw, L_.xw2};
     const int dxr[2] = {L_.dxr, L_.dxr2}, er[2] = {L_.e, L_.e2};
-    for (int set = 0; set < 2; set++)
-    { // forward: 1 = right-hand side, 3 = xw; backward: 1 = output, 2 = accumulated solution, 3 = xw
-        P.fw_ld[set][0] = variant(H_.fw.ld, rhs[set], 0, xw[set]);
-        P.fw_ld[set][1] = variant(H_.fw.ld, er[set], 0, xw[set]);
-        P.bw_ld[set][0] = variant(H_.bwp.ld, sol[set], 0, xw[set]);
-        P.bw_ld[set][1] = variant(H_.bw.ld, dxr[set], sol[set], xw[set]);
-        P.mv_ld[set] = variant(H_.mv.ld, rhs[set], sol[set], L_.lpv, er[set]);
+    for (int v = 0; v < M_VARIANTS; v++)
+    {
+        prog(H_.fw[v], P.fw[v]);
+        prog(H_.bw[v], P.bw[v]);
+        prog(H_.bwp[v], P.bwp[v]);
+        prog(H_.mv[v], P.mv[v], &dmv_ops_[v]);
+        prog(H_.rs[v], P.rs[v], &drs_ops_[v]);
+        prog(H_.fa[v], P.fa[v], &dfa_ops_[v]);
+        for (int set = 0; set < 2; set++)
+        { // forward: 1 = right-hand side, 3 = xw; backward: 1 = output, 2 = accumulated solution, 3 = xw
+            P.fw_ld[v][set][0] = variant(H_.fw[v].ld, rhs[set], 0, xw[set]);
+            P.fw_ld[v][set][1] = variant(H_.fw[v].ld, er[set], 0, xw[set]);
+            P.bw_ld[v][set][0] = variant(H_.bwp[v].ld, sol[set], 0, xw[set]);
+            P.bw_ld[v][set][1] = variant(H_.bw[v].ld, dxr[set], sol[set], xw[set]);
+            P.mv_ld[v][set] = variant(H_.mv[v].ld, rhs[set], sol[set], L_.lpv, er[set]);
+        }
+        P.rs_ld[v] = variant(H_.rs[v].ld, L_.chb, L_.w, L_.s, L_.r, L_.sc);
+        P.fa_ld[v] = variant(H_.fa[v].ld, 0, 0, 0);
     }
-    P.rs_ld = variant(H_.rs.ld, L_.chb, L_.w, L_.s, L_.r, L_.sc);
     P.mv_rows = H_.mv_rows;
-    P.fa = upload(H_.fa, owned_, st);
-    P.fa_ld = upload(H_.fa_ld, owned_, st);
-    P.fa_val = dfa_val_ = upload(H_.fa_val, owned_, st);
     ivec vk;
     for (int k = 0; k < S.l; k++)
         vk.push_back(0);
@@ -299,10 +317,13 @@ void Engine::upload_values(const Symbolic &S)
     be::h2d(dxeq_, S.xeq.data(), S.xeq.size() * sizeof(double), st);
     be::h2d(dAeq_, S.Aeq.data(), S.Aeq.size() * sizeof(double), st);
     be::h2d(dGeq_, ge.data(), ge.size() * sizeof(double), st);
-    be::h2d(dfa_val_, H_.fa_val.data(), H_.fa_val.size() * sizeof(double), st);
-    // the mat-vec programs carry the shared coefficients inline
-    be::h2d(dmv_ops_[0], H_.mv.ops.data(), H_.mv.ops.size() * sizeof(int), st);
-    be::h2d(dmv_ops_[1], H_.rs.ops.data(), H_.rs.ops.size() * sizeof(int), st);
+    // the mat-vec and factor programs carry the shared coefficients inline
+    for (int v = 0; v < M_VARIANTS; v++)
+    {
+        be::h2d(dmv_ops_[v], H_.mv[v].ops.data(), H_.mv[v].ops.size() * sizeof(int), st);
+        be::h2d(drs_ops_[v], H_.rs[v].ops.data(), H_.rs[v].ops.size() * sizeof(int), st);
+        be::h2d(dfa_ops_[v], H_.fa[v].ops.data(), H_.fa[v].ops.size() * sizeof(int), st);
+    }
     be::sync(st);
 }
 
@@ -311,8 +332,10 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
       pim_(instance_matrices), nnzG_(S.G.nnz()), nnzA_(S.A.nnz())
 {
     be::set_device(device_);
+    if (const char *v = std::getenv("EICOS_RING_VARIANT")) // (diagnostics / tests) pin the ring depth of every launch
+        force_variant_ = std::atoi(v);
     stream_ = (void *)(intptr_t)be::make_stream();
-    build_layout(S);
+    build_layout(S, false);
     upload_pattern(S);
     cap_tiles_ = std::max<long long>(1, (capacity_instances + TILE - 1) / TILE);
     ws_bytes_ = (size_t)cap_tiles_ * L_.rows_total * TILE * sizeof(double);
@@ -331,26 +354,26 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
     moves_dev_ = (int *)be::alloc(2 * slots * sizeof(int));
     status_host_ = (int *)be::pinned(slots * sizeof(int));
     moves_host_ = (int *)be::pinned(2 * slots * sizeof(int));
-    // program kernels (one warp per tile): stream buffers + FIFO ring + slots; vector kernels: reduction rows only
-    const size_t smem_base = ((size_t)2 * STAGE_SLOTS * TILE + PS_DOUBLES) * sizeof(double);
-    smem_prog_ = machine_smem_doubles(P_.sw_rows) * sizeof(double);
-    smem_common_ = workers_ > 1 ? (size_t)workers_ * KRED * TILE * sizeof(double) : 0;
-    xrows_factor_ = H_.fa_slots + (H_.fa_fast ? 0 : 2 * S.maxcol); // record form keeps the column in registers
-#ifndef EICOS_EMU
-    if (!H_.fa_fast && 2 * S.maxcol > MAX_COLBUF_ROWS)
-    { // the column buffers of the factorisation spill to global memory (one slab per tile)
-        acc_global_ = (double *)be::alloc((size_t)cap_tiles_ * 2 * S.maxcol * TILE * sizeof(double));
-        xrows_factor_ = H_.fa_slots;
-    }
-#endif
-    smem_factor_ = smem_base + (size_t)xrows_factor_ * TILE * sizeof(double);
-#ifndef EICOS_EMU
-    if (smem_factor_ > 48 * 1024)
-        EI_CUDA(cudaFuncSetAttribute(eicos_ldl_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_factor_));
-    if (smem_prog_ > 48 * 1024)
+    // program kernels (one warp per tile): the shared memory of the FMA machine; vector kernels: reduction rows only
+    for (int v = 0; v < M_VARIANTS; v++)
     {
-        EI_CUDA(cudaFuncSetAttribute(eicos_solve_kkt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prog_));
-        EI_CUDA(cudaFuncSetAttribute(eicos_residuals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prog_));
+        smem_prog_[v] = machine_smem_doubles(P_.sw_budget, M_VARIANT_GROUPS[v]) * sizeof(double);
+        smem_factor_[v] = machine_smem_doubles(P_.fa_budget, M_VARIANT_GROUPS[v]) * sizeof(double);
+    }
+    smem_common_ = workers_ > 1 ? (size_t)workers_ * KRED * TILE * sizeof(double) : 0;
+#ifndef EICOS_EMU
+    {
+        const size_t top_f = std::max(smem_factor_[0], smem_factor_[M_VARIANTS - 1]), top_p = std::max(smem_prog_[0], smem_prog_[M_VARIANTS - 1]);
+        if (top_f > 48 * 1024)
+            EI_CUDA(cudaFuncSetAttribute(eicos_ldl_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)top_f));
+        if (top_p > 48 * 1024)
+        {
+            EI_CUDA(cudaFuncSetAttribute(eicos_solve_kkt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)top_p));
+            EI_CUDA(cudaFuncSetAttribute(eicos_residuals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)top_p));
+        }
+        int dev_sms = 148;
+        EI_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, device_));
+        sms_ = dev_sms;
     }
     if (smem_common_ > 48 * 1024)
     {
@@ -376,7 +399,6 @@ Engine::~Engine()
         be::dfree(p);
     be::dfree(ws_);
     be::dfree(iws_);
-    be::dfree(acc_global_);
     be::dfree(base_vec_);
     be::dfree(base_mat_);
     be::dfree(active_count_);
@@ -410,14 +432,14 @@ ProgramStats Engine::program_stats() const
     ProgramStats p;
     p.sw_slots = H_.sw_slots;
     p.fa_slots = H_.fa_slots;
-    p.fa_fast = H_.fa_fast;
+    p.fa_fast = 1;
     p.sw_far = H_.sw_far;
-    p.sw_direct = H_.sw_direct;
+    p.sw_direct = 0;
     p.fa_home = H_.fa_home;
-    p.fw_loads = H_.fw.nld - (int)H_.fw.pads;
-    p.bw_loads = H_.bw.nld - (int)H_.bw.pads;
-    p.fa_loads = H_.fa_nld;
-    p.mv_loads = H_.mv.nld - (int)H_.mv.pads;
+    p.fw_loads = H_.fw[0].nld - (int)H_.fw[0].pads;
+    p.bw_loads = H_.bw[0].nld - (int)H_.bw[0].pads;
+    p.fa_loads = H_.fa[0].nld - (int)H_.fa[0].pads;
+    p.mv_loads = H_.mv[0].nld - (int)H_.mv[0].pads;
     return p;
 }
 
@@ -443,7 +465,6 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
     a.L = L_;
     a.ws = ws_;
     a.iws = iws_;
-    a.acc_global = acc_global_;
     a.in_c = d_c;
     a.in_h = d_h;
     a.in_b = d_b;
@@ -476,7 +497,6 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
     a.active_count = active_count_;
     a.ir_rounds = ir_rounds_;
     a.njobs = 1;
-    a.xrows = 0;
     be::zero(ir_rounds_, 8 * sizeof(unsigned long long), st);
 
     const int threads = workers_ * (LANES == 1 ? 1 : 32), threads1 = LANES == 1 ? 1 : 32;
@@ -541,11 +561,12 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
         a.first = (int)first;
         stt.chunks++;
 
+        // ring depth of a launch: deep when its CTAs would leave most of the machine's shared memory idle
+        auto pick = [&](int ctas) { a.variant = deep_ring(ctas) ? M_VARIANTS - 1 : 0; };
         auto factor = [&]() {
-            a.xrows = xrows_factor_;
-            EI_TIMED(0, EI_LAUNCH(eicos_ldl_factor, tile_factor, tiles, threads1, smem_factor_, st, a));
-            a.xrows = 0;
-            stt.factor_launches++;
+            pick(tiles);
+            EI_TIMED(0, EI_LAUNCH(eicos_ldl_factor, tile_factor, tiles, threads1, smem_factor_[a.variant], st, a));
+                    stt.factor_launches++;
             stt.factor_launch_tiles += tiles;
         };
         // solveKKT launches: one job, or the two solves of an iteration that share the factor and do
@@ -556,7 +577,8 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
             a.job[1] = {L_.rhs2, L_.sol2, nit2, 1};
             a.njobs = 2;
             a.initialize = init;
-            EI_TIMED(1, EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt, tiles, 2, threads1, smem_prog_, st, a));
+            pick(2 * tiles);
+            EI_TIMED(1, EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt, tiles, 2, threads1, smem_prog_[a.variant], st, a));
             stt.solve_launches++;
             stt.solve_launch_tiles += (long long)tiles * 2;
         };
@@ -564,7 +586,8 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
             a.job[0] = {L_.rhs2, L_.sol2, nitrow, 1};
             a.njobs = 1;
             a.initialize = 0;
-            EI_TIMED(1, EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt, tiles, 1, threads1, smem_prog_, st, a));
+            pick(tiles);
+            EI_TIMED(1, EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt, tiles, 1, threads1, smem_prog_[a.variant], st, a));
             stt.solve_launches++;
             stt.solve_launch_tiles += tiles;
         };
@@ -580,7 +603,8 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
         for (int it = 0; it <= Settings::iter_max + 1; it++)
         {
             be::zero(active_count_, sizeof(unsigned int), st);
-            EI_TIMED(2, EI_LAUNCH(eicos_residuals, tile_resid, tiles, threads1, smem_prog_, st, a));
+            pick(tiles);
+            EI_TIMED(2, EI_LAUNCH(eicos_residuals, tile_resid, tiles, threads1, smem_prog_[a.variant], st, a));
             EI_TIMED(2, EI_LAUNCH(eicos_iter_head, tile_head, tiles, threads, smem_common_, st, a));
             stt.ipm_iterations++;
             be::d2h(host_pinned_, active_count_, sizeof(unsigned int), st);
@@ -690,7 +714,6 @@ void Engine::debug_factor_init(int batch, const double *d_c, const double *d_h, 
     a.L = L_;
     a.ws = ws_;
     a.iws = iws_;
-    a.acc_global = acc_global_;
     a.in_c = d_c;
     a.in_h = d_h;
     a.in_b = d_b;
@@ -706,7 +729,6 @@ void Engine::debug_factor_init(int batch, const double *d_c, const double *d_h, 
     be::sync(st);
     a.batch = batch;
     a.first = 0;
-    a.xrows = 0;
     const int tiles = (batch + TILE - 1) / TILE;
     const int threads = workers_ * (LANES == 1 ? 1 : 32), threads1 = LANES == 1 ? 1 : 32;
     (void)threads;
@@ -719,14 +741,13 @@ void Engine::debug_factor_init(int batch, const double *d_c, const double *d_h, 
     if (pim_)
         EI_LAUNCH(eicos_equilibrate, tile_equil, tiles, threads, smem_common_, st, a);
     EI_LAUNCH(eicos_init, tile_init, tiles, threads, smem_common_, st, a);
-    a.xrows = xrows_factor_;
-    EI_LAUNCH(eicos_ldl_factor, tile_factor, tiles, threads1, smem_factor_, st, a);
-    a.xrows = 0;
+    a.variant = deep_ring(2 * tiles) ? M_VARIANTS - 1 : 0;
+    EI_LAUNCH(eicos_ldl_factor, tile_factor, tiles, threads1, smem_factor_[a.variant], st, a);
     a.initialize = 1;
     a.njobs = 2;
     a.job[0] = {L_.rhs1, L_.sol1, J_NIT1, 0};
     a.job[1] = {L_.rhs2, L_.sol2, J_NIT2, 1};
-    EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt, tiles, 2, threads1, smem_prog_, st, a);
+    EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt, tiles, 2, threads1, smem_prog_[a.variant], st, a);
     be::sync(st);
     // gather rows back to instance-major host arrays; L comes back in CSC order
     const size_t tile_doubles = (size_t)L_.rows_total * TILE;
@@ -750,7 +771,9 @@ void Engine::debug_factor_init(int batch, const double *d_c, const double *d_h, 
             if (h_Lx)
                 for (int u = 0; u < P_.nnzL; u++)
                     h_Lx[inst * P_.nnzL + u] = buf[(size_t)(L_.Lx + u) * TILE + lane];
-            grab(h_D, L_.D, P_.N);
+            if (h_D) // the factorisation keeps 1 / D only (what the sweeps read)
+                for (int r = 0; r < P_.N; r++)
+                    h_D[inst * P_.N + r] = 1.0 / buf[(size_t)(L_.Dinv + r) * TILE + lane];
             grab(h_sol1, L_.sol1, P_.N);
             grab(h_sol2, L_.sol2, P_.N);
             if (h_nit)

@@ -40,7 +40,7 @@ struct SolveStats
 // what the program compiler (streams.cpp) produced for this pattern
 struct ProgramStats
 {
-    int sw_slots = 0, fa_slots = 0, fa_fast = 0;
+    int sw_slots = 0, fa_slots = 0, fa_fast = 0; // fa_fast: the factorisation is a machine program (always 1)
     long long sw_far = 0, sw_direct = 0, fa_home = 0; // operands served by far gathers / direct loads / home rows
     int fw_loads = 0, bw_loads = 0, fa_loads = 0, mv_loads = 0; // rows each program reads from HBM per run
 };
@@ -92,7 +92,7 @@ class Engine
     static int tile_width();
 
   private:
-    void build_layout(const Symbolic &S);
+    void build_layout(const Symbolic &S, bool acc_rows);
     void upload_pattern(const Symbolic &S);
 
     int device_ = 0, workers_ = 4;
@@ -107,20 +107,19 @@ class Engine
     DevPattern P_{};
     double *ws_ = nullptr;
     int *iws_ = nullptr;
-    double *acc_global_ = nullptr;
     double *base_vec_ = nullptr; // device copy of base c|h|b
     unsigned int *active_count_ = nullptr;
     unsigned long long *ir_rounds_ = nullptr;
     unsigned int *host_pinned_ = nullptr;
     int *moves_dev_ = nullptr, *status_host_ = nullptr, *moves_host_ = nullptr; // active-set compaction
     bool compaction_ = true;
-    size_t smem_factor_ = 0, smem_common_ = 0, smem_prog_ = 0; // factor kernel / vector kernels / solveKKT + residual kernels
-    int xrows_factor_ = 0; // shared-memory rows behind the FIFO ring in the factor kernel (slots + column buffers)
+    size_t smem_factor_[M_VARIANTS] = {0, 0}, smem_common_ = 0, smem_prog_[M_VARIANTS] = {0, 0}; // factor kernel / vector kernels / solveKKT + residual kernels (per ring variant)
+    int sms_ = 148, force_variant_ = -1;
+    bool deep_ring(int ctas) const;
     std::vector<void *> owned_; // device allocations holding pattern data
     // positions of value arrays that upload_values() rewrites
     double *dxeq_ = nullptr, *dAeq_ = nullptr, *dGeq_ = nullptr;
-    int *dmv_ops_[2] = {nullptr, nullptr};
-    double *dfa_val_ = nullptr;
+    int *dmv_ops_[M_VARIANTS] = {nullptr, nullptr}, *drs_ops_[M_VARIANTS] = {nullptr, nullptr}, *dfa_ops_[M_VARIANTS] = {nullptr, nullptr};
     HostStreams H_;        // host copy of the instruction streams (value streams are rebuilt on updateData)
     std::vector<int> Lp_;  // column pointers of L (debug extraction)
     std::vector<void *> events_;

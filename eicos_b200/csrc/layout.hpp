@@ -83,6 +83,7 @@ struct Layout
     int Gx, Ax, eq;                 // per-instance-matrices mode: equilibrated G / A values (CSC order), and the
                                     // equilibration vectors KKT-shaped [x_equil | A_equil | G_equil expanded] (N rows)
     int sc;                         // S_COUNT scalar rows
+    int acc;                        // home rows of the factorisation's accumulators (nnzL rows), or -1: they live in slots only
     int rows_total;
     int irows_total;                // integer rows (J_COUNT)
 };
@@ -91,7 +92,10 @@ struct Layout
 struct DevMachine
 {
     const int *ops;
-    int nchunks;
+    int nchunks;     // 1 KB chunks of the record stream
+    int nld_chunks;  // 1 KB chunks of its load lists
+    int ring_groups; // depth of the data ring it was compiled for
+    int ring_row0;   // shared-memory row the ring starts at
 };
 
 enum ConeParam : int
@@ -110,19 +114,18 @@ struct DevPattern
     // of the tile): a job set is (rhs1, sol1) with work vectors xw / dxr / e (set 0) or (rhs2, sol2) with
     // xw2 / dxr2 / e2 (set 1); [set][first solve | refinement round].  The backward sweep of a first solve
     // runs the plain program bwp, a refinement round the accumulating program bw.
-    DevMachine fw, bw, bwp, mv, rs;
-    const int *fw_ld[2][2], *bw_ld[2][2], *mv_ld[2], *rs_ld;
+    // Every program exists for two depths of the data ring (first index; streams.hpp: M_VARIANT_GROUPS).
+    DevMachine fw[2], bw[2], bwp[2], mv[2], rs[2];
+    const int *fw_ld[2][2][2], *bw_ld[2][2][2], *mv_ld[2][2], *rs_ld[2];
     int mv_rows;
-    int sw_rows; // shared-memory rows behind M_ROW_SLOT0 the programs use
-    // factor program (FIFO form)
-    const int *fa, *fa_ld;
-    int fa_nld, fa_slots;
-    int fa_fast;   // the factor program is in record form (streams.hpp)
+    int sw_budget, fa_budget; // slot rows of the solveKKT / residual programs and of the factor program
+    // factor program (absolute rows: its load list needs no materialisation)
+    DevMachine fa[2];
+    const int *fa_ld[2];
     // per-instance-matrices mode (every instance has its own G / A values): 1, and the index arrays
     // the on-device equilibration walks (CSC of G and A, their CSR views as row pointer + value index)
     int pim, nnzG, nnzA;
     const int *Gp, *Gi, *Ap, *Ai, *Grp, *Grv, *Arp, *Arv, *cone_z;
-    const double *fa_val;
     const int *Vkind; // per V entry: what resetKKTScalings writes (0 -> -1, 1 -> 0, 2 -> +1)
 };
 

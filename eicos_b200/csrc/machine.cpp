@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstring>
 #include <cstdlib>
+#include <queue>
 #include <set>
 #include <stdexcept>
 
@@ -61,18 +62,53 @@ void schedule(const MProgram &P, int window, std::vector<ivec> &bundles, ivec &b
             prio[t] = std::max(prio[t], 1 + prio[c]);
     // values without a home row must find a slot: their operations go first, while slots are free
     for (int t = 0; t < n; t++)
-        if (P.ops[t].dst >= 0 && P.vals[P.ops[t].dst].home_sel < 0)
+        if (P.ops[t].dst >= 0 && P.vals[P.ops[t].dst].home_sel < 0 && npred[t] == 0)
             prio[t] = INT_MAX / 2;
     // Only operations close to the oldest unscheduled one (program order = elimination order, whose values
     // are short-lived) are candidates: running far ahead would fill the slots with values nobody reads soon.
+    bundle_of.assign(n, -1);
+    bundles.clear();
+    ivec fresh;
+    if (window >= n)
+    { // no window: a heap by (priority, program order)
+        typedef std::pair<int, int> key;
+        std::priority_queue<key> heap;
+        for (int t = 0; t < n; t++)
+            if (npred[t] == 0)
+                heap.push({prio[t], -t});
+        int done = 0;
+        while (done < n)
+        {
+            if (heap.empty())
+                throw std::logic_error("machine: dependency cycle");
+            ivec cur;
+            while (!heap.empty() && (int)cur.size() < M_U)
+            {
+                cur.push_back(-heap.top().second);
+                heap.pop();
+            }
+            std::sort(cur.begin(), cur.end());
+            const int b = (int)bundles.size();
+            fresh.clear();
+            for (int t : cur)
+            {
+                bundle_of[t] = b;
+                done++;
+                for (int c : succ[t])
+                    if (--npred[c] == 0)
+                        fresh.push_back(c);
+            }
+            for (int c : fresh)
+                heap.push({prio[c], -c});
+            bundles.push_back(cur);
+        }
+        return;
+    }
     std::set<int> ready; // by index
     for (int t = 0; t < n; t++)
         if (npred[t] == 0)
             ready.insert(t);
-    bundle_of.assign(n, -1);
-    bundles.clear();
     int done = 0, oldest = 0;
-    ivec fresh;
     std::vector<std::pair<int, int>> cand; // (-priority, index)
     while (done < n)
     {
@@ -108,10 +144,15 @@ void schedule(const MProgram &P, int window, std::vector<ivec> &bundles, ivec &b
 
 void verify(const MProgram &P, const std::vector<ivec> &bundles, const MachineCode &mc);
 
-void compile_with_window(const MProgram &P, int max_slots, int window, MachineCode &out)
+void compile_with_window(const MProgram &P, int max_slots, int window, int RG, MachineCode &out)
 {
+    if (RG < 2 || RG > M_MAX_RING_GROUPS)
+        throw std::logic_error("machine: ring depth out of range");
+    const int RING_ROWS = RG * M_RING_GROUP, ring0 = M_ROW_SLOT0 + std::max(max_slots, 0);
     out = MachineCode();
     out.window = window;
+    out.ring_groups = RG;
+    out.slot_budget = std::max(max_slots, 0);
     const int n = (int)P.ops.size(), nv = (int)P.vals.size();
     std::vector<ivec> bundles;
     ivec bundle_of;
@@ -158,7 +199,7 @@ void compile_with_window(const MProgram &P, int max_slots, int window, MachineCo
     std::vector<long long> first_pop(nb + 1, 0);
     const auto push_pop = [&](int word) {
         out.ld.push_back(word);
-        return (int)(npop++ % M_RING_ROWS);
+        return ring0 + (int)(npop++ % RING_ROWS);
     };
     const auto pad_to = [&](long long target) {
         while (npop < target)
@@ -175,7 +216,7 @@ void compile_with_window(const MProgram &P, int max_slots, int window, MachineCo
         if (prev_ctrl_at < 0)
             return;
         const int nrel = (int)(npop / M_RING_GROUP) - released;
-        if (nrel < 0 || nrel > 7)
+        if (nrel < 0 || nrel > 31)
             throw std::logic_error("machine: bundle releases too many ring groups");
         released += nrel;
         out.ops[(size_t)prev_ctrl_at] |= (prev_wait << MF_WAIT_SHIFT) | (nrel << MF_NREL_SHIFT);
@@ -207,7 +248,7 @@ void compile_with_window(const MProgram &P, int max_slots, int window, MachineCo
             pad_to((first_pop[pbmax] / M_RING_GROUP + 2) * M_RING_GROUP);
         close_prev();
         first_pop[b] = npop;
-        const long long window_end = (first_pop[b] / M_RING_GROUP + M_RING_GROUPS) * M_RING_GROUP; // rows issued so far
+        const long long window_end = (first_pop[b] / M_RING_GROUP + RG) * M_RING_GROUP; // rows issued so far
 
         // ---- records; pops of single-use rows first, re-reads of written values last (they need late ring positions)
         const size_t rec0 = out.ops.size();
@@ -311,7 +352,7 @@ void compile_with_window(const MProgram &P, int max_slots, int window, MachineCo
         {
             const int v = rr.val, pb = written_at[v];
             if (pb >= 0)
-                pad_to((first_pop[pb] / M_RING_GROUP + M_RING_GROUPS) * M_RING_GROUP);
+                pad_to((first_pop[pb] / M_RING_GROUP + RG) * M_RING_GROUP);
             const MVal &mv = P.vals[v];
             out.ops[rr.at] = field(push_pop((mv.home_sel << M_LD_SEL_SHIFT) | mv.home_row));
             out.far++;
@@ -369,7 +410,7 @@ void compile_with_window(const MProgram &P, int max_slots, int window, MachineCo
             { // a partial sum without a slot waits in its home row
                 const MVal &mv = P.vals[v];
                 if (mv.home_sel < 0)
-                    throw std::logic_error("machine: out of slots for a value without a home row");
+                    throw MachineOutOfSlots("machine: out of slots for a value without a home row");
                 out.ops[d.f_at] |= MF_OUT;
                 out.ops[d.f_at + 1] = mv.home_row;
                 written_at[v] = b;
@@ -395,10 +436,12 @@ void compile_with_window(const MProgram &P, int max_slots, int window, MachineCo
             const int g_need = (int)((npop - 1) / M_RING_GROUP);
             if (g_need > waited_upto)
             {
-                const int allowed = M_RING_GROUPS + released - 1 - g_need;
-                if (allowed < 0 || allowed >= M_RING_GROUPS)
+                const int allowed = RG + released - 1 - g_need;
+                if (allowed < 0 || allowed >= RG)
                     throw std::logic_error("machine: wait depth out of range");
-                prev_wait = allowed + 1;
+                prev_wait = 1;
+                while (prev_wait + 1 < M_WAIT_CODES && M_WAIT_N[prev_wait + 1] <= allowed)
+                    prev_wait++;
                 waited_upto = g_need;
             }
         }
@@ -423,9 +466,10 @@ void compile_with_window(const MProgram &P, int max_slots, int window, MachineCo
     out.nchunks = (out.nbundles + M_CHUNK_BUNDLES - 1) / M_CHUNK_BUNDLES;
     out.ops.resize((size_t)(out.nchunks + 1) * M_CHUNK_WORDS, 0); // + one chunk the record look-ahead may touch
     out.nld = (int)out.ld.size();
-    while (out.ld.size() % M_RING_ROWS)
+    out.ld.insert(out.ld.end(), (size_t)RING_ROWS, M_LD_NONE); // refills run RG groups ahead of the consumer
+    while (out.ld.size() % M_LD_CHUNK_WORDS)
         out.ld.push_back(M_LD_NONE);
-    out.ld.insert(out.ld.end(), (size_t)2 * M_RING_ROWS, M_LD_NONE); // refills run GROUPS groups ahead, their words one more
+    out.nld_chunks = (int)(out.ld.size() / M_LD_CHUNK_WORDS);
     out.slot_rows = slot_top;
     if (P.ops.size() <= 400000 || std::getenv("EICOS_VERIFY_PROGRAMS"))
         verify(P, bundles, out);
@@ -443,7 +487,8 @@ void verify(const MProgram &P, const std::vector<ivec> &bundles, const MachineCo
         int kind = 0; // 0 unknown, 1 ring copy (word, version), 2 value
         int word = 0, ver = -3, val = -1;
     };
-    const int nrows = M_ROW_SLOT0 + std::max(mc.slot_rows, 1);
+    const int RING_ROWS = mc.ring_groups * M_RING_GROUP, ring0 = M_ROW_SLOT0 + mc.slot_budget;
+    const int nrows = ring0 + RING_ROWS;
     std::vector<Tag> rows((size_t)nrows);
     std::vector<std::pair<long long, int>> gl; // sorted (home word, value id last written)
     std::vector<int> gver;                     // parallel hash: use a map keyed by word
@@ -479,7 +524,7 @@ void verify(const MProgram &P, const std::vector<ivec> &bundles, const MachineCo
             const int w = mc.ld[(size_t)idx];
             if (w == M_LD_NONE)
                 continue;
-            Tag &t = rows[(size_t)(idx % M_RING_ROWS)];
+            Tag &t = rows[(size_t)(ring0 + idx % RING_ROWS)];
             t.kind = 1;
             t.word = w;
             const int s = slot_of_word(w);
@@ -487,7 +532,7 @@ void verify(const MProgram &P, const std::vector<ivec> &bundles, const MachineCo
         }
         issued++;
     };
-    for (int g = 0; g < M_RING_GROUPS; g++)
+    for (int g = 0; g < mc.ring_groups; g++)
         refill();
     const auto fail = [&](int b, int u, const char *what) {
         throw std::logic_error("machine verify: bundle " + std::to_string(b) + " op " + std::to_string(u) + ": " + what);
@@ -529,7 +574,11 @@ void verify(const MProgram &P, const std::vector<ivec> &bundles, const MachineCo
                     const int want = producer[s.val] < 0 ? -1 : s.val;
                     if (t.kind == 1 && mv.home_sel >= 0 && t.word == ((mv.home_sel << M_LD_SEL_SHIFT) | mv.home_row) && t.ver == want)
                         break;
-                    fail(b, u, name);
+                    fail(b, u, (std::string(name) + ": wants value " + std::to_string(s.val) + " (home word " +
+                                std::to_string(mv.home_sel >= 0 ? ((mv.home_sel << M_LD_SEL_SHIFT) | mv.home_row) : -1) + ", producer " +
+                                std::to_string(producer[s.val]) + "), row " + std::to_string(row) + " holds kind " + std::to_string(t.kind) +
+                                " word " + std::to_string(t.word) + " ver " + std::to_string(t.ver) + " val " + std::to_string(t.val))
+                                   .c_str());
                 }
                 }
             };
@@ -547,7 +596,7 @@ void verify(const MProgram &P, const std::vector<ivec> &bundles, const MachineCo
             const int krow = w[3] >> M_FIELD_SHIFT;
             if (krow != M_ROW_TRASH)
             {
-                if (krow < M_ROW_SLOT0 || krow >= nrows)
+                if (krow < M_ROW_SLOT0 || krow >= ring0)
                     fail(b, u, "destination is not a slot");
                 rows[(size_t)krow].kind = 2;
                 rows[(size_t)krow].val = op.dst;
@@ -562,13 +611,13 @@ void verify(const MProgram &P, const std::vector<ivec> &bundles, const MachineCo
             if (w[4] & MF_BKEEP)
             {
                 const int row = w[5] >> M_FIELD_SHIFT;
-                if (op.b.kind != MS_VAL || row < M_ROW_SLOT0 || row >= nrows)
+                if (op.b.kind != MS_VAL || row < M_ROW_SLOT0 || row >= ring0)
                     fail(b, u, "bad keep");
                 rows[(size_t)row].kind = 2;
                 rows[(size_t)row].val = op.b.val;
             }
         }
-        for (int k = (rec[4] >> MF_NREL_SHIFT) & 7; k > 0; k--)
+        for (int k = (rec[4] >> MF_NREL_SHIFT) & 31; k > 0; k--)
             refill();
     }
 }
@@ -578,39 +627,43 @@ void verify(const MProgram &P, const std::vector<ivec> &bundles, const MachineCo
 // The look-ahead window of the scheduler trades bundles (latency of one tile) against re-reads (HBM traffic of
 // the batch); which one wins depends on the shape of the dependency graph, so a few windows are compiled and
 // the cheapest program is kept: cost = bundles + rows read from global memory (+ a little for padding pops).
-void machine_compile(const MProgram &P, int max_slots, MachineCode &out, int tune_slots)
+void machine_compile(const MProgram &P, int max_slots, MachineCode &out, int tune_slots, int ring_groups, int window)
 {
     if (tune_slots < max_slots)
         tune_slots = max_slots;
     if (const char *v = std::getenv("EICOS_SCHED_WINDOW"))
+        window = std::max(M_U, std::atoi(v));
+    if (window <= 0)
     {
-        compile_with_window(P, max_slots, std::max(M_U, std::atoi(v)), out);
-        return;
-    }
-    const int windows[] = {16, 32, 64, 128, 512, INT_MAX / 2};
-    double best = 0;
-    bool have = false;
-    for (int w : windows)
-    {
-        MachineCode c;
-        compile_with_window(P, tune_slots, w, c);
-        const double cost = (double)c.nbundles + (double)(c.nld - c.pads) + 0.25 * (double)c.pads;
-        if (!have || cost < best)
+        const int windows[] = {16, 32, 64, 128, 512, INT_MAX / 2};
+        double best = 0;
+        for (int w : windows)
         {
-            best = cost;
-            have = true;
-            out = std::move(c);
+            if ((long long)P.ops.size() > 300000)
+            { // huge programs (dense fronts): no tuning
+                window = 128;
+                break;
+            }
+            MachineCode c;
+            try
+            {
+                compile_with_window(P, tune_slots, w, 4, c);
+            }
+            catch (const MachineOutOfSlots &)
+            { // this order of operations keeps more values without a home row alive than there are slots
+                continue;
+            }
+            const double cost = (double)c.nbundles + (double)(c.nld - c.pads) + 0.25 * (double)c.pads;
+            if (window <= 0 || cost < best)
+            {
+                best = cost;
+                window = w;
+            }
         }
-        if ((long long)P.ops.size() > 4000000)
-            break; // huge programs: one compile
+        if (window <= 0)
+            throw MachineOutOfSlots("machine: no order of the operations fits the slots");
     }
-    // the window is a property of the pattern (chosen with the roomy budget): a tighter slot budget changes where
-    // values wait, never the order of the operations
-    if (tune_slots != max_slots)
-    {
-        const int w = out.window;
-        compile_with_window(P, max_slots, w, out);
-    }
+    compile_with_window(P, max_slots, window, ring_groups, out);
 }
 
 } // namespace eicos

@@ -10,7 +10,9 @@
 // traffic are known to the host.  The host therefore compiles each kernel into a statically scheduled
 // program for a small 3-address machine:
 //   * operands live in shared-memory rows: a RING that global rows are gathered into by cp.async a few
-//     groups ahead of use (the program's load list, in consumption order), SLOTS that hold computed
+//     groups ahead of use (the program's load list, in consumption order; the ring depth is what bounds
+//     the bytes one tile has in flight, so every program is compiled for a shallow ring - full machine -
+//     and a deep one - few tiles per SM), SLOTS that hold computed
 //     values for their live range (Belady allocation, evicted values are re-read from their home row),
 //     and three constant rows (0, -0, scratch);
 //   * operations are 32-byte records {A, B, C, K, flags, out, constant}; M_U of them form a BUNDLE of
@@ -25,6 +27,7 @@
 
 #include "symbolic.hpp"
 
+#include <stdexcept>
 #include <vector>
 
 namespace eicos
@@ -36,8 +39,15 @@ constexpr int M_BUNDLE_WORDS = M_U * M_REC_WORDS;
 constexpr int M_CHUNK_BUNDLES = 8; // bundles per TMA chunk of the record stream (1 KB)
 constexpr int M_CHUNK_WORDS = M_CHUNK_BUNDLES * M_BUNDLE_WORDS;
 constexpr int M_CHUNKS = 4;        // chunks in the shared-memory ops ring
-constexpr int M_RING_GROUP = 8, M_RING_GROUPS = 4, M_RING_ROWS = M_RING_GROUP * M_RING_GROUPS;
-constexpr int M_ROW_ZERO = M_RING_ROWS, M_ROW_NEGZERO = M_RING_ROWS + 1, M_ROW_TRASH = M_RING_ROWS + 2, M_ROW_SLOT0 = M_RING_ROWS + 3;
+constexpr int M_RING_GROUP = 8;    // rows per ring group (= one cp.async commit group)
+constexpr int M_MAX_RING_GROUPS = 16;
+// shared-memory rows: 0, -0, scratch, the slots (the program's slot budget), then the ring
+constexpr int M_ROW_ZERO = 0, M_ROW_NEGZERO = 1, M_ROW_TRASH = 2, M_ROW_SLOT0 = 3;
+// the load list arrives in shared memory like the records: chunks of M_LD_CHUNK_WORDS words by TMA
+constexpr int M_LD_CHUNK_WORDS = 256, M_LD_CHUNK_GROUPS = M_LD_CHUNK_WORDS / M_RING_GROUP, M_LD_CHUNKS = 2;
+// WAIT codes of the bundle control: cp.async.wait_group takes an immediate, deep rings get the nearest one below
+constexpr int M_WAIT_CODES = 8;
+constexpr int M_WAIT_N[M_WAIT_CODES] = {-1, 0, 1, 2, 3, 5, 8, 12};
 constexpr int M_FIELD_SHIFT = 9;   // a field is row << 9: the byte offset of a 512-byte row on the device
 constexpr int M_LD_NONE = -1;      // load-list word: no copy (padding)
 constexpr int M_LD_SEL_SHIFT = 28; // load-list word before materialisation: selector << 28 | row
@@ -52,7 +62,7 @@ constexpr int M_LD_ROW_MASK = (1 << M_LD_SEL_SHIFT) - 1;
 //   MF_AONE:  A = 1.0 when the run's `a_one` switch is set (the LP scaling term of the refinement residual
 //             while the scalings are the identity, src/eicos.cpp:1557-1559)
 // bundle control, in the flags of a bundle's first record:
-//   WAIT  n > 0: cp.async.wait_group(n - 1) before the operand loads
+//   WAIT  code > 0: cp.async.wait_group(M_WAIT_N[code]) before the operand loads
 //   NREL  ring groups consumed by the end of this bundle: each is refilled with the next group of the load list
 //   END   last bundle
 enum : int
@@ -68,7 +78,7 @@ enum : int
     MF_KIND_SHIFT = 8, // 4 bits
     MF_X3 = 1 << 12,   // field w6 names a fourth operand row (set by the compiler)
     MF_WAIT_SHIFT = 16, // 3 bits
-    MF_NREL_SHIFT = 20, // 3 bits
+    MF_NREL_SHIFT = 25, // 5 bits
     MF_END = 1 << 24,
     MF_POS = (int)0x80000000u
 };
@@ -145,20 +155,29 @@ struct MProgram
     }
 };
 
+// thrown when a value without a home row finds no slot (the caller may retry with home rows for those values)
+struct MachineOutOfSlots : std::runtime_error
+{
+    using std::runtime_error::runtime_error;
+};
+
 // ---- what the compiler produces
 struct MachineCode
 {
     ivec ops;  // records, bundle after bundle, padded to whole chunks (+ one chunk of look-ahead)
     ivec ld;   // load list: selector << M_LD_SEL_SHIFT | row, or M_LD_NONE; padded
-    int nbundles = 0, nchunks = 0, nld = 0;
+    int nbundles = 0, nchunks = 0, nld = 0, nld_chunks = 0;
+    int ring_groups = 4;         // ring rows / M_RING_GROUP the code was compiled for
+    int slot_budget = 0;         // the ring starts at row M_ROW_SLOT0 + slot_budget
     int window = 0;              // look-ahead window of the scheduler that produced it
     int slot_rows = 0;           // rows used behind M_ROW_SLOT0
     long long nops = 0, nnop = 0; // real operations / padding operations
     long long far = 0, pads = 0, spills = 0; // values re-read from their home row / padding pops / partial sums sent home
 };
 
-// list-schedules the program into bundles and allocates ring rows and slots (at most max_slots);
-// tune_slots: the slot budget the scheduler's look-ahead window is chosen for (>= max_slots)
-void machine_compile(const MProgram &P, int max_slots, MachineCode &out, int tune_slots = 0);
+// list-schedules the program into bundles and allocates ring rows (ring_groups groups of M_RING_GROUP) and
+// slots (at most max_slots).  window: look-ahead of the scheduler, 0 = choose (for a 4-group ring and
+// tune_slots >= max_slots slots, so that the order of the operations depends on the pattern alone)
+void machine_compile(const MProgram &P, int max_slots, MachineCode &out, int tune_slots = 0, int ring_groups = 4, int window = 0);
 
 } // namespace eicos

@@ -12,90 +12,6 @@ namespace eicos
 {
 namespace
 {
-void align_chunk(ivec &s)
-{
-    while (s.size() % STREAM_CHUNK)
-        s.push_back(0);
-}
-void align_chunk(dvec &s)
-{
-    while (s.size() % STREAM_CHUNK)
-        s.push_back(0.0);
-}
-void pad_tail(ivec &s)
-{
-    align_chunk(s);
-    s.insert(s.end(), STREAM_PAD, 0);
-}
-void pad_tail(dvec &s)
-{
-    align_chunk(s);
-    s.insert(s.end(), STREAM_PAD, 0.0);
-}
-
-// Shared-memory slots for the live ranges of a slot program (linear scan: a value gets a slot when
-// it is first touched and gives it back after its last use; when none is free it lives at home).
-struct SlotPool
-{
-    ivec free_;
-    int top = 0; // slots ever used
-    long long home = 0;
-    explicit SlotPool(int n)
-    {
-        for (int s = n - 1; s >= 0; s--)
-            free_.push_back(s);
-    }
-    int take(int home_row)
-    {
-        if (free_.empty())
-        {
-            home++;
-            return SLOT_HOME + home_row;
-        }
-        const int s = free_.back();
-        free_.pop_back();
-        top = std::max(top, s + 1);
-        return s;
-    }
-    void give(int code)
-    {
-        if (code >= 0 && code < SLOT_HOME)
-            free_.push_back(code);
-    }
-};
-
-// Host model of the device FIFO: every pop appends the row to the load list and returns the ring row
-// the device will find it in.
-struct FifoSim
-{
-    ivec &ld;
-    int npop = 0;
-    explicit FifoSim(ivec &l) : ld(l) {}
-    int pop(int base, int row)
-    {
-        if (row < 0 || row > LD_ROW_MASK)
-            throw std::logic_error("load list: row out of range");
-        ld.push_back((base << LD_BASE_SHIFT) | row);
-        return npop++ % FIFO_ROWS;
-    }
-    // does a check point that makes `pops` pops, the first one being pop number `first`, enter a new group?
-    static bool crosses(int first, int pops)
-    {
-        if (pops <= 0)
-            return false;
-        const int before = first == 0 ? 0 : (first - 1) / FIFO_GROUP + 1;
-        return (first + pops - 1) / FIFO_GROUP + 1 > before;
-    }
-    // A value written to global memory when `prod` pops had been made may be loaded through the FIFO as
-    // pop number j only if the group of j is issued afterwards (sync points come up to FIFO_GROUP - 1
-    // pops early, the first FIFO_AHEAD groups are issued before the program starts).
-    static bool far_safe(int prod, int j)
-    {
-        const int g = j / FIFO_GROUP;
-        return g >= FIFO_AHEAD && prod <= (g - FIFO_AHEAD) * FIFO_GROUP - FIFO_GROUP;
-    }
-};
-
 // ------------------------------------------------------------------ machine programs (machine.hpp)
 
 // ---- forward sweep  xw = L^-1 P rhs, rows of L in dot form in ascending column order (the summation
@@ -364,18 +280,26 @@ ivec ag_rows(const Symbolic &S, const Layout &L)
     return row;
 }
 
-// ---- numeric factorisation, right-looking in elimination order.  Every entry (i,j) of L and every
-// pivot owns an accumulator that starts from the KKT value (shared constant, per-instance scaling
-// value, or 0 for fill) on its first touch.  Step k: d = acc(k,k); for the rows i of column k
-// a_i = acc(i,k), l_i = a_i / d (stored, column-major = the order both sweeps stream it in); then
-// for every pair i1 >= i2 of the column  acc(i1,i2) -= l_i2 * a_i1  (the products Eigen's
-// up-looking kernel forms, accumulated in ascending k).
-//   ops:   [src_d, cnt, cnt x src, cnt(cnt+1)/2 x target]   constants in fa_val, V rows in the load list
-void build_factor(const Symbolic &S, const Layout &L, int max_slots, HostStreams &H, bool pim)
+// ---- numeric factorisation (Eigen's ldlt.factorize, src/eicos.cpp:900,1164), right-looking in elimination
+// order, as a machine program.  Every entry (i,j) of L and every pivot owns an accumulator that starts from
+// its KKT value (shared constant, per-instance row of the scaling block / of the instance's matrices, or 0
+// for fill) on its first touch.  Step k:
+//     rd = 1 / acc(k,k)                              -> row Dinv + k   (the sweeps multiply by it, like Eigen's
+//                                                       diag.inverse() * x; the finish functor flags rd = inf)
+//     l_i = acc(i,k) * rd  for the rows i of column k -> row Lx + u    (column-major = the order the sweeps stream it in)
+//     acc(i1,i2) -= l_i2 * acc(i1,k)  for every pair i1 >= i2 of the column   (the products Eigen's up-looking
+//                                                       kernel forms, accumulated in ascending k)
+// Accumulators are values of the program: they sit in slots between their updates; when the slots run out
+// they wait in home rows of their own (Layout::acc, allocated only for patterns that need them; the D row
+// for a pivot).  Untouched per-instance entries are
+// external values (gathered when first used, kept while they have further uses); shared constants ride in
+// the records.  HBM traffic: the scaling block in, L and 1/D out.  Selector 0 only (absolute rows).
+void build_factor(const Symbolic &S, const Layout &L, MProgram &P, bool pim)
 {
     struct Init
     {
-        int kind = OPK_ZERO, vrow = -1;
+        int kind = 0; // 0 zero (fill), 1 constant, 2 row
+        int vrow = -1;
         double c = 0.0;
     };
     const ivec agrow = pim ? ag_rows(S, L) : ivec(S.Ki.size(), -1);
@@ -387,183 +311,73 @@ void build_factor(const Symbolic &S, const Layout &L, int max_slots, HostStreams
             Init &t = pos < 0 ? di[j] : ei[S.Lp[j] + pos];
             if (vi >= 0 || agrow[slot] >= 0)
             {
-                t.kind = OPK_FIFO;
+                t.kind = 2;
                 t.vrow = vi >= 0 ? L.V + vi : agrow[slot];
             }
             else
             {
-                t.kind = OPK_CONST;
+                t.kind = 1;
                 t.c = S.Kshared[slot];
             }
         }
-    SlotPool pool(max_slots);
-    ivec dcode(S.N, -1), ecode(S.nnzL, -1);
-    const auto source = [&](int code, const Init &t) {
-        if (code >= 0)
-            H.fa.push_back(code);
-        else if (t.kind == OPK_FIFO)
-        {
-            H.fa.push_back(SRC_FIFO);
-            H.fa_ld.push_back(t.vrow);
-        }
-        else if (t.kind == OPK_CONST)
-        {
-            H.fa.push_back(SRC_CONST);
-            H.fa_val.push_back(t.c);
-        }
-        else
-            H.fa.push_back(SRC_ZERO);
+    P.keep_loads = true;
+    ivec dcur(S.N, -1), ecur(S.nnzL, -1); // current value of a touched accumulator
+    const auto start = [&](const Init &t) { // first-touch value of an accumulator, as a C operand
+        return t.kind == 2 ? MSrc::load(0, t.vrow) : (t.kind == 1 ? MSrc::constant(t.c) : MSrc::zero());
     };
-    const auto target = [&](int &code, const Init &t, int home_row) {
-        if (code >= 0)
-        {
-            H.fa.push_back(code);
-            return;
-        }
-        code = pool.take(home_row);
-        H.fa.push_back(code | (t.kind << OPK_SHIFT));
-        if (t.kind == OPK_FIFO)
-            H.fa_ld.push_back(t.vrow);
-        else if (t.kind == OPK_CONST)
-            H.fa_val.push_back(t.c);
-    };
+    std::vector<MSrc> av, lv;
     for (int k = 0; k < S.N; k++)
     {
         const int u0 = S.Lp[k], cnt = S.Lp[k + 1] - u0;
-        source(dcode[k], di[k]);
-        H.fa.push_back(cnt);
-        for (int e = 0; e < cnt; e++)
-            source(ecode[u0 + e], ei[u0 + e]);
-        for (int e1 = 0; e1 < cnt; e1++)
+        int rd;
         {
-            const int i1 = S.Li[u0 + e1];
-            for (int e2 = 0; e2 < e1; e2++)
-            {
-                const int i2 = S.Li[u0 + e2];
-                const int *b = S.Li.data() + S.Lp[i2], *e = S.Li.data() + S.Lp[i2 + 1];
-                const int *f = std::lower_bound(b, e, i1);
-                if (f == e || *f != i1)
-                    throw std::logic_error("factor program: update outside the pattern of L");
-                const int ut = (int)(f - S.Li.data());
-                target(ecode[ut], ei[ut], L.Lx + ut);
-            }
-            target(dcode[i1], di[i1], L.D + i1);
+            MOp op;
+            op.c = dcur[k] >= 0 ? MSrc::value(dcur[k]) : start(di[k]);
+            op.flags |= MF_RECIP | MF_OUT | MF_FIN | (FIN_PIVOT << MF_KIND_SHIFT);
+            op.out_row = L.Dinv + k;
+            op.dst = rd = P.new_value(0, L.Dinv + k);
+            P.ops.push_back(op);
         }
-        pool.give(dcode[k]);
+        if (cnt == 0)
+            continue;
+        // the finished accumulators of the column: a value, a shared constant, or an untouched per-instance row
+        av.assign(cnt, MSrc());
+        lv.assign(cnt, MSrc());
         for (int e = 0; e < cnt; e++)
-            pool.give(ecode[u0 + e]);
-    }
-    H.fa_nld = (int)H.fa_ld.size();
-    H.fa_slots = pool.top;
-    H.fa_home = pool.home;
-    pad_tail(H.fa);
-    pad_tail(H.fa_ld);
-    pad_tail(H.fa_val);
-}
-// ---- numeric factorisation in record form (streams.hpp); same right-looking algorithm and the
-// same arithmetic as build_factor, but every operand is a shared-memory row known to the host.
-// Returns false (leaving H untouched) when the pattern does not qualify.
-bool build_factor_fast(const Symbolic &S, const Layout &L, int max_slots, HostStreams &H, bool pim)
-{
-    if (S.maxcol > FA_FAST_COL)
-        return false;
-    struct Init
-    {
-        int kind = FA_ZERO, vrow = -1;
-        double c = 0.0;
-    };
-    const ivec agrow = pim ? ag_rows(S, L) : ivec(S.Ki.size(), -1);
-    std::vector<Init> di(S.N), ei(S.nnzL);
-    for (int j = 0; j < S.N; j++)
-        for (int e = S.KLp[j]; e < S.KLp[j + 1]; e++)
         {
-            const int slot = S.KLslot[e], vi = S.Kvidx[slot], pos = S.KLpos[e];
-            Init &t = pos < 0 ? di[j] : ei[S.Lp[j] + pos];
-            if (vi >= 0 || agrow[slot] >= 0)
+            const Init &t = ei[u0 + e];
+            if (ecur[u0 + e] >= 0)
+                av[e] = MSrc::value(ecur[u0 + e]);
+            else if (t.kind == 2)
+                av[e] = MSrc::value(P.new_value(0, t.vrow)); // external: lives in its row
+            else
+                av[e] = MSrc::constant(t.kind == 1 ? t.c : 0.0);
+            MOp op; // l = a * rd  (a product: + (-0))
+            op.c = MSrc::negzero();
+            op.flags |= MF_POS | MF_OUT;
+            op.out_row = L.Lx + u0 + e;
+            if (av[e].kind == MS_CONST)
             {
-                t.kind = FA_ROW;
-                t.vrow = vi >= 0 ? L.V + vi : agrow[slot];
+                op.a = av[e];
+                op.b = MSrc::value(rd);
             }
             else
             {
-                t.kind = FA_CONST;
-                t.c = S.Kshared[slot];
+                op.a = MSrc::value(rd);
+                op.b = av[e];
             }
+            op.dst = P.new_value(0, L.Lx + u0 + e);
+            lv[e] = MSrc::value(op.dst);
+            P.ops.push_back(op);
         }
-    ivec ops, ld;
-    dvec val;
-    SlotPool pool(max_slots);
-    FifoSim F(ld);
-    ivec dcode(S.N, -1), ecode(S.nnzL, -1); // slot of a touched accumulator
-    const int slot0 = FIFO_ROWS;
-    const auto source = [&](int code, const Init &t) {
-        if (code >= 0)
-            return slot0 + code;
-        if (t.kind == FA_ROW)
-            return F.pop(0, t.vrow);
-        if (t.kind == FA_CONST)
-        {
-            val.push_back(t.c);
-            return FA_CONST << FA_KIND_SHIFT;
-        }
-        return FA_ZERO << FA_KIND_SHIFT;
-    };
-    bool ok = true;
-    const auto target = [&](int &code, const Init &t, int home_row) {
-        if (code >= 0)
-            return (slot0 + code) | ((slot0 + code) << 8);
-        code = pool.take(home_row);
-        if (code >= SLOT_HOME)
-        {
-            ok = false;
-            return 0;
-        }
-        const int row = slot0 + code;
-        if (t.kind == FA_ROW)
-            return row | (F.pop(0, t.vrow) << 8);
-        if (t.kind == FA_CONST)
-        {
-            val.push_back(t.c);
-            return row | (FA_CONST << FA_KIND_SHIFT);
-        }
-        return row | (FA_ZERO << FA_KIND_SHIFT);
-    };
-    // a record = 4 words whose pops start at `first`
-    const auto close_record = [&](size_t at, int first) {
-        if (FifoSim::crosses(first, F.npop - first))
-            ops[at] |= FA_SYNC;
-    };
-    for (int k = 0; k < S.N && ok; k++)
-    {
-        const int u0 = S.Lp[k], cnt = S.Lp[k + 1] - u0;
-        int first = F.npop;
-        size_t at = ops.size();
-        ops.push_back(source(dcode[k], di[k]));
-        ops.push_back(cnt);
-        for (int e = 0; e < 2; e++)
-            ops.push_back(e < cnt ? source(ecode[u0 + e], ei[u0 + e]) : 0);
-        close_record(at, first);
-        if (cnt > 2)
-        {
-            first = F.npop;
-            at = ops.size();
-            for (int e = 2; e < 4; e++)
-                ops.push_back(e < cnt ? source(ecode[u0 + e], ei[u0 + e]) : 0);
-            ops.push_back(0);
-            ops.push_back(0);
-            close_record(at, first);
-        }
-        int inrec = 0;
-        for (int e1 = 0; e1 < cnt && ok; e1++)
+        for (int e1 = 0; e1 < cnt; e1++)
         {
             const int i1 = S.Li[u0 + e1];
-            for (int e2 = 0; e2 <= e1 && ok; e2++)
+            for (int e2 = 0; e2 <= e1; e2++)
             {
-                if (inrec == 0)
-                {
-                    first = F.npop;
-                    at = ops.size();
-                }
+                int *cur;
+                const Init *init;
+                int home;
                 if (e2 < e1)
                 {
                     const int i2 = S.Li[u0 + e2];
@@ -572,48 +386,52 @@ bool build_factor_fast(const Symbolic &S, const Layout &L, int max_slots, HostSt
                     if (f == e || *f != i1)
                         throw std::logic_error("factor program: update outside the pattern of L");
                     const int ut = (int)(f - S.Li.data());
-                    ops.push_back(target(ecode[ut], ei[ut], L.Lx + ut));
+                    cur = &ecur[ut];
+                    init = &ei[ut];
+                    // (not the row of the L entry: the finished accumulator is still read after l has been written there)
+                    home = L.acc >= 0 ? L.acc + ut : -1;
                 }
                 else
-                    ops.push_back(target(dcode[i1], di[i1], L.D + i1));
-                if (++inrec == 4)
                 {
-                    close_record(at, first);
-                    inrec = 0;
+                    cur = &dcur[i1];
+                    init = &di[i1];
+                    home = L.D + i1;
                 }
+                MOp op; // acc -= l(i2) * a(i1)
+                op.c = *cur >= 0 ? MSrc::value(*cur) : start(*init);
+                if (op.c.kind == MS_CONST && av[e1].kind == MS_CONST)
+                { // a record carries one constant: the accumulator starts as a value of its own
+                    MOp mv;
+                    mv.c = op.c;
+                    mv.dst = P.new_value(home >= 0 ? 0 : -1, std::max(home, 0));
+                    P.ops.push_back(mv);
+                    op.c = MSrc::value(mv.dst);
+                }
+                if (av[e1].kind == MS_CONST)
+                {
+                    op.a = av[e1];
+                    op.b = lv[e2];
+                }
+                else
+                {
+                    op.a = lv[e2];
+                    op.b = av[e1];
+                }
+                op.dst = *cur = P.new_value(home >= 0 ? 0 : -1, std::max(home, 0));
+                P.ops.push_back(op);
             }
         }
-        if (inrec > 0)
-        {
-            while (inrec++ < 4)
-                ops.push_back(0);
-            close_record(at, first);
-        }
-        pool.give(dcode[k]);
-        for (int e = 0; e < cnt; e++)
-            pool.give(ecode[u0 + e]);
     }
-    if (!ok || slot0 + pool.top > 255)
-        return false;
-    H.fa.swap(ops);
-    H.fa_ld.swap(ld);
-    H.fa_val.swap(val);
-    H.fa_nld = (int)H.fa_ld.size();
-    H.fa_slots = pool.top;
-    H.fa_home = 0;
-    H.fa_fast = 1;
-    pad_tail(H.fa);
-    pad_tail(H.fa_ld);
-    pad_tail(H.fa_val);
-    return true;
 }
 } // namespace
 
 void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, int max_fa_slots, HostStreams &H, bool pim)
 {
-    constexpr int MACHINE_TUNE_SLOTS = 24; // = the engine's default budget (engine.cu: MAX_SW_SLOTS)
+    constexpr int MACHINE_TUNE_SLOTS = 24, MACHINE_TUNE_FA_SLOTS = 32; // = the engine's default budgets (engine.cu: MAX_SW_SLOTS, MAX_FA_SLOTS)
     H = HostStreams();
     H.workers = W;
+    H.sw_budget = max_sw_slots;
+    H.fa_budget = max_fa_slots;
     for (int k = 0; k < S.N; k++)
         for (int u = S.Lp[k]; u + 1 < S.Lp[k + 1]; u++)
             if (S.Li[u] >= S.Li[u + 1])
@@ -632,48 +450,47 @@ void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, 
         build_backward(S, L, pbp, false);
         build_matvec(S, L, pm, H.mv_rows, pim);
         build_resid(S, L, pr, pim);
-        const auto compile = [&](const char *name, const MProgram &p, MachineCode &c) {
+        const auto compile = [&](const char *name, const MProgram &p, MachineCode (&c)[M_VARIANTS], int budget, int tune) {
             // (diagnostics) EICOS_SCHED_WINDOW_<name> pins the scheduler window of one program
             const std::string key = std::string("EICOS_SCHED_WINDOW_") + name;
-            if (const char *v = std::getenv(key.c_str()))
-            {
-                setenv("EICOS_SCHED_WINDOW", v, 1);
-                machine_compile(p, slots, c, MACHINE_TUNE_SLOTS);
-                unsetenv("EICOS_SCHED_WINDOW");
-            }
-            else
-                machine_compile(p, slots, c, MACHINE_TUNE_SLOTS);
+            const char *v = std::getenv(key.c_str());
+            machine_compile(p, budget, c[0], tune, M_VARIANT_GROUPS[0], v ? std::max(M_U, std::atoi(v)) : 0);
+            for (int k = 1; k < M_VARIANTS; k++) // same order of operations, deeper ring
+                machine_compile(p, budget, c[k], tune, M_VARIANT_GROUPS[k], c[0].window);
+            if (std::getenv("EICOS_DBG_PROGRAMS"))
+                for (int k = 0; k < M_VARIANTS; k++)
+                    std::fprintf(stderr, "machine %s[%d]: ops %lld nop %lld bundles %d loads %d far %lld pads %lld spills %lld slots %d window %d\n",
+                                 name, k, c[k].nops, c[k].nnop, c[k].nbundles, c[k].nld, c[k].far, c[k].pads, c[k].spills, c[k].slot_rows,
+                                 c[k].window);
         };
-        compile("fw", pf, H.fw);
-        compile("bw", pb, H.bw);
-        compile("bwp", pbp, H.bwp);
-        compile("mv", pm, H.mv);
-        compile("rs", pr, H.rs);
-        for (const MachineCode *q : {&H.fw, &H.bw, &H.bwp, &H.mv, &H.rs})
-            H.sw_slots = std::max(H.sw_slots, q->slot_rows);
-        H.sw_far = H.fw.far + H.bwp.far;
-        if (std::getenv("EICOS_DBG_PROGRAMS"))
-            for (auto nq : {std::make_pair("fw", &H.fw), std::make_pair("bw", &H.bw), std::make_pair("bwp", &H.bwp),
-                            std::make_pair("mv", &H.mv), std::make_pair("rs", &H.rs)})
-                std::fprintf(stderr, "machine %s: ops %lld nop %lld bundles %d loads %d far %lld pads %lld spills %lld slots %d\n", nq.first,
-                             nq.second->nops, nq.second->nnop, nq.second->nbundles, nq.second->nld, nq.second->far, nq.second->pads,
-                             nq.second->spills, nq.second->slot_rows, nq.second->window);
+        compile("fw", pf, H.fw, slots, MACHINE_TUNE_SLOTS);
+        compile("bw", pb, H.bw, slots, MACHINE_TUNE_SLOTS);
+        compile("bwp", pbp, H.bwp, slots, MACHINE_TUNE_SLOTS);
+        compile("mv", pm, H.mv, slots, MACHINE_TUNE_SLOTS);
+        compile("rs", pr, H.rs, slots, MACHINE_TUNE_SLOTS);
+        MProgram pa;
+        build_factor(S, L, pa, pim);
+        compile("fa", pa, H.fa, std::max(2, max_fa_slots), MACHINE_TUNE_FA_SLOTS);
+        for (int k = 0; k < M_VARIANTS; k++)
+            for (const MachineCode *q : {&H.fw[k], &H.bw[k], &H.bwp[k], &H.mv[k], &H.rs[k]})
+                H.sw_slots = std::max(H.sw_slots, q->slot_rows);
+        H.sw_far = H.fw[0].far + H.bwp[0].far;
+        H.fa_slots = std::max(H.fa[0].slot_rows, H.fa[1].slot_rows);
+        H.fa_home = H.fa[0].spills + H.fa[0].far;
     }
-    if (!build_factor_fast(S, L, max_fa_slots, H, pim))
-        build_factor(S, L, max_fa_slots, H, pim);
 }
 
 void refresh_stream_values(const Symbolic &S, const Layout &L, HostStreams &H, bool pim)
 {
     HostStreams fresh;
-    build_streams(S, L, H.workers, std::max(H.sw_slots, 1), std::max(H.fa_slots, 1), fresh, pim);
-    H.fa_val.swap(fresh.fa_val);
-    for (auto pq : {std::make_pair(&H.mv, &fresh.mv), std::make_pair(&H.rs, &fresh.rs)})
-    { // the mat-vec programs carry the shared coefficients inline
-        if (pq.second->ops.size() != pq.first->ops.size())
-            throw std::logic_error("mat-vec program changed shape on a value refresh");
-        pq.first->ops.swap(pq.second->ops);
-    }
+    build_streams(S, L, H.workers, std::max(H.sw_budget, 2), std::max(H.fa_budget, 2), fresh, pim);
+    for (int k = 0; k < M_VARIANTS; k++)
+        for (auto pq : {std::make_pair(&H.mv[k], &fresh.mv[k]), std::make_pair(&H.rs[k], &fresh.rs[k]), std::make_pair(&H.fa[k], &fresh.fa[k])})
+        { // the mat-vec and factor programs carry the shared coefficients inline
+            if (pq.second->ops.size() != pq.first->ops.size())
+                throw std::logic_error("machine program changed shape on a value refresh");
+            pq.first->ops.swap(pq.second->ops);
+        }
 }
 
 } // namespace eicos

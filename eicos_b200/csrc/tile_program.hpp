@@ -237,8 +237,6 @@ struct KArgs
     Layout L;
     double *ws; // [tiles][rows_total][TILE]
     int *iws;   // [tiles][irows_total][TILE]
-    double *acc_global; // factor column buffers [tile][2 maxcol][TILE] when they do not fit shared memory, else null
-    int xrows;  // rows of shared memory between worker 0's staging buffers and the other workers' (slots, column buffers)
     int batch;  // instances handled by this launch's chunk
     int first;  // global index (within the device's batch) of the chunk's first instance
     // instance-major device buffers for load/store (any may be null)
@@ -257,6 +255,7 @@ struct KArgs
         int rhs, sol, nitrow, set;
     } job[2];
     int njobs, initialize;
+    int variant; // which ring depth of the programs this launch runs (streams.hpp: M_VARIANT_GROUPS)
     int keep_sticky;
     int pre_equilibrated; // inputs are already divided by the equilibration vectors
     unsigned int *active_count; // device counter: instances still iterating after the head step
@@ -270,9 +269,7 @@ struct Team
     int wk, nwk;
     int job;       // eicos_solve_kkt: which of the launch's solveKKT jobs this CTA runs
     double *red;   // [nwk][KRED][TILE]
-    double *stage; // this worker's staging slots + lane: slot s lives at stage[s * TILE]
-    double *extra; // shared memory behind the staging buffers (+ lane): slots of the slot programs, column buffers
-    double *pbuf;  // worker 0: PS_STREAMS x PS_BYTES of shared memory for the program-stream readers (no lane offset)
+    double *pbuf;  // worker 0: shared memory of the FMA machine (no lane offset)
 #ifdef EICOS_EMU
     std::barrier<> *bar; // workers of a tile are real threads in the emulator
     void sync() const
@@ -516,406 +513,6 @@ EI_DEV vd line_search(const Team &tm, const KArgs &a, double *T, int lam, int ds
     return res;
 }
 
-// ------------------------------------------------------------------ program-stream reader
-// Sequential reader of a program stream (16-byte records).  L1 allocates by 32-byte sector, so
-// record-sized loads from global memory pay an L2 round trip every other record (profiles/r01e).
-// Instead the warp fetches the stream 512 bytes at a time (one coalesced 16-byte load per lane, a
-// whole chunk ahead of use), parks it in a 1 KB double buffer in shared memory and reads records
-// from there with broadcast 128-bit loads, one record ahead of use.
-constexpr int PS_BYTES = 1024; // shared memory per stream
-constexpr int PS_STREAMS = 3;  // streams a kernel reads at the same time (ops, load list, coefficients)
-constexpr int PS_DOUBLES = PS_STREAMS * PS_BYTES / 8;
-#ifdef EICOS_EMU
-struct PStream
-{
-    const int *p;
-    EI_DEV void open(const Team &, const void *base, int) { p = (const int *)base; }
-    EI_DEV i4 get()
-    {
-        const i4 r = ldg4(p);
-        p += 4;
-        return r;
-    }
-};
-#else
-struct PStream
-{
-    const int *g; // next chunk to fetch from global memory (+ this lane's 16 bytes)
-    i4 nextv;     // the chunk after the two in the buffer (this lane's part)
-    i4 look;      // the record get() will return
-    unsigned buf, pa;
-    static __device__ __forceinline__ i4 lds(unsigned a)
-    {
-        i4 r;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
-        return r;
-    }
-    static __device__ __forceinline__ void sts(unsigned a, i4 v)
-    {
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-    }
-    __device__ __forceinline__ void open(const Team &tm, const void *base, int k)
-    {
-        const int *b = (const int *)base + 4 * tm.pl;
-        buf = (unsigned)__cvta_generic_to_shared(tm.pbuf) + (unsigned)k * PS_BYTES;
-        __syncwarp();
-        sts(buf + 16 * tm.pl, ldg4(b));
-        sts(buf + 512 + 16 * tm.pl, ldg4(b + 128));
-        g = b + 256;
-        nextv = ldg4(g);
-        g += 128;
-        __syncwarp();
-        look = lds(buf);
-        pa = 16;
-    }
-    __device__ __forceinline__ i4 get()
-    {
-        const i4 r = look;
-        look = lds(buf + pa);
-        pa += 16;
-        if ((pa & 511) == 0)
-        { // the half behind pa has been read completely: it takes the prefetched chunk
-            const unsigned half = (pa & 512) ^ 512;
-            __syncwarp();
-            sts(buf + half + 16 * (threadIdx.x & 31), nextv);
-            nextv = ldg4(g);
-            g += 128;
-            __syncwarp();
-            pa &= PS_BYTES - 1;
-        }
-        return r;
-    }
-};
-#endif
-// word-at-a-time views of a program stream (factor program)
-struct WStream
-{
-    PStream ps;
-    i4 cur;
-    int k;
-    EI_DEV void open(const Team &tm, const void *base, int stream)
-    {
-        ps.open(tm, base, stream);
-        k = 4;
-    }
-    EI_DEV int get()
-    {
-        if (k == 4)
-        {
-            cur = ps.get();
-            k = 0;
-        }
-        const int w = k == 0 ? cur.x : (k == 1 ? cur.y : (k == 2 ? cur.z : cur.w));
-        k++;
-        return w;
-    }
-};
-EI_DEV d2 as_d2(i4 r)
-{
-#ifdef EICOS_EMU
-    d2 v;
-    std::memcpy(&v, &r, sizeof(v));
-    return v;
-#else
-    return d2{__hiloint2double(r.y, r.x), __hiloint2double(r.w, r.z)};
-#endif
-}
-
-struct DWStream
-{
-    PStream ps;
-    d2 cur;
-    int k;
-    EI_DEV void open(const Team &tm, const void *base, int stream)
-    {
-        ps.open(tm, base, stream);
-        k = 2;
-    }
-    EI_DEV double get()
-    {
-        if (k == 2)
-        {
-            cur = as_d2(ps.get());
-            k = 0;
-        }
-        const double v = k == 0 ? cur.x : cur.y;
-        k++;
-        return v;
-    }
-};
-
-// ------------------------------------------------------------------ FIFO of asynchronously loaded rows
-// Every global read of the factorisation and of the sweeps is known to the host in consumption
-// order (the program's load list).  The warp keeps FIFO_AHEAD cp.async groups of FIFO_GROUP rows in
-// flight ahead of the group it is consuming, so the memory latency never meets a dependent
-// instruction.  The host simulates the ring while it builds a program: operands name their ring
-// row directly and sync points are flags in the program (streams.hpp).  Each lane copies and later
-// reads only its own 8 * VEC bytes of a row, so cp.async.wait_group is the only synchronisation.
-// The load list itself is read one group (two 16-byte records) ahead.
-struct Fifo
-{
-    PStream ld;                  // the load list: FIFO_GROUP words = two records per group
-    smem_t ring;                 // FIFO_ROWS rows of shared memory (this lane's part)
-    const double *b0;            // tile base (+ lane); the words of the (materialised, layout.hpp) load list are rows of the tile
-    int left;                    // words left in the load list
-    int head;                    // producer ring row
-
-    EI_DEV void issue_row(int r, int w) const { sm_fill(ring, head + r, b0 + (size_t)w * TILE); }
-    EI_DEV void issue_group()
-    {
-        const i4 a = ld.get(), b = ld.get();
-        if (left >= FIFO_GROUP)
-        {
-            issue_row(0, a.x);
-            issue_row(1, a.y);
-            issue_row(2, a.z);
-            issue_row(3, a.w);
-            issue_row(4, b.x);
-            issue_row(5, b.y);
-            issue_row(6, b.z);
-            issue_row(7, b.w);
-            left -= FIFO_GROUP;
-        }
-        else
-        {
-            const int w[FIFO_GROUP] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int r = 0; r < FIFO_GROUP; r++)
-                if (r < left)
-                    issue_row(r, w[r]);
-            left = 0;
-        }
-        head = head + FIFO_GROUP == FIFO_ROWS ? 0 : head + FIFO_GROUP;
-        stage_commit();
-    }
-    // stream: which PStream buffer of the worker the load list uses
-    EI_DEV void open(const Team &tm, const int *list, int nwords, const double *T, int stream)
-    {
-        static_assert(FIFO_GROUP == 8, "issue_group reads the load list as two 4-word records");
-        ld.open(tm, list, stream);
-        ring = smem_of(tm.stage);
-        b0 = T;
-        left = nwords;
-        head = 0;
-        for (int g = 0; g < FIFO_AHEAD; g++)
-            issue_group();
-    }
-    EI_DEV void sync() // entering a new group: issue the next one, wait for this one
-    {
-        issue_group();
-#ifndef EICOS_EMU
-        asm volatile("cp.async.wait_group %0;" ::"n"(FIFO_AHEAD) : "memory");
-#endif
-    }
-    // sequential consumption (factor program): the device counts the rows itself
-    int tail;
-    EI_DEV vd pop()
-    {
-        if ((tail & (FIFO_GROUP - 1)) == 0)
-            sync();
-        const vd v = sm_load(ring, tail);
-        tail = tail + 1 == FIFO_ROWS ? 0 : tail + 1;
-        return v;
-    }
-    EI_DEV void close() { stage_wait(); }
-};
-
-// operand of a slot program: shared-memory slot or home row (streams.hpp)
-EI_DEV double *opnd(double *slots, double *home, int code)
-{
-    return code < SLOT_HOME ? slots + (size_t)code * TILE : home + (size_t)(code - SLOT_HOME) * TILE;
-}
-
-// ------------------------------------------------------------------ numeric LDL', record form (streams.hpp: FA_*)
-// Columns of at most FA_FAST_COL entries: the column lives in registers, the Schur updates are
-// unrolled, every operand is a shared-memory row named by the program.
-EI_DEV void tile_factor_fast(const Team &tm, const KArgs &a, const TileMem &t, vb act)
-{
-    const DevPattern &P = a.P;
-    const Layout &L = a.L;
-    double *T = t.T;
-    const smem_t sm = smem_of(tm.stage); // ring rows, then the slots
-    vb zero_pivot = vbset(false);
-    PStream ops;
-    DWStream ds;
-    Fifo ff;
-    ops.open(tm, P.fa, 1);
-    ds.open(tm, P.fa_val, 2);
-    ff.open(tm, P.fa_ld, P.fa_nld, T, 0);
-    const auto src = [&](int w) -> vd {
-        const int kind = (w >> FA_KIND_SHIFT) & 3;
-        if (kind == FA_ROW)
-            return sm_load(sm, w & 0xff);
-        return vset(kind == FA_CONST ? ds.get() : 0.0);
-    };
-    const auto upd = [&](int w, vd l2, vd a1) {
-        const int kind = (w >> FA_KIND_SHIFT) & 3;
-        vd init;
-        if (kind == FA_ROW)
-            init = sm_load(sm, (w >> 8) & 0xff);
-        else
-            init = vset(kind == FA_CONST ? ds.get() : 0.0);
-        sm_store(sm, w & 0xff, init - l2 * a1);
-    };
-    double *Dp = T + (size_t)L.D * TILE, *Lp = T + (size_t)L.Lx * TILE;
-    const size_t dinv_off = (size_t)(L.Dinv - L.D) * TILE;
-    for (int k = 0; k < P.N; k++, Dp += TILE)
-    {
-        const i4 r0 = ops.get();
-        if (r0.x & FA_SYNC)
-            ff.sync();
-        const int cnt = r0.y;
-        const vd d = src(r0.x);
-        const vd rd = 1.0 / d;
-        vstore(Dp, d);
-        vstore(Dp + dinv_off, rd);
-        VFOR zero_pivot.v[c_] = zero_pivot.v[c_] || (d.v[c_] == 0.0);
-        if (cnt == 0)
-            continue;
-        vd av[FA_FAST_COL], lv[FA_FAST_COL];
-        av[0] = src(r0.z);
-        lv[0] = av[0] * rd;
-        vstore(Lp, lv[0]);
-        Lp += TILE;
-        if (cnt > 1)
-        {
-            av[1] = src(r0.w);
-            lv[1] = av[1] * rd;
-            vstore(Lp, lv[1]);
-            Lp += TILE;
-        }
-        if (cnt > 2)
-        {
-            const i4 r1 = ops.get();
-            if (r1.x & FA_SYNC)
-                ff.sync();
-            av[2] = src(r1.x);
-            lv[2] = av[2] * rd;
-            vstore(Lp, lv[2]);
-            Lp += TILE;
-            if (cnt > 3)
-            {
-                av[3] = src(r1.y);
-                lv[3] = av[3] * rd;
-                vstore(Lp, lv[3]);
-                Lp += TILE;
-            }
-        }
-        // Schur updates, pairs (e1, e2 <= e1) in order: acc(i1, i2) -= l(i2) * a(i1)
-        const i4 t0 = ops.get();
-        if (t0.x & FA_SYNC)
-            ff.sync();
-        upd(t0.x, lv[0], av[0]);
-        if (cnt > 1)
-        {
-            upd(t0.y, lv[0], av[1]);
-            upd(t0.z, lv[1], av[1]);
-            if (cnt > 2)
-            {
-                upd(t0.w, lv[0], av[2]);
-                const i4 t1 = ops.get();
-                if (t1.x & FA_SYNC)
-                    ff.sync();
-                upd(t1.x, lv[1], av[2]);
-                upd(t1.y, lv[2], av[2]);
-                if (cnt > 3)
-                {
-                    upd(t1.z, lv[0], av[3]);
-                    upd(t1.w, lv[1], av[3]);
-                    const i4 t2 = ops.get();
-                    if (t2.x & FA_SYNC)
-                        ff.sync();
-                    upd(t2.x, lv[2], av[3]);
-                    upd(t2.y, lv[3], av[3]);
-                }
-            }
-        }
-    }
-    ff.close();
-    VFOR if (zero_pivot.v[c_] && act.v[c_]) ROWC(t.I, J_STATUS, c_) = EXIT_FATAL;
-}
-
-// ------------------------------------------------------------------ numeric LDL' (Eigen factorize, src/eicos.cpp:900,1164)
-// Right-looking in elimination order, one warp per tile, driven by the factor program
-// (streams.cpp: build_factor).  Step k takes the finished accumulators of column k, writes the pivot
-// and the column of L (column-major, contiguous), and applies the Schur updates of the column to the
-// accumulators of later entries - shared-memory slots for the (short) live range of each entry.
-// HBM traffic: the scaling block V in (FIFO), L and D out.  Same products as Eigen's up-looking
-// kernel (l_small_row * unscaled a_large_row), accumulated in ascending column order.
-EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
-{
-    const TileMem t = tile_mem(tm, a, tile);
-    const vb act = lane_active(tm, t);
-    if (!tm.any(act))
-        return;
-    if (tm.wk != 0)
-        return;
-    if (a.P.fa_fast)
-    {
-        tile_factor_fast(tm, a, t, act);
-        return;
-    }
-    const DevPattern &P = a.P;
-    const Layout &L = a.L;
-    double *T = t.T;
-    double *slots = tm.extra;
-    double *colA = a.acc_global ? a.acc_global + (size_t)tile * 2 * P.maxcol * TILE + tm.lane : tm.extra + (size_t)P.fa_slots * TILE;
-    double *colL = colA + (size_t)P.maxcol * TILE;
-    vb zero_pivot = vbset(false);
-    WStream is;
-    DWStream ds;
-    Fifo ff;
-    is.open(tm, P.fa, 1);
-    ds.open(tm, P.fa_val, 2);
-    ff.open(tm, P.fa_ld, P.fa_nld, T, 0);
-    ff.tail = 0;
-    const auto fetch = [&](int src) -> vd {
-        if (src >= 0)
-            return vload(opnd(slots, T, src));
-        if (src == SRC_FIFO)
-            return ff.pop();
-        return vset(src == SRC_CONST ? ds.get() : 0.0);
-    };
-    double *Dp = T + (size_t)L.D * TILE, *Lp = T + (size_t)L.Lx * TILE;
-    const size_t dinv_off = (size_t)(L.Dinv - L.D) * TILE;
-    for (int k = 0; k < P.N; k++, Dp += TILE)
-    {
-        const int dsrc = is.get(), cnt = is.get();
-        const vd d = fetch(dsrc);
-        vstore(Dp, d);
-        vstore(Dp + dinv_off, 1.0 / d); // the backward sweep multiplies by the reciprocal, like Eigen
-        VFOR zero_pivot.v[c_] = zero_pivot.v[c_] || (d.v[c_] == 0.0); // Eigen: NumericalIssue only on an exactly zero pivot
-        for (int e = 0; e < cnt; e++, Lp += TILE)
-        {
-            const vd av = fetch(is.get());
-            const vd lv = av / d;
-            vstore(colA + (size_t)e * TILE, av);
-            vstore(colL + (size_t)e * TILE, lv);
-            vstore(Lp, lv);
-        }
-        for (int e1 = 0; e1 < cnt; e1++)
-        {
-            const vd a1 = vload(colA + (size_t)e1 * TILE);
-            for (int e2 = 0; e2 <= e1; e2++)
-            {
-                const int tw = is.get();
-                const int kind = tw >> OPK_SHIFT;
-                double *tp = opnd(slots, T, tw & OP_CODE_MASK);
-                vd init;
-                if (kind == OPK_RMW)
-                    init = vload(tp);
-                else if (kind == OPK_FIFO)
-                    init = ff.pop();
-                else
-                    init = vset(kind == OPK_CONST ? ds.get() : 0.0);
-                vstore(tp, init - vload(colL + (size_t)e2 * TILE) * a1);
-            }
-        }
-    }
-    ff.close();
-    VFOR if (zero_pivot.v[c_] && act.v[c_]) ROWC(t.I, J_STATUS, c_) = EXIT_FATAL;
-}
-
 // ------------------------------------------------------------------ TMA bulk copies and mbarriers (sm_100a)
 #ifndef EICOS_EMU
 EI_DEV void mbar_init(unsigned bar, unsigned count)
@@ -958,17 +555,22 @@ EI_DEV void proxy_fence() { asm volatile("fence.proxy.async;" ::: "memory"); }
 #endif
 
 // ------------------------------------------------------------------ the FMA machine (machine.hpp)
-// Shared memory of one program warp: [ops ring][mbarriers][rows: data ring, 0, -0, scratch, slots].
+// Shared memory of one program warp: [ops ring][load-list ring][mbarriers][rows: 0, -0, scratch, slots, data ring].
 constexpr int ROW_BYTES = TILE * (int)sizeof(double);
 constexpr int M_CHUNK_BYTES = M_CHUNK_WORDS * 4;
 constexpr int M_OPS_RING_BYTES = M_CHUNKS * M_CHUNK_BYTES;
-constexpr int M_BAR_BYTES = 64; // M_CHUNKS mbarriers
-constexpr int M_HEAD_DOUBLES = (M_OPS_RING_BYTES + M_BAR_BYTES) / 8;
+constexpr int M_LD_CHUNK_BYTES = M_LD_CHUNK_WORDS * 4;
+constexpr int M_LD_RING_BYTES = M_LD_CHUNKS * M_LD_CHUNK_BYTES;
+constexpr int M_BAR_BYTES = 64; // M_CHUNKS + M_LD_CHUNKS mbarriers
+constexpr int M_HEAD_DOUBLES = (M_OPS_RING_BYTES + M_LD_RING_BYTES + M_BAR_BYTES) / 8;
 constexpr int M_BUNDLE_BYTES = M_BUNDLE_WORDS * 4;
 #ifndef EICOS_EMU
 static_assert(ROW_BYTES == (1 << M_FIELD_SHIFT), "a field is the byte offset of a 512-byte row");
 #endif
-inline size_t machine_smem_doubles(int slot_rows) { return M_HEAD_DOUBLES + (size_t)(M_ROW_SLOT0 + slot_rows) * TILE; }
+inline size_t machine_smem_doubles(int slot_budget, int ring_groups)
+{
+    return M_HEAD_DOUBLES + (size_t)(M_ROW_SLOT0 + slot_budget + ring_groups * M_RING_GROUP) * TILE;
+}
 
 // what the interpreter compiles in for a kernel (everything else costs no instructions)
 enum : int
@@ -993,16 +595,15 @@ struct MRun
     bool a_one;
 };
 
-EI_DEV d2 words_d2(int lo, int hi)
+EI_DEV double words_double(int lo, int hi)
 {
 #ifdef EICOS_EMU
-    d2 v;
-    int w[4] = {lo, hi, 0, 0};
-    std::memcpy(&v.x, w, 8);
-    v.y = 0.0;
+    double v;
+    const int w[2] = {lo, hi};
+    std::memcpy(&v, w, 8);
     return v;
 #else
-    return d2{__hiloint2double(hi, lo), 0.0};
+    return __hiloint2double(hi, lo);
 #endif
 }
 
@@ -1022,6 +623,7 @@ struct Machine
             rows[(size_t)M_ROW_ZERO * TILE + c] = 0.0;
             rows[(size_t)M_ROW_NEGZERO * TILE + c] = -0.0;
         }
+        const int ring_rows = r.prog.ring_groups * M_RING_GROUP;
         long long issued = 0; // ring groups copied so far
         const auto refill = [&]() {
             for (int k = 0; k < M_RING_GROUP; k++)
@@ -1029,11 +631,11 @@ struct Machine
                 const long long idx = issued * M_RING_GROUP + k;
                 const int w = r.ld[idx];
                 if (w != M_LD_NONE)
-                    std::memcpy(rows + (size_t)(idx % M_RING_ROWS) * TILE, r.Tb + (size_t)w * TILE, ROW_BYTES);
+                    std::memcpy(rows + (size_t)(r.prog.ring_row0 + idx % ring_rows) * TILE, r.Tb + (size_t)w * TILE, ROW_BYTES);
             }
             issued++;
         };
-        for (int g = 0; g < M_RING_GROUPS; g++)
+        for (int g = 0; g < r.prog.ring_groups; g++)
             refill();
         const int *rec = r.prog.ops;
         for (;; rec += M_BUNDLE_WORDS)
@@ -1044,7 +646,7 @@ struct Machine
             {
                 const int *w = rec + u * M_REC_WORDS;
                 const int f = w[4];
-                const double cst = words_d2(w[6], w[7]).x;
+                const double cst = words_double(w[6], w[7]);
                 xv[u] = (CFG & MC_X3) && (f & MF_X3) ? ld(w[6]) : vset(0.0);
                 vd a = (CFG & MC_CONST) && (f & MF_ACONST) ? vset(cst) : ld(w[0]);
                 const vd b = ld(w[1]);
@@ -1071,7 +673,7 @@ struct Machine
                 if ((CFG & MC_FIN) && (f & MF_FIN))
                     fin((f >> MF_KIND_SHIFT) & 15, w[5], res[u], bv[u], xv[u]);
             }
-            for (int k = (ctrl >> MF_NREL_SHIFT) & 7; k > 0; k--)
+            for (int k = (ctrl >> MF_NREL_SHIFT) & 31; k > 0; k--)
                 refill();
             if (ctrl & MF_END)
                 break;
@@ -1080,14 +682,18 @@ struct Machine
 #else
     unsigned rows; // shared address of the rows region + this lane's 16 bytes
     unsigned opsb; // shared address of the ops ring
-    unsigned bars; // mbarriers of the ops chunks
+    unsigned ldb;  // shared address of the load-list ring
+    unsigned bars; // mbarriers: M_CHUNKS of the ops chunks, then M_LD_CHUNKS of the load-list chunks
     int pl;
     bool inited;
     // data ring: every lane moves its 16 bytes of a row (cp.async), one commit group per ring group
-    const int *listp; // load list, one group ahead of the refill
-    i4 nw0, nw1;      // the words of the next refill
     const char *Tl;   // tile base + this lane's 16 bytes
-    unsigned head;    // ring group the next refill lands in
+    unsigned ring0;   // shared address of ring row 0 (+ lane)
+    int rg;           // ring groups
+    int head;         // ring group the next refill lands in
+    int lgroup;       // load-list group the next refill reads
+    const int *ldg;   // global pointer of the next load-list chunk to fetch
+    int ld_nchunks, ld_fetched;
     // ops ring: the record stream arrives in 1 KB chunks by TMA bulk copies (one elected lane)
     const int *opsg;  // global pointer of the next chunk to fetch
     int nchunks, fetched;
@@ -1096,7 +702,8 @@ struct Machine
     {
         pl = tm.pl;
         opsb = (unsigned)__cvta_generic_to_shared(mem);
-        bars = opsb + M_OPS_RING_BYTES;
+        ldb = opsb + M_OPS_RING_BYTES;
+        bars = ldb + M_LD_RING_BYTES;
         rows = bars + M_BAR_BYTES + 16u * pl;
         inited = false;
     }
@@ -1121,9 +728,36 @@ struct Machine
         if (w != M_LD_NONE)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(Tl + (size_t)w * ROW_BYTES) : "memory");
     }
+    __device__ __forceinline__ void fetch_ld_chunk()
+    { // next chunk of the load list into its ring position
+        if (pl == 0)
+        {
+            const unsigned slot = (unsigned)ld_fetched % M_LD_CHUNKS;
+            const unsigned bar = bars + 8u * (M_CHUNKS + slot);
+            mbar_arrive_expect(bar, M_LD_CHUNK_BYTES);
+            bulk_g2s(ldb + slot * M_LD_CHUNK_BYTES, ldg, M_LD_CHUNK_BYTES, bar);
+        }
+        ld_fetched++;
+        ldg += M_LD_CHUNK_WORDS;
+    }
     __device__ __forceinline__ void issue_group()
-    { // the next M_RING_GROUP words of the load list into ring group `head`; their successors are fetched for next time
-        const unsigned d = rows + head * (M_RING_GROUP * ROW_BYTES);
+    { // the next M_RING_GROUP words of the load list into ring group `head`
+        const int gc = lgroup % M_LD_CHUNK_GROUPS;
+        if (gc == 0)
+        { // entering a new chunk of the load list: the one before it is free, this one must have landed
+            const int c = lgroup / M_LD_CHUNK_GROUPS;
+            if (c > 0 && ld_fetched < ld_nchunks)
+            {
+                if (pl == 0)
+                    proxy_fence();
+                fetch_ld_chunk();
+            }
+            mbar_wait(bars + 8u * (M_CHUNKS + (unsigned)c % M_LD_CHUNKS), ((unsigned)c / M_LD_CHUNKS) & 1u);
+        }
+        const unsigned la = ldb + (unsigned)(lgroup % (M_LD_CHUNKS * M_LD_CHUNK_GROUPS)) * (M_RING_GROUP * 4);
+        const i4 nw0 = lds4(la), nw1 = lds4(la + 16);
+        lgroup++;
+        const unsigned d = ring0 + (unsigned)head * (M_RING_GROUP * ROW_BYTES);
         issue_row(d, nw0.x);
         issue_row(d + ROW_BYTES, nw0.y);
         issue_row(d + 2 * ROW_BYTES, nw0.z);
@@ -1133,10 +767,7 @@ struct Machine
         issue_row(d + 6 * ROW_BYTES, nw1.z);
         issue_row(d + 7 * ROW_BYTES, nw1.w);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        head = (head + 1) % M_RING_GROUPS;
-        nw0 = ldg4(listp);
-        nw1 = ldg4(listp + 4);
-        listp += M_RING_GROUP;
+        head = head + 1 == rg ? 0 : head + 1;
     }
     __device__ __forceinline__ void issue_chunk()
     { // next chunk of the record stream into its ring position (lane 0 only)
@@ -1145,26 +776,44 @@ struct Machine
         mbar_arrive_expect(bar, M_CHUNK_BYTES);
         bulk_g2s(opsb + slot * M_CHUNK_BYTES, opsg, M_CHUNK_BYTES, bar);
     }
-    static __device__ __forceinline__ void wait_groups(int n)
-    { // n = allowed pending groups + 1
-        if (n == 1)
+    static __device__ __forceinline__ void wait_groups(int code)
+    { // machine.hpp: M_WAIT_N
+        static_assert(M_WAIT_N[1] == 0 && M_WAIT_N[2] == 1 && M_WAIT_N[3] == 2 && M_WAIT_N[4] == 3 && M_WAIT_N[5] == 5 &&
+                          M_WAIT_N[6] == 8 && M_WAIT_N[7] == 12,
+                      "wait codes");
+        switch (code)
+        {
+        case 1:
             asm volatile("cp.async.wait_group 0;" ::: "memory");
-        else if (n == 2)
+            break;
+        case 2:
             asm volatile("cp.async.wait_group 1;" ::: "memory");
-        else if (n == 3)
+            break;
+        case 3:
             asm volatile("cp.async.wait_group 2;" ::: "memory");
-        else
+            break;
+        case 4:
             asm volatile("cp.async.wait_group 3;" ::: "memory");
+            break;
+        case 5:
+            asm volatile("cp.async.wait_group 5;" ::: "memory");
+            break;
+        case 6:
+            asm volatile("cp.async.wait_group 8;" ::: "memory");
+            break;
+        default:
+            asm volatile("cp.async.wait_group 12;" ::: "memory");
+            break;
+        }
     }
 
     template <int CFG, class Fin>
     __device__ __forceinline__ void run(const Team &, const MRun &r, Fin &fin)
     {
-        static_assert(M_RING_GROUP == 8 && M_RING_GROUPS == 4, "issue_group / wait_groups are written for 4 groups of 8 rows");
         __syncwarp();
         if (pl == 0)
         {
-            for (int b = 0; b < M_CHUNKS; b++)
+            for (int b = 0; b < M_CHUNKS + M_LD_CHUNKS; b++)
             {
                 if (inited)
                     mbar_inval(bars + 8u * b);
@@ -1176,7 +825,7 @@ struct Machine
         __syncwarp();
         asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(rows + M_ROW_ZERO * ROW_BYTES), "d"(0.0) : "memory");
         asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(rows + M_ROW_NEGZERO * ROW_BYTES), "d"(-0.0) : "memory");
-        // ops ring
+        // ops ring and load-list ring
         nchunks = r.prog.nchunks;
         opsg = r.prog.ops;
         fetched = 0;
@@ -1187,13 +836,18 @@ struct Machine
             fetched++;
             opsg += M_CHUNK_WORDS;
         }
-        // data ring: the first M_RING_GROUPS groups of the load list (the list is padded with M_LD_NONE)
+        ld_nchunks = r.prog.nld_chunks;
+        ldg = r.ld;
+        ld_fetched = 0;
+        for (int c = 0; c < M_LD_CHUNKS && c < ld_nchunks; c++)
+            fetch_ld_chunk();
+        // data ring: the first groups of the load list (the list is padded with M_LD_NONE)
         Tl = (const char *)r.Tb + 16 * pl;
+        rg = r.prog.ring_groups;
+        ring0 = rows + (unsigned)r.prog.ring_row0 * ROW_BYTES;
         head = 0;
-        nw0 = ldg4(r.ld);
-        nw1 = ldg4(r.ld + 4);
-        listp = r.ld + M_RING_GROUP;
-        for (int g = 0; g < M_RING_GROUPS; g++)
+        lgroup = 0;
+        for (int g = 0; g < rg; g++)
             issue_group();
         mbar_wait(bars, 0);
         unsigned pos = 0; // byte position of the current bundle in the ops ring
@@ -1303,7 +957,7 @@ struct Machine
                     fin((fl[u] >> MF_KIND_SHIFT) & 15, w5[u], res[u], b[u], (CFG & MC_X3) ? x3[u] : vset(0.0));
             }
             // ---- refills of the ring groups this bundle finished with
-            for (int k = (ctrl >> MF_NREL_SHIFT) & 7; k > 0; k--)
+            for (int k = (ctrl >> MF_NREL_SHIFT) & 31; k > 0; k--)
                 issue_group();
             if (last)
                 break;
@@ -1312,6 +966,8 @@ struct Machine
         asm volatile("cp.async.wait_all;" ::: "memory");
         for (int c = cons + 1; c < fetched; c++)
             mbar_wait(bars + 8u * ((unsigned)c % M_CHUNKS), ((unsigned)c / M_CHUNKS) & 1u);
+        for (int c = (lgroup + M_LD_CHUNK_GROUPS - 1) / M_LD_CHUNK_GROUPS; c < ld_fetched; c++)
+            mbar_wait(bars + 8u * (M_CHUNKS + (unsigned)c % M_LD_CHUNKS), ((unsigned)c / M_LD_CHUNKS) & 1u);
     }
 #endif
 };
@@ -1320,6 +976,40 @@ struct NoFin
 {
     EI_DEV void operator()(int, int, vd, vd, vd) {}
 };
+
+// ------------------------------------------------------------------ numeric LDL' (Eigen factorize, src/eicos.cpp:900,1164)
+// Right-looking in elimination order, one warp per tile, as a machine program (streams.cpp: build_factor):
+// HBM traffic is the scaling block V in, L and 1/D out.  Like Eigen the factorisation fails only on an
+// exactly zero pivot (the reciprocal is infinite).
+struct PivotFin
+{
+    vb zero_pivot;
+    EI_DEV void operator()(int, int, vd res, vd, vd)
+    {
+        VFOR zero_pivot.v[c_] = zero_pivot.v[c_] || fabs(res.v[c_]) > DBL_MAX;
+    }
+};
+EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
+{
+    const TileMem t = tile_mem(tm, a, tile);
+    const vb act = lane_active(tm, t);
+    if (!tm.any(act))
+        return;
+    if (tm.wk != 0)
+        return;
+    Machine mm;
+    mm.init(tm, tm.pbuf);
+    PivotFin fin;
+    fin.zero_pivot = vbset(false);
+    MRun r;
+    r.prog = a.P.fa[a.variant];
+    r.ld = a.P.fa_ld[a.variant];
+    r.Tb = t.Tb;
+    r.out = r.out2 = t.T;
+    r.a_one = false;
+    mm.run<MC_CONST | MC_POS | MC_BKEEP | MC_RECIP | MC_FIN>(tm, r, fin);
+    VFOR if (fin.zero_pivot.v[c_] && act.v[c_]) ROWC(t.I, J_STATUS, c_) = EXIT_FATAL;
+}
 
 // ------------------------------------------------------------------ triangular solves and KKT residual (machine programs)
 // forward:  xw = L^-1 P rhs         rows of L in dot form, ascending columns (the summation order of Eigen's
@@ -1358,7 +1048,7 @@ EI_DEV void kkt_residual(const Team &tm, const KArgs &a, Machine &mm, const Tile
         AbsMaxFin fin;
         fin.nerr = vset(0.0);
         MRun r;
-        r.prog = P.mv;
+        r.prog = P.mv[a.variant];
         r.ld = mvld;
         r.Tb = t.Tb;
         r.out = T + (size_t)erow * TILE;
@@ -1444,8 +1134,8 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
         MRun r;
         r.Tb = t.Tb;
         r.a_one = false;
-        r.prog = P.fw;
-        r.ld = P.fw_ld[set][round];
+        r.prog = P.fw[a.variant];
+        r.ld = P.fw_ld[a.variant][set][round];
         r.out = r.out2 = T + (size_t)xw * TILE;
         NoFin nofin;
         mm.run<0>(tm, r, nofin);
@@ -1455,15 +1145,15 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
             AccFin fin;
             fin.cont = cont;
             fin.x = T + (size_t)sol * TILE;
-            r.prog = P.bw;
-            r.ld = P.bw_ld[set][1];
+            r.prog = P.bw[a.variant];
+            r.ld = P.bw_ld[a.variant][set][1];
             r.out = r.out2 = T + (size_t)dxr * TILE;
             mm.run<MC_POS | MC_FIN | MC_X3>(tm, r, fin);
         }
         else
         {
-            r.prog = P.bwp;
-            r.ld = P.bw_ld[set][0];
+            r.prog = P.bwp[a.variant];
+            r.ld = P.bw_ld[a.variant][set][0];
             r.out = r.out2 = T + (size_t)sol * TILE;
             mm.run<MC_POS>(tm, r, nofin);
         }
@@ -1481,7 +1171,7 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
     for (;;)
     {
         vd nerr;
-        kkt_residual(tm, a, mm, t, P.mv_ld[set], sol, erow, init, nerr);
+        kkt_residual(tm, a, mm, t, P.mv_ld[a.variant][set], sol, erow, init, nerr);
         EI_PHASE(3);
         vb rollback = vbset(false);
         VFOR
@@ -1880,8 +1570,8 @@ EI_DEV void tile_resid(const Team &tm, const KArgs &a, int tile)
         Machine mm;
         mm.init(tm, tm.pbuf);
         MRun r;
-        r.prog = P.rs;
-        r.ld = P.rs_ld;
+        r.prog = P.rs[a.variant];
+        r.ld = P.rs_ld[a.variant];
         r.Tb = t.Tb;
         r.out = r.out2 = T + (size_t)L.r * TILE;
         r.a_one = false;

@@ -122,7 +122,8 @@ def test_initial_factor_and_solves(oracle_mod, emu_lib):
             # left-looking (kernel) and up-looking (Eigen/oracle) summation orders agree to ~1e-9,
             # not to machine precision.  Iterative refinement (solveKKT) is what removes this.
             assert np.max(np.abs(r["D"][b] - Do) / np.maximum(1.0, np.abs(Do))) <= 1e-7
-            assert np.max(np.abs(r["Lx"][b] - Lo), initial=0.0) <= 1e-9 * max(1.0, np.max(np.abs(Lo), initial=0.0))
+            # (the machine multiplies by the reciprocal pivot where Eigen divides: one more rounding per entry)
+            assert np.max(np.abs(r["Lx"][b] - Lo), initial=0.0) <= 2e-9 * max(1.0, np.max(np.abs(Lo), initial=0.0))
 
 
 def test_compaction_is_transparent(oracle_mod, emu_lib):

@@ -18,13 +18,14 @@ def _budget(monkeypatch, sw, fa):
 
 
 def test_mpc02_program_is_slot_resident(oracle_mod, emu_lib):
-    """The benchmark pattern: record-form factor, a handful of slots, nothing read directly from HBM."""
+    """The benchmark pattern: every value of the factorisation and all but the dense row's operands of the
+    sweeps live in slots; HBM reads are the algorithmic minimum."""
     from eicos_b200.binding import BatchSolver
     P = oracle_mod.load_fixture("MPC02")
     B = BatchSolver(P, lib=emu_lib, capacity=1)
     ps, d = B.program_stats(), B.dims()
     assert ps["fa_fast"] == 1 and ps["fa_home"] == 0 and ps["sw_direct"] == 0
-    assert ps["sw_slots"] <= 24 and ps["fa_slots"] <= 20
+    assert ps["sw_slots"] <= 24 and ps["fa_slots"] <= 32
     N, nnzL, nnzV = d["dim_K"], d["nnzL"], d["nnzV"]
     # HBM reads per run = the algorithmic minimum plus the re-reads of values that lost their slot
     # (the operands of the one dense row); sw_far counts the forward and the plain backward sweep
@@ -34,8 +35,8 @@ def test_mpc02_program_is_slot_resident(oracle_mod, emu_lib):
     assert ps["sw_far"] <= 0.15 * nnzL
 
 
-@pytest.mark.parametrize("name,sw,fa", [("update_data_1", 3, 2), ("update_data_1", 2, 1), ("lp_afiro", 3, 4),
-                                        ("issue98", 2, 1), ("lp_blend", 4, 6), ("unboundedLP1", 2, 1)])
+@pytest.mark.parametrize("name,sw,fa", [("update_data_1", 3, 2), ("update_data_1", 2, 2), ("lp_afiro", 3, 4),
+                                        ("issue98", 2, 2), ("lp_blend", 4, 6), ("unboundedLP1", 2, 2)])
 def test_parity_with_starved_slots(oracle_mod, emu_lib, monkeypatch, name, sw, fa):
     """Tiny slot budgets force evictions, re-reads of home rows through the ring (with the padding pops that
     keep them behind their writers), partial sums parked in their home rows and the general-form factor
@@ -47,7 +48,7 @@ def test_parity_with_starved_slots(oracle_mod, emu_lib, monkeypatch, name, sw, f
     B = BatchSolver(P, lib=emu_lib, capacity=1)
     ps = B.program_stats()
     assert ps["sw_slots"] <= sw and ps["fa_slots"] <= fa
-    assert ps["sw_far"] + ps["sw_direct"] > 0 and (ps["fa_home"] > 0 or ps["fa_fast"] == 1)
+    assert ps["sw_far"] + ps["sw_direct"] > 0 and ps["fa_home"] > 0
     O = oracle_mod.OracleSolver(P)
     co = O.solve()
     S = Solver(P, lib=emu_lib)
