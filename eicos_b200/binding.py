@@ -36,7 +36,10 @@ class BatchStats(C.Structure):
                 ("ms_solve", C.c_double), ("ms_other", C.c_double),
                 ("factor_launch_tiles", C.c_longlong), ("solve_launch_tiles", C.c_longlong),
                 ("factor_launches", C.c_int), ("solve_launches", C.c_int), ("compactions", C.c_int),
-                ("kkt_phase_cycles", C.c_ulonglong * 5)]
+                ("kkt_phase_cycles", C.c_ulonglong * 5),
+                ("ms_resid", C.c_double), ("ms_vector", C.c_double),
+                ("resid_launch_tiles", C.c_longlong), ("vector_launch_tiles", C.c_longlong),
+                ("resid_launches", C.c_int), ("vector_launches", C.c_int), ("lane_rounds", C.c_ulonglong)]
 
     def asdict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_}
@@ -239,11 +242,12 @@ class BatchSolver:
     def __init__(self, problem, device=0, capacity=0, workers=0, lib=None, instance_matrices=False):
         self.lib = lib or load()
         self._keep, args, (self.n, self.m, self.p) = _problem_args(problem)
-        self.nnzG, self.nnzA = int(np.asarray(problem["Gpr"]).size), int(np.asarray(problem["Apr"]).size)
         self.h = self.lib.L.eicos_batch_setup_ex(*args, int(device), int(capacity), int(workers),
                                                  self.INSTANCE_MATRICES if instance_matrices else 0)
         if not self.h:
             raise RuntimeError("eicos_batch_setup failed: " + self.lib.last_error())
+        d = self.dims()  # problems without G or A have no "Gpr" / "Apr" entry (or None): the handle knows
+        self.nnzG, self.nnzA = d["nnzG"], d["nnzA"]
 
     def close(self):
         if getattr(self, "h", None):

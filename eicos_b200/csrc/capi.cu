@@ -371,6 +371,13 @@ int eicos_batch_get_stats(const eicos_batch *bt, eicos_batch_stats *o)
     o->compactions = s.compactions;
     for (int k = 0; k < 5; k++)
         o->kkt_phase_cycles[k] = s.kkt_phase_cycles[k];
+    o->ms_resid = s.ms_resid;
+    o->ms_vector = s.ms_vector;
+    o->resid_launch_tiles = s.resid_launch_tiles;
+    o->vector_launch_tiles = s.vector_launch_tiles;
+    o->resid_launches = s.resid_launches;
+    o->vector_launches = s.vector_launches;
+    o->lane_rounds = s.lane_rounds;
     return 0;
 }
 
@@ -458,6 +465,8 @@ int eicos_batch_debug_init(eicos_batch *bt, int batch, const double *cs, const d
         be::h2d(dh, hs, nh_ * sizeof(double), st);
         be::h2d(db, bs, nb_ * sizeof(double), st);
         be::sync(st);
+        if (bt->eng->instance_matrices()) // the shared raw matrices stand in for every instance
+            bt->eng->set_matrices(nullptr, nullptr, bt->rawG.data(), bt->rawA.data());
         bt->eng->debug_factor_init(batch, dc, dh, db, bt->c.data(), bt->h.data(), bt->b.data(), Lx, D, sol1, sol2, nitref);
         return 0;
     }
@@ -559,6 +568,11 @@ static int update_common(eicos_solver *s, bool full, const double *Gpr, const do
         }
         else
         { // pointer overload (src/eicos.cpp:2053-2082)
+            // every argument is checked before anything is touched: a rejected update leaves the solver as it was
+            if (Gpr && S.m && !h)
+                throw std::invalid_argument("eicos_update_data: h must accompany Gpr");
+            if (Apr && S.p && !b)
+                throw std::invalid_argument("eicos_update_data: b must accompany Apr");
             if (s->equilibrated)
             { // unsetEquilibration :389-404
                 unequilibrate(S);
@@ -570,20 +584,10 @@ static int update_common(eicos_solver *s, bool full, const double *Gpr, const do
                     s->h[k] *= S.Geq[k];
                 s->equilibrated = false;
             }
-            if (Gpr)
-            {
-                if (S.m && !h)
-                    throw std::invalid_argument("eicos_update_data: h must accompany Gpr");
-                if (S.m)
-                    s->h.assign(h, h + S.m);
-            }
-            if (Apr)
-            {
-                if (S.p && !b)
-                    throw std::invalid_argument("eicos_update_data: b must accompany Apr");
-                if (S.p)
-                    s->b.assign(b, b + S.p);
-            }
+            if (Gpr && S.m)
+                s->h.assign(h, h + S.m);
+            if (Apr && S.p)
+                s->b.assign(b, b + S.p);
             if (c)
                 s->c.assign(c, c + S.n);
             refresh_values(S, Gpr, Apr);

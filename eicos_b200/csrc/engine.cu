@@ -108,7 +108,7 @@ static void eicos_compact_emu(const KArgs &a, const MoveRanges &mr, const int *m
 
 // shared-memory budget of the slot programs (rows of TILE doubles per CTA)
 // (one warp per tile wants 7 CTAs per SM: ring 32 rows + 28 rows here = 30 KB per CTA at TILE = 64)
-constexpr int MAX_SW_SLOTS = 24, MAX_FA_SLOTS = 32;
+constexpr int MAX_SW_SLOTS = 16, MAX_FA_SLOTS = 24;
 
 int Engine::tile_width() { return TILE; }
 
@@ -264,7 +264,8 @@ void Engine::upload_pattern(const Symbolic &S)
         ivec out(list.size());
         const int off[8] = {0, a1, a2, a3, a4, a5, 0, 0};
         for (size_t k = 0; k < list.size(); k++)
-            out[k] = list[k] == M_LD_NONE ? M_LD_NONE : (list[k] & M_LD_ROW_MASK) + off[((unsigned)list[k] >> M_LD_SEL_SHIFT) & 7];
+            // (padding words copy row 0 of the tile into a ring row nobody reads: cheaper than a test per copy)
+            out[k] = list[k] == M_LD_NONE ? 0 : (list[k] & M_LD_ROW_MASK) + off[((unsigned)list[k] >> M_LD_SEL_SHIFT) & 7];
         return upload(out, owned_, st);
     };
     P.sw_budget = H_.fw[0].slot_budget;
@@ -604,8 +605,10 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
         {
             be::zero(active_count_, sizeof(unsigned int), st);
             pick(tiles);
-            EI_TIMED(2, EI_LAUNCH(eicos_residuals, tile_resid, tiles, threads1, smem_prog_[a.variant], st, a));
-            EI_TIMED(2, EI_LAUNCH(eicos_iter_head, tile_head, tiles, threads, smem_common_, st, a));
+            EI_TIMED(3, EI_LAUNCH(eicos_residuals, tile_resid, tiles, threads1, smem_prog_[a.variant], st, a));
+            EI_TIMED(4, EI_LAUNCH(eicos_iter_head, tile_head, tiles, threads, smem_common_, st, a));
+            stt.resid_launches++, stt.vector_launches++;
+            stt.resid_launch_tiles += tiles, stt.vector_launch_tiles += tiles;
             stt.ipm_iterations++;
             be::d2h(host_pinned_, active_count_, sizeof(unsigned int), st);
             be::sync(st);
@@ -666,9 +669,11 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
             }
             factor();
             kkt_pair(0, -1, -1);
-            EI_TIMED(2, EI_LAUNCH(eicos_iter_mid, tile_mid, tiles, threads, smem_common_, st, a));
+            EI_TIMED(4, EI_LAUNCH(eicos_iter_mid, tile_mid, tiles, threads, smem_common_, st, a));
             kkt_rhs2(J_NIT3);
-            EI_TIMED(2, EI_LAUNCH(eicos_iter_tail, tile_tail, tiles, threads, smem_common_, st, a));
+            EI_TIMED(4, EI_LAUNCH(eicos_iter_tail, tile_tail, tiles, threads, smem_common_, st, a));
+            stt.vector_launches += 2;
+            stt.vector_launch_tiles += 2 * (long long)tiles;
         }
         EI_TIMED(2, EI_LAUNCH(eicos_store_outputs, tile_store, tiles, threads, smem_common_, st, a));
     }
@@ -683,6 +688,7 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
 #endif
     be::sync(st);
     std::memcpy(&stt.ir_rounds, host_pinned_ + 2, sizeof(unsigned long long));
+    std::memcpy(&stt.lane_rounds, host_pinned_ + 2 + 2 * 6, sizeof(unsigned long long));
     std::memcpy(stt.kkt_phase_cycles, host_pinned_ + 4, 5 * sizeof(unsigned long long));
 #ifndef EICOS_EMU
     if (timing)
@@ -694,6 +700,10 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
         {
             EI_CUDA(cudaEventElapsedTime(&ms, sp.a, sp.b));
             (sp.cls == 0 ? stt.ms_factor : sp.cls == 1 ? stt.ms_solve : stt.ms_other) += ms;
+            if (sp.cls == 3)
+                stt.ms_resid += ms;
+            if (sp.cls == 4)
+                stt.ms_vector += ms;
         }
     }
 #endif

@@ -23,6 +23,10 @@ struct SolveStats
     double ms_total = 0, ms_factor = 0, ms_solve = 0, ms_other = 0; // device time by kernel class (CUDA events)
     long long factor_launch_tiles = 0, solve_launch_tiles = 0;      // tiles covered by the timed launches
     int factor_launches = 0, solve_launches = 0;
+    double ms_resid = 0, ms_vector = 0; // part of ms_other: eicos_residuals / the three per-iteration vector kernels
+    long long resid_launch_tiles = 0, vector_launch_tiles = 0;
+    int resid_launches = 0, vector_launches = 0;
+    unsigned long long lane_rounds = 0; // solve rounds the instances needed themselves (ir_rounds counts whole tiles)
 
     SolveStats &operator+=(const SolveStats &o)
     { // a batch solved in several segments (capi.cu)
@@ -33,6 +37,10 @@ struct SolveStats
         ms_total += o.ms_total, ms_factor += o.ms_factor, ms_solve += o.ms_solve, ms_other += o.ms_other;
         factor_launch_tiles += o.factor_launch_tiles, solve_launch_tiles += o.solve_launch_tiles;
         factor_launches += o.factor_launches, solve_launches += o.solve_launches;
+        ms_resid += o.ms_resid, ms_vector += o.ms_vector;
+        resid_launch_tiles += o.resid_launch_tiles, vector_launch_tiles += o.vector_launch_tiles;
+        resid_launches += o.resid_launches, vector_launches += o.vector_launches;
+        lane_rounds += o.lane_rounds;
         return *this;
     }
 };

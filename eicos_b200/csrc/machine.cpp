@@ -647,7 +647,7 @@ void machine_compile(const MProgram &P, int max_slots, MachineCode &out, int tun
             MachineCode c;
             try
             {
-                compile_with_window(P, tune_slots, w, 4, c);
+                compile_with_window(P, tune_slots, w, 3, c);
             }
             catch (const MachineOutOfSlots &)
             { // this order of operations keeps more values without a home row alive than there are slots

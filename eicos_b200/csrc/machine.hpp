@@ -38,13 +38,13 @@ constexpr int M_REC_WORDS = 8;  // 32-byte records
 constexpr int M_BUNDLE_WORDS = M_U * M_REC_WORDS;
 constexpr int M_CHUNK_BUNDLES = 8; // bundles per TMA chunk of the record stream (1 KB)
 constexpr int M_CHUNK_WORDS = M_CHUNK_BUNDLES * M_BUNDLE_WORDS;
-constexpr int M_CHUNKS = 4;        // chunks in the shared-memory ops ring
+constexpr int M_CHUNKS = 2;        // chunks in the shared-memory ops ring
 constexpr int M_RING_GROUP = 8;    // rows per ring group (= one cp.async commit group)
 constexpr int M_MAX_RING_GROUPS = 16;
 // shared-memory rows: 0, -0, scratch, the slots (the program's slot budget), then the ring
 constexpr int M_ROW_ZERO = 0, M_ROW_NEGZERO = 1, M_ROW_TRASH = 2, M_ROW_SLOT0 = 3;
 // the load list arrives in shared memory like the records: chunks of M_LD_CHUNK_WORDS words by TMA
-constexpr int M_LD_CHUNK_WORDS = 256, M_LD_CHUNK_GROUPS = M_LD_CHUNK_WORDS / M_RING_GROUP, M_LD_CHUNKS = 2;
+constexpr int M_LD_CHUNK_WORDS = 128, M_LD_CHUNK_GROUPS = M_LD_CHUNK_WORDS / M_RING_GROUP, M_LD_CHUNKS = 2;
 // WAIT codes of the bundle control: cp.async.wait_group takes an immediate, deep rings get the nearest one below
 constexpr int M_WAIT_CODES = 8;
 constexpr int M_WAIT_N[M_WAIT_CODES] = {-1, 0, 1, 2, 3, 5, 8, 12};

@@ -427,7 +427,7 @@ void build_factor(const Symbolic &S, const Layout &L, MProgram &P, bool pim)
 
 void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, int max_fa_slots, HostStreams &H, bool pim)
 {
-    constexpr int MACHINE_TUNE_SLOTS = 24, MACHINE_TUNE_FA_SLOTS = 32; // = the engine's default budgets (engine.cu: MAX_SW_SLOTS, MAX_FA_SLOTS)
+    constexpr int MACHINE_TUNE_SLOTS = 16, MACHINE_TUNE_FA_SLOTS = 24; // = the engine's default budgets (engine.cu: MAX_SW_SLOTS, MAX_FA_SLOTS)
     H = HostStreams();
     H.workers = W;
     H.sw_budget = max_sw_slots;

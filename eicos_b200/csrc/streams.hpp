@@ -22,7 +22,7 @@ namespace eicos
 // tiles per SM share the memory latency), the deep one when there are few tiles per SM and the bytes ONE
 // tile has in flight are what bounds its speed.
 constexpr int M_VARIANTS = 2;
-constexpr int M_VARIANT_GROUPS[M_VARIANTS] = {4, 16};
+constexpr int M_VARIANT_GROUPS[M_VARIANTS] = {3, 16};
 
 constexpr long long MAX_FACTOR_UPDATES = 20LL * 1000 * 1000; // Schur updates per factorisation a factor program may hold (32 bytes each)
 

@@ -338,6 +338,20 @@ void analyze(Symbolic &S, int n, int m, int p, int ncones, const int *q,
     S.n = n;
     S.m = hasG ? m : 0;
     S.p = hasA ? p : 0;
+    if (n < 0 || m < 0 || p < 0 || ncones < 0)
+        throw std::invalid_argument("negative dimension");
+    if (hasG && ncones > 0 && !q)
+        throw std::invalid_argument("cone dimensions missing");
+    // column pointers come from the caller: they must start at 0 and never decrease before they are walked
+    for (const int *jc : {hasG ? Gjc : nullptr, hasA ? Ajc : nullptr})
+        if (jc)
+        {
+            if (jc[0] != 0)
+                throw std::invalid_argument("CSC column pointers must start at 0");
+            for (int j = 0; j < n; j++)
+                if (jc[j] > jc[j + 1])
+                    throw std::invalid_argument("CSC column pointers must be non-decreasing");
+        }
     S.q.assign(q, q + (hasG ? ncones : 0));
     S.nc = (int)S.q.size();
     int sumq = 0;

@@ -630,8 +630,7 @@ struct Machine
             {
                 const long long idx = issued * M_RING_GROUP + k;
                 const int w = r.ld[idx];
-                if (w != M_LD_NONE)
-                    std::memcpy(rows + (size_t)(r.prog.ring_row0 + idx % ring_rows) * TILE, r.Tb + (size_t)w * TILE, ROW_BYTES);
+                std::memcpy(rows + (size_t)(r.prog.ring_row0 + idx % ring_rows) * TILE, r.Tb + (size_t)w * TILE, ROW_BYTES);
             }
             issued++;
         };
@@ -724,9 +723,8 @@ struct Machine
         asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(rows + (unsigned)f), "d"(v.v[0]), "d"(v.v[1]) : "memory");
     }
     __device__ __forceinline__ void issue_row(unsigned dst, int w) const
-    { // ring row <- workspace row w of the tile (M_LD_NONE: padding, nothing to copy)
-        if (w != M_LD_NONE)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(Tl + (size_t)w * ROW_BYTES) : "memory");
+    { // ring row <- workspace row w of the tile (padding words of the materialised list name row 0)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(Tl + (long long)w * ROW_BYTES) : "memory");
     }
     __device__ __forceinline__ void fetch_ld_chunk()
     { // next chunk of the load list into its ring position
@@ -746,12 +744,10 @@ struct Machine
         if (gc == 0)
         { // entering a new chunk of the load list: the one before it is free, this one must have landed
             const int c = lgroup / M_LD_CHUNK_GROUPS;
+            // (the words of the chunk being replaced were read - and used - long ago: no cross-proxy fence needed
+            //  between those generic reads and the bulk copy's write; a fence here waits for every copy in flight)
             if (c > 0 && ld_fetched < ld_nchunks)
-            {
-                if (pl == 0)
-                    proxy_fence();
                 fetch_ld_chunk();
-            }
             mbar_wait(bars + 8u * (M_CHUNKS + (unsigned)c % M_LD_CHUNKS), ((unsigned)c / M_LD_CHUNKS) & 1u);
         }
         const unsigned la = ldb + (unsigned)(lgroup % (M_LD_CHUNKS * M_LD_CHUNK_GROUPS)) * (M_RING_GROUP * 4);
@@ -781,30 +777,21 @@ struct Machine
         static_assert(M_WAIT_N[1] == 0 && M_WAIT_N[2] == 1 && M_WAIT_N[3] == 2 && M_WAIT_N[4] == 3 && M_WAIT_N[5] == 5 &&
                           M_WAIT_N[6] == 8 && M_WAIT_N[7] == 12,
                       "wait codes");
-        switch (code)
-        {
-        case 1:
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            break;
-        case 2:
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-            break;
-        case 3:
+        // (an if-chain, commonest first - all but the newest ring groups - instead of a jump table)
+        if (code == 3)
             asm volatile("cp.async.wait_group 2;" ::: "memory");
-            break;
-        case 4:
-            asm volatile("cp.async.wait_group 3;" ::: "memory");
-            break;
-        case 5:
-            asm volatile("cp.async.wait_group 5;" ::: "memory");
-            break;
-        case 6:
-            asm volatile("cp.async.wait_group 8;" ::: "memory");
-            break;
-        default:
+        else if (code == 2)
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else if (code == 1)
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        else if (code == 7)
             asm volatile("cp.async.wait_group 12;" ::: "memory");
-            break;
-        }
+        else if (code == 6)
+            asm volatile("cp.async.wait_group 8;" ::: "memory");
+        else if (code == 5)
+            asm volatile("cp.async.wait_group 5;" ::: "memory");
+        else
+            asm volatile("cp.async.wait_group 3;" ::: "memory");
     }
 
     template <int CFG, class Fin>
@@ -852,6 +839,7 @@ struct Machine
         mbar_wait(bars, 0);
         unsigned pos = 0; // byte position of the current bundle in the ops ring
         int cons = 0;     // chunk being consumed
+        const int aone_mask = r.a_one ? MF_AONE : 0;
         i4 ra[M_U], rb[M_U];
 #pragma unroll
         for (int u = 0; u < M_U; u++)
@@ -862,9 +850,8 @@ struct Machine
         for (;;)
         {
             const int ctrl = rb[0].x;
-            const int nwait = (ctrl >> MF_WAIT_SHIFT) & 7;
-            if (nwait)
-                wait_groups(nwait);
+            if (ctrl & (7 << MF_WAIT_SHIFT))
+                wait_groups((ctrl >> MF_WAIT_SHIFT) & 7);
             // ---- operand loads
             vd a[M_U], b[M_U], c[M_U], x3[M_U];
             int fl[M_U], kf[M_U], w5[M_U];
@@ -909,10 +896,7 @@ struct Machine
                 if (fetched < nchunks)
                 {
                     if (pl == 0)
-                    {
-                        proxy_fence();
                         issue_chunk();
-                    }
                     fetched++;
                     opsg += M_CHUNK_WORDS;
                 }
@@ -933,7 +917,7 @@ struct Machine
             for (int u = 0; u < M_U; u++)
             {
                 vd av = a[u];
-                if ((CFG & MC_AONE) && (fl[u] & MF_AONE) && r.a_one)
+                if ((CFG & MC_AONE) && (fl[u] & aone_mask))
                     av = vset(1.0);
                 if (CFG & MC_POS)
                 { // flip the sign of A where the flag (bit 31) is set
@@ -941,7 +925,10 @@ struct Machine
                 }
                 vd v = vfnma(c[u], av, b[u]);
                 if ((CFG & MC_RECIP) && (fl[u] & MF_RECIP))
+                { // (a real branch: the division is long and rare)
+                    asm volatile("" ::: "memory");
                     v = 1.0 / c[u];
+                }
                 res[u] = v;
             }
             // ---- stores

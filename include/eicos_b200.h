@@ -151,6 +151,12 @@ typedef struct eicos_batch_stats
     /* SM clock cycles the tiles spent in the phases of eicos_solve_kkt, summed over tiles and launches:
      * right-hand-side norm, forward sweep, backward sweep, refinement residual, bookkeeping */
     unsigned long long kkt_phase_cycles[5];
+    /* part of ms_other: eicos_residuals (computeResiduals) and the three per-iteration vector kernels
+     * (eicos_iter_head / _mid / _tail), with the tiles their launches covered */
+    double ms_resid, ms_vector;
+    long long resid_launch_tiles, vector_launch_tiles;
+    int resid_launches, vector_launches;
+    unsigned long long lane_rounds; /* solve rounds the instances needed themselves (ir_rounds counts whole tiles) */
 } eicos_batch_stats;
 
 /* Per-kernel-class device timing of the LAST eicos_batch_solve* call (enable first). */

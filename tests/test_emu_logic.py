@@ -56,6 +56,22 @@ def test_update_data_paths(oracle_mod, emu_lib):
     assert relerr(S.solution(), O.solution()[0]) <= TOL
 
 
+def test_rejected_update_leaves_the_solver_unchanged(oracle_mod, emu_lib):
+    """eicos_update_data checks its arguments before it touches anything: after a rejected call (Gpr without h)
+    the next solve gives the same answer as before, not a mix of raw and equilibrated data."""
+    from eicos_b200.binding import Solver
+    P1, P2 = oracle_mod.load_fixture("update_data_1"), oracle_mod.load_fixture("update_data_2")
+    S = Solver(P1, lib=emu_lib)
+    assert S.solve() == 0
+    x0 = S.solution()
+    with pytest.raises(RuntimeError):
+        S.update_data(P2["Gpr"], None, None, None, None)  # h must accompany Gpr
+    with pytest.raises(RuntimeError):
+        S.update_data(None, P2["Apr"], P2["c"], None, None)  # b must accompany Apr
+    assert S.solve() == 0
+    assert np.array_equal(S.solution(), x0)
+
+
 @pytest.mark.parametrize("name,rel,batch", [("update_data_1", 0.05, 24), ("lp_afiro", 0.02, 9), ("MPC02", {"h": 0.002, "b": 0.02}, 5)])
 def test_batched_perturbed_parity(oracle_mod, emu_lib, name, rel, batch):
     from eicos_b200.binding import BatchSolver

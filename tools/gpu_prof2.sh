@@ -26,7 +26,7 @@ for r in rows:
 for k, (n, ms, inst) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print("%-28s launches %4d  total %9.2f ms  avg %8.3f ms  inst/launch %.3e" % (k, n, ms, ms / max(n, 1), inst / max(n, 1)))
 PY
-for K in eicos_solve_kkt_pair eicos_solve_kkt eicos_residuals eicos_ldl_factor; do
+for K in eicos_solve_kkt eicos_residuals eicos_ldl_factor; do
   echo "== ncu full: $K"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:^$K\$ -s 4 -c 1 -f -o $OUT/prof_$K $SMALL > $OUT/prof_$K.log 2>&1
 done
