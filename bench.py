@@ -39,9 +39,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mpc02", choices=["mpc02", "mpc02pim", "socmpc", "lp25fv47"])
-    ap.add_argument("--batch", type=int, default=65536, help="instances per GPU (weak) or in total (strong)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--workload", default="mpc02", choices=["mpc02", "mpc02pct5", "mpc02pim", "socmpc", "lp25fv47"])
+    ap.add_argument("--batch", type=int, default=65536, help="instances in total (strong, the metric's configuration) or per GPU (weak)")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
     ap.add_argument("--workers", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -56,7 +56,7 @@ def make_problem(workload):
         P = {k: d[k] for k in d.files}
         for k in ("n", "m", "p", "l", "ncones"):
             P[k] = int(P[k])
-        name = ("MPC02 (reference test/MPC/MPC02.h) x{B} per GPU, per-instance G*(1+-0.1%) A*(1+-0.1%) values on the shared "
+        name = ("MPC02 (reference test/MPC/MPC02.h) x{B}, per-instance G*(1+-0.1%) A*(1+-0.1%) values on the shared "
                 "pattern plus h*(1+-0.2%) b*(1+-2%), via updateData(Gpr, Apr, c, h, b); equilibration per instance on the device")
 
         def gen(batch, seed):
@@ -65,12 +65,20 @@ def make_problem(workload):
             W["Gs"], W["As"] = M["Gs"], M["As"]
             return W
         return P, name, gen
+    if workload == "mpc02pct5":  # SURVEY.md 8d config 3 as written: h and b perturbed by +-5 % (most instances turn infeasible)
+        d = np.load(os.path.join(ROOT, "tests", "golden", "fixtures", "MPC02.npz"))
+        P = {k: d[k] for k in d.files}
+        for k in ("n", "m", "p", "l", "ncones"):
+            P[k] = int(P[k])
+        name = ("MPC02 (reference test/MPC/MPC02.h) x{B}, h*(1+-5%) b*(1+-5%) per instance via updateData "
+                "(the survey's recipe: a mix of optimal and primal-infeasible instances), G/A/c shared")
+        return P, name, lambda batch, seed: perturbed(P, batch, rel=0.05, seed=seed)
     if workload == "mpc02":
         d = np.load(os.path.join(ROOT, "tests", "golden", "fixtures", "MPC02.npz"))
         P = {k: d[k] for k in d.files}
         for k in ("n", "m", "p", "l", "ncones"):
             P[k] = int(P[k])
-        name = ("MPC02 (reference test/MPC/MPC02.h; stands in for the missing MPC01) x{B} per GPU, "
+        name = ("MPC02 (reference test/MPC/MPC02.h; stands in for the missing MPC01) x{B}, "
                 "h*(1+-0.2%) b*(1+-2%) per instance via updateData, G/A/c shared")
         return P, name, lambda batch, seed: perturbed(P, batch, rel=MPC_REL, seed=seed)
     if workload == "lp25fv47":  # BASELINE.json configs[4]: c and b perturbed by 1 %
@@ -78,10 +86,10 @@ def make_problem(workload):
         P = {k: d[k] for k in d.files}
         for k in ("n", "m", "p", "l", "ncones"):
             P[k] = int(P[k])
-        name = "lp_25fv47 (reference test/LPnetlib/lp_25fv47.h) x{B} per GPU, c*(1+-1%) b*(1+-1%) per instance, G/A/h shared"
+        name = "lp_25fv47 (reference test/LPnetlib/lp_25fv47.h) x{B}, c*(1+-1%) b*(1+-1%) per instance, G/A/h shared"
         return P, name, lambda batch, seed: perturbed(P, batch, rel=0.01, seed=seed, vary=("c", "b"))
     P = soc_mpc(T=40)
-    name = "builder-defined SOC MPC (2-D double integrator, T=40, 80 cones of dim 3/5) x{B} per GPU, x0/ref per instance"
+    name = "builder-defined SOC MPC (2-D double integrator, T=40, 80 cones of dim 3/5) x{B}, x0/ref per instance"
     return P, name, lambda batch, seed: soc_mpc_batch(P, batch, seed=seed)
 
 
@@ -103,6 +111,8 @@ def cpu_baseline(P, gen, cores, seconds_target=15.0):
     W = gen(sample, 992)
     r = oracle.batch_run(P, sample, Gs=W.get("Gs"), As=W.get("As"), hs=W["hs"], bs=W["bs"], cs=W.get("cs"), nthreads=cores, want_solution=False)
     return {"value": sample / r["seconds"], "unit": "solves/s", "cores": cores, "kind": "port",
+            "exit_flags": {int(k): int(v) for k, v in zip(*np.unique(r["exit"], return_counts=True))},
+            "iterations_mean": float(r["iter"].mean()),
             "sample": f"{sample} instances of the same workload, {cores} threads, one solver per thread, "
                       f"updateData+solve per instance (includes re-equilibration and the per-solve AMD ordering), "
                       f"{r['seconds']:.1f} s; exit flags {dict(zip(*[a.tolist() for a in np.unique(r['exit'], return_counts=True)]))}, "
@@ -174,7 +184,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "SOCP solves/sec", "value": value, "unit": "solves/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name.format(B=args.batch), "reference_impl": "CPU oracle port of EiCOS (Eigen absent: the reference itself cannot be built)"},
+            "config": {"workload": name.format(B=args.batch * (args.gpus if args.scaling == "weak" else 1)), "reference_impl": "CPU oracle port of EiCOS (Eigen absent: the reference itself cannot be built)"},
             "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -258,6 +268,7 @@ def main():
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
+        timed.local_ms = ms
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -273,6 +284,7 @@ def main():
         sampler.start()
     stats = []
     ms = timed(step_device, args.steps, stats.append)
+    local_ms = timed.local_ms
     clocks = sampler.stop() if rank == 0 else None
     solver.set_timing(False)
     total_batch = batch * world if args.scaling == "weak" else args.batch
@@ -294,6 +306,16 @@ def main():
                        "eicos_batch_solve (include/eicos_b200.h): pinned host h,b in; x and exit flags out")}
         assert np.array_equal(exit_h.numpy(), exits)
 
+    # per-rank step time and iteration counts (the slowest rank sets the job's time: its slowest instance runs the
+    # most interior-point iterations, and every one of them is at least a latency floor long)
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([0.0, float(iters.max()), float(iters.mean()), float(batch)], dtype=torch.float64, device=dev)
+        mine[0] = local_ms / args.steps
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"rank": r, "ms_per_step": float(t[0]), "iterations_max": int(t[1]), "iterations_mean": float(t[2]),
+                     "instances": int(t[3])} for r, t in enumerate(allr)]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -312,6 +334,12 @@ def main():
     ms_other = sum(s["ms_other"] for s in stats)
     ms_kernels = ms_solve + ms_factor + ms_other
     rounds = sum(s["ir_rounds"] for s in stats)
+    lane_rounds = sum(s["lane_rounds"] for s in stats)
+    ms_resid = sum(s["ms_resid"] for s in stats)
+    ms_vector = sum(s["ms_vector"] for s in stats)
+    resid_tiles = sum(s["resid_launch_tiles"] for s in stats)
+    vector_tiles = sum(s["vector_launch_tiles"] for s in stats)
+    mt = m  # rows of a z-shaped vector (+ 2 per cone, none in the LP workloads)
     solve_launches = sum(s["solve_launches"] for s in stats)
     factor_launches = sum(s["factor_launches"] for s in stats)
     factor_tiles = sum(s["factor_launch_tiles"] for s in stats)
@@ -335,11 +363,27 @@ def main():
                 "algorithmic_bytes_per_launch": rounds * bytes_round / max(solve_launches, 1),
                 "avg_launch_ms": ms_solve / max(solve_launches, 1),
                 "share_of_step": ms_solve / ms_kernels if ms_kernels else None,
+                "units": "tile-rounds x %d lanes: one unit = one solve round (forward + backward sweep + refinement residual) of one "
+                         "instance, 8 (2 nnzL + 7 N) bytes (SURVEY.md 8d: B_sol + B_res, shared-A/G variant); finished lanes of a live "
+                         "tile count (frac_lane_rounds counts only the rounds each instance needed itself)" % tile,
+                "frac_lane_rounds": (lane_rounds * bytes_round / tile / (ms_solve * 1e-3) / 1e9 / peak) if ms_solve > 0 else None,
                 "ldl_factor": {"kernel": "eicos_ldl_factor", "achieved": factor_gbs, "frac": factor_gbs / peak,
                                "algorithmic_bytes_per_launch": factor_tiles * bytes_factor / max(factor_launches, 1),
                                "avg_launch_ms": ms_factor / max(factor_launches, 1),
                                "share_of_step": ms_factor / ms_kernels if ms_kernels else None,
-                               "traffic": (traffic or {}).get("eicos_ldl_factor")}}
+                               "traffic": (traffic or {}).get("eicos_ldl_factor")},
+                # computeResiduals: [c|b|h], [x|y|z], s in, r out (+ the instance's G / A values); the three vector
+                # kernels of an iteration: about 22 N-row passes together
+                "residuals": {"kernel": "eicos_residuals",
+                              "achieved": (resid_tiles * 8.0 * (3 * N + mt + nnzGA) * tile / (ms_resid * 1e-3) / 1e9) if ms_resid > 0 else 0.0,
+                              "avg_launch_ms": ms_resid / max(sum(s["resid_launches"] for s in stats), 1),
+                              "share_of_step": ms_resid / ms_kernels if ms_kernels else None},
+                "vector_kernels": {"kernel": "eicos_iter_head + eicos_iter_mid + eicos_iter_tail",
+                                   "achieved": (vector_tiles * 8.0 * (22.0 / 3.0) * N * tile / (ms_vector * 1e-3) / 1e9) if ms_vector > 0 else 0.0,
+                                   "avg_launch_ms": ms_vector / max(sum(s["vector_launches"] for s in stats), 1),
+                                   "share_of_step": ms_vector / ms_kernels if ms_kernels else None}}
+    for k in ("residuals", "vector_kernels"):
+        roofline[k]["frac"] = roofline[k]["achieved"] / peak
 
     # where the tiles spend their time inside eicos_solve_kkt (clock64 per phase, summed over tiles)
     pc = np.sum([s["kkt_phase_cycles"] for s in stats], axis=0).astype(float)
@@ -355,7 +399,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": name.format(B=batch), "batch_per_gpu": batch, "total_batch": total_batch,
+            "config": {"workload": name.format(B=total_batch), "batch_per_gpu": batch, "total_batch": total_batch,
                        "n": n, "m": m, "p": p, "dim_K": N, "nnzK": dims["nnzK"], "nnzL": nnzL,
                        "etree_height": dims["etree_height"], "workers_per_tile": dims["workers"],
                        "l2": "inputs and workspace (%.1f GB) are far larger than L2" % (dims["workspace_bytes"] / 1e9),
@@ -364,8 +408,9 @@ def main():
                        "parallelism": f"batch sharded by instance over {world} GPU(s), no collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(sum(s["launches"] for s in stats)),
-            "kernel_ms": {"solve_kkt": ms_solve, "ldl_factor": ms_factor, "other": ms_other},
+            "kernel_ms": {"solve_kkt": ms_solve, "ldl_factor": ms_factor, "other": ms_other, "residuals": ms_resid, "vector": ms_vector},
             "kkt_phase_share": phase_share,
+            "per_rank": per_rank,
             "clocks": clocks}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -72,7 +72,7 @@ EXPORTS = [
     "eicos_batch_setup", "eicos_batch_setup_ex", "eicos_batch_update_matrices", "eicos_batch_solve",
     "eicos_batch_solve_matrices", "eicos_batch_solve_device", "eicos_batch_solve_matrices_device",
     "eicos_batch_set_timing", "eicos_batch_set_compaction", "eicos_batch_get_stats", "eicos_batch_get_dims", "eicos_batch_get_program_stats", "eicos_batch_get_symbolic",
-    "eicos_batch_debug_init", "eicos_batch_stream", "eicos_batch_cleanup",
+    "eicos_batch_debug_init", "eicos_batch_debug_line_search", "eicos_batch_stream", "eicos_batch_cleanup",
     "eicos_last_error", "eicos_device_count",
 ]
 
@@ -144,6 +144,8 @@ class Library:
         L.eicos_batch_get_symbolic.argtypes = [C.c_void_p] + [_ip] * 6
         L.eicos_batch_debug_init.restype = C.c_int
         L.eicos_batch_debug_init.argtypes = [C.c_void_p, C.c_int] + [_dp] * 7 + [_ip]
+        L.eicos_batch_debug_line_search.restype = C.c_int
+        L.eicos_batch_debug_line_search.argtypes = [C.c_void_p, C.c_int] + [_dp] * 5
         L.eicos_batch_stream.restype = C.c_void_p
         L.eicos_batch_stream.argtypes = [C.c_void_p]
         L.eicos_batch_cleanup.restype = None
@@ -323,6 +325,13 @@ class BatchSolver:
         """Raw device pointers (ints); results stay in HBM."""
         self.lib.check(self.lib.L.eicos_batch_solve_matrices_device(
             self.h, int(batch), *[C.c_void_p(int(v) or None) for v in (d_Gs, d_As, d_cs, d_hs, d_bs, d_x, d_y, d_z, d_s, d_exit, d_iter)]))
+
+    def debug_line_search(self, lam, ds, dz, scalars):
+        """lineSearch on caller data: lam, ds, dz [batch x m] in z order, scalars [batch x 4] = tau, dtau, kap, dkap."""
+        lam, ds, dz, scalars = (np.ascontiguousarray(v, np.float64) for v in (lam, ds, dz, scalars))
+        alpha = np.zeros(lam.shape[0])
+        self.lib.check(self.lib.L.eicos_batch_debug_line_search(self.h, int(lam.shape[0]), _d(lam), _d(ds), _d(dz), _d(scalars), _d(alpha)))
+        return alpha
 
     def debug_init(self, batch, cs=None, hs=None, bs=None):
         d = self.dims()

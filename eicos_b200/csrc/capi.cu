@@ -480,6 +480,26 @@ int eicos_batch_debug_init(eicos_batch *bt, int batch, const double *cs, const d
     }
 }
 
+int eicos_batch_debug_line_search(eicos_batch *bt, int batch, const double *lambda, const double *ds, const double *dz,
+                                  const double *scalars, double *alpha)
+{
+    if (!bt || batch <= 0 || !lambda || !ds || !dz || !scalars || !alpha)
+        return fail(EICOS_ERR_INVALID, "null argument or empty batch");
+    try
+    {
+        bt->eng->debug_line_search(batch, lambda, ds, dz, scalars, alpha);
+        return 0;
+    }
+    catch (const std::invalid_argument &e)
+    {
+        return fail(EICOS_ERR_INVALID, e.what());
+    }
+    catch (const std::exception &e)
+    {
+        return fail(EICOS_ERR_DEVICE, e.what());
+    }
+}
+
 void *eicos_batch_stream(const eicos_batch *bt) { return bt ? bt->eng->stream() : nullptr; }
 
 void eicos_batch_cleanup(eicos_batch *bt)

@@ -39,13 +39,15 @@ EI_DEFINE_KERNEL(eicos_load_inputs, tile_load, 2)
 EI_DEFINE_KERNEL(eicos_equilibrate, tile_equil, 2)
 EI_DEFINE_KERNEL(eicos_init, tile_init, 2)
 EI_DEFINE_KERNEL1(eicos_ldl_factor, tile_factor)
-EI_DEFINE_KERNEL_(eicos_solve_kkt, tile_solve_kkt, 32, 8, 1) /* CTA = (tile, job): one solveKKT each */
+EI_DEFINE_KERNEL_(eicos_solve_kkt, tile_solve_kkt<1>, 32, 8, 1) /* CTA = (tile, job): one solveKKT each */
+EI_DEFINE_KERNEL_(eicos_solve_kkt_pair, tile_solve_kkt<2>, 32, 7, 0) /* two solveKKT that share the factor, one pass over L */
 EI_DEFINE_KERNEL(eicos_init_point, tile_init_point, 2)
 EI_DEFINE_KERNEL1(eicos_residuals, tile_resid)
 EI_DEFINE_KERNEL(eicos_iter_head, tile_head, 2)
 EI_DEFINE_KERNEL(eicos_iter_mid, tile_mid, 2)
 EI_DEFINE_KERNEL(eicos_iter_tail, tile_tail, 2)
 EI_DEFINE_KERNEL(eicos_store_outputs, tile_store, 2)
+EI_DEFINE_KERNEL(eicos_debug_line_search, tile_debug_line_search, 2)
 
 #define EI_LAUNCH(name, fn, tiles, threads, smem, stream, args) name<<<(tiles), (threads), (smem), (stream)>>>(args)
 #define EI_LAUNCH_JOBS(name, fn, tiles, njobs, threads, smem, stream, args) \
@@ -68,7 +70,7 @@ __global__ void eicos_compact(const __grid_constant__ KArgs a, const __grid_cons
     {                                                                                             \
         const int nw_ = (threads), nj_ = (njobs);                                                                \
         std::vector<double> red_((size_t)nw_ * KRED * TILE + 8);                                  \
-        std::vector<double> pb_(machine_smem_doubles(std::max((args).P.sw_budget, (args).P.fa_budget), M_MAX_RING_GROUPS) + 8); \
+        std::vector<double> pb_(machine_smem_doubles(std::max(std::max((args).P.sw_budget, (args).P.fa_budget), (args).P.pair_budget), M_MAX_RING_GROUPS, 2) + 8); \
         for (int cta_ = 0; cta_ < (tiles) * nj_; cta_++)                                          \
         {                                                                                         \
             const int tile_ = cta_ / nj_;                                                         \
@@ -114,6 +116,12 @@ int Engine::tile_width() { return TILE; }
 
 // A launch of `ctas` one-warp CTAs runs the deep-ring programs when all of them are resident at the deep
 // ring's shared-memory footprint (then nothing is lost by giving each tile more rows in flight).
+// The two solves of an iteration that share the factor run as CTAs (tile, job); EICOS_PAIR_SOLVES = 1 runs them as ONE
+// CTA per tile with the two-job programs instead (one pass over L for both right-hand sides: less HBM traffic, but on
+// B200 the wider operations cost more shared-memory bandwidth than the shared L saves - measured slower, kept as an
+// option and as a parity check of the two-job machine).
+bool Engine::pair_solves(int) const { return force_pair_ > 0; }
+
 bool Engine::deep_ring(int ctas) const
 {
     if (force_variant_ >= 0)
@@ -256,16 +264,25 @@ void Engine::upload_pattern(const Symbolic &S)
         d.nchunks = h.nchunks;
         d.nld_chunks = h.nld_chunks;
         d.ring_groups = h.ring_groups;
-        d.ring_row0 = M_ROW_SLOT0 + h.slot_budget;
+        d.ring_row0 = m_row_slot0(h.nr) + h.nr * h.slot_budget;
         if (keep)
             *keep = o;
     };
-    const auto variant = [&](const ivec &list, int a1, int a2, int a3, int a4 = 0, int a5 = 0) {
+    // offsets of the vectors the selectors 1.. stand for: job A, then job B (two-job programs)
+    const auto variant = [&](const ivec &list, std::initializer_list<int> va, std::initializer_list<int> vb = {}) {
         ivec out(list.size());
-        const int off[8] = {0, a1, a2, a3, a4, a5, 0, 0};
-        for (size_t k = 0; k < list.size(); k++)
-            // (padding words copy row 0 of the tile into a ring row nobody reads: cheaper than a test per copy)
-            out[k] = list[k] == M_LD_NONE ? 0 : (list[k] & M_LD_ROW_MASK) + off[((unsigned)list[k] >> M_LD_SEL_SHIFT) & 7];
+        int off[16] = {0};
+        int k = 1;
+        for (int o : va)
+            off[k++] = o;
+        k = 9;
+        for (int o : vb)
+            off[k++] = o;
+        for (size_t q = 0; q < list.size(); q++)
+        { // (padding words copy row 0 of the tile into a ring row nobody reads: cheaper than a test per copy)
+            const int w = list[q];
+            out[q] = w == M_LD_NONE ? 0 : (w & M_LD_ROW_MASK) + off[(((unsigned)w >> M_LD_SEL_SHIFT) & 7) + ((w & M_LD_JOB_B) ? 8 : 0)];
+        }
         return upload(out, owned_, st);
     };
     P.sw_budget = H_.fw[0].slot_budget;
@@ -282,15 +299,26 @@ void Engine::upload_pattern(const Symbolic &S)
         prog(H_.fa[v], P.fa[v], &dfa_ops_[v]);
         for (int set = 0; set < 2; set++)
         { // forward: 1 = right-hand side, 3 = xw; backward: 1 = output, 2 = accumulated solution, 3 = xw
-            P.fw_ld[v][set][0] = variant(H_.fw[v].ld, rhs[set], 0, xw[set]);
-            P.fw_ld[v][set][1] = variant(H_.fw[v].ld, er[set], 0, xw[set]);
-            P.bw_ld[v][set][0] = variant(H_.bwp[v].ld, sol[set], 0, xw[set]);
-            P.bw_ld[v][set][1] = variant(H_.bw[v].ld, dxr[set], sol[set], xw[set]);
-            P.mv_ld[v][set] = variant(H_.mv[v].ld, rhs[set], sol[set], L_.lpv, er[set]);
+            P.fw_ld[v][set][0] = variant(H_.fw[v].ld, {rhs[set], 0, xw[set]});
+            P.fw_ld[v][set][1] = variant(H_.fw[v].ld, {er[set], 0, xw[set]});
+            P.bw_ld[v][set][0] = variant(H_.bwp[v].ld, {sol[set], 0, xw[set]});
+            P.bw_ld[v][set][1] = variant(H_.bw[v].ld, {dxr[set], sol[set], xw[set]});
+            P.mv_ld[v][set] = variant(H_.mv[v].ld, {rhs[set], sol[set], L_.lpv, er[set]});
         }
-        P.rs_ld[v] = variant(H_.rs[v].ld, L_.chb, L_.w, L_.s, L_.r, L_.sc);
-        P.fa_ld[v] = variant(H_.fa[v].ld, 0, 0, 0);
+        P.rs_ld[v] = variant(H_.rs[v].ld, {L_.chb, L_.w, L_.s, L_.r, L_.sc});
+        P.fa_ld[v] = variant(H_.fa[v].ld, {});
     }
+    // two-job programs: job A = set 0 (rhs1 / sol1), job B = set 1 (rhs2 / sol2)
+    P.pair_budget = H_.pair_budget;
+    prog(H_.fw2, P.fw2);
+    prog(H_.bw2, P.bw2);
+    prog(H_.bwp2, P.bwp2);
+    prog(H_.mv2, P.mv2, &dmv2_ops_);
+    P.fw2_ld[0] = variant(H_.fw2.ld, {rhs[0], 0, xw[0]}, {rhs[1], 0, xw[1]});
+    P.fw2_ld[1] = variant(H_.fw2.ld, {er[0], 0, xw[0]}, {er[1], 0, xw[1]});
+    P.bw2_ld[0] = variant(H_.bwp2.ld, {sol[0], 0, xw[0]}, {sol[1], 0, xw[1]});
+    P.bw2_ld[1] = variant(H_.bw2.ld, {dxr[0], sol[0], xw[0]}, {dxr[1], sol[1], xw[1]});
+    P.mv2_ld = variant(H_.mv2.ld, {rhs[0], sol[0], L_.lpv, er[0]}, {rhs[1], sol[1], L_.lpv, er[1]});
     P.mv_rows = H_.mv_rows;
     ivec vk;
     for (int k = 0; k < S.l; k++)
@@ -325,6 +353,7 @@ void Engine::upload_values(const Symbolic &S)
         be::h2d(drs_ops_[v], H_.rs[v].ops.data(), H_.rs[v].ops.size() * sizeof(int), st);
         be::h2d(dfa_ops_[v], H_.fa[v].ops.data(), H_.fa[v].ops.size() * sizeof(int), st);
     }
+    be::h2d(dmv2_ops_, H_.mv2.ops.data(), H_.mv2.ops.size() * sizeof(int), st);
     be::sync(st);
 }
 
@@ -335,6 +364,8 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
     be::set_device(device_);
     if (const char *v = std::getenv("EICOS_RING_VARIANT")) // (diagnostics / tests) pin the ring depth of every launch
         force_variant_ = std::atoi(v);
+    if (const char *v = std::getenv("EICOS_PAIR_SOLVES")) // ... and the form of the paired solves
+        force_pair_ = std::atoi(v);
     stream_ = (void *)(intptr_t)be::make_stream();
     build_layout(S, false);
     upload_pattern(S);
@@ -358,12 +389,15 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
     // program kernels (one warp per tile): the shared memory of the FMA machine; vector kernels: reduction rows only
     for (int v = 0; v < M_VARIANTS; v++)
     {
-        smem_prog_[v] = machine_smem_doubles(P_.sw_budget, M_VARIANT_GROUPS[v]) * sizeof(double);
-        smem_factor_[v] = machine_smem_doubles(P_.fa_budget, M_VARIANT_GROUPS[v]) * sizeof(double);
+        smem_prog_[v] = machine_smem_doubles(P_.sw_budget, variant_groups(v)) * sizeof(double);
+        smem_factor_[v] = machine_smem_doubles(P_.fa_budget, variant_groups(v)) * sizeof(double);
     }
+    smem_pair_ = machine_smem_doubles(P_.pair_budget, M_PAIR_GROUPS, 2) * sizeof(double);
     smem_common_ = workers_ > 1 ? (size_t)workers_ * KRED * TILE * sizeof(double) : 0;
 #ifndef EICOS_EMU
     {
+        if (smem_pair_ > 48 * 1024)
+            EI_CUDA(cudaFuncSetAttribute(eicos_solve_kkt_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pair_));
         const size_t top_f = std::max(smem_factor_[0], smem_factor_[M_VARIANTS - 1]), top_p = std::max(smem_prog_[0], smem_prog_[M_VARIANTS - 1]);
         if (top_f > 48 * 1024)
             EI_CUDA(cudaFuncSetAttribute(eicos_ldl_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)top_f));
@@ -426,6 +460,40 @@ void Engine::set_matrices(const double *d_G, const double *d_A, const double *ba
     if (base_A)
         be::h2d(base_mat_ + nnzG_, base_A, (size_t)nnzA_ * sizeof(double), st);
     be::sync(st);
+}
+
+void Engine::debug_line_search(int batch, const double *h_lambda, const double *h_ds, const double *h_dz, const double *h_scalars,
+                               double *h_alpha)
+{
+    be::set_device(device_);
+    be::stream_t st = S_(stream_);
+    if (batch <= 0 || batch > cap_tiles_ * TILE)
+        throw std::invalid_argument("debug_line_search: batch exceeds workspace capacity");
+    const size_t zm = (size_t)batch * P_.m;
+    double *d = (double *)be::alloc((3 * zm + 5 * (size_t)batch) * sizeof(double));
+    be::h2d(d, h_lambda, zm * sizeof(double), st);
+    be::h2d(d + zm, h_ds, zm * sizeof(double), st);
+    be::h2d(d + 2 * zm, h_dz, zm * sizeof(double), st);
+    be::h2d(d + 3 * zm, h_scalars, 4 * (size_t)batch * sizeof(double), st);
+    KArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.P = P_;
+    a.L = L_;
+    a.ws = ws_;
+    a.iws = iws_;
+    a.batch = batch;
+    a.in_h = d;
+    a.in_G = d + zm;
+    a.in_A = d + 2 * zm;
+    a.in_b = d + 3 * zm;
+    a.out_x = d + 3 * zm + 4 * (size_t)batch;
+    const int tiles = (batch + TILE - 1) / TILE;
+    const int threads = workers_ * (LANES == 1 ? 1 : 32);
+    (void)threads;
+    EI_LAUNCH(eicos_debug_line_search, tile_debug_line_search, tiles, threads, smem_common_, st, a);
+    be::d2h(h_alpha, a.out_x, (size_t)batch * sizeof(double), st);
+    be::sync(st);
+    be::dfree(d);
 }
 
 ProgramStats Engine::program_stats() const
@@ -579,7 +647,13 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
             a.njobs = 2;
             a.initialize = init;
             pick(2 * tiles);
-            EI_TIMED(1, EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt, tiles, 2, threads1, smem_prog_[a.variant], st, a));
+            if (pair_solves(tiles))
+            { // both solves in one pass over L (one CTA per tile)
+                a.njobs = 1;
+                EI_TIMED(1, EI_LAUNCH(eicos_solve_kkt_pair, tile_solve_kkt<2>, tiles, threads1, smem_pair_, st, a));
+            }
+            else
+                EI_TIMED(1, EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt<1>, tiles, 2, threads1, smem_prog_[a.variant], st, a));
             stt.solve_launches++;
             stt.solve_launch_tiles += (long long)tiles * 2;
         };
@@ -588,7 +662,7 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
             a.njobs = 1;
             a.initialize = 0;
             pick(tiles);
-            EI_TIMED(1, EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt, tiles, 1, threads1, smem_prog_[a.variant], st, a));
+            EI_TIMED(1, EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt<1>, tiles, 1, threads1, smem_prog_[a.variant], st, a));
             stt.solve_launches++;
             stt.solve_launch_tiles += tiles;
         };
@@ -757,7 +831,13 @@ void Engine::debug_factor_init(int batch, const double *d_c, const double *d_h, 
     a.njobs = 2;
     a.job[0] = {L_.rhs1, L_.sol1, J_NIT1, 0};
     a.job[1] = {L_.rhs2, L_.sol2, J_NIT2, 1};
-    EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt, tiles, 2, threads1, smem_prog_[a.variant], st, a);
+    if (pair_solves(tiles))
+    {
+        a.njobs = 1;
+        EI_LAUNCH(eicos_solve_kkt_pair, tile_solve_kkt<2>, tiles, threads1, smem_pair_, st, a);
+    }
+    else
+        EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt<1>, tiles, 2, threads1, smem_prog_[a.variant], st, a);
     be::sync(st);
     // gather rows back to instance-major host arrays; L comes back in CSC order
     const size_t tile_doubles = (size_t)L_.rows_total * TILE;

@@ -89,6 +89,11 @@ class Engine
                            const double *base_c, const double *base_h, const double *base_b,
                            double *h_Lx, double *h_D, double *h_sol1, double *h_sol2, int *h_nit);
 
+    // lineSearch (src/eicos.cpp:1380-1469) on caller data: lambda, ds, dz instance-major in compact z order [batch x m],
+    // scalars = tau, dtau, kap, dkap per instance [batch x 4]; all host pointers
+    void debug_line_search(int batch, const double *h_lambda, const double *h_ds, const double *h_dz, const double *h_scalars,
+                           double *h_alpha);
+
     ProgramStats program_stats() const;
     void *stream() const { return stream_; }
     int device() const { return device_; }
@@ -122,12 +127,14 @@ class Engine
     int *moves_dev_ = nullptr, *status_host_ = nullptr, *moves_host_ = nullptr; // active-set compaction
     bool compaction_ = true;
     size_t smem_factor_[M_VARIANTS] = {0, 0}, smem_common_ = 0, smem_prog_[M_VARIANTS] = {0, 0}; // factor kernel / vector kernels / solveKKT + residual kernels (per ring variant)
-    int sms_ = 148, force_variant_ = -1;
+    size_t smem_pair_ = 0; // two-job solveKKT kernel
+    int sms_ = 148, force_variant_ = -1, force_pair_ = -1;
     bool deep_ring(int ctas) const;
+    bool pair_solves(int tiles) const;
     std::vector<void *> owned_; // device allocations holding pattern data
     // positions of value arrays that upload_values() rewrites
     double *dxeq_ = nullptr, *dAeq_ = nullptr, *dGeq_ = nullptr;
-    int *dmv_ops_[M_VARIANTS] = {nullptr, nullptr}, *drs_ops_[M_VARIANTS] = {nullptr, nullptr}, *dfa_ops_[M_VARIANTS] = {nullptr, nullptr};
+    int *dmv_ops_[M_VARIANTS] = {nullptr, nullptr}, *drs_ops_[M_VARIANTS] = {nullptr, nullptr}, *dfa_ops_[M_VARIANTS] = {nullptr, nullptr}, *dmv2_ops_ = nullptr;
     HostStreams H_;        // host copy of the instruction streams (value streams are rebuilt on updateData)
     std::vector<int> Lp_;  // column pointers of L (debug extraction)
     std::vector<void *> events_;

@@ -117,8 +117,11 @@ struct DevPattern
     // Every program exists for two depths of the data ring (first index; streams.hpp: M_VARIANT_GROUPS).
     DevMachine fw[2], bw[2], bwp[2], mv[2], rs[2];
     const int *fw_ld[2][2][2], *bw_ld[2][2][2], *mv_ld[2][2], *rs_ld[2];
+    // two-job programs (both job sets in one pass, shallow ring): [first solve | refinement round]
+    DevMachine fw2, bw2, bwp2, mv2;
+    const int *fw2_ld[2], *bw2_ld[2], *mv2_ld;
     int mv_rows;
-    int sw_budget, fa_budget; // slot rows of the solveKKT / residual programs and of the factor program
+    int sw_budget, fa_budget, pair_budget; // slots of the solveKKT / residual programs, the factor program, the two-job programs
     // factor program (absolute rows: its load list needs no materialisation)
     DevMachine fa[2];
     const int *fa_ld[2];

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <string>
 #include <cstdint>
 #include <cstring>
 #include <cstdlib>
@@ -144,39 +145,50 @@ void schedule(const MProgram &P, int window, std::vector<ivec> &bundles, ivec &b
 
 void verify(const MProgram &P, const std::vector<ivec> &bundles, const MachineCode &mc);
 
+// ---- pass 2: ring rows, slots, control words.
+// NR = P.nr right-hand sides per pass: a VECTOR operand (B, C, x3, the destination) is NR adjacent rows (one per
+// job), an A operand one row.  Vector pops take NR consecutive ring rows starting at a multiple of NR.
 void compile_with_window(const MProgram &P, int max_slots, int window, int RG, MachineCode &out)
 {
     if (RG < 2 || RG > M_MAX_RING_GROUPS)
         throw std::logic_error("machine: ring depth out of range");
-    const int RING_ROWS = RG * M_RING_GROUP, ring0 = M_ROW_SLOT0 + std::max(max_slots, 0);
+    const int NR = P.nr;
+    if (NR != 1 && NR != 2)
+        throw std::logic_error("machine: one or two right-hand sides per pass");
+    const int RING_ROWS = RG * M_RING_GROUP, ring0 = m_row_slot0(NR) + NR * std::max(max_slots, 0);
     out = MachineCode();
     out.window = window;
     out.ring_groups = RG;
     out.slot_budget = std::max(max_slots, 0);
+    out.nr = NR;
     const int n = (int)P.ops.size(), nv = (int)P.vals.size();
     std::vector<ivec> bundles;
     ivec bundle_of;
     schedule(P, window, bundles, bundle_of);
-    const int nb = (int)bundles.size();
 
-    // use times (bundle numbers) of every value, in order
+    // uses of every value: the operations that read it, in schedule order; their times are bundle keys
+    // (16 x the scheduled bundle number, + 1 for every time an operation is pushed into an inserted bundle)
+    std::vector<long long> optime(n, 0);
     std::vector<ivec> uses(nv);
-    for (int b = 0; b < nb; b++)
+    for (int b = 0; b < (int)bundles.size(); b++)
         for (int t : bundles[b])
         {
+            optime[t] = 16LL * b;
             const MSrc *src[4] = {&P.ops[t].a, &P.ops[t].b, &P.ops[t].c, &P.ops[t].x3};
             for (const MSrc *s : src)
                 if (s->kind == MS_VAL)
-                    uses[s->val].push_back(b);
+                    uses[s->val].push_back(t);
         }
     ivec uptr(nv, 0);
-    const auto next_use = [&](int v) { return uptr[v] < (int)uses[v].size() ? uses[v][uptr[v]] : INT_MAX; };
+    const long long NEVER = LLONG_MAX;
+    const auto next_use = [&](int v) { return uptr[v] < (int)uses[v].size() ? optime[uses[v][uptr[v]]] : NEVER; };
 
-    // slots
+    // slots (one slot = NR rows)
     ivec slot_of(nv, -1), holder(std::max(max_slots, 0), -1), stamp(std::max(max_slots, 0), -1), free_slots;
     for (int s = (int)holder.size() - 1; s >= 0; s--)
         free_slots.push_back(s);
     int slot_top = 0;
+    const auto slot_row = [&](int s) { return m_row_slot0(NR) + NR * s; };
     // where a value can be re-read from: bundle whose store phase wrote its home row (-1: before the program), -2: nowhere
     ivec written_at(nv, -2);
     {
@@ -196,11 +208,7 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
     // ring bookkeeping
     long long npop = 0;
     int released = 0, waited_upto = -1;
-    std::vector<long long> first_pop(nb + 1, 0);
-    const auto push_pop = [&](int word) {
-        out.ld.push_back(word);
-        return ring0 + (int)(npop++ % RING_ROWS);
-    };
+    std::vector<long long> first_pop;
     const auto pad_to = [&](long long target) {
         while (npop < target)
         {
@@ -208,6 +216,21 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
             npop++;
             out.pads++;
         }
+    };
+    const auto push_single = [&](int word) {
+        out.ld.push_back(word);
+        return ring0 + (int)(npop++ % RING_ROWS);
+    };
+    const auto push_vector = [&](int word) { // NR rows, one per job, at a multiple of NR
+        if (npop % NR)
+            pad_to(npop + 1);
+        const int row = ring0 + (int)(npop % RING_ROWS);
+        for (int j = 0; j < NR; j++)
+        {
+            out.ld.push_back(word | (j ? M_LD_JOB_B : 0));
+            npop++;
+        }
+        return row;
     };
     // control word of the previous bundle is closed once the next bundle knows how much padding it needs
     long long prev_ctrl_at = -1;
@@ -221,6 +244,19 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
         released += nrel;
         out.ops[(size_t)prev_ctrl_at] |= (prev_wait << MF_WAIT_SHIFT) | (nrel << MF_NREL_SHIFT);
     };
+    // rows an operation pops, given what is in the slots now: (rows of one-use loads, rows of re-reads); the
+    // one-use loads of a bundle need at most one alignment pad together, every re-read of a vector one of its own
+    const auto pops_of = [&](const MOp &op, int &regular, int &reread) {
+        const MSrc *src[4] = {&op.a, &op.b, &op.c, &op.x3};
+        for (int k = 0; k < 4; k++)
+        {
+            const bool vec = k != 0;
+            if (src[k]->kind == MS_LOAD)
+                regular += vec ? NR : 1;
+            else if (src[k]->kind == MS_VAL && slot_of[src[k]->val] < 0)
+                reread += vec ? NR + (NR - 1) : 1;
+        }
+    };
 
     struct Pending
     {
@@ -228,8 +264,32 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
         size_t k_at; // word index of the K field
         size_t f_at; // word index of the flags
     };
-    for (int b = 0; b < nb; b++)
+    for (int b = 0; b < (int)bundles.size(); b++)
     {
+        // ---- a bundle's pops must fit the rows in flight: 16 rows are kept for its re-reads (see below), the rest of
+        // the window for its one-use loads; operations that do not fit move into a bundle of their own behind it
+        {
+            ivec &cur = bundles[b];
+            int keep = 0, regular = NR - 1, reread = 0;
+            for (; keep < (int)cur.size(); keep++)
+            {
+                int r1 = regular, r2 = reread;
+                pops_of(P.ops[cur[keep]], r1, r2);
+                if (keep > 0 && (r2 > 16 || r1 + r2 > RING_ROWS - 8))
+                    break;
+                regular = r1, reread = r2;
+            }
+            if (regular + reread > RING_ROWS - 8 || reread > 16)
+                throw std::logic_error("machine: one operation pops more rows than the ring holds");
+            if (keep < (int)cur.size())
+            {
+                ivec rest(cur.begin() + keep, cur.end());
+                cur.resize(keep);
+                for (int t : rest)
+                    optime[t]++;
+                bundles.insert(bundles.begin() + b + 1, rest);
+            }
+        }
         const ivec &cur = bundles[b];
         // ---- how far back were the values written that this bundle re-reads from their home rows?
         int pbmax = -1;
@@ -247,7 +307,7 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
         if (pbmax >= 0) // two group boundaries between the writer's first pop and ours (see the safety rule below)
             pad_to((first_pop[pbmax] / M_RING_GROUP + 2) * M_RING_GROUP);
         close_prev();
-        first_pop[b] = npop;
+        first_pop.push_back(npop);
         const long long window_end = (first_pop[b] / M_RING_GROUP + RG) * M_RING_GROUP; // rows issued so far
 
         // ---- records; pops of single-use rows first, re-reads of written values last (they need late ring positions)
@@ -257,9 +317,16 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
         {
             size_t at; // word to receive the field
             int val;
-            bool keep_b;
+            bool vec, keep_b;
             size_t f_at, w5_at;
         };
+        struct Load
+        {
+            size_t at;
+            int word;
+            bool vec;
+        };
+        std::vector<Load> loads; // one-use loads of the bundle, laid out once all are known
         std::vector<Reread> rereads;
         std::vector<Pending> dsts;
         ivec last_used; // values whose last use is in this bundle
@@ -270,7 +337,7 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
             if (u >= (int)cur.size())
             { // padding operation: scratch = 0 - 0 * 0
                 w[0] = w[1] = w[2] = field(M_ROW_ZERO);
-                w[3] = field(M_ROW_TRASH);
+                w[3] = field(m_row_trash(NR));
                 out.nnop++;
                 continue;
             }
@@ -281,19 +348,22 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
             double cval = 0.0;
             const auto resolve = [&](const MSrc &s, int which) { // which: 0 A, 1 B, 2 C, 3 x3
                 const size_t at = r + (which == 3 ? 6 : which);
+                const bool vec = which != 0;
                 switch (s.kind)
                 {
                 case MS_ZERO:
                     out.ops[at] = field(M_ROW_ZERO);
                     break;
                 case MS_NEGZERO:
-                    out.ops[at] = field(M_ROW_NEGZERO);
+                    out.ops[at] = field(m_row_negzero(NR));
                     break;
                 case MS_LOAD:
-                    if (s.row < 0 || s.row > M_LD_ROW_MASK)
+                {
+                    if (s.row < 0 || s.row > M_LD_ROW_MASK || s.sel < 0 || s.sel > 7)
                         throw std::logic_error("machine: load row out of range");
-                    out.ops[at] = field(push_pop((s.sel << M_LD_SEL_SHIFT) | s.row));
+                    loads.push_back({at, (s.sel << M_LD_SEL_SHIFT) | s.row, vec && NR > 1});
                     break;
+                }
                 case MS_CONST:
                     if (which != 0 && which != 2)
                         throw std::logic_error("machine: constant in a B / x3 operand");
@@ -307,10 +377,12 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
                 case MS_VAL:
                 {
                     const int v = s.val;
+                    if (!vec && NR > 1)
+                        throw std::logic_error("machine: a value as the A operand of a two-job program");
                     if (slot_of[v] >= 0)
-                        out.ops[at] = field(M_ROW_SLOT0 + slot_of[v]);
+                        out.ops[at] = field(slot_row(slot_of[v]));
                     else
-                        rereads.push_back({at, v, which == 1, r + 4, r + 5});
+                        rereads.push_back({at, v, vec, which == 1, r + 4, r + 5});
                     uptr[v]++;
                     if (uptr[v] == (int)uses[v].size())
                         last_used.push_back(v);
@@ -337,11 +409,33 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
                 w[7] = cw[1];
             }
             w = out.ops.data() + r;
-            w[3] = field(M_ROW_TRASH);
+            w[3] = field(m_row_trash(NR));
             w[4] = flags;
             w[5] = (flags & MF_OUT) ? op.out_row : 0;
             if (op.dst >= 0)
                 dsts.push_back({op.dst, r + 3, r + 4});
+        }
+        // ---- one-use loads: the vector pops want a position that is a multiple of NR, so a one-row pop goes first
+        // when the ring position is odd, then all vectors, then the remaining one-row pops
+        {
+            size_t next_single = 0;
+            const auto place_single = [&]() {
+                while (next_single < loads.size() && loads[next_single].vec)
+                    next_single++;
+                if (next_single == loads.size())
+                    return false;
+                out.ops[loads[next_single].at] = field(push_single(loads[next_single].word));
+                next_single++;
+                return true;
+            };
+            if (NR > 1 && npop % NR)
+                place_single();
+            for (const Load &l : loads)
+                if (l.vec)
+                    out.ops[l.at] = field(push_vector(l.word));
+            while (place_single())
+            {
+            }
         }
         // ---- re-reads.  The home row of value v was written in the store phase of bundle pb; ring group g is
         // refilled at the end of the first bundle t with  pops(<= t) >= 8 (g - GROUPS + 1),  so the copy of pop
@@ -354,7 +448,8 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
             if (pb >= 0)
                 pad_to((first_pop[pb] / M_RING_GROUP + RG) * M_RING_GROUP);
             const MVal &mv = P.vals[v];
-            out.ops[rr.at] = field(push_pop((mv.home_sel << M_LD_SEL_SHIFT) | mv.home_row));
+            const int word = (mv.home_sel << M_LD_SEL_SHIFT) | mv.home_row;
+            out.ops[rr.at] = field(rr.vec ? push_vector(word) : push_single(word));
             out.far++;
         }
         if (npop > window_end)
@@ -370,7 +465,7 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
         // ---- a slot for a value: free one, or the one whose holder is needed furthest in the future (if that
         // is later than our own next use and the holder can be re-read from its home row)
         const auto take_slot = [&](int v) -> int {
-            if (next_use(v) == INT_MAX)
+            if (next_use(v) == NEVER)
                 return -1;
             int s = -1;
             if (!free_slots.empty())
@@ -405,8 +500,8 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
                 written_at[v] = b;
             const int s = take_slot(v);
             if (s >= 0)
-                out.ops[d.k_at] = field(M_ROW_SLOT0 + s);
-            else if (next_use(v) != INT_MAX && !has_out)
+                out.ops[d.k_at] = field(slot_row(s));
+            else if (next_use(v) != NEVER && !has_out)
             { // a partial sum without a slot waits in its home row
                 const MVal &mv = P.vals[v];
                 if (mv.home_sel < 0)
@@ -426,7 +521,7 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
                     if (s >= 0)
                     {
                         out.ops[rr.f_at] |= MF_BKEEP;
-                        out.ops[rr.w5_at] = field(M_ROW_SLOT0 + s);
+                        out.ops[rr.w5_at] = field(slot_row(s));
                     }
                 }
         // ---- control: wait for the newest group this bundle reads
@@ -447,6 +542,7 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
         }
         prev_ctrl_at = (long long)rec0 + 4;
     }
+    const int nb = (int)bundles.size();
     if (nb == 0)
     { // an empty program still needs its END bundle
         const size_t rec0 = out.ops.size();
@@ -455,7 +551,7 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
         {
             int *w = out.ops.data() + rec0 + (size_t)u * M_REC_WORDS;
             w[0] = w[1] = w[2] = field(M_ROW_ZERO);
-            w[3] = field(M_ROW_TRASH);
+            w[3] = field(m_row_trash(NR));
         }
         prev_ctrl_at = (long long)rec0 + 4;
         prev_wait = 0;
@@ -470,11 +566,10 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
     while (out.ld.size() % M_LD_CHUNK_WORDS)
         out.ld.push_back(M_LD_NONE);
     out.nld_chunks = (int)(out.ld.size() / M_LD_CHUNK_WORDS);
-    out.slot_rows = slot_top;
+    out.slot_rows = NR * slot_top;
     if (P.ops.size() <= 400000 || std::getenv("EICOS_VERIFY_PROGRAMS"))
         verify(P, bundles, out);
 }
-
 
 // Symbolic execution of compiled code against the program it came from: every operand field must hold the
 // value the operation means to read at the time the device reads it (ring refills happen where the device
@@ -484,29 +579,23 @@ void verify(const MProgram &P, const std::vector<ivec> &bundles, const MachineCo
 {
     struct Tag
     {
-        int kind = 0; // 0 unknown, 1 ring copy (word, version), 2 value
-        int word = 0, ver = -3, val = -1;
+        int kind = 0; // 0 unknown, 1 ring copy (word, version), 2 value (of job `job`)
+        int word = 0, ver = -3, val = -1, job = 0;
     };
-    const int RING_ROWS = mc.ring_groups * M_RING_GROUP, ring0 = M_ROW_SLOT0 + mc.slot_budget;
+    const int NR = mc.nr;
+    const int RING_ROWS = mc.ring_groups * M_RING_GROUP, ring0 = m_row_slot0(NR) + NR * mc.slot_budget;
     const int nrows = ring0 + RING_ROWS;
     std::vector<Tag> rows((size_t)nrows);
-    std::vector<std::pair<long long, int>> gl; // sorted (home word, value id last written)
-    std::vector<int> gver;                     // parallel hash: use a map keyed by word
-    std::vector<std::pair<int, int>> dummy;
-    (void)gl;
-    (void)gver;
-    (void)dummy;
-    std::vector<int> written_val; // per distinct home word -> value
-    std::vector<int> words;
-    // map home word -> index
+    // home words (job A) -> value currently stored there (-1: what was there before the program); jobs move together
     std::vector<int> key;
     for (const MVal &v : P.vals)
         if (v.home_sel >= 0)
             key.push_back((v.home_sel << M_LD_SEL_SHIFT) | v.home_row);
     std::sort(key.begin(), key.end());
     key.erase(std::unique(key.begin(), key.end()), key.end());
-    std::vector<int> cur(key.size(), -1); // value currently stored at that home row (-1: what was there before the program)
+    std::vector<int> cur(key.size(), -1);
     const auto slot_of_word = [&](int w) -> int {
+        w &= ~M_LD_JOB_B;
         auto it = std::lower_bound(key.begin(), key.end(), w);
         return it != key.end() && *it == w ? (int)(it - key.begin()) : -1;
     };
@@ -534,7 +623,7 @@ void verify(const MProgram &P, const std::vector<ivec> &bundles, const MachineCo
     };
     for (int g = 0; g < mc.ring_groups; g++)
         refill();
-    const auto fail = [&](int b, int u, const char *what) {
+    const auto fail = [&](int b, int u, const std::string &what) {
         throw std::logic_error("machine verify: bundle " + std::to_string(b) + " op " + std::to_string(u) + ": " + what);
     };
     for (int b = 0; b < (int)bundles.size(); b++)
@@ -545,48 +634,52 @@ void verify(const MProgram &P, const std::vector<ivec> &bundles, const MachineCo
         {
             const MOp &op = P.ops[bundles[b][u]];
             const int *w = rec + u * M_REC_WORDS;
-            const auto check = [&](const MSrc &s, int f, const char *name) {
-                const int row = f >> M_FIELD_SHIFT;
-                if (row < 0 || row >= nrows)
-                    fail(b, u, "field out of range");
-                const Tag &t = rows[(size_t)row];
-                switch (s.kind)
+            const auto check = [&](const MSrc &s, int f, bool vec, const char *name) {
+                const int row0 = f >> M_FIELD_SHIFT;
+                for (int j = 0; j < (vec ? NR : 1); j++)
                 {
-                case MS_ZERO:
-                    if (row != M_ROW_ZERO)
-                        fail(b, u, name);
-                    break;
-                case MS_NEGZERO:
-                    if (row != M_ROW_NEGZERO)
-                        fail(b, u, name);
-                    break;
-                case MS_CONST:
-                    break;
-                case MS_LOAD:
-                    if (t.kind != 1 || t.word != ((s.sel << M_LD_SEL_SHIFT) | s.row))
-                        fail(b, u, name);
-                    break;
-                case MS_VAL:
-                {
-                    if (t.kind == 2 && t.val == s.val)
+                    const int row = row0 + j;
+                    if (row < 0 || row >= nrows)
+                        fail(b, u, "field out of range");
+                    const Tag &t = rows[(size_t)row];
+                    switch (s.kind)
+                    {
+                    case MS_ZERO:
+                        if (row0 != M_ROW_ZERO)
+                            fail(b, u, name);
                         break;
-                    const MVal &mv = P.vals[s.val];
-                    const int want = producer[s.val] < 0 ? -1 : s.val;
-                    if (t.kind == 1 && mv.home_sel >= 0 && t.word == ((mv.home_sel << M_LD_SEL_SHIFT) | mv.home_row) && t.ver == want)
+                    case MS_NEGZERO:
+                        if (row0 != m_row_negzero(NR))
+                            fail(b, u, name);
                         break;
-                    fail(b, u, (std::string(name) + ": wants value " + std::to_string(s.val) + " (home word " +
-                                std::to_string(mv.home_sel >= 0 ? ((mv.home_sel << M_LD_SEL_SHIFT) | mv.home_row) : -1) + ", producer " +
-                                std::to_string(producer[s.val]) + "), row " + std::to_string(row) + " holds kind " + std::to_string(t.kind) +
-                                " word " + std::to_string(t.word) + " ver " + std::to_string(t.ver) + " val " + std::to_string(t.val))
-                                   .c_str());
-                }
+                    case MS_CONST:
+                        break;
+                    case MS_LOAD:
+                        if (t.kind != 1 || t.word != (((s.sel << M_LD_SEL_SHIFT) | s.row) | (j ? M_LD_JOB_B : 0)))
+                            fail(b, u, name);
+                        break;
+                    case MS_VAL:
+                    {
+                        if (t.kind == 2 && t.val == s.val && t.job == j)
+                            break;
+                        const MVal &mv = P.vals[s.val];
+                        const int want = producer[s.val] < 0 ? -1 : s.val;
+                        const int hw = mv.home_sel >= 0 ? (((mv.home_sel << M_LD_SEL_SHIFT) | mv.home_row) | (j ? M_LD_JOB_B : 0)) : -1;
+                        if (t.kind == 1 && mv.home_sel >= 0 && t.word == hw && t.ver == want)
+                            break;
+                        fail(b, u, std::string(name) + ": wants value " + std::to_string(s.val) + " job " + std::to_string(j) + " (home word " +
+                                       std::to_string(hw) + ", producer " + std::to_string(producer[s.val]) + "), row " + std::to_string(row) +
+                                       " holds kind " + std::to_string(t.kind) + " word " + std::to_string(t.word) + " ver " +
+                                       std::to_string(t.ver) + " val " + std::to_string(t.val));
+                    }
+                    }
                 }
             };
-            check(op.a, w[0], "operand A");
-            check(op.b, w[1], "operand B");
-            check(op.c, w[2], "operand C");
+            check(op.a, w[0], false, "operand A");
+            check(op.b, w[1], true, "operand B");
+            check(op.c, w[2], true, "operand C");
             if (op.x3.kind != MS_ZERO)
-                check(op.x3, w[6], "operand x3");
+                check(op.x3, w[6], true, "operand x3");
         }
         // store phase
         for (int u = 0; u < (int)bundles[b].size(); u++)
@@ -594,12 +687,16 @@ void verify(const MProgram &P, const std::vector<ivec> &bundles, const MachineCo
             const MOp &op = P.ops[bundles[b][u]];
             const int *w = rec + u * M_REC_WORDS;
             const int krow = w[3] >> M_FIELD_SHIFT;
-            if (krow != M_ROW_TRASH)
+            if (krow != m_row_trash(NR))
             {
-                if (krow < M_ROW_SLOT0 || krow >= ring0)
+                if (krow < m_row_slot0(NR) || krow + NR > ring0)
                     fail(b, u, "destination is not a slot");
-                rows[(size_t)krow].kind = 2;
-                rows[(size_t)krow].val = op.dst;
+                for (int j = 0; j < NR; j++)
+                {
+                    rows[(size_t)krow + j].kind = 2;
+                    rows[(size_t)krow + j].val = op.dst;
+                    rows[(size_t)krow + j].job = j;
+                }
             }
             if (w[4] & MF_OUT)
             {
@@ -611,10 +708,14 @@ void verify(const MProgram &P, const std::vector<ivec> &bundles, const MachineCo
             if (w[4] & MF_BKEEP)
             {
                 const int row = w[5] >> M_FIELD_SHIFT;
-                if (op.b.kind != MS_VAL || row < M_ROW_SLOT0 || row >= ring0)
+                if (op.b.kind != MS_VAL || row < m_row_slot0(NR) || row + NR > ring0)
                     fail(b, u, "bad keep");
-                rows[(size_t)row].kind = 2;
-                rows[(size_t)row].val = op.b.val;
+                for (int j = 0; j < NR; j++)
+                {
+                    rows[(size_t)row + j].kind = 2;
+                    rows[(size_t)row + j].val = op.b.val;
+                    rows[(size_t)row + j].job = j;
+                }
             }
         }
         for (int k = (rec[4] >> MF_NREL_SHIFT) & 31; k > 0; k--)
@@ -626,7 +727,8 @@ void verify(const MProgram &P, const std::vector<ivec> &bundles, const MachineCo
 
 // The look-ahead window of the scheduler trades bundles (latency of one tile) against re-reads (HBM traffic of
 // the batch); which one wins depends on the shape of the dependency graph, so a few windows are compiled and
-// the cheapest program is kept: cost = bundles + rows read from global memory (+ a little for padding pops).
+// the cheapest program is kept: cost = 8 x bundles + rows copied from global memory (a bundle costs the warp about
+// a hundred instructions whether it is full or not, a copied row three or four and 512 bytes of traffic).
 void machine_compile(const MProgram &P, int max_slots, MachineCode &out, int tune_slots, int ring_groups, int window)
 {
     if (tune_slots < max_slots)
@@ -653,7 +755,7 @@ void machine_compile(const MProgram &P, int max_slots, MachineCode &out, int tun
             { // this order of operations keeps more values without a home row alive than there are slots
                 continue;
             }
-            const double cost = (double)c.nbundles + (double)(c.nld - c.pads) + 0.25 * (double)c.pads;
+            const double cost = 8.0 * (double)c.nbundles + (double)c.nld;
             if (window <= 0 || cost < best)
             {
                 best = cost;

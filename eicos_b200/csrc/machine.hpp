@@ -42,16 +42,21 @@ constexpr int M_CHUNKS = 2;        // chunks in the shared-memory ops ring
 constexpr int M_RING_GROUP = 8;    // rows per ring group (= one cp.async commit group)
 constexpr int M_MAX_RING_GROUPS = 16;
 // shared-memory rows: 0, -0, scratch, the slots (the program's slot budget), then the ring
-constexpr int M_ROW_ZERO = 0, M_ROW_NEGZERO = 1, M_ROW_TRASH = 2, M_ROW_SLOT0 = 3;
+// (the three constant operands are vectors like any B / C operand: nr rows each)
+constexpr int M_ROW_ZERO = 0;
+constexpr int m_row_negzero(int nr) { return nr; }
+constexpr int m_row_trash(int nr) { return 2 * nr; }
+constexpr int m_row_slot0(int nr) { return 3 * nr; }
 // the load list arrives in shared memory like the records: chunks of M_LD_CHUNK_WORDS words by TMA
-constexpr int M_LD_CHUNK_WORDS = 128, M_LD_CHUNK_GROUPS = M_LD_CHUNK_WORDS / M_RING_GROUP, M_LD_CHUNKS = 2;
+constexpr int M_LD_CHUNK_WORDS = 64, M_LD_CHUNK_GROUPS = M_LD_CHUNK_WORDS / M_RING_GROUP, M_LD_CHUNKS = 2;
 // WAIT codes of the bundle control: cp.async.wait_group takes an immediate, deep rings get the nearest one below
 constexpr int M_WAIT_CODES = 8;
 constexpr int M_WAIT_N[M_WAIT_CODES] = {-1, 0, 1, 2, 3, 5, 8, 12};
 constexpr int M_FIELD_SHIFT = 9;   // a field is row << 9: the byte offset of a 512-byte row on the device
 constexpr int M_LD_NONE = -1;      // load-list word: no copy (padding)
-constexpr int M_LD_SEL_SHIFT = 28; // load-list word before materialisation: selector << 28 | row
+constexpr int M_LD_SEL_SHIFT = 27; // load-list word before materialisation: job B << 30 | selector << 27 | row
 constexpr int M_LD_ROW_MASK = (1 << M_LD_SEL_SHIFT) - 1;
+constexpr int M_LD_JOB_B = 1 << 30; // the row of the second job's vector (two-job programs)
 
 // record = [A, B, C, K, flags, w5, w6, w7]
 //   result = C - A * B   (MF_POS: C + A * B;  MF_RECIP: 1 / C)   -> row K, and
@@ -145,6 +150,8 @@ struct MProgram
     std::vector<MOp> ops;   // in a valid sequential order (every value is defined before it is used)
     std::vector<MVal> vals;
     bool keep_loads = false; // gathered values with further uses may be parked in a slot (MF_BKEEP)
+    int nr = 1;              // right-hand sides per pass: B, C, x3 and the destination are vectors of nr adjacent rows
+                             // (one per job), A operands (matrix values, constants) are shared by the jobs
     int new_value(int home_sel = -1, int home_row = 0)
     {
         MVal v;
@@ -167,8 +174,9 @@ struct MachineCode
     ivec ops;  // records, bundle after bundle, padded to whole chunks (+ one chunk of look-ahead)
     ivec ld;   // load list: selector << M_LD_SEL_SHIFT | row, or M_LD_NONE; padded
     int nbundles = 0, nchunks = 0, nld = 0, nld_chunks = 0;
+    int nr = 1;                  // right-hand sides per pass (MProgram::nr)
     int ring_groups = 4;         // ring rows / M_RING_GROUP the code was compiled for
-    int slot_budget = 0;         // the ring starts at row M_ROW_SLOT0 + slot_budget
+    int slot_budget = 0;         // slots (of nr rows) the code may use: the ring starts at row M_ROW_SLOT0 + nr * slot_budget
     int window = 0;              // look-ahead window of the scheduler that produced it
     int slot_rows = 0;           // rows used behind M_ROW_SLOT0
     long long nops = 0, nnop = 0; // real operations / padding operations

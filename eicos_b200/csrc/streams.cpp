@@ -454,9 +454,9 @@ void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, 
             // (diagnostics) EICOS_SCHED_WINDOW_<name> pins the scheduler window of one program
             const std::string key = std::string("EICOS_SCHED_WINDOW_") + name;
             const char *v = std::getenv(key.c_str());
-            machine_compile(p, budget, c[0], tune, M_VARIANT_GROUPS[0], v ? std::max(M_U, std::atoi(v)) : 0);
+            machine_compile(p, budget, c[0], tune, variant_groups(0), v ? std::max(M_U, std::atoi(v)) : 0);
             for (int k = 1; k < M_VARIANTS; k++) // same order of operations, deeper ring
-                machine_compile(p, budget, c[k], tune, M_VARIANT_GROUPS[k], c[0].window);
+                machine_compile(p, budget, c[k], tune, variant_groups(k), c[0].window);
             if (std::getenv("EICOS_DBG_PROGRAMS"))
                 for (int k = 0; k < M_VARIANTS; k++)
                     std::fprintf(stderr, "machine %s[%d]: ops %lld nop %lld bundles %d loads %d far %lld pads %lld spills %lld slots %d window %d\n",
@@ -468,6 +468,22 @@ void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, 
         compile("bwp", pbp, H.bwp, slots, MACHINE_TUNE_SLOTS);
         compile("mv", pm, H.mv, slots, MACHINE_TUNE_SLOTS);
         compile("rs", pr, H.rs, slots, MACHINE_TUNE_SLOTS);
+        // two-job forms: the same operations, every vector operand two rows wide
+        {
+            const int pslots = std::max(2, std::min(14, max_sw_slots * 14 / 16)); // (14 two-row slots: seven tiles per SM)
+            H.pair_budget = pslots;
+            const auto pair = [&](const char *name, MProgram &p, MachineCode &c, int window) {
+                p.nr = 2; // (same order of the operations as the one-job form)
+                machine_compile(p, pslots, c, 0, M_PAIR_GROUPS, window);
+                if (std::getenv("EICOS_DBG_PROGRAMS"))
+                    std::fprintf(stderr, "machine %s: ops %lld nop %lld bundles %d loads %d far %lld pads %lld spills %lld slots %d window %d\n", name,
+                                 c.nops, c.nnop, c.nbundles, c.nld, c.far, c.pads, c.spills, c.slot_rows, c.window);
+            };
+            pair("fw2", pf, H.fw2, H.fw[0].window);
+            pair("bw2", pb, H.bw2, H.bw[0].window);
+            pair("bwp2", pbp, H.bwp2, H.bwp[0].window);
+            pair("mv2", pm, H.mv2, H.mv[0].window);
+        }
         MProgram pa;
         build_factor(S, L, pa, pim);
         compile("fa", pa, H.fa, std::max(2, max_fa_slots), MACHINE_TUNE_FA_SLOTS);
@@ -484,13 +500,16 @@ void refresh_stream_values(const Symbolic &S, const Layout &L, HostStreams &H, b
 {
     HostStreams fresh;
     build_streams(S, L, H.workers, std::max(H.sw_budget, 2), std::max(H.fa_budget, 2), fresh, pim);
+    std::vector<std::pair<MachineCode *, MachineCode *>> pq = {{&H.mv2, &fresh.mv2}};
     for (int k = 0; k < M_VARIANTS; k++)
-        for (auto pq : {std::make_pair(&H.mv[k], &fresh.mv[k]), std::make_pair(&H.rs[k], &fresh.rs[k]), std::make_pair(&H.fa[k], &fresh.fa[k])})
-        { // the mat-vec and factor programs carry the shared coefficients inline
-            if (pq.second->ops.size() != pq.first->ops.size())
-                throw std::logic_error("machine program changed shape on a value refresh");
-            pq.first->ops.swap(pq.second->ops);
-        }
+        for (auto q : {std::make_pair(&H.mv[k], &fresh.mv[k]), std::make_pair(&H.rs[k], &fresh.rs[k]), std::make_pair(&H.fa[k], &fresh.fa[k])})
+            pq.push_back(q);
+    for (auto &q : pq)
+    { // the mat-vec and factor programs carry the shared coefficients inline
+        if (q.second->ops.size() != q.first->ops.size())
+            throw std::logic_error("machine program changed shape on a value refresh");
+        q.first->ops.swap(q.second->ops);
+    }
 }
 
 } // namespace eicos

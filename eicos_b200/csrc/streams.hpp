@@ -12,6 +12,8 @@
 #include "machine.hpp"
 #include "symbolic.hpp"
 
+#include <algorithm>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -23,6 +25,15 @@ namespace eicos
 // tile has in flight are what bounds its speed.
 constexpr int M_VARIANTS = 2;
 constexpr int M_VARIANT_GROUPS[M_VARIANTS] = {3, 16};
+// (diagnostics) EICOS_SHALLOW_GROUPS overrides the depth of the shallow ring
+inline int variant_groups(int v)
+{
+    if (v == 0)
+        if (const char *e = std::getenv("EICOS_SHALLOW_GROUPS"))
+            return std::max(2, std::min(M_MAX_RING_GROUPS, std::atoi(e)));
+    return M_VARIANT_GROUPS[v];
+}
+constexpr int M_PAIR_GROUPS = 3; // ring depth of the two-job programs
 
 constexpr long long MAX_FACTOR_UPDATES = 20LL * 1000 * 1000; // Schur updates per factorisation a factor program may hold (32 bytes each)
 
@@ -59,6 +70,9 @@ struct HostStreams
     MachineCode fw[M_VARIANTS], bw[M_VARIANTS], bwp[M_VARIANTS], mv[M_VARIANTS], rs[M_VARIANTS];
     int mv_rows = 0;
     MachineCode fa[M_VARIANTS]; // numeric factorisation
+    // two-job programs: the sweeps and the refinement residual for both job sets in one pass (shallow ring)
+    MachineCode fw2, bw2, bwp2, mv2;
+    int pair_budget = 0; // slots (of two rows) they were compiled with
     int sw_slots = 0, fa_slots = 0; // slot rows the sweeps / mat-vecs and the factorisation use
     long long sw_far = 0, fa_home = 0; // values re-read from their home rows (forward + plain backward sweep) / accumulators that wait in their home rows (factor)
 };

@@ -421,9 +421,89 @@ EI_DEV void cone_scale(const Team &tm, const KArgs &a, double *T, int in, int ou
 
 // ------------------------------------------------------------------ line search (src/eicos.cpp:1380-1469)
 // lambda, ds, dz are z-shaped row offsets.  Returns the clamped step for every instance.
-// TODO(parity): the reference's `continue` on lknorm2<=0 skips the cone offset advance; here later
-// cones keep their own offsets (differs only after lambda has already left the cone).
 // lp = false: the caller has already folded the LP rows into m0 = min ds/lambda, m1 = min dz/lambda.
+//
+// The reference walks the cones with a running offset and `continue`s past a cone whose lambda has left the
+// cone (lknorm2 <= 0) WITHOUT advancing that offset (:1423-1424 against :1462): every later cone is then read
+// at the skipped cone's position, with its own dimension.  cone_step() evaluates one cone at a given compact
+// z offset; the fast path below uses every cone's own offset, and only instances that hit the `continue` are
+// walked again sequentially with the reference's running offset (line_search_misaligned).
+struct ConeStep
+{
+    bool skipped; // lknorm2 <= 0
+    double inv;   // 1 / conic_step, or DBL_MAX when the cone does not bound the step
+};
+// entry k of the cone evaluated at compact z offset `cs`: expanded row zk[cs + k]
+template <class RowOf>
+EI_DEV ConeStep cone_step(double *T, int lam, int ds, int dz, int d, RowOf row, int c_)
+{
+    ConeStep r;
+    r.skipped = false;
+    r.inv = DBL_MAX;
+    const double l0 = ROWC(T, lam + row(0), c_);
+    double sq = 0.0;
+    for (int k = 1; k < d; k++)
+    {
+        const double v = ROWC(T, lam + row(k), c_);
+        sq += v * v;
+    }
+    const double lknorm2 = l0 * l0 - sq;
+    if (lknorm2 <= 0.)
+    {
+        r.skipped = true;
+        return r;
+    }
+    const double lknorm = sqrt(lknorm2);
+    const double lknorminv = 1. / lknorm;
+    const double lk0 = l0 / lknorm;
+    double dsdot = 0.0, dzdot = 0.0;
+    for (int k = 1; k < d; k++)
+    {
+        const double lkb = ROWC(T, lam + row(k), c_) / lknorm;
+        dsdot += lkb * ROWC(T, ds + row(k), c_);
+        dzdot += lkb * ROWC(T, dz + row(k), c_);
+    }
+    const double ds0 = ROWC(T, ds + row(0), c_), dz0 = ROWC(T, dz + row(0), c_);
+    const double lds = lk0 * ds0 - dsdot, ldz = lk0 * dz0 - dzdot;
+    const double rho0 = lknorminv * lds, sig0 = lknorminv * ldz;
+    const double frho = (lds + ds0) / (lk0 + 1.), fsig = (ldz + dz0) / (lk0 + 1.);
+    double ar = 0.0, as = 0.0;
+    for (int k = 1; k < d; k++)
+    {
+        const double lkb = ROWC(T, lam + row(k), c_) / lknorm;
+        const double rr = lknorminv * (ROWC(T, ds + row(k), c_) - frho * lkb);
+        const double ss = lknorminv * (ROWC(T, dz + row(k), c_) - fsig * lkb);
+        ar += rr * rr;
+        as += ss * ss;
+    }
+    const double rhonorm = sqrt(ar) - rho0, signorm = sqrt(as) - sig0;
+    const double conic_step = dmax(0., dmax(signorm, rhonorm));
+    if (conic_step != 0.)
+        r.inv = 1. / conic_step;
+    return r;
+}
+// One instance (element c_ of this lane), all cones in order with the reference's running offset.
+EI_DEV double line_search_misaligned(const KArgs &a, double *T, int lam, int ds, int dz, int c_)
+{
+    const DevPattern &P = a.P;
+    double best = DBL_MAX;
+    int cs = P.l; // compact z offset (the LP rows come first)
+    for (int c = 0; c < P.nc; c++)
+    {
+        const int d = EI_LDG(P.cone_dim + c);
+        const int base = cs;
+        // (a misaligned cone may reach past the last z entry in the reference - undefined behaviour there; here the
+        //  walk stops at the end of z)
+        if (base + d > P.m)
+            break;
+        const ConeStep r = cone_step(T, lam, ds, dz, d, [&](int k) { return EI_LDG(P.zk + base + k); }, c_);
+        if (r.skipped)
+            continue; // the offset stays where it is
+        best = dmin(best, r.inv);
+        cs += d;
+    }
+    return best;
+}
 EI_DEV vd line_search(const Team &tm, const KArgs &a, double *T, int lam, int ds, int dz,
                       vd tau, vd dtau, vd kap, vd dkap, bool lp = true, vd m0 = vset(DBL_MAX), vd m1 = vset(DBL_MAX))
 {
@@ -437,48 +517,30 @@ EI_DEV vd line_search(const Team &tm, const KArgs &a, double *T, int lam, int ds
             mn[1] = vmin(mn[1], x[2] / x[0]);
         });
     }
+    vd skipped[1] = {vset(0.0)}; // 1 where an instance has hit the `continue` with cones still to come
     for (int c = tm.wk; c < P.nc; c += tm.nwk)
     {
         const int d = EI_LDG(P.cone_dim + c), zs = EI_LDG(P.cone_k + c);
         VFOR
         {
-            const double l0 = ROWC(T, lam + zs, c_);
-            double sq = 0.0;
-            for (int k = 1; k < d; k++)
+            const ConeStep r = cone_step(T, lam, ds, dz, d, [&](int k) { return zs + k; }, c_);
+            if (r.skipped)
             {
-                const double v = ROWC(T, lam + zs + k, c_);
-                sq += v * v;
-            }
-            const double lknorm2 = l0 * l0 - sq;
-            if (lknorm2 <= 0.)
+                if (c + 1 < P.nc)
+                    skipped[0].v[c_] = 1.0;
                 continue;
-            const double lknorm = sqrt(lknorm2);
-            const double lknorminv = 1. / lknorm;
-            const double lk0 = l0 / lknorm;
-            double dsdot = 0.0, dzdot = 0.0;
-            for (int k = 1; k < d; k++)
-            {
-                const double lkb = ROWC(T, lam + zs + k, c_) / lknorm;
-                dsdot += lkb * ROWC(T, ds + zs + k, c_);
-                dzdot += lkb * ROWC(T, dz + zs + k, c_);
             }
-            const double ds0 = ROWC(T, ds + zs, c_), dz0 = ROWC(T, dz + zs, c_);
-            const double lds = lk0 * ds0 - dsdot, ldz = lk0 * dz0 - dzdot;
-            const double rho0 = lknorminv * lds, sig0 = lknorminv * ldz;
-            const double frho = (lds + ds0) / (lk0 + 1.), fsig = (ldz + dz0) / (lk0 + 1.);
-            double ar = 0.0, as = 0.0;
-            for (int k = 1; k < d; k++)
-            {
-                const double lkb = ROWC(T, lam + zs + k, c_) / lknorm;
-                const double r = lknorminv * (ROWC(T, ds + zs + k, c_) - frho * lkb);
-                const double s = lknorminv * (ROWC(T, dz + zs + k, c_) - fsig * lkb);
-                ar += r * r;
-                as += s * s;
-            }
-            const double rhonorm = sqrt(ar) - rho0, signorm = sqrt(as) - sig0;
-            const double conic_step = dmax(0., dmax(signorm, rhonorm));
-            if (conic_step != 0.)
-                mn[2].v[c_] = dmin(mn[2].v[c_], 1. / conic_step);
+            mn[2].v[c_] = dmin(mn[2].v[c_], r.inv);
+        }
+    }
+    team_max<1>(tm, skipped);
+    {
+        vb sk;
+        VFOR sk.v[c_] = skipped[0].v[c_] != 0.0;
+        if (tm.any(sk))
+        { // rare: walk those instances again the way the reference does (every worker computes the same values)
+            team_min<3>(tm, mn);
+            VFOR if (sk.v[c_]) mn[2].v[c_] = line_search_misaligned(a, T, lam, ds, dz, c_);
         }
     }
     team_min<3>(tm, mn);
@@ -567,9 +629,9 @@ constexpr int M_BUNDLE_BYTES = M_BUNDLE_WORDS * 4;
 #ifndef EICOS_EMU
 static_assert(ROW_BYTES == (1 << M_FIELD_SHIFT), "a field is the byte offset of a 512-byte row");
 #endif
-inline size_t machine_smem_doubles(int slot_budget, int ring_groups)
+inline size_t machine_smem_doubles(int slot_budget, int ring_groups, int nr = 1)
 {
-    return M_HEAD_DOUBLES + (size_t)(M_ROW_SLOT0 + slot_budget + ring_groups * M_RING_GROUP) * TILE;
+    return M_HEAD_DOUBLES + (size_t)(m_row_slot0(nr) + nr * slot_budget + ring_groups * M_RING_GROUP) * TILE;
 }
 
 // what the interpreter compiles in for a kernel (everything else costs no instructions)
@@ -592,6 +654,7 @@ struct MRun
     const int *ld;     // materialised load list of this use
     const double *Tb;  // tile base (row 0, lane 0)
     double *out, *out2; // out bases (+ this lane's element offset)
+    double *outB, *out2B; // ... of the second job (two-job programs)
     bool a_one;
 };
 
@@ -615,14 +678,15 @@ struct Machine
     EI_DEV vd ld(int f) const { return vload(rows + (size_t)(f >> M_FIELD_SHIFT) * TILE); }
     EI_DEV void st(int f, vd v) const { vstore(rows + (size_t)(f >> M_FIELD_SHIFT) * TILE, v); }
 
-    template <int CFG, class Fin>
+    template <int CFG, int NR, class Fin>
     EI_DEV void run(const Team &, const MRun &r, Fin &fin)
     {
         for (int c = 0; c < VEC; c++)
-        {
-            rows[(size_t)M_ROW_ZERO * TILE + c] = 0.0;
-            rows[(size_t)M_ROW_NEGZERO * TILE + c] = -0.0;
-        }
+            for (int j = 0; j < NR; j++)
+            {
+                rows[(size_t)(M_ROW_ZERO + j) * TILE + c] = 0.0;
+                rows[(size_t)(m_row_negzero(NR) + j) * TILE + c] = -0.0;
+            }
         const int ring_rows = r.prog.ring_groups * M_RING_GROUP;
         long long issued = 0; // ring groups copied so far
         const auto refill = [&]() {
@@ -637,38 +701,48 @@ struct Machine
         for (int g = 0; g < r.prog.ring_groups; g++)
             refill();
         const int *rec = r.prog.ops;
+        const int JB = 1 << M_FIELD_SHIFT; // field offset of the second job's row
         for (;; rec += M_BUNDLE_WORDS)
         {
             const int ctrl = rec[4];
-            vd res[M_U], bv[M_U], xv[M_U];
+            vd res[M_U][NR], bv[M_U][NR], xv[M_U][NR];
             for (int u = 0; u < M_U; u++)
             {
                 const int *w = rec + u * M_REC_WORDS;
                 const int f = w[4];
                 const double cst = words_double(w[6], w[7]);
-                xv[u] = (CFG & MC_X3) && (f & MF_X3) ? ld(w[6]) : vset(0.0);
                 vd a = (CFG & MC_CONST) && (f & MF_ACONST) ? vset(cst) : ld(w[0]);
-                const vd b = ld(w[1]);
-                const vd c = (CFG & MC_CONST) && (f & MF_CCONST) ? vset(cst) : ld(w[2]);
                 if ((CFG & MC_AONE) && (f & MF_AONE) && r.a_one)
                     a = vset(1.0);
                 if ((CFG & MC_POS) && f < 0)
                     a = -a;
-                vd v = vfnma(c, a, b);
-                if ((CFG & MC_RECIP) && (f & MF_RECIP))
-                    v = 1.0 / c;
-                res[u] = v;
-                bv[u] = b;
+                for (int j = 0; j < NR; j++)
+                {
+                    xv[u][j] = (CFG & MC_X3) && (f & MF_X3) ? ld(w[6] + j * JB) : vset(0.0);
+                    const vd b = ld(w[1] + j * JB);
+                    const vd c = (CFG & MC_CONST) && (f & MF_CCONST) ? vset(cst) : ld(w[2] + j * JB);
+                    vd v = vfnma(c, a, b);
+                    if ((CFG & MC_RECIP) && (f & MF_RECIP))
+                        v = 1.0 / c;
+                    res[u][j] = v;
+                    bv[u][j] = b;
+                }
             }
             for (int u = 0; u < M_U; u++)
             {
                 const int *w = rec + u * M_REC_WORDS;
                 const int f = w[4];
-                st(w[3], res[u]);
-                if (f & MF_OUT)
-                    vstore(((CFG & MC_OUT2) && (f & MF_OUT2) ? r.out2 : r.out) + (size_t)w[5] * TILE, res[u]);
-                if ((CFG & MC_BKEEP) && (f & MF_BKEEP))
-                    st(w[5], bv[u]);
+                for (int j = 0; j < NR; j++)
+                {
+                    st(w[3] + j * JB, res[u][j]);
+                    if (f & MF_OUT)
+                    {
+                        double *o = (CFG & MC_OUT2) && (f & MF_OUT2) ? (j ? r.out2B : r.out2) : (j ? r.outB : r.out);
+                        vstore(o + (size_t)w[5] * TILE, res[u][j]);
+                    }
+                    if ((CFG & MC_BKEEP) && (f & MF_BKEEP))
+                        st(w[5] + j * JB, bv[u][j]);
+                }
                 if ((CFG & MC_FIN) && (f & MF_FIN))
                     fin((f >> MF_KIND_SHIFT) & 15, w[5], res[u], bv[u], xv[u]);
             }
@@ -722,9 +796,23 @@ struct Machine
     {
         asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(rows + (unsigned)f), "d"(v.v[0]), "d"(v.v[1]) : "memory");
     }
+    // the row behind it (the second job's row of a vector operand)
+    __device__ __forceinline__ vd ldB(int f) const
+    {
+        vd r;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+512];" : "=d"(r.v[0]), "=d"(r.v[1]) : "r"(rows + (unsigned)f));
+        return r;
+    }
+    __device__ __forceinline__ void stB(int f, vd v) const
+    {
+        asm volatile("st.shared.v2.f64 [%0+512], {%1, %2};" ::"r"(rows + (unsigned)f), "d"(v.v[0]), "d"(v.v[1]) : "memory");
+    }
     __device__ __forceinline__ void issue_row(unsigned dst, int w) const
-    { // ring row <- workspace row w of the tile (padding words of the materialised list name row 0)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(Tl + (long long)w * ROW_BYTES) : "memory");
+    { // ring row <- workspace row w of the tile (padding words of the materialised list name row 0).
+      // One IMAD.WIDE for the address: left to itself the compiler re-derives it from the tile index (7 instructions).
+        unsigned long long src;
+        asm volatile("mad.wide.s32 %0, %1, 512, %2;" : "=l"(src) : "r"(w), "l"(Tl));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     }
     __device__ __forceinline__ void fetch_ld_chunk()
     { // next chunk of the load list into its ring position
@@ -773,30 +861,25 @@ struct Machine
         bulk_g2s(opsb + slot * M_CHUNK_BYTES, opsg, M_CHUNK_BYTES, bar);
     }
     static __device__ __forceinline__ void wait_groups(int code)
-    { // machine.hpp: M_WAIT_N
+    { // machine.hpp: M_WAIT_N.  Predicated waits instead of a jump table: no branch latency in front of the loads.
         static_assert(M_WAIT_N[1] == 0 && M_WAIT_N[2] == 1 && M_WAIT_N[3] == 2 && M_WAIT_N[4] == 3 && M_WAIT_N[5] == 5 &&
                           M_WAIT_N[6] == 8 && M_WAIT_N[7] == 12,
                       "wait codes");
-        // (an if-chain, commonest first - all but the newest ring groups - instead of a jump table)
-        if (code == 3)
-            asm volatile("cp.async.wait_group 2;" ::: "memory");
-        else if (code == 2)
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        else if (code == 1)
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        else if (code == 7)
-            asm volatile("cp.async.wait_group 12;" ::: "memory");
-        else if (code == 6)
-            asm volatile("cp.async.wait_group 8;" ::: "memory");
-        else if (code == 5)
-            asm volatile("cp.async.wait_group 5;" ::: "memory");
-        else
-            asm volatile("cp.async.wait_group 3;" ::: "memory");
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "setp.eq.s32 p, %0, 3;\n\t@p cp.async.wait_group 2;\n\t"
+                     "setp.eq.s32 p, %0, 2;\n\t@p cp.async.wait_group 1;\n\t"
+                     "setp.eq.s32 p, %0, 1;\n\t@p cp.async.wait_group 0;\n\t"
+                     "setp.eq.s32 p, %0, 4;\n\t@p cp.async.wait_group 3;\n\t"
+                     "setp.eq.s32 p, %0, 5;\n\t@p cp.async.wait_group 5;\n\t"
+                     "setp.eq.s32 p, %0, 6;\n\t@p cp.async.wait_group 8;\n\t"
+                     "setp.eq.s32 p, %0, 7;\n\t@p cp.async.wait_group 12;\n\t}" ::"r"(code)
+                     : "memory");
     }
 
-    template <int CFG, class Fin>
+    template <int CFG, int NR, class Fin>
     __device__ __forceinline__ void run(const Team &, const MRun &r, Fin &fin)
     {
+        static_assert(ROW_BYTES == 512, "ldB / stB address the next row as +512");
         __syncwarp();
         if (pl == 0)
         {
@@ -810,8 +893,13 @@ struct Machine
         }
         inited = true;
         __syncwarp();
-        asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(rows + M_ROW_ZERO * ROW_BYTES), "d"(0.0) : "memory");
-        asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(rows + M_ROW_NEGZERO * ROW_BYTES), "d"(-0.0) : "memory");
+        st(M_ROW_ZERO * ROW_BYTES, vset(0.0));
+        st((NR * ROW_BYTES), vset(-0.0));
+        if (NR == 2)
+        {
+            stB(M_ROW_ZERO * ROW_BYTES, vset(0.0));
+            stB((NR * ROW_BYTES), vset(-0.0));
+        }
         // ops ring and load-list ring
         nchunks = r.prog.nchunks;
         opsg = r.prog.ops;
@@ -850,10 +938,9 @@ struct Machine
         for (;;)
         {
             const int ctrl = rb[0].x;
-            if (ctrl & (7 << MF_WAIT_SHIFT))
-                wait_groups((ctrl >> MF_WAIT_SHIFT) & 7);
-            // ---- operand loads
-            vd a[M_U], b[M_U], c[M_U], x3[M_U];
+            wait_groups((ctrl >> MF_WAIT_SHIFT) & 7);
+            // ---- operand loads (A: one row; B, C, x3: one row per job)
+            vd a[M_U], b[M_U][NR], c[M_U][NR], x3[M_U][NR];
             int fl[M_U], kf[M_U], w5[M_U];
 #pragma unroll
             for (int u = 0; u < M_U; u++)
@@ -861,13 +948,23 @@ struct Machine
                 fl[u] = rb[u].x;
                 kf[u] = ra[u].w;
                 w5[u] = rb[u].y;
-                b[u] = ld(ra[u].y);
+                b[u][0] = ld(ra[u].y);
+                if (NR == 2)
+                    b[u][NR - 1] = ldB(ra[u].y);
                 if (CFG & MC_X3)
                 {
                     if (fl[u] & MF_X3)
-                        x3[u] = ld(rb[u].z);
+                    {
+                        x3[u][0] = ld(rb[u].z);
+                        if (NR == 2)
+                            x3[u][NR - 1] = ldB(rb[u].z);
+                    }
                     else
-                        x3[u] = vset(0.0);
+                    {
+#pragma unroll
+                        for (int j = 0; j < NR; j++)
+                            x3[u][j] = vset(0.0);
+                    }
                 }
                 if (CFG & MC_CONST)
                 {
@@ -877,14 +974,24 @@ struct Machine
                     else
                         a[u] = ld(ra[u].x);
                     if (fl[u] & MF_CCONST)
-                        c[u] = vset(cst);
+                    {
+#pragma unroll
+                        for (int j = 0; j < NR; j++)
+                            c[u][j] = vset(cst);
+                    }
                     else
-                        c[u] = ld(ra[u].z);
+                    {
+                        c[u][0] = ld(ra[u].z);
+                        if (NR == 2)
+                            c[u][NR - 1] = ldB(ra[u].z);
+                    }
                 }
                 else
                 {
                     a[u] = ld(ra[u].x);
-                    c[u] = ld(ra[u].z);
+                    c[u][0] = ld(ra[u].z);
+                    if (NR == 2)
+                        c[u][NR - 1] = ldB(ra[u].z);
                 }
             }
             // ---- the records of the next bundle (the chunk behind a boundary was fetched M_CHUNKS - 1 chunks ago)
@@ -912,7 +1019,7 @@ struct Machine
                 rb[u] = lds4(opsb + pos + 32u * u + 16u);
             }
             // ---- multiply-adds
-            vd res[M_U];
+            vd res[M_U][NR];
 #pragma unroll
             for (int u = 0; u < M_U; u++)
             {
@@ -923,25 +1030,39 @@ struct Machine
                 { // flip the sign of A where the flag (bit 31) is set
                     VFOR av.v[c_] = __hiloint2double(__double2hiint(av.v[c_]) ^ (fl[u] & (int)0x80000000), __double2loint(av.v[c_]));
                 }
-                vd v = vfnma(c[u], av, b[u]);
+#pragma unroll
+                for (int j = 0; j < NR; j++)
+                    res[u][j] = vfnma(c[u][j], av, b[u][j]);
                 if ((CFG & MC_RECIP) && (fl[u] & MF_RECIP))
                 { // (a real branch: the division is long and rare)
                     asm volatile("" ::: "memory");
-                    v = 1.0 / c[u];
+#pragma unroll
+                    for (int j = 0; j < NR; j++)
+                        res[u][j] = 1.0 / c[u][j];
                 }
-                res[u] = v;
             }
             // ---- stores
 #pragma unroll
             for (int u = 0; u < M_U; u++)
             {
-                st(kf[u], res[u]);
+                st(kf[u], res[u][0]);
+                if (NR == 2)
+                    stB(kf[u], res[u][NR - 1]);
                 if (fl[u] & MF_OUT)
-                    vstore(((CFG & MC_OUT2) && (fl[u] & MF_OUT2) ? r.out2 : r.out) + (size_t)w5[u] * TILE, res[u]);
+                {
+                    const bool second = (CFG & MC_OUT2) && (fl[u] & MF_OUT2);
+                    vstore((second ? r.out2 : r.out) + (size_t)w5[u] * TILE, res[u][0]);
+                    if (NR == 2)
+                        vstore((second ? r.out2B : r.outB) + (size_t)w5[u] * TILE, res[u][NR - 1]);
+                }
                 if ((CFG & MC_BKEEP) && (fl[u] & MF_BKEEP))
-                    st(w5[u], b[u]);
+                {
+                    st(w5[u], b[u][0]);
+                    if (NR == 2)
+                        stB(w5[u], b[u][NR - 1]);
+                }
                 if ((CFG & MC_FIN) && (fl[u] & MF_FIN))
-                    fin((fl[u] >> MF_KIND_SHIFT) & 15, w5[u], res[u], b[u], (CFG & MC_X3) ? x3[u] : vset(0.0));
+                    fin((fl[u] >> MF_KIND_SHIFT) & 15, w5[u], res[u], b[u], x3[u]);
             }
             // ---- refills of the ring groups this bundle finished with
             for (int k = (ctrl >> MF_NREL_SHIFT) & 31; k > 0; k--)
@@ -959,9 +1080,11 @@ struct Machine
 #endif
 };
 
+// finish functors see (kind, w5, result[NR], B[NR], x3[NR])
 struct NoFin
 {
-    EI_DEV void operator()(int, int, vd, vd, vd) {}
+    template <int NR>
+    EI_DEV void operator()(int, int, const vd (&)[NR], const vd (&)[NR], const vd (&)[NR]) {}
 };
 
 // ------------------------------------------------------------------ numeric LDL' (Eigen factorize, src/eicos.cpp:900,1164)
@@ -971,9 +1094,9 @@ struct NoFin
 struct PivotFin
 {
     vb zero_pivot;
-    EI_DEV void operator()(int, int, vd res, vd, vd)
+    EI_DEV void operator()(int, int, const vd (&res)[1], const vd (&)[1], const vd (&)[1])
     {
-        VFOR zero_pivot.v[c_] = zero_pivot.v[c_] || fabs(res.v[c_]) > DBL_MAX;
+        VFOR zero_pivot.v[c_] = zero_pivot.v[c_] || fabs(res[0].v[c_]) > DBL_MAX;
     }
 };
 EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
@@ -992,9 +1115,9 @@ EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
     r.prog = a.P.fa[a.variant];
     r.ld = a.P.fa_ld[a.variant];
     r.Tb = t.Tb;
-    r.out = r.out2 = t.T;
+    r.out = r.out2 = r.outB = r.out2B = t.T;
     r.a_one = false;
-    mm.run<MC_CONST | MC_POS | MC_BKEEP | MC_RECIP | MC_FIN>(tm, r, fin);
+    mm.run<MC_CONST | MC_POS | MC_BKEEP | MC_RECIP | MC_FIN, 1>(tm, r, fin);
     VFOR if (fin.zero_pivot.v[c_] && act.v[c_]) ROWC(t.I, J_STATUS, c_) = EXIT_FATAL;
 }
 
@@ -1005,47 +1128,60 @@ EI_DEV void tile_factor(const Team &tm, const KArgs &a, int tile)
 //                                   accumulating form also does x += out for the instances with `cont`.
 // residual: e = rhs - Ktrue * x     with the un-regularised scaling block (src/eicos.cpp:1511-1576)
 // All three are programs of the FMA machine (streams.cpp: build_forward / build_backward / build_matvec).
+template <int NR>
 struct AccFin
 {
-    vb cont;
-    double *x; // accumulated solution (+ lane)
-    EI_DEV void operator()(int, int row, vd res, vd, vd xa)
+    vb cont[NR];
+    double *x[NR]; // accumulated solutions (+ lane)
+    EI_DEV void operator()(int, int row, const vd (&res)[NR], const vd (&)[NR], const vd (&xa)[NR])
     {
-        vstore(x + (size_t)row * TILE, xa + vsel(cont, res, vset(0.0)));
+#pragma unroll
+        for (int j = 0; j < NR; j++)
+            vstore(x[j] + (size_t)row * TILE, xa[j] + vsel(cont[j], res[j], vset(0.0)));
     }
 };
+template <int NR>
 struct AbsMaxFin
 {
-    vd nerr;
-    EI_DEV void operator()(int, int, vd res, vd, vd) { nerr = vmax(nerr, vabs(res)); }
+    vd nerr[NR];
+    EI_DEV void operator()(int, int, const vd (&res)[NR], const vd (&)[NR], const vd (&)[NR])
+    {
+#pragma unroll
+        for (int j = 0; j < NR; j++)
+            nerr[j] = vmax(nerr[j], vabs(res[j]));
+    }
 };
 
-// e = rhs - Ktrue * x, nerr = ||e||_inf per instance.  mvld: the materialised mat-vec load list of this use.
-EI_DEV void kkt_residual(const Team &tm, const KArgs &a, Machine &mm, const TileMem &t, const int *mvld, int x, int erow,
-                         bool initialize, vd &nerr)
+// e[j] = rhs[j] - Ktrue * x[j], nerr[j] = ||e[j]||_inf per instance.  mvld: the materialised mat-vec load list of this use.
+template <int NR>
+EI_DEV void kkt_residual(const Team &tm, const KArgs &a, Machine &mm, const TileMem &t, const DevMachine &prog, const int *mvld,
+                         const int (&x)[NR], const int (&erow)[NR], bool initialize, vd (&nerr)[NR])
 {
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     double *T = t.T;
     const double delta = Settings::deltastat;
     const int zb = P.n + P.p;
-    nerr = vset(0.0);
+#pragma unroll
+    for (int j = 0; j < NR; j++)
+        nerr[j] = vset(0.0);
     if (tm.wk == 0 && P.mv_rows > 0)
     {
-        AbsMaxFin fin;
-        fin.nerr = vset(0.0);
+        AbsMaxFin<NR> fin;
+#pragma unroll
+        for (int j = 0; j < NR; j++)
+            fin.nerr[j] = vset(0.0);
         MRun r;
-        r.prog = P.mv[a.variant];
+        r.prog = prog;
         r.ld = mvld;
         r.Tb = t.Tb;
-        r.out = T + (size_t)erow * TILE;
-        r.out2 = r.out;
+        r.out = r.out2 = T + (size_t)erow[0] * TILE;
+        r.outB = r.out2B = T + (size_t)erow[NR - 1] * TILE;
         r.a_one = initialize;
-        if (P.pim)
-            mm.run<MC_CONST | MC_POS | MC_BKEEP | MC_FIN | MC_AONE>(tm, r, fin);
-        else
-            mm.run<MC_CONST | MC_POS | MC_BKEEP | MC_FIN | MC_AONE>(tm, r, fin);
-        nerr = fin.nerr;
+        mm.run<MC_CONST | MC_POS | MC_BKEEP | MC_FIN | MC_AONE, NR>(tm, r, fin);
+#pragma unroll
+        for (int j = 0; j < NR; j++)
+            nerr[j] = fin.nerr[j];
     }
     if (P.nc > 0)
     {
@@ -1057,45 +1193,51 @@ EI_DEV void kkt_residual(const Team &tm, const KArgs &a, Machine &mm, const Tile
             const int cp = L.cpar + c * CP_COUNT;
             const vd eta2 = ROWD(T, cp + CP_ETA2), d1 = ROWD(T, cp + CP_D1), u0 = ROWD(T, cp + CP_U0);
             const vd u1 = ROWD(T, cp + CP_U1), v1 = ROWD(T, cp + CP_V1);
-            const int xj = x, ej = erow;
-            const vd x1 = ROWD(T, xj + kb), x3 = ROWD(T, xj + kb + d), x4 = ROWD(T, xj + kb + d + 1);
-            vd qtx2 = vset(0.0);
-            for (int k = 1; k < d; k++)
-                qtx2 += vd(ROWD(T, L.cq + qo + k - 1)) * vd(ROWD(T, xj + kb + k));
-            const vd vu = v1 * x3 + u1 * x4;
-            for (int k = 0; k < d; k++)
+            for (int j = 0; j < NR; j++)
             {
-                const vd xk = ROWD(T, xj + kb + k);
-                vd v = ROWD(T, ej + kb + k); // rhs - G x from the mat-vec program
-                if (k < d - 1)
-                    v += delta * xk;
-                else
-                    v -= delta * xk;
-                if (initialize)
-                    v += xk;
-                else if (k == 0)
-                    v += eta2 * (d1 * x1 + u0 * x4);
-                else
-                    v += eta2 * (xk + vu * vd(ROWD(T, L.cq + qo + k - 1)));
-                ROWD(T, ej + kb + k) = v;
-                nerr = vmax(nerr, vabs(v));
+                const int xj = x[j], ej = erow[j];
+                const vd x1 = ROWD(T, xj + kb), x3 = ROWD(T, xj + kb + d), x4 = ROWD(T, xj + kb + d + 1);
+                vd qtx2 = vset(0.0);
+                for (int k = 1; k < d; k++)
+                    qtx2 += vd(ROWD(T, L.cq + qo + k - 1)) * vd(ROWD(T, xj + kb + k));
+                const vd vu = v1 * x3 + u1 * x4;
+                for (int k = 0; k < d; k++)
+                {
+                    const vd xk = ROWD(T, xj + kb + k);
+                    vd v = ROWD(T, ej + kb + k); // rhs - G x from the mat-vec program
+                    if (k < d - 1)
+                        v += delta * xk;
+                    else
+                        v -= delta * xk;
+                    if (initialize)
+                        v += xk;
+                    else if (k == 0)
+                        v += eta2 * (d1 * x1 + u0 * x4);
+                    else
+                        v += eta2 * (xk + vu * vd(ROWD(T, L.cq + qo + k - 1)));
+                    ROWD(T, ej + kb + k) = v;
+                    nerr[j] = vmax(nerr[j], vabs(v));
+                }
+                const vd e3 = initialize ? x3 : eta2 * (v1 * qtx2 + x3);
+                const vd e4 = initialize ? x4 : eta2 * (u0 * x1 + u1 * qtx2 - x4);
+                ROWD(T, ej + kb + d) = e3;
+                ROWD(T, ej + kb + d + 1) = e4;
+                nerr[j] = vmax(nerr[j], vmax(vabs(e3), vabs(e4)));
             }
-            const vd e3 = initialize ? x3 : eta2 * (v1 * qtx2 + x3);
-            const vd e4 = initialize ? x4 : eta2 * (u0 * x1 + u1 * qtx2 - x4);
-            ROWD(T, ej + kb + d) = e3;
-            ROWD(T, ej + kb + d + 1) = e4;
-            nerr = vmax(nerr, vmax(vabs(e3), vabs(e4)));
         }
     }
-    vd nn[1] = {nerr};
-    team_max<1>(tm, nn);
-    nerr = nn[0];
+    team_max<NR>(tm, nerr);
 }
 
 // ------------------------------------------------------------------ solveKKT (src/eicos.cpp:1471-1620)
 // sol = K^-1 rhs followed by up to nitref refinement rounds; every instance stops on its own
-// criterion, the tile loops until all of its instances have stopped.  CTA = (tile, job): the two solves
-// of an iteration that share the factor (rhs1 -> sol1, rhs2 -> sol2) run side by side.
+// criterion, the tile loops until all of its instances have stopped.
+//   NR = 1: CTA = (tile, job) - the two solves of an iteration that share the factor (rhs1 -> sol1,
+//           rhs2 -> sol2) run side by side as separate CTAs (few tiles: twice the parallelism);
+//   NR = 2: one CTA runs both in ONE pass over L per sweep (two-job programs: every record is decoded
+//           once for two right-hand sides; a job whose instances have all stopped rides along with its
+//           accumulation masked off) - the form for a full machine.
+template <int NR>
 EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
 {
     const TileMem t = tile_mem(tm, a, tile);
@@ -1106,108 +1248,169 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
     const Layout &L = a.L;
     double *T = t.T;
     const bool init = a.initialize != 0;
-    const KArgs::KktJob jb = a.job[tm.job];
-    const int set = jb.set; // (jb.rhs is baked into the materialised load lists of the set)
-    const int sol = jb.sol, nitrow = jb.nitrow;
-    const int xw = set ? L.xw2 : L.xw, dxr = set ? L.dxr2 : L.dxr, erow = set ? L.e2 : L.e;
-    // max |rhs| is kept up to date by the kernels that write the right-hand sides (src/eicos.cpp:1590)
-    const vd threshold = (1. + vd(ROWD(T, L.sc + (set ? S_RHSMAX2 : S_RHSMAX1)))) * Settings::linsysacc;
+    int sol[NR], xw[NR], dxr[NR], erow[NR], nitrow[NR];
+    vd threshold[NR];
+#pragma unroll
+    for (int j = 0; j < NR; j++)
+    {
+        const KArgs::KktJob jb = a.job[NR == 1 ? tm.job : j];
+        const int set = jb.set; // (jb.rhs is baked into the materialised load lists of the set)
+        sol[j] = jb.sol;
+        nitrow[j] = jb.nitrow;
+        xw[j] = set ? L.xw2 : L.xw;
+        dxr[j] = set ? L.dxr2 : L.dxr;
+        erow[j] = set ? L.e2 : L.e;
+        // max |rhs| is kept up to date by the kernels that write the right-hand sides (src/eicos.cpp:1590)
+        threshold[j] = (1. + vd(ROWD(T, L.sc + (set ? S_RHSMAX2 : S_RHSMAX1)))) * Settings::linsysacc;
+    }
+    const int set0 = a.job[NR == 1 ? tm.job : 0].set, v = a.variant;
+    // programs and load lists of this launch: [first solve | refinement round]
+    const DevMachine &pfw = NR == 1 ? P.fw[v] : P.fw2, &pbw = NR == 1 ? P.bw[v] : P.bw2;
+    const DevMachine &pbwp = NR == 1 ? P.bwp[v] : P.bwp2, &pmv = NR == 1 ? P.mv[v] : P.mv2;
+    const int *fw_ld[2], *bw_ld[2], *mv_ld;
+    if (NR == 1)
+    {
+        fw_ld[0] = P.fw_ld[v][set0][0], fw_ld[1] = P.fw_ld[v][set0][1];
+        bw_ld[0] = P.bw_ld[v][set0][0], bw_ld[1] = P.bw_ld[v][set0][1];
+        mv_ld = P.mv_ld[v][set0];
+    }
+    else
+    {
+        fw_ld[0] = P.fw2_ld[0], fw_ld[1] = P.fw2_ld[1];
+        bw_ld[0] = P.bw2_ld[0], bw_ld[1] = P.bw2_ld[1];
+        mv_ld = P.mv2_ld;
+    }
     Machine mm;
     mm.init(tm, tm.pbuf);
 
     long long ck[5] = {0, 0, 0, 0, 0}, c0 = EI_CLOCK(), c1;
 #define EI_PHASE(k) (c1 = EI_CLOCK(), ck[k] += c1 - c0, c0 = c1)
-    const auto sweeps = [&](int round, bool accumulate, vb cont) {
+    const auto sweeps = [&](int round, bool accumulate, const vb (&cont)[NR]) {
         MRun r;
         r.Tb = t.Tb;
         r.a_one = false;
-        r.prog = P.fw[a.variant];
-        r.ld = P.fw_ld[a.variant][set][round];
-        r.out = r.out2 = T + (size_t)xw * TILE;
+        r.prog = pfw;
+        r.ld = fw_ld[round];
+        r.out = r.out2 = T + (size_t)xw[0] * TILE;
+        r.outB = r.out2B = T + (size_t)xw[NR - 1] * TILE;
         NoFin nofin;
-        mm.run<0>(tm, r, nofin);
+        mm.run<0, NR>(tm, r, nofin);
         EI_PHASE(1);
         if (accumulate)
         {
-            AccFin fin;
-            fin.cont = cont;
-            fin.x = T + (size_t)sol * TILE;
-            r.prog = P.bw[a.variant];
-            r.ld = P.bw_ld[a.variant][set][1];
-            r.out = r.out2 = T + (size_t)dxr * TILE;
-            mm.run<MC_POS | MC_FIN | MC_X3>(tm, r, fin);
+            AccFin<NR> fin;
+#pragma unroll
+            for (int j = 0; j < NR; j++)
+            {
+                fin.cont[j] = cont[j];
+                fin.x[j] = T + (size_t)sol[j] * TILE;
+            }
+            r.prog = pbw;
+            r.ld = bw_ld[1];
+            r.out = r.out2 = T + (size_t)dxr[0] * TILE;
+            r.outB = r.out2B = T + (size_t)dxr[NR - 1] * TILE;
+            mm.run<MC_POS | MC_FIN | MC_X3, NR>(tm, r, fin);
         }
         else
         {
-            r.prog = P.bwp[a.variant];
-            r.ld = P.bw_ld[a.variant][set][0];
-            r.out = r.out2 = T + (size_t)sol * TILE;
-            mm.run<MC_POS>(tm, r, nofin);
+            r.prog = pbwp;
+            r.ld = bw_ld[0];
+            r.out = r.out2 = T + (size_t)sol[0] * TILE;
+            r.outB = r.out2B = T + (size_t)sol[NR - 1] * TILE;
+            mm.run<MC_POS, NR>(tm, r, nofin);
         }
         EI_PHASE(2);
     };
+    vb nocont[NR];
+#pragma unroll
+    for (int j = 0; j < NR; j++)
+        nocont[j] = vbset(false);
     if (tm.wk == 0)
-        sweeps(0, false, vbset(false));
+        sweeps(0, false, nocont);
     tm.sync();
 
-    vd nerr_prev = vset(DBL_MAX);
-    int kref[VEC];
-    vb done = !act;
-    VFOR kref[c_] = 0;
+    vd nerr_prev[NR];
+    int kref[NR][VEC];
+    vb done[NR];
+#pragma unroll
+    for (int j = 0; j < NR; j++)
+    {
+        nerr_prev[j] = vset(DBL_MAX);
+        done[j] = !act;
+        VFOR kref[j][c_] = 0;
+    }
     unsigned rounds = 0;
     for (;;)
     {
-        vd nerr;
-        kkt_residual(tm, a, mm, t, P.mv_ld[a.variant][set], sol, erow, init, nerr);
+        vd nerr[NR];
+        kkt_residual<NR>(tm, a, mm, t, pmv, mv_ld, sol, erow, init, nerr);
         EI_PHASE(3);
-        vb rollback = vbset(false);
-        VFOR
+        bool all_done = true;
+#pragma unroll
+        for (int j = 0; j < NR; j++)
         {
-            if (done.v[c_])
-                continue;
-            if (kref[c_] > 0 && nerr.v[c_] > nerr_prev.v[c_])
+            vb rollback = vbset(false);
+            VFOR
             {
-                rollback.v[c_] = true;
-                kref[c_]--;
-                done.v[c_] = true;
+                if (done[j].v[c_])
+                    continue;
+                if (kref[j][c_] > 0 && nerr[j].v[c_] > nerr_prev[j].v[c_])
+                {
+                    rollback.v[c_] = true;
+                    kref[j][c_]--;
+                    done[j].v[c_] = true;
+                }
+                else if (kref[j][c_] == Settings::nitref || nerr[j].v[c_] < threshold[j].v[c_] ||
+                         (kref[j][c_] > 0 && nerr_prev[j].v[c_] < Settings::irerrfact * nerr[j].v[c_]))
+                    done[j].v[c_] = true;
+                else
+                    nerr_prev[j].v[c_] = nerr[j].v[c_];
             }
-            else if (kref[c_] == Settings::nitref || nerr.v[c_] < threshold.v[c_] ||
-                     (kref[c_] > 0 && nerr_prev.v[c_] < Settings::irerrfact * nerr.v[c_]))
-                done.v[c_] = true;
-            else
-                nerr_prev.v[c_] = nerr.v[c_];
+            if (tm.any(rollback))
+            { // x -= dx_ref for the instances whose last refinement made things worse
+                for (int r = tm.wk; r < P.N; r += tm.nwk)
+                    ROWD(T, sol[j] + r) -= vsel(rollback, ROWD(T, dxr[j] + r), vset(0.0));
+            }
+            all_done = all_done && tm.all(done[j]);
         }
-        if (tm.any(rollback))
-        { // x -= dx_ref for the instances whose last refinement made things worse
-            for (int r = tm.wk; r < P.N; r += tm.nwk)
-                ROWD(T, sol + r) -= vsel(rollback, ROWD(T, dxr + r), vset(0.0));
-        }
-        if (tm.all(done))
+        if (all_done)
             break;
         tm.sync(); // e complete before the forward sweep loads it
         EI_PHASE(4);
         if (tm.wk == 0)
-            sweeps(1, true, !done);
+        {
+            vb cont[NR];
+#pragma unroll
+            for (int j = 0; j < NR; j++)
+                cont[j] = !done[j];
+            sweeps(1, true, cont);
+        }
         tm.sync();
-        VFOR if (!done.v[c_]) kref[c_]++;
+#pragma unroll
+        for (int j = 0; j < NR; j++)
+            VFOR if (!done[j].v[c_]) kref[j][c_]++;
         rounds++;
     }
     tm.sync();
     if (tm.wk == 0)
     {
-        if (nitrow >= 0)
-            VFOR if (act.v[c_]) ROWC(t.I, nitrow, c_) = kref[c_];
+#pragma unroll
+        for (int j = 0; j < NR; j++)
+            if (nitrow[j] >= 0)
+                VFOR if (act.v[c_]) ROWC(t.I, nitrow[j], c_) = kref[j][c_];
 #ifndef EICOS_EMU
         if (a.ir_rounds)
         {
-            // [0] tile-rounds (sweep pairs), [6] lane-rounds: sweep pairs each instance needed
+            // [0] tile-rounds (sweep pairs x jobs), [6] lane-rounds: sweep pairs each instance needed
             int lane_rounds = 0;
-            VFOR if (act.v[c_]) lane_rounds += kref[c_] + 1;
+#pragma unroll
+            for (int j = 0; j < NR; j++)
+                VFOR if (act.v[c_]) lane_rounds += kref[j][c_] + 1;
             for (int o = 16; o > 0; o >>= 1)
                 lane_rounds += __shfl_xor_sync(0xffffffffu, lane_rounds, o);
             if (tm.pl == 0)
             {
-                atomicAdd(a.ir_rounds, (unsigned long long)(rounds + 1));
+                atomicAdd(a.ir_rounds, (unsigned long long)(rounds + 1) * NR);
                 atomicAdd(a.ir_rounds + 6, (unsigned long long)lane_rounds);
                 EI_PHASE(4);
                 for (int k = 0; k < 5; k++)
@@ -1499,8 +1702,9 @@ enum { RS_HX2, RS_RX2, RS_CX, RS_NX2, RS_HY2, RS_RY2, RS_BY, RS_NY2, RS_HZ2, RS_
 struct ResidFin
 {
     vd r[RS_NRED];
-    EI_DEV void operator()(int kind, int, vd res, vd b, vd own)
+    EI_DEV void operator()(int kind, int, const vd (&resv)[1], const vd (&bv)[1], const vd (&ownv)[1])
     {
+        const vd res = resv[0], b = bv[0], own = ownv[0];
         // PRE: res = the row before its tau term; FIN: res = the finished row, b = c_j / b_i / h_i, f3 -> x_j / y_i / z_i;
         // FIRST_Z: res = s_i, f3 -> z_i
         if (kind == RS_PRE_X)
@@ -1560,9 +1764,9 @@ EI_DEV void tile_resid(const Team &tm, const KArgs &a, int tile)
         r.prog = P.rs[a.variant];
         r.ld = P.rs_ld[a.variant];
         r.Tb = t.Tb;
-        r.out = r.out2 = T + (size_t)L.r * TILE;
+        r.out = r.out2 = r.outB = r.out2B = T + (size_t)L.r * TILE;
         r.a_one = false;
-        mm.run<MC_CONST | MC_POS | MC_BKEEP | MC_FIN | MC_X3>(tm, r, fin);
+        mm.run<MC_CONST | MC_POS | MC_BKEEP | MC_FIN | MC_X3, 1>(tm, r, fin);
     }
     if (tm.wk == 0)
         for (int k = 0; k < RS_NRED; k++)
@@ -2407,6 +2611,37 @@ EI_DEV void tile_store(const Team &tm, const KArgs &a, int tile)
     tm.sync();
     if (tm.wk == 0)
         VFOR if (ROWC(t.I, J_INST, c_) >= 0 && ROWC(t.I, J_STATUS, c_) != ST_ACTIVE) ROWC(t.I, J_STORED, c_) = 1;
+}
+
+// ------------------------------------------------------------------ debug: lineSearch on caller data (unit tests)
+// in_h / in_G / in_A: lambda, ds, dz (instance-major, compact z order); in_b: tau, dtau, kap, dkap per instance;
+// out_x: the step length.  Lets a test drive the line search into states a solve hardly ever reaches.
+EI_DEV void tile_debug_line_search(const Team &tm, const KArgs &a, int tile)
+{
+    const TileMem t = tile_mem(tm, a, tile);
+    const DevPattern &P = a.P;
+    const Layout &L = a.L;
+    double *T = t.T;
+    const int base = tile * TILE + tm.lane;
+    for (int i = tm.wk; i < P.m; i += tm.nwk)
+    {
+        const int e = EI_LDG(P.zk + i);
+        VFOR
+        {
+            const int inst = base + c_;
+            const bool ok = inst < a.batch;
+            ROWC(T, L.lam + e, c_) = ok ? a.in_h[(size_t)inst * P.m + i] : 1.0;
+            ROWC(T, L.dsw + e, c_) = ok ? a.in_G[(size_t)inst * P.m + i] : 0.0;
+            ROWC(T, L.wdz + e, c_) = ok ? a.in_A[(size_t)inst * P.m + i] : 0.0;
+        }
+    }
+    tm.sync();
+    vd sc[4];
+    for (int k = 0; k < 4; k++)
+        VFOR sc[k].v[c_] = base + c_ < a.batch ? a.in_b[(size_t)(base + c_) * 4 + k] : 1.0;
+    const vd alpha = line_search(tm, a, T, L.lam, L.dsw, L.wdz, sc[0], sc[1], sc[2], sc[3]);
+    if (tm.wk == 0)
+        VFOR if (base + c_ < a.batch) a.out_x[base + c_] = alpha.v[c_];
 }
 
 // ------------------------------------------------------------------ active-set compaction

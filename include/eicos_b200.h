@@ -199,6 +199,10 @@ int eicos_batch_get_symbolic(const eicos_batch *bt, int *pinv, int *parent, int 
  * Lx [batch x nnzL], D [batch x dim_K], sol1/sol2 [batch x dim_K], nitref [batch x 2]. */
 int eicos_batch_debug_init(eicos_batch *bt, int batch, const double *cs, const double *hs, const double *bs,
                            double *Lx, double *D, double *sol1, double *sol2, int *nitref);
+/* Test hook: lineSearch (reference src/eicos.cpp:1380-1469) on caller data - lambda, ds, dz instance-major in z
+ * order [batch x m], scalars = tau, dtau, kap, dkap per instance [batch x 4], alpha out [batch] (host pointers). */
+int eicos_batch_debug_line_search(eicos_batch *bt, int batch, const double *lambda, const double *ds, const double *dz,
+                                  const double *scalars, double *alpha);
 
 void *eicos_batch_stream(const eicos_batch *bt); /* cudaStream_t the engine launches on */
 void eicos_batch_cleanup(eicos_batch *bt);

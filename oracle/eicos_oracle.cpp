@@ -34,8 +34,23 @@
 #include <thread>
 #include <vector>
 
+/* -DORA_LONG_DOUBLE builds the same algorithm in 80-bit extended precision (tests/test_oracle.py uses it to
+ * see which way a knife-edge decision of the double-precision run would go with 11 more bits); the C API
+ * below stays double and converts at the boundary. */
+typedef double ora_api_real; /* what crosses the C API, whatever the arithmetic type is */
+#ifdef ORA_LONG_DOUBLE
+#define double long double
+#endif
+
 namespace ora
 {
+/* std::max over mixed literal / variable types (the long double build) */
+template <class A, class B>
+inline auto rmax(A a, B b) -> decltype(a + b)
+{
+    typedef decltype(a + b) T;
+    return std::max<T>(a, b);
+}
 
 using std::size_t;
 typedef std::vector<double> vec;
@@ -132,7 +147,7 @@ static double norminf(const double *v, size_t n)
 {
     double s = 0; /* Eigen lpNorm<Infinity> returns 0 for an empty vector */
     for (size_t k = 0; k < n; k++)
-        s = std::max(s, std::fabs(v[k]));
+        s = rmax(s, std::fabs(v[k]));
     return s;
 }
 
@@ -190,7 +205,7 @@ static ivec amd_order(int n, const ivec &Ap, const ivec &Ai)
         perm.resize(0);
         return perm;
     }
-    int dense = std::max(16, (int)(10 * std::sqrt((double)n)));
+    int dense = rmax(16, (int)(10 * std::sqrt((double)n)));
     dense = std::min(n - 2, dense);
 
     int cnz = Ap[n];
@@ -431,7 +446,7 @@ static ivec amd_order(int n, const ivec &Ap, const ivec &Ai)
             }
         }
         degree[k] = dk;
-        lemax = std::max(lemax, dk);
+        lemax = rmax(lemax, dk);
         mark = wclear(mark + lemax, lemax, w, n);
 
         /* supernode detection */
@@ -592,7 +607,7 @@ struct Ldlt
         ivec c2(n + 1, 0);
         for (int j = 0; j < n; j++)
             for (int k = K.p[j]; k < K.p[j + 1]; k++)
-                c2[std::max(P[K.i[k]], P[j]) + 1]++;
+                c2[rmax(P[K.i[k]], P[j]) + 1]++;
         for (int j = 0; j < n; j++)
             c2[j + 1] += c2[j];
         Up = c2;
@@ -603,7 +618,7 @@ struct Ldlt
             for (int k = K.p[j]; k < K.p[j + 1]; k++)
             {
                 const int ip = P[K.i[k]], jp = P[j];
-                const int q = fill[std::max(ip, jp)]++;
+                const int q = fill[rmax(ip, jp)]++;
                 Ui[q] = std::min(ip, jp);
                 Umap[q] = k;
             }
@@ -769,6 +784,7 @@ struct Work /* include/eicos.hpp:97-114 */
 struct Solver
 {
     int n = 0, p = 0, m = 0, l = 0, nc = 0, N = 0; /* n_var n_eq n_ineq n_lc n_sc dim_K */
+    long long misaligned_cones = 0; /* test hook: line searches that skipped the offset advance (src/eicos.cpp:1423-1424) with cones still to come */
     Work w, wbest;
     vec lpv, lpw;
     std::vector<SOCone> cones;
@@ -788,9 +804,9 @@ struct Solver
 
     /* ---- construction: src/eicos.cpp:91-120 + build :132-187 + allocate :209-249 */
     void build(int n_, int m_, int p_, int ncones, const int *q,
-               const double *Gpr, const int *Gjc, const int *Gir,
-               const double *Apr, const int *Ajc, const int *Air,
-               const double *c_, const double *h_, const double *b_)
+               const ora_api_real *Gpr, const int *Gjc, const int *Gir,
+               const ora_api_real *Apr, const int *Ajc, const int *Air,
+               const ora_api_real *c_, const ora_api_real *h_, const ora_api_real *b_)
     {
         /* pointer ctor :103-117: a NULL triple leaves the matrix 0x0 and its vector empty */
         int ncz = 0;
@@ -872,11 +888,11 @@ struct Solver
             for (const Csc *M : {&A, &G}) /* maxCols :267 */
                 for (int j = 0; j < M->cols; j++)
                     for (int k = M->p[j]; k < M->p[j + 1]; k++)
-                        xt[j] = std::max(std::fabs(M->x[k]), xt[j]);
+                        xt[j] = rmax(std::fabs(M->x[k]), xt[j]);
             for (int k = 0; k < A.nnz(); k++) /* maxRows :256 */
-                At_[A.i[k]] = std::max(std::fabs(A.x[k]), At_[A.i[k]]);
+                At_[A.i[k]] = rmax(std::fabs(A.x[k]), At_[A.i[k]]);
             for (int k = 0; k < G.nnz(); k++)
-                Gt_[G.i[k]] = std::max(std::fabs(G.x[k]), Gt_[G.i[k]]);
+                Gt_[G.i[k]] = rmax(std::fabs(G.x[k]), Gt_[G.i[k]]);
             int ind = l; /* collapse each cone to the sum over its rows :338-344 */
             for (const SOCone &sc : cones)
             {
@@ -1117,7 +1133,7 @@ struct Solver
             const double ww = sqnorm(sc.q.data(), d - 1);
             const double cc = (1. + a) + ww / (1. + a);
             const double dd = 1. + 2. / (1. + a) + ww / ((1. + a) * (1. + a));
-            const double d1 = std::max(0., 0.5 * (a * a + ww * (1. - (cc * cc) / (1. + ww * dd))));
+            const double d1 = rmax(0., 0.5 * (a * a + ww * (1. - (cc * cc) / (1. + ww * dd))));
             const double u0_square = a * a + ww - d1;
             const double c2byu02 = (cc * cc) / u0_square;
             if (c2byu02 - dd <= 0)
@@ -1259,19 +1275,19 @@ struct Solver
         }
         else
             i.has_relgap = false;
-        const double nry = p > 0 ? norm2(ry.data(), p) / std::max(resy0 + nx, 1.) : 0.;
-        const double nrz = norm2(rz.data(), m) / std::max(resz0 + nx + ns, 1.);
-        i.pres = std::max(nry, nrz) / w.tau;
-        i.dres = norm2(rx.data(), n) / std::max(resx0 + ny + nz, 1.) / w.tau;
-        if ((w.hz + w.by) / std::max(ny + nz, 1.) < -RELTOL)
+        const double nry = p > 0 ? norm2(ry.data(), p) / rmax(resy0 + nx, 1.) : 0.;
+        const double nrz = norm2(rz.data(), m) / rmax(resz0 + nx + ns, 1.);
+        i.pres = rmax(nry, nrz) / w.tau;
+        i.dres = norm2(rx.data(), n) / rmax(resx0 + ny + nz, 1.) / w.tau;
+        if ((w.hz + w.by) / rmax(ny + nz, 1.) < -RELTOL)
         {
             i.has_pinfres = true;
-            i.pinfres = hresx / std::max(ny + nz, 1.);
+            i.pinfres = hresx / rmax(ny + nz, 1.);
         }
-        if (w.cx / std::max(nx, 1.) < -RELTOL)
+        if (w.cx / rmax(nx, 1.) < -RELTOL)
         {
             i.has_dinfres = true;
-            i.dinfres = std::max(hresy / std::max(nx, 1.), hresz / std::max(nx + ns, 1.));
+            i.dinfres = rmax(hresy / rmax(nx, 1.), hresz / rmax(nx + ns, 1.));
         }
     }
 
@@ -1382,7 +1398,11 @@ struct Solver
             const int d = sc.dim;
             const double lknorm2 = lambda[cs] * lambda[cs] - sqnorm(&lambda[cs] + 1, d - 1);
             if (lknorm2 <= 0.)
+            {
+                if (&sc != &cones.back())
+                    misaligned_cones++;
                 continue;
+            }
             const double lknorm = std::sqrt(lknorm2);
             const double lknorminv = 1. / lknorm;
             const double lk0 = lambda[cs] / lknorm;
@@ -1413,12 +1433,12 @@ struct Solver
                 acc += r * r;
             }
             const double sigmanorm = std::sqrt(acc) - sigma0;
-            const double conic_step = std::max(0., std::max(sigmanorm, rhonorm));
+            const double conic_step = rmax(0., rmax(sigmanorm, rhonorm));
             if (conic_step != 0.)
                 alpha = std::min(1. / conic_step, alpha);
             cs += d;
         }
-        return std::min(std::max(alpha, STEPMIN), STEPMAX);
+        return std::min(rmax(alpha, STEPMIN), STEPMAX);
     }
 
     /* src/eicos.cpp:1471-1620 */
@@ -1490,9 +1510,9 @@ struct Solver
             else
                 scale2add(dz_true, ez.data());
             const double nez = norminf(ez.data(), mt);
-            double nerr = std::max(nex, nez);
+            double nerr = rmax(nex, nez);
             if (p > 0)
-                nerr = std::max(nerr, ney);
+                nerr = rmax(nerr, ney);
             if (k_ref > 0 && nerr > nerr_prev)
             {
                 for (int k = 0; k < N; k++)
@@ -1620,9 +1640,9 @@ struct Solver
         std::fill(rhs2.begin(), rhs2.end(), 0.0);
         for (int k = 0; k < n; k++)
             rhs2[k] = -c[k];
-        resx0 = std::max(1., norm2(c.data(), n));
-        resy0 = std::max(1., norm2(b.data(), p));
-        resz0 = std::max(1., norm2(h.data(), m));
+        resx0 = rmax(1., norm2(c.data(), n));
+        resy0 = rmax(1., norm2(b.data(), p));
+        resz0 = rmax(1., norm2(h.data(), m));
     }
 
     /* src/eicos.cpp:848-1262 */
@@ -1663,9 +1683,12 @@ struct Solver
             compute_residuals();
             update_statistics();
             if (verbose)
-                std::printf("%2d  %+5.3e  %+5.3e  %+2.0e  %2.0e  %2.0e  %2.0e  %2.0e  step=%6.4f sigma=%2.0e IR %d/%d/%d tau=%g kap=%g pinfres=%g(%d) dinfres=%g(%d)\n",
-                            w.i.iter, w.i.pcost, w.i.dcost, w.i.gap, w.i.pres, w.i.dres, w.i.kapovert, w.i.mu, w.i.step, w.i.sigma,
-                            w.i.nitref1, w.i.nitref2, w.i.nitref3, w.tau, w.kap, w.i.pinfres, (int)w.i.has_pinfres, w.i.dinfres, (int)w.i.has_dinfres);
+                std::printf("%2d  %+5.3e  %+5.3e  %+2.0e  %2.0e  %2.0e  %2.0e  %2.0e  step=%6.4f sigma=%2.0e IR %d/%d/%d tau=%g kap=%g pinfres=%.17g(%d) dinfres=%.17g(%d) pres=%.17g pres_prev=%.17g\n",
+                            w.i.iter, (ora_api_real)w.i.pcost, (ora_api_real)w.i.dcost, (ora_api_real)w.i.gap, (ora_api_real)w.i.pres,
+                            (ora_api_real)w.i.dres, (ora_api_real)w.i.kapovert, (ora_api_real)w.i.mu, (ora_api_real)w.i.step,
+                            (ora_api_real)w.i.sigma, w.i.nitref1, w.i.nitref2, w.i.nitref3, (ora_api_real)w.tau, (ora_api_real)w.kap,
+                            (ora_api_real)w.i.pinfres, (int)w.i.has_pinfres, (ora_api_real)w.i.dinfres, (int)w.i.has_dinfres,
+                            (ora_api_real)w.i.pres, (ora_api_real)pres_prev);
 
             if (w.i.iter > 0 && (w.i.pres > SAFEGUARD * pres_prev || w.i.gap < 0.))
             {
@@ -1734,7 +1757,7 @@ struct Solver
             const double dkapaff = -w.kap - w.kap / w.tau * dtauaff;
             w.i.step_aff = line_search(w.lambda, dsaff_by_W, W_times_dzaff, w.tau, dtauaff, w.kap, dkapaff);
             const double t = 1. - w.i.step_aff;
-            const double sigma = std::min(std::max(t * t * t, SIGMAMIN), SIGMAMAX);
+            const double sigma = std::min(rmax(t * t * t, SIGMAMIN), SIGMAMAX);
             w.i.sigma = sigma;
 
             rhs_combined();
@@ -1769,7 +1792,7 @@ struct Solver
     }
 
     /* src/eicos.cpp:2053-2082 : h only follows Gpr, b only follows Apr */
-    void update_data_ptr(const double *Gpr, const double *Apr, const double *c_, const double *h_, const double *b_)
+    void update_data_ptr(const ora_api_real *Gpr, const ora_api_real *Apr, const ora_api_real *c_, const ora_api_real *h_, const ora_api_real *b_)
     {
         if (equilibrated)
             unset_equilibration();
@@ -1792,7 +1815,7 @@ struct Solver
     }
 
     /* src/eicos.cpp:2032-2051 */
-    void update_data_full(const double *Gpr, const double *Apr, const double *c_, const double *h_, const double *b_)
+    void update_data_full(const ora_api_real *Gpr, const ora_api_real *Apr, const ora_api_real *c_, const ora_api_real *h_, const ora_api_real *b_)
     {
         std::copy(Gpr, Gpr + G.nnz(), G.x.begin());
         std::copy(Apr, Apr + A.nnz(), A.x.begin());
@@ -1810,6 +1833,10 @@ struct Solver
 
 /* ------------------------------------------------------------------ C ABI */
 using ora::Solver;
+
+#ifdef ORA_LONG_DOUBLE
+#undef double
+#endif
 
 extern "C"
 {
@@ -1835,6 +1862,17 @@ void ora_update_data_full(void *sv, const double *Gpr, const double *Apr, const 
 }
 
 int ora_solve(void *sv) { return ((Solver *)sv)->solve(); }
+
+/* test hook: lineSearch on caller data (lambda, ds, dz of length m) */
+double ora_debug_line_search(void *sv, const double *lambda, const double *ds, const double *dz, double tau, double dtau, double kap,
+                             double dkap)
+{
+    Solver *s = (Solver *)sv;
+    return s->line_search(ora::vec(lambda, lambda + s->m), ora::vec(ds, ds + s->m), ora::vec(dz, dz + s->m), tau, dtau, kap, dkap);
+}
+
+/* test hook: how often lineSearch left `cone_start` behind (the reference's `continue` quirk) in this solver's life */
+long long ora_misaligned_cones(void *sv) { return ((Solver *)sv)->misaligned_cones; }
 
 void ora_get_solution(void *sv, double *x, double *y, double *z, double *s)
 {
@@ -1932,7 +1970,13 @@ void ora_debug_get_K(void *sv, double *Kx)
     std::copy(S->K.x.begin(), S->K.x.end(), Kx);
 }
 
-void ora_debug_ldl_solve(void *sv, const double *rhs, double *x) { ((Solver *)sv)->ldlt.solve(rhs, x); }
+void ora_debug_ldl_solve(void *sv, const double *rhs, double *x)
+{
+    Solver *S = (Solver *)sv;
+    ora::vec r(rhs, rhs + S->N), o(S->N);
+    S->ldlt.solve(r.data(), o.data());
+    std::copy(o.begin(), o.end(), x);
+}
 
 int ora_debug_solve_kkt(void *sv, const double *rhs, double *dx, double *dy, double *dz, int initialize)
 {

@@ -8,6 +8,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_build", "libeicos_oracle.so")
+LIB_LD = os.path.join(HERE, "_build", "libeicos_oracle_ld.so")  # the same restatement in 80-bit extended precision
 FIXTURE_DIR = os.path.join(os.path.dirname(HERE), "tests", "golden", "fixtures")
 
 _lib = None
@@ -15,7 +16,7 @@ _lib = None
 
 def build(force=False):
     src = [os.path.join(HERE, f) for f in ("eicos_oracle.cpp", "eicos_oracle.h", "Makefile")]
-    if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in src):
+    if force or not os.path.exists(LIB) or not os.path.exists(LIB_LD) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in src):
         subprocess.check_call(["make", "-C", HERE, "-s"])
     return LIB
 
@@ -57,6 +58,10 @@ def lib():
             f.argtypes = [C.c_void_p] + [_dp] * 5
         L.ora_solve.restype = C.c_int
         L.ora_solve.argtypes = [C.c_void_p]
+        L.ora_debug_line_search.restype = C.c_double
+        L.ora_debug_line_search.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.ora_misaligned_cones.restype = C.c_longlong
+        L.ora_misaligned_cones.argtypes = [C.c_void_p]
         L.ora_get_solution.restype = None
         L.ora_get_solution.argtypes = [C.c_void_p] + [_dp] * 4
         L.ora_get_info.restype = None
@@ -114,6 +119,33 @@ def _problem_args(P):
     return keep, args
 
 
+def solve_extended_precision(P, trace=False):
+    """Exit flag of the long-double build of the oracle on problem P (and, with trace=True, the per-iteration lines
+    it prints under ORA_VERBOSE: run in a subprocess so that the output can be captured)."""
+    import sys
+    code = ("import ctypes as C, sys; sys.path.insert(0, %r); import oracle; from oracle.oracle import _problem_args, LIB_LD, _dp, _ip;"
+            "P = oracle.load_fixture(%r) if isinstance(%r, str) else None;"
+            "L = C.CDLL(LIB_LD); L.ora_setup.restype = C.c_void_p;"
+            "L.ora_setup.argtypes = [C.c_int] * 5 + [_ip, _dp, _ip, _ip, _dp, _ip, _ip, _dp, _dp, _dp];"
+            "L.ora_solve.restype = C.c_int; L.ora_solve.argtypes = [C.c_void_p];"
+            "keep, args = _problem_args(P); h = L.ora_setup(*args); print('EXIT', L.ora_solve(h))") % (os.path.dirname(HERE), P, P)
+    env = dict(os.environ)
+    if trace:
+        env["ORA_VERBOSE"] = "1"
+    out = subprocess.check_output([sys.executable, "-c", code], env=env, text=True)
+    exitflag = int([l for l in out.splitlines() if l.startswith("EXIT")][-1].split()[1])
+    return (exitflag, out) if trace else exitflag
+
+
+def solve_trace(name):
+    """Exit flag and ORA_VERBOSE trace of the double-precision oracle on fixture `name` (subprocess)."""
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import oracle; S = oracle.OracleSolver(oracle.load_fixture(%r)); print('EXIT', S.solve())"
+            % (os.path.dirname(HERE), name))
+    out = subprocess.check_output([sys.executable, "-c", code], env=dict(os.environ, ORA_VERBOSE="1"), text=True)
+    return int([l for l in out.splitlines() if l.startswith("EXIT")][-1].split()[1]), out
+
+
 class OracleSolver:
     """Mirrors EiCOS::Solver's pointer interface (include/eicos.hpp:151-163 of the reference)."""
 
@@ -140,6 +172,14 @@ class OracleSolver:
 
     def solve(self):
         return lib().ora_solve(self.h)
+
+    def line_search(self, lam, ds, dz, tau, dtau, kap, dkap):
+        a = [np.ascontiguousarray(v, np.float64) for v in (lam, ds, dz)]
+        return float(lib().ora_debug_line_search(self.h, *[v.ctypes.data_as(_dp) for v in a], tau, dtau, kap, dkap))
+
+    def misaligned_cones(self):
+        """How often lineSearch skipped the cone-offset advance with cones still to come (src/eicos.cpp:1423-1424)."""
+        return int(lib().ora_misaligned_cones(self.h))
 
     def update_data(self, Gpr=None, Apr=None, c=None, h=None, b=None, full=False):
         a = [None if v is None else np.ascontiguousarray(v, dtype=np.float64) for v in (Gpr, Apr, c, h, b)]

@@ -22,8 +22,9 @@ def test_single_instance_parity(oracle_mod, gpu_lib, name):
     S = Solver(P, lib=gpu_lib)
     cg = S.solve()
     io, ig = O.info(), S.info()
-    if name == "unboundedMaxSqrt":  # rounding-chaotic (tests/test_oracle.py): DINF is what the reference's test expects
-        assert cg in (2, co)
+    if name == "unboundedMaxSqrt":  # a rounding knife edge (tests/test_oracle.py::test_unbounded_maxsqrt_is_a_rounding_knife_edge):
+        # two double-precision roundings of this unbounded problem need not take the same side
+        assert cg in (2, -2) and co in (2, -2)
         return
     assert cg == co
     for k in ("iter", "nitref1", "nitref2", "pinf", "dinf"):
@@ -216,6 +217,29 @@ def test_compaction_is_transparent(oracle_mod, gpu_lib):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name,rel", [("update_data_1", 0.05), ("MPC02", None), ("issue98", 0.01)])
+def test_program_forms_agree_bitwise_on_device(oracle_mod, gpu_lib, monkeypatch, name, rel):
+    """Shallow / deep data ring, two CTAs per tile or one two-job pass over L (the engine chooses by occupancy):
+    the CUDA kernels must give bit-identical results in every form."""
+    from eicos_b200.binding import BatchSolver
+    from eicos_b200.workloads import MPC_REL, perturbed
+    P = oracle_mod.load_fixture(name)
+    batch = 70
+    W = perturbed(P, batch, rel=MPC_REL if rel is None else rel, seed=12)
+    outs = []
+    for ring, pair in (("0", "0"), ("1", "0"), ("0", "1")):
+        monkeypatch.setenv("EICOS_RING_VARIANT", ring)
+        monkeypatch.setenv("EICOS_PAIR_SOLVES", pair)
+        B = BatchSolver(P, lib=gpu_lib, capacity=batch)
+        outs.append(B.solve(batch, hs=W["hs"], bs=W["bs"]))
+    for o in outs[1:]:
+        for k in ("x", "y", "z", "s", "iter", "exit"):
+            assert np.array_equal(outs[0][k], o[k]), k
+    ref = oracle_mod.batch_run(P, batch, hs=W["hs"], bs=W["bs"], nthreads=8)
+    assert np.array_equal(outs[0]["exit"], ref["exit"]) and np.array_equal(outs[0]["iter"], ref["iter"])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name,sw,fa", [("update_data_1", 2, 2), ("lp_afiro", 3, 4), ("MPC02", 3, 6)])
 def test_starved_slots_on_device(oracle_mod, gpu_lib, monkeypatch, name, sw, fa):
     """Shrunk slot budgets push the CUDA kernels through the far-gather, direct-operand and
@@ -362,3 +386,21 @@ def test_instance_matrices_compaction(oracle_mod, gpu_lib):
     assert np.array_equal(a["exit"], ref["exit"]) and np.array_equal(a["iter"], ref["iter"])
     ok = ref["exit"] == 0
     assert relerr(a["x"][ok], ref["x"][ok]) <= TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cones,l", [([3, 5, 2, 4], 3), ([2, 6, 3, 3, 5], 1)])
+def test_line_search_misaligned_cones_on_device(oracle_mod, gpu_lib, cones, l):
+    """lineSearch with lambda outside some cones: the reference's walk leaves its cone offset behind
+    (src/eicos.cpp:1423-1424 against :1462) and the CUDA kernel follows it (line_search_misaligned)."""
+    from eicos_b200.binding import BatchSolver
+    from test_emu_logic import _line_search_cases, _soc_problem
+    rng = np.random.default_rng(5)
+    P = _soc_problem(rng, cones, l=l)
+    batch = 150  # three tiles, the last one ragged
+    lam, ds, dz, sc = _line_search_cases(rng, P, batch)
+    O = oracle_mod.OracleSolver(P)
+    want = np.array([O.line_search(lam[b], ds[b], dz[b], *sc[b]) for b in range(batch)])
+    assert O.misaligned_cones() > 0
+    got = BatchSolver(P, lib=gpu_lib, capacity=batch).debug_line_search(lam, ds, dz, sc)
+    assert np.allclose(got, want, rtol=1e-12, atol=0)

@@ -11,28 +11,56 @@ from conftest import FIXTURES, ROOT, relerr
 
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_objectives.json")))
 
-# unboundedMaxSqrt: the reference's test expects DINF (test/unboundedProblems/unboundedMaxSqrt.h:33).
-# The oracle stops one iteration short with NUMERICS: at iteration 11 the primal residual jumps by a
-# factor ~600 (> safeguard 500, src/eicos.cpp:1010) while dinfres is 1.6e-8 (> feastol 1e-8).  The
-# outcome is rounding-chaotic: about half of the other pivot orders give DINF, and which half changes
-# with compiler flags (test_oracle_chaotic_case).
-KNOWN_DEVIATION = {"unboundedMaxSqrt": -2}
+# unboundedMaxSqrt (3-cone SOCP, test/unboundedProblems/unboundedMaxSqrt.h:33 expects DINF) is the one expectation the
+# double-precision restatement does not reproduce; test_unbounded_maxsqrt_is_a_rounding_knife_edge below establishes
+# why, and tests/test_reference_tester.py carries the one xfail for it.
+ROUNDING_KNIFE_EDGE = {"unboundedMaxSqrt"}
 
 
-@pytest.mark.parametrize("name", FIXTURES)
+@pytest.mark.parametrize("name", [n for n in FIXTURES if n not in ROUNDING_KNIFE_EDGE])
 def test_exit_flags_match_reference_tests(oracle_mod, name):
     P = oracle_mod.load_fixture(name)
     S = oracle_mod.OracleSolver(P)
     code = S.solve()
-    if name in KNOWN_DEVIATION:
-        assert code == KNOWN_DEVIATION[name]
-    else:
-        assert code in P["expect"], (name, code)
+    assert code in P["expect"], (name, code)
     if name in GOLD:
         x = S.solution()[0]
         obj = float(P["c"] @ x)
         assert abs(obj - GOLD[name]) <= 1e-7 * max(1.0, abs(GOLD[name])), (name, obj, GOLD[name])
         assert abs(S.info()["pcost"] * 1.0 - S.info()["pcost"]) == 0.0
+
+
+def _trace_column(trace, key):
+    import re
+    return [float(m.group(1)) for m in re.finditer(key + r"=([-+0-9.e]+)", trace)]
+
+
+def test_unbounded_maxsqrt_is_a_rounding_knife_edge(oracle_mod, capsys):
+    """The reference expects DINF for unboundedMaxSqrt.  The same restatement in 80-bit extended precision (11 more
+    mantissa bits, oracle/_build/libeicos_oracle_ld.so) ends with DINF: dinfres drops below feastol = 1e-8 and the
+    dual-infeasibility test of checkExitConditions (src/eicos.cpp:573-596) fires.  In double precision the iterates
+    have separated from that trajectory by iteration 11 (the problem is unbounded: the KKT systems lose all accuracy
+    as tau -> 0), dinfres hovers just above feastol for five iterations and the run ends in the safeguard
+    `pres > 500 pres_prev` (:1010) with NUMERICS.  The margin by which the double run misses DINF is printed."""
+    P = oracle_mod.load_fixture("unboundedMaxSqrt")
+    assert 2 in P["expect"]
+    code_ld, trace_ld = oracle_mod.solve_extended_precision("unboundedMaxSqrt", trace=True)
+    assert code_ld == 2, "extended precision reaches the reference's DINF"
+    code_d, trace_d = oracle_mod.solve_trace("unboundedMaxSqrt")
+    assert code_d in (2, -2)
+    dinf_d, dinf_ld = _trace_column(trace_d, "dinfres"), _trace_column(trace_ld, "dinfres")
+    pres_d, prev_d = _trace_column(trace_d, "pres"), _trace_column(trace_d, "pres_prev")
+    feastol = 1e-8
+    assert min(v for v in dinf_ld if v > 0) < feastol
+    with capsys.disabled():
+        print("\n  unboundedMaxSqrt: extended precision -> exit %d after %d iterations (min dinfres %.3e < feastol)"
+              % (code_ld, len(dinf_ld) - 1, min(v for v in dinf_ld if v > 0)))
+        print("  double precision   -> exit %d after %d iterations; closest approach dinfres = %.4e = %.2f x feastol; "
+              "last safeguard ratio pres / pres_prev = %.3g (limit 500)"
+              % (code_d, len(dinf_d) - 1, min(v for v in dinf_d if v > 0), min(v for v in dinf_d if v > 0) / feastol,
+                 pres_d[-1] / prev_d[-1]))
+    if code_d == -2:
+        assert min(v for v in dinf_d if v > 0) < 2 * feastol  # a near miss, not a different answer
 
 
 def test_oracle_chaotic_case(oracle_mod):

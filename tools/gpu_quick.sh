@@ -3,7 +3,7 @@
 TAG=${1:-quick}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-echo "== pytest -m gpu (slice)"; timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "single_instance or batched_perturbed or starved or lanes" 2>&1 | tail -5 | tee $OUT/pytest_gpu.txt
+echo "== pytest -m gpu (slice)"; timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "single_instance or batched_perturbed or starved or lanes or forms" 2>&1 | tail -5 | tee $OUT/pytest_gpu.txt
 for B in ${2:-65536 8192}; do
   echo "== bench batch $B"
   timeout 600 python bench.py --batch $B --steps 2 --warmup 3 --no-e2e --no-cpu-baseline 2>$OUT/bench_$B.err | tee $OUT/bench_$B.json | python -c "
