@@ -73,6 +73,7 @@ EXPORTS = [
     "eicos_batch_solve_matrices", "eicos_batch_solve_device", "eicos_batch_solve_matrices_device",
     "eicos_batch_set_timing", "eicos_batch_set_compaction", "eicos_batch_get_stats", "eicos_batch_get_dims", "eicos_batch_get_program_stats", "eicos_batch_get_symbolic",
     "eicos_batch_debug_init", "eicos_batch_debug_line_search", "eicos_batch_stream", "eicos_batch_cleanup",
+    "eicos_multi_setup", "eicos_multi_solve", "eicos_multi_ngpu", "eicos_multi_slice", "eicos_multi_cleanup",
     "eicos_last_error", "eicos_device_count",
 ]
 
@@ -146,6 +147,16 @@ class Library:
         L.eicos_batch_debug_init.argtypes = [C.c_void_p, C.c_int] + [_dp] * 7 + [_ip]
         L.eicos_batch_debug_line_search.restype = C.c_int
         L.eicos_batch_debug_line_search.argtypes = [C.c_void_p, C.c_int] + [_dp] * 5
+        L.eicos_multi_setup.restype = C.c_void_p
+        L.eicos_multi_setup.argtypes = setup_args + [C.c_int, _ip, C.c_longlong, C.c_int, C.c_int]
+        L.eicos_multi_solve.restype = C.c_int
+        L.eicos_multi_solve.argtypes = [C.c_void_p, C.c_int] + [_dp] * 9 + [_ip, C.POINTER(Info)]
+        L.eicos_multi_ngpu.restype = C.c_int
+        L.eicos_multi_ngpu.argtypes = [C.c_void_p]
+        L.eicos_multi_slice.restype = C.c_int
+        L.eicos_multi_slice.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip, _ip]
+        L.eicos_multi_cleanup.restype = None
+        L.eicos_multi_cleanup.argtypes = [C.c_void_p]
         L.eicos_batch_stream.restype = C.c_void_p
         L.eicos_batch_stream.argtypes = [C.c_void_p]
         L.eicos_batch_cleanup.restype = None
@@ -342,3 +353,45 @@ class BatchSolver:
         self.lib.check(self.lib.L.eicos_batch_debug_init(self.h, int(batch), _d(cs), _d(hs), _d(bs),
                                                          _d(Lx), _d(D), _d(s1), _d(s2), _i(nit)))
         return dict(Lx=Lx, D=D, sol1=s1, sol2=s2, nitref=nit)
+
+
+class MultiBatchSolver:
+    """The batched overload over several GPUs of one node (eicos_multi_*): contiguous slices of the batch, one
+    device and one host thread each, results gathered into the caller's arrays; no collective."""
+
+    def __init__(self, problem, devices=(0,), capacity=0, workers=0, lib=None, instance_matrices=False):
+        self.lib = lib or load()
+        self._keep, args, (self.n, self.m, self.p) = _problem_args(problem)
+        dev = np.ascontiguousarray(list(devices), dtype=np.int32)
+        self.h = self.lib.L.eicos_multi_setup(*args, int(dev.size), _i(dev), int(capacity), int(workers),
+                                              BatchSolver.INSTANCE_MATRICES if instance_matrices else 0)
+        if not self.h:
+            raise RuntimeError("eicos_multi_setup failed: " + self.lib.last_error())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.L.eicos_multi_cleanup(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def ngpu(self):
+        return int(self.lib.L.eicos_multi_ngpu(self.h))
+
+    def slice(self, batch, k):
+        first, count = C.c_int(), C.c_int()
+        self.lib.check(self.lib.L.eicos_multi_slice(self.h, int(batch), int(k), C.byref(first), C.byref(count)))
+        return first.value, count.value
+
+    def solve(self, batch, cs=None, hs=None, bs=None, Gs=None, As=None):
+        a = [_arr(v, np.float64) for v in (Gs, As, cs, hs, bs)]
+        x, y = np.zeros((batch, self.n)), np.zeros((batch, self.p))
+        z, s = np.zeros((batch, self.m)), np.zeros((batch, self.m))
+        ex = np.zeros(batch, np.int32)
+        info = (Info * batch)()
+        self.lib.check(self.lib.L.eicos_multi_solve(self.h, int(batch), *[_d(v) for v in a], _d(x), _d(y), _d(z), _d(s), _i(ex), info))
+        return dict(x=x, y=y, z=z, s=s, exit=ex, iter=np.array([i.iter for i in info], np.int32), info=info)

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstring>
 #include <memory>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -498,6 +499,103 @@ int eicos_batch_debug_line_search(eicos_batch *bt, int batch, const double *lamb
     {
         return fail(EICOS_ERR_DEVICE, e.what());
     }
+}
+
+// ---------------------------------------------------------------- several devices behind one handle
+struct eicos_multi
+{
+    std::vector<eicos_batch *> part;
+    int n = 0, m = 0, p = 0, nnzG = 0, nnzA = 0;
+};
+
+static void multi_slice(int batch, int parts, int k, int &first, int &count)
+{ // contiguous, sizes differ by at most one (the same cut as eicos_b200/sharding.py: shard_range)
+    const int base = batch / parts, rem = batch % parts;
+    first = k * base + std::min(k, rem);
+    count = base + (k < rem ? 1 : 0);
+}
+
+eicos_multi *eicos_multi_setup(int n, int m, int p, int l, int ncones, const int *q,
+                               const double *Gpr, const int *Gjc, const int *Gir,
+                               const double *Apr, const int *Ajc, const int *Air,
+                               const double *c, const double *h, const double *b,
+                               int ngpu, const int *devices, long long capacity, int workers, int flags)
+{
+    if (ngpu < 1)
+    {
+        g_error = "eicos_multi_setup: ngpu must be at least 1";
+        return nullptr;
+    }
+    std::unique_ptr<eicos_multi> mt(new eicos_multi());
+    for (int k = 0; k < ngpu; k++)
+    {
+        eicos_batch *bt = eicos_batch_setup_ex(n, m, p, l, ncones, q, Gpr, Gjc, Gir, Apr, Ajc, Air, c, h, b,
+                                               devices ? devices[k] : k, capacity, workers, flags);
+        if (!bt)
+        { // g_error says why
+            for (eicos_batch *o : mt->part)
+                eicos_batch_cleanup(o);
+            return nullptr;
+        }
+        mt->part.push_back(bt);
+    }
+    const Symbolic &S = mt->part[0]->S;
+    mt->n = S.n, mt->m = S.m, mt->p = S.p, mt->nnzG = S.G.nnz(), mt->nnzA = S.A.nnz();
+    return mt.release();
+}
+
+int eicos_multi_ngpu(const eicos_multi *mt) { return mt ? (int)mt->part.size() : 0; }
+
+int eicos_multi_slice(const eicos_multi *mt, int batch, int k, int *first, int *count)
+{
+    if (!mt || k < 0 || k >= (int)mt->part.size() || batch < 0 || !first || !count)
+        return fail(EICOS_ERR_INVALID, "eicos_multi_slice: bad argument");
+    multi_slice(batch, (int)mt->part.size(), k, *first, *count);
+    return 0;
+}
+
+int eicos_multi_solve(eicos_multi *mt, int batch, const double *Gs, const double *As,
+                      const double *cs, const double *hs, const double *bs,
+                      double *x, double *y, double *z, double *s, int *exitflag, eicos_info *info)
+{
+    if (!mt || batch <= 0)
+        return fail(EICOS_ERR_INVALID, "null handle or empty batch");
+    const int parts = (int)mt->part.size();
+    std::vector<int> rc(parts, 0);
+    std::vector<std::string> err(parts);
+    std::vector<std::thread> th;
+    const auto run = [&](int k) {
+        int first, count;
+        multi_slice(batch, parts, k, first, count);
+        if (count == 0)
+            return;
+        const size_t f = (size_t)first;
+        const auto at = [&](const double *ptr, int width) { return ptr ? ptr + f * (size_t)width : nullptr; };
+        const auto atw = [&](double *ptr, int width) { return ptr ? ptr + f * (size_t)width : nullptr; };
+        rc[k] = eicos_batch_solve_matrices(mt->part[k], count, at(Gs, mt->nnzG), at(As, mt->nnzA), at(cs, mt->n), at(hs, mt->m),
+                                           at(bs, mt->p), atw(x, mt->n), atw(y, mt->p), atw(z, mt->m), atw(s, mt->m),
+                                           exitflag ? exitflag + f : nullptr, info ? info + f : nullptr);
+        if (rc[k] != 0)
+            err[k] = g_error; // (thread-local: carried back to the caller's thread below)
+    };
+    for (int k = 1; k < parts; k++)
+        th.emplace_back(run, k);
+    run(0);
+    for (std::thread &t : th)
+        t.join();
+    for (int k = 0; k < parts; k++)
+        if (rc[k] != 0)
+            return fail(rc[k], ("device slice " + std::to_string(k) + ": " + err[k]).c_str());
+    return 0;
+}
+
+void eicos_multi_cleanup(eicos_multi *mt)
+{
+    if (!mt)
+        return;
+    for (eicos_batch *bt : mt->part)
+        eicos_batch_cleanup(bt);
+    delete mt;
 }
 
 void *eicos_batch_stream(const eicos_batch *bt) { return bt ? bt->eng->stream() : nullptr; }

@@ -199,6 +199,26 @@ int eicos_batch_get_symbolic(const eicos_batch *bt, int *pinv, int *parent, int 
  * Lx [batch x nnzL], D [batch x dim_K], sol1/sol2 [batch x dim_K], nitref [batch x 2]. */
 int eicos_batch_debug_init(eicos_batch *bt, int batch, const double *cs, const double *hs, const double *bs,
                            double *Lx, double *D, double *sol1, double *sol2, int *nitref);
+/* ---- several GPUs of one node behind one handle.  Instances are independent (no reduction
+ * across instances anywhere in src/eicos.cpp:848-1262), so the batch is cut into contiguous slices, one per
+ * device; every device gets its own eicos_batch (symbolic data and programs replicated, ~1 MB) and its own host
+ * thread; results land in the caller's buffers by per-device copies - no collective.
+ * devices: ngpu CUDA ordinals, or NULL for 0 .. ngpu-1.  capacity: instances resident per device (0 = default). */
+typedef struct eicos_multi eicos_multi;
+eicos_multi *eicos_multi_setup(int n, int m, int p, int l, int ncones, const int *q,
+                               const double *Gpr, const int *Gjc, const int *Gir,
+                               const double *Apr, const int *Ajc, const int *Air,
+                               const double *c, const double *h, const double *b,
+                               int ngpu, const int *devices, long long capacity, int workers, int flags);
+/* Host buffers, instance-major, as eicos_batch_solve_matrices (any input NULL = the setup data for every instance). */
+int eicos_multi_solve(eicos_multi *mt, int batch, const double *Gs, const double *As,
+                      const double *cs, const double *hs, const double *bs,
+                      double *x, double *y, double *z, double *s, int *exitflag, eicos_info *info);
+int eicos_multi_ngpu(const eicos_multi *mt);
+/* slice of device k in a batch of `batch` instances: [*first, *first + *count) */
+int eicos_multi_slice(const eicos_multi *mt, int batch, int k, int *first, int *count);
+void eicos_multi_cleanup(eicos_multi *mt);
+
 /* Test hook: lineSearch (reference src/eicos.cpp:1380-1469) on caller data - lambda, ds, dz instance-major in z
  * order [batch x m], scalars = tau, dtau, kap, dkap per instance [batch x 4], alpha out [batch] (host pointers). */
 int eicos_batch_debug_line_search(eicos_batch *bt, int batch, const double *lambda, const double *ds, const double *dz,

@@ -333,3 +333,23 @@ def test_line_search_misaligned_cones(oracle_mod, emu_lib, cones, l):
     assert O.misaligned_cones() > 0
     got = BatchSolver(P, lib=emu_lib, capacity=batch, workers=3).debug_line_search(lam, ds, dz, sc)
     assert np.allclose(got, want, rtol=1e-12, atol=0), (got, want)
+
+
+@pytest.mark.parametrize("parts", [2, 3])
+def test_multi_device_handle_matches_single(oracle_mod, emu_lib, parts):
+    """eicos_multi_*: the batch cut into contiguous slices over several device handles (the emulator ignores the
+    ordinals, so this exercises the host logic - slicing, per-slice threads, gathering) gives what one handle gives,
+    bit for bit."""
+    from eicos_b200.binding import BatchSolver, MultiBatchSolver
+    from eicos_b200.workloads import perturbed
+    P = oracle_mod.load_fixture("update_data_1")
+    batch = 23
+    W = perturbed(P, batch, rel=0.05, seed=21)
+    one = BatchSolver(P, lib=emu_lib, capacity=batch).solve(batch, hs=W["hs"], bs=W["bs"])
+    M = MultiBatchSolver(P, devices=list(range(parts)), capacity=batch, lib=emu_lib)
+    assert M.ngpu() == parts
+    cover = [M.slice(batch, k) for k in range(parts)]
+    assert cover[0][0] == 0 and sum(c for _, c in cover) == batch and all(cover[k][0] + cover[k][1] == cover[k + 1][0] for k in range(parts - 1))
+    many = M.solve(batch, hs=W["hs"], bs=W["bs"])
+    for k in ("x", "y", "z", "s", "exit", "iter"):
+        assert np.array_equal(one[k], many[k]), k

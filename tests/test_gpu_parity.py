@@ -404,3 +404,24 @@ def test_line_search_misaligned_cones_on_device(oracle_mod, gpu_lib, cones, l):
     assert O.misaligned_cones() > 0
     got = BatchSolver(P, lib=gpu_lib, capacity=batch).debug_line_search(lam, ds, dz, sc)
     assert np.allclose(got, want, rtol=1e-12, atol=0)
+
+
+@pytest.mark.gpu
+def test_multi_gpu_handle_matches_single(oracle_mod, gpu_lib):
+    """eicos_multi_* (SURVEY.md 8b / 8e): a batch cut over the devices of the node gives, bit for bit, what one device
+    gives.  With one visible GPU both slices run on it (two handles, two host threads, one device); with two or
+    more, on distinct devices."""
+    from eicos_b200.binding import BatchSolver, MultiBatchSolver
+    from eicos_b200.workloads import MPC_REL, perturbed
+    P = oracle_mod.load_fixture("MPC02")
+    batch = 150
+    W = perturbed(P, batch, rel=MPC_REL, seed=31)
+    one = BatchSolver(P, lib=gpu_lib, capacity=batch).solve(batch, hs=W["hs"], bs=W["bs"])
+    ndev = gpu_lib.L.eicos_device_count()
+    devices = [0, 1] if ndev >= 2 else [0, 0]
+    M = MultiBatchSolver(P, devices=devices, capacity=batch, lib=gpu_lib)
+    many = M.solve(batch, hs=W["hs"], bs=W["bs"])
+    for k in ("x", "y", "z", "s", "exit", "iter"):
+        assert np.array_equal(one[k], many[k]), k
+    ref = oracle_mod.batch_run(P, batch, hs=W["hs"], bs=W["bs"], nthreads=8)
+    assert np.array_equal(many["exit"], ref["exit"]) and np.array_equal(many["iter"], ref["iter"])

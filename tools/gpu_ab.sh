@@ -21,5 +21,3 @@ for l in sys.stdin:
 }
 BATCHES="${BATCHES:-65536 8192}"
 run base X=1
-run split EICOS_PAIR_SOLVES=0
-run pair EICOS_PAIR_SOLVES=1
