@@ -252,13 +252,33 @@ class BatchSolver
         if (!h_)
             throw std::runtime_error(std::string("EiCOS::BatchSolver: ") + eicos_last_error());
     }
-    ~BatchSolver() { eicos_batch_cleanup(h_); }
+    // several GPUs of one node: the batch is cut into contiguous slices, one per entry of `devices` (eicos_multi_*:
+    // one device handle and one host thread per slice, results gathered into the Result; no collective)
+    BatchSolver(int n, int m, int p, int l, int ncones, const int *q,
+                const double *Gpr, const int *Gjc, const int *Gir,
+                const double *Apr, const int *Ajc, const int *Air,
+                const double *c, const double *h, const double *b,
+                const std::vector<int> &devices, bool instance_matrices = false, long long capacity = 0, int workers = 0)
+        : n_(n), m_(m), p_(p), nnzG_(Gjc ? Gjc[n] : 0), nnzA_(Ajc ? Ajc[n] : 0)
+    {
+        mh_ = eicos_multi_setup(n, m, p, l, ncones, q, Gpr, Gjc, Gir, Apr, Ajc, Air, c, h, b, (int)devices.size(), devices.data(),
+                                capacity, workers, instance_matrices ? EICOS_BATCH_INSTANCE_MATRICES : 0);
+        if (!mh_)
+            throw std::runtime_error(std::string("EiCOS::BatchSolver: ") + eicos_last_error());
+    }
+    ~BatchSolver()
+    {
+        eicos_batch_cleanup(h_);
+        eicos_multi_cleanup(mh_);
+    }
     BatchSolver(const BatchSolver &) = delete;
     BatchSolver &operator=(const BatchSolver &) = delete;
 
     // new matrix values shared by every instance (updateData with Gpr / Apr, src/eicos.cpp:2076-2081)
     void updateMatrices(const double *Gpr, const double *Apr)
     {
+        if (mh_)
+            throw std::runtime_error("EiCOS::BatchSolver::updateMatrices: not available on a multi-device solver");
         detail::check(eicos_batch_update_matrices(h_, Gpr, Apr), "EiCOS::BatchSolver::updateMatrices");
     }
 
@@ -275,10 +295,10 @@ class BatchSolver
         r.exitflag.assign(B, (int)exitcode::not_converged_yet);
         if (want_info)
             r.info.resize(B);
-        detail::check(eicos_batch_solve_matrices(h_, batch, Gs, As, cs, hs, bs, r.x.data(),
-                                                 want_duals ? r.y.data() : nullptr, want_duals ? r.z.data() : nullptr,
-                                                 want_duals ? r.s.data() : nullptr, r.exitflag.data(),
-                                                 want_info ? r.info.data() : nullptr),
+        double *y = want_duals ? r.y.data() : nullptr, *z = want_duals ? r.z.data() : nullptr, *s = want_duals ? r.s.data() : nullptr;
+        eicos_info *info = want_info ? r.info.data() : nullptr;
+        detail::check(mh_ ? eicos_multi_solve(mh_, batch, Gs, As, cs, hs, bs, r.x.data(), y, z, s, r.exitflag.data(), info)
+                          : eicos_batch_solve_matrices(h_, batch, Gs, As, cs, hs, bs, r.x.data(), y, z, s, r.exitflag.data(), info),
                       "EiCOS::BatchSolver::solve");
         return r;
     }
@@ -286,9 +306,11 @@ class BatchSolver
     int nnzG() const { return nnzG_; }
     int nnzA() const { return nnzA_; }
     eicos_batch *handle() const { return h_; }
+    int devices() const { return mh_ ? eicos_multi_ngpu(mh_) : 1; }
 
   private:
     eicos_batch *h_ = nullptr;
+    eicos_multi *mh_ = nullptr; // set instead of h_ by the multi-device constructor
     int n_ = 0, m_ = 0, p_ = 0, nnzG_ = 0, nnzA_ = 0;
 };
 

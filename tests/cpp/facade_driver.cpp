@@ -119,6 +119,16 @@ int main(int argc, char **argv)
                 print_vec("z", r.z.data() + (size_t)k * m, (size_t)m);
                 print_vec("s", r.s.data() + (size_t)k * m, (size_t)m);
             }
+            // the same batch through the multi-device constructor (two slices; both on device 0 when that is all
+            // there is): must reproduce the single-handle result bit for bit
+            EiCOS::BatchSolver many(n, m, p, l, ncones, q.data(), Gpr.data(), Gjc.data(), Gir.data(),
+                                    hasA ? Apr.data() : nullptr, hasA ? Ajc.data() : nullptr, hasA ? Air.data() : nullptr,
+                                    c.data(), h.data(), b.data(), std::vector<int>{0, 0}, /*instance_matrices=*/(mask & 3) != 0);
+            const EiCOS::BatchSolver::Result r2 =
+                many.solve(batch, mask & 4 ? cs.data() : nullptr, mask & 8 ? hs.data() : nullptr, mask & 16 ? bs.data() : nullptr,
+                           mask & 1 ? Gs.data() : nullptr, mask & 2 ? As.data() : nullptr);
+            const bool same = many.devices() == 2 && r2.x == r.x && r2.y == r.y && r2.z == r.z && r2.s == r.s && r2.exitflag == r.exitflag;
+            printf("multi-device %s\n", same ? "ok" : "MISMATCH");
         }
         // error behaviour: a malformed pattern must throw, not crash or fall back
         try

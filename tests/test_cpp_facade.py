@@ -61,8 +61,8 @@ def _run(binary, script):
             solves.append(cur)
         elif t[0] in "xyzs":
             cur[t[0]] = np.array([float(v) for v in t[1:]])
-        elif t[0] == "error-check":
-            solves.append({"kind": "error-check", "result": t[1]})
+        elif t[0] in ("error-check", "multi-device"):
+            solves.append({"kind": t[0], "result": t[1]})
     return solves
 
 
@@ -101,6 +101,7 @@ def _check_sequence(oracle_mod, binary, tmp_path):
         assert g["exit"] == ref["exit"][k] and g["iter"] == ref["iter"][k]
         for key in "xyzs":
             assert relerr(g[key], ref[key][k]) <= TOL, key
+    assert {"kind": "multi-device", "result": "ok"} in got  # BatchSolver(..., devices): bit-identical to one handle
     assert got[-1] == {"kind": "error-check", "result": "ok"}  # malformed pattern -> exception, no fallback
 
 

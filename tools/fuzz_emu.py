@@ -18,7 +18,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def random_mpc(seed):
     """Banded MPC-like LP (scalar or 2-state dynamics, box bounds, optional input-norm cones): narrow
-    columns of L, so the record-form factor program (streams.hpp: fa_fast) is the one exercised."""
+    columns of L, so every value of the factor program stays in its slots."""
     from eicos_b200.workloads import _csc
     rng = np.random.default_rng(seed)
     nx, T = int(rng.integers(1, 3)), int(rng.integers(3, 25))
