@@ -98,7 +98,7 @@ struct eicos_solver
 static int default_workers(long long instances)
 {
     (void)instances;
-    return 4;
+    return 8; // measured on B200 (profiles/r02a): 8 against 4 warps per tile, +5 % at 8 192 instances, +1 % at 65 536
 }
 
 extern "C"

@@ -136,3 +136,15 @@ def test_facade_sequence_gpu(oracle_mod, gpu_lib, tmp_path):
 @pytest.mark.parametrize("name", ["lp_afiro", "infeasible1", "MPC02"])
 def test_facade_fixtures_gpu(oracle_mod, gpu_lib, tmp_path, name):
     _check_fixture(oracle_mod, _build("facade_gpu"), tmp_path, name)
+
+
+def test_eigen_typed_overloads_compile_and_run(emu_lib):
+    """The Eigen-typed constructor / updateData / solution() of include/eicos.hpp (reference include/eicos.hpp:138-148)
+    against tests/cpp/mock_eigen (Eigen itself is not in the image): a 2-variable problem with one LP row and one
+    second-order cone, then updateData with the Eigen signature."""
+    out = subprocess.run([_build("eigen_overloads_emu")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    rows = [l.split() for l in out.stdout.splitlines()]
+    assert [r[1] for r in rows] == ["0", "0"]
+    assert np.allclose([float(v) for v in rows[0][3:]], [1.0, 2.0], atol=1e-6)
+    assert np.allclose([float(v) for v in rows[1][3:]], [3.0, 5.0], atol=1e-6)
