@@ -2,14 +2,15 @@
 """Benchmark of the batched SOCP interior-point hot path (BASELINE.json metric: SOCP solves/sec).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload mpc02|socmpc] [--batch B] [--scaling weak|strong]
+                    [--workload mpc02|mpc02pct5|mpc02pim|socmpc|lp25fv47] [--batch B] [--scaling strong|weak]
 
 A "step" is one pass of the hot path over one batch: updateData (per-instance h, b) + solve for
 every instance of the batch.  Workload at N=1: BASELINE.json configs[2] - the reference's MPC data
 set x65536 with perturbed h/b.  The checkout lacks data_MPC01.hpp / test/MPC/MPC01.h,
 so the reference's own sibling fixture MPC02 (test/MPC/MPC02.h) stands in; `--workload socmpc` runs a
 builder-defined SOC-bearing MPC instead.  One process per GPU (torchrun), the batch is sharded by
-instance, no data-path collective.
+instance, no data-path collective; --scaling strong (default) = --batch instances IN TOTAL (the metric's
+configuration: 65536 over 1/2/4/8 GPUs), weak = per GPU.
 
 JSON line (rank 0): value = whole-job solves/s with inputs resident in HBM (device-timed, max over
 ranks); e2e = the same through the C ABI with HOST buffers (H2D of h,b and D2H of x + exit flags in

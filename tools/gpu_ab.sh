@@ -3,7 +3,6 @@
 TAG=${1:-ab}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-echo "== pytest -m gpu (slice)"; timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "single_instance or batched_perturbed or starved or lanes or forms or line_search" 2>&1 | tail -5 | tee $OUT/pytest_gpu.txt
 run() {
   name=$1; shift
   for B in $BATCHES; do
@@ -19,5 +18,8 @@ for l in sys.stdin:
     tail -2 $OUT/${name}_$B.err
   done
 }
-BATCHES="${BATCHES:-65536 8192}"
-run base X=1
+BATCHES="${BATCHES:-65536}"
+run g3 EICOS_SHALLOW_GROUPS=3
+run g5 EICOS_SHALLOW_GROUPS=5
+run g6 EICOS_SHALLOW_GROUPS=6
+run g3again EICOS_SHALLOW_GROUPS=3
