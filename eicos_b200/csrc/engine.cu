@@ -108,8 +108,9 @@ static void eicos_compact_emu(const KArgs &a, const MoveRanges &mr, const int *m
 }
 #endif
 
-// shared-memory budget of the slot programs (rows of TILE doubles per CTA)
-// (one warp per tile wants 7 CTAs per SM: ring 32 rows + 28 rows here = 30 KB per CTA at TILE = 64)
+// slot budgets of the machine programs (a slot = one row of TILE doubles; two rows in the two-job programs).
+// With the shallow ring (24 rows) a solveKKT / residual CTA takes 25 KB of shared memory: 9 per SM; a factor CTA 29 KB: 7 per SM,
+// one wave for the 1024 tiles of the benchmark batch.
 constexpr int MAX_SW_SLOTS = 16, MAX_FA_SLOTS = 24;
 
 int Engine::tile_width() { return TILE; }

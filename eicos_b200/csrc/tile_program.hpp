@@ -5,11 +5,11 @@
 // per-instance array is moved with ONE 16-byte access per lane (512 B per warp for VEC = 2): every
 // index decode, address computation and loop step is amortised over VEC instances, and the
 // sparsity pattern never diverges inside a warp.
-//   * Program kernels (numeric LDL', triangular sweeps, KKT mat-vecs): ONE warp per tile walks a
-//     program compiled on the host (streams.hpp) in elimination order.  Global reads arrive through
-//     a cp.async FIFO whose ring rows the program names directly; intermediate values sit in
-//     shared-memory slots for their live range; the program itself is read through a small
-//     shared-memory double buffer.  Nothing inside such a kernel needs a barrier.
+//   * Program kernels (numeric LDL', triangular sweeps, KKT mat-vecs): ONE warp per tile interprets
+//     machine code compiled on the host (machine.hpp, streams.hpp): bundles of independent 3-address
+//     operations on shared-memory rows.  Global reads arrive through a cp.async ring whose rows the
+//     code names directly; intermediate values sit in shared-memory slots for their live range; the
+//     code itself and its load list arrive by TMA bulk copies.  Nothing inside such a kernel needs a barrier.
 //   * Vector kernels (statistics, scalings, right-hand sides, line search, iterate update): the
 //     warps ("workers") of the CTA split the rows; per-instance reductions run down the rows in
 //     each worker and are combined through shared memory in a fixed order, so every warp holds
@@ -32,13 +32,11 @@
 #include <barrier>
 #define EI_DEV inline
 #define EI_LDG(p) (*(p))
-#define EI_PREFETCH(p) ((void)0)
 #define EI_CLOCK() 0ll
 #else
 #include <cuda_runtime.h>
 #define EI_DEV __device__ __forceinline__
 #define EI_LDG(p) __ldg(p)
-#define EI_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
 #define EI_CLOCK() clock64()
 #endif
 
@@ -159,61 +157,6 @@ EI_DEV d2 ldg2(const double *p)
     return d2{v.x, v.y};
 #endif
 }
-
-// Rows of the worker's shared memory (FIFO ring, zero row, slots) addressed by row number.  On the
-// device these are 32-bit shared-window addresses and explicit ld/st.shared, so that the compiler
-// neither widens them to generic pointers nor reorders them around the cp.async traffic.
-#ifdef EICOS_EMU
-typedef double *smem_t;
-EI_DEV smem_t smem_of(double *p) { return p; }
-EI_DEV vd sm_load(smem_t b, int row) { return vload(b + (size_t)row * TILE); }
-EI_DEV void sm_store(smem_t b, int row, vd v) { vstore(b + (size_t)row * TILE, v); }
-EI_DEV void sm_fill(smem_t b, int row, const double *src) { vstore(b + (size_t)row * TILE, vload(src)); }
-#else
-typedef unsigned smem_t;
-EI_DEV smem_t smem_of(double *p) { return (unsigned)__cvta_generic_to_shared(p); }
-EI_DEV vd sm_load(smem_t b, int row)
-{
-    vd r;
-    const unsigned a = b + (unsigned)row * (unsigned)(TILE * sizeof(double));
-    if (VEC % 2 == 0)
-    {
-#pragma unroll
-        for (int c = 0; c < VEC; c += 2)
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.v[c]), "=d"(r.v[c + 1]) : "r"(a + 8 * c));
-    }
-    else
-        for (int c = 0; c < VEC; c++)
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r.v[c]) : "r"(a + 8 * c));
-    return r;
-}
-EI_DEV void sm_store(smem_t b, int row, vd v)
-{
-    const unsigned a = b + (unsigned)row * (unsigned)(TILE * sizeof(double));
-    if (VEC % 2 == 0)
-    {
-#pragma unroll
-        for (int c = 0; c < VEC; c += 2)
-            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a + 8 * c), "d"(v.v[c]), "d"(v.v[c + 1]) : "memory");
-    }
-    else
-        for (int c = 0; c < VEC; c++)
-            asm volatile("st.shared.f64 [%0], %1;" ::"r"(a + 8 * c), "d"(v.v[c]) : "memory");
-}
-EI_DEV void sm_fill(smem_t b, int row, const double *src) // asynchronous copy of one row (this lane's part)
-{
-    const unsigned a = b + (unsigned)row * (unsigned)(TILE * sizeof(double));
-    if (VEC % 2 == 0)
-    {
-#pragma unroll
-        for (int c = 0; c < VEC; c += 2)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a + 8 * c), "l"(src + c) : "memory");
-    }
-    else
-        for (int c = 0; c < VEC; c++)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(a + 8 * c), "l"(src + c) : "memory");
-}
-#endif
 
 // proxy for one row of the tile as seen by this lane (VEC instances)
 struct RowRef
@@ -349,19 +292,6 @@ EI_DEV vb lane_active(const Team &tm, const TileMem &t)
     return r;
 }
 
-// ------------------------------------------------------------------ cp.async group control (the FIFO below)
-EI_DEV void stage_commit()
-{
-#ifndef EICOS_EMU
-    asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
-}
-EI_DEV void stage_wait()
-{
-#ifndef EICOS_EMU
-    asm volatile("cp.async.wait_all;" ::: "memory");
-#endif
-}
 EI_DEV const double *rowp(const Team &, const double *T, int row) { return T + (size_t)row * TILE; }
 
 // Elementwise pass over `count` rows with NIN input arrays (row offsets in[k]): a worker takes U
@@ -612,8 +542,6 @@ EI_DEV void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar
                  "r"(bytes), "r"(bar)
                  : "memory");
 }
-// global / shared writes made through the generic proxy before this point are visible to later bulk copies
-EI_DEV void proxy_fence() { asm volatile("fence.proxy.async;" ::: "memory"); }
 #endif
 
 // ------------------------------------------------------------------ the FMA machine (machine.hpp)
