@@ -41,6 +41,9 @@ EI_DEFINE_KERNEL(eicos_init, tile_init, 2)
 EI_DEFINE_KERNEL1(eicos_ldl_factor, tile_factor)
 EI_DEFINE_KERNEL_(eicos_solve_kkt, tile_solve_kkt<1>, 32, 8, 1) /* CTA = (tile, job): one solveKKT each */
 EI_DEFINE_KERNEL_(eicos_solve_kkt_pair, tile_solve_kkt<2>, 32, 7, 0) /* two solveKKT that share the factor, one pass over L */
+/* few tiles: four warps per CTA, the residual rows split over them (M_MV_PARTS machines side by side) */
+EI_DEFINE_KERNEL_(eicos_solve_kkt_wide, tile_solve_kkt<1>, 32 * M_MV_PARTS, 2, 1)
+EI_DEFINE_KERNEL_(eicos_residuals_wide, tile_resid, 32 * M_MV_PARTS, 2, 0)
 EI_DEFINE_KERNEL(eicos_init_point, tile_init_point, 2)
 EI_DEFINE_KERNEL1(eicos_residuals, tile_resid)
 EI_DEFINE_KERNEL(eicos_iter_head, tile_head, 2)
@@ -70,7 +73,7 @@ __global__ void eicos_compact(const __grid_constant__ KArgs a, const __grid_cons
     {                                                                                             \
         const int nw_ = (threads), nj_ = (njobs);                                                                \
         std::vector<double> red_((size_t)nw_ * KRED * TILE + 8);                                  \
-        std::vector<double> pb_(machine_smem_doubles(std::max(std::max((args).P.sw_budget, (args).P.fa_budget), (args).P.pair_budget), M_MAX_RING_GROUPS, 2) + 8); \
+        std::vector<double> pb_(M_MV_PARTS * machine_smem_doubles(std::max(std::max((args).P.sw_budget, (args).P.fa_budget), (args).P.pair_budget), M_MAX_RING_GROUPS, 2) + 8); \
         for (int cta_ = 0; cta_ < (tiles) * nj_; cta_++)                                          \
         {                                                                                         \
             const int tile_ = cta_ / nj_;                                                         \
@@ -123,13 +126,18 @@ int Engine::tile_width() { return TILE; }
 // option and as a parity check of the two-job machine).
 bool Engine::pair_solves(int) const { return force_pair_ > 0; }
 
-bool Engine::deep_ring(int ctas) const
+// The deep-ring programs are an option (EICOS_RING_VARIANT = 1): on B200 a deeper ring measured no faster at any
+// batch (the program warps are bound by their instruction stream, not by memory latency).
+bool Engine::deep_ring(int) const { return force_variant_ > 0; }
+
+// A launch with few CTAs (all resident at the wide kernels' shared-memory footprint) runs the wide kernels: four warps
+// per CTA, the rows of the mat-vec programs split over them.  EICOS_WIDE = 0 / 1 pins the choice.
+bool Engine::wide_launch(int ctas) const
 {
-    if (force_variant_ >= 0)
-        return force_variant_ > 0;
-    const size_t deep = std::max(smem_prog_[M_VARIANTS - 1], smem_factor_[M_VARIANTS - 1]) + 1024;
-    const long long per_sm = (long long)((size_t)227 * 1024 / deep);
-    return (long long)ctas <= per_sm * sms_;
+    if (force_wide_ >= 0)
+        return force_wide_ > 0;
+    const long long per_sm = (long long)((size_t)227 * 1024 / (smem_wide_ + 1024));
+    return per_sm > 0 && (long long)ctas <= per_sm * sms_;
 }
 
 namespace
@@ -296,7 +304,6 @@ void Engine::upload_pattern(const Symbolic &S)
         prog(H_.bw[v], P.bw[v]);
         prog(H_.bwp[v], P.bwp[v]);
         prog(H_.mv[v], P.mv[v], &dmv_ops_[v]);
-        prog(H_.rs[v], P.rs[v], &drs_ops_[v]);
         prog(H_.fa[v], P.fa[v], &dfa_ops_[v]);
         for (int set = 0; set < 2; set++)
         { // forward: 1 = right-hand side, 3 = xw; backward: 1 = output, 2 = accumulated solution, 3 = xw
@@ -306,8 +313,16 @@ void Engine::upload_pattern(const Symbolic &S)
             P.bw_ld[v][set][1] = variant(H_.bw[v].ld, {dxr[set], sol[set], xw[set]});
             P.mv_ld[v][set] = variant(H_.mv[v].ld, {rhs[set], sol[set], L_.lpv, er[set]});
         }
-        P.rs_ld[v] = variant(H_.rs[v].ld, {L_.chb, L_.w, L_.s, L_.r, L_.sc});
         P.fa_ld[v] = variant(H_.fa[v].ld, {});
+    }
+    // the mat-vec programs in parts
+    for (int k = 0; k < M_MV_PARTS; k++)
+    {
+        prog(H_.rs[k], P.rs[k], &drs_ops_[k]);
+        prog(H_.mvw[k], P.mvw[k], &dmvw_ops_[k]);
+        P.rs_ld[k] = variant(H_.rs[k].ld, {L_.chb, L_.w, L_.s, L_.r, L_.sc});
+        for (int set = 0; set < 2; set++)
+            P.mvw_ld[set][k] = variant(H_.mvw[k].ld, {rhs[set], sol[set], L_.lpv, er[set]});
     }
     // two-job programs: job A = set 0 (rhs1 / sol1), job B = set 1 (rhs2 / sol2)
     P.pair_budget = H_.pair_budget;
@@ -351,10 +366,14 @@ void Engine::upload_values(const Symbolic &S)
     for (int v = 0; v < M_VARIANTS; v++)
     {
         be::h2d(dmv_ops_[v], H_.mv[v].ops.data(), H_.mv[v].ops.size() * sizeof(int), st);
-        be::h2d(drs_ops_[v], H_.rs[v].ops.data(), H_.rs[v].ops.size() * sizeof(int), st);
         be::h2d(dfa_ops_[v], H_.fa[v].ops.data(), H_.fa[v].ops.size() * sizeof(int), st);
     }
     be::h2d(dmv2_ops_, H_.mv2.ops.data(), H_.mv2.ops.size() * sizeof(int), st);
+    for (int k = 0; k < M_MV_PARTS; k++)
+    {
+        be::h2d(drs_ops_[k], H_.rs[k].ops.data(), H_.rs[k].ops.size() * sizeof(int), st);
+        be::h2d(dmvw_ops_[k], H_.mvw[k].ops.data(), H_.mvw[k].ops.size() * sizeof(int), st);
+    }
     be::sync(st);
 }
 
@@ -367,6 +386,8 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
         force_variant_ = std::atoi(v);
     if (const char *v = std::getenv("EICOS_PAIR_SOLVES")) // ... and the form of the paired solves
         force_pair_ = std::atoi(v);
+    if (const char *v = std::getenv("EICOS_WIDE")) // ... and the wide kernels
+        force_wide_ = std::atoi(v);
     stream_ = (void *)(intptr_t)be::make_stream();
     build_layout(S, false);
     upload_pattern(S);
@@ -394,11 +415,23 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
         smem_factor_[v] = machine_smem_doubles(P_.fa_budget, variant_groups(v)) * sizeof(double);
     }
     smem_pair_ = machine_smem_doubles(P_.pair_budget, M_PAIR_GROUPS, 2) * sizeof(double);
+    // one-warp residual kernel: the parts one after the other in one machine; wide kernels: reduction rows + one machine per
+    // warp (the sweeps' machine of warp 0 lies over the same memory: it is idle while the parts run)
+    part_doubles_ = machine_smem_doubles(P_.sw_budget, M_PART_GROUPS);
+    smem_resid_ = part_doubles_ * sizeof(double);
+    smem_wide_ = ((size_t)M_MV_PARTS * KRED * TILE + std::max((size_t)M_MV_PARTS * part_doubles_, machine_smem_doubles(P_.sw_budget, variant_groups(0)))) * sizeof(double);
     smem_common_ = workers_ > 1 ? (size_t)workers_ * KRED * TILE * sizeof(double) : 0;
 #ifndef EICOS_EMU
     {
         if (smem_pair_ > 48 * 1024)
             EI_CUDA(cudaFuncSetAttribute(eicos_solve_kkt_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pair_));
+        if (smem_wide_ > 48 * 1024)
+        {
+            EI_CUDA(cudaFuncSetAttribute(eicos_solve_kkt_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wide_));
+            EI_CUDA(cudaFuncSetAttribute(eicos_residuals_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wide_));
+        }
+        if (smem_resid_ > 48 * 1024)
+            EI_CUDA(cudaFuncSetAttribute(eicos_residuals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_resid_));
         const size_t top_f = std::max(smem_factor_[0], smem_factor_[M_VARIANTS - 1]), top_p = std::max(smem_prog_[0], smem_prog_[M_VARIANTS - 1]);
         if (top_f > 48 * 1024)
             EI_CUDA(cudaFuncSetAttribute(eicos_ldl_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)top_f));
@@ -570,8 +603,11 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
     be::zero(ir_rounds_, 8 * sizeof(unsigned long long), st);
 
     const int threads = workers_ * (LANES == 1 ? 1 : 32), threads1 = LANES == 1 ? 1 : 32;
+    const int threads_wide = M_MV_PARTS * (LANES == 1 ? 1 : 32);
     (void)threads;
     (void)threads1;
+    (void)threads_wide;
+    a.part_doubles = (int)part_doubles_;
 
 #ifndef EICOS_EMU
     // event pool for per-class device timing
@@ -653,6 +689,11 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
                 a.njobs = 1;
                 EI_TIMED(1, EI_LAUNCH(eicos_solve_kkt_pair, tile_solve_kkt<2>, tiles, threads1, smem_pair_, st, a));
             }
+            else if (wide_launch(2 * tiles))
+            {
+                a.variant = 0;
+                EI_TIMED(1, EI_LAUNCH_JOBS(eicos_solve_kkt_wide, tile_solve_kkt<1>, tiles, 2, threads_wide, smem_wide_, st, a));
+            }
             else
                 EI_TIMED(1, EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt<1>, tiles, 2, threads1, smem_prog_[a.variant], st, a));
             stt.solve_launches++;
@@ -663,7 +704,13 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
             a.njobs = 1;
             a.initialize = 0;
             pick(tiles);
-            EI_TIMED(1, EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt<1>, tiles, 1, threads1, smem_prog_[a.variant], st, a));
+            if (wide_launch(tiles))
+            {
+                a.variant = 0;
+                EI_TIMED(1, EI_LAUNCH_JOBS(eicos_solve_kkt_wide, tile_solve_kkt<1>, tiles, 1, threads_wide, smem_wide_, st, a));
+            }
+            else
+                EI_TIMED(1, EI_LAUNCH_JOBS(eicos_solve_kkt, tile_solve_kkt<1>, tiles, 1, threads1, smem_prog_[a.variant], st, a));
             stt.solve_launches++;
             stt.solve_launch_tiles += tiles;
         };
@@ -679,8 +726,10 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
         for (int it = 0; it <= Settings::iter_max + 1; it++)
         {
             be::zero(active_count_, sizeof(unsigned int), st);
-            pick(tiles);
-            EI_TIMED(3, EI_LAUNCH(eicos_residuals, tile_resid, tiles, threads1, smem_prog_[a.variant], st, a));
+            if (wide_launch(tiles))
+                EI_TIMED(3, EI_LAUNCH(eicos_residuals_wide, tile_resid, tiles, threads_wide, smem_wide_, st, a));
+            else
+                EI_TIMED(3, EI_LAUNCH(eicos_residuals, tile_resid, tiles, threads1, smem_resid_, st, a));
             EI_TIMED(4, EI_LAUNCH(eicos_iter_head, tile_head, tiles, threads, smem_common_, st, a));
             stt.resid_launches++, stt.vector_launches++;
             stt.resid_launch_tiles += tiles, stt.vector_launch_tiles += tiles;

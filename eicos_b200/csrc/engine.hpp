@@ -128,13 +128,16 @@ class Engine
     bool compaction_ = true;
     size_t smem_factor_[M_VARIANTS] = {0, 0}, smem_common_ = 0, smem_prog_[M_VARIANTS] = {0, 0}; // factor kernel / vector kernels / solveKKT + residual kernels (per ring variant)
     size_t smem_pair_ = 0; // two-job solveKKT kernel
+    size_t smem_resid_ = 0, smem_wide_ = 0, part_doubles_ = 0; // one-warp residual kernel; wide kernels; one part machine (doubles)
+    int force_wide_ = -1;
+    bool wide_launch(int ctas) const;
     int sms_ = 148, force_variant_ = -1, force_pair_ = -1;
     bool deep_ring(int ctas) const;
     bool pair_solves(int tiles) const;
     std::vector<void *> owned_; // device allocations holding pattern data
     // positions of value arrays that upload_values() rewrites
     double *dxeq_ = nullptr, *dAeq_ = nullptr, *dGeq_ = nullptr;
-    int *dmv_ops_[M_VARIANTS] = {nullptr, nullptr}, *drs_ops_[M_VARIANTS] = {nullptr, nullptr}, *dfa_ops_[M_VARIANTS] = {nullptr, nullptr}, *dmv2_ops_ = nullptr;
+    int *dmv_ops_[M_VARIANTS] = {nullptr, nullptr}, *drs_ops_[M_MV_PARTS] = {nullptr, nullptr, nullptr, nullptr}, *dmvw_ops_[M_MV_PARTS] = {nullptr, nullptr, nullptr, nullptr}, *dfa_ops_[M_VARIANTS] = {nullptr, nullptr}, *dmv2_ops_ = nullptr;
     HostStreams H_;        // host copy of the instruction streams (value streams are rebuilt on updateData)
     std::vector<int> Lp_;  // column pointers of L (debug extraction)
     std::vector<void *> events_;

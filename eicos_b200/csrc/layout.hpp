@@ -115,8 +115,11 @@ struct DevPattern
     // xw2 / dxr2 / e2 (set 1); [set][first solve | refinement round].  The backward sweep of a first solve
     // runs the plain program bwp, a refinement round the accumulating program bw.
     // Every program exists for two depths of the data ring (first index; streams.hpp: M_VARIANT_GROUPS).
-    DevMachine fw[2], bw[2], bwp[2], mv[2], rs[2];
-    const int *fw_ld[2][2][2], *bw_ld[2][2][2], *mv_ld[2][2], *rs_ld[2];
+    DevMachine fw[2], bw[2], bwp[2], mv[2];
+    const int *fw_ld[2][2][2], *bw_ld[2][2][2], *mv_ld[2][2];
+    // computeResiduals, and the refinement residual once more, in 4 independent parts (streams.hpp: M_MV_PARTS)
+    DevMachine rs[4], mvw[4];
+    const int *rs_ld[4], *mvw_ld[2][4]; // mvw_ld: [set][part]
     // two-job programs (both job sets in one pass, shallow ring): [first solve | refinement round]
     DevMachine fw2, bw2, bwp2, mv2;
     const int *fw2_ld[2], *bw2_ld[2], *mv2_ld;

@@ -136,6 +136,21 @@ void matvec_rows(const Symbolic &S, const Layout &L, MatvecRows &R)
             R.crow[zb + S.zk[i]].push_back(L.Gx + S.Gr.v[t]);
         }
 }
+// rows [first, last) of part `part` of `parts`: contiguous stretches of the elimination order with about the same
+// number of entries (the mat-vec rows are independent of each other, so parts can run on different warps)
+void matvec_part(const MatvecRows &R, int part, int parts, size_t &first, size_t &last)
+{
+    std::vector<size_t> weight(R.order.size() + 1, 0);
+    for (size_t k = 0; k < R.order.size(); k++)
+        weight[k + 1] = weight[k] + 2 + R.ent[R.order[k]].size();
+    const auto cut = [&](int q) {
+        const size_t target = weight.back() * (size_t)q / (size_t)parts;
+        return (size_t)(std::lower_bound(weight.begin(), weight.end(), target) - weight.begin());
+    };
+    first = part == 0 ? 0 : std::min(cut(part), R.order.size());
+    last = part + 1 == parts ? R.order.size() : std::min(cut(part + 1), R.order.size());
+}
+
 int mv_kind(const Symbolic &S, int r)
 {
     const int zb = S.n + S.p;
@@ -148,18 +163,21 @@ int mv_kind(const Symbolic &S, int r)
 //   rows of second-order cones stop after the sum (the cone block is applied cone by cone afterwards).
 // The vector x is an external value per row: gathered once, parked in a slot while it has further uses.
 // Selectors: 1 = rhs, 2 = x, 3 = LP scalings, 4 = e (out vector).
-void build_matvec(const Symbolic &S, const Layout &L, MProgram &P, int &mv_rows, bool pim)
+void build_matvec(const Symbolic &S, const Layout &L, MProgram &P, int &mv_rows, bool pim, int part = 0, int parts = 1)
 {
     MatvecRows R;
     matvec_rows(S, L, R);
+    size_t first, last;
+    matvec_part(R, part, parts, first, last);
     const int zb = S.n + S.p;
     const double delta = Settings::deltastat;
     P.keep_loads = true;
     ivec xv(S.N);
     for (int c = 0; c < S.N; c++)
         xv[c] = P.new_value(2, c);
-    for (int r : R.order)
+    for (size_t at = first; at < last; at++)
     {
+        const int r = R.order[at];
         const int kind = mv_kind(S, r);
         std::vector<MOp> row;
         for (size_t q = 0; q < R.ent[r].size(); q++)
@@ -211,10 +229,12 @@ void build_matvec(const Symbolic &S, const Layout &L, MProgram &P, int &mv_rows,
 //   y row:  v = 0 + sum;  PRE;  v -= tau b_i -> out;  FIN (b_i, y_i)
 //   z row:  v = s_i (FIRST: s_i, z_i);  v += sum;  PRE;  v -= tau h_i -> out;  FIN (h_i, z_i)
 // Selectors: 1 = [c | b | h], 2 = [x | y | z], 3 = s, 4 = r (out vector), 5 = scalar rows.
-void build_resid(const Symbolic &S, const Layout &L, MProgram &P, bool pim)
+void build_resid(const Symbolic &S, const Layout &L, MProgram &P, bool pim, int part, int parts)
 {
     MatvecRows R;
     matvec_rows(S, L, R);
+    size_t first, last;
+    matvec_part(R, part, parts, first, last);
     const int zb = S.n + S.p;
     P.keep_loads = true;
     ivec xv(S.N);
@@ -229,8 +249,9 @@ void build_resid(const Symbolic &S, const Layout &L, MProgram &P, bool pim)
         op.dst = tau;
         P.ops.push_back(op);
     }
-    for (int r : R.order)
+    for (size_t at = first; at < last; at++)
     {
+        const int r = R.order[at];
         const int kind = mv_kind(S, r);
         const bool zrow = kind >= MV_Z;
         const int pre = kind == MV_X ? RS_PRE_X : (kind == MV_Y ? RS_PRE_Y : RS_PRE_Z);
@@ -444,12 +465,11 @@ void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, 
                                  " Schur updates per factorisation; limit " + std::to_string(MAX_FACTOR_UPDATES) + ")");
     {
         const int slots = std::max(2, max_sw_slots);
-        MProgram pf, pb, pbp, pm, pr;
+        MProgram pf, pb, pbp, pm;
         build_forward(S, L, pf);
         build_backward(S, L, pb, true);
         build_backward(S, L, pbp, false);
         build_matvec(S, L, pm, H.mv_rows, pim);
-        build_resid(S, L, pr, pim);
         const auto compile = [&](const char *name, const MProgram &p, MachineCode (&c)[M_VARIANTS], int budget, int tune) {
             // (diagnostics) EICOS_SCHED_WINDOW_<name> pins the scheduler window of one program
             const std::string key = std::string("EICOS_SCHED_WINDOW_") + name;
@@ -467,7 +487,24 @@ void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, 
         compile("bw", pb, H.bw, slots, MACHINE_TUNE_SLOTS);
         compile("bwp", pbp, H.bwp, slots, MACHINE_TUNE_SLOTS);
         compile("mv", pm, H.mv, slots, MACHINE_TUNE_SLOTS);
-        compile("rs", pr, H.rs, slots, MACHINE_TUNE_SLOTS);
+        // The rows of a mat-vec do not depend on each other: computeResiduals is compiled as M_MV_PARTS programs over
+        // contiguous stretches of the rows (its fourteen sums are then combined in a fixed order, whichever way the
+        // parts are run), and the refinement residual a second time in that form - for launches with few tiles, where
+        // the parts run on different warps of the CTA, each with a machine of its own (shallow ring).
+        for (int k = 0; k < M_MV_PARTS; k++)
+        {
+            MProgram pr, pw;
+            int rows_unused = 0;
+            build_resid(S, L, pr, pim, k, M_MV_PARTS);
+            build_matvec(S, L, pw, rows_unused, pim, k, M_MV_PARTS);
+            machine_compile(pr, slots, H.rs[k], MACHINE_TUNE_SLOTS, M_PART_GROUPS, 0);
+            machine_compile(pw, slots, H.mvw[k], MACHINE_TUNE_SLOTS, M_PART_GROUPS, 0);
+            if (std::getenv("EICOS_DBG_PROGRAMS"))
+                for (auto nq : {std::make_pair("rs", &H.rs[k]), std::make_pair("mvw", &H.mvw[k])})
+                    std::fprintf(stderr, "machine %s part %d: ops %lld nop %lld bundles %d loads %d far %lld pads %lld spills %lld slots %d window %d\n",
+                                 nq.first, k, nq.second->nops, nq.second->nnop, nq.second->nbundles, nq.second->nld, nq.second->far,
+                                 nq.second->pads, nq.second->spills, nq.second->slot_rows, nq.second->window);
+        }
         // two-job forms: the same operations, every vector operand two rows wide
         {
             const int pslots = std::max(2, std::min(14, max_sw_slots * 14 / 16)); // (14 two-row slots: seven tiles per SM)
@@ -488,8 +525,10 @@ void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, 
         build_factor(S, L, pa, pim);
         compile("fa", pa, H.fa, std::max(2, max_fa_slots), MACHINE_TUNE_FA_SLOTS);
         for (int k = 0; k < M_VARIANTS; k++)
-            for (const MachineCode *q : {&H.fw[k], &H.bw[k], &H.bwp[k], &H.mv[k], &H.rs[k]})
+            for (const MachineCode *q : {&H.fw[k], &H.bw[k], &H.bwp[k], &H.mv[k]})
                 H.sw_slots = std::max(H.sw_slots, q->slot_rows);
+        for (int k = 0; k < M_MV_PARTS; k++)
+            H.sw_slots = std::max(H.sw_slots, std::max(H.rs[k].slot_rows, H.mvw[k].slot_rows));
         H.sw_far = H.fw[0].far + H.bwp[0].far;
         H.fa_slots = std::max(H.fa[0].slot_rows, H.fa[1].slot_rows);
         H.fa_home = H.fa[0].spills + H.fa[0].far;
@@ -502,7 +541,10 @@ void refresh_stream_values(const Symbolic &S, const Layout &L, HostStreams &H, b
     build_streams(S, L, H.workers, std::max(H.sw_budget, 2), std::max(H.fa_budget, 2), fresh, pim);
     std::vector<std::pair<MachineCode *, MachineCode *>> pq = {{&H.mv2, &fresh.mv2}};
     for (int k = 0; k < M_VARIANTS; k++)
-        for (auto q : {std::make_pair(&H.mv[k], &fresh.mv[k]), std::make_pair(&H.rs[k], &fresh.rs[k]), std::make_pair(&H.fa[k], &fresh.fa[k])})
+        for (auto q : {std::make_pair(&H.mv[k], &fresh.mv[k]), std::make_pair(&H.fa[k], &fresh.fa[k])})
+            pq.push_back(q);
+    for (int k = 0; k < M_MV_PARTS; k++)
+        for (auto q : {std::make_pair(&H.rs[k], &fresh.rs[k]), std::make_pair(&H.mvw[k], &fresh.mvw[k])})
             pq.push_back(q);
     for (auto &q : pq)
     { // the mat-vec and factor programs carry the shared coefficients inline

@@ -34,6 +34,8 @@ inline int variant_groups(int v)
     return M_VARIANT_GROUPS[v];
 }
 constexpr int M_PAIR_GROUPS = 3; // ring depth of the two-job programs
+constexpr int M_MV_PARTS = 4;    // the mat-vec programs exist split into this many independent parts (one warp each when tiles are few)
+constexpr int M_PART_GROUPS = 4; // ring depth of those parts
 
 constexpr long long MAX_FACTOR_UPDATES = 20LL * 1000 * 1000; // Schur updates per factorisation a factor program may hold (32 bytes each)
 
@@ -67,7 +69,8 @@ struct HostStreams
     int sw_budget = 0, fa_budget = 0; // slot budgets the programs were compiled with
     // machine programs: forward sweep, backward sweep (accumulating / plain), refinement residual, computeResiduals
     // (index = ring variant, streams.hpp: M_VARIANT_GROUPS)
-    MachineCode fw[M_VARIANTS], bw[M_VARIANTS], bwp[M_VARIANTS], mv[M_VARIANTS], rs[M_VARIANTS];
+    MachineCode fw[M_VARIANTS], bw[M_VARIANTS], bwp[M_VARIANTS], mv[M_VARIANTS];
+    MachineCode rs[M_MV_PARTS], mvw[M_MV_PARTS]; // computeResiduals / the refinement residual in M_MV_PARTS independent parts
     int mv_rows = 0;
     MachineCode fa[M_VARIANTS]; // numeric factorisation
     // two-job programs: the sweeps and the refinement residual for both job sets in one pass (shallow ring)

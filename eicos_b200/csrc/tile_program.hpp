@@ -199,6 +199,7 @@ struct KArgs
     } job[2];
     int njobs, initialize;
     int variant; // which ring depth of the programs this launch runs (streams.hpp: M_VARIANT_GROUPS)
+    int part_doubles; // wide launches: shared memory (doubles) of one warp's machine
     int keep_sticky;
     int pre_equilibrated; // inputs are already divided by the equilibration vectors
     unsigned int *active_count; // device counter: instances still iterating after the head step
@@ -686,7 +687,6 @@ struct Machine
     unsigned ldb;  // shared address of the load-list ring
     unsigned bars; // mbarriers: M_CHUNKS of the ops chunks, then M_LD_CHUNKS of the load-list chunks
     int pl;
-    bool inited;
     // data ring: every lane moves its 16 bytes of a row (cp.async), one commit group per ring group
     const char *Tl;   // tile base + this lane's 16 bytes
     unsigned ring0;   // shared address of ring row 0 (+ lane)
@@ -706,7 +706,6 @@ struct Machine
         ldb = opsb + M_OPS_RING_BYTES;
         bars = ldb + M_LD_RING_BYTES;
         rows = bars + M_BAR_BYTES + 16u * pl;
-        inited = false;
     }
     static __device__ __forceinline__ i4 lds4(unsigned a)
     {
@@ -810,16 +809,11 @@ struct Machine
         static_assert(ROW_BYTES == 512, "ldB / stB address the next row as +512");
         __syncwarp();
         if (pl == 0)
-        {
+        { // (every run invalidates its barriers when it is done, so the memory may be another machine's next time)
             for (int b = 0; b < M_CHUNKS + M_LD_CHUNKS; b++)
-            {
-                if (inited)
-                    mbar_inval(bars + 8u * b);
                 mbar_init(bars + 8u * b, 1);
-            }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        inited = true;
         __syncwarp();
         st(M_ROW_ZERO * ROW_BYTES, vset(0.0));
         st((NR * ROW_BYTES), vset(-0.0));
@@ -1004,6 +998,11 @@ struct Machine
             mbar_wait(bars + 8u * ((unsigned)c % M_CHUNKS), ((unsigned)c / M_CHUNKS) & 1u);
         for (int c = (lgroup + M_LD_CHUNK_GROUPS - 1) / M_LD_CHUNK_GROUPS; c < ld_fetched; c++)
             mbar_wait(bars + 8u * (M_CHUNKS + (unsigned)c % M_LD_CHUNKS), ((unsigned)c / M_LD_CHUNKS) & 1u);
+        __syncwarp();
+        if (pl == 0)
+            for (int b = 0; b < M_CHUNKS + M_LD_CHUNKS; b++)
+                mbar_inval(bars + 8u * b);
+        __syncwarp();
     }
 #endif
 };
@@ -1081,9 +1080,10 @@ struct AbsMaxFin
 };
 
 // e[j] = rhs[j] - Ktrue * x[j], nerr[j] = ||e[j]||_inf per instance.  mvld: the materialised mat-vec load list of this use.
+// set: job set of a one-job solve (selects the load lists of the part programs in a wide launch)
 template <int NR>
 EI_DEV void kkt_residual(const Team &tm, const KArgs &a, Machine &mm, const TileMem &t, const DevMachine &prog, const int *mvld,
-                         const int (&x)[NR], const int (&erow)[NR], bool initialize, vd (&nerr)[NR])
+                         const int (&x)[NR], const int (&erow)[NR], bool initialize, vd (&nerr)[NR], int set = 0)
 {
     const DevPattern &P = a.P;
     const Layout &L = a.L;
@@ -1093,27 +1093,34 @@ EI_DEV void kkt_residual(const Team &tm, const KArgs &a, Machine &mm, const Tile
 #pragma unroll
     for (int j = 0; j < NR; j++)
         nerr[j] = vset(0.0);
-    if (tm.wk == 0 && P.mv_rows > 0)
+    // wide launch (one-job solves only): the rows are split into M_MV_PARTS independent programs, one warp each, every
+    // warp with a machine of its own; max |e| is combined by team_max below (order-independent: same bits as one warp)
+    const bool wide = NR == 1 && tm.nwk >= M_MV_PARTS;
+    if ((wide ? tm.wk < M_MV_PARTS : tm.wk == 0) && P.mv_rows > 0)
     {
         AbsMaxFin<NR> fin;
 #pragma unroll
         for (int j = 0; j < NR; j++)
             fin.nerr[j] = vset(0.0);
+        Machine mw;
+        if (wide)
+            mw.init(tm, tm.pbuf + (size_t)tm.wk * a.part_doubles);
+        Machine &mrun = wide ? mw : mm;
         MRun r;
-        r.prog = prog;
-        r.ld = mvld;
+        r.prog = wide ? P.mvw[tm.wk] : prog;
+        r.ld = wide ? P.mvw_ld[set][tm.wk] : mvld;
         r.Tb = t.Tb;
         r.out = r.out2 = T + (size_t)erow[0] * TILE;
         r.outB = r.out2B = T + (size_t)erow[NR - 1] * TILE;
         r.a_one = initialize;
-        mm.run<MC_CONST | MC_POS | MC_BKEEP | MC_FIN | MC_AONE, NR>(tm, r, fin);
+        mrun.template run<MC_CONST | MC_POS | MC_BKEEP | MC_FIN | MC_AONE, NR>(tm, r, fin);
 #pragma unroll
         for (int j = 0; j < NR; j++)
             nerr[j] = fin.nerr[j];
     }
     if (P.nc > 0)
     {
-        tm.sync(); // (workers > 1) the partial cone rows written by worker 0 are visible
+        tm.sync(); // (workers > 1) the partial cone rows written by the program warps are visible
         for (int c = tm.wk; c < P.nc; c += tm.nwk)
         {
             const int d = EI_LDG(P.cone_dim + c), ks = EI_LDG(P.cone_k + c), qo = EI_LDG(P.cone_q + c);
@@ -1271,7 +1278,7 @@ EI_DEV void tile_solve_kkt(const Team &tm, const KArgs &a, int tile)
     for (;;)
     {
         vd nerr[NR];
-        kkt_residual<NR>(tm, a, mm, t, pmv, mv_ld, sol, erow, init, nerr);
+        kkt_residual<NR>(tm, a, mm, t, pmv, mv_ld, sol, erow, init, nerr, set0);
         EI_PHASE(3);
         bool all_done = true;
 #pragma unroll
@@ -1681,24 +1688,44 @@ EI_DEV void tile_resid(const Team &tm, const KArgs &a, int tile)
     const DevPattern &P = a.P;
     const Layout &L = a.L;
     double *T = t.T;
-    ResidFin fin;
+    // The program exists in M_MV_PARTS independent parts (streams.cpp).  A wide launch (one warp per part, each with a
+    // machine of its own) runs them side by side, a one-warp launch one after the other; the fourteen sums are the
+    // parts' sums added in part order either way, so both launches give the same bits.
+    const bool wide = tm.nwk >= M_MV_PARTS;
+    vd tot[RS_NRED];
     for (int k = 0; k < RS_NRED; k++)
-        fin.r[k] = vset(0.0);
-    if (tm.wk == 0 && P.mv_rows > 0)
-    {
+        tot[k] = vset(0.0);
+    const auto run_part = [&](int part, double *mem) {
+        ResidFin fin;
+        for (int k = 0; k < RS_NRED; k++)
+            fin.r[k] = vset(0.0);
         Machine mm;
-        mm.init(tm, tm.pbuf);
+        mm.init(tm, mem);
         MRun r;
-        r.prog = P.rs[a.variant];
-        r.ld = P.rs_ld[a.variant];
+        r.prog = P.rs[part];
+        r.ld = P.rs_ld[part];
         r.Tb = t.Tb;
         r.out = r.out2 = r.outB = r.out2B = T + (size_t)L.r * TILE;
         r.a_one = false;
         mm.run<MC_CONST | MC_POS | MC_BKEEP | MC_FIN | MC_X3, 1>(tm, r, fin);
+        for (int k = 0; k < RS_NRED; k++)
+            tot[k] = part == 0 || wide ? fin.r[k] : tot[k] + fin.r[k];
+    };
+    if (P.mv_rows > 0)
+    {
+        if (wide)
+        {
+            if (tm.wk < M_MV_PARTS)
+                run_part(tm.wk, tm.pbuf + (size_t)tm.wk * a.part_doubles);
+            team_sum<RS_NRED>(tm, tot); // worker order = part order
+        }
+        else if (tm.wk == 0)
+            for (int part = 0; part < M_MV_PARTS; part++)
+                run_part(part, tm.pbuf);
     }
     if (tm.wk == 0)
         for (int k = 0; k < RS_NRED; k++)
-            ROWD(T, L.sc + S_RED + k) = fin.r[k];
+            ROWD(T, L.sc + S_RED + k) = tot[k];
 }
 
 // ------------------------------------------------------------------ head of an iteration

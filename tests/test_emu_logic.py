@@ -59,17 +59,19 @@ def test_update_data_paths(oracle_mod, emu_lib):
 
 @pytest.mark.parametrize("name,rel", [("update_data_1", 0.05), ("lp_blend", 0.02), ("issue98", 0.01)])
 def test_program_forms_agree_bitwise(oracle_mod, emu_lib, monkeypatch, name, rel):
-    """The engine picks the form of its programs by occupancy - shallow or deep data ring, the two solves of an
-    iteration as two CTAs or as one two-job pass over L.  The forms only differ in where values wait and in how
+    """The engine has several forms of its programs - shallow or deep data ring, the two solves of an iteration as
+    two CTAs or as one two-job pass over L, one warp per tile or (few tiles) four warps with the mat-vec rows split
+    over them.  The forms only differ in where values wait and in how
     many right-hand sides share a record: every instance must come out bit-identical."""
     from eicos_b200.binding import BatchSolver
     from eicos_b200.workloads import perturbed
     P = oracle_mod.load_fixture(name)
     W = perturbed(P, 5, rel=rel, seed=11)
     outs = []
-    for ring, pair in (("0", "0"), ("1", "0"), ("0", "1")):
+    for ring, pair, wide in (("0", "0", "0"), ("1", "0", "0"), ("0", "1", "0"), ("0", "0", "1")):
         monkeypatch.setenv("EICOS_RING_VARIANT", ring)
         monkeypatch.setenv("EICOS_PAIR_SOLVES", pair)
+        monkeypatch.setenv("EICOS_WIDE", wide)
         B = BatchSolver(P, lib=emu_lib, capacity=5)
         outs.append(B.solve(5, hs=W["hs"], bs=W["bs"]))
     for o in outs[1:]:

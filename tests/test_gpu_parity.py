@@ -280,7 +280,8 @@ def test_compaction_is_transparent(oracle_mod, gpu_lib):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,rel", [("update_data_1", 0.05), ("MPC02", None), ("issue98", 0.01)])
 def test_program_forms_agree_bitwise_on_device(oracle_mod, gpu_lib, monkeypatch, name, rel):
-    """Shallow / deep data ring, two CTAs per tile or one two-job pass over L (the engine chooses by occupancy):
+    """Shallow / deep data ring, two CTAs per tile or one two-job pass over L, one warp per tile or four with the
+    mat-vec rows split over them (the engine chooses by occupancy):
     the CUDA kernels must give bit-identical results in every form."""
     from eicos_b200.binding import BatchSolver
     from eicos_b200.workloads import MPC_REL, perturbed
@@ -288,9 +289,10 @@ def test_program_forms_agree_bitwise_on_device(oracle_mod, gpu_lib, monkeypatch,
     batch = 70
     W = perturbed(P, batch, rel=MPC_REL if rel is None else rel, seed=12)
     outs = []
-    for ring, pair in (("0", "0"), ("1", "0"), ("0", "1")):
+    for ring, pair, wide in (("0", "0", "0"), ("1", "0", "0"), ("0", "1", "0"), ("0", "0", "1")):
         monkeypatch.setenv("EICOS_RING_VARIANT", ring)
         monkeypatch.setenv("EICOS_PAIR_SOLVES", pair)
+        monkeypatch.setenv("EICOS_WIDE", wide)
         B = BatchSolver(P, lib=gpu_lib, capacity=batch)
         outs.append(B.solve(batch, hs=W["hs"], bs=W["bs"]))
     for o in outs[1:]:
