@@ -46,6 +46,9 @@ def parse_args():
     ap.add_argument("--workers", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-handles", type=int, default=4,
+                    help="end-to-end arm: handles (one stream and one host thread each) on the device behind eicos_multi_solve; "
+                         "copies of one slice overlap the kernels of the others (1 = eicos_batch_solve on the device arm's handle)")
     return ap.parse_args()
 
 
@@ -243,12 +246,22 @@ def main():
         solver.solve_device(batch, d_Gs=dptr["Gs"], d_As=dptr["As"], d_cs=dptr["cs"], d_hs=dptr["hs"], d_bs=dptr["bs"], d_x=x_d.data_ptr(),
                             d_exit=exit_d.data_ptr(), d_iter=iter_d.data_ptr())
 
+    lib = solver.lib
+    e2e_handles = max(1, args.e2e_handles)
+    multi = []  # the end-to-end arm's handle (built after the device arm has released its workspace)
+
     def step_host():
-        L = solver.lib.L
+        L = lib.L
         import ctypes as C
         dp = C.POINTER(C.c_double)
         hp = {k: (C.cast(v.data_ptr(), dp) if v is not None else None) for k, v in host.items()}
-        solver.lib.check(L.eicos_batch_solve_matrices(
+        if multi:
+            lib.check(L.eicos_multi_solve(
+                multi[0].h, batch, hp["Gs"], hp["As"], hp["cs"], hp["hs"], hp["bs"],
+                C.cast(x_h.data_ptr(), dp), None, None, None,
+                C.cast(exit_h.data_ptr(), C.POINTER(C.c_int)), None))
+            return
+        lib.check(L.eicos_batch_solve_matrices(
             solver.h, batch, hp["Gs"], hp["As"], hp["cs"], hp["hs"], hp["bs"],
             C.cast(x_h.data_ptr(), dp), None, None, None,
             C.cast(exit_h.data_ptr(), C.POINTER(C.c_int)), None))
@@ -258,15 +271,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, collect=None):
+    def timed(fn, steps, collect=None, ev_stream=None):
+        # events on the stream the kernels are launched on (device arm), or - for the synchronous host-buffer calls,
+        # which return when their streams have drained - on torch's current stream
+        ev_stream = ev_stream or stream
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        e0.record(stream)
+        e0.record(ev_stream)
         for _ in range(steps):
             fn()
             if collect is not None:
                 collect(solver.stats())
-        e1.record(stream)
+        e1.record(ev_stream)
         barrier()
         ms = e0.elapsed_time(e1)
         timed.local_ms = ms
@@ -296,15 +312,28 @@ def main():
     # ---- end to end through the C ABI with host buffers
     e2e = None
     if not args.no_e2e:
+        ev_stream = None
+        if e2e_handles > 1:
+            # several handles on THIS device behind one eicos_multi handle: contiguous slices, one stream and one host
+            # thread each, so the H2D / D2H copies of one slice overlap the kernels of the others
+            solver.close()
+            del devb, x_d, exit_d, iter_d
+            torch.cuda.empty_cache()
+            multi.append(eicos_b200.MultiBatchSolver(P, devices=[local] * e2e_handles, capacity=-(-batch // e2e_handles),
+                                                     workers=args.workers, lib=lib, instance_matrices=pim))
+            ev_stream = torch.cuda.current_stream()
         for _ in range(max(1, min(args.warmup, 3))):
             step_host()
-        ms_e = timed(step_host, args.steps)
+        ms_e = timed(step_host, args.steps, ev_stream=ev_stream)
+        what = "pinned host G,A,h,b in" if pim else "pinned host h,b in"
         e2e = {"value": total_batch * args.steps / (ms_e * 1e-3), "unit": "solves/s",
                "h2d_bytes_per_step": int(sum(v.numel() * 8 for v in host.values() if v is not None)),
                "d2h_bytes_per_step": int(batch * (n * 8 + 4)),
                "ms_per_step": ms_e / args.steps,
-               "api": ("eicos_batch_solve_matrices (include/eicos_b200.h): pinned host G,A,h,b in; x and exit flags out" if pim else
-                       "eicos_batch_solve (include/eicos_b200.h): pinned host h,b in; x and exit flags out")}
+               "handles_on_device": e2e_handles,
+               "api": ("eicos_multi_solve (include/eicos_b200.h) over %d handles on the device: %s; x and exit flags out" % (e2e_handles, what)
+                       if e2e_handles > 1 else
+                       ("eicos_batch_solve_matrices" if pim else "eicos_batch_solve") + " (include/eicos_b200.h): " + what + "; x and exit flags out")}
         assert np.array_equal(exit_h.numpy(), exits)
 
     # per-rank step time and iteration counts (the slowest rank sets the job's time: its slowest instance runs the

@@ -33,7 +33,10 @@
 namespace eicos
 {
 
-constexpr int M_U = 4;          // operations per bundle
+#ifndef EICOS_M_U
+#define EICOS_M_U 4
+#endif
+constexpr int M_U = EICOS_M_U; // operations per bundle
 constexpr int M_REC_WORDS = 8;  // 32-byte records
 constexpr int M_BUNDLE_WORDS = M_U * M_REC_WORDS;
 constexpr int M_CHUNK_BUNDLES = 8; // bundles per TMA chunk of the record stream (1 KB)

@@ -175,6 +175,16 @@ void build_matvec(const Symbolic &S, const Layout &L, MProgram &P, int &mv_rows,
     ivec xv(S.N);
     for (int c = 0; c < S.N; c++)
         xv[c] = P.new_value(2, c);
+    // A row is one dependent chain (Eigen's summation order).  A row much longer than the others (a dense column of
+    // G' or A': MPC02 has one of 1 497 entries) would run alone at the end of the program, one operation per bundle;
+    // its operations are spread over the whole program instead, so that the scheduler's look-ahead window always has
+    // the chain's next link next to short rows.  The order inside every row - and so every result - is unchanged.
+    std::vector<std::vector<MOp>> chains; // long rows
+    std::vector<MOp> shorts;              // operations of all other rows, row after row
+    size_t total_ops = 0;
+    for (size_t at = first; at < last; at++)
+        total_ops += R.ent[R.order[at]].size() + 2;
+    const size_t long_row = std::max<size_t>(128, total_ops / 64);
     for (size_t at = first; at < last; at++)
     {
         const int r = R.order[at];
@@ -217,7 +227,38 @@ void build_matvec(const Symbolic &S, const Layout &L, MProgram &P, int &mv_rows,
                 if (kind != MV_ZC)
                     op.flags |= MF_FIN | (FIN_ABSMAX << MF_KIND_SHIFT);
             }
+        }
+        if (row.size() >= long_row)
+            chains.push_back(row);
+        else
+            shorts.insert(shorts.end(), row.begin(), row.end());
+    }
+    {
+        size_t nlong = 0;
+        for (const auto &c : chains)
+            nlong += c.size();
+        // one link of a long row after every `gap` operations of short rows (the long rows one after the other)
+        const size_t gap = nlong ? std::max<size_t>(1, shorts.size() / nlong) : 0;
+        size_t ci = 0, cq = 0, since = 0;
+        const auto link = [&]() {
+            if (ci == chains.size())
+                return false;
+            P.ops.push_back(chains[ci][cq]);
+            if (++cq == chains[ci].size())
+                ci++, cq = 0;
+            return true;
+        };
+        for (const MOp &op : shorts)
+        {
             P.ops.push_back(op);
+            if (gap && ++since >= gap)
+            {
+                since = 0;
+                link();
+            }
+        }
+        while (link())
+        {
         }
     }
     mv_rows = (int)R.order.size();

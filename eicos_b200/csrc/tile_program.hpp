@@ -741,6 +741,12 @@ struct Machine
         asm volatile("mad.wide.s32 %0, %1, 512, %2;" : "=l"(src) : "r"(w), "l"(Tl));
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     }
+    static __device__ __forceinline__ void out_row(const double *base, int w, vd v)
+    { // global row w behind an out base (one IMAD.WIDE for the address, like issue_row)
+        unsigned long long dst;
+        asm volatile("mad.wide.s32 %0, %1, 512, %2;" : "=l"(dst) : "r"(w), "l"(base));
+        asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(v.v[0]), "d"(v.v[1]) : "memory");
+    }
     __device__ __forceinline__ void fetch_ld_chunk()
     { // next chunk of the load list into its ring position
         if (pl == 0)
@@ -788,19 +794,25 @@ struct Machine
         bulk_g2s(opsb + slot * M_CHUNK_BYTES, opsg, M_CHUNK_BYTES, bar);
     }
     static __device__ __forceinline__ void wait_groups(int code)
-    { // machine.hpp: M_WAIT_N.  Predicated waits instead of a jump table: no branch latency in front of the loads.
+    { // machine.hpp: M_WAIT_N.  Called only when code > 0 (most bundles read rows of groups that were waited for
+      // already: one test instead of seven); the shallow ring's codes first.
         static_assert(M_WAIT_N[1] == 0 && M_WAIT_N[2] == 1 && M_WAIT_N[3] == 2 && M_WAIT_N[4] == 3 && M_WAIT_N[5] == 5 &&
                           M_WAIT_N[6] == 8 && M_WAIT_N[7] == 12,
                       "wait codes");
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "setp.eq.s32 p, %0, 3;\n\t@p cp.async.wait_group 2;\n\t"
-                     "setp.eq.s32 p, %0, 2;\n\t@p cp.async.wait_group 1;\n\t"
-                     "setp.eq.s32 p, %0, 1;\n\t@p cp.async.wait_group 0;\n\t"
-                     "setp.eq.s32 p, %0, 4;\n\t@p cp.async.wait_group 3;\n\t"
-                     "setp.eq.s32 p, %0, 5;\n\t@p cp.async.wait_group 5;\n\t"
-                     "setp.eq.s32 p, %0, 6;\n\t@p cp.async.wait_group 8;\n\t"
-                     "setp.eq.s32 p, %0, 7;\n\t@p cp.async.wait_group 12;\n\t}" ::"r"(code)
-                     : "memory");
+        if (code == 3)
+            asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else if (code == 2)
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else if (code == 1)
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        else if (code == 4)
+            asm volatile("cp.async.wait_group 3;" ::: "memory");
+        else if (code == 5)
+            asm volatile("cp.async.wait_group 5;" ::: "memory");
+        else if (code == 6)
+            asm volatile("cp.async.wait_group 8;" ::: "memory");
+        else
+            asm volatile("cp.async.wait_group 12;" ::: "memory");
     }
 
     template <int CFG, int NR, class Fin>
@@ -860,7 +872,8 @@ struct Machine
         for (;;)
         {
             const int ctrl = rb[0].x;
-            wait_groups((ctrl >> MF_WAIT_SHIFT) & 7);
+            if (ctrl & (7 << MF_WAIT_SHIFT))
+                wait_groups((ctrl >> MF_WAIT_SHIFT) & 7);
             // ---- operand loads (A: one row; B, C, x3: one row per job)
             vd a[M_U], b[M_U][NR], c[M_U][NR], x3[M_U][NR];
             int fl[M_U], kf[M_U], w5[M_U];
@@ -973,9 +986,9 @@ struct Machine
                 if (fl[u] & MF_OUT)
                 {
                     const bool second = (CFG & MC_OUT2) && (fl[u] & MF_OUT2);
-                    vstore((second ? r.out2 : r.out) + (size_t)w5[u] * TILE, res[u][0]);
+                    out_row(second ? r.out2 : r.out, w5[u], res[u][0]);
                     if (NR == 2)
-                        vstore((second ? r.out2B : r.outB) + (size_t)w5[u] * TILE, res[u][NR - 1]);
+                        out_row(second ? r.out2B : r.outB, w5[u], res[u][NR - 1]);
                 }
                 if ((CFG & MC_BKEEP) && (fl[u] & MF_BKEEP))
                 {

@@ -18,8 +18,9 @@ for l in sys.stdin:
     tail -2 $OUT/${name}_$B.err
   done
 }
-BATCHES="${BATCHES:-65536}"
-run g3 EICOS_SHALLOW_GROUPS=3
-run g5 EICOS_SHALLOW_GROUPS=5
-run g6 EICOS_SHALLOW_GROUPS=6
-run g3again EICOS_SHALLOW_GROUPS=3
+BATCHES="${BATCHES:-65536 8192}"
+echo "== pytest -m gpu (slice)"; timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "single_instance or batched_perturbed or starved or forms" 2>&1 | tail -5 | tee $OUT/pytest_gpu.txt
+run base EICOS_NO_TRAFFIC_FLAGS=1 EICOS_L2_PREFETCH=0
+run flags EICOS_L2_PREFETCH=0
+run pf EICOS_NO_TRAFFIC_FLAGS=1
+run both X=1
