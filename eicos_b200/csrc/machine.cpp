@@ -234,7 +234,8 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
     };
     // control word of the previous bundle is closed once the next bundle knows how much padding it needs
     long long prev_ctrl_at = -1;
-    int prev_wait = 0;
+    int prev_wait = 0, prev_newg = 0;
+    std::vector<long long> released_at; // control word of the bundle that released ring group g (its refill copies group g + RG)
     const auto close_prev = [&]() {
         if (prev_ctrl_at < 0)
             return;
@@ -242,7 +243,8 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
         if (nrel < 0 || nrel > 31)
             throw std::logic_error("machine: bundle releases too many ring groups");
         released += nrel;
-        out.ops[(size_t)prev_ctrl_at] |= (prev_wait << MF_WAIT_SHIFT) | (nrel << MF_NREL_SHIFT);
+        released_at.resize((size_t)released, prev_ctrl_at);
+        out.ops[(size_t)prev_ctrl_at] |= (prev_wait << MF_WAIT_SHIFT) | (nrel << MF_NREL_SHIFT) | (prev_newg << MF_NEWG_SHIFT);
     };
     // rows an operation pops, given what is in the slots now: (rows of one-use loads, rows of re-reads); the
     // one-use loads of a bundle need at most one alignment pad together, every re-read of a vector one of its own
@@ -449,6 +451,19 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
                 pad_to((first_pop[pb] / M_RING_GROUP + RG) * M_RING_GROUP);
             const MVal &mv = P.vals[v];
             const int word = (mv.home_sel << M_LD_SEL_SHIFT) | mv.home_row;
+            if (pb >= 0)
+            { // the row was written by the program: the refill that copies it (issued by the bundle that released the
+              // group RG places earlier - a bundle behind pb, by the rule above) needs the proxy fence
+                if (rr.vec && npop % NR)
+                    pad_to(npop + 1);
+                for (long long pp = npop; pp < npop + (rr.vec ? NR : 1); pp++)
+                {
+                    const long long g = pp / M_RING_GROUP - RG;
+                    if (g < 0 || g >= (long long)released_at.size())
+                        throw std::logic_error("machine: re-read of a written row in a group nobody refilled");
+                    out.ops[(size_t)released_at[(size_t)g]] |= MF_FENCE;
+                }
+            }
             out.ops[rr.at] = field(rr.vec ? push_vector(word) : push_single(word));
             out.far++;
         }
@@ -526,11 +541,15 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
                 }
         // ---- control: wait for the newest group this bundle reads
         prev_wait = 0;
+        prev_newg = 0;
         if (npop > first_pop[b])
         {
             const int g_need = (int)((npop - 1) / M_RING_GROUP);
             if (g_need > waited_upto)
             {
+                prev_newg = g_need - waited_upto;
+                if (prev_newg > 31)
+                    throw std::logic_error("machine: a bundle opens too many ring groups");
                 const int allowed = RG + released - 1 - g_need;
                 if (allowed < 0 || allowed >= RG)
                     throw std::logic_error("machine: wait depth out of range");
@@ -555,6 +574,7 @@ void compile_with_window(const MProgram &P, int max_slots, int window, int RG, M
         }
         prev_ctrl_at = (long long)rec0 + 4;
         prev_wait = 0;
+        prev_newg = 0;
     }
     close_prev();
     out.ops[(size_t)prev_ctrl_at] |= MF_END;

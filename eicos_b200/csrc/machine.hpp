@@ -70,7 +70,9 @@ constexpr int M_LD_JOB_B = 1 << 30; // the row of the second job's vector (two-j
 //   MF_AONE:  A = 1.0 when the run's `a_one` switch is set (the LP scaling term of the refinement residual
 //             while the scalings are the identity, src/eicos.cpp:1557-1559)
 // bundle control, in the flags of a bundle's first record:
-//   WAIT  code > 0: cp.async.wait_group(M_WAIT_N[code]) before the operand loads
+//   WAIT  code > 0: cp.async.wait_group(M_WAIT_N[code]) before the operand loads (cp.async form of the data ring)
+//   NEWG  ring groups this bundle is the first to read: their mbarriers are waited for (TMA form of the data ring)
+//   FENCE proxy fence in front of this bundle's refills (TMA form)
 //   NREL  ring groups consumed by the end of this bundle: each is refilled with the next group of the load list
 //   END   last bundle
 enum : int
@@ -85,6 +87,11 @@ enum : int
     MF_AONE = 1 << 7,
     MF_KIND_SHIFT = 8, // 4 bits
     MF_X3 = 1 << 12,   // field w6 names a fourth operand row (set by the compiler)
+    // bundle control for the TMA data ring (tile_program.hpp: the rows of a ring group arrive by eight bulk copies
+    // counted on the group's mbarrier):
+    MF_FENCE = 1 << 13,     // the refills at the end of this bundle copy a home row the program itself has written:
+                            // a generic -> async proxy fence goes in front of them
+    MF_NEWG_SHIFT = 19,     // 5 bits: ring groups this bundle is the first to read (it waits for their mbarriers)
     MF_WAIT_SHIFT = 16, // 3 bits
     MF_NREL_SHIFT = 25, // 5 bits
     MF_END = 1 << 24,

