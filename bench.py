@@ -46,9 +46,10 @@ def parse_args():
     ap.add_argument("--workers", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-handles", type=int, default=4,
+    ap.add_argument("--e2e-handles", type=int, default=0,
                     help="end-to-end arm: handles (one stream and one host thread each) on the device behind eicos_multi_solve; "
-                         "copies of one slice overlap the kernels of the others (1 = eicos_batch_solve on the device arm's handle)")
+                         "copies of one slice overlap the kernels of the others (1 = eicos_batch_solve on the device arm's handle; "
+                         "0 = choose: one handle per 16384 instances of this GPU's share, at most 4)")
     return ap.parse_args()
 
 
@@ -247,7 +248,8 @@ def main():
                             d_exit=exit_d.data_ptr(), d_iter=iter_d.data_ptr())
 
     lib = solver.lib
-    e2e_handles = max(1, args.e2e_handles)
+    # (slices below ~16k instances run at the per-tile latency floor: splitting further only adds launches)
+    e2e_handles = args.e2e_handles if args.e2e_handles > 0 else max(1, min(4, batch // 16384))
     multi = []  # the end-to-end arm's handle (built after the device arm has released its workspace)
 
     def step_host():
