@@ -72,7 +72,7 @@ EXPORTS = [
     "eicos_batch_setup", "eicos_batch_setup_ex", "eicos_batch_update_matrices", "eicos_batch_solve",
     "eicos_batch_solve_matrices", "eicos_batch_solve_device", "eicos_batch_solve_matrices_device",
     "eicos_batch_set_timing", "eicos_batch_set_compaction", "eicos_batch_get_stats", "eicos_batch_get_dims", "eicos_batch_get_program_stats", "eicos_batch_get_symbolic",
-    "eicos_batch_debug_init", "eicos_batch_debug_line_search", "eicos_batch_stream", "eicos_batch_cleanup",
+    "eicos_batch_debug_init", "eicos_batch_debug_line_search", "eicos_batch_debug_set_iter_max", "eicos_batch_stream", "eicos_batch_cleanup",
     "eicos_multi_setup", "eicos_multi_solve", "eicos_multi_ngpu", "eicos_multi_slice", "eicos_multi_cleanup",
     "eicos_last_error", "eicos_device_count",
 ]
@@ -145,6 +145,8 @@ class Library:
         L.eicos_batch_get_symbolic.argtypes = [C.c_void_p] + [_ip] * 6
         L.eicos_batch_debug_init.restype = C.c_int
         L.eicos_batch_debug_init.argtypes = [C.c_void_p, C.c_int] + [_dp] * 7 + [_ip]
+        L.eicos_batch_debug_set_iter_max.restype = C.c_int
+        L.eicos_batch_debug_set_iter_max.argtypes = [C.c_void_p, C.c_int]
         L.eicos_batch_debug_line_search.restype = C.c_int
         L.eicos_batch_debug_line_search.argtypes = [C.c_void_p, C.c_int] + [_dp] * 5
         L.eicos_multi_setup.restype = C.c_void_p
@@ -298,6 +300,10 @@ class BatchSolver:
 
     def set_timing(self, on=True):
         self.lib.check(self.lib.L.eicos_batch_set_timing(self.h, int(on)))
+
+    def debug_set_iter_max(self, iter_max):
+        """Test hook: cap the interior-point iterations (0 = the reference's 100)."""
+        self.lib.check(self.lib.L.eicos_batch_debug_set_iter_max(self.h, int(iter_max)))
 
     def set_compaction(self, on=True):
         self.lib.check(self.lib.L.eicos_batch_set_compaction(self.h, int(on)))

@@ -501,6 +501,14 @@ int eicos_batch_debug_line_search(eicos_batch *bt, int batch, const double *lamb
     }
 }
 
+int eicos_batch_debug_set_iter_max(eicos_batch *bt, int iter_max)
+{
+    if (!bt)
+        return fail(EICOS_ERR_INVALID, "null handle");
+    bt->eng->set_iter_max(iter_max > 0 ? std::min(iter_max, (int)Settings::iter_max) : (int)Settings::iter_max);
+    return 0;
+}
+
 // ---------------------------------------------------------------- several devices behind one handle
 struct eicos_multi
 {

@@ -596,6 +596,7 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
     a.out_info = d_info;
     a.out_iinfo = d_iinfo;
     a.keep_sticky = keep_sticky ? 1 : 0;
+    a.iter_max = iter_max_;
     a.pre_equilibrated = pre_equilibrated ? 1 : 0;
     a.active_count = active_count_;
     a.ir_rounds = ir_rounds_;
@@ -723,7 +724,7 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
         kkt_pair(1, J_NIT1, J_NIT2);
         EI_TIMED(2, EI_LAUNCH(eicos_init_point, tile_init_point, tiles, threads, smem_common_, st, a));
 
-        for (int it = 0; it <= Settings::iter_max + 1; it++)
+        for (int it = 0; it <= iter_max_ + 1; it++)
         {
             be::zero(active_count_, sizeof(unsigned int), st);
             if (wide_launch(tiles))

@@ -201,6 +201,7 @@ struct KArgs
     int variant; // which ring depth of the programs this launch runs (streams.hpp: M_VARIANT_GROUPS)
     int part_doubles; // wide launches: shared memory (doubles) of one warp's machine
     int keep_sticky;
+    int iter_max; // Settings::iter_max, or the test hook's cap
     int pre_equilibrated; // inputs are already divided by the equilibration vectors
     unsigned int *active_count; // device counter: instances still iterating after the head step
     unsigned long long *ir_rounds; // device counters: [0] solve rounds executed (tile-rounds), [1..5] cycles per solve_kkt phase
@@ -1907,7 +1908,7 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
                         if (code == EXIT_NOT_CONVERGED)
                             code = EXIT_NUMERICS;
                     }
-                    else if (iter == Settings::iter_max)
+                    else if (iter == a.iter_max)
                     {
                         if (!ws_better(w, best))
                         {

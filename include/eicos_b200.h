@@ -224,6 +224,12 @@ void eicos_multi_cleanup(eicos_multi *mt);
 int eicos_batch_debug_line_search(eicos_batch *bt, int batch, const double *lambda, const double *ds, const double *dz,
                                   const double *scalars, double *alpha);
 
+/* Test hook: cap the interior-point iterations of this handle (the reference's Settings::iter_max, include/eicos.hpp:45,
+ * is a compile-time 100).  A capped solve ends with exit flag -1 (maxit) and the iterate src/eicos.cpp:1082-1106
+ * returns after `iter_max` iterations, which the parity tests compare with a CPU solve under the same cap:
+ * a check of every kernel's result iteration by iteration.  iter_max <= 0 restores the default. */
+int eicos_batch_debug_set_iter_max(eicos_batch *bt, int iter_max);
+
 void *eicos_batch_stream(const eicos_batch *bt); /* cudaStream_t the engine launches on */
 void eicos_batch_cleanup(eicos_batch *bt);
 

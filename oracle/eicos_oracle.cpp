@@ -62,6 +62,10 @@ static const double GAMMA = 0.99, DELTASTAT = 7e-8;
 static const double FEASTOL = 1e-8, ABSTOL = 1e-8, RELTOL = 1e-8;
 static const double FEASTOL_INACC = 1e-4, ABSTOL_INACC = 5e-5, RELTOL_INACC = 5e-5;
 static const int NITREF = 9, EQUIL_ITERS = 3, ITER_MAX = 100;
+// test hook (ora_debug_set_iter_max): a cap on the iterations of every solve in this process, 0 = ITER_MAX.  The
+// reference's iter_max is a compile-time constant (include/eicos.hpp:45); capping it exposes the iterate after k
+// iterations (src/eicos.cpp:1082-1106) to the per-iteration parity tests.
+static int g_debug_iter_max = 0;
 static const double LINSYSACC = 1e-14, IRERRFACT = 6, STEPMIN = 1e-6, STEPMAX = 0.999;
 static const double SIGMAMIN = 1e-4, SIGMAMAX = 1.0, SAFEGUARD = 500;
 
@@ -1675,7 +1679,7 @@ struct Solver
         w.i.step_aff = 0.;
         w.i.pinf = false;
         w.i.dinf = false;
-        w.i.iter_max = ITER_MAX;
+        w.i.iter_max = g_debug_iter_max > 0 ? g_debug_iter_max : ITER_MAX;
         double pres_prev = std::numeric_limits<double>::max();
 
         for (w.i.iter = 0; w.i.iter <= w.i.iter_max; w.i.iter++)
@@ -2014,6 +2018,8 @@ void ora_debug_get_data(void *sv, double *Gpr, double *Apr, double *c, double *h
     if (b)
         std::copy(S->b.begin(), S->b.end(), b);
 }
+
+void ora_debug_set_iter_max(int iter_max) { ora::g_debug_iter_max = iter_max > 0 ? (iter_max < ora::ITER_MAX ? iter_max : ora::ITER_MAX) : 0; }
 
 double ora_batch_run(int n, int m, int p, int l, int ncones, const int *q,
                      const double *Gpr, const int *Gjc, const int *Gir,

@@ -81,6 +81,9 @@ void ora_debug_get_data(void *solver, double *Gpr, double *Apr, double *c, doubl
  * reference Solver would (they are never cleared there, src/eicos.cpp:720-728).
  * Returns wall seconds spent in the update+solve loop (construction excluded).
  */
+/* test hook: cap the interior-point iterations of every later solve in this process (0 = the reference's 100) */
+void ora_debug_set_iter_max(int iter_max);
+
 double ora_batch_run(int n, int m, int p, int l, int ncones, const int *q,
                      const double *Gpr, const int *Gjc, const int *Gir,
                      const double *Apr, const int *Ajc, const int *Air,

@@ -89,8 +89,15 @@ def lib():
         L.ora_batch_run.restype = C.c_double
         L.ora_batch_run.argtypes = ([C.c_int] * 5 + [_ip, _dp, _ip, _ip, _dp, _ip, _ip, _dp, _dp, _dp] +
                                     [C.c_int] + [_dp] * 5 + [C.c_int, C.c_int] + [_ip, _ip] + [_dp] * 5)
+        L.ora_debug_set_iter_max.restype = None
+        L.ora_debug_set_iter_max.argtypes = [C.c_int]
         _lib = L
     return _lib
+
+
+def debug_set_iter_max(iter_max):
+    """Test hook: cap the iterations of every later solve (0 restores the reference's 100)."""
+    lib().ora_debug_set_iter_max(int(iter_max))
 
 
 def load_fixture(name):

@@ -355,3 +355,53 @@ def test_multi_device_handle_matches_single(oracle_mod, emu_lib, parts):
     many = M.solve(batch, hs=W["hs"], bs=W["bs"])
     for k in ("x", "y", "z", "s", "exit", "iter"):
         assert np.array_equal(one[k], many[k]), k
+
+
+def iterates_after_k(oracle_mod, lib, name, rel, batch, caps, soc=False):
+    """Both engines capped at k interior-point iterations (test hooks eicos_batch_debug_set_iter_max /
+    ora_debug_set_iter_max: the reference's iter_max is a compile-time constant): the iterate src/eicos.cpp:1082-1106
+    returns after k iterations must agree.  Every kernel's output feeds the next iteration, so this checks the
+    factorisation, the solves with their refinement, the line searches, the scalings and the bookkeeping iteration
+    by iteration, not only at the end.  Returns the largest relative deviation seen."""
+    from eicos_b200.binding import BatchSolver
+    from eicos_b200.workloads import perturbed, soc_mpc, soc_mpc_batch
+    if soc:
+        P = soc_mpc(T=6)
+        W = soc_mpc_batch(P, batch, seed=5)
+    else:
+        P = oracle_mod.load_fixture(name)
+        W = perturbed(P, batch, rel=rel, seed=3)
+    kw = {k: W[k] for k in ("cs", "hs", "bs") if W.get(k) is not None}
+    bs = BatchSolver(P, lib=lib, capacity=batch)
+    worst = 0.0
+    try:
+        for k in caps:
+            bs.debug_set_iter_max(k)
+            oracle_mod.debug_set_iter_max(k)
+            out = bs.solve(batch, **kw)
+            ref = oracle_mod.batch_run(P, batch, nthreads=2, **kw)
+            assert np.array_equal(out["exit"], ref["exit"]), (k, out["exit"], ref["exit"])
+            assert np.array_equal(out["iter"], ref["iter"]), (k, out["iter"], ref["iter"])
+            for v in "xyzs":
+                if ref[v].size:
+                    worst = max(worst, relerr(out[v], ref[v]))
+            pc = np.array([i["pcost"] for i in out["info"]])
+            worst = max(worst, float(np.max(np.abs(pc - ref["pcost"]) / np.maximum(1.0, np.abs(ref["pcost"])))))
+    finally:
+        oracle_mod.debug_set_iter_max(0)
+        bs.debug_set_iter_max(0)
+    return worst
+
+
+@pytest.mark.parametrize("name,rel,batch", [("update_data_1", 0.05, 5), ("lp_afiro", 0.02, 4), ("lp_blend", 0.02, 3),
+                                            ("MPC02", {"h": 0.002, "b": 0.02}, 3)])
+def test_iterates_agree_after_k_iterations(oracle_mod, emu_lib, name, rel, batch):
+    worst = iterates_after_k(oracle_mod, emu_lib, name, rel, batch, (1, 2, 3, 4, 6, 9))
+    print("\n%s: largest relative deviation of x, y, z, s, pcost over the capped solves: %.2e" % (name, worst))
+    assert worst <= 1e-9
+
+
+def test_iterates_agree_after_k_iterations_soc(oracle_mod, emu_lib):
+    worst = iterates_after_k(oracle_mod, emu_lib, None, None, 4, (1, 2, 3, 5, 8), soc=True)
+    print("\nSOC MPC: largest relative deviation over the capped solves: %.2e" % worst)
+    assert worst <= 1e-9

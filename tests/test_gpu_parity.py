@@ -504,3 +504,23 @@ def test_multi_gpu_handle_matches_single(oracle_mod, gpu_lib):
         assert np.array_equal(one[k], many[k]), k
     ref = oracle_mod.batch_run(P, batch, hs=W["hs"], bs=W["bs"], nthreads=8)
     assert np.array_equal(many["exit"], ref["exit"]) and np.array_equal(many["iter"], ref["iter"])
+
+
+# ---------------------------------------------------------------- iteration by iteration
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,rel,batch", [("update_data_1", 0.05, 70), ("lp_afiro", 0.02, 40), ("MPC02", {"h": 0.002, "b": 0.02}, 96)])
+def test_iterates_agree_after_k_iterations(oracle_mod, gpu_lib, name, rel, batch):
+    """Engine and oracle capped at k = 1, 2, 3, 4, 6, 9 interior-point iterations: the iterates they return agree
+    (tests/test_emu_logic.py::iterates_after_k) - every kernel checked through its effect on the next iteration."""
+    from test_emu_logic import iterates_after_k
+    worst = iterates_after_k(oracle_mod, gpu_lib, name, rel, batch, (1, 2, 3, 4, 6, 9))
+    print("\n%s x%d: largest relative deviation of x, y, z, s, pcost over the capped solves: %.2e" % (name, batch, worst))
+    assert worst <= 1e-9
+
+
+@pytest.mark.gpu
+def test_iterates_agree_after_k_iterations_soc(oracle_mod, gpu_lib):
+    from test_emu_logic import iterates_after_k
+    worst = iterates_after_k(oracle_mod, gpu_lib, None, None, 70, (1, 2, 3, 5, 8), soc=True)
+    print("\nSOC MPC x70: largest relative deviation over the capped solves: %.2e" % worst)
+    assert worst <= 1e-9
