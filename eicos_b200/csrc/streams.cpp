@@ -159,7 +159,7 @@ int mv_kind(const Symbolic &S, int r)
 
 // ---- residual of the iterative refinement  e = rhs - Ktrue x  (src/eicos.cpp:1511-1576), LP part:
 //   row r:  v = rhs_r - sum_k coefficient_k x_k;  x rows: v -= delta x_r;  y rows: v += delta x_r;
-//   LP z rows: v += delta x_r, v += w_r^2 x_r (x_r alone while the scalings are the identity: MF_AONE);
+//   LP z rows: v += delta x_r, v -= (-w_r^2) x_r (the scalings row holds -w^2, -1 while the scalings are the identity);
 //   rows of second-order cones stop after the sum (the cone block is applied cone by cone afterwards).
 // The vector x is an external value per row: gathered once, parked in a slot while it has further uses.
 // Selectors: 1 = rhs, 2 = x, 3 = LP scalings, 4 = e (out vector).
@@ -207,9 +207,8 @@ void build_matvec(const Symbolic &S, const Layout &L, MProgram &P, int &mv_rows,
         if (kind == MV_Z)
         {
             MOp op;
-            op.a = MSrc::load(3, r - zb);
+            op.a = MSrc::load(3, r - zb); // (the row holds -w^2, and -1 during the initial solves: no MF_POS, no MF_AONE)
             op.b = MSrc::value(xv[r]);
-            op.flags |= MF_POS | MF_AONE;
             row.push_back(op);
         }
         if (row.empty())

@@ -1188,8 +1188,8 @@ EI_DEV void kkt_residual(const Team &tm, const KArgs &a, Machine &mm, const Tile
         r.Tb = t.Tb;
         r.out = r.out2 = T + (size_t)erow[0] * TILE;
         r.outB = r.out2B = T + (size_t)erow[NR - 1] * TILE;
-        r.a_one = initialize;
-        mrun.template run<MC_CONST | MC_POS | MC_BKEEP | MC_FIN | MC_AONE, NR>(tm, r, fin);
+        r.a_one = false;
+        mrun.template run<MC_CONST | MC_BKEEP | MC_FIN, NR>(tm, r, fin);
 #pragma unroll
         for (int j = 0; j < NR; j++)
             nerr[j] = fin.nerr[j];
@@ -1465,6 +1465,10 @@ EI_DEV void tile_init(const Team &tm, const KArgs &a, int tile)
         const int kind = EI_LDG(P.Vkind + k);
         ROWD(T, L.V + k) = kind == 0 ? -1.0 : (kind == 1 ? 0.0 : 1.0);
     }
+    // the LP scalings as the refinement residual reads them: MINUS w^2 (the mat-vec program then needs neither a sign
+    // flag nor a special case for the identity scalings of the initial solves, src/eicos.cpp:1557-1559)
+    for (int k = tm.wk; k < P.l; k += tm.nwk)
+        ROWD(T, L.lpv + k) = -1.0;
     // rhs1 = [0; b; h], rhs2 = [-c; 0; 0]; resx0.. = max(1, ||c||), ... (:865-894)
     vd nr[3] = {vset(0.0), vset(0.0), vset(0.0)};
     vd mx[2] = {vset(0.0), vset(0.0)}; // max |rhs1|, max |rhs2| (solveKKT's stopping threshold, src/eicos.cpp:1590)
@@ -2034,7 +2038,7 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
         ew_rows<2, 6>(tm, T, P.l, ins, [&](int k, const vd *x) {
             const vd v = x[0] / x[1];
             const vd w = vsqrt(v);
-            ROWD(T, L.lpv + k) = v;
+            ROWD(T, L.lpv + k) = -v;
             ROWD(T, L.lpw + k) = w;
             ROWD(T, L.V + k) = -v - Settings::deltastat; // updateKKTScalings, LP part (:1696-1699)
             ROWD(T, L.lam + k) = w * x[1];                // scale(): lambda = W z
@@ -2045,11 +2049,11 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
         const int ins[5] = {L.s, sz, L.lpv, L.lpw, L.lam};
         ew_rows<5, 2>(tm, T, P.l, ins, [&](int k, const vd *x) {
             const vd v = x[0] / x[1];
-            const vd vn = vsel(cont, v, x[2]);
+            const vd nvn = vsel(cont, -v, x[2]); // (lpv holds -w^2)
             const vd wn = vsel(cont, vsqrt(v), x[3]);
-            ROWD(T, L.lpv + k) = vn;
+            ROWD(T, L.lpv + k) = nvn;
             ROWD(T, L.lpw + k) = wn;
-            ROWD(T, L.V + k) = -vn - Settings::deltastat;
+            ROWD(T, L.V + k) = nvn - Settings::deltastat;
             ROWD(T, L.lam + k) = vsel(cont, wn * x[1], x[4]);
         });
     }
@@ -2058,10 +2062,10 @@ EI_DEV void tile_head(const Team &tm, const KArgs &a, int tile)
         const int ins[4] = {L.s, sz, L.lpv, L.lpw};
         ew_rows<4, 3>(tm, T, P.l, ins, [&](int k, const vd *x) {
             const vd v = x[0] / x[1];
-            const vd vn = vsel(cont, v, x[2]);
-            ROWD(T, L.lpv + k) = vn;
+            const vd nvn = vsel(cont, -v, x[2]); // (lpv holds -w^2)
+            ROWD(T, L.lpv + k) = nvn;
             ROWD(T, L.lpw + k) = vsel(cont, vsqrt(v), x[3]);
-            ROWD(T, L.V + k) = -vn - Settings::deltastat; // updateKKTScalings, LP part (:1696-1699)
+            ROWD(T, L.V + k) = nvn - Settings::deltastat; // updateKKTScalings, LP part (:1696-1699)
         });
     }
     vb nofail = vbset(true);
