@@ -327,7 +327,7 @@ def main():
         for _ in range(max(1, min(args.warmup, 3))):
             step_host()
         ms_e = timed(step_host, args.steps, ev_stream=ev_stream)
-        what = "pinned host G,A,h,b in" if pim else "pinned host h,b in"
+        what = "pinned host " + ",".join(k[:-1] for k in ("Gs", "As", "cs", "hs", "bs") if host[k] is not None) + " in"
         e2e = {"value": total_batch * args.steps / (ms_e * 1e-3), "unit": "solves/s",
                "h2d_bytes_per_step": int(sum(v.numel() * 8 for v in host.values() if v is not None)),
                "d2h_bytes_per_step": int(batch * (n * 8 + 4)),
