@@ -163,7 +163,9 @@ eicos_batch *eicos_batch_setup_ex(int n, int m, int p, int l, int ncones, const 
         }
         be::set_device(device);
         if (capacity <= 0)
-        {
+        { // default: what fits 80 % of the free device memory; -r: that divided by r (r handles share the device)
+            const long long share = capacity < 0 ? -capacity : 1;
+            (void)share;
             capacity = 4096;
 #ifndef EICOS_EMU
             size_t fr = 0, tot = 0;
@@ -172,7 +174,7 @@ eicos_batch *eicos_batch_setup_ex(int n, int m, int p, int l, int ncones, const 
             const double per_inst = 8.0 * (2.0 * S.nnzL + 13.0 * S.N + 12.0 * S.m + 4.0 * S.n + 4.0 * S.p + 2.0 * S.l +
                                            S.Vslot.size() + 8.0 * S.nc + S.qtot + S_COUNT + J_COUNT +
                                            (pim ? (double)S.G.nnz() + S.A.nnz() + S.N : 0.0));
-            capacity = (long long)(0.80 * (double)fr / std::max(per_inst, 8.0));
+            capacity = (long long)(0.80 * (double)fr / std::max(per_inst, 8.0)) / share;
             capacity = std::max<long long>(32, std::min<long long>(capacity, 1 << 20));
             capacity -= capacity % 32;
 #endif
@@ -537,8 +539,17 @@ eicos_multi *eicos_multi_setup(int n, int m, int p, int l, int ncones, const int
     std::unique_ptr<eicos_multi> mt(new eicos_multi());
     for (int k = 0; k < ngpu; k++)
     {
+        // default capacity on a device that is listed r times: 1 / r of what fits it, taken while its first handle is built
+        long long cap_k = capacity;
+        if (capacity <= 0 && devices)
+        {
+            int later = 0;
+            for (int j = k; j < ngpu; j++)
+                later += devices[j] == devices[k];
+            cap_k = -(long long)later; // (the earlier handles of this device have taken their share of the free memory already)
+        }
         eicos_batch *bt = eicos_batch_setup_ex(n, m, p, l, ncones, q, Gpr, Gjc, Gir, Apr, Ajc, Air, c, h, b,
-                                               devices ? devices[k] : k, capacity, workers, flags);
+                                               devices ? devices[k] : k, cap_k, workers, flags);
         if (!bt)
         { // g_error says why
             for (eicos_batch *o : mt->part)

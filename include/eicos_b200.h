@@ -203,7 +203,9 @@ int eicos_batch_debug_init(eicos_batch *bt, int batch, const double *cs, const d
  * across instances anywhere in src/eicos.cpp:848-1262), so the batch is cut into contiguous slices, one per
  * device; every device gets its own eicos_batch (symbolic data and programs replicated, ~1 MB) and its own host
  * thread; results land in the caller's buffers by per-device copies - no collective.
- * devices: ngpu CUDA ordinals, or NULL for 0 .. ngpu-1.  capacity: instances resident per device (0 = default). */
+ * devices: ngpu CUDA ordinals, or NULL for 0 .. ngpu-1; an ordinal may be listed several times: every mention is a
+ * slice with its own stream, staging buffers and host thread, so that the copies of one slice overlap the kernels
+ * of the others.  capacity: instances resident per slice (0 = default: an equal share of what fits the device). */
 typedef struct eicos_multi eicos_multi;
 eicos_multi *eicos_multi_setup(int n, int m, int p, int l, int ncones, const int *q,
                                const double *Gpr, const int *Gjc, const int *Gir,

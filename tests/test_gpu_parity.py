@@ -506,6 +506,23 @@ def test_multi_gpu_handle_matches_single(oracle_mod, gpu_lib):
     assert np.array_equal(many["exit"], ref["exit"]) and np.array_equal(many["iter"], ref["iter"])
 
 
+@pytest.mark.gpu
+def test_several_handles_on_one_device_default_capacity(oracle_mod, gpu_lib):
+    """A device listed three times with the default capacity: every mention takes an equal share of what fits the
+    device (include/eicos_b200.h), and the slices give what one handle gives, bit for bit."""
+    from eicos_b200.binding import BatchSolver, MultiBatchSolver
+    from eicos_b200.workloads import perturbed
+    P = oracle_mod.load_fixture("update_data_1")
+    batch = 200
+    W = perturbed(P, batch, rel=0.05, seed=33)
+    one = BatchSolver(P, lib=gpu_lib, capacity=batch).solve(batch, hs=W["hs"], bs=W["bs"])
+    M = MultiBatchSolver(P, devices=[0, 0, 0], capacity=0, lib=gpu_lib)
+    many = M.solve(batch, hs=W["hs"], bs=W["bs"])
+    for k in ("x", "y", "z", "s", "exit", "iter"):
+        assert np.array_equal(one[k], many[k]), k
+    M.close()
+
+
 # ---------------------------------------------------------------- iteration by iteration (SURVEY.md section 7 step 4)
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,rel,batch", [("update_data_1", 0.05, 70), ("lp_afiro", 0.02, 40), ("MPC02", {"h": 0.002, "b": 0.02}, 96)])
