@@ -126,9 +126,18 @@ int Engine::tile_width() { return TILE; }
 // option and as a parity check of the two-job machine).
 bool Engine::pair_solves(int) const { return force_pair_ > 0; }
 
-// The deep-ring programs are an option (EICOS_RING_VARIANT = 1): on B200 a deeper ring measured no faster at any
-// batch (the program warps are bound by their instruction stream, not by memory latency).
-bool Engine::deep_ring(int) const { return force_variant_ > 0; }
+// Ring depth of a launch.  The bytes ONE tile has in flight bound its pace when few tiles share an SM (a sweep of
+// MPC02 copies 11 MB per tile through a ring of 12 KB: 12 KB per memory latency); with the machine full the shallow
+// ring's smaller footprint (9 tiles per SM instead of 6) wins (65 536 instances: 41.0 k solves/s at 3 groups, 37.6 k at
+// 5 or 6).  Measured crossover: every launch deep gains 5.7 % at 16 384 instances (512 CTAs in the paired solve) and
+// loses 4.5 % at 32 768 (1 024 CTAs), so a launch takes the deep programs when it has at most four CTAs per SM; the
+// wide launches always do for their sweeps.  EICOS_RING_VARIANT = 0 / 1 pins the choice for every launch.
+bool Engine::deep_ring(int ctas) const
+{
+    if (force_variant_ >= 0)
+        return force_variant_ > 0;
+    return (long long)ctas <= 4LL * sms_;
+}
 
 // A launch with few CTAs (all resident at the wide kernels' shared-memory footprint) runs the wide kernels: four warps
 // per CTA, the rows of the mat-vec programs split over them.  EICOS_WIDE = 0 / 1 pins the choice.
@@ -309,8 +318,8 @@ void Engine::upload_pattern(const Symbolic &S)
         { // forward: 1 = right-hand side, 3 = xw; backward: 1 = output, 2 = accumulated solution, 3 = xw
             P.fw_ld[v][set][0] = variant(H_.fw[v].ld, {rhs[set], 0, xw[set]});
             P.fw_ld[v][set][1] = variant(H_.fw[v].ld, {er[set], 0, xw[set]});
-            P.bw_ld[v][set][0] = variant(H_.bwp[v].ld, {sol[set], 0, xw[set]});
-            P.bw_ld[v][set][1] = variant(H_.bw[v].ld, {dxr[set], sol[set], xw[set]});
+            P.bw_ld[v][set][0] = variant(H_.bwp[v].ld, {sol[set], 0, xw[set], rhs[set]});
+            P.bw_ld[v][set][1] = variant(H_.bw[v].ld, {dxr[set], sol[set], xw[set], er[set]});
             P.mv_ld[v][set] = variant(H_.mv[v].ld, {rhs[set], sol[set], L_.lpv, er[set]});
         }
         P.fa_ld[v] = variant(H_.fa[v].ld, {});
@@ -332,8 +341,8 @@ void Engine::upload_pattern(const Symbolic &S)
     prog(H_.mv2, P.mv2, &dmv2_ops_);
     P.fw2_ld[0] = variant(H_.fw2.ld, {rhs[0], 0, xw[0]}, {rhs[1], 0, xw[1]});
     P.fw2_ld[1] = variant(H_.fw2.ld, {er[0], 0, xw[0]}, {er[1], 0, xw[1]});
-    P.bw2_ld[0] = variant(H_.bwp2.ld, {sol[0], 0, xw[0]}, {sol[1], 0, xw[1]});
-    P.bw2_ld[1] = variant(H_.bw2.ld, {dxr[0], sol[0], xw[0]}, {dxr[1], sol[1], xw[1]});
+    P.bw2_ld[0] = variant(H_.bwp2.ld, {sol[0], 0, xw[0], rhs[0]}, {sol[1], 0, xw[1], rhs[1]});
+    P.bw2_ld[1] = variant(H_.bw2.ld, {dxr[0], sol[0], xw[0], er[0]}, {dxr[1], sol[1], xw[1], er[1]});
     P.mv2_ld = variant(H_.mv2.ld, {rhs[0], sol[0], L_.lpv, er[0]}, {rhs[1], sol[1], L_.lpv, er[1]});
     P.mv_rows = H_.mv_rows;
     ivec vk;
@@ -419,7 +428,9 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
     // warp (the sweeps' machine of warp 0 lies over the same memory: it is idle while the parts run)
     part_doubles_ = machine_smem_doubles(P_.sw_budget, M_PART_GROUPS);
     smem_resid_ = part_doubles_ * sizeof(double);
-    smem_wide_ = ((size_t)M_MV_PARTS * KRED * TILE + std::max((size_t)M_MV_PARTS * part_doubles_, machine_smem_doubles(P_.sw_budget, variant_groups(0)))) * sizeof(double);
+    smem_wide_ = ((size_t)M_MV_PARTS * KRED * TILE +
+                  std::max((size_t)M_MV_PARTS * part_doubles_, machine_smem_doubles(P_.sw_budget, std::max(variant_groups(0), variant_groups(M_VARIANTS - 1))))) *
+                 sizeof(double);
     smem_common_ = workers_ > 1 ? (size_t)workers_ * KRED * TILE * sizeof(double) : 0;
 #ifndef EICOS_EMU
     {
@@ -692,7 +703,7 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
             }
             else if (wide_launch(2 * tiles))
             {
-                a.variant = 0;
+                a.variant = force_variant_ == 0 ? 0 : M_VARIANTS - 1; // (the sweeps of warp 0: deep ring)
                 EI_TIMED(1, EI_LAUNCH_JOBS(eicos_solve_kkt_wide, tile_solve_kkt<1>, tiles, 2, threads_wide, smem_wide_, st, a));
             }
             else
@@ -707,7 +718,7 @@ void Engine::solve(int batch, const double *d_c, const double *d_h, const double
             pick(tiles);
             if (wide_launch(tiles))
             {
-                a.variant = 0;
+                a.variant = force_variant_ == 0 ? 0 : M_VARIANTS - 1; // (the sweeps of warp 0: deep ring)
                 EI_TIMED(1, EI_LAUNCH_JOBS(eicos_solve_kkt_wide, tile_solve_kkt<1>, tiles, 1, threads_wide, smem_wide_, st, a));
             }
             else

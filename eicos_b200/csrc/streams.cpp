@@ -24,18 +24,22 @@ void build_forward(const Symbolic &S, const Layout &L, MProgram &P)
     for (int i = 0; i < S.N; i++)
     {
         const int t0 = S.Lr.p[i], cnt = S.Lr.p[i + 1] - t0;
+        if (cnt == 0)
+        { // a row of L without entries: xw_i IS the right-hand side entry (rhs - 0 * 0 leaves every bit, -0 included).
+          // No operation and no copy: whoever reads xw_i - later rows here, the backward sweep's first product -
+          // reads the right-hand side instead (MPC02: 3 497 of 5 991 rows, 22 % of the sweep's operations).
+            xval[i] = P.new_value(1, S.pinv[i]);
+            continue;
+        }
         int prev = -1;
-        for (int q = 0; q < std::max(cnt, 1); q++)
+        for (int q = 0; q < cnt; q++)
         {
             MOp op;
             op.c = q == 0 ? MSrc::load(1, S.pinv[i]) : MSrc::value(prev);
-            if (cnt > 0)
-            {
-                op.a = MSrc::load(0, L.Lx + S.Lr.v[t0 + q]);
-                op.b = MSrc::value(xval[S.Lr.j[t0 + q]]);
-            }
+            op.a = MSrc::load(0, L.Lx + S.Lr.v[t0 + q]);
+            op.b = MSrc::value(xval[S.Lr.j[t0 + q]]);
             op.dst = prev = P.new_value(3, i);
-            if (q == std::max(cnt, 1) - 1)
+            if (q == cnt - 1)
             {
                 op.flags |= MF_OUT;
                 op.out_row = i;
@@ -50,7 +54,7 @@ void build_forward(const Symbolic &S, const Layout &L, MProgram &P)
 // order); results land in KKT order.  Column k:  v = (1/d_k) xw_k;  v -= L(i,k) x_i for the rows of the
 // column; out[pinv k] = v.  accumulate: the last operation of a column also hands the row of the accumulated
 // solution to the finish functor (x += v for the instances that continue refining).
-// Selectors: 1 = output vector, 2 = accumulated solution, 3 = xw.
+// Selectors: 1 = output vector, 2 = accumulated solution, 3 = xw, 4 = the right-hand side of the forward sweep.
 void build_backward(const Symbolic &S, const Layout &L, MProgram &P, bool accumulate)
 {
     ivec xval(S.N, -1);
@@ -65,7 +69,8 @@ void build_backward(const Symbolic &S, const Layout &L, MProgram &P, bool accumu
             { // Eigen: diag.inverse() * x  (a product: 1/d * xw + (-0))
                 op.c = MSrc::negzero();
                 op.a = MSrc::load(0, L.Dinv + k);
-                op.b = MSrc::load(3, k);
+                // (a row of L without entries has no xw: the forward sweep left its right-hand side entry in place)
+                op.b = S.Lr.p[k + 1] == S.Lr.p[k] ? MSrc::load(4, S.pinv[k]) : MSrc::load(3, k);
                 op.flags |= MF_POS;
             }
             else

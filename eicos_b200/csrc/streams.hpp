@@ -24,7 +24,7 @@ namespace eicos
 // tiles per SM share the memory latency), the deep one when there are few tiles per SM and the bytes ONE
 // tile has in flight are what bounds its speed.
 constexpr int M_VARIANTS = 2;
-constexpr int M_VARIANT_GROUPS[M_VARIANTS] = {3, 16};
+constexpr int M_VARIANT_GROUPS[M_VARIANTS] = {3, 5}; // (measured on B200: 5, 6, 8 and 10 groups are equally good for few tiles, 16 is not)
 // (diagnostics) EICOS_SHALLOW_GROUPS overrides the depth of the shallow ring
 inline int variant_groups(int v)
 {
@@ -43,7 +43,8 @@ constexpr long long MAX_FACTOR_UPDATES = 20LL * 1000 * 1000; // Schur updates pe
 // Load-list selectors (bits 28.. of a load-list word; materialised into absolute tile rows per use):
 //   0 = absolute row of the tile (L, 1/D, per-instance matrix values, scalar rows)
 //   forward:   1 = right-hand side (KKT order), 3 = work vector xw (the program's out vector)
-//   backward:  1 = output vector (the program's out vector), 2 = accumulated solution, 3 = xw
+//   backward:  1 = output vector (the program's out vector), 2 = accumulated solution, 3 = xw, 4 = the forward sweep's
+//              right-hand side (rows of L without entries have no xw: build_forward)
 //   mat-vec:   1 = vector of the row's start value (rhs), 2 = operand vector, 3 = LP scalings, 4 = out vector e
 //   residuals: 1 = [c | b | h], 2 = iterate [x | y | z], 3 = s, 4 = out vector r, 5 = scalar rows
 //   factor:    0 only (the out base is the tile base)

@@ -32,7 +32,9 @@ def test_mpc02_program_is_slot_resident(oracle_mod, emu_lib):
     assert ps["fa_loads"] == nnzV
     assert N + nnzL <= ps["fw_loads"] <= N + nnzL + ps["sw_far"]
     assert 3 * N + nnzL <= ps["bw_loads"] <= 3 * N + nnzL + ps["sw_far"]
-    assert ps["sw_far"] <= 0.15 * nnzL
+    # (rows of L without entries are read from the right-hand side wherever they are used - build_forward - which
+    #  trades the 3 497 copies of MPC02's forward sweep for ~5 000 re-reads)
+    assert ps["sw_far"] <= 0.6 * nnzL
 
 
 @pytest.mark.parametrize("name,sw,fa", [("update_data_1", 3, 2), ("update_data_1", 2, 2), ("lp_afiro", 3, 4),
