@@ -130,13 +130,18 @@ bool Engine::pair_solves(int) const { return force_pair_ > 0; }
 // MPC02 copies 11 MB per tile through a ring of 12 KB: 12 KB per memory latency); with the machine full the shallow
 // ring's smaller footprint (9 tiles per SM instead of 6) wins (65 536 instances: 41.0 k solves/s at 3 groups, 37.6 k at
 // 5 or 6).  Measured crossover: every launch deep gains 5.7 % at 16 384 instances (512 CTAs in the paired solve) and
-// loses 4.5 % at 32 768 (1 024 CTAs), so a launch takes the deep programs when it has at most four CTAs per SM; the
-// wide launches always do for their sweeps.  EICOS_RING_VARIANT = 0 / 1 pins the choice for every launch.
+// loses 4.5 % at 32 768 (1 024 CTAs: two waves at the deep footprint), so a launch takes the deep programs when all
+// its CTAs are resident with them; the wide launches always do for their sweeps.  EICOS_RING_VARIANT = 0 / 1 pins the choice for every launch.
 bool Engine::deep_ring(int ctas) const
 {
     if (force_variant_ >= 0)
         return force_variant_ > 0;
-    return (long long)ctas <= 4LL * sms_;
+    // ... when all of its CTAs are resident at the deep programs' footprint (MPC02: six per SM; measured 4 / 5 / 6 per
+    // SM: 44.29 k / 44.30 k / 44.50 k solves/s at 65 536 instances, 39.96 k / 40.04 k / 40.36 k at 49 152)
+    long long per_sm = (long long)((size_t)227 * 1024 / (smem_prog_[M_VARIANTS - 1] + 1024));
+    if (const char *v = std::getenv("EICOS_DEEP_CTAS_PER_SM")) // (diagnostics)
+        per_sm = std::atoi(v);
+    return (long long)ctas <= per_sm * sms_;
 }
 
 // A launch with few CTAs (all resident at the wide kernels' shared-memory footprint) runs the wide kernels: four warps
