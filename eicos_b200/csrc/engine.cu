@@ -425,7 +425,9 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
     // program kernels (one warp per tile): the shared memory of the FMA machine; vector kernels: reduction rows only
     for (int v = 0; v < M_VARIANTS; v++)
     {
-        smem_prog_[v] = machine_smem_doubles(P_.sw_budget, variant_groups(v)) * sizeof(double);
+        // (the programs of a variant share one machine: its slots are the largest budget among them)
+        const int sw_v = std::max(std::max(H_.fw[v].slot_budget, H_.bw[v].slot_budget), std::max(H_.bwp[v].slot_budget, H_.mv[v].slot_budget));
+        smem_prog_[v] = machine_smem_doubles(sw_v, variant_groups(v)) * sizeof(double);
         smem_factor_[v] = machine_smem_doubles(P_.fa_budget, variant_groups(v)) * sizeof(double);
     }
     smem_pair_ = machine_smem_doubles(P_.pair_budget, M_PAIR_GROUPS, 2) * sizeof(double);
@@ -434,7 +436,7 @@ Engine::Engine(const Symbolic &S, int device, long long capacity_instances, int 
     part_doubles_ = machine_smem_doubles(P_.sw_budget, M_PART_GROUPS);
     smem_resid_ = part_doubles_ * sizeof(double);
     smem_wide_ = ((size_t)M_MV_PARTS * KRED * TILE +
-                  std::max((size_t)M_MV_PARTS * part_doubles_, machine_smem_doubles(P_.sw_budget, std::max(variant_groups(0), variant_groups(M_VARIANTS - 1))))) *
+                  std::max((size_t)M_MV_PARTS * part_doubles_, std::max(smem_prog_[0], smem_prog_[M_VARIANTS - 1]) / sizeof(double))) *
                  sizeof(double);
     smem_common_ = workers_ > 1 ? (size_t)workers_ * KRED * TILE * sizeof(double) : 0;
 #ifndef EICOS_EMU

@@ -515,23 +515,27 @@ void build_streams(const Symbolic &S, const Layout &L, int W, int max_sw_slots, 
         build_backward(S, L, pb, true);
         build_backward(S, L, pbp, false);
         build_matvec(S, L, pm, H.mv_rows, pim);
-        const auto compile = [&](const char *name, const MProgram &p, MachineCode (&c)[M_VARIANTS], int budget, int tune) {
+        // deep = slots of the deeper-ring variants (k >= 1): those run few tiles per SM, where shared memory is free
+        // (MPC02 with 32 instead of 16 slots: the mat-vec copies 18.0 k instead of 25.7 k rows per pass)
+        const auto compile = [&](const char *name, const MProgram &p, MachineCode (&c)[M_VARIANTS], int budget, int tune, int deep = 0) {
             // (diagnostics) EICOS_SCHED_WINDOW_<name> pins the scheduler window of one program
             const std::string key = std::string("EICOS_SCHED_WINDOW_") + name;
             const char *v = std::getenv(key.c_str());
             machine_compile(p, budget, c[0], tune, variant_groups(0), v ? std::max(M_U, std::atoi(v)) : 0);
             for (int k = 1; k < M_VARIANTS; k++) // same order of operations, deeper ring
-                machine_compile(p, budget, c[k], tune, variant_groups(k), c[0].window);
+                machine_compile(p, deep > 0 ? deep : budget, c[k], tune, variant_groups(k), c[0].window);
             if (std::getenv("EICOS_DBG_PROGRAMS"))
                 for (int k = 0; k < M_VARIANTS; k++)
                     std::fprintf(stderr, "machine %s[%d]: ops %lld nop %lld bundles %d loads %d far %lld pads %lld spills %lld slots %d window %d\n",
                                  name, k, c[k].nops, c[k].nnop, c[k].nbundles, c[k].nld, c[k].far, c[k].pads, c[k].spills, c[k].slot_rows,
                                  c[k].window);
         };
-        compile("fw", pf, H.fw, slots, MACHINE_TUNE_SLOTS);
-        compile("bw", pb, H.bw, slots, MACHINE_TUNE_SLOTS);
-        compile("bwp", pbp, H.bwp, slots, MACHINE_TUNE_SLOTS);
-        compile("mv", pm, H.mv, slots, MACHINE_TUNE_SLOTS);
+        // (a budget pinned from the environment - the tests starve the slots on purpose - holds for every variant)
+        const int deep_slots = std::getenv("EICOS_MAX_SW_SLOTS") ? slots : 2 * slots;
+        compile("fw", pf, H.fw, slots, MACHINE_TUNE_SLOTS, deep_slots);
+        compile("bw", pb, H.bw, slots, MACHINE_TUNE_SLOTS, deep_slots);
+        compile("bwp", pbp, H.bwp, slots, MACHINE_TUNE_SLOTS, deep_slots);
+        compile("mv", pm, H.mv, slots, MACHINE_TUNE_SLOTS, deep_slots);
         // The rows of a mat-vec do not depend on each other: computeResiduals is compiled as M_MV_PARTS programs over
         // contiguous stretches of the rows (its fourteen sums are then combined in a fixed order, whichever way the
         // parts are run), and the refinement residual a second time in that form - for launches with few tiles, where

@@ -25,7 +25,7 @@ def test_mpc02_program_is_slot_resident(oracle_mod, emu_lib):
     B = BatchSolver(P, lib=emu_lib, capacity=1)
     ps, d = B.program_stats(), B.dims()
     assert ps["fa_fast"] == 1 and ps["fa_home"] == 0 and ps["sw_direct"] == 0
-    assert ps["sw_slots"] <= 24 and ps["fa_slots"] <= 32
+    assert ps["sw_slots"] <= 32 and ps["fa_slots"] <= 32  # (the deeper-ring variants get twice the 16 slots)
     N, nnzL, nnzV = d["dim_K"], d["nnzL"], d["nnzV"]
     # HBM reads per run = the algorithmic minimum plus the re-reads of values that lost their slot
     # (the operands of the one dense row); sw_far counts the forward and the plain backward sweep
